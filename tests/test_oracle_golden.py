@@ -1,0 +1,284 @@
+"""Pins the CPU oracle against every known-answer fixture the reference's own tests hold for the
+Matcher+Solver path. Each test names the reference test it ports.
+
+CPU-only (`-m "not gpu"`).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as orc
+from tests import icp_harness
+from tests.fixtures import (
+    pt2pl_fixture_global,
+    pt2pt_fixture_global,
+    two_local_points,
+)
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+DEG = np.pi / 180.0
+
+
+# ---------------------------------------------------------------------------------------------
+# tests/test-mp2p_matcher_pt2pt.cpp:26-107 — exact (localIdx, globalIdx) for 3 poses + identity
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize(
+    "pose,expected",
+    [
+        ((0, 0, 0, 0, 0, 0), []),  # :68-74
+        ((0, 5, 0, 0, 0, 0), [(0, 0)]),  # :78-86  (localIdx, globalIdx)
+        ((-2, 5, 0, 0, 0, 0), [(1, 0)]),  # :88-96
+        ((8.5, -1.0, 1, 45 * DEG, 0, 0), [(1, 19)]),  # :98-107
+    ],
+)
+def test_matcher_pt2pt_known_answers(pose, expected):
+    gx, gy, gz = pt2pt_fixture_global()
+    lx, ly, lz = two_local_points()
+    tree = orc.KDTree(gx, gy, gz)
+    prm = orc.MatchPt2PtParams(threshold=1.05, thresholdAngularDeg=0.001)
+    pairs, pot = orc.match_pt2pt(tree, lx, ly, lz, orc.pose_from_xyzypr(*pose), prm)
+    assert [(int(p["localIdx"]), int(p["globalIdx"])) for p in pairs] == expected
+    assert pot == 2
+
+
+# ---------------------------------------------------------------------------------------------
+# tests/test-mp2p_matcher_pt2pl.cpp:29-168 (DISABLED upstream, tests/CMakeLists.txt:37): the only
+# known answers that exist for pt2pl matching.
+# ---------------------------------------------------------------------------------------------
+PT2PL_PRM = dict(distanceThreshold=0.1, searchRadius=0.1, minimumPlanePoints=5, knn=5, planeEigenThreshold=0.1)
+
+
+def test_matcher_pt2pl_known_answers():
+    gx, gy, gz = pt2pl_fixture_global()
+    lx, ly, lz = two_local_points()
+    tree = orc.KDTree(gx, gy, gz)
+    prm = orc.MatchPt2PlParams(**PT2PL_PRM)
+
+    pairs, _ = orc.match_pt2pl(tree, lx, ly, lz, orc.pose_from_xyzypr(0, 0, 0), prm)
+    assert len(pairs) == 0  # :85-91
+
+    pairs, _ = orc.match_pt2pl(tree, lx, ly, lz, orc.pose_from_xyzypr(0, 5, 0), prm)
+    assert len(pairs) == 1  # :93-100
+
+    pairs, _ = orc.match_pt2pl(tree, lx, ly, lz, orc.pose_from_xyzypr(8.04, 0, 0), prm)
+    assert len(pairs) == 1  # :102-123
+    p0 = pairs[0]
+    np.testing.assert_allclose(p0["local"], [2.0, 0.0, 0.0], atol=1e-3)
+    np.testing.assert_allclose(p0["centroid"], [10.0, 0.0, 0.0], atol=0.01)
+    np.testing.assert_allclose(p0["coefs"], [1.0, 0.0, 0.0, -10.0], atol=1e-3)
+
+    pairs, _ = orc.match_pt2pl(tree, lx, ly, lz, orc.pose_from_xyzypr(18.053, 0.05, 0.03), prm)
+    assert len(pairs) == 0  # :125-131
+
+
+@pytest.mark.parametrize("allow,expected_total", [(True, 2), (False, 1)])
+def test_matcher_pt2pl_then_pt2pt_pipeline(allow, expected_total):
+    """:133-168 — run_matchers({pt2pl, pt2pt}) sharing one MatchState (Matcher.cpp:46-88)."""
+    gx, gy, gz = pt2pl_fixture_global()
+    lx, ly, lz = two_local_points()
+    tree = orc.KDTree(gx, gy, gz)
+    T = orc.pose_from_xyzypr(8.04, 0, 0)
+    local_paired = np.zeros(2, np.uint8)
+    global_paired = np.zeros(tree.n, np.uint8)
+    p2l, _ = orc.match_pt2pl(tree, lx, ly, lz, T, orc.MatchPt2PlParams(**PT2PL_PRM), local_paired)
+    p2p, _ = orc.match_pt2pt(
+        tree, lx, ly, lz, T,
+        orc.MatchPt2PtParams(threshold=0.1, thresholdAngularDeg=0.0, allowMatchAlreadyMatchedPoints=allow),
+        local_paired, global_paired,
+    )
+    assert len(p2l) == 1
+    assert len(p2l) + len(p2p) == expected_total
+
+
+# ---------------------------------------------------------------------------------------------
+# tests/test-mp2p_optimize_pt2pl.cpp:36-128 — GN on 3 pt2pl + 1 pt2pt recovers 15 GT poses (1e-3)
+# ---------------------------------------------------------------------------------------------
+GT_POSES_PT2PL = [
+    (0, 0, 0, 0, 0, 0), (1, 0, 0, 0, 0, 0), (0, 1, 0, 0, 0, 0), (0, 0, 1, 0, 0, 0),
+    (-2, 0, 0, 0, 0, 0), (0, -3, 0, 0, 0, 0), (0, 0, -4, 0, 0, 0),
+    (0, 0, 0, 20 * DEG, 0, 0), (0, 0, 0, -20 * DEG, 0, 0),
+    (0, 0, 0, 0, 10 * DEG, 0), (0, 0, 0, 0, -10 * DEG, 0),
+    (0, 0, 0, 0, 0, 15 * DEG), (0, 0, 0, 0, 0, -15 * DEG),
+    (1, 2, 3, 0, 0, 0), (1, 2, 3, -10 * DEG, 5 * DEG, 30 * DEG),
+]
+
+
+def _inv_compose_point(T, g):
+    T = np.asarray(T).reshape(3, 4)
+    return T[:, :3].T @ (np.asarray(g, float) - T[:, 3])
+
+
+def make_pt2pl_case(gt):
+    p2l = np.zeros(3, orc.PAIR_PT2PL)
+    for k, (normal, g) in enumerate([((0, 0, 1), (0.5, 0, 0)), ((1, 0, 0), (0, 0.8, 0)), ((0, 1, 0), (0, 0, 0.3))]):
+        p2l[k]["coefs"] = [*normal, 0.0]  # TPlane::FromPointAndNormal({0,0,0}, n)
+        p2l[k]["centroid"] = 0
+        p2l[k]["local"] = _inv_compose_point(gt, g).astype(np.float32)
+    p2p = np.zeros(1, orc.PAIR_PT2PT)
+    p2p[0]["global"] = 0
+    p2p[0]["local"] = _inv_compose_point(gt, (0, 0, 0)).astype(np.float32)
+    return p2p, p2l
+
+
+@pytest.mark.parametrize("gt", GT_POSES_PT2PL)
+def test_gn_pt2pl_known_answers(gt):
+    GT = orc.pose_from_xyzypr(*gt)
+    p2p, p2l = make_pt2pl_case(GT)
+    ok, T, _ = orc.optimal_tf_gauss_newton(p2p, p2l, orc.GNParams(maxInnerLoopIterations=25), np.eye(3, 4))
+    assert ok
+    assert np.linalg.norm(orc.se3_log(orc.inverse_compose(T, GT))) < 1e-3
+
+
+# tests/test-mp2p_optimize_with_prior.cpp:38-52,81-89 — case 0 (no prior): 3 pt2pt pairings
+def test_gn_pt2pt_no_prior_known_answer():
+    GT = orc.pose_from_xyzypr(1.0, 2.0, 3.0, -10 * DEG, 5 * DEG, 30 * DEG)
+    p2p = np.zeros(3, orc.PAIR_PT2PT)
+    for k, g in enumerate(np.eye(3)):
+        p2p[k]["global"] = g
+        p2p[k]["local"] = _inv_compose_point(GT, g).astype(np.float32)
+    ok, T, _ = orc.optimal_tf_gauss_newton(p2p, None, orc.GNParams(maxInnerLoopIterations=25), np.eye(3, 4))
+    assert ok
+    assert np.linalg.norm(orc.se3_log(orc.inverse_compose(T, GT))) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# tests/test-mp2p_error_terms_jacobians.cpp:45-102,186-252 — analytic J vs finite differences
+# on D*exp(eps), step 1e-6, tolerance 1e-5, 1000 random draws, seed 1234.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", [0, 1])
+def test_jacobians_vs_finite_differences(kind):
+    rng = np.random.default_rng(1234)
+    for _ in range(1000):
+        D = orc.pose_from_xyzypr(*rng.normal(0, 10, 3), rng.uniform(-np.pi, np.pi), *rng.uniform(-np.pi / 2, np.pi / 2, 2))
+        if kind == 0:
+            pair = np.zeros(1, orc.PAIR_PT2PT)
+            pair["global"] = rng.normal(0, 20, 3)
+            pair["local"] = rng.normal(0, 20, 3)
+        else:
+            pair = np.zeros(1, orc.PAIR_PT2PL)
+            n = rng.normal(0, 1, 3)
+            n /= np.linalg.norm(n)
+            c = rng.normal(0, 20, 3)
+            pair["coefs"] = [*n, -n @ c]
+            pair["centroid"] = c
+            pair["local"] = rng.normal(0, 20, 3)
+        _, J = orc.error_and_jacobian(kind, pair, D)
+        num = np.zeros((3, 6))
+        for a in range(6):
+            ep, em = np.zeros(6), np.zeros(6)
+            ep[a], em[a] = 1e-6, -1e-6
+            e_p, _ = orc.error_and_jacobian(kind, pair, orc.compose(D, orc.se3_exp(ep)))
+            e_m, _ = orc.error_and_jacobian(kind, pair, orc.compose(D, orc.se3_exp(em)))
+            num[:, a] = (e_p - e_m) / 2e-6
+        assert np.abs(num - J).max() < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# tests/test-mp2p_optimal_tf_algos.cpp:49-63,112-157,285,369-377 — Horn on random pairings with
+# sigma_xyz = 1 mm noise: SO(3) error < min(1, 0.2 + 10*sigma_xyz + 50*sigma_n) (outlier-free).
+# We also check the far stronger property that the noiseless case is exact.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [3, 4, 10, 100, 1000])
+def test_horn_random_pairings(n):
+    rng = np.random.default_rng(1234 + n)
+    for sigma in (0.0, 1e-3):
+        A = rng.uniform(0, 50, (n, 3))
+        gt = orc.pose_from_xyzypr(*rng.uniform(-1, 1, 3), *(rng.uniform(-5, 5, 3) * DEG))
+        B = (A - gt[:, 3]) @ gt[:, :3] + rng.normal(0, sigma, (n, 3)) if sigma else (A - gt[:, 3]) @ gt[:, :3]
+        pairs = np.zeros(n, orc.PAIR_PT2PT)
+        pairs["globalIdx"] = pairs["localIdx"] = np.arange(n)
+        pairs["global"], pairs["local"] = A, B
+        ok, T = orc.optimal_tf_horn(pairs)
+        assert ok
+        err = orc.se3_log(orc.inverse_compose(T, gt))
+        if sigma == 0.0:
+            assert np.linalg.norm(err) < 2e-4  # float32 storage of the pairings
+        else:
+            assert np.linalg.norm(err[3:]) < min(1.0, 0.2 + 10 * sigma)
+
+
+def test_horn_needs_three_pairings():
+    pairs = np.zeros(2, orc.PAIR_PT2PT)  # optimal_tf_horn.cpp:96
+    ok, _ = orc.optimal_tf_horn(pairs)
+    assert not ok
+
+
+# ---------------------------------------------------------------------------------------------
+# tests/test-mp2p_icp_algos.cpp:85-108,161-169,187-223 — full ICP::align on bunny / buddha:
+# GT pose within +-15 % bbox and +-10 deg, threshold = 0.40*max_dim, thresholdAngularDeg = 0,
+# maxIterations 100, identity guess; assert |log(GT - est)| < 0.1.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model", ["bunny_decim.xyz.gz", "happy_buddha_decim.xyz.gz"])
+@pytest.mark.parametrize("solver", ["horn", "gn"])
+def test_icp_align_protocol(model, solver):
+    x, y, z = icp_harness.load_xyz_gz(os.path.join(GOLD, model))
+    x, y, z = x[::10], y[::10], z[::10]  # decimation 10 (:250-262)
+    P = np.stack([x, y, z], 1).astype(np.float64)
+    size = P.max(0) - P.min(0)
+    rng = np.random.default_rng(1234)
+    tree = orc.KDTree(x, y, z)
+    for _ in range(3):
+        gt = orc.pose_from_xyzypr(*(rng.uniform(-0.15, 0.15, 3) * size), *(rng.uniform(-10, 10, 3) * DEG))
+        L = ((P - gt[:, 3]) @ gt[:, :3]).astype(np.float32)  # changeCoordinatesReference(pts, -gt)
+        lx, ly, lz = (np.ascontiguousarray(L[:, k]) for k in range(3))
+        prm = orc.MatchPt2PtParams(threshold=0.40 * size.max(), thresholdAngularDeg=0.0)
+
+        def match(pose, it):
+            return orc.match_pt2pt(tree, lx, ly, lz, pose, prm, nthreads=4)[0]
+
+        def solve(pairs, guess, it):
+            if solver == "horn":
+                return orc.optimal_tf_horn(pairs)
+            ok, T, _ = orc.optimal_tf_gauss_newton(pairs, None, orc.GNParams(maxInnerLoopIterations=6), guess)
+            return ok, T
+
+        res = icp_harness.align(match, solve, np.eye(3, 4), icp_harness.IcpParams(maxIterations=100))
+        assert np.linalg.norm(orc.se3_log(orc.inverse_compose(res.pose, gt))) < 0.1
+
+
+# ---------------------------------------------------------------------------------------------
+# Oracle-internal cross checks (SURVEY §4 plan item 2): KD-tree == brute force == scipy cKDTree
+# ---------------------------------------------------------------------------------------------
+def test_kdtree_matches_bruteforce_and_scipy():
+    from scipy.spatial import cKDTree
+
+    rng = np.random.default_rng(7)
+    M = rng.uniform(0, 20, (20000, 3)).astype(np.float32)
+    Q = rng.uniform(-1, 21, (2000, 3)).astype(np.float32)
+    tree = orc.KDTree(M[:, 0], M[:, 1], M[:, 2])
+    for k, r2 in [(1, np.inf), (5, np.inf), (8, 1.5), (3, 0.05)]:
+        i1, d1, f1 = tree.knn(Q[:, 0], Q[:, 1], Q[:, 2], k, r2)
+        i2, d2, f2 = tree.knn(Q[:, 0], Q[:, 1], Q[:, 2], k, r2, bruteforce=True)
+        assert np.array_equal(f1, f2)
+        for q in range(len(Q)):
+            assert np.array_equal(i1[q, : f1[q]], i2[q, : f1[q]])
+            assert np.array_equal(d1[q, : f1[q]], d2[q, : f1[q]])
+    # scipy (float64 metric): identical 1-NN except float32-rounding near-ties
+    i1, _, _ = tree.knn(Q[:, 0], Q[:, 1], Q[:, 2], 1)
+    _, isp = cKDTree(M.astype(np.float64)).query(Q.astype(np.float64), k=1)
+    assert (i1[:, 0] != isp).sum() <= 2
+
+
+def test_kdtree_ties_lowest_index_wins():
+    # duplicate points: nanoflann's winner is traversal dependent (unpinned); ours is the lowest index
+    x = np.array([1, 1, 1, 5, 1], np.float32)
+    tree = orc.KDTree(x, np.zeros(5, np.float32), np.zeros(5, np.float32), leaf_max=1)
+    i, d, f = tree.knn(np.array([1.0]), np.array([0.0]), np.array([0.0]), 3)
+    assert list(i[0]) == [0, 1, 2] and f[0] == 3
+
+
+def test_transform_is_double_then_float():
+    """Matcher_Points_Base.cpp:216 — composePoint(float...) computes in double, rounds once."""
+    rng = np.random.default_rng(3)
+    l = rng.normal(0, 50, (1000, 3)).astype(np.float32)
+    T = orc.pose_from_xyzypr(3.3, -7.1, 0.4, 0.7, -0.2, 0.1)
+    gx, gy, gz, bmin, bmax = orc.transform_local_to_global(l[:, 0], l[:, 1], l[:, 2], T)
+    ref = (l.astype(np.float64) @ T[:, :3].T + T[:, 3])
+    # numpy's matmul may reassociate; allow 1 ulp but require exact equality for the explicit formula
+    exp = np.empty_like(ref)
+    for r in range(3):
+        exp[:, r] = ((T[r, 0] * l[:, 0].astype(np.float64) + T[r, 1] * l[:, 1].astype(np.float64)) + T[r, 2] * l[:, 2].astype(np.float64)) + T[r, 3]
+    assert np.array_equal(np.stack([gx, gy, gz], 1), exp.astype(np.float32))
+    assert np.allclose(ref, exp)
+    assert np.array_equal(bmin, exp.astype(np.float32).min(0)) and np.array_equal(bmax, exp.astype(np.float32).max(0))
