@@ -1,0 +1,248 @@
+/* mp2p_b200.h — C ABI of the B200-native mp2p_icp Matcher+Solver hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, `int` status codes, no
+ * exceptions, no torch / MRPT types. The C++ plugin classes that derive from the reference's
+ * `mp2p_icp::Matcher_Points_Base` / `mp2p_icp::Solver` (mp2p_icp_b200/host/mrpt_plugin.cpp, built
+ * only where MRPT exists) and the MRPT-free host mirror (mp2p_icp_b200/host/) call exactly these
+ * entry points. Every entry point names the reference interface it replaces (paths relative to the
+ * reference checkout).
+ *
+ * Conventions
+ *  - poses: `double[12]`, row-major 3x4 [R | t]  (mrpt::poses::CPose3D rotation + translation).
+ *  - `*_on_device` flags: 0 = the pointer is HOST memory (pinned memory is DMA'd directly, pageable
+ *    memory goes through the CUDA staging path), 1 = the pointer is DEVICE memory on the context's
+ *    GPU (lets a caller keep pairings resident between matcher and solver).
+ *  - return value: 0 = MP2P_B200_OK, negative = error; text via mp2p_b200_last_error().
+ *  - There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    MP2P_B200_ERR_CUDA.
+ */
+#ifndef MP2P_B200_H
+#define MP2P_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MP2P_B200_OK 0
+#define MP2P_B200_ERR_ARG (-1)
+#define MP2P_B200_ERR_CUDA (-2)
+#define MP2P_B200_ERR_CAPACITY (-3)
+#define MP2P_B200_ERR_NOMEM (-4)
+
+#define MP2P_B200_MAX_KNN 32
+
+typedef struct mp2p_b200_ctx mp2p_b200_ctx; /* one per (process, GPU): stream + scratch */
+typedef struct mp2p_b200_map mp2p_b200_map; /* device-resident global layer + NN index   */
+
+/* mrpt::tfest::TMatchingPair — 36 bytes, the element of Pairings::paired_pt2pt
+ * (fields written at mp2p_icp/src/Matcher_Points_DistanceThreshold.cpp:106-113). */
+#pragma pack(push, 1)
+typedef struct
+{
+    uint32_t globalIdx, localIdx;
+    float    global_x, global_y, global_z;
+    float    local_x, local_y, local_z; /* ORIGINAL (untransformed) local point */
+    float    errorSquareAfterTransformation;
+} mp2p_b200_pair_pt2pt;
+#pragma pack(pop)
+
+/* mp2p_icp::point_plane_pair_t — 72 bytes, the element of Pairings::paired_pt2pl
+ * (mp2p_icp_map/include/mp2p_icp/point_plane_pair_t.h:34-38, plane_patch.h:30-34). */
+typedef struct
+{
+    double plane_coefs[4]; /* TPlane: A x + B y + C z + D = 0, unit normal */
+    double centroid[3];
+    float  local_x, local_y, local_z; /* ORIGINAL local point */
+    float  _pad;
+} mp2p_b200_pair_pt2pl;
+
+/* Parameters of Matcher_Points_DistanceThreshold (+ Matcher_Points_Base):
+ * mp2p_icp/src/Matcher_Points_DistanceThreshold.cpp:39-46, Matcher_Points_Base.cpp:132-181. */
+typedef struct
+{
+    double   threshold;
+    double   thresholdAngularDeg;
+    uint32_t pairingsPerPoint;
+    int32_t  allowMatchAlreadyMatchedPoints;
+    int32_t  allowMatchAlreadyMatchedGlobalPoints;
+    double   bounding_box_intersection_check_epsilon; /* default 0.20 */
+} mp2p_b200_pt2pt_params;
+
+/* Parameters of Matcher_Point2Plane (mp2p_icp/src/Matcher_Point2Plane.cpp:35-39) plus the
+ * plane-fit parameters of the NearestPlaneCapable implementation over a point layer
+ * (names from tests/test-mp2p_matcher_pt2pl.cpp:74-81; definition SURVEY.md §8a-7'). */
+typedef struct
+{
+    double   distanceThreshold;
+    double   searchRadius;
+    uint32_t knn;
+    uint32_t minimumPlanePoints;
+    double   planeEigenThreshold;
+    int32_t  allowMatchAlreadyMatchedPoints;
+    double   bounding_box_intersection_check_epsilon;
+} mp2p_b200_pt2pl_params;
+
+/* mp2p_icp::WeightParameters as used by Solver_Horn
+ * (mp2p_icp/include/mp2p_icp/WeightParameters.h:36-63). robust_kernel: 0 None, 1 GemanMcClure,
+ * 2 Cauchy (mp2p_icp/include/mp2p_icp/robust_kernels.h:33-44). */
+typedef struct
+{
+    int32_t use_scale_outlier_detector;
+    double  scale_outlier_threshold;
+    double  w_pt2pt;
+    int32_t robust_kernel;
+    double  robust_kernel_param;
+    double  currentEstimateForRobust[12];
+} mp2p_b200_horn_params;
+
+/* mp2p_icp::OptimalTF_GN_Parameters (mp2p_icp/include/mp2p_icp/optimal_tf_gauss_newton.h:32-61),
+ * restricted to the pt2pt and pt2pl terms; the prior term stays host-side. */
+typedef struct
+{
+    uint32_t maxInnerLoopIterations;
+    double   minDelta;
+    double   maxCost;
+    double   w_pt2pt, w_pt2pl;
+    int32_t  kernel;
+    double   kernelParam;
+} mp2p_b200_gn_params;
+
+typedef struct
+{
+    uint64_t n_points;
+    float    bbox_min[3], bbox_max[3];
+    float    finest_cell_size; /* metres */
+    uint32_t n_levels;
+    uint64_t n_finest_cells;
+    uint64_t index_bytes;
+    float    build_ms; /* device time of the index build (CUDA events) */
+} mp2p_b200_map_info;
+
+/* Accumulator packets (32 doubles each; what a multi-GPU caller all-reduces with SUM):
+ *  GN   : [0..20] upper triangle of H row-major, [21..26] g, [27] sum w|e|^2, [28] pair count
+ *  HORN1: [0..2] sum local, [3..5] sum global, [6] count (non-outlier pairs)
+ *  HORN2: [0..8] S row-major (sum w r b^T), [9] w_sum, [10] new outliers, [11] pairs used   */
+#define MP2P_B200_PACKET_DOUBLES 32
+
+/* ------------------------------------------------------------------------------------------ */
+const char* mp2p_b200_last_error(void);
+int         mp2p_b200_device_count(void);
+
+/* `cuda_stream` = a cudaStream_t the caller owns (e.g. torch's current stream) or NULL to let the
+ * context create its own non-blocking stream. */
+int  mp2p_b200_ctx_create(int device, void* cuda_stream, mp2p_b200_ctx** out);
+void mp2p_b200_ctx_destroy(mp2p_b200_ctx* ctx);
+int  mp2p_b200_ctx_synchronize(mp2p_b200_ctx* ctx);
+/* number of kernels this context launched so far (bench.py's `gpu_launches`). */
+uint64_t mp2p_b200_ctx_launch_count(const mp2p_b200_ctx* ctx);
+
+/* Upload a global map layer and build its NN index. Replaces
+ * mrpt::maps::NearestNeighborsCapable::nn_prepare_for_3d_queries() on a CPointsMap
+ * (call site mp2p_icp/src/Matcher_Points_DistanceThreshold.cpp:92); rebuilt whenever the layer is
+ * modified (Matcher_Points_Base.cpp:105-114). x/y/z = CPointsMap::getPointsBufferRef_x/y/z(). */
+int  mp2p_b200_map_create(mp2p_b200_ctx* ctx, const float* x, const float* y, const float* z,
+                          uint64_t n, int on_device, mp2p_b200_map** out);
+void mp2p_b200_map_destroy(mp2p_b200_map* map);
+int  mp2p_b200_map_get_info(const mp2p_b200_map* map, mp2p_b200_map_info* out);
+
+/* Raw k-NN of already-transformed query points (ascending (d2, index), d2 < radius2 strictly;
+ * out_idx/out_d2 are [nq*k], out_found [nq]); replaces nn_single_search / nn_multiple_search /
+ * nn_radius_search (Matcher_Points_DistanceThreshold.cpp:161-163,174-177,246-248). Host pointers. */
+int mp2p_b200_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const float* qy,
+                  const float* qz, uint64_t nq, uint32_t k, float radius2, uint32_t* out_idx,
+                  float* out_d2, int32_t* out_found);
+
+/* Matcher_Points_DistanceThreshold::implMatchOneLayer
+ * (mp2p_icp/src/Matcher_Points_DistanceThreshold.cpp:48-269, serial-branch semantics) including
+ * transform_local_to_global (Matcher_Points_Base.cpp:183-249) and the bounding-box gate.
+ *  local_paired_bits / global_paired_bits: MatchState bitfields on entry (bit i of word i/32;
+ *  NULL = none set), HOST memory (Matcher.cpp:46-88, pointcloud_bitfield.h:46-133). The caller
+ *  marks the bits of the returned pairs (lambdaAddPair, :116-120).
+ *  out_pairs: capacity records; *out_count = pairs produced (ascending localIdx, then rank);
+ *  *potential_pairings is incremented by n_local*pairingsPerPoint (:64). */
+int mp2p_b200_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                          const float* lz, uint64_t n_local, int local_on_device,
+                          const double pose[12], const mp2p_b200_pt2pt_params* params,
+                          const uint32_t* local_paired_bits, const uint32_t* global_paired_bits,
+                          mp2p_b200_pair_pt2pt* out_pairs, uint64_t capacity, int out_on_device,
+                          uint64_t* out_count, uint64_t* potential_pairings);
+
+/* Matcher_Point2Plane::implMatchOneLayer (mp2p_icp/src/Matcher_Point2Plane.cpp:41-114) with
+ * NearestPlaneCapable::nn_search_pt2pl (mp2p_icp_map/include/mp2p_icp/NearestPlaneCapable.h:39-51)
+ * realised over the point layer as k-NN + estimate_points_eigen
+ * (mp2p_icp_map/src/estimate_points_eigen.cpp:27-123) + planarity test
+ * (mp2p_icp/src/Matcher_Adaptive.cpp:229-253). */
+int mp2p_b200_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                          const float* lz, uint64_t n_local, int local_on_device,
+                          const double pose[12], const mp2p_b200_pt2pl_params* params,
+                          const uint32_t* local_paired_bits, mp2p_b200_pair_pt2pl* out_pairs,
+                          uint64_t capacity, int out_on_device, uint64_t* out_count,
+                          uint64_t* potential_pairings);
+
+/* optimal_tf_horn (mp2p_icp/src/optimal_tf_horn.cpp:201-252) over pt2pt pairings:
+ * eval_centroids_robust (Pairings.cpp:68-110) + visit_correspondences S accumulation
+ * (visit_correspondences.h:39-221) on the GPU; 4x4 eigen-solve on the host.
+ * weight_counts/values: Pairings::point_weights run-length blocks (NULL/0 = all 1.0).
+ * *solved = 0 mirrors `return false` (fewer than 3 pairings, optimal_tf_horn.cpp:96). */
+int mp2p_b200_solve_horn(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* pairs, uint64_t n,
+                         int pairs_on_device, const mp2p_b200_horn_params* params,
+                         const uint64_t* weight_counts, const double* weight_values,
+                         uint64_t n_weight_blocks, double pose_out[12], int32_t* solved);
+
+/* optimal_tf_gauss_newton (mp2p_icp/src/optimal_tf_gauss_newton.cpp:36-372), pt2pt + pt2pl terms
+ * (error_point2point / error_point2plane, errorTerms.cpp:36-66,115-161; robust_kernels.h:57-94).
+ * H and g are zeroed every inner iteration. */
+int mp2p_b200_solve_gauss_newton(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* pairs_pt2pt,
+                                 uint64_t n_pt2pt, const mp2p_b200_pair_pt2pl* pairs_pt2pl,
+                                 uint64_t n_pt2pl, int pairs_on_device,
+                                 const mp2p_b200_gn_params* params, const double pose_init[12],
+                                 double pose_out[12], uint32_t* iterations_done, int32_t* solved);
+
+/* ---- building blocks for query-sharded multi-GPU runs: each rank accumulates
+ * over its shard, the caller all-reduces the 32-double packet (SUM), every rank finishes the
+ * solve redundantly. `packet` may be host or device memory (packet_on_device). ---- */
+int mp2p_b200_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* pairs_pt2pt,
+                            uint64_t n_pt2pt, const mp2p_b200_pair_pt2pl* pairs_pt2pl,
+                            uint64_t n_pt2pl, int pairs_on_device, const mp2p_b200_gn_params* params,
+                            const double pose[12], double* packet, int packet_on_device);
+/* host-side step from a reduced GN packet: delta = -H^{-1} g (LDLT), pose_out = pose (+) exp(delta);
+ * *converged = 1 if |delta| < minDelta or sqrt(err) <= maxCost (optimal_tf_gauss_newton.cpp:344-365). */
+int mp2p_b200_gn_step_from_packet(const double packet[MP2P_B200_PACKET_DOUBLES],
+                                  const mp2p_b200_gn_params* params, const double pose[12],
+                                  double pose_out[12], int32_t* converged);
+int mp2p_b200_horn_sums(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* pairs, uint64_t n,
+                        int pairs_on_device, double* packet, int packet_on_device);
+int mp2p_b200_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* pairs, uint64_t n,
+                           int pairs_on_device, const mp2p_b200_horn_params* params,
+                           const double* sums_packet /* reduced HORN1 */, int sums_on_device,
+                           uint64_t n_total_pairs, double* packet, int packet_on_device);
+/* host-side finish from reduced HORN1 + HORN2 packets (optimal_tf_horn.cpp:132-174,238-247). */
+int mp2p_b200_horn_finish(const double sums_packet[MP2P_B200_PACKET_DOUBLES],
+                          const double moments_packet[MP2P_B200_PACKET_DOUBLES], double pose_out[12],
+                          int32_t* solved);
+
+/* ---- measurement hooks (bench.py): per-kernel CUDA-event timing and search statistics ----
+ * With profiling on, every public call records CUDA events around its kernels on the context
+ * stream; mp2p_b200_ctx_get_timings returns the durations (ms) of the LAST call:
+ *   [0] NN search kernel (k_match_pt2pt / k_match_pt2pl)   [1] compaction kernel
+ *   [2] Horn sums  [3] Horn moments  [4] GN accumulate (sum over inner iterations)
+ *   [5] whole call, device time                             (unused slots = 0)
+ * mp2p_b200_ctx_get_search_stats returns counters of the LAST match call when stats are on:
+ *   [0] hash-table probes (16 B each)  [1] candidate points read (16 B each)
+ *   [2] valid candidates written       [3] queries that climbed above the finest level  */
+#define MP2P_B200_N_TIMINGS 8
+int mp2p_b200_ctx_set_profiling(mp2p_b200_ctx* ctx, int timings_on, int search_stats_on);
+int mp2p_b200_ctx_get_timings(mp2p_b200_ctx* ctx, float ms[MP2P_B200_N_TIMINGS]);
+int mp2p_b200_ctx_get_search_stats(mp2p_b200_ctx* ctx, uint64_t stats[4]);
+
+/* Pinned host memory helpers (so callers in any language can give the library DMA-able buffers). */
+int  mp2p_b200_host_alloc(size_t bytes, void** out);
+void mp2p_b200_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MP2P_B200_H */

@@ -1,0 +1,411 @@
+"""ctypes binding of include/mp2p_b200.h (the drop-in C ABI).
+
+Mirrors the C structs one to one. Host numpy arrays are passed as plain pointers; device-resident
+buffers (torch tensors) are passed as integer addresses with ``on_device=True``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libmp2p_b200.so")
+
+PACKET_DOUBLES = 32
+MAX_KNN = 32
+
+PAIR_PT2PT = np.dtype(
+    [("globalIdx", "<u4"), ("localIdx", "<u4"), ("global", "<f4", 3), ("local", "<f4", 3), ("errSq", "<f4")]
+)
+PAIR_PT2PL = np.dtype([("coefs", "<f8", 4), ("centroid", "<f8", 3), ("local", "<f4", 3), ("_pad", "<f4")])
+assert PAIR_PT2PT.itemsize == 36 and PAIR_PT2PL.itemsize == 72
+
+KERNELS = {"None": 0, "GemanMcClure": 1, "Cauchy": 2}
+
+
+class Mp2pError(RuntimeError):
+    pass
+
+
+class _Pt2PtParams(C.Structure):
+    _fields_ = [
+        ("threshold", C.c_double),
+        ("thresholdAngularDeg", C.c_double),
+        ("pairingsPerPoint", C.c_uint32),
+        ("allowMatchAlreadyMatchedPoints", C.c_int32),
+        ("allowMatchAlreadyMatchedGlobalPoints", C.c_int32),
+        ("bounding_box_intersection_check_epsilon", C.c_double),
+    ]
+
+
+class _Pt2PlParams(C.Structure):
+    _fields_ = [
+        ("distanceThreshold", C.c_double),
+        ("searchRadius", C.c_double),
+        ("knn", C.c_uint32),
+        ("minimumPlanePoints", C.c_uint32),
+        ("planeEigenThreshold", C.c_double),
+        ("allowMatchAlreadyMatchedPoints", C.c_int32),
+        ("bounding_box_intersection_check_epsilon", C.c_double),
+    ]
+
+
+class _HornParams(C.Structure):
+    _fields_ = [
+        ("use_scale_outlier_detector", C.c_int32),
+        ("scale_outlier_threshold", C.c_double),
+        ("w_pt2pt", C.c_double),
+        ("robust_kernel", C.c_int32),
+        ("robust_kernel_param", C.c_double),
+        ("currentEstimateForRobust", C.c_double * 12),
+    ]
+
+
+class _GNParams(C.Structure):
+    _fields_ = [
+        ("maxInnerLoopIterations", C.c_uint32),
+        ("minDelta", C.c_double),
+        ("maxCost", C.c_double),
+        ("w_pt2pt", C.c_double),
+        ("w_pt2pl", C.c_double),
+        ("kernel", C.c_int32),
+        ("kernelParam", C.c_double),
+    ]
+
+
+class _MapInfo(C.Structure):
+    _fields_ = [
+        ("n_points", C.c_uint64),
+        ("bbox_min", C.c_float * 3),
+        ("bbox_max", C.c_float * 3),
+        ("finest_cell_size", C.c_float),
+        ("n_levels", C.c_uint32),
+        ("n_finest_cells", C.c_uint64),
+        ("index_bytes", C.c_uint64),
+        ("build_ms", C.c_float),
+    ]
+
+
+@dataclass
+class Pt2PtParams:
+    """Parameters of Matcher_Points_DistanceThreshold (same names as the reference's YAML keys)."""
+
+    threshold: float
+    thresholdAngularDeg: float = 0.0
+    pairingsPerPoint: int = 1
+    allowMatchAlreadyMatchedPoints: bool = False
+    allowMatchAlreadyMatchedGlobalPoints: bool = False
+    bounding_box_intersection_check_epsilon: float = 0.20
+
+    def c(self):
+        return _Pt2PtParams(self.threshold, self.thresholdAngularDeg, self.pairingsPerPoint, int(self.allowMatchAlreadyMatchedPoints), int(self.allowMatchAlreadyMatchedGlobalPoints), self.bounding_box_intersection_check_epsilon)
+
+
+@dataclass
+class Pt2PlParams:
+    distanceThreshold: float
+    searchRadius: float
+    knn: int = 5
+    minimumPlanePoints: int = 5
+    planeEigenThreshold: float = 0.01
+    allowMatchAlreadyMatchedPoints: bool = False
+    bounding_box_intersection_check_epsilon: float = 0.20
+
+    def c(self):
+        return _Pt2PlParams(self.distanceThreshold, self.searchRadius, self.knn, self.minimumPlanePoints, self.planeEigenThreshold, int(self.allowMatchAlreadyMatchedPoints), self.bounding_box_intersection_check_epsilon)
+
+
+@dataclass
+class HornParams:
+    use_scale_outlier_detector: bool = False
+    scale_outlier_threshold: float = 1.20
+    w_pt2pt: float = 1.0
+    robust_kernel: str = "None"
+    robust_kernel_param: float = 1.0
+    currentEstimateForRobust: np.ndarray = field(default_factory=lambda: np.eye(3, 4))
+
+    def c(self):
+        T = np.ascontiguousarray(self.currentEstimateForRobust, dtype=np.float64).reshape(-1)
+        return _HornParams(int(self.use_scale_outlier_detector), self.scale_outlier_threshold, self.w_pt2pt, KERNELS[self.robust_kernel], self.robust_kernel_param, (C.c_double * 12)(*T))
+
+
+@dataclass
+class GNParams:
+    maxInnerLoopIterations: int = 6
+    minDelta: float = 1e-7
+    maxCost: float = 0.0
+    w_pt2pt: float = 1.0
+    w_pt2pl: float = 1.0
+    kernel: str = "None"
+    kernelParam: float = 1.0
+
+    def c(self):
+        return _GNParams(self.maxInnerLoopIterations, self.minDelta, self.maxCost, self.w_pt2pt, self.w_pt2pl, KERNELS[self.kernel], self.kernelParam)
+
+
+EXPORTS = [
+    "mp2p_b200_last_error", "mp2p_b200_device_count", "mp2p_b200_ctx_create", "mp2p_b200_ctx_destroy",
+    "mp2p_b200_ctx_synchronize", "mp2p_b200_ctx_launch_count", "mp2p_b200_map_create", "mp2p_b200_map_destroy",
+    "mp2p_b200_map_get_info", "mp2p_b200_knn", "mp2p_b200_match_pt2pt", "mp2p_b200_match_pt2pl",
+    "mp2p_b200_solve_horn", "mp2p_b200_solve_gauss_newton", "mp2p_b200_gn_accumulate",
+    "mp2p_b200_gn_step_from_packet", "mp2p_b200_horn_sums", "mp2p_b200_horn_moments", "mp2p_b200_horn_finish",
+    "mp2p_b200_host_alloc", "mp2p_b200_host_free", "mp2p_b200_ctx_set_profiling",
+    "mp2p_b200_ctx_get_timings", "mp2p_b200_ctx_get_search_stats",
+]
+
+_lib = None
+
+
+def library_path() -> str:
+    return _SO
+
+
+def load_library():
+    """Load libmp2p_b200.so. Fails loudly if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise Mp2pError(f"{_SO} not built: run `python -c 'import __graft_entry__ as g; g.build()'` (or make -C mp2p_icp_b200/csrc)")
+    L = C.CDLL(_SO)
+    L.mp2p_b200_last_error.restype = C.c_char_p
+    L.mp2p_b200_ctx_launch_count.restype = C.c_uint64
+    L.mp2p_b200_ctx_launch_count.argtypes = [C.c_void_p]
+    L.mp2p_b200_ctx_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.mp2p_b200_ctx_destroy.argtypes = [C.c_void_p]
+    L.mp2p_b200_ctx_synchronize.argtypes = [C.c_void_p]
+    L.mp2p_b200_map_destroy.argtypes = [C.c_void_p]
+    L.mp2p_b200_host_free.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise Mp2pError(f"mp2p_b200 error {rc}: {load_library().mp2p_b200_last_error().decode()}")
+
+
+def _ptr(a):
+    """numpy array -> void*, int (device address) -> void*, None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return a if isinstance(a, (int, np.integer)) else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _pose(T):
+    T = np.ascontiguousarray(T, dtype=np.float64).reshape(-1)
+    assert T.size == 12
+    return T
+
+
+def pack_bits(flags) -> np.ndarray:
+    """bool/uint8 per point -> uint32 words, bit i of word i//32 (MatchState bitfield layout)."""
+    flags = np.asarray(flags).astype(bool)
+    pad = (-len(flags)) % 32
+    b = np.concatenate([flags, np.zeros(pad, bool)]).reshape(-1, 32)
+    return (b.astype(np.uint32) << np.arange(32, dtype=np.uint32)).sum(1).astype(np.uint32)
+
+
+class Context:
+    """One per (process, GPU). `stream` = a cudaStream_t address (e.g. torch's) or None."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        L = load_library()
+        h = C.c_void_p()
+        _check(L.mp2p_b200_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().mp2p_b200_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _check(load_library().mp2p_b200_ctx_synchronize(self._h))
+
+    def set_profiling(self, timings: bool, search_stats: bool = False):
+        _check(load_library().mp2p_b200_ctx_set_profiling(self._h, int(timings), int(search_stats)))
+
+    def timings(self) -> dict:
+        ms = (C.c_float * 8)()
+        _check(load_library().mp2p_b200_ctx_get_timings(self._h, ms))
+        names = ["nn_search", "compact", "horn_sums", "horn_moments", "gn_accumulate", "call_total"]
+        return {n: float(ms[i]) for i, n in enumerate(names)}
+
+    def search_stats(self) -> dict:
+        st = (C.c_uint64 * 4)()
+        _check(load_library().mp2p_b200_ctx_get_search_stats(self._h, st))
+        return {"probes": int(st[0]), "candidates": int(st[1]), "valid": int(st[2]), "climbed": int(st[3])}
+
+    @property
+    def launch_count(self) -> int:
+        return int(load_library().mp2p_b200_ctx_launch_count(self._h))
+
+    # ---------------------------------------------------------------- solvers
+    def solve_horn(self, pairs, n=None, prm: HornParams = None, point_weights=None, on_device=False):
+        prm = prm or HornParams()
+        if not on_device:
+            pairs = np.ascontiguousarray(pairs, dtype=PAIR_PT2PT)
+            n = pairs.size
+        cp = prm.c()
+        wc = wv = None
+        nb = 0
+        if point_weights:
+            wc = np.array([c for c, _ in point_weights], np.uint64)
+            wv = np.array([w for _, w in point_weights], np.float64)
+            nb = len(point_weights)
+        T = np.zeros(12)
+        solved = C.c_int32(0)
+        _check(load_library().mp2p_b200_solve_horn(self._h, _ptr(pairs), C.c_uint64(n), int(on_device), C.byref(cp), _ptr(wc), _ptr(wv), C.c_uint64(nb), _ptr(T), C.byref(solved)))
+        return bool(solved.value), T.reshape(3, 4)
+
+    def solve_gauss_newton(self, p2p, p2l, prm: GNParams, T_init, n2p=None, n2l=None, on_device=False):
+        if not on_device:
+            p2p = np.ascontiguousarray(p2p if p2p is not None else np.zeros(0, PAIR_PT2PT), dtype=PAIR_PT2PT)
+            p2l = np.ascontiguousarray(p2l if p2l is not None else np.zeros(0, PAIR_PT2PL), dtype=PAIR_PT2PL)
+            n2p, n2l = p2p.size, p2l.size
+        cp = prm.c()
+        T = np.zeros(12)
+        it, solved = C.c_uint32(0), C.c_int32(0)
+        _check(load_library().mp2p_b200_solve_gauss_newton(self._h, _ptr(p2p) if n2p else None, C.c_uint64(n2p or 0), _ptr(p2l) if n2l else None, C.c_uint64(n2l or 0), int(on_device), C.byref(cp), _ptr(_pose(T_init)), _ptr(T), C.byref(it), C.byref(solved)))
+        return bool(solved.value), T.reshape(3, 4), it.value
+
+    def gn_accumulate(self, p2p, p2l, prm: GNParams, T, n2p=None, n2l=None, on_device=False, packet=None, packet_on_device=False):
+        if not on_device:
+            p2p = np.ascontiguousarray(p2p if p2p is not None else np.zeros(0, PAIR_PT2PT), dtype=PAIR_PT2PT)
+            p2l = np.ascontiguousarray(p2l if p2l is not None else np.zeros(0, PAIR_PT2PL), dtype=PAIR_PT2PL)
+            n2p, n2l = p2p.size, p2l.size
+        cp = prm.c()
+        if packet is None:
+            packet = np.zeros(PACKET_DOUBLES)
+        _check(load_library().mp2p_b200_gn_accumulate(self._h, _ptr(p2p) if n2p else None, C.c_uint64(n2p or 0), _ptr(p2l) if n2l else None, C.c_uint64(n2l or 0), int(on_device), C.byref(cp), _ptr(_pose(T)), _ptr(packet), int(packet_on_device)))
+        return packet
+
+    def horn_sums(self, pairs, n=None, on_device=False, packet=None, packet_on_device=False):
+        if not on_device:
+            pairs = np.ascontiguousarray(pairs, dtype=PAIR_PT2PT)
+            n = pairs.size
+        if packet is None:
+            packet = np.zeros(PACKET_DOUBLES)
+        _check(load_library().mp2p_b200_horn_sums(self._h, _ptr(pairs) if n else None, C.c_uint64(n), int(on_device), _ptr(packet), int(packet_on_device)))
+        return packet
+
+    def horn_moments(self, pairs, sums_packet, n_total, n=None, prm: HornParams = None, on_device=False, sums_on_device=False, packet=None, packet_on_device=False):
+        prm = prm or HornParams()
+        if not on_device:
+            pairs = np.ascontiguousarray(pairs, dtype=PAIR_PT2PT)
+            n = pairs.size
+        if packet is None:
+            packet = np.zeros(PACKET_DOUBLES)
+        cp = prm.c()
+        _check(load_library().mp2p_b200_horn_moments(self._h, _ptr(pairs) if n else None, C.c_uint64(n), int(on_device), C.byref(cp), _ptr(sums_packet), int(sums_on_device), C.c_uint64(n_total), _ptr(packet), int(packet_on_device)))
+        return packet
+
+
+def gn_step_from_packet(packet, prm: GNParams, T):
+    out = np.zeros(12)
+    conv = C.c_int32(0)
+    cp = prm.c()
+    _check(load_library().mp2p_b200_gn_step_from_packet(_ptr(np.ascontiguousarray(packet, dtype=np.float64)), C.byref(cp), _ptr(_pose(T)), _ptr(out), C.byref(conv)))
+    return out.reshape(3, 4), bool(conv.value)
+
+
+def horn_finish(sums, moments):
+    out = np.zeros(12)
+    solved = C.c_int32(0)
+    _check(load_library().mp2p_b200_horn_finish(_ptr(np.ascontiguousarray(sums, dtype=np.float64)), _ptr(np.ascontiguousarray(moments, dtype=np.float64)), _ptr(out), C.byref(solved)))
+    return bool(solved.value), out.reshape(3, 4)
+
+
+class Map:
+    """A global map layer resident on the GPU with its NN index (nn_prepare_for_3d_queries)."""
+
+    def __init__(self, ctx: Context, x, y, z, n=None, on_device=False):
+        self.ctx = ctx
+        if not on_device:
+            x, y, z = _f32(x), _f32(y), _f32(z)
+            n = x.size
+        h = C.c_void_p()
+        _check(load_library().mp2p_b200_map_create(ctx._h, _ptr(x), _ptr(y), _ptr(z), C.c_uint64(n), int(on_device), C.byref(h)))
+        self._h = h
+        self.n = n
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().mp2p_b200_map_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def info(self) -> dict:
+        inf = _MapInfo()
+        _check(load_library().mp2p_b200_map_get_info(self._h, C.byref(inf)))
+        return {
+            "n_points": inf.n_points, "bbox_min": list(inf.bbox_min), "bbox_max": list(inf.bbox_max),
+            "finest_cell_size": inf.finest_cell_size, "n_levels": inf.n_levels,
+            "n_finest_cells": inf.n_finest_cells, "index_bytes": inf.index_bytes, "build_ms": inf.build_ms,
+        }
+
+    def knn(self, qx, qy, qz, k: int, radius2: float = np.inf):
+        qx, qy, qz = _f32(qx), _f32(qy), _f32(qz)
+        nq = qx.size
+        idx = np.zeros((nq, k), np.uint32)
+        d2 = np.full((nq, k), np.inf, np.float32)
+        found = np.zeros(nq, np.int32)
+        r2 = np.float32(min(radius2, 3.0e38))
+        _check(load_library().mp2p_b200_knn(self.ctx._h, self._h, _ptr(qx), _ptr(qy), _ptr(qz), C.c_uint64(nq), C.c_uint32(k), C.c_float(r2), _ptr(idx), _ptr(d2), _ptr(found)))
+        return idx, d2, found
+
+    def match_pt2pt(self, lx, ly, lz, T, prm: Pt2PtParams, local_paired=None, global_paired=None, n_local=None, local_on_device=False, out=None, out_on_device=False, capacity=None):
+        """Returns (pairs, potential_pairings); `pairs` is a numpy view of `out[:count]` for host
+        output, or the count for device output."""
+        if not local_on_device:
+            lx, ly, lz = _f32(lx), _f32(ly), _f32(lz)
+            n_local = lx.size
+        cap = capacity if capacity is not None else n_local * prm.pairingsPerPoint
+        if out is None and not out_on_device:
+            out = np.empty(max(cap, 1), PAIR_PT2PT)
+        lb = pack_bits(local_paired) if local_paired is not None else None
+        gb = pack_bits(global_paired) if global_paired is not None else None
+        cp = prm.c()
+        cnt, pot = C.c_uint64(0), C.c_uint64(0)
+        _check(load_library().mp2p_b200_match_pt2pt(self.ctx._h, self._h, _ptr(lx), _ptr(ly), _ptr(lz), C.c_uint64(n_local), int(local_on_device), _ptr(_pose(T)), C.byref(cp), _ptr(lb), _ptr(gb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt), C.byref(pot)))
+        if out_on_device:
+            return cnt.value, pot.value
+        return out[: cnt.value], pot.value
+
+    def match_pt2pl(self, lx, ly, lz, T, prm: Pt2PlParams, local_paired=None, n_local=None, local_on_device=False, out=None, out_on_device=False, capacity=None):
+        if not local_on_device:
+            lx, ly, lz = _f32(lx), _f32(ly), _f32(lz)
+            n_local = lx.size
+        cap = capacity if capacity is not None else n_local
+        if out is None and not out_on_device:
+            out = np.empty(max(cap, 1), PAIR_PT2PL)
+        lb = pack_bits(local_paired) if local_paired is not None else None
+        cp = prm.c()
+        cnt, pot = C.c_uint64(0), C.c_uint64(0)
+        _check(load_library().mp2p_b200_match_pt2pl(self.ctx._h, self._h, _ptr(lx), _ptr(ly), _ptr(lz), C.c_uint64(n_local), int(local_on_device), _ptr(_pose(T)), C.byref(cp), _ptr(lb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt), C.byref(pot)))
+        if out_on_device:
+            return cnt.value, pot.value
+        return out[: cnt.value], pot.value

@@ -1,0 +1,587 @@
+// C-ABI entry points (include/mp2p_b200.h). Product code: no oracle, no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "host_math.hpp"
+
+namespace mp2p
+{
+static thread_local char g_err[512] = "";
+void                     set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void prof_reset(mp2p_b200_ctx* c)
+{
+    if (!c->prof_timings) return;
+    for (int k = 0; k < 8; k++) c->pev_used[k] = false;
+    prof_begin(c, 5);
+}
+void prof_collect(mp2p_b200_ctx* c)
+{
+    if (!c->prof_timings) return;
+    prof_end(c, 5);
+    cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < MP2P_B200_N_TIMINGS; k++)
+    {
+        c->timings[k] = 0.f;
+        if (k < 8 && c->pev_used[k]) cudaEventElapsedTime(&c->timings[k], c->pev[2 * k], c->pev[2 * k + 1]);
+    }
+}
+
+namespace
+{
+// RAII bracket of one public compute call: timing slot 5 = whole call (device time)
+struct ProfScope
+{
+    mp2p_b200_ctx* c;
+    explicit ProfScope(mp2p_b200_ctx* ctx) : c(ctx) { prof_reset(c); }
+    ~ProfScope() { prof_collect(c); }
+};
+
+struct DeviceGuard
+{
+    int  prev = -1;
+    bool ok   = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+double* pinned_packets(mp2p_b200_ctx* c) { return reinterpret_cast<double*>(static_cast<char*>(c->h_pinned) + 256); }
+
+template <class Rec>
+int stage_pairs(mp2p_b200_ctx* ctx, DevBuf& buf, const Rec* pairs, uint64_t n, int on_device, const Rec** d_out)
+{
+    if (on_device || n == 0)
+    {
+        *d_out = pairs;
+        return 0;
+    }
+    MP2P_TRY(buf.ensure(n * sizeof(Rec)));
+    MP2P_CUDA_TRY(cudaMemcpyAsync(buf.p, pairs, n * sizeof(Rec), cudaMemcpyHostToDevice, ctx->stream));
+    *d_out = buf.as<Rec>();
+    return 0;
+}
+
+int packet_out(mp2p_b200_ctx* ctx, const double* d_packet, double* packet, int packet_on_device)
+{
+    if (packet_on_device)
+    {
+        if (packet != d_packet)
+            MP2P_CUDA_TRY(cudaMemcpyAsync(packet, d_packet, MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        return 0;
+    }
+    double* hp = pinned_packets(ctx);
+    MP2P_CUDA_TRY(cudaMemcpyAsync(hp, d_packet, MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    MP2P_CUDA_TRY(cudaGetLastError());
+    std::memcpy(packet, hp, MP2P_B200_PACKET_DOUBLES * 8);
+    return 0;
+}
+
+void unpack_H(const double* packet, double H[36], double g[6])
+{
+    int idx = 0;
+    for (int i = 0; i < 6; i++)
+        for (int j = i; j < 6; j++) H[6 * i + j] = H[6 * j + i] = packet[idx++];
+    for (int i = 0; i < 6; i++) g[i] = packet[21 + i];
+}
+}  // namespace
+}  // namespace mp2p
+
+using namespace mp2p;
+
+extern "C"
+{
+    const char* mp2p_b200_last_error(void) { return g_err; }
+
+    int mp2p_b200_device_count(void)
+    {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return 0;
+        }
+        return n;
+    }
+
+    int mp2p_b200_ctx_create(int device, void* cuda_stream, mp2p_b200_ctx** out)
+    {
+        if (!out)
+        {
+            set_error("ctx_create: out is NULL");
+            return MP2P_B200_ERR_ARG;
+        }
+        *out = nullptr;
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+        {
+            set_error("no CUDA device available (this library has no CPU fallback): %s",
+                      cudaGetErrorString(cudaGetLastError()));
+            return MP2P_B200_ERR_CUDA;
+        }
+        if (device < 0 || device >= n)
+        {
+            set_error("ctx_create: device %d out of range [0,%d)", device, n);
+            return MP2P_B200_ERR_ARG;
+        }
+        MP2P_CUDA_TRY(cudaSetDevice(device));
+        auto* c   = new (std::nothrow) mp2p_b200_ctx();
+        if (!c) return MP2P_B200_ERR_NOMEM;
+        c->device = device;
+        if (cuda_stream)
+            c->stream = static_cast<cudaStream_t>(cuda_stream), c->own_stream = false;
+        else
+        {
+            if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
+            {
+                set_error("cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+                delete c;
+                return MP2P_B200_ERR_CUDA;
+            }
+            c->own_stream = true;
+        }
+        cudaEventCreate(&c->ev0);
+        cudaEventCreate(&c->ev1);
+        for (auto& e : c->pev) cudaEventCreate(&e);
+        if (cudaHostAlloc(&c->h_pinned, 4096, cudaHostAllocDefault) != cudaSuccess)
+        {
+            set_error("cudaHostAlloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+            delete c;
+            return MP2P_B200_ERR_CUDA;
+        }
+        if (c->d_packet.ensure(8 * MP2P_B200_PACKET_DOUBLES * sizeof(double)) || c->d_pose.ensure(256))
+        {
+            delete c;
+            return MP2P_B200_ERR_NOMEM;
+        }
+        *out = c;
+        return 0;
+    }
+
+    void mp2p_b200_ctx_destroy(mp2p_b200_ctx* c)
+    {
+        if (!c) return;
+        DeviceGuard g(c->device);
+        cudaStreamSynchronize(c->stream);
+        for (DevBuf* b : {&c->d_lx, &c->d_ly, &c->d_lz, &c->d_cand, &c->d_lbits, &c->d_gbits, &c->d_scan,
+                          &c->d_small, &c->d_out2p, &c->d_out2l, &c->d_plcand, &c->d_knn_idx, &c->d_knn_d2,
+                          &c->d_knn_found, &c->d_pairs2p, &c->d_pairs2l, &c->d_partials, &c->d_packet,
+                          &c->d_pose, &c->d_weights, &c->d_outlier})
+            b->release();
+        if (c->h_pinned) cudaFreeHost(c->h_pinned);
+        if (c->ev0) cudaEventDestroy(c->ev0);
+        if (c->ev1) cudaEventDestroy(c->ev1);
+        for (auto& e : c->pev)
+            if (e) cudaEventDestroy(e);
+        c->d_stats.release();
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+        delete c;
+    }
+
+    int mp2p_b200_ctx_synchronize(mp2p_b200_ctx* c)
+    {
+        if (!c) return MP2P_B200_ERR_ARG;
+        DeviceGuard g(c->device);
+        MP2P_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+
+    uint64_t mp2p_b200_ctx_launch_count(const mp2p_b200_ctx* c) { return c ? c->launches : 0; }
+
+    int mp2p_b200_map_create(mp2p_b200_ctx* ctx, const float* x, const float* y, const float* z,
+                             uint64_t n, int on_device, mp2p_b200_map** out)
+    {
+        if (!ctx || !out || (n && (!x || !y || !z)))
+        {
+            set_error("map_create: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        *out = nullptr;
+        DeviceGuard g(ctx->device);
+        auto*       m = new (std::nothrow) mp2p_b200_map();
+        if (!m) return MP2P_B200_ERR_NOMEM;
+        const int rc = build_index(ctx, m, x, y, z, n, on_device);
+        if (rc != 0)
+        {
+            mp2p_b200_map_destroy(m);
+            return rc;
+        }
+        *out = m;
+        return 0;
+    }
+
+    void mp2p_b200_map_destroy(mp2p_b200_map* m)
+    {
+        if (!m) return;
+        if (m->ctx)
+        {
+            DeviceGuard g(m->ctx->device);
+            cudaStreamSynchronize(m->ctx->stream);
+            m->d_pts.release(), m->d_pts_orig.release(), m->d_table.release(), m->d_claim.release();
+        }
+        delete m;
+    }
+
+    int mp2p_b200_map_get_info(const mp2p_b200_map* m, mp2p_b200_map_info* out)
+    {
+        if (!m || !out) return MP2P_B200_ERR_ARG;
+        *out = m->info;
+        return 0;
+    }
+
+    int mp2p_b200_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const float* qy,
+                      const float* qz, uint64_t nq, uint32_t k, float radius2, uint32_t* out_idx,
+                      float* out_d2, int32_t* out_found)
+    {
+        if (!ctx || !map || (nq && (!qx || !qy || !qz || !out_idx || !out_d2 || !out_found)))
+        {
+            set_error("knn: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        DeviceGuard g(ctx->device);
+        return run_knn(ctx, map, qx, qy, qz, nq, k, radius2, out_idx, out_d2, out_found);
+    }
+
+    int mp2p_b200_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                              const float* lz, uint64_t n_local, int local_on_device,
+                              const double pose[12], const mp2p_b200_pt2pt_params* prm,
+                              const uint32_t* local_paired_bits, const uint32_t* global_paired_bits,
+                              mp2p_b200_pair_pt2pt* out_pairs, uint64_t capacity, int out_on_device,
+                              uint64_t* out_count, uint64_t* potential_pairings)
+    {
+        if (!ctx || !map || !pose || !prm || !out_count || (n_local && (!lx || !ly || !lz)) ||
+            (capacity && !out_pairs))
+        {
+            set_error("match_pt2pt: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        // ASSERT_(pairingsPerPoint >= 1); ASSERT_GT_(threshold, .0); ASSERT_GE_(thresholdAngularDeg, .0)
+        // (Matcher_Points_DistanceThreshold.cpp:57-59)
+        if (prm->pairingsPerPoint < 1 || prm->pairingsPerPoint > MP2P_B200_MAX_KNN || !(prm->threshold > 0.0) ||
+            !(prm->thresholdAngularDeg >= 0.0))
+        {
+            set_error("match_pt2pt: need 1 <= pairingsPerPoint <= %d, threshold > 0, thresholdAngularDeg >= 0",
+                      MP2P_B200_MAX_KNN);
+            return MP2P_B200_ERR_ARG;
+        }
+        if (potential_pairings) *potential_pairings += n_local * prm->pairingsPerPoint;  // :64
+        DeviceGuard g(ctx->device);
+        ProfScope   ps(ctx);
+        return run_match_pt2pt(ctx, map, lx, ly, lz, n_local, local_on_device, pose, prm, local_paired_bits,
+                               global_paired_bits, out_pairs, capacity, out_on_device, out_count);
+    }
+
+    int mp2p_b200_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                              const float* lz, uint64_t n_local, int local_on_device,
+                              const double pose[12], const mp2p_b200_pt2pl_params* prm,
+                              const uint32_t* local_paired_bits, mp2p_b200_pair_pt2pl* out_pairs,
+                              uint64_t capacity, int out_on_device, uint64_t* out_count,
+                              uint64_t* potential_pairings)
+    {
+        if (!ctx || !map || !pose || !prm || !out_count || (n_local && (!lx || !ly || !lz)) ||
+            (capacity && !out_pairs))
+        {
+            set_error("match_pt2pl: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        if (!(prm->distanceThreshold > 0.0) || !(prm->searchRadius > 0.0))
+        {
+            set_error("match_pt2pl: distanceThreshold and searchRadius must be > 0");
+            return MP2P_B200_ERR_ARG;
+        }
+        if (potential_pairings) *potential_pairings += n_local;  // Matcher_Point2Plane.cpp:54
+        DeviceGuard g(ctx->device);
+        ProfScope   ps(ctx);
+        return run_match_pt2pl(ctx, map, lx, ly, lz, n_local, local_on_device, pose, prm, local_paired_bits,
+                               out_pairs, capacity, out_on_device, out_count);
+    }
+
+    // ------------------------------------------------------------------------------ Horn
+    int mp2p_b200_horn_sums(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* pairs, uint64_t n,
+                            int pairs_on_device, double* packet, int packet_on_device)
+    {
+        if (!ctx || !packet || (n && !pairs)) return MP2P_B200_ERR_ARG;
+        DeviceGuard                 g(ctx->device);
+        ProfScope   ps(ctx);
+        const mp2p_b200_pair_pt2pt* d;
+        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2p, pairs, n, pairs_on_device, &d));
+        double* dp = packet_on_device ? packet : ctx->d_packet.as<double>();
+        MP2P_TRY(run_horn_sums(ctx, d, n, nullptr, dp));
+        return packet_out(ctx, dp, packet, packet_on_device);
+    }
+
+    int mp2p_b200_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* pairs, uint64_t n,
+                               int pairs_on_device, const mp2p_b200_horn_params* prm,
+                               const double* sums_packet, int sums_on_device, uint64_t n_total_pairs,
+                               double* packet, int packet_on_device)
+    {
+        if (!ctx || !packet || !prm || !sums_packet || (n && !pairs)) return MP2P_B200_ERR_ARG;
+        DeviceGuard                 g(ctx->device);
+        ProfScope   ps(ctx);
+        const mp2p_b200_pair_pt2pt* d;
+        // note: if horn_sums staged the same host pairs just before, this re-uploads them; callers
+        // that care keep the pairings on the device (pairs_on_device = 1).
+        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2p, pairs, n, pairs_on_device, &d));
+        const double* ds = sums_packet;
+        if (!sums_on_device)
+        {
+            double* tmp = ctx->d_packet.as<double>() + 2 * MP2P_B200_PACKET_DOUBLES;
+            MP2P_CUDA_TRY(cudaMemcpyAsync(tmp, sums_packet, MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyHostToDevice, ctx->stream));
+            ds = tmp;
+        }
+        double* dp = packet_on_device ? packet : ctx->d_packet.as<double>() + MP2P_B200_PACKET_DOUBLES;
+        MP2P_TRY(run_horn_moments(ctx, d, n, prm, ds, n_total_pairs, nullptr, nullptr, 0, nullptr, dp));
+        return packet_out(ctx, dp, packet, packet_on_device);
+    }
+
+    int mp2p_b200_horn_finish(const double sums[MP2P_B200_PACKET_DOUBLES],
+                              const double mom[MP2P_B200_PACKET_DOUBLES], double pose_out[12], int32_t* solved)
+    {
+        if (!sums || !mom || !pose_out || !solved) return MP2P_B200_ERR_ARG;
+        *solved = 0;
+        if (!(sums[6] > 0)) return 0;
+        const double wc = 1.0 / sums[6];
+        const double cl[3] = {sums[0] * wc, sums[1] * wc, sums[2] * wc};
+        const double cg[3] = {sums[3] * wc, sums[4] * wc, sums[5] * wc};
+        double       S[9];
+        for (int k = 0; k < 9; k++) S[k] = mom[k];
+        if (mom[9] > 0)
+            for (double& s : S) s *= 1.0 / mom[9];  // optimal_tf_horn.cpp:121-124
+        double N[16];  // optimal_tf_horn.cpp:132-152
+        N[0] = S[0] + S[4] + S[8], N[1] = S[5] - S[7], N[2] = S[6] - S[2], N[3] = S[1] - S[3];
+        N[4] = N[1], N[5] = S[0] - S[4] - S[8], N[6] = S[1] + S[3], N[7] = S[6] + S[2];
+        N[8] = N[2], N[9] = N[6], N[10] = -S[0] + S[4] - S[8], N[11] = S[5] + S[7];
+        N[12] = N[3], N[13] = N[7], N[14] = N[11], N[15] = -S[0] - S[4] + S[8];
+        double q[4];
+        hm::eig_sym4_largest(N, q);  // :156-160
+        if (q[0] < 0)
+            for (double& v : q) v = -v;  // :165-171
+        hm::Pose34 R = hm::pose_from_quat(q);  // :238
+        for (int r = 0; r < 3; r++)              // :242-247  t = c_g - R c_l
+            R.m[4 * r + 3] = cg[r] - (R.m[4 * r] * cl[0] + R.m[4 * r + 1] * cl[1] + R.m[4 * r + 2] * cl[2]);
+        std::memcpy(pose_out, R.m, sizeof(R.m));
+        *solved = 1;
+        return 0;
+    }
+
+    int mp2p_b200_solve_horn(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* pairs, uint64_t n,
+                             int pairs_on_device, const mp2p_b200_horn_params* prm,
+                             const uint64_t* weight_counts, const double* weight_values,
+                             uint64_t n_weight_blocks, double pose_out[12], int32_t* solved)
+    {
+        if (!ctx || !prm || !pose_out || !solved || (n && !pairs))
+        {
+            set_error("solve_horn: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        *solved = 0;
+        if (n < 3) return 0;  // optimal_tf_horn.cpp:96
+        if (!(prm->w_pt2pt > 0.0))
+        {
+            set_error("solve_horn: pair weight pt2pt must be > 0");  // visit_correspondences.h:83
+            return MP2P_B200_ERR_ARG;
+        }
+        DeviceGuard                 g(ctx->device);
+        ProfScope   ps(ctx);
+        const mp2p_b200_pair_pt2pt* d;
+        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2p, pairs, n, pairs_on_device, &d));
+
+        const uint64_t* d_wprefix = nullptr;
+        const double*   d_wvalue  = nullptr;
+        if (n_weight_blocks && weight_counts && weight_values)
+        {
+            std::vector<uint64_t> prefix(n_weight_blocks + 1, 0);
+            for (uint64_t b = 0; b < n_weight_blocks; b++) prefix[b + 1] = prefix[b] + weight_counts[b];
+            const size_t pb = (n_weight_blocks + 1) * 8, vb = n_weight_blocks * 8;
+            MP2P_TRY(ctx->d_weights.ensure(pb + vb));
+            MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_weights.p, prefix.data(), pb, cudaMemcpyHostToDevice, ctx->stream));
+            MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_weights.as<char>() + pb, weight_values, vb, cudaMemcpyHostToDevice, ctx->stream));
+            MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // `prefix` is a local
+            d_wprefix = ctx->d_weights.as<uint64_t>();
+            d_wvalue  = reinterpret_cast<const double*>(ctx->d_weights.as<char>() + pb);
+        }
+        uint8_t* d_outl = nullptr;
+        if (prm->use_scale_outlier_detector)
+        {
+            MP2P_TRY(ctx->d_outlier.ensure(n));
+            MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_outlier.p, 0, n, ctx->stream));
+            d_outl = ctx->d_outlier.as<uint8_t>();
+        }
+        double* dp0 = ctx->d_packet.as<double>();
+        double* dp1 = dp0 + MP2P_B200_PACKET_DOUBLES;
+        double* hp  = pinned_packets(ctx);
+        // round 1 (optimal_tf_horn.cpp:216-221): centroids over all pairs, then S
+        MP2P_TRY(run_horn_sums(ctx, d, n, nullptr, dp0));
+        MP2P_TRY(run_horn_moments(ctx, d, n, prm, dp0, n, d_wprefix, d_wvalue, (uint32_t)n_weight_blocks, d_outl, dp1));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(hp, dp0, 2 * MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        MP2P_CUDA_TRY(cudaGetLastError());
+        if (prm->use_scale_outlier_detector && hp[MP2P_B200_PACKET_DOUBLES + 10] > 0)  // :224-235
+        {
+            if (hp[MP2P_B200_PACKET_DOUBLES + 10] >= (double)n)
+            {
+                set_error("solve_horn: every pairing was flagged as a scale outlier");  // Pairings.cpp:74
+                return MP2P_B200_ERR_ARG;
+            }
+            MP2P_TRY(run_horn_sums(ctx, d, n, d_outl, dp0));
+            MP2P_TRY(run_horn_moments(ctx, d, n, prm, dp0, n, d_wprefix, d_wvalue, (uint32_t)n_weight_blocks, d_outl, dp1));
+            MP2P_CUDA_TRY(cudaMemcpyAsync(hp, dp0, 2 * MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            MP2P_CUDA_TRY(cudaGetLastError());
+        }
+        return mp2p_b200_horn_finish(hp, hp + MP2P_B200_PACKET_DOUBLES, pose_out, solved);
+    }
+
+    // ------------------------------------------------------------------------------ Gauss-Newton
+    int mp2p_b200_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* p2p, uint64_t n2p,
+                                const mp2p_b200_pair_pt2pl* p2l, uint64_t n2l, int pairs_on_device,
+                                const mp2p_b200_gn_params* prm, const double pose[12], double* packet,
+                                int packet_on_device)
+    {
+        if (!ctx || !prm || !pose || !packet || (n2p && !p2p) || (n2l && !p2l)) return MP2P_B200_ERR_ARG;
+        DeviceGuard                 g(ctx->device);
+        ProfScope   ps(ctx);
+        const mp2p_b200_pair_pt2pt* d2p;
+        const mp2p_b200_pair_pt2pl* d2l;
+        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2p, p2p, n2p, pairs_on_device, &d2p));
+        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2l, p2l, n2l, pairs_on_device, &d2l));
+        double* hpose = reinterpret_cast<double*>(static_cast<char*>(ctx->h_pinned) + 2048);
+        std::memcpy(hpose, pose, 96);
+        MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_pose.p, hpose, 96, cudaMemcpyHostToDevice, ctx->stream));
+        double* dp = packet_on_device ? packet : ctx->d_packet.as<double>();
+        MP2P_TRY(run_gn_accumulate(ctx, d2p, n2p, d2l, n2l, prm, ctx->d_pose.as<double>(), dp));
+        return packet_out(ctx, dp, packet, packet_on_device);
+    }
+
+    int mp2p_b200_gn_step_from_packet(const double packet[MP2P_B200_PACKET_DOUBLES],
+                                      const mp2p_b200_gn_params* prm, const double pose[12],
+                                      double pose_out[12], int32_t* converged)
+    {
+        if (!packet || !prm || !pose || !pose_out || !converged) return MP2P_B200_ERR_ARG;
+        *converged = 0;
+        if (std::sqrt(packet[27]) <= prm->maxCost)  // optimal_tf_gauss_newton.cpp:344-346
+        {
+            std::memcpy(pose_out, pose, 96);
+            *converged = 1;
+            return 0;
+        }
+        double H[36], gv[6], mg[6], delta[6];
+        unpack_H(packet, H, gv);
+        for (int k = 0; k < 6; k++) mg[k] = -gv[k];
+        hm::ldlt_solve6(H, mg, delta);  // :351
+        hm::Pose34 P;
+        std::memcpy(P.m, pose, 96);
+        const hm::Pose34 Pn = hm::compose(P, hm::se3_exp(delta));  // :354-356
+        std::memcpy(pose_out, Pn.m, 96);
+        double nrm = 0;
+        for (double d : delta) nrm += d * d;
+        if (std::sqrt(nrm) < prm->minDelta) *converged = 1;  // :365
+        return 0;
+    }
+
+    int mp2p_b200_solve_gauss_newton(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* p2p, uint64_t n2p,
+                                     const mp2p_b200_pair_pt2pl* p2l, uint64_t n2l, int pairs_on_device,
+                                     const mp2p_b200_gn_params* prm, const double pose_init[12],
+                                     double pose_out[12], uint32_t* iterations_done, int32_t* solved)
+    {
+        if (!ctx || !prm || !pose_init || !pose_out || !solved || (n2p && !p2p) || (n2l && !p2l))
+        {
+            set_error("solve_gauss_newton: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        *solved = 0;
+        DeviceGuard                 g(ctx->device);
+        ProfScope   ps(ctx);
+        const mp2p_b200_pair_pt2pt* d2p;
+        const mp2p_b200_pair_pt2pl* d2l;
+        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2p, p2p, n2p, pairs_on_device, &d2p));
+        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2l, p2l, n2l, pairs_on_device, &d2l));
+        double  pose[12];
+        std::memcpy(pose, pose_init, 96);  // optimal_tf_gauss_newton.cpp:50
+        double* hpose = reinterpret_cast<double*>(static_cast<char*>(ctx->h_pinned) + 2048);
+        double* hp    = pinned_packets(ctx);
+        double* dp    = ctx->d_packet.as<double>();
+        uint32_t it   = 0;
+        for (; it < prm->maxInnerLoopIterations; it++)  // :70
+        {
+            std::memcpy(hpose, pose, 96);
+            MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_pose.p, hpose, 96, cudaMemcpyHostToDevice, ctx->stream));
+            MP2P_TRY(run_gn_accumulate(ctx, d2p, n2p, d2l, n2l, prm, ctx->d_pose.as<double>(), dp));
+            MP2P_CUDA_TRY(cudaMemcpyAsync(hp, dp, MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            MP2P_CUDA_TRY(cudaGetLastError());
+            if (std::sqrt(hp[27]) <= prm->maxCost) break;
+            double  next[12];
+            int32_t conv = 0;
+            MP2P_TRY(mp2p_b200_gn_step_from_packet(hp, prm, pose, next, &conv));
+            std::memcpy(pose, next, 96);
+            if (conv)
+            {
+                it++;
+                break;
+            }
+        }
+        std::memcpy(pose_out, pose, 96);
+        if (iterations_done) *iterations_done = it;
+        *solved = 1;
+        return 0;
+    }
+
+    int mp2p_b200_ctx_set_profiling(mp2p_b200_ctx* ctx, int timings_on, int search_stats_on)
+    {
+        if (!ctx) return MP2P_B200_ERR_ARG;
+        ctx->prof_timings = timings_on != 0;
+        ctx->prof_stats   = search_stats_on != 0;
+        return 0;
+    }
+    int mp2p_b200_ctx_get_timings(mp2p_b200_ctx* ctx, float ms[MP2P_B200_N_TIMINGS])
+    {
+        if (!ctx || !ms) return MP2P_B200_ERR_ARG;
+        for (int k = 0; k < MP2P_B200_N_TIMINGS; k++) ms[k] = ctx->timings[k];
+        return 0;
+    }
+    int mp2p_b200_ctx_get_search_stats(mp2p_b200_ctx* ctx, uint64_t stats[4])
+    {
+        if (!ctx || !stats) return MP2P_B200_ERR_ARG;
+        for (int k = 0; k < 4; k++) stats[k] = 0;
+        if (!ctx->d_stats.p) return 0;
+        DeviceGuard g(ctx->device);
+        MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->h_pinned, ctx->d_stats.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        std::memcpy(stats, ctx->h_pinned, 32);
+        return 0;
+    }
+
+    int mp2p_b200_host_alloc(size_t bytes, void** out)
+    {
+        if (!out) return MP2P_B200_ERR_ARG;
+        *out = nullptr;
+        if (cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess)
+        {
+            set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+            return MP2P_B200_ERR_CUDA;
+        }
+        return 0;
+    }
+    void mp2p_b200_host_free(void* p)
+    {
+        if (p) cudaFreeHost(p);
+    }
+}

@@ -1,0 +1,185 @@
+// Shared declarations of the B200 hot-path library (product code; never includes oracle/).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "mp2p_b200.h"
+
+namespace mp2p
+{
+void set_error(const char* fmt, ...);
+
+#define MP2P_CUDA_TRY(expr)                                                                   \
+    do                                                                                        \
+    {                                                                                         \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+        {                                                                                     \
+            ::mp2p::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                   \
+                              cudaGetErrorString(e_));                                        \
+            return MP2P_B200_ERR_CUDA;                                                        \
+        }                                                                                     \
+    } while (0)
+
+#define MP2P_TRY(expr)            \
+    do                            \
+    {                             \
+        int rc_ = (expr);         \
+        if (rc_ != 0) return rc_; \
+    } while (0)
+
+constexpr int      kGridBits  = 21;  // finest quantisation: 2^21 cells along the longest axis
+constexpr int      kMaxLevels = 22;  // levels 0..21 (level L: cell = s0 * 2^L)
+constexpr uint32_t kQueryTile = 256; // queries per CTA tile (TMA bulk copies of 1 KiB per axis)
+
+// One occupied voxel of one level: 16 bytes, fetched with a single 128-bit load.
+struct __align__(16) CellEntry
+{
+    unsigned long long key;  // cx | cy<<21 | cz<<42 ; ~0 = empty slot
+    uint32_t           start;  // first point (Morton-sorted order)
+    uint32_t           count;
+};
+constexpr unsigned long long kEmptyKey = ~0ull;
+
+// Read-only view of a map index, passed BY VALUE to kernels (lives in constant/param space).
+struct GridView
+{
+    const float4*    pts;       // Morton-sorted points: x,y,z, original index (int bits)
+    const float4*    pts_orig;  // original order: x,y,z,0  (for emitting TMatchingPair::global)
+    const CellEntry* table;     // all level tables back to back
+    float            ox, oy, oz;  // grid origin = map bbox min
+    float            inv_s0;      // 1 / finest quantum
+    float            s0_lo;       // finest quantum, rounded DOWN (conservative bounds)
+    int              level_first; // absolute level of table 0
+    int              n_levels;    // tables for levels level_first .. level_first+n_levels-1
+    uint32_t         level_off[kMaxLevels];    // entry offset of each table
+    uint32_t         level_shift[kMaxLevels];  // 64 - log2(capacity)
+    float            bbmin[3], bbmax[3];
+    uint32_t         n_points;
+};
+
+struct DevBuf
+{
+    void*  p     = nullptr;
+    size_t bytes = 0;
+    int    ensure(size_t need)
+    {
+        if (need <= bytes) return 0;
+        if (p) cudaFree(p);
+        p     = nullptr;
+        bytes = 0;
+        // grow geometrically to avoid re-allocations when cloud sizes jitter between calls
+        size_t want = need + need / 4 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess)
+        {
+            set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(cudaGetLastError()));
+            return MP2P_B200_ERR_NOMEM;
+        }
+        bytes = want;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p     = nullptr;
+        bytes = 0;
+    }
+    template <class T>
+    T* as() const
+    {
+        return static_cast<T*>(p);
+    }
+};
+
+}  // namespace mp2p
+
+// ---- opaque handles -------------------------------------------------------------------------
+struct mp2p_b200_ctx
+{
+    int          device     = 0;
+    cudaStream_t stream     = nullptr;
+    bool         own_stream = false;
+    uint64_t     launches   = 0;
+    cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+    // measurement hooks
+    bool         prof_timings = false, prof_stats = false;
+    cudaEvent_t  pev[16]      = {};     // pairs (2k, 2k+1) bracket timing slot k
+    bool         pev_used[8]  = {};
+    float        timings[MP2P_B200_N_TIMINGS] = {};
+    mp2p::DevBuf d_stats;               // 4 x u64 search counters
+
+    // matcher scratch
+    mp2p::DevBuf d_lx, d_ly, d_lz;     // local cloud staging (padded to kQueryTile)
+    mp2p::DevBuf d_cand;               // u64 [n_local*K]  (d2 bits << 32 | map index)
+    mp2p::DevBuf d_lbits, d_gbits;     // MatchState bitfields
+    mp2p::DevBuf d_scan;               // tile status words + counters
+    mp2p::DevBuf d_small;              // bbox (6 u32) + count (u64) + misc
+    mp2p::DevBuf d_out2p, d_out2l;     // compacted pairs when the caller wants them on the host
+    mp2p::DevBuf d_plcand;             // per-query plane candidates (pt2pl)
+    mp2p::DevBuf d_knn_idx, d_knn_d2, d_knn_found;
+    // solver scratch
+    mp2p::DevBuf d_pairs2p, d_pairs2l; // H2D staging of host pairings
+    mp2p::DevBuf d_partials;           // per-block partial sums
+    mp2p::DevBuf d_packet;             // 4 packets of 32 doubles
+    mp2p::DevBuf d_pose;               // 12 doubles + flags
+    mp2p::DevBuf d_weights;            // run-length point weights
+    mp2p::DevBuf d_outlier;            // Horn scale-outlier flags
+    // pinned host scratch
+    void* h_pinned = nullptr;  // 4 KiB: counts, packets, poses
+};
+
+struct mp2p_b200_map
+{
+    mp2p_b200_ctx*     ctx = nullptr;
+    mp2p::GridView     view{};
+    mp2p_b200_map_info info{};
+    mp2p::DevBuf       d_pts, d_pts_orig, d_table, d_claim;
+    uint32_t           epoch = 0;  // first-claim epoch (see match.cu)
+};
+
+namespace mp2p
+{
+inline void count_launch(mp2p_b200_ctx* c, uint64_t n = 1) { c->launches += n; }
+// timing slot brackets (no-ops unless profiling is on)
+inline void prof_begin(mp2p_b200_ctx* c, int slot)
+{
+    if (c->prof_timings) cudaEventRecord(c->pev[2 * slot], c->stream);
+}
+inline void prof_end(mp2p_b200_ctx* c, int slot)
+{
+    if (c->prof_timings) cudaEventRecord(c->pev[2 * slot + 1], c->stream), c->pev_used[slot] = true;
+}
+void prof_reset(mp2p_b200_ctx* c);    // api.cu: start of a public call
+void prof_collect(mp2p_b200_ctx* c);  // api.cu: after the call's final synchronize
+
+// index.cu
+int build_index(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* x, const float* y,
+                const float* z, uint64_t n, int on_device);
+// match.cu
+int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                    const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
+                    const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits, const uint32_t* gbits,
+                    mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device,
+                    uint64_t* out_count);
+int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                    const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
+                    const mp2p_b200_pt2pl_params* prm, const uint32_t* lbits,
+                    mp2p_b200_pair_pt2pl* out, uint64_t capacity, int out_on_device,
+                    uint64_t* out_count);
+int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const float* qy,
+            const float* qz, uint64_t nq, uint32_t k, float radius2, uint32_t* out_idx,
+            float* out_d2, int32_t* out_found);
+// solve.cu
+int run_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p,
+                      const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l, const mp2p_b200_gn_params* prm,
+                      const double* d_pose, double* d_packet);
+int run_horn_sums(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n,
+                  const uint8_t* d_outlier, double* d_packet);
+int run_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n,
+                     const mp2p_b200_horn_params* prm, const double* d_sums_packet,
+                     uint64_t n_total_pairs, const uint64_t* d_wcount_prefix, const double* d_wvalue,
+                     uint32_t n_wblocks, uint8_t* d_outlier, double* d_packet);
+}  // namespace mp2p

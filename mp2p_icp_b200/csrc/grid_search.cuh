@@ -1,0 +1,230 @@
+// Device-side exact k-NN over the multi-resolution hashed voxel index (product code).
+//
+// Index layout (built in index.cu): map points are sorted by the 63-bit Morton code of their
+// finest-level voxel coordinates (2^21 voxels along the longest bbox axis), so the voxel of ANY
+// level L (cell = s0 * 2^L) is one contiguous run of the sorted array. For each level from the
+// chosen finest one upwards there is an open-addressing hash table  (cx,cy,cz) -> (start,count).
+//
+// Search for one query: visit the 3x3x3 voxel block around the query at the finest level, keep
+// the K best candidates ordered by the pair (d2, original index); the block guarantees that every
+// unvisited point is farther than `m` (distance from the query to the block's faces). If the K-th
+// best d2 <= m^2 the result is exact and the search stops, otherwise it is repeated one level up
+// (voxels twice as large) — the top level is a single voxel, so termination is unconditional.
+// Voxels whose box lower bound exceeds the current K-th distance are skipped without a lookup.
+//
+// Exactness w.r.t. the reference metric (nanoflann L2_Simple on float, see oracle/kdtree.hpp):
+// d2 = ((dx*dx)+dy*dy)+dz*dz with non-fused float ops; bounds are made conservative by 4 finest
+// quanta (covers the float rounding of the voxel coordinate function, which is monotonic) and a
+// 1e-6 relative margin; candidates compare on (d2, index) so exact ties resolve to the lowest
+// original index, the rule the oracle pins.
+#pragma once
+#include "common.cuh"
+
+namespace mp2p
+{
+__device__ __forceinline__ unsigned long long morton_expand21(uint32_t v)
+{
+    unsigned long long x = v & 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+__device__ __forceinline__ unsigned long long morton63(uint32_t x, uint32_t y, uint32_t z)
+{
+    return morton_expand21(x) | (morton_expand21(y) << 1) | (morton_expand21(z) << 2);
+}
+
+// voxel coordinate function (float, monotonic in p): u = (p - o) * inv_s0
+__device__ __forceinline__ float grid_u(float p, float o, float inv_s0)
+{
+    return __fmul_rn(__fsub_rn(p, o), inv_s0);
+}
+
+__device__ __forceinline__ unsigned long long cell_key(uint32_t cx, uint32_t cy, uint32_t cz)
+{
+    return (unsigned long long)cx | ((unsigned long long)cy << 21) | ((unsigned long long)cz << 42);
+}
+__device__ __forceinline__ uint32_t cell_hash(unsigned long long key, uint32_t shift)
+{
+    return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> shift);
+}
+
+__device__ __forceinline__ bool grid_lookup(const GridView& g, int rl, uint32_t cx, uint32_t cy,
+                                            uint32_t cz, uint32_t& start, uint32_t& count)
+{
+    const unsigned long long key   = cell_key(cx, cy, cz);
+    const uint32_t           shift = g.level_shift[rl];
+    const uint32_t           mask  = (1u << (64 - shift)) - 1u;
+    const CellEntry*         t     = g.table + g.level_off[rl];
+    uint32_t                 h     = cell_hash(key, shift);
+    while (true)
+    {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(t + h));
+        const unsigned long long k = (unsigned long long)raw.x | ((unsigned long long)raw.y << 32);
+        if (k == key)
+        {
+            start = raw.z;
+            count = raw.w;
+            return true;
+        }
+        if (k == kEmptyKey) return false;
+        h = (h + 1) & mask;
+    }
+}
+
+// reference float metric, never fused
+__device__ __forceinline__ float dist2_ref(float qx, float qy, float qz, float px, float py, float pz)
+{
+    const float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
+    float       d  = __fmul_rn(dx, dx);
+    d              = __fadd_rn(d, __fmul_rn(dy, dy));
+    d              = __fadd_rn(d, __fmul_rn(dz, dz));
+    return d;
+}
+
+template <int K>
+struct TopK
+{
+    unsigned long long v[K];  // ascending; (d2 bits << 32) | original index
+    __device__ __forceinline__ void init(unsigned long long sentinel)
+    {
+#pragma unroll
+        for (int j = 0; j < K; j++) v[j] = sentinel;
+    }
+    __device__ __forceinline__ unsigned long long worst(int k_runtime) const
+    {
+        unsigned long long w = v[K - 1];
+#pragma unroll
+        for (int j = 0; j < K - 1; j++)
+            if (j == k_runtime - 1) w = v[j];
+        return w;
+    }
+    __device__ __forceinline__ void insert(unsigned long long c)
+    {
+#pragma unroll
+        for (int j = 0; j < K; j++)
+        {
+            if (c == v[j]) c = ~0ull;  // the same point seen again at a coarser level
+            if (c < v[j])
+            {
+                const unsigned long long t = v[j];
+                v[j]                       = c;
+                c                          = t;
+            }
+        }
+    }
+};
+
+// 27 neighbour offsets ordered centre, 6 faces, 12 edges, 8 corners: bits [1:0]=dx+1, [3:2]=dy+1,
+// [5:4]=dz+1
+__constant__ uint8_t kNeighbourOrder[27] = {
+    0x15,                                                                    // (0,0,0)
+    0x14, 0x16, 0x11, 0x19, 0x05, 0x25,                                      // faces
+    0x10, 0x12, 0x18, 0x1a, 0x04, 0x06, 0x24, 0x26, 0x01, 0x09, 0x21, 0x29,  // edges
+    0x00, 0x02, 0x08, 0x0a, 0x20, 0x22, 0x28, 0x2a};                         // corners
+
+// Exact K-nearest (k_runtime <= K) of (qx,qy,qz) among points with d2 < radius2 (strict).
+// On return top.v[0..k_runtime) ascending; entries >= sentinel are "not found".
+struct SearchCounters
+{
+    uint32_t probes = 0, cands = 0, levels = 0;
+};
+
+template <int K>
+__device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy, float qz,
+                                           float radius2, int k_runtime, TopK<K>& top,
+                                           SearchCounters& sc)
+{
+    const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
+    top.init(sentinel);
+    if (!(radius2 > 0.f)) return;
+
+    // reject queries farther than the radius from the map bbox (conservative: strictly greater)
+    {
+        const float ex = fmaxf(fmaxf(g.bbmin[0] - qx, qx - g.bbmax[0]), 0.f);
+        const float ey = fmaxf(fmaxf(g.bbmin[1] - qy, qy - g.bbmax[1]), 0.f);
+        const float ez = fmaxf(fmaxf(g.bbmin[2] - qz, qz - g.bbmax[2]), 0.f);
+        const float e2 = ex * ex + ey * ey + ez * ez;
+        if (e2 * 0.999999f > radius2) return;
+    }
+
+    const float lim = 4194304.f;  // 2^22
+    const float ux  = fminf(fmaxf(grid_u(qx, g.ox, g.inv_s0), -lim), lim);
+    const float uy  = fminf(fmaxf(grid_u(qy, g.oy, g.inv_s0), -lim), lim);
+    const float uz  = fminf(fmaxf(grid_u(qz, g.oz, g.inv_s0), -lim), lim);
+    const int   Ix = (int)floorf(ux), Iy = (int)floorf(uy), Iz = (int)floorf(uz);
+
+    float kth = radius2;
+    for (int rl = 0; rl < g.n_levels; rl++)
+    {
+        const int   L      = g.level_first + rl;
+        const int   cmax   = ((1 << kGridBits) - 1) >> L;
+        const float s      = (float)(1 << L);  // voxel edge in finest quanta
+        const int   cx = Ix >> L, cy = Iy >> L, cz = Iz >> L;
+        const float fx = ux - (float)cx * s, fy = uy - (float)cy * s, fz = uz - (float)cz * s;
+        // per-axis gap (in quanta, made conservative) to the -1 / +1 neighbour slabs
+        const float gxl = fmaxf(fx - 4.f, 0.f), gxh = fmaxf(s - fx - 4.f, 0.f);
+        const float gyl = fmaxf(fy - 4.f, 0.f), gyh = fmaxf(s - fy - 4.f, 0.f);
+        const float gzl = fmaxf(fz - 4.f, 0.f), gzh = fmaxf(s - fz - 4.f, 0.f);
+        const float q2  = g.s0_lo * g.s0_lo * 0.999999f;  // quanta^2 -> metres^2, rounded down
+
+#pragma unroll 1
+        for (int nb = 0; nb < 27; nb++)
+        {
+            const uint32_t code = kNeighbourOrder[nb];
+            const int      dx = (int)(code & 3u) - 1, dy = (int)((code >> 2) & 3u) - 1,
+                      dz = (int)((code >> 4) & 3u) - 1;
+            const float bx = dx < 0 ? gxl : (dx > 0 ? gxh : 0.f);
+            const float by = dy < 0 ? gyl : (dy > 0 ? gyh : 0.f);
+            const float bz = dz < 0 ? gzl : (dz > 0 ? gzh : 0.f);
+            const float lb = (bx * bx + by * by + bz * bz) * q2;
+            if (lb > kth) continue;  // strict: an equal-distance lower index must still be seen
+            const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
+            if ((unsigned)nx > (unsigned)cmax || (unsigned)ny > (unsigned)cmax ||
+                (unsigned)nz > (unsigned)cmax)
+                continue;
+            uint32_t start, count;
+            sc.probes++;
+            if (!grid_lookup(g, rl, (uint32_t)nx, (uint32_t)ny, (uint32_t)nz, start, count)) continue;
+            sc.cands += count;
+            for (uint32_t j = start; j < start + count; j++)
+            {
+                const float4 p  = __ldg(g.pts + j);
+                const float  d2 = dist2_ref(qx, qy, qz, p.x, p.y, p.z);
+                const unsigned long long c =
+                    ((unsigned long long)__float_as_uint(d2) << 32) | (uint32_t)__float_as_int(p.w);
+                if (c < top.worst(k_runtime))
+                {
+                    top.insert(c);
+                    kth = __uint_as_float((uint32_t)(top.worst(k_runtime) >> 32));
+                }
+            }
+        }
+        // everything outside the 3x3x3 block is at least m quanta away
+        const float mx = s + fminf(fx, s - fx), my = s + fminf(fy, s - fy), mz = s + fminf(fz, s - fz);
+        const float m  = fmaxf(fminf(mx, fminf(my, mz)) - 4.f, 0.f);
+        sc.levels++;
+        if (kth <= m * m * q2) break;
+    }
+}
+
+// warp-aggregated accumulation of the per-thread counters into stats[0..3] (measurement hook)
+__device__ __forceinline__ void flush_search_stats(const SearchCounters& sc, uint32_t n_valid,
+                                                   unsigned long long* stats)
+{
+    if (!stats) return;
+    uint32_t a = sc.probes, b = sc.cands, c = n_valid, d = sc.levels > 1 ? 1u : 0u;
+    const unsigned mask = __activemask();
+    a = __reduce_add_sync(mask, a), b = __reduce_add_sync(mask, b);
+    c = __reduce_add_sync(mask, c), d = __reduce_add_sync(mask, d);
+    if ((threadIdx.x & 31) == (__ffs(mask) - 1))
+    {
+        atomicAdd(stats + 0, (unsigned long long)a), atomicAdd(stats + 1, (unsigned long long)b);
+        atomicAdd(stats + 2, (unsigned long long)c), atomicAdd(stats + 3, (unsigned long long)d);
+    }
+}
+
+}  // namespace mp2p

@@ -1,0 +1,810 @@
+// Matcher kernels (product code): the per-ICP-iteration correspondence search.
+//
+//   k_match_pt2pt  = transform_local_to_global (Matcher_Points_Base.cpp:183-220) +
+//                    nn_single_search / nn_multiple_search (MRPT/nanoflann, external) +
+//                    distance-threshold test (Matcher_Points_DistanceThreshold.cpp:214-259) +
+//                    first-claim proposal on the global point.
+//   k_compact_pt2pt = lambdaAddPair (…DistanceThreshold.cpp:94-121): bounding-box gate (:73-75),
+//                    first-claim acceptance, stream compaction into 36-byte TMatchingPair records
+//                    in ascending (localIdx, rank) order.
+//   k_match_pt2pl / k_compact_pt2pl = Matcher_Point2Plane.cpp:41-114 with the k-NN + PCA plane fit.
+//
+// Query tiles (256 points x 3 axes) are staged into shared memory with TMA bulk copies
+// (cp.async.bulk … mbarrier::complete_tx) so the per-thread search starts from on-chip data.
+//
+// First-claim semantics on a parallel machine: in the serial reference a proposal (i,k) -> g is
+// rejected iff g was taken by a lexicographically smaller (i',k'). Every proposer does
+// atomicMin(claim[g], tag | (i*K+k)); the proposal whose word survives is the accepted one.
+// `tag` = (0xFFFFFFFF - epoch) << 32 decreases with every call, so words of earlier calls always
+// lose and the claim array never needs clearing.
+#include <cuda/std/limits>
+
+#include "grid_search.cuh"
+#include "plane_fit.cuh"
+
+namespace mp2p
+{
+namespace
+{
+// ------------------------------------------------------------------------------------------
+// TMA bulk-copy helpers (sm_90+/sm_100a): 1-D global -> shared copies completing on an mbarrier.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                            uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+struct QueryTile
+{
+    alignas(128) float x[kQueryTile];
+    alignas(128) float y[kQueryTile];
+    alignas(128) float z[kQueryTile];
+    alignas(8) uint64_t bar;
+};
+
+// All threads of the CTA call this; afterwards tile.x/y/z hold queries [base, base+kQueryTile).
+// The staging arrays are padded to a multiple of kQueryTile, so the copy size is constant.
+__device__ __forceinline__ void load_query_tile(QueryTile& tile, const float* lx, const float* ly,
+                                                const float* lz, size_t base)
+{
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&tile.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        constexpr uint32_t bytes = kQueryTile * sizeof(float);
+        mbar_expect_tx(&tile.bar, 3 * bytes);
+        tma_load_1d(tile.x, lx + base, bytes, &tile.bar);
+        tma_load_1d(tile.y, ly + base, bytes, &tile.bar);
+        tma_load_1d(tile.z, lz + base, bytes, &tile.bar);
+    }
+    mbar_wait(&tile.bar, 0);
+}
+
+struct PoseArg
+{
+    double m[12];
+};
+
+// CPose3D::composePoint(float…): double arithmetic left to right, one rounding to float.
+__device__ __forceinline__ void compose_point_f(const PoseArg& T, float lx, float ly, float lz,
+                                                float& gx, float& gy, float& gz)
+{
+    const double x = lx, y = ly, z = lz;
+    gx = __double2float_rn(__dadd_rn(
+        __dadd_rn(__dadd_rn(__dmul_rn(T.m[0], x), __dmul_rn(T.m[1], y)), __dmul_rn(T.m[2], z)), T.m[3]));
+    gy = __double2float_rn(__dadd_rn(
+        __dadd_rn(__dadd_rn(__dmul_rn(T.m[4], x), __dmul_rn(T.m[5], y)), __dmul_rn(T.m[6], z)), T.m[7]));
+    gz = __double2float_rn(__dadd_rn(
+        __dadd_rn(__dadd_rn(__dmul_rn(T.m[8], x), __dmul_rn(T.m[9], y)), __dmul_rn(T.m[10], z)), T.m[11]));
+}
+
+__device__ __forceinline__ uint32_t f2ord(float f)
+{
+    const uint32_t u = __float_as_uint(f);
+    return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o)
+{
+    return __uint_as_float(o ^ (((o >> 31) - 1u) | 0x80000000u));
+}
+
+// CTA-wide min/max of the transformed cloud -> 6 global atomics per CTA.
+__device__ __forceinline__ void block_bbox_update(float gx, float gy, float gz, bool valid,
+                                                  uint32_t* bbox)
+{
+    float mn[3] = {valid ? gx : 3.4e38f, valid ? gy : 3.4e38f, valid ? gz : 3.4e38f};
+    float mx[3] = {valid ? gx : -3.4e38f, valid ? gy : -3.4e38f, valid ? gz : -3.4e38f};
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+        }
+    if ((threadIdx.x & 31) == 0)
+    {
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+        {
+            atomicMin(bbox + d, f2ord(mn[d]));
+            atomicMax(bbox + 3 + d, f2ord(mx[d]));
+        }
+    }
+}
+
+__device__ __forceinline__ bool bit_set(const uint32_t* bits, uint32_t i)
+{
+    return bits && ((bits[i >> 5] >> (i & 31)) & 1u);
+}
+
+struct Pt2PtArgs
+{
+    PoseArg  pose;
+    float    maxDistSq, angSq;
+    uint32_t n_local, K;
+    int      allowLocal, allowGlobal;
+    unsigned long long tag;  // (0xFFFFFFFF - epoch) << 32
+};
+
+// ------------------------------------------------------------------------------------------
+template <int KT>
+__global__ void __launch_bounds__(kQueryTile)
+    k_match_pt2pt(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
+                  const float* __restrict__ lz, const uint32_t* __restrict__ lbits,
+                  const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim,
+                  unsigned long long* __restrict__ cand, uint32_t* __restrict__ bbox,
+                  unsigned long long* __restrict__ stats)
+{
+    __shared__ QueryTile tile;
+    const size_t         base = (size_t)blockIdx.x * kQueryTile;
+    load_query_tile(tile, lx, ly, lz, base);
+    const uint32_t i     = (uint32_t)base + threadIdx.x;
+    const bool     valid = i < a.n_local;
+
+    float gx = 0, gy = 0, gz = 0;
+    if (valid) compose_point_f(a.pose, tile.x[threadIdx.x], tile.y[threadIdx.x], tile.z[threadIdx.x], gx, gy, gz);
+    block_bbox_update(gx, gy, gz, valid, bbox);
+    if (!valid) return;
+
+    const int K = (int)a.K;
+    // …DistanceThreshold.cpp:230,256-257 (float, unfused)
+    const float normSq = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+    const float thr2   = __fadd_rn(a.maxDistSq, __fmul_rn(a.angSq, normSq));
+    const unsigned long long sentinel = (unsigned long long)__float_as_uint(thr2) << 32;
+
+    TopK<KT>       top;
+    SearchCounters sc;
+    if (!a.allowLocal && bit_set(lbits, i))
+        top.init(sentinel);  // :218-220 skip, already paired
+    else
+        knn_search<KT>(g, gx, gy, gz, thr2, K, top, sc);
+
+    uint32_t n_valid = 0;
+#pragma unroll
+    for (int k = 0; k < KT; k++)
+    {
+        if (k < K)
+        {
+            // unused ranks are marked with an impossible map index (all ones)
+            const unsigned long long c = top.v[k] < sentinel ? top.v[k] : ~0ull;
+            n_valid += (c != ~0ull);
+            cand[(size_t)i * K + k]    = c;
+            if (c != ~0ull && !a.allowGlobal)
+            {
+                const uint32_t gi = (uint32_t)c;
+                if (!bit_set(gbits, gi)) atomicMin(claim + gi, a.tag | (unsigned long long)(i * (uint32_t)K + k));
+            }
+        }
+    }
+    flush_search_stats(sc, n_valid, stats);
+}
+
+// ------------------------------------------------------------------------------------------
+// Single-pass stream compaction (decoupled look-back over 1024-slot tiles).
+// status word: [63:62] 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix; [61:0] value
+// ------------------------------------------------------------------------------------------
+constexpr int      kScanThreads = 256;
+constexpr int      kScanItems   = 4;
+constexpr uint32_t kScanTile    = kScanThreads * kScanItems;
+
+struct ScanSmem
+{
+    uint32_t warp_sums[kScanThreads / 32];
+    uint32_t tile_id;
+    unsigned long long tile_base;
+};
+
+// returns this thread's exclusive offset inside the grid-wide output; *total_out written by the
+// last tile. `local` = number of outputs of this thread (its kScanItems consecutive slots).
+__device__ __forceinline__ unsigned long long grid_exclusive_scan(
+    ScanSmem& sm, uint32_t tile, uint32_t n_tiles, uint32_t local, unsigned long long* status,
+    unsigned long long* total_out)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t       incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) sm.warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t warp_off = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; w++)
+    {
+        const uint32_t s = sm.warp_sums[w];
+        if (w < (int)warp) warp_off += s;
+        block_total += s;
+    }
+    if (threadIdx.x == 0)
+    {
+        unsigned long long base = 0;
+        if (tile > 0)
+        {
+            // publish aggregate, then look back
+            __threadfence();
+            atomicExch(status + tile, (1ull << 62) | block_total);
+            int t = (int)tile - 1;
+            while (t >= 0)
+            {
+                unsigned long long s;
+                do
+                {
+                    s = atomicAdd(status + t, 0ull);
+                } while ((s >> 62) == 0);
+                base += s & ((1ull << 62) - 1);
+                if ((s >> 62) == 2) break;
+                t--;
+            }
+        }
+        atomicExch(status + tile, (2ull << 62) | (base + block_total));
+        sm.tile_base = base;
+        if (tile == n_tiles - 1) *total_out = base + block_total;
+    }
+    __syncthreads();
+    return sm.tile_base + warp_off + (incl - local);
+}
+
+struct CompactArgs
+{
+    uint32_t n_local, K;
+    int      allowGlobal;
+    unsigned long long tag;
+    float    gate_eps;  // threshold + bounding_box_intersection_check_epsilon (float)
+    uint64_t capacity;
+};
+
+__device__ __forceinline__ bool bbox_gate(const GridView& g, const uint32_t* bbox, float eps)
+{
+    // mrpt TBoundingBoxf::intersection(other, epsilon) has a value (…DistanceThreshold.cpp:73-75)
+    const float lmin[3] = {ord2f(bbox[0]), ord2f(bbox[1]), ord2f(bbox[2])};
+    const float lmax[3] = {ord2f(bbox[3]), ord2f(bbox[4]), ord2f(bbox[5])};
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+    {
+        if (__fsub_rn(lmin[d], eps) > g.bbmax[d]) return false;
+        if (__fadd_rn(lmax[d], eps) < g.bbmin[d]) return false;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+    k_compact_pt2pt(GridView g, CompactArgs a, const float* __restrict__ lx,
+                    const float* __restrict__ ly, const float* __restrict__ lz,
+                    const uint32_t* __restrict__ gbits, const unsigned long long* __restrict__ claim,
+                    const unsigned long long* __restrict__ cand, const uint32_t* __restrict__ bbox,
+                    unsigned long long* __restrict__ status, uint32_t* __restrict__ tile_counter,
+                    mp2p_b200_pair_pt2pt* __restrict__ out, unsigned long long* __restrict__ out_count)
+{
+    __shared__ ScanSmem sm;
+    if (threadIdx.x == 0) sm.tile_id = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile    = sm.tile_id;
+    const uint64_t n_slots = (uint64_t)a.n_local * a.K;
+    const uint32_t n_tiles = (uint32_t)((n_slots + kScanTile - 1) / kScanTile);
+    const bool     gate    = bbox_gate(g, bbox, a.gate_eps);
+
+    const uint64_t     slot0 = (uint64_t)tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    unsigned long long c[kScanItems];
+    uint32_t           flags = 0, local = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++)
+    {
+        const uint64_t slot = slot0 + j;
+        bool           ok   = false;
+        if (gate && slot < n_slots)
+        {
+            c[j] = cand[slot];
+            ok = ((uint32_t)c[j] != 0xFFFFFFFFu);  // unused ranks carry an all-ones map index
+            if (ok && !a.allowGlobal)
+            {
+                const uint32_t gi = (uint32_t)c[j];
+                ok = !bit_set(gbits, gi) && (claim[gi] == (a.tag | (unsigned long long)slot));
+            }
+        }
+        if (ok) flags |= 1u << j, local++;
+    }
+    const unsigned long long off = grid_exclusive_scan(sm, tile, n_tiles, local, status, out_count);
+    unsigned long long       w   = off;
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++)
+    {
+        if (!(flags & (1u << j))) continue;
+        if (w < a.capacity)
+        {
+            const uint64_t slot = slot0 + j;
+            const uint32_t i    = (uint32_t)(slot / a.K);
+            const uint32_t gi   = (uint32_t)c[j];
+            const float4   gp   = __ldg(g.pts_orig + gi);
+            uint32_t*      o    = reinterpret_cast<uint32_t*>(out + w);  // 36-byte records, 4-aligned
+            o[0] = gi, o[1] = i;
+            o[2] = __float_as_uint(gp.x), o[3] = __float_as_uint(gp.y), o[4] = __float_as_uint(gp.z);
+            o[5] = __float_as_uint(lx[i]), o[6] = __float_as_uint(ly[i]), o[7] = __float_as_uint(lz[i]);
+            o[8] = (uint32_t)(c[j] >> 32);
+        }
+        w++;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// pt2pl
+// ------------------------------------------------------------------------------------------
+struct Pt2PlArgs
+{
+    PoseArg  pose;
+    float    radiusSq, distThr;
+    double   planeEigenThreshold;
+    uint32_t n_local, K, minPts;
+    int      allowLocal;
+    float    gate_eps;
+    uint64_t capacity;
+};
+
+template <int KT>
+__global__ void __launch_bounds__(kQueryTile)
+    k_match_pt2pl(GridView g, Pt2PlArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
+                  const float* __restrict__ lz, const uint32_t* __restrict__ lbits,
+                  PlaneCandidate* __restrict__ plc, uint8_t* __restrict__ ok_flags,
+                  uint32_t* __restrict__ bbox, unsigned long long* __restrict__ stats)
+{
+    __shared__ QueryTile tile;
+    const size_t         base = (size_t)blockIdx.x * kQueryTile;
+    load_query_tile(tile, lx, ly, lz, base);
+    const uint32_t i     = (uint32_t)base + threadIdx.x;
+    const bool     valid = i < a.n_local;
+    float          gx = 0, gy = 0, gz = 0;
+    if (valid) compose_point_f(a.pose, tile.x[threadIdx.x], tile.y[threadIdx.x], tile.z[threadIdx.x], gx, gy, gz);
+    block_bbox_update(gx, gy, gz, valid, bbox);
+    if (!valid) return;
+
+    uint8_t        ok = 0;
+    SearchCounters sc;
+    uint32_t       n_valid = 0;
+    if (a.allowLocal || !bit_set(lbits, i))
+    {
+        TopK<KT> top;
+        const int K = (int)a.K;
+        knn_search<KT>(g, gx, gy, gz, a.radiusSq, K, top, sc);
+        const unsigned long long sentinel = (unsigned long long)__float_as_uint(a.radiusSq) << 32;
+        int                      cnt      = 0;
+#pragma unroll
+        for (int k = 0; k < KT; k++)
+            if (k < K && top.v[k] < sentinel) cnt++;
+        n_valid = (uint32_t)cnt;
+        if (cnt >= 3 && cnt >= (int)a.minPts)
+        {
+            // estimate_points_eigen.cpp:45-63 — float mean, double centred moments, ascending
+            // (d2, index) neighbour order
+            float px[KT], py[KT], pz[KT];
+#pragma unroll
+            for (int k = 0; k < KT; k++)
+                if (k < cnt)
+                {
+                    const float4 p = __ldg(g.pts_orig + (uint32_t)top.v[k]);
+                    px[k] = p.x, py[k] = p.y, pz[k] = p.z;
+                }
+            PlaneCandidate pc;
+            if (fit_plane<KT>(px, py, pz, cnt, gx, gy, gz, a.planeEigenThreshold, a.distThr, pc))
+            {
+                plc[i] = pc;
+                ok     = 1;
+            }
+        }
+    }
+    ok_flags[i] = ok;
+    flush_search_stats(sc, n_valid, stats);
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+    k_compact_pt2pl(GridView g, uint32_t n_local, float gate_eps, uint64_t capacity,
+                    const float* __restrict__ lx, const float* __restrict__ ly,
+                    const float* __restrict__ lz, const PlaneCandidate* __restrict__ plc,
+                    const uint8_t* __restrict__ ok_flags, const uint32_t* __restrict__ bbox,
+                    unsigned long long* __restrict__ status, uint32_t* __restrict__ tile_counter,
+                    mp2p_b200_pair_pt2pl* __restrict__ out, unsigned long long* __restrict__ out_count)
+{
+    __shared__ ScanSmem sm;
+    if (threadIdx.x == 0) sm.tile_id = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile    = sm.tile_id;
+    const uint32_t n_tiles = (n_local + kScanTile - 1) / kScanTile;
+    const bool     gate    = bbox_gate(g, bbox, gate_eps);
+    const uint32_t i0      = tile * kScanTile + threadIdx.x * kScanItems;
+    uint32_t       flags = 0, local = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++)
+    {
+        const uint32_t i = i0 + j;
+        if (gate && i < n_local && ok_flags[i]) flags |= 1u << j, local++;
+    }
+    const unsigned long long off = grid_exclusive_scan(sm, tile, n_tiles, local, status, out_count);
+    unsigned long long       w   = off;
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++)
+    {
+        if (!(flags & (1u << j))) continue;
+        if (w < capacity)
+        {
+            const uint32_t       i  = i0 + j;
+            const PlaneCandidate pc = plc[i];
+            mp2p_b200_pair_pt2pl r;
+            r.plane_coefs[0] = pc.coefs[0], r.plane_coefs[1] = pc.coefs[1];
+            r.plane_coefs[2] = pc.coefs[2], r.plane_coefs[3] = pc.coefs[3];
+            r.centroid[0] = pc.centroid[0], r.centroid[1] = pc.centroid[1], r.centroid[2] = pc.centroid[2];
+            r.local_x = lx[i], r.local_y = ly[i], r.local_z = lz[i];  // ORIGINAL point (:105)
+            r._pad = 0.f;
+            out[w] = r;
+        }
+        w++;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// raw k-NN (already transformed queries) — nn_* parity tests
+// ------------------------------------------------------------------------------------------
+template <int KT>
+__global__ void __launch_bounds__(256)
+    k_knn(GridView g, const float* __restrict__ qx, const float* __restrict__ qy,
+          const float* __restrict__ qz, uint32_t nq, uint32_t K, float radius2,
+          uint32_t* __restrict__ out_idx, float* __restrict__ out_d2, int32_t* __restrict__ out_found)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    TopK<KT>       top;
+    SearchCounters sc;
+    knn_search<KT>(g, qx[i], qy[i], qz[i], radius2, (int)K, top, sc);
+    const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
+    int                      cnt      = 0;
+#pragma unroll
+    for (int k = 0; k < KT; k++)
+        if (k < (int)K)
+        {
+            const bool f                 = top.v[k] < sentinel;
+            out_idx[(size_t)i * K + k]   = f ? (uint32_t)top.v[k] : 0u;
+            out_d2[(size_t)i * K + k]    = f ? __uint_as_float((uint32_t)(top.v[k] >> 32))
+                                             : cuda::std::numeric_limits<float>::infinity();
+            cnt += f;
+        }
+    out_found[i] = cnt;
+}
+
+__global__ void k_init_small(uint32_t* bbox, unsigned long long* count, uint32_t* tile_counter)
+{
+    if (threadIdx.x < 3) bbox[threadIdx.x] = 0xffffffffu;
+    if (threadIdx.x >= 3 && threadIdx.x < 6) bbox[threadIdx.x] = 0u;
+    if (threadIdx.x == 6) *count = 0ull;
+    if (threadIdx.x == 7) *tile_counter = 0u;
+}
+
+int pick_kt(uint32_t K)
+{
+    if (K <= 1) return 1;
+    if (K <= 4) return 4;
+    if (K <= 8) return 8;
+    if (K <= 16) return 16;
+    return 32;
+}
+
+// stage the local cloud into kQueryTile-padded device arrays (TMA needs 16-byte granules and must
+// not read past the caller's buffers)
+int stage_local(mp2p_b200_ctx* ctx, const float* lx, const float* ly, const float* lz, uint64_t n,
+                int on_device)
+{
+    const size_t padded = ((n + kQueryTile - 1) / kQueryTile) * kQueryTile * sizeof(float);
+    MP2P_TRY(ctx->d_lx.ensure(padded));
+    MP2P_TRY(ctx->d_ly.ensure(padded));
+    MP2P_TRY(ctx->d_lz.ensure(padded));
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_lx.p, lx, n * 4, kind, ctx->stream));
+    MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_ly.p, ly, n * 4, kind, ctx->stream));
+    MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_lz.p, lz, n * 4, kind, ctx->stream));
+    return 0;
+}
+
+int upload_bits(mp2p_b200_ctx* ctx, DevBuf& buf, const uint32_t* bits, uint64_t n_bits,
+                const uint32_t** d_out)
+{
+    *d_out = nullptr;
+    if (!bits) return 0;
+    const size_t bytes = ((n_bits + 31) / 32) * 4;
+    MP2P_TRY(buf.ensure(bytes));
+    MP2P_CUDA_TRY(cudaMemcpyAsync(buf.p, bits, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *d_out = buf.as<uint32_t>();
+    return 0;
+}
+
+struct SmallView
+{
+    uint32_t*           bbox;
+    unsigned long long* count;
+    uint32_t*           tile_counter;
+};
+int prepare_small(mp2p_b200_ctx* ctx, uint64_t n_tiles, SmallView& sv, unsigned long long** status)
+{
+    MP2P_TRY(ctx->d_small.ensure(64));
+    sv.bbox         = ctx->d_small.as<uint32_t>();
+    sv.count        = reinterpret_cast<unsigned long long*>(ctx->d_small.as<char>() + 32);
+    sv.tile_counter = reinterpret_cast<uint32_t*>(ctx->d_small.as<char>() + 40);
+    MP2P_TRY(ctx->d_scan.ensure((n_tiles + 1) * 8));
+    *status = ctx->d_scan.as<unsigned long long>();
+    MP2P_CUDA_TRY(cudaMemsetAsync(*status, 0, (n_tiles + 1) * 8, ctx->stream));
+    k_init_small<<<1, 32, 0, ctx->stream>>>(sv.bbox, sv.count, sv.tile_counter);
+    count_launch(ctx);
+    return 0;
+}
+
+int prepare_stats(mp2p_b200_ctx* ctx, unsigned long long** stats)
+{
+    *stats = nullptr;
+    if (!ctx->prof_stats) return 0;
+    MP2P_TRY(ctx->d_stats.ensure(32));
+    MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_stats.p, 0, 32, ctx->stream));
+    *stats = ctx->d_stats.as<unsigned long long>();
+    return 0;
+}
+
+template <class Rec>
+int fetch_results(mp2p_b200_ctx* ctx, const unsigned long long* d_count, const Rec* d_pairs,
+                  Rec* out, uint64_t capacity, int out_on_device, uint64_t* out_count)
+{
+    unsigned long long* h_count = static_cast<unsigned long long*>(ctx->h_pinned);
+    MP2P_CUDA_TRY(cudaMemcpyAsync(h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    MP2P_CUDA_TRY(cudaGetLastError());
+    const uint64_t cnt = *h_count;
+    *out_count         = cnt;
+    if (cnt > capacity)
+    {
+        set_error("output capacity %llu too small for %llu pairings", (unsigned long long)capacity,
+                  (unsigned long long)cnt);
+        return MP2P_B200_ERR_CAPACITY;
+    }
+    if (!out_on_device && cnt)
+    {
+        MP2P_CUDA_TRY(cudaMemcpyAsync(out, d_pairs, cnt * sizeof(Rec), cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+}  // namespace
+
+// ==========================================================================================
+int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                    const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
+                    const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits, const uint32_t* gbits,
+                    mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device,
+                    uint64_t* out_count)
+{
+    *out_count          = 0;
+    const uint32_t K    = prm->pairingsPerPoint;
+    const uint64_t nmap = map->view.n_points;
+    if (nmap == 0 || n_local == 0) return 0;  // …DistanceThreshold.cpp:67
+    if (n_local * (uint64_t)K >= 0xFFFFFFFFull)
+    {
+        set_error("n_local*pairingsPerPoint must be < 2^32-1");
+        return MP2P_B200_ERR_ARG;
+    }
+    cudaStream_t st = ctx->stream;
+    MP2P_TRY(stage_local(ctx, lx, ly, lz, n_local, local_on_device));
+    const uint32_t *d_lbits, *d_gbits;
+    MP2P_TRY(upload_bits(ctx, ctx->d_lbits, lbits, n_local, &d_lbits));
+    MP2P_TRY(upload_bits(ctx, ctx->d_gbits, gbits, nmap, &d_gbits));
+    const uint64_t n_slots = n_local * K;
+    const uint64_t n_tiles = (n_slots + kScanTile - 1) / kScanTile;
+    SmallView           sv;
+    unsigned long long* status;
+    MP2P_TRY(prepare_small(ctx, n_tiles, sv, &status));
+    MP2P_TRY(ctx->d_cand.ensure(n_slots * 8));
+
+    if (++map->epoch == 0xFFFFFFFFu)  // tags exhausted: restart the claim words
+    {
+        MP2P_CUDA_TRY(cudaMemsetAsync(map->d_claim.p, 0xff, nmap * 8, st));
+        map->epoch = 1;
+    }
+
+    Pt2PtArgs a{};
+    for (int k = 0; k < 12; k++) a.pose.m[k] = pose[k];
+    a.maxDistSq = (float)(prm->threshold * prm->threshold);  // …DistanceThreshold.cpp:82
+    const double ang = prm->thresholdAngularDeg * 3.14159265358979323846 / 180.0;
+    a.angSq     = (float)(ang * ang);  // :83
+    a.n_local = (uint32_t)n_local, a.K = K;
+    a.allowLocal = prm->allowMatchAlreadyMatchedPoints, a.allowGlobal = prm->allowMatchAlreadyMatchedGlobalPoints;
+    a.tag = (unsigned long long)(0xFFFFFFFFu - map->epoch) << 32;
+
+    const uint32_t blocks = (uint32_t)((n_local + kQueryTile - 1) / kQueryTile);
+    const float *  dlx = ctx->d_lx.as<float>(), *dly = ctx->d_ly.as<float>(), *dlz = ctx->d_lz.as<float>();
+    auto*          claim = map->d_claim.as<unsigned long long>();
+    auto*          cand  = ctx->d_cand.as<unsigned long long>();
+    unsigned long long* stats = nullptr;
+    MP2P_TRY(prepare_stats(ctx, &stats));
+    prof_begin(ctx, 0);
+#define LAUNCH_MATCH(KT) \
+    k_match_pt2pt<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, sv.bbox, stats)
+    switch (pick_kt(K))
+    {
+        case 1: LAUNCH_MATCH(1); break;
+        case 4: LAUNCH_MATCH(4); break;
+        case 8: LAUNCH_MATCH(8); break;
+        case 16: LAUNCH_MATCH(16); break;
+        default: LAUNCH_MATCH(32); break;
+    }
+#undef LAUNCH_MATCH
+    prof_end(ctx, 0);
+    count_launch(ctx);
+
+    mp2p_b200_pair_pt2pt* d_out = out;
+    if (!out_on_device)
+    {
+        MP2P_TRY(ctx->d_out2p.ensure(std::min<uint64_t>(capacity, n_slots) * sizeof(mp2p_b200_pair_pt2pt)));
+        d_out = ctx->d_out2p.as<mp2p_b200_pair_pt2pt>();
+    }
+    CompactArgs c{};
+    c.n_local = (uint32_t)n_local, c.K = K, c.allowGlobal = a.allowGlobal, c.tag = a.tag;
+    c.gate_eps = (float)(prm->threshold + prm->bounding_box_intersection_check_epsilon);
+    c.capacity = std::min<uint64_t>(capacity, n_slots);
+    prof_begin(ctx, 1);
+    k_compact_pt2pt<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, c, dlx, dly, dlz, d_gbits,
+                                                               claim, cand, sv.bbox, status,
+                                                               sv.tile_counter, d_out, sv.count);
+    prof_end(ctx, 1);
+    count_launch(ctx);
+    return fetch_results(ctx, sv.count, d_out, out, capacity, out_on_device, out_count);
+}
+
+int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                    const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
+                    const mp2p_b200_pt2pl_params* prm, const uint32_t* lbits,
+                    mp2p_b200_pair_pt2pl* out, uint64_t capacity, int out_on_device,
+                    uint64_t* out_count)
+{
+    *out_count          = 0;
+    const uint64_t nmap = map->view.n_points;
+    if (nmap == 0 || n_local == 0) return 0;
+    if (n_local >= 0xFFFFFFFFull || prm->knn < 1 || prm->knn > MP2P_B200_MAX_KNN)
+    {
+        set_error("pt2pl: knn must be in [1,%d] and n_local < 2^32-1", MP2P_B200_MAX_KNN);
+        return MP2P_B200_ERR_ARG;
+    }
+    cudaStream_t st = ctx->stream;
+    MP2P_TRY(stage_local(ctx, lx, ly, lz, n_local, local_on_device));
+    const uint32_t* d_lbits;
+    MP2P_TRY(upload_bits(ctx, ctx->d_lbits, lbits, n_local, &d_lbits));
+    const uint64_t      n_tiles = (n_local + kScanTile - 1) / kScanTile;
+    SmallView           sv;
+    unsigned long long* status;
+    MP2P_TRY(prepare_small(ctx, n_tiles, sv, &status));
+    MP2P_TRY(ctx->d_plcand.ensure(n_local * sizeof(PlaneCandidate)));
+    MP2P_TRY(ctx->d_cand.ensure(n_local));  // ok flags (bytes)
+
+    Pt2PlArgs a{};
+    for (int k = 0; k < 12; k++) a.pose.m[k] = pose[k];
+    a.radiusSq = (float)(prm->searchRadius * prm->searchRadius);
+    a.distThr  = (float)prm->distanceThreshold;
+    a.planeEigenThreshold = prm->planeEigenThreshold;
+    a.n_local = (uint32_t)n_local, a.K = prm->knn, a.minPts = prm->minimumPlanePoints;
+    a.allowLocal = prm->allowMatchAlreadyMatchedPoints;
+    const float gate_eps = (float)(prm->distanceThreshold + prm->bounding_box_intersection_check_epsilon);
+
+    const uint32_t blocks = (uint32_t)((n_local + kQueryTile - 1) / kQueryTile);
+    const float *  dlx = ctx->d_lx.as<float>(), *dly = ctx->d_ly.as<float>(), *dlz = ctx->d_lz.as<float>();
+    auto*          plc = ctx->d_plcand.as<PlaneCandidate>();
+    auto*          okf = ctx->d_cand.as<uint8_t>();
+    unsigned long long* stats = nullptr;
+    MP2P_TRY(prepare_stats(ctx, &stats));
+    prof_begin(ctx, 0);
+#define LAUNCH_PL(KT) \
+    k_match_pt2pl<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, plc, okf, sv.bbox, stats)
+    switch (pick_kt(prm->knn))
+    {
+        case 1:
+        case 4: LAUNCH_PL(4); break;
+        case 8: LAUNCH_PL(8); break;
+        case 16: LAUNCH_PL(16); break;
+        default: LAUNCH_PL(32); break;
+    }
+#undef LAUNCH_PL
+    prof_end(ctx, 0);
+    count_launch(ctx);
+
+    mp2p_b200_pair_pt2pl* d_out = out;
+    const uint64_t        cap   = std::min<uint64_t>(capacity, n_local);
+    if (!out_on_device)
+    {
+        MP2P_TRY(ctx->d_out2l.ensure(cap * sizeof(mp2p_b200_pair_pt2pl)));
+        d_out = ctx->d_out2l.as<mp2p_b200_pair_pt2pl>();
+    }
+    prof_begin(ctx, 1);
+    k_compact_pt2pl<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, (uint32_t)n_local, gate_eps,
+                                                               cap, dlx, dly, dlz, plc, okf, sv.bbox,
+                                                               status, sv.tile_counter, d_out, sv.count);
+    prof_end(ctx, 1);
+    count_launch(ctx);
+    return fetch_results(ctx, sv.count, d_out, out, capacity, out_on_device, out_count);
+}
+
+int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const float* qy,
+            const float* qz, uint64_t nq, uint32_t K, float radius2, uint32_t* out_idx,
+            float* out_d2, int32_t* out_found)
+{
+    if (nq == 0) return 0;
+    if (K < 1 || K > MP2P_B200_MAX_KNN || nq >= 0xFFFFFFFFull)
+    {
+        set_error("knn: k must be in [1,%d]", MP2P_B200_MAX_KNN);
+        return MP2P_B200_ERR_ARG;
+    }
+    cudaStream_t st = ctx->stream;
+    MP2P_TRY(stage_local(ctx, qx, qy, qz, nq, 0));
+    MP2P_TRY(ctx->d_knn_idx.ensure(nq * K * 4));
+    MP2P_TRY(ctx->d_knn_d2.ensure(nq * K * 4));
+    MP2P_TRY(ctx->d_knn_found.ensure(nq * 4));
+    if (map->view.n_points == 0)
+    {
+        MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_knn_found.p, 0, nq * 4, st));
+    }
+    else
+    {
+        const uint32_t blocks = (uint32_t)((nq + 255) / 256);
+        const float *  dqx = ctx->d_lx.as<float>(), *dqy = ctx->d_ly.as<float>(), *dqz = ctx->d_lz.as<float>();
+        auto *oi = ctx->d_knn_idx.as<uint32_t>();
+        auto *od = ctx->d_knn_d2.as<float>();
+        auto *of = ctx->d_knn_found.as<int32_t>();
+#define LAUNCH_KNN(KT) k_knn<KT><<<blocks, 256, 0, st>>>(map->view, dqx, dqy, dqz, (uint32_t)nq, K, radius2, oi, od, of)
+        switch (pick_kt(K))
+        {
+            case 1: LAUNCH_KNN(1); break;
+            case 4: LAUNCH_KNN(4); break;
+            case 8: LAUNCH_KNN(8); break;
+            case 16: LAUNCH_KNN(16); break;
+            default: LAUNCH_KNN(32); break;
+        }
+#undef LAUNCH_KNN
+        count_launch(ctx);
+    }
+    MP2P_CUDA_TRY(cudaMemcpyAsync(out_idx, ctx->d_knn_idx.p, nq * K * 4, cudaMemcpyDeviceToHost, st));
+    MP2P_CUDA_TRY(cudaMemcpyAsync(out_d2, ctx->d_knn_d2.p, nq * K * 4, cudaMemcpyDeviceToHost, st));
+    MP2P_CUDA_TRY(cudaMemcpyAsync(out_found, ctx->d_knn_found.p, nq * 4, cudaMemcpyDeviceToHost, st));
+    MP2P_CUDA_TRY(cudaStreamSynchronize(st));
+    MP2P_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+}  // namespace mp2p

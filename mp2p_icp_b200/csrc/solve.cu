@@ -1,0 +1,401 @@
+// Solver kernels (product code): the O(N_pairs) accumulations of Solver_Horn / Solver_GaussNewton.
+//
+//   k_gn_accumulate   pt2pt loop (optimal_tf_gauss_newton.cpp:149-180) and pt2pl loop (:267-286):
+//                     residual + Jacobian (errorTerms.cpp:36-66,115-161) in the closed form
+//                     Ji = A [R | -R [l]x]  (A = I for pt2pt, -n n^T/|n|^2 for pt2pl), robust weight
+//                     (robust_kernels.h:57-94), H += w Ji^T Ji (upper triangle, 21), g += w Ji^T e (6).
+//   k_horn_sums       eval_centroids_robust (Pairings.cpp:68-110).
+//   k_horn_moments    visit_correspondences (visit_correspondences.h:100-212) + S accumulation
+//                     (optimal_tf_horn.cpp:101-117).
+//
+// Reduction skeleton (shared by all three): every thread keeps NV double accumulators over a
+// grid-stride range, warp-shuffle tree -> one partial per warp in shared memory -> one partial per
+// CTA in global memory -> k_final_reduce sums the CTA partials in FIXED order into a 32-double
+// packet. Grid size is a pure function of N, so results are run-to-run bit-stable. The packet is
+// what a multi-GPU caller all-reduces.
+//
+// Pair records are AoS (36 / 72 bytes). A warp stages 32 consecutive records with fully coalesced
+// 128-byte loads into shared memory and each lane then reads its own record (stride 9 / 18 words).
+#include "common.cuh"
+
+namespace mp2p
+{
+namespace
+{
+constexpr int kSolveThreads = 256;
+constexpr int kWarps        = kSolveThreads / 32;
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&acc)[NV], double* __restrict__ partial_out)
+{
+    __shared__ double sh[kWarps][NV];
+    const int         lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int v = 0; v < NV; v++)
+    {
+        double x = acc[v];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) sh[warp][v] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV)
+    {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; w++) s += sh[w][threadIdx.x];
+        partial_out[(size_t)blockIdx.x * NV + threadIdx.x] = s;
+    }
+}
+
+// packet[v] (+)= sum over CTA partials, fixed order
+__global__ void __launch_bounds__(64)
+    k_final_reduce(const double* __restrict__ partials, int n_blocks, int nv, double* __restrict__ packet,
+                   int accumulate)
+{
+    const int v = threadIdx.x;
+    if (v >= MP2P_B200_PACKET_DOUBLES) return;
+    double s = 0;
+    if (v < nv)
+        for (int b = 0; b < n_blocks; b++) s += partials[(size_t)b * nv + v];
+    packet[v] = (accumulate ? packet[v] : 0.0) + s;
+}
+
+// Stage 32 records of WORDS 4-byte words each into this warp's shared buffer, coalesced.
+template <int WORDS>
+__device__ __forceinline__ void warp_stage_records(const uint32_t* __restrict__ src_words,
+                                                   uint64_t first_rec, uint64_t n_rec, uint32_t* sh)
+{
+    const int      lane  = threadIdx.x & 31;
+    const uint64_t w0    = first_rec * WORDS;
+    const uint64_t w_end = n_rec * WORDS;
+#pragma unroll
+    for (int k = 0; k < WORDS; k++)
+    {
+        const uint64_t w = w0 + (uint64_t)k * 32 + lane;
+        sh[k * 32 + lane] = (w < w_end) ? __ldg(src_words + w) : 0u;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ double robust_weight(int kernel, double param, double e2)
+{
+    // robust_kernels.h:57-94 — argument is the SQUARED error
+    if (kernel == 1)
+    {
+        const double d = e2 + param;  // GemanMcClure: c^2/(e^2+c)^2
+        return (param * param) / (d * d);
+    }
+    if (kernel == 2) return (param * param) / (e2 + param * param);  // Cauchy
+    return 1.0;
+}
+
+struct GNArgs
+{
+    uint64_t n2p, n2l;
+    double   w2p, w2l;
+    int      kernel;
+    double   kparam;
+};
+
+constexpr int kGNV = 29;  // 21 H + 6 g + err + count
+
+// acc += w * (a a^T upper, a r) for a 1x6 row a and scalar residual r
+__device__ __forceinline__ void add_row(double (&acc)[kGNV], const double (&a)[6], double r, double w)
+{
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+    {
+        const double wa = w * a[i];
+#pragma unroll
+        for (int j = i; j < 6; j++) acc[idx++] += wa * a[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) acc[21 + i] += w * a[i] * r;
+}
+
+__global__ void __launch_bounds__(kSolveThreads)
+    k_gn_accumulate(const uint32_t* __restrict__ p2p, const uint32_t* __restrict__ p2l, GNArgs a,
+                    const double* __restrict__ pose, double* __restrict__ partials)
+{
+    __shared__ uint32_t stage[kWarps][32 * 18];
+    const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t*           sh = stage[warp];
+    double              R[9], t[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+    {
+        R[3 * r] = pose[4 * r], R[3 * r + 1] = pose[4 * r + 1], R[3 * r + 2] = pose[4 * r + 2];
+        t[r] = pose[4 * r + 3];
+    }
+    double acc[kGNV];
+#pragma unroll
+    for (int v = 0; v < kGNV; v++) acc[v] = 0;
+
+    const uint64_t warp_global = (uint64_t)blockIdx.x * kWarps + warp;
+    const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
+
+    // ---- point-to-point: e = R l + t - g ; J = [R | -R [l]x]
+    for (uint64_t base = warp_global * 32; base < a.n2p; base += warp_stride * 32)
+    {
+        warp_stage_records<9>(p2p, base, a.n2p, sh);
+        if (base + lane < a.n2p)
+        {
+            const uint32_t* rec = sh + lane * 9;
+            const double    gx = __uint_as_float(rec[2]), gy = __uint_as_float(rec[3]), gz = __uint_as_float(rec[4]);
+            const double    lx = __uint_as_float(rec[5]), ly = __uint_as_float(rec[6]), lz = __uint_as_float(rec[7]);
+            double          e[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) e[r] = R[3 * r] * lx + R[3 * r + 1] * ly + R[3 * r + 2] * lz + t[r];
+            e[0] -= gx, e[1] -= gy, e[2] -= gz;
+            const double e2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+            double       w  = a.w2p;
+            if (a.kernel) w *= robust_weight(a.kernel, a.kparam, e2);
+            acc[27] += w * e2;
+            acc[28] += 1.0;
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+            {
+                const double R0 = R[3 * r], R1 = R[3 * r + 1], R2 = R[3 * r + 2];
+                const double row[6] = {R0, R1, R2, R2 * ly - R1 * lz, R0 * lz - R2 * lx, R1 * lx - R0 * ly};
+                add_row(acc, row, e[r], w);
+            }
+        }
+        __syncwarp();
+    }
+    // ---- point-to-plane: scalar residual r = (n.g + d)/|n|, row a = n^T/|n| [R | -R [l]x];
+    //      identical to the reference's 3-vector form since (n n^T/|n|^2)^2 = n n^T/|n|^2.
+    for (uint64_t base = warp_global * 32; base < a.n2l; base += warp_stride * 32)
+    {
+        warp_stage_records<18>(p2l, base, a.n2l, sh);
+        if (base + lane < a.n2l)
+        {
+            const uint32_t* rec = sh + lane * 18;
+            double          c[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                c[k] = __longlong_as_double(((long long)rec[2 * k + 1] << 32) | (long long)rec[2 * k]);
+            const double lx = __uint_as_float(rec[14]), ly = __uint_as_float(rec[15]), lz = __uint_as_float(rec[16]);
+            double       g[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) g[r] = R[3 * r] * lx + R[3 * r + 1] * ly + R[3 * r + 2] * lz + t[r];
+            const double mod_n = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+            const double ev    = c[0] * g[0] + c[1] * g[1] + c[2] * g[2] + c[3];
+            const double e2    = ev * ev / mod_n;  // |e|^2 of the reference's 3-vector error
+            double       w     = a.w2l;
+            if (a.kernel) w *= robust_weight(a.kernel, a.kparam, e2);
+            acc[27] += w * e2;
+            acc[28] += 1.0;
+            const double inv_n = 1.0 / sqrt(mod_n);
+            const double n0 = c[0] * inv_n, n1 = c[1] * inv_n, n2 = c[2] * inv_n;
+            // nR = n^T R
+            const double q0 = n0 * R[0] + n1 * R[3] + n2 * R[6];
+            const double q1 = n0 * R[1] + n1 * R[4] + n2 * R[7];
+            const double q2 = n0 * R[2] + n1 * R[5] + n2 * R[8];
+            const double row[6] = {q0, q1, q2, q2 * ly - q1 * lz, q0 * lz - q2 * lx, q1 * lx - q0 * ly};
+            add_row(acc, row, ev * inv_n, w);
+        }
+        __syncwarp();
+    }
+    block_reduce_store<kGNV>(acc, partials);
+}
+
+// ------------------------------------------------------------------------------------------
+constexpr int kH1V = 7;  // sum local(3), sum global(3), count
+
+__global__ void __launch_bounds__(kSolveThreads)
+    k_horn_sums(const uint32_t* __restrict__ p2p, uint64_t n, const uint8_t* __restrict__ outlier,
+                double* __restrict__ partials)
+{
+    __shared__ uint32_t stage[kWarps][32 * 9];
+    const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t*           sh = stage[warp];
+    double              acc[kH1V];
+#pragma unroll
+    for (int v = 0; v < kH1V; v++) acc[v] = 0;
+    const uint64_t warp_global = (uint64_t)blockIdx.x * kWarps + warp;
+    const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
+    for (uint64_t base = warp_global * 32; base < n; base += warp_stride * 32)
+    {
+        warp_stage_records<9>(p2p, base, n, sh);
+        const uint64_t i = base + lane;
+        if (i < n && !(outlier && outlier[i]))
+        {
+            const uint32_t* rec = sh + lane * 9;
+            acc[3] += (double)__uint_as_float(rec[2]), acc[4] += (double)__uint_as_float(rec[3]);
+            acc[5] += (double)__uint_as_float(rec[4]);
+            acc[0] += (double)__uint_as_float(rec[5]), acc[1] += (double)__uint_as_float(rec[6]);
+            acc[2] += (double)__uint_as_float(rec[7]);
+            acc[6] += 1.0;
+        }
+        __syncwarp();
+    }
+    block_reduce_store<kH1V>(acc, partials);
+}
+
+struct HornArgs
+{
+    uint64_t n, n_total;
+    int      use_scale_outlier;
+    double   scale_thr, w_pt2pt;
+    int      kernel;
+    double   kparam;
+    double   Rref[9];  // rotation+translation of currentEstimateForRobust
+    double   tref[3];
+    uint32_t n_wblocks;
+};
+
+constexpr int kH2V = 12;  // S(9), w_sum, new outliers, pairs used
+
+__global__ void __launch_bounds__(kSolveThreads)
+    k_horn_moments(const uint32_t* __restrict__ p2p, HornArgs a, const double* __restrict__ sums,
+                   const uint64_t* __restrict__ wprefix, const double* __restrict__ wvalue,
+                   uint8_t* __restrict__ outlier, uint64_t first_global_index,
+                   double* __restrict__ partials)
+{
+    __shared__ uint32_t stage[kWarps][32 * 9];
+    const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t*           sh = stage[warp];
+    // centroids (Pairings.cpp:78,104-106): sums * 1/(n - outliers)
+    const double wc   = 1.0 / sums[6];
+    const double cl[3] = {sums[0] * wc, sums[1] * wc, sums[2] * wc};
+    const double cg[3] = {sums[3] * wc, sums[4] * wc, sums[5] * wc};
+    // visit_correspondences.h:85-87: waPoints = wPt / (wPt * nPt2Pt)
+    const double waPoints = a.w_pt2pt / (a.w_pt2pt * (double)a.n_total);
+    double       acc[kH2V];
+#pragma unroll
+    for (int v = 0; v < kH2V; v++) acc[v] = 0;
+    const uint64_t warp_global = (uint64_t)blockIdx.x * kWarps + warp;
+    const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
+    for (uint64_t base = warp_global * 32; base < a.n; base += warp_stride * 32)
+    {
+        warp_stage_records<9>(p2p, base, a.n, sh);
+        const uint64_t i = base + lane;
+        if (i < a.n && !(outlier && outlier[i]))
+        {
+            const uint32_t* rec = sh + lane * 9;
+            const double    bi[3] = {(double)__uint_as_float(rec[2]) - cg[0], (double)__uint_as_float(rec[3]) - cg[1],
+                                     (double)__uint_as_float(rec[4]) - cg[2]};
+            const double    ri[3] = {(double)__uint_as_float(rec[5]) - cl[0], (double)__uint_as_float(rec[6]) - cl[1],
+                                     (double)__uint_as_float(rec[7]) - cl[2]};
+            const double bn = sqrt(bi[0] * bi[0] + bi[1] * bi[1] + bi[2] * bi[2]);
+            const double rn = sqrt(ri[0] * ri[0] + ri[1] * ri[1] + ri[2] * ri[2]);
+            bool         use = !(bn < 1e-4 || rn < 1e-4);  // visit_correspondences.h:141-146
+            if (use && a.use_scale_outlier)                  // :158-169
+            {
+                const double mism = fmax(bn, rn) / fmin(bn, rn);
+                if (mism > a.scale_thr)
+                {
+                    use = false;
+                    if (outlier) outlier[i] = 1;
+                    acc[10] += 1.0;
+                }
+            }
+            if (use)
+            {
+                double wi = waPoints;
+                if (a.n_wblocks)  // Pairings::point_weights run-length blocks (:127-133)
+                {
+                    const uint64_t gi = first_global_index + i;
+                    uint32_t       lo = 0, hi = a.n_wblocks - 1;
+                    while (lo < hi)
+                    {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (gi < wprefix[mid + 1])
+                            hi = mid;
+                        else
+                            lo = mid + 1;
+                    }
+                    wi *= wvalue[lo];
+                }
+                if (a.kernel)  // :200-210
+                {
+                    double r2[3];
+#pragma unroll
+                    for (int r = 0; r < 3; r++)
+                        r2[r] = a.Rref[3 * r] * ri[0] + a.Rref[3 * r + 1] * ri[1] + a.Rref[3 * r + 2] * ri[2] + a.tref[r];
+                    const double e2 = (r2[0] - bi[0]) * (r2[0] - bi[0]) + (r2[1] - bi[1]) * (r2[1] - bi[1]) +
+                                      (r2[2] - bi[2]) * (r2[2] - bi[2]);
+                    wi *= robust_weight(a.kernel, a.kparam, e2);
+                }
+                acc[9] += wi;
+                acc[11] += 1.0;
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) acc[3 * r + c] += wi * ri[r] * bi[c];  // S += w r b^T
+            }
+        }
+        __syncwarp();
+    }
+    block_reduce_store<kH2V>(acc, partials);
+}
+
+int solve_grid(uint64_t n)
+{
+    // one warp handles 32 records per trip; aim for >= 4 trips per warp, cap at 4 CTAs per SM
+    const uint64_t warps  = (n + 127) / 128;
+    const uint64_t blocks = (warps + kWarps - 1) / kWarps;
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(blocks, 148 * 4));
+}
+}  // namespace
+
+int run_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p,
+                      const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l, const mp2p_b200_gn_params* prm,
+                      const double* d_pose, double* d_packet)
+{
+    const int blocks = solve_grid(std::max(n2p, n2l));
+    MP2P_TRY(ctx->d_partials.ensure((size_t)blocks * 32 * sizeof(double)));
+    GNArgs a{n2p, n2l, prm->w_pt2pt, prm->w_pt2pl, prm->kernel, prm->kernelParam};
+    prof_begin(ctx, 4);
+    k_gn_accumulate<<<blocks, kSolveThreads, 0, ctx->stream>>>(
+        reinterpret_cast<const uint32_t*>(d2p), reinterpret_cast<const uint32_t*>(d2l), a, d_pose,
+        ctx->d_partials.as<double>());
+    k_final_reduce<<<1, 64, 0, ctx->stream>>>(ctx->d_partials.as<double>(), blocks, kGNV, d_packet, 0);
+    prof_end(ctx, 4);
+    count_launch(ctx, 2);
+    return 0;
+}
+
+int run_horn_sums(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n,
+                  const uint8_t* d_outlier, double* d_packet)
+{
+    const int blocks = solve_grid(n);
+    MP2P_TRY(ctx->d_partials.ensure((size_t)blocks * 32 * sizeof(double)));
+    prof_begin(ctx, 2);
+    k_horn_sums<<<blocks, kSolveThreads, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d2p), n,
+                                                          d_outlier, ctx->d_partials.as<double>());
+    k_final_reduce<<<1, 64, 0, ctx->stream>>>(ctx->d_partials.as<double>(), blocks, kH1V, d_packet, 0);
+    prof_end(ctx, 2);
+    count_launch(ctx, 2);
+    return 0;
+}
+
+int run_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n,
+                     const mp2p_b200_horn_params* prm, const double* d_sums_packet,
+                     uint64_t n_total_pairs, const uint64_t* d_wcount_prefix, const double* d_wvalue,
+                     uint32_t n_wblocks, uint8_t* d_outlier, double* d_packet)
+{
+    const int blocks = solve_grid(n);
+    MP2P_TRY(ctx->d_partials.ensure((size_t)blocks * 32 * sizeof(double)));
+    HornArgs a{};
+    a.n = n, a.n_total = n_total_pairs;
+    a.use_scale_outlier = prm->use_scale_outlier_detector, a.scale_thr = prm->scale_outlier_threshold;
+    a.w_pt2pt = prm->w_pt2pt, a.kernel = prm->robust_kernel, a.kparam = prm->robust_kernel_param;
+    for (int r = 0; r < 3; r++)
+    {
+        for (int c = 0; c < 3; c++) a.Rref[3 * r + c] = prm->currentEstimateForRobust[4 * r + c];
+        a.tref[r] = prm->currentEstimateForRobust[4 * r + 3];
+    }
+    a.n_wblocks = n_wblocks;
+    prof_begin(ctx, 3);
+    k_horn_moments<<<blocks, kSolveThreads, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d2p), a,
+                                                             d_sums_packet, d_wcount_prefix, d_wvalue,
+                                                             d_outlier, 0, ctx->d_partials.as<double>());
+    k_final_reduce<<<1, 64, 0, ctx->stream>>>(ctx->d_partials.as<double>(), blocks, kH2V, d_packet, 0);
+    prof_end(ctx, 3);
+    count_launch(ctx, 2);
+    return 0;
+}
+}  // namespace mp2p
