@@ -182,6 +182,33 @@ int mp2p_b200_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* l
                           uint64_t capacity, int out_on_device, uint64_t* out_count,
                           uint64_t* potential_pairings);
 
+/* ---- query-sharded pt2pt matching, one process per GPU --------------------------
+ * The local cloud of n_total points is split in contiguous shards; rank r owns
+ * [index_offset, index_offset + n_local). The map (and its index) is replicated on every GPU.
+ *  phase A `..._shard_search`: transform + NN search of the shard; writes n_local*pairingsPerPoint
+ *     64-bit candidate words and the shard's bounding box (6 floats: min xyz, max xyz) to DEVICE
+ *     memory owned by the caller;
+ *  (caller) all-gather the candidate words of all shards into cand_all[n_total*pairingsPerPoint] and
+ *     the boxes into bbox_parts[n_shards*6] — NCCL all_gather over NVLink;
+ *  phase B `..._shard_resolve`: replays every shard's proposals on this GPU's first-claim array
+ *     with the global proposal numbering, applies the bounding-box gate of the WHOLE cloud and
+ *     compacts this shard's accepted pairs (localIdx = index in the whole cloud).
+ * Concatenating the shards' outputs in rank order gives exactly the single-GPU result.
+ * Phase B must follow phase A on the same context (the staged shard is reused). */
+int mp2p_b200_match_pt2pt_shard_search(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx,
+                                       const float* ly, const float* lz, uint64_t n_local,
+                                       int local_on_device, const double pose[12],
+                                       const mp2p_b200_pt2pt_params* params,
+                                       const uint32_t* local_paired_bits, uint64_t* cand_out_device,
+                                       float* bbox6_out_device);
+int mp2p_b200_match_pt2pt_shard_resolve(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_local,
+                                        uint64_t index_offset, uint64_t n_total,
+                                        const uint64_t* cand_all_device, const float* bbox_parts_device,
+                                        uint32_t n_shards, const mp2p_b200_pt2pt_params* params,
+                                        const uint32_t* global_paired_bits,
+                                        mp2p_b200_pair_pt2pt* out_pairs, uint64_t capacity,
+                                        int out_on_device, uint64_t* out_count);
+
 /* optimal_tf_horn (mp2p_icp/src/optimal_tf_horn.cpp:201-252) over pt2pt pairings:
  * eval_centroids_robust (Pairings.cpp:68-110) + visit_correspondences S accumulation
  * (visit_correspondences.h:39-221) on the GPU; 4x4 eigen-solve on the host.

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -154,6 +155,7 @@ EXPORTS = [
     "mp2p_b200_gn_step_from_packet", "mp2p_b200_horn_sums", "mp2p_b200_horn_moments", "mp2p_b200_horn_finish",
     "mp2p_b200_host_alloc", "mp2p_b200_host_free", "mp2p_b200_ctx_set_profiling",
     "mp2p_b200_ctx_get_timings", "mp2p_b200_ctx_get_search_stats",
+    "mp2p_b200_match_pt2pt_shard_search", "mp2p_b200_match_pt2pt_shard_resolve",
 ]
 
 _lib = None
@@ -224,9 +226,12 @@ class Context:
         _check(L.mp2p_b200_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
         self._h = h
         self.device = device
+        self._maps = weakref.WeakSet()
 
     def close(self):
         if getattr(self, "_h", None):
+            for m in list(self._maps):  # maps hold device memory of this context: free them first
+                m.close()
             load_library().mp2p_b200_ctx_destroy(self._h)
             self._h = None
 
@@ -345,10 +350,12 @@ class Map:
         _check(load_library().mp2p_b200_map_create(ctx._h, _ptr(x), _ptr(y), _ptr(z), C.c_uint64(n), int(on_device), C.byref(h)))
         self._h = h
         self.n = n
+        ctx._maps.add(self)
 
     def close(self):
         if getattr(self, "_h", None):
-            load_library().mp2p_b200_map_destroy(self._h)
+            if getattr(self.ctx, "_h", None):  # a map never outlives its context
+                load_library().mp2p_b200_map_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -394,6 +401,27 @@ class Map:
         if out_on_device:
             return cnt.value, pot.value
         return out[: cnt.value], pot.value
+
+    def shard_search_pt2pt(self, lx, ly, lz, T, prm: Pt2PtParams, cand_out: int, bbox6_out: int, n_local=None, local_on_device=False, local_paired=None):
+        """Phase A of the query-sharded matcher; cand_out / bbox6_out are DEVICE addresses."""
+        if not local_on_device:
+            lx, ly, lz = _f32(lx), _f32(ly), _f32(lz)
+            n_local = lx.size
+        lb = pack_bits(local_paired) if local_paired is not None else None
+        cp = prm.c()
+        _check(load_library().mp2p_b200_match_pt2pt_shard_search(self.ctx._h, self._h, _ptr(lx), _ptr(ly), _ptr(lz), C.c_uint64(n_local), int(local_on_device), _ptr(_pose(T)), C.byref(cp), _ptr(lb), C.c_void_p(cand_out), C.c_void_p(bbox6_out)))
+
+    def shard_resolve_pt2pt(self, n_local, index_offset, n_total, cand_all: int, bbox_parts: int, n_shards, prm: Pt2PtParams, global_paired=None, out=None, out_on_device=False, capacity=None):
+        cap = capacity if capacity is not None else n_local * prm.pairingsPerPoint
+        if out is None and not out_on_device:
+            out = np.empty(max(cap, 1), PAIR_PT2PT)
+        gb = pack_bits(global_paired) if global_paired is not None else None
+        cp = prm.c()
+        cnt = C.c_uint64(0)
+        _check(load_library().mp2p_b200_match_pt2pt_shard_resolve(self.ctx._h, self._h, C.c_uint64(n_local), C.c_uint64(index_offset), C.c_uint64(n_total), C.c_void_p(cand_all), C.c_void_p(bbox_parts), C.c_uint32(n_shards), C.byref(cp), _ptr(gb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt)))
+        if out_on_device:
+            return cnt.value
+        return out[: cnt.value]
 
     def match_pt2pl(self, lx, ly, lz, T, prm: Pt2PlParams, local_paired=None, n_local=None, local_on_device=False, out=None, out_on_device=False, capacity=None):
         if not local_on_device:

@@ -313,6 +313,52 @@ extern "C"
                                out_pairs, capacity, out_on_device, out_count);
     }
 
+    int mp2p_b200_match_pt2pt_shard_search(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx,
+                                           const float* ly, const float* lz, uint64_t n_local,
+                                           int local_on_device, const double pose[12],
+                                           const mp2p_b200_pt2pt_params* prm,
+                                           const uint32_t* local_paired_bits, uint64_t* cand_out_device,
+                                           float* bbox6_out_device)
+    {
+        if (!ctx || !map || !pose || !prm || !bbox6_out_device || (n_local && (!lx || !ly || !lz || !cand_out_device)))
+        {
+            set_error("shard_search: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        if (prm->pairingsPerPoint < 1 || prm->pairingsPerPoint > MP2P_B200_MAX_KNN || !(prm->threshold > 0.0) ||
+            !(prm->thresholdAngularDeg >= 0.0))
+        {
+            set_error("shard_search: bad matcher parameters");
+            return MP2P_B200_ERR_ARG;
+        }
+        DeviceGuard g(ctx->device);
+        ProfScope   ps(ctx);
+        return run_shard_search_pt2pt(ctx, map, lx, ly, lz, n_local, local_on_device, pose, prm, local_paired_bits,
+                                      reinterpret_cast<unsigned long long*>(cand_out_device), bbox6_out_device);
+    }
+
+    int mp2p_b200_match_pt2pt_shard_resolve(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_local,
+                                            uint64_t index_offset, uint64_t n_total,
+                                            const uint64_t* cand_all_device, const float* bbox_parts_device,
+                                            uint32_t n_shards, const mp2p_b200_pt2pt_params* prm,
+                                            const uint32_t* global_paired_bits,
+                                            mp2p_b200_pair_pt2pt* out_pairs, uint64_t capacity,
+                                            int out_on_device, uint64_t* out_count)
+    {
+        if (!ctx || !map || !prm || !out_count || !cand_all_device || !bbox_parts_device || n_shards == 0 ||
+            (capacity && !out_pairs))
+        {
+            set_error("shard_resolve: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        DeviceGuard g(ctx->device);
+        ProfScope   ps(ctx);
+        return run_shard_resolve_pt2pt(ctx, map, n_local, index_offset, n_total,
+                                       reinterpret_cast<const unsigned long long*>(cand_all_device),
+                                       bbox_parts_device, n_shards, prm, global_paired_bits, out_pairs, capacity,
+                                       out_on_device, out_count);
+    }
+
     // ------------------------------------------------------------------------------ Horn
     int mp2p_b200_horn_sums(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* pairs, uint64_t n,
                             int pairs_on_device, double* packet, int packet_on_device)

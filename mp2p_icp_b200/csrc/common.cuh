@@ -169,6 +169,16 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
                     const mp2p_b200_pt2pl_params* prm, const uint32_t* lbits,
                     mp2p_b200_pair_pt2pl* out, uint64_t capacity, int out_on_device,
                     uint64_t* out_count);
+int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                           const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
+                           const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits,
+                           unsigned long long* d_cand_out, float* d_bbox6_out);
+int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_local, uint64_t index_offset,
+                            uint64_t n_total, const unsigned long long* d_cand_all,
+                            const float* d_bbox_parts, uint32_t n_bbox_parts,
+                            const mp2p_b200_pt2pt_params* prm, const uint32_t* gbits,
+                            mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device,
+                            uint64_t* out_count);
 int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const float* qy,
             const float* qz, uint64_t nq, uint32_t k, float radius2, uint32_t* out_idx,
             float* out_d2, int32_t* out_found);

@@ -171,6 +171,22 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
         const float gzl = fmaxf(fz - 4.f, 0.f), gzh = fmaxf(s - fz - 4.f, 0.f);
         const float q2  = g.s0_lo * g.s0_lo * 0.999999f;  // quanta^2 -> metres^2, rounded down
 
+        if (L == kGridBits)
+        {
+            // top level: the single voxel holds every point; a query outside the grid (possible only
+            // with a radius larger than its distance to the bbox) must still see all of them
+            sc.probes++, sc.cands += g.n_points, sc.levels++;
+            for (uint32_t j = 0; j < g.n_points; j++)
+            {
+                const float4 p  = __ldg(g.pts + j);
+                const float  d2 = dist2_ref(qx, qy, qz, p.x, p.y, p.z);
+                const unsigned long long c =
+                    ((unsigned long long)__float_as_uint(d2) << 32) | (uint32_t)__float_as_int(p.w);
+                if (c < top.worst(k_runtime)) top.insert(c);
+            }
+            break;
+        }
+
 #pragma unroll 1
         for (int nb = 0; nb < 27; nb++)
         {

@@ -115,38 +115,75 @@ __device__ __forceinline__ void compose_point_f(const PoseArg& T, float lx, floa
         __dadd_rn(__dadd_rn(__dmul_rn(T.m[8], x), __dmul_rn(T.m[9], y)), __dmul_rn(T.m[10], z)), T.m[11]));
 }
 
-__device__ __forceinline__ uint32_t f2ord(float f)
+// Bounding box of the transformed local cloud (TransformedLocalPointCloud::localMin/localMax,
+// Matcher_Points_Base.h:98-112) without same-address atomics: every CTA writes its 6 partial
+// extrema, takes a ticket, and the LAST CTA to finish folds all partials into bbox_final[6].
+// Must be called by every thread of the CTA (contains __syncthreads).
+struct BBoxSmem
 {
-    const uint32_t u = __float_as_uint(f);
-    return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
-}
-__device__ __forceinline__ float ord2f(uint32_t o)
+    float    w[kQueryTile / 32][6];
+    uint32_t is_last;
+};
+__device__ __forceinline__ void block_bbox_finalize(BBoxSmem& sm, float gx, float gy, float gz, bool valid,
+                                                    float* __restrict__ bbox_part,
+                                                    uint32_t* __restrict__ done_counter,
+                                                    float* __restrict__ bbox_final)
 {
-    return __uint_as_float(o ^ (((o >> 31) - 1u) | 0x80000000u));
-}
-
-// CTA-wide min/max of the transformed cloud -> 6 global atomics per CTA.
-__device__ __forceinline__ void block_bbox_update(float gx, float gy, float gz, bool valid,
-                                                  uint32_t* bbox)
-{
-    float mn[3] = {valid ? gx : 3.4e38f, valid ? gy : 3.4e38f, valid ? gz : 3.4e38f};
-    float mx[3] = {valid ? gx : -3.4e38f, valid ? gy : -3.4e38f, valid ? gz : -3.4e38f};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float     v[6] = {valid ? gx : 3.4e38f,  valid ? gy : 3.4e38f,  valid ? gz : 3.4e38f,
+                      valid ? gx : -3.4e38f, valid ? gy : -3.4e38f, valid ? gz : -3.4e38f};
 #pragma unroll
-    for (int d = 0; d < 3; d++)
+    for (int d = 0; d < 6; d++)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
         {
-            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
-            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+            const float t = __shfl_xor_sync(0xffffffffu, v[d], o);
+            v[d]          = d < 3 ? fminf(v[d], t) : fmaxf(v[d], t);
         }
-    if ((threadIdx.x & 31) == 0)
-    {
+    if (lane == 0)
 #pragma unroll
-        for (int d = 0; d < 3; d++)
+        for (int d = 0; d < 6; d++) sm.w[warp][d] = v[d];
+    __syncthreads();
+    if (threadIdx.x < 6)
+    {
+        const int d = threadIdx.x;
+        float     r = sm.w[0][d];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = d < 3 ? fminf(r, sm.w[w][d]) : fmaxf(r, sm.w[w][d]);
+        bbox_part[(size_t)blockIdx.x * 6 + d] = r;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sm.is_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!sm.is_last) return;
+    __threadfence();
+    float a[6] = {3.4e38f, 3.4e38f, 3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f};
+    for (uint32_t b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+#pragma unroll
+        for (int d = 0; d < 6; d++)
         {
-            atomicMin(bbox + d, f2ord(mn[d]));
-            atomicMax(bbox + 3 + d, f2ord(mx[d]));
+            const float t = __ldcg(bbox_part + (size_t)b * 6 + d);
+            a[d]          = d < 3 ? fminf(a[d], t) : fmaxf(a[d], t);
         }
+#pragma unroll
+    for (int d = 0; d < 6; d++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const float t = __shfl_xor_sync(0xffffffffu, a[d], o);
+            a[d]          = d < 3 ? fminf(a[d], t) : fmaxf(a[d], t);
+        }
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int d = 0; d < 6; d++) sm.w[warp][d] = a[d];
+    __syncthreads();
+    if (threadIdx.x < 6)
+    {
+        const int d = threadIdx.x;
+        float     r = sm.w[0][d];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = d < 3 ? fminf(r, sm.w[w][d]) : fmaxf(r, sm.w[w][d]);
+        bbox_final[d] = r;
     }
 }
 
@@ -170,51 +207,54 @@ __global__ void __launch_bounds__(kQueryTile)
     k_match_pt2pt(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
                   const float* __restrict__ lz, const uint32_t* __restrict__ lbits,
                   const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim,
-                  unsigned long long* __restrict__ cand, uint32_t* __restrict__ bbox,
+                  unsigned long long* __restrict__ cand, float* __restrict__ bbox_part,
+                  uint32_t* __restrict__ done_counter, float* __restrict__ bbox_final,
                   unsigned long long* __restrict__ stats)
 {
     __shared__ QueryTile tile;
+    __shared__ BBoxSmem  bsm;
     const size_t         base = (size_t)blockIdx.x * kQueryTile;
     load_query_tile(tile, lx, ly, lz, base);
     const uint32_t i     = (uint32_t)base + threadIdx.x;
     const bool     valid = i < a.n_local;
 
     float gx = 0, gy = 0, gz = 0;
-    if (valid) compose_point_f(a.pose, tile.x[threadIdx.x], tile.y[threadIdx.x], tile.z[threadIdx.x], gx, gy, gz);
-    block_bbox_update(gx, gy, gz, valid, bbox);
-    if (!valid) return;
-
-    const int K = (int)a.K;
-    // …DistanceThreshold.cpp:230,256-257 (float, unfused)
-    const float normSq = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
-    const float thr2   = __fadd_rn(a.maxDistSq, __fmul_rn(a.angSq, normSq));
-    const unsigned long long sentinel = (unsigned long long)__float_as_uint(thr2) << 32;
-
-    TopK<KT>       top;
-    SearchCounters sc;
-    if (!a.allowLocal && bit_set(lbits, i))
-        top.init(sentinel);  // :218-220 skip, already paired
-    else
-        knn_search<KT>(g, gx, gy, gz, thr2, K, top, sc);
-
-    uint32_t n_valid = 0;
-#pragma unroll
-    for (int k = 0; k < KT; k++)
+    if (valid)
     {
-        if (k < K)
+        compose_point_f(a.pose, tile.x[threadIdx.x], tile.y[threadIdx.x], tile.z[threadIdx.x], gx, gy, gz);
+        const int K = (int)a.K;
+        // …DistanceThreshold.cpp:230,256-257 (float, unfused)
+        const float normSq = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+        const float thr2   = __fadd_rn(a.maxDistSq, __fmul_rn(a.angSq, normSq));
+        const unsigned long long sentinel = (unsigned long long)__float_as_uint(thr2) << 32;
+
+        TopK<KT>       top;
+        SearchCounters sc;
+        if (!a.allowLocal && bit_set(lbits, i))
+            top.init(sentinel);  // :218-220 skip, already paired
+        else
+            knn_search<KT>(g, gx, gy, gz, thr2, K, top, sc);
+
+        uint32_t n_valid = 0;
+#pragma unroll
+        for (int k = 0; k < KT; k++)
         {
-            // unused ranks are marked with an impossible map index (all ones)
-            const unsigned long long c = top.v[k] < sentinel ? top.v[k] : ~0ull;
-            n_valid += (c != ~0ull);
-            cand[(size_t)i * K + k]    = c;
-            if (c != ~0ull && !a.allowGlobal)
+            if (k < K)
             {
-                const uint32_t gi = (uint32_t)c;
-                if (!bit_set(gbits, gi)) atomicMin(claim + gi, a.tag | (unsigned long long)(i * (uint32_t)K + k));
+                // unused ranks are marked with an impossible map index (all ones)
+                const unsigned long long c = top.v[k] < sentinel ? top.v[k] : ~0ull;
+                n_valid += (c != ~0ull);
+                cand[(size_t)i * K + k] = c;
+                if (c != ~0ull && !a.allowGlobal)
+                {
+                    const uint32_t gi = (uint32_t)c;
+                    if (!bit_set(gbits, gi)) atomicMin(claim + gi, a.tag | (unsigned long long)(i * (uint32_t)K + k));
+                }
             }
         }
+        flush_search_stats(sc, n_valid, stats);
     }
-    flush_search_stats(sc, n_valid, stats);
+    block_bbox_finalize(bsm, gx, gy, gz, valid, bbox_part, done_counter, bbox_final);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -292,18 +332,18 @@ struct CompactArgs
     unsigned long long tag;
     float    gate_eps;  // threshold + bounding_box_intersection_check_epsilon (float)
     uint64_t capacity;
+    uint64_t slot_offset;   // sharded runs: first global proposal slot of this shard (index_offset*K)
+    uint32_t index_offset;  // sharded runs: first global local-point index of this shard
 };
 
-__device__ __forceinline__ bool bbox_gate(const GridView& g, const uint32_t* bbox, float eps)
+__device__ __forceinline__ bool bbox_gate(const GridView& g, const float* __restrict__ bbox, float eps)
 {
     // mrpt TBoundingBoxf::intersection(other, epsilon) has a value (…DistanceThreshold.cpp:73-75)
-    const float lmin[3] = {ord2f(bbox[0]), ord2f(bbox[1]), ord2f(bbox[2])};
-    const float lmax[3] = {ord2f(bbox[3]), ord2f(bbox[4]), ord2f(bbox[5])};
 #pragma unroll
     for (int d = 0; d < 3; d++)
     {
-        if (__fsub_rn(lmin[d], eps) > g.bbmax[d]) return false;
-        if (__fadd_rn(lmax[d], eps) < g.bbmin[d]) return false;
+        if (__fsub_rn(__ldcg(bbox + d), eps) > g.bbmax[d]) return false;
+        if (__fadd_rn(__ldcg(bbox + 3 + d), eps) < g.bbmin[d]) return false;
     }
     return true;
 }
@@ -312,7 +352,7 @@ __global__ void __launch_bounds__(kScanThreads)
     k_compact_pt2pt(GridView g, CompactArgs a, const float* __restrict__ lx,
                     const float* __restrict__ ly, const float* __restrict__ lz,
                     const uint32_t* __restrict__ gbits, const unsigned long long* __restrict__ claim,
-                    const unsigned long long* __restrict__ cand, const uint32_t* __restrict__ bbox,
+                    const unsigned long long* __restrict__ cand, const float* __restrict__ bbox,
                     unsigned long long* __restrict__ status, uint32_t* __restrict__ tile_counter,
                     mp2p_b200_pair_pt2pt* __restrict__ out, unsigned long long* __restrict__ out_count)
 {
@@ -339,7 +379,7 @@ __global__ void __launch_bounds__(kScanThreads)
             if (ok && !a.allowGlobal)
             {
                 const uint32_t gi = (uint32_t)c[j];
-                ok = !bit_set(gbits, gi) && (claim[gi] == (a.tag | (unsigned long long)slot));
+                ok = !bit_set(gbits, gi) && (claim[gi] == (a.tag | (unsigned long long)(slot + a.slot_offset)));
             }
         }
         if (ok) flags |= 1u << j, local++;
@@ -357,7 +397,7 @@ __global__ void __launch_bounds__(kScanThreads)
             const uint32_t gi   = (uint32_t)c[j];
             const float4   gp   = __ldg(g.pts_orig + gi);
             uint32_t*      o    = reinterpret_cast<uint32_t*>(out + w);  // 36-byte records, 4-aligned
-            o[0] = gi, o[1] = i;
+            o[0] = gi, o[1] = i + a.index_offset;
             o[2] = __float_as_uint(gp.x), o[3] = __float_as_uint(gp.y), o[4] = __float_as_uint(gp.z);
             o[5] = __float_as_uint(lx[i]), o[6] = __float_as_uint(ly[i]), o[7] = __float_as_uint(lz[i]);
             o[8] = (uint32_t)(c[j] >> 32);
@@ -385,61 +425,64 @@ __global__ void __launch_bounds__(kQueryTile)
     k_match_pt2pl(GridView g, Pt2PlArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
                   const float* __restrict__ lz, const uint32_t* __restrict__ lbits,
                   PlaneCandidate* __restrict__ plc, uint8_t* __restrict__ ok_flags,
-                  uint32_t* __restrict__ bbox, unsigned long long* __restrict__ stats)
+                  float* __restrict__ bbox_part, uint32_t* __restrict__ done_counter,
+                  float* __restrict__ bbox_final, unsigned long long* __restrict__ stats)
 {
     __shared__ QueryTile tile;
+    __shared__ BBoxSmem  bsm;
     const size_t         base = (size_t)blockIdx.x * kQueryTile;
     load_query_tile(tile, lx, ly, lz, base);
     const uint32_t i     = (uint32_t)base + threadIdx.x;
     const bool     valid = i < a.n_local;
     float          gx = 0, gy = 0, gz = 0;
-    if (valid) compose_point_f(a.pose, tile.x[threadIdx.x], tile.y[threadIdx.x], tile.z[threadIdx.x], gx, gy, gz);
-    block_bbox_update(gx, gy, gz, valid, bbox);
-    if (!valid) return;
-
-    uint8_t        ok = 0;
-    SearchCounters sc;
-    uint32_t       n_valid = 0;
-    if (a.allowLocal || !bit_set(lbits, i))
+    if (valid)
     {
-        TopK<KT> top;
-        const int K = (int)a.K;
-        knn_search<KT>(g, gx, gy, gz, a.radiusSq, K, top, sc);
-        const unsigned long long sentinel = (unsigned long long)__float_as_uint(a.radiusSq) << 32;
-        int                      cnt      = 0;
-#pragma unroll
-        for (int k = 0; k < KT; k++)
-            if (k < K && top.v[k] < sentinel) cnt++;
-        n_valid = (uint32_t)cnt;
-        if (cnt >= 3 && cnt >= (int)a.minPts)
+        compose_point_f(a.pose, tile.x[threadIdx.x], tile.y[threadIdx.x], tile.z[threadIdx.x], gx, gy, gz);
+        uint8_t        ok = 0;
+        SearchCounters sc;
+        uint32_t       n_valid = 0;
+        if (a.allowLocal || !bit_set(lbits, i))
         {
-            // estimate_points_eigen.cpp:45-63 — float mean, double centred moments, ascending
-            // (d2, index) neighbour order
-            float px[KT], py[KT], pz[KT];
+            TopK<KT>  top;
+            const int K = (int)a.K;
+            knn_search<KT>(g, gx, gy, gz, a.radiusSq, K, top, sc);
+            const unsigned long long sentinel = (unsigned long long)__float_as_uint(a.radiusSq) << 32;
+            int                      cnt      = 0;
 #pragma unroll
             for (int k = 0; k < KT; k++)
-                if (k < cnt)
-                {
-                    const float4 p = __ldg(g.pts_orig + (uint32_t)top.v[k]);
-                    px[k] = p.x, py[k] = p.y, pz[k] = p.z;
-                }
-            PlaneCandidate pc;
-            if (fit_plane<KT>(px, py, pz, cnt, gx, gy, gz, a.planeEigenThreshold, a.distThr, pc))
+                if (k < K && top.v[k] < sentinel) cnt++;
+            n_valid = (uint32_t)cnt;
+            if (cnt >= 3 && cnt >= (int)a.minPts)
             {
-                plc[i] = pc;
-                ok     = 1;
+                // estimate_points_eigen.cpp:45-63 — float mean, double centred moments, ascending
+                // (d2, index) neighbour order
+                float px[KT], py[KT], pz[KT];
+#pragma unroll
+                for (int k = 0; k < KT; k++)
+                    if (k < cnt)
+                    {
+                        const float4 p = __ldg(g.pts_orig + (uint32_t)top.v[k]);
+                        px[k] = p.x, py[k] = p.y, pz[k] = p.z;
+                    }
+                PlaneCandidate pc;
+                if (fit_plane<KT>(px, py, pz, cnt, gx, gy, gz, a.planeEigenThreshold, a.distThr, pc))
+                {
+                    plc[i] = pc;
+                    ok     = 1;
+                }
             }
         }
+        ok_flags[i] = ok;
+        flush_search_stats(sc, n_valid, stats);
     }
-    ok_flags[i] = ok;
-    flush_search_stats(sc, n_valid, stats);
+    block_bbox_finalize(bsm, gx, gy, gz, valid, bbox_part, done_counter, bbox_final);
 }
 
 __global__ void __launch_bounds__(kScanThreads)
     k_compact_pt2pl(GridView g, uint32_t n_local, float gate_eps, uint64_t capacity,
                     const float* __restrict__ lx, const float* __restrict__ ly,
                     const float* __restrict__ lz, const PlaneCandidate* __restrict__ plc,
-                    const uint8_t* __restrict__ ok_flags, const uint32_t* __restrict__ bbox,
+                    const uint8_t* __restrict__ ok_flags, const float* __restrict__ bbox,
                     unsigned long long* __restrict__ status, uint32_t* __restrict__ tile_counter,
                     mp2p_b200_pair_pt2pl* __restrict__ out, unsigned long long* __restrict__ out_count)
 {
@@ -508,12 +551,11 @@ __global__ void __launch_bounds__(256)
     out_found[i] = cnt;
 }
 
-__global__ void k_init_small(uint32_t* bbox, unsigned long long* count, uint32_t* tile_counter)
+__global__ void k_init_small(unsigned long long* count, uint32_t* tile_counter, uint32_t* done_counter)
 {
-    if (threadIdx.x < 3) bbox[threadIdx.x] = 0xffffffffu;
-    if (threadIdx.x >= 3 && threadIdx.x < 6) bbox[threadIdx.x] = 0u;
-    if (threadIdx.x == 6) *count = 0ull;
-    if (threadIdx.x == 7) *tile_counter = 0u;
+    if (threadIdx.x == 0) *count = 0ull;
+    if (threadIdx.x == 1) *tile_counter = 0u;
+    if (threadIdx.x == 2) *done_counter = 0u;
 }
 
 int pick_kt(uint32_t K)
@@ -555,20 +597,26 @@ int upload_bits(mp2p_b200_ctx* ctx, DevBuf& buf, const uint32_t* bits, uint64_t 
 
 struct SmallView
 {
-    uint32_t*           bbox;
+    float*              bbox_final;    // 6 floats: min xyz, max xyz of the transformed local cloud
+    float*              bbox_part;     // 6 floats per CTA of the match kernel
     unsigned long long* count;
     uint32_t*           tile_counter;
+    uint32_t*           done_counter;
 };
-int prepare_small(mp2p_b200_ctx* ctx, uint64_t n_tiles, SmallView& sv, unsigned long long** status)
+int prepare_small(mp2p_b200_ctx* ctx, uint64_t n_tiles, uint64_t n_match_blocks, SmallView& sv,
+                  unsigned long long** status)
 {
-    MP2P_TRY(ctx->d_small.ensure(64));
-    sv.bbox         = ctx->d_small.as<uint32_t>();
-    sv.count        = reinterpret_cast<unsigned long long*>(ctx->d_small.as<char>() + 32);
-    sv.tile_counter = reinterpret_cast<uint32_t*>(ctx->d_small.as<char>() + 40);
+    MP2P_TRY(ctx->d_small.ensure(64 + n_match_blocks * 24));
+    char* base      = ctx->d_small.as<char>();
+    sv.bbox_final   = reinterpret_cast<float*>(base);
+    sv.count        = reinterpret_cast<unsigned long long*>(base + 32);
+    sv.tile_counter = reinterpret_cast<uint32_t*>(base + 40);
+    sv.done_counter = reinterpret_cast<uint32_t*>(base + 44);
+    sv.bbox_part    = reinterpret_cast<float*>(base + 64);
     MP2P_TRY(ctx->d_scan.ensure((n_tiles + 1) * 8));
     *status = ctx->d_scan.as<unsigned long long>();
     MP2P_CUDA_TRY(cudaMemsetAsync(*status, 0, (n_tiles + 1) * 8, ctx->stream));
-    k_init_small<<<1, 32, 0, ctx->stream>>>(sv.bbox, sv.count, sv.tile_counter);
+    k_init_small<<<1, 32, 0, ctx->stream>>>(sv.count, sv.tile_counter, sv.done_counter);
     count_launch(ctx);
     return 0;
 }
@@ -633,7 +681,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     const uint64_t n_tiles = (n_slots + kScanTile - 1) / kScanTile;
     SmallView           sv;
     unsigned long long* status;
-    MP2P_TRY(prepare_small(ctx, n_tiles, sv, &status));
+    MP2P_TRY(prepare_small(ctx, n_tiles, (n_local + kQueryTile - 1) / kQueryTile, sv, &status));
     MP2P_TRY(ctx->d_cand.ensure(n_slots * 8));
 
     if (++map->epoch == 0xFFFFFFFFu)  // tags exhausted: restart the claim words
@@ -659,7 +707,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     MP2P_TRY(prepare_stats(ctx, &stats));
     prof_begin(ctx, 0);
 #define LAUNCH_MATCH(KT) \
-    k_match_pt2pt<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, sv.bbox, stats)
+    k_match_pt2pt<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, sv.bbox_part, sv.done_counter, sv.bbox_final, stats)
     switch (pick_kt(K))
     {
         case 1: LAUNCH_MATCH(1); break;
@@ -684,8 +732,149 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     c.capacity = std::min<uint64_t>(capacity, n_slots);
     prof_begin(ctx, 1);
     k_compact_pt2pt<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, c, dlx, dly, dlz, d_gbits,
-                                                               claim, cand, sv.bbox, status,
+                                                               claim, cand, sv.bbox_final, status,
                                                                sv.tile_counter, d_out, sv.count);
+    prof_end(ctx, 1);
+    count_launch(ctx);
+    return fetch_results(ctx, sv.count, d_out, out, capacity, out_on_device, out_count);
+}
+
+// ------------------------------------------------------------------------------------------
+// Query-sharded matching (one process per GPU): phase A searches the shard, the caller all-gathers
+// the candidate words of all shards, phase B replays EVERY shard's proposals into this GPU's claim
+// array with one global slot numbering (slot = globalLocalIdx*K + rank) and compacts its own shard.
+// The result is bit-identical to a single-GPU run over the whole cloud.
+// ------------------------------------------------------------------------------------------
+namespace
+{
+__global__ void __launch_bounds__(256)
+    k_claim_all(const unsigned long long* __restrict__ cand_all, uint64_t n_slots, unsigned long long tag,
+                const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim)
+{
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < n_slots; s += (uint64_t)gridDim.x * blockDim.x)
+    {
+        const unsigned long long c = cand_all[s];
+        if ((uint32_t)c == 0xFFFFFFFFu) continue;
+        const uint32_t gi = (uint32_t)c;
+        if (!bit_set(gbits, gi)) atomicMin(claim + gi, tag | s);
+    }
+}
+// fold the per-shard bounding boxes (6 floats each, min xyz / max xyz) into one
+__global__ void k_fold_bbox(const float* __restrict__ parts, uint32_t n_parts, float* __restrict__ out)
+{
+    const int d = threadIdx.x;
+    if (d >= 6) return;
+    float r = parts[d];
+    for (uint32_t p = 1; p < n_parts; p++) r = d < 3 ? fminf(r, parts[p * 6 + d]) : fmaxf(r, parts[p * 6 + d]);
+    out[d] = r;
+}
+}  // namespace
+
+int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                           const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
+                           const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits,
+                           unsigned long long* d_cand_out, float* d_bbox6_out)
+{
+    const uint32_t K = prm->pairingsPerPoint;
+    cudaStream_t   st = ctx->stream;
+    if (n_local == 0 || map->view.n_points == 0)
+    {
+        // an empty shard still has to contribute "nothing": all-ones candidates, inverted bbox
+        if (n_local) MP2P_CUDA_TRY(cudaMemsetAsync(d_cand_out, 0xff, n_local * K * 8, st));
+        const float inv[6] = {3.4e38f, 3.4e38f, 3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f};
+        MP2P_CUDA_TRY(cudaMemcpyAsync(d_bbox6_out, inv, sizeof(inv), cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+    MP2P_TRY(stage_local(ctx, lx, ly, lz, n_local, local_on_device));
+    const uint32_t* d_lbits;
+    MP2P_TRY(upload_bits(ctx, ctx->d_lbits, lbits, n_local, &d_lbits));
+    SmallView           sv;
+    unsigned long long* status;
+    const uint32_t      blocks = (uint32_t)((n_local + kQueryTile - 1) / kQueryTile);
+    MP2P_TRY(prepare_small(ctx, 1, blocks, sv, &status));
+    Pt2PtArgs a{};
+    for (int k = 0; k < 12; k++) a.pose.m[k] = pose[k];
+    a.maxDistSq = (float)(prm->threshold * prm->threshold);
+    const double ang = prm->thresholdAngularDeg * 3.14159265358979323846 / 180.0;
+    a.angSq     = (float)(ang * ang);
+    a.n_local = (uint32_t)n_local, a.K = K;
+    a.allowLocal = prm->allowMatchAlreadyMatchedPoints, a.allowGlobal = 1;  // claims happen in phase B
+    a.tag = 0;
+    const float *dlx = ctx->d_lx.as<float>(), *dly = ctx->d_ly.as<float>(), *dlz = ctx->d_lz.as<float>();
+    unsigned long long* stats = nullptr;
+    MP2P_TRY(prepare_stats(ctx, &stats));
+    prof_begin(ctx, 0);
+#define LAUNCH_MATCH(KT) \
+    k_match_pt2pt<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, nullptr, nullptr, d_cand_out, sv.bbox_part, sv.done_counter, d_bbox6_out, stats)
+    switch (pick_kt(K))
+    {
+        case 1: LAUNCH_MATCH(1); break;
+        case 4: LAUNCH_MATCH(4); break;
+        case 8: LAUNCH_MATCH(8); break;
+        case 16: LAUNCH_MATCH(16); break;
+        default: LAUNCH_MATCH(32); break;
+    }
+#undef LAUNCH_MATCH
+    prof_end(ctx, 0);
+    count_launch(ctx);
+    return 0;
+}
+
+int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_local, uint64_t index_offset,
+                            uint64_t n_total, const unsigned long long* d_cand_all,
+                            const float* d_bbox_parts, uint32_t n_bbox_parts,
+                            const mp2p_b200_pt2pt_params* prm, const uint32_t* gbits,
+                            mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device,
+                            uint64_t* out_count)
+{
+    *out_count        = 0;
+    const uint32_t K  = prm->pairingsPerPoint;
+    const uint64_t nmap = map->view.n_points;
+    if (nmap == 0 || n_local == 0) return 0;
+    if (n_total * (uint64_t)K >= 0xFFFFFFFFull || index_offset + n_local > n_total)
+    {
+        set_error("shard_resolve: need n_total*pairingsPerPoint < 2^32-1 and a shard inside the cloud");
+        return MP2P_B200_ERR_ARG;
+    }
+    cudaStream_t    st = ctx->stream;
+    const uint32_t* d_gbits;
+    MP2P_TRY(upload_bits(ctx, ctx->d_gbits, gbits, nmap, &d_gbits));
+    const uint64_t      n_slots = n_local * K;
+    const uint64_t      n_tiles = (n_slots + kScanTile - 1) / kScanTile;
+    SmallView           sv;
+    unsigned long long* status;
+    MP2P_TRY(prepare_small(ctx, n_tiles, 1, sv, &status));
+    k_fold_bbox<<<1, 32, 0, st>>>(d_bbox_parts, n_bbox_parts, sv.bbox_final);
+    count_launch(ctx);
+    if (++map->epoch == 0xFFFFFFFFu)
+    {
+        MP2P_CUDA_TRY(cudaMemsetAsync(map->d_claim.p, 0xff, nmap * 8, st));
+        map->epoch = 1;
+    }
+    const unsigned long long tag   = (unsigned long long)(0xFFFFFFFFu - map->epoch) << 32;
+    auto*                    claim = map->d_claim.as<unsigned long long>();
+    if (!prm->allowMatchAlreadyMatchedGlobalPoints)
+    {
+        const uint64_t all_slots = n_total * K;
+        const uint32_t blocks    = (uint32_t)std::min<uint64_t>((all_slots + 255) / 256, 148 * 16);
+        k_claim_all<<<blocks, 256, 0, st>>>(d_cand_all, all_slots, tag, d_gbits, claim);
+        count_launch(ctx);
+    }
+    mp2p_b200_pair_pt2pt* d_out = out;
+    if (!out_on_device)
+    {
+        MP2P_TRY(ctx->d_out2p.ensure(std::min<uint64_t>(capacity, n_slots) * sizeof(mp2p_b200_pair_pt2pt)));
+        d_out = ctx->d_out2p.as<mp2p_b200_pair_pt2pt>();
+    }
+    CompactArgs c{};
+    c.n_local = (uint32_t)n_local, c.K = K, c.allowGlobal = prm->allowMatchAlreadyMatchedGlobalPoints, c.tag = tag;
+    c.gate_eps = (float)(prm->threshold + prm->bounding_box_intersection_check_epsilon);
+    c.capacity = std::min<uint64_t>(capacity, n_slots);
+    c.slot_offset = index_offset * K, c.index_offset = (uint32_t)index_offset;
+    prof_begin(ctx, 1);
+    k_compact_pt2pt<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(
+        map->view, c, ctx->d_lx.as<float>(), ctx->d_ly.as<float>(), ctx->d_lz.as<float>(), d_gbits, claim,
+        d_cand_all + index_offset * K, sv.bbox_final, status, sv.tile_counter, d_out, sv.count);
     prof_end(ctx, 1);
     count_launch(ctx);
     return fetch_results(ctx, sv.count, d_out, out, capacity, out_on_device, out_count);
@@ -712,7 +901,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     const uint64_t      n_tiles = (n_local + kScanTile - 1) / kScanTile;
     SmallView           sv;
     unsigned long long* status;
-    MP2P_TRY(prepare_small(ctx, n_tiles, sv, &status));
+    MP2P_TRY(prepare_small(ctx, n_tiles, (n_local + kQueryTile - 1) / kQueryTile, sv, &status));
     MP2P_TRY(ctx->d_plcand.ensure(n_local * sizeof(PlaneCandidate)));
     MP2P_TRY(ctx->d_cand.ensure(n_local));  // ok flags (bytes)
 
@@ -733,7 +922,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     MP2P_TRY(prepare_stats(ctx, &stats));
     prof_begin(ctx, 0);
 #define LAUNCH_PL(KT) \
-    k_match_pt2pl<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, plc, okf, sv.bbox, stats)
+    k_match_pt2pl<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, plc, okf, sv.bbox_part, sv.done_counter, sv.bbox_final, stats)
     switch (pick_kt(prm->knn))
     {
         case 1:
@@ -755,7 +944,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     }
     prof_begin(ctx, 1);
     k_compact_pt2pl<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, (uint32_t)n_local, gate_eps,
-                                                               cap, dlx, dly, dlz, plc, okf, sv.bbox,
+                                                               cap, dlx, dly, dlz, plc, okf, sv.bbox_final,
                                                                status, sv.tile_counter, d_out, sv.count);
     prof_end(ctx, 1);
     count_launch(ctx);

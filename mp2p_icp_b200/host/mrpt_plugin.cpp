@@ -1,0 +1,207 @@
+// Reference-side binding: the mp2p_icp plugin classes that put the B200 hot path under the
+// reference's own Matcher / Solver interfaces. Built ONLY where MRPT and mp2p_icp headers exist
+// (`make -C mp2p_icp_b200/host plugin MRPT=1`); this container has neither, so the
+// file is compile-guarded and has not been compiled here — INTEGRATION.md says so explicitly.
+//
+// Usage from a pipeline YAML (the reference loads the .so through its `plugin:` key,
+// mp2p_icp_map/src/load_plugin.cpp:70-134, then creates the class by name, ICP.cpp:507-516):
+//
+//   matchers:
+//     - class: mp2p_icp::Matcher_Points_DistanceThreshold_B200
+//       plugin: libmp2p_icp_b200_plugin.so
+//       params: { threshold: 1.0, thresholdAngularDeg: 0, pairingsPerPoint: 1 }
+//   solvers:
+//     - class: mp2p_icp::Solver_Horn_B200
+//       plugin: libmp2p_icp_b200_plugin.so
+#if defined(MP2P_B200_WITH_MRPT)
+
+#include <mp2p_icp/Matcher_Points_Base.h>
+#include <mp2p_icp/Solver.h>
+#include <mp2p_icp/Solver_GaussNewton.h>
+#include <mp2p_icp/Solver_Horn.h>
+#include <mp2p_icp/metricmap.h>
+#include <mrpt/core/initializer.h>
+#include <mrpt/maps/CPointsMap.h>
+#include <mrpt/rtti/CObject.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "mp2p_b200.h"
+
+namespace mp2p_icp
+{
+namespace b200_detail
+{
+inline void check(int rc)
+{
+    if (rc != MP2P_B200_OK) THROW_EXCEPTION_FMT("mp2p_b200: %s", mp2p_b200_last_error());
+}
+inline mp2p_b200_ctx* ctx()
+{
+    static mp2p_b200_ctx* c = []
+    {
+        mp2p_b200_ctx* p = nullptr;
+        check(mp2p_b200_ctx_create(0, nullptr, &p));
+        return p;
+    }();
+    return c;
+}
+inline void pose12(const mrpt::poses::CPose3D& p, double out[12])
+{
+    const auto& R = p.getRotationMatrix();
+    for (int r = 0; r < 3; r++)
+    {
+        for (int c = 0; c < 3; c++) out[4 * r + c] = R(r, c);
+        out[4 * r + 3] = p.m_coords[r];
+    }
+}
+// Device copies of global layers, keyed on the layer object and rebuilt when its size or buffer
+// address changes (the reference relies on MRPT's own "kd-tree up to date" flag; methods are const
+// so the cache is mutable, SURVEY.md §8b "Ownership").
+struct MapCache
+{
+    struct Entry
+    {
+        mp2p_b200_map* map = nullptr;
+        const float*   x   = nullptr;
+        size_t         n   = 0;
+    };
+    std::mutex                                                   mtx;
+    std::unordered_map<const mrpt::maps::CMetricMap*, Entry>     entries;
+    mp2p_b200_map* get(const mrpt::maps::CMetricMap& layer)
+    {
+        const auto* pts = mp2p_icp::MapToPointsMap(layer);
+        ASSERTMSG_(pts, "B200 matchers need a CPointsMap global layer");
+        const auto&                 xs = pts->getPointsBufferRef_x();
+        std::lock_guard<std::mutex> lk(mtx);
+        auto&                       e = entries[&layer];
+        if (!e.map || e.x != xs.data() || e.n != xs.size())
+        {
+            if (e.map) mp2p_b200_map_destroy(e.map);
+            check(mp2p_b200_map_create(ctx(), xs.data(), pts->getPointsBufferRef_y().data(),
+                                       pts->getPointsBufferRef_z().data(), xs.size(), 0, &e.map));
+            e.x = xs.data(), e.n = xs.size();
+        }
+        return e.map;
+    }
+};
+inline MapCache& cache()
+{
+    static MapCache c;
+    return c;
+}
+inline std::vector<uint32_t> to_bits(const pointcloud_bitfield_t::DenseOrSparseBitField& bf, size_t n)
+{
+    std::vector<uint32_t> w((n + 31) / 32, 0u);
+    for (size_t i = 0; i < n; i++)
+        if (bf[i]) w[i >> 5] |= 1u << (i & 31);
+    return w;
+}
+}  // namespace b200_detail
+
+/** Drop-in for Matcher_Points_DistanceThreshold (same parameters, same results). */
+class Matcher_Points_DistanceThreshold_B200 : public Matcher_Points_Base
+{
+    DEFINE_MRPT_OBJECT(Matcher_Points_DistanceThreshold_B200, mp2p_icp)
+   public:
+    void initialize(const mrpt::containers::yaml& params) override
+    {
+        Matcher_Points_Base::initialize(params);
+        DECLARE_PARAMETER_REQ(params, threshold);
+        DECLARE_PARAMETER_REQ(params, thresholdAngularDeg);
+        DECLARE_PARAMETER_OPT(params, pairingsPerPoint);
+    }
+    double   threshold = 0.5, thresholdAngularDeg = 0.0;
+    uint32_t pairingsPerPoint = 1;
+
+   private:
+    void implMatchOneLayer(const mrpt::maps::CMetricMap& pcGlobal, const mrpt::maps::CPointsMap& pcLocal,
+                           const mrpt::poses::CPose3D& localPose, MatchState& ms,
+                           const layer_name_t& globalName, const layer_name_t& localName,
+                           Pairings& out) const override
+    {
+        using namespace b200_detail;
+        checkAllParametersAreRealized();
+        ASSERT_(pairingsPerPoint >= 1);
+        ASSERT_GT_(threshold, .0);
+        ASSERT_GE_(thresholdAngularDeg, .0);
+        mp2p_b200_map* gmap = cache().get(pcGlobal);
+        const auto &   lx = pcLocal.getPointsBufferRef_x(), &ly = pcLocal.getPointsBufferRef_y(),
+                   &lz = pcLocal.getPointsBufferRef_z();
+        double T[12];
+        pose12(localPose, T);
+        mp2p_b200_pt2pt_params p{threshold, thresholdAngularDeg, pairingsPerPoint,
+                                 allowMatchAlreadyMatchedPoints_, allowMatchAlreadyMatchedGlobalPoints_,
+                                 bounding_box_intersection_check_epsilon_};
+        auto&      lbf   = ms.localPairedBitField.point_layers[localName];
+        auto&      gbf   = ms.globalPairedBitField.point_layers[globalName];
+        const auto lbits = to_bits(lbf, lx.size());
+        const auto gbits = to_bits(gbf, mp2p_icp::MapToNN(pcGlobal, true)->nn_index_count());
+        const size_t before = out.paired_pt2pt.size();
+        out.paired_pt2pt.resize(before + lx.size() * pairingsPerPoint);
+        static_assert(sizeof(mrpt::tfest::TMatchingPair) == sizeof(mp2p_b200_pair_pt2pt));
+        uint64_t cnt = 0, pot = 0;
+        check(mp2p_b200_match_pt2pt(ctx(), gmap, lx.data(), ly.data(), lz.data(), lx.size(), 0, T, &p,
+                                    lbits.data(), gbits.data(),
+                                    reinterpret_cast<mp2p_b200_pair_pt2pt*>(out.paired_pt2pt.data() + before),
+                                    lx.size() * pairingsPerPoint, 0, &cnt, &pot));
+        out.paired_pt2pt.resize(before + cnt);
+        out.potential_pairings += pot;
+        if (!allowMatchAlreadyMatchedGlobalPoints_)  // lambdaAddPair, …DistanceThreshold.cpp:116-120
+            for (size_t i = before; i < out.paired_pt2pt.size(); i++)
+            {
+                lbf.mark_as_set(out.paired_pt2pt[i].localIdx);
+                gbf.mark_as_set(out.paired_pt2pt[i].globalIdx);
+            }
+    }
+};
+IMPLEMENTS_MRPT_OBJECT(Matcher_Points_DistanceThreshold_B200, Matcher, mp2p_icp)
+
+/** Drop-in for Solver_Horn: pt2pt accumulation on the GPU. pt2ln / pt2pl pairings are first
+ *  projected by the reference's own pt2ln_pl_to_pt2pt (host). */
+class Solver_Horn_B200 : public Solver_Horn
+{
+    DEFINE_MRPT_OBJECT(Solver_Horn_B200, mp2p_icp)
+   protected:
+    bool impl_optimal_pose(const Pairings& pairings, OptimalTF_Result& out, const SolverContext& sc) const override
+    {
+        using namespace b200_detail;
+        if (!pairings.paired_pt2ln.empty() || !pairings.paired_pt2pl.empty() ||
+            !pairings.paired_ln2ln.empty() || !pairings.paired_pl2pl.empty())
+            return Solver_Horn::impl_optimal_pose(pairings, out, sc);  // terms that stay host-side
+        out = OptimalTF_Result();
+        const auto&           wp = pairingsWeightParameters;
+        mp2p_b200_horn_params p{};
+        p.use_scale_outlier_detector = wp.use_scale_outlier_detector;
+        p.scale_outlier_threshold    = wp.scale_outlier_threshold;
+        p.w_pt2pt                    = wp.pair_weights.pt2pt;
+        p.robust_kernel              = static_cast<int>(wp.robust_kernel);
+        p.robust_kernel_param        = wp.robust_kernel_param;
+        if (wp.currentEstimateForRobust) pose12(*wp.currentEstimateForRobust, p.currentEstimateForRobust);
+        std::vector<uint64_t> wc;
+        std::vector<double>   wv;
+        for (const auto& [cnt, w] : pairings.point_weights) wc.push_back(cnt), wv.push_back(w);
+        double  T[12];
+        int32_t solved = 0;
+        check(mp2p_b200_solve_horn(ctx(), reinterpret_cast<const mp2p_b200_pair_pt2pt*>(pairings.paired_pt2pt.data()),
+                                   pairings.paired_pt2pt.size(), 0, &p, wc.data(), wv.data(), wc.size(), T, &solved));
+        if (!solved) return false;
+        mrpt::math::CMatrixDouble44 M = mrpt::math::CMatrixDouble44::Identity();
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 4; c++) M(r, c) = T[4 * r + c];
+        out.optimalPose = mrpt::poses::CPose3D(M);
+        return true;
+    }
+};
+IMPLEMENTS_MRPT_OBJECT(Solver_Horn_B200, Solver, mp2p_icp)
+
+MRPT_INITIALIZER(register_mp2p_icp_b200)
+{
+    using mrpt::rtti::registerClass;
+    registerClass(CLASS_ID(mp2p_icp::Matcher_Points_DistanceThreshold_B200));
+    registerClass(CLASS_ID(mp2p_icp::Solver_Horn_B200));
+}
+}  // namespace mp2p_icp
+
+#endif  // MP2P_B200_WITH_MRPT

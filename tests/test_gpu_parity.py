@@ -126,8 +126,9 @@ def test_match_pt2pt_bit_exact_c2_small(ctx, kw):
         p0, pot0 = orc.match_pt2pt(tree, *xyz(L), pose, orc.MatchPt2PtParams(**kw), nthreads=8)
         p1, pot1 = gmap.match_pt2pt(*xyz(L), pose, b200.Pt2PtParams(**kw))
         assert pot0 == pot1
-        assert len(p0) == len(p1) and len(p0) > 1000
+        assert len(p0) == len(p1)
         assert p0.tobytes() == p1.tobytes()  # every field of every record, bit for bit
+    assert len(p1) > 1000  # at the GT pose the clouds overlap
 
 
 def test_match_pt2pt_matchstate_bitfields(ctx):
@@ -338,3 +339,38 @@ def test_icp_align_bunny_matches_oracle(ctx, solver):
     # of a transformed query once in a while; the first iteration (identical pose) must be identical.
     assert log["cpu"][0].tobytes() == log["gpu"][0].tobytes()
     assert same >= len(log["cpu"]) - 2
+
+
+# --------------------------------------------------------------------------- query sharding (§8e)
+@pytest.mark.parametrize("kw", [dict(threshold=1.0), dict(threshold=2.0, pairingsPerPoint=3), dict(threshold=1.0, allowMatchAlreadyMatchedGlobalPoints=True)])
+def test_sharded_match_equals_unsharded(ctx, kw):
+    """Phase A (search per shard) + gathered candidates + phase B (global first-claim replay) must
+    reproduce the single-call result bit for bit. The shards are run one after another on the one
+    GPU here; across processes the only difference is who owns which slice (tests/test_multi_gloo.py
+    covers the host-side exchange)."""
+    import torch
+
+    M, L, gt = _c2(150_000, 5)
+    L = np.concatenate([L, L[:4000] + np.float32(2e-3)])  # cross-shard duplicate claims
+    gmap = b200.Map(ctx, *xyz(M))
+    prm = b200.Pt2PtParams(**kw)
+    K = prm.pairingsPerPoint
+    ref, _ = gmap.match_pt2pt(*xyz(L), gt, prm)
+    ref = ref.copy()
+    n_total, n_sh = len(L), 3
+    bounds = np.linspace(0, n_total, n_sh + 1).astype(int)
+    cand_all = torch.empty(n_total * K, dtype=torch.int64, device="cuda")
+    boxes = torch.empty(n_sh * 6, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    for s in range(n_sh):
+        a, b = bounds[s], bounds[s + 1]
+        gmap.shard_search_pt2pt(*xyz(L[a:b]), gt, prm, cand_all.data_ptr() + a * K * 8, boxes.data_ptr() + s * 24)
+    ctx.synchronize()
+    parts = []
+    for s in range(n_sh):
+        a, b = bounds[s], bounds[s + 1]
+        # phase B reuses the shard staged by phase A on this context: restage it
+        gmap.shard_search_pt2pt(*xyz(L[a:b]), gt, prm, cand_all.data_ptr() + a * K * 8, boxes.data_ptr() + s * 24)
+        parts.append(gmap.shard_resolve_pt2pt(b - a, a, n_total, cand_all.data_ptr(), boxes.data_ptr(), n_sh, prm).copy())
+    got = np.concatenate(parts)
+    assert len(got) == len(ref) and got.tobytes() == ref.tobytes()
