@@ -409,7 +409,7 @@ class Map:
             n_local = lx.size
         lb = pack_bits(local_paired) if local_paired is not None else None
         cp = prm.c()
-        _check(load_library().mp2p_b200_match_pt2pt_shard_search(self.ctx._h, self._h, _ptr(lx), _ptr(ly), _ptr(lz), C.c_uint64(n_local), int(local_on_device), _ptr(_pose(T)), C.byref(cp), _ptr(lb), C.c_void_p(cand_out), C.c_void_p(bbox6_out)))
+        _check(load_library().mp2p_b200_match_pt2pt_shard_search(self.ctx._h, self._h, _ptr(lx), _ptr(ly), _ptr(lz), C.c_uint64(n_local), int(local_on_device), _ptr(_pose(T)), C.byref(cp), _ptr(lb), C.c_void_p(int(cand_out)), C.c_void_p(int(bbox6_out))))
 
     def shard_resolve_pt2pt(self, n_local, index_offset, n_total, cand_all: int, bbox_parts: int, n_shards, prm: Pt2PtParams, global_paired=None, out=None, out_on_device=False, capacity=None):
         cap = capacity if capacity is not None else n_local * prm.pairingsPerPoint
@@ -418,7 +418,7 @@ class Map:
         gb = pack_bits(global_paired) if global_paired is not None else None
         cp = prm.c()
         cnt = C.c_uint64(0)
-        _check(load_library().mp2p_b200_match_pt2pt_shard_resolve(self.ctx._h, self._h, C.c_uint64(n_local), C.c_uint64(index_offset), C.c_uint64(n_total), C.c_void_p(cand_all), C.c_void_p(bbox_parts), C.c_uint32(n_shards), C.byref(cp), _ptr(gb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt)))
+        _check(load_library().mp2p_b200_match_pt2pt_shard_resolve(self.ctx._h, self._h, C.c_uint64(n_local), C.c_uint64(index_offset), C.c_uint64(n_total), C.c_void_p(int(cand_all)), C.c_void_p(int(bbox_parts)), C.c_uint32(n_shards), C.byref(cp), _ptr(gb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt)))
         if out_on_device:
             return cnt.value
         return out[: cnt.value]

@@ -103,6 +103,7 @@ struct mp2p_b200_ctx
     cudaStream_t stream     = nullptr;
     bool         own_stream = false;
     uint64_t     launches   = 0;
+    uint32_t     scan_epoch = 0;  // stamps look-back status words (match.cu)
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
     // measurement hooks
     bool         prof_timings = false, prof_stats = false;

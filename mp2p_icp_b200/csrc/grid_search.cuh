@@ -126,20 +126,73 @@ __constant__ uint8_t kNeighbourOrder[27] = {
     0x10, 0x12, 0x18, 0x1a, 0x04, 0x06, 0x24, 0x26, 0x01, 0x09, 0x21, 0x29,  // edges
     0x00, 0x02, 0x08, 0x0a, 0x20, 0x22, 0x28, 0x2a};                         // corners
 
-// Exact K-nearest (k_runtime <= K) of (qx,qy,qz) among points with d2 < radius2 (strict).
-// On return top.v[0..k_runtime) ascending; entries >= sentinel are "not found".
 struct SearchCounters
 {
     uint32_t probes = 0, cands = 0, levels = 0;
 };
 
-template <int K>
+// ---- sub-warp cooperative search --------------------------------------------------------------
+// A query is processed by a GROUP of G consecutive lanes (G = 8: four queries per warp). The group
+// members hold the same query; work is split so that memory requests of one query are issued by
+// different lanes in the same instruction (memory-level parallelism instead of one thread's serial
+// chain of dependent loads):
+//   1. centre voxel: one broadcast hash probe, its points scanned G at a time;
+//   2. group all-reduce of the best key -> K-th distance bound;
+//   3. the 26 neighbour voxels are dealt to the lanes (lane l takes 1+l, 1+G+l, ...): each lane
+//      prunes with the box bound, probes and scans its own voxels;
+//   4. group merge (K rounds of "pop the group minimum") -> exact K best of the level, replicated
+//      in every lane; termination test; otherwise one level up with fresh per-lane lists.
+constexpr int kGroup = 8;
+
+template <int G>
+__device__ __forceinline__ unsigned long long group_min_u64(unsigned long long v, unsigned gmask)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1)
+    {
+        const unsigned long long t = __shfl_xor_sync(gmask, v, o);
+        v                          = t < v ? t : v;
+    }
+    return v;
+}
+
+// Merge the G per-lane ascending lists into the ascending K best of their union (replicated).
+// Keys are unique (they embed the point index) except for sentinels.
+template <int K, int G>
+__device__ __forceinline__ void group_merge(TopK<K>& lane, TopK<K>& out, unsigned gmask)
+{
+#pragma unroll
+    for (int r = 0; r < K; r++)
+    {
+        const unsigned long long head = lane.v[0];
+        const unsigned long long m    = group_min_u64<G>(head, gmask);
+        out.v[r]                      = m;
+        if (head == m)
+        {
+#pragma unroll
+            for (int j = 0; j < K - 1; j++) lane.v[j] = lane.v[j + 1];
+            lane.v[K - 1] = ~0ull;
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned long long point_key(float qx, float qy, float qz, const float4 p)
+{
+    const float d2 = dist2_ref(qx, qy, qz, p.x, p.y, p.z);
+    return ((unsigned long long)__float_as_uint(d2) << 32) | (uint32_t)__float_as_int(p.w);
+}
+
+// Exact K-nearest (k_runtime <= K) of (qx,qy,qz) among points with d2 < radius2 (strict).
+// Called by all G lanes of a group with identical arguments; `sub` = lane index inside the group,
+// `gmask` = the group's lanes. On return res.v[0..k_runtime) ascending, identical in all lanes;
+// entries >= (radius2 bits << 32) are "not found".
+template <int K, int G>
 __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy, float qz,
-                                           float radius2, int k_runtime, TopK<K>& top,
-                                           SearchCounters& sc)
+                                           float radius2, int k_runtime, TopK<K>& res, unsigned gmask,
+                                           int sub, SearchCounters& sc)
 {
     const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
-    top.init(sentinel);
+    res.init(sentinel);
     if (!(radius2 > 0.f)) return;
 
     // reject queries farther than the radius from the map bbox (conservative: strictly greater)
@@ -156,39 +209,63 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
     const float uy  = fminf(fmaxf(grid_u(qy, g.oy, g.inv_s0), -lim), lim);
     const float uz  = fminf(fmaxf(grid_u(qz, g.oz, g.inv_s0), -lim), lim);
     const int   Ix = (int)floorf(ux), Iy = (int)floorf(uy), Iz = (int)floorf(uz);
+    const float q2 = g.s0_lo * g.s0_lo * 0.999999f;  // quanta^2 -> metres^2, rounded down
 
-    float kth = radius2;
+    float kth = radius2;  // upper bound of the K-th best distance found so far (all levels)
     for (int rl = 0; rl < g.n_levels; rl++)
     {
-        const int   L      = g.level_first + rl;
-        const int   cmax   = ((1 << kGridBits) - 1) >> L;
-        const float s      = (float)(1 << L);  // voxel edge in finest quanta
+        const int L = g.level_first + rl;
+        TopK<K>   mine;  // this lane's candidates of this level
+        mine.init(sentinel);
+
+        if (L == kGridBits)
+        {
+            // top level: the single voxel holds every point; a query outside the grid (possible only
+            // with a radius larger than its distance to the bbox) must still see all of them
+            if (sub == 0) sc.probes++, sc.cands += g.n_points;
+            for (uint32_t j = sub; j < g.n_points; j += G)
+            {
+                const unsigned long long c = point_key(qx, qy, qz, __ldg(g.pts + j));
+                if (c < mine.worst(k_runtime)) mine.insert(c);
+            }
+            group_merge<K, G>(mine, res, gmask);
+            if (sub == 0) sc.levels++;
+            break;
+        }
+
+        const int   cmax = ((1 << kGridBits) - 1) >> L;
+        const float s    = (float)(1 << L);  // voxel edge in finest quanta
         const int   cx = Ix >> L, cy = Iy >> L, cz = Iz >> L;
         const float fx = ux - (float)cx * s, fy = uy - (float)cy * s, fz = uz - (float)cz * s;
         // per-axis gap (in quanta, made conservative) to the -1 / +1 neighbour slabs
         const float gxl = fmaxf(fx - 4.f, 0.f), gxh = fmaxf(s - fx - 4.f, 0.f);
         const float gyl = fmaxf(fy - 4.f, 0.f), gyh = fmaxf(s - fy - 4.f, 0.f);
         const float gzl = fmaxf(fz - 4.f, 0.f), gzh = fmaxf(s - fz - 4.f, 0.f);
-        const float q2  = g.s0_lo * g.s0_lo * 0.999999f;  // quanta^2 -> metres^2, rounded down
 
-        if (L == kGridBits)
+        // ---- 1. centre voxel, scanned by the whole group
+        if ((unsigned)cx <= (unsigned)cmax && (unsigned)cy <= (unsigned)cmax && (unsigned)cz <= (unsigned)cmax)
         {
-            // top level: the single voxel holds every point; a query outside the grid (possible only
-            // with a radius larger than its distance to the bbox) must still see all of them
-            sc.probes++, sc.cands += g.n_points, sc.levels++;
-            for (uint32_t j = 0; j < g.n_points; j++)
+            uint32_t start, count;
+            if (sub == 0) sc.probes++;
+            if (grid_lookup(g, rl, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, start, count))
             {
-                const float4 p  = __ldg(g.pts + j);
-                const float  d2 = dist2_ref(qx, qy, qz, p.x, p.y, p.z);
-                const unsigned long long c =
-                    ((unsigned long long)__float_as_uint(d2) << 32) | (uint32_t)__float_as_int(p.w);
-                if (c < top.worst(k_runtime)) top.insert(c);
+                if (sub == 0) sc.cands += count;
+                for (uint32_t j = start + sub; j < start + count; j += G)
+                {
+                    const unsigned long long c = point_key(qx, qy, qz, __ldg(g.pts + j));
+                    if (c < mine.worst(k_runtime)) mine.insert(c);
+                }
             }
-            break;
         }
-
+        // ---- 2. bound for pruning the neighbours. K == 1: exact group minimum. K > 1: any lane that
+        // already holds k candidates bounds the K-th distance of the union from above.
+        {
+            const unsigned long long w = group_min_u64<G>(mine.worst(k_runtime), gmask);
+            kth                        = fminf(kth, __uint_as_float((uint32_t)(w >> 32)));
+        }
+        // ---- 3. the 26 neighbours, dealt round-robin to the lanes
 #pragma unroll 1
-        for (int nb = 0; nb < 27; nb++)
+        for (int nb = 1 + sub; nb < 27; nb += G)
         {
             const uint32_t code = kNeighbourOrder[nb];
             const int      dx = (int)(code & 3u) - 1, dy = (int)((code >> 2) & 3u) - 1,
@@ -208,21 +285,21 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
             sc.cands += count;
             for (uint32_t j = start; j < start + count; j++)
             {
-                const float4 p  = __ldg(g.pts + j);
-                const float  d2 = dist2_ref(qx, qy, qz, p.x, p.y, p.z);
-                const unsigned long long c =
-                    ((unsigned long long)__float_as_uint(d2) << 32) | (uint32_t)__float_as_int(p.w);
-                if (c < top.worst(k_runtime))
+                const unsigned long long c = point_key(qx, qy, qz, __ldg(g.pts + j));
+                if (c < mine.worst(k_runtime))
                 {
-                    top.insert(c);
-                    kth = __uint_as_float((uint32_t)(top.worst(k_runtime) >> 32));
+                    mine.insert(c);
+                    kth = fminf(kth, __uint_as_float((uint32_t)(mine.worst(k_runtime) >> 32)));
                 }
             }
         }
+        // ---- 4. exact K best of this level, replicated; termination test
+        group_merge<K, G>(mine, res, gmask);
+        kth = fminf(kth, __uint_as_float((uint32_t)(res.worst(k_runtime) >> 32)));
         // everything outside the 3x3x3 block is at least m quanta away
         const float mx = s + fminf(fx, s - fx), my = s + fminf(fy, s - fy), mz = s + fminf(fz, s - fz);
         const float m  = fmaxf(fminf(mx, fminf(my, mz)) - 4.f, 0.f);
-        sc.levels++;
+        if (sub == 0) sc.levels++;
         if (kth <= m * m * q2) break;
     }
 }

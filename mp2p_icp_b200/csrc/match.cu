@@ -67,15 +67,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "memory");
 }
 
+// A CTA of kQueryTile threads serves kQueryTile / kGroup queries (kGroup lanes cooperate per query).
+constexpr uint32_t kQueriesPerBlock = kQueryTile / kGroup;
+
 struct QueryTile
 {
-    alignas(128) float x[kQueryTile];
-    alignas(128) float y[kQueryTile];
-    alignas(128) float z[kQueryTile];
+    alignas(128) float x[kQueriesPerBlock];
+    alignas(128) float y[kQueriesPerBlock];
+    alignas(128) float z[kQueriesPerBlock];
     alignas(8) uint64_t bar;
 };
 
-// All threads of the CTA call this; afterwards tile.x/y/z hold queries [base, base+kQueryTile).
+// All threads of the CTA call this; afterwards tile.x/y/z hold queries [base, base+kQueriesPerBlock).
 // The staging arrays are padded to a multiple of kQueryTile, so the copy size is constant.
 __device__ __forceinline__ void load_query_tile(QueryTile& tile, const float* lx, const float* ly,
                                                 const float* lz, size_t base)
@@ -88,7 +91,7 @@ __device__ __forceinline__ void load_query_tile(QueryTile& tile, const float* lx
     __syncthreads();
     if (threadIdx.x == 0)
     {
-        constexpr uint32_t bytes = kQueryTile * sizeof(float);
+        constexpr uint32_t bytes = kQueriesPerBlock * sizeof(float);
         mbar_expect_tx(&tile.bar, 3 * bytes);
         tma_load_1d(tile.x, lx + base, bytes, &tile.bar);
         tma_load_1d(tile.y, ly + base, bytes, &tile.bar);
@@ -157,6 +160,7 @@ __device__ __forceinline__ void block_bbox_finalize(BBoxSmem& sm, float gx, floa
     __syncthreads();
     if (!sm.is_last) return;
     __threadfence();
+    if (threadIdx.x == 0) *done_counter = 0u;  // re-arm for the next launch
     float a[6] = {3.4e38f, 3.4e38f, 3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f};
     for (uint32_t b = threadIdx.x; b < gridDim.x; b += blockDim.x)
 #pragma unroll
@@ -213,15 +217,17 @@ __global__ void __launch_bounds__(kQueryTile)
 {
     __shared__ QueryTile tile;
     __shared__ BBoxSmem  bsm;
-    const size_t         base = (size_t)blockIdx.x * kQueryTile;
+    const size_t         base = (size_t)blockIdx.x * kQueriesPerBlock;
     load_query_tile(tile, lx, ly, lz, base);
-    const uint32_t i     = (uint32_t)base + threadIdx.x;
+    const int      sub   = threadIdx.x % kGroup, ql = threadIdx.x / kGroup;
+    const unsigned gmask = ((1u << kGroup) - 1u) << ((threadIdx.x & 31) / kGroup * kGroup);
+    const uint32_t i     = (uint32_t)base + ql;
     const bool     valid = i < a.n_local;
 
     float gx = 0, gy = 0, gz = 0;
     if (valid)
     {
-        compose_point_f(a.pose, tile.x[threadIdx.x], tile.y[threadIdx.x], tile.z[threadIdx.x], gx, gy, gz);
+        compose_point_f(a.pose, tile.x[ql], tile.y[ql], tile.z[ql], gx, gy, gz);
         const int K = (int)a.K;
         // …DistanceThreshold.cpp:230,256-257 (float, unfused)
         const float normSq = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
@@ -233,33 +239,38 @@ __global__ void __launch_bounds__(kQueryTile)
         if (!a.allowLocal && bit_set(lbits, i))
             top.init(sentinel);  // :218-220 skip, already paired
         else
-            knn_search<KT>(g, gx, gy, gz, thr2, K, top, sc);
+            knn_search<KT, kGroup>(g, gx, gy, gz, thr2, K, top, gmask, sub, sc);
 
         uint32_t n_valid = 0;
-#pragma unroll
-        for (int k = 0; k < KT; k++)
+        if (sub == 0)
         {
-            if (k < K)
+#pragma unroll
+            for (int k = 0; k < KT; k++)
             {
-                // unused ranks are marked with an impossible map index (all ones)
-                const unsigned long long c = top.v[k] < sentinel ? top.v[k] : ~0ull;
-                n_valid += (c != ~0ull);
-                cand[(size_t)i * K + k] = c;
-                if (c != ~0ull && !a.allowGlobal)
+                if (k < K)
                 {
-                    const uint32_t gi = (uint32_t)c;
-                    if (!bit_set(gbits, gi)) atomicMin(claim + gi, a.tag | (unsigned long long)(i * (uint32_t)K + k));
+                    // unused ranks are marked with an impossible map index (all ones)
+                    const unsigned long long c = top.v[k] < sentinel ? top.v[k] : ~0ull;
+                    n_valid += (c != ~0ull);
+                    cand[(size_t)i * K + k] = c;
+                    if (c != ~0ull && !a.allowGlobal)
+                    {
+                        const uint32_t gi = (uint32_t)c;
+                        if (!bit_set(gbits, gi)) atomicMin(claim + gi, a.tag | (unsigned long long)(i * (uint32_t)K + k));
+                    }
                 }
             }
         }
         flush_search_stats(sc, n_valid, stats);
     }
-    block_bbox_finalize(bsm, gx, gy, gz, valid, bbox_part, done_counter, bbox_final);
+    block_bbox_finalize(bsm, gx, gy, gz, valid && sub == 0, bbox_part, done_counter, bbox_final);
 }
 
 // ------------------------------------------------------------------------------------------
 // Single-pass stream compaction (decoupled look-back over 1024-slot tiles).
-// status word: [63:62] 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix; [61:0] value
+// status word: [63:62] 1 = tile aggregate, 2 = inclusive prefix; [61:40] call epoch (22 bits);
+// [39:0] value. A word whose epoch is not the current call's reads as "not ready", so the status
+// array is never cleared between calls.
 // ------------------------------------------------------------------------------------------
 constexpr int      kScanThreads = 256;
 constexpr int      kScanItems   = 4;
@@ -276,7 +287,7 @@ struct ScanSmem
 // last tile. `local` = number of outputs of this thread (its kScanItems consecutive slots).
 __device__ __forceinline__ unsigned long long grid_exclusive_scan(
     ScanSmem& sm, uint32_t tile, uint32_t n_tiles, uint32_t local, unsigned long long* status,
-    unsigned long long* total_out)
+    unsigned long long* total_out, uint32_t epoch22)
 {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t       incl = local;
@@ -296,30 +307,47 @@ __device__ __forceinline__ unsigned long long grid_exclusive_scan(
         if (w < (int)warp) warp_off += s;
         block_total += s;
     }
-    if (threadIdx.x == 0)
+    if (warp == 0)
     {
-        unsigned long long base = 0;
-        if (tile > 0)
+        // decoupled look-back, one WARP wide: lane l inspects tile (t - l); the nearest tile that
+        // already published an inclusive prefix ends the walk.
+        constexpr unsigned long long kVal = (1ull << 40) - 1;
+        const unsigned long long     ep   = (unsigned long long)(epoch22 & 0x3FFFFFu) << 40;
+        volatile unsigned long long* vstatus = status;
+        if (tile > 0 && lane == 0)
         {
-            // publish aggregate, then look back
             __threadfence();
-            atomicExch(status + tile, (1ull << 62) | block_total);
-            int t = (int)tile - 1;
-            while (t >= 0)
+            vstatus[tile] = (1ull << 62) | ep | block_total;  // aggregate available
+        }
+        unsigned long long base = 0;
+        int                t    = (int)tile - 1;
+        while (t >= 0)
+        {
+            const int          idx = t - (int)lane;
+            unsigned long long sw  = (2ull << 62) | ep;  // tiles before the first: prefix 0
+            if (idx >= 0)
             {
-                unsigned long long s;
                 do
                 {
-                    s = atomicAdd(status + t, 0ull);
-                } while ((s >> 62) == 0);
-                base += s & ((1ull << 62) - 1);
-                if ((s >> 62) == 2) break;
-                t--;
+                    sw = vstatus[idx];
+                } while ((sw >> 62) == 0 || (sw & (0x3FFFFFull << 40)) != ep);
             }
+            const unsigned pm   = __ballot_sync(0xffffffffu, (sw >> 62) == 2);
+            const int      stop = pm ? __ffs(pm) - 1 : 31;  // nearest published prefix, if any
+            unsigned long long v = ((int)lane <= stop) ? (sw & kVal) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            base += v;
+            if (pm) break;  // (tiles before the first count as prefix 0, so this always triggers)
+            t -= 32;
         }
-        atomicExch(status + tile, (2ull << 62) | (base + block_total));
-        sm.tile_base = base;
-        if (tile == n_tiles - 1) *total_out = base + block_total;
+        if (lane == 0)
+        {
+            __threadfence();
+            vstatus[tile] = (2ull << 62) | ep | (base + block_total);
+            sm.tile_base  = base;
+            if (tile == n_tiles - 1) *total_out = base + block_total;
+        }
     }
     __syncthreads();
     return sm.tile_base + warp_off + (incl - local);
@@ -332,6 +360,7 @@ struct CompactArgs
     unsigned long long tag;
     float    gate_eps;  // threshold + bounding_box_intersection_check_epsilon (float)
     uint64_t capacity;
+    uint32_t scan_epoch;    // stamps the look-back status words of this call
     uint64_t slot_offset;   // sharded runs: first global proposal slot of this shard (index_offset*K)
     uint32_t index_offset;  // sharded runs: first global local-point index of this shard
 };
@@ -357,11 +386,15 @@ __global__ void __launch_bounds__(kScanThreads)
                     mp2p_b200_pair_pt2pt* __restrict__ out, unsigned long long* __restrict__ out_count)
 {
     __shared__ ScanSmem sm;
-    if (threadIdx.x == 0) sm.tile_id = atomicAdd(tile_counter, 1u);
-    __syncthreads();
-    const uint32_t tile    = sm.tile_id;
     const uint64_t n_slots = (uint64_t)a.n_local * a.K;
     const uint32_t n_tiles = (uint32_t)((n_slots + kScanTile - 1) / kScanTile);
+    if (threadIdx.x == 0)
+    {
+        sm.tile_id = atomicAdd(tile_counter, 1u);
+        if (sm.tile_id == n_tiles - 1) *tile_counter = 0u;  // last ticket handed out: re-arm
+    }
+    __syncthreads();
+    const uint32_t tile    = sm.tile_id;
     const bool     gate    = bbox_gate(g, bbox, a.gate_eps);
 
     const uint64_t     slot0 = (uint64_t)tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
@@ -384,7 +417,7 @@ __global__ void __launch_bounds__(kScanThreads)
         }
         if (ok) flags |= 1u << j, local++;
     }
-    const unsigned long long off = grid_exclusive_scan(sm, tile, n_tiles, local, status, out_count);
+    const unsigned long long off = grid_exclusive_scan(sm, tile, n_tiles, local, status, out_count, a.scan_epoch);
     unsigned long long       w   = off;
 #pragma unroll
     for (int j = 0; j < kScanItems; j++)
@@ -430,14 +463,16 @@ __global__ void __launch_bounds__(kQueryTile)
 {
     __shared__ QueryTile tile;
     __shared__ BBoxSmem  bsm;
-    const size_t         base = (size_t)blockIdx.x * kQueryTile;
+    const size_t         base = (size_t)blockIdx.x * kQueriesPerBlock;
     load_query_tile(tile, lx, ly, lz, base);
-    const uint32_t i     = (uint32_t)base + threadIdx.x;
+    const int      sub   = threadIdx.x % kGroup, ql = threadIdx.x / kGroup;
+    const unsigned gmask = ((1u << kGroup) - 1u) << ((threadIdx.x & 31) / kGroup * kGroup);
+    const uint32_t i     = (uint32_t)base + ql;
     const bool     valid = i < a.n_local;
     float          gx = 0, gy = 0, gz = 0;
     if (valid)
     {
-        compose_point_f(a.pose, tile.x[threadIdx.x], tile.y[threadIdx.x], tile.z[threadIdx.x], gx, gy, gz);
+        compose_point_f(a.pose, tile.x[ql], tile.y[ql], tile.z[ql], gx, gy, gz);
         uint8_t        ok = 0;
         SearchCounters sc;
         uint32_t       n_valid = 0;
@@ -445,14 +480,14 @@ __global__ void __launch_bounds__(kQueryTile)
         {
             TopK<KT>  top;
             const int K = (int)a.K;
-            knn_search<KT>(g, gx, gy, gz, a.radiusSq, K, top, sc);
+            knn_search<KT, kGroup>(g, gx, gy, gz, a.radiusSq, K, top, gmask, sub, sc);
             const unsigned long long sentinel = (unsigned long long)__float_as_uint(a.radiusSq) << 32;
             int                      cnt      = 0;
 #pragma unroll
             for (int k = 0; k < KT; k++)
                 if (k < K && top.v[k] < sentinel) cnt++;
-            n_valid = (uint32_t)cnt;
-            if (cnt >= 3 && cnt >= (int)a.minPts)
+            if (sub == 0) n_valid = (uint32_t)cnt;
+            if (sub == 0 && cnt >= 3 && cnt >= (int)a.minPts)
             {
                 // estimate_points_eigen.cpp:45-63 — float mean, double centred moments, ascending
                 // (d2, index) neighbour order
@@ -472,10 +507,10 @@ __global__ void __launch_bounds__(kQueryTile)
                 }
             }
         }
-        ok_flags[i] = ok;
+        if (sub == 0) ok_flags[i] = ok;
         flush_search_stats(sc, n_valid, stats);
     }
-    block_bbox_finalize(bsm, gx, gy, gz, valid, bbox_part, done_counter, bbox_final);
+    block_bbox_finalize(bsm, gx, gy, gz, valid && sub == 0, bbox_part, done_counter, bbox_final);
 }
 
 __global__ void __launch_bounds__(kScanThreads)
@@ -484,13 +519,18 @@ __global__ void __launch_bounds__(kScanThreads)
                     const float* __restrict__ lz, const PlaneCandidate* __restrict__ plc,
                     const uint8_t* __restrict__ ok_flags, const float* __restrict__ bbox,
                     unsigned long long* __restrict__ status, uint32_t* __restrict__ tile_counter,
-                    mp2p_b200_pair_pt2pl* __restrict__ out, unsigned long long* __restrict__ out_count)
+                    mp2p_b200_pair_pt2pl* __restrict__ out, unsigned long long* __restrict__ out_count,
+                    uint32_t scan_epoch)
 {
     __shared__ ScanSmem sm;
-    if (threadIdx.x == 0) sm.tile_id = atomicAdd(tile_counter, 1u);
+    const uint32_t n_tiles = (n_local + kScanTile - 1) / kScanTile;
+    if (threadIdx.x == 0)
+    {
+        sm.tile_id = atomicAdd(tile_counter, 1u);
+        if (sm.tile_id == n_tiles - 1) *tile_counter = 0u;
+    }
     __syncthreads();
     const uint32_t tile    = sm.tile_id;
-    const uint32_t n_tiles = (n_local + kScanTile - 1) / kScanTile;
     const bool     gate    = bbox_gate(g, bbox, gate_eps);
     const uint32_t i0      = tile * kScanTile + threadIdx.x * kScanItems;
     uint32_t       flags = 0, local = 0;
@@ -500,7 +540,7 @@ __global__ void __launch_bounds__(kScanThreads)
         const uint32_t i = i0 + j;
         if (gate && i < n_local && ok_flags[i]) flags |= 1u << j, local++;
     }
-    const unsigned long long off = grid_exclusive_scan(sm, tile, n_tiles, local, status, out_count);
+    const unsigned long long off = grid_exclusive_scan(sm, tile, n_tiles, local, status, out_count, scan_epoch);
     unsigned long long       w   = off;
 #pragma unroll
     for (int j = 0; j < kScanItems; j++)
@@ -531,11 +571,14 @@ __global__ void __launch_bounds__(256)
           const float* __restrict__ qz, uint32_t nq, uint32_t K, float radius2,
           uint32_t* __restrict__ out_idx, float* __restrict__ out_d2, int32_t* __restrict__ out_found)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
+    const int      sub   = threadIdx.x % kGroup;
+    const unsigned gmask = ((1u << kGroup) - 1u) << ((threadIdx.x & 31) / kGroup * kGroup);
+    const uint32_t i     = (blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
+    if (i >= nq) return;  // whole groups leave together
     TopK<KT>       top;
     SearchCounters sc;
-    knn_search<KT>(g, qx[i], qy[i], qz[i], radius2, (int)K, top, sc);
+    knn_search<KT, kGroup>(g, qx[i], qy[i], qz[i], radius2, (int)K, top, gmask, sub, sc);
+    if (sub != 0) return;
     const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
     int                      cnt      = 0;
 #pragma unroll
@@ -549,13 +592,6 @@ __global__ void __launch_bounds__(256)
             cnt += f;
         }
     out_found[i] = cnt;
-}
-
-__global__ void k_init_small(unsigned long long* count, uint32_t* tile_counter, uint32_t* done_counter)
-{
-    if (threadIdx.x == 0) *count = 0ull;
-    if (threadIdx.x == 1) *tile_counter = 0u;
-    if (threadIdx.x == 2) *done_counter = 0u;
 }
 
 int pick_kt(uint32_t K)
@@ -606,18 +642,28 @@ struct SmallView
 int prepare_small(mp2p_b200_ctx* ctx, uint64_t n_tiles, uint64_t n_match_blocks, SmallView& sv,
                   unsigned long long** status)
 {
-    MP2P_TRY(ctx->d_small.ensure(64 + n_match_blocks * 24));
+    // counters re-arm themselves inside the kernels and the scan status words carry a call epoch,
+    // so nothing is cleared per call: buffers are zeroed once when they are (re)allocated.
+    const size_t need_small = 64 + n_match_blocks * 24;
+    if (need_small > ctx->d_small.bytes)
+    {
+        MP2P_TRY(ctx->d_small.ensure(need_small));
+        MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_small.p, 0, ctx->d_small.bytes, ctx->stream));
+    }
+    const size_t need_scan = (n_tiles + 1) * 8;
+    if (need_scan > ctx->d_scan.bytes)
+    {
+        MP2P_TRY(ctx->d_scan.ensure(need_scan));
+        MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_scan.p, 0, ctx->d_scan.bytes, ctx->stream));
+    }
     char* base      = ctx->d_small.as<char>();
     sv.bbox_final   = reinterpret_cast<float*>(base);
     sv.count        = reinterpret_cast<unsigned long long*>(base + 32);
     sv.tile_counter = reinterpret_cast<uint32_t*>(base + 40);
     sv.done_counter = reinterpret_cast<uint32_t*>(base + 44);
     sv.bbox_part    = reinterpret_cast<float*>(base + 64);
-    MP2P_TRY(ctx->d_scan.ensure((n_tiles + 1) * 8));
-    *status = ctx->d_scan.as<unsigned long long>();
-    MP2P_CUDA_TRY(cudaMemsetAsync(*status, 0, (n_tiles + 1) * 8, ctx->stream));
-    k_init_small<<<1, 32, 0, ctx->stream>>>(sv.count, sv.tile_counter, sv.done_counter);
-    count_launch(ctx);
+    *status         = ctx->d_scan.as<unsigned long long>();
+    ctx->scan_epoch = (ctx->scan_epoch % 0x3FFFFEu) + 1;  // 1 .. 2^22-2, never 0 (= cleared memory)
     return 0;
 }
 
@@ -681,7 +727,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     const uint64_t n_tiles = (n_slots + kScanTile - 1) / kScanTile;
     SmallView           sv;
     unsigned long long* status;
-    MP2P_TRY(prepare_small(ctx, n_tiles, (n_local + kQueryTile - 1) / kQueryTile, sv, &status));
+    MP2P_TRY(prepare_small(ctx, n_tiles, (n_local + kQueriesPerBlock - 1) / kQueriesPerBlock, sv, &status));
     MP2P_TRY(ctx->d_cand.ensure(n_slots * 8));
 
     if (++map->epoch == 0xFFFFFFFFu)  // tags exhausted: restart the claim words
@@ -699,7 +745,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     a.allowLocal = prm->allowMatchAlreadyMatchedPoints, a.allowGlobal = prm->allowMatchAlreadyMatchedGlobalPoints;
     a.tag = (unsigned long long)(0xFFFFFFFFu - map->epoch) << 32;
 
-    const uint32_t blocks = (uint32_t)((n_local + kQueryTile - 1) / kQueryTile);
+    const uint32_t blocks = (uint32_t)((n_local + kQueriesPerBlock - 1) / kQueriesPerBlock);
     const float *  dlx = ctx->d_lx.as<float>(), *dly = ctx->d_ly.as<float>(), *dlz = ctx->d_lz.as<float>();
     auto*          claim = map->d_claim.as<unsigned long long>();
     auto*          cand  = ctx->d_cand.as<unsigned long long>();
@@ -730,6 +776,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     c.n_local = (uint32_t)n_local, c.K = K, c.allowGlobal = a.allowGlobal, c.tag = a.tag;
     c.gate_eps = (float)(prm->threshold + prm->bounding_box_intersection_check_epsilon);
     c.capacity = std::min<uint64_t>(capacity, n_slots);
+    c.scan_epoch = ctx->scan_epoch;
     prof_begin(ctx, 1);
     k_compact_pt2pt<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, c, dlx, dly, dlz, d_gbits,
                                                                claim, cand, sv.bbox_final, status,
@@ -790,7 +837,7 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     MP2P_TRY(upload_bits(ctx, ctx->d_lbits, lbits, n_local, &d_lbits));
     SmallView           sv;
     unsigned long long* status;
-    const uint32_t      blocks = (uint32_t)((n_local + kQueryTile - 1) / kQueryTile);
+    const uint32_t      blocks = (uint32_t)((n_local + kQueriesPerBlock - 1) / kQueriesPerBlock);
     MP2P_TRY(prepare_small(ctx, 1, blocks, sv, &status));
     Pt2PtArgs a{};
     for (int k = 0; k < 12; k++) a.pose.m[k] = pose[k];
@@ -871,6 +918,7 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
     c.gate_eps = (float)(prm->threshold + prm->bounding_box_intersection_check_epsilon);
     c.capacity = std::min<uint64_t>(capacity, n_slots);
     c.slot_offset = index_offset * K, c.index_offset = (uint32_t)index_offset;
+    c.scan_epoch = ctx->scan_epoch;
     prof_begin(ctx, 1);
     k_compact_pt2pt<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(
         map->view, c, ctx->d_lx.as<float>(), ctx->d_ly.as<float>(), ctx->d_lz.as<float>(), d_gbits, claim,
@@ -901,7 +949,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     const uint64_t      n_tiles = (n_local + kScanTile - 1) / kScanTile;
     SmallView           sv;
     unsigned long long* status;
-    MP2P_TRY(prepare_small(ctx, n_tiles, (n_local + kQueryTile - 1) / kQueryTile, sv, &status));
+    MP2P_TRY(prepare_small(ctx, n_tiles, (n_local + kQueriesPerBlock - 1) / kQueriesPerBlock, sv, &status));
     MP2P_TRY(ctx->d_plcand.ensure(n_local * sizeof(PlaneCandidate)));
     MP2P_TRY(ctx->d_cand.ensure(n_local));  // ok flags (bytes)
 
@@ -914,7 +962,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     a.allowLocal = prm->allowMatchAlreadyMatchedPoints;
     const float gate_eps = (float)(prm->distanceThreshold + prm->bounding_box_intersection_check_epsilon);
 
-    const uint32_t blocks = (uint32_t)((n_local + kQueryTile - 1) / kQueryTile);
+    const uint32_t blocks = (uint32_t)((n_local + kQueriesPerBlock - 1) / kQueriesPerBlock);
     const float *  dlx = ctx->d_lx.as<float>(), *dly = ctx->d_ly.as<float>(), *dlz = ctx->d_lz.as<float>();
     auto*          plc = ctx->d_plcand.as<PlaneCandidate>();
     auto*          okf = ctx->d_cand.as<uint8_t>();
@@ -945,7 +993,8 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     prof_begin(ctx, 1);
     k_compact_pt2pl<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, (uint32_t)n_local, gate_eps,
                                                                cap, dlx, dly, dlz, plc, okf, sv.bbox_final,
-                                                               status, sv.tile_counter, d_out, sv.count);
+                                                               status, sv.tile_counter, d_out, sv.count,
+                                                               ctx->scan_epoch);
     prof_end(ctx, 1);
     count_launch(ctx);
     return fetch_results(ctx, sv.count, d_out, out, capacity, out_on_device, out_count);
@@ -972,7 +1021,7 @@ int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const
     }
     else
     {
-        const uint32_t blocks = (uint32_t)((nq + 255) / 256);
+        const uint32_t blocks = (uint32_t)((nq * kGroup + 255) / 256);
         const float *  dqx = ctx->d_lx.as<float>(), *dqy = ctx->d_ly.as<float>(), *dqz = ctx->d_lz.as<float>();
         auto *oi = ctx->d_knn_idx.as<uint32_t>();
         auto *od = ctx->d_knn_d2.as<float>();

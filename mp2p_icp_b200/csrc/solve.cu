@@ -25,11 +25,19 @@ namespace
 constexpr int kSolveThreads = 256;
 constexpr int kWarps        = kSolveThreads / 32;
 
+// Block reduction + grid fold without a second launch: every CTA stores its NV partial sums and
+// takes a ticket; the LAST CTA to arrive sums the partials of all CTAs in a FIXED order (8 chunks
+// of CTAs in parallel, then the 8 chunk sums in order) into the 32-double packet and re-arms the
+// ticket counter for the next launch. Summation order depends only on gridDim => bit-stable.
 template <int NV>
-__device__ __forceinline__ void block_reduce_store(double (&acc)[NV], double* __restrict__ partial_out)
+__device__ __forceinline__ void block_reduce_to_packet(double (&acc)[NV], double* __restrict__ partials,
+                                                       unsigned int* __restrict__ ticket,
+                                                       double* __restrict__ packet)
 {
-    __shared__ double sh[kWarps][NV];
-    const int         lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    static_assert(NV <= 32, "packet holds 32 doubles");
+    __shared__ double   sh[kWarps][32];
+    __shared__ unsigned is_last;
+    const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int v = 0; v < NV; v++)
     {
@@ -44,21 +52,34 @@ __device__ __forceinline__ void block_reduce_store(double (&acc)[NV], double* __
         double s = 0;
 #pragma unroll
         for (int w = 0; w < kWarps; w++) s += sh[w][threadIdx.x];
-        partial_out[(size_t)blockIdx.x * NV + threadIdx.x] = s;
+        partials[(size_t)blockIdx.x * NV + threadIdx.x] = s;
+        __threadfence();
     }
-}
-
-// packet[v] (+)= sum over CTA partials, fixed order
-__global__ void __launch_bounds__(64)
-    k_final_reduce(const double* __restrict__ partials, int n_blocks, int nv, double* __restrict__ packet,
-                   int accumulate)
-{
-    const int v = threadIdx.x;
-    if (v >= MP2P_B200_PACKET_DOUBLES) return;
-    double s = 0;
-    if (v < nv)
-        for (int b = 0; b < n_blocks; b++) s += partials[(size_t)b * nv + v];
-    packet[v] = (accumulate ? packet[v] : 0.0) + s;
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // thread (warp = chunk, lane = value): chunk c sums CTAs [c*per, (c+1)*per) in order
+    const unsigned per = (gridDim.x + kWarps - 1) / kWarps;
+    double         s   = 0;
+    if (lane < NV)
+    {
+        const unsigned b0 = warp * per, b1 = min(b0 + per, gridDim.x);
+        for (unsigned b = b0; b < b1; b++) s += __ldcg(partials + (size_t)b * NV + lane);
+    }
+    __syncthreads();
+    sh[warp][lane] = s;
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        double t = 0;
+        if (threadIdx.x < NV)
+#pragma unroll
+            for (int w = 0; w < kWarps; w++) t += sh[w][threadIdx.x];
+        packet[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
 }
 
 // Stage 32 records of WORDS 4-byte words each into this warp's shared buffer, coalesced.
@@ -117,7 +138,8 @@ __device__ __forceinline__ void add_row(double (&acc)[kGNV], const double (&a)[6
 
 __global__ void __launch_bounds__(kSolveThreads)
     k_gn_accumulate(const uint32_t* __restrict__ p2p, const uint32_t* __restrict__ p2l, GNArgs a,
-                    const double* __restrict__ pose, double* __restrict__ partials)
+                    const double* __restrict__ pose, double* __restrict__ partials,
+                    unsigned int* __restrict__ ticket, double* __restrict__ packet)
 {
     __shared__ uint32_t stage[kWarps][32 * 18];
     const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -198,7 +220,7 @@ __global__ void __launch_bounds__(kSolveThreads)
         }
         __syncwarp();
     }
-    block_reduce_store<kGNV>(acc, partials);
+    block_reduce_to_packet<kGNV>(acc, partials, ticket, packet);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -206,7 +228,8 @@ constexpr int kH1V = 7;  // sum local(3), sum global(3), count
 
 __global__ void __launch_bounds__(kSolveThreads)
     k_horn_sums(const uint32_t* __restrict__ p2p, uint64_t n, const uint8_t* __restrict__ outlier,
-                double* __restrict__ partials)
+                double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                double* __restrict__ packet)
 {
     __shared__ uint32_t stage[kWarps][32 * 9];
     const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -231,7 +254,7 @@ __global__ void __launch_bounds__(kSolveThreads)
         }
         __syncwarp();
     }
-    block_reduce_store<kH1V>(acc, partials);
+    block_reduce_to_packet<kH1V>(acc, partials, ticket, packet);
 }
 
 struct HornArgs
@@ -252,7 +275,8 @@ __global__ void __launch_bounds__(kSolveThreads)
     k_horn_moments(const uint32_t* __restrict__ p2p, HornArgs a, const double* __restrict__ sums,
                    const uint64_t* __restrict__ wprefix, const double* __restrict__ wvalue,
                    uint8_t* __restrict__ outlier, uint64_t first_global_index,
-                   double* __restrict__ partials)
+                   double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                   double* __restrict__ packet)
 {
     __shared__ uint32_t stage[kWarps][32 * 9];
     const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -329,7 +353,21 @@ __global__ void __launch_bounds__(kSolveThreads)
         }
         __syncwarp();
     }
-    block_reduce_store<kH2V>(acc, partials);
+    block_reduce_to_packet<kH2V>(acc, partials, ticket, packet);
+}
+
+// partial sums of all CTAs followed by the (self re-arming) ticket counter
+int solve_scratch(mp2p_b200_ctx* ctx, int blocks, unsigned int** ticket)
+{
+    constexpr size_t kPartialBytes = (size_t)148 * 4 * 32 * sizeof(double);  // the largest grid
+    (void)blocks;
+    if (ctx->d_partials.bytes < kPartialBytes + 64)
+    {
+        MP2P_TRY(ctx->d_partials.ensure(kPartialBytes + 64));
+        MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_partials.p, 0, ctx->d_partials.bytes, ctx->stream));
+    }
+    *ticket = reinterpret_cast<unsigned int*>(ctx->d_partials.as<char>() + kPartialBytes);
+    return 0;
 }
 
 int solve_grid(uint64_t n)
@@ -346,15 +384,15 @@ int run_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint6
                       const double* d_pose, double* d_packet)
 {
     const int blocks = solve_grid(std::max(n2p, n2l));
-    MP2P_TRY(ctx->d_partials.ensure((size_t)blocks * 32 * sizeof(double)));
+    unsigned int* ticket;
+    MP2P_TRY(solve_scratch(ctx, blocks, &ticket));
     GNArgs a{n2p, n2l, prm->w_pt2pt, prm->w_pt2pl, prm->kernel, prm->kernelParam};
     prof_begin(ctx, 4);
     k_gn_accumulate<<<blocks, kSolveThreads, 0, ctx->stream>>>(
         reinterpret_cast<const uint32_t*>(d2p), reinterpret_cast<const uint32_t*>(d2l), a, d_pose,
-        ctx->d_partials.as<double>());
-    k_final_reduce<<<1, 64, 0, ctx->stream>>>(ctx->d_partials.as<double>(), blocks, kGNV, d_packet, 0);
+        ctx->d_partials.as<double>(), ticket, d_packet);
     prof_end(ctx, 4);
-    count_launch(ctx, 2);
+    count_launch(ctx);
     return 0;
 }
 
@@ -362,13 +400,14 @@ int run_horn_sums(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t 
                   const uint8_t* d_outlier, double* d_packet)
 {
     const int blocks = solve_grid(n);
-    MP2P_TRY(ctx->d_partials.ensure((size_t)blocks * 32 * sizeof(double)));
+    unsigned int* ticket;
+    MP2P_TRY(solve_scratch(ctx, blocks, &ticket));
     prof_begin(ctx, 2);
     k_horn_sums<<<blocks, kSolveThreads, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d2p), n,
-                                                          d_outlier, ctx->d_partials.as<double>());
-    k_final_reduce<<<1, 64, 0, ctx->stream>>>(ctx->d_partials.as<double>(), blocks, kH1V, d_packet, 0);
+                                                          d_outlier, ctx->d_partials.as<double>(), ticket,
+                                                          d_packet);
     prof_end(ctx, 2);
-    count_launch(ctx, 2);
+    count_launch(ctx);
     return 0;
 }
 
@@ -377,8 +416,9 @@ int run_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64
                      uint64_t n_total_pairs, const uint64_t* d_wcount_prefix, const double* d_wvalue,
                      uint32_t n_wblocks, uint8_t* d_outlier, double* d_packet)
 {
-    const int blocks = solve_grid(n);
-    MP2P_TRY(ctx->d_partials.ensure((size_t)blocks * 32 * sizeof(double)));
+    const int     blocks = solve_grid(n);
+    unsigned int* ticket;
+    MP2P_TRY(solve_scratch(ctx, blocks, &ticket));
     HornArgs a{};
     a.n = n, a.n_total = n_total_pairs;
     a.use_scale_outlier = prm->use_scale_outlier_detector, a.scale_thr = prm->scale_outlier_threshold;
@@ -392,10 +432,10 @@ int run_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64
     prof_begin(ctx, 3);
     k_horn_moments<<<blocks, kSolveThreads, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d2p), a,
                                                              d_sums_packet, d_wcount_prefix, d_wvalue,
-                                                             d_outlier, 0, ctx->d_partials.as<double>());
-    k_final_reduce<<<1, 64, 0, ctx->stream>>>(ctx->d_partials.as<double>(), blocks, kH2V, d_packet, 0);
+                                                             d_outlier, 0, ctx->d_partials.as<double>(), ticket,
+                                                             d_packet);
     prof_end(ctx, 3);
-    count_launch(ctx, 2);
+    count_launch(ctx);
     return 0;
 }
 }  // namespace mp2p

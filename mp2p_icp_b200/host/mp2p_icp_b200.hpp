@@ -1,0 +1,712 @@
+// MRPT-free C++ host mirror of the reference's Matcher / Solver plugin interface for the hot path.
+//
+// Same class names, parameter names, argument meaning and error behaviour as the reference
+// (exceptions for bad parameters, `false` for "did not run"), over minimal stand-ins for the MRPT /
+// mp2p_icp_map types the path touches. Everything computes through the C ABI (mp2p_b200.h): no CPU
+// implementation of the path lives here. With MRPT available the real plugin classes are in
+// mrpt_plugin.cpp; this header is what can be built and tested without MRPT.
+//
+// Reference interfaces mirrored (paths relative to the reference checkout):
+//   Matcher, MatchContext, MatchState, run_matchers   mp2p_icp/include/mp2p_icp/Matcher.h:36-109, src/Matcher.cpp:35-88
+//   Matcher_Points_Base                              mp2p_icp/src/Matcher_Points_Base.cpp:30-181
+//   Matcher_Points_DistanceThreshold                 mp2p_icp/src/Matcher_Points_DistanceThreshold.cpp:39-269
+//   Matcher_Point2Plane                              mp2p_icp/src/Matcher_Point2Plane.cpp:35-114
+//   Solver, SolverContext                            mp2p_icp/include/mp2p_icp/Solver.h:43-102, src/Solver.cpp:28-64
+//   Solver_Horn / Solver_GaussNewton                 mp2p_icp/src/Solver_Horn.cpp:33-61, Solver_GaussNewton.cpp:29-67
+//   Pairings                                         mp2p_icp/include/mp2p_icp/Pairings.h:84-194, src/Pairings.cpp:123-147
+//   ICP::align loop (the caller)                     mp2p_icp/src/ICP.cpp:108-308
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <optional>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "mp2p_b200.h"
+
+namespace mp2p_icp_b200
+{
+using layer_name_t = std::string;
+
+inline void check(int rc, const char* what)
+{
+    if (rc != MP2P_B200_OK) throw std::runtime_error(std::string(what) + ": " + mp2p_b200_last_error());
+}
+
+// ---- mrpt::poses::CPose3D stand-in: 3x4 row-major [R|t] -----------------------------------
+struct CPose3D
+{
+    double m[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    CPose3D()    = default;
+    CPose3D(double x, double y, double z, double yaw, double pitch, double roll)
+    {
+        const double cy = std::cos(yaw), sy = std::sin(yaw), cp = std::cos(pitch), sp = std::sin(pitch),
+                     cr = std::cos(roll), sr = std::sin(roll);
+        const double v[12] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr, x,
+                              sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr, y,
+                              -sp,     cp * sr,                cp * cr,                z};
+        std::memcpy(m, v, sizeof(m));
+    }
+    static CPose3D Identity() { return {}; }
+    CPose3D        operator+(const CPose3D& b) const  // composition a (+) b
+    {
+        CPose3D o;
+        for (int r = 0; r < 3; r++)
+        {
+            for (int c = 0; c < 3; c++)
+                o.m[4 * r + c] = m[4 * r] * b.m[c] + m[4 * r + 1] * b.m[4 + c] + m[4 * r + 2] * b.m[8 + c];
+            o.m[4 * r + 3] = m[4 * r] * b.m[3] + m[4 * r + 1] * b.m[7] + m[4 * r + 2] * b.m[11] + m[4 * r + 3];
+        }
+        return o;
+    }
+    CPose3D inverse() const
+    {
+        CPose3D o;
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) o.m[4 * r + c] = m[4 * c + r];
+        for (int r = 0; r < 3; r++) o.m[4 * r + 3] = -(m[r] * m[3] + m[4 + r] * m[7] + m[8 + r] * m[11]);
+        return o;
+    }
+    CPose3D operator-(const CPose3D& b) const { return b.inverse() + *this; }  // a (-) b = b^-1 (+) a
+    void    inverseComposePoint(double gx, double gy, double gz, double& lx, double& ly, double& lz) const
+    {
+        const double dx = gx - m[3], dy = gy - m[7], dz = gz - m[11];
+        lx = m[0] * dx + m[4] * dy + m[8] * dz;
+        ly = m[1] * dx + m[5] * dy + m[9] * dz;
+        lz = m[2] * dx + m[6] * dy + m[10] * dz;
+    }
+    /** SE(3) log as (v, w): only the norms are needed by the ICP termination rule (ICP.cpp:194-229). */
+    void log_norms(double& n_xyz, double& n_rot) const
+    {
+        const double tr = m[0] + m[5] + m[10];
+        double       c  = 0.5 * (tr - 1.0);
+        c               = c > 1 ? 1 : (c < -1 ? -1 : c);
+        const double th = std::acos(c);
+        n_rot           = th;
+        // v = V^-1 t ;  |v| via V^-1 = I - 1/2 W + D W^2
+        double w[3] = {m[9] - m[6], m[2] - m[8], m[4] - m[1]};
+        double k    = th < 1e-7 ? 0.5 * (1.0 + th * th / 6.0) : th / (2.0 * std::sin(th));
+        if (M_PI - th < 1e-6) k = 0;  // not reached by ICP increments
+        for (double& x : w) x *= k;
+        const double th2 = th * th;
+        double       D;
+        if (th < 1e-6)
+            D = 1.0 / 12.0 + th2 / 720.0;
+        else
+        {
+            const double A = std::sin(th) / th, B = (1.0 - std::cos(th)) / th2;
+            D              = (1.0 - A / (2.0 * B)) / th2;
+        }
+        const double t[3] = {m[3], m[7], m[11]};
+        const double wxt[3] = {w[1] * t[2] - w[2] * t[1], w[2] * t[0] - w[0] * t[2], w[0] * t[1] - w[1] * t[0]};
+        const double wxwxt[3] = {w[1] * wxt[2] - w[2] * wxt[1], w[2] * wxt[0] - w[0] * wxt[2], w[0] * wxt[1] - w[1] * wxt[0]};
+        double       v2 = 0;
+        for (int i = 0; i < 3; i++)
+        {
+            const double v = t[i] - 0.5 * wxt[i] + D * wxwxt[i];
+            v2 += v * v;
+        }
+        n_xyz = std::sqrt(v2);
+    }
+};
+
+// ---- mrpt::maps::CPointsMap stand-in: three SoA float buffers + a modification stamp ---------
+class CPointsMap
+{
+   public:
+    using Ptr = std::shared_ptr<CPointsMap>;
+    static Ptr Create() { return std::make_shared<CPointsMap>(); }
+    void       insertPoint(float x, float y, float z)
+    {
+        xs_.push_back(x), ys_.push_back(y), zs_.push_back(z);
+        mark_as_modified();
+    }
+    void                      insertPointFast(float x, float y, float z) { insertPoint(x, y, z); }
+    size_t                    size() const { return xs_.size(); }
+    bool                      empty() const { return xs_.empty(); }
+    const std::vector<float>& getPointsBufferRef_x() const { return xs_; }
+    const std::vector<float>& getPointsBufferRef_y() const { return ys_; }
+    const std::vector<float>& getPointsBufferRef_z() const { return zs_; }
+    void                      mark_as_modified() { stamp_++; }  // invalidates the NN index
+    uint64_t                  stamp() const { return stamp_; }
+    void                      reserve(size_t n) { xs_.reserve(n), ys_.reserve(n), zs_.reserve(n); }
+
+   private:
+    std::vector<float> xs_, ys_, zs_;
+    uint64_t           stamp_ = 0;
+};
+
+/** mp2p_icp::metric_map_t: named point layers (metricmap.h:64-151). */
+struct metric_map_t
+{
+    static constexpr const char*               PT_LAYER_RAW = "raw";
+    std::map<layer_name_t, CPointsMap::Ptr>    layers;
+};
+
+/** mp2p_icp::Pairings restricted to the pairing kinds of the hot path (Pairings.h:84-194). */
+struct Pairings
+{
+    std::vector<mp2p_b200_pair_pt2pt>           paired_pt2pt;
+    std::vector<mp2p_b200_pair_pt2pl>           paired_pt2pl;
+    std::vector<std::pair<std::size_t, double>> point_weights;
+    uint64_t                                    potential_pairings = 0;
+    bool        empty() const { return paired_pt2pt.empty() && paired_pt2pl.empty(); }
+    std::size_t size() const { return paired_pt2pt.size() + paired_pt2pl.size(); }
+    /** Pairings::push_back(const Pairings&): appends the lists and potential_pairings but NOT
+     *  point_weights (Pairings.cpp:123-131) — kept as is. */
+    void push_back(const Pairings& o)
+    {
+        paired_pt2pt.insert(paired_pt2pt.end(), o.paired_pt2pt.begin(), o.paired_pt2pt.end());
+        paired_pt2pl.insert(paired_pt2pl.end(), o.paired_pt2pl.begin(), o.paired_pt2pl.end());
+        potential_pairings += o.potential_pairings;
+    }
+};
+
+struct MatchContext
+{
+    uint32_t icpIteration = 0;
+};
+
+/** MatchState: one "already paired" flag per point and layer (Matcher.h:36-70, pointcloud_bitfield.h). */
+struct MatchState
+{
+    MatchState(const metric_map_t& pcGlobal, const metric_map_t& pcLocal)
+    {
+        for (const auto& kv : pcGlobal.layers) globalPaired[kv.first].assign((kv.second->size() + 31) / 32, 0u);
+        for (const auto& kv : pcLocal.layers) localPaired[kv.first].assign((kv.second->size() + 31) / 32, 0u);
+    }
+    std::map<layer_name_t, std::vector<uint32_t>> globalPaired, localPaired;
+    static void mark(std::vector<uint32_t>& w, size_t i) { w[i >> 5] |= 1u << (i & 31); }
+};
+
+/** Flat stand-in for mrpt::containers::yaml maps: key -> scalar text. */
+class ParameterMap
+{
+   public:
+    ParameterMap() = default;
+    ParameterMap(std::initializer_list<std::pair<const std::string, std::string>> il) : kv_(il) {}
+    template <class T>
+    void set(const std::string& k, const T& v)
+    {
+        std::ostringstream s;
+        s.precision(17);
+        s << v;
+        kv_[k] = s.str();
+    }
+    bool has(const std::string& k) const { return kv_.count(k) != 0; }
+    template <class T>
+    T get(const std::string& k) const
+    {
+        std::istringstream s(kv_.at(k));
+        T                  v{};
+        if (kv_.at(k) == "true") return static_cast<T>(1);
+        if (kv_.at(k) == "false") return static_cast<T>(0);
+        s >> v;
+        return v;
+    }
+    template <class T>
+    T getOrDefault(const std::string& k, const T& d) const
+    {
+        return has(k) ? get<T>(k) : d;
+    }
+    /** DECLARE_PARAMETER_REQ: std::invalid_argument if missing (Parameterizable.h:176-181). */
+    template <class T>
+    T required(const std::string& k) const
+    {
+        if (!has(k)) throw std::invalid_argument("Required parameter `" + k + "` not an existing key");
+        return get<T>(k);
+    }
+    std::string getString(const std::string& k, const std::string& d) const { return has(k) ? kv_.at(k) : d; }
+
+   private:
+    std::map<std::string, std::string> kv_;
+};
+
+// ---- device context + map cache ------------------------------------------------------------
+class Device
+{
+   public:
+    static Device& instance(int device = 0)
+    {
+        static Device d(device);
+        return d;
+    }
+    mp2p_b200_ctx* ctx() { return ctx_; }
+    /** nn_prepare_for_3d_queries(): index of a global layer, rebuilt when the layer was modified. */
+    mp2p_b200_map* map_for(const CPointsMap& layer)
+    {
+        Entry& e = cache_[&layer];
+        if (!e.map || e.stamp != layer.stamp() || e.n != layer.size())
+        {
+            if (e.map) mp2p_b200_map_destroy(e.map);
+            e.map = nullptr;
+            check(mp2p_b200_map_create(ctx_, layer.getPointsBufferRef_x().data(), layer.getPointsBufferRef_y().data(),
+                                       layer.getPointsBufferRef_z().data(), layer.size(), 0, &e.map),
+                  "mp2p_b200_map_create");
+            e.stamp = layer.stamp(), e.n = layer.size();
+        }
+        return e.map;
+    }
+    void forget(const CPointsMap& layer)
+    {
+        auto it = cache_.find(&layer);
+        if (it == cache_.end()) return;
+        if (it->second.map) mp2p_b200_map_destroy(it->second.map);
+        cache_.erase(it);
+    }
+    ~Device()
+    {
+        for (auto& kv : cache_)
+            if (kv.second.map) mp2p_b200_map_destroy(kv.second.map);
+        mp2p_b200_ctx_destroy(ctx_);
+    }
+
+   private:
+    explicit Device(int device) { check(mp2p_b200_ctx_create(device, nullptr, &ctx_), "mp2p_b200_ctx_create"); }
+    struct Entry
+    {
+        mp2p_b200_map* map   = nullptr;
+        uint64_t       stamp = 0;
+        size_t         n     = 0;
+    };
+    mp2p_b200_ctx*                      ctx_ = nullptr;
+    std::map<const CPointsMap*, Entry>  cache_;
+};
+
+// ---- Matcher hierarchy -----------------------------------------------------------------------
+class Matcher
+{
+   public:
+    using Ptr          = std::shared_ptr<Matcher>;
+    virtual ~Matcher() = default;
+    virtual void initialize(const ParameterMap& params)  // Matcher.cpp:28-33
+    {
+        runFromIteration = params.getOrDefault<uint32_t>("runFromIteration", runFromIteration);
+        runUpToIteration = params.getOrDefault<uint32_t>("runUpToIteration", runUpToIteration);
+        enabled          = params.getOrDefault<int>("enabled", enabled ? 1 : 0) != 0;
+    }
+    /** Matcher.cpp:35-44; returns false if the matcher did not run. */
+    bool match(const metric_map_t& pcGlobal, const metric_map_t& pcLocal, const CPose3D& localPose,
+               const MatchContext& mc, MatchState& ms, Pairings& out) const
+    {
+        if (!enabled) return false;
+        if (mc.icpIteration < runFromIteration) return false;
+        if (runUpToIteration > 0 && mc.icpIteration > runUpToIteration) return false;
+        return impl_match(pcGlobal, pcLocal, localPose, mc, ms, out);
+    }
+    uint32_t runFromIteration = 0, runUpToIteration = 0;
+    bool     enabled = true;
+
+   protected:
+    virtual bool impl_match(const metric_map_t& pcGlobal, const metric_map_t& pcLocal, const CPose3D& localPose,
+                            const MatchContext& mc, MatchState& ms, Pairings& out) const = 0;
+};
+using matcher_list_t = std::vector<Matcher::Ptr>;
+
+class Matcher_Points_Base : public Matcher
+{
+   public:
+    /** w["globalLayer"]["localLayer"] = weight (Matcher_Points_Base.h:45-53) */
+    std::map<std::string, std::map<std::string, double>> weight_pt2pt_layers;
+    bool   allowMatchAlreadyMatchedPoints_       = false;
+    bool   allowMatchAlreadyMatchedGlobalPoints_ = false;
+    double bounding_box_intersection_check_epsilon_ = 0.20;
+
+    void initialize(const ParameterMap& params) override  // Matcher_Points_Base.cpp:132-181
+    {
+        Matcher::initialize(params);
+        if (params.getOrDefault<uint64_t>("maxLocalPointsPerLayer", 0) != 0)
+            throw std::invalid_argument("maxLocalPointsPerLayer != 0 is not offered (reference bug Q1/Q2, see DESIGN.md)");
+        allowMatchAlreadyMatchedPoints_ = params.getOrDefault<int>("allowMatchAlreadyMatchedPoints", 0) != 0;
+        allowMatchAlreadyMatchedGlobalPoints_ = params.getOrDefault<int>("allowMatchAlreadyMatchedGlobalPoints", 0) != 0;
+        bounding_box_intersection_check_epsilon_ =
+            params.getOrDefault<double>("bounding_box_intersection_check_epsilon", bounding_box_intersection_check_epsilon_);
+    }
+
+   protected:
+    bool impl_match(const metric_map_t& pcGlobal, const metric_map_t& pcLocal, const CPose3D& localPose,
+                    const MatchContext&, MatchState& ms, Pairings& out) const final  // Matcher_Points_Base.cpp:30-130
+    {
+        out = Pairings();
+        for (const auto& glKV : pcGlobal.layers)
+        {
+            std::map<std::string, std::optional<double>> localLayers;
+            if (!weight_pt2pt_layers.empty())
+            {
+                const auto it = weight_pt2pt_layers.find(glKV.first);
+                if (it == weight_pt2pt_layers.end()) continue;
+                for (const auto& kv : it->second) localLayers[kv.first] = kv.second;
+            }
+            else
+                localLayers[glKV.first] = {};
+            for (const auto& lw : localLayers)
+            {
+                const auto itLocal = pcLocal.layers.find(lw.first);
+                if (itLocal == pcLocal.layers.end())
+                {
+                    if (!lw.second.has_value()) continue;
+                    throw std::runtime_error("Local pointcloud layer '" + lw.first + "' not found matching global layer '" + glKV.first + "'");
+                }
+                if (!glKV.second || !itLocal->second) throw std::runtime_error("null layer");
+                const size_t nBefore = out.paired_pt2pt.size();
+                implMatchOneLayer(*glKV.second, *itLocal->second, localPose, ms, glKV.first, lw.first, out);
+                const size_t nAfter = out.paired_pt2pt.size();
+                if (lw.second.has_value() && nAfter != nBefore) out.point_weights.emplace_back(nAfter - nBefore, *lw.second);
+            }
+        }
+        return true;
+    }
+
+   private:
+    virtual void implMatchOneLayer(const CPointsMap& pcGlobal, const CPointsMap& pcLocal, const CPose3D& localPose,
+                                   MatchState& ms, const layer_name_t& globalName, const layer_name_t& localName,
+                                   Pairings& out) const = 0;
+};
+
+class Matcher_Points_DistanceThreshold : public Matcher_Points_Base
+{
+   public:
+    double   threshold           = 0.50;
+    double   thresholdAngularDeg = 0.50;
+    uint32_t pairingsPerPoint    = 1;
+    void     initialize(const ParameterMap& params) override  // …DistanceThreshold.cpp:39-46
+    {
+        Matcher_Points_Base::initialize(params);
+        threshold           = params.required<double>("threshold");
+        thresholdAngularDeg = params.required<double>("thresholdAngularDeg");
+        pairingsPerPoint    = params.getOrDefault<uint32_t>("pairingsPerPoint", pairingsPerPoint);
+    }
+
+   private:
+    void implMatchOneLayer(const CPointsMap& pcGlobal, const CPointsMap& pcLocal, const CPose3D& localPose,
+                           MatchState& ms, const layer_name_t& globalName, const layer_name_t& localName,
+                           Pairings& out) const override
+    {
+        if (!(pairingsPerPoint >= 1)) throw std::runtime_error("Assert failed: pairingsPerPoint >= 1");  // :57-59
+        if (!(threshold > .0)) throw std::runtime_error("Assert failed: threshold > 0");
+        if (!(thresholdAngularDeg >= .0)) throw std::runtime_error("Assert failed: thresholdAngularDeg >= 0");
+        Device&                dev = Device::instance();
+        mp2p_b200_pt2pt_params p{threshold, thresholdAngularDeg, pairingsPerPoint, allowMatchAlreadyMatchedPoints_,
+                                 allowMatchAlreadyMatchedGlobalPoints_, bounding_box_intersection_check_epsilon_};
+        auto&        lbits  = ms.localPaired.at(localName);
+        auto&        gbits  = ms.globalPaired.at(globalName);
+        const size_t before = out.paired_pt2pt.size(), cap = pcLocal.size() * pairingsPerPoint;
+        out.paired_pt2pt.resize(before + cap);
+        uint64_t cnt = 0, pot = 0;
+        check(mp2p_b200_match_pt2pt(dev.ctx(), dev.map_for(pcGlobal), pcLocal.getPointsBufferRef_x().data(),
+                                    pcLocal.getPointsBufferRef_y().data(), pcLocal.getPointsBufferRef_z().data(),
+                                    pcLocal.size(), 0, localPose.m, &p, lbits.data(), gbits.data(),
+                                    out.paired_pt2pt.data() + before, cap, 0, &cnt, &pot),
+              "mp2p_b200_match_pt2pt");
+        out.paired_pt2pt.resize(before + cnt);
+        out.potential_pairings += pot;
+        if (!allowMatchAlreadyMatchedGlobalPoints_)  // lambdaAddPair :116-120
+            for (size_t i = before; i < out.paired_pt2pt.size(); i++)
+            {
+                MatchState::mark(lbits, out.paired_pt2pt[i].localIdx);
+                MatchState::mark(gbits, out.paired_pt2pt[i].globalIdx);
+            }
+    }
+};
+
+class Matcher_Point2Plane : public Matcher_Points_Base
+{
+   public:
+    double   distanceThreshold = 0.50, searchRadius = 1.0, planeEigenThreshold = 0.01;
+    uint32_t knn = 5, minimumPlanePoints = 5;
+    void     initialize(const ParameterMap& params) override  // Matcher_Point2Plane.cpp:35-39 (+ plane-fit params)
+    {
+        Matcher_Points_Base::initialize(params);
+        distanceThreshold   = params.required<double>("distanceThreshold");
+        searchRadius        = params.getOrDefault<double>("searchRadius", searchRadius);
+        knn                 = params.getOrDefault<uint32_t>("knn", knn);
+        minimumPlanePoints  = static_cast<uint32_t>(params.getOrDefault<double>("minimumPlanePoints", minimumPlanePoints));
+        planeEigenThreshold = params.getOrDefault<double>("planeEigenThreshold", planeEigenThreshold);
+    }
+
+   private:
+    void implMatchOneLayer(const CPointsMap& pcGlobal, const CPointsMap& pcLocal, const CPose3D& localPose,
+                           MatchState& ms, const layer_name_t&, const layer_name_t& localName, Pairings& out) const override
+    {
+        Device&                dev = Device::instance();
+        mp2p_b200_pt2pl_params p{distanceThreshold, searchRadius, knn, minimumPlanePoints, planeEigenThreshold,
+                                 allowMatchAlreadyMatchedPoints_, bounding_box_intersection_check_epsilon_};
+        auto&        lbits  = ms.localPaired.at(localName);
+        const size_t before = out.paired_pt2pl.size(), cap = pcLocal.size();
+        out.paired_pt2pl.resize(before + cap);
+        uint64_t cnt = 0, pot = 0;
+        check(mp2p_b200_match_pt2pl(dev.ctx(), dev.map_for(pcGlobal), pcLocal.getPointsBufferRef_x().data(),
+                                    pcLocal.getPointsBufferRef_y().data(), pcLocal.getPointsBufferRef_z().data(),
+                                    pcLocal.size(), 0, localPose.m, &p, lbits.data(), out.paired_pt2pl.data() + before,
+                                    cap, 0, &cnt, &pot),
+              "mp2p_b200_match_pt2pl");
+        out.paired_pt2pl.resize(before + cnt);
+        out.potential_pairings += pot;
+        // Matcher_Point2Plane.cpp:109 — the local point is marked; which one it was is recoverable
+        // from pt_local only through the coordinates, so re-identify by a parallel walk (the output
+        // is in ascending local index and each local point pairs at most once).
+        const auto &lx = pcLocal.getPointsBufferRef_x(), &ly = pcLocal.getPointsBufferRef_y(),
+                   &lz = pcLocal.getPointsBufferRef_z();
+        size_t i = 0;
+        for (size_t k = before; k < out.paired_pt2pl.size(); k++)
+        {
+            const auto& r = out.paired_pt2pl[k];
+            while (i < lx.size() && !(lx[i] == r.local_x && ly[i] == r.local_y && lz[i] == r.local_z &&
+                                      !((lbits[i >> 5] >> (i & 31)) & 1u)))
+                i++;
+            if (i < lx.size()) MatchState::mark(lbits, i++);
+        }
+    }
+};
+
+/** run_matchers (Matcher.cpp:46-88) */
+inline Pairings run_matchers(const matcher_list_t& matchers, const metric_map_t& pcGlobal, const metric_map_t& pcLocal,
+                             const CPose3D& local_wrt_global, const MatchContext& mc, MatchState* userMS = nullptr)
+{
+    Pairings                  pairings;
+    std::optional<MatchState> localMS;
+    MatchState*               ms = userMS;
+    if (!ms)
+    {
+        localMS.emplace(pcGlobal, pcLocal);
+        ms = &*localMS;
+    }
+    for (const auto& m : matchers)
+    {
+        if (!m) throw std::runtime_error("null matcher");
+        Pairings pc;
+        m->match(pcGlobal, pcLocal, local_wrt_global, mc, *ms, pc);
+        pairings.push_back(pc);
+    }
+    return pairings;
+}
+
+// ---- Solver hierarchy -------------------------------------------------------------------------
+struct OptimalTF_Result
+{
+    CPose3D optimalPose;
+};
+struct SolverContext
+{
+    std::optional<uint32_t> icpIteration;
+    std::optional<CPose3D>  guessRelativePose;
+    std::optional<CPose3D>  lastIcpStepIncrement;
+    mutable std::map<const void*, bool> perSolverFinished;  // perSolverPersistentData["finished"]
+};
+
+class Solver
+{
+   public:
+    using Ptr         = std::shared_ptr<Solver>;
+    virtual ~Solver() = default;
+    virtual void initialize(const ParameterMap& p)  // Solver.cpp:28-34
+    {
+        runFromIteration = p.getOrDefault<uint32_t>("runFromIteration", runFromIteration);
+        runUpToIteration = p.getOrDefault<uint32_t>("runUpToIteration", runUpToIteration);
+        enabled          = p.getOrDefault<int>("enabled", enabled ? 1 : 0) != 0;
+        runUntilTranslationCorrectionSmallerThan =
+            p.getOrDefault<double>("runUntilTranslationCorrectionSmallerThan", runUntilTranslationCorrectionSmallerThan);
+    }
+    bool optimal_pose(const Pairings& pairings, OptimalTF_Result& out, const SolverContext& sc) const  // Solver.cpp:36-64
+    {
+        if (!enabled) return false;
+        if (sc.icpIteration && *sc.icpIteration < runFromIteration) return false;
+        if (sc.icpIteration && runUpToIteration > 0 && *sc.icpIteration > runUpToIteration) return false;
+        if (runUntilTranslationCorrectionSmallerThan > 0)
+        {
+            if (sc.perSolverFinished.count(this)) return false;
+            if (sc.lastIcpStepIncrement)
+            {
+                const auto&  d = sc.lastIcpStepIncrement->m;
+                const double n = std::sqrt(d[3] * d[3] + d[7] * d[7] + d[11] * d[11]);
+                if (n < runUntilTranslationCorrectionSmallerThan)
+                {
+                    sc.perSolverFinished[this] = true;
+                    return false;
+                }
+            }
+        }
+        return impl_optimal_pose(pairings, out, sc);
+    }
+    uint32_t runFromIteration = 0, runUpToIteration = 0;
+    bool     enabled = true;
+    double   runUntilTranslationCorrectionSmallerThan = 0;
+
+   protected:
+    virtual bool impl_optimal_pose(const Pairings& pairings, OptimalTF_Result& out, const SolverContext& sc) const = 0;
+};
+using solver_list_t = std::vector<Solver::Ptr>;
+
+inline int robust_kernel_from_string(const std::string& s)
+{
+    if (s == "None" || s == "RobustKernel::None") return 0;
+    if (s == "GemanMcClure" || s == "RobustKernel::GemanMcClure") return 1;
+    if (s == "Cauchy" || s == "RobustKernel::Cauchy") return 2;
+    throw std::invalid_argument("Unknown kernel type");  // robust_kernels.h:91
+}
+
+class Solver_Horn : public Solver
+{
+   public:
+    mp2p_b200_horn_params pairingsWeightParameters{0, 1.20, 1.0, 0, 1.0, {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}};
+    void                  initialize(const ParameterMap& p) override  // Solver_Horn.cpp:33-39
+    {
+        Solver::initialize(p);
+        auto& w                      = pairingsWeightParameters;
+        w.use_scale_outlier_detector = p.getOrDefault<int>("use_scale_outlier_detector", w.use_scale_outlier_detector);
+        w.scale_outlier_threshold    = p.getOrDefault<double>("scale_outlier_threshold", w.scale_outlier_threshold);
+        w.robust_kernel              = robust_kernel_from_string(p.getString("robust_kernel", "None"));
+        w.robust_kernel_param        = p.getOrDefault<double>("robust_kernel_param", w.robust_kernel_param);
+    }
+
+   protected:
+    bool impl_optimal_pose(const Pairings& pairings, OptimalTF_Result& out, const SolverContext& sc) const override
+    {
+        out = OptimalTF_Result();
+        if (!pairings.paired_pt2pl.empty())
+            throw std::runtime_error("Solver_Horn on pt2pl pairings needs pt2ln_pl_to_pt2pt (host-side in the reference)");
+        mp2p_b200_horn_params prm = pairingsWeightParameters;
+        if (prm.robust_kernel != 0)
+        {
+            if (!sc.guessRelativePose) throw std::runtime_error("Assert failed: currentEstimateForRobust.has_value()");
+            std::memcpy(prm.currentEstimateForRobust, sc.guessRelativePose->m, sizeof(prm.currentEstimateForRobust));
+        }
+        std::vector<uint64_t> wc;
+        std::vector<double>   wv;
+        for (const auto& b : pairings.point_weights) wc.push_back(b.first), wv.push_back(b.second);
+        int32_t solved = 0;
+        check(mp2p_b200_solve_horn(Device::instance().ctx(), pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size(), 0,
+                                   &prm, wc.data(), wv.data(), wc.size(), out.optimalPose.m, &solved),
+              "mp2p_b200_solve_horn");
+        return solved != 0;
+    }
+};
+
+class Solver_GaussNewton : public Solver
+{
+   public:
+    uint32_t    maxIterations = 5;
+    std::string robustKernel  = "None";
+    double      robustKernelParam = 1.0, w_pt2pt = 1.0, w_pt2pl = 1.0;
+    void        initialize(const ParameterMap& p) override  // Solver_GaussNewton.cpp:29-40
+    {
+        Solver::initialize(p);
+        maxIterations     = p.required<uint32_t>("maxIterations");
+        robustKernel      = p.getString("robustKernel", robustKernel);
+        robustKernelParam = p.getOrDefault<double>("robustKernelParam", robustKernelParam);
+        robust_kernel_from_string(robustKernel);
+    }
+
+   protected:
+    bool impl_optimal_pose(const Pairings& pairings, OptimalTF_Result& out, const SolverContext& sc) const override
+    {
+        out = OptimalTF_Result();
+        if (!sc.guessRelativePose) throw std::runtime_error("Assert failed: sc.guessRelativePose.has_value()");  // :57
+        mp2p_b200_gn_params prm{maxIterations, 1e-7, 0.0, w_pt2pt, w_pt2pl, robust_kernel_from_string(robustKernel), robustKernelParam};
+        uint32_t            iters  = 0;
+        int32_t             solved = 0;
+        check(mp2p_b200_solve_gauss_newton(Device::instance().ctx(), pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size(),
+                                           pairings.paired_pt2pl.data(), pairings.paired_pt2pl.size(), 0, &prm,
+                                           sc.guessRelativePose->m, out.optimalPose.m, &iters, &solved),
+              "mp2p_b200_solve_gauss_newton");
+        return solved != 0;
+    }
+};
+
+// ---- the caller: ICP::align (ICP.cpp:108-308), restated so whole alignments can be run --------
+enum class IterTermReason
+{
+    Undefined,
+    NoPairings,
+    SolverError,
+    MaxIterations,
+    Stalled
+};
+struct Parameters  // Parameters.h:42-52
+{
+    uint32_t maxIterations    = 40;
+    double   minAbsStep_trans = 5e-4, minAbsStep_rot = 1e-4;
+};
+struct Results
+{
+    CPose3D        optimal_tf;
+    uint32_t       nIterations       = 0;
+    IterTermReason terminationReason = IterTermReason::Undefined;
+    Pairings       finalPairings;
+};
+
+class ICP
+{
+   public:
+    matcher_list_t& matchers() { return matchers_; }
+    solver_list_t&  solvers() { return solvers_; }
+    void align(const metric_map_t& pcLocal, const metric_map_t& pcGlobal, const CPose3D& initialGuess,
+               const Parameters& p, Results& result)
+    {
+        result           = Results();
+        CPose3D current  = initialGuess, prev = initialGuess;
+        std::optional<CPose3D> prev2, lastCorrection;
+        SolverContext          sc;
+        Pairings               pairings;
+        result.terminationReason = IterTermReason::MaxIterations;
+        for (result.nIterations = 0; result.nIterations < p.maxIterations; result.nIterations++)
+        {
+            MatchContext mc;
+            mc.icpIteration = result.nIterations;
+            pairings        = run_matchers(matchers_, pcGlobal, pcLocal, current, mc);  // :143
+            if (pairings.empty())
+            {
+                result.terminationReason = IterTermReason::NoPairings;  // :148
+                break;
+            }
+            sc.icpIteration = result.nIterations;
+            sc.guessRelativePose    = current;
+            sc.lastIcpStepIncrement = lastCorrection;
+            OptimalTF_Result sol;
+            bool             solvedOk = false;
+            for (const auto& s : solvers_)  // run_solvers, ICP.cpp:469-479
+                if (s->optimal_pose(pairings, sol, sc))
+                {
+                    solvedOk = true;
+                    break;
+                }
+            if (!solvedOk)
+            {
+                result.terminationReason = IterTermReason::SolverError;
+                break;
+            }
+            current            = sol.optimalPose;
+            const CPose3D dSol = current - prev;  // :203
+            lastCorrection     = dSol;
+            double dxyz, drot;
+            dSol.log_norms(dxyz, drot);
+            if (prev2)  // :208-215
+            {
+                double d2x, d2r;
+                (current - *prev2).log_norms(d2x, d2r);
+                dxyz = std::min(dxyz, d2x), drot = std::min(drot, d2r);
+            }
+            if (std::abs(dxyz) < p.minAbsStep_trans && std::abs(drot) < p.minAbsStep_rot)  // :228-229
+            {
+                result.terminationReason = IterTermReason::Stalled;
+                break;
+            }
+            prev2 = prev;
+            prev  = current;
+        }
+        result.optimal_tf    = current;
+        result.finalPairings = std::move(pairings);
+    }
+
+   private:
+    matcher_list_t matchers_;
+    solver_list_t  solvers_;
+};
+
+}  // namespace mp2p_icp_b200
