@@ -227,7 +227,14 @@ def run_ours(args):
             return sh.solve_horn(d_pairs.data_ptr(), n_pairs, sprm)[1]
         return sh.solve_gauss_newton(None, 0, d_pairs.data_ptr(), n_pairs, sprm, pose)[1]
 
+    fused = None
+    if world == 1:  # both plugins ours: fused iteration, pairings stay in HBM, one synchronisation
+        fused = gmap.make_iterator(d_l[0].data_ptr(), d_l[1].data_ptr(), d_l[2].data_ptr(), nq, mprm, sprm, d_pairs.data_ptr(), cap)
+
     def step_device():
+        if fused is not None:
+            ok, T, n_pairs = fused(pose)
+            return n_pairs, T
         lp = (d_l[0].data_ptr(), d_l[1].data_ptr(), d_l[2].data_ptr())
         if w["matcher"] == "pt2pt":
             if world > 1:  # exact cross-shard first-claim dedup: search -> all_gather -> resolve
@@ -350,7 +357,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32 metric / f64 solve", "data": "synthetic",
         "config": {"workload": w["name"], "detail": w["desc"], "queries_per_gpu": nq, "map_points": len(w["map"]),
                    "pairs": int(n_pairs), "l2": "flushed between timed steps (256 MiB memset, outside the event bracket)",
-                   "unit_note": "at N GPUs one step is one query-sharded iteration over N x queries_per_gpu; value counts N iteration-equivalents per step",
+                   "device_path": "fused mp2p_b200_iterate_* call (N=1) / sharded search+all_gather+resolve+all_reduce (N>1)", "unit_note": "at N GPUs one step is one query-sharded iteration over N x queries_per_gpu; value counts N iteration-equivalents per step",
                    "index": {"build_ms": info["build_ms"], "finest_cell_m": info["finest_cell_size"], "levels": info["n_levels"], "bytes": info["index_bytes"]}},
         "e2e": {"value": unit_scale * 1e3 / ms_e2e, "unit": "iterations/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "timing": "wall clock around the C-ABI calls, pinned host buffers"},

@@ -186,8 +186,8 @@ int mp2p_b200_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* l
  * The local cloud of n_total points is split in contiguous shards; rank r owns
  * [index_offset, index_offset + n_local). The map (and its index) is replicated on every GPU.
  *  phase A `..._shard_search`: transform + NN search of the shard; writes n_local*pairingsPerPoint
- *     64-bit candidate words and the shard's bounding box (6 floats: min xyz, max xyz) to DEVICE
- *     memory owned by the caller;
+ *     64-bit candidate words and the shard's bounding box (24 opaque bytes: 6 order-preserving
+ *     32-bit words, min xyz / max xyz) to DEVICE memory owned by the caller;
  *  (caller) all-gather the candidate words of all shards into cand_all[n_total*pairingsPerPoint] and
  *     the boxes into bbox_parts[n_shards*6] — NCCL all_gather over NVLink;
  *  phase B `..._shard_resolve`: replays every shard's proposals on this GPU's first-claim array
@@ -200,10 +200,10 @@ int mp2p_b200_match_pt2pt_shard_search(mp2p_b200_ctx* ctx, mp2p_b200_map* map, c
                                        int local_on_device, const double pose[12],
                                        const mp2p_b200_pt2pt_params* params,
                                        const uint32_t* local_paired_bits, uint64_t* cand_out_device,
-                                       float* bbox6_out_device);
+                                       void* bbox6_out_device);
 int mp2p_b200_match_pt2pt_shard_resolve(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_local,
                                         uint64_t index_offset, uint64_t n_total,
-                                        const uint64_t* cand_all_device, const float* bbox_parts_device,
+                                        const uint64_t* cand_all_device, const void* bbox_parts_device,
                                         uint32_t n_shards, const mp2p_b200_pt2pt_params* params,
                                         const uint32_t* global_paired_bits,
                                         mp2p_b200_pair_pt2pt* out_pairs, uint64_t capacity,
@@ -227,6 +227,26 @@ int mp2p_b200_solve_gauss_newton(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt*
                                  uint64_t n_pt2pl, int pairs_on_device,
                                  const mp2p_b200_gn_params* params, const double pose_init[12],
                                  double pose_out[12], uint32_t* iterations_done, int32_t* solved);
+
+/* ---- fused iterations: when BOTH plugins of an ICP iteration are ours, run_matchers + run_solvers
+ * (mp2p_icp/src/ICP.cpp:143,170) are enqueued back to back on the device — the pairings never
+ * leave HBM and the call synchronises ONCE. `pairs_device` (optional, DEVICE memory, `capacity`
+ * records) receives the pairings so that the caller can still fetch them (Results::finalPairings,
+ * hooks, logging: ICP.cpp:232-241,286-303,331); NULL = library scratch. `*solved` = 0 mirrors a
+ * solver returning false (no / too few pairings). MatchState bitfields are not taken: one matcher
+ * per iteration starts from an empty MatchState (Matcher.cpp:58-66). ---- */
+int mp2p_b200_iterate_pt2pt_horn(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                                 const float* lz, uint64_t n_local, int local_on_device,
+                                 const double pose[12], const mp2p_b200_pt2pt_params* matcher_params,
+                                 const mp2p_b200_horn_params* solver_params,
+                                 mp2p_b200_pair_pt2pt* pairs_device, uint64_t capacity, double pose_out[12],
+                                 int32_t* solved, uint64_t* n_pairs, uint64_t* potential_pairings);
+int mp2p_b200_iterate_pt2pl_gn(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                               const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
+                               const mp2p_b200_pt2pl_params* matcher_params,
+                               const mp2p_b200_gn_params* solver_params, mp2p_b200_pair_pt2pl* pairs_device,
+                               uint64_t capacity, double pose_out[12], int32_t* solved, uint64_t* n_pairs,
+                               uint32_t* iterations_done, uint64_t* potential_pairings);
 
 /* ---- building blocks for query-sharded multi-GPU runs: each rank accumulates
  * over its shard, the caller all-reduces the 32-double packet (SUM), every rank finishes the

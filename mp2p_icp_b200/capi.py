@@ -156,6 +156,7 @@ EXPORTS = [
     "mp2p_b200_host_alloc", "mp2p_b200_host_free", "mp2p_b200_ctx_set_profiling",
     "mp2p_b200_ctx_get_timings", "mp2p_b200_ctx_get_search_stats",
     "mp2p_b200_match_pt2pt_shard_search", "mp2p_b200_match_pt2pt_shard_resolve",
+    "mp2p_b200_iterate_pt2pt_horn", "mp2p_b200_iterate_pt2pl_gn",
 ]
 
 _lib = None
@@ -422,6 +423,30 @@ class Map:
         if out_on_device:
             return cnt.value
         return out[: cnt.value]
+
+    def make_iterator(self, lx, ly, lz, n_local, matcher_prm, solver_prm, pairs_device: int = 0, capacity: int = 0):
+        """Pre-binds a fused ICP iteration (device-resident local cloud) and returns a function
+        pose(3x4) -> (solved, pose_out 3x4, n_pairs). All ctypes marshalling happens once here."""
+        L = load_library()
+        is_pt2pt = isinstance(matcher_prm, Pt2PtParams)
+        mp, sp = matcher_prm.c(), solver_prm.c()
+        pose_in, pose_out = (C.c_double * 12)(), (C.c_double * 12)()
+        solved, n_pairs, iters, pot = C.c_int32(0), C.c_uint64(0), C.c_uint32(0), C.c_uint64(0)
+        args = [self.ctx._h, self._h, C.c_void_p(int(lx)), C.c_void_p(int(ly)), C.c_void_p(int(lz)), C.c_uint64(n_local), 1, pose_in, C.byref(mp), C.byref(sp), C.c_void_p(int(pairs_device)) if pairs_device else None, C.c_uint64(capacity), pose_out, C.byref(solved), C.byref(n_pairs)]
+        if is_pt2pt:
+            fn, args = L.mp2p_b200_iterate_pt2pt_horn, args + [C.byref(pot)]
+        else:
+            fn, args = L.mp2p_b200_iterate_pt2pl_gn, args + [C.byref(iters), C.byref(pot)]
+        keep = (mp, sp)  # noqa: F841  (keeps the structs alive as long as the closure)
+
+        def step(T):
+            pose_in[:] = np.asarray(T, dtype=np.float64).reshape(-1).tolist()
+            rc = fn(*args)
+            if rc != 0:
+                _check(rc)
+            return bool(solved.value), np.array(pose_out[:]).reshape(3, 4), int(n_pairs.value)
+
+        return step
 
     def match_pt2pl(self, lx, ly, lz, T, prm: Pt2PlParams, local_paired=None, n_local=None, local_on_device=False, out=None, out_on_device=False, capacity=None):
         if not local_on_device:

@@ -318,7 +318,7 @@ extern "C"
                                            int local_on_device, const double pose[12],
                                            const mp2p_b200_pt2pt_params* prm,
                                            const uint32_t* local_paired_bits, uint64_t* cand_out_device,
-                                           float* bbox6_out_device)
+                                           void* bbox6_out_device)
     {
         if (!ctx || !map || !pose || !prm || !bbox6_out_device || (n_local && (!lx || !ly || !lz || !cand_out_device)))
         {
@@ -334,12 +334,13 @@ extern "C"
         DeviceGuard g(ctx->device);
         ProfScope   ps(ctx);
         return run_shard_search_pt2pt(ctx, map, lx, ly, lz, n_local, local_on_device, pose, prm, local_paired_bits,
-                                      reinterpret_cast<unsigned long long*>(cand_out_device), bbox6_out_device);
+                                      reinterpret_cast<unsigned long long*>(cand_out_device),
+                                      reinterpret_cast<uint32_t*>(bbox6_out_device));
     }
 
     int mp2p_b200_match_pt2pt_shard_resolve(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_local,
                                             uint64_t index_offset, uint64_t n_total,
-                                            const uint64_t* cand_all_device, const float* bbox_parts_device,
+                                            const uint64_t* cand_all_device, const void* bbox_parts_device,
                                             uint32_t n_shards, const mp2p_b200_pt2pt_params* prm,
                                             const uint32_t* global_paired_bits,
                                             mp2p_b200_pair_pt2pt* out_pairs, uint64_t capacity,
@@ -355,7 +356,7 @@ extern "C"
         ProfScope   ps(ctx);
         return run_shard_resolve_pt2pt(ctx, map, n_local, index_offset, n_total,
                                        reinterpret_cast<const unsigned long long*>(cand_all_device),
-                                       bbox_parts_device, n_shards, prm, global_paired_bits, out_pairs, capacity,
+                                       reinterpret_cast<const uint32_t*>(bbox_parts_device), n_shards, prm, global_paired_bits, out_pairs, capacity,
                                        out_on_device, out_count);
     }
 
@@ -559,33 +560,130 @@ extern "C"
         const mp2p_b200_pair_pt2pl* d2l;
         MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2p, p2p, n2p, pairs_on_device, &d2p));
         MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2l, p2l, n2l, pairs_on_device, &d2l));
-        double  pose[12];
-        std::memcpy(pose, pose_init, 96);  // optimal_tf_gauss_newton.cpp:50
-        double* hpose = reinterpret_cast<double*>(static_cast<char*>(ctx->h_pinned) + 2048);
-        double* hp    = pinned_packets(ctx);
-        double* dp    = ctx->d_packet.as<double>();
-        uint32_t it   = 0;
-        for (; it < prm->maxInnerLoopIterations; it++)  // :70
+        // the whole inner loop runs on the device (accumulate -> LDL^T step -> pose update, repeated),
+        // one synchronisation at the end
+        double*   hpose = reinterpret_cast<double*>(static_cast<char*>(ctx->h_pinned) + 2048);
+        uint32_t* hst   = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->h_pinned) + 2048 + 128);
+        std::memcpy(hpose, pose_init, 96);  // optimal_tf_gauss_newton.cpp:50
+        double*   d_pose  = ctx->d_pose.as<double>();
+        uint32_t* d_state = reinterpret_cast<uint32_t*>(ctx->d_pose.as<char>() + 128);
+        MP2P_CUDA_TRY(cudaMemcpyAsync(d_pose, hpose, 96, cudaMemcpyHostToDevice, ctx->stream));
+        MP2P_TRY(run_gn_device_loop(ctx, d2p, n2p, d2l, n2l, prm, d_pose, d_state, ctx->d_packet.as<double>()));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(hpose, d_pose, 96, cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(hst, d_state, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        MP2P_CUDA_TRY(cudaGetLastError());
+        std::memcpy(pose_out, hpose, 96);
+        if (iterations_done) *iterations_done = hst[1];
+        *solved = 1;
+        return 0;
+    }
+
+    // ------------------------------------------------------------------------------ fused iterations
+    int mp2p_b200_iterate_pt2pt_horn(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                                     const float* lz, uint64_t n_local, int local_on_device,
+                                     const double pose[12], const mp2p_b200_pt2pt_params* mprm,
+                                     const mp2p_b200_horn_params* sprm, mp2p_b200_pair_pt2pt* pairs_device,
+                                     uint64_t capacity, double pose_out[12], int32_t* solved,
+                                     uint64_t* n_pairs, uint64_t* potential_pairings)
+    {
+        if (!ctx || !map || !pose || !mprm || !sprm || !pose_out || !solved || !n_pairs || (n_local && (!lx || !ly || !lz)))
         {
-            std::memcpy(hpose, pose, 96);
-            MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_pose.p, hpose, 96, cudaMemcpyHostToDevice, ctx->stream));
-            MP2P_TRY(run_gn_accumulate(ctx, d2p, n2p, d2l, n2l, prm, ctx->d_pose.as<double>(), dp));
-            MP2P_CUDA_TRY(cudaMemcpyAsync(hp, dp, MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            MP2P_CUDA_TRY(cudaGetLastError());
-            if (std::sqrt(hp[27]) <= prm->maxCost) break;
-            double  next[12];
-            int32_t conv = 0;
-            MP2P_TRY(mp2p_b200_gn_step_from_packet(hp, prm, pose, next, &conv));
-            std::memcpy(pose, next, 96);
-            if (conv)
-            {
-                it++;
-                break;
-            }
+            set_error("iterate_pt2pt_horn: NULL argument");
+            return MP2P_B200_ERR_ARG;
         }
-        std::memcpy(pose_out, pose, 96);
-        if (iterations_done) *iterations_done = it;
+        if (mprm->pairingsPerPoint < 1 || mprm->pairingsPerPoint > MP2P_B200_MAX_KNN || !(mprm->threshold > 0.0) ||
+            !(mprm->thresholdAngularDeg >= 0.0) || sprm->use_scale_outlier_detector)
+        {
+            set_error("iterate_pt2pt_horn: bad matcher parameters, or use_scale_outlier_detector (needs the two-call path)");
+            return MP2P_B200_ERR_ARG;
+        }
+        *solved = 0, *n_pairs = 0;
+        if (potential_pairings) *potential_pairings += n_local * mprm->pairingsPerPoint;
+        DeviceGuard g(ctx->device);
+        ProfScope   ps(ctx);
+        const uint64_t cap = pairs_device ? capacity : n_local * mprm->pairingsPerPoint;
+        if (!pairs_device)
+        {
+            MP2P_TRY(ctx->d_out2p.ensure(cap * sizeof(mp2p_b200_pair_pt2pt)));
+            pairs_device = ctx->d_out2p.as<mp2p_b200_pair_pt2pt>();
+        }
+        DeviceMatch dm;
+        uint64_t    dummy = 0;
+        MP2P_TRY(run_match_pt2pt(ctx, map, lx, ly, lz, n_local, local_on_device, pose, mprm, nullptr, nullptr,
+                                 pairs_device, cap, 1, &dummy, &dm));
+        if (!dm.d_count) return 0;  // empty map or cloud: no pairings (ICP: NoPairings)
+        const auto* d2p = static_cast<const mp2p_b200_pair_pt2pt*>(dm.d_pairs);
+        double*     dp0 = ctx->d_packet.as<double>();
+        double*     dp1 = dp0 + MP2P_B200_PACKET_DOUBLES;
+        MP2P_TRY(run_horn_sums(ctx, d2p, dm.capacity, nullptr, dp0, dm.d_count));
+        MP2P_TRY(run_horn_moments(ctx, d2p, dm.capacity, sprm, dp0, dm.capacity, nullptr, nullptr, 0, nullptr, dp1, dm.d_count));
+        double*             hp = pinned_packets(ctx);
+        unsigned long long* hc = static_cast<unsigned long long*>(ctx->h_pinned);
+        MP2P_CUDA_TRY(cudaMemcpyAsync(hp, dp0, 2 * MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(hc, dm.d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        MP2P_CUDA_TRY(cudaGetLastError());
+        *n_pairs = *hc;
+        if (*n_pairs > dm.capacity)
+        {
+            set_error("iterate_pt2pt_horn: pairings buffer too small");
+            return MP2P_B200_ERR_CAPACITY;
+        }
+        if (*n_pairs < 3) return 0;  // optimal_tf_horn.cpp:96
+        return mp2p_b200_horn_finish(hp, hp + MP2P_B200_PACKET_DOUBLES, pose_out, solved);
+    }
+
+    int mp2p_b200_iterate_pt2pl_gn(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                                   const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
+                                   const mp2p_b200_pt2pl_params* mprm, const mp2p_b200_gn_params* sprm,
+                                   mp2p_b200_pair_pt2pl* pairs_device, uint64_t capacity, double pose_out[12],
+                                   int32_t* solved, uint64_t* n_pairs, uint32_t* iterations_done,
+                                   uint64_t* potential_pairings)
+    {
+        if (!ctx || !map || !pose || !mprm || !sprm || !pose_out || !solved || !n_pairs || (n_local && (!lx || !ly || !lz)))
+        {
+            set_error("iterate_pt2pl_gn: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        if (!(mprm->distanceThreshold > 0.0) || !(mprm->searchRadius > 0.0))
+        {
+            set_error("iterate_pt2pl_gn: distanceThreshold and searchRadius must be > 0");
+            return MP2P_B200_ERR_ARG;
+        }
+        *solved = 0, *n_pairs = 0;
+        if (potential_pairings) *potential_pairings += n_local;
+        DeviceGuard g(ctx->device);
+        ProfScope   ps(ctx);
+        const uint64_t cap = pairs_device ? capacity : n_local;
+        if (!pairs_device)
+        {
+            MP2P_TRY(ctx->d_out2l.ensure(cap * sizeof(mp2p_b200_pair_pt2pl)));
+            pairs_device = ctx->d_out2l.as<mp2p_b200_pair_pt2pl>();
+        }
+        DeviceMatch dm;
+        uint64_t    dummy = 0;
+        MP2P_TRY(run_match_pt2pl(ctx, map, lx, ly, lz, n_local, local_on_device, pose, mprm, nullptr, pairs_device, cap, 1,
+                                 &dummy, &dm));
+        if (!dm.d_count) return 0;
+        double*             hpose = reinterpret_cast<double*>(static_cast<char*>(ctx->h_pinned) + 2048);
+        uint32_t*           hst   = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->h_pinned) + 2048 + 128);
+        unsigned long long* hc    = static_cast<unsigned long long*>(ctx->h_pinned);
+        std::memcpy(hpose, pose, 96);  // Solver_GaussNewton.cpp:57-59: start from the current guess
+        double*   d_pose  = ctx->d_pose.as<double>();
+        uint32_t* d_state = reinterpret_cast<uint32_t*>(ctx->d_pose.as<char>() + 128);
+        MP2P_CUDA_TRY(cudaMemcpyAsync(d_pose, hpose, 96, cudaMemcpyHostToDevice, ctx->stream));
+        MP2P_TRY(run_gn_device_loop(ctx, nullptr, 0, static_cast<const mp2p_b200_pair_pt2pl*>(dm.d_pairs), dm.capacity, sprm,
+                                    d_pose, d_state, ctx->d_packet.as<double>(), nullptr, dm.d_count));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(hpose, d_pose, 96, cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(hst, d_state, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(hc, dm.d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        MP2P_CUDA_TRY(cudaGetLastError());
+        *n_pairs = *hc;
+        if (iterations_done) *iterations_done = hst[1];
+        if (*n_pairs == 0) return 0;
+        std::memcpy(pose_out, hpose, 96);
         *solved = 1;
         return 0;
     }

@@ -113,6 +113,8 @@ struct mp2p_b200_ctx
     mp2p::DevBuf d_stats;               // 4 x u64 search counters
 
     // matcher scratch
+    const float *cur_lx = nullptr, *cur_ly = nullptr, *cur_lz = nullptr;  // local cloud the kernels read
+    bool         cur_tma_ok = false;
     mp2p::DevBuf d_lx, d_ly, d_lz;     // local cloud staging (padded to kQueryTile)
     mp2p::DevBuf d_cand;               // u64 [n_local*K]  (d2 bits << 32 | map index)
     mp2p::DevBuf d_lbits, d_gbits;     // MatchState bitfields
@@ -156,6 +158,14 @@ inline void prof_end(mp2p_b200_ctx* c, int slot)
 void prof_reset(mp2p_b200_ctx* c);    // api.cu: start of a public call
 void prof_collect(mp2p_b200_ctx* c);  // api.cu: after the call's final synchronize
 
+// result of a matcher call whose pairings stay on the device (fused iteration path)
+struct DeviceMatch
+{
+    const unsigned long long* d_count  = nullptr;  // number of pairings, device memory
+    const void*               d_pairs  = nullptr;  // compacted records, device memory
+    uint64_t                  capacity = 0;        // upper bound of *d_count
+};
+
 // index.cu
 int build_index(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* x, const float* y,
                 const float* z, uint64_t n, int on_device);
@@ -164,19 +174,19 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
                     const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
                     const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits, const uint32_t* gbits,
                     mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device,
-                    uint64_t* out_count);
+                    uint64_t* out_count, DeviceMatch* keep_on_device = nullptr);
 int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
                     const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
                     const mp2p_b200_pt2pl_params* prm, const uint32_t* lbits,
                     mp2p_b200_pair_pt2pl* out, uint64_t capacity, int out_on_device,
-                    uint64_t* out_count);
+                    uint64_t* out_count, DeviceMatch* keep_on_device = nullptr);
 int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
                            const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
                            const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits,
-                           unsigned long long* d_cand_out, float* d_bbox6_out);
+                           unsigned long long* d_cand_out, uint32_t* d_bbox6_out);
 int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_local, uint64_t index_offset,
                             uint64_t n_total, const unsigned long long* d_cand_all,
-                            const float* d_bbox_parts, uint32_t n_bbox_parts,
+                            const uint32_t* d_bbox_parts, uint32_t n_bbox_parts,
                             const mp2p_b200_pt2pt_params* prm, const uint32_t* gbits,
                             mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device,
                             uint64_t* out_count);
@@ -184,13 +194,23 @@ int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const
             const float* qz, uint64_t nq, uint32_t k, float radius2, uint32_t* out_idx,
             float* out_d2, int32_t* out_found);
 // solve.cu
+// `d_n*` (optional): pair counts read from DEVICE memory at kernel time (n* then are upper bounds
+// used for the grid size) — lets a solver be enqueued behind a matcher without a host round trip.
 int run_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p,
                       const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l, const mp2p_b200_gn_params* prm,
-                      const double* d_pose, double* d_packet);
+                      const double* d_pose, double* d_packet, const unsigned long long* d_n2p = nullptr,
+                      const unsigned long long* d_n2l = nullptr, const uint32_t* d_done = nullptr);
+// whole inner loop of optimal_tf_gauss_newton on the device: (accumulate, solve+update) x maxIter,
+// no host synchronisation; d_pose in/out, d_state = {done flag, iterations done}
+int run_gn_device_loop(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p,
+                       const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l, const mp2p_b200_gn_params* prm,
+                       double* d_pose, uint32_t* d_state, double* d_packet,
+                       const unsigned long long* d_n2p = nullptr, const unsigned long long* d_n2l = nullptr);
 int run_horn_sums(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n,
-                  const uint8_t* d_outlier, double* d_packet);
+                  const uint8_t* d_outlier, double* d_packet, const unsigned long long* d_n = nullptr);
 int run_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n,
                      const mp2p_b200_horn_params* prm, const double* d_sums_packet,
                      uint64_t n_total_pairs, const uint64_t* d_wcount_prefix, const double* d_wvalue,
-                     uint32_t n_wblocks, uint8_t* d_outlier, double* d_packet);
+                     uint32_t n_wblocks, uint8_t* d_outlier, double* d_packet,
+                     const unsigned long long* d_n = nullptr);
 }  // namespace mp2p

@@ -8,6 +8,12 @@
 #include <cmath>
 #include <cstring>
 
+#ifdef __CUDACC__
+#define MP2P_HD __host__ __device__
+#else
+#define MP2P_HD
+#endif
+
 namespace mp2p
 {
 namespace hm
@@ -17,7 +23,7 @@ struct Pose34
     double m[12];
 };
 
-inline Pose34 compose(const Pose34& a, const Pose34& b)
+MP2P_HD inline Pose34 compose(const Pose34& a, const Pose34& b)
 {
     Pose34 o;
     for (int r = 0; r < 3; r++)
@@ -30,15 +36,15 @@ inline Pose34 compose(const Pose34& a, const Pose34& b)
 }
 
 // xi = (v, w): R = exp([w]x), t = V(w) v
-inline Pose34 se3_exp(const double xi[6])
+MP2P_HD inline Pose34 se3_exp(const double xi[6])
 {
     const double wx = xi[3], wy = xi[4], wz = xi[5];
-    const double th2 = wx * wx + wy * wy + wz * wz, th = std::sqrt(th2);
+    const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
     double       A, B, C;
     if (th < 1e-6)
         A = 1.0 - th2 / 6.0, B = 0.5 - th2 / 24.0, C = 1.0 / 6.0 - th2 / 120.0;
     else
-        A = std::sin(th) / th, B = (1.0 - std::cos(th)) / th2, C = (th - std::sin(th)) / (th2 * th);
+        A = sin(th) / th, B = (1.0 - cos(th)) / th2, C = (th - sin(th)) / (th2 * th);
     const double W[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
     double       W2[9];
     for (int r = 0; r < 3; r++)
@@ -59,29 +65,41 @@ inline Pose34 se3_exp(const double xi[6])
 }
 
 // x = H^{-1} b for symmetric 6x6 H, LDL^T with diagonal pivoting; null pivots contribute zero.
-inline void ldlt_solve6(const double Hin[36], const double b[6], double x[6])
+MP2P_HD inline void ldlt_solve6(const double Hin[36], const double b[6], double x[6])
 {
     const int N = 6;
     double    A[36];
-    std::memcpy(A, Hin, sizeof(A));
+    for (int i = 0; i < 36; i++) A[i] = Hin[i];
     int perm[6] = {0, 1, 2, 3, 4, 5};
     double maxdiag = 0;
-    for (int i = 0; i < N; i++) maxdiag = std::fmax(maxdiag, std::fabs(A[i * N + i]));
+    for (int i = 0; i < N; i++) maxdiag = fmax(maxdiag, fabs(A[i * N + i]));
     const double tol = maxdiag * 2.220446049250313e-16 * N;
     for (int k = 0; k < N; k++)
     {
         int    piv = k;
-        double best = std::fabs(A[k * N + k]);
+        double best = fabs(A[k * N + k]);
         for (int i = k + 1; i < N; i++)
-            if (std::fabs(A[i * N + i]) > best) best = std::fabs(A[i * N + i]), piv = i;
+            if (fabs(A[i * N + i]) > best) best = fabs(A[i * N + i]), piv = i;
         if (piv != k)
         {
-            for (int c = 0; c < N; c++) std::swap(A[k * N + c], A[piv * N + c]);
-            for (int r = 0; r < N; r++) std::swap(A[r * N + k], A[r * N + piv]);
-            std::swap(perm[k], perm[piv]);
+            for (int c = 0; c < N; c++)
+            {
+                const double t = A[k * N + c];
+                A[k * N + c]   = A[piv * N + c];
+                A[piv * N + c] = t;
+            }
+            for (int r = 0; r < N; r++)
+            {
+                const double t = A[r * N + k];
+                A[r * N + k]   = A[r * N + piv];
+                A[r * N + piv] = t;
+            }
+            const int tp = perm[k];
+            perm[k]      = perm[piv];
+            perm[piv]    = tp;
         }
         const double d = A[k * N + k];
-        if (std::fabs(d) <= tol) continue;
+        if (fabs(d) <= tol) continue;
         double col[6];
         for (int i = k + 1; i < N; i++) col[i] = A[i * N + k];
         for (int i = k + 1; i < N; i++)
@@ -102,7 +120,7 @@ inline void ldlt_solve6(const double Hin[36], const double b[6], double x[6])
     for (int i = 0; i < N; i++)
     {
         const double d = A[i * N + i];
-        y[i]           = (std::fabs(d) > tol) ? y[i] / d : 0.0;
+        y[i]           = (fabs(d) > tol) ? y[i] / d : 0.0;
     }
     for (int i = N - 1; i >= 0; i--)
         for (int j = i + 1; j < N; j++) y[i] -= A[j * N + i] * y[j];

@@ -67,31 +67,46 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "memory");
 }
 
-// A CTA of kQueryTile threads serves kQueryTile / kGroup queries (kGroup lanes cooperate per query).
+// A CTA of kQueryTile threads serves kQueryTile / kGroup queries in the group-cooperative kernels
+// (kGroup lanes per query) and kNN1Threads queries in the lane-per-query K = 1 kernel.
 constexpr uint32_t kQueriesPerBlock = kQueryTile / kGroup;
+constexpr uint32_t kNN1Threads      = 128;
 
+template <uint32_t NQ>
 struct QueryTile
 {
-    alignas(128) float x[kQueriesPerBlock];
-    alignas(128) float y[kQueriesPerBlock];
-    alignas(128) float z[kQueriesPerBlock];
+    alignas(128) float x[NQ];
+    alignas(128) float y[NQ];
+    alignas(128) float z[NQ];
     alignas(8) uint64_t bar;
 };
 
 // All threads of the CTA call this; afterwards tile.x/y/z hold queries [base, base+kQueriesPerBlock).
 // The staging arrays are padded to a multiple of kQueryTile, so the copy size is constant.
-__device__ __forceinline__ void load_query_tile(QueryTile& tile, const float* lx, const float* ly,
-                                                const float* lz, size_t base)
+// Full tiles of 16-byte aligned arrays come in by TMA; the ragged last tile (or a caller's
+// unaligned device arrays, used in place without a staging copy) by plain predicated loads.
+template <uint32_t NQ>
+__device__ __forceinline__ void load_query_tile(QueryTile<NQ>& tile, const float* lx, const float* ly,
+                                                const float* lz, size_t base, size_t n_total, bool tma_ok)
 {
-    if (threadIdx.x == 0)
+    const bool use_tma = tma_ok && base + NQ <= n_total;  // CTA-uniform
+    if (use_tma && threadIdx.x == 0)
     {
         mbar_init(&tile.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (!use_tma)
+        for (uint32_t t = threadIdx.x; t < NQ; t += blockDim.x)
+        {
+            const size_t idx = base + t;
+            const bool   in  = idx < n_total;
+            tile.x[t] = in ? lx[idx] : 0.f, tile.y[t] = in ? ly[idx] : 0.f, tile.z[t] = in ? lz[idx] : 0.f;
+        }
     __syncthreads();
+    if (!use_tma) return;
     if (threadIdx.x == 0)
     {
-        constexpr uint32_t bytes = kQueriesPerBlock * sizeof(float);
+        constexpr uint32_t bytes = NQ * sizeof(float);
         mbar_expect_tx(&tile.bar, 3 * bytes);
         tma_load_1d(tile.x, lx + base, bytes, &tile.bar);
         tma_load_1d(tile.y, ly + base, bytes, &tile.bar);
@@ -119,75 +134,61 @@ __device__ __forceinline__ void compose_point_f(const PoseArg& T, float lx, floa
 }
 
 // Bounding box of the transformed local cloud (TransformedLocalPointCloud::localMin/localMax,
-// Matcher_Points_Base.h:98-112) without same-address atomics: every CTA writes its 6 partial
-// extrema, takes a ticket, and the LAST CTA to finish folds all partials into bbox_final[6].
-// Must be called by every thread of the CTA (contains __syncthreads).
-struct BBoxSmem
+// Matcher_Points_Base.h:98-112) as 6 order-preserving 32-bit words (min xyz, max xyz), without
+// any CTA barrier: warp redux -> shared atomics -> the last warp of the CTA to arrive pushes the
+// CTA's extrema to the global words with (fire-and-forget) atomics. Warps never wait for each
+// other, so a warp whose queries are done retires immediately.
+__device__ __forceinline__ uint32_t f2ord(float f)
 {
-    float    w[kQueryTile / 32][6];
-    uint32_t is_last;
+    const uint32_t u = __float_as_uint(f);
+    return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o)
+{
+    return __uint_as_float(o ^ (((o >> 31) - 1u) | 0x80000000u));
+}
+struct BBoxAcc
+{
+    uint32_t v[6];
+    uint32_t warps_done;
 };
-__device__ __forceinline__ void block_bbox_finalize(BBoxSmem& sm, float gx, float gy, float gz, bool valid,
-                                                    float* __restrict__ bbox_part,
-                                                    uint32_t* __restrict__ done_counter,
-                                                    float* __restrict__ bbox_final)
+// call by every thread BEFORE the CTA's first __syncthreads
+__device__ __forceinline__ void bbox_init(BBoxAcc& b)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float     v[6] = {valid ? gx : 3.4e38f,  valid ? gy : 3.4e38f,  valid ? gz : 3.4e38f,
-                      valid ? gx : -3.4e38f, valid ? gy : -3.4e38f, valid ? gz : -3.4e38f};
+    if (threadIdx.x < 3) b.v[threadIdx.x] = 0xFFFFFFFFu;
+    if (threadIdx.x >= 3 && threadIdx.x < 6) b.v[threadIdx.x] = 0u;
+    if (threadIdx.x == 6) b.warps_done = 0u;
+}
+// call by all 32 lanes of every warp of the CTA, exactly once
+__device__ __forceinline__ void bbox_accumulate(BBoxAcc& b, float gx, float gy, float gz, bool contributes,
+                                                uint32_t* __restrict__ g_words)
+{
+    const uint32_t lo[3] = {contributes ? f2ord(gx) : 0xFFFFFFFFu, contributes ? f2ord(gy) : 0xFFFFFFFFu,
+                            contributes ? f2ord(gz) : 0xFFFFFFFFu};
+    const uint32_t hi[3] = {contributes ? f2ord(gx) : 0u, contributes ? f2ord(gy) : 0u,
+                            contributes ? f2ord(gz) : 0u};
+    uint32_t r[6];
 #pragma unroll
-    for (int d = 0; d < 6; d++)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-        {
-            const float t = __shfl_xor_sync(0xffffffffu, v[d], o);
-            v[d]          = d < 3 ? fminf(v[d], t) : fmaxf(v[d], t);
-        }
-    if (lane == 0)
-#pragma unroll
-        for (int d = 0; d < 6; d++) sm.w[warp][d] = v[d];
-    __syncthreads();
-    if (threadIdx.x < 6)
+    for (int d = 0; d < 3; d++)
     {
-        const int d = threadIdx.x;
-        float     r = sm.w[0][d];
-        for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = d < 3 ? fminf(r, sm.w[w][d]) : fmaxf(r, sm.w[w][d]);
-        bbox_part[(size_t)blockIdx.x * 6 + d] = r;
-        __threadfence();
+        r[d]     = __reduce_min_sync(0xffffffffu, lo[d]);
+        r[3 + d] = __reduce_max_sync(0xffffffffu, hi[d]);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) sm.is_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
-    __syncthreads();
-    if (!sm.is_last) return;
-    __threadfence();
-    if (threadIdx.x == 0) *done_counter = 0u;  // re-arm for the next launch
-    float a[6] = {3.4e38f, 3.4e38f, 3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f};
-    for (uint32_t b = threadIdx.x; b < gridDim.x; b += blockDim.x)
-#pragma unroll
-        for (int d = 0; d < 6; d++)
-        {
-            const float t = __ldcg(bbox_part + (size_t)b * 6 + d);
-            a[d]          = d < 3 ? fminf(a[d], t) : fmaxf(a[d], t);
-        }
-#pragma unroll
-    for (int d = 0; d < 6; d++)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-        {
-            const float t = __shfl_xor_sync(0xffffffffu, a[d], o);
-            a[d]          = d < 3 ? fminf(a[d], t) : fmaxf(a[d], t);
-        }
-    __syncthreads();
-    if (lane == 0)
-#pragma unroll
-        for (int d = 0; d < 6; d++) sm.w[warp][d] = a[d];
-    __syncthreads();
-    if (threadIdx.x < 6)
+    if ((threadIdx.x & 31) == 0)
     {
-        const int d = threadIdx.x;
-        float     r = sm.w[0][d];
-        for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = d < 3 ? fminf(r, sm.w[w][d]) : fmaxf(r, sm.w[w][d]);
-        bbox_final[d] = r;
+#pragma unroll
+        for (int d = 0; d < 3; d++) atomicMin(&b.v[d], r[d]), atomicMax(&b.v[3 + d], r[3 + d]);
+        __threadfence_block();
+        if (atomicAdd(&b.warps_done, 1u) == (blockDim.x >> 5) - 1)
+        {
+            __threadfence_block();
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+            {
+                atomicMin(g_words + d, *(volatile uint32_t*)&b.v[d]);
+                atomicMax(g_words + 3 + d, *(volatile uint32_t*)&b.v[3 + d]);
+            }
+        }
     }
 }
 
@@ -203,6 +204,7 @@ struct Pt2PtArgs
     uint32_t n_local, K;
     int      allowLocal, allowGlobal;
     unsigned long long tag;  // (0xFFFFFFFF - epoch) << 32
+    int      tma_ok;         // local arrays are 16-byte aligned
 };
 
 // ------------------------------------------------------------------------------------------
@@ -211,23 +213,24 @@ __global__ void __launch_bounds__(kQueryTile)
     k_match_pt2pt(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
                   const float* __restrict__ lz, const uint32_t* __restrict__ lbits,
                   const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim,
-                  unsigned long long* __restrict__ cand, float* __restrict__ bbox_part,
-                  uint32_t* __restrict__ done_counter, float* __restrict__ bbox_final,
+                  unsigned long long* __restrict__ cand, uint32_t* __restrict__ bbox_words,
                   unsigned long long* __restrict__ stats)
 {
-    __shared__ QueryTile tile;
-    __shared__ BBoxSmem  bsm;
+    __shared__ QueryTile<kQueriesPerBlock> tile;
+    __shared__ BBoxAcc   bacc;
     const size_t         base = (size_t)blockIdx.x * kQueriesPerBlock;
-    load_query_tile(tile, lx, ly, lz, base);
+    bbox_init(bacc);
+    load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
     const int      sub   = threadIdx.x % kGroup, ql = threadIdx.x / kGroup;
     const unsigned gmask = ((1u << kGroup) - 1u) << ((threadIdx.x & 31) / kGroup * kGroup);
     const uint32_t i     = (uint32_t)base + ql;
     const bool     valid = i < a.n_local;
 
     float gx = 0, gy = 0, gz = 0;
+    if (valid) compose_point_f(a.pose, tile.x[ql], tile.y[ql], tile.z[ql], gx, gy, gz);
+    bbox_accumulate(bacc, gx, gy, gz, valid && sub == 0, bbox_words);
     if (valid)
     {
-        compose_point_f(a.pose, tile.x[ql], tile.y[ql], tile.z[ql], gx, gy, gz);
         const int K = (int)a.K;
         // …DistanceThreshold.cpp:230,256-257 (float, unfused)
         const float normSq = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
@@ -263,7 +266,212 @@ __global__ void __launch_bounds__(kQueryTile)
         }
         flush_search_stats(sc, n_valid, stats);
     }
-    block_bbox_finalize(bsm, gx, gy, gz, valid && sub == 0, bbox_part, done_counter, bbox_final);
+}
+
+// ------------------------------------------------------------------------------------------
+// K = 1 matcher: one LANE per query for the scalar part (transform, threshold, centre voxel), then
+// the neighbour voxels that survive the box bound — a few per query, 0 for most — are pooled over
+// the warp and dealt out again one (query, voxel) item per lane ("warp work redistribution"), so
+// the hash probes and point reads of 32 different items are in flight together instead of one
+// thread walking 27 voxels. Item results flow back to the owner through a shared-memory
+// atomicMin on the 64-bit (d2, index) key. Exactness argument unchanged: every voxel with box
+// bound <= current best distance is visited, candidates compare on (d2, index).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNN1Threads)
+    k_match_pt2pt_nn1(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
+                      const float* __restrict__ lz, const uint32_t* __restrict__ lbits,
+                      const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim,
+                      unsigned long long* __restrict__ cand, uint32_t* __restrict__ bbox_words,
+                      unsigned long long* __restrict__ stats)
+{
+    __shared__ QueryTile<kNN1Threads> tile;
+    __shared__ BBoxAcc                bacc;
+    __shared__ unsigned long long     s_best[kNN1Threads / 32][32];
+    const size_t                      base = (size_t)blockIdx.x * kNN1Threads;
+    bbox_init(bacc);
+    load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
+    const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t i     = (uint32_t)base + threadIdx.x;
+    const bool     valid = i < a.n_local;
+    const unsigned FULL  = 0xffffffffu;
+
+    float gx = 0, gy = 0, gz = 0;
+    if (valid) compose_point_f(a.pose, tile.x[threadIdx.x], tile.y[threadIdx.x], tile.z[threadIdx.x], gx, gy, gz);
+    bbox_accumulate(bacc, gx, gy, gz, valid, bbox_words);
+
+    // …DistanceThreshold.cpp:230,256-257 (float, unfused); skipped locals (:218-220) get radius 0
+    float thr2 = 0.f;
+    if (valid && (a.allowLocal || !bit_set(lbits, i)))
+    {
+        const float normSq = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+        thr2               = __fadd_rn(a.maxDistSq, __fmul_rn(a.angSq, normSq));
+    }
+    const unsigned long long sentinel = (unsigned long long)__float_as_uint(thr2) << 32;
+    unsigned long long       best     = sentinel;
+    float                    kth      = thr2;
+    bool                     active   = thr2 > 0.f;
+    if (active)
+    {
+        const float ex = fmaxf(fmaxf(g.bbmin[0] - gx, gx - g.bbmax[0]), 0.f);
+        const float ey = fmaxf(fmaxf(g.bbmin[1] - gy, gy - g.bbmax[1]), 0.f);
+        const float ez = fmaxf(fmaxf(g.bbmin[2] - gz, gz - g.bbmax[2]), 0.f);
+        if ((ex * ex + ey * ey + ez * ez) * 0.999999f > thr2) active = false;
+    }
+    const float lim = 4194304.f;  // 2^22
+    const float ux  = fminf(fmaxf(grid_u(gx, g.ox, g.inv_s0), -lim), lim);
+    const float uy  = fminf(fmaxf(grid_u(gy, g.oy, g.inv_s0), -lim), lim);
+    const float uz  = fminf(fmaxf(grid_u(gz, g.oz, g.inv_s0), -lim), lim);
+    const int   Ix = (int)floorf(ux), Iy = (int)floorf(uy), Iz = (int)floorf(uz);
+    const float q2 = g.s0_lo * g.s0_lo * 0.999999f;
+    SearchCounters sc;
+
+    for (int rl = 0; rl < g.n_levels; rl++)
+    {
+        if (!__any_sync(FULL, active)) break;
+        const int L = g.level_first + rl;
+        if (L == kGridBits)
+        {
+            // top level = every point (see grid_search.cuh); reached only by queries whose radius
+            // exceeds half the map extent
+            if (active)
+            {
+                sc.probes++, sc.cands += g.n_points, sc.levels++;
+                for (uint32_t j = 0; j < g.n_points; j++)
+                {
+                    const unsigned long long c = point_key(gx, gy, gz, __ldg(g.pts + j));
+                    best                       = c < best ? c : best;
+                }
+            }
+            break;
+        }
+        const int   cmax = ((1 << kGridBits) - 1) >> L;
+        const float s    = (float)(1 << L);
+        const int   cx = Ix >> L, cy = Iy >> L, cz = Iz >> L;
+        const float fx = ux - (float)cx * s, fy = uy - (float)cy * s, fz = uz - (float)cz * s;
+
+        // ---- centre voxel, own query
+        if (active && (unsigned)cx <= (unsigned)cmax && (unsigned)cy <= (unsigned)cmax && (unsigned)cz <= (unsigned)cmax)
+        {
+            uint32_t start, count;
+            sc.probes++;
+            if (grid_lookup(g, rl, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, start, count))
+            {
+                sc.cands += count;
+                for (uint32_t j = start; j < start + count; j++)
+                {
+                    const unsigned long long c = point_key(gx, gy, gz, __ldg(g.pts + j));
+                    best                       = c < best ? c : best;
+                }
+            }
+        }
+        kth = fminf(kth, __uint_as_float((uint32_t)(best >> 32)));
+
+        // ---- which of the 26 neighbours can hold something better: bit b = dz*9 + dy*3 + dx (each 0..2)
+        uint32_t mask = 0;
+        if (active)
+        {
+            // squared conservative gaps (metres^2) to the -1 / 0 / +1 slabs per axis
+            const float glx = fmaxf(fx - 4.f, 0.f), ghx = fmaxf(s - fx - 4.f, 0.f);
+            const float gly = fmaxf(fy - 4.f, 0.f), ghy = fmaxf(s - fy - 4.f, 0.f);
+            const float glz = fmaxf(fz - 4.f, 0.f), ghz = fmaxf(s - fz - 4.f, 0.f);
+            const float ax[3] = {glx * glx * q2, 0.f, ghx * ghx * q2};
+            const float ay[3] = {gly * gly * q2, 0.f, ghy * ghy * q2};
+            const float az[3] = {glz * glz * q2, 0.f, ghz * ghz * q2};
+#pragma unroll
+            for (int dz = 0; dz < 3; dz++)
+            {
+                if (az[dz] > kth || (unsigned)(cz + dz - 1) > (unsigned)cmax) continue;
+#pragma unroll
+                for (int dy = 0; dy < 3; dy++)
+                {
+                    const float t = az[dz] + ay[dy];
+                    if (t > kth || (unsigned)(cy + dy - 1) > (unsigned)cmax) continue;
+#pragma unroll
+                    for (int dx = 0; dx < 3; dx++)
+                    {
+                        if (dx == 1 && dy == 1 && dz == 1) continue;
+                        if (t + ax[dx] > kth || (unsigned)(cx + dx - 1) > (unsigned)cmax) continue;  // strict >
+                        mask |= 1u << (dz * 9 + dy * 3 + dx);
+                    }
+                }
+            }
+        }
+        // ---- pool the (query, voxel) items of the warp and deal them out one per lane
+        const uint32_t cnt  = __popc(mask);
+        uint32_t       incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t excl  = incl - cnt;
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        s_best[warp][lane]   = best;
+        __syncwarp();
+        for (uint32_t b0 = 0; b0 < total; b0 += 32)
+        {
+            const uint32_t id = b0 + lane;
+            int            owner = 0;  // largest lane q with excl[q] <= id
+#pragma unroll
+            for (int st = 16; st > 0; st >>= 1)
+            {
+                const int      probe = owner + st;
+                const uint32_t e     = __shfl_sync(FULL, excl, probe & 31);
+                if (probe < 32 && e <= id) owner = probe;
+            }
+            const float    oqx = __shfl_sync(FULL, gx, owner), oqy = __shfl_sync(FULL, gy, owner),
+                        oqz = __shfl_sync(FULL, gz, owner);
+            const int      ocx = __shfl_sync(FULL, cx, owner), ocy = __shfl_sync(FULL, cy, owner),
+                      ocz = __shfl_sync(FULL, cz, owner);
+            const uint32_t omask = __shfl_sync(FULL, mask, owner), oexcl = __shfl_sync(FULL, excl, owner);
+            if (id < total)
+            {
+                const uint32_t bit = __fns(omask, 0, (int)(id - oexcl) + 1);
+                const int      dz = (int)(bit / 9u), dy = (int)((bit % 9u) / 3u), dx = (int)(bit % 3u);
+                uint32_t       start, count;
+                sc.probes++;
+                if (grid_lookup(g, rl, (uint32_t)(ocx + dx - 1), (uint32_t)(ocy + dy - 1), (uint32_t)(ocz + dz - 1), start, count))
+                {
+                    sc.cands += count;
+                    unsigned long long m = ~0ull;
+                    for (uint32_t j = start; j < start + count; j++)
+                    {
+                        const unsigned long long c = point_key(oqx, oqy, oqz, __ldg(g.pts + j));
+                        m                          = c < m ? c : m;
+                    }
+                    atomicMin(&s_best[warp][owner], m);
+                }
+            }
+        }
+        __syncwarp();
+        best = s_best[warp][lane];
+        __syncwarp();
+        kth = fminf(kth, __uint_as_float((uint32_t)(best >> 32)));
+        // everything outside the 3x3x3 block is at least m quanta away
+        const float mx = s + fminf(fx, s - fx), my = s + fminf(fy, s - fy), mz = s + fminf(fz, s - fz);
+        const float m  = fmaxf(fminf(mx, fminf(my, mz)) - 4.f, 0.f);
+        if (active)
+        {
+            sc.levels++;
+            if (kth <= m * m * q2) active = false;
+        }
+    }
+
+    uint32_t n_valid = 0;
+    if (valid)
+    {
+        // unused ranks are marked with an impossible map index (all ones)
+        const unsigned long long c = best < sentinel ? best : ~0ull;
+        n_valid                    = (c != ~0ull);
+        cand[i]                    = c;
+        if (c != ~0ull && !a.allowGlobal)
+        {
+            const uint32_t gi = (uint32_t)c;
+            if (!bit_set(gbits, gi)) atomicMin(claim + gi, a.tag | (unsigned long long)i);
+        }
+    }
+    flush_search_stats(sc, n_valid, stats);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -365,27 +573,34 @@ struct CompactArgs
     uint32_t index_offset;  // sharded runs: first global local-point index of this shard
 };
 
-__device__ __forceinline__ bool bbox_gate(const GridView& g, const float* __restrict__ bbox, float eps)
+__device__ __forceinline__ bool bbox_gate(const GridView& g, const uint32_t* __restrict__ words, float eps)
 {
     // mrpt TBoundingBoxf::intersection(other, epsilon) has a value (…DistanceThreshold.cpp:73-75)
 #pragma unroll
     for (int d = 0; d < 3; d++)
     {
-        if (__fsub_rn(__ldcg(bbox + d), eps) > g.bbmax[d]) return false;
-        if (__fadd_rn(__ldcg(bbox + 3 + d), eps) < g.bbmin[d]) return false;
+        if (__fsub_rn(ord2f(__ldcg(words + d)), eps) > g.bbmax[d]) return false;
+        if (__fadd_rn(ord2f(__ldcg(words + 3 + d)), eps) < g.bbmin[d]) return false;
     }
     return true;
+}
+// the two bbox slots alternate between calls: the consumer of slot e re-arms slot e^1
+__device__ __forceinline__ void bbox_rearm(uint32_t* __restrict__ next_words)
+{
+    if (blockIdx.x == 0 && threadIdx.x < 6) next_words[threadIdx.x] = threadIdx.x < 3 ? 0xFFFFFFFFu : 0u;
 }
 
 __global__ void __launch_bounds__(kScanThreads)
     k_compact_pt2pt(GridView g, CompactArgs a, const float* __restrict__ lx,
                     const float* __restrict__ ly, const float* __restrict__ lz,
                     const uint32_t* __restrict__ gbits, const unsigned long long* __restrict__ claim,
-                    const unsigned long long* __restrict__ cand, const float* __restrict__ bbox,
-                    unsigned long long* __restrict__ status, uint32_t* __restrict__ tile_counter,
-                    mp2p_b200_pair_pt2pt* __restrict__ out, unsigned long long* __restrict__ out_count)
+                    const unsigned long long* __restrict__ cand, const uint32_t* __restrict__ bbox,
+                    uint32_t* __restrict__ bbox_next, unsigned long long* __restrict__ status,
+                    uint32_t* __restrict__ tile_counter, mp2p_b200_pair_pt2pt* __restrict__ out,
+                    unsigned long long* __restrict__ out_count)
 {
     __shared__ ScanSmem sm;
+    bbox_rearm(bbox_next);
     const uint64_t n_slots = (uint64_t)a.n_local * a.K;
     const uint32_t n_tiles = (uint32_t)((n_slots + kScanTile - 1) / kScanTile);
     if (threadIdx.x == 0)
@@ -451,6 +666,7 @@ struct Pt2PlArgs
     int      allowLocal;
     float    gate_eps;
     uint64_t capacity;
+    int      tma_ok;
 };
 
 template <int KT>
@@ -458,21 +674,22 @@ __global__ void __launch_bounds__(kQueryTile)
     k_match_pt2pl(GridView g, Pt2PlArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
                   const float* __restrict__ lz, const uint32_t* __restrict__ lbits,
                   PlaneCandidate* __restrict__ plc, uint8_t* __restrict__ ok_flags,
-                  float* __restrict__ bbox_part, uint32_t* __restrict__ done_counter,
-                  float* __restrict__ bbox_final, unsigned long long* __restrict__ stats)
+                  uint32_t* __restrict__ bbox_words, unsigned long long* __restrict__ stats)
 {
-    __shared__ QueryTile tile;
-    __shared__ BBoxSmem  bsm;
+    __shared__ QueryTile<kQueriesPerBlock> tile;
+    __shared__ BBoxAcc   bacc;
     const size_t         base = (size_t)blockIdx.x * kQueriesPerBlock;
-    load_query_tile(tile, lx, ly, lz, base);
+    bbox_init(bacc);
+    load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
     const int      sub   = threadIdx.x % kGroup, ql = threadIdx.x / kGroup;
     const unsigned gmask = ((1u << kGroup) - 1u) << ((threadIdx.x & 31) / kGroup * kGroup);
     const uint32_t i     = (uint32_t)base + ql;
     const bool     valid = i < a.n_local;
     float          gx = 0, gy = 0, gz = 0;
+    if (valid) compose_point_f(a.pose, tile.x[ql], tile.y[ql], tile.z[ql], gx, gy, gz);
+    bbox_accumulate(bacc, gx, gy, gz, valid && sub == 0, bbox_words);
     if (valid)
     {
-        compose_point_f(a.pose, tile.x[ql], tile.y[ql], tile.z[ql], gx, gy, gz);
         uint8_t        ok = 0;
         SearchCounters sc;
         uint32_t       n_valid = 0;
@@ -510,19 +727,20 @@ __global__ void __launch_bounds__(kQueryTile)
         if (sub == 0) ok_flags[i] = ok;
         flush_search_stats(sc, n_valid, stats);
     }
-    block_bbox_finalize(bsm, gx, gy, gz, valid && sub == 0, bbox_part, done_counter, bbox_final);
 }
 
 __global__ void __launch_bounds__(kScanThreads)
     k_compact_pt2pl(GridView g, uint32_t n_local, float gate_eps, uint64_t capacity,
                     const float* __restrict__ lx, const float* __restrict__ ly,
                     const float* __restrict__ lz, const PlaneCandidate* __restrict__ plc,
-                    const uint8_t* __restrict__ ok_flags, const float* __restrict__ bbox,
-                    unsigned long long* __restrict__ status, uint32_t* __restrict__ tile_counter,
+                    const uint8_t* __restrict__ ok_flags, const uint32_t* __restrict__ bbox,
+                    uint32_t* __restrict__ bbox_next, unsigned long long* __restrict__ status,
+                    uint32_t* __restrict__ tile_counter,
                     mp2p_b200_pair_pt2pl* __restrict__ out, unsigned long long* __restrict__ out_count,
                     uint32_t scan_epoch)
 {
     __shared__ ScanSmem sm;
+    bbox_rearm(bbox_next);
     const uint32_t n_tiles = (n_local + kScanTile - 1) / kScanTile;
     if (threadIdx.x == 0)
     {
@@ -603,19 +821,27 @@ int pick_kt(uint32_t K)
     return 32;
 }
 
-// stage the local cloud into kQueryTile-padded device arrays (TMA needs 16-byte granules and must
-// not read past the caller's buffers)
+// Host clouds are copied into (aligned) staging arrays; device-resident clouds are used in place.
+// Sets ctx->cur_l{x,y,z} (what the kernels read) and ctx->cur_tma_ok.
 int stage_local(mp2p_b200_ctx* ctx, const float* lx, const float* ly, const float* lz, uint64_t n,
                 int on_device)
 {
-    const size_t padded = ((n + kQueryTile - 1) / kQueryTile) * kQueryTile * sizeof(float);
-    MP2P_TRY(ctx->d_lx.ensure(padded));
-    MP2P_TRY(ctx->d_ly.ensure(padded));
-    MP2P_TRY(ctx->d_lz.ensure(padded));
-    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_lx.p, lx, n * 4, kind, ctx->stream));
-    MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_ly.p, ly, n * 4, kind, ctx->stream));
-    MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_lz.p, lz, n * 4, kind, ctx->stream));
+    if (on_device)
+    {
+        ctx->cur_lx = lx, ctx->cur_ly = ly, ctx->cur_lz = lz;
+        ctx->cur_tma_ok = ((reinterpret_cast<uintptr_t>(lx) | reinterpret_cast<uintptr_t>(ly) |
+                            reinterpret_cast<uintptr_t>(lz)) & 15u) == 0;
+        return 0;
+    }
+    const size_t bytes = n * sizeof(float);
+    MP2P_TRY(ctx->d_lx.ensure(bytes));
+    MP2P_TRY(ctx->d_ly.ensure(bytes));
+    MP2P_TRY(ctx->d_lz.ensure(bytes));
+    MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_lx.p, lx, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_ly.p, ly, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_lz.p, lz, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->cur_lx = ctx->d_lx.as<float>(), ctx->cur_ly = ctx->d_ly.as<float>(), ctx->cur_lz = ctx->d_lz.as<float>();
+    ctx->cur_tma_ok = true;
     return 0;
 }
 
@@ -633,22 +859,22 @@ int upload_bits(mp2p_b200_ctx* ctx, DevBuf& buf, const uint32_t* bits, uint64_t 
 
 struct SmallView
 {
-    float*              bbox_final;    // 6 floats: min xyz, max xyz of the transformed local cloud
-    float*              bbox_part;     // 6 floats per CTA of the match kernel
+    uint32_t*           bbox;       // this call's 6 ordered words (min xyz, max xyz)
+    uint32_t*           bbox_next;  // the other slot, re-armed by this call's compaction kernel
     unsigned long long* count;
     uint32_t*           tile_counter;
-    uint32_t*           done_counter;
 };
-int prepare_small(mp2p_b200_ctx* ctx, uint64_t n_tiles, uint64_t n_match_blocks, SmallView& sv,
-                  unsigned long long** status)
+int prepare_small(mp2p_b200_ctx* ctx, uint64_t n_tiles, SmallView& sv, unsigned long long** status)
 {
     // counters re-arm themselves inside the kernels and the scan status words carry a call epoch,
-    // so nothing is cleared per call: buffers are zeroed once when they are (re)allocated.
-    const size_t need_small = 64 + n_match_blocks * 24;
-    if (need_small > ctx->d_small.bytes)
+    // so nothing is cleared per call: buffers are initialised once when they are (re)allocated.
+    if (ctx->d_small.bytes < 128)
     {
-        MP2P_TRY(ctx->d_small.ensure(need_small));
+        MP2P_TRY(ctx->d_small.ensure(128));
         MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_small.p, 0, ctx->d_small.bytes, ctx->stream));
+        const uint32_t init[12] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0,
+                                   0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
+        MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_small.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     }
     const size_t need_scan = (n_tiles + 1) * 8;
     if (need_scan > ctx->d_scan.bytes)
@@ -656,14 +882,13 @@ int prepare_small(mp2p_b200_ctx* ctx, uint64_t n_tiles, uint64_t n_match_blocks,
         MP2P_TRY(ctx->d_scan.ensure(need_scan));
         MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_scan.p, 0, ctx->d_scan.bytes, ctx->stream));
     }
-    char* base      = ctx->d_small.as<char>();
-    sv.bbox_final   = reinterpret_cast<float*>(base);
-    sv.count        = reinterpret_cast<unsigned long long*>(base + 32);
-    sv.tile_counter = reinterpret_cast<uint32_t*>(base + 40);
-    sv.done_counter = reinterpret_cast<uint32_t*>(base + 44);
-    sv.bbox_part    = reinterpret_cast<float*>(base + 64);
-    *status         = ctx->d_scan.as<unsigned long long>();
     ctx->scan_epoch = (ctx->scan_epoch % 0x3FFFFEu) + 1;  // 1 .. 2^22-2, never 0 (= cleared memory)
+    char* base      = ctx->d_small.as<char>();
+    sv.bbox         = reinterpret_cast<uint32_t*>(base) + 6 * (ctx->scan_epoch & 1u);
+    sv.bbox_next    = reinterpret_cast<uint32_t*>(base) + 6 * ((ctx->scan_epoch & 1u) ^ 1u);
+    sv.count        = reinterpret_cast<unsigned long long*>(base + 64);
+    sv.tile_counter = reinterpret_cast<uint32_t*>(base + 72);
+    *status         = ctx->d_scan.as<unsigned long long>();
     return 0;
 }
 
@@ -707,9 +932,10 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
                     const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
                     const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits, const uint32_t* gbits,
                     mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device,
-                    uint64_t* out_count)
+                    uint64_t* out_count, DeviceMatch* keep_on_device)
 {
     *out_count          = 0;
+    if (keep_on_device) *keep_on_device = DeviceMatch{};
     const uint32_t K    = prm->pairingsPerPoint;
     const uint64_t nmap = map->view.n_points;
     if (nmap == 0 || n_local == 0) return 0;  // …DistanceThreshold.cpp:67
@@ -727,7 +953,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     const uint64_t n_tiles = (n_slots + kScanTile - 1) / kScanTile;
     SmallView           sv;
     unsigned long long* status;
-    MP2P_TRY(prepare_small(ctx, n_tiles, (n_local + kQueriesPerBlock - 1) / kQueriesPerBlock, sv, &status));
+    MP2P_TRY(prepare_small(ctx, n_tiles, sv, &status));
     MP2P_TRY(ctx->d_cand.ensure(n_slots * 8));
 
     if (++map->epoch == 0xFFFFFFFFu)  // tags exhausted: restart the claim words
@@ -744,19 +970,23 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     a.n_local = (uint32_t)n_local, a.K = K;
     a.allowLocal = prm->allowMatchAlreadyMatchedPoints, a.allowGlobal = prm->allowMatchAlreadyMatchedGlobalPoints;
     a.tag = (unsigned long long)(0xFFFFFFFFu - map->epoch) << 32;
+    a.tma_ok = ctx->cur_tma_ok;
 
     const uint32_t blocks = (uint32_t)((n_local + kQueriesPerBlock - 1) / kQueriesPerBlock);
-    const float *  dlx = ctx->d_lx.as<float>(), *dly = ctx->d_ly.as<float>(), *dlz = ctx->d_lz.as<float>();
+    const float *  dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;
     auto*          claim = map->d_claim.as<unsigned long long>();
     auto*          cand  = ctx->d_cand.as<unsigned long long>();
     unsigned long long* stats = nullptr;
     MP2P_TRY(prepare_stats(ctx, &stats));
     prof_begin(ctx, 0);
 #define LAUNCH_MATCH(KT) \
-    k_match_pt2pt<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, sv.bbox_part, sv.done_counter, sv.bbox_final, stats)
+    k_match_pt2pt<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, sv.bbox, stats)
     switch (pick_kt(K))
     {
-        case 1: LAUNCH_MATCH(1); break;
+        case 1:
+            k_match_pt2pt_nn1<<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
+                map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, sv.bbox, stats);
+            break;
         case 4: LAUNCH_MATCH(4); break;
         case 8: LAUNCH_MATCH(8); break;
         case 16: LAUNCH_MATCH(16); break;
@@ -779,10 +1009,15 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     c.scan_epoch = ctx->scan_epoch;
     prof_begin(ctx, 1);
     k_compact_pt2pt<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, c, dlx, dly, dlz, d_gbits,
-                                                               claim, cand, sv.bbox_final, status,
+                                                               claim, cand, sv.bbox, sv.bbox_next, status,
                                                                sv.tile_counter, d_out, sv.count);
     prof_end(ctx, 1);
     count_launch(ctx);
+    if (keep_on_device)  // fused iteration: the caller enqueues the solver and synchronises once
+    {
+        keep_on_device->d_count = sv.count, keep_on_device->d_pairs = d_out, keep_on_device->capacity = c.capacity;
+        return 0;
+    }
     return fetch_results(ctx, sv.count, d_out, out, capacity, out_on_device, out_count);
 }
 
@@ -806,13 +1041,13 @@ __global__ void __launch_bounds__(256)
         if (!bit_set(gbits, gi)) atomicMin(claim + gi, tag | s);
     }
 }
-// fold the per-shard bounding boxes (6 floats each, min xyz / max xyz) into one
-__global__ void k_fold_bbox(const float* __restrict__ parts, uint32_t n_parts, float* __restrict__ out)
+// fold the per-shard bounding boxes (6 ordered words each: min xyz / max xyz) into one
+__global__ void k_fold_bbox(const uint32_t* __restrict__ parts, uint32_t n_parts, uint32_t* __restrict__ out)
 {
     const int d = threadIdx.x;
     if (d >= 6) return;
-    float r = parts[d];
-    for (uint32_t p = 1; p < n_parts; p++) r = d < 3 ? fminf(r, parts[p * 6 + d]) : fmaxf(r, parts[p * 6 + d]);
+    uint32_t r = parts[d];
+    for (uint32_t p = 1; p < n_parts; p++) r = d < 3 ? min(r, parts[p * 6 + d]) : max(r, parts[p * 6 + d]);
     out[d] = r;
 }
 }  // namespace
@@ -820,7 +1055,7 @@ __global__ void k_fold_bbox(const float* __restrict__ parts, uint32_t n_parts, f
 int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
                            const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
                            const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits,
-                           unsigned long long* d_cand_out, float* d_bbox6_out)
+                           unsigned long long* d_cand_out, uint32_t* d_bbox6_out)
 {
     const uint32_t K = prm->pairingsPerPoint;
     cudaStream_t   st = ctx->stream;
@@ -828,17 +1063,18 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     {
         // an empty shard still has to contribute "nothing": all-ones candidates, inverted bbox
         if (n_local) MP2P_CUDA_TRY(cudaMemsetAsync(d_cand_out, 0xff, n_local * K * 8, st));
-        const float inv[6] = {3.4e38f, 3.4e38f, 3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f};
+        const uint32_t inv[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
         MP2P_CUDA_TRY(cudaMemcpyAsync(d_bbox6_out, inv, sizeof(inv), cudaMemcpyHostToDevice, st));
         return 0;
     }
     MP2P_TRY(stage_local(ctx, lx, ly, lz, n_local, local_on_device));
     const uint32_t* d_lbits;
     MP2P_TRY(upload_bits(ctx, ctx->d_lbits, lbits, n_local, &d_lbits));
-    SmallView           sv;
-    unsigned long long* status;
-    const uint32_t      blocks = (uint32_t)((n_local + kQueriesPerBlock - 1) / kQueriesPerBlock);
-    MP2P_TRY(prepare_small(ctx, 1, blocks, sv, &status));
+    const uint32_t blocks = (uint32_t)((n_local + kQueriesPerBlock - 1) / kQueriesPerBlock);
+    {
+        const uint32_t init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
+        MP2P_CUDA_TRY(cudaMemcpyAsync(d_bbox6_out, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
     Pt2PtArgs a{};
     for (int k = 0; k < 12; k++) a.pose.m[k] = pose[k];
     a.maxDistSq = (float)(prm->threshold * prm->threshold);
@@ -847,15 +1083,19 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     a.n_local = (uint32_t)n_local, a.K = K;
     a.allowLocal = prm->allowMatchAlreadyMatchedPoints, a.allowGlobal = 1;  // claims happen in phase B
     a.tag = 0;
-    const float *dlx = ctx->d_lx.as<float>(), *dly = ctx->d_ly.as<float>(), *dlz = ctx->d_lz.as<float>();
+    a.tma_ok = ctx->cur_tma_ok;
+    const float *dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;
     unsigned long long* stats = nullptr;
     MP2P_TRY(prepare_stats(ctx, &stats));
     prof_begin(ctx, 0);
 #define LAUNCH_MATCH(KT) \
-    k_match_pt2pt<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, nullptr, nullptr, d_cand_out, sv.bbox_part, sv.done_counter, d_bbox6_out, stats)
+    k_match_pt2pt<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, nullptr, nullptr, d_cand_out, d_bbox6_out, stats)
     switch (pick_kt(K))
     {
-        case 1: LAUNCH_MATCH(1); break;
+        case 1:
+            k_match_pt2pt_nn1<<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
+                map->view, a, dlx, dly, dlz, d_lbits, nullptr, nullptr, d_cand_out, d_bbox6_out, stats);
+            break;
         case 4: LAUNCH_MATCH(4); break;
         case 8: LAUNCH_MATCH(8); break;
         case 16: LAUNCH_MATCH(16); break;
@@ -869,7 +1109,7 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
 
 int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_local, uint64_t index_offset,
                             uint64_t n_total, const unsigned long long* d_cand_all,
-                            const float* d_bbox_parts, uint32_t n_bbox_parts,
+                            const uint32_t* d_bbox_parts, uint32_t n_bbox_parts,
                             const mp2p_b200_pt2pt_params* prm, const uint32_t* gbits,
                             mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device,
                             uint64_t* out_count)
@@ -890,8 +1130,8 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
     const uint64_t      n_tiles = (n_slots + kScanTile - 1) / kScanTile;
     SmallView           sv;
     unsigned long long* status;
-    MP2P_TRY(prepare_small(ctx, n_tiles, 1, sv, &status));
-    k_fold_bbox<<<1, 32, 0, st>>>(d_bbox_parts, n_bbox_parts, sv.bbox_final);
+    MP2P_TRY(prepare_small(ctx, n_tiles, sv, &status));
+    k_fold_bbox<<<1, 32, 0, st>>>(d_bbox_parts, n_bbox_parts, sv.bbox);
     count_launch(ctx);
     if (++map->epoch == 0xFFFFFFFFu)
     {
@@ -921,8 +1161,8 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
     c.scan_epoch = ctx->scan_epoch;
     prof_begin(ctx, 1);
     k_compact_pt2pt<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(
-        map->view, c, ctx->d_lx.as<float>(), ctx->d_ly.as<float>(), ctx->d_lz.as<float>(), d_gbits, claim,
-        d_cand_all + index_offset * K, sv.bbox_final, status, sv.tile_counter, d_out, sv.count);
+        map->view, c, ctx->cur_lx, ctx->cur_ly, ctx->cur_lz, d_gbits, claim,
+        d_cand_all + index_offset * K, sv.bbox, sv.bbox_next, status, sv.tile_counter, d_out, sv.count);
     prof_end(ctx, 1);
     count_launch(ctx);
     return fetch_results(ctx, sv.count, d_out, out, capacity, out_on_device, out_count);
@@ -932,9 +1172,10 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
                     const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
                     const mp2p_b200_pt2pl_params* prm, const uint32_t* lbits,
                     mp2p_b200_pair_pt2pl* out, uint64_t capacity, int out_on_device,
-                    uint64_t* out_count)
+                    uint64_t* out_count, DeviceMatch* keep_on_device)
 {
     *out_count          = 0;
+    if (keep_on_device) *keep_on_device = DeviceMatch{};
     const uint64_t nmap = map->view.n_points;
     if (nmap == 0 || n_local == 0) return 0;
     if (n_local >= 0xFFFFFFFFull || prm->knn < 1 || prm->knn > MP2P_B200_MAX_KNN)
@@ -949,7 +1190,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     const uint64_t      n_tiles = (n_local + kScanTile - 1) / kScanTile;
     SmallView           sv;
     unsigned long long* status;
-    MP2P_TRY(prepare_small(ctx, n_tiles, (n_local + kQueriesPerBlock - 1) / kQueriesPerBlock, sv, &status));
+    MP2P_TRY(prepare_small(ctx, n_tiles, sv, &status));
     MP2P_TRY(ctx->d_plcand.ensure(n_local * sizeof(PlaneCandidate)));
     MP2P_TRY(ctx->d_cand.ensure(n_local));  // ok flags (bytes)
 
@@ -960,17 +1201,18 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     a.planeEigenThreshold = prm->planeEigenThreshold;
     a.n_local = (uint32_t)n_local, a.K = prm->knn, a.minPts = prm->minimumPlanePoints;
     a.allowLocal = prm->allowMatchAlreadyMatchedPoints;
+    a.tma_ok     = ctx->cur_tma_ok;
     const float gate_eps = (float)(prm->distanceThreshold + prm->bounding_box_intersection_check_epsilon);
 
     const uint32_t blocks = (uint32_t)((n_local + kQueriesPerBlock - 1) / kQueriesPerBlock);
-    const float *  dlx = ctx->d_lx.as<float>(), *dly = ctx->d_ly.as<float>(), *dlz = ctx->d_lz.as<float>();
+    const float *  dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;
     auto*          plc = ctx->d_plcand.as<PlaneCandidate>();
     auto*          okf = ctx->d_cand.as<uint8_t>();
     unsigned long long* stats = nullptr;
     MP2P_TRY(prepare_stats(ctx, &stats));
     prof_begin(ctx, 0);
 #define LAUNCH_PL(KT) \
-    k_match_pt2pl<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, plc, okf, sv.bbox_part, sv.done_counter, sv.bbox_final, stats)
+    k_match_pt2pl<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, plc, okf, sv.bbox, stats)
     switch (pick_kt(prm->knn))
     {
         case 1:
@@ -992,11 +1234,16 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     }
     prof_begin(ctx, 1);
     k_compact_pt2pl<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, (uint32_t)n_local, gate_eps,
-                                                               cap, dlx, dly, dlz, plc, okf, sv.bbox_final,
+                                                               cap, dlx, dly, dlz, plc, okf, sv.bbox, sv.bbox_next,
                                                                status, sv.tile_counter, d_out, sv.count,
                                                                ctx->scan_epoch);
     prof_end(ctx, 1);
     count_launch(ctx);
+    if (keep_on_device)
+    {
+        keep_on_device->d_count = sv.count, keep_on_device->d_pairs = d_out, keep_on_device->capacity = cap;
+        return 0;
+    }
     return fetch_results(ctx, sv.count, d_out, out, capacity, out_on_device, out_count);
 }
 
@@ -1022,7 +1269,7 @@ int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const
     else
     {
         const uint32_t blocks = (uint32_t)((nq * kGroup + 255) / 256);
-        const float *  dqx = ctx->d_lx.as<float>(), *dqy = ctx->d_ly.as<float>(), *dqz = ctx->d_lz.as<float>();
+        const float *  dqx = ctx->cur_lx, *dqy = ctx->cur_ly, *dqz = ctx->cur_lz;
         auto *oi = ctx->d_knn_idx.as<uint32_t>();
         auto *od = ctx->d_knn_d2.as<float>();
         auto *of = ctx->d_knn_found.as<int32_t>();

@@ -17,6 +17,7 @@
 // Pair records are AoS (36 / 72 bytes). A warp stages 32 consecutive records with fully coalesced
 // 128-byte loads into shared memory and each lane then reads its own record (stride 9 / 18 words).
 #include "common.cuh"
+#include "host_math.hpp"
 
 namespace mp2p
 {
@@ -139,8 +140,13 @@ __device__ __forceinline__ void add_row(double (&acc)[kGNV], const double (&a)[6
 __global__ void __launch_bounds__(kSolveThreads)
     k_gn_accumulate(const uint32_t* __restrict__ p2p, const uint32_t* __restrict__ p2l, GNArgs a,
                     const double* __restrict__ pose, double* __restrict__ partials,
-                    unsigned int* __restrict__ ticket, double* __restrict__ packet)
+                    unsigned int* __restrict__ ticket, double* __restrict__ packet,
+                    const unsigned long long* __restrict__ d_n2p, const unsigned long long* __restrict__ d_n2l,
+                    const uint32_t* __restrict__ d_done)
 {
+    if (d_done && *d_done) return;  // the device-side GN loop already converged
+    if (d_n2p) a.n2p = *d_n2p;
+    if (d_n2l) a.n2l = *d_n2l;
     __shared__ uint32_t stage[kWarps][32 * 18];
     const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t*           sh = stage[warp];
@@ -229,8 +235,9 @@ constexpr int kH1V = 7;  // sum local(3), sum global(3), count
 __global__ void __launch_bounds__(kSolveThreads)
     k_horn_sums(const uint32_t* __restrict__ p2p, uint64_t n, const uint8_t* __restrict__ outlier,
                 double* __restrict__ partials, unsigned int* __restrict__ ticket,
-                double* __restrict__ packet)
+                double* __restrict__ packet, const unsigned long long* __restrict__ d_n)
 {
+    if (d_n) n = *d_n;
     __shared__ uint32_t stage[kWarps][32 * 9];
     const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t*           sh = stage[warp];
@@ -276,8 +283,9 @@ __global__ void __launch_bounds__(kSolveThreads)
                    const uint64_t* __restrict__ wprefix, const double* __restrict__ wvalue,
                    uint8_t* __restrict__ outlier, uint64_t first_global_index,
                    double* __restrict__ partials, unsigned int* __restrict__ ticket,
-                   double* __restrict__ packet)
+                   double* __restrict__ packet, const unsigned long long* __restrict__ d_n)
 {
+    if (d_n) a.n = a.n_total = *d_n;
     __shared__ uint32_t stage[kWarps][32 * 9];
     const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t*           sh = stage[warp];
@@ -381,7 +389,8 @@ int solve_grid(uint64_t n)
 
 int run_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p,
                       const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l, const mp2p_b200_gn_params* prm,
-                      const double* d_pose, double* d_packet)
+                      const double* d_pose, double* d_packet, const unsigned long long* d_n2p,
+                      const unsigned long long* d_n2l, const uint32_t* d_done)
 {
     const int blocks = solve_grid(std::max(n2p, n2l));
     unsigned int* ticket;
@@ -390,14 +399,56 @@ int run_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint6
     prof_begin(ctx, 4);
     k_gn_accumulate<<<blocks, kSolveThreads, 0, ctx->stream>>>(
         reinterpret_cast<const uint32_t*>(d2p), reinterpret_cast<const uint32_t*>(d2l), a, d_pose,
-        ctx->d_partials.as<double>(), ticket, d_packet);
+        ctx->d_partials.as<double>(), ticket, d_packet, d_n2p, d_n2l, d_done);
     prof_end(ctx, 4);
     count_launch(ctx);
     return 0;
 }
 
+// One Gauss-Newton update on the device (single thread): delta = -H^{-1} g by LDL^T, pose <- pose (+)
+// exp(delta), convergence flags (optimal_tf_gauss_newton.cpp:344-365). state[0] = done, state[1] = updates.
+__global__ void k_gn_step(const double* __restrict__ packet, double minDelta, double maxCost,
+                          double* __restrict__ pose, uint32_t* __restrict__ state)
+{
+    if (threadIdx.x != 0 || state[0]) return;
+    if (sqrt(packet[27]) <= maxCost)
+    {
+        state[0] = 1;
+        return;
+    }
+    double H[36], g[6], delta[6];
+    int    idx = 0;
+    for (int i = 0; i < 6; i++)
+        for (int j = i; j < 6; j++) H[6 * i + j] = H[6 * j + i] = packet[idx++];
+    for (int i = 0; i < 6; i++) g[i] = -packet[21 + i];
+    hm::ldlt_solve6(H, g, delta);
+    hm::Pose34 P;
+    for (int k = 0; k < 12; k++) P.m[k] = pose[k];
+    const hm::Pose34 Pn = hm::compose(P, hm::se3_exp(delta));
+    for (int k = 0; k < 12; k++) pose[k] = Pn.m[k];
+    state[1] += 1;
+    double nrm = 0;
+    for (int k = 0; k < 6; k++) nrm += delta[k] * delta[k];
+    if (sqrt(nrm) < minDelta) state[0] = 1;
+}
+
+int run_gn_device_loop(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p,
+                       const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l, const mp2p_b200_gn_params* prm,
+                       double* d_pose, uint32_t* d_state, double* d_packet,
+                       const unsigned long long* d_n2p, const unsigned long long* d_n2l)
+{
+    MP2P_CUDA_TRY(cudaMemsetAsync(d_state, 0, 8, ctx->stream));
+    for (uint32_t it = 0; it < prm->maxInnerLoopIterations; it++)  // optimal_tf_gauss_newton.cpp:70
+    {
+        MP2P_TRY(run_gn_accumulate(ctx, d2p, n2p, d2l, n2l, prm, d_pose, d_packet, d_n2p, d_n2l, d_state));
+        k_gn_step<<<1, 32, 0, ctx->stream>>>(d_packet, prm->minDelta, prm->maxCost, d_pose, d_state);
+        count_launch(ctx);
+    }
+    return 0;
+}
+
 int run_horn_sums(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n,
-                  const uint8_t* d_outlier, double* d_packet)
+                  const uint8_t* d_outlier, double* d_packet, const unsigned long long* d_n)
 {
     const int blocks = solve_grid(n);
     unsigned int* ticket;
@@ -405,7 +456,7 @@ int run_horn_sums(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t 
     prof_begin(ctx, 2);
     k_horn_sums<<<blocks, kSolveThreads, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d2p), n,
                                                           d_outlier, ctx->d_partials.as<double>(), ticket,
-                                                          d_packet);
+                                                          d_packet, d_n);
     prof_end(ctx, 2);
     count_launch(ctx);
     return 0;
@@ -414,7 +465,7 @@ int run_horn_sums(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t 
 int run_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n,
                      const mp2p_b200_horn_params* prm, const double* d_sums_packet,
                      uint64_t n_total_pairs, const uint64_t* d_wcount_prefix, const double* d_wvalue,
-                     uint32_t n_wblocks, uint8_t* d_outlier, double* d_packet)
+                     uint32_t n_wblocks, uint8_t* d_outlier, double* d_packet, const unsigned long long* d_n)
 {
     const int     blocks = solve_grid(n);
     unsigned int* ticket;
@@ -433,7 +484,7 @@ int run_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64
     k_horn_moments<<<blocks, kSolveThreads, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d2p), a,
                                                              d_sums_packet, d_wcount_prefix, d_wvalue,
                                                              d_outlier, 0, ctx->d_partials.as<double>(), ticket,
-                                                             d_packet);
+                                                             d_packet, d_n);
     prof_end(ctx, 3);
     count_launch(ctx);
     return 0;

@@ -374,3 +374,51 @@ def test_sharded_match_equals_unsharded(ctx, kw):
         parts.append(gmap.shard_resolve_pt2pt(b - a, a, n_total, cand_all.data_ptr(), boxes.data_ptr(), n_sh, prm).copy())
     got = np.concatenate(parts)
     assert len(got) == len(ref) and got.tobytes() == ref.tobytes()
+
+
+# --------------------------------------------------------------------------- fused iterations
+def test_fused_iteration_pt2pt_horn_equals_two_calls(ctx):
+    """mp2p_b200_iterate_pt2pt_horn (pairings never leave HBM, one sync) == match + solve_horn."""
+    import torch
+
+    M, L, gt = _c2(200_000, 10)
+    gmap = b200.Map(ctx, *xyz(M))
+    guess = fx.pose_xyzypr(0.25, -0.15, 0.08, 1.7 * DEG, -0.8 * DEG, 1.2 * DEG)
+    mprm, sprm = b200.Pt2PtParams(threshold=1.0), b200.HornParams()
+    pairs, _ = gmap.match_pt2pt(*xyz(L), guess, mprm)
+    ok_ref, T_ref = ctx.solve_horn(pairs)
+    d = [torch.from_numpy(a).cuda() for a in xyz(L)]
+    d_pairs = torch.zeros(len(L) * 36, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    step = gmap.make_iterator(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), len(L), mprm, sprm, d_pairs.data_ptr(), len(L))
+    for _ in range(3):
+        ok, T, n = step(guess)
+        assert ok and ok_ref and n == len(pairs)
+        assert np.array_equal(T, T_ref)  # same kernels, same fixed-order reductions
+    got = d_pairs.cpu().numpy().view(b200.PAIR_PT2PT)[:n]
+    assert got.tobytes() == pairs.tobytes()
+    ok0, T0 = orc.optimal_tf_horn(pairs)
+    assert_pose_close(T, T0)
+
+
+def test_fused_iteration_pt2pl_gn_equals_two_calls(ctx):
+    import torch
+
+    M = fx.make_street_scene(n_map=300_000, length=50.0)
+    S = fx.make_lidar_scan((25.0, 0.5, 0.0), n_rings=32, n_az=500, length=50.0)
+    guess = fx.pose_xyzypr(25.08, 0.46, 0.02, 0.02, 0.001, -0.001)
+    gmap = b200.Map(ctx, *xyz(M))
+    mkw = dict(distanceThreshold=0.5, searchRadius=1.0, knn=8, minimumPlanePoints=5, planeEigenThreshold=0.01)
+    skw = dict(maxInnerLoopIterations=3, kernel="GemanMcClure", kernelParam=0.15)
+    pairs, _ = gmap.match_pt2pl(*xyz(S), guess, b200.Pt2PlParams(**mkw))
+    ok_ref, T_ref, it_ref = ctx.solve_gauss_newton(None, pairs, b200.GNParams(**skw), guess)
+    d = [torch.from_numpy(a).cuda() for a in xyz(S)]
+    torch.cuda.synchronize()
+    step = gmap.make_iterator(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), len(S), b200.Pt2PlParams(**mkw), b200.GNParams(**skw))
+    ok, T, n = step(guess)
+    assert ok and n == len(pairs) and np.array_equal(T, T_ref)
+    tree = orc.KDTree(*xyz(M))
+    p0, _ = orc.match_pt2pl(tree, *xyz(S), guess, orc.MatchPt2PlParams(**mkw), nthreads=8)
+    ok0, T0, it0 = orc.optimal_tf_gauss_newton(None, p0, orc.GNParams(**skw), guess, nthreads=8)
+    assert it0 == it_ref
+    assert_pose_close(T, T0)
