@@ -180,8 +180,8 @@ extern "C"
         if (!c) return;
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
-        for (DevBuf* b : {&c->d_lx, &c->d_ly, &c->d_lz, &c->d_cand, &c->d_lbits, &c->d_gbits, &c->d_scan,
-                          &c->d_small, &c->d_out2p, &c->d_out2l, &c->d_plcand, &c->d_knn_idx, &c->d_knn_d2,
+        for (DevBuf* b : {&c->d_lx, &c->d_ly, &c->d_lz, &c->d_cand, &c->d_candxyz, &c->d_lbits, &c->d_gbits, &c->d_scan,
+                          &c->d_small, &c->d_out2p, &c->d_out2l, &c->d_plcand, &c->d_okflags, &c->d_knn_idx, &c->d_knn_d2,
                           &c->d_knn_found, &c->d_pairs2p, &c->d_pairs2l, &c->d_partials, &c->d_packet,
                           &c->d_pose, &c->d_weights, &c->d_outlier})
             b->release();
@@ -608,15 +608,15 @@ extern "C"
             MP2P_TRY(ctx->d_out2p.ensure(cap * sizeof(mp2p_b200_pair_pt2pt)));
             pairs_device = ctx->d_out2p.as<mp2p_b200_pair_pt2pt>();
         }
+        double*     dp0 = ctx->d_packet.as<double>();
+        double*     dp1 = dp0 + MP2P_B200_PACKET_DOUBLES;
         DeviceMatch dm;
+        dm.want_horn_sums = dp0;  // eval_centroids_robust folded into the compaction kernel
         uint64_t    dummy = 0;
         MP2P_TRY(run_match_pt2pt(ctx, map, lx, ly, lz, n_local, local_on_device, pose, mprm, nullptr, nullptr,
                                  pairs_device, cap, 1, &dummy, &dm));
         if (!dm.d_count) return 0;  // empty map or cloud: no pairings (ICP: NoPairings)
         const auto* d2p = static_cast<const mp2p_b200_pair_pt2pt*>(dm.d_pairs);
-        double*     dp0 = ctx->d_packet.as<double>();
-        double*     dp1 = dp0 + MP2P_B200_PACKET_DOUBLES;
-        MP2P_TRY(run_horn_sums(ctx, d2p, dm.capacity, nullptr, dp0, dm.d_count));
         MP2P_TRY(run_horn_moments(ctx, d2p, dm.capacity, sprm, dp0, dm.capacity, nullptr, nullptr, 0, nullptr, dp1, dm.d_count));
         double*             hp = pinned_packets(ctx);
         unsigned long long* hc = static_cast<unsigned long long*>(ctx->h_pinned);

@@ -117,11 +117,12 @@ struct mp2p_b200_ctx
     bool         cur_tma_ok = false;
     mp2p::DevBuf d_lx, d_ly, d_lz;     // local cloud staging (padded to kQueryTile)
     mp2p::DevBuf d_cand;               // u64 [n_local*K]  (d2 bits << 32 | map index)
+    mp2p::DevBuf d_candxyz;            // float4 [n_local] coordinates of the K = 1 candidate
     mp2p::DevBuf d_lbits, d_gbits;     // MatchState bitfields
     mp2p::DevBuf d_scan;               // tile status words + counters
     mp2p::DevBuf d_small;              // bbox (6 u32) + count (u64) + misc
     mp2p::DevBuf d_out2p, d_out2l;     // compacted pairs when the caller wants them on the host
-    mp2p::DevBuf d_plcand;             // per-query plane candidates (pt2pl)
+    mp2p::DevBuf d_plcand, d_okflags;  // per-query plane candidates + accepted flags (pt2pl)
     mp2p::DevBuf d_knn_idx, d_knn_d2, d_knn_found;
     // solver scratch
     mp2p::DevBuf d_pairs2p, d_pairs2l; // H2D staging of host pairings
@@ -164,6 +165,7 @@ struct DeviceMatch
     const unsigned long long* d_count  = nullptr;  // number of pairings, device memory
     const void*               d_pairs  = nullptr;  // compacted records, device memory
     uint64_t                  capacity = 0;        // upper bound of *d_count
+    double*                   want_horn_sums = nullptr;  // in: device packet to receive the HORN1 sums
 };
 
 // index.cu

@@ -6,20 +6,19 @@
 // Steps (all on the context stream):
 //   k_bbox          min/max of the layer                      N*12 B read
 //   k_morton_keys   63-bit Morton key of the finest voxel     N*12 B read, N*12 B write
-//   radix sort      (key,idx) pairs — cub::DeviceRadixSort, STOP-GAP: the only library kernel in
-//                   this library, build step only; a hand-written onesweep replaces it next.
+//   radix sort      (key,idx) pairs — hand-written stable LSD radix sort, 8 passes of 8 bits
+//                   (radix_sort.cuh); no library kernel anywhere in this library
 //   k_gather        sorted float4 {x,y,z,idx} + original-order float4
 //   k_level_hist    for every sorted position, the coarsest level at which it opens a new voxel
 //   (host)          choose the finest level with >= kTargetOccupancy points per occupied voxel
 //   k_insert_cells  each voxel opener finds its run end (galloping) and inserts (key,start,count)
 //                   into that level's open-addressing table
-#include <cub/device/device_radix_sort.cuh>
-
 #include <algorithm>
 #include <cmath>
 #include <vector>
 
 #include "grid_search.cuh"
+#include "radix_sort.cuh"
 
 namespace mp2p
 {
@@ -305,15 +304,10 @@ int build_index(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* x, const fl
                                                    k0.as<unsigned long long>(), v0.as<uint32_t>());
     count_launch(ctx);
     {
-        cub::DoubleBuffer<unsigned long long> dk(k0.as<unsigned long long>(), k1.as<unsigned long long>());
-        cub::DoubleBuffer<uint32_t>           dv(v0.as<uint32_t>(), v1.as<uint32_t>());
-        size_t                                tb = 0;
-        MP2P_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)n, 0, 63, st));
-        MP2P_TRY(tmp.ensure(tb));
-        MP2P_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, (int)n, 0, 63, st));
-        count_launch(ctx, 8);
-        if (dk.Current() != k0.as<unsigned long long>()) std::swap(k0, k1);
-        if (dv.Current() != v0.as<uint32_t>()) std::swap(v0, v1);
+        const uint32_t n_tiles = (n + rs::kTile - 1) / rs::kTile;
+        MP2P_TRY(tmp.ensure(((size_t)256 * n_tiles + 256) * sizeof(uint32_t)));
+        MP2P_TRY(rs::sort_pairs(ctx, k0.as<unsigned long long>(), v0.as<uint32_t>(), k1.as<unsigned long long>(),
+                                v1.as<uint32_t>(), n, 63, tmp.as<uint32_t>()));
     }
     const unsigned long long* d_keys = k0.as<unsigned long long>();
     const uint32_t*           d_vals = v0.as<uint32_t>();

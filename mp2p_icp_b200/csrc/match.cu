@@ -21,6 +21,7 @@
 
 #include "grid_search.cuh"
 #include "plane_fit.cuh"
+#include "reduce.cuh"
 
 namespace mp2p
 {
@@ -281,12 +282,13 @@ __global__ void __launch_bounds__(kNN1Threads)
     k_match_pt2pt_nn1(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
                       const float* __restrict__ lz, const uint32_t* __restrict__ lbits,
                       const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim,
-                      unsigned long long* __restrict__ cand, uint32_t* __restrict__ bbox_words,
-                      unsigned long long* __restrict__ stats)
+                      unsigned long long* __restrict__ cand, float4* __restrict__ cand_xyz,
+                      uint32_t* __restrict__ bbox_words, unsigned long long* __restrict__ stats)
 {
     __shared__ QueryTile<kNN1Threads> tile;
     __shared__ BBoxAcc                bacc;
     __shared__ unsigned long long     s_best[kNN1Threads / 32][32];
+    __shared__ float                  s_xyz[kNN1Threads / 32][32][3];  // coordinates of s_best's point
     const size_t                      base = (size_t)blockIdx.x * kNN1Threads;
     bbox_init(bacc);
     load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
@@ -308,6 +310,7 @@ __global__ void __launch_bounds__(kNN1Threads)
     }
     const unsigned long long sentinel = (unsigned long long)__float_as_uint(thr2) << 32;
     unsigned long long       best     = sentinel;
+    float                    bpx = 0.f, bpy = 0.f, bpz = 0.f;  // the best candidate's coordinates
     float                    kth      = thr2;
     bool                     active   = thr2 > 0.f;
     if (active)
@@ -338,8 +341,9 @@ __global__ void __launch_bounds__(kNN1Threads)
                 sc.probes++, sc.cands += g.n_points, sc.levels++;
                 for (uint32_t j = 0; j < g.n_points; j++)
                 {
-                    const unsigned long long c = point_key(gx, gy, gz, __ldg(g.pts + j));
-                    best                       = c < best ? c : best;
+                    const float4             p = __ldg(g.pts + j);
+                    const unsigned long long c = point_key(gx, gy, gz, p);
+                    if (c < best) best = c, bpx = p.x, bpy = p.y, bpz = p.z;
                 }
             }
             break;
@@ -359,8 +363,9 @@ __global__ void __launch_bounds__(kNN1Threads)
                 sc.cands += count;
                 for (uint32_t j = start; j < start + count; j++)
                 {
-                    const unsigned long long c = point_key(gx, gy, gz, __ldg(g.pts + j));
-                    best                       = c < best ? c : best;
+                    const float4             p = __ldg(g.pts + j);
+                    const unsigned long long c = point_key(gx, gy, gz, p);
+                    if (c < best) best = c, bpx = p.x, bpy = p.y, bpz = p.z;
                 }
             }
         }
@@ -408,44 +413,99 @@ __global__ void __launch_bounds__(kNN1Threads)
         const uint32_t excl  = incl - cnt;
         const uint32_t total = __shfl_sync(FULL, incl, 31);
         s_best[warp][lane]   = best;
+        s_xyz[warp][lane][0] = bpx, s_xyz[warp][lane][1] = bpy, s_xyz[warp][lane][2] = bpz;
         __syncwarp();
-        for (uint32_t b0 = 0; b0 < total; b0 += 32)
+        // kItemRounds rounds of 32 items are software-pipelined: all hash probes of the chunk are
+        // issued first, then all first-point loads, then the scans — 3 overlapped memory round trips
+        // per chunk instead of 2 per round.
+        constexpr int kItemRounds = 4;
+        for (uint32_t b0 = 0; b0 < total; b0 += 32 * kItemRounds)
         {
-            const uint32_t id = b0 + lane;
-            int            owner = 0;  // largest lane q with excl[q] <= id
+            int                owner[kItemRounds];
+            float              oq[kItemRounds][3];
+            unsigned long long ckey[kItemRounds];
+            uint32_t           h[kItemRounds], start[kItemRounds], count[kItemRounds];
+            uint4              raw[kItemRounds];
+            float4             p0[kItemRounds];
+            const uint32_t     shift = g.level_shift[rl], hmask = (1u << (64 - shift)) - 1u;
+            const CellEntry*   tab   = g.table + g.level_off[rl];
+            // ---- phase A: who owns item (b0 + r*32 + lane), which voxel is it, issue the probe
 #pragma unroll
-            for (int st = 16; st > 0; st >>= 1)
+            for (int r = 0; r < kItemRounds; r++)
             {
-                const int      probe = owner + st;
-                const uint32_t e     = __shfl_sync(FULL, excl, probe & 31);
-                if (probe < 32 && e <= id) owner = probe;
-            }
-            const float    oqx = __shfl_sync(FULL, gx, owner), oqy = __shfl_sync(FULL, gy, owner),
-                        oqz = __shfl_sync(FULL, gz, owner);
-            const int      ocx = __shfl_sync(FULL, cx, owner), ocy = __shfl_sync(FULL, cy, owner),
-                      ocz = __shfl_sync(FULL, cz, owner);
-            const uint32_t omask = __shfl_sync(FULL, mask, owner), oexcl = __shfl_sync(FULL, excl, owner);
-            if (id < total)
-            {
-                const uint32_t bit = __fns(omask, 0, (int)(id - oexcl) + 1);
-                const int      dz = (int)(bit / 9u), dy = (int)((bit % 9u) / 3u), dx = (int)(bit % 3u);
-                uint32_t       start, count;
-                sc.probes++;
-                if (grid_lookup(g, rl, (uint32_t)(ocx + dx - 1), (uint32_t)(ocy + dy - 1), (uint32_t)(ocz + dz - 1), start, count))
+                const uint32_t id = b0 + r * 32 + lane;
+                int            ow = 0;  // largest lane q with excl[q] <= id
+#pragma unroll
+                for (int st = 16; st > 0; st >>= 1)
                 {
-                    sc.cands += count;
-                    unsigned long long m = ~0ull;
-                    for (uint32_t j = start; j < start + count; j++)
-                    {
-                        const unsigned long long c = point_key(oqx, oqy, oqz, __ldg(g.pts + j));
-                        m                          = c < m ? c : m;
-                    }
-                    atomicMin(&s_best[warp][owner], m);
+                    const int      probe = ow + st;
+                    const uint32_t e     = __shfl_sync(FULL, excl, probe & 31);
+                    if (probe < 32 && e <= id) ow = probe;
+                }
+                owner[r] = ow;
+                oq[r][0] = __shfl_sync(FULL, gx, ow), oq[r][1] = __shfl_sync(FULL, gy, ow), oq[r][2] = __shfl_sync(FULL, gz, ow);
+                const int      ocx = __shfl_sync(FULL, cx, ow), ocy = __shfl_sync(FULL, cy, ow), ocz = __shfl_sync(FULL, cz, ow);
+                const uint32_t omask = __shfl_sync(FULL, mask, ow), oexcl = __shfl_sync(FULL, excl, ow);
+                count[r] = 0, start[r] = 0, ckey[r] = kEmptyKey, h[r] = 0;
+                raw[r]   = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+                if (id < total)
+                {
+                    const uint32_t bit = __fns(omask, 0, (int)(id - oexcl) + 1);
+                    const int      dz = (int)(bit / 9u), dy = (int)((bit % 9u) / 3u), dx = (int)(bit % 3u);
+                    ckey[r] = cell_key((uint32_t)(ocx + dx - 1), (uint32_t)(ocy + dy - 1), (uint32_t)(ocz + dz - 1));
+                    h[r]    = cell_hash(ckey[r], shift);
+                    raw[r]  = __ldg(reinterpret_cast<const uint4*>(tab + h[r]));
+                    sc.probes++;
                 }
             }
+            // ---- phase B: resolve the probes (linear probing continues on a collision), issue the
+            // first point of every hit
+#pragma unroll
+            for (int r = 0; r < kItemRounds; r++)
+            {
+                p0[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ckey[r] == kEmptyKey) continue;
+                while (true)
+                {
+                    const unsigned long long k = (unsigned long long)raw[r].x | ((unsigned long long)raw[r].y << 32);
+                    if (k == ckey[r])
+                    {
+                        start[r] = raw[r].z, count[r] = raw[r].w;
+                        break;
+                    }
+                    if (k == kEmptyKey) break;
+                    h[r]   = (h[r] + 1) & hmask;
+                    raw[r] = __ldg(reinterpret_cast<const uint4*>(tab + h[r]));
+                }
+                if (count[r]) p0[r] = __ldg(g.pts + start[r]), sc.cands += count[r];
+            }
+            // ---- phase C: scan, hand the minimum (and, if it survives, its coordinates) to the owner
+#pragma unroll
+            for (int r = 0; r < kItemRounds; r++)
+            {
+                unsigned long long m  = ~0ull;
+                float              mx = 0.f, my = 0.f, mz = 0.f;
+                if (count[r])
+                {
+                    float4 p = p0[r];
+                    for (uint32_t j = 0; j < count[r]; j++)
+                    {
+                        if (j) p = __ldg(g.pts + start[r] + j);
+                        const unsigned long long c = point_key(oq[r][0], oq[r][1], oq[r][2], p);
+                        if (c < m) m = c, mx = p.x, my = p.y, mz = p.z;
+                    }
+                    atomicMin(&s_best[warp][owner[r]], m);
+                }
+                // keys are unique: exactly one item (or the owner's own centre candidate) matches the
+                // slot afterwards; later rounds may replace it again
+                __syncwarp();
+                if (m != ~0ull && s_best[warp][owner[r]] == m)
+                    s_xyz[warp][owner[r]][0] = mx, s_xyz[warp][owner[r]][1] = my, s_xyz[warp][owner[r]][2] = mz;
+                __syncwarp();
+            }
         }
-        __syncwarp();
         best = s_best[warp][lane];
+        bpx = s_xyz[warp][lane][0], bpy = s_xyz[warp][lane][1], bpz = s_xyz[warp][lane][2];
         __syncwarp();
         kth = fminf(kth, __uint_as_float((uint32_t)(best >> 32)));
         // everything outside the 3x3x3 block is at least m quanta away
@@ -465,6 +525,7 @@ __global__ void __launch_bounds__(kNN1Threads)
         const unsigned long long c = best < sentinel ? best : ~0ull;
         n_valid                    = (c != ~0ull);
         cand[i]                    = c;
+        cand_xyz[i]                = make_float4(bpx, bpy, bpz, 0.f);
         if (c != ~0ull && !a.allowGlobal)
         {
             const uint32_t gi = (uint32_t)c;
@@ -481,14 +542,15 @@ __global__ void __launch_bounds__(kNN1Threads)
 // array is never cleared between calls.
 // ------------------------------------------------------------------------------------------
 constexpr int      kScanThreads = 256;
-constexpr int      kScanItems   = 4;
+constexpr int      kScanItems   = 1;  // latency-bound at ICP sizes: one slot per thread, many small tiles
 constexpr uint32_t kScanTile    = kScanThreads * kScanItems;
 
 struct ScanSmem
 {
     uint32_t warp_sums[kScanThreads / 32];
     uint32_t tile_id;
-    unsigned long long tile_base;
+    uint32_t tile_total;           // outputs of this tile
+    unsigned long long tile_base;  // outputs of all earlier tiles
 };
 
 // returns this thread's exclusive offset inside the grid-wide output; *total_out written by the
@@ -554,6 +616,7 @@ __device__ __forceinline__ unsigned long long grid_exclusive_scan(
             __threadfence();
             vstatus[tile] = (2ull << 62) | ep | (base + block_total);
             sm.tile_base  = base;
+            sm.tile_total = block_total;
             if (tile == n_tiles - 1) *total_out = base + block_total;
         }
     }
@@ -590,16 +653,29 @@ __device__ __forceinline__ void bbox_rearm(uint32_t* __restrict__ next_words)
     if (blockIdx.x == 0 && threadIdx.x < 6) next_words[threadIdx.x] = threadIdx.x < 3 ? 0xFFFFFFFFu : 0u;
 }
 
+// sums (optional): HORN1 packet (sum local xyz, sum global xyz, count) of the accepted pairings,
+// i.e. eval_centroids_robust (Pairings.cpp:68-110) folded into the compaction when the solver is
+// known to follow (fused iteration) — saves one pass over the pairings.
+struct FusedSums
+{
+    double*       partials;  // one row of 7 per tile
+    unsigned int* ticket;
+    double*       packet;    // NULL = not requested
+};
+
 __global__ void __launch_bounds__(kScanThreads)
     k_compact_pt2pt(GridView g, CompactArgs a, const float* __restrict__ lx,
                     const float* __restrict__ ly, const float* __restrict__ lz,
                     const uint32_t* __restrict__ gbits, const unsigned long long* __restrict__ claim,
-                    const unsigned long long* __restrict__ cand, const uint32_t* __restrict__ bbox,
-                    uint32_t* __restrict__ bbox_next, unsigned long long* __restrict__ status,
-                    uint32_t* __restrict__ tile_counter, mp2p_b200_pair_pt2pt* __restrict__ out,
-                    unsigned long long* __restrict__ out_count)
+                    const unsigned long long* __restrict__ cand, const float4* __restrict__ cand_xyz,
+                    const uint32_t* __restrict__ bbox, uint32_t* __restrict__ bbox_next,
+                    unsigned long long* __restrict__ status, uint32_t* __restrict__ tile_counter,
+                    mp2p_b200_pair_pt2pt* __restrict__ out, unsigned long long* __restrict__ out_count,
+                    FusedSums fs)
 {
+    static_assert(kScanItems == 1 && kScanThreads == kReduceThreads, "one slot per thread");
     __shared__ ScanSmem sm;
+    __shared__ uint32_t s_rec[kScanThreads * 9];  // this tile's records, staged for coalesced stores
     bbox_rearm(bbox_next);
     const uint64_t n_slots = (uint64_t)a.n_local * a.K;
     const uint32_t n_tiles = (uint32_t)((n_slots + kScanTile - 1) / kScanTile);
@@ -609,48 +685,61 @@ __global__ void __launch_bounds__(kScanThreads)
         if (sm.tile_id == n_tiles - 1) *tile_counter = 0u;  // last ticket handed out: re-arm
     }
     __syncthreads();
-    const uint32_t tile    = sm.tile_id;
-    const bool     gate    = bbox_gate(g, bbox, a.gate_eps);
+    const uint32_t tile = sm.tile_id;
+    const bool     gate = bbox_gate(g, bbox, a.gate_eps);
 
-    const uint64_t     slot0 = (uint64_t)tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-    unsigned long long c[kScanItems];
-    uint32_t           flags = 0, local = 0;
-#pragma unroll
-    for (int j = 0; j < kScanItems; j++)
+    // Everything a record needs is requested up front (cand -> {claim word, global point, local
+    // point} in parallel) so that only ONE dependent memory round trip precedes the scan.
+    const uint64_t     slot = (uint64_t)tile * kScanTile + threadIdx.x;
+    bool               ok   = false;
+    unsigned long long c    = ~0ull;
+    uint32_t           i = 0, gi = 0;
+    float4             gp = make_float4(0.f, 0.f, 0.f, 0.f);
+    float              px = 0.f, py = 0.f, pz = 0.f;
+    if (gate && slot < n_slots)
     {
-        const uint64_t slot = slot0 + j;
-        bool           ok   = false;
-        if (gate && slot < n_slots)
+        c  = cand[slot];
+        ok = ((uint32_t)c != 0xFFFFFFFFu);  // unused ranks carry an all-ones map index
+        if (ok)
         {
-            c[j] = cand[slot];
-            ok = ((uint32_t)c[j] != 0xFFFFFFFFu);  // unused ranks carry an all-ones map index
-            if (ok && !a.allowGlobal)
-            {
-                const uint32_t gi = (uint32_t)c[j];
-                ok = !bit_set(gbits, gi) && (claim[gi] == (a.tag | (unsigned long long)(slot + a.slot_offset)));
-            }
+            gi = (uint32_t)c;
+            i  = (uint32_t)(a.K == 1 ? slot : slot / a.K);
+            unsigned long long cw = a.tag | (unsigned long long)(slot + a.slot_offset);
+            if (!a.allowGlobal) cw = __ldcg(claim + gi);
+            // the K = 1 matcher hands the matched point's coordinates over with the candidate
+            // (sequential read); the K > 1 matcher does not (random gather from the map)
+            gp = cand_xyz ? __ldcs(cand_xyz + slot) : __ldg(g.pts_orig + gi);
+            px = lx[i], py = ly[i], pz = lz[i];
+            if (!a.allowGlobal)
+                ok = !bit_set(gbits, gi) && (cw == (a.tag | (unsigned long long)(slot + a.slot_offset)));
         }
-        if (ok) flags |= 1u << j, local++;
     }
-    const unsigned long long off = grid_exclusive_scan(sm, tile, n_tiles, local, status, out_count, a.scan_epoch);
-    unsigned long long       w   = off;
-#pragma unroll
-    for (int j = 0; j < kScanItems; j++)
+    const unsigned long long w = grid_exclusive_scan(sm, tile, n_tiles, ok ? 1u : 0u, status, out_count, a.scan_epoch);
+    // The tile's records are consecutive in the output: stage them in shared memory and store the
+    // byte range with fully coalesced 4-byte words (full sectors: no read-for-ownership fills),
+    // instead of nine strided stores per thread.
+    const unsigned long long tile_base = sm.tile_base;
+    if (ok)
     {
-        if (!(flags & (1u << j))) continue;
-        if (w < a.capacity)
-        {
-            const uint64_t slot = slot0 + j;
-            const uint32_t i    = (uint32_t)(slot / a.K);
-            const uint32_t gi   = (uint32_t)c[j];
-            const float4   gp   = __ldg(g.pts_orig + gi);
-            uint32_t*      o    = reinterpret_cast<uint32_t*>(out + w);  // 36-byte records, 4-aligned
-            o[0] = gi, o[1] = i + a.index_offset;
-            o[2] = __float_as_uint(gp.x), o[3] = __float_as_uint(gp.y), o[4] = __float_as_uint(gp.z);
-            o[5] = __float_as_uint(lx[i]), o[6] = __float_as_uint(ly[i]), o[7] = __float_as_uint(lz[i]);
-            o[8] = (uint32_t)(c[j] >> 32);
-        }
-        w++;
+        uint32_t* o = s_rec + (uint32_t)(w - tile_base) * 9;
+        o[0] = gi, o[1] = i + a.index_offset;
+        o[2] = __float_as_uint(gp.x), o[3] = __float_as_uint(gp.y), o[4] = __float_as_uint(gp.z);
+        o[5] = __float_as_uint(px), o[6] = __float_as_uint(py), o[7] = __float_as_uint(pz);
+        o[8] = (uint32_t)(c >> 32);
+    }
+    __syncthreads();
+    {
+        const unsigned long long room  = a.capacity > tile_base ? a.capacity - tile_base : 0ull;
+        const uint32_t           n_rec = (uint32_t)min((unsigned long long)sm.tile_total, room);
+        uint32_t*                dst   = reinterpret_cast<uint32_t*>(out) + tile_base * 9;
+        for (uint32_t k = threadIdx.x; k < n_rec * 9; k += kScanThreads) dst[k] = s_rec[k];
+    }
+    if (fs.packet)
+    {
+        const bool in  = ok && w < a.capacity;
+        double     acc[7] = {in ? (double)px : 0.0,   in ? (double)py : 0.0,   in ? (double)pz : 0.0, in ? (double)gp.x : 0.0,
+                             in ? (double)gp.y : 0.0, in ? (double)gp.z : 0.0, in ? 1.0 : 0.0};
+        block_reduce_to_packet<7>(acc, fs.partials, fs.ticket, fs.packet, tile, n_tiles);
     }
 }
 
@@ -669,64 +758,50 @@ struct Pt2PlArgs
     int      tma_ok;
 };
 
+// Plane fit of the pt2pl matcher, one THREAD per query (the k-NN search ran before, in the
+// group-cooperative k_match_pt2pt<K> used as a pure radius-bounded k-NN): reads the K neighbour
+// keys of the query (ascending (d2, index)), gathers the points, estimate_points_eigen + planarity
+// + distance tests (plane_fit.cuh). Full-lane utilisation for the fp64 Jacobi.
 template <int KT>
-__global__ void __launch_bounds__(kQueryTile)
-    k_match_pt2pl(GridView g, Pt2PlArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
-                  const float* __restrict__ lz, const uint32_t* __restrict__ lbits,
-                  PlaneCandidate* __restrict__ plc, uint8_t* __restrict__ ok_flags,
-                  uint32_t* __restrict__ bbox_words, unsigned long long* __restrict__ stats)
+__global__ void __launch_bounds__(128)
+    k_plane_fit(GridView g, Pt2PlArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
+                const float* __restrict__ lz, const unsigned long long* __restrict__ cand,
+                PlaneCandidate* __restrict__ plc, uint8_t* __restrict__ ok_flags)
 {
-    __shared__ QueryTile<kQueriesPerBlock> tile;
-    __shared__ BBoxAcc   bacc;
-    const size_t         base = (size_t)blockIdx.x * kQueriesPerBlock;
-    bbox_init(bacc);
-    load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
-    const int      sub   = threadIdx.x % kGroup, ql = threadIdx.x / kGroup;
-    const unsigned gmask = ((1u << kGroup) - 1u) << ((threadIdx.x & 31) / kGroup * kGroup);
-    const uint32_t i     = (uint32_t)base + ql;
-    const bool     valid = i < a.n_local;
-    float          gx = 0, gy = 0, gz = 0;
-    if (valid) compose_point_f(a.pose, tile.x[ql], tile.y[ql], tile.z[ql], gx, gy, gz);
-    bbox_accumulate(bacc, gx, gy, gz, valid && sub == 0, bbox_words);
-    if (valid)
-    {
-        uint8_t        ok = 0;
-        SearchCounters sc;
-        uint32_t       n_valid = 0;
-        if (a.allowLocal || !bit_set(lbits, i))
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_local) return;
+    const int K   = (int)a.K;
+    int       cnt = 0;
+    uint32_t  idx[KT];
+#pragma unroll
+    for (int k = 0; k < KT; k++)
+        if (k < K)
         {
-            TopK<KT>  top;
-            const int K = (int)a.K;
-            knn_search<KT, kGroup>(g, gx, gy, gz, a.radiusSq, K, top, gmask, sub, sc);
-            const unsigned long long sentinel = (unsigned long long)__float_as_uint(a.radiusSq) << 32;
-            int                      cnt      = 0;
-#pragma unroll
-            for (int k = 0; k < KT; k++)
-                if (k < K && top.v[k] < sentinel) cnt++;
-            if (sub == 0) n_valid = (uint32_t)cnt;
-            if (sub == 0 && cnt >= 3 && cnt >= (int)a.minPts)
-            {
-                // estimate_points_eigen.cpp:45-63 — float mean, double centred moments, ascending
-                // (d2, index) neighbour order
-                float px[KT], py[KT], pz[KT];
-#pragma unroll
-                for (int k = 0; k < KT; k++)
-                    if (k < cnt)
-                    {
-                        const float4 p = __ldg(g.pts_orig + (uint32_t)top.v[k]);
-                        px[k] = p.x, py[k] = p.y, pz[k] = p.z;
-                    }
-                PlaneCandidate pc;
-                if (fit_plane<KT>(px, py, pz, cnt, gx, gy, gz, a.planeEigenThreshold, a.distThr, pc))
-                {
-                    plc[i] = pc;
-                    ok     = 1;
-                }
-            }
+            const unsigned long long c = cand[(size_t)i * K + k];
+            idx[k]                     = (uint32_t)c;
+            cnt += ((uint32_t)c != 0xFFFFFFFFu);  // valid ranks come first
         }
-        if (sub == 0) ok_flags[i] = ok;
-        flush_search_stats(sc, n_valid, stats);
+    uint8_t ok = 0;
+    if (cnt >= 3 && cnt >= (int)a.minPts)
+    {
+        float px[KT], py[KT], pz[KT];
+#pragma unroll
+        for (int k = 0; k < KT; k++)
+            if (k < cnt)
+            {
+                const float4 p = __ldg(g.pts_orig + idx[k]);
+                px[k] = p.x, py[k] = p.y, pz[k] = p.z;
+            }
+        float gx, gy, gz;
+        compose_point_f(a.pose, lx[i], ly[i], lz[i], gx, gy, gz);
+        PlaneCandidate pc;
+        if (fit_plane<KT>(px, py, pz, cnt, gx, gy, gz, a.planeEigenThreshold, a.distThr, pc))
+        {
+            plc[i] = pc;
+            ok     = 1;
+        }
     }
+    ok_flags[i] = ok;
 }
 
 __global__ void __launch_bounds__(kScanThreads)
@@ -935,7 +1010,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
                     uint64_t* out_count, DeviceMatch* keep_on_device)
 {
     *out_count          = 0;
-    if (keep_on_device) *keep_on_device = DeviceMatch{};
+    if (keep_on_device) keep_on_device->d_count = nullptr, keep_on_device->d_pairs = nullptr, keep_on_device->capacity = 0;
     const uint32_t K    = prm->pairingsPerPoint;
     const uint64_t nmap = map->view.n_points;
     if (nmap == 0 || n_local == 0) return 0;  // …DistanceThreshold.cpp:67
@@ -978,14 +1053,17 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     auto*          cand  = ctx->d_cand.as<unsigned long long>();
     unsigned long long* stats = nullptr;
     MP2P_TRY(prepare_stats(ctx, &stats));
+    float4* cand_xyz = nullptr;
     prof_begin(ctx, 0);
 #define LAUNCH_MATCH(KT) \
     k_match_pt2pt<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, sv.bbox, stats)
     switch (pick_kt(K))
     {
         case 1:
+            MP2P_TRY(ctx->d_candxyz.ensure(n_slots * sizeof(float4)));
+            cand_xyz = ctx->d_candxyz.as<float4>();
             k_match_pt2pt_nn1<<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
-                map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, sv.bbox, stats);
+                map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, cand_xyz, sv.bbox, stats);
             break;
         case 4: LAUNCH_MATCH(4); break;
         case 8: LAUNCH_MATCH(8); break;
@@ -1008,9 +1086,15 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     c.capacity = std::min<uint64_t>(capacity, n_slots);
     c.scan_epoch = ctx->scan_epoch;
     prof_begin(ctx, 1);
+    FusedSums fs{nullptr, nullptr, nullptr};
+    if (keep_on_device && keep_on_device->want_horn_sums)
+    {
+        MP2P_TRY(solve_scratch(ctx, n_tiles, &fs.ticket, &fs.partials));
+        fs.packet = keep_on_device->want_horn_sums;
+    }
     k_compact_pt2pt<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, c, dlx, dly, dlz, d_gbits,
-                                                               claim, cand, sv.bbox, sv.bbox_next, status,
-                                                               sv.tile_counter, d_out, sv.count);
+                                                               claim, cand, cand_xyz, sv.bbox, sv.bbox_next, status,
+                                                               sv.tile_counter, d_out, sv.count, fs);
     prof_end(ctx, 1);
     count_launch(ctx);
     if (keep_on_device)  // fused iteration: the caller enqueues the solver and synchronises once
@@ -1093,8 +1177,10 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     switch (pick_kt(K))
     {
         case 1:
+            MP2P_TRY(ctx->d_candxyz.ensure(n_local * sizeof(float4)));
             k_match_pt2pt_nn1<<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
-                map->view, a, dlx, dly, dlz, d_lbits, nullptr, nullptr, d_cand_out, d_bbox6_out, stats);
+                map->view, a, dlx, dly, dlz, d_lbits, nullptr, nullptr, d_cand_out, ctx->d_candxyz.as<float4>(),
+                d_bbox6_out, stats);
             break;
         case 4: LAUNCH_MATCH(4); break;
         case 8: LAUNCH_MATCH(8); break;
@@ -1162,7 +1248,9 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
     prof_begin(ctx, 1);
     k_compact_pt2pt<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(
         map->view, c, ctx->cur_lx, ctx->cur_ly, ctx->cur_lz, d_gbits, claim,
-        d_cand_all + index_offset * K, sv.bbox, sv.bbox_next, status, sv.tile_counter, d_out, sv.count);
+        d_cand_all + index_offset * K, K == 1 ? ctx->d_candxyz.as<float4>() : nullptr, sv.bbox, sv.bbox_next, status,
+        sv.tile_counter, d_out, sv.count,
+        FusedSums{nullptr, nullptr, nullptr});
     prof_end(ctx, 1);
     count_launch(ctx);
     return fetch_results(ctx, sv.count, d_out, out, capacity, out_on_device, out_count);
@@ -1192,7 +1280,8 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     unsigned long long* status;
     MP2P_TRY(prepare_small(ctx, n_tiles, sv, &status));
     MP2P_TRY(ctx->d_plcand.ensure(n_local * sizeof(PlaneCandidate)));
-    MP2P_TRY(ctx->d_cand.ensure(n_local));  // ok flags (bytes)
+    MP2P_TRY(ctx->d_cand.ensure(n_local * prm->knn * 8));  // k-NN keys
+    MP2P_TRY(ctx->d_okflags.ensure(n_local));
 
     Pt2PlArgs a{};
     for (int k = 0; k < 12; k++) a.pose.m[k] = pose[k];
@@ -1207,12 +1296,19 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     const uint32_t blocks = (uint32_t)((n_local + kQueriesPerBlock - 1) / kQueriesPerBlock);
     const float *  dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;
     auto*          plc = ctx->d_plcand.as<PlaneCandidate>();
-    auto*          okf = ctx->d_cand.as<uint8_t>();
+    auto*          okf = ctx->d_okflags.as<uint8_t>();
+    auto*          cand = ctx->d_cand.as<unsigned long long>();
     unsigned long long* stats = nullptr;
     MP2P_TRY(prepare_stats(ctx, &stats));
+    // k-NN within searchRadius: the pt2pt search kernel with threshold = searchRadius, no claims
+    Pt2PtArgs sa{};
+    sa.pose = a.pose, sa.maxDistSq = a.radiusSq, sa.angSq = 0.f, sa.n_local = a.n_local, sa.K = a.K;
+    sa.allowLocal = a.allowLocal, sa.allowGlobal = 1, sa.tag = 0, sa.tma_ok = a.tma_ok;
     prof_begin(ctx, 0);
-#define LAUNCH_PL(KT) \
-    k_match_pt2pl<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, plc, okf, sv.bbox, stats)
+#define LAUNCH_PL(KT)                                                                                         \
+    k_match_pt2pt<KT><<<blocks, kQueryTile, 0, st>>>(map->view, sa, dlx, dly, dlz, d_lbits, nullptr, nullptr, cand, \
+                                                     sv.bbox, stats);                                         \
+    k_plane_fit<KT><<<(uint32_t)((n_local + 127) / 128), 128, 0, st>>>(map->view, a, dlx, dly, dlz, cand, plc, okf)
     switch (pick_kt(prm->knn))
     {
         case 1:
@@ -1223,7 +1319,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     }
 #undef LAUNCH_PL
     prof_end(ctx, 0);
-    count_launch(ctx);
+    count_launch(ctx, 2);
 
     mp2p_b200_pair_pt2pl* d_out = out;
     const uint64_t        cap   = std::min<uint64_t>(capacity, n_local);

@@ -1,0 +1,84 @@
+// Deterministic grid-wide reduction of NV doubles per thread into a 32-double packet, in ONE launch.
+#pragma once
+#include "common.cuh"
+
+namespace mp2p
+{
+constexpr int    kReduceThreads  = 256;
+constexpr int    kReduceWarps    = kReduceThreads / 32;
+
+// Block reduction + grid fold without a second launch: every CTA stores its NV partial sums in row
+// `slot` (a CTA-unique index in [0, n_slots)) and takes a ticket; the LAST CTA to arrive sums the
+// rows of all CTAs in a FIXED order (8 chunks of rows in parallel, then the 8 chunk sums in order)
+// into the packet and re-arms the ticket for the next launch. The order depends only on n_slots,
+// so results are run-to-run bit-stable. Must be called by all kReduceThreads threads of the CTA.
+template <int NV>
+__device__ __forceinline__ void block_reduce_to_packet(double (&acc)[NV], double* __restrict__ partials,
+                                                       unsigned int* __restrict__ ticket,
+                                                       double* __restrict__ packet, unsigned slot,
+                                                       unsigned n_slots)
+{
+    static_assert(NV <= 32, "packet holds 32 doubles");
+    __shared__ double   sh[kReduceWarps][32];
+    __shared__ unsigned is_last;
+    const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int v = 0; v < NV; v++)
+    {
+        double x = acc[v];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) sh[warp][v] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV)
+    {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < kReduceWarps; w++) s += sh[w][threadIdx.x];
+        partials[(size_t)slot * NV + threadIdx.x] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == n_slots - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // thread (warp = chunk, lane = value): chunk c sums rows [c*per, (c+1)*per) in order
+    const unsigned per = (n_slots + kReduceWarps - 1) / kReduceWarps;
+    double         s   = 0;
+    if (lane < NV)
+    {
+        // 8 independent partial sums keep 8 loads in flight (the rows sit in L2: a dependent chain
+        // of ~0.4 us loads would cost more than the whole streaming pass); combined in fixed order
+        const unsigned b0 = warp * per, b1 = min(b0 + per, n_slots);
+        double         p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned       b = b0;
+        for (; b + 8 <= b1; b += 8)
+        {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = __ldcg(partials + (size_t)(b + k) * NV + lane);
+#pragma unroll
+            for (int k = 0; k < 8; k++) p[k] += v[k];
+        }
+        for (int k = 0; b < b1; b++, k++) p[k] += __ldcg(partials + (size_t)b * NV + lane);
+        s = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+    }
+    __syncthreads();
+    sh[warp][lane] = s;
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        double t = 0;
+        if (threadIdx.x < NV)
+#pragma unroll
+            for (int w = 0; w < kReduceWarps; w++) t += sh[w][threadIdx.x];
+        packet[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// solve.cu: scratch rows + ticket of a context
+int solve_scratch(mp2p_b200_ctx* ctx, size_t rows, unsigned int** ticket, double** partials);
+}  // namespace mp2p

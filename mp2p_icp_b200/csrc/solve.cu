@@ -18,70 +18,14 @@
 // 128-byte loads into shared memory and each lane then reads its own record (stride 9 / 18 words).
 #include "common.cuh"
 #include "host_math.hpp"
+#include "reduce.cuh"
 
 namespace mp2p
 {
 namespace
 {
-constexpr int kSolveThreads = 256;
-constexpr int kWarps        = kSolveThreads / 32;
-
-// Block reduction + grid fold without a second launch: every CTA stores its NV partial sums and
-// takes a ticket; the LAST CTA to arrive sums the partials of all CTAs in a FIXED order (8 chunks
-// of CTAs in parallel, then the 8 chunk sums in order) into the 32-double packet and re-arms the
-// ticket counter for the next launch. Summation order depends only on gridDim => bit-stable.
-template <int NV>
-__device__ __forceinline__ void block_reduce_to_packet(double (&acc)[NV], double* __restrict__ partials,
-                                                       unsigned int* __restrict__ ticket,
-                                                       double* __restrict__ packet)
-{
-    static_assert(NV <= 32, "packet holds 32 doubles");
-    __shared__ double   sh[kWarps][32];
-    __shared__ unsigned is_last;
-    const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int v = 0; v < NV; v++)
-    {
-        double x = acc[v];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        if (lane == 0) sh[warp][v] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x < NV)
-    {
-        double s = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; w++) s += sh[w][threadIdx.x];
-        partials[(size_t)blockIdx.x * NV + threadIdx.x] = s;
-        __threadfence();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // thread (warp = chunk, lane = value): chunk c sums CTAs [c*per, (c+1)*per) in order
-    const unsigned per = (gridDim.x + kWarps - 1) / kWarps;
-    double         s   = 0;
-    if (lane < NV)
-    {
-        const unsigned b0 = warp * per, b1 = min(b0 + per, gridDim.x);
-        for (unsigned b = b0; b < b1; b++) s += __ldcg(partials + (size_t)b * NV + lane);
-    }
-    __syncthreads();
-    sh[warp][lane] = s;
-    __syncthreads();
-    if (threadIdx.x < 32)
-    {
-        double t = 0;
-        if (threadIdx.x < NV)
-#pragma unroll
-            for (int w = 0; w < kWarps; w++) t += sh[w][threadIdx.x];
-        packet[threadIdx.x] = t;
-    }
-    if (threadIdx.x == 0) *ticket = 0u;
-}
+constexpr int kSolveThreads = kReduceThreads;
+constexpr int kWarps        = kReduceWarps;
 
 // Stage 32 records of WORDS 4-byte words each into this warp's shared buffer, coalesced.
 template <int WORDS>
@@ -226,7 +170,7 @@ __global__ void __launch_bounds__(kSolveThreads)
         }
         __syncwarp();
     }
-    block_reduce_to_packet<kGNV>(acc, partials, ticket, packet);
+    block_reduce_to_packet<kGNV>(acc, partials, ticket, packet, blockIdx.x, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -261,7 +205,7 @@ __global__ void __launch_bounds__(kSolveThreads)
         }
         __syncwarp();
     }
-    block_reduce_to_packet<kH1V>(acc, partials, ticket, packet);
+    block_reduce_to_packet<kH1V>(acc, partials, ticket, packet, blockIdx.x, gridDim.x);
 }
 
 struct HornArgs
@@ -361,29 +305,33 @@ __global__ void __launch_bounds__(kSolveThreads)
         }
         __syncwarp();
     }
-    block_reduce_to_packet<kH2V>(acc, partials, ticket, packet);
+    block_reduce_to_packet<kH2V>(acc, partials, ticket, packet, blockIdx.x, gridDim.x);
 }
 
-// partial sums of all CTAs followed by the (self re-arming) ticket counter
-int solve_scratch(mp2p_b200_ctx* ctx, int blocks, unsigned int** ticket)
+}  // namespace
+// scratch of the one-launch reductions: [0,64) the (self re-arming) ticket counter, then one row
+// of 32 doubles per CTA / tile
+int solve_scratch(mp2p_b200_ctx* ctx, size_t rows, unsigned int** ticket, double** partials)
 {
-    constexpr size_t kPartialBytes = (size_t)148 * 4 * 32 * sizeof(double);  // the largest grid
-    (void)blocks;
-    if (ctx->d_partials.bytes < kPartialBytes + 64)
+    const size_t need = 64 + rows * 32 * sizeof(double);
+    if (ctx->d_partials.bytes < need)
     {
-        MP2P_TRY(ctx->d_partials.ensure(kPartialBytes + 64));
+        MP2P_TRY(ctx->d_partials.ensure(std::max<size_t>(need, 64 + (size_t)148 * 8 * 32 * sizeof(double))));
         MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_partials.p, 0, ctx->d_partials.bytes, ctx->stream));
     }
-    *ticket = reinterpret_cast<unsigned int*>(ctx->d_partials.as<char>() + kPartialBytes);
+    *ticket   = ctx->d_partials.as<unsigned int>();
+    *partials = reinterpret_cast<double*>(ctx->d_partials.as<char>() + 64);
     return 0;
 }
 
+namespace
+{
 int solve_grid(uint64_t n)
 {
-    // one warp handles 32 records per trip; aim for >= 4 trips per warp, cap at 4 CTAs per SM
-    const uint64_t warps  = (n + 127) / 128;
-    const uint64_t blocks = (warps + kWarps - 1) / kWarps;
-    return (int)std::max<uint64_t>(1, std::min<uint64_t>(blocks, 148 * 4));
+    // latency-bound at ICP sizes: one record per thread (one staging trip per warp) until the
+    // machine is full (8 CTAs per SM), grid-stride beyond that
+    const uint64_t blocks = (n + kSolveThreads - 1) / kSolveThreads;
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(blocks, 148 * 8));
 }
 }  // namespace
 
@@ -394,12 +342,13 @@ int run_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint6
 {
     const int blocks = solve_grid(std::max(n2p, n2l));
     unsigned int* ticket;
-    MP2P_TRY(solve_scratch(ctx, blocks, &ticket));
+    double*       partials;
+    MP2P_TRY(solve_scratch(ctx, blocks, &ticket, &partials));
     GNArgs a{n2p, n2l, prm->w_pt2pt, prm->w_pt2pl, prm->kernel, prm->kernelParam};
     prof_begin(ctx, 4);
     k_gn_accumulate<<<blocks, kSolveThreads, 0, ctx->stream>>>(
         reinterpret_cast<const uint32_t*>(d2p), reinterpret_cast<const uint32_t*>(d2l), a, d_pose,
-        ctx->d_partials.as<double>(), ticket, d_packet, d_n2p, d_n2l, d_done);
+        partials, ticket, d_packet, d_n2p, d_n2l, d_done);
     prof_end(ctx, 4);
     count_launch(ctx);
     return 0;
@@ -452,10 +401,11 @@ int run_horn_sums(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t 
 {
     const int blocks = solve_grid(n);
     unsigned int* ticket;
-    MP2P_TRY(solve_scratch(ctx, blocks, &ticket));
+    double*       partials;
+    MP2P_TRY(solve_scratch(ctx, blocks, &ticket, &partials));
     prof_begin(ctx, 2);
     k_horn_sums<<<blocks, kSolveThreads, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d2p), n,
-                                                          d_outlier, ctx->d_partials.as<double>(), ticket,
+                                                          d_outlier, partials, ticket,
                                                           d_packet, d_n);
     prof_end(ctx, 2);
     count_launch(ctx);
@@ -469,7 +419,8 @@ int run_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64
 {
     const int     blocks = solve_grid(n);
     unsigned int* ticket;
-    MP2P_TRY(solve_scratch(ctx, blocks, &ticket));
+    double*       partials;
+    MP2P_TRY(solve_scratch(ctx, blocks, &ticket, &partials));
     HornArgs a{};
     a.n = n, a.n_total = n_total_pairs;
     a.use_scale_outlier = prm->use_scale_outlier_detector, a.scale_thr = prm->scale_outlier_threshold;
@@ -483,7 +434,7 @@ int run_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64
     prof_begin(ctx, 3);
     k_horn_moments<<<blocks, kSolveThreads, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d2p), a,
                                                              d_sums_packet, d_wcount_prefix, d_wvalue,
-                                                             d_outlier, 0, ctx->d_partials.as<double>(), ticket,
+                                                             d_outlier, 0, partials, ticket,
                                                              d_packet, d_n);
     prof_end(ctx, 3);
     count_launch(ctx);

@@ -394,7 +394,7 @@ def test_fused_iteration_pt2pt_horn_equals_two_calls(ctx):
     for _ in range(3):
         ok, T, n = step(guess)
         assert ok and ok_ref and n == len(pairs)
-        assert np.array_equal(T, T_ref)  # same kernels, same fixed-order reductions
+        assert_pose_close(T, T_ref, 1e-9)  # same kernels; the reduction grid differs (capacity vs count)
     got = d_pairs.cpu().numpy().view(b200.PAIR_PT2PT)[:n]
     assert got.tobytes() == pairs.tobytes()
     ok0, T0 = orc.optimal_tf_horn(pairs)
@@ -416,7 +416,8 @@ def test_fused_iteration_pt2pl_gn_equals_two_calls(ctx):
     torch.cuda.synchronize()
     step = gmap.make_iterator(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), len(S), b200.Pt2PlParams(**mkw), b200.GNParams(**skw))
     ok, T, n = step(guess)
-    assert ok and n == len(pairs) and np.array_equal(T, T_ref)
+    assert ok and n == len(pairs)
+    assert_pose_close(T, T_ref, 1e-9)
     tree = orc.KDTree(*xyz(M))
     p0, _ = orc.match_pt2pl(tree, *xyz(S), guess, orc.MatchPt2PlParams(**mkw), nthreads=8)
     ok0, T0, it0 = orc.optimal_tf_gauss_newton(None, p0, orc.GNParams(**skw), guess, nthreads=8)
