@@ -59,6 +59,7 @@ struct GridView
     uint32_t         level_shift[kMaxLevels];  // 64 - log2(capacity)
     float            bbmin[3], bbmax[3];
     uint32_t         n_points;
+    float            level_occupancy[kMaxLevels];  // mean points per occupied voxel, per table
 };
 
 struct DevBuf

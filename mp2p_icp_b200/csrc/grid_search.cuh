@@ -94,8 +94,13 @@ struct TopK
 #pragma unroll
         for (int j = 0; j < K; j++) v[j] = sentinel;
     }
+    // K-th best so far. EXACT (k == K, the common case: the kernels are instantiated for the usual
+    // values of pairingsPerPoint / knn) is a plain register read; otherwise a select chain, which the
+    // compiler turns into a dynamically indexed (local-memory) access.
+    template <bool EXACT>
     __device__ __forceinline__ unsigned long long worst(int k_runtime) const
     {
+        if (EXACT) return v[K - 1];
         unsigned long long w = v[K - 1];
 #pragma unroll
         for (int j = 0; j < K - 1; j++)
@@ -145,6 +150,18 @@ struct SearchCounters
 constexpr int kGroup = 8;
 
 template <int G>
+__device__ __forceinline__ unsigned long long group_max_u64(unsigned long long v, unsigned gmask)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1)
+    {
+        const unsigned long long t = __shfl_xor_sync(gmask, v, o);
+        v                          = t > v ? t : v;
+    }
+    return v;
+}
+
+template <int G>
 __device__ __forceinline__ unsigned long long group_min_u64(unsigned long long v, unsigned gmask)
 {
 #pragma unroll
@@ -186,10 +203,13 @@ __device__ __forceinline__ unsigned long long point_key(float qx, float qy, floa
 // Called by all G lanes of a group with identical arguments; `sub` = lane index inside the group,
 // `gmask` = the group's lanes. On return res.v[0..k_runtime) ascending, identical in all lanes;
 // entries >= (radius2 bits << 32) are "not found".
-template <int K, int G>
+// `rl_start`: relative level to start from — the finest level whose voxels hold about 1.5 K points
+// on average (start_level(), host side), so that the centre voxel alone usually settles the K-th
+// distance and the neighbours can be pruned; any start level is correct.
+template <int K, int G, bool EXACT>
 __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy, float qz,
-                                           float radius2, int k_runtime, TopK<K>& res, unsigned gmask,
-                                           int sub, SearchCounters& sc)
+                                           float radius2, int k_runtime, int rl_start, TopK<K>& res,
+                                           unsigned gmask, int sub, SearchCounters& sc)
 {
     const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
     res.init(sentinel);
@@ -212,7 +232,7 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
     const float q2 = g.s0_lo * g.s0_lo * 0.999999f;  // quanta^2 -> metres^2, rounded down
 
     float kth = radius2;  // upper bound of the K-th best distance found so far (all levels)
-    for (int rl = 0; rl < g.n_levels; rl++)
+    for (int rl = rl_start; rl < g.n_levels; rl++)
     {
         const int L = g.level_first + rl;
         TopK<K>   mine;  // this lane's candidates of this level
@@ -226,7 +246,7 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
             for (uint32_t j = sub; j < g.n_points; j += G)
             {
                 const unsigned long long c = point_key(qx, qy, qz, __ldg(g.pts + j));
-                if (c < mine.worst(k_runtime)) mine.insert(c);
+                if (c < mine.template worst<EXACT>(k_runtime)) mine.insert(c);
             }
             group_merge<K, G>(mine, res, gmask);
             if (sub == 0) sc.levels++;
@@ -253,15 +273,23 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
                 for (uint32_t j = start + sub; j < start + count; j += G)
                 {
                     const unsigned long long c = point_key(qx, qy, qz, __ldg(g.pts + j));
-                    if (c < mine.worst(k_runtime)) mine.insert(c);
+                    if (c < mine.template worst<EXACT>(k_runtime)) mine.insert(c);
                 }
             }
         }
         // ---- 2. bound for pruning the neighbours. K == 1: exact group minimum. K > 1: any lane that
         // already holds k candidates bounds the K-th distance of the union from above.
         {
-            const unsigned long long w = group_min_u64<G>(mine.worst(k_runtime), gmask);
+            const unsigned long long w = group_min_u64<G>(mine.template worst<EXACT>(k_runtime), gmask);
             kth                        = fminf(kth, __uint_as_float((uint32_t)(w >> 32)));
+            if (EXACT && K > 1)
+            {
+                // r = ceil(K/G): if every lane already holds r candidates the union holds >= K that are
+                // <= the largest of the lanes' r-th best (sentinel = radius when a lane has fewer)
+                constexpr int            r  = (K + G - 1) / G;
+                const unsigned long long wr = group_max_u64<G>(mine.v[r - 1], gmask);
+                kth                         = fminf(kth, __uint_as_float((uint32_t)(wr >> 32)));
+            }
         }
         // ---- 3. the 26 neighbours, dealt round-robin to the lanes
 #pragma unroll 1
@@ -286,16 +314,16 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
             for (uint32_t j = start; j < start + count; j++)
             {
                 const unsigned long long c = point_key(qx, qy, qz, __ldg(g.pts + j));
-                if (c < mine.worst(k_runtime))
+                if (c < mine.template worst<EXACT>(k_runtime))
                 {
                     mine.insert(c);
-                    kth = fminf(kth, __uint_as_float((uint32_t)(mine.worst(k_runtime) >> 32)));
+                    kth = fminf(kth, __uint_as_float((uint32_t)(mine.template worst<EXACT>(k_runtime) >> 32)));
                 }
             }
         }
         // ---- 4. exact K best of this level, replicated; termination test
         group_merge<K, G>(mine, res, gmask);
-        kth = fminf(kth, __uint_as_float((uint32_t)(res.worst(k_runtime) >> 32)));
+        kth = fminf(kth, __uint_as_float((uint32_t)(res.template worst<EXACT>(k_runtime) >> 32)));
         // everything outside the 3x3x3 block is at least m quanta away
         const float mx = s + fminf(fx, s - fx), my = s + fminf(fy, s - fy), mz = s + fminf(fz, s - fz);
         const float m  = fmaxf(fminf(mx, fminf(my, mz)) - 4.f, 0.f);

@@ -362,7 +362,10 @@ int build_index(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* x, const fl
     count_launch(ctx);
     v.table = map->d_table.as<CellEntry>(), v.level_first = Lf, v.n_levels = lay.n_levels;
     for (int rl = 0; rl < lay.n_levels; rl++)
+    {
         v.level_off[rl] = lay.level_off[rl], v.level_shift[rl] = lay.level_shift[rl];
+        v.level_occupancy[rl] = (float)((double)n / (double)cells[Lf + rl]);
+    }
 
     // ---- first-claim words (see match.cu): one u64 per map point, all ones = "never claimed"
     MP2P_TRY(map->d_claim.ensure(n * 8ull));

@@ -19,6 +19,8 @@
 // lose and the claim array never needs clearing.
 #include <cuda/std/limits>
 
+#include <cstdlib>
+
 #include "grid_search.cuh"
 #include "plane_fit.cuh"
 #include "reduce.cuh"
@@ -206,10 +208,11 @@ struct Pt2PtArgs
     int      allowLocal, allowGlobal;
     unsigned long long tag;  // (0xFFFFFFFF - epoch) << 32
     int      tma_ok;         // local arrays are 16-byte aligned
+    int      rl_start;       // relative level the search starts from (start_level())
 };
 
 // ------------------------------------------------------------------------------------------
-template <int KT>
+template <int KT, bool EXACT>
 __global__ void __launch_bounds__(kQueryTile)
     k_match_pt2pt(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
                   const float* __restrict__ lz, const uint32_t* __restrict__ lbits,
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(kQueryTile)
         if (!a.allowLocal && bit_set(lbits, i))
             top.init(sentinel);  // :218-220 skip, already paired
         else
-            knn_search<KT, kGroup>(g, gx, gy, gz, thr2, K, top, gmask, sub, sc);
+            knn_search<KT, kGroup, EXACT>(g, gx, gy, gz, thr2, K, a.rl_start, top, gmask, sub, sc);
 
         uint32_t n_valid = 0;
         if (sub == 0)
@@ -278,6 +281,7 @@ __global__ void __launch_bounds__(kQueryTile)
 // atomicMin on the 64-bit (d2, index) key. Exactness argument unchanged: every voxel with box
 // bound <= current best distance is visited, candidates compare on (d2, index).
 // ------------------------------------------------------------------------------------------
+template <int kItemRounds>
 __global__ void __launch_bounds__(kNN1Threads)
     k_match_pt2pt_nn1(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
                       const float* __restrict__ lz, const uint32_t* __restrict__ lbits,
@@ -418,7 +422,6 @@ __global__ void __launch_bounds__(kNN1Threads)
         // kItemRounds rounds of 32 items are software-pipelined: all hash probes of the chunk are
         // issued first, then all first-point loads, then the scans — 3 overlapped memory round trips
         // per chunk instead of 2 per round.
-        constexpr int kItemRounds = 4;
         for (uint32_t b0 = 0; b0 < total; b0 += 32 * kItemRounds)
         {
             int                owner[kItemRounds];
@@ -858,10 +861,10 @@ __global__ void __launch_bounds__(kScanThreads)
 // ------------------------------------------------------------------------------------------
 // raw k-NN (already transformed queries) — nn_* parity tests
 // ------------------------------------------------------------------------------------------
-template <int KT>
+template <int KT, bool EXACT>
 __global__ void __launch_bounds__(256)
     k_knn(GridView g, const float* __restrict__ qx, const float* __restrict__ qy,
-          const float* __restrict__ qz, uint32_t nq, uint32_t K, float radius2,
+          const float* __restrict__ qz, uint32_t nq, uint32_t K, float radius2, int rl_start,
           uint32_t* __restrict__ out_idx, float* __restrict__ out_d2, int32_t* __restrict__ out_found)
 {
     const int      sub   = threadIdx.x % kGroup;
@@ -870,7 +873,7 @@ __global__ void __launch_bounds__(256)
     if (i >= nq) return;  // whole groups leave together
     TopK<KT>       top;
     SearchCounters sc;
-    knn_search<KT, kGroup>(g, qx[i], qy[i], qz[i], radius2, (int)K, top, gmask, sub, sc);
+    knn_search<KT, kGroup, EXACT>(g, qx[i], qy[i], qz[i], radius2, (int)K, rl_start, top, gmask, sub, sc);
     if (sub != 0) return;
     const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
     int                      cnt      = 0;
@@ -887,6 +890,16 @@ __global__ void __launch_bounds__(256)
     out_found[i] = cnt;
 }
 
+// tuning knob (measurement only): item rounds software-pipelined per chunk in the K = 1 matcher
+int nn1_rounds()
+{
+    static const int v = [] {
+        const char* e = getenv("MP2P_NN1_ROUNDS");
+        return (e && atoi(e) == 4) ? 4 : 1;
+    }();
+    return v;
+}
+
 int pick_kt(uint32_t K)
 {
     if (K <= 1) return 1;
@@ -894,6 +907,43 @@ int pick_kt(uint32_t K)
     if (K <= 8) return 8;
     if (K <= 16) return 16;
     return 32;
+}
+
+// The search kernels are instantiated EXACTLY for the usual k (1..10, 12, 16, 20, 24, 32): the K-th
+// best is then a fixed register. Any other k <= 32 runs on the next capacity with a runtime k.
+#define MP2P_DISPATCH_K(K, CALL)      \
+    switch (K)                        \
+    {                                 \
+        case 1: CALL(1, true); break; \
+        case 2: CALL(2, true); break; \
+        case 3: CALL(3, true); break; \
+        case 4: CALL(4, true); break; \
+        case 5: CALL(5, true); break; \
+        case 6: CALL(6, true); break; \
+        case 7: CALL(7, true); break; \
+        case 8: CALL(8, true); break; \
+        case 9: CALL(9, true); break; \
+        case 10: CALL(10, true); break; \
+        case 12: CALL(12, true); break; \
+        case 16: CALL(16, true); break; \
+        case 20: CALL(20, true); break; \
+        case 24: CALL(24, true); break; \
+        case 32: CALL(32, true); break; \
+        default:                      \
+            if (K <= 16)              \
+                CALL(16, false);      \
+            else                      \
+                CALL(32, false);      \
+            break;                    \
+    }
+
+// finest table whose voxels hold ~1.5 k points on average (k = 1: the finest table)
+int start_level(const GridView& v, uint32_t K)
+{
+    if (K <= 1) return 0;
+    for (int rl = 0; rl < v.n_levels; rl++)
+        if (v.level_occupancy[rl] >= 1.5f * (float)K) return rl;
+    return v.n_levels - 1;
 }
 
 // Host clouds are copied into (aligned) staging arrays; device-resident clouds are used in place.
@@ -1046,6 +1096,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     a.allowLocal = prm->allowMatchAlreadyMatchedPoints, a.allowGlobal = prm->allowMatchAlreadyMatchedGlobalPoints;
     a.tag = (unsigned long long)(0xFFFFFFFFu - map->epoch) << 32;
     a.tma_ok = ctx->cur_tma_ok;
+    a.rl_start = start_level(map->view, K);
 
     const uint32_t blocks = (uint32_t)((n_local + kQueriesPerBlock - 1) / kQueriesPerBlock);
     const float *  dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;
@@ -1055,20 +1106,22 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     MP2P_TRY(prepare_stats(ctx, &stats));
     float4* cand_xyz = nullptr;
     prof_begin(ctx, 0);
-#define LAUNCH_MATCH(KT) \
-    k_match_pt2pt<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, sv.bbox, stats)
-    switch (pick_kt(K))
+#define LAUNCH_MATCH(KT, EX) \
+    k_match_pt2pt<KT, EX><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, sv.bbox, stats)
+    if (K == 1)
     {
-        case 1:
-            MP2P_TRY(ctx->d_candxyz.ensure(n_slots * sizeof(float4)));
-            cand_xyz = ctx->d_candxyz.as<float4>();
-            k_match_pt2pt_nn1<<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
+        MP2P_TRY(ctx->d_candxyz.ensure(n_slots * sizeof(float4)));
+        cand_xyz = ctx->d_candxyz.as<float4>();
+        if (nn1_rounds() == 1)
+            k_match_pt2pt_nn1<1><<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
                 map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, cand_xyz, sv.bbox, stats);
-            break;
-        case 4: LAUNCH_MATCH(4); break;
-        case 8: LAUNCH_MATCH(8); break;
-        case 16: LAUNCH_MATCH(16); break;
-        default: LAUNCH_MATCH(32); break;
+        else
+            k_match_pt2pt_nn1<4><<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
+                map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, cand_xyz, sv.bbox, stats);
+    }
+    else
+    {
+        MP2P_DISPATCH_K(K, LAUNCH_MATCH)
     }
 #undef LAUNCH_MATCH
     prof_end(ctx, 0);
@@ -1168,24 +1221,28 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     a.allowLocal = prm->allowMatchAlreadyMatchedPoints, a.allowGlobal = 1;  // claims happen in phase B
     a.tag = 0;
     a.tma_ok = ctx->cur_tma_ok;
+    a.rl_start = start_level(map->view, K);
     const float *dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;
     unsigned long long* stats = nullptr;
     MP2P_TRY(prepare_stats(ctx, &stats));
     prof_begin(ctx, 0);
-#define LAUNCH_MATCH(KT) \
-    k_match_pt2pt<KT><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, nullptr, nullptr, d_cand_out, d_bbox6_out, stats)
-    switch (pick_kt(K))
+#define LAUNCH_MATCH(KT, EX) \
+    k_match_pt2pt<KT, EX><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, nullptr, nullptr, d_cand_out, d_bbox6_out, stats)
+    if (K == 1)
     {
-        case 1:
-            MP2P_TRY(ctx->d_candxyz.ensure(n_local * sizeof(float4)));
-            k_match_pt2pt_nn1<<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
+        MP2P_TRY(ctx->d_candxyz.ensure(n_local * sizeof(float4)));
+        if (nn1_rounds() == 1)
+            k_match_pt2pt_nn1<1><<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
                 map->view, a, dlx, dly, dlz, d_lbits, nullptr, nullptr, d_cand_out, ctx->d_candxyz.as<float4>(),
                 d_bbox6_out, stats);
-            break;
-        case 4: LAUNCH_MATCH(4); break;
-        case 8: LAUNCH_MATCH(8); break;
-        case 16: LAUNCH_MATCH(16); break;
-        default: LAUNCH_MATCH(32); break;
+        else
+            k_match_pt2pt_nn1<4><<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
+                map->view, a, dlx, dly, dlz, d_lbits, nullptr, nullptr, d_cand_out, ctx->d_candxyz.as<float4>(),
+                d_bbox6_out, stats);
+    }
+    else
+    {
+        MP2P_DISPATCH_K(K, LAUNCH_MATCH)
     }
 #undef LAUNCH_MATCH
     prof_end(ctx, 0);
@@ -1305,18 +1362,23 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     sa.pose = a.pose, sa.maxDistSq = a.radiusSq, sa.angSq = 0.f, sa.n_local = a.n_local, sa.K = a.K;
     sa.allowLocal = a.allowLocal, sa.allowGlobal = 1, sa.tag = 0, sa.tma_ok = a.tma_ok;
     prof_begin(ctx, 0);
-#define LAUNCH_PL(KT)                                                                                         \
-    k_match_pt2pt<KT><<<blocks, kQueryTile, 0, st>>>(map->view, sa, dlx, dly, dlz, d_lbits, nullptr, nullptr, cand, \
-                                                     sv.bbox, stats);                                         \
+#define LAUNCH_SEARCH(KT, EX) \
+    k_match_pt2pt<KT, EX><<<blocks, kQueryTile, 0, st>>>(map->view, sa, dlx, dly, dlz, d_lbits, nullptr, nullptr, cand, sv.bbox, stats)
+#define LAUNCH_FIT(KT) \
     k_plane_fit<KT><<<(uint32_t)((n_local + 127) / 128), 128, 0, st>>>(map->view, a, dlx, dly, dlz, cand, plc, okf)
+    sa.rl_start = start_level(map->view, prm->knn);
+    MP2P_DISPATCH_K(prm->knn, LAUNCH_SEARCH)
     switch (pick_kt(prm->knn))
     {
         case 1:
-        case 4: LAUNCH_PL(4); break;
-        case 8: LAUNCH_PL(8); break;
-        case 16: LAUNCH_PL(16); break;
-        default: LAUNCH_PL(32); break;
+        case 4: LAUNCH_FIT(4); break;
+        case 8: LAUNCH_FIT(8); break;
+        case 16: LAUNCH_FIT(16); break;
+        default: LAUNCH_FIT(32); break;
     }
+#undef LAUNCH_SEARCH
+#undef LAUNCH_FIT
+#define LAUNCH_PL(KT)
 #undef LAUNCH_PL
     prof_end(ctx, 0);
     count_launch(ctx, 2);
@@ -1369,15 +1431,9 @@ int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const
         auto *oi = ctx->d_knn_idx.as<uint32_t>();
         auto *od = ctx->d_knn_d2.as<float>();
         auto *of = ctx->d_knn_found.as<int32_t>();
-#define LAUNCH_KNN(KT) k_knn<KT><<<blocks, 256, 0, st>>>(map->view, dqx, dqy, dqz, (uint32_t)nq, K, radius2, oi, od, of)
-        switch (pick_kt(K))
-        {
-            case 1: LAUNCH_KNN(1); break;
-            case 4: LAUNCH_KNN(4); break;
-            case 8: LAUNCH_KNN(8); break;
-            case 16: LAUNCH_KNN(16); break;
-            default: LAUNCH_KNN(32); break;
-        }
+        const int rl0 = start_level(map->view, K);
+#define LAUNCH_KNN(KT, EX) k_knn<KT, EX><<<blocks, 256, 0, st>>>(map->view, dqx, dqy, dqz, (uint32_t)nq, K, radius2, rl0, oi, od, of)
+        MP2P_DISPATCH_K(K, LAUNCH_KNN)
 #undef LAUNCH_KNN
         count_launch(ctx);
     }

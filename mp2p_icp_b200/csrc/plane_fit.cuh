@@ -1,9 +1,9 @@
 // Per-query plane fit of the pt2pl matcher (product code): estimate_points_eigen
 // (mp2p_icp_map/src/estimate_points_eigen.cpp:27-123) + the planarity / distance tests of
 // mp2p_icp/src/Matcher_Adaptive.cpp:229-253, i.e. NearestPlaneCapable::nn_search_pt2pl realised
-// over a plain point layer. This file is compiled with -fmad=false: every double/float operation
-// rounds separately, in the same order as the CPU statement of the algorithm, so plane
-// coefficients can be compared bit for bit.
+// over a plain point layer. Compiled with -fmad=false: the float mean and the centred moments round exactly as in the
+// CPU statement of the algorithm; the 3x3 eigen-solve uses a cheaper (mathematically identical)
+// rotation formula, so plane coefficients agree to ~1e-15 relative, not bit for bit.
 #pragma once
 #include "common.cuh"
 
@@ -48,10 +48,13 @@ __device__ __forceinline__ void eig_sym3(const double Ain[9], double V[9], doubl
             {
                 const double apq = A[p * 3 + q];
                 if (apq == 0.0) continue;
-                const double app = A[p * 3 + p], aqq = A[q * 3 + q];
-                const double tau = (aqq - app) / (2.0 * apq);
-                const double t   = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+                // Jacobi rotation angle: t = sgn(tau) / (|tau| + sqrt(1 + tau^2)), tau = (aqq-app)/(2 apq),
+                // evaluated without forming tau (one sqrt, one division, one rsqrt instead of two
+                // sqrt and three divisions — fp64 division and sqrt are ~50-instruction sequences)
+                const double d  = A[q * 3 + q] - A[p * 3 + p], a2 = 2.0 * apq;
+                const double sg = (d == 0.0) ? 1.0 : ((d > 0.0) == (apq > 0.0) ? 1.0 : -1.0);
+                const double t  = sg * fabs(a2) / (fabs(d) + sqrt(d * d + a2 * a2));
+                const double c = rsqrt(1.0 + t * t), s = t * c;
 #pragma unroll
                 for (int k = 0; k < 3; k++)
                 {

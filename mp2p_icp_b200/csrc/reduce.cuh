@@ -62,7 +62,9 @@ __device__ __forceinline__ void block_reduce_to_packet(double (&acc)[NV], double
 #pragma unroll
             for (int k = 0; k < 8; k++) p[k] += v[k];
         }
-        for (int k = 0; b < b1; b++, k++) p[k] += __ldcg(partials + (size_t)b * NV + lane);
+#pragma unroll
+        for (int k = 0; k < 8; k++)  // remainder, static indices (a dynamic p[k] would go to local memory)
+            if (b + k < b1) p[k] += __ldcg(partials + (size_t)(b + k) * NV + lane);
         s = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
     }
     __syncthreads();

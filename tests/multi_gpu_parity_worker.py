@@ -1,0 +1,70 @@
+"""torchrun worker: N-GPU query-sharded iteration == 1-GPU iteration (SURVEY.md §4 plan item 5).
+
+Every rank builds the same map, owns a contiguous shard of the local cloud, runs the sharded
+matcher (search -> NCCL all_gather -> resolve) and the all-reduced Horn / GN solvers. Rank 0 also
+runs the whole cloud on its own GPU and checks: concatenated pairings identical bit for bit, poses
+within 1e-9 (different reduction grouping only).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import mp2p_icp_b200 as b200  # noqa: E402
+from mp2p_icp_b200.sharded import ShardedMatcherSolver  # noqa: E402
+from tests import fixtures as fx  # noqa: E402
+
+
+def xyz(a):
+    return np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 1]), np.ascontiguousarray(a[:, 2])
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dev = torch.device("cuda", lr)
+    dist.init_process_group("nccl", device_id=dev)
+    M, L, gt = fx.make_c2(n_map=300_000, decim=5)
+    L = np.concatenate([L, L[:5000] + np.float32(2e-3)])  # duplicate claims across shards
+    L = L[: (len(L) // world) * world]
+    pose = fx.pose_xyzypr(0.25, -0.15, 0.08, np.deg2rad(1.7), np.deg2rad(-0.8), np.deg2rad(1.2))
+    ctx = b200.Context(lr, stream=torch.cuda.current_stream().cuda_stream)
+    gmap = b200.Map(ctx, *xyz(M))
+    n_total = len(L)
+    sh = ShardedMatcherSolver(ctx, gmap, rank, world, n_total, k_max=1)
+    mine = L[sh.lo : sh.hi]
+    d_l = [torch.from_numpy(a).to(dev) for a in xyz(mine)]
+    d_pairs = torch.zeros(len(mine) * 36, dtype=torch.uint8, device=dev)
+    prm = b200.Pt2PtParams(threshold=1.0)
+    n_pairs = sh.match_pt2pt(d_l[0].data_ptr(), d_l[1].data_ptr(), d_l[2].data_ptr(), pose, prm, d_pairs.data_ptr(), len(mine))
+    ok_h, T_h = sh.solve_horn(d_pairs.data_ptr(), n_pairs, b200.HornParams())
+    gprm = b200.GNParams(maxInnerLoopIterations=4, kernel="Cauchy", kernelParam=0.3)
+    ok_g, T_g, it_g = sh.solve_gauss_newton(d_pairs.data_ptr(), n_pairs, None, 0, gprm, pose)
+    # gather the shards' pairings on rank 0
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([n_pairs], dtype=torch.int64, device=dev))
+    bufs = [torch.zeros(len(mine) * 36, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(bufs, d_pairs)
+    fail = 0
+    if rank == 0:
+        got = np.concatenate([b.cpu().numpy().view(b200.PAIR_PT2PT)[: int(c.item())] for b, c in zip(bufs, counts)])
+        ref, _ = gmap.match_pt2pt(*xyz(L), pose, prm)
+        ok_r, T_r = ctx.solve_horn(ref)
+        ok_r2, T_r2, it_r = ctx.solve_gauss_newton(ref, None, gprm, pose)
+        same = len(got) == len(ref) and got.tobytes() == ref.tobytes()
+        dh, dg = np.abs(T_h - T_r).max(), np.abs(T_g - T_r2).max()
+        print(f"world={world} pairs={len(got)} identical={same} horn_diff={dh:.2e} gn_diff={dg:.2e} gn_iters={it_g}/{it_r}")
+        fail = int(not (same and ok_h and ok_g and dh < 1e-9 and dg < 1e-9 and it_g == it_r))
+    t = torch.tensor([fail], device=dev)
+    dist.broadcast(t, 0)
+    dist.destroy_process_group()
+    sys.exit(int(t.item()))
+
+
+if __name__ == "__main__":
+    main()

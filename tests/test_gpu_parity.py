@@ -423,3 +423,21 @@ def test_fused_iteration_pt2pl_gn_equals_two_calls(ctx):
     ok0, T0, it0 = orc.optimal_tf_gauss_newton(None, p0, orc.GNParams(**skw), guess, nthreads=8)
     assert it0 == it_ref
     assert_pose_close(T, T0)
+
+
+# --------------------------------------------------------------------------- multi-GPU (needs >= 2 GPUs)
+def test_multi_gpu_sharded_iteration_equals_single_gpu():
+    import subprocess
+    import sys
+
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run under `gpurun --gpus 2`)")
+    world = 2 if n < 4 else 4
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.join(here, "multi_gpu_parity_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "identical=True" in r.stdout
