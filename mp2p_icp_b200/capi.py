@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libmp2p_b200.so")
+_SO = os.environ.get("MP2P_B200_LIB") or os.path.join(_HERE, "libmp2p_b200.so")  # env override: A/B builds only
 
 PACKET_DOUBLES = 32
 MAX_KNN = 32

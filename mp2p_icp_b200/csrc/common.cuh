@@ -105,6 +105,7 @@ struct mp2p_b200_ctx
     bool         own_stream = false;
     uint64_t     launches   = 0;
     uint32_t     scan_epoch = 0;  // stamps look-back status words (match.cu)
+    uint64_t     hint_pt2pt = ~0ull, hint_pt2pl = ~0ull;  // previous pairing counts (speculative D2H size)
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
     // measurement hooks
     bool         prof_timings = false, prof_stats = false;

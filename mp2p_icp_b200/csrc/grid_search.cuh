@@ -107,18 +107,17 @@ struct TopK
             if (j == k_runtime - 1) w = v[j];
         return w;
     }
+    // sorted insert as a chain of (min, max) exchanges; every key is offered at most once per list
+    // (the lists are rebuilt at every level), so no duplicate test is needed
     __device__ __forceinline__ void insert(unsigned long long c)
     {
 #pragma unroll
         for (int j = 0; j < K; j++)
         {
-            if (c == v[j]) c = ~0ull;  // the same point seen again at a coarser level
-            if (c < v[j])
-            {
-                const unsigned long long t = v[j];
-                v[j]                       = c;
-                c                          = t;
-            }
+            const bool               lt = c < v[j];
+            const unsigned long long lo = lt ? c : v[j], hi = lt ? v[j] : c;
+            v[j]                        = lo;
+            c                           = hi;
         }
     }
 };
@@ -137,7 +136,8 @@ struct SearchCounters
 };
 
 // ---- sub-warp cooperative search --------------------------------------------------------------
-// A query is processed by a GROUP of G consecutive lanes (G = 8: four queries per warp). The group
+// A query is processed by a GROUP of G consecutive lanes (G = 8: four queries per warp; measured
+// faster than G = 4 on the C3 workload, profiles/r01_c3_group_ab.txt). The group
 // members hold the same query; work is split so that memory requests of one query are issued by
 // different lanes in the same instruction (memory-level parallelism instead of one thread's serial
 // chain of dependent loads):
@@ -147,7 +147,10 @@ struct SearchCounters
 //      prunes with the box bound, probes and scans its own voxels;
 //   4. group merge (K rounds of "pop the group minimum") -> exact K best of the level, replicated
 //      in every lane; termination test; otherwise one level up with fresh per-lane lists.
-constexpr int kGroup = 8;
+#ifndef MP2P_GROUP
+#define MP2P_GROUP 8
+#endif
+constexpr int kGroup = MP2P_GROUP;
 
 template <int G>
 __device__ __forceinline__ unsigned long long group_max_u64(unsigned long long v, unsigned gmask)
@@ -199,11 +202,22 @@ __device__ __forceinline__ unsigned long long point_key(float qx, float qy, floa
     return ((unsigned long long)__float_as_uint(d2) << 32) | (uint32_t)__float_as_int(p.w);
 }
 
+// position of offset (dz,dy,dx in 0..2, index dz*9+dy*3+dx) inside kNeighbourOrder
+__host__ __device__ constexpr int neighbour_rank(int idx)
+{
+    constexpr int order[27] = {0x15, 0x14, 0x16, 0x11, 0x19, 0x05, 0x25, 0x10, 0x12, 0x18, 0x1a, 0x04, 0x06, 0x24,
+                               0x26, 0x01, 0x09, 0x21, 0x29, 0x00, 0x02, 0x08, 0x0a, 0x20, 0x22, 0x28, 0x2a};
+    const int     code      = (idx % 3) | (((idx / 3) % 3) << 2) | ((idx / 9) << 4);
+    for (int i = 0; i < 27; i++)
+        if (order[i] == code) return i;
+    return 0;
+}
+
 // Exact K-nearest (k_runtime <= K) of (qx,qy,qz) among points with d2 < radius2 (strict).
 // Called by all G lanes of a group with identical arguments; `sub` = lane index inside the group,
 // `gmask` = the group's lanes. On return res.v[0..k_runtime) ascending, identical in all lanes;
 // entries >= (radius2 bits << 32) are "not found".
-// `rl_start`: relative level to start from — the finest level whose voxels hold about 1.5 K points
+// `rl_start`: relative level to start from — the finest level whose voxels hold about 0.75 K points
 // on average (start_level(), host side), so that the centre voxel alone usually settles the K-th
 // distance and the neighbours can be pruned; any start level is correct.
 template <int K, int G, bool EXACT>
@@ -262,62 +276,76 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
         const float gyl = fmaxf(fy - 4.f, 0.f), gyh = fmaxf(s - fy - 4.f, 0.f);
         const float gzl = fmaxf(fz - 4.f, 0.f), gzh = fmaxf(s - fz - 4.f, 0.f);
 
-        // ---- 1. centre voxel, scanned by the whole group
-        if ((unsigned)cx <= (unsigned)cmax && (unsigned)cy <= (unsigned)cmax && (unsigned)cz <= (unsigned)cmax)
+        // ---- 1-3. the voxels of the 3x3x3 block, centre first then faces/edges/corners, visited by
+        // the WHOLE group in lock step: one broadcast hash probe per surviving voxel, its points
+        // scanned G at a time, then the K-th bound is refreshed for the group. (Dealing different
+        // voxels to different lanes left most lanes idle: only the few voxels that survive the box
+        // bound have any work.) After the centre, the survivors are collected once in a bit mask
+        // (hierarchically: a slab or a row that is too far drops all its voxels at once) and only
+        // those are iterated, re-checked against the bound as it tightens.
+        const float ax[3] = {gxl * gxl * q2, 0.f, gxh * gxh * q2};
+        const float ay[3] = {gyl * gyl * q2, 0.f, gyh * gyh * q2};
+        const float az[3] = {gzl * gzl * q2, 0.f, gzh * gzh * q2};
+        uint32_t    todo  = 1u;  // bit i <-> kNeighbourOrder[i]; start with the centre
+        bool        first = true;
+        while (todo)
         {
-            uint32_t start, count;
-            if (sub == 0) sc.probes++;
-            if (grid_lookup(g, rl, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, start, count))
-            {
-                if (sub == 0) sc.cands += count;
-                for (uint32_t j = start + sub; j < start + count; j += G)
-                {
-                    const unsigned long long c = point_key(qx, qy, qz, __ldg(g.pts + j));
-                    if (c < mine.template worst<EXACT>(k_runtime)) mine.insert(c);
-                }
-            }
-        }
-        // ---- 2. bound for pruning the neighbours. K == 1: exact group minimum. K > 1: any lane that
-        // already holds k candidates bounds the K-th distance of the union from above.
-        {
-            const unsigned long long w = group_min_u64<G>(mine.template worst<EXACT>(k_runtime), gmask);
-            kth                        = fminf(kth, __uint_as_float((uint32_t)(w >> 32)));
-            if (EXACT && K > 1)
-            {
-                // r = ceil(K/G): if every lane already holds r candidates the union holds >= K that are
-                // <= the largest of the lanes' r-th best (sentinel = radius when a lane has fewer)
-                constexpr int            r  = (K + G - 1) / G;
-                const unsigned long long wr = group_max_u64<G>(mine.v[r - 1], gmask);
-                kth                         = fminf(kth, __uint_as_float((uint32_t)(wr >> 32)));
-            }
-        }
-        // ---- 3. the 26 neighbours, dealt round-robin to the lanes
-#pragma unroll 1
-        for (int nb = 1 + sub; nb < 27; nb += G)
-        {
+            const int nb = __ffs(todo) - 1;
+            todo &= todo - 1;
             const uint32_t code = kNeighbourOrder[nb];
             const int      dx = (int)(code & 3u) - 1, dy = (int)((code >> 2) & 3u) - 1,
                       dz = (int)((code >> 4) & 3u) - 1;
-            const float bx = dx < 0 ? gxl : (dx > 0 ? gxh : 0.f);
-            const float by = dy < 0 ? gyl : (dy > 0 ? gyh : 0.f);
-            const float bz = dz < 0 ? gzl : (dz > 0 ? gzh : 0.f);
-            const float lb = (bx * bx + by * by + bz * bz) * q2;
-            if (lb > kth) continue;  // strict: an equal-distance lower index must still be seen
+            const float lb = (dx < 0 ? ax[0] : (dx > 0 ? ax[2] : 0.f)) + (dy < 0 ? ay[0] : (dy > 0 ? ay[2] : 0.f)) +
+                             (dz < 0 ? az[0] : (dz > 0 ? az[2] : 0.f));
             const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
-            if ((unsigned)nx > (unsigned)cmax || (unsigned)ny > (unsigned)cmax ||
-                (unsigned)nz > (unsigned)cmax)
-                continue;
-            uint32_t start, count;
-            sc.probes++;
-            if (!grid_lookup(g, rl, (uint32_t)nx, (uint32_t)ny, (uint32_t)nz, start, count)) continue;
-            sc.cands += count;
-            for (uint32_t j = start; j < start + count; j++)
+            uint32_t  start, count;
+            // strict `>`: an equal-distance lower index must still be seen
+            if (!(lb > kth) && (unsigned)nx <= (unsigned)cmax && (unsigned)ny <= (unsigned)cmax &&
+                (unsigned)nz <= (unsigned)cmax)
             {
-                const unsigned long long c = point_key(qx, qy, qz, __ldg(g.pts + j));
-                if (c < mine.template worst<EXACT>(k_runtime))
+                if (sub == 0) sc.probes++;
+                if (grid_lookup(g, rl, (uint32_t)nx, (uint32_t)ny, (uint32_t)nz, start, count))
                 {
-                    mine.insert(c);
-                    kth = fminf(kth, __uint_as_float((uint32_t)(mine.template worst<EXACT>(k_runtime) >> 32)));
+                    if (sub == 0) sc.cands += count;
+                    for (uint32_t j = start + sub; j < start + count; j += G)
+                    {
+                        const unsigned long long c = point_key(qx, qy, qz, __ldg(g.pts + j));
+                        if (__uint_as_float((uint32_t)(c >> 32)) <= kth && c < mine.template worst<EXACT>(k_runtime))
+                            mine.insert(c);
+                    }
+                    // bound for pruning what follows. A lane that holds k candidates bounds the K-th
+                    // distance of the union from above; with r = ceil(K/G), if every lane holds r
+                    // candidates the union holds >= K that are <= the largest of the lanes' r-th best.
+                    const unsigned long long w = group_min_u64<G>(mine.template worst<EXACT>(k_runtime), gmask);
+                    kth                        = fminf(kth, __uint_as_float((uint32_t)(w >> 32)));
+                    if (EXACT && K > 1)
+                    {
+                        constexpr int            r  = (K + G - 1) / G;
+                        const unsigned long long wr = group_max_u64<G>(mine.v[r - 1], gmask);
+                        kth                         = fminf(kth, __uint_as_float((uint32_t)(wr >> 32)));
+                    }
+                }
+            }
+            if (first)
+            {
+                first = false;
+#pragma unroll
+                for (int dz3 = 0; dz3 < 3; dz3++)
+                {
+                    if (az[dz3] > kth) continue;
+#pragma unroll
+                    for (int dy3 = 0; dy3 < 3; dy3++)
+                    {
+                        const float t = az[dz3] + ay[dy3];
+                        if (t > kth) continue;
+#pragma unroll
+                        for (int dx3 = 0; dx3 < 3; dx3++)
+                        {
+                            if (dx3 == 1 && dy3 == 1 && dz3 == 1) continue;
+                            if (t + ax[dx3] > kth) continue;
+                            todo |= 1u << neighbour_rank(dz3 * 9 + dy3 * 3 + dx3);
+                        }
+                    }
                 }
             }
         }

@@ -127,6 +127,57 @@ MP2P_HD inline void ldlt_solve6(const double Hin[36], const double b[6], double 
     for (int i = 0; i < N; i++) x[perm[i]] = y[i];
 }
 
+// Same solve without pivoting, all loops fully unrolled on static indices (registers only — the
+// device-side GN step is a single thread, where the pivoted version's dynamically indexed arrays
+// live in local memory). Returns false if a pivot is numerically null; callers then fall back to
+// the pivoted solve. For a positive definite H the two agree to rounding.
+MP2P_HD inline bool ldlt_solve6_nopivot(const double Hin[36], const double b[6], double x[6])
+{
+    double A[36];
+#pragma unroll
+    for (int i = 0; i < 36; i++) A[i] = Hin[i];
+    double maxdiag = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) maxdiag = fmax(maxdiag, fabs(A[i * 6 + i]));
+    const double tol = maxdiag * 2.220446049250313e-16 * 6 * 1e3;
+    bool         ok  = true;
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+    {
+        const double d = A[k * 6 + k];
+        if (!(fabs(d) > tol)) ok = false;
+        const double inv = 1.0 / d;
+#pragma unroll
+        for (int i = k + 1; i < 6; i++)
+        {
+            const double l = A[i * 6 + k] * inv;
+#pragma unroll
+            for (int j = k + 1; j <= i; j++) A[i * 6 + j] -= l * A[j * 6 + k];
+            A[k * 6 + i] = l;  // L^T above the diagonal; column k below it stays the original a_ik
+        }
+    }
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+    {
+        double v = b[i];
+#pragma unroll
+        for (int j = 0; j < i; j++) v -= A[j * 6 + i] * y[j];
+        y[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) y[i] = y[i] / A[i * 6 + i];
+#pragma unroll
+    for (int i = 5; i >= 0; i--)
+    {
+        double v = y[i];
+#pragma unroll
+        for (int j = i + 1; j < 6; j++) v -= A[i * 6 + j] * x[j];
+        x[i] = v;
+    }
+    return ok;
+}
+
 // eigenvector (unit) of the LARGEST eigenvalue of a symmetric 4x4, by cyclic Jacobi.
 inline void eig_sym4_largest(const double Nin[16], double q[4])
 {

@@ -15,6 +15,7 @@
 //                   into that level's open-addressing table
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "grid_search.cuh"
@@ -24,7 +25,17 @@ namespace mp2p
 {
 namespace
 {
-constexpr float kTargetOccupancy = 2.5f;
+// finest level = the finest one with at least this many points per occupied voxel (measurement
+// knob: MP2P_TARGET_OCC overrides the default)
+float target_occupancy()
+{
+    static const float v = [] {
+        const char* e = getenv("MP2P_TARGET_OCC");
+        const float f = e ? (float)atof(e) : 0.f;
+        return f > 0.5f ? f : 2.5f;
+    }();
+    return v;
+}
 
 __device__ __forceinline__ uint32_t f2ord(float f)
 {
@@ -333,7 +344,7 @@ int build_index(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* x, const fl
     }
     int Lf = kGridBits;  // the single-voxel level always qualifies
     for (int L = 0; L <= kGridBits; L++)
-        if ((double)n / (double)cells[L] >= kTargetOccupancy)
+        if ((double)n / (double)cells[L] >= target_occupancy())
         {
             Lf = L;
             break;

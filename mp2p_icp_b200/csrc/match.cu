@@ -539,6 +539,247 @@ __global__ void __launch_bounds__(kNN1Threads)
 }
 
 // ------------------------------------------------------------------------------------------
+// k > 1 matcher / k-NN of the pt2pl matcher, one LANE per query (k <= 16): the K = 1 scheme
+// (k_match_pt2pt_nn1) generalised. Each lane keeps its query's K best in registers and scans the
+// centre voxel itself; the surviving neighbour voxels of the 32 queries are pooled and dealt out
+// one (query, voxel) item per lane; an item's candidates that beat the owner's current K-th
+// distance are appended to the owner's slot list in shared memory (atomic slot counter), which the
+// owner drains into its register list afterwards. If a list overflows (kKnnBuf entries) the owner
+// re-scans its voxels itself — rare, and exact either way. Lists are rebuilt at every level, as in
+// the group kernel, so no candidate is ever offered twice.
+// ------------------------------------------------------------------------------------------
+constexpr int kKnnBuf = 24;
+
+template <int K>
+__global__ void __launch_bounds__(kNN1Threads)
+    k_match_knn_lane(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
+                     const float* __restrict__ lz, const uint32_t* __restrict__ lbits,
+                     const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim,
+                     unsigned long long* __restrict__ cand, uint32_t* __restrict__ bbox_words,
+                     unsigned long long* __restrict__ stats)
+{
+    __shared__ QueryTile<kNN1Threads> tile;
+    __shared__ BBoxAcc                bacc;
+    __shared__ uint32_t               s_cnt[kNN1Threads / 32][32];
+    __shared__ unsigned long long     s_buf[kNN1Threads / 32][32][kKnnBuf];
+    const size_t                      base = (size_t)blockIdx.x * kNN1Threads;
+    bbox_init(bacc);
+    load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
+    const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t i     = (uint32_t)base + threadIdx.x;
+    const bool     valid = i < a.n_local;
+    const unsigned FULL  = 0xffffffffu;
+
+    float gx = 0, gy = 0, gz = 0;
+    if (valid) compose_point_f(a.pose, tile.x[threadIdx.x], tile.y[threadIdx.x], tile.z[threadIdx.x], gx, gy, gz);
+    bbox_accumulate(bacc, gx, gy, gz, valid, bbox_words);
+
+    float thr2 = 0.f;
+    if (valid && (a.allowLocal || !bit_set(lbits, i)))
+    {
+        const float normSq = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+        thr2               = __fadd_rn(a.maxDistSq, __fmul_rn(a.angSq, normSq));
+    }
+    const unsigned long long sentinel = (unsigned long long)__float_as_uint(thr2) << 32;
+    TopK<K>                  top;
+    top.init(sentinel);
+    float kth    = thr2;
+    bool  active = thr2 > 0.f;
+    if (active)
+    {
+        const float ex = fmaxf(fmaxf(g.bbmin[0] - gx, gx - g.bbmax[0]), 0.f);
+        const float ey = fmaxf(fmaxf(g.bbmin[1] - gy, gy - g.bbmax[1]), 0.f);
+        const float ez = fmaxf(fmaxf(g.bbmin[2] - gz, gz - g.bbmax[2]), 0.f);
+        if ((ex * ex + ey * ey + ez * ez) * 0.999999f > thr2) active = false;
+    }
+    const float lim = 4194304.f;  // 2^22
+    const float ux  = fminf(fmaxf(grid_u(gx, g.ox, g.inv_s0), -lim), lim);
+    const float uy  = fminf(fmaxf(grid_u(gy, g.oy, g.inv_s0), -lim), lim);
+    const float uz  = fminf(fmaxf(grid_u(gz, g.oz, g.inv_s0), -lim), lim);
+    const int   Ix = (int)floorf(ux), Iy = (int)floorf(uy), Iz = (int)floorf(uz);
+    const float q2 = g.s0_lo * g.s0_lo * 0.999999f;
+    SearchCounters sc;
+
+    // offer one point of a voxel to this lane's own list
+    auto offer = [&](const float4 p)
+    {
+        const unsigned long long c = point_key(gx, gy, gz, p);
+        if (__uint_as_float((uint32_t)(c >> 32)) <= kth && c < top.v[K - 1])
+        {
+            top.insert(c);
+            kth = fminf(kth, __uint_as_float((uint32_t)(top.v[K - 1] >> 32)));
+        }
+    };
+
+    for (int rl = a.rl_start; rl < g.n_levels; rl++)
+    {
+        if (!__any_sync(FULL, active)) break;
+        const int L = g.level_first + rl;
+        if (active) top.init(sentinel);  // rebuilt per level (kth keeps bounding from above)
+        if (L == kGridBits)
+        {
+            if (active)
+            {
+                sc.probes++, sc.cands += g.n_points, sc.levels++;
+                for (uint32_t j = 0; j < g.n_points; j++) offer(__ldg(g.pts + j));
+            }
+            break;
+        }
+        const int   cmax = ((1 << kGridBits) - 1) >> L;
+        const float s    = (float)(1 << L);
+        const int   cx = Ix >> L, cy = Iy >> L, cz = Iz >> L;
+        const float fx = ux - (float)cx * s, fy = uy - (float)cy * s, fz = uz - (float)cz * s;
+
+        // ---- centre voxel, own query
+        if (active && (unsigned)cx <= (unsigned)cmax && (unsigned)cy <= (unsigned)cmax && (unsigned)cz <= (unsigned)cmax)
+        {
+            uint32_t start, count;
+            sc.probes++;
+            if (grid_lookup(g, rl, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, start, count))
+            {
+                sc.cands += count;
+                for (uint32_t j = start; j < start + count; j++) offer(__ldg(g.pts + j));
+            }
+        }
+        // ---- surviving neighbours: bit b = dz*9 + dy*3 + dx (each 0..2)
+        uint32_t mask = 0;
+        if (active)
+        {
+            const float glx = fmaxf(fx - 4.f, 0.f), ghx = fmaxf(s - fx - 4.f, 0.f);
+            const float gly = fmaxf(fy - 4.f, 0.f), ghy = fmaxf(s - fy - 4.f, 0.f);
+            const float glz = fmaxf(fz - 4.f, 0.f), ghz = fmaxf(s - fz - 4.f, 0.f);
+            const float ax[3] = {glx * glx * q2, 0.f, ghx * ghx * q2};
+            const float ay[3] = {gly * gly * q2, 0.f, ghy * ghy * q2};
+            const float az[3] = {glz * glz * q2, 0.f, ghz * ghz * q2};
+#pragma unroll
+            for (int dz = 0; dz < 3; dz++)
+            {
+                if (az[dz] > kth || (unsigned)(cz + dz - 1) > (unsigned)cmax) continue;
+#pragma unroll
+                for (int dy = 0; dy < 3; dy++)
+                {
+                    const float t = az[dz] + ay[dy];
+                    if (t > kth || (unsigned)(cy + dy - 1) > (unsigned)cmax) continue;
+#pragma unroll
+                    for (int dx = 0; dx < 3; dx++)
+                    {
+                        if (dx == 1 && dy == 1 && dz == 1) continue;
+                        if (t + ax[dx] > kth || (unsigned)(cx + dx - 1) > (unsigned)cmax) continue;  // strict >
+                        mask |= 1u << (dz * 9 + dy * 3 + dx);
+                    }
+                }
+            }
+        }
+        // ---- pool the (query, voxel) items of the warp and deal them out one per lane
+        const uint32_t cnt  = __popc(mask);
+        uint32_t       incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t excl  = incl - cnt;
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        s_cnt[warp][lane]    = 0;
+        __syncwarp();
+        for (uint32_t b0 = 0; b0 < total; b0 += 32)
+        {
+            const uint32_t id = b0 + lane;
+            int            owner = 0;  // largest lane q with excl[q] <= id
+#pragma unroll
+            for (int st = 16; st > 0; st >>= 1)
+            {
+                const int      probe = owner + st;
+                const uint32_t e     = __shfl_sync(FULL, excl, probe & 31);
+                if (probe < 32 && e <= id) owner = probe;
+            }
+            const float    oqx = __shfl_sync(FULL, gx, owner), oqy = __shfl_sync(FULL, gy, owner),
+                        oqz = __shfl_sync(FULL, gz, owner), okth = __shfl_sync(FULL, kth, owner);
+            const int      ocx = __shfl_sync(FULL, cx, owner), ocy = __shfl_sync(FULL, cy, owner),
+                      ocz = __shfl_sync(FULL, cz, owner);
+            const uint32_t omask = __shfl_sync(FULL, mask, owner), oexcl = __shfl_sync(FULL, excl, owner);
+            if (id < total)
+            {
+                const uint32_t bit = __fns(omask, 0, (int)(id - oexcl) + 1);
+                const int      dz = (int)(bit / 9u), dy = (int)((bit % 9u) / 3u), dx = (int)(bit % 3u);
+                uint32_t       start, count;
+                sc.probes++;
+                if (grid_lookup(g, rl, (uint32_t)(ocx + dx - 1), (uint32_t)(ocy + dy - 1), (uint32_t)(ocz + dz - 1), start, count))
+                {
+                    sc.cands += count;
+                    for (uint32_t j = start; j < start + count; j++)
+                    {
+                        const unsigned long long c = point_key(oqx, oqy, oqz, __ldg(g.pts + j));
+                        if (__uint_as_float((uint32_t)(c >> 32)) <= okth)
+                        {
+                            const uint32_t slot = atomicAdd(&s_cnt[warp][owner], 1u);
+                            if (slot < (uint32_t)kKnnBuf) s_buf[warp][owner][slot] = c;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---- the owner drains its list
+        {
+            const uint32_t n = s_cnt[warp][lane];
+            if (n <= (uint32_t)kKnnBuf)
+            {
+                for (uint32_t t = 0; t < n; t++)
+                {
+                    const unsigned long long c = s_buf[warp][lane][t];
+                    if (c < top.v[K - 1]) top.insert(c);
+                }
+                kth = fminf(kth, __uint_as_float((uint32_t)(top.v[K - 1] >> 32)));
+            }
+            else
+            {
+                // overflow: the list is incomplete — scan the surviving voxels again, serially
+                uint32_t m = mask;
+                while (m)
+                {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int dz = bit / 9, dy = (bit % 9) / 3, dx = bit % 3;
+                    uint32_t  start, count;
+                    if (grid_lookup(g, rl, (uint32_t)(cx + dx - 1), (uint32_t)(cy + dy - 1), (uint32_t)(cz + dz - 1), start, count))
+                        for (uint32_t j = start; j < start + count; j++) offer(__ldg(g.pts + j));
+                }
+            }
+        }
+        __syncwarp();
+        // everything outside the 3x3x3 block is at least m quanta away
+        const float mx = s + fminf(fx, s - fx), my = s + fminf(fy, s - fy), mz = s + fminf(fz, s - fz);
+        const float m  = fmaxf(fminf(mx, fminf(my, mz)) - 4.f, 0.f);
+        if (active)
+        {
+            sc.levels++;
+            if (kth <= m * m * q2) active = false;
+        }
+    }
+
+    uint32_t n_valid = 0;
+    if (valid)
+    {
+#pragma unroll
+        for (int k = 0; k < K; k++)
+        {
+            // unused ranks are marked with an impossible map index (all ones)
+            const unsigned long long c = top.v[k] < sentinel ? top.v[k] : ~0ull;
+            n_valid += (c != ~0ull);
+            cand[(size_t)i * K + k] = c;
+            if (c != ~0ull && !a.allowGlobal)
+            {
+                const uint32_t gi = (uint32_t)c;
+                if (!bit_set(gbits, gi)) atomicMin(claim + gi, a.tag | (unsigned long long)(i * (uint32_t)K + k));
+            }
+        }
+    }
+    flush_search_stats(sc, n_valid, stats);
+}
+
+// ------------------------------------------------------------------------------------------
 // Single-pass stream compaction (decoupled look-back over 1024-slot tiles).
 // status word: [63:62] 1 = tile aggregate, 2 = inclusive prefix; [61:40] call epoch (22 bits);
 // [39:0] value. A word whose epoch is not the current call's reads as "not ready", so the status
@@ -890,6 +1131,16 @@ __global__ void __launch_bounds__(256)
     out_found[i] = cnt;
 }
 
+// tuning knob (measurement only): MP2P_KNN_LANE=0 falls back to the group kernel for every k > 1
+bool knn_lane_enabled()
+{
+    static const bool v = [] {
+        const char* e = getenv("MP2P_KNN_LANE");
+        return !(e && atoi(e) == 0);
+    }();
+    return v;
+}
+
 // tuning knob (measurement only): item rounds software-pipelined per chunk in the K = 1 matcher
 int nn1_rounds()
 {
@@ -911,6 +1162,24 @@ int pick_kt(uint32_t K)
 
 // The search kernels are instantiated EXACTLY for the usual k (1..10, 12, 16, 20, 24, 32): the K-th
 // best is then a fixed register. Any other k <= 32 runs on the next capacity with a runtime k.
+// lane-per-query kernel (k_match_knn_lane) for the exact k up to 16; others use the group kernel
+#define MP2P_DISPATCH_LANE_K(K, CALL, ELSE) \
+    switch (K)                              \
+    {                                       \
+        case 2: CALL(2); break;             \
+        case 3: CALL(3); break;             \
+        case 4: CALL(4); break;             \
+        case 5: CALL(5); break;             \
+        case 6: CALL(6); break;             \
+        case 7: CALL(7); break;             \
+        case 8: CALL(8); break;             \
+        case 9: CALL(9); break;             \
+        case 10: CALL(10); break;           \
+        case 12: CALL(12); break;           \
+        case 16: CALL(16); break;           \
+        default: ELSE; break;               \
+    }
+
 #define MP2P_DISPATCH_K(K, CALL)      \
     switch (K)                        \
     {                                 \
@@ -937,12 +1206,12 @@ int pick_kt(uint32_t K)
             break;                    \
     }
 
-// finest table whose voxels hold ~1.5 k points on average (k = 1: the finest table)
+// finest table whose voxels hold at least ~0.75 k points on average (k = 1: the finest table)
 int start_level(const GridView& v, uint32_t K)
 {
     if (K <= 1) return 0;
     for (int rl = 0; rl < v.n_levels; rl++)
-        if (v.level_occupancy[rl] >= 1.5f * (float)K) return rl;
+        if (v.level_occupancy[rl] >= 0.75f * (float)K) return rl;
     return v.n_levels - 1;
 }
 
@@ -1027,25 +1296,35 @@ int prepare_stats(mp2p_b200_ctx* ctx, unsigned long long** stats)
     return 0;
 }
 
+// Pairings back to the host with ONE synchronisation in the steady state: the record copy is
+// issued speculatively right behind the compaction, sized from the previous call's count (+12.5 %),
+// together with the count; only if the guess was too small a second copy fetches the remainder.
 template <class Rec>
 int fetch_results(mp2p_b200_ctx* ctx, const unsigned long long* d_count, const Rec* d_pairs,
-                  Rec* out, uint64_t capacity, int out_on_device, uint64_t* out_count)
+                  Rec* out, uint64_t capacity, int out_on_device, uint64_t* out_count, uint64_t* hint)
 {
     unsigned long long* h_count = static_cast<unsigned long long*>(ctx->h_pinned);
     MP2P_CUDA_TRY(cudaMemcpyAsync(h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    uint64_t spec = 0;
+    if (!out_on_device && capacity)
+    {
+        spec = *hint == ~0ull ? capacity : std::min<uint64_t>(capacity, *hint + *hint / 8 + 1024);
+        MP2P_CUDA_TRY(cudaMemcpyAsync(out, d_pairs, spec * sizeof(Rec), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     MP2P_CUDA_TRY(cudaGetLastError());
     const uint64_t cnt = *h_count;
     *out_count         = cnt;
+    *hint              = cnt;
     if (cnt > capacity)
     {
         set_error("output capacity %llu too small for %llu pairings", (unsigned long long)capacity,
                   (unsigned long long)cnt);
         return MP2P_B200_ERR_CAPACITY;
     }
-    if (!out_on_device && cnt)
+    if (!out_on_device && cnt > spec)
     {
-        MP2P_CUDA_TRY(cudaMemcpyAsync(out, d_pairs, cnt * sizeof(Rec), cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(out + spec, d_pairs + spec, (cnt - spec) * sizeof(Rec), cudaMemcpyDeviceToHost, ctx->stream));
         MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
     return 0;
@@ -1121,7 +1400,17 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     }
     else
     {
-        MP2P_DISPATCH_K(K, LAUNCH_MATCH)
+#define LAUNCH_LANE(KT) \
+    k_match_knn_lane<KT><<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, sv.bbox, stats)
+        if (knn_lane_enabled())
+        {
+            MP2P_DISPATCH_LANE_K(K, LAUNCH_LANE, { MP2P_DISPATCH_K(K, LAUNCH_MATCH) })
+        }
+        else
+        {
+            MP2P_DISPATCH_K(K, LAUNCH_MATCH)
+        }
+#undef LAUNCH_LANE
     }
 #undef LAUNCH_MATCH
     prof_end(ctx, 0);
@@ -1155,7 +1444,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
         keep_on_device->d_count = sv.count, keep_on_device->d_pairs = d_out, keep_on_device->capacity = c.capacity;
         return 0;
     }
-    return fetch_results(ctx, sv.count, d_out, out, capacity, out_on_device, out_count);
+    return fetch_results(ctx, sv.count, d_out, out, c.capacity, out_on_device, out_count, &ctx->hint_pt2pt);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1310,7 +1599,7 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
         FusedSums{nullptr, nullptr, nullptr});
     prof_end(ctx, 1);
     count_launch(ctx);
-    return fetch_results(ctx, sv.count, d_out, out, capacity, out_on_device, out_count);
+    return fetch_results(ctx, sv.count, d_out, out, c.capacity, out_on_device, out_count, &ctx->hint_pt2pt);
 }
 
 int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
@@ -1367,7 +1656,17 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
 #define LAUNCH_FIT(KT) \
     k_plane_fit<KT><<<(uint32_t)((n_local + 127) / 128), 128, 0, st>>>(map->view, a, dlx, dly, dlz, cand, plc, okf)
     sa.rl_start = start_level(map->view, prm->knn);
-    MP2P_DISPATCH_K(prm->knn, LAUNCH_SEARCH)
+#define LAUNCH_LANE(KT) \
+    k_match_knn_lane<KT><<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(map->view, sa, dlx, dly, dlz, d_lbits, nullptr, nullptr, cand, sv.bbox, stats)
+    if (knn_lane_enabled())
+    {
+        MP2P_DISPATCH_LANE_K(prm->knn, LAUNCH_LANE, { MP2P_DISPATCH_K(prm->knn, LAUNCH_SEARCH) })
+    }
+    else
+    {
+        MP2P_DISPATCH_K(prm->knn, LAUNCH_SEARCH)
+    }
+#undef LAUNCH_LANE
     switch (pick_kt(prm->knn))
     {
         case 1:
@@ -1402,7 +1701,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
         keep_on_device->d_count = sv.count, keep_on_device->d_pairs = d_out, keep_on_device->capacity = cap;
         return 0;
     }
-    return fetch_results(ctx, sv.count, d_out, out, capacity, out_on_device, out_count);
+    return fetch_results(ctx, sv.count, d_out, out, cap, out_on_device, out_count, &ctx->hint_pt2pl);
 }
 
 int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const float* qy,

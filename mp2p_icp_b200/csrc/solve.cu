@@ -370,7 +370,7 @@ __global__ void k_gn_step(const double* __restrict__ packet, double minDelta, do
     for (int i = 0; i < 6; i++)
         for (int j = i; j < 6; j++) H[6 * i + j] = H[6 * j + i] = packet[idx++];
     for (int i = 0; i < 6; i++) g[i] = -packet[21 + i];
-    hm::ldlt_solve6(H, g, delta);
+    if (!hm::ldlt_solve6_nopivot(H, g, delta)) hm::ldlt_solve6(H, g, delta);
     hm::Pose34 P;
     for (int k = 0; k < 12; k++) P.m[k] = pose[k];
     const hm::Pose34 Pn = hm::compose(P, hm::se3_exp(delta));
