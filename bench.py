@@ -299,6 +299,23 @@ def run_ours(args):
     ms_e2e, (n_pairs_e, T_e2e) = timed(step_e2e, args.steps, max(3, args.warmup), wall=True)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- PCIe reference for the e2e number: pinned 16 MiB H2D and D2H copies (best of 5)
+    def pcie_gbs():
+        hb = torch.empty(16 << 20, dtype=torch.uint8).pin_memory()
+        db = torch.empty(16 << 20, dtype=torch.uint8, device=dev)
+        best = [0.0, 0.0]
+        for _ in range(5):
+            for k, (dst, src) in enumerate(((db, hb), (hb, db))):
+                s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record(stream)
+                dst.copy_(src, non_blocking=True)
+                e0.record(stream)
+                torch.cuda.synchronize()
+                best[k] = max(best[k], (16 << 20) / (s0.elapsed_time(e0) * 1e-3) / 1e9)
+        return best
+
+    pcie = pcie_gbs()
+
     # ---- roofline pass: per-kernel CUDA events (stats OFF: the counters add same-address atomics),
     # then ONE untimed call with the search statistics on. Not part of the timed region above.
     def match_once():
@@ -334,6 +351,14 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of this command
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = tj[w["name"]]["dram_bytes_read"] + tj[w["name"]]["dram_bytes_write"]
+    except Exception:
+        pass
+
     # ---- CPU baseline (rank 0, N=1 only), bounded sample
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -365,10 +390,12 @@ def run_ours(args):
                    "device_path": "fused mp2p_b200_iterate_* call (N=1) / sharded search+all_gather+resolve+all_reduce (N>1)", "unit_note": "at N GPUs one step is one query-sharded iteration over N x queries_per_gpu; value counts N iteration-equivalents per step",
                    "index": {"build_ms": info["build_ms"], "finest_cell_m": info["finest_cell_size"], "levels": info["n_levels"], "bytes": info["index_bytes"]}},
         "e2e": {"value": unit_scale * 1e3 / ms_e2e, "unit": "iterations/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "timing": "wall clock around the C-ABI calls, pinned host buffers"},
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "timing": "wall clock around the C-ABI calls, pinned host buffers",
+                "pcie_h2d_gbs": pcie[0], "pcie_d2h_gbs": pcie[1],
+                "pcie_floor_ms": (h2d / (pcie[0] * 1e9) + d2h / (pcie[1] * 1e9)) * 1e3},
         "gpu_launches": int(launches * args.steps),
         "roofline": {"kernel": "k_match_" + w["matcher"], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": nn_ms_mean,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": nn_ms_mean,
                      "algorithmic_bytes": int(alg_bytes), "probes": st["probes"], "candidates": st["candidates"],
                      "climbed_queries": st["climbed"], "other_kernels_ms": {k: v for k, v in tm.items() if k != "nn_search"}},
         "cpu_baseline": cpu,

@@ -603,6 +603,11 @@ extern "C"
         DeviceGuard g(ctx->device);
         ProfScope   ps(ctx);
         const uint64_t cap = pairs_device ? capacity : n_local * mprm->pairingsPerPoint;
+        if (cap < n_local * mprm->pairingsPerPoint)
+        {
+            set_error("iterate_pt2pt_horn: pairs_device must hold n_local*pairingsPerPoint records");
+            return MP2P_B200_ERR_CAPACITY;
+        }
         if (!pairs_device)
         {
             MP2P_TRY(ctx->d_out2p.ensure(cap * sizeof(mp2p_b200_pair_pt2pt)));
@@ -618,13 +623,13 @@ extern "C"
         if (!dm.d_count) return 0;  // empty map or cloud: no pairings (ICP: NoPairings)
         const auto* d2p = static_cast<const mp2p_b200_pair_pt2pt*>(dm.d_pairs);
         MP2P_TRY(run_horn_moments(ctx, d2p, dm.capacity, sprm, dp0, dm.capacity, nullptr, nullptr, 0, nullptr, dp1, dm.d_count));
-        double*             hp = pinned_packets(ctx);
-        unsigned long long* hc = static_cast<unsigned long long*>(ctx->h_pinned);
+        // one D2H copy brings both packets; the pairing count rides in the HORN1 packet ([6], exact
+        // in a double up to 2^53)
+        double* hp = pinned_packets(ctx);
         MP2P_CUDA_TRY(cudaMemcpyAsync(hp, dp0, 2 * MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        MP2P_CUDA_TRY(cudaMemcpyAsync(hc, dm.d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
         MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         MP2P_CUDA_TRY(cudaGetLastError());
-        *n_pairs = *hc;
+        *n_pairs = (uint64_t)hp[6];
         if (*n_pairs > dm.capacity)
         {
             set_error("iterate_pt2pt_horn: pairings buffer too small");

@@ -1131,12 +1131,15 @@ __global__ void __launch_bounds__(256)
     out_found[i] = cnt;
 }
 
-// tuning knob (measurement only): MP2P_KNN_LANE=0 falls back to the group kernel for every k > 1
+// MP2P_KNN_LANE=1 selects the lane-per-query kernel (k_match_knn_lane) for k in 2..16. Measured on
+// C3 (119k queries, k = 8): half the instructions of the group kernel but 3x slower — 3.7k warps of
+// long serial chains cannot hide latency, the group kernel's 30k warps can
+// (profiles/r01_c3_knn_lane_ab.txt). Kept for query counts >= ~1M per GPU; default = group kernel.
 bool knn_lane_enabled()
 {
     static const bool v = [] {
         const char* e = getenv("MP2P_KNN_LANE");
-        return !(e && atoi(e) == 0);
+        return e && atoi(e) == 1;
     }();
     return v;
 }

@@ -43,18 +43,18 @@ def allreduce_gn_solve(accumulate_fn, prm: capi.GNParams, pose0, dist, group=Non
     """accumulate_fn(pose 3x4) -> tensor[32] (GN packet of the shard at that pose).
     optimal_tf_gauss_newton.cpp:70-366 with the reduction spread over ranks."""
     T = np.array(pose0, dtype=np.float64).reshape(3, 4)
-    it = 0
-    for it in range(prm.maxInnerLoopIterations):
+    updates = 0  # number of pose updates applied (what mp2p_b200_solve_gauss_newton reports)
+    for _ in range(prm.maxInnerLoopIterations):
         pk = accumulate_fn(T)
         dist.all_reduce(pk, group=group)
         h = pk.detach().cpu().numpy()
         if np.sqrt(h[27]) <= prm.maxCost:
             break
         T, conv = capi.gn_step_from_packet(h, prm, T)
+        updates += 1
         if conv:
-            it += 1
             break
-    return True, T, it
+    return True, T, updates
 
 
 class _SingleProcess:

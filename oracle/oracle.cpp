@@ -679,7 +679,7 @@ extern "C"
                                     double T_out[12], uint32_t* iters_done, int nthreads)
     {
         Pose     pose = to_pose(T_init);  // :50
-        uint32_t it   = 0;
+        uint32_t it = 0, updates = 0;
         for (; it < prm->maxInnerLoopIterations; it++)
         {
             double H[36], g[6], errSq = 0;
@@ -689,16 +689,13 @@ extern "C"
             for (int k = 0; k < 6; k++) mg[k] = -g[k];
             ldlt_solve6(H, mg, delta);  // :351
             pose = compose(pose, se3_exp(delta));  // :354-356
+            updates++;
             double nrm = 0;
             for (double d : delta) nrm += d * d;
-            if (std::sqrt(nrm) < prm->minDelta)  // :365
-            {
-                it++;
-                break;
-            }
+            if (std::sqrt(nrm) < prm->minDelta) break;  // :365
         }
         std::memcpy(T_out, pose.m, sizeof(pose.m));
-        if (iters_done) *iters_done = it;
+        if (iters_done) *iters_done = updates;  // number of pose updates applied
         return 1;
     }
 
