@@ -188,7 +188,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     w = make_workload(args.workload, shard=rank, n_shards=world)
-    stream = torch.cuda.current_stream()
+    # one explicit stream for everything: our kernels, torch's copies / events, NCCL collectives
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     ctx = b200.Context(local_rank, stream=stream.cuda_stream)
     gmap = b200.Map(ctx, *xyz(w["map"]))
     info = gmap.info
@@ -227,22 +229,27 @@ def run_ours(args):
             return sh.solve_horn(d_pairs.data_ptr(), n_pairs, sprm)[1]
         return sh.solve_gauss_newton(None, 0, d_pairs.data_ptr(), n_pairs, sprm, pose)[1]
 
+    # the local layer is constant over an align(): resident cloud, uploaded + Morton-sorted once
+    # (like the map index; reported as config.local_cloud.build_ms, outside the per-iteration time)
+    cloud = None
+    if args.local == "cloud":
+        cloud = b200.Cloud(ctx, d_l[0].data_ptr(), d_l[1].data_ptr(), d_l[2].data_ptr(), n=nq, on_device=True)
+    lp = (cloud, None, None) if cloud is not None else (d_l[0].data_ptr(), d_l[1].data_ptr(), d_l[2].data_ptr())
     fused = None
     if world == 1:  # both plugins ours: fused iteration, pairings stay in HBM, one synchronisation
-        fused = gmap.make_iterator(d_l[0].data_ptr(), d_l[1].data_ptr(), d_l[2].data_ptr(), nq, mprm, sprm, d_pairs.data_ptr(), cap)
+        fused = gmap.make_iterator(*lp, nq, mprm, sprm, d_pairs.data_ptr(), cap)
 
     def step_device():
         if fused is not None:
             ok, T, n_pairs = fused(pose)
             return n_pairs, T
-        lp = (d_l[0].data_ptr(), d_l[1].data_ptr(), d_l[2].data_ptr())
         if w["matcher"] == "pt2pt":
-            if world > 1:  # exact cross-shard first-claim dedup: search -> all_gather -> resolve
-                n_pairs = sh.match_pt2pt(*lp, pose, mprm, d_pairs.data_ptr(), cap)
-            else:
-                n_pairs, _ = gmap.match_pt2pt(*lp, pose, mprm, n_local=nq, local_on_device=True, out=d_pairs.data_ptr(), out_on_device=True, capacity=cap)
-        else:  # pt2pl never dedups global points (Matcher_Point2Plane.cpp:87-90): shards are independent
-            n_pairs, _ = gmap.match_pt2pl(*lp, pose, mprm, n_local=nq, local_on_device=True, out=d_pairs.data_ptr(), out_on_device=True, capacity=cap)
+            # exact cross-shard first-claim dedup: search -> in-place all_gather of the exchange
+            # records -> resolve (+HORN1 sums) -> all_reduce -> HORN2 -> all_reduce, ONE host sync
+            ok, T, n_all = sh.iterate_pt2pt_horn(lp, pose, mprm, sprm, d_pairs.data_ptr(), cap)
+            return n_all, T
+        # pt2pl never dedups global points (Matcher_Point2Plane.cpp:87-90): shards are independent
+        n_pairs, _ = gmap.match_pt2pl(*lp, pose, mprm, n_local=nq, local_on_device=True, out=d_pairs.data_ptr(), out_on_device=True, capacity=cap)
         return n_pairs, solve_device(n_pairs)
 
     def step_e2e():
@@ -319,7 +326,6 @@ def run_ours(args):
     # ---- roofline pass: per-kernel CUDA events (stats OFF: the counters add same-address atomics),
     # then ONE untimed call with the search statistics on. Not part of the timed region above.
     def match_once():
-        lp = (d_l[0].data_ptr(), d_l[1].data_ptr(), d_l[2].data_ptr())
         if w["matcher"] == "pt2pt":
             gmap.match_pt2pt(*lp, pose, mprm, n_local=nq, local_on_device=True, out=d_pairs.data_ptr(), out_on_device=True, capacity=cap)
         else:
@@ -388,6 +394,7 @@ def run_ours(args):
                    "pairs": int(n_pairs), "l2": "flushed between timed steps (256 MiB memset, outside the event bracket)",
                    "ms_per_step_l2_warm_informative": ms_warm,
                    "device_path": "fused mp2p_b200_iterate_* call (N=1) / sharded search+all_gather+resolve+all_reduce (N>1)", "unit_note": "at N GPUs one step is one query-sharded iteration over N x queries_per_gpu; value counts N iteration-equivalents per step",
+                   "local_cloud": ({"resident": True, "order": "Morton-sorted copy, built once per align()", "build_ms": cloud.info["build_ms"]} if cloud is not None else {"resident": False}),
                    "index": {"build_ms": info["build_ms"], "finest_cell_m": info["finest_cell_size"], "levels": info["n_levels"], "bytes": info["index_bytes"]}},
         "e2e": {"value": unit_scale * 1e3 / ms_e2e, "unit": "iterations/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "timing": "wall clock around the C-ABI calls, pinned host buffers",
@@ -414,6 +421,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C2", "C3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--local", default="cloud", choices=["cloud", "arrays"], help="device path: resident Morton-sorted local cloud (default) or plain device arrays in the caller's order")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -121,9 +121,16 @@ typedef struct
     float    build_ms; /* device time of the index build (CUDA events) */
 } mp2p_b200_map_info;
 
+typedef struct
+{
+    uint64_t     n_points;
+    float        build_ms;                       /* device time of upload + sort (CUDA events) */
+    const float *x_device, *y_device, *z_device; /* the cloud in the caller's order, device memory */
+} mp2p_b200_cloud_info;
+
 /* Accumulator packets (32 doubles each; what a multi-GPU caller all-reduces with SUM):
  *  GN   : [0..20] upper triangle of H row-major, [21..26] g, [27] sum w|e|^2, [28] pair count
- *  HORN1: [0..2] sum local, [3..5] sum global, [6] count (non-outlier pairs)
+ *  HORN1: [0..2] sum local, [3..5] sum global, [6] count (non-outlier pairs), [7] pairs (all)
  *  HORN2: [0..8] S row-major (sum w r b^T), [9] w_sum, [10] new outliers, [11] pairs used   */
 #define MP2P_B200_PACKET_DOUBLES 32
 
@@ -147,6 +154,24 @@ int  mp2p_b200_map_create(mp2p_b200_ctx* ctx, const float* x, const float* y, co
                           uint64_t n, int on_device, mp2p_b200_map** out);
 void mp2p_b200_map_destroy(mp2p_b200_map* map);
 int  mp2p_b200_map_get_info(const mp2p_b200_map* map, mp2p_b200_map_info* out);
+
+/* A LOCAL cloud kept on the device for a whole ICP::align(): the local layer does not change
+ * between iterations (ICP.cpp:123-308 only moves the pose), so it is uploaded once and a second
+ * copy is sorted along a Morton curve — warps of the search kernels then work on spatially
+ * neighbouring queries and share hash cells / map points in L1/L2. Results are always reported
+ * under the caller's original indices and in the reference's order; the sort is invisible.
+ * Every entry point below that takes `lx, ly, lz, n_local, local_on_device` accepts
+ *   local_on_device = 0  host arrays (copied on every call),
+ *                     1  device arrays (used in place, caller's order),
+ *                     2  `lx` is a mp2p_b200_cloud* (cast), `ly`/`lz` ignored, n_local = its size. */
+typedef struct mp2p_b200_cloud mp2p_b200_cloud;
+#define MP2P_B200_LOCAL_HOST 0
+#define MP2P_B200_LOCAL_DEVICE 1
+#define MP2P_B200_LOCAL_CLOUD 2
+int  mp2p_b200_cloud_create(mp2p_b200_ctx* ctx, const float* x, const float* y, const float* z,
+                            uint64_t n, int on_device, mp2p_b200_cloud** out);
+void mp2p_b200_cloud_destroy(mp2p_b200_cloud* cloud);
+int  mp2p_b200_cloud_get_info(const mp2p_b200_cloud* cloud, mp2p_b200_cloud_info* out);
 
 /* Raw k-NN of already-transformed query points (ascending (d2, index), d2 < radius2 strictly;
  * out_idx/out_d2 are [nq*k], out_found [nq]); replaces nn_single_search / nn_multiple_search /
@@ -183,31 +208,41 @@ int mp2p_b200_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* l
                           uint64_t* potential_pairings);
 
 /* ---- query-sharded pt2pt matching, one process per GPU --------------------------
- * The local cloud of n_total points is split in contiguous shards; rank r owns
- * [index_offset, index_offset + n_local). The map (and its index) is replicated on every GPU.
- *  phase A `..._shard_search`: transform + NN search of the shard; writes n_local*pairingsPerPoint
- *     64-bit candidate words and the shard's bounding box (24 opaque bytes: 6 order-preserving
- *     32-bit words, min xyz / max xyz) to DEVICE memory owned by the caller;
- *  (caller) all-gather the candidate words of all shards into cand_all[n_total*pairingsPerPoint] and
- *     the boxes into bbox_parts[n_shards*6] — NCCL all_gather over NVLink;
+ * The local cloud is split in contiguous shards of `per_shard` points (the last may be shorter, or
+ * empty); shard r owns the local indices [r*per_shard, r*per_shard + n_local_r). The map (and its
+ * index) is replicated on every GPU. The shards talk through fixed-size EXCHANGE RECORDS of
+ * mp2p_b200_shard_record_words(per_shard, pairingsPerPoint) 64-bit words:
+ *     [per_shard*pairingsPerPoint candidate words | 24 opaque bytes: the shard's bounding box | pad]
+ *  phase A `..._shard_search`: transform + NN search of the shard; writes the shard's record to
+ *     DEVICE memory of the caller (asynchronous: no host synchronisation);
+ *  (caller) all-gather the records of all shards, rank order, contiguous — ONE collective
+ *     (NCCL all_gather over NVLink), nothing to repack on either side;
  *  phase B `..._shard_resolve`: replays every shard's proposals on this GPU's first-claim array
  *     with the global proposal numbering, applies the bounding-box gate of the WHOLE cloud and
- *     compacts this shard's accepted pairs (localIdx = index in the whole cloud).
+ *     compacts this shard's accepted pairs (localIdx = index in the whole cloud). Optionally the
+ *     HORN1 sums of the shard's pairs are produced in the same pass (horn_sums_packet_device).
+ *     With out_count == NULL (device output only) the call is asynchronous as well: the pairing
+ *     count stays on the device and the solver building blocks below take it from there when
+ *     given n = MP2P_B200_COUNT_ON_DEVICE — a whole sharded iteration then needs ONE host
+ *     synchronisation (reading the final packets).
  * Concatenating the shards' outputs in rank order gives exactly the single-GPU result.
  * Phase B must follow phase A on the same context (the staged shard is reused). */
+#define MP2P_B200_COUNT_ON_DEVICE UINT64_MAX
+uint64_t mp2p_b200_shard_record_words(uint64_t per_shard, uint32_t pairingsPerPoint);
 int mp2p_b200_match_pt2pt_shard_search(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx,
                                        const float* ly, const float* lz, uint64_t n_local,
                                        int local_on_device, const double pose[12],
                                        const mp2p_b200_pt2pt_params* params,
-                                       const uint32_t* local_paired_bits, uint64_t* cand_out_device,
-                                       void* bbox6_out_device);
+                                       const uint32_t* local_paired_bits, uint64_t per_shard,
+                                       uint64_t* record_out_device);
 int mp2p_b200_match_pt2pt_shard_resolve(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_local,
-                                        uint64_t index_offset, uint64_t n_total,
-                                        const uint64_t* cand_all_device, const void* bbox_parts_device,
-                                        uint32_t n_shards, const mp2p_b200_pt2pt_params* params,
+                                        uint32_t shard_rank, uint32_t n_shards, uint64_t per_shard,
+                                        const uint64_t* records_device,
+                                        const mp2p_b200_pt2pt_params* params,
                                         const uint32_t* global_paired_bits,
                                         mp2p_b200_pair_pt2pt* out_pairs, uint64_t capacity,
-                                        int out_on_device, uint64_t* out_count);
+                                        int out_on_device, uint64_t* out_count /* may be NULL */,
+                                        double* horn_sums_packet_device /* may be NULL */);
 
 /* optimal_tf_horn (mp2p_icp/src/optimal_tf_horn.cpp:201-252) over pt2pt pairings:
  * eval_centroids_robust (Pairings.cpp:68-110) + visit_correspondences S accumulation
@@ -250,7 +285,11 @@ int mp2p_b200_iterate_pt2pl_gn(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const flo
 
 /* ---- building blocks for query-sharded multi-GPU runs: each rank accumulates
  * over its shard, the caller all-reduces the 32-double packet (SUM), every rank finishes the
- * solve redundantly. `packet` may be host or device memory (packet_on_device). ---- */
+ * solve redundantly. `packet` may be host or device memory (packet_on_device); with device pairs
+ * AND a device packet the calls only enqueue work. `n` / `n_pt2pt` = MP2P_B200_COUNT_ON_DEVICE: the
+ * pairs are the device output of the preceding shard_resolve, whose count is read on the device.
+ * horn_moments: n_total_pairs = 0 takes the pair count of the WHOLE cloud from the reduced HORN1
+ * packet ([7]) on the device instead of from the host. ---- */
 int mp2p_b200_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* pairs_pt2pt,
                             uint64_t n_pt2pt, const mp2p_b200_pair_pt2pl* pairs_pt2pl,
                             uint64_t n_pt2pl, int pairs_on_device, const mp2p_b200_gn_params* params,

@@ -9,6 +9,7 @@ anywhere, every compute call needs the built library and a CUDA device.
 from .capi import (  # noqa: F401
     PAIR_PT2PL,
     PAIR_PT2PT,
+    Cloud,
     Context,
     GNParams,
     HornParams,

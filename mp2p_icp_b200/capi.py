@@ -157,7 +157,10 @@ EXPORTS = [
     "mp2p_b200_ctx_get_timings", "mp2p_b200_ctx_get_search_stats",
     "mp2p_b200_match_pt2pt_shard_search", "mp2p_b200_match_pt2pt_shard_resolve",
     "mp2p_b200_iterate_pt2pt_horn", "mp2p_b200_iterate_pt2pl_gn",
+    "mp2p_b200_cloud_create", "mp2p_b200_cloud_destroy", "mp2p_b200_cloud_get_info",
+    "mp2p_b200_shard_record_words",
 ]
+COUNT_ON_DEVICE = (1 << 64) - 1  # MP2P_B200_COUNT_ON_DEVICE
 
 _lib = None
 
@@ -181,9 +184,16 @@ def load_library():
     L.mp2p_b200_ctx_destroy.argtypes = [C.c_void_p]
     L.mp2p_b200_ctx_synchronize.argtypes = [C.c_void_p]
     L.mp2p_b200_map_destroy.argtypes = [C.c_void_p]
+    L.mp2p_b200_cloud_destroy.argtypes = [C.c_void_p]
+    L.mp2p_b200_shard_record_words.restype = C.c_uint64
+    L.mp2p_b200_shard_record_words.argtypes = [C.c_uint64, C.c_uint32]
     L.mp2p_b200_host_free.argtypes = [C.c_void_p]
     _lib = L
     return L
+
+
+def shard_record_words(per_shard: int, k: int) -> int:
+    return int(load_library().mp2p_b200_shard_record_words(per_shard, k))
 
 
 def _check(rc: int):
@@ -224,9 +234,13 @@ class Context:
     def __init__(self, device: int = 0, stream: int | None = None):
         L = load_library()
         h = C.c_void_p()
+        if stream is not None and int(stream) == 0:
+            # handle 0 is the legacy default stream; the C ABI reads NULL as "create a private stream"
+            raise Mp2pError("cannot share the legacy default stream (handle 0): make a torch.cuda.Stream() current and pass its .cuda_stream")
         _check(L.mp2p_b200_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
         self._h = h
         self.device = device
+        self.stream = int(stream) if stream else None  # None: the context owns a private stream
         self._maps = weakref.WeakSet()
 
     def close(self):
@@ -339,6 +353,54 @@ def horn_finish(sums, moments):
     return bool(solved.value), out.reshape(3, 4)
 
 
+class _CloudInfo(C.Structure):
+    _fields_ = [("n_points", C.c_uint64), ("build_ms", C.c_float), ("x_device", C.c_void_p), ("y_device", C.c_void_p), ("z_device", C.c_void_p)]
+
+
+class Cloud:
+    """A LOCAL cloud resident on the GPU for a whole align(): caller-order copy + Morton-sorted copy
+    (mp2p_b200_cloud_create). Pass it as `lx` (ly = lz = None) to the matchers / iterators."""
+
+    def __init__(self, ctx: Context, x, y, z, n=None, on_device=False):
+        self.ctx = ctx
+        if not on_device:
+            x, y, z = _f32(x), _f32(y), _f32(z)
+            n = x.size
+        h = C.c_void_p()
+        _check(load_library().mp2p_b200_cloud_create(ctx._h, _ptr(x), _ptr(y), _ptr(z), C.c_uint64(n), int(on_device), C.byref(h)))
+        self._h = h
+        self.n = int(n)
+        ctx._maps.add(self)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            if getattr(self.ctx, "_h", None):
+                load_library().mp2p_b200_cloud_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def info(self) -> dict:
+        inf = _CloudInfo()
+        _check(load_library().mp2p_b200_cloud_get_info(self._h, C.byref(inf)))
+        return {"n_points": inf.n_points, "build_ms": inf.build_ms, "x_device": inf.x_device, "y_device": inf.y_device, "z_device": inf.z_device}
+
+
+def _local(lx, ly, lz, n_local, local_on_device):
+    """-> (lx, ly, lz as void*, n_local, kind) for the `lx, ly, lz, n_local, local_on_device` arguments."""
+    if isinstance(lx, Cloud):
+        return lx._h, None, None, lx.n, 2
+    if not local_on_device:
+        lx, ly, lz = _f32(lx), _f32(ly), _f32(lz)
+        return _ptr(lx), _ptr(ly), _ptr(lz), lx.size, 0
+    return _ptr(lx), _ptr(ly), _ptr(lz), n_local, 1
+
+
 class Map:
     """A global map layer resident on the GPU with its NN index (nn_prepare_for_3d_queries)."""
 
@@ -388,9 +450,7 @@ class Map:
     def match_pt2pt(self, lx, ly, lz, T, prm: Pt2PtParams, local_paired=None, global_paired=None, n_local=None, local_on_device=False, out=None, out_on_device=False, capacity=None):
         """Returns (pairs, potential_pairings); `pairs` is a numpy view of `out[:count]` for host
         output, or the count for device output."""
-        if not local_on_device:
-            lx, ly, lz = _f32(lx), _f32(ly), _f32(lz)
-            n_local = lx.size
+        plx, ply, plz, n_local, kind = _local(lx, ly, lz, n_local, local_on_device)
         cap = capacity if capacity is not None else n_local * prm.pairingsPerPoint
         if out is None and not out_on_device:
             out = np.empty(max(cap, 1), PAIR_PT2PT)
@@ -398,28 +458,31 @@ class Map:
         gb = pack_bits(global_paired) if global_paired is not None else None
         cp = prm.c()
         cnt, pot = C.c_uint64(0), C.c_uint64(0)
-        _check(load_library().mp2p_b200_match_pt2pt(self.ctx._h, self._h, _ptr(lx), _ptr(ly), _ptr(lz), C.c_uint64(n_local), int(local_on_device), _ptr(_pose(T)), C.byref(cp), _ptr(lb), _ptr(gb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt), C.byref(pot)))
+        _check(load_library().mp2p_b200_match_pt2pt(self.ctx._h, self._h, plx, ply, plz, C.c_uint64(n_local), kind, _ptr(_pose(T)), C.byref(cp), _ptr(lb), _ptr(gb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt), C.byref(pot)))
         if out_on_device:
             return cnt.value, pot.value
         return out[: cnt.value], pot.value
 
-    def shard_search_pt2pt(self, lx, ly, lz, T, prm: Pt2PtParams, cand_out: int, bbox6_out: int, n_local=None, local_on_device=False, local_paired=None):
-        """Phase A of the query-sharded matcher; cand_out / bbox6_out are DEVICE addresses."""
-        if not local_on_device:
-            lx, ly, lz = _f32(lx), _f32(ly), _f32(lz)
-            n_local = lx.size
+    def shard_search_pt2pt(self, lx, ly, lz, T, prm: Pt2PtParams, per_shard: int, record_out: int, n_local=None, local_on_device=False, local_paired=None):
+        """Phase A of the query-sharded matcher; record_out is a DEVICE address with room for
+        shard_record_words(per_shard, K) 64-bit words. Asynchronous."""
+        plx, ply, plz, n_local, kind = _local(lx, ly, lz, n_local, local_on_device)
         lb = pack_bits(local_paired) if local_paired is not None else None
         cp = prm.c()
-        _check(load_library().mp2p_b200_match_pt2pt_shard_search(self.ctx._h, self._h, _ptr(lx), _ptr(ly), _ptr(lz), C.c_uint64(n_local), int(local_on_device), _ptr(_pose(T)), C.byref(cp), _ptr(lb), C.c_void_p(int(cand_out)), C.c_void_p(int(bbox6_out))))
+        _check(load_library().mp2p_b200_match_pt2pt_shard_search(self.ctx._h, self._h, plx, ply, plz, C.c_uint64(n_local), kind, _ptr(_pose(T)), C.byref(cp), _ptr(lb), C.c_uint64(per_shard), C.c_void_p(int(record_out))))
 
-    def shard_resolve_pt2pt(self, n_local, index_offset, n_total, cand_all: int, bbox_parts: int, n_shards, prm: Pt2PtParams, global_paired=None, out=None, out_on_device=False, capacity=None):
+    def shard_resolve_pt2pt(self, n_local, shard_rank, n_shards, per_shard, records: int, prm: Pt2PtParams, global_paired=None, out=None, out_on_device=False, capacity=None, sync=True, horn_sums: int = 0):
+        """Phase B. sync=False (device output only): nothing is read back, returns None; the count
+        stays on the device for solver calls given n=COUNT_ON_DEVICE."""
         cap = capacity if capacity is not None else n_local * prm.pairingsPerPoint
         if out is None and not out_on_device:
             out = np.empty(max(cap, 1), PAIR_PT2PT)
         gb = pack_bits(global_paired) if global_paired is not None else None
         cp = prm.c()
         cnt = C.c_uint64(0)
-        _check(load_library().mp2p_b200_match_pt2pt_shard_resolve(self.ctx._h, self._h, C.c_uint64(n_local), C.c_uint64(index_offset), C.c_uint64(n_total), C.c_void_p(int(cand_all)), C.c_void_p(int(bbox_parts)), C.c_uint32(n_shards), C.byref(cp), _ptr(gb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt)))
+        _check(load_library().mp2p_b200_match_pt2pt_shard_resolve(self.ctx._h, self._h, C.c_uint64(n_local), C.c_uint32(shard_rank), C.c_uint32(n_shards), C.c_uint64(per_shard), C.c_void_p(int(records)), C.byref(cp), _ptr(gb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt) if sync else None, C.c_void_p(int(horn_sums)) if horn_sums else None))
+        if not sync:
+            return None
         if out_on_device:
             return cnt.value
         return out[: cnt.value]
@@ -432,7 +495,8 @@ class Map:
         mp, sp = matcher_prm.c(), solver_prm.c()
         pose_in, pose_out = (C.c_double * 12)(), (C.c_double * 12)()
         solved, n_pairs, iters, pot = C.c_int32(0), C.c_uint64(0), C.c_uint32(0), C.c_uint64(0)
-        args = [self.ctx._h, self._h, C.c_void_p(int(lx)), C.c_void_p(int(ly)), C.c_void_p(int(lz)), C.c_uint64(n_local), 1, pose_in, C.byref(mp), C.byref(sp), C.c_void_p(int(pairs_device)) if pairs_device else None, C.c_uint64(capacity), pose_out, C.byref(solved), C.byref(n_pairs)]
+        plx, ply, plz, n_local, kind = _local(lx, ly, lz, n_local, True)
+        args = [self.ctx._h, self._h, plx, ply, plz, C.c_uint64(n_local), kind, pose_in, C.byref(mp), C.byref(sp), C.c_void_p(int(pairs_device)) if pairs_device else None, C.c_uint64(capacity), pose_out, C.byref(solved), C.byref(n_pairs)]
         if is_pt2pt:
             fn, args = L.mp2p_b200_iterate_pt2pt_horn, args + [C.byref(pot)]
         else:
@@ -449,16 +513,14 @@ class Map:
         return step
 
     def match_pt2pl(self, lx, ly, lz, T, prm: Pt2PlParams, local_paired=None, n_local=None, local_on_device=False, out=None, out_on_device=False, capacity=None):
-        if not local_on_device:
-            lx, ly, lz = _f32(lx), _f32(ly), _f32(lz)
-            n_local = lx.size
+        plx, ply, plz, n_local, kind = _local(lx, ly, lz, n_local, local_on_device)
         cap = capacity if capacity is not None else n_local
         if out is None and not out_on_device:
             out = np.empty(max(cap, 1), PAIR_PT2PL)
         lb = pack_bits(local_paired) if local_paired is not None else None
         cp = prm.c()
         cnt, pot = C.c_uint64(0), C.c_uint64(0)
-        _check(load_library().mp2p_b200_match_pt2pl(self.ctx._h, self._h, _ptr(lx), _ptr(ly), _ptr(lz), C.c_uint64(n_local), int(local_on_device), _ptr(_pose(T)), C.byref(cp), _ptr(lb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt), C.byref(pot)))
+        _check(load_library().mp2p_b200_match_pt2pl(self.ctx._h, self._h, plx, ply, plz, C.c_uint64(n_local), kind, _ptr(_pose(T)), C.byref(cp), _ptr(lb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt), C.byref(pot)))
         if out_on_device:
             return cnt.value, pot.value
         return out[: cnt.value], pot.value

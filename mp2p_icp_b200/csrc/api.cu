@@ -47,6 +47,13 @@ struct ProfScope
     ~ProfScope() { prof_collect(c); }
 };
 
+// local cloud arguments: kind 2 = `lx` is a mp2p_b200_cloud handle (ly, lz unused)
+inline bool bad_local(const float* lx, const float* ly, const float* lz, int kind)
+{
+    if (kind < 0 || kind > 2) return true;
+    return kind == 2 ? !lx : (!lx || !ly || !lz);
+}
+
 struct DeviceGuard
 {
     int  prev = -1;
@@ -63,6 +70,21 @@ struct DeviceGuard
 };
 
 double* pinned_packets(mp2p_b200_ctx* c) { return reinterpret_cast<double*>(static_cast<char*>(c->h_pinned) + 256); }
+
+// n == MP2P_B200_COUNT_ON_DEVICE: the pairs are the previous matcher call's device output and
+// their count never left the device; the kernels read it there (n becomes the grid-size bound).
+int count_on_device(mp2p_b200_ctx* ctx, uint64_t* n, int pairs_on_device, const unsigned long long** d_n)
+{
+    *d_n = nullptr;
+    if (*n != MP2P_B200_COUNT_ON_DEVICE) return 0;
+    if (!pairs_on_device)
+    {
+        set_error("MP2P_B200_COUNT_ON_DEVICE needs pairs_on_device");
+        return MP2P_B200_ERR_ARG;
+    }
+    *n = ctx->last_count ? ctx->last_capacity : 0, *d_n = ctx->last_count;
+    return 0;
+}
 
 template <class Rec>
 int stage_pairs(mp2p_b200_ctx* ctx, DevBuf& buf, const Rec* pairs, uint64_t n, int on_device, const Rec** d_out)
@@ -246,6 +268,49 @@ extern "C"
         return 0;
     }
 
+    // ------------------------------------------------------------------------------ resident cloud
+    int mp2p_b200_cloud_create(mp2p_b200_ctx* ctx, const float* x, const float* y, const float* z, uint64_t n,
+                               int on_device, mp2p_b200_cloud** out)
+    {
+        if (!ctx || !out || (n && (!x || !y || !z)))
+        {
+            set_error("cloud_create: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        *out = nullptr;
+        DeviceGuard g(ctx->device);
+        auto*       c = new (std::nothrow) mp2p_b200_cloud();
+        if (!c) return MP2P_B200_ERR_NOMEM;
+        const int rc = build_cloud(ctx, c, x, y, z, n, on_device);
+        if (rc != 0)
+        {
+            mp2p_b200_cloud_destroy(c);
+            return rc;
+        }
+        *out = c;
+        return 0;
+    }
+
+    void mp2p_b200_cloud_destroy(mp2p_b200_cloud* c)
+    {
+        if (!c) return;
+        if (c->ctx)
+        {
+            DeviceGuard g(c->ctx->device);
+            cudaStreamSynchronize(c->ctx->stream);
+            for (DevBuf* b : {&c->d_x, &c->d_y, &c->d_z, &c->d_sx, &c->d_sy, &c->d_sz, &c->d_perm}) b->release();
+        }
+        delete c;
+    }
+
+    int mp2p_b200_cloud_get_info(const mp2p_b200_cloud* c, mp2p_b200_cloud_info* out)
+    {
+        if (!c || !out) return MP2P_B200_ERR_ARG;
+        out->n_points = c->n, out->build_ms = c->build_ms;
+        out->x_device = c->d_x.as<float>(), out->y_device = c->d_y.as<float>(), out->z_device = c->d_z.as<float>();
+        return 0;
+    }
+
     int mp2p_b200_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const float* qy,
                       const float* qz, uint64_t nq, uint32_t k, float radius2, uint32_t* out_idx,
                       float* out_d2, int32_t* out_found)
@@ -266,7 +331,7 @@ extern "C"
                               mp2p_b200_pair_pt2pt* out_pairs, uint64_t capacity, int out_on_device,
                               uint64_t* out_count, uint64_t* potential_pairings)
     {
-        if (!ctx || !map || !pose || !prm || !out_count || (n_local && (!lx || !ly || !lz)) ||
+        if (!ctx || !map || !pose || !prm || !out_count || (n_local && bad_local(lx, ly, lz, local_on_device)) ||
             (capacity && !out_pairs))
         {
             set_error("match_pt2pt: NULL argument");
@@ -295,7 +360,7 @@ extern "C"
                               uint64_t capacity, int out_on_device, uint64_t* out_count,
                               uint64_t* potential_pairings)
     {
-        if (!ctx || !map || !pose || !prm || !out_count || (n_local && (!lx || !ly || !lz)) ||
+        if (!ctx || !map || !pose || !prm || !out_count || (n_local && bad_local(lx, ly, lz, local_on_device)) ||
             (capacity && !out_pairs))
         {
             set_error("match_pt2pl: NULL argument");
@@ -313,14 +378,19 @@ extern "C"
                                out_pairs, capacity, out_on_device, out_count);
     }
 
+    uint64_t mp2p_b200_shard_record_words(uint64_t per_shard, uint32_t pairingsPerPoint)
+    {
+        return shard_record_words(per_shard, pairingsPerPoint);
+    }
+
     int mp2p_b200_match_pt2pt_shard_search(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx,
                                            const float* ly, const float* lz, uint64_t n_local,
                                            int local_on_device, const double pose[12],
                                            const mp2p_b200_pt2pt_params* prm,
-                                           const uint32_t* local_paired_bits, uint64_t* cand_out_device,
-                                           void* bbox6_out_device)
+                                           const uint32_t* local_paired_bits, uint64_t per_shard,
+                                           uint64_t* record_out_device)
     {
-        if (!ctx || !map || !pose || !prm || !bbox6_out_device || (n_local && (!lx || !ly || !lz || !cand_out_device)))
+        if (!ctx || !map || !pose || !prm || !record_out_device || (n_local && bad_local(lx, ly, lz, local_on_device)))
         {
             set_error("shard_search: NULL argument");
             return MP2P_B200_ERR_ARG;
@@ -334,30 +404,28 @@ extern "C"
         DeviceGuard g(ctx->device);
         ProfScope   ps(ctx);
         return run_shard_search_pt2pt(ctx, map, lx, ly, lz, n_local, local_on_device, pose, prm, local_paired_bits,
-                                      reinterpret_cast<unsigned long long*>(cand_out_device),
-                                      reinterpret_cast<uint32_t*>(bbox6_out_device));
+                                      per_shard, reinterpret_cast<unsigned long long*>(record_out_device));
     }
 
     int mp2p_b200_match_pt2pt_shard_resolve(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_local,
-                                            uint64_t index_offset, uint64_t n_total,
-                                            const uint64_t* cand_all_device, const void* bbox_parts_device,
-                                            uint32_t n_shards, const mp2p_b200_pt2pt_params* prm,
-                                            const uint32_t* global_paired_bits,
-                                            mp2p_b200_pair_pt2pt* out_pairs, uint64_t capacity,
-                                            int out_on_device, uint64_t* out_count)
+                                            uint32_t shard_rank, uint32_t n_shards, uint64_t per_shard,
+                                            const uint64_t* records_device, const mp2p_b200_pt2pt_params* prm,
+                                            const uint32_t* global_paired_bits, mp2p_b200_pair_pt2pt* out_pairs,
+                                            uint64_t capacity, int out_on_device, uint64_t* out_count,
+                                            double* horn_sums_packet_device)
     {
-        if (!ctx || !map || !prm || !out_count || !cand_all_device || !bbox_parts_device || n_shards == 0 ||
-            (capacity && !out_pairs))
+        if (!ctx || !map || !prm || !records_device || n_shards == 0 || (capacity && !out_pairs) ||
+            (!out_count && !out_on_device))
         {
-            set_error("shard_resolve: NULL argument");
+            set_error("shard_resolve: NULL argument (out_count may only be NULL with device output)");
             return MP2P_B200_ERR_ARG;
         }
         DeviceGuard g(ctx->device);
         ProfScope   ps(ctx);
-        return run_shard_resolve_pt2pt(ctx, map, n_local, index_offset, n_total,
-                                       reinterpret_cast<const unsigned long long*>(cand_all_device),
-                                       reinterpret_cast<const uint32_t*>(bbox_parts_device), n_shards, prm, global_paired_bits, out_pairs, capacity,
-                                       out_on_device, out_count);
+        return run_shard_resolve_pt2pt(ctx, map, n_local, shard_rank, n_shards, per_shard,
+                                       reinterpret_cast<const unsigned long long*>(records_device), prm,
+                                       global_paired_bits, out_pairs, capacity, out_on_device, out_count,
+                                       horn_sums_packet_device);
     }
 
     // ------------------------------------------------------------------------------ Horn
@@ -367,10 +435,12 @@ extern "C"
         if (!ctx || !packet || (n && !pairs)) return MP2P_B200_ERR_ARG;
         DeviceGuard                 g(ctx->device);
         ProfScope   ps(ctx);
+        const unsigned long long*   d_n;
+        MP2P_TRY(count_on_device(ctx, &n, pairs_on_device, &d_n));
         const mp2p_b200_pair_pt2pt* d;
         MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2p, pairs, n, pairs_on_device, &d));
         double* dp = packet_on_device ? packet : ctx->d_packet.as<double>();
-        MP2P_TRY(run_horn_sums(ctx, d, n, nullptr, dp));
+        MP2P_TRY(run_horn_sums(ctx, d, n, nullptr, dp, d_n));
         return packet_out(ctx, dp, packet, packet_on_device);
     }
 
@@ -382,6 +452,8 @@ extern "C"
         if (!ctx || !packet || !prm || !sums_packet || (n && !pairs)) return MP2P_B200_ERR_ARG;
         DeviceGuard                 g(ctx->device);
         ProfScope   ps(ctx);
+        const unsigned long long*   d_n;
+        MP2P_TRY(count_on_device(ctx, &n, pairs_on_device, &d_n));
         const mp2p_b200_pair_pt2pt* d;
         // note: if horn_sums staged the same host pairs just before, this re-uploads them; callers
         // that care keep the pairings on the device (pairs_on_device = 1).
@@ -394,7 +466,8 @@ extern "C"
             ds = tmp;
         }
         double* dp = packet_on_device ? packet : ctx->d_packet.as<double>() + MP2P_B200_PACKET_DOUBLES;
-        MP2P_TRY(run_horn_moments(ctx, d, n, prm, ds, n_total_pairs, nullptr, nullptr, 0, nullptr, dp));
+        MP2P_TRY(run_horn_moments(ctx, d, n, prm, ds, n_total_pairs, nullptr, nullptr, 0, nullptr, dp, d_n,
+                                  n_total_pairs ? 0 : 2));
         return packet_out(ctx, dp, packet, packet_on_device);
     }
 
@@ -505,6 +578,8 @@ extern "C"
         if (!ctx || !prm || !pose || !packet || (n2p && !p2p) || (n2l && !p2l)) return MP2P_B200_ERR_ARG;
         DeviceGuard                 g(ctx->device);
         ProfScope   ps(ctx);
+        const unsigned long long*   d_n2p;
+        MP2P_TRY(count_on_device(ctx, &n2p, pairs_on_device, &d_n2p));
         const mp2p_b200_pair_pt2pt* d2p;
         const mp2p_b200_pair_pt2pl* d2l;
         MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2p, p2p, n2p, pairs_on_device, &d2p));
@@ -513,7 +588,7 @@ extern "C"
         std::memcpy(hpose, pose, 96);
         MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_pose.p, hpose, 96, cudaMemcpyHostToDevice, ctx->stream));
         double* dp = packet_on_device ? packet : ctx->d_packet.as<double>();
-        MP2P_TRY(run_gn_accumulate(ctx, d2p, n2p, d2l, n2l, prm, ctx->d_pose.as<double>(), dp));
+        MP2P_TRY(run_gn_accumulate(ctx, d2p, n2p, d2l, n2l, prm, ctx->d_pose.as<double>(), dp, d_n2p));
         return packet_out(ctx, dp, packet, packet_on_device);
     }
 
@@ -587,7 +662,7 @@ extern "C"
                                      uint64_t capacity, double pose_out[12], int32_t* solved,
                                      uint64_t* n_pairs, uint64_t* potential_pairings)
     {
-        if (!ctx || !map || !pose || !mprm || !sprm || !pose_out || !solved || !n_pairs || (n_local && (!lx || !ly || !lz)))
+        if (!ctx || !map || !pose || !mprm || !sprm || !pose_out || !solved || !n_pairs || (n_local && bad_local(lx, ly, lz, local_on_device)))
         {
             set_error("iterate_pt2pt_horn: NULL argument");
             return MP2P_B200_ERR_ARG;
@@ -622,7 +697,7 @@ extern "C"
                                  pairs_device, cap, 1, &dummy, &dm));
         if (!dm.d_count) return 0;  // empty map or cloud: no pairings (ICP: NoPairings)
         const auto* d2p = static_cast<const mp2p_b200_pair_pt2pt*>(dm.d_pairs);
-        MP2P_TRY(run_horn_moments(ctx, d2p, dm.capacity, sprm, dp0, dm.capacity, nullptr, nullptr, 0, nullptr, dp1, dm.d_count));
+        MP2P_TRY(run_horn_moments(ctx, d2p, dm.capacity, sprm, dp0, dm.capacity, nullptr, nullptr, 0, nullptr, dp1, dm.d_count, 1));
         // one D2H copy brings both packets; the pairing count rides in the HORN1 packet ([6], exact
         // in a double up to 2^53)
         double* hp = pinned_packets(ctx);
@@ -646,7 +721,7 @@ extern "C"
                                    int32_t* solved, uint64_t* n_pairs, uint32_t* iterations_done,
                                    uint64_t* potential_pairings)
     {
-        if (!ctx || !map || !pose || !mprm || !sprm || !pose_out || !solved || !n_pairs || (n_local && (!lx || !ly || !lz)))
+        if (!ctx || !map || !pose || !mprm || !sprm || !pose_out || !solved || !n_pairs || (n_local && bad_local(lx, ly, lz, local_on_device)))
         {
             set_error("iterate_pt2pl_gn: NULL argument");
             return MP2P_B200_ERR_ARG;

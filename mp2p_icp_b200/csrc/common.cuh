@@ -106,6 +106,10 @@ struct mp2p_b200_ctx
     uint64_t     launches   = 0;
     uint32_t     scan_epoch = 0;  // stamps look-back status words (match.cu)
     uint64_t     hint_pt2pt = ~0ull, hint_pt2pl = ~0ull;  // previous pairing counts (speculative D2H size)
+    // pairing count a matcher call left on the device without reading it back (shard_resolve with
+    // out_count == NULL), consumed by solver calls given n = MP2P_B200_COUNT_ON_DEVICE
+    const unsigned long long* last_count    = nullptr;
+    uint64_t                  last_capacity = 0;
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
     // measurement hooks
     bool         prof_timings = false, prof_stats = false;
@@ -115,8 +119,12 @@ struct mp2p_b200_ctx
     mp2p::DevBuf d_stats;               // 4 x u64 search counters
 
     // matcher scratch
-    const float *cur_lx = nullptr, *cur_ly = nullptr, *cur_lz = nullptr;  // local cloud the kernels read
-    bool         cur_tma_ok = false;
+    const float *cur_lx = nullptr, *cur_ly = nullptr, *cur_lz = nullptr;  // local cloud, caller's order
+    // what the SEARCH kernels read: the same arrays, or a resident cloud's Morton-sorted copy
+    // (then cur_perm[j] = caller's index of sorted position j)
+    const float *   cur_qx = nullptr, *cur_qy = nullptr, *cur_qz = nullptr;
+    const uint32_t* cur_perm   = nullptr;
+    bool            cur_tma_ok = false;
     mp2p::DevBuf d_lx, d_ly, d_lz;     // local cloud staging (padded to kQueryTile)
     mp2p::DevBuf d_cand;               // u64 [n_local*K]  (d2 bits << 32 | map index)
     mp2p::DevBuf d_candxyz;            // float4 [n_local] coordinates of the K = 1 candidate
@@ -146,6 +154,18 @@ struct mp2p_b200_map
     uint32_t           epoch = 0;  // first-claim epoch (see match.cu)
 };
 
+// A local cloud kept resident on the device for a whole align(): caller-order SoA plus a
+// Morton-sorted copy (spatially coherent warps in the search kernels) and the permutation.
+struct mp2p_b200_cloud
+{
+    mp2p_b200_ctx* ctx = nullptr;
+    uint64_t       n   = 0;
+    mp2p::DevBuf   d_x, d_y, d_z;     // caller order
+    mp2p::DevBuf   d_sx, d_sy, d_sz;  // sorted by Morton code of the cloud's own bounding box
+    mp2p::DevBuf   d_perm;            // u32 [n]: sorted position -> caller index
+    float          build_ms = 0.f;
+};
+
 namespace mp2p
 {
 inline void count_launch(mp2p_b200_ctx* c, uint64_t n = 1) { c->launches += n; }
@@ -173,7 +193,9 @@ struct DeviceMatch
 // index.cu
 int build_index(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* x, const float* y,
                 const float* z, uint64_t n, int on_device);
-// match.cu
+int build_cloud(mp2p_b200_ctx* ctx, mp2p_b200_cloud* cloud, const float* x, const float* y, const float* z,
+                uint64_t n, int on_device);
+// match.cu — `local_on_device`: 0 host arrays, 1 device arrays, 2 = lx is a mp2p_b200_cloud*
 int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
                     const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
                     const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits, const uint32_t* gbits,
@@ -184,16 +206,16 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
                     const mp2p_b200_pt2pl_params* prm, const uint32_t* lbits,
                     mp2p_b200_pair_pt2pl* out, uint64_t capacity, int out_on_device,
                     uint64_t* out_count, DeviceMatch* keep_on_device = nullptr);
+uint64_t shard_record_words(uint64_t per_shard, uint32_t K);
 int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
                            const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
-                           const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits,
-                           unsigned long long* d_cand_out, uint32_t* d_bbox6_out);
-int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_local, uint64_t index_offset,
-                            uint64_t n_total, const unsigned long long* d_cand_all,
-                            const uint32_t* d_bbox_parts, uint32_t n_bbox_parts,
+                           const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits, uint64_t per_shard,
+                           unsigned long long* d_record);
+int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_local, uint32_t shard_rank,
+                            uint32_t n_shards, uint64_t per_shard, const unsigned long long* d_records,
                             const mp2p_b200_pt2pt_params* prm, const uint32_t* gbits,
                             mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device,
-                            uint64_t* out_count);
+                            uint64_t* out_count, double* d_horn_sums);
 int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const float* qy,
             const float* qz, uint64_t nq, uint32_t k, float radius2, uint32_t* out_idx,
             float* out_d2, int32_t* out_found);
@@ -216,5 +238,5 @@ int run_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64
                      const mp2p_b200_horn_params* prm, const double* d_sums_packet,
                      uint64_t n_total_pairs, const uint64_t* d_wcount_prefix, const double* d_wvalue,
                      uint32_t n_wblocks, uint8_t* d_outlier, double* d_packet,
-                     const unsigned long long* d_n = nullptr);
+                     const unsigned long long* d_n = nullptr, int n_total_mode = 0);
 }  // namespace mp2p

@@ -225,7 +225,113 @@ __global__ void k_fill_u64(unsigned long long* p, size_t n, unsigned long long v
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         p[i] = v;
 }
+// resident local cloud: coarse (30-bit) Morton keys of the cloud's own bounding box
+__global__ void __launch_bounds__(256)
+    k_cloud_keys(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z, uint32_t n,
+                 float ox, float oy, float oz, float inv_s0, unsigned long long* __restrict__ keys,
+                 uint32_t* __restrict__ vals)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cmax = (1 << kGridBits) - 1;
+    const int ix = min(max((int)floorf(grid_u(x[i], ox, inv_s0)), 0), cmax);
+    const int iy = min(max((int)floorf(grid_u(y[i], oy, inv_s0)), 0), cmax);
+    const int iz = min(max((int)floorf(grid_u(z[i], oz, inv_s0)), 0), cmax);
+    keys[i]      = morton63((uint32_t)ix, (uint32_t)iy, (uint32_t)iz) >> 33;  // 10 bits per axis
+    vals[i]      = i;
+}
+
+__global__ void __launch_bounds__(256)
+    k_cloud_gather(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
+                   const uint32_t* __restrict__ vals, uint32_t n, float* __restrict__ sx, float* __restrict__ sy,
+                   float* __restrict__ sz)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t i = vals[j];
+    sx[j] = x[i], sy[j] = y[i], sz[j] = z[i];
+}
 }  // namespace
+
+// Upload (or copy) a local cloud and sort a second copy along a Morton curve. The order only
+// affects which queries share a warp — results are written back under the caller's indices — so
+// any finite quantisation is valid; non-finite points simply land in the first/last cell.
+int build_cloud(mp2p_b200_ctx* ctx, mp2p_b200_cloud* cloud, const float* x, const float* y, const float* z,
+                uint64_t n64, int on_device)
+{
+    if (n64 >= (1ull << 31))
+    {
+        set_error("local cloud too large: %llu points (max 2^31-1)", (unsigned long long)n64);
+        return MP2P_B200_ERR_ARG;
+    }
+    const uint32_t n  = (uint32_t)n64;
+    cudaStream_t   st = ctx->stream;
+    cloud->ctx = ctx, cloud->n = n;
+    if (n == 0) return 0;
+    MP2P_CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+    // padded like the staging buffers of stage_local (whole query tiles are always readable)
+    const size_t bytes = ((size_t)n + kQueryTile) / kQueryTile * kQueryTile * sizeof(float);
+    for (DevBuf* b : {&cloud->d_x, &cloud->d_y, &cloud->d_z, &cloud->d_sx, &cloud->d_sy, &cloud->d_sz})
+    {
+        MP2P_TRY(b->ensure(bytes));
+        MP2P_CUDA_TRY(cudaMemsetAsync(b->p, 0, bytes, st));
+    }
+    MP2P_TRY(cloud->d_perm.ensure((size_t)n * 4));
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    MP2P_CUDA_TRY(cudaMemcpyAsync(cloud->d_x.p, x, (size_t)n * 4, kind, st));
+    MP2P_CUDA_TRY(cudaMemcpyAsync(cloud->d_y.p, y, (size_t)n * 4, kind, st));
+    MP2P_CUDA_TRY(cudaMemcpyAsync(cloud->d_z.p, z, (size_t)n * 4, kind, st));
+    const float *dx = cloud->d_x.as<float>(), *dy = cloud->d_y.as<float>(), *dz = cloud->d_z.as<float>();
+
+    DevBuf small, k0, k1, v1, tmp;
+    auto   cleanup = [&]() { small.release(), k0.release(), k1.release(), v1.release(), tmp.release(); };
+    MP2P_TRY(small.ensure(64));
+    uint32_t* d_bbox = small.as<uint32_t>();
+    {
+        const uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0};
+        MP2P_CUDA_TRY(cudaMemcpyAsync(d_bbox, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        k_bbox<<<(int)std::min<uint32_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(dx, dy, dz, n, d_bbox);
+        count_launch(ctx);
+    }
+    uint32_t h_bbox[6];
+    MP2P_CUDA_TRY(cudaMemcpyAsync(h_bbox, d_bbox, sizeof(h_bbox), cudaMemcpyDeviceToHost, st));
+    MP2P_CUDA_TRY(cudaStreamSynchronize(st));
+    float  bmin[3];
+    double extent = 0;
+    for (int d = 0; d < 3; d++)
+    {
+        bmin[d]        = ord2f(h_bbox[d]);
+        const float mx = ord2f(h_bbox[3 + d]);
+        if (!std::isfinite(bmin[d])) bmin[d] = -3.0e38f;
+        if (std::isfinite(mx)) extent = std::max(extent, (double)mx - (double)bmin[d]);
+    }
+    if (!(extent >= 1e-6)) extent = 1e-6;
+    if (!(extent < 1e38)) extent = 1e38;
+    const float inv_s0 = (float)((double)(1u << kGridBits) / (extent * (1.0 + 1e-4)));
+
+    MP2P_TRY(k0.ensure(n * 8ull));
+    MP2P_TRY(k1.ensure(n * 8ull));
+    MP2P_TRY(v1.ensure(n * 4ull));
+    k_cloud_keys<<<(n + 255) / 256, 256, 0, st>>>(dx, dy, dz, n, bmin[0], bmin[1], bmin[2], inv_s0,
+                                                  k0.as<unsigned long long>(), cloud->d_perm.as<uint32_t>());
+    count_launch(ctx);
+    {
+        const uint32_t n_tiles = (n + rs::kTile - 1) / rs::kTile;
+        MP2P_TRY(tmp.ensure(((size_t)256 * n_tiles + 256) * sizeof(uint32_t)));
+        MP2P_TRY(rs::sort_pairs(ctx, k0.as<unsigned long long>(), cloud->d_perm.as<uint32_t>(),
+                                k1.as<unsigned long long>(), v1.as<uint32_t>(), n, 30, tmp.as<uint32_t>()));
+    }
+    k_cloud_gather<<<(n + 255) / 256, 256, 0, st>>>(dx, dy, dz, cloud->d_perm.as<uint32_t>(), n,
+                                                    cloud->d_sx.as<float>(), cloud->d_sy.as<float>(),
+                                                    cloud->d_sz.as<float>());
+    count_launch(ctx);
+    MP2P_CUDA_TRY(cudaEventRecord(ctx->ev1, st));
+    MP2P_CUDA_TRY(cudaStreamSynchronize(st));
+    MP2P_CUDA_TRY(cudaGetLastError());
+    cudaEventElapsedTime(&cloud->build_ms, ctx->ev0, ctx->ev1);
+    cleanup();
+    return 0;
+}
 
 int build_index(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* x, const float* y,
                 const float* z, uint64_t n64, int on_device)

@@ -209,13 +209,15 @@ struct Pt2PtArgs
     unsigned long long tag;  // (0xFFFFFFFF - epoch) << 32
     int      tma_ok;         // local arrays are 16-byte aligned
     int      rl_start;       // relative level the search starts from (start_level())
+    int      cand_sorted;    // candidate words go to the query's SORTED position (pt2pl path)
 };
 
 // ------------------------------------------------------------------------------------------
 template <int KT, bool EXACT>
 __global__ void __launch_bounds__(kQueryTile)
     k_match_pt2pt(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
-                  const float* __restrict__ lz, const uint32_t* __restrict__ lbits,
+                  const float* __restrict__ lz, const uint32_t* __restrict__ perm,
+                  const uint32_t* __restrict__ lbits,
                   const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim,
                   unsigned long long* __restrict__ cand, uint32_t* __restrict__ bbox_words,
                   unsigned long long* __restrict__ stats)
@@ -227,8 +229,10 @@ __global__ void __launch_bounds__(kQueryTile)
     load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
     const int      sub   = threadIdx.x % kGroup, ql = threadIdx.x / kGroup;
     const unsigned gmask = ((1u << kGroup) - 1u) << ((threadIdx.x & 31) / kGroup * kGroup);
-    const uint32_t i     = (uint32_t)base + ql;
-    const bool     valid = i < a.n_local;
+    const uint32_t qpos  = (uint32_t)base + ql;  // position in the array walked (sorted if perm)
+    const bool     valid = qpos < a.n_local;
+    const uint32_t i     = (perm && valid) ? __ldg(perm + qpos) : qpos;  // the caller's index of this query
+    const uint32_t co    = a.cand_sorted ? qpos : i;                     // where its candidate words go
 
     float gx = 0, gy = 0, gz = 0;
     if (valid) compose_point_f(a.pose, tile.x[ql], tile.y[ql], tile.z[ql], gx, gy, gz);
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(kQueryTile)
                     // unused ranks are marked with an impossible map index (all ones)
                     const unsigned long long c = top.v[k] < sentinel ? top.v[k] : ~0ull;
                     n_valid += (c != ~0ull);
-                    cand[(size_t)i * K + k] = c;
+                    cand[(size_t)co * K + k] = c;
                     if (c != ~0ull && !a.allowGlobal)
                     {
                         const uint32_t gi = (uint32_t)c;
@@ -284,7 +288,8 @@ __global__ void __launch_bounds__(kQueryTile)
 template <int kItemRounds>
 __global__ void __launch_bounds__(kNN1Threads)
     k_match_pt2pt_nn1(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
-                      const float* __restrict__ lz, const uint32_t* __restrict__ lbits,
+                      const float* __restrict__ lz, const uint32_t* __restrict__ perm,
+                      const uint32_t* __restrict__ lbits,
                       const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim,
                       unsigned long long* __restrict__ cand, float4* __restrict__ cand_xyz,
                       uint32_t* __restrict__ bbox_words, unsigned long long* __restrict__ stats)
@@ -297,8 +302,9 @@ __global__ void __launch_bounds__(kNN1Threads)
     bbox_init(bacc);
     load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
     const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t i     = (uint32_t)base + threadIdx.x;
-    const bool     valid = i < a.n_local;
+    const uint32_t qpos  = (uint32_t)base + threadIdx.x;  // position in the array walked (sorted if perm)
+    const bool     valid = qpos < a.n_local;
+    const uint32_t i     = (perm && valid) ? __ldg(perm + qpos) : qpos;  // the caller's index of this query
     const unsigned FULL  = 0xffffffffu;
 
     float gx = 0, gy = 0, gz = 0;
@@ -539,247 +545,6 @@ __global__ void __launch_bounds__(kNN1Threads)
 }
 
 // ------------------------------------------------------------------------------------------
-// k > 1 matcher / k-NN of the pt2pl matcher, one LANE per query (k <= 16): the K = 1 scheme
-// (k_match_pt2pt_nn1) generalised. Each lane keeps its query's K best in registers and scans the
-// centre voxel itself; the surviving neighbour voxels of the 32 queries are pooled and dealt out
-// one (query, voxel) item per lane; an item's candidates that beat the owner's current K-th
-// distance are appended to the owner's slot list in shared memory (atomic slot counter), which the
-// owner drains into its register list afterwards. If a list overflows (kKnnBuf entries) the owner
-// re-scans its voxels itself — rare, and exact either way. Lists are rebuilt at every level, as in
-// the group kernel, so no candidate is ever offered twice.
-// ------------------------------------------------------------------------------------------
-constexpr int kKnnBuf = 24;
-
-template <int K>
-__global__ void __launch_bounds__(kNN1Threads)
-    k_match_knn_lane(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
-                     const float* __restrict__ lz, const uint32_t* __restrict__ lbits,
-                     const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim,
-                     unsigned long long* __restrict__ cand, uint32_t* __restrict__ bbox_words,
-                     unsigned long long* __restrict__ stats)
-{
-    __shared__ QueryTile<kNN1Threads> tile;
-    __shared__ BBoxAcc                bacc;
-    __shared__ uint32_t               s_cnt[kNN1Threads / 32][32];
-    __shared__ unsigned long long     s_buf[kNN1Threads / 32][32][kKnnBuf];
-    const size_t                      base = (size_t)blockIdx.x * kNN1Threads;
-    bbox_init(bacc);
-    load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
-    const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t i     = (uint32_t)base + threadIdx.x;
-    const bool     valid = i < a.n_local;
-    const unsigned FULL  = 0xffffffffu;
-
-    float gx = 0, gy = 0, gz = 0;
-    if (valid) compose_point_f(a.pose, tile.x[threadIdx.x], tile.y[threadIdx.x], tile.z[threadIdx.x], gx, gy, gz);
-    bbox_accumulate(bacc, gx, gy, gz, valid, bbox_words);
-
-    float thr2 = 0.f;
-    if (valid && (a.allowLocal || !bit_set(lbits, i)))
-    {
-        const float normSq = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
-        thr2               = __fadd_rn(a.maxDistSq, __fmul_rn(a.angSq, normSq));
-    }
-    const unsigned long long sentinel = (unsigned long long)__float_as_uint(thr2) << 32;
-    TopK<K>                  top;
-    top.init(sentinel);
-    float kth    = thr2;
-    bool  active = thr2 > 0.f;
-    if (active)
-    {
-        const float ex = fmaxf(fmaxf(g.bbmin[0] - gx, gx - g.bbmax[0]), 0.f);
-        const float ey = fmaxf(fmaxf(g.bbmin[1] - gy, gy - g.bbmax[1]), 0.f);
-        const float ez = fmaxf(fmaxf(g.bbmin[2] - gz, gz - g.bbmax[2]), 0.f);
-        if ((ex * ex + ey * ey + ez * ez) * 0.999999f > thr2) active = false;
-    }
-    const float lim = 4194304.f;  // 2^22
-    const float ux  = fminf(fmaxf(grid_u(gx, g.ox, g.inv_s0), -lim), lim);
-    const float uy  = fminf(fmaxf(grid_u(gy, g.oy, g.inv_s0), -lim), lim);
-    const float uz  = fminf(fmaxf(grid_u(gz, g.oz, g.inv_s0), -lim), lim);
-    const int   Ix = (int)floorf(ux), Iy = (int)floorf(uy), Iz = (int)floorf(uz);
-    const float q2 = g.s0_lo * g.s0_lo * 0.999999f;
-    SearchCounters sc;
-
-    // offer one point of a voxel to this lane's own list
-    auto offer = [&](const float4 p)
-    {
-        const unsigned long long c = point_key(gx, gy, gz, p);
-        if (__uint_as_float((uint32_t)(c >> 32)) <= kth && c < top.v[K - 1])
-        {
-            top.insert(c);
-            kth = fminf(kth, __uint_as_float((uint32_t)(top.v[K - 1] >> 32)));
-        }
-    };
-
-    for (int rl = a.rl_start; rl < g.n_levels; rl++)
-    {
-        if (!__any_sync(FULL, active)) break;
-        const int L = g.level_first + rl;
-        if (active) top.init(sentinel);  // rebuilt per level (kth keeps bounding from above)
-        if (L == kGridBits)
-        {
-            if (active)
-            {
-                sc.probes++, sc.cands += g.n_points, sc.levels++;
-                for (uint32_t j = 0; j < g.n_points; j++) offer(__ldg(g.pts + j));
-            }
-            break;
-        }
-        const int   cmax = ((1 << kGridBits) - 1) >> L;
-        const float s    = (float)(1 << L);
-        const int   cx = Ix >> L, cy = Iy >> L, cz = Iz >> L;
-        const float fx = ux - (float)cx * s, fy = uy - (float)cy * s, fz = uz - (float)cz * s;
-
-        // ---- centre voxel, own query
-        if (active && (unsigned)cx <= (unsigned)cmax && (unsigned)cy <= (unsigned)cmax && (unsigned)cz <= (unsigned)cmax)
-        {
-            uint32_t start, count;
-            sc.probes++;
-            if (grid_lookup(g, rl, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, start, count))
-            {
-                sc.cands += count;
-                for (uint32_t j = start; j < start + count; j++) offer(__ldg(g.pts + j));
-            }
-        }
-        // ---- surviving neighbours: bit b = dz*9 + dy*3 + dx (each 0..2)
-        uint32_t mask = 0;
-        if (active)
-        {
-            const float glx = fmaxf(fx - 4.f, 0.f), ghx = fmaxf(s - fx - 4.f, 0.f);
-            const float gly = fmaxf(fy - 4.f, 0.f), ghy = fmaxf(s - fy - 4.f, 0.f);
-            const float glz = fmaxf(fz - 4.f, 0.f), ghz = fmaxf(s - fz - 4.f, 0.f);
-            const float ax[3] = {glx * glx * q2, 0.f, ghx * ghx * q2};
-            const float ay[3] = {gly * gly * q2, 0.f, ghy * ghy * q2};
-            const float az[3] = {glz * glz * q2, 0.f, ghz * ghz * q2};
-#pragma unroll
-            for (int dz = 0; dz < 3; dz++)
-            {
-                if (az[dz] > kth || (unsigned)(cz + dz - 1) > (unsigned)cmax) continue;
-#pragma unroll
-                for (int dy = 0; dy < 3; dy++)
-                {
-                    const float t = az[dz] + ay[dy];
-                    if (t > kth || (unsigned)(cy + dy - 1) > (unsigned)cmax) continue;
-#pragma unroll
-                    for (int dx = 0; dx < 3; dx++)
-                    {
-                        if (dx == 1 && dy == 1 && dz == 1) continue;
-                        if (t + ax[dx] > kth || (unsigned)(cx + dx - 1) > (unsigned)cmax) continue;  // strict >
-                        mask |= 1u << (dz * 9 + dy * 3 + dx);
-                    }
-                }
-            }
-        }
-        // ---- pool the (query, voxel) items of the warp and deal them out one per lane
-        const uint32_t cnt  = __popc(mask);
-        uint32_t       incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            const uint32_t t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const uint32_t excl  = incl - cnt;
-        const uint32_t total = __shfl_sync(FULL, incl, 31);
-        s_cnt[warp][lane]    = 0;
-        __syncwarp();
-        for (uint32_t b0 = 0; b0 < total; b0 += 32)
-        {
-            const uint32_t id = b0 + lane;
-            int            owner = 0;  // largest lane q with excl[q] <= id
-#pragma unroll
-            for (int st = 16; st > 0; st >>= 1)
-            {
-                const int      probe = owner + st;
-                const uint32_t e     = __shfl_sync(FULL, excl, probe & 31);
-                if (probe < 32 && e <= id) owner = probe;
-            }
-            const float    oqx = __shfl_sync(FULL, gx, owner), oqy = __shfl_sync(FULL, gy, owner),
-                        oqz = __shfl_sync(FULL, gz, owner), okth = __shfl_sync(FULL, kth, owner);
-            const int      ocx = __shfl_sync(FULL, cx, owner), ocy = __shfl_sync(FULL, cy, owner),
-                      ocz = __shfl_sync(FULL, cz, owner);
-            const uint32_t omask = __shfl_sync(FULL, mask, owner), oexcl = __shfl_sync(FULL, excl, owner);
-            if (id < total)
-            {
-                const uint32_t bit = __fns(omask, 0, (int)(id - oexcl) + 1);
-                const int      dz = (int)(bit / 9u), dy = (int)((bit % 9u) / 3u), dx = (int)(bit % 3u);
-                uint32_t       start, count;
-                sc.probes++;
-                if (grid_lookup(g, rl, (uint32_t)(ocx + dx - 1), (uint32_t)(ocy + dy - 1), (uint32_t)(ocz + dz - 1), start, count))
-                {
-                    sc.cands += count;
-                    for (uint32_t j = start; j < start + count; j++)
-                    {
-                        const unsigned long long c = point_key(oqx, oqy, oqz, __ldg(g.pts + j));
-                        if (__uint_as_float((uint32_t)(c >> 32)) <= okth)
-                        {
-                            const uint32_t slot = atomicAdd(&s_cnt[warp][owner], 1u);
-                            if (slot < (uint32_t)kKnnBuf) s_buf[warp][owner][slot] = c;
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        // ---- the owner drains its list
-        {
-            const uint32_t n = s_cnt[warp][lane];
-            if (n <= (uint32_t)kKnnBuf)
-            {
-                for (uint32_t t = 0; t < n; t++)
-                {
-                    const unsigned long long c = s_buf[warp][lane][t];
-                    if (c < top.v[K - 1]) top.insert(c);
-                }
-                kth = fminf(kth, __uint_as_float((uint32_t)(top.v[K - 1] >> 32)));
-            }
-            else
-            {
-                // overflow: the list is incomplete — scan the surviving voxels again, serially
-                uint32_t m = mask;
-                while (m)
-                {
-                    const int bit = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int dz = bit / 9, dy = (bit % 9) / 3, dx = bit % 3;
-                    uint32_t  start, count;
-                    if (grid_lookup(g, rl, (uint32_t)(cx + dx - 1), (uint32_t)(cy + dy - 1), (uint32_t)(cz + dz - 1), start, count))
-                        for (uint32_t j = start; j < start + count; j++) offer(__ldg(g.pts + j));
-                }
-            }
-        }
-        __syncwarp();
-        // everything outside the 3x3x3 block is at least m quanta away
-        const float mx = s + fminf(fx, s - fx), my = s + fminf(fy, s - fy), mz = s + fminf(fz, s - fz);
-        const float m  = fmaxf(fminf(mx, fminf(my, mz)) - 4.f, 0.f);
-        if (active)
-        {
-            sc.levels++;
-            if (kth <= m * m * q2) active = false;
-        }
-    }
-
-    uint32_t n_valid = 0;
-    if (valid)
-    {
-#pragma unroll
-        for (int k = 0; k < K; k++)
-        {
-            // unused ranks are marked with an impossible map index (all ones)
-            const unsigned long long c = top.v[k] < sentinel ? top.v[k] : ~0ull;
-            n_valid += (c != ~0ull);
-            cand[(size_t)i * K + k] = c;
-            if (c != ~0ull && !a.allowGlobal)
-            {
-                const uint32_t gi = (uint32_t)c;
-                if (!bit_set(gbits, gi)) atomicMin(claim + gi, a.tag | (unsigned long long)(i * (uint32_t)K + k));
-            }
-        }
-    }
-    flush_search_stats(sc, n_valid, stats);
-}
-
-// ------------------------------------------------------------------------------------------
 // Single-pass stream compaction (decoupled look-back over 1024-slot tiles).
 // status word: [63:62] 1 = tile aggregate, 2 = inclusive prefix; [61:40] call epoch (22 bits);
 // [39:0] value. A word whose epoch is not the current call's reads as "not ready", so the status
@@ -902,7 +667,7 @@ __device__ __forceinline__ void bbox_rearm(uint32_t* __restrict__ next_words)
 // known to follow (fused iteration) — saves one pass over the pairings.
 struct FusedSums
 {
-    double*       partials;  // one row of 7 per tile
+    double*       partials;  // one row of 8 per tile
     unsigned int* ticket;
     double*       packet;    // NULL = not requested
 };
@@ -981,9 +746,9 @@ __global__ void __launch_bounds__(kScanThreads)
     if (fs.packet)
     {
         const bool in  = ok && w < a.capacity;
-        double     acc[7] = {in ? (double)px : 0.0,   in ? (double)py : 0.0,   in ? (double)pz : 0.0, in ? (double)gp.x : 0.0,
-                             in ? (double)gp.y : 0.0, in ? (double)gp.z : 0.0, in ? 1.0 : 0.0};
-        block_reduce_to_packet<7>(acc, fs.partials, fs.ticket, fs.packet, tile, n_tiles);
+        double     acc[8] = {in ? (double)px : 0.0,   in ? (double)py : 0.0,   in ? (double)pz : 0.0, in ? (double)gp.x : 0.0,
+                             in ? (double)gp.y : 0.0, in ? (double)gp.z : 0.0, in ? 1.0 : 0.0,       in ? 1.0 : 0.0};
+        block_reduce_to_packet<8>(acc, fs.partials, fs.ticket, fs.packet, tile, n_tiles);
     }
 }
 
@@ -1008,12 +773,16 @@ struct Pt2PlArgs
 // + distance tests (plane_fit.cuh). Full-lane utilisation for the fp64 Jacobi.
 template <int KT>
 __global__ void __launch_bounds__(128)
-    k_plane_fit(GridView g, Pt2PlArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
-                const float* __restrict__ lz, const unsigned long long* __restrict__ cand,
-                PlaneCandidate* __restrict__ plc, uint8_t* __restrict__ ok_flags)
+    k_plane_fit(GridView g, Pt2PlArgs a, const float* __restrict__ qx, const float* __restrict__ qy,
+                const float* __restrict__ qz, const uint32_t* __restrict__ perm,
+                const unsigned long long* __restrict__ cand, PlaneCandidate* __restrict__ plc,
+                uint8_t* __restrict__ ok_flags)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_local) return;
+    // walks the same (possibly Morton-sorted) query array as the search did: neighbouring threads
+    // gather overlapping neighbour sets; results go to the caller's index i
+    const uint32_t qpos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qpos >= a.n_local) return;
+    const uint32_t i = perm ? __ldg(perm + qpos) : qpos;
     const int K   = (int)a.K;
     int       cnt = 0;
     uint32_t  idx[KT];
@@ -1021,7 +790,7 @@ __global__ void __launch_bounds__(128)
     for (int k = 0; k < KT; k++)
         if (k < K)
         {
-            const unsigned long long c = cand[(size_t)i * K + k];
+            const unsigned long long c = cand[(size_t)qpos * K + k];
             idx[k]                     = (uint32_t)c;
             cnt += ((uint32_t)c != 0xFFFFFFFFu);  // valid ranks come first
         }
@@ -1037,7 +806,7 @@ __global__ void __launch_bounds__(128)
                 px[k] = p.x, py[k] = p.y, pz[k] = p.z;
             }
         float gx, gy, gz;
-        compose_point_f(a.pose, lx[i], ly[i], lz[i], gx, gy, gz);
+        compose_point_f(a.pose, qx[qpos], qy[qpos], qz[qpos], gx, gy, gz);
         PlaneCandidate pc;
         if (fit_plane<KT>(px, py, pz, cnt, gx, gy, gz, a.planeEigenThreshold, a.distThr, pc))
         {
@@ -1131,19 +900,6 @@ __global__ void __launch_bounds__(256)
     out_found[i] = cnt;
 }
 
-// MP2P_KNN_LANE=1 selects the lane-per-query kernel (k_match_knn_lane) for k in 2..16. Measured on
-// C3 (119k queries, k = 8): half the instructions of the group kernel but 3x slower — 3.7k warps of
-// long serial chains cannot hide latency, the group kernel's 30k warps can
-// (profiles/r01_c3_knn_lane_ab.txt). Kept for query counts >= ~1M per GPU; default = group kernel.
-bool knn_lane_enabled()
-{
-    static const bool v = [] {
-        const char* e = getenv("MP2P_KNN_LANE");
-        return e && atoi(e) == 1;
-    }();
-    return v;
-}
-
 // tuning knob (measurement only): item rounds software-pipelined per chunk in the K = 1 matcher
 int nn1_rounds()
 {
@@ -1165,24 +921,6 @@ int pick_kt(uint32_t K)
 
 // The search kernels are instantiated EXACTLY for the usual k (1..10, 12, 16, 20, 24, 32): the K-th
 // best is then a fixed register. Any other k <= 32 runs on the next capacity with a runtime k.
-// lane-per-query kernel (k_match_knn_lane) for the exact k up to 16; others use the group kernel
-#define MP2P_DISPATCH_LANE_K(K, CALL, ELSE) \
-    switch (K)                              \
-    {                                       \
-        case 2: CALL(2); break;             \
-        case 3: CALL(3); break;             \
-        case 4: CALL(4); break;             \
-        case 5: CALL(5); break;             \
-        case 6: CALL(6); break;             \
-        case 7: CALL(7); break;             \
-        case 8: CALL(8); break;             \
-        case 9: CALL(9); break;             \
-        case 10: CALL(10); break;           \
-        case 12: CALL(12); break;           \
-        case 16: CALL(16); break;           \
-        default: ELSE; break;               \
-    }
-
 #define MP2P_DISPATCH_K(K, CALL)      \
     switch (K)                        \
     {                                 \
@@ -1223,9 +961,24 @@ int start_level(const GridView& v, uint32_t K)
 int stage_local(mp2p_b200_ctx* ctx, const float* lx, const float* ly, const float* lz, uint64_t n,
                 int on_device)
 {
+    ctx->cur_perm = nullptr;
+    if (on_device == 2)  // resident cloud: search kernels walk the Morton-sorted copy
+    {
+        const auto* c = reinterpret_cast<const mp2p_b200_cloud*>(lx);
+        if (c->ctx != ctx || c->n != n)
+        {
+            set_error("local cloud handle belongs to another context, or n_local differs from its size");
+            return MP2P_B200_ERR_ARG;
+        }
+        ctx->cur_lx = c->d_x.as<float>(), ctx->cur_ly = c->d_y.as<float>(), ctx->cur_lz = c->d_z.as<float>();
+        ctx->cur_qx = c->d_sx.as<float>(), ctx->cur_qy = c->d_sy.as<float>(), ctx->cur_qz = c->d_sz.as<float>();
+        ctx->cur_perm   = c->d_perm.as<uint32_t>();
+        ctx->cur_tma_ok = true;
+        return 0;
+    }
     if (on_device)
     {
-        ctx->cur_lx = lx, ctx->cur_ly = ly, ctx->cur_lz = lz;
+        ctx->cur_lx = ctx->cur_qx = lx, ctx->cur_ly = ctx->cur_qy = ly, ctx->cur_lz = ctx->cur_qz = lz;
         ctx->cur_tma_ok = ((reinterpret_cast<uintptr_t>(lx) | reinterpret_cast<uintptr_t>(ly) |
                             reinterpret_cast<uintptr_t>(lz)) & 15u) == 0;
         return 0;
@@ -1237,7 +990,8 @@ int stage_local(mp2p_b200_ctx* ctx, const float* lx, const float* ly, const floa
     MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_lx.p, lx, bytes, cudaMemcpyHostToDevice, ctx->stream));
     MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_ly.p, ly, bytes, cudaMemcpyHostToDevice, ctx->stream));
     MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_lz.p, lz, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->cur_lx = ctx->d_lx.as<float>(), ctx->cur_ly = ctx->d_ly.as<float>(), ctx->cur_lz = ctx->d_lz.as<float>();
+    ctx->cur_lx = ctx->cur_qx = ctx->d_lx.as<float>(), ctx->cur_ly = ctx->cur_qy = ctx->d_ly.as<float>();
+    ctx->cur_lz = ctx->cur_qz = ctx->d_lz.as<float>();
     ctx->cur_tma_ok = true;
     return 0;
 }
@@ -1381,7 +1135,8 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     a.rl_start = start_level(map->view, K);
 
     const uint32_t blocks = (uint32_t)((n_local + kQueriesPerBlock - 1) / kQueriesPerBlock);
-    const float *  dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;
+    const float *  dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;  // caller order (records)
+    const float *  dqx = ctx->cur_qx, *dqy = ctx->cur_qy, *dqz = ctx->cur_qz;  // what the search walks
     auto*          claim = map->d_claim.as<unsigned long long>();
     auto*          cand  = ctx->d_cand.as<unsigned long long>();
     unsigned long long* stats = nullptr;
@@ -1389,31 +1144,21 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     float4* cand_xyz = nullptr;
     prof_begin(ctx, 0);
 #define LAUNCH_MATCH(KT, EX) \
-    k_match_pt2pt<KT, EX><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, sv.bbox, stats)
+    k_match_pt2pt<KT, EX><<<blocks, kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, sv.bbox, stats)
     if (K == 1)
     {
         MP2P_TRY(ctx->d_candxyz.ensure(n_slots * sizeof(float4)));
         cand_xyz = ctx->d_candxyz.as<float4>();
         if (nn1_rounds() == 1)
             k_match_pt2pt_nn1<1><<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
-                map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, cand_xyz, sv.bbox, stats);
+                map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, cand_xyz, sv.bbox, stats);
         else
             k_match_pt2pt_nn1<4><<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
-                map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, cand_xyz, sv.bbox, stats);
+                map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, cand_xyz, sv.bbox, stats);
     }
     else
     {
-#define LAUNCH_LANE(KT) \
-    k_match_knn_lane<KT><<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, d_gbits, claim, cand, sv.bbox, stats)
-        if (knn_lane_enabled())
-        {
-            MP2P_DISPATCH_LANE_K(K, LAUNCH_LANE, { MP2P_DISPATCH_K(K, LAUNCH_MATCH) })
-        }
-        else
-        {
-            MP2P_DISPATCH_K(K, LAUNCH_MATCH)
-        }
-#undef LAUNCH_LANE
+        MP2P_DISPATCH_K(K, LAUNCH_MATCH)
     }
 #undef LAUNCH_MATCH
     prof_end(ctx, 0);
@@ -1458,52 +1203,65 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
 // ------------------------------------------------------------------------------------------
 namespace
 {
+// records: n_shards exchange records of `rec_words` 64-bit words each, laid out
+// [per_k candidate words | 3 words = 6 ordered bbox words | 1 pad]; global slot = shard*per_k + j
 __global__ void __launch_bounds__(256)
-    k_claim_all(const unsigned long long* __restrict__ cand_all, uint64_t n_slots, unsigned long long tag,
-                const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim)
+    k_claim_all(const unsigned long long* __restrict__ records, uint32_t n_shards, uint64_t per_k, uint64_t rec_words,
+                unsigned long long tag, const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim)
 {
+    const uint64_t n_slots = per_k * n_shards;
     for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < n_slots; s += (uint64_t)gridDim.x * blockDim.x)
     {
-        const unsigned long long c = cand_all[s];
+        const uint64_t           r = s / per_k, j = s - r * per_k;
+        const unsigned long long c = records[r * rec_words + j];
         if ((uint32_t)c == 0xFFFFFFFFu) continue;
         const uint32_t gi = (uint32_t)c;
         if (!bit_set(gbits, gi)) atomicMin(claim + gi, tag | s);
     }
 }
 // fold the per-shard bounding boxes (6 ordered words each: min xyz / max xyz) into one
-__global__ void k_fold_bbox(const uint32_t* __restrict__ parts, uint32_t n_parts, uint32_t* __restrict__ out)
+__global__ void k_fold_bbox(const unsigned long long* __restrict__ records, uint32_t n_shards, uint64_t per_k,
+                            uint64_t rec_words, uint32_t* __restrict__ out)
 {
     const int d = threadIdx.x;
     if (d >= 6) return;
-    uint32_t r = parts[d];
-    for (uint32_t p = 1; p < n_parts; p++) r = d < 3 ? min(r, parts[p * 6 + d]) : max(r, parts[p * 6 + d]);
+    uint32_t r = d < 3 ? 0xFFFFFFFFu : 0u;
+    for (uint32_t p = 0; p < n_shards; p++)
+    {
+        const uint32_t v = reinterpret_cast<const uint32_t*>(records + p * rec_words + per_k)[d];
+        r                = d < 3 ? min(r, v) : max(r, v);
+    }
     out[d] = r;
 }
 }  // namespace
 
+uint64_t shard_record_words(uint64_t per_shard, uint32_t K) { return per_shard * K + 4; }
+
 int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
                            const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
-                           const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits,
-                           unsigned long long* d_cand_out, uint32_t* d_bbox6_out)
+                           const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits, uint64_t per_shard,
+                           unsigned long long* d_record)
 {
-    const uint32_t K = prm->pairingsPerPoint;
+    const uint32_t K  = prm->pairingsPerPoint;
     cudaStream_t   st = ctx->stream;
-    if (n_local == 0 || map->view.n_points == 0)
+    if (n_local > per_shard)
     {
-        // an empty shard still has to contribute "nothing": all-ones candidates, inverted bbox
-        if (n_local) MP2P_CUDA_TRY(cudaMemsetAsync(d_cand_out, 0xff, n_local * K * 8, st));
-        const uint32_t inv[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
-        MP2P_CUDA_TRY(cudaMemcpyAsync(d_bbox6_out, inv, sizeof(inv), cudaMemcpyHostToDevice, st));
-        return 0;
+        set_error("shard_search: n_local exceeds per_shard");
+        return MP2P_B200_ERR_ARG;
     }
+    uint32_t* d_bbox6 = reinterpret_cast<uint32_t*>(d_record + per_shard * K);
+    // bbox = inverted (nothing seen yet); slots of a short or empty shard = "no candidate"
+    const uint32_t init[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0, 0, 0};
+    MP2P_CUDA_TRY(cudaMemcpyAsync(d_bbox6, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const bool nothing = n_local == 0 || map->view.n_points == 0;
+    const uint64_t first_pad = nothing ? 0 : n_local;
+    if (first_pad < per_shard)
+        MP2P_CUDA_TRY(cudaMemsetAsync(d_record + first_pad * K, 0xff, (per_shard - first_pad) * K * 8, st));
+    if (nothing) return 0;
     MP2P_TRY(stage_local(ctx, lx, ly, lz, n_local, local_on_device));
     const uint32_t* d_lbits;
     MP2P_TRY(upload_bits(ctx, ctx->d_lbits, lbits, n_local, &d_lbits));
     const uint32_t blocks = (uint32_t)((n_local + kQueriesPerBlock - 1) / kQueriesPerBlock);
-    {
-        const uint32_t init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
-        MP2P_CUDA_TRY(cudaMemcpyAsync(d_bbox6_out, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    }
     Pt2PtArgs a{};
     for (int k = 0; k < 12; k++) a.pose.m[k] = pose[k];
     a.maxDistSq = (float)(prm->threshold * prm->threshold);
@@ -1514,23 +1272,22 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     a.tag = 0;
     a.tma_ok = ctx->cur_tma_ok;
     a.rl_start = start_level(map->view, K);
-    const float *dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;
+    const float *dqx = ctx->cur_qx, *dqy = ctx->cur_qy, *dqz = ctx->cur_qz;
     unsigned long long* stats = nullptr;
     MP2P_TRY(prepare_stats(ctx, &stats));
     prof_begin(ctx, 0);
 #define LAUNCH_MATCH(KT, EX) \
-    k_match_pt2pt<KT, EX><<<blocks, kQueryTile, 0, st>>>(map->view, a, dlx, dly, dlz, d_lbits, nullptr, nullptr, d_cand_out, d_bbox6_out, stats)
+    k_match_pt2pt<KT, EX><<<blocks, kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, d_record, d_bbox6, stats)
     if (K == 1)
     {
         MP2P_TRY(ctx->d_candxyz.ensure(n_local * sizeof(float4)));
+        const uint32_t nb = (uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads);
         if (nn1_rounds() == 1)
-            k_match_pt2pt_nn1<1><<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
-                map->view, a, dlx, dly, dlz, d_lbits, nullptr, nullptr, d_cand_out, ctx->d_candxyz.as<float4>(),
-                d_bbox6_out, stats);
+            k_match_pt2pt_nn1<1><<<nb, kNN1Threads, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr,
+                                                             nullptr, d_record, ctx->d_candxyz.as<float4>(), d_bbox6, stats);
         else
-            k_match_pt2pt_nn1<4><<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
-                map->view, a, dlx, dly, dlz, d_lbits, nullptr, nullptr, d_cand_out, ctx->d_candxyz.as<float4>(),
-                d_bbox6_out, stats);
+            k_match_pt2pt_nn1<4><<<nb, kNN1Threads, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr,
+                                                             nullptr, d_record, ctx->d_candxyz.as<float4>(), d_bbox6, stats);
     }
     else
     {
@@ -1542,23 +1299,30 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     return 0;
 }
 
-int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_local, uint64_t index_offset,
-                            uint64_t n_total, const unsigned long long* d_cand_all,
-                            const uint32_t* d_bbox_parts, uint32_t n_bbox_parts,
+// out_count == NULL: nothing is read back and the stream is not synchronised — the count stays on
+// the device (ctx->last_count) for solver calls that pass MP2P_B200_COUNT_ON_DEVICE.
+int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_local, uint32_t shard_rank,
+                            uint32_t n_shards, uint64_t per_shard, const unsigned long long* d_records,
                             const mp2p_b200_pt2pt_params* prm, const uint32_t* gbits,
                             mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device,
-                            uint64_t* out_count)
+                            uint64_t* out_count, double* d_horn_sums)
 {
-    *out_count        = 0;
-    const uint32_t K  = prm->pairingsPerPoint;
+    if (out_count) *out_count = 0;
+    ctx->last_count = nullptr, ctx->last_capacity = 0;
+    const uint32_t K    = prm->pairingsPerPoint;
     const uint64_t nmap = map->view.n_points;
-    if (nmap == 0 || n_local == 0) return 0;
-    if (n_total * (uint64_t)K >= 0xFFFFFFFFull || index_offset + n_local > n_total)
+    const uint64_t per_k = per_shard * K, rec_words = shard_record_words(per_shard, K);
+    if (per_k * n_shards >= 0xFFFFFFFFull || shard_rank >= n_shards || n_local > per_shard)
     {
-        set_error("shard_resolve: need n_total*pairingsPerPoint < 2^32-1 and a shard inside the cloud");
+        set_error("shard_resolve: need n_shards*per_shard*pairingsPerPoint < 2^32-1, shard_rank < n_shards, n_local <= per_shard");
         return MP2P_B200_ERR_ARG;
     }
-    cudaStream_t    st = ctx->stream;
+    cudaStream_t st = ctx->stream;
+    if (nmap == 0 || n_local == 0)
+    {
+        if (d_horn_sums) MP2P_CUDA_TRY(cudaMemsetAsync(d_horn_sums, 0, MP2P_B200_PACKET_DOUBLES * 8, st));
+        return 0;  // last_count stays NULL: the solver calls that follow see zero pairings
+    }
     const uint32_t* d_gbits;
     MP2P_TRY(upload_bits(ctx, ctx->d_gbits, gbits, nmap, &d_gbits));
     const uint64_t      n_slots = n_local * K;
@@ -1566,7 +1330,7 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
     SmallView           sv;
     unsigned long long* status;
     MP2P_TRY(prepare_small(ctx, n_tiles, sv, &status));
-    k_fold_bbox<<<1, 32, 0, st>>>(d_bbox_parts, n_bbox_parts, sv.bbox);
+    k_fold_bbox<<<1, 32, 0, st>>>(d_records, n_shards, per_k, rec_words, sv.bbox);
     count_launch(ctx);
     if (++map->epoch == 0xFFFFFFFFu)
     {
@@ -1577,9 +1341,9 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
     auto*                    claim = map->d_claim.as<unsigned long long>();
     if (!prm->allowMatchAlreadyMatchedGlobalPoints)
     {
-        const uint64_t all_slots = n_total * K;
+        const uint64_t all_slots = per_k * n_shards;
         const uint32_t blocks    = (uint32_t)std::min<uint64_t>((all_slots + 255) / 256, 148 * 16);
-        k_claim_all<<<blocks, 256, 0, st>>>(d_cand_all, all_slots, tag, d_gbits, claim);
+        k_claim_all<<<blocks, 256, 0, st>>>(d_records, n_shards, per_k, rec_words, tag, d_gbits, claim);
         count_launch(ctx);
     }
     mp2p_b200_pair_pt2pt* d_out = out;
@@ -1592,16 +1356,23 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
     c.n_local = (uint32_t)n_local, c.K = K, c.allowGlobal = prm->allowMatchAlreadyMatchedGlobalPoints, c.tag = tag;
     c.gate_eps = (float)(prm->threshold + prm->bounding_box_intersection_check_epsilon);
     c.capacity = std::min<uint64_t>(capacity, n_slots);
-    c.slot_offset = index_offset * K, c.index_offset = (uint32_t)index_offset;
+    c.slot_offset = (uint64_t)shard_rank * per_k, c.index_offset = (uint32_t)(shard_rank * per_shard);
     c.scan_epoch = ctx->scan_epoch;
+    FusedSums fs{nullptr, nullptr, nullptr};
+    if (d_horn_sums)
+    {
+        MP2P_TRY(solve_scratch(ctx, n_tiles, &fs.ticket, &fs.partials));
+        fs.packet = d_horn_sums;
+    }
     prof_begin(ctx, 1);
     k_compact_pt2pt<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(
         map->view, c, ctx->cur_lx, ctx->cur_ly, ctx->cur_lz, d_gbits, claim,
-        d_cand_all + index_offset * K, K == 1 ? ctx->d_candxyz.as<float4>() : nullptr, sv.bbox, sv.bbox_next, status,
-        sv.tile_counter, d_out, sv.count,
-        FusedSums{nullptr, nullptr, nullptr});
+        d_records + (uint64_t)shard_rank * rec_words, K == 1 ? ctx->d_candxyz.as<float4>() : nullptr, sv.bbox,
+        sv.bbox_next, status, sv.tile_counter, d_out, sv.count, fs);
     prof_end(ctx, 1);
     count_launch(ctx);
+    ctx->last_count = sv.count, ctx->last_capacity = c.capacity;
+    if (!out_count) return 0;
     return fetch_results(ctx, sv.count, d_out, out, c.capacity, out_on_device, out_count, &ctx->hint_pt2pt);
 }
 
@@ -1643,7 +1414,8 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     const float gate_eps = (float)(prm->distanceThreshold + prm->bounding_box_intersection_check_epsilon);
 
     const uint32_t blocks = (uint32_t)((n_local + kQueriesPerBlock - 1) / kQueriesPerBlock);
-    const float *  dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;
+    const float *  dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;  // caller order (records)
+    const float *  dqx = ctx->cur_qx, *dqy = ctx->cur_qy, *dqz = ctx->cur_qz;  // what the search walks
     auto*          plc = ctx->d_plcand.as<PlaneCandidate>();
     auto*          okf = ctx->d_okflags.as<uint8_t>();
     auto*          cand = ctx->d_cand.as<unsigned long long>();
@@ -1653,23 +1425,14 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     Pt2PtArgs sa{};
     sa.pose = a.pose, sa.maxDistSq = a.radiusSq, sa.angSq = 0.f, sa.n_local = a.n_local, sa.K = a.K;
     sa.allowLocal = a.allowLocal, sa.allowGlobal = 1, sa.tag = 0, sa.tma_ok = a.tma_ok;
+    sa.cand_sorted = 1;  // the plane fit walks the same order
     prof_begin(ctx, 0);
 #define LAUNCH_SEARCH(KT, EX) \
-    k_match_pt2pt<KT, EX><<<blocks, kQueryTile, 0, st>>>(map->view, sa, dlx, dly, dlz, d_lbits, nullptr, nullptr, cand, sv.bbox, stats)
+    k_match_pt2pt<KT, EX><<<blocks, kQueryTile, 0, st>>>(map->view, sa, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, cand, sv.bbox, stats)
 #define LAUNCH_FIT(KT) \
-    k_plane_fit<KT><<<(uint32_t)((n_local + 127) / 128), 128, 0, st>>>(map->view, a, dlx, dly, dlz, cand, plc, okf)
+    k_plane_fit<KT><<<(uint32_t)((n_local + 127) / 128), 128, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, cand, plc, okf)
     sa.rl_start = start_level(map->view, prm->knn);
-#define LAUNCH_LANE(KT) \
-    k_match_knn_lane<KT><<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(map->view, sa, dlx, dly, dlz, d_lbits, nullptr, nullptr, cand, sv.bbox, stats)
-    if (knn_lane_enabled())
-    {
-        MP2P_DISPATCH_LANE_K(prm->knn, LAUNCH_LANE, { MP2P_DISPATCH_K(prm->knn, LAUNCH_SEARCH) })
-    }
-    else
-    {
-        MP2P_DISPATCH_K(prm->knn, LAUNCH_SEARCH)
-    }
-#undef LAUNCH_LANE
+    MP2P_DISPATCH_K(prm->knn, LAUNCH_SEARCH)
     switch (pick_kt(prm->knn))
     {
         case 1:

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kSolveThreads)
 }
 
 // ------------------------------------------------------------------------------------------
-constexpr int kH1V = 7;  // sum local(3), sum global(3), count
+constexpr int kH1V = 8;  // sum local(3), sum global(3), count (non-outliers), pairs (all)
 
 __global__ void __launch_bounds__(kSolveThreads)
     k_horn_sums(const uint32_t* __restrict__ p2p, uint64_t n, const uint8_t* __restrict__ outlier,
@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(kSolveThreads)
     {
         warp_stage_records<9>(p2p, base, n, sh);
         const uint64_t i = base + lane;
+        if (i < n) acc[7] += 1.0;
         if (i < n && !(outlier && outlier[i]))
         {
             const uint32_t* rec = sh + lane * 9;
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(kSolveThreads)
 struct HornArgs
 {
     uint64_t n, n_total;
+    int      n_total_mode;  // 0: n_total given; 1: = *d_n (single GPU, fused); 2: = sums[7] (all-reduced)
     int      use_scale_outlier;
     double   scale_thr, w_pt2pt;
     int      kernel;
@@ -229,7 +231,9 @@ __global__ void __launch_bounds__(kSolveThreads)
                    double* __restrict__ partials, unsigned int* __restrict__ ticket,
                    double* __restrict__ packet, const unsigned long long* __restrict__ d_n)
 {
-    if (d_n) a.n = a.n_total = *d_n;
+    if (d_n) a.n = *d_n;
+    if (a.n_total_mode == 1) a.n_total = a.n;
+    if (a.n_total_mode == 2) a.n_total = (uint64_t)sums[7];
     __shared__ uint32_t stage[kWarps][32 * 9];
     const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t*           sh = stage[warp];
@@ -415,14 +419,15 @@ int run_horn_sums(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t 
 int run_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n,
                      const mp2p_b200_horn_params* prm, const double* d_sums_packet,
                      uint64_t n_total_pairs, const uint64_t* d_wcount_prefix, const double* d_wvalue,
-                     uint32_t n_wblocks, uint8_t* d_outlier, double* d_packet, const unsigned long long* d_n)
+                     uint32_t n_wblocks, uint8_t* d_outlier, double* d_packet, const unsigned long long* d_n,
+                     int n_total_mode)
 {
     const int     blocks = solve_grid(n);
     unsigned int* ticket;
     double*       partials;
     MP2P_TRY(solve_scratch(ctx, blocks, &ticket, &partials));
     HornArgs a{};
-    a.n = n, a.n_total = n_total_pairs;
+    a.n = n, a.n_total = n_total_pairs, a.n_total_mode = n_total_mode;
     a.use_scale_outlier = prm->use_scale_outlier_detector, a.scale_thr = prm->scale_outlier_threshold;
     a.w_pt2pt = prm->w_pt2pt, a.kernel = prm->robust_kernel, a.kparam = prm->robust_kernel_param;
     for (int r = 0; r < 3; r++)

@@ -4,8 +4,9 @@ NVLink on GPUs, gloo in the CPU tests) as plumbing around the C-ABI building blo
 The local cloud is split into contiguous shards (rank r owns [offsets[r], offsets[r+1])), the map
 and its index are replicated. Per ICP iteration:
 
-  matcher   shard_search (phase A)  ->  ONE all_gather of [candidate words | shard bbox]
-            ->  shard_resolve (phase B: global first-claim replay + compaction of the own shard)
+  matcher   shard_search (phase A)  ->  ONE in-place all_gather of the exchange records
+            [candidate words | shard bbox]  ->  shard_resolve (phase B: global first-claim replay +
+            compaction of the own shard, HORN1 sums in the same pass)
   solver    accumulate the shard into a 32-double packet -> all_reduce(SUM) -> every rank finishes the
             4x4 / 6x6 solve redundantly (mp2p_b200_horn_finish / mp2p_b200_gn_step_from_packet).
 
@@ -66,48 +67,80 @@ class _SingleProcess:
 
 
 class ShardedMatcherSolver:
-    """GPU side: owns the exchange buffers of one rank."""
+    """GPU side: owns the exchange buffers of one rank.
+
+    Exchange layout (include/mp2p_b200.h, "EXCHANGE RECORDS"): `records` holds world records of
+    rec_words 64-bit words; this rank's phase A writes its record IN PLACE at records[rank], the
+    all_gather is NCCL's in-place form (send = recv + rank*count), phase B reads the gathered
+    records where they are — no packing or unpacking kernels on either side.
+    """
 
     def __init__(self, ctx: capi.Context, gmap: capi.Map, rank: int, world: int, n_total: int, k_max: int = 1):
         import torch
         import torch.distributed as dist
 
+        if ctx.stream is None or ctx.stream != torch.cuda.current_stream(ctx.device).cuda_stream:
+            # NCCL collectives and the packet read-back are ordered on torch's current stream
+            raise ValueError("create the Context on torch's current stream: Context(dev, stream=torch.cuda.current_stream().cuda_stream)")
         self.torch, self.dist = torch, (dist if world > 1 else _SingleProcess)
         self.ctx, self.map, self.rank, self.world, self.n_total = ctx, gmap, rank, world, n_total
         self.bounds, self.per = shard_bounds(n_total, world)
         self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
         self.n_local = self.hi - self.lo
         dev = torch.device("cuda", ctx.device)
-        self.k_max = k_max
-        # one exchange record per rank: per*K candidate words followed by 6 bbox floats (+2 pad)
-        self.rec_words = self.per * k_max + 4
-        self.send = torch.full((self.rec_words,), -1, dtype=torch.int64, device=dev)
-        self.recv = torch.empty((world * self.rec_words,), dtype=torch.int64, device=dev)
-        self.cand_all = torch.empty((world * self.per * k_max,), dtype=torch.int64, device=dev)
-        self.boxes = torch.empty((world * 6,), dtype=torch.float32, device=dev)
+        self.k = k_max
+        self.rec_words = capi.shard_record_words(self.per, k_max)
+        self.records = torch.empty((world * self.rec_words,), dtype=torch.int64, device=dev)
+        self.mine = self.records[rank * self.rec_words : (rank + 1) * self.rec_words]
         self.packets = torch.zeros((64,), dtype=torch.float64, device=dev)
+        self.h_packets = torch.zeros((64,), dtype=torch.float64).pin_memory()
 
-    def match_pt2pt(self, d_lx: int, d_ly: int, d_lz: int, pose, prm: capi.Pt2PtParams, d_out: int, capacity: int):
-        """Device addresses of THIS rank's shard; returns the number of pairs written to d_out."""
-        t, K = self.torch, prm.pairingsPerPoint
-        assert K <= self.k_max
-        if K != self.k_max:
+    # ---- matcher -------------------------------------------------------------------------------
+    def _search_gather(self, local, pose, prm):
+        if prm.pairingsPerPoint != self.k:
             raise ValueError("exchange buffers were sized for another pairingsPerPoint")
-        bbox_ptr = self.send.data_ptr() + self.per * K * 8
-        self.send[: self.per * K].fill_(-1)  # padding slots of a short last shard stay invalid
-        self.map.shard_search_pt2pt(d_lx, d_ly, d_lz, pose, prm, self.send.data_ptr(), bbox_ptr, n_local=self.n_local, local_on_device=True)
+        lx, ly, lz = local
+        self.map.shard_search_pt2pt(lx, ly, lz, pose, prm, self.per, self.mine.data_ptr(), n_local=self.n_local, local_on_device=True)
         if self.world > 1:
-            self.dist.all_gather_into_tensor(self.recv, self.send)
-            r = self.recv.view(self.world, self.rec_words)
-        else:
-            r = self.send.view(1, self.rec_words)
-        # padded layout -> the library's dense global slot numbering uses offsets[r]*K, which equals
-        # r*per*K for every rank but possibly a shorter tail: keep the padded numbering end to end.
-        self.cand_all.view(self.world, self.per * K).copy_(r[:, : self.per * K])
-        self.boxes.view(self.world, 6).copy_(r[:, self.per * K : self.per * K + 3].contiguous().view(t.float32).view(self.world, 6))
-        n_total_padded = self.world * self.per
-        return self.map.shard_resolve_pt2pt(self.n_local, self.rank * self.per, n_total_padded, self.cand_all.data_ptr(), self.boxes.data_ptr(), self.world, prm, out=d_out, out_on_device=True, capacity=capacity)
+            self.dist.all_gather_into_tensor(self.records, self.mine)
 
+    def match_pt2pt(self, d_lx, d_ly, d_lz, pose, prm: capi.Pt2PtParams, d_out: int, capacity: int):
+        """(d_lx, d_ly, d_lz) = device addresses of THIS rank's shard, or (Cloud, None, None).
+        Returns the number of pairs written to d_out (synchronises)."""
+        self._search_gather((d_lx, d_ly, d_lz), pose, prm)
+        return self.map.shard_resolve_pt2pt(self.n_local, self.rank, self.world, self.per, self.records.data_ptr(), prm, out=d_out, out_on_device=True, capacity=capacity)
+
+    # ---- whole iterations, ONE host synchronisation ----------------------------------------------
+    def iterate_pt2pt_horn(self, local, pose, mprm: capi.Pt2PtParams, sprm: capi.HornParams, d_pairs: int, capacity: int):
+        """Matcher_Points_DistanceThreshold + Solver_Horn over the sharded cloud. Enqueues
+        search -> all_gather -> resolve(+HORN1 sums) -> all_reduce -> HORN2 moments -> all_reduce
+        and reads the two packets back once. Returns (solved, pose 3x4, pairs in the whole cloud)."""
+        if sprm.use_scale_outlier_detector:
+            raise ValueError("use_scale_outlier_detector needs the two-call path (match_pt2pt + solve_horn)")
+        p = self.packets
+        self._search_gather(local, pose, mprm)
+        self.map.shard_resolve_pt2pt(self.n_local, self.rank, self.world, self.per, self.records.data_ptr(), mprm, out=d_pairs, out_on_device=True, capacity=capacity, sync=False, horn_sums=p.data_ptr())
+        self.dist.all_reduce(p[:32])
+        self.ctx.horn_moments(d_pairs, p.data_ptr(), 0, n=capi.COUNT_ON_DEVICE, prm=sprm, on_device=True, sums_on_device=True, packet=p[32:].data_ptr(), packet_on_device=True)
+        self.dist.all_reduce(p[32:])
+        self.h_packets.copy_(p, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        h = self.h_packets.numpy()
+        n_pairs = int(h[7])
+        if n_pairs < 3:  # optimal_tf_horn.cpp:96
+            return False, np.eye(3, 4), n_pairs
+        ok, T = capi.horn_finish(h[:32], h[32:])
+        return ok, T, n_pairs
+
+    def iterate_pt2pt_gn(self, local, pose, mprm: capi.Pt2PtParams, sprm: capi.GNParams, d_pairs: int, capacity: int):
+        """Matcher_Points_DistanceThreshold + Solver_GaussNewton over the sharded cloud:
+        one synchronisation per inner Gauss-Newton iteration (the reduced 6x6 system comes to the host)."""
+        self._search_gather(local, pose, mprm)
+        self.map.shard_resolve_pt2pt(self.n_local, self.rank, self.world, self.per, self.records.data_ptr(), mprm, out=d_pairs, out_on_device=True, capacity=capacity, sync=False)
+        ok, T, updates = self.solve_gauss_newton(d_pairs, capi.COUNT_ON_DEVICE, None, 0, sprm, pose)
+        return ok, T, updates
+
+    # ---- solvers over pairings already on the device -------------------------------------------
     def solve_horn(self, d_pairs: int, n_pairs: int, prm: capi.HornParams):
         p = self.packets
 

@@ -33,6 +33,7 @@ def main():
     L = np.concatenate([L, L[:5000] + np.float32(2e-3)])  # duplicate claims across shards
     L = L[: (len(L) // world) * world]
     pose = fx.pose_xyzypr(0.25, -0.15, 0.08, np.deg2rad(1.7), np.deg2rad(-0.8), np.deg2rad(1.2))
+    torch.cuda.set_stream(torch.cuda.Stream(dev))  # one stream for our kernels, torch and NCCL
     ctx = b200.Context(lr, stream=torch.cuda.current_stream().cuda_stream)
     gmap = b200.Map(ctx, *xyz(M))
     n_total = len(L)
@@ -45,6 +46,16 @@ def main():
     ok_h, T_h = sh.solve_horn(d_pairs.data_ptr(), n_pairs, b200.HornParams())
     gprm = b200.GNParams(maxInnerLoopIterations=4, kernel="Cauchy", kernelParam=0.3)
     ok_g, T_g, it_g = sh.solve_gauss_newton(d_pairs.data_ptr(), n_pairs, None, 0, gprm, pose)
+    # the same iteration through the one-synchronisation path, on a resident (Morton-sorted) shard
+    cloud = b200.Cloud(ctx, *xyz(mine))
+    d_pairs2 = torch.zeros(len(mine) * 36, dtype=torch.uint8, device=dev)
+    ok_f, T_f, n_all = sh.iterate_pt2pt_horn((cloud, None, None), pose, prm, b200.HornParams(), d_pairs2.data_ptr(), len(mine))
+    ok_fg, T_fg, it_fg = sh.iterate_pt2pt_gn((cloud, None, None), pose, prm, gprm, d_pairs2.data_ptr(), len(mine))
+    torch.cuda.synchronize()
+    fused_same = bool((d_pairs2[: n_pairs * 36] == d_pairs[: n_pairs * 36]).all().item())
+    df = max(np.abs(T_f - T_h).max(), np.abs(T_fg - T_g).max())
+    fused_ok = torch.tensor([int(fused_same and ok_f and ok_fg and df < 1e-9 and it_fg == it_g)], device=dev)
+    dist.all_reduce(fused_ok, op=dist.ReduceOp.MIN)
     # gather the shards' pairings on rank 0
     counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(counts, torch.tensor([n_pairs], dtype=torch.int64, device=dev))
@@ -58,8 +69,8 @@ def main():
         ok_r2, T_r2, it_r = ctx.solve_gauss_newton(ref, None, gprm, pose)
         same = len(got) == len(ref) and got.tobytes() == ref.tobytes()
         dh, dg = np.abs(T_h - T_r).max(), np.abs(T_g - T_r2).max()
-        print(f"world={world} pairs={len(got)} identical={same} horn_diff={dh:.2e} gn_diff={dg:.2e} gn_iters={it_g}/{it_r}")
-        fail = int(not (same and ok_h and ok_g and dh < 1e-9 and dg < 1e-9 and it_g == it_r))
+        print(f"world={world} pairs={len(got)} identical={same} horn_diff={dh:.2e} gn_diff={dg:.2e} gn_iters={it_g}/{it_r} one_sync_path_ok={int(fused_ok.item())} n_all={n_all}")
+        fail = int(not (same and ok_h and ok_g and dh < 1e-9 and dg < 1e-9 and it_g == it_r and int(fused_ok.item()) == 1 and n_all == len(ref)))
     t = torch.tensor([fail], device=dev)
     dist.broadcast(t, 0)
     dist.destroy_process_group()

@@ -357,23 +357,86 @@ def test_sharded_match_equals_unsharded(ctx, kw):
     K = prm.pairingsPerPoint
     ref, _ = gmap.match_pt2pt(*xyz(L), gt, prm)
     ref = ref.copy()
+    ok_ref, T_ref = ctx.solve_horn(ref)
     n_total, n_sh = len(L), 3
-    bounds = np.linspace(0, n_total, n_sh + 1).astype(int)
-    cand_all = torch.empty(n_total * K, dtype=torch.int64, device="cuda")
-    boxes = torch.empty(n_sh * 6, dtype=torch.float32, device="cuda")
+    per = -(-n_total // n_sh)  # the last shard is shorter: its padding slots must stay inert
+    words = b200.capi.shard_record_words(per, K)
+    assert words == per * K + 4
+    records = torch.empty(n_sh * words, dtype=torch.int64, device="cuda")
+    sums = torch.zeros(32 * n_sh, dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
-    for s in range(n_sh):
-        a, b = bounds[s], bounds[s + 1]
-        gmap.shard_search_pt2pt(*xyz(L[a:b]), gt, prm, cand_all.data_ptr() + a * K * 8, boxes.data_ptr() + s * 24)
-    ctx.synchronize()
-    parts = []
-    for s in range(n_sh):
-        a, b = bounds[s], bounds[s + 1]
-        # phase B reuses the shard staged by phase A on this context: restage it
-        gmap.shard_search_pt2pt(*xyz(L[a:b]), gt, prm, cand_all.data_ptr() + a * K * 8, boxes.data_ptr() + s * 24)
-        parts.append(gmap.shard_resolve_pt2pt(b - a, a, n_total, cand_all.data_ptr(), boxes.data_ptr(), n_sh, prm).copy())
-    got = np.concatenate(parts)
-    assert len(got) == len(ref) and got.tobytes() == ref.tobytes()
+    bounds = [min(s * per, n_total) for s in range(n_sh + 1)]
+    for use_cloud in (False, True):
+        records.fill_(0x5A5A5A5A)  # stale garbage: every word of a record must be rewritten by phase A
+        shard = []
+        for s in range(n_sh):
+            a, b = bounds[s], bounds[s + 1]
+            shard.append((b200.Cloud(ctx, *xyz(L[a:b])), None, None) if use_cloud else xyz(L[a:b]))
+            gmap.shard_search_pt2pt(*shard[s], gt, prm, per, records.data_ptr() + s * words * 8)
+        ctx.synchronize()
+        parts = []
+        for s in range(n_sh):
+            a, b = bounds[s], bounds[s + 1]
+            # phase B reuses the shard staged by phase A on this context: restage it
+            gmap.shard_search_pt2pt(*shard[s], gt, prm, per, records.data_ptr() + s * words * 8)
+            parts.append(gmap.shard_resolve_pt2pt(b - a, s, n_sh, per, records.data_ptr(), prm, horn_sums=sums.data_ptr() + s * 256).copy())
+        got = np.concatenate(parts)
+        assert len(got) == len(ref) and got.tobytes() == ref.tobytes()
+        # HORN1 sums produced by the compaction pass: summed over shards = sums of the whole cloud
+        h = sums.cpu().numpy().reshape(n_sh, 32).sum(axis=0)
+        assert h[6] == len(ref) and h[7] == len(ref)
+        np.testing.assert_allclose(h[0:3], ref["local"].astype(np.float64).sum(axis=0), rtol=1e-12)
+        np.testing.assert_allclose(h[3:6], ref["global"].astype(np.float64).sum(axis=0), rtol=1e-12)
+    del ok_ref, T_ref
+
+
+def test_sharded_iteration_one_sync_world1():
+    """ShardedMatcherSolver.iterate_* (asynchronous phases, counts stay on the device) at world = 1
+    must equal the fused single-GPU iteration and the two-call path."""
+    import torch
+
+    from mp2p_icp_b200.sharded import ShardedMatcherSolver
+
+    with pytest.raises(ValueError):  # a context on a private stream cannot be ordered with NCCL
+        ShardedMatcherSolver(b200.Context(0), None, 0, 1, 10)
+    prev = torch.cuda.current_stream()
+    torch.cuda.set_stream(torch.cuda.Stream())
+    try:
+        _sharded_iteration_world1(b200.Context(0, stream=torch.cuda.current_stream().cuda_stream))
+    finally:
+        torch.cuda.set_stream(prev)
+
+
+def _sharded_iteration_world1(ctx):
+    import torch
+
+    from mp2p_icp_b200.sharded import ShardedMatcherSolver
+
+    M, L, gt = _c2(150_000, 5)
+    gmap = b200.Map(ctx, *xyz(M))
+    guess = fx.pose_xyzypr(0.25, -0.15, 0.08, 1.7 * DEG, -0.8 * DEG, 1.2 * DEG)
+    mprm = b200.Pt2PtParams(threshold=1.0)
+    pairs, _ = gmap.match_pt2pt(*xyz(L), guess, mprm)
+    pairs = pairs.copy()
+    ok_ref, T_ref = ctx.solve_horn(pairs)
+    cloud = b200.Cloud(ctx, *xyz(L))
+    d_pairs = torch.zeros(len(L) * 36, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    sh = ShardedMatcherSolver(ctx, gmap, 0, 1, len(L), k_max=1)
+    for _ in range(3):
+        ok, T, n = sh.iterate_pt2pt_horn((cloud, None, None), guess, mprm, b200.HornParams(), d_pairs.data_ptr(), len(L))
+        assert ok and ok_ref and n == len(pairs)
+        assert_pose_close(T, T_ref, 1e-9)
+    assert d_pairs.cpu().numpy().view(b200.PAIR_PT2PT)[:n].tobytes() == pairs.tobytes()
+    gprm = b200.GNParams(maxInnerLoopIterations=4, kernel="Cauchy", kernelParam=0.3)
+    ok_g, T_g, it_g = sh.iterate_pt2pt_gn((cloud, None, None), guess, mprm, gprm, d_pairs.data_ptr(), len(L))
+    ok_r, T_r, it_r = ctx.solve_gauss_newton(pairs, None, gprm, guess)
+    assert ok_g and ok_r and it_g == it_r
+    assert_pose_close(T_g, T_r, 1e-9)
+    # nothing matches: the on-device count is zero, the iteration reports "not solved"
+    far = fx.pose_xyzypr(500, 0, 0)
+    ok, T, n = sh.iterate_pt2pt_horn((cloud, None, None), far, mprm, b200.HornParams(), d_pairs.data_ptr(), len(L))
+    assert not ok and n == 0
 
 
 # --------------------------------------------------------------------------- fused iterations
@@ -423,6 +486,77 @@ def test_fused_iteration_pt2pl_gn_equals_two_calls(ctx):
     ok0, T0, it0 = orc.optimal_tf_gauss_newton(None, p0, orc.GNParams(**skw), guess, nthreads=8)
     assert it0 == it_ref
     assert_pose_close(T, T0)
+
+
+# --------------------------------------------------------------------------- resident (Morton-sorted) local cloud
+@pytest.mark.parametrize("kw", [dict(threshold=1.0), dict(threshold=2.5, pairingsPerPoint=3), dict(threshold=1.0, thresholdAngularDeg=0.5, allowMatchAlreadyMatchedGlobalPoints=True)])
+def test_resident_cloud_pt2pt_is_invisible(ctx, kw):
+    """mp2p_b200_cloud: the search walks a Morton-sorted copy, the records must not change by a bit
+    (same order, same indices) — against the array path AND the oracle."""
+    M, L, gt = _c2(200_000, 10)
+    L = np.concatenate([L, L[:3000] + np.float32(1e-3)])  # duplicates: first-claim dedup must keep caller order
+    rng = np.random.default_rng(5)
+    lp = (rng.random(len(L)) < 0.2).astype(np.uint8)
+    gp = (rng.random(len(M)) < 0.2).astype(np.uint8)
+    tree, gmap = orc.KDTree(*xyz(M)), b200.Map(ctx, *xyz(M))
+    cloud = b200.Cloud(ctx, *xyz(L))
+    assert cloud.info["n_points"] == len(L)
+    for pose in (np.eye(3, 4), gt):
+        for bits in (dict(), dict(local_paired=lp, global_paired=gp)):
+            ref, pot0 = gmap.match_pt2pt(*xyz(L), pose, b200.Pt2PtParams(**kw), **bits)
+            ref = ref.copy()
+            got, pot1 = gmap.match_pt2pt(cloud, None, None, pose, b200.Pt2PtParams(**kw), **bits)
+            assert pot0 == pot1 and ref.tobytes() == got.tobytes()
+    p0, _ = orc.match_pt2pt(tree, *xyz(L), gt, orc.MatchPt2PtParams(**kw), lp.copy(), gp.copy(), nthreads=8)
+    assert len(p0) > 1000 and p0.tobytes() == got.tobytes()
+    with pytest.raises(b200.Mp2pError):
+        gmap.match_pt2pt(cloud, None, None, gt, b200.Pt2PtParams(threshold=-1.0))
+
+
+def test_resident_cloud_pt2pl_and_fused_iterations(ctx):
+    M = fx.make_street_scene(n_map=300_000, length=50.0)
+    S = fx.make_lidar_scan((25.0, 0.5, 0.0), n_rings=32, n_az=500, length=50.0)
+    guess = fx.pose_xyzypr(25.08, 0.46, 0.02, 0.02, 0.001, -0.001)
+    gmap, cloud = b200.Map(ctx, *xyz(M)), b200.Cloud(ctx, *xyz(S))
+    mkw = dict(distanceThreshold=0.5, searchRadius=1.0, knn=8, minimumPlanePoints=5, planeEigenThreshold=0.01)
+    skw = dict(maxInnerLoopIterations=3, kernel="GemanMcClure", kernelParam=0.15)
+    lp = (np.random.default_rng(6).random(len(S)) < 0.2).astype(np.uint8)
+    for bits in (dict(), dict(local_paired=lp)):
+        ref, _ = gmap.match_pt2pl(*xyz(S), guess, b200.Pt2PlParams(**mkw), **bits)
+        ref = ref.copy()
+        got, _ = gmap.match_pt2pl(cloud, None, None, guess, b200.Pt2PlParams(**mkw), **bits)
+        assert len(ref) > 2000 and ref.tobytes() == got.tobytes()
+    ref, _ = gmap.match_pt2pl(*xyz(S), guess, b200.Pt2PlParams(**mkw))
+    ok_ref, T_ref, _ = ctx.solve_gauss_newton(None, ref, b200.GNParams(**skw), guess)
+    ok, T, n = gmap.make_iterator(cloud, None, None, None, b200.Pt2PlParams(**mkw), b200.GNParams(**skw))(guess)
+    assert ok and ok_ref and n == len(ref)
+    assert_pose_close(T, T_ref, 1e-9)
+    # pt2pt + Horn on the same data
+    mprm = b200.Pt2PtParams(threshold=0.5)
+    pairs, _ = gmap.match_pt2pt(*xyz(S), guess, mprm)
+    ok_ref, T_ref = ctx.solve_horn(pairs)
+    ok, T, n = gmap.make_iterator(cloud, None, None, None, mprm, b200.HornParams())(guess)
+    assert ok and ok_ref and n == len(pairs)
+    assert_pose_close(T, T_ref, 1e-9)
+
+
+def test_resident_cloud_edge_cases(ctx):
+    z = np.zeros(0, np.float32)
+    M, L, gt = _c2(20_000, 10)
+    gmap = b200.Map(ctx, *xyz(M))
+    empty = b200.Cloud(ctx, z, z, z)
+    p, pot = gmap.match_pt2pt(empty, None, None, gt, b200.Pt2PtParams(threshold=1.0))
+    assert len(p) == 0 and pot == 0
+    for n in (1, 31, 257):  # ragged tiles
+        c = b200.Cloud(ctx, *xyz(L[:n]))
+        ref, _ = gmap.match_pt2pt(*xyz(L[:n]), gt, b200.Pt2PtParams(threshold=1.0))
+        got, _ = gmap.match_pt2pt(c, None, None, gt, b200.Pt2PtParams(threshold=1.0))
+        assert ref.tobytes() == got.tobytes()
+    same = np.repeat(L[:1], 1000, axis=0)  # zero-extent cloud
+    c = b200.Cloud(ctx, *xyz(same))
+    ref, _ = gmap.match_pt2pt(*xyz(same), gt, b200.Pt2PtParams(threshold=1.0))
+    got, _ = gmap.match_pt2pt(c, None, None, gt, b200.Pt2PtParams(threshold=1.0))
+    assert len(ref) == 1 and ref.tobytes() == got.tobytes()
 
 
 # --------------------------------------------------------------------------- multi-GPU (needs >= 2 GPUs)
