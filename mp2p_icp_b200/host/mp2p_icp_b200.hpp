@@ -253,17 +253,38 @@ class Device
         }
         return e.map;
     }
+    /** Device-resident copy of a LOCAL layer (mp2p_b200_cloud: caller order + Morton-sorted copy),
+     *  cached like the index of a global layer: ICP::align() matches the same, unmodified local
+     *  layer at every iteration (ICP.cpp:123-308), so it crosses PCIe once per align(). */
+    const float* cloud_for(const CPointsMap& layer)
+    {
+        Entry& e = cache_[&layer];
+        if (!e.cloud || e.cloud_stamp != layer.stamp() || e.cloud_n != layer.size())
+        {
+            if (e.cloud) mp2p_b200_cloud_destroy(e.cloud);
+            e.cloud = nullptr;
+            check(mp2p_b200_cloud_create(ctx_, layer.getPointsBufferRef_x().data(), layer.getPointsBufferRef_y().data(),
+                                         layer.getPointsBufferRef_z().data(), layer.size(), 0, &e.cloud),
+                  "mp2p_b200_cloud_create");
+            e.cloud_stamp = layer.stamp(), e.cloud_n = layer.size();
+        }
+        return reinterpret_cast<const float*>(e.cloud);  // passed as `lx` with MP2P_B200_LOCAL_CLOUD
+    }
     void forget(const CPointsMap& layer)
     {
         auto it = cache_.find(&layer);
         if (it == cache_.end()) return;
         if (it->second.map) mp2p_b200_map_destroy(it->second.map);
+        if (it->second.cloud) mp2p_b200_cloud_destroy(it->second.cloud);
         cache_.erase(it);
     }
     ~Device()
     {
         for (auto& kv : cache_)
+        {
             if (kv.second.map) mp2p_b200_map_destroy(kv.second.map);
+            if (kv.second.cloud) mp2p_b200_cloud_destroy(kv.second.cloud);
+        }
         mp2p_b200_ctx_destroy(ctx_);
     }
 
@@ -271,9 +292,12 @@ class Device
     explicit Device(int device) { check(mp2p_b200_ctx_create(device, nullptr, &ctx_), "mp2p_b200_ctx_create"); }
     struct Entry
     {
-        mp2p_b200_map* map   = nullptr;
-        uint64_t       stamp = 0;
-        size_t         n     = 0;
+        mp2p_b200_map*   map   = nullptr;
+        uint64_t         stamp = 0;
+        size_t           n     = 0;
+        mp2p_b200_cloud* cloud = nullptr;
+        uint64_t         cloud_stamp = 0;
+        size_t           cloud_n     = 0;
     };
     mp2p_b200_ctx*                      ctx_ = nullptr;
     std::map<const CPointsMap*, Entry>  cache_;
@@ -399,9 +423,8 @@ class Matcher_Points_DistanceThreshold : public Matcher_Points_Base
         const size_t before = out.paired_pt2pt.size(), cap = pcLocal.size() * pairingsPerPoint;
         out.paired_pt2pt.resize(before + cap);
         uint64_t cnt = 0, pot = 0;
-        check(mp2p_b200_match_pt2pt(dev.ctx(), dev.map_for(pcGlobal), pcLocal.getPointsBufferRef_x().data(),
-                                    pcLocal.getPointsBufferRef_y().data(), pcLocal.getPointsBufferRef_z().data(),
-                                    pcLocal.size(), 0, localPose.m, &p, lbits.data(), gbits.data(),
+        check(mp2p_b200_match_pt2pt(dev.ctx(), dev.map_for(pcGlobal), dev.cloud_for(pcLocal), nullptr, nullptr,
+                                    pcLocal.size(), MP2P_B200_LOCAL_CLOUD, localPose.m, &p, lbits.data(), gbits.data(),
                                     out.paired_pt2pt.data() + before, cap, 0, &cnt, &pot),
               "mp2p_b200_match_pt2pt");
         out.paired_pt2pt.resize(before + cnt);
@@ -441,9 +464,8 @@ class Matcher_Point2Plane : public Matcher_Points_Base
         const size_t before = out.paired_pt2pl.size(), cap = pcLocal.size();
         out.paired_pt2pl.resize(before + cap);
         uint64_t cnt = 0, pot = 0;
-        check(mp2p_b200_match_pt2pl(dev.ctx(), dev.map_for(pcGlobal), pcLocal.getPointsBufferRef_x().data(),
-                                    pcLocal.getPointsBufferRef_y().data(), pcLocal.getPointsBufferRef_z().data(),
-                                    pcLocal.size(), 0, localPose.m, &p, lbits.data(), out.paired_pt2pl.data() + before,
+        check(mp2p_b200_match_pt2pl(dev.ctx(), dev.map_for(pcGlobal), dev.cloud_for(pcLocal), nullptr, nullptr,
+                                    pcLocal.size(), MP2P_B200_LOCAL_CLOUD, localPose.m, &p, lbits.data(), out.paired_pt2pl.data() + before,
                                     cap, 0, &cnt, &pot),
               "mp2p_b200_match_pt2pl");
         out.paired_pt2pl.resize(before + cnt);

@@ -63,9 +63,12 @@ struct MapCache
 {
     struct Entry
     {
-        mp2p_b200_map* map = nullptr;
-        const float*   x   = nullptr;
-        size_t         n   = 0;
+        mp2p_b200_map*   map = nullptr;
+        const float*     x   = nullptr;
+        size_t           n   = 0;
+        mp2p_b200_cloud* cloud = nullptr;  // the same layer used as the LOCAL cloud of an align()
+        const float*     cx    = nullptr;
+        size_t           cn    = 0;
     };
     std::mutex                                                   mtx;
     std::unordered_map<const mrpt::maps::CMetricMap*, Entry>     entries;
@@ -84,6 +87,21 @@ struct MapCache
             e.x = xs.data(), e.n = xs.size();
         }
         return e.map;
+    }
+    // local layer: uploaded (and Morton-sorted) once, reused by every ICP iteration of the align()
+    const float* get_local(const mrpt::maps::CPointsMap& pts)
+    {
+        const auto&                 xs = pts.getPointsBufferRef_x();
+        std::lock_guard<std::mutex> lk(mtx);
+        auto&                       e = entries[&pts];
+        if (!e.cloud || e.cx != xs.data() || e.cn != xs.size())
+        {
+            if (e.cloud) mp2p_b200_cloud_destroy(e.cloud);
+            check(mp2p_b200_cloud_create(ctx(), xs.data(), pts.getPointsBufferRef_y().data(),
+                                         pts.getPointsBufferRef_z().data(), xs.size(), 0, &e.cloud));
+            e.cx = xs.data(), e.cn = xs.size();
+        }
+        return reinterpret_cast<const float*>(e.cloud);
     }
 };
 inline MapCache& cache()
@@ -127,8 +145,7 @@ class Matcher_Points_DistanceThreshold_B200 : public Matcher_Points_Base
         ASSERT_GT_(threshold, .0);
         ASSERT_GE_(thresholdAngularDeg, .0);
         mp2p_b200_map* gmap = cache().get(pcGlobal);
-        const auto &   lx = pcLocal.getPointsBufferRef_x(), &ly = pcLocal.getPointsBufferRef_y(),
-                   &lz = pcLocal.getPointsBufferRef_z();
+        const auto& lx = pcLocal.getPointsBufferRef_x();
         double T[12];
         pose12(localPose, T);
         mp2p_b200_pt2pt_params p{threshold, thresholdAngularDeg, pairingsPerPoint,
@@ -142,7 +159,8 @@ class Matcher_Points_DistanceThreshold_B200 : public Matcher_Points_Base
         out.paired_pt2pt.resize(before + lx.size() * pairingsPerPoint);
         static_assert(sizeof(mrpt::tfest::TMatchingPair) == sizeof(mp2p_b200_pair_pt2pt));
         uint64_t cnt = 0, pot = 0;
-        check(mp2p_b200_match_pt2pt(ctx(), gmap, lx.data(), ly.data(), lz.data(), lx.size(), 0, T, &p,
+        check(mp2p_b200_match_pt2pt(ctx(), gmap, cache().get_local(pcLocal), nullptr, nullptr, lx.size(),
+                                    MP2P_B200_LOCAL_CLOUD, T, &p,
                                     lbits.data(), gbits.data(),
                                     reinterpret_cast<mp2p_b200_pair_pt2pt*>(out.paired_pt2pt.data() + before),
                                     lx.size() * pairingsPerPoint, 0, &cnt, &pot));
