@@ -285,7 +285,28 @@ __global__ void __launch_bounds__(kQueryTile)
 // atomicMin on the 64-bit (d2, index) key. Exactness argument unchanged: every voxel with box
 // bound <= current best distance is visited, candidates compare on (d2, index).
 // ------------------------------------------------------------------------------------------
-template <int kItemRounds>
+// scan `count` consecutive points for the smallest (d2, index) key: loads go out four at a time
+// (clamped to the last point of the run — a duplicate never wins the strict compare), so a voxel
+// of <= 4 points costs ONE memory round trip; returns the key, *best_j = position inside the run
+__device__ __forceinline__ unsigned long long scan_run_min(const float4* __restrict__ run, uint32_t count, float qx,
+                                                           float qy, float qz, unsigned long long m, uint32_t& best_j)
+{
+    const uint32_t last = count - 1;
+    for (uint32_t j0 = 0; j0 < count; j0 += 4)
+    {
+        float4 q[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) q[k] = __ldg(run + min(j0 + k, last));
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            const unsigned long long c = point_key(qx, qy, qz, q[k]);
+            if (c < m) m = c, best_j = min(j0 + k, last);
+        }
+    }
+    return m;
+}
+
 __global__ void __launch_bounds__(kNN1Threads)
     k_match_pt2pt_nn1(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
                       const float* __restrict__ lz, const uint32_t* __restrict__ perm,
@@ -294,10 +315,12 @@ __global__ void __launch_bounds__(kNN1Threads)
                       unsigned long long* __restrict__ cand, float4* __restrict__ cand_xyz,
                       uint32_t* __restrict__ bbox_words, unsigned long long* __restrict__ stats)
 {
+    constexpr int kWarpsNN1 = kNN1Threads / 32;
     __shared__ QueryTile<kNN1Threads> tile;
     __shared__ BBoxAcc                bacc;
-    __shared__ unsigned long long     s_best[kNN1Threads / 32][32];
-    __shared__ float                  s_xyz[kNN1Threads / 32][32][3];  // coordinates of s_best's point
+    __shared__ unsigned long long     s_best[kWarpsNN1][32];
+    __shared__ uint32_t               s_run[kWarpsNN1][32];         // map position of s_best's point
+    __shared__ uint16_t               s_item[kWarpsNN1][32 * 26];   // (owner lane << 5) | neighbour bit
     const size_t                      base = (size_t)blockIdx.x * kNN1Threads;
     bbox_init(bacc);
     load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
@@ -320,7 +343,7 @@ __global__ void __launch_bounds__(kNN1Threads)
     }
     const unsigned long long sentinel = (unsigned long long)__float_as_uint(thr2) << 32;
     unsigned long long       best     = sentinel;
-    float                    bpx = 0.f, bpy = 0.f, bpz = 0.f;  // the best candidate's coordinates
+    uint32_t                 best_pos = 0;  // position in g.pts of the best candidate
     float                    kth      = thr2;
     bool                     active   = thr2 > 0.f;
     if (active)
@@ -349,12 +372,9 @@ __global__ void __launch_bounds__(kNN1Threads)
             if (active)
             {
                 sc.probes++, sc.cands += g.n_points, sc.levels++;
-                for (uint32_t j = 0; j < g.n_points; j++)
-                {
-                    const float4             p = __ldg(g.pts + j);
-                    const unsigned long long c = point_key(gx, gy, gz, p);
-                    if (c < best) best = c, bpx = p.x, bpy = p.y, bpz = p.z;
-                }
+                uint32_t j = 0;
+                best       = scan_run_min(g.pts, g.n_points, gx, gy, gz, best, j);
+                if (best < sentinel) best_pos = j;  // j is only meaningful if something won
             }
             break;
         }
@@ -371,12 +391,9 @@ __global__ void __launch_bounds__(kNN1Threads)
             if (grid_lookup(g, rl, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, start, count))
             {
                 sc.cands += count;
-                for (uint32_t j = start; j < start + count; j++)
-                {
-                    const float4             p = __ldg(g.pts + j);
-                    const unsigned long long c = point_key(gx, gy, gz, p);
-                    if (c < best) best = c, bpx = p.x, bpy = p.y, bpz = p.z;
-                }
+                uint32_t                 j = 0;
+                const unsigned long long m = scan_run_min(g.pts + start, count, gx, gy, gz, best, j);
+                if (m < best) best = m, best_pos = start + j;
             }
         }
         kth = fminf(kth, __uint_as_float((uint32_t)(best >> 32)));
@@ -411,7 +428,8 @@ __global__ void __launch_bounds__(kNN1Threads)
                 }
             }
         }
-        // ---- pool the (query, voxel) items of the warp and deal them out one per lane
+        // ---- pool the (query, voxel) items of the warp: every owner lists its items in shared
+        // memory at its exclusive offset, then item `id` goes to lane id % 32
         const uint32_t cnt  = __popc(mask);
         uint32_t       incl = cnt;
 #pragma unroll
@@ -420,101 +438,70 @@ __global__ void __launch_bounds__(kNN1Threads)
             const uint32_t t = __shfl_up_sync(FULL, incl, o);
             if (lane >= o) incl += t;
         }
-        const uint32_t excl  = incl - cnt;
         const uint32_t total = __shfl_sync(FULL, incl, 31);
-        s_best[warp][lane]   = best;
-        s_xyz[warp][lane][0] = bpx, s_xyz[warp][lane][1] = bpy, s_xyz[warp][lane][2] = bpz;
-        __syncwarp();
-        // kItemRounds rounds of 32 items are software-pipelined: all hash probes of the chunk are
-        // issued first, then all first-point loads, then the scans — 3 overlapped memory round trips
-        // per chunk instead of 2 per round.
-        for (uint32_t b0 = 0; b0 < total; b0 += 32 * kItemRounds)
         {
-            int                owner[kItemRounds];
-            float              oq[kItemRounds][3];
-            unsigned long long ckey[kItemRounds];
-            uint32_t           h[kItemRounds], start[kItemRounds], count[kItemRounds];
-            uint4              raw[kItemRounds];
-            float4             p0[kItemRounds];
-            const uint32_t     shift = g.level_shift[rl], hmask = (1u << (64 - shift)) - 1u;
-            const CellEntry*   tab   = g.table + g.level_off[rl];
-            // ---- phase A: who owns item (b0 + r*32 + lane), which voxel is it, issue the probe
-#pragma unroll
-            for (int r = 0; r < kItemRounds; r++)
+            uint32_t pos = incl - cnt, m = mask;
+            while (m)
             {
-                const uint32_t id = b0 + r * 32 + lane;
-                int            ow = 0;  // largest lane q with excl[q] <= id
-#pragma unroll
-                for (int st = 16; st > 0; st >>= 1)
-                {
-                    const int      probe = ow + st;
-                    const uint32_t e     = __shfl_sync(FULL, excl, probe & 31);
-                    if (probe < 32 && e <= id) ow = probe;
-                }
-                owner[r] = ow;
-                oq[r][0] = __shfl_sync(FULL, gx, ow), oq[r][1] = __shfl_sync(FULL, gy, ow), oq[r][2] = __shfl_sync(FULL, gz, ow);
-                const int      ocx = __shfl_sync(FULL, cx, ow), ocy = __shfl_sync(FULL, cy, ow), ocz = __shfl_sync(FULL, cz, ow);
-                const uint32_t omask = __shfl_sync(FULL, mask, ow), oexcl = __shfl_sync(FULL, excl, ow);
-                count[r] = 0, start[r] = 0, ckey[r] = kEmptyKey, h[r] = 0;
-                raw[r]   = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
-                if (id < total)
-                {
-                    const uint32_t bit = __fns(omask, 0, (int)(id - oexcl) + 1);
-                    const int      dz = (int)(bit / 9u), dy = (int)((bit % 9u) / 3u), dx = (int)(bit % 3u);
-                    ckey[r] = cell_key((uint32_t)(ocx + dx - 1), (uint32_t)(ocy + dy - 1), (uint32_t)(ocz + dz - 1));
-                    h[r]    = cell_hash(ckey[r], shift);
-                    raw[r]  = __ldg(reinterpret_cast<const uint4*>(tab + h[r]));
-                    sc.probes++;
-                }
+                const uint32_t bit = __ffs(m) - 1;
+                m &= m - 1;
+                s_item[warp][pos++] = (uint16_t)((lane << 5) | bit);
             }
-            // ---- phase B: resolve the probes (linear probing continues on a collision), issue the
-            // first point of every hit
-#pragma unroll
-            for (int r = 0; r < kItemRounds; r++)
+        }
+        s_best[warp][lane] = best;
+        s_run[warp][lane]  = best_pos;
+        __syncwarp();
+        const uint32_t   shift = g.level_shift[rl], hmask = (1u << (64 - shift)) - 1u;
+        const CellEntry* tab   = g.table + g.level_off[rl];
+        for (uint32_t b0 = 0; b0 < total; b0 += 32)
+        {
+            const uint32_t id = b0 + lane;
+            // the shuffles below are executed by all lanes; lanes past the end mirror item 0's owner
+            const uint32_t it    = id < total ? s_item[warp][id] : 0u;
+            const int      owner = (int)(it >> 5);
+            const uint32_t bit   = it & 31u;
+            const float    oqx = __shfl_sync(FULL, gx, owner), oqy = __shfl_sync(FULL, gy, owner), oqz = __shfl_sync(FULL, gz, owner);
+            const int      ocx = __shfl_sync(FULL, cx, owner), ocy = __shfl_sync(FULL, cy, owner), ocz = __shfl_sync(FULL, cz, owner);
+            unsigned long long m   = ~0ull;
+            uint32_t           pos = 0;
+            if (id < total)
             {
-                p0[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ckey[r] == kEmptyKey) continue;
-                while (true)
+                const int dz = (int)(bit / 9u), dy = (int)((bit % 9u) / 3u), dx = (int)(bit % 3u);
+                const unsigned long long ckey =
+                    cell_key((uint32_t)(ocx + dx - 1), (uint32_t)(ocy + dy - 1), (uint32_t)(ocz + dz - 1));
+                uint32_t h     = cell_hash(ckey, shift);
+                uint32_t start = 0, count = 0;
+                sc.probes++;
+                while (true)  // linear probing continues on a collision
                 {
-                    const unsigned long long k = (unsigned long long)raw[r].x | ((unsigned long long)raw[r].y << 32);
-                    if (k == ckey[r])
+                    const uint4              raw = __ldg(reinterpret_cast<const uint4*>(tab + h));
+                    const unsigned long long k   = (unsigned long long)raw.x | ((unsigned long long)raw.y << 32);
+                    if (k == ckey)
                     {
-                        start[r] = raw[r].z, count[r] = raw[r].w;
+                        start = raw.z, count = raw.w;
                         break;
                     }
                     if (k == kEmptyKey) break;
-                    h[r]   = (h[r] + 1) & hmask;
-                    raw[r] = __ldg(reinterpret_cast<const uint4*>(tab + h[r]));
+                    h = (h + 1) & hmask;
                 }
-                if (count[r]) p0[r] = __ldg(g.pts + start[r]), sc.cands += count[r];
-            }
-            // ---- phase C: scan, hand the minimum (and, if it survives, its coordinates) to the owner
-#pragma unroll
-            for (int r = 0; r < kItemRounds; r++)
-            {
-                unsigned long long m  = ~0ull;
-                float              mx = 0.f, my = 0.f, mz = 0.f;
-                if (count[r])
+                if (count)
                 {
-                    float4 p = p0[r];
-                    for (uint32_t j = 0; j < count[r]; j++)
-                    {
-                        if (j) p = __ldg(g.pts + start[r] + j);
-                        const unsigned long long c = point_key(oq[r][0], oq[r][1], oq[r][2], p);
-                        if (c < m) m = c, mx = p.x, my = p.y, mz = p.z;
-                    }
-                    atomicMin(&s_best[warp][owner[r]], m);
+                    sc.cands += count;
+                    uint32_t j = 0;
+                    m          = scan_run_min(g.pts + start, count, oqx, oqy, oqz, ~0ull, j);
+                    pos        = start + j;
+                    atomicMin(&s_best[warp][owner], m);
                 }
-                // keys are unique: exactly one item (or the owner's own centre candidate) matches the
-                // slot afterwards; later rounds may replace it again
-                __syncwarp();
-                if (m != ~0ull && s_best[warp][owner[r]] == m)
-                    s_xyz[warp][owner[r]][0] = mx, s_xyz[warp][owner[r]][1] = my, s_xyz[warp][owner[r]][2] = mz;
-                __syncwarp();
             }
+            // keys are unique (the map index is part of the key): once all items of the round have
+            // offered theirs, at most one of them equals the owner's slot — that one records where
+            // its point sits (the owner's own centre candidate keeps its position otherwise)
+            __syncwarp();
+            if (m != ~0ull && s_best[warp][owner] == m) s_run[warp][owner] = pos;
+            __syncwarp();
         }
-        best = s_best[warp][lane];
-        bpx = s_xyz[warp][lane][0], bpy = s_xyz[warp][lane][1], bpz = s_xyz[warp][lane][2];
+        best     = s_best[warp][lane];
+        best_pos = s_run[warp][lane];
         __syncwarp();
         kth = fminf(kth, __uint_as_float((uint32_t)(best >> 32)));
         // everything outside the 3x3x3 block is at least m quanta away
@@ -534,7 +521,9 @@ __global__ void __launch_bounds__(kNN1Threads)
         const unsigned long long c = best < sentinel ? best : ~0ull;
         n_valid                    = (c != ~0ull);
         cand[i]                    = c;
-        cand_xyz[i]                = make_float4(bpx, bpy, bpz, 0.f);
+        float4 bp                  = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n_valid) bp = __ldg(g.pts + best_pos);  // just read by some lane of this warp: L1/L2 hit
+        cand_xyz[i] = make_float4(bp.x, bp.y, bp.z, 0.f);
         if (c != ~0ull && !a.allowGlobal)
         {
             const uint32_t gi = (uint32_t)c;
@@ -900,16 +889,6 @@ __global__ void __launch_bounds__(256)
     out_found[i] = cnt;
 }
 
-// tuning knob (measurement only): item rounds software-pipelined per chunk in the K = 1 matcher
-int nn1_rounds()
-{
-    static const int v = [] {
-        const char* e = getenv("MP2P_NN1_ROUNDS");
-        return (e && atoi(e) == 4) ? 4 : 1;
-    }();
-    return v;
-}
-
 int pick_kt(uint32_t K)
 {
     if (K <= 1) return 1;
@@ -1149,12 +1128,8 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     {
         MP2P_TRY(ctx->d_candxyz.ensure(n_slots * sizeof(float4)));
         cand_xyz = ctx->d_candxyz.as<float4>();
-        if (nn1_rounds() == 1)
-            k_match_pt2pt_nn1<1><<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
-                map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, cand_xyz, sv.bbox, stats);
-        else
-            k_match_pt2pt_nn1<4><<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
-                map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, cand_xyz, sv.bbox, stats);
+        k_match_pt2pt_nn1<<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
+            map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, cand_xyz, sv.bbox, stats);
     }
     else
     {
@@ -1282,12 +1257,8 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     {
         MP2P_TRY(ctx->d_candxyz.ensure(n_local * sizeof(float4)));
         const uint32_t nb = (uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads);
-        if (nn1_rounds() == 1)
-            k_match_pt2pt_nn1<1><<<nb, kNN1Threads, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr,
-                                                             nullptr, d_record, ctx->d_candxyz.as<float4>(), d_bbox6, stats);
-        else
-            k_match_pt2pt_nn1<4><<<nb, kNN1Threads, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr,
-                                                             nullptr, d_record, ctx->d_candxyz.as<float4>(), d_bbox6, stats);
+        k_match_pt2pt_nn1<<<nb, kNN1Threads, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr,
+                                                      d_record, ctx->d_candxyz.as<float4>(), d_bbox6, stats);
     }
     else
     {
