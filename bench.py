@@ -248,9 +248,10 @@ def run_ours(args):
             # records -> resolve (+HORN1 sums) -> all_reduce -> HORN2 -> all_reduce, ONE host sync
             ok, T, n_all = sh.iterate_pt2pt_horn(lp, pose, mprm, sprm, d_pairs.data_ptr(), cap)
             return n_all, T
-        # pt2pl never dedups global points (Matcher_Point2Plane.cpp:87-90): shards are independent
-        n_pairs, _ = gmap.match_pt2pl(*lp, pose, mprm, n_local=nq, local_on_device=True, out=d_pairs.data_ptr(), out_on_device=True, capacity=cap)
-        return n_pairs, solve_device(n_pairs)
+        # pt2pl never dedups global points (Matcher_Point2Plane.cpp:87-90): shards match independently,
+        # GN inner loop with the pose on the device and one all_reduce per inner iteration, ONE host sync
+        ok, T, updates = sh.iterate_pt2pl_gn(lp, pose, mprm, sprm, d_pairs.data_ptr(), cap)
+        return -1, T
 
     def step_e2e():
         hx, hy, hz = (t.numpy() for t in h_l)
@@ -391,7 +392,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 metric / f64 solve", "data": "synthetic",
         "config": {"workload": w["name"], "detail": w["desc"], "queries_per_gpu": nq, "map_points": len(w["map"]),
-                   "pairs": int(n_pairs), "l2": "flushed between timed steps (256 MiB memset, outside the event bracket)",
+                   "pairs": int(n_pairs) if n_pairs >= 0 else None, "l2": "flushed between timed steps (256 MiB memset, outside the event bracket)",
                    "ms_per_step_l2_warm_informative": ms_warm,
                    "device_path": "fused mp2p_b200_iterate_* call (N=1) / sharded search+all_gather+resolve+all_reduce (N>1)", "unit_note": "at N GPUs one step is one query-sharded iteration over N x queries_per_gpu; value counts N iteration-equivalents per step",
                    "local_cloud": ({"resident": True, "order": "Morton-sorted copy, built once per align()", "build_ms": cloud.info["build_ms"]} if cloud is not None else {"resident": False}),

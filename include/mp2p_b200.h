@@ -221,7 +221,8 @@ int mp2p_b200_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* l
  *     with the global proposal numbering, applies the bounding-box gate of the WHOLE cloud and
  *     compacts this shard's accepted pairs (localIdx = index in the whole cloud). Optionally the
  *     HORN1 sums of the shard's pairs are produced in the same pass (horn_sums_packet_device).
- *     With out_count == NULL (device output only) the call is asynchronous as well: the pairing
+ *     With out_count == NULL (device output only; also accepted by mp2p_b200_match_pt2pt and
+ *     mp2p_b200_match_pt2pl) the call is asynchronous as well: the pairing
  *     count stays on the device and the solver building blocks below take it from there when
  *     given n = MP2P_B200_COUNT_ON_DEVICE — a whole sharded iteration then needs ONE host
  *     synchronisation (reading the final packets).
@@ -294,6 +295,21 @@ int mp2p_b200_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* pair
                             uint64_t n_pt2pt, const mp2p_b200_pair_pt2pl* pairs_pt2pl,
                             uint64_t n_pt2pl, int pairs_on_device, const mp2p_b200_gn_params* params,
                             const double pose[12], double* packet, int packet_on_device);
+/* Gauss-Newton inner loop with the pose kept on the DEVICE (no host round trip per inner iteration;
+ * a multi-GPU caller enqueues  begin, then maxInnerLoopIterations x { accumulate, all_reduce(packet),
+ * step }  and reads the state back once). state_device: MP2P_B200_GN_STATE_DOUBLES doubles =
+ * [0..11] pose, then two uint32 {done flag, pose updates applied}. Once `done` is set (converged,
+ * optimal_tf_gauss_newton.cpp:344-365) accumulate and step become no-ops, so every rank can run the
+ * same fixed number of rounds. Pairings must be device memory; n = MP2P_B200_COUNT_ON_DEVICE allowed
+ * for the list the last matcher call produced. All three calls only enqueue work. */
+#define MP2P_B200_GN_STATE_DOUBLES 16
+int mp2p_b200_gn_device_begin(mp2p_b200_ctx* ctx, const double pose[12], double* state_device);
+int mp2p_b200_gn_device_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* pairs_pt2pt,
+                                   uint64_t n_pt2pt, const mp2p_b200_pair_pt2pl* pairs_pt2pl,
+                                   uint64_t n_pt2pl, const mp2p_b200_gn_params* params,
+                                   const double* state_device, double* packet_device);
+int mp2p_b200_gn_device_step(mp2p_b200_ctx* ctx, const double* packet_device,
+                             const mp2p_b200_gn_params* params, double* state_device);
 /* host-side step from a reduced GN packet: delta = -H^{-1} g (LDLT), pose_out = pose (+) exp(delta);
  * *converged = 1 if |delta| < minDelta or sqrt(err) <= maxCost (optimal_tf_gauss_newton.cpp:344-365). */
 int mp2p_b200_gn_step_from_packet(const double packet[MP2P_B200_PACKET_DOUBLES],

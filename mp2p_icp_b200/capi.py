@@ -159,7 +159,9 @@ EXPORTS = [
     "mp2p_b200_iterate_pt2pt_horn", "mp2p_b200_iterate_pt2pl_gn",
     "mp2p_b200_cloud_create", "mp2p_b200_cloud_destroy", "mp2p_b200_cloud_get_info",
     "mp2p_b200_shard_record_words",
+    "mp2p_b200_gn_device_begin", "mp2p_b200_gn_device_accumulate", "mp2p_b200_gn_device_step",
 ]
+GN_STATE_DOUBLES = 16
 COUNT_ON_DEVICE = (1 << 64) - 1  # MP2P_B200_COUNT_ON_DEVICE
 
 _lib = None
@@ -317,6 +319,16 @@ class Context:
         _check(load_library().mp2p_b200_gn_accumulate(self._h, _ptr(p2p) if n2p else None, C.c_uint64(n2p or 0), _ptr(p2l) if n2l else None, C.c_uint64(n2l or 0), int(on_device), C.byref(cp), _ptr(_pose(T)), _ptr(packet), int(packet_on_device)))
         return packet
 
+    # device-resident Gauss-Newton loop (multi-GPU building blocks): all three only enqueue work
+    def gn_device_begin(self, T, state: int):
+        _check(load_library().mp2p_b200_gn_device_begin(self._h, _ptr(_pose(T)), C.c_void_p(int(state))))
+
+    def gn_device_accumulate(self, d_p2p, n2p, d_p2l, n2l, prm_c, state: int, packet: int):
+        _check(load_library().mp2p_b200_gn_device_accumulate(self._h, C.c_void_p(int(d_p2p)) if d_p2p else None, C.c_uint64(n2p or 0), C.c_void_p(int(d_p2l)) if d_p2l else None, C.c_uint64(n2l or 0), C.byref(prm_c), C.c_void_p(int(state)), C.c_void_p(int(packet))))
+
+    def gn_device_step(self, packet: int, prm_c, state: int):
+        _check(load_library().mp2p_b200_gn_device_step(self._h, C.c_void_p(int(packet)), C.byref(prm_c), C.c_void_p(int(state))))
+
     def horn_sums(self, pairs, n=None, on_device=False, packet=None, packet_on_device=False):
         if not on_device:
             pairs = np.ascontiguousarray(pairs, dtype=PAIR_PT2PT)
@@ -447,7 +459,7 @@ class Map:
         _check(load_library().mp2p_b200_knn(self.ctx._h, self._h, _ptr(qx), _ptr(qy), _ptr(qz), C.c_uint64(nq), C.c_uint32(k), C.c_float(r2), _ptr(idx), _ptr(d2), _ptr(found)))
         return idx, d2, found
 
-    def match_pt2pt(self, lx, ly, lz, T, prm: Pt2PtParams, local_paired=None, global_paired=None, n_local=None, local_on_device=False, out=None, out_on_device=False, capacity=None):
+    def match_pt2pt(self, lx, ly, lz, T, prm: Pt2PtParams, local_paired=None, global_paired=None, n_local=None, local_on_device=False, out=None, out_on_device=False, capacity=None, sync=True):
         """Returns (pairs, potential_pairings); `pairs` is a numpy view of `out[:count]` for host
         output, or the count for device output."""
         plx, ply, plz, n_local, kind = _local(lx, ly, lz, n_local, local_on_device)
@@ -458,7 +470,9 @@ class Map:
         gb = pack_bits(global_paired) if global_paired is not None else None
         cp = prm.c()
         cnt, pot = C.c_uint64(0), C.c_uint64(0)
-        _check(load_library().mp2p_b200_match_pt2pt(self.ctx._h, self._h, plx, ply, plz, C.c_uint64(n_local), kind, _ptr(_pose(T)), C.byref(cp), _ptr(lb), _ptr(gb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt), C.byref(pot)))
+        _check(load_library().mp2p_b200_match_pt2pt(self.ctx._h, self._h, plx, ply, plz, C.c_uint64(n_local), kind, _ptr(_pose(T)), C.byref(cp), _ptr(lb), _ptr(gb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt) if sync else None, C.byref(pot)))
+        if not sync:
+            return None, pot.value
         if out_on_device:
             return cnt.value, pot.value
         return out[: cnt.value], pot.value
@@ -512,7 +526,7 @@ class Map:
 
         return step
 
-    def match_pt2pl(self, lx, ly, lz, T, prm: Pt2PlParams, local_paired=None, n_local=None, local_on_device=False, out=None, out_on_device=False, capacity=None):
+    def match_pt2pl(self, lx, ly, lz, T, prm: Pt2PlParams, local_paired=None, n_local=None, local_on_device=False, out=None, out_on_device=False, capacity=None, sync=True):
         plx, ply, plz, n_local, kind = _local(lx, ly, lz, n_local, local_on_device)
         cap = capacity if capacity is not None else n_local
         if out is None and not out_on_device:
@@ -520,7 +534,9 @@ class Map:
         lb = pack_bits(local_paired) if local_paired is not None else None
         cp = prm.c()
         cnt, pot = C.c_uint64(0), C.c_uint64(0)
-        _check(load_library().mp2p_b200_match_pt2pl(self.ctx._h, self._h, plx, ply, plz, C.c_uint64(n_local), kind, _ptr(_pose(T)), C.byref(cp), _ptr(lb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt), C.byref(pot)))
+        _check(load_library().mp2p_b200_match_pt2pl(self.ctx._h, self._h, plx, ply, plz, C.c_uint64(n_local), kind, _ptr(_pose(T)), C.byref(cp), _ptr(lb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt) if sync else None, C.byref(pot)))
+        if not sync:
+            return None, pot.value
         if out_on_device:
             return cnt.value, pot.value
         return out[: cnt.value], pot.value

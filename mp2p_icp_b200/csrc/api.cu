@@ -331,10 +331,10 @@ extern "C"
                               mp2p_b200_pair_pt2pt* out_pairs, uint64_t capacity, int out_on_device,
                               uint64_t* out_count, uint64_t* potential_pairings)
     {
-        if (!ctx || !map || !pose || !prm || !out_count || (n_local && bad_local(lx, ly, lz, local_on_device)) ||
-            (capacity && !out_pairs))
+        if (!ctx || !map || !pose || !prm || (!out_count && !out_on_device) ||
+            (n_local && bad_local(lx, ly, lz, local_on_device)) || (capacity && !out_pairs))
         {
-            set_error("match_pt2pt: NULL argument");
+            set_error("match_pt2pt: NULL argument (out_count may only be NULL with device output)");
             return MP2P_B200_ERR_ARG;
         }
         // ASSERT_(pairingsPerPoint >= 1); ASSERT_GT_(threshold, .0); ASSERT_GE_(thresholdAngularDeg, .0)
@@ -349,8 +349,17 @@ extern "C"
         if (potential_pairings) *potential_pairings += n_local * prm->pairingsPerPoint;  // :64
         DeviceGuard g(ctx->device);
         ProfScope   ps(ctx);
-        return run_match_pt2pt(ctx, map, lx, ly, lz, n_local, local_on_device, pose, prm, local_paired_bits,
-                               global_paired_bits, out_pairs, capacity, out_on_device, out_count);
+        if (out_count)
+            return run_match_pt2pt(ctx, map, lx, ly, lz, n_local, local_on_device, pose, prm, local_paired_bits,
+                                   global_paired_bits, out_pairs, capacity, out_on_device, out_count);
+        // asynchronous form: the count stays on the device (MP2P_B200_COUNT_ON_DEVICE)
+        DeviceMatch dm;
+        uint64_t    dummy = 0;
+        ctx->last_count = nullptr, ctx->last_capacity = 0;
+        MP2P_TRY(run_match_pt2pt(ctx, map, lx, ly, lz, n_local, local_on_device, pose, prm, local_paired_bits,
+                                 global_paired_bits, out_pairs, capacity, 1, &dummy, &dm));
+        ctx->last_count = dm.d_count, ctx->last_capacity = dm.d_count ? dm.capacity : 0;
+        return 0;
     }
 
     int mp2p_b200_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
@@ -360,10 +369,10 @@ extern "C"
                               uint64_t capacity, int out_on_device, uint64_t* out_count,
                               uint64_t* potential_pairings)
     {
-        if (!ctx || !map || !pose || !prm || !out_count || (n_local && bad_local(lx, ly, lz, local_on_device)) ||
-            (capacity && !out_pairs))
+        if (!ctx || !map || !pose || !prm || (!out_count && !out_on_device) ||
+            (n_local && bad_local(lx, ly, lz, local_on_device)) || (capacity && !out_pairs))
         {
-            set_error("match_pt2pl: NULL argument");
+            set_error("match_pt2pl: NULL argument (out_count may only be NULL with device output)");
             return MP2P_B200_ERR_ARG;
         }
         if (!(prm->distanceThreshold > 0.0) || !(prm->searchRadius > 0.0))
@@ -374,8 +383,16 @@ extern "C"
         if (potential_pairings) *potential_pairings += n_local;  // Matcher_Point2Plane.cpp:54
         DeviceGuard g(ctx->device);
         ProfScope   ps(ctx);
-        return run_match_pt2pl(ctx, map, lx, ly, lz, n_local, local_on_device, pose, prm, local_paired_bits,
-                               out_pairs, capacity, out_on_device, out_count);
+        if (out_count)
+            return run_match_pt2pl(ctx, map, lx, ly, lz, n_local, local_on_device, pose, prm, local_paired_bits,
+                                   out_pairs, capacity, out_on_device, out_count);
+        DeviceMatch dm;  // asynchronous form: the count stays on the device (MP2P_B200_COUNT_ON_DEVICE)
+        uint64_t    dummy = 0;
+        ctx->last_count = nullptr, ctx->last_capacity = 0;
+        MP2P_TRY(run_match_pt2pl(ctx, map, lx, ly, lz, n_local, local_on_device, pose, prm, local_paired_bits,
+                                 out_pairs, capacity, 1, &dummy, &dm));
+        ctx->last_count = dm.d_count, ctx->last_capacity = dm.d_count ? dm.capacity : 0;
+        return 0;
     }
 
     uint64_t mp2p_b200_shard_record_words(uint64_t per_shard, uint32_t pairingsPerPoint)
@@ -590,6 +607,47 @@ extern "C"
         double* dp = packet_on_device ? packet : ctx->d_packet.as<double>();
         MP2P_TRY(run_gn_accumulate(ctx, d2p, n2p, d2l, n2l, prm, ctx->d_pose.as<double>(), dp, d_n2p));
         return packet_out(ctx, dp, packet, packet_on_device);
+    }
+
+    // ---- device-resident Gauss-Newton state: [0..11] pose, [12] = {done flag u32, updates u32}
+    int mp2p_b200_gn_device_begin(mp2p_b200_ctx* ctx, const double pose[12], double* state_device)
+    {
+        if (!ctx || !pose || !state_device) return MP2P_B200_ERR_ARG;
+        DeviceGuard g(ctx->device);
+        double*     h = reinterpret_cast<double*>(static_cast<char*>(ctx->h_pinned) + 2048);
+        std::memcpy(h, pose, 96);
+        std::memset(h + 12, 0, 32);
+        MP2P_CUDA_TRY(cudaMemcpyAsync(state_device, h, MP2P_B200_GN_STATE_DOUBLES * 8, cudaMemcpyHostToDevice, ctx->stream));
+        return 0;
+    }
+
+    int mp2p_b200_gn_device_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* p2p, uint64_t n2p,
+                                       const mp2p_b200_pair_pt2pl* p2l, uint64_t n2l,
+                                       const mp2p_b200_gn_params* prm, const double* state_device,
+                                       double* packet_device)
+    {
+        if (!ctx || !prm || !state_device || !packet_device) return MP2P_B200_ERR_ARG;
+        if (n2p == MP2P_B200_COUNT_ON_DEVICE && n2l == MP2P_B200_COUNT_ON_DEVICE)
+        {
+            set_error("gn_device_accumulate: only one of the two lists can be the last matcher's output");
+            return MP2P_B200_ERR_ARG;
+        }
+        DeviceGuard               g(ctx->device);
+        ProfScope                 ps(ctx);
+        const unsigned long long *d_n2p, *d_n2l;
+        MP2P_TRY(count_on_device(ctx, &n2p, 1, &d_n2p));
+        MP2P_TRY(count_on_device(ctx, &n2l, 1, &d_n2l));
+        if ((n2p && !p2p) || (n2l && !p2l)) return MP2P_B200_ERR_ARG;
+        return run_gn_accumulate(ctx, p2p, n2p, p2l, n2l, prm, state_device, packet_device, d_n2p, d_n2l,
+                                 reinterpret_cast<const uint32_t*>(state_device + 12));
+    }
+
+    int mp2p_b200_gn_device_step(mp2p_b200_ctx* ctx, const double* packet_device, const mp2p_b200_gn_params* prm,
+                                 double* state_device)
+    {
+        if (!ctx || !packet_device || !prm || !state_device) return MP2P_B200_ERR_ARG;
+        DeviceGuard g(ctx->device);
+        return run_gn_step(ctx, packet_device, prm, state_device, reinterpret_cast<uint32_t*>(state_device + 12));
     }
 
     int mp2p_b200_gn_step_from_packet(const double packet[MP2P_B200_PACKET_DOUBLES],

@@ -232,6 +232,8 @@ int run_gn_device_loop(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint
                        const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l, const mp2p_b200_gn_params* prm,
                        double* d_pose, uint32_t* d_state, double* d_packet,
                        const unsigned long long* d_n2p = nullptr, const unsigned long long* d_n2l = nullptr);
+int run_gn_step(mp2p_b200_ctx* ctx, const double* d_packet, const mp2p_b200_gn_params* prm, double* d_pose,
+                uint32_t* d_state);
 int run_horn_sums(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n,
                   const uint8_t* d_outlier, double* d_packet, const unsigned long long* d_n = nullptr);
 int run_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n,

@@ -400,6 +400,14 @@ int run_gn_device_loop(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint
     return 0;
 }
 
+int run_gn_step(mp2p_b200_ctx* ctx, const double* d_packet, const mp2p_b200_gn_params* prm, double* d_pose,
+                uint32_t* d_state)
+{
+    k_gn_step<<<1, 32, 0, ctx->stream>>>(d_packet, prm->minDelta, prm->maxCost, d_pose, d_state);
+    count_launch(ctx);
+    return 0;
+}
+
 int run_horn_sums(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n,
                   const uint8_t* d_outlier, double* d_packet, const unsigned long long* d_n)
 {

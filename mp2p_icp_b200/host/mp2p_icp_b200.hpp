@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <atomic>
 #include <map>
 #include <memory>
 #include <optional>
@@ -133,13 +134,28 @@ class CPointsMap
     const std::vector<float>& getPointsBufferRef_x() const { return xs_; }
     const std::vector<float>& getPointsBufferRef_y() const { return ys_; }
     const std::vector<float>& getPointsBufferRef_z() const { return zs_; }
-    void                      mark_as_modified() { stamp_++; }  // invalidates the NN index
+    // Stamps are unique across ALL objects and modifications (process-wide counter), so a device
+    // cache keyed on (address, stamp) can never mistake a new map that reuses a freed address for
+    // the one it cached. Copies get a fresh stamp as well.
+    void                      mark_as_modified() { stamp_ = next_stamp(); }  // invalidates the NN index
     uint64_t                  stamp() const { return stamp_; }
+    CPointsMap() = default;
+    CPointsMap(const CPointsMap& o) : xs_(o.xs_), ys_(o.ys_), zs_(o.zs_) {}
+    CPointsMap& operator=(const CPointsMap& o)
+    {
+        xs_ = o.xs_, ys_ = o.ys_, zs_ = o.zs_, stamp_ = next_stamp();
+        return *this;
+    }
     void                      reserve(size_t n) { xs_.reserve(n), ys_.reserve(n), zs_.reserve(n); }
 
    private:
+    static uint64_t next_stamp()
+    {
+        static std::atomic<uint64_t> counter{0};
+        return ++counter;
+    }
     std::vector<float> xs_, ys_, zs_;
-    uint64_t           stamp_ = 0;
+    uint64_t           stamp_ = next_stamp();
 };
 
 /** mp2p_icp::metric_map_t: named point layers (metricmap.h:64-151). */

@@ -66,9 +66,7 @@ struct MapCache
         mp2p_b200_map*   map = nullptr;
         const float*     x   = nullptr;
         size_t           n   = 0;
-        mp2p_b200_cloud* cloud = nullptr;  // the same layer used as the LOCAL cloud of an align()
-        const float*     cx    = nullptr;
-        size_t           cn    = 0;
+        mp2p_b200_cloud* cloud = nullptr;  // set while a B200LocalCloudScope pins this layer as a LOCAL cloud
     };
     std::mutex                                                   mtx;
     std::unordered_map<const mrpt::maps::CMetricMap*, Entry>     entries;
@@ -88,20 +86,32 @@ struct MapCache
         }
         return e.map;
     }
-    // local layer: uploaded (and Morton-sorted) once, reused by every ICP iteration of the align()
-    const float* get_local(const mrpt::maps::CPointsMap& pts)
+    // A local layer is uploaded (and Morton-sorted) once and reused by every ICP iteration ONLY while
+    // the caller vouches that it does not change: MRPT exposes no modification counter for the point
+    // buffers, so the plugin cannot detect edits by itself. B200LocalCloudScope (below) is that
+    // promise; without it the matchers pass the host buffers on every call (MP2P_B200_LOCAL_HOST).
+    const float* pinned_local(const mrpt::maps::CPointsMap& pts)
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        auto                        it = entries.find(&pts);
+        return (it == entries.end() || !it->second.cloud) ? nullptr : reinterpret_cast<const float*>(it->second.cloud);
+    }
+    void pin_local(const mrpt::maps::CPointsMap& pts)
     {
         const auto&                 xs = pts.getPointsBufferRef_x();
         std::lock_guard<std::mutex> lk(mtx);
         auto&                       e = entries[&pts];
-        if (!e.cloud || e.cx != xs.data() || e.cn != xs.size())
-        {
-            if (e.cloud) mp2p_b200_cloud_destroy(e.cloud);
-            check(mp2p_b200_cloud_create(ctx(), xs.data(), pts.getPointsBufferRef_y().data(),
-                                         pts.getPointsBufferRef_z().data(), xs.size(), 0, &e.cloud));
-            e.cx = xs.data(), e.cn = xs.size();
-        }
-        return reinterpret_cast<const float*>(e.cloud);
+        if (e.cloud) mp2p_b200_cloud_destroy(e.cloud), e.cloud = nullptr;
+        check(mp2p_b200_cloud_create(ctx(), xs.data(), pts.getPointsBufferRef_y().data(),
+                                     pts.getPointsBufferRef_z().data(), xs.size(), 0, &e.cloud));
+    }
+    void unpin_local(const mrpt::maps::CPointsMap& pts)
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        auto                        it = entries.find(&pts);
+        if (it == entries.end() || !it->second.cloud) return;
+        mp2p_b200_cloud_destroy(it->second.cloud);
+        it->second.cloud = nullptr;
     }
 };
 inline MapCache& cache()
@@ -117,6 +127,21 @@ inline std::vector<uint32_t> to_bits(const pointcloud_bitfield_t::DenseOrSparseB
     return w;
 }
 }  // namespace b200_detail
+
+/** RAII promise that a local layer stays unmodified (e.g. for the duration of one ICP::align()):
+ *  the layer is kept on the device, Morton-sorted, instead of crossing PCIe at every iteration.
+ *      { mp2p_icp::B200LocalCloudScope keep(*pcLocal); icp.align(pcLocal, pcGlobal, ...); }        */
+class B200LocalCloudScope
+{
+   public:
+    explicit B200LocalCloudScope(const mrpt::maps::CPointsMap& pts) : pts_(pts) { b200_detail::cache().pin_local(pts_); }
+    ~B200LocalCloudScope() { b200_detail::cache().unpin_local(pts_); }
+    B200LocalCloudScope(const B200LocalCloudScope&)            = delete;
+    B200LocalCloudScope& operator=(const B200LocalCloudScope&) = delete;
+
+   private:
+    const mrpt::maps::CPointsMap& pts_;
+};
 
 /** Drop-in for Matcher_Points_DistanceThreshold (same parameters, same results). */
 class Matcher_Points_DistanceThreshold_B200 : public Matcher_Points_Base
@@ -159,8 +184,11 @@ class Matcher_Points_DistanceThreshold_B200 : public Matcher_Points_Base
         out.paired_pt2pt.resize(before + lx.size() * pairingsPerPoint);
         static_assert(sizeof(mrpt::tfest::TMatchingPair) == sizeof(mp2p_b200_pair_pt2pt));
         uint64_t cnt = 0, pot = 0;
-        check(mp2p_b200_match_pt2pt(ctx(), gmap, cache().get_local(pcLocal), nullptr, nullptr, lx.size(),
-                                    MP2P_B200_LOCAL_CLOUD, T, &p,
+        const float* resident = cache().pinned_local(pcLocal);
+        check(mp2p_b200_match_pt2pt(ctx(), gmap, resident ? resident : lx.data(),
+                                    resident ? nullptr : pcLocal.getPointsBufferRef_y().data(),
+                                    resident ? nullptr : pcLocal.getPointsBufferRef_z().data(), lx.size(),
+                                    resident ? MP2P_B200_LOCAL_CLOUD : MP2P_B200_LOCAL_HOST, T, &p,
                                     lbits.data(), gbits.data(),
                                     reinterpret_cast<mp2p_b200_pair_pt2pt*>(out.paired_pt2pt.data() + before),
                                     lx.size() * pairingsPerPoint, 0, &cnt, &pot));

@@ -94,6 +94,8 @@ class ShardedMatcherSolver:
         self.mine = self.records[rank * self.rec_words : (rank + 1) * self.rec_words]
         self.packets = torch.zeros((64,), dtype=torch.float64, device=dev)
         self.h_packets = torch.zeros((64,), dtype=torch.float64).pin_memory()
+        self.gn_state = torch.zeros((capi.GN_STATE_DOUBLES + 32,), dtype=torch.float64, device=dev)  # state | last packet
+        self.h_gn_state = torch.zeros((capi.GN_STATE_DOUBLES + 32,), dtype=torch.float64).pin_memory()
 
     # ---- matcher -------------------------------------------------------------------------------
     def _search_gather(self, local, pose, prm):
@@ -137,8 +139,31 @@ class ShardedMatcherSolver:
         one synchronisation per inner Gauss-Newton iteration (the reduced 6x6 system comes to the host)."""
         self._search_gather(local, pose, mprm)
         self.map.shard_resolve_pt2pt(self.n_local, self.rank, self.world, self.per, self.records.data_ptr(), mprm, out=d_pairs, out_on_device=True, capacity=capacity, sync=False)
-        ok, T, updates = self.solve_gauss_newton(d_pairs, capi.COUNT_ON_DEVICE, None, 0, sprm, pose)
-        return ok, T, updates
+        return self.gn_device_loop(d_pairs, capi.COUNT_ON_DEVICE, None, 0, sprm, pose)
+
+    def iterate_pt2pl_gn(self, local, pose, mprm: capi.Pt2PlParams, sprm: capi.GNParams, d_pairs: int, capacity: int):
+        """Matcher_Point2Plane + Solver_GaussNewton (C3). pt2pl never dedups global points
+        (Matcher_Point2Plane.cpp:87-90), so the shards match independently; the solver all-reduces one
+        packet per inner iteration with the pose on the device. ONE host synchronisation."""
+        lx, ly, lz = local
+        self.map.match_pt2pl(lx, ly, lz, pose, mprm, n_local=self.n_local, local_on_device=True, out=d_pairs, out_on_device=True, capacity=capacity, sync=False)
+        return self.gn_device_loop(None, 0, d_pairs, capi.COUNT_ON_DEVICE, sprm, pose)
+
+    def gn_device_loop(self, d_p2p, n2p, d_p2l, n2l, prm: capi.GNParams, pose0):
+        """optimal_tf_gauss_newton.cpp:70-366 with the reduction spread over ranks and the pose kept
+        on the device: maxInnerLoopIterations x {accumulate, all_reduce, step} enqueued back to back
+        (after convergence the remaining rounds are no-ops on every rank alike), one read-back."""
+        st, p, cp = self.gn_state, self.gn_state[capi.GN_STATE_DOUBLES :], prm.c()
+        self.ctx.gn_device_begin(pose0, st.data_ptr())
+        for _ in range(prm.maxInnerLoopIterations):
+            self.ctx.gn_device_accumulate(d_p2p, n2p, d_p2l, n2l, cp, st.data_ptr(), p.data_ptr())
+            self.dist.all_reduce(p)
+            self.ctx.gn_device_step(p.data_ptr(), cp, st.data_ptr())
+        self.h_gn_state.copy_(st, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        h = self.h_gn_state.numpy()
+        flags = h[12:13].view(np.uint32)
+        return True, h[:12].reshape(3, 4).copy(), int(flags[1])
 
     # ---- solvers over pairings already on the device -------------------------------------------
     def solve_horn(self, d_pairs: int, n_pairs: int, prm: capi.HornParams):

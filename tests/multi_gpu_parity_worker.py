@@ -56,6 +56,18 @@ def main():
     df = max(np.abs(T_f - T_h).max(), np.abs(T_fg - T_g).max())
     fused_ok = torch.tensor([int(fused_same and ok_f and ok_fg and df < 1e-9 and it_fg == it_g)], device=dev)
     dist.all_reduce(fused_ok, op=dist.ReduceOp.MIN)
+    # pt2pl + Gauss-Newton over a sharded scan (independent shards, device-resident GN loop)
+    Ms = fx.make_street_scene(n_map=200_000, length=40.0)
+    S = fx.make_lidar_scan((20.0, 0.5, 0.0), n_rings=32, n_az=400, length=40.0)
+    S = S[: (len(S) // world) * world]
+    g2 = fx.pose_xyzypr(20.08, 0.46, 0.02, 0.02, 0.001, -0.001)
+    smap = b200.Map(ctx, *xyz(Ms))
+    sh2 = ShardedMatcherSolver(ctx, smap, rank, world, len(S), k_max=1)
+    mine2 = S[sh2.lo : sh2.hi]
+    mkw = b200.Pt2PlParams(distanceThreshold=0.5, searchRadius=1.0, knn=8, minimumPlanePoints=5, planeEigenThreshold=0.01)
+    skw = b200.GNParams(maxInnerLoopIterations=3, kernel="GemanMcClure", kernelParam=0.15)
+    d_pl = torch.zeros(len(mine2) * 72, dtype=torch.uint8, device=dev)
+    ok_p, T_p, it_p = sh2.iterate_pt2pl_gn((b200.Cloud(ctx, *xyz(mine2)), None, None), g2, mkw, skw, d_pl.data_ptr(), len(mine2))
     # gather the shards' pairings on rank 0
     counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(counts, torch.tensor([n_pairs], dtype=torch.int64, device=dev))
@@ -70,6 +82,11 @@ def main():
         same = len(got) == len(ref) and got.tobytes() == ref.tobytes()
         dh, dg = np.abs(T_h - T_r).max(), np.abs(T_g - T_r2).max()
         print(f"world={world} pairs={len(got)} identical={same} horn_diff={dh:.2e} gn_diff={dg:.2e} gn_iters={it_g}/{it_r} one_sync_path_ok={int(fused_ok.item())} n_all={n_all}")
+        ref_l, _ = smap.match_pt2pl(*xyz(S), g2, mkw)
+        ok_pr, T_pr, it_pr = ctx.solve_gauss_newton(None, ref_l, skw, g2)
+        dp = np.abs(T_p - T_pr).max()
+        print(f"pt2pl+GN sharded: pairs(ref)={len(ref_l)} pose_diff={dp:.2e} iters={it_p}/{it_pr}")
+        same = same and ok_p and ok_pr and dp < 1e-9 and it_p == it_pr
         fail = int(not (same and ok_h and ok_g and dh < 1e-9 and dg < 1e-9 and it_g == it_r and int(fused_ok.item()) == 1 and n_all == len(ref)))
     t = torch.tensor([fail], device=dev)
     dist.broadcast(t, 0)

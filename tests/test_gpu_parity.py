@@ -433,6 +433,21 @@ def _sharded_iteration_world1(ctx):
     ok_r, T_r, it_r = ctx.solve_gauss_newton(pairs, None, gprm, guess)
     assert ok_g and ok_r and it_g == it_r
     assert_pose_close(T_g, T_r, 1e-9)
+    # pt2pl + GN through the asynchronous matcher form and the device-resident GN loop
+    Ms = fx.make_street_scene(n_map=200_000, length=40.0)
+    S = fx.make_lidar_scan((20.0, 0.5, 0.0), n_rings=32, n_az=400, length=40.0)
+    g2 = fx.pose_xyzypr(20.08, 0.46, 0.02, 0.02, 0.001, -0.001)
+    smap, scloud = b200.Map(ctx, *xyz(Ms)), b200.Cloud(ctx, *xyz(S))
+    mkw = b200.Pt2PlParams(distanceThreshold=0.5, searchRadius=1.0, knn=8, minimumPlanePoints=5, planeEigenThreshold=0.01)
+    skw = b200.GNParams(maxInnerLoopIterations=3, kernel="GemanMcClure", kernelParam=0.15)
+    ref_l, _ = smap.match_pt2pl(*xyz(S), g2, mkw)
+    ok_r, T_r, it_r = ctx.solve_gauss_newton(None, ref_l, skw, g2)
+    d_pl = torch.zeros(len(S) * 72, dtype=torch.uint8, device="cuda")
+    sh2 = ShardedMatcherSolver(ctx, smap, 0, 1, len(S), k_max=1)
+    ok_g, T_g, it_g = sh2.iterate_pt2pl_gn((scloud, None, None), g2, mkw, skw, d_pl.data_ptr(), len(S))
+    assert ok_g and ok_r and it_g == it_r and len(ref_l) > 1000
+    assert_pose_close(T_g, T_r, 1e-9)
+    assert d_pl.cpu().numpy().view(b200.PAIR_PT2PL)[: len(ref_l)].tobytes() == ref_l.tobytes()
     # nothing matches: the on-device count is zero, the iteration reports "not solved"
     far = fx.pose_xyzypr(500, 0, 0)
     ok, T, n = sh.iterate_pt2pt_horn((cloud, None, None), far, mprm, b200.HornParams(), d_pairs.data_ptr(), len(L))
