@@ -85,43 +85,6 @@ __device__ __forceinline__ float dist2_ref(float qx, float qy, float qz, float p
     return d;
 }
 
-template <int K>
-struct TopK
-{
-    unsigned long long v[K];  // ascending; (d2 bits << 32) | original index
-    __device__ __forceinline__ void init(unsigned long long sentinel)
-    {
-#pragma unroll
-        for (int j = 0; j < K; j++) v[j] = sentinel;
-    }
-    // K-th best so far. EXACT (k == K, the common case: the kernels are instantiated for the usual
-    // values of pairingsPerPoint / knn) is a plain register read; otherwise a select chain, which the
-    // compiler turns into a dynamically indexed (local-memory) access.
-    template <bool EXACT>
-    __device__ __forceinline__ unsigned long long worst(int k_runtime) const
-    {
-        if (EXACT) return v[K - 1];
-        unsigned long long w = v[K - 1];
-#pragma unroll
-        for (int j = 0; j < K - 1; j++)
-            if (j == k_runtime - 1) w = v[j];
-        return w;
-    }
-    // sorted insert as a chain of (min, max) exchanges; every key is offered at most once per list
-    // (the lists are rebuilt at every level), so no duplicate test is needed
-    __device__ __forceinline__ void insert(unsigned long long c)
-    {
-#pragma unroll
-        for (int j = 0; j < K; j++)
-        {
-            const bool               lt = c < v[j];
-            const unsigned long long lo = lt ? c : v[j], hi = lt ? v[j] : c;
-            v[j]                        = lo;
-            c                           = hi;
-        }
-    }
-};
-
 // 27 neighbour offsets ordered centre, 6 faces, 12 edges, 8 corners: bits [1:0]=dx+1, [3:2]=dy+1,
 // [5:4]=dz+1
 __constant__ uint8_t kNeighbourOrder[27] = {
@@ -136,66 +99,13 @@ struct SearchCounters
 };
 
 // ---- sub-warp cooperative search --------------------------------------------------------------
-// A query is processed by a GROUP of G consecutive lanes (G = 8: four queries per warp; measured
-// faster than G = 4 on the C3 workload, profiles/r01_c3_group_ab.txt). The group
-// members hold the same query; work is split so that memory requests of one query are issued by
-// different lanes in the same instruction (memory-level parallelism instead of one thread's serial
-// chain of dependent loads):
-//   1. centre voxel: one broadcast hash probe, its points scanned G at a time;
-//   2. group all-reduce of the best key -> K-th distance bound;
-//   3. the 26 neighbour voxels are dealt to the lanes (lane l takes 1+l, 1+G+l, ...): each lane
-//      prunes with the box bound, probes and scans its own voxels;
-//   4. group merge (K rounds of "pop the group minimum") -> exact K best of the level, replicated
-//      in every lane; termination test; otherwise one level up with fresh per-lane lists.
-#ifndef MP2P_GROUP
-#define MP2P_GROUP 8
-#endif
-constexpr int kGroup = MP2P_GROUP;
-
-template <int G>
-__device__ __forceinline__ unsigned long long group_max_u64(unsigned long long v, unsigned gmask)
-{
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1)
-    {
-        const unsigned long long t = __shfl_xor_sync(gmask, v, o);
-        v                          = t > v ? t : v;
-    }
-    return v;
-}
-
-template <int G>
-__device__ __forceinline__ unsigned long long group_min_u64(unsigned long long v, unsigned gmask)
-{
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1)
-    {
-        const unsigned long long t = __shfl_xor_sync(gmask, v, o);
-        v                          = t < v ? t : v;
-    }
-    return v;
-}
-
-// Merge the G per-lane ascending lists into the ascending K best of their union (replicated).
-// Keys are unique (they embed the point index) except for sentinels.
-template <int K, int G>
-__device__ __forceinline__ void group_merge(TopK<K>& lane, TopK<K>& out, unsigned gmask)
-{
-#pragma unroll
-    for (int r = 0; r < K; r++)
-    {
-        const unsigned long long head = lane.v[0];
-        const unsigned long long m    = group_min_u64<G>(head, gmask);
-        out.v[r]                      = m;
-        if (head == m)
-        {
-#pragma unroll
-            for (int j = 0; j < K - 1; j++) lane.v[j] = lane.v[j + 1];
-            lane.v[K - 1] = ~0ull;
-        }
-    }
-}
-
+// A query is processed by a GROUP of G consecutive lanes, G = 8, 16 or 32 (the smallest >= k: four,
+// two or one query per warp). The group members hold the same query and
+//   * read a voxel's points G at a time (one coalesced request per step);
+//   * keep the K best of the current level DISTRIBUTED over the group, one 64-bit key per lane,
+//     ascending by lane (lane r holds the r-th smallest): the K-th distance is one shuffle away,
+//     exact at all times, and a new candidate enters with one shuffle-up (group_insert) — no
+//     per-lane lists, no merge pass, two registers of state.
 __device__ __forceinline__ unsigned long long point_key(float qx, float qy, float qz, const float4 p)
 {
     const float d2 = dist2_ref(qx, qy, qz, p.x, p.y, p.z);
@@ -213,20 +123,29 @@ __host__ __device__ constexpr int neighbour_rank(int idx)
     return 0;
 }
 
-// Exact K-nearest (k_runtime <= K) of (qx,qy,qz) among points with d2 < radius2 (strict).
-// Called by all G lanes of a group with identical arguments; `sub` = lane index inside the group,
-// `gmask` = the group's lanes. On return res.v[0..k_runtime) ascending, identical in all lanes;
-// entries >= (radius2 bits << 32) are "not found".
-// `rl_start`: relative level to start from — the finest level whose voxels hold about 0.75 K points
-// on average (start_level(), host side), so that the centre voxel alone usually settles the K-th
+// Insert a candidate (uniform over the group) into the distributed ascending list.
+template <int G>
+__device__ __forceinline__ void group_insert(unsigned long long& mine, unsigned long long c, int sub, unsigned gmask)
+{
+    const unsigned long long up = __shfl_up_sync(gmask, mine, 1, G);  // left neighbour's key
+    // the lanes with c < mine form a suffix of the group: its first lane takes c, the others shift
+    if (c < mine) mine = (sub == 0 || !(c < up)) ? c : up;
+}
+
+// Exact k nearest neighbours (k <= G) of (qx,qy,qz) within radius2 (strict <), by (d2, index).
+// `gmask` = the group's lanes, `sub` = lane index inside the group. On return lane r of the group
+// holds the r-th best key in `mine` (ascending); keys >= (radius2 bits << 32) are "not found".
+// `rl_start`: relative level to start from — the finest level whose voxels hold about 0.75 k points
+// on average (start_level(), host side), so that the centre voxel alone usually settles the k-th
 // distance and the neighbours can be pruned; any start level is correct.
-template <int K, int G, bool EXACT>
-__device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy, float qz,
-                                           float radius2, int k_runtime, int rl_start, TopK<K>& res,
-                                           unsigned gmask, int sub, SearchCounters& sc)
+template <int G>
+__device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy, float qz, float radius2, int K,
+                                           int rl_start, unsigned long long& mine, unsigned gmask, int sub,
+                                           SearchCounters& sc)
 {
     const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
-    res.init(sentinel);
+    const int                kth_lane = (__ffs(gmask) - 1) + K - 1;  // warp lane holding the K-th best
+    mine                              = sentinel;
     if (!(radius2 > 0.f)) return;
 
     // reject queries farther than the radius from the map bbox (conservative: strictly greater)
@@ -246,24 +165,41 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
     const float q2 = g.s0_lo * g.s0_lo * 0.999999f;  // quanta^2 -> metres^2, rounded down
 
     float kth = radius2;  // upper bound of the K-th best distance found so far (all levels)
+
+    // offer `count` consecutive points, G per step (index clamped to the run: a lane past the end
+    // re-reads the last point and is masked out), then refresh the bound from the K-th key
+    auto scan_run = [&](const float4* __restrict__ run, uint32_t count)
+    {
+        const uint32_t last = count - 1;
+        for (uint32_t j0 = 0; j0 < count; j0 += G)
+        {
+            const uint32_t           j    = j0 + sub;
+            const unsigned long long c    = point_key(qx, qy, qz, __ldg(run + min(j, last)));
+            const unsigned long long kkey = __shfl_sync(gmask, mine, kth_lane);
+            const bool pass = j <= last && c < kkey && __uint_as_float((uint32_t)(c >> 32)) <= kth;
+            unsigned   pm   = __ballot_sync(gmask, pass) & gmask;
+            while (pm)  // group-uniform
+            {
+                const int src = __ffs(pm) - 1;
+                pm &= pm - 1;
+                group_insert<G>(mine, __shfl_sync(gmask, c, src), sub, gmask);
+            }
+        }
+        const unsigned long long kkey = __shfl_sync(gmask, mine, kth_lane);
+        kth                           = fminf(kth, __uint_as_float((uint32_t)(kkey >> 32)));
+    };
+
     for (int rl = rl_start; rl < g.n_levels; rl++)
     {
         const int L = g.level_first + rl;
-        TopK<K>   mine;  // this lane's candidates of this level
-        mine.init(sentinel);
+        mine        = sentinel;  // the list is rebuilt at every level: no key is ever offered twice
 
         if (L == kGridBits)
         {
             // top level: the single voxel holds every point; a query outside the grid (possible only
             // with a radius larger than its distance to the bbox) must still see all of them
-            if (sub == 0) sc.probes++, sc.cands += g.n_points;
-            for (uint32_t j = sub; j < g.n_points; j += G)
-            {
-                const unsigned long long c = point_key(qx, qy, qz, __ldg(g.pts + j));
-                if (c < mine.template worst<EXACT>(k_runtime)) mine.insert(c);
-            }
-            group_merge<K, G>(mine, res, gmask);
-            if (sub == 0) sc.levels++;
+            if (sub == 0) sc.probes++, sc.cands += g.n_points, sc.levels++;
+            scan_run(g.pts, g.n_points);
             break;
         }
 
@@ -276,11 +212,9 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
         const float gyl = fmaxf(fy - 4.f, 0.f), gyh = fmaxf(s - fy - 4.f, 0.f);
         const float gzl = fmaxf(fz - 4.f, 0.f), gzh = fmaxf(s - fz - 4.f, 0.f);
 
-        // ---- 1-3. the voxels of the 3x3x3 block, centre first then faces/edges/corners, visited by
-        // the WHOLE group in lock step: one broadcast hash probe per surviving voxel, its points
-        // scanned G at a time, then the K-th bound is refreshed for the group. (Dealing different
-        // voxels to different lanes left most lanes idle: only the few voxels that survive the box
-        // bound have any work.) After the centre, the survivors are collected once in a bit mask
+        // The voxels of the 3x3x3 block, centre first then faces/edges/corners, are visited by the
+        // whole group in lock step: one broadcast hash probe per surviving voxel, its points offered
+        // G at a time. After the centre, the survivors are collected once in a bit mask
         // (hierarchically: a slab or a row that is too far drops all its voxels at once) and only
         // those are iterated, re-checked against the bound as it tightens.
         const float ax[3] = {gxl * gxl * q2, 0.f, gxh * gxh * q2};
@@ -307,23 +241,7 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
                 if (grid_lookup(g, rl, (uint32_t)nx, (uint32_t)ny, (uint32_t)nz, start, count))
                 {
                     if (sub == 0) sc.cands += count;
-                    for (uint32_t j = start + sub; j < start + count; j += G)
-                    {
-                        const unsigned long long c = point_key(qx, qy, qz, __ldg(g.pts + j));
-                        if (__uint_as_float((uint32_t)(c >> 32)) <= kth && c < mine.template worst<EXACT>(k_runtime))
-                            mine.insert(c);
-                    }
-                    // bound for pruning what follows. A lane that holds k candidates bounds the K-th
-                    // distance of the union from above; with r = ceil(K/G), if every lane holds r
-                    // candidates the union holds >= K that are <= the largest of the lanes' r-th best.
-                    const unsigned long long w = group_min_u64<G>(mine.template worst<EXACT>(k_runtime), gmask);
-                    kth                        = fminf(kth, __uint_as_float((uint32_t)(w >> 32)));
-                    if (EXACT && K > 1)
-                    {
-                        constexpr int            r  = (K + G - 1) / G;
-                        const unsigned long long wr = group_max_u64<G>(mine.v[r - 1], gmask);
-                        kth                         = fminf(kth, __uint_as_float((uint32_t)(wr >> 32)));
-                    }
+                    scan_run(g.pts + start, count);
                 }
             }
             if (first)
@@ -349,10 +267,8 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
                 }
             }
         }
-        // ---- 4. exact K best of this level, replicated; termination test
-        group_merge<K, G>(mine, res, gmask);
-        kth = fminf(kth, __uint_as_float((uint32_t)(res.template worst<EXACT>(k_runtime) >> 32)));
-        // everything outside the 3x3x3 block is at least m quanta away
+        // `mine` now holds the exact K best of this level's block; everything outside the 3x3x3
+        // block is at least m quanta away
         const float mx = s + fminf(fx, s - fx), my = s + fminf(fy, s - fy), mz = s + fminf(fz, s - fz);
         const float m  = fmaxf(fminf(mx, fminf(my, mz)) - 4.f, 0.f);
         if (sub == 0) sc.levels++;

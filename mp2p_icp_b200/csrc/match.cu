@@ -70,10 +70,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "memory");
 }
 
-// A CTA of kQueryTile threads serves kQueryTile / kGroup queries in the group-cooperative kernels
-// (kGroup lanes per query) and kNN1Threads queries in the lane-per-query K = 1 kernel.
-constexpr uint32_t kQueriesPerBlock = kQueryTile / kGroup;
-constexpr uint32_t kNN1Threads      = 128;
+// A CTA of kQueryTile threads serves kQueryTile / G queries in the group-cooperative kernels
+// (G = 8, 16 or 32 lanes per query) and kNN1Threads queries in the lane-per-query K = 1 kernel.
+constexpr uint32_t kNN1Threads = 128;
 
 template <uint32_t NQ>
 struct QueryTile
@@ -84,7 +83,7 @@ struct QueryTile
     alignas(8) uint64_t bar;
 };
 
-// All threads of the CTA call this; afterwards tile.x/y/z hold queries [base, base+kQueriesPerBlock).
+// All threads of the CTA call this; afterwards tile.x/y/z hold queries [base, base+NQ).
 // The staging arrays are padded to a multiple of kQueryTile, so the copy size is constant.
 // Full tiles of 16-byte aligned arrays come in by TMA; the ragged last tile (or a caller's
 // unaligned device arrays, used in place without a staging copy) by plain predicated loads.
@@ -213,7 +212,7 @@ struct Pt2PtArgs
 };
 
 // ------------------------------------------------------------------------------------------
-template <int KT, bool EXACT>
+template <int G>
 __global__ void __launch_bounds__(kQueryTile)
     k_match_pt2pt(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
                   const float* __restrict__ lz, const uint32_t* __restrict__ perm,
@@ -222,13 +221,14 @@ __global__ void __launch_bounds__(kQueryTile)
                   unsigned long long* __restrict__ cand, uint32_t* __restrict__ bbox_words,
                   unsigned long long* __restrict__ stats)
 {
-    __shared__ QueryTile<kQueriesPerBlock> tile;
-    __shared__ BBoxAcc   bacc;
-    const size_t         base = (size_t)blockIdx.x * kQueriesPerBlock;
+    constexpr uint32_t NQ = kQueryTile / G;  // queries per CTA
+    __shared__ QueryTile<NQ> tile;
+    __shared__ BBoxAcc       bacc;
+    const size_t             base = (size_t)blockIdx.x * NQ;
     bbox_init(bacc);
     load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
-    const int      sub   = threadIdx.x % kGroup, ql = threadIdx.x / kGroup;
-    const unsigned gmask = ((1u << kGroup) - 1u) << ((threadIdx.x & 31) / kGroup * kGroup);
+    const int      sub   = threadIdx.x % G, ql = threadIdx.x / G;
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << ((threadIdx.x & 31) / G * G);
     const uint32_t qpos  = (uint32_t)base + ql;  // position in the array walked (sorted if perm)
     const bool     valid = qpos < a.n_local;
     const uint32_t i     = (perm && valid) ? __ldg(perm + qpos) : qpos;  // the caller's index of this query
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(kQueryTile)
     float gx = 0, gy = 0, gz = 0;
     if (valid) compose_point_f(a.pose, tile.x[ql], tile.y[ql], tile.z[ql], gx, gy, gz);
     bbox_accumulate(bacc, gx, gy, gz, valid && sub == 0, bbox_words);
-    if (valid)
+    if (valid)  // whole groups take the branch together
     {
         const int K = (int)a.K;
         // …DistanceThreshold.cpp:230,256-257 (float, unfused)
@@ -245,34 +245,23 @@ __global__ void __launch_bounds__(kQueryTile)
         const float thr2   = __fadd_rn(a.maxDistSq, __fmul_rn(a.angSq, normSq));
         const unsigned long long sentinel = (unsigned long long)__float_as_uint(thr2) << 32;
 
-        TopK<KT>       top;
-        SearchCounters sc;
-        if (!a.allowLocal && bit_set(lbits, i))
-            top.init(sentinel);  // :218-220 skip, already paired
-        else
-            knn_search<KT, kGroup, EXACT>(g, gx, gy, gz, thr2, K, a.rl_start, top, gmask, sub, sc);
+        unsigned long long mine = sentinel;  // lane `sub` ends up with the sub-th best key
+        SearchCounters     sc;
+        if (a.allowLocal || !bit_set(lbits, i))  // :218-220 skip, already paired
+            knn_search<G>(g, gx, gy, gz, thr2, K, a.rl_start, mine, gmask, sub, sc);
 
-        uint32_t n_valid = 0;
-        if (sub == 0)
+        // lane r < K writes rank r; unused ranks are marked with an impossible map index (all ones)
+        const unsigned long long c = (sub < K && mine < sentinel) ? mine : ~0ull;
+        if (sub < K)
         {
-#pragma unroll
-            for (int k = 0; k < KT; k++)
+            cand[(size_t)co * K + sub] = c;
+            if (c != ~0ull && !a.allowGlobal)
             {
-                if (k < K)
-                {
-                    // unused ranks are marked with an impossible map index (all ones)
-                    const unsigned long long c = top.v[k] < sentinel ? top.v[k] : ~0ull;
-                    n_valid += (c != ~0ull);
-                    cand[(size_t)co * K + k] = c;
-                    if (c != ~0ull && !a.allowGlobal)
-                    {
-                        const uint32_t gi = (uint32_t)c;
-                        if (!bit_set(gbits, gi)) atomicMin(claim + gi, a.tag | (unsigned long long)(i * (uint32_t)K + k));
-                    }
-                }
+                const uint32_t gi = (uint32_t)c;
+                if (!bit_set(gbits, gi)) atomicMin(claim + gi, a.tag | (unsigned long long)(i * (uint32_t)K + sub));
             }
         }
-        flush_search_stats(sc, n_valid, stats);
+        flush_search_stats(sc, c != ~0ull ? 1u : 0u, stats);
     }
 }
 
@@ -860,34 +849,32 @@ __global__ void __launch_bounds__(kScanThreads)
 // ------------------------------------------------------------------------------------------
 // raw k-NN (already transformed queries) — nn_* parity tests
 // ------------------------------------------------------------------------------------------
-template <int KT, bool EXACT>
+template <int G>
 __global__ void __launch_bounds__(256)
     k_knn(GridView g, const float* __restrict__ qx, const float* __restrict__ qy,
           const float* __restrict__ qz, uint32_t nq, uint32_t K, float radius2, int rl_start,
           uint32_t* __restrict__ out_idx, float* __restrict__ out_d2, int32_t* __restrict__ out_found)
 {
-    const int      sub   = threadIdx.x % kGroup;
-    const unsigned gmask = ((1u << kGroup) - 1u) << ((threadIdx.x & 31) / kGroup * kGroup);
-    const uint32_t i     = (blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
+    const int      sub   = threadIdx.x % G;
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << ((threadIdx.x & 31) / G * G);
+    const uint32_t i     = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     if (i >= nq) return;  // whole groups leave together
-    TopK<KT>       top;
-    SearchCounters sc;
-    knn_search<KT, kGroup, EXACT>(g, qx[i], qy[i], qz[i], radius2, (int)K, rl_start, top, gmask, sub, sc);
-    if (sub != 0) return;
+    unsigned long long mine;
+    SearchCounters     sc;
+    knn_search<G>(g, qx[i], qy[i], qz[i], radius2, (int)K, rl_start, mine, gmask, sub, sc);
     const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
-    int                      cnt      = 0;
-#pragma unroll
-    for (int k = 0; k < KT; k++)
-        if (k < (int)K)
-        {
-            const bool f                 = top.v[k] < sentinel;
-            out_idx[(size_t)i * K + k]   = f ? (uint32_t)top.v[k] : 0u;
-            out_d2[(size_t)i * K + k]    = f ? __uint_as_float((uint32_t)(top.v[k] >> 32))
-                                             : cuda::std::numeric_limits<float>::infinity();
-            cnt += f;
-        }
-    out_found[i] = cnt;
+    const bool               f        = sub < (int)K && mine < sentinel;
+    if (sub < (int)K)
+    {
+        out_idx[(size_t)i * K + sub] = f ? (uint32_t)mine : 0u;
+        out_d2[(size_t)i * K + sub]  = f ? __uint_as_float((uint32_t)(mine >> 32)) : cuda::std::numeric_limits<float>::infinity();
+    }
+    const unsigned found = __ballot_sync(gmask, f) & gmask;
+    if (sub == 0) out_found[i] = __popc(found);
 }
+
+// lanes per query of the group-cooperative kernels: the smallest supported group that holds k keys
+int group_size(uint32_t K) { return K <= 8 ? 8 : (K <= 16 ? 16 : 32); }
 
 int pick_kt(uint32_t K)
 {
@@ -898,32 +885,13 @@ int pick_kt(uint32_t K)
     return 32;
 }
 
-// The search kernels are instantiated EXACTLY for the usual k (1..10, 12, 16, 20, 24, 32): the K-th
-// best is then a fixed register. Any other k <= 32 runs on the next capacity with a runtime k.
-#define MP2P_DISPATCH_K(K, CALL)      \
-    switch (K)                        \
-    {                                 \
-        case 1: CALL(1, true); break; \
-        case 2: CALL(2, true); break; \
-        case 3: CALL(3, true); break; \
-        case 4: CALL(4, true); break; \
-        case 5: CALL(5, true); break; \
-        case 6: CALL(6, true); break; \
-        case 7: CALL(7, true); break; \
-        case 8: CALL(8, true); break; \
-        case 9: CALL(9, true); break; \
-        case 10: CALL(10, true); break; \
-        case 12: CALL(12, true); break; \
-        case 16: CALL(16, true); break; \
-        case 20: CALL(20, true); break; \
-        case 24: CALL(24, true); break; \
-        case 32: CALL(32, true); break; \
-        default:                      \
-            if (K <= 16)              \
-                CALL(16, false);      \
-            else                      \
-                CALL(32, false);      \
-            break;                    \
+// group-cooperative kernels are instantiated for G = 8, 16, 32 lanes per query (group_size(k))
+#define MP2P_DISPATCH_G(K, CALL)  \
+    switch (group_size(K))        \
+    {                             \
+        case 8: CALL(8); break;   \
+        case 16: CALL(16); break; \
+        default: CALL(32); break; \
     }
 
 // finest table whose voxels hold at least ~0.75 k points on average (k = 1: the finest table)
@@ -1113,7 +1081,6 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     a.tma_ok = ctx->cur_tma_ok;
     a.rl_start = start_level(map->view, K);
 
-    const uint32_t blocks = (uint32_t)((n_local + kQueriesPerBlock - 1) / kQueriesPerBlock);
     const float *  dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;  // caller order (records)
     const float *  dqx = ctx->cur_qx, *dqy = ctx->cur_qy, *dqz = ctx->cur_qz;  // what the search walks
     auto*          claim = map->d_claim.as<unsigned long long>();
@@ -1122,8 +1089,8 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     MP2P_TRY(prepare_stats(ctx, &stats));
     float4* cand_xyz = nullptr;
     prof_begin(ctx, 0);
-#define LAUNCH_MATCH(KT, EX) \
-    k_match_pt2pt<KT, EX><<<blocks, kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, sv.bbox, stats)
+#define LAUNCH_MATCH(G) \
+    k_match_pt2pt<G><<<(uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile), kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, sv.bbox, stats)
     if (K == 1)
     {
         MP2P_TRY(ctx->d_candxyz.ensure(n_slots * sizeof(float4)));
@@ -1133,7 +1100,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     }
     else
     {
-        MP2P_DISPATCH_K(K, LAUNCH_MATCH)
+        MP2P_DISPATCH_G(K, LAUNCH_MATCH)
     }
 #undef LAUNCH_MATCH
     prof_end(ctx, 0);
@@ -1236,7 +1203,6 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     MP2P_TRY(stage_local(ctx, lx, ly, lz, n_local, local_on_device));
     const uint32_t* d_lbits;
     MP2P_TRY(upload_bits(ctx, ctx->d_lbits, lbits, n_local, &d_lbits));
-    const uint32_t blocks = (uint32_t)((n_local + kQueriesPerBlock - 1) / kQueriesPerBlock);
     Pt2PtArgs a{};
     for (int k = 0; k < 12; k++) a.pose.m[k] = pose[k];
     a.maxDistSq = (float)(prm->threshold * prm->threshold);
@@ -1251,8 +1217,8 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     unsigned long long* stats = nullptr;
     MP2P_TRY(prepare_stats(ctx, &stats));
     prof_begin(ctx, 0);
-#define LAUNCH_MATCH(KT, EX) \
-    k_match_pt2pt<KT, EX><<<blocks, kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, d_record, d_bbox6, stats)
+#define LAUNCH_MATCH(G) \
+    k_match_pt2pt<G><<<(uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile), kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, d_record, d_bbox6, stats)
     if (K == 1)
     {
         MP2P_TRY(ctx->d_candxyz.ensure(n_local * sizeof(float4)));
@@ -1262,7 +1228,7 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     }
     else
     {
-        MP2P_DISPATCH_K(K, LAUNCH_MATCH)
+        MP2P_DISPATCH_G(K, LAUNCH_MATCH)
     }
 #undef LAUNCH_MATCH
     prof_end(ctx, 0);
@@ -1384,7 +1350,6 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     a.tma_ok     = ctx->cur_tma_ok;
     const float gate_eps = (float)(prm->distanceThreshold + prm->bounding_box_intersection_check_epsilon);
 
-    const uint32_t blocks = (uint32_t)((n_local + kQueriesPerBlock - 1) / kQueriesPerBlock);
     const float *  dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;  // caller order (records)
     const float *  dqx = ctx->cur_qx, *dqy = ctx->cur_qy, *dqz = ctx->cur_qz;  // what the search walks
     auto*          plc = ctx->d_plcand.as<PlaneCandidate>();
@@ -1398,12 +1363,12 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     sa.allowLocal = a.allowLocal, sa.allowGlobal = 1, sa.tag = 0, sa.tma_ok = a.tma_ok;
     sa.cand_sorted = 1;  // the plane fit walks the same order
     prof_begin(ctx, 0);
-#define LAUNCH_SEARCH(KT, EX) \
-    k_match_pt2pt<KT, EX><<<blocks, kQueryTile, 0, st>>>(map->view, sa, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, cand, sv.bbox, stats)
+#define LAUNCH_SEARCH(G) \
+    k_match_pt2pt<G><<<(uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile), kQueryTile, 0, st>>>(map->view, sa, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, cand, sv.bbox, stats)
 #define LAUNCH_FIT(KT) \
     k_plane_fit<KT><<<(uint32_t)((n_local + 127) / 128), 128, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, cand, plc, okf)
     sa.rl_start = start_level(map->view, prm->knn);
-    MP2P_DISPATCH_K(prm->knn, LAUNCH_SEARCH)
+    MP2P_DISPATCH_G(prm->knn, LAUNCH_SEARCH)
     switch (pick_kt(prm->knn))
     {
         case 1:
@@ -1414,8 +1379,6 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     }
 #undef LAUNCH_SEARCH
 #undef LAUNCH_FIT
-#define LAUNCH_PL(KT)
-#undef LAUNCH_PL
     prof_end(ctx, 0);
     count_launch(ctx, 2);
 
@@ -1462,14 +1425,13 @@ int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const
     }
     else
     {
-        const uint32_t blocks = (uint32_t)((nq * kGroup + 255) / 256);
         const float *  dqx = ctx->cur_lx, *dqy = ctx->cur_ly, *dqz = ctx->cur_lz;
         auto *oi = ctx->d_knn_idx.as<uint32_t>();
         auto *od = ctx->d_knn_d2.as<float>();
         auto *of = ctx->d_knn_found.as<int32_t>();
         const int rl0 = start_level(map->view, K);
-#define LAUNCH_KNN(KT, EX) k_knn<KT, EX><<<blocks, 256, 0, st>>>(map->view, dqx, dqy, dqz, (uint32_t)nq, K, radius2, rl0, oi, od, of)
-        MP2P_DISPATCH_K(K, LAUNCH_KNN)
+#define LAUNCH_KNN(G) k_knn<G><<<(uint32_t)((nq * G + 255) / 256), 256, 0, st>>>(map->view, dqx, dqy, dqz, (uint32_t)nq, K, radius2, rl0, oi, od, of)
+        MP2P_DISPATCH_G(K, LAUNCH_KNN)
 #undef LAUNCH_KNN
         count_launch(ctx);
     }
