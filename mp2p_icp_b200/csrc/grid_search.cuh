@@ -123,38 +123,36 @@ __host__ __device__ constexpr int neighbour_rank(int idx)
     return 0;
 }
 
-// Insert a candidate (uniform over the group) into the distributed ascending list.
-template <int G>
-__device__ __forceinline__ void group_insert(unsigned long long& mine, unsigned long long c, int sub, unsigned gmask)
-{
-    const unsigned long long up = __shfl_up_sync(gmask, mine, 1, G);  // left neighbour's key
-    // the lanes with c < mine form a suffix of the group: its first lane takes c, the others shift
-    if (c < mine) mine = (sub == 0 || !(c < up)) ? c : up;
-}
-
 // Exact k nearest neighbours (k <= G) of (qx,qy,qz) within radius2 (strict <), by (d2, index).
-// `gmask` = the group's lanes, `sub` = lane index inside the group. On return lane r of the group
-// holds the r-th best key in `mine` (ascending); keys >= (radius2 bits << 32) are "not found".
+// MUST be called by all 32 lanes of the warp, converged (`enabled` = false for lanes without a
+// query): the groups of a warp run ONE control flow — every loop below is warp-uniform and the
+// bodies are predicated per group — so the 32/G queries of a warp share every instruction issue
+// and their memory requests go out together. (Letting each group run its own loops serialises the
+// groups: measured 0.9k warp-instructions per QUERY, profiles/r01_c3_search_*.txt.)
+// `sub` = lane index inside the group. On return lane r of the group holds the r-th best key in
+// `mine` (ascending); keys >= (radius2 bits << 32) are "not found".
 // `rl_start`: relative level to start from — the finest level whose voxels hold about 0.75 k points
 // on average (start_level(), host side), so that the centre voxel alone usually settles the k-th
 // distance and the neighbours can be pruned; any start level is correct.
 template <int G>
-__device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy, float qz, float radius2, int K,
-                                           int rl_start, unsigned long long& mine, unsigned gmask, int sub,
+__device__ __forceinline__ void knn_search(const GridView& g, bool enabled, float qx, float qy, float qz,
+                                           float radius2, int K, int rl_start, unsigned long long& mine, int sub,
                                            SearchCounters& sc)
 {
+    constexpr unsigned       FULL     = 0xffffffffu;
+    const int                lane     = threadIdx.x & 31;
+    const unsigned           gmask    = (G == 32 ? FULL : ((1u << (G & 31)) - 1u)) << (lane - sub);
+    const int                kth_lane = (lane - sub) + K - 1;  // warp lane holding the K-th best
     const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
-    const int                kth_lane = (__ffs(gmask) - 1) + K - 1;  // warp lane holding the K-th best
     mine                              = sentinel;
-    if (!(radius2 > 0.f)) return;
-
-    // reject queries farther than the radius from the map bbox (conservative: strictly greater)
+    bool live = enabled && radius2 > 0.f;  // group-uniform
+    if (live)
     {
+        // reject queries farther than the radius from the map bbox (conservative: strictly greater)
         const float ex = fmaxf(fmaxf(g.bbmin[0] - qx, qx - g.bbmax[0]), 0.f);
         const float ey = fmaxf(fmaxf(g.bbmin[1] - qy, qy - g.bbmax[1]), 0.f);
         const float ez = fmaxf(fmaxf(g.bbmin[2] - qz, qz - g.bbmax[2]), 0.f);
-        const float e2 = ex * ex + ey * ey + ez * ez;
-        if (e2 * 0.999999f > radius2) return;
+        if ((ex * ex + ey * ey + ez * ez) * 0.999999f > radius2) live = false;
     }
 
     const float lim = 4194304.f;  // 2^22
@@ -166,40 +164,49 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
 
     float kth = radius2;  // upper bound of the K-th best distance found so far (all levels)
 
-    // offer `count` consecutive points, G per step (index clamped to the run: a lane past the end
-    // re-reads the last point and is masked out), then refresh the bound from the K-th key
+    // Offer the group's run of `count` consecutive points (count = 0: nothing for this group), G per
+    // step; all groups of the warp step together. The K best stay distributed over the group, one
+    // key per lane, ascending: the K-th key is one shuffle away, a passing candidate enters with one
+    // shuffle-up — the lanes with cc < mine form a suffix of the group, its first lane takes cc, the
+    // others take their left neighbour's key.
     auto scan_run = [&](const float4* __restrict__ run, uint32_t count)
     {
-        const uint32_t last = count - 1;
-        for (uint32_t j0 = 0; j0 < count; j0 += G)
+        const uint32_t steps = __reduce_max_sync(FULL, count);
+        for (uint32_t j0 = 0; j0 < steps; j0 += G)
         {
-            const uint32_t           j    = j0 + sub;
-            const unsigned long long c    = point_key(qx, qy, qz, __ldg(run + min(j, last)));
-            const unsigned long long kkey = __shfl_sync(gmask, mine, kth_lane);
-            const bool pass = j <= last && c < kkey && __uint_as_float((uint32_t)(c >> 32)) <= kth;
-            unsigned   pm   = __ballot_sync(gmask, pass) & gmask;
-            while (pm)  // group-uniform
+            const uint32_t     j  = j0 + sub;
+            const bool         in = j < count;
+            unsigned long long c  = ~0ull;
+            if (in) c = point_key(qx, qy, qz, __ldg(run + j));
+            const unsigned long long kkey = __shfl_sync(FULL, mine, kth_lane);
+            const bool pass = in && c < kkey && __uint_as_float((uint32_t)(c >> 32)) <= kth;
+            unsigned   pm   = __ballot_sync(FULL, pass) & gmask;
+            while (__any_sync(FULL, pm != 0))
             {
-                const int src = __ffs(pm) - 1;
+                const bool ins = pm != 0;
+                const int  src = ins ? __ffs(pm) - 1 : lane;
                 pm &= pm - 1;
-                group_insert<G>(mine, __shfl_sync(gmask, c, src), sub, gmask);
+                const unsigned long long cc = __shfl_sync(FULL, c, src);
+                const unsigned long long up = __shfl_up_sync(FULL, mine, 1, G);  // left neighbour's key
+                if (ins && cc < mine) mine = (sub == 0 || !(cc < up)) ? cc : up;
             }
         }
-        const unsigned long long kkey = __shfl_sync(gmask, mine, kth_lane);
-        kth                           = fminf(kth, __uint_as_float((uint32_t)(kkey >> 32)));
+        const unsigned long long kkey = __shfl_sync(FULL, mine, kth_lane);
+        if (count) kth = fminf(kth, __uint_as_float((uint32_t)(kkey >> 32)));
     };
 
     for (int rl = rl_start; rl < g.n_levels; rl++)
     {
+        if (!__any_sync(FULL, live)) break;
         const int L = g.level_first + rl;
-        mine        = sentinel;  // the list is rebuilt at every level: no key is ever offered twice
+        if (live) mine = sentinel;  // the list is rebuilt at every level: no key is ever offered twice
 
         if (L == kGridBits)
         {
             // top level: the single voxel holds every point; a query outside the grid (possible only
             // with a radius larger than its distance to the bbox) must still see all of them
-            if (sub == 0) sc.probes++, sc.cands += g.n_points, sc.levels++;
-            scan_run(g.pts, g.n_points);
+            if (live && sub == 0) sc.probes++, sc.cands += g.n_points, sc.levels++;
+            scan_run(g.pts, live ? g.n_points : 0u);
             break;
         }
 
@@ -212,19 +219,20 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
         const float gyl = fmaxf(fy - 4.f, 0.f), gyh = fmaxf(s - fy - 4.f, 0.f);
         const float gzl = fmaxf(fz - 4.f, 0.f), gzh = fmaxf(s - fz - 4.f, 0.f);
 
-        // The voxels of the 3x3x3 block, centre first then faces/edges/corners, are visited by the
-        // whole group in lock step: one broadcast hash probe per surviving voxel, its points offered
-        // G at a time. After the centre, the survivors are collected once in a bit mask
-        // (hierarchically: a slab or a row that is too far drops all its voxels at once) and only
-        // those are iterated, re-checked against the bound as it tightens.
+        // The voxels of the 3x3x3 block, centre first then faces/edges/corners: per round every live
+        // group takes its next surviving voxel (one broadcast hash probe, points offered G at a
+        // time). After the centre, a group collects its survivors once in a bit mask
+        // (hierarchically: a slab or a row that is too far drops all its voxels at once); they are
+        // re-checked against the bound as it tightens.
         const float ax[3] = {gxl * gxl * q2, 0.f, gxh * gxh * q2};
         const float ay[3] = {gyl * gyl * q2, 0.f, gyh * gyh * q2};
         const float az[3] = {gzl * gzl * q2, 0.f, gzh * gzh * q2};
-        uint32_t    todo  = 1u;  // bit i <-> kNeighbourOrder[i]; start with the centre
-        bool        first = true;
-        while (todo)
+        uint32_t    todo  = live ? 1u : 0u;  // bit i <-> kNeighbourOrder[i]; start with the centre
+        bool        first = live;
+        while (__any_sync(FULL, todo != 0))
         {
-            const int nb = __ffs(todo) - 1;
+            const bool act = todo != 0;
+            const int  nb  = act ? __ffs(todo) - 1 : 0;
             todo &= todo - 1;
             const uint32_t code = kNeighbourOrder[nb];
             const int      dx = (int)(code & 3u) - 1, dy = (int)((code >> 2) & 3u) - 1,
@@ -232,18 +240,16 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
             const float lb = (dx < 0 ? ax[0] : (dx > 0 ? ax[2] : 0.f)) + (dy < 0 ? ay[0] : (dy > 0 ? ay[2] : 0.f)) +
                              (dz < 0 ? az[0] : (dz > 0 ? az[2] : 0.f));
             const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
-            uint32_t  start, count;
+            uint32_t  start = 0, count = 0;
             // strict `>`: an equal-distance lower index must still be seen
-            if (!(lb > kth) && (unsigned)nx <= (unsigned)cmax && (unsigned)ny <= (unsigned)cmax &&
+            if (act && !(lb > kth) && (unsigned)nx <= (unsigned)cmax && (unsigned)ny <= (unsigned)cmax &&
                 (unsigned)nz <= (unsigned)cmax)
             {
                 if (sub == 0) sc.probes++;
-                if (grid_lookup(g, rl, (uint32_t)nx, (uint32_t)ny, (uint32_t)nz, start, count))
-                {
-                    if (sub == 0) sc.cands += count;
-                    scan_run(g.pts + start, count);
-                }
+                if (!grid_lookup(g, rl, (uint32_t)nx, (uint32_t)ny, (uint32_t)nz, start, count)) count = 0;
+                if (sub == 0) sc.cands += count;
             }
+            scan_run(g.pts + start, count);
             if (first)
             {
                 first = false;
@@ -271,8 +277,11 @@ __device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy
         // block is at least m quanta away
         const float mx = s + fminf(fx, s - fx), my = s + fminf(fy, s - fy), mz = s + fminf(fz, s - fz);
         const float m  = fmaxf(fminf(mx, fminf(my, mz)) - 4.f, 0.f);
-        if (sub == 0) sc.levels++;
-        if (kth <= m * m * q2) break;
+        if (live)
+        {
+            if (sub == 0) sc.levels++;
+            if (kth <= m * m * q2) live = false;
+        }
     }
 }
 

@@ -228,7 +228,6 @@ __global__ void __launch_bounds__(kQueryTile)
     bbox_init(bacc);
     load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
     const int      sub   = threadIdx.x % G, ql = threadIdx.x / G;
-    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << ((threadIdx.x & 31) / G * G);
     const uint32_t qpos  = (uint32_t)base + ql;  // position in the array walked (sorted if perm)
     const bool     valid = qpos < a.n_local;
     const uint32_t i     = (perm && valid) ? __ldg(perm + qpos) : qpos;  // the caller's index of this query
@@ -237,19 +236,19 @@ __global__ void __launch_bounds__(kQueryTile)
     float gx = 0, gy = 0, gz = 0;
     if (valid) compose_point_f(a.pose, tile.x[ql], tile.y[ql], tile.z[ql], gx, gy, gz);
     bbox_accumulate(bacc, gx, gy, gz, valid && sub == 0, bbox_words);
-    if (valid)  // whole groups take the branch together
+    const int K = (int)a.K;
+    // …DistanceThreshold.cpp:230,256-257 (float, unfused)
+    const float normSq = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+    const float thr2   = __fadd_rn(a.maxDistSq, __fmul_rn(a.angSq, normSq));
+    const unsigned long long sentinel = (unsigned long long)__float_as_uint(thr2) << 32;
+
+    unsigned long long mine;  // lane `sub` ends up with the sub-th best key
+    SearchCounters     sc;
+    // all lanes take part (warp-uniform search); lanes past the end and already paired locals
+    // (:218-220) are disabled
+    knn_search<G>(g, valid && (a.allowLocal || !bit_set(lbits, i)), gx, gy, gz, thr2, K, a.rl_start, mine, sub, sc);
+    if (valid)
     {
-        const int K = (int)a.K;
-        // …DistanceThreshold.cpp:230,256-257 (float, unfused)
-        const float normSq = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
-        const float thr2   = __fadd_rn(a.maxDistSq, __fmul_rn(a.angSq, normSq));
-        const unsigned long long sentinel = (unsigned long long)__float_as_uint(thr2) << 32;
-
-        unsigned long long mine = sentinel;  // lane `sub` ends up with the sub-th best key
-        SearchCounters     sc;
-        if (a.allowLocal || !bit_set(lbits, i))  // :218-220 skip, already paired
-            knn_search<G>(g, gx, gy, gz, thr2, K, a.rl_start, mine, gmask, sub, sc);
-
         // lane r < K writes rank r; unused ranks are marked with an impossible map index (all ones)
         const unsigned long long c = (sub < K && mine < sentinel) ? mine : ~0ull;
         if (sub < K)
@@ -745,12 +744,18 @@ struct Pt2PlArgs
     int      tma_ok;
 };
 
-// Plane fit of the pt2pl matcher, one THREAD per query (the k-NN search ran before, in the
-// group-cooperative k_match_pt2pt<K> used as a pure radius-bounded k-NN): reads the K neighbour
-// keys of the query (ascending (d2, index)), gathers the points, estimate_points_eigen + planarity
-// + distance tests (plane_fit.cuh). Full-lane utilisation for the fp64 Jacobi.
+// Plane fit of the pt2pl matcher, one THREAD per query that has enough neighbours (the k-NN search
+// ran before, in the group-cooperative k_match_pt2pt<G> used as a pure radius-bounded k-NN). A CTA
+// owns kFitQueries consecutive queries: it first lists the ones whose k-NN holds at least
+// max(3, minimumPlanePoints) points (one 8-byte read each: valid ranks come first), then the
+// threads work through that dense list — the fp64 Jacobi runs on full warps instead of on the
+// ~half of the lanes whose query qualifies. Per listed query: gather the K neighbour points
+// (ascending (d2, index)), estimate_points_eigen + planarity + distance tests (plane_fit.cuh).
+constexpr int kFitThreads = 128;
+constexpr int kFitQueries = 4 * kFitThreads;
+
 template <int KT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kFitThreads)
     k_plane_fit(GridView g, Pt2PlArgs a, const float* __restrict__ qx, const float* __restrict__ qy,
                 const float* __restrict__ qz, const uint32_t* __restrict__ perm,
                 const unsigned long long* __restrict__ cand, PlaneCandidate* __restrict__ plc,
@@ -758,23 +763,45 @@ __global__ void __launch_bounds__(128)
 {
     // walks the same (possibly Morton-sorted) query array as the search did: neighbouring threads
     // gather overlapping neighbour sets; results go to the caller's index i
-    const uint32_t qpos = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qpos >= a.n_local) return;
-    const uint32_t i = perm ? __ldg(perm + qpos) : qpos;
-    const int K   = (int)a.K;
-    int       cnt = 0;
-    uint32_t  idx[KT];
+    __shared__ uint32_t s_list[kFitQueries];
+    __shared__ uint32_t s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int      K    = (int)a.K;
+    const int      need = max(3, (int)a.minPts);
+    const uint32_t q0   = blockIdx.x * kFitQueries;
 #pragma unroll
-    for (int k = 0; k < KT; k++)
-        if (k < K)
-        {
-            const unsigned long long c = cand[(size_t)qpos * K + k];
-            idx[k]                     = (uint32_t)c;
-            cnt += ((uint32_t)c != 0xFFFFFFFFu);  // valid ranks come first
-        }
-    uint8_t ok = 0;
-    if (cnt >= 3 && cnt >= (int)a.minPts)
+    for (int r = 0; r < kFitQueries / kFitThreads; r++)
     {
+        const uint32_t qpos = q0 + r * kFitThreads + threadIdx.x;
+        bool           act  = false;
+        if (qpos < a.n_local)
+        {
+            act = need <= K && (uint32_t)cand[(size_t)qpos * K + need - 1] != 0xFFFFFFFFu;
+            if (!act) ok_flags[perm ? __ldg(perm + qpos) : qpos] = 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        uint32_t       base = 0;
+        if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(&s_n, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (act) s_list[base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = qpos;
+    }
+    __syncthreads();
+    const uint32_t n_act = s_n;
+    for (uint32_t t = threadIdx.x; t < n_act; t += kFitThreads)
+    {
+        const uint32_t qpos = s_list[t];
+        const uint32_t i    = perm ? __ldg(perm + qpos) : qpos;
+        int            cnt  = 0;
+        uint32_t       idx[KT];
+#pragma unroll
+        for (int k = 0; k < KT; k++)
+            if (k < K)
+            {
+                const unsigned long long c = cand[(size_t)qpos * K + k];
+                idx[k]                     = (uint32_t)c;
+                cnt += ((uint32_t)c != 0xFFFFFFFFu);  // valid ranks come first
+            }
         float px[KT], py[KT], pz[KT];
 #pragma unroll
         for (int k = 0; k < KT; k++)
@@ -786,13 +813,14 @@ __global__ void __launch_bounds__(128)
         float gx, gy, gz;
         compose_point_f(a.pose, qx[qpos], qy[qpos], qz[qpos], gx, gy, gz);
         PlaneCandidate pc;
+        uint8_t        ok = 0;
         if (fit_plane<KT>(px, py, pz, cnt, gx, gy, gz, a.planeEigenThreshold, a.distThr, pc))
         {
             plc[i] = pc;
             ok     = 1;
         }
+        ok_flags[i] = ok;
     }
-    ok_flags[i] = ok;
 }
 
 __global__ void __launch_bounds__(kScanThreads)
@@ -858,10 +886,11 @@ __global__ void __launch_bounds__(256)
     const int      sub   = threadIdx.x % G;
     const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << ((threadIdx.x & 31) / G * G);
     const uint32_t i     = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-    if (i >= nq) return;  // whole groups leave together
+    const bool     have  = i < nq;
     unsigned long long mine;
     SearchCounters     sc;
-    knn_search<G>(g, qx[i], qy[i], qz[i], radius2, (int)K, rl_start, mine, gmask, sub, sc);
+    knn_search<G>(g, have, have ? qx[i] : 0.f, have ? qy[i] : 0.f, have ? qz[i] : 0.f, radius2, (int)K, rl_start, mine, sub, sc);
+    if (!have) return;  // whole groups leave together
     const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
     const bool               f        = sub < (int)K && mine < sentinel;
     if (sub < (int)K)
@@ -1366,7 +1395,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
 #define LAUNCH_SEARCH(G) \
     k_match_pt2pt<G><<<(uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile), kQueryTile, 0, st>>>(map->view, sa, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, cand, sv.bbox, stats)
 #define LAUNCH_FIT(KT) \
-    k_plane_fit<KT><<<(uint32_t)((n_local + 127) / 128), 128, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, cand, plc, okf)
+    k_plane_fit<KT><<<(uint32_t)((n_local + kFitQueries - 1) / kFitQueries), kFitThreads, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, cand, plc, okf)
     sa.rl_start = start_level(map->view, prm->knn);
     MP2P_DISPATCH_G(prm->knn, LAUNCH_SEARCH)
     switch (pick_kt(prm->knn))
