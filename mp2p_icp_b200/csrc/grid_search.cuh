@@ -172,23 +172,37 @@ __device__ __forceinline__ void knn_search(const GridView& g, bool enabled, floa
     auto scan_run = [&](const float4* __restrict__ run, uint32_t count)
     {
         const uint32_t steps = __reduce_max_sync(FULL, count);
-        for (uint32_t j0 = 0; j0 < steps; j0 += G)
+        constexpr int  kAhead = 4;  // steps whose loads are issued together: a long run (a coarse
+                                    // voxel of a query that had to climb) is latency-bound otherwise
+        for (uint32_t j0 = 0; j0 < steps; j0 += kAhead * G)
         {
-            const uint32_t     j  = j0 + sub;
-            const bool         in = j < count;
-            unsigned long long c  = ~0ull;
-            if (in) c = point_key(qx, qy, qz, __ldg(run + j));
-            const unsigned long long kkey = __shfl_sync(FULL, mine, kth_lane);
-            const bool pass = in && c < kkey && __uint_as_float((uint32_t)(c >> 32)) <= kth;
-            unsigned   pm   = __ballot_sync(FULL, pass) & gmask;
-            while (__any_sync(FULL, pm != 0))
+            float4 p[kAhead];
+#pragma unroll
+            for (int u = 0; u < kAhead; u++)
             {
-                const bool ins = pm != 0;
-                const int  src = ins ? __ffs(pm) - 1 : lane;
-                pm &= pm - 1;
-                const unsigned long long cc = __shfl_sync(FULL, c, src);
-                const unsigned long long up = __shfl_up_sync(FULL, mine, 1, G);  // left neighbour's key
-                if (ins && cc < mine) mine = (sub == 0 || !(cc < up)) ? cc : up;
+                const uint32_t j = j0 + u * G + sub;
+                p[u]             = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < count) p[u] = __ldg(run + j);
+            }
+#pragma unroll
+            for (int u = 0; u < kAhead; u++)
+            {
+                if (j0 + u * G >= steps) break;  // warp-uniform
+                const uint32_t           j    = j0 + u * G + sub;
+                const bool               in   = j < count;
+                const unsigned long long c    = in ? point_key(qx, qy, qz, p[u]) : ~0ull;
+                const unsigned long long kkey = __shfl_sync(FULL, mine, kth_lane);
+                const bool pass = in && c < kkey && __uint_as_float((uint32_t)(c >> 32)) <= kth;
+                unsigned   pm   = __ballot_sync(FULL, pass) & gmask;
+                while (__any_sync(FULL, pm != 0))
+                {
+                    const bool ins = pm != 0;
+                    const int  src = ins ? __ffs(pm) - 1 : lane;
+                    pm &= pm - 1;
+                    const unsigned long long cc = __shfl_sync(FULL, c, src);
+                    const unsigned long long up = __shfl_up_sync(FULL, mine, 1, G);  // left neighbour's key
+                    if (ins && cc < mine) mine = (sub == 0 || !(cc < up)) ? cc : up;
+                }
             }
         }
         const unsigned long long kkey = __shfl_sync(FULL, mine, kth_lane);

@@ -212,8 +212,11 @@ struct Pt2PtArgs
 };
 
 // ------------------------------------------------------------------------------------------
+#ifndef MP2P_MATCH_MIN_BLOCKS
+#define MP2P_MATCH_MIN_BLOCKS 4  // CTAs of 256 threads per SM the register allocation must allow
+#endif
 template <int G>
-__global__ void __launch_bounds__(kQueryTile)
+__global__ void __launch_bounds__(kQueryTile, MP2P_MATCH_MIN_BLOCKS)
     k_match_pt2pt(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
                   const float* __restrict__ lz, const uint32_t* __restrict__ perm,
                   const uint32_t* __restrict__ lbits,
@@ -927,8 +930,13 @@ int pick_kt(uint32_t K)
 int start_level(const GridView& v, uint32_t K)
 {
     if (K <= 1) return 0;
+    static const float factor = [] {  // tuning knob (measurement only): MP2P_START_OCC, default 0.75
+        const char* e = getenv("MP2P_START_OCC");
+        const float f = e ? (float)atof(e) : 0.f;
+        return f > 0.01f ? f : 0.75f;
+    }();
     for (int rl = 0; rl < v.n_levels; rl++)
-        if (v.level_occupancy[rl] >= 0.75f * (float)K) return rl;
+        if (v.level_occupancy[rl] >= factor * (float)K) return rl;
     return v.n_levels - 1;
 }
 
