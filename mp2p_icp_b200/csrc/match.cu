@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(kQueryTile, MP2P_MATCH_MIN_BLOCKS)
     constexpr uint32_t NQ = kQueryTile / G;  // queries per CTA
     __shared__ QueryTile<NQ> tile;
     __shared__ BBoxAcc       bacc;
+    __shared__ uint32_t      s_stack[NQ][kSearchStack];  // per-query descent stack of knn_search
     const size_t             base = (size_t)blockIdx.x * NQ;
     bbox_init(bacc);
     load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kQueryTile, MP2P_MATCH_MIN_BLOCKS)
     SearchCounters     sc;
     // all lanes take part (warp-uniform search); lanes past the end and already paired locals
     // (:218-220) are disabled
-    knn_search<G>(g, valid && (a.allowLocal || !bit_set(lbits, i)), gx, gy, gz, thr2, K, a.rl_start, mine, sub, sc);
+    knn_search<G>(g, valid && (a.allowLocal || !bit_set(lbits, i)), gx, gy, gz, thr2, K, a.rl_start, mine, sub, sc, s_stack[ql]);
     if (valid)
     {
         // lane r < K writes rank r; unused ranks are marked with an impossible map index (all ones)
@@ -890,9 +891,10 @@ __global__ void __launch_bounds__(256)
     const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << ((threadIdx.x & 31) / G * G);
     const uint32_t i     = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const bool     have  = i < nq;
+    __shared__ uint32_t s_stack[256 / G][kSearchStack];
     unsigned long long mine;
     SearchCounters     sc;
-    knn_search<G>(g, have, have ? qx[i] : 0.f, have ? qy[i] : 0.f, have ? qz[i] : 0.f, radius2, (int)K, rl_start, mine, sub, sc);
+    knn_search<G>(g, have, have ? qx[i] : 0.f, have ? qy[i] : 0.f, have ? qz[i] : 0.f, radius2, (int)K, rl_start, mine, sub, sc, s_stack[threadIdx.x / G]);
     if (!have) return;  // whole groups leave together
     const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
     const bool               f        = sub < (int)K && mine < sentinel;
