@@ -405,7 +405,7 @@ def run_ours(args):
         "roofline": {"kernel": "k_match_" + w["matcher"], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": nn_ms_mean,
                      "algorithmic_bytes": int(alg_bytes), "probes": st["probes"], "candidates": st["candidates"],
-                     "climbed_queries": st["climbed"], "other_kernels_ms": {k: v for k, v in tm.items() if k != "nn_search"}},
+                     "climbed_queries": st["climbed"], "per_query_max": {"candidates": st["max_candidates_per_query"], "probes": st["max_probes_per_query"], "levels": st["max_levels"], "warps_with_gt2000_candidates": st["heavy_warps"]}, "other_kernels_ms": {k: v for k, v in tm.items() if k != "nn_search"}},
         "cpu_baseline": cpu,
         "clocks": clocks,
     }

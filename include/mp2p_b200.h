@@ -334,11 +334,13 @@ int mp2p_b200_horn_finish(const double sums_packet[MP2P_B200_PACKET_DOUBLES],
  *   [5] whole call, device time                             (unused slots = 0)
  * mp2p_b200_ctx_get_search_stats returns counters of the LAST match call when stats are on:
  *   [0] hash-table probes (16 B each)  [1] candidate points read (16 B each)
- *   [2] valid candidates written       [3] queries that climbed above the finest level  */
+ *   [2] valid candidates written       [3] queries that climbed above the finest level
+ *   [4] largest candidate count of one query  [5] largest probe count  [6] most levels visited
+ *   [7] warps holding a query with more than 2000 candidates (the stragglers of a launch)  */
 #define MP2P_B200_N_TIMINGS 8
 int mp2p_b200_ctx_set_profiling(mp2p_b200_ctx* ctx, int timings_on, int search_stats_on);
 int mp2p_b200_ctx_get_timings(mp2p_b200_ctx* ctx, float ms[MP2P_B200_N_TIMINGS]);
-int mp2p_b200_ctx_get_search_stats(mp2p_b200_ctx* ctx, uint64_t stats[4]);
+int mp2p_b200_ctx_get_search_stats(mp2p_b200_ctx* ctx, uint64_t stats[8]);
 
 /* Pinned host memory helpers (so callers in any language can give the library DMA-able buffers). */
 int  mp2p_b200_host_alloc(size_t bytes, void** out);

@@ -271,9 +271,10 @@ class Context:
         return {n: float(ms[i]) for i, n in enumerate(names)}
 
     def search_stats(self) -> dict:
-        st = (C.c_uint64 * 4)()
+        st = (C.c_uint64 * 8)()
         _check(load_library().mp2p_b200_ctx_get_search_stats(self._h, st))
-        return {"probes": int(st[0]), "candidates": int(st[1]), "valid": int(st[2]), "climbed": int(st[3])}
+        return {"probes": int(st[0]), "candidates": int(st[1]), "valid": int(st[2]), "climbed": int(st[3]),
+                "max_candidates_per_query": int(st[4]), "max_probes_per_query": int(st[5]), "max_levels": int(st[6]), "heavy_warps": int(st[7])}
 
     @property
     def launch_count(self) -> int:

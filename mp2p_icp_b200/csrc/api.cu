@@ -839,15 +839,15 @@ extern "C"
         for (int k = 0; k < MP2P_B200_N_TIMINGS; k++) ms[k] = ctx->timings[k];
         return 0;
     }
-    int mp2p_b200_ctx_get_search_stats(mp2p_b200_ctx* ctx, uint64_t stats[4])
+    int mp2p_b200_ctx_get_search_stats(mp2p_b200_ctx* ctx, uint64_t stats[8])
     {
         if (!ctx || !stats) return MP2P_B200_ERR_ARG;
-        for (int k = 0; k < 4; k++) stats[k] = 0;
+        for (int k = 0; k < 8; k++) stats[k] = 0;
         if (!ctx->d_stats.p) return 0;
         DeviceGuard g(ctx->device);
-        MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->h_pinned, ctx->d_stats.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->h_pinned, ctx->d_stats.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
         MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        std::memcpy(stats, ctx->h_pinned, 32);
+        std::memcpy(stats, ctx->h_pinned, 64);
         return 0;
     }
 

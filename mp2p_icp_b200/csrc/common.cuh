@@ -116,7 +116,7 @@ struct mp2p_b200_ctx
     cudaEvent_t  pev[16]      = {};     // pairs (2k, 2k+1) bracket timing slot k
     bool         pev_used[8]  = {};
     float        timings[MP2P_B200_N_TIMINGS] = {};
-    mp2p::DevBuf d_stats;               // 4 x u64 search counters
+    mp2p::DevBuf d_stats;               // 8 x u64 search counters
 
     // matcher scratch
     const float *cur_lx = nullptr, *cur_ly = nullptr, *cur_lz = nullptr;  // local cloud, caller's order

@@ -140,7 +140,7 @@ constexpr int kSearchStack = 7 * kMaxDescent + 8;  // DFS: one node popped, <= 8
 template <int G>
 __device__ __forceinline__ void knn_search(const GridView& g, bool enabled, float qx, float qy, float qz,
                                            float radius2, int K, int rl_start, unsigned long long& mine, int sub,
-                                           SearchCounters& sc, uint32_t* __restrict__ stack)
+                                           SearchCounters& sc, uint32_t* __restrict__ stack, int max_descent)
 {
     constexpr unsigned       FULL     = 0xffffffffu;
     const int                lane     = threadIdx.x & 31;
@@ -262,8 +262,11 @@ __device__ __forceinline__ void knn_search(const GridView& g, bool enabled, floa
         const float ax[3] = {gxl * gxl * q2, 0.f, gxh * gxh * q2};
         const float ay[3] = {gyl * gyl * q2, 0.f, gyh * gyh * q2};
         const float az[3] = {gzl * gzl * q2, 0.f, gzh * gzh * q2};
-        const bool  climbed = rl > rl_start;
-        const int   rl_leaf = max(rl_start, rl - kMaxDescent);
+        // max_descent = 0: plain scheme — every level scans its 27 voxels whole, the list is rebuilt
+        // per level so that no key is offered twice
+        if (live && max_descent == 0) mine = sentinel;
+        const bool  climbed = rl > rl_start && max_descent > 0;
+        const int   rl_leaf = max(rl_start, rl - max_descent);
         const int   Lp  = L > 0 ? L - 1 : 0;
         const int   pcx = Ix >> Lp, pcy = Iy >> Lp, pcz = Iz >> Lp;  // previous block's centre (if climbed)
         uint32_t    todo  = live ? 1u : 0u;  // bit i <-> kNeighbourOrder[i]; start with the centre
@@ -374,10 +377,15 @@ __device__ __forceinline__ void flush_search_stats(const SearchCounters& sc, uin
     const unsigned mask = __activemask();
     a = __reduce_add_sync(mask, a), b = __reduce_add_sync(mask, b);
     c = __reduce_add_sync(mask, c), d = __reduce_add_sync(mask, d);
+    const uint32_t mc = __reduce_max_sync(mask, sc.cands), mp = __reduce_max_sync(mask, sc.probes);
+    const uint32_t ml = __reduce_max_sync(mask, sc.levels);
     if ((threadIdx.x & 31) == (__ffs(mask) - 1))
     {
         atomicAdd(stats + 0, (unsigned long long)a), atomicAdd(stats + 1, (unsigned long long)b);
         atomicAdd(stats + 2, (unsigned long long)c), atomicAdd(stats + 3, (unsigned long long)d);
+        atomicMax(stats + 4, (unsigned long long)mc), atomicMax(stats + 5, (unsigned long long)mp);
+        atomicMax(stats + 6, (unsigned long long)ml);
+        if (mc > 2000u) atomicAdd(stats + 7, 1ull);  // warps holding a query with > 2000 candidates
     }
 }
 

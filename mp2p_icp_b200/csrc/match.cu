@@ -209,6 +209,9 @@ struct Pt2PtArgs
     int      tma_ok;         // local arrays are 16-byte aligned
     int      rl_start;       // relative level the search starts from (start_level())
     int      cand_sorted;    // candidate words go to the query's SORTED position (pt2pl path)
+    int      max_descent;    // levels a climbing query descends below its current level (0 = scan whole voxels)
+    uint32_t tile_stride;    // CTA b serves query tile (b * tile_stride) % n_tiles: spreads expensive
+                             // neighbourhoods (sparse map regions cluster in any spatial order) over the grid
 };
 
 // ------------------------------------------------------------------------------------------
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(kQueryTile, MP2P_MATCH_MIN_BLOCKS)
     __shared__ QueryTile<NQ> tile;
     __shared__ BBoxAcc       bacc;
     __shared__ uint32_t      s_stack[NQ][kSearchStack];  // per-query descent stack of knn_search
-    const size_t             base = (size_t)blockIdx.x * NQ;
+    const size_t             base = (size_t)(((unsigned long long)blockIdx.x * a.tile_stride) % gridDim.x) * NQ;
     bbox_init(bacc);
     load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
     const int      sub   = threadIdx.x % G, ql = threadIdx.x / G;
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(kQueryTile, MP2P_MATCH_MIN_BLOCKS)
     SearchCounters     sc;
     // all lanes take part (warp-uniform search); lanes past the end and already paired locals
     // (:218-220) are disabled
-    knn_search<G>(g, valid && (a.allowLocal || !bit_set(lbits, i)), gx, gy, gz, thr2, K, a.rl_start, mine, sub, sc, s_stack[ql]);
+    knn_search<G>(g, valid && (a.allowLocal || !bit_set(lbits, i)), gx, gy, gz, thr2, K, a.rl_start, mine, sub, sc, s_stack[ql], a.max_descent);
     if (valid)
     {
         // lane r < K writes rank r; unused ranks are marked with an impossible map index (all ones)
@@ -894,7 +897,7 @@ __global__ void __launch_bounds__(256)
     __shared__ uint32_t s_stack[256 / G][kSearchStack];
     unsigned long long mine;
     SearchCounters     sc;
-    knn_search<G>(g, have, have ? qx[i] : 0.f, have ? qy[i] : 0.f, have ? qz[i] : 0.f, radius2, (int)K, rl_start, mine, sub, sc, s_stack[threadIdx.x / G]);
+    knn_search<G>(g, have, have ? qx[i] : 0.f, have ? qy[i] : 0.f, have ? qz[i] : 0.f, radius2, (int)K, rl_start, mine, sub, sc, s_stack[threadIdx.x / G], kMaxDescent);
     if (!have) return;  // whole groups leave together
     const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
     const bool               f        = sub < (int)K && mine < sentinel;
@@ -923,12 +926,41 @@ int pick_kt(uint32_t K)
 #define MP2P_DISPATCH_G(K, CALL)  \
     switch (group_size(K))        \
     {                             \
-        case 8: CALL(8); break;   \
-        case 16: CALL(16); break; \
-        default: CALL(32); break; \
+        case 8: CALL(8) break;   \
+        case 16: CALL(16) break; \
+        default: CALL(32) break; \
     }
 
 // finest table whose voxels hold at least ~0.75 k points on average (k = 1: the finest table)
+// odd stride near 0.618 n, coprime to n: b -> (b * stride) % n is a permutation of the tiles
+uint32_t tile_stride_for(uint64_t n_tiles)
+{
+    static const bool off = [] {
+        const char* e = getenv("MP2P_TILE_STRIDE");
+        return e && atoi(e) == 0;
+    }();
+    if (off || n_tiles < 8) return 1;
+    uint64_t s = (uint64_t)((double)n_tiles * 0.6180339887) | 1ull;
+    auto     gcd = [](uint64_t a, uint64_t b) {
+        while (b)
+        {
+            const uint64_t t = a % b;
+            a = b, b = t;
+        }
+        return a;
+    };
+    while (gcd(s, n_tiles) != 1) s += 2;
+    return (uint32_t)(s % n_tiles);
+}
+int max_descent()
+{
+    static const int v = [] {  // tuning knob (measurement only)
+        const char* e = getenv("MP2P_DESCENT");
+        return e ? std::max(0, std::min(atoi(e), kMaxDescent)) : 0;
+    }();
+    return v;
+}
+
 int start_level(const GridView& v, uint32_t K)
 {
     if (K <= 1) return 0;
@@ -1033,8 +1065,8 @@ int prepare_stats(mp2p_b200_ctx* ctx, unsigned long long** stats)
 {
     *stats = nullptr;
     if (!ctx->prof_stats) return 0;
-    MP2P_TRY(ctx->d_stats.ensure(32));
-    MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_stats.p, 0, 32, ctx->stream));
+    MP2P_TRY(ctx->d_stats.ensure(64));
+    MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_stats.p, 0, 64, ctx->stream));
     *stats = ctx->d_stats.as<unsigned long long>();
     return 0;
 }
@@ -1128,8 +1160,12 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     MP2P_TRY(prepare_stats(ctx, &stats));
     float4* cand_xyz = nullptr;
     prof_begin(ctx, 0);
-#define LAUNCH_MATCH(G) \
-    k_match_pt2pt<G><<<(uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile), kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, sv.bbox, stats)
+#define LAUNCH_MATCH(G)                                                                                    \
+    {                                                                                                      \
+        const uint32_t nb = (uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile);                       \
+        a.tile_stride = tile_stride_for(nb), a.max_descent = max_descent();                                \
+        k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, sv.bbox, stats); \
+    }
     if (K == 1)
     {
         MP2P_TRY(ctx->d_candxyz.ensure(n_slots * sizeof(float4)));
@@ -1256,8 +1292,12 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     unsigned long long* stats = nullptr;
     MP2P_TRY(prepare_stats(ctx, &stats));
     prof_begin(ctx, 0);
-#define LAUNCH_MATCH(G) \
-    k_match_pt2pt<G><<<(uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile), kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, d_record, d_bbox6, stats)
+#define LAUNCH_MATCH(G)                                                                                    \
+    {                                                                                                      \
+        const uint32_t nb = (uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile);                       \
+        a.tile_stride = tile_stride_for(nb), a.max_descent = max_descent();                                \
+        k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, d_record, d_bbox6, stats); \
+    }
     if (K == 1)
     {
         MP2P_TRY(ctx->d_candxyz.ensure(n_local * sizeof(float4)));
@@ -1402,8 +1442,12 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     sa.allowLocal = a.allowLocal, sa.allowGlobal = 1, sa.tag = 0, sa.tma_ok = a.tma_ok;
     sa.cand_sorted = 1;  // the plane fit walks the same order
     prof_begin(ctx, 0);
-#define LAUNCH_SEARCH(G) \
-    k_match_pt2pt<G><<<(uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile), kQueryTile, 0, st>>>(map->view, sa, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, cand, sv.bbox, stats)
+#define LAUNCH_SEARCH(G)                                                                                   \
+    {                                                                                                      \
+        const uint32_t nb = (uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile);                       \
+        sa.tile_stride = tile_stride_for(nb), sa.max_descent = max_descent();                              \
+        k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, sa, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, cand, sv.bbox, stats); \
+    }
 #define LAUNCH_FIT(KT) \
     k_plane_fit<KT><<<(uint32_t)((n_local + kFitQueries - 1) / kFitQueries), kFitThreads, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, cand, plc, okf)
     sa.rl_start = start_level(map->view, prm->knn);
@@ -1469,7 +1513,7 @@ int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const
         auto *od = ctx->d_knn_d2.as<float>();
         auto *of = ctx->d_knn_found.as<int32_t>();
         const int rl0 = start_level(map->view, K);
-#define LAUNCH_KNN(G) k_knn<G><<<(uint32_t)((nq * G + 255) / 256), 256, 0, st>>>(map->view, dqx, dqy, dqz, (uint32_t)nq, K, radius2, rl0, oi, od, of)
+#define LAUNCH_KNN(G) k_knn<G><<<(uint32_t)((nq * G + 255) / 256), 256, 0, st>>>(map->view, dqx, dqy, dqz, (uint32_t)nq, K, radius2, rl0, oi, od, of);
         MP2P_DISPATCH_G(K, LAUNCH_KNN)
 #undef LAUNCH_KNN
         count_launch(ctx);

@@ -6,7 +6,7 @@ show() { python - "$1" <<'P'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); r=d['roofline']
-    print(sys.argv[1], 'ms', round(d['ms_per_step'],4), 'warm', round(d['config'].get('ms_per_step_l2_warm_informative',0),4), 'e2e', round(d['e2e']['ms_per_step'],4), 'nn_ms', round(r['kernel_ms'],4), 'frac', round(r['frac'],3), 'probes', r['probes'], 'cands', r['candidates'], r['other_kernels_ms'])
+    print(sys.argv[1], 'ms', round(d['ms_per_step'],4), 'warm', round(d['config'].get('ms_per_step_l2_warm_informative',0),4), 'e2e', round(d['e2e']['ms_per_step'],4), 'nn_ms', round(r['kernel_ms'],4), 'frac', round(r['frac'],3), 'probes', r['probes'], 'cands', r['candidates'], r.get('per_query_max'), r['other_kernels_ms'])
 except Exception as e:
     print(sys.argv[1], 'unreadable', e)
 P
