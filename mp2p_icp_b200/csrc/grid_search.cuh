@@ -135,6 +135,7 @@ __host__ __device__ constexpr int neighbour_rank(int idx)
 // on average (start_level(), host side), so that the centre voxel alone usually settles the k-th
 // distance and the neighbours can be pruned; any start level is correct.
 // `stack`: kSearchStack 32-bit words of shared memory owned by this group (pruned descent, below).
+constexpr uint32_t kLongRun = 96;                 // points from which a run is scanned by the whole warp
 constexpr int kMaxDescent  = 6;                    // levels a climbing query descends below its current level
 constexpr int kSearchStack = 7 * kMaxDescent + 8;  // DFS: one node popped, <= 8 children pushed per level
 template <int G>
@@ -174,6 +175,59 @@ __device__ __forceinline__ void knn_search(const GridView& g, bool enabled, floa
     // others take their left neighbour's key.
     auto scan_run = [&](const float4* __restrict__ run, uint32_t count)
     {
+        // A LONG run (a coarse voxel of a query that had to climb) is scanned by the whole warp for
+        // its owner group — 32 points per step, kAhead steps of loads in flight — instead of by the
+        // G lanes of the group while the other groups of the warp wait: such queries are rare but a
+        // single one otherwise outlives the rest of the launch.
+        if (G < 32)
+        {
+            unsigned big = __ballot_sync(FULL, count >= kLongRun && sub == 0);
+            while (big)  // warp-uniform
+            {
+                const int o = __ffs(big) - 1;  // first lane of the owner group
+                big &= big - 1;
+                const float4* __restrict__ orun = reinterpret_cast<const float4*>(
+                    __shfl_sync(FULL, reinterpret_cast<unsigned long long>(run), o));
+                const uint32_t ocount = __shfl_sync(FULL, count, o);
+                const float    oqx = __shfl_sync(FULL, qx, o), oqy = __shfl_sync(FULL, qy, o), oqz = __shfl_sync(FULL, qz, o);
+                const float    okth  = __shfl_sync(FULL, kth, o);
+                const int      okl   = o + K - 1;                   // lane holding the owner's K-th key
+                const bool     owner = (unsigned)(lane - o) < (unsigned)G;
+                constexpr int  kAheadW = 4;
+                for (uint32_t j0 = 0; j0 < ocount; j0 += kAheadW * 32)
+                {
+                    float4 p[kAheadW];
+#pragma unroll
+                    for (int u = 0; u < kAheadW; u++)
+                    {
+                        const uint32_t j = j0 + u * 32 + lane;
+                        p[u]             = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (j < ocount) p[u] = __ldg(orun + j);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kAheadW; u++)
+                    {
+                        if (j0 + u * 32 >= ocount) break;  // warp-uniform
+                        const uint32_t           j    = j0 + u * 32 + lane;
+                        const bool               in   = j < ocount;
+                        const unsigned long long c    = in ? point_key(oqx, oqy, oqz, p[u]) : ~0ull;
+                        const unsigned long long kkey = __shfl_sync(FULL, mine, okl);
+                        const bool pass = in && c < kkey && __uint_as_float((uint32_t)(c >> 32)) <= okth;
+                        unsigned   pm   = __ballot_sync(FULL, pass);
+                        while (pm)  // warp-uniform
+                        {
+                            const int src = __ffs(pm) - 1;
+                            pm &= pm - 1;
+                            const unsigned long long cc = __shfl_sync(FULL, c, src);
+                            const unsigned long long up = __shfl_up_sync(FULL, mine, 1, G);
+                            if (owner && cc < mine) mine = (sub == 0 || !(cc < up)) ? cc : up;
+                        }
+                    }
+                }
+                const unsigned long long kkey = __shfl_sync(FULL, mine, okl);
+                if (owner) kth = fminf(kth, __uint_as_float((uint32_t)(kkey >> 32))), count = 0;
+            }
+        }
         const uint32_t steps = __reduce_max_sync(FULL, count);
         constexpr int  kAhead = 4;  // steps whose loads are issued together: a long run (a coarse
                                     // voxel of a query that had to climb) is latency-bound otherwise

@@ -242,11 +242,121 @@ class Solver_Horn_B200 : public Solver_Horn
 };
 IMPLEMENTS_MRPT_OBJECT(Solver_Horn_B200, Solver, mp2p_icp)
 
+/** Drop-in for Matcher_Point2Plane over a plain point layer: NearestPlaneCapable::nn_search_pt2pl is
+ *  realised on the GPU as k-NN + PCA plane (SURVEY.md §8a-7'; the reference ships no implementer of
+ *  that interface, tests/CMakeLists.txt:37). `distanceThreshold` as in the reference
+ *  (Matcher_Point2Plane.cpp:36-39); the plane-detection parameters are those of Matcher_Adaptive
+ *  (Matcher_Adaptive.cpp:229-253) with the same names and defaults. */
+class Matcher_Point2Plane_B200 : public Matcher_Points_Base
+{
+    DEFINE_MRPT_OBJECT(Matcher_Point2Plane_B200, mp2p_icp)
+   public:
+    void initialize(const mrpt::containers::yaml& params) override
+    {
+        Matcher_Points_Base::initialize(params);
+        DECLARE_PARAMETER_REQ(params, distanceThreshold);
+        DECLARE_PARAMETER_OPT(params, searchRadius);
+        DECLARE_PARAMETER_OPT(params, knn);
+        DECLARE_PARAMETER_OPT(params, minimumPlanePoints);
+        DECLARE_PARAMETER_OPT(params, planeEigenThreshold);
+    }
+    double   distanceThreshold = 0.50, searchRadius = 1.0, planeEigenThreshold = 0.01;
+    uint32_t knn = 8, minimumPlanePoints = 5;
+
+   private:
+    void implMatchOneLayer(const mrpt::maps::CMetricMap& pcGlobal, const mrpt::maps::CPointsMap& pcLocal,
+                           const mrpt::poses::CPose3D& localPose, MatchState& ms,
+                           const layer_name_t& globalName, const layer_name_t& localName,
+                           Pairings& out) const override
+    {
+        using namespace b200_detail;
+        (void)globalName;
+        checkAllParametersAreRealized();
+        mp2p_b200_map* gmap = cache().get(pcGlobal);
+        const auto&    lx   = pcLocal.getPointsBufferRef_x();
+        double         T[12];
+        pose12(localPose, T);
+        mp2p_b200_pt2pl_params p{distanceThreshold, searchRadius, knn, minimumPlanePoints, planeEigenThreshold,
+                                 allowMatchAlreadyMatchedPoints_, bounding_box_intersection_check_epsilon_};
+        auto&                  lbf   = ms.localPairedBitField.point_layers.at(localName);
+        const auto             lbits = to_bits(lbf, lx.size());
+        const size_t           before = out.paired_pt2pl.size();
+        out.paired_pt2pl.resize(before + lx.size());
+        static_assert(sizeof(mp2p_icp::point_plane_pair_t) == sizeof(mp2p_b200_pair_pt2pl));
+        uint64_t     cnt = 0, pot = 0;
+        const float* resident = cache().pinned_local(pcLocal);
+        check(mp2p_b200_match_pt2pl(ctx(), gmap, resident ? resident : lx.data(),
+                                    resident ? nullptr : pcLocal.getPointsBufferRef_y().data(),
+                                    resident ? nullptr : pcLocal.getPointsBufferRef_z().data(), lx.size(),
+                                    resident ? MP2P_B200_LOCAL_CLOUD : MP2P_B200_LOCAL_HOST, T, &p, lbits.data(),
+                                    reinterpret_cast<mp2p_b200_pair_pt2pl*>(out.paired_pt2pl.data() + before),
+                                    lx.size(), 0, &cnt, &pot));
+        out.paired_pt2pl.resize(before + cnt);
+        out.potential_pairings += pot;
+        // Matcher_Point2Plane.cpp:105-109: only the local point is marked. point_plane_pair_t carries
+        // the local COORDINATES, not the index: re-identify by a parallel walk (the output is in
+        // ascending local index and each local point pairs at most once)
+        const auto& ly = pcLocal.getPointsBufferRef_y();
+        const auto& lz = pcLocal.getPointsBufferRef_z();
+        size_t      i  = 0;
+        for (size_t k = before; k < out.paired_pt2pl.size(); k++)
+        {
+            const auto& pl = out.paired_pt2pl[k].pt_local;
+            while (i < lx.size() && !(lx[i] == pl.x && ly[i] == pl.y && lz[i] == pl.z && !lbf[i])) i++;
+            if (i < lx.size()) lbf.mark_as_set(i++);
+        }
+    }
+};
+IMPLEMENTS_MRPT_OBJECT(Matcher_Point2Plane_B200, Matcher, mp2p_icp)
+
+/** Drop-in for Solver_GaussNewton: pt2pt and pt2pl terms accumulated on the GPU (whole inner loop on
+ *  the device); any other term or a prior sends the call to the reference implementation. */
+class Solver_GaussNewton_B200 : public Solver_GaussNewton
+{
+    DEFINE_MRPT_OBJECT(Solver_GaussNewton_B200, mp2p_icp)
+   protected:
+    bool impl_optimal_pose(const Pairings& pairings, OptimalTF_Result& out, const SolverContext& sc) const override
+    {
+        using namespace b200_detail;
+        if (sc.prior.has_value() || !pairings.paired_pt2ln.empty() || !pairings.paired_ln2ln.empty() ||
+            !pairings.paired_pl2pl.empty())
+            return Solver_GaussNewton::impl_optimal_pose(pairings, out, sc);  // terms that stay host-side
+        checkAllParametersAreRealized();
+        out = OptimalTF_Result();
+        ASSERT_(sc.guessRelativePose.has_value());
+        mp2p_b200_gn_params p{};
+        p.maxInnerLoopIterations = maxIterations;
+        p.minDelta               = 1e-7;  // OptimalTF_GN_Parameters defaults (optimal_tf_gauss_newton.h:46-50)
+        p.maxCost                = 0;
+        p.w_pt2pt                = pairWeights.pt2pt;
+        p.w_pt2pl                = pairWeights.pt2pl;
+        p.kernel                 = static_cast<int>(robustKernel);
+        p.kernelParam            = robustKernelParam;
+        double T0[12], T[12];
+        pose12(mrpt::poses::CPose3D(sc.guessRelativePose.value()), T0);
+        int32_t  solved = 0;
+        uint32_t iters  = 0;
+        check(mp2p_b200_solve_gauss_newton(ctx(), reinterpret_cast<const mp2p_b200_pair_pt2pt*>(pairings.paired_pt2pt.data()),
+                                           pairings.paired_pt2pt.size(),
+                                           reinterpret_cast<const mp2p_b200_pair_pt2pl*>(pairings.paired_pt2pl.data()),
+                                           pairings.paired_pt2pl.size(), 0, &p, T0, T, &iters, &solved));
+        if (!solved) return false;
+        mrpt::math::CMatrixDouble44 M = mrpt::math::CMatrixDouble44::Identity();
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 4; c++) M(r, c) = T[4 * r + c];
+        out.optimalPose = mrpt::poses::CPose3D(M);
+        return true;
+    }
+};
+IMPLEMENTS_MRPT_OBJECT(Solver_GaussNewton_B200, Solver, mp2p_icp)
+
 MRPT_INITIALIZER(register_mp2p_icp_b200)
 {
     using mrpt::rtti::registerClass;
     registerClass(CLASS_ID(mp2p_icp::Matcher_Points_DistanceThreshold_B200));
     registerClass(CLASS_ID(mp2p_icp::Solver_Horn_B200));
+    registerClass(CLASS_ID(mp2p_icp::Matcher_Point2Plane_B200));
+    registerClass(CLASS_ID(mp2p_icp::Solver_GaussNewton_B200));
 }
 }  // namespace mp2p_icp
 

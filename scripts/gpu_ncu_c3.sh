@@ -1,5 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
-ncu --set full --clock-control none --import-source on -k regex:"k_match_pt2pt" -s 4 -c 1 -f -o gpurun_out/prof_c3_search python bench.py --workload C3 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_C3s.log 2>&1; echo "full C3 search rc=$?"
-ls -la gpurun_out/*.ncu-rep
+ncu --set full --clock-control none --import-source on -k regex:"k_match_pt2pt" -s 4 -c 1 -f -o gpurun_out/prof_c3_search3 python bench.py --workload C3 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_C3s.log 2>&1; echo "full C3 search rc=$?"
