@@ -134,14 +134,11 @@ __host__ __device__ constexpr int neighbour_rank(int idx)
 // `rl_start`: relative level to start from — the finest level whose voxels hold about 0.75 k points
 // on average (start_level(), host side), so that the centre voxel alone usually settles the k-th
 // distance and the neighbours can be pruned; any start level is correct.
-// `stack`: kSearchStack 32-bit words of shared memory owned by this group (pruned descent, below).
 constexpr uint32_t kLongRun = 96;                 // points from which a run is scanned by the whole warp
-constexpr int kMaxDescent  = 6;                    // levels a climbing query descends below its current level
-constexpr int kSearchStack = 7 * kMaxDescent + 8;  // DFS: one node popped, <= 8 children pushed per level
 template <int G>
 __device__ __forceinline__ void knn_search(const GridView& g, bool enabled, float qx, float qy, float qz,
                                            float radius2, int K, int rl_start, unsigned long long& mine, int sub,
-                                           SearchCounters& sc, uint32_t* __restrict__ stack, int max_descent)
+                                           SearchCounters& sc)
 {
     constexpr unsigned       FULL     = 0xffffffffu;
     const int                lane     = threadIdx.x & 31;
@@ -266,28 +263,16 @@ __device__ __forceinline__ void knn_search(const GridView& g, bool enabled, floa
         if (count) kth = fminf(kth, __uint_as_float((uint32_t)(kkey >> 32)));
     };
 
-    // squared conservative distance (metres^2) from the query to voxel (vx,vy,vz) of edge `s`
-    // quanta: per-axis gap to the box, shrunk by 4 quanta, like the neighbour slabs below
-    auto box_bound = [&](int vx, int vy, int vz, float s) -> float
-    {
-        const float ax0 = (float)vx * s, ay0 = (float)vy * s, az0 = (float)vz * s;  // exact: < 2^22
-        const float dx = fmaxf(fmaxf(ax0 - ux, ux - (ax0 + s)) - 4.f, 0.f);
-        const float dy = fmaxf(fmaxf(ay0 - uy, uy - (ay0 + s)) - 4.f, 0.f);
-        const float dz = fmaxf(fmaxf(az0 - uz, uz - (az0 + s)) - 4.f, 0.f);
-        return (dx * dx + dy * dy + dz * dz) * q2;
-    };
-
-    uint32_t sp = 0;  // this group's stack pointer (group-uniform)
     for (int rl = rl_start; rl < g.n_levels; rl++)
     {
         if (!__any_sync(FULL, live)) break;
         const int L = g.level_first + rl;
+        if (live) mine = sentinel;  // the list is rebuilt at every level: no key is ever offered twice
 
         if (L == kGridBits)
         {
             // top level: the single voxel holds every point; a query outside the grid (possible only
             // with a radius larger than its distance to the bbox) must still see all of them
-            if (live) mine = sentinel;  // everything is offered again here
             if (live && sub == 0) sc.probes++, sc.cands += g.n_points, sc.levels++;
             scan_run(g.pts, live ? g.n_points : 0u);
             break;
@@ -302,92 +287,62 @@ __device__ __forceinline__ void knn_search(const GridView& g, bool enabled, floa
         const float gyl = fmaxf(fy - 4.f, 0.f), gyh = fmaxf(s - fy - 4.f, 0.f);
         const float gzl = fmaxf(fz - 4.f, 0.f), gzh = fmaxf(s - fz - 4.f, 0.f);
 
-        // The 3x3x3 block of this level, centre first then faces/edges/corners; per round every live
-        // group takes ONE node: the next entry of its stack if it has one, else its next surviving
-        // block voxel (after the centre, the survivors are collected once in a bit mask —
-        // hierarchically: a slab or a row that is too far drops all its voxels at once).
-        //   * At the start level a node is a small voxel: one broadcast hash probe, points offered.
-        //   * A level reached by CLIMBING (the K-th neighbour was not settled below) has big voxels,
-        //     mostly far outside the ball of radius sqrt(kth): such a node is not scanned but split
-        //     into its 8 children one level down, pushed on the group's stack and, when popped,
-        //     re-checked against the (tightening) bound — a pruned descent to the start level.
-        //     Children inside the previous level's 3x3x3 block are skipped: that block was examined
-        //     completely one level down and `mine` is kept across levels, so no point is offered twice.
+        // The 3x3x3 block of this level, centre first then faces/edges/corners. Per round a group
+        // takes up to G voxels of its to-do mask, ONE PER LANE: each lane bounds and hash-probes its
+        // own voxel (the probes of a round are in flight together — a dependent chain of one probe
+        // per voxel is what a query that climbs through sparse space would otherwise pay), then the
+        // runs found are offered one after the other, each re-checked against the bound the
+        // previous ones tightened. After the centre, the survivors are collected once in the mask
+        // (hierarchically: a slab or a row that is too far drops all its voxels at once).
         const float ax[3] = {gxl * gxl * q2, 0.f, gxh * gxh * q2};
         const float ay[3] = {gyl * gyl * q2, 0.f, gyh * gyh * q2};
         const float az[3] = {gzl * gzl * q2, 0.f, gzh * gzh * q2};
-        // max_descent = 0: plain scheme — every level scans its 27 voxels whole, the list is rebuilt
-        // per level so that no key is offered twice
-        if (live && max_descent == 0) mine = sentinel;
-        const bool  climbed = rl > rl_start && max_descent > 0;
-        const int   rl_leaf = max(rl_start, rl - max_descent);
-        const int   Lp  = L > 0 ? L - 1 : 0;
-        const int   pcx = Ix >> Lp, pcy = Iy >> Lp, pcz = Iz >> Lp;  // previous block's centre (if climbed)
         uint32_t    todo  = live ? 1u : 0u;  // bit i <-> kNeighbourOrder[i]; start with the centre
         bool        first = live;
-        while (__any_sync(FULL, todo != 0 || sp != 0))
+        while (__any_sync(FULL, todo != 0))
         {
-            int   nl = rl, nx = 0, ny = 0, nz = 0;
-            bool  have = false;
-            float lb   = 0.f;
-            if (sp)
+            // lane `sub` takes the sub-th pending voxel
+            const int      n_take = min(__popc(todo), G);
+            uint32_t       start = 0, count = 0;
+            float          lb    = 0.f;
+            uint32_t       taken = 0;  // bit of my voxel
+            if (sub < n_take)
             {
-                const uint32_t e = stack[--sp];
-                nl               = (int)(e >> 24);
-                const int Ln     = g.level_first + nl;
-                nx = (Ix >> Ln) + (int)(int8_t)(e >> 16), ny = (Iy >> Ln) + (int)(int8_t)(e >> 8), nz = (Iz >> Ln) + (int)(int8_t)e;
-                lb   = box_bound(nx, ny, nz, (float)(1 << Ln));
-                have = true;  // in range by construction
-            }
-            else if (todo)
-            {
-                const int nb = __ffs(todo) - 1;
-                todo &= todo - 1;
+                const int nb = (int)__fns(todo, 0, sub + 1);
+                taken        = 1u << nb;
                 const uint32_t code = kNeighbourOrder[nb];
                 const int      dx = (int)(code & 3u) - 1, dy = (int)((code >> 2) & 3u) - 1,
                           dz = (int)((code >> 4) & 3u) - 1;
                 lb = (dx < 0 ? ax[0] : (dx > 0 ? ax[2] : 0.f)) + (dy < 0 ? ay[0] : (dy > 0 ? ay[2] : 0.f)) +
                      (dz < 0 ? az[0] : (dz > 0 ? az[2] : 0.f));
-                nx = cx + dx, ny = cy + dy, nz = cz + dz;
-                have = (unsigned)nx <= (unsigned)cmax && (unsigned)ny <= (unsigned)cmax && (unsigned)nz <= (unsigned)cmax;
-            }
-            __syncwarp();  // every lane has read its stack entry before anyone pushes again
-            uint32_t start = 0, count = 0;
-            // strict `>`: an equal-distance lower index must still be seen
-            if (have && !(lb > kth))
-            {
-                if (sub == 0) sc.probes++;
-                if (!grid_lookup(g, nl, (uint32_t)nx, (uint32_t)ny, (uint32_t)nz, start, count)) count = 0;
-            }
-            if (count && climbed && nl > rl_leaf)
-            {
-                // does this node contain part of the previous level's block? (only possible at nl == rl)
-                const bool over = nl == rl && 2 * nx + 1 >= pcx - 1 && 2 * nx <= pcx + 1 && 2 * ny + 1 >= pcy - 1 &&
-                                  2 * ny <= pcy + 1 && 2 * nz + 1 >= pcz - 1 && 2 * nz <= pcz + 1;
-                if (over || count > 4u * G)
+                const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
+                // strict `>`: an equal-distance lower index must still be seen
+                if (!(lb > kth) && (unsigned)nx <= (unsigned)cmax && (unsigned)ny <= (unsigned)cmax &&
+                    (unsigned)nz <= (unsigned)cmax)
                 {
-                    // split: children one level down, relative to the query's own voxel there
-                    const int Lc  = g.level_first + nl - 1;
-                    const int ccx = Ix >> Lc, ccy = Iy >> Lc, ccz = Iz >> Lc;
-#pragma unroll
-                    for (int c = 0; c < 8; c++)
-                    {
-                        const int kx = 2 * nx + (c & 1), ky = 2 * ny + ((c >> 1) & 1), kz = 2 * nz + (c >> 2);
-                        const bool seen = nl == rl && kx >= pcx - 1 && kx <= pcx + 1 && ky >= pcy - 1 && ky <= pcy + 1 &&
-                                          kz >= pcz - 1 && kz <= pcz + 1;
-                        if (seen) continue;
-                        if (sub == 0)
-                            stack[sp] = ((uint32_t)(nl - 1) << 24) | (((uint32_t)(kx - ccx) & 255u) << 16) |
-                                        (((uint32_t)(ky - ccy) & 255u) << 8) | ((uint32_t)(kz - ccz) & 255u);
-                        sp++;
-                    }
-                    count = 0;
+                    sc.probes++;
+                    if (!grid_lookup(g, rl, (uint32_t)nx, (uint32_t)ny, (uint32_t)nz, start, count)) count = 0;
                 }
             }
-            __syncwarp();  // stack writes of lane 0 of each group -> visible to the group
-            if (sub == 0) sc.cands += count;
-            scan_run(g.pts + start, count);
-            if (first && sp == 0)  // the centre (and, when climbing, its whole subtree) is done
+            // drop the voxels taken this round from the group's mask (OR over the group's lanes)
+            {
+                uint32_t t = taken;
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) t |= __shfl_xor_sync(FULL, t, o);
+                todo &= ~t;
+            }
+            // offer the runs in voxel order; a run whose bound fell behind is skipped
+            const int rounds = __reduce_max_sync(FULL, (unsigned)n_take);
+            for (int t = 0; t < rounds; t++)
+            {
+                const int      src = (lane - sub) + t;
+                const uint32_t rs = __shfl_sync(FULL, start, src), rc = __shfl_sync(FULL, count, src);
+                const float    rlb = __shfl_sync(FULL, lb, src);
+                const uint32_t c   = (t < n_take && !(rlb > kth)) ? rc : 0u;
+                if (sub == 0) sc.cands += c;
+                scan_run(g.pts + rs, c);
+            }
+            if (first)
             {
                 first = false;
 #pragma unroll
@@ -410,8 +365,8 @@ __device__ __forceinline__ void knn_search(const GridView& g, bool enabled, floa
                 }
             }
         }
-        // `mine` now holds the exact K best of everything inside this level's block; everything
-        // outside the 3x3x3 block is at least m quanta away
+        // `mine` now holds the exact K best of this level's block; everything outside the 3x3x3
+        // block is at least m quanta away
         const float mx = s + fminf(fx, s - fx), my = s + fminf(fy, s - fy), mz = s + fminf(fz, s - fz);
         const float m  = fmaxf(fminf(mx, fminf(my, mz)) - 4.f, 0.f);
         if (live)

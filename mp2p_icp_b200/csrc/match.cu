@@ -209,7 +209,6 @@ struct Pt2PtArgs
     int      tma_ok;         // local arrays are 16-byte aligned
     int      rl_start;       // relative level the search starts from (start_level())
     int      cand_sorted;    // candidate words go to the query's SORTED position (pt2pl path)
-    int      max_descent;    // levels a climbing query descends below its current level (0 = scan whole voxels)
     uint32_t tile_stride;    // CTA b serves query tile (b * tile_stride) % n_tiles: spreads expensive
                              // neighbourhoods (sparse map regions cluster in any spatial order) over the grid
 };
@@ -230,7 +229,6 @@ __global__ void __launch_bounds__(kQueryTile, MP2P_MATCH_MIN_BLOCKS)
     constexpr uint32_t NQ = kQueryTile / G;  // queries per CTA
     __shared__ QueryTile<NQ> tile;
     __shared__ BBoxAcc       bacc;
-    __shared__ uint32_t      s_stack[NQ][kSearchStack];  // per-query descent stack of knn_search
     const size_t             base = (size_t)(((unsigned long long)blockIdx.x * a.tile_stride) % gridDim.x) * NQ;
     bbox_init(bacc);
     load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
@@ -253,7 +251,7 @@ __global__ void __launch_bounds__(kQueryTile, MP2P_MATCH_MIN_BLOCKS)
     SearchCounters     sc;
     // all lanes take part (warp-uniform search); lanes past the end and already paired locals
     // (:218-220) are disabled
-    knn_search<G>(g, valid && (a.allowLocal || !bit_set(lbits, i)), gx, gy, gz, thr2, K, a.rl_start, mine, sub, sc, s_stack[ql], a.max_descent);
+    knn_search<G>(g, valid && (a.allowLocal || !bit_set(lbits, i)), gx, gy, gz, thr2, K, a.rl_start, mine, sub, sc);
     if (valid)
     {
         // lane r < K writes rank r; unused ranks are marked with an impossible map index (all ones)
@@ -894,10 +892,9 @@ __global__ void __launch_bounds__(256)
     const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << ((threadIdx.x & 31) / G * G);
     const uint32_t i     = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const bool     have  = i < nq;
-    __shared__ uint32_t s_stack[256 / G][kSearchStack];
     unsigned long long mine;
     SearchCounters     sc;
-    knn_search<G>(g, have, have ? qx[i] : 0.f, have ? qy[i] : 0.f, have ? qz[i] : 0.f, radius2, (int)K, rl_start, mine, sub, sc, s_stack[threadIdx.x / G], kMaxDescent);
+    knn_search<G>(g, have, have ? qx[i] : 0.f, have ? qy[i] : 0.f, have ? qz[i] : 0.f, radius2, (int)K, rl_start, mine, sub, sc);
     if (!have) return;  // whole groups leave together
     const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
     const bool               f        = sub < (int)K && mine < sentinel;
@@ -952,15 +949,6 @@ uint32_t tile_stride_for(uint64_t n_tiles)
     while (gcd(s, n_tiles) != 1) s += 2;
     return (uint32_t)(s % n_tiles);
 }
-int max_descent()
-{
-    static const int v = [] {  // tuning knob (measurement only)
-        const char* e = getenv("MP2P_DESCENT");
-        return e ? std::max(0, std::min(atoi(e), kMaxDescent)) : 0;
-    }();
-    return v;
-}
-
 int start_level(const GridView& v, uint32_t K)
 {
     if (K <= 1) return 0;
@@ -1163,7 +1151,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
 #define LAUNCH_MATCH(G)                                                                                    \
     {                                                                                                      \
         const uint32_t nb = (uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile);                       \
-        a.tile_stride = tile_stride_for(nb), a.max_descent = max_descent();                                \
+        a.tile_stride = tile_stride_for(nb);                                                                \
         k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, sv.bbox, stats); \
     }
     if (K == 1)
@@ -1295,7 +1283,7 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
 #define LAUNCH_MATCH(G)                                                                                    \
     {                                                                                                      \
         const uint32_t nb = (uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile);                       \
-        a.tile_stride = tile_stride_for(nb), a.max_descent = max_descent();                                \
+        a.tile_stride = tile_stride_for(nb);                                                                \
         k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, d_record, d_bbox6, stats); \
     }
     if (K == 1)
@@ -1445,7 +1433,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
 #define LAUNCH_SEARCH(G)                                                                                   \
     {                                                                                                      \
         const uint32_t nb = (uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile);                       \
-        sa.tile_stride = tile_stride_for(nb), sa.max_descent = max_descent();                              \
+        sa.tile_stride = tile_stride_for(nb);                                                              \
         k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, sa, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, cand, sv.bbox, stats); \
     }
 #define LAUNCH_FIT(KT) \
