@@ -203,7 +203,7 @@ extern "C"
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
         for (DevBuf* b : {&c->d_lx, &c->d_ly, &c->d_lz, &c->d_cand, &c->d_candxyz, &c->d_lbits, &c->d_gbits, &c->d_scan,
-                          &c->d_small, &c->d_out2p, &c->d_out2l, &c->d_plcand, &c->d_okflags, &c->d_knn_idx, &c->d_knn_d2,
+                          &c->d_small, &c->d_out2p, &c->d_out2l, &c->d_plcand, &c->d_okflags, &c->d_fitlist, &c->d_knn_idx, &c->d_knn_d2,
                           &c->d_knn_found, &c->d_pairs2p, &c->d_pairs2l, &c->d_partials, &c->d_packet,
                           &c->d_pose, &c->d_weights, &c->d_outlier})
             b->release();

@@ -133,6 +133,7 @@ struct mp2p_b200_ctx
     mp2p::DevBuf d_small;              // bbox (6 u32) + count (u64) + misc
     mp2p::DevBuf d_out2p, d_out2l;     // compacted pairs when the caller wants them on the host
     mp2p::DevBuf d_plcand, d_okflags;  // per-query plane candidates + accepted flags (pt2pl)
+    mp2p::DevBuf d_fitlist;            // [0] count, [1..] queries that qualify for a plane fit
     mp2p::DevBuf d_knn_idx, d_knn_d2, d_knn_found;
     // solver scratch
     mp2p::DevBuf d_pairs2p, d_pairs2l; // H2D staging of host pairings
@@ -225,7 +226,8 @@ int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const
 int run_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p,
                       const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l, const mp2p_b200_gn_params* prm,
                       const double* d_pose, double* d_packet, const unsigned long long* d_n2p = nullptr,
-                      const unsigned long long* d_n2l = nullptr, const uint32_t* d_done = nullptr);
+                      const unsigned long long* d_n2l = nullptr, const uint32_t* d_done = nullptr,
+                      uint32_t* d_step_state = nullptr /* != NULL: the launch also applies the GN update */);
 // whole inner loop of optimal_tf_gauss_newton on the device: (accumulate, solve+update) x maxIter,
 // no host synchronisation; d_pose in/out, d_state = {done flag, iterations done}
 int run_gn_device_loop(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p,

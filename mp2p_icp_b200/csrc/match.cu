@@ -214,6 +214,17 @@ struct Pt2PtArgs
 };
 
 // ------------------------------------------------------------------------------------------
+// pt2pl: the search kernel lists the queries whose k-NN holds at least `need` points (list order =
+// arrival order: results are written under the query's index, so any order is fine) and clears the
+// accepted-flag of the others; the plane fit then runs one thread per LISTED query on full warps.
+struct FitList
+{
+    uint32_t* list;   // NULL = not requested
+    uint32_t* count;  // zeroed by the host before the launch
+    uint8_t*  ok_flags;
+    int       need;
+};
+
 #ifndef MP2P_MATCH_MIN_BLOCKS
 #define MP2P_MATCH_MIN_BLOCKS 4  // CTAs of 256 threads per SM the register allocation must allow
 #endif
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(kQueryTile, MP2P_MATCH_MIN_BLOCKS)
                   const uint32_t* __restrict__ lbits,
                   const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim,
                   unsigned long long* __restrict__ cand, uint32_t* __restrict__ bbox_words,
-                  unsigned long long* __restrict__ stats)
+                  unsigned long long* __restrict__ stats, FitList fit)
 {
     constexpr uint32_t NQ = kQueryTile / G;  // queries per CTA
     __shared__ QueryTile<NQ> tile;
@@ -266,6 +277,19 @@ __global__ void __launch_bounds__(kQueryTile, MP2P_MATCH_MIN_BLOCKS)
             }
         }
         flush_search_stats(sc, c != ~0ull ? 1u : 0u, stats);
+    }
+    if (fit.list)  // all lanes: warp-aggregated append of the queries that qualify for a plane fit
+    {
+        const bool     q_lane = valid && sub == fit.need - 1;  // the lane holding rank need-1
+        const bool     has    = q_lane && fit.need <= K && mine < sentinel;
+        const unsigned m      = __ballot_sync(0xffffffffu, has);
+        const int      lane   = threadIdx.x & 31;
+        uint32_t       at     = 0;
+        if (m && lane == __ffs(m) - 1) at = atomicAdd(fit.count, (uint32_t)__popc(m));
+        at = __shfl_sync(0xffffffffu, at, m ? __ffs(m) - 1 : 0);
+        if (has) fit.list[at + __popc(m & ((1u << lane) - 1u))] = qpos;
+        if (q_lane && !has) fit.ok_flags[i] = 0;
+        if (valid && fit.need > G && sub == 0) fit.ok_flags[i] = 0;  // cannot hold `need` neighbours at all
     }
 }
 
@@ -749,83 +773,54 @@ struct Pt2PlArgs
     int      tma_ok;
 };
 
-// Plane fit of the pt2pl matcher, one THREAD per query that has enough neighbours (the k-NN search
-// ran before, in the group-cooperative k_match_pt2pt<G> used as a pure radius-bounded k-NN). A CTA
-// owns kFitQueries consecutive queries: it first lists the ones whose k-NN holds at least
-// max(3, minimumPlanePoints) points (one 8-byte read each: valid ranks come first), then the
-// threads work through that dense list — the fp64 Jacobi runs on full warps instead of on the
-// ~half of the lanes whose query qualifies. Per listed query: gather the K neighbour points
+// Plane fit of the pt2pl matcher, one THREAD per LISTED query (FitList: the k-NN search listed the
+// queries whose neighbourhood holds at least max(3, minimumPlanePoints) points; the grid is sized
+// for the worst case and CTAs past the list's end leave at once). Full warps in the fp64 Jacobi
+// instead of the ~half of the lanes whose query qualifies. Per query: gather the K neighbour points
 // (ascending (d2, index)), estimate_points_eigen + planarity + distance tests (plane_fit.cuh).
 constexpr int kFitThreads = 128;
-constexpr int kFitQueries = 4 * kFitThreads;
 
 template <int KT>
 __global__ void __launch_bounds__(kFitThreads)
     k_plane_fit(GridView g, Pt2PlArgs a, const float* __restrict__ qx, const float* __restrict__ qy,
                 const float* __restrict__ qz, const uint32_t* __restrict__ perm,
-                const unsigned long long* __restrict__ cand, PlaneCandidate* __restrict__ plc,
+                const unsigned long long* __restrict__ cand, const uint32_t* __restrict__ fit_list,
+                const uint32_t* __restrict__ fit_count, PlaneCandidate* __restrict__ plc,
                 uint8_t* __restrict__ ok_flags)
 {
-    // walks the same (possibly Morton-sorted) query array as the search did: neighbouring threads
-    // gather overlapping neighbour sets; results go to the caller's index i
-    __shared__ uint32_t s_list[kFitQueries];
-    __shared__ uint32_t s_n;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
+    const uint32_t t = blockIdx.x * kFitThreads + threadIdx.x;
+    if (t >= *fit_count) return;
     const int      K    = (int)a.K;
-    const int      need = max(3, (int)a.minPts);
-    const uint32_t q0   = blockIdx.x * kFitQueries;
+    const uint32_t qpos = fit_list[t];  // position in the (possibly Morton-sorted) array the search walked
+    const uint32_t i    = perm ? __ldg(perm + qpos) : qpos;
+    int            cnt  = 0;
+    uint32_t       idx[KT];
 #pragma unroll
-    for (int r = 0; r < kFitQueries / kFitThreads; r++)
-    {
-        const uint32_t qpos = q0 + r * kFitThreads + threadIdx.x;
-        bool           act  = false;
-        if (qpos < a.n_local)
+    for (int k = 0; k < KT; k++)
+        if (k < K)
         {
-            act = need <= K && (uint32_t)cand[(size_t)qpos * K + need - 1] != 0xFFFFFFFFu;
-            if (!act) ok_flags[perm ? __ldg(perm + qpos) : qpos] = 0;
+            const unsigned long long c = cand[(size_t)qpos * K + k];
+            idx[k]                     = (uint32_t)c;
+            cnt += ((uint32_t)c != 0xFFFFFFFFu);  // valid ranks come first
         }
-        const unsigned m = __ballot_sync(0xffffffffu, act);
-        uint32_t       base = 0;
-        if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(&s_n, (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (act) s_list[base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = qpos;
-    }
-    __syncthreads();
-    const uint32_t n_act = s_n;
-    for (uint32_t t = threadIdx.x; t < n_act; t += kFitThreads)
-    {
-        const uint32_t qpos = s_list[t];
-        const uint32_t i    = perm ? __ldg(perm + qpos) : qpos;
-        int            cnt  = 0;
-        uint32_t       idx[KT];
+    float px[KT], py[KT], pz[KT];
 #pragma unroll
-        for (int k = 0; k < KT; k++)
-            if (k < K)
-            {
-                const unsigned long long c = cand[(size_t)qpos * K + k];
-                idx[k]                     = (uint32_t)c;
-                cnt += ((uint32_t)c != 0xFFFFFFFFu);  // valid ranks come first
-            }
-        float px[KT], py[KT], pz[KT];
-#pragma unroll
-        for (int k = 0; k < KT; k++)
-            if (k < cnt)
-            {
-                const float4 p = __ldg(g.pts_orig + idx[k]);
-                px[k] = p.x, py[k] = p.y, pz[k] = p.z;
-            }
-        float gx, gy, gz;
-        compose_point_f(a.pose, qx[qpos], qy[qpos], qz[qpos], gx, gy, gz);
-        PlaneCandidate pc;
-        uint8_t        ok = 0;
-        if (fit_plane<KT>(px, py, pz, cnt, gx, gy, gz, a.planeEigenThreshold, a.distThr, pc))
+    for (int k = 0; k < KT; k++)
+        if (k < cnt)
         {
-            plc[i] = pc;
-            ok     = 1;
+            const float4 p = __ldg(g.pts_orig + idx[k]);
+            px[k] = p.x, py[k] = p.y, pz[k] = p.z;
         }
-        ok_flags[i] = ok;
+    float gx, gy, gz;
+    compose_point_f(a.pose, qx[qpos], qy[qpos], qz[qpos], gx, gy, gz);
+    PlaneCandidate pc;
+    uint8_t        ok = 0;
+    if (fit_plane<KT>(px, py, pz, cnt, gx, gy, gz, a.planeEigenThreshold, a.distThr, pc))
+    {
+        plc[i] = pc;
+        ok     = 1;
     }
+    ok_flags[i] = ok;
 }
 
 __global__ void __launch_bounds__(kScanThreads)
@@ -1152,7 +1147,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     {                                                                                                      \
         const uint32_t nb = (uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile);                       \
         a.tile_stride = tile_stride_for(nb);                                                                \
-        k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, sv.bbox, stats); \
+        k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, sv.bbox, stats, FitList{nullptr, nullptr, nullptr, 0}); \
     }
     if (K == 1)
     {
@@ -1284,7 +1279,7 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     {                                                                                                      \
         const uint32_t nb = (uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile);                       \
         a.tile_stride = tile_stride_for(nb);                                                                \
-        k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, d_record, d_bbox6, stats); \
+        k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, d_record, d_bbox6, stats, FitList{nullptr, nullptr, nullptr, 0}); \
     }
     if (K == 1)
     {
@@ -1429,15 +1424,19 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     sa.pose = a.pose, sa.maxDistSq = a.radiusSq, sa.angSq = 0.f, sa.n_local = a.n_local, sa.K = a.K;
     sa.allowLocal = a.allowLocal, sa.allowGlobal = 1, sa.tag = 0, sa.tma_ok = a.tma_ok;
     sa.cand_sorted = 1;  // the plane fit walks the same order
+    MP2P_TRY(ctx->d_fitlist.ensure((n_local + 1) * 4));
+    MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_fitlist.p, 0, 4, st));
+    const FitList fit{ctx->d_fitlist.as<uint32_t>() + 1, ctx->d_fitlist.as<uint32_t>(), okf,
+                      (int)std::max<uint32_t>(3u, prm->minimumPlanePoints)};
     prof_begin(ctx, 0);
 #define LAUNCH_SEARCH(G)                                                                                   \
     {                                                                                                      \
         const uint32_t nb = (uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile);                       \
         sa.tile_stride = tile_stride_for(nb);                                                              \
-        k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, sa, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, cand, sv.bbox, stats); \
+        k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, sa, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, cand, sv.bbox, stats, fit); \
     }
 #define LAUNCH_FIT(KT) \
-    k_plane_fit<KT><<<(uint32_t)((n_local + kFitQueries - 1) / kFitQueries), kFitThreads, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, cand, plc, okf)
+    k_plane_fit<KT><<<(uint32_t)((n_local + kFitThreads - 1) / kFitThreads), kFitThreads, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, cand, fit.list, fit.count, plc, okf)
     sa.rl_start = start_level(map->view, prm->knn);
     MP2P_DISPATCH_G(prm->knn, LAUNCH_SEARCH)
     switch (pick_kt(prm->knn))

@@ -40,7 +40,10 @@ __device__ __forceinline__ void eig_sym3(const double Ain[9], double V[9], doubl
                     off += A[r * 3 + c] * A[r * 3 + c];
                 else
                     diag += A[r * 3 + c] * A[r * 3 + c];
-        if (off <= 1e-300 || off <= 1e-32 * diag) break;
+        // |off| <= 1e-13 |diag|: the sweep after that would bring it to ~1e-26 (quadratic convergence),
+        // far below what the planarity / distance tests or the 1e-9 parity bound can see; a tighter
+        // bound sits at the rounding level and makes a few lanes spin for extra sweeps
+        if (off <= 1e-300 || off <= 1e-26 * diag) break;
 #pragma unroll
         for (int p = 0; p < 2; p++)
 #pragma unroll

@@ -12,8 +12,9 @@ constexpr int    kReduceWarps    = kReduceThreads / 32;
 // rows of all CTAs in a FIXED order (8 chunks of rows in parallel, then the 8 chunk sums in order)
 // into the packet and re-arms the ticket for the next launch. The order depends only on n_slots,
 // so results are run-to-run bit-stable. Must be called by all kReduceThreads threads of the CTA.
+// Returns true (to every thread of the CTA) in the CTA that folded the packet, false elsewhere.
 template <int NV>
-__device__ __forceinline__ void block_reduce_to_packet(double (&acc)[NV], double* __restrict__ partials,
+__device__ __forceinline__ bool block_reduce_to_packet(double (&acc)[NV], double* __restrict__ partials,
                                                        unsigned int* __restrict__ ticket,
                                                        double* __restrict__ packet, unsigned slot,
                                                        unsigned n_slots)
@@ -42,7 +43,7 @@ __device__ __forceinline__ void block_reduce_to_packet(double (&acc)[NV], double
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == n_slots - 1) ? 1u : 0u;
     __syncthreads();
-    if (!is_last) return;
+    if (!is_last) return false;
     __threadfence();
     // thread (warp = chunk, lane = value): chunk c sums rows [c*per, (c+1)*per) in order
     const unsigned per = (n_slots + kReduceWarps - 1) / kReduceWarps;
@@ -79,6 +80,7 @@ __device__ __forceinline__ void block_reduce_to_packet(double (&acc)[NV], double
         packet[threadIdx.x] = t;
     }
     if (threadIdx.x == 0) *ticket = 0u;
+    return true;
 }
 
 // solve.cu: scratch rows + ticket of a context

@@ -81,12 +81,43 @@ __device__ __forceinline__ void add_row(double (&acc)[kGNV], const double (&a)[6
     for (int i = 0; i < 6; i++) acc[21 + i] += w * a[i] * r;
 }
 
+// One Gauss-Newton update (single thread): delta = -H^{-1} g by LDL^T, pose <- pose (+) exp(delta),
+// convergence flags (optimal_tf_gauss_newton.cpp:344-365). state[0] = done, state[1] = updates.
+__device__ __forceinline__ void gn_step_device(const double* packet, double minDelta, double maxCost, double* pose,
+                                               uint32_t* state)
+{
+    if (state[0]) return;
+    if (sqrt(packet[27]) <= maxCost)
+    {
+        state[0] = 1;
+        return;
+    }
+    double H[36], g[6], delta[6];
+    int    idx = 0;
+    for (int i = 0; i < 6; i++)
+        for (int j = i; j < 6; j++) H[6 * i + j] = H[6 * j + i] = packet[idx++];
+    for (int i = 0; i < 6; i++) g[i] = -packet[21 + i];
+    if (!hm::ldlt_solve6_nopivot(H, g, delta)) hm::ldlt_solve6(H, g, delta);
+    hm::Pose34 P;
+    for (int k = 0; k < 12; k++) P.m[k] = pose[k];
+    const hm::Pose34 Pn = hm::compose(P, hm::se3_exp(delta));
+    for (int k = 0; k < 12; k++) pose[k] = Pn.m[k];
+    state[1] += 1;
+    double nrm = 0;
+    for (int k = 0; k < 6; k++) nrm += delta[k] * delta[k];
+    if (sqrt(nrm) < minDelta) state[0] = 1;
+}
+
+// `step_state` != NULL: the CTA that folds the packet also applies the Gauss-Newton update to `pose`
+// (every other CTA has read the pose long before: they all passed the ticket) — the single-GPU inner
+// loop is then ONE launch per iteration. A multi-GPU caller all-reduces the packet first and uses
+// k_gn_step.
 __global__ void __launch_bounds__(kSolveThreads)
     k_gn_accumulate(const uint32_t* __restrict__ p2p, const uint32_t* __restrict__ p2l, GNArgs a,
-                    const double* __restrict__ pose, double* __restrict__ partials,
+                    double* pose, double* __restrict__ partials,
                     unsigned int* __restrict__ ticket, double* __restrict__ packet,
                     const unsigned long long* __restrict__ d_n2p, const unsigned long long* __restrict__ d_n2l,
-                    const uint32_t* __restrict__ d_done)
+                    const uint32_t* d_done, uint32_t* step_state, double minDelta, double maxCost)
 {
     if (d_done && *d_done) return;  // the device-side GN loop already converged
     if (d_n2p) a.n2p = *d_n2p;
@@ -170,7 +201,12 @@ __global__ void __launch_bounds__(kSolveThreads)
         }
         __syncwarp();
     }
-    block_reduce_to_packet<kGNV>(acc, partials, ticket, packet, blockIdx.x, gridDim.x);
+    const bool folded = block_reduce_to_packet<kGNV>(acc, partials, ticket, packet, blockIdx.x, gridDim.x);
+    if (folded && step_state && threadIdx.x < 32)
+    {
+        __syncwarp();  // the packet was written by this warp's lanes
+        if (threadIdx.x == 0) gn_step_device(packet, minDelta, maxCost, pose, step_state);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -342,7 +378,7 @@ int solve_grid(uint64_t n)
 int run_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p,
                       const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l, const mp2p_b200_gn_params* prm,
                       const double* d_pose, double* d_packet, const unsigned long long* d_n2p,
-                      const unsigned long long* d_n2l, const uint32_t* d_done)
+                      const unsigned long long* d_n2l, const uint32_t* d_done, uint32_t* d_step_state)
 {
     const int blocks = solve_grid(std::max(n2p, n2l));
     unsigned int* ticket;
@@ -351,38 +387,17 @@ int run_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint6
     GNArgs a{n2p, n2l, prm->w_pt2pt, prm->w_pt2pl, prm->kernel, prm->kernelParam};
     prof_begin(ctx, 4);
     k_gn_accumulate<<<blocks, kSolveThreads, 0, ctx->stream>>>(
-        reinterpret_cast<const uint32_t*>(d2p), reinterpret_cast<const uint32_t*>(d2l), a, d_pose,
-        partials, ticket, d_packet, d_n2p, d_n2l, d_done);
+        reinterpret_cast<const uint32_t*>(d2p), reinterpret_cast<const uint32_t*>(d2l), a, const_cast<double*>(d_pose),
+        partials, ticket, d_packet, d_n2p, d_n2l, d_done, d_step_state, prm->minDelta, prm->maxCost);
     prof_end(ctx, 4);
     count_launch(ctx);
     return 0;
 }
 
-// One Gauss-Newton update on the device (single thread): delta = -H^{-1} g by LDL^T, pose <- pose (+)
-// exp(delta), convergence flags (optimal_tf_gauss_newton.cpp:344-365). state[0] = done, state[1] = updates.
 __global__ void k_gn_step(const double* __restrict__ packet, double minDelta, double maxCost,
                           double* __restrict__ pose, uint32_t* __restrict__ state)
 {
-    if (threadIdx.x != 0 || state[0]) return;
-    if (sqrt(packet[27]) <= maxCost)
-    {
-        state[0] = 1;
-        return;
-    }
-    double H[36], g[6], delta[6];
-    int    idx = 0;
-    for (int i = 0; i < 6; i++)
-        for (int j = i; j < 6; j++) H[6 * i + j] = H[6 * j + i] = packet[idx++];
-    for (int i = 0; i < 6; i++) g[i] = -packet[21 + i];
-    if (!hm::ldlt_solve6_nopivot(H, g, delta)) hm::ldlt_solve6(H, g, delta);
-    hm::Pose34 P;
-    for (int k = 0; k < 12; k++) P.m[k] = pose[k];
-    const hm::Pose34 Pn = hm::compose(P, hm::se3_exp(delta));
-    for (int k = 0; k < 12; k++) pose[k] = Pn.m[k];
-    state[1] += 1;
-    double nrm = 0;
-    for (int k = 0; k < 6; k++) nrm += delta[k] * delta[k];
-    if (sqrt(nrm) < minDelta) state[0] = 1;
+    if (threadIdx.x == 0) gn_step_device(packet, minDelta, maxCost, pose, state);
 }
 
 int run_gn_device_loop(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p,
@@ -393,9 +408,8 @@ int run_gn_device_loop(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint
     MP2P_CUDA_TRY(cudaMemsetAsync(d_state, 0, 8, ctx->stream));
     for (uint32_t it = 0; it < prm->maxInnerLoopIterations; it++)  // optimal_tf_gauss_newton.cpp:70
     {
-        MP2P_TRY(run_gn_accumulate(ctx, d2p, n2p, d2l, n2l, prm, d_pose, d_packet, d_n2p, d_n2l, d_state));
-        k_gn_step<<<1, 32, 0, ctx->stream>>>(d_packet, prm->minDelta, prm->maxCost, d_pose, d_state);
-        count_launch(ctx);
+        // accumulate + update in one launch (the folding CTA applies the step)
+        MP2P_TRY(run_gn_accumulate(ctx, d2p, n2p, d2l, n2l, prm, d_pose, d_packet, d_n2p, d_n2l, d_state, d_state));
     }
     return 0;
 }
