@@ -518,12 +518,15 @@ class Map:
             fn, args = L.mp2p_b200_iterate_pt2pl_gn, args + [C.byref(iters), C.byref(pot)]
         keep = (mp, sp)  # noqa: F841  (keeps the structs alive as long as the closure)
 
+        pose_in_np = np.frombuffer(pose_in, dtype=np.float64)  # views of the ctypes arrays: no per-call marshalling
+        pose_out_np = np.frombuffer(pose_out, dtype=np.float64).reshape(3, 4)
+
         def step(T):
-            pose_in[:] = np.asarray(T, dtype=np.float64).reshape(-1).tolist()
+            pose_in_np[:] = np.asarray(T, dtype=np.float64).reshape(-1)
             rc = fn(*args)
             if rc != 0:
                 _check(rc)
-            return bool(solved.value), np.array(pose_out[:]).reshape(3, 4), int(n_pairs.value)
+            return bool(solved.value), pose_out_np.copy(), int(n_pairs.value)
 
         return step
 

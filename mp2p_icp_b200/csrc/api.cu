@@ -203,7 +203,7 @@ extern "C"
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
         for (DevBuf* b : {&c->d_lx, &c->d_ly, &c->d_lz, &c->d_cand, &c->d_candxyz, &c->d_lbits, &c->d_gbits, &c->d_scan,
-                          &c->d_small, &c->d_out2p, &c->d_out2l, &c->d_plcand, &c->d_okflags, &c->d_fitlist, &c->d_knn_idx, &c->d_knn_d2,
+                          &c->d_small, &c->d_out2p, &c->d_out2l, &c->d_plcand, &c->d_okflags, &c->d_fitlist, &c->d_coop, &c->d_knn_idx, &c->d_knn_d2,
                           &c->d_knn_found, &c->d_pairs2p, &c->d_pairs2l, &c->d_partials, &c->d_packet,
                           &c->d_pose, &c->d_weights, &c->d_outlier})
             b->release();
@@ -750,12 +750,14 @@ extern "C"
         double*     dp1 = dp0 + MP2P_B200_PACKET_DOUBLES;
         DeviceMatch dm;
         dm.want_horn_sums = dp0;  // eval_centroids_robust folded into the compaction kernel
+        if (sprm->robust_kernel == 0 && sprm->w_pt2pt > 0.0) dm.fuse_moments_w = sprm->w_pt2pt;  // plain Horn: one launch
         uint64_t    dummy = 0;
         MP2P_TRY(run_match_pt2pt(ctx, map, lx, ly, lz, n_local, local_on_device, pose, mprm, nullptr, nullptr,
                                  pairs_device, cap, 1, &dummy, &dm));
         if (!dm.d_count) return 0;  // empty map or cloud: no pairings (ICP: NoPairings)
         const auto* d2p = static_cast<const mp2p_b200_pair_pt2pt*>(dm.d_pairs);
-        MP2P_TRY(run_horn_moments(ctx, d2p, dm.capacity, sprm, dp0, dm.capacity, nullptr, nullptr, 0, nullptr, dp1, dm.d_count, 1));
+        if (!dm.moments_done)
+            MP2P_TRY(run_horn_moments(ctx, d2p, dm.capacity, sprm, dp0, dm.capacity, nullptr, nullptr, 0, nullptr, dp1, dm.d_count, 1));
         // one D2H copy brings both packets; the pairing count rides in the HORN1 packet ([6], exact
         // in a double up to 2^53)
         double* hp = pinned_packets(ctx);

@@ -110,6 +110,10 @@ struct mp2p_b200_ctx
     // out_count == NULL), consumed by solver calls given n = MP2P_B200_COUNT_ON_DEVICE
     const unsigned long long* last_count    = nullptr;
     uint64_t                  last_capacity = 0;
+    // grid barrier state of the single-launch iteration (match.cu): counters only ever grow
+    mp2p::DevBuf       d_coop;
+    unsigned long long coop_arrivals = 0;
+    unsigned int       coop_epoch    = 0;
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
     // measurement hooks
     bool         prof_timings = false, prof_stats = false;
@@ -189,6 +193,10 @@ struct DeviceMatch
     const void*               d_pairs  = nullptr;  // compacted records, device memory
     uint64_t                  capacity = 0;        // upper bound of *d_count
     double*                   want_horn_sums = nullptr;  // in: device packet to receive the HORN1 sums
+    // in: > 0 = pair weight pt2pt: the caller also wants the HORN2 moments (plain Horn: no robust
+    // kernel, weights or scale-outlier pass) in want_horn_sums[32..64) if the matcher can fuse them
+    double                    fuse_moments_w = 0.0;
+    bool                      moments_done   = false;    // out: the matcher produced the moments too
 };
 
 // index.cu

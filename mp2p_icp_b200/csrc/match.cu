@@ -324,21 +324,23 @@ __device__ __forceinline__ unsigned long long scan_run_min(const float4* __restr
     return m;
 }
 
-__global__ void __launch_bounds__(kNN1Threads)
-    k_match_pt2pt_nn1(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
-                      const float* __restrict__ lz, const uint32_t* __restrict__ perm,
-                      const uint32_t* __restrict__ lbits,
-                      const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim,
-                      unsigned long long* __restrict__ cand, float4* __restrict__ cand_xyz,
-                      uint32_t* __restrict__ bbox_words, unsigned long long* __restrict__ stats)
+// Body of the K = 1 matcher for a CTA of NT threads (NT queries); shared by the stand-alone kernel
+// and by the fused single-launch iteration (k_iterate_nn1_horn).
+template <int NT>
+__device__ __forceinline__ void nn1_body(const GridView& g, const Pt2PtArgs& a, const float* __restrict__ lx,
+                                         const float* __restrict__ ly, const float* __restrict__ lz,
+                                         const uint32_t* __restrict__ perm, const uint32_t* __restrict__ lbits,
+                                         const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim,
+                                         unsigned long long* __restrict__ cand, float4* __restrict__ cand_xyz,
+                                         uint32_t* __restrict__ bbox_words, unsigned long long* __restrict__ stats)
 {
-    constexpr int kWarpsNN1 = kNN1Threads / 32;
-    __shared__ QueryTile<kNN1Threads> tile;
+    constexpr int kWarpsNN1 = NT / 32;
+    __shared__ QueryTile<NT> tile;
     __shared__ BBoxAcc                bacc;
     __shared__ unsigned long long     s_best[kWarpsNN1][32];
     __shared__ uint32_t               s_run[kWarpsNN1][32];         // map position of s_best's point
     __shared__ uint16_t               s_item[kWarpsNN1][32 * 26];   // (owner lane << 5) | neighbour bit
-    const size_t                      base = (size_t)blockIdx.x * kNN1Threads;
+    const size_t                      base = (size_t)blockIdx.x * NT;
     bbox_init(bacc);
     load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
     const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -550,6 +552,17 @@ __global__ void __launch_bounds__(kNN1Threads)
     flush_search_stats(sc, n_valid, stats);
 }
 
+__global__ void __launch_bounds__(kNN1Threads)
+    k_match_pt2pt_nn1(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
+                      const float* __restrict__ lz, const uint32_t* __restrict__ perm,
+                      const uint32_t* __restrict__ lbits,
+                      const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim,
+                      unsigned long long* __restrict__ cand, float4* __restrict__ cand_xyz,
+                      uint32_t* __restrict__ bbox_words, unsigned long long* __restrict__ stats)
+{
+    nn1_body<kNN1Threads>(g, a, lx, ly, lz, perm, lbits, gbits, claim, cand, cand_xyz, bbox_words, stats);
+}
+
 // ------------------------------------------------------------------------------------------
 // Single-pass stream compaction (decoupled look-back over 1024-slot tiles).
 // status word: [63:62] 1 = tile aggregate, 2 = inclusive prefix; [61:40] call epoch (22 bits);
@@ -678,30 +691,20 @@ struct FusedSums
     double*       packet;    // NULL = not requested
 };
 
-__global__ void __launch_bounds__(kScanThreads)
-    k_compact_pt2pt(GridView g, CompactArgs a, const float* __restrict__ lx,
-                    const float* __restrict__ ly, const float* __restrict__ lz,
-                    const uint32_t* __restrict__ gbits, const unsigned long long* __restrict__ claim,
-                    const unsigned long long* __restrict__ cand, const float4* __restrict__ cand_xyz,
-                    const uint32_t* __restrict__ bbox, uint32_t* __restrict__ bbox_next,
-                    unsigned long long* __restrict__ status, uint32_t* __restrict__ tile_counter,
-                    mp2p_b200_pair_pt2pt* __restrict__ out, unsigned long long* __restrict__ out_count,
-                    FusedSums fs)
+// Body of the pt2pt compaction for tile `tile` of a CTA of kScanThreads threads. On return the
+// tile's accepted records sit in s_rec[0 .. n_rec*9) (n_rec returned); shared by the stand-alone
+// kernel and by the fused single-launch iteration.
+__device__ __forceinline__ uint32_t compact_pt2pt_body(
+    const GridView& g, const CompactArgs& a, const float* __restrict__ lx, const float* __restrict__ ly,
+    const float* __restrict__ lz, const uint32_t* __restrict__ gbits, const unsigned long long* __restrict__ claim,
+    const unsigned long long* __restrict__ cand, const float4* __restrict__ cand_xyz, const uint32_t* __restrict__ bbox,
+    unsigned long long* __restrict__ status, mp2p_b200_pair_pt2pt* __restrict__ out,
+    unsigned long long* __restrict__ out_count, const FusedSums& fs, uint32_t tile, ScanSmem& sm, uint32_t* s_rec,
+    bool* folded_sums = nullptr)
 {
-    static_assert(kScanItems == 1 && kScanThreads == kReduceThreads, "one slot per thread");
-    __shared__ ScanSmem sm;
-    __shared__ uint32_t s_rec[kScanThreads * 9];  // this tile's records, staged for coalesced stores
-    bbox_rearm(bbox_next);
     const uint64_t n_slots = (uint64_t)a.n_local * a.K;
     const uint32_t n_tiles = (uint32_t)((n_slots + kScanTile - 1) / kScanTile);
-    if (threadIdx.x == 0)
-    {
-        sm.tile_id = atomicAdd(tile_counter, 1u);
-        if (sm.tile_id == n_tiles - 1) *tile_counter = 0u;  // last ticket handed out: re-arm
-    }
-    __syncthreads();
-    const uint32_t tile = sm.tile_id;
-    const bool     gate = bbox_gate(g, bbox, a.gate_eps);
+    const bool     gate    = bbox_gate(g, bbox, a.gate_eps);
 
     // Everything a record needs is requested up front (cand -> {claim word, global point, local
     // point} in parallel) so that only ONE dependent memory round trip precedes the scan.
@@ -743,10 +746,10 @@ __global__ void __launch_bounds__(kScanThreads)
         o[8] = (uint32_t)(c >> 32);
     }
     __syncthreads();
+    const unsigned long long room  = a.capacity > tile_base ? a.capacity - tile_base : 0ull;
+    const uint32_t           n_rec = (uint32_t)min((unsigned long long)sm.tile_total, room);
     {
-        const unsigned long long room  = a.capacity > tile_base ? a.capacity - tile_base : 0ull;
-        const uint32_t           n_rec = (uint32_t)min((unsigned long long)sm.tile_total, room);
-        uint32_t*                dst   = reinterpret_cast<uint32_t*>(out) + tile_base * 9;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out) + tile_base * 9;
         for (uint32_t k = threadIdx.x; k < n_rec * 9; k += kScanThreads) dst[k] = s_rec[k];
     }
     if (fs.packet)
@@ -754,8 +757,131 @@ __global__ void __launch_bounds__(kScanThreads)
         const bool in  = ok && w < a.capacity;
         double     acc[8] = {in ? (double)px : 0.0,   in ? (double)py : 0.0,   in ? (double)pz : 0.0, in ? (double)gp.x : 0.0,
                              in ? (double)gp.y : 0.0, in ? (double)gp.z : 0.0, in ? 1.0 : 0.0,       in ? 1.0 : 0.0};
-        block_reduce_to_packet<8>(acc, fs.partials, fs.ticket, fs.packet, tile, n_tiles);
+        const bool folded = block_reduce_to_packet<8>(acc, fs.partials, fs.ticket, fs.packet, tile, n_tiles);
+        if (folded_sums) *folded_sums = folded;
     }
+    return n_rec;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+    k_compact_pt2pt(GridView g, CompactArgs a, const float* __restrict__ lx,
+                    const float* __restrict__ ly, const float* __restrict__ lz,
+                    const uint32_t* __restrict__ gbits, const unsigned long long* __restrict__ claim,
+                    const unsigned long long* __restrict__ cand, const float4* __restrict__ cand_xyz,
+                    const uint32_t* __restrict__ bbox, uint32_t* __restrict__ bbox_next,
+                    unsigned long long* __restrict__ status, uint32_t* __restrict__ tile_counter,
+                    mp2p_b200_pair_pt2pt* __restrict__ out, unsigned long long* __restrict__ out_count,
+                    FusedSums fs)
+{
+    static_assert(kScanItems == 1 && kScanThreads == kReduceThreads, "one slot per thread");
+    __shared__ ScanSmem sm;
+    __shared__ uint32_t s_rec[kScanThreads * 9];  // this tile's records, staged for coalesced stores
+    bbox_rearm(bbox_next);
+    const uint64_t n_slots = (uint64_t)a.n_local * a.K;
+    const uint32_t n_tiles = (uint32_t)((n_slots + kScanTile - 1) / kScanTile);
+    if (threadIdx.x == 0)
+    {
+        sm.tile_id = atomicAdd(tile_counter, 1u);
+        if (sm.tile_id == n_tiles - 1) *tile_counter = 0u;  // last ticket handed out: re-arm
+    }
+    __syncthreads();
+    compact_pt2pt_body(g, a, lx, ly, lz, gbits, claim, cand, cand_xyz, bbox, status, out, out_count, fs, sm.tile_id, sm,
+                       s_rec);
+}
+
+// ------------------------------------------------------------------------------------------
+// One ICP iteration (Matcher_Points_DistanceThreshold, k = 1, + Solver_Horn without robust kernel /
+// weights / scale-outlier pass) in ONE cooperative launch of co-resident CTAs:
+//   phase 1  nn1_body: search, candidate words, first-claim proposals, bounding box
+//   -------- grid barrier (claims and the box are complete)
+//   phase 2  compact_pt2pt_body: acceptance, look-back scan, records out, HORN1 sums -> packet[0..32)
+//   -------- every CTA waits for the folded sums (flag written by the folding CTA)
+//   phase 3  S moments of the tile's records straight from shared memory -> packet[32..64)
+// Saves two launches, the solver's re-read of the pairings and the launch gaps; the numbers are the
+// same sums in a different grouping (poses agree to ~1e-15 with the three-kernel path).
+// ------------------------------------------------------------------------------------------
+struct CoopSync
+{
+    unsigned long long* arrivals;  // monotonically increasing across launches (never reset)
+    unsigned long long  target;    // arrivals value that completes this launch's barrier
+    unsigned int*       sums_flag; // epoch of the launch whose HORN1 packet is complete
+    unsigned int        epoch;
+};
+
+__device__ __forceinline__ void grid_barrier(const CoopSync& cs)
+{
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        atomicAdd(cs.arrivals, 1ull);
+        while (*reinterpret_cast<volatile unsigned long long*>(cs.arrivals) < cs.target) __nanosleep(32);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kScanThreads, 3)
+    k_iterate_nn1_horn(GridView g, Pt2PtArgs a, CompactArgs ca, const float* __restrict__ qx, const float* __restrict__ qy,
+                       const float* __restrict__ qz, const float* __restrict__ lx, const float* __restrict__ ly,
+                       const float* __restrict__ lz, const uint32_t* __restrict__ perm, unsigned long long* __restrict__ claim,
+                       unsigned long long* __restrict__ cand, float4* __restrict__ cand_xyz, uint32_t* __restrict__ bbox,
+                       uint32_t* __restrict__ bbox_next, unsigned long long* __restrict__ status,
+                       mp2p_b200_pair_pt2pt* __restrict__ out, unsigned long long* __restrict__ out_count, FusedSums fs,
+                       double* __restrict__ mom_partials, unsigned int* __restrict__ mom_ticket, double w_pt2pt, CoopSync cs)
+{
+    __shared__ ScanSmem sm;
+    __shared__ uint32_t s_rec[kScanThreads * 9];
+    // ---- phase 1
+    nn1_body<kScanThreads>(g, a, qx, qy, qz, perm, nullptr, nullptr, claim, cand, cand_xyz, bbox, nullptr);
+    grid_barrier(cs);
+    // ---- phase 2 (tile = CTA index: all CTAs are resident, the look-back cannot starve)
+    bbox_rearm(bbox_next);
+    bool           folded = false;  // CTA-uniform
+    const uint32_t n_rec  = compact_pt2pt_body(g, ca, lx, ly, lz, nullptr, claim, cand, cand_xyz, bbox, status, out, out_count, fs,
+                                               blockIdx.x, sm, s_rec, &folded);
+    // ---- the CTA that folded the HORN1 packet publishes it; everybody waits for it
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        if (folded)
+        {
+            __threadfence();
+            atomicExch(cs.sums_flag, cs.epoch);
+        }
+        while (*reinterpret_cast<volatile unsigned int*>(cs.sums_flag) != cs.epoch) __nanosleep(32);
+        __threadfence();
+    }
+    __syncthreads();
+    // ---- phase 3: visit_correspondences (visit_correspondences.h:100-212) over the tile's records
+    const double* sums = fs.packet;
+    const double  wc   = 1.0 / __ldcg(sums + 6);
+    const double  cl[3] = {__ldcg(sums + 0) * wc, __ldcg(sums + 1) * wc, __ldcg(sums + 2) * wc};
+    const double  cg[3] = {__ldcg(sums + 3) * wc, __ldcg(sums + 4) * wc, __ldcg(sums + 5) * wc};
+    const double  waPoints = w_pt2pt / (w_pt2pt * __ldcg(sums + 7));  // :85-87
+    double        acc[12];
+#pragma unroll
+    for (int v = 0; v < 12; v++) acc[v] = 0;
+    if (threadIdx.x < n_rec)
+    {
+        const uint32_t* rec = s_rec + threadIdx.x * 9;
+        const double    bi[3] = {(double)__uint_as_float(rec[2]) - cg[0], (double)__uint_as_float(rec[3]) - cg[1],
+                                 (double)__uint_as_float(rec[4]) - cg[2]};
+        const double    ri[3] = {(double)__uint_as_float(rec[5]) - cl[0], (double)__uint_as_float(rec[6]) - cl[1],
+                                 (double)__uint_as_float(rec[7]) - cl[2]};
+        const double bn = sqrt(bi[0] * bi[0] + bi[1] * bi[1] + bi[2] * bi[2]);
+        const double rn = sqrt(ri[0] * ri[0] + ri[1] * ri[1] + ri[2] * ri[2]);
+        if (!(bn < 1e-4 || rn < 1e-4))  // :141-146
+        {
+            acc[9] += waPoints;
+            acc[11] += 1.0;
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) acc[3 * r + c] += waPoints * ri[r] * bi[c];  // S += w r b^T
+        }
+    }
+    block_reduce_to_packet<12>(acc, mom_partials, mom_ticket, fs.packet + MP2P_B200_PACKET_DOUBLES, blockIdx.x, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1089,6 +1215,65 @@ int fetch_results(mp2p_b200_ctx* ctx, const unsigned long long* d_count, const R
 }
 }  // namespace
 
+// Launches k_iterate_nn1_horn if the whole grid can be co-resident; returns 1 if it cannot (the
+// caller then takes the three-kernel path), 0 after a successful launch.
+static int launch_iterate_nn1_horn(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const Pt2PtArgs& a, const CompactArgs& c,
+                                   const SmallView& sv, unsigned long long* status, unsigned long long* cand,
+                                   float4* cand_xyz, mp2p_b200_pair_pt2pt* d_out, double* d_packets, double w_pt2pt,
+                                   uint32_t n_tiles)
+{
+    static int blocks_per_sm = -1, n_sm = 0;
+    if (blocks_per_sm < 0)
+    {
+        int dev = 0, coop = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        blocks_per_sm = 0;
+        if (coop) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_iterate_nn1_horn, kScanThreads, 0);
+        const char* e = getenv("MP2P_FUSED_ITERATION");
+        if (e && atoi(e) == 0) blocks_per_sm = 0;
+    }
+    if ((uint64_t)n_tiles > (uint64_t)blocks_per_sm * (uint64_t)n_sm) return 1;
+    if (!ctx->d_coop.p)
+    {
+        MP2P_TRY(ctx->d_coop.ensure(64));
+        MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_coop.p, 0, 64, ctx->stream));
+        ctx->coop_arrivals = 0, ctx->coop_epoch = 0;
+    }
+    FusedSums fs{};
+    MP2P_TRY(solve_scratch(ctx, 2 * (size_t)n_tiles, &fs.ticket, &fs.partials));
+    fs.packet                 = d_packets;
+    double*       mom_partials = fs.partials + (size_t)n_tiles * 32;
+    unsigned int* mom_ticket   = fs.ticket + 1;
+    CoopSync      cs{};
+    cs.arrivals  = ctx->d_coop.as<unsigned long long>();
+    cs.target    = ctx->coop_arrivals + n_tiles;
+    cs.sums_flag = reinterpret_cast<unsigned int*>(ctx->d_coop.as<char>() + 16);
+    cs.epoch     = ctx->coop_epoch + 1;
+    GridView       gv = map->view;
+    Pt2PtArgs      aa = a;
+    CompactArgs    cc = c;
+    const float *  qx = ctx->cur_qx, *qy = ctx->cur_qy, *qz = ctx->cur_qz, *lx = ctx->cur_lx, *ly = ctx->cur_ly, *lz = ctx->cur_lz;
+    const uint32_t*     perm  = ctx->cur_perm;
+    unsigned long long* claim = map->d_claim.as<unsigned long long>();
+    uint32_t *          bbox = sv.bbox, *bbox_next = sv.bbox_next;
+    unsigned long long* count = sv.count;
+    void* args[] = {&gv, &aa, &cc, &qx, &qy, &qz, &lx, &ly, &lz, &perm, &claim, &cand, &cand_xyz, &bbox, &bbox_next, &status,
+                    &d_out, &count, &fs, &mom_partials, &mom_ticket, &w_pt2pt, &cs};
+    const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_iterate_nn1_horn), dim3(n_tiles),
+                                                      dim3(kScanThreads), args, 0, ctx->stream);
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        set_error("cooperative launch failed: %s", cudaGetErrorString(e));
+        return MP2P_B200_ERR_CUDA;
+    }
+    ctx->coop_arrivals += n_tiles, ctx->coop_epoch += 1;
+    count_launch(ctx);
+    return 0;
+}
+
 // ==========================================================================================
 int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
                     const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
@@ -1142,6 +1327,38 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     unsigned long long* stats = nullptr;
     MP2P_TRY(prepare_stats(ctx, &stats));
     float4* cand_xyz = nullptr;
+
+    mp2p_b200_pair_pt2pt* d_out = out;
+    if (!out_on_device)
+    {
+        MP2P_TRY(ctx->d_out2p.ensure(std::min<uint64_t>(capacity, n_slots) * sizeof(mp2p_b200_pair_pt2pt)));
+        d_out = ctx->d_out2p.as<mp2p_b200_pair_pt2pt>();
+    }
+    CompactArgs c{};
+    c.n_local = (uint32_t)n_local, c.K = K, c.allowGlobal = a.allowGlobal, c.tag = a.tag;
+    c.gate_eps = (float)(prm->threshold + prm->bounding_box_intersection_check_epsilon);
+    c.capacity = std::min<uint64_t>(capacity, n_slots);
+    c.scan_epoch = ctx->scan_epoch;
+
+    // whole iteration in one cooperative launch (k = 1, Horn sums AND moments wanted, no MatchState
+    // bits, no search statistics), when the grid fits on the device
+    if (K == 1 && keep_on_device && keep_on_device->want_horn_sums && keep_on_device->fuse_moments_w > 0.0 && !lbits &&
+        !gbits && !stats)
+    {
+        MP2P_TRY(ctx->d_candxyz.ensure(n_slots * sizeof(float4)));
+        cand_xyz = ctx->d_candxyz.as<float4>();
+        prof_begin(ctx, 0);
+        const int rc = launch_iterate_nn1_horn(ctx, map, a, c, sv, status, cand, cand_xyz, d_out, keep_on_device->want_horn_sums,
+                                               keep_on_device->fuse_moments_w, (uint32_t)n_tiles);
+        if (rc < 0) return rc;
+        if (rc == 0)
+        {
+            prof_end(ctx, 0);
+            keep_on_device->d_count = sv.count, keep_on_device->d_pairs = d_out, keep_on_device->capacity = c.capacity;
+            keep_on_device->moments_done = true;
+            return 0;
+        }
+    }
     prof_begin(ctx, 0);
 #define LAUNCH_MATCH(G)                                                                                    \
     {                                                                                                      \
@@ -1164,17 +1381,6 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     prof_end(ctx, 0);
     count_launch(ctx);
 
-    mp2p_b200_pair_pt2pt* d_out = out;
-    if (!out_on_device)
-    {
-        MP2P_TRY(ctx->d_out2p.ensure(std::min<uint64_t>(capacity, n_slots) * sizeof(mp2p_b200_pair_pt2pt)));
-        d_out = ctx->d_out2p.as<mp2p_b200_pair_pt2pt>();
-    }
-    CompactArgs c{};
-    c.n_local = (uint32_t)n_local, c.K = K, c.allowGlobal = a.allowGlobal, c.tag = a.tag;
-    c.gate_eps = (float)(prm->threshold + prm->bounding_box_intersection_check_epsilon);
-    c.capacity = std::min<uint64_t>(capacity, n_slots);
-    c.scan_epoch = ctx->scan_epoch;
     prof_begin(ctx, 1);
     FusedSums fs{nullptr, nullptr, nullptr};
     if (keep_on_device && keep_on_device->want_horn_sums)
