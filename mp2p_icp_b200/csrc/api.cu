@@ -1,6 +1,8 @@
 // C-ABI entry points (include/mp2p_b200.h). Product code: no oracle, no CPU fallback.
 #include <algorithm>
 #include <cmath>
+#include <atomic>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -182,6 +184,19 @@ extern "C"
         cudaEventCreate(&c->ev0);
         cudaEventCreate(&c->ev1);
         for (auto& e : c->pev) cudaEventCreate(&e);
+        {
+            void* hm = nullptr;
+            if (cudaHostAlloc(&hm, 1024, cudaHostAllocMapped) == cudaSuccess)
+            {
+                void* dm = nullptr;
+                std::memset(hm, 0, 1024);
+                if (cudaHostGetDevicePointer(&dm, hm, 0) == cudaSuccess)
+                    c->h_mapped = static_cast<double*>(hm), c->h_mapped_dev = static_cast<double*>(dm);
+                else
+                    cudaFreeHost(hm);
+            }
+            cudaGetLastError();
+        }
         if (cudaHostAlloc(&c->h_pinned, 4096, cudaHostAllocDefault) != cudaSuccess)
         {
             set_error("cudaHostAlloc failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -208,6 +223,7 @@ extern "C"
                           &c->d_pose, &c->d_weights, &c->d_outlier})
             b->release();
         if (c->h_pinned) cudaFreeHost(c->h_pinned);
+        if (c->h_mapped) cudaFreeHost(c->h_mapped);
         if (c->ev0) cudaEventDestroy(c->ev0);
         if (c->ev1) cudaEventDestroy(c->ev1);
         for (auto& e : c->pev)
@@ -761,9 +777,31 @@ extern "C"
         // one D2H copy brings both packets; the pairing count rides in the HORN1 packet ([6], exact
         // in a double up to 2^53)
         double* hp = pinned_packets(ctx);
-        MP2P_CUDA_TRY(cudaMemcpyAsync(hp, dp0, 2 * MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        MP2P_CUDA_TRY(cudaGetLastError());
+        bool    got = false;
+        if (dm.moments_done && ctx->h_mapped)
+        {
+            // the single-launch iteration wrote both packets into mapped host memory and raised its
+            // epoch flag: poll (bounded), no DMA copy, no stream synchronise
+            volatile unsigned int* flag = reinterpret_cast<volatile unsigned int*>(ctx->h_mapped + 2 * MP2P_B200_PACKET_DOUBLES);
+            const auto             t0   = std::chrono::steady_clock::now();
+            unsigned               spins = 0;
+            while (*flag != ctx->coop_epoch)
+            {
+                if ((++spins & 0xFFFu) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) break;
+            }
+            if (*flag == ctx->coop_epoch)
+            {
+                std::atomic_thread_fence(std::memory_order_acquire);
+                for (int k = 0; k < 2 * MP2P_B200_PACKET_DOUBLES; k++) hp[k] = ctx->h_mapped[k];
+                got = true;
+            }
+        }
+        if (!got)
+        {
+            MP2P_CUDA_TRY(cudaMemcpyAsync(hp, dp0, 2 * MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            MP2P_CUDA_TRY(cudaGetLastError());
+        }
         *n_pairs = (uint64_t)hp[6];
         if (*n_pairs > dm.capacity)
         {

@@ -148,6 +148,9 @@ struct mp2p_b200_ctx
     mp2p::DevBuf d_outlier;            // Horn scale-outlier flags
     // pinned host scratch
     void* h_pinned = nullptr;  // 4 KiB: counts, packets, poses
+    // 1 KiB of MAPPED pinned memory a kernel writes results into directly (host view / device view)
+    double* h_mapped = nullptr;
+    double* h_mapped_dev = nullptr;
 };
 
 struct mp2p_b200_map

@@ -652,6 +652,78 @@ __device__ __forceinline__ unsigned long long grid_exclusive_scan(
     return sm.tile_base + warp_off + (incl - local);
 }
 
+struct CoopSync
+{
+    unsigned long long* arrivals;  // monotonically increasing across launches (never reset)
+    unsigned long long  target;    // arrivals value that completes this launch's FIRST barrier (+ grid per further one)
+    unsigned int*       sums_flag; // epoch of the launch whose HORN1 packet is complete
+    unsigned int        epoch;
+    double*             host_out;  // mapped pinned host memory: 64 packet doubles, then the flag word
+};
+
+// barrier number `which` (0, 1, ...) of a cooperative launch: all CTAs are resident, so spinning is safe
+__device__ __forceinline__ void grid_barrier(const CoopSync& cs, unsigned which)
+{
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const unsigned long long target = cs.target + (unsigned long long)which * gridDim.x;
+        __threadfence();
+        atomicAdd(cs.arrivals, 1ull);
+        while (*reinterpret_cast<volatile unsigned long long*>(cs.arrivals) < target) __nanosleep(20);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// Exclusive scan for CO-RESIDENT tiles (cooperative launch): every tile publishes its count, one grid
+// barrier, every tile adds up the counts before it — two memory round trips instead of a look-back
+// chain that is fully serialised when all tiles start at the same moment.
+__device__ __forceinline__ unsigned long long grid_exclusive_scan_resident(
+    ScanSmem& sm, uint32_t tile, uint32_t n_tiles, uint32_t local, unsigned long long* counts,
+    unsigned long long* total_out, const CoopSync& cs, unsigned barrier_no)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t       incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) sm.warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t warp_off = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; w++)
+    {
+        const uint32_t s = sm.warp_sums[w];
+        if (w < (int)warp) warp_off += s;
+        block_total += s;
+    }
+    if (threadIdx.x == 0) counts[tile] = block_total;
+    grid_barrier(cs, barrier_no);
+    unsigned long long part = 0;
+    for (uint32_t t = threadIdx.x; t < tile; t += kScanThreads) part += __ldcg(counts + t);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __shared__ unsigned long long s_part[kScanThreads / 32];
+    if (lane == 0) s_part[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        unsigned long long base = 0;
+#pragma unroll
+        for (int w = 0; w < kScanThreads / 32; w++) base += s_part[w];
+        sm.tile_base  = base;
+        sm.tile_total = block_total;
+        if (tile == n_tiles - 1) *total_out = base + block_total;
+    }
+    __syncthreads();
+    return sm.tile_base + warp_off + (incl - local);
+}
+
+
 struct CompactArgs
 {
     uint32_t n_local, K;
@@ -700,7 +772,7 @@ __device__ __forceinline__ uint32_t compact_pt2pt_body(
     const unsigned long long* __restrict__ cand, const float4* __restrict__ cand_xyz, const uint32_t* __restrict__ bbox,
     unsigned long long* __restrict__ status, mp2p_b200_pair_pt2pt* __restrict__ out,
     unsigned long long* __restrict__ out_count, const FusedSums& fs, uint32_t tile, ScanSmem& sm, uint32_t* s_rec,
-    bool* folded_sums = nullptr)
+    bool* folded_sums = nullptr, const CoopSync* resident = nullptr)
 {
     const uint64_t n_slots = (uint64_t)a.n_local * a.K;
     const uint32_t n_tiles = (uint32_t)((n_slots + kScanTile - 1) / kScanTile);
@@ -732,7 +804,9 @@ __device__ __forceinline__ uint32_t compact_pt2pt_body(
                 ok = !bit_set(gbits, gi) && (cw == (a.tag | (unsigned long long)(slot + a.slot_offset)));
         }
     }
-    const unsigned long long w = grid_exclusive_scan(sm, tile, n_tiles, ok ? 1u : 0u, status, out_count, a.scan_epoch);
+    const unsigned long long w =
+        resident ? grid_exclusive_scan_resident(sm, tile, n_tiles, ok ? 1u : 0u, status, out_count, *resident, 1)
+                 : grid_exclusive_scan(sm, tile, n_tiles, ok ? 1u : 0u, status, out_count, a.scan_epoch);
     // The tile's records are consecutive in the output: stage them in shared memory and store the
     // byte range with fully coalesced 4-byte words (full sectors: no read-for-ownership fills),
     // instead of nine strided stores per thread.
@@ -800,27 +874,6 @@ __global__ void __launch_bounds__(kScanThreads)
 // Saves two launches, the solver's re-read of the pairings and the launch gaps; the numbers are the
 // same sums in a different grouping (poses agree to ~1e-15 with the three-kernel path).
 // ------------------------------------------------------------------------------------------
-struct CoopSync
-{
-    unsigned long long* arrivals;  // monotonically increasing across launches (never reset)
-    unsigned long long  target;    // arrivals value that completes this launch's barrier
-    unsigned int*       sums_flag; // epoch of the launch whose HORN1 packet is complete
-    unsigned int        epoch;
-};
-
-__device__ __forceinline__ void grid_barrier(const CoopSync& cs)
-{
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        __threadfence();
-        atomicAdd(cs.arrivals, 1ull);
-        while (*reinterpret_cast<volatile unsigned long long*>(cs.arrivals) < cs.target) __nanosleep(32);
-        __threadfence();
-    }
-    __syncthreads();
-}
-
 __global__ void __launch_bounds__(kScanThreads, 3)
     k_iterate_nn1_horn(GridView g, Pt2PtArgs a, CompactArgs ca, const float* __restrict__ qx, const float* __restrict__ qy,
                        const float* __restrict__ qz, const float* __restrict__ lx, const float* __restrict__ ly,
@@ -834,12 +887,12 @@ __global__ void __launch_bounds__(kScanThreads, 3)
     __shared__ uint32_t s_rec[kScanThreads * 9];
     // ---- phase 1
     nn1_body<kScanThreads>(g, a, qx, qy, qz, perm, nullptr, nullptr, claim, cand, cand_xyz, bbox, nullptr);
-    grid_barrier(cs);
+    grid_barrier(cs, 0);
     // ---- phase 2 (tile = CTA index: all CTAs are resident, the look-back cannot starve)
     bbox_rearm(bbox_next);
     bool           folded = false;  // CTA-uniform
     const uint32_t n_rec  = compact_pt2pt_body(g, ca, lx, ly, lz, nullptr, claim, cand, cand_xyz, bbox, status, out, out_count, fs,
-                                               blockIdx.x, sm, s_rec, &folded);
+                                               blockIdx.x, sm, s_rec, &folded, &cs);
     // ---- the CTA that folded the HORN1 packet publishes it; everybody waits for it
     __syncthreads();
     if (threadIdx.x == 0)
@@ -881,7 +934,23 @@ __global__ void __launch_bounds__(kScanThreads, 3)
                 for (int c = 0; c < 3; c++) acc[3 * r + c] += waPoints * ri[r] * bi[c];  // S += w r b^T
         }
     }
-    block_reduce_to_packet<12>(acc, mom_partials, mom_ticket, fs.packet + MP2P_B200_PACKET_DOUBLES, blockIdx.x, gridDim.x);
+    const bool last = block_reduce_to_packet<12>(acc, mom_partials, mom_ticket, fs.packet + MP2P_B200_PACKET_DOUBLES,
+                                                 blockIdx.x, gridDim.x);
+    if (last && cs.host_out)
+    {
+        // the CTA that folded the moments hands both packets to the host through mapped pinned memory
+        // and raises the flag: the caller polls it instead of paying a DMA copy + stream synchronise
+        __syncthreads();
+        if (threadIdx.x < 2 * MP2P_B200_PACKET_DOUBLES)
+            reinterpret_cast<volatile double*>(cs.host_out)[threadIdx.x] = __ldcg(fs.packet + threadIdx.x);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            *reinterpret_cast<volatile unsigned int*>(cs.host_out + 2 * MP2P_B200_PACKET_DOUBLES) = cs.epoch;
+            __threadfence_system();
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1248,9 +1317,10 @@ static int launch_iterate_nn1_horn(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const
     unsigned int* mom_ticket   = fs.ticket + 1;
     CoopSync      cs{};
     cs.arrivals  = ctx->d_coop.as<unsigned long long>();
-    cs.target    = ctx->coop_arrivals + n_tiles;
+    cs.target    = ctx->coop_arrivals + n_tiles;  // barrier 0; barrier 1 completes at + 2 n_tiles
     cs.sums_flag = reinterpret_cast<unsigned int*>(ctx->d_coop.as<char>() + 16);
     cs.epoch     = ctx->coop_epoch + 1;
+    cs.host_out  = ctx->h_mapped_dev;  // NULL if the mapping is not available: the caller then copies
     GridView       gv = map->view;
     Pt2PtArgs      aa = a;
     CompactArgs    cc = c;
@@ -1269,7 +1339,7 @@ static int launch_iterate_nn1_horn(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const
         set_error("cooperative launch failed: %s", cudaGetErrorString(e));
         return MP2P_B200_ERR_CUDA;
     }
-    ctx->coop_arrivals += n_tiles, ctx->coop_epoch += 1;
+    ctx->coop_arrivals += 2ull * n_tiles, ctx->coop_epoch += 1;
     count_launch(ctx);
     return 0;
 }
