@@ -12,6 +12,12 @@
  *  - `*_on_device` flags: 0 = the pointer is HOST memory (pinned memory is DMA'd directly, pageable
  *    memory goes through the CUDA staging path), 1 = the pointer is DEVICE memory on the context's
  *    GPU (lets a caller keep pairings resident between matcher and solver).
+ *  - `pairs_on_device` additionally accepts MP2P_B200_PAIRS_LAST_MATCH (2): the HOST records handed
+ *    in are, unmodified, what the last matcher call on this context returned to the host (true
+ *    between run_matchers and run_solvers, mp2p_icp/src/ICP.cpp:143-170: nothing touches the
+ *    Pairings in between). The solver then reads the copy that matcher call left in device memory
+ *    instead of uploading the same bytes again; the count must match or the call fails with
+ *    MP2P_B200_ERR_ARG. The caller vouches for the identity — the library only checks the count.
  *  - return value: 0 = MP2P_B200_OK, negative = error; text via mp2p_b200_last_error().
  *  - There is NO CPU fallback: without a CUDA device every compute entry point fails with
  *    MP2P_B200_ERR_CUDA.
@@ -33,6 +39,7 @@ extern "C" {
 #define MP2P_B200_ERR_NOMEM (-4)
 
 #define MP2P_B200_MAX_KNN 32
+#define MP2P_B200_PAIRS_LAST_MATCH 2
 
 typedef struct mp2p_b200_ctx mp2p_b200_ctx; /* one per (process, GPU): stream + scratch */
 typedef struct mp2p_b200_map mp2p_b200_map; /* device-resident global layer + NN index   */

@@ -17,6 +17,7 @@ _SO = os.environ.get("MP2P_B200_LIB") or os.path.join(_HERE, "libmp2p_b200.so") 
 
 PACKET_DOUBLES = 32
 MAX_KNN = 32
+PAIRS_LAST_MATCH = 2  # MP2P_B200_PAIRS_LAST_MATCH
 
 PAIR_PT2PT = np.dtype(
     [("globalIdx", "<u4"), ("localIdx", "<u4"), ("global", "<f4", 3), ("local", "<f4", 3), ("errSq", "<f4")]
@@ -281,9 +282,13 @@ class Context:
         return int(load_library().mp2p_b200_ctx_launch_count(self._h))
 
     # ---------------------------------------------------------------- solvers
-    def solve_horn(self, pairs, n=None, prm: HornParams = None, point_weights=None, on_device=False):
+    def solve_horn(self, pairs, n=None, prm: HornParams = None, point_weights=None, on_device=False, last_match=False):
+        """last_match=True: `pairs` is the unmodified host output of the last matcher call on this
+        context; the solver reads the copy that call left on the device (MP2P_B200_PAIRS_LAST_MATCH)."""
         prm = prm or HornParams()
-        if not on_device:
+        if last_match:
+            on_device, n = PAIRS_LAST_MATCH, len(pairs)
+        elif not on_device:
             pairs = np.ascontiguousarray(pairs, dtype=PAIR_PT2PT)
             n = pairs.size
         cp = prm.c()
@@ -298,8 +303,10 @@ class Context:
         _check(load_library().mp2p_b200_solve_horn(self._h, _ptr(pairs), C.c_uint64(n), int(on_device), C.byref(cp), _ptr(wc), _ptr(wv), C.c_uint64(nb), _ptr(T), C.byref(solved)))
         return bool(solved.value), T.reshape(3, 4)
 
-    def solve_gauss_newton(self, p2p, p2l, prm: GNParams, T_init, n2p=None, n2l=None, on_device=False):
-        if not on_device:
+    def solve_gauss_newton(self, p2p, p2l, prm: GNParams, T_init, n2p=None, n2l=None, on_device=False, last_match=False):
+        if last_match:  # see solve_horn
+            on_device, n2p, n2l = PAIRS_LAST_MATCH, (len(p2p) if p2p is not None else 0), (len(p2l) if p2l is not None else 0)
+        elif not on_device:
             p2p = np.ascontiguousarray(p2p if p2p is not None else np.zeros(0, PAIR_PT2PT), dtype=PAIR_PT2PT)
             p2l = np.ascontiguousarray(p2l if p2l is not None else np.zeros(0, PAIR_PT2PL), dtype=PAIR_PT2PL)
             n2p, n2l = p2p.size, p2l.size
@@ -502,15 +509,19 @@ class Map:
             return cnt.value
         return out[: cnt.value]
 
-    def make_iterator(self, lx, ly, lz, n_local, matcher_prm, solver_prm, pairs_device: int = 0, capacity: int = 0):
-        """Pre-binds a fused ICP iteration (device-resident local cloud) and returns a function
+    def make_iterator(self, lx, ly, lz, n_local, matcher_prm, solver_prm, pairs_device: int = 0, capacity: int = 0, local_on_device=True):
+        """Pre-binds a fused ICP iteration (device-resident local cloud, or host arrays uploaded by
+        every call with local_on_device=False) and returns a function
         pose(3x4) -> (solved, pose_out 3x4, n_pairs). All ctypes marshalling happens once here."""
         L = load_library()
         is_pt2pt = isinstance(matcher_prm, Pt2PtParams)
         mp, sp = matcher_prm.c(), solver_prm.c()
         pose_in, pose_out = (C.c_double * 12)(), (C.c_double * 12)()
         solved, n_pairs, iters, pot = C.c_int32(0), C.c_uint64(0), C.c_uint32(0), C.c_uint64(0)
-        plx, ply, plz, n_local, kind = _local(lx, ly, lz, n_local, True)
+        if not local_on_device and not isinstance(lx, Cloud):
+            lx, ly, lz = _f32(lx), _f32(ly), _f32(lz)
+        plx, ply, plz, n_local, kind = _local(lx, ly, lz, n_local, local_on_device)
+        keep_local = (lx, ly, lz)  # noqa: F841
         args = [self.ctx._h, self._h, plx, ply, plz, C.c_uint64(n_local), kind, pose_in, C.byref(mp), C.byref(sp), C.c_void_p(int(pairs_device)) if pairs_device else None, C.c_uint64(capacity), pose_out, C.byref(solved), C.byref(n_pairs)]
         if is_pt2pt:
             fn, args = L.mp2p_b200_iterate_pt2pt_horn, args + [C.byref(pot)]
@@ -527,6 +538,59 @@ class Map:
             if rc != 0:
                 _check(rc)
             return bool(solved.value), pose_out_np.copy(), int(n_pairs.value)
+
+        return step
+
+    def make_plugin_step(self, hx, hy, hz, matcher_prm, solver_prm, out_pairs, reuse_device_pairs=True):
+        """Pre-binds what the reference's ICP loop does per iteration through the two plugin classes
+        (run_matchers then run_solvers, ICP.cpp:143,170) over HOST buffers: a matcher call that
+        uploads the local cloud `hx, hy, hz` and returns the pairings into `out_pairs` (host), then a
+        solver call over those host pairings. reuse_device_pairs: the solver names them as the
+        unmodified output of the last matcher call (MP2P_B200_PAIRS_LAST_MATCH, what the plugin's
+        witness check does) instead of uploading them again. Returns pose(3x4) -> (solved, pose_out,
+        n_pairs); all ctypes marshalling happens once here."""
+        L = load_library()
+        is_pt2pt = isinstance(matcher_prm, Pt2PtParams)
+        mp, sp = matcher_prm.c(), solver_prm.c()
+        hx, hy, hz = _f32(hx), _f32(hy), _f32(hz)
+        n_local = hx.size
+        pose_in, pose_out = (C.c_double * 12)(), (C.c_double * 12)()
+        solved, cnt, pot, iters = C.c_int32(0), C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+        cap = out_pairs.size
+        origin = PAIRS_LAST_MATCH if reuse_device_pairs else 0
+        n_arg = C.c_uint64(0)
+        if is_pt2pt:
+            m_fn = L.mp2p_b200_match_pt2pt
+            m_args = [self.ctx._h, self._h, _ptr(hx), _ptr(hy), _ptr(hz), C.c_uint64(n_local), 0, pose_in, C.byref(mp), None, None, _ptr(out_pairs), C.c_uint64(cap), 0, C.byref(cnt), C.byref(pot)]
+        else:
+            m_fn = L.mp2p_b200_match_pt2pl
+            m_args = [self.ctx._h, self._h, _ptr(hx), _ptr(hy), _ptr(hz), C.c_uint64(n_local), 0, pose_in, C.byref(mp), None, _ptr(out_pairs), C.c_uint64(cap), 0, C.byref(cnt), C.byref(pot)]
+        if isinstance(solver_prm, HornParams):
+            s_fn = L.mp2p_b200_solve_horn
+            s_args = [self.ctx._h, _ptr(out_pairs), n_arg, origin, C.byref(sp), None, None, C.c_uint64(0), pose_out, C.byref(solved)]
+            n_idx = 2
+        elif is_pt2pt:
+            s_fn = L.mp2p_b200_solve_gauss_newton
+            s_args = [self.ctx._h, _ptr(out_pairs), n_arg, None, C.c_uint64(0), origin, C.byref(sp), pose_in, pose_out, C.byref(iters), C.byref(solved)]
+            n_idx = 2
+        else:
+            s_fn = L.mp2p_b200_solve_gauss_newton
+            s_args = [self.ctx._h, None, C.c_uint64(0), _ptr(out_pairs), n_arg, origin, C.byref(sp), pose_in, pose_out, C.byref(iters), C.byref(solved)]
+            n_idx = 4
+        keep = (mp, sp, hx, hy, hz, out_pairs)  # noqa: F841
+        pose_in_np = np.frombuffer(pose_in, dtype=np.float64)
+        pose_out_np = np.frombuffer(pose_out, dtype=np.float64).reshape(3, 4)
+
+        def step(T):
+            pose_in_np[:] = np.asarray(T, dtype=np.float64).reshape(-1)
+            rc = m_fn(*m_args)
+            if rc != 0:
+                _check(rc)
+            s_args[n_idx] = C.c_uint64(cnt.value)
+            rc = s_fn(*s_args)
+            if rc != 0:
+                _check(rc)
+            return bool(solved.value), pose_out_np.copy(), int(cnt.value)
 
         return step
 

@@ -91,6 +91,20 @@ int count_on_device(mp2p_b200_ctx* ctx, uint64_t* n, int pairs_on_device, const 
 template <class Rec>
 int stage_pairs(mp2p_b200_ctx* ctx, DevBuf& buf, const Rec* pairs, uint64_t n, int on_device, const Rec** d_out)
 {
+    if (on_device == MP2P_B200_PAIRS_LAST_MATCH && n)
+    {
+        // the caller's host records ARE the output of the last matcher call (it vouches for that):
+        // read the copy that call left in device memory instead of uploading them again
+        const mp2p_b200_ctx::LastMatch& lm = sizeof(Rec) == sizeof(mp2p_b200_pair_pt2pt) ? ctx->last2p : ctx->last2l;
+        if (!lm.valid || lm.n != n)
+        {
+            set_error("MP2P_B200_PAIRS_LAST_MATCH: no device copy of %llu pairings (the last matcher call left %llu%s)",
+                      (unsigned long long)n, (unsigned long long)lm.n, lm.valid ? "" : ", invalid");
+            return MP2P_B200_ERR_ARG;
+        }
+        *d_out = static_cast<const Rec*>(lm.dev);
+        return 0;
+    }
     if (on_device || n == 0)
     {
         *d_out = pairs;
@@ -580,10 +594,21 @@ extern "C"
         double* dp0 = ctx->d_packet.as<double>();
         double* dp1 = dp0 + MP2P_B200_PACKET_DOUBLES;
         double* hp  = pinned_packets(ctx);
-        // round 1 (optimal_tf_horn.cpp:216-221): centroids over all pairs, then S
-        MP2P_TRY(run_horn_sums(ctx, d, n, nullptr, dp0));
-        MP2P_TRY(run_horn_moments(ctx, d, n, prm, dp0, n, d_wprefix, d_wvalue, (uint32_t)n_weight_blocks, d_outl, dp1));
-        MP2P_CUDA_TRY(cudaMemcpyAsync(hp, dp0, 2 * MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        // round 1 (optimal_tf_horn.cpp:216-221): centroids over all pairs, then S. The centroid sums
+        // of the last matcher call's output were already produced by its compaction kernel.
+        const double* dsums = dp0;
+        if (pairs_on_device == MP2P_B200_PAIRS_LAST_MATCH && ctx->last2p.sums)
+            dsums = ctx->last2p.sums;
+        else
+            MP2P_TRY(run_horn_sums(ctx, d, n, nullptr, dp0));
+        MP2P_TRY(run_horn_moments(ctx, d, n, prm, dsums, n, d_wprefix, d_wvalue, (uint32_t)n_weight_blocks, d_outl, dp1));
+        if (dsums == dp0)
+            MP2P_CUDA_TRY(cudaMemcpyAsync(hp, dp0, 2 * MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        else
+        {
+            MP2P_CUDA_TRY(cudaMemcpyAsync(hp, dsums, MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            MP2P_CUDA_TRY(cudaMemcpyAsync(hp + MP2P_B200_PACKET_DOUBLES, dp1, MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        }
         MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         MP2P_CUDA_TRY(cudaGetLastError());
         if (prm->use_scale_outlier_detector && hp[MP2P_B200_PACKET_DOUBLES + 10] > 0)  // :224-235

@@ -110,6 +110,16 @@ struct mp2p_b200_ctx
     // out_count == NULL), consumed by solver calls given n = MP2P_B200_COUNT_ON_DEVICE
     const unsigned long long* last_count    = nullptr;
     uint64_t                  last_capacity = 0;
+    // device-resident copy of the pairings the last matcher call returned to the HOST (d_out2p /
+    // d_out2l): a solver call given pairs_on_device = MP2P_B200_PAIRS_LAST_MATCH reads it instead of
+    // uploading the same records again
+    struct LastMatch
+    {
+        const void*   dev   = nullptr;
+        uint64_t      n     = 0;
+        bool          valid = false;
+        const double* sums  = nullptr;  // pt2pt: HORN1 packet the compaction produced on the way (device)
+    } last2p, last2l;
     // grid barrier state of the single-launch iteration (match.cu): counters only ever grow
     mp2p::DevBuf       d_coop;
     unsigned long long coop_arrivals = 0;

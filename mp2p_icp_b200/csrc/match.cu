@@ -1269,6 +1269,11 @@ int fetch_results(mp2p_b200_ctx* ctx, const unsigned long long* d_count, const R
     const uint64_t cnt = *h_count;
     *out_count         = cnt;
     *hint              = cnt;
+    if (!out_on_device)  // the device copy outlives the call: solver calls may name it (PAIRS_LAST_MATCH)
+    {
+        mp2p_b200_ctx::LastMatch& lm = sizeof(Rec) == sizeof(mp2p_b200_pair_pt2pt) ? ctx->last2p : ctx->last2l;
+        lm.dev = d_pairs, lm.n = cnt, lm.valid = cnt <= capacity;
+    }
     if (cnt > capacity)
     {
         set_error("output capacity %llu too small for %llu pairings", (unsigned long long)capacity,
@@ -1353,6 +1358,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
 {
     *out_count          = 0;
     if (keep_on_device) keep_on_device->d_count = nullptr, keep_on_device->d_pairs = nullptr, keep_on_device->capacity = 0;
+    ctx->last2p.valid = false, ctx->last2p.sums = nullptr;
     const uint32_t K    = prm->pairingsPerPoint;
     const uint64_t nmap = map->view.n_points;
     if (nmap == 0 || n_local == 0) return 0;  // …DistanceThreshold.cpp:67
@@ -1457,6 +1463,14 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     {
         MP2P_TRY(solve_scratch(ctx, n_tiles, &fs.ticket, &fs.partials));
         fs.packet = keep_on_device->want_horn_sums;
+    }
+    else if (!keep_on_device && !out_on_device)
+    {
+        // host output: the records also stay in d_out2p for a solver call that names them
+        // (PAIRS_LAST_MATCH); the centroid sums of Solver_Horn's first pass cost nothing here
+        MP2P_TRY(solve_scratch(ctx, n_tiles, &fs.ticket, &fs.partials));
+        fs.packet        = ctx->d_packet.as<double>() + 4 * MP2P_B200_PACKET_DOUBLES;
+        ctx->last2p.sums = fs.packet;
     }
     k_compact_pt2pt<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, c, dlx, dly, dlz, d_gbits,
                                                                claim, cand, cand_xyz, sv.bbox, sv.bbox_next, status,
@@ -1584,6 +1598,7 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
 {
     if (out_count) *out_count = 0;
     ctx->last_count = nullptr, ctx->last_capacity = 0;
+    ctx->last2p.valid = false, ctx->last2p.sums = nullptr;
     const uint32_t K    = prm->pairingsPerPoint;
     const uint64_t nmap = map->view.n_points;
     const uint64_t per_k = per_shard * K, rec_words = shard_record_words(per_shard, K);
@@ -1659,6 +1674,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
 {
     *out_count          = 0;
     if (keep_on_device) *keep_on_device = DeviceMatch{};
+    ctx->last2l.valid   = false;
     const uint64_t nmap = map->view.n_points;
     if (nmap == 0 || n_local == 0) return 0;
     if (n_local >= 0xFFFFFFFFull || prm->knn < 1 || prm->knn > MP2P_B200_MAX_KNN)

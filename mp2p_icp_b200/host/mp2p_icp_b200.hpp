@@ -286,6 +286,27 @@ class Device
         }
         return reinterpret_cast<const float*>(e.cloud);  // passed as `lx` with MP2P_B200_LOCAL_CLOUD
     }
+    /** Witness of the pairings a matcher call just returned to the host: the count and 8 sample
+     *  records. A solver that is handed a list with the same count and the same samples takes it
+     *  for that output (nothing modifies the Pairings between run_matchers and run_solvers,
+     *  ICP.cpp:143-170) and lets the library read its device-resident copy
+     *  (MP2P_B200_PAIRS_LAST_MATCH) instead of uploading the records again. */
+    template <class Rec>
+    void note_match_output(const Rec* recs, size_t n)
+    {
+        Witness& w = sizeof(Rec) == sizeof(mp2p_b200_pair_pt2pt) ? wit2p_ : wit2l_;
+        w.n        = n;
+        for (size_t k = 0; k < 8 && n; k++) std::memcpy(w.sample[k], &recs[k * (n - 1) / 7], sizeof(Rec));
+    }
+    template <class Rec>
+    bool is_last_match_output(const Rec* recs, size_t n) const
+    {
+        const Witness& w = sizeof(Rec) == sizeof(mp2p_b200_pair_pt2pt) ? wit2p_ : wit2l_;
+        if (!n || w.n != n) return false;
+        for (size_t k = 0; k < 8; k++)
+            if (std::memcmp(w.sample[k], &recs[k * (n - 1) / 7], sizeof(Rec)) != 0) return false;
+        return true;
+    }
     void forget(const CPointsMap& layer)
     {
         auto it = cache_.find(&layer);
@@ -315,8 +336,14 @@ class Device
         uint64_t         cloud_stamp = 0;
         size_t           cloud_n     = 0;
     };
+    struct Witness
+    {
+        size_t        n = ~size_t(0);
+        unsigned char sample[8][sizeof(mp2p_b200_pair_pt2pl)];
+    };
     mp2p_b200_ctx*                      ctx_ = nullptr;
     std::map<const CPointsMap*, Entry>  cache_;
+    Witness                             wit2p_, wit2l_;
 };
 
 // ---- Matcher hierarchy -----------------------------------------------------------------------
@@ -445,6 +472,7 @@ class Matcher_Points_DistanceThreshold : public Matcher_Points_Base
               "mp2p_b200_match_pt2pt");
         out.paired_pt2pt.resize(before + cnt);
         out.potential_pairings += pot;
+        dev.note_match_output(out.paired_pt2pt.data() + before, before == 0 ? cnt : 0);
         if (!allowMatchAlreadyMatchedGlobalPoints_)  // lambdaAddPair :116-120
             for (size_t i = before; i < out.paired_pt2pt.size(); i++)
             {
@@ -486,6 +514,7 @@ class Matcher_Point2Plane : public Matcher_Points_Base
               "mp2p_b200_match_pt2pl");
         out.paired_pt2pl.resize(before + cnt);
         out.potential_pairings += pot;
+        dev.note_match_output(out.paired_pt2pl.data() + before, before == 0 ? cnt : 0);
         // Matcher_Point2Plane.cpp:109 — the local point is marked; which one it was is recoverable
         // from pt_local only through the coordinates, so re-identify by a parallel walk (the output
         // is in ascending local index and each local point pairs at most once).
@@ -619,7 +648,11 @@ class Solver_Horn : public Solver
         std::vector<double>   wv;
         for (const auto& b : pairings.point_weights) wc.push_back(b.first), wv.push_back(b.second);
         int32_t solved = 0;
-        check(mp2p_b200_solve_horn(Device::instance().ctx(), pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size(), 0,
+        Device&   dev    = Device::instance();
+        const int origin = dev.is_last_match_output(pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size())
+                               ? MP2P_B200_PAIRS_LAST_MATCH
+                               : 0;
+        check(mp2p_b200_solve_horn(dev.ctx(), pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size(), origin,
                                    &prm, wc.data(), wv.data(), wc.size(), out.optimalPose.m, &solved),
               "mp2p_b200_solve_horn");
         return solved != 0;
@@ -649,8 +682,15 @@ class Solver_GaussNewton : public Solver
         mp2p_b200_gn_params prm{maxIterations, 1e-7, 0.0, w_pt2pt, w_pt2pl, robust_kernel_from_string(robustKernel), robustKernelParam};
         uint32_t            iters  = 0;
         int32_t             solved = 0;
-        check(mp2p_b200_solve_gauss_newton(Device::instance().ctx(), pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size(),
-                                           pairings.paired_pt2pl.data(), pairings.paired_pt2pl.size(), 0, &prm,
+        Device&    dev   = Device::instance();
+        const auto &l2p = pairings.paired_pt2pt;
+        const auto &l2l = pairings.paired_pt2pl;
+        // every non-empty list must be the witnessed output of the last matcher call of its kind
+        const bool last  = (l2p.empty() || dev.is_last_match_output(l2p.data(), l2p.size())) &&
+                          (l2l.empty() || dev.is_last_match_output(l2l.data(), l2l.size())) && !pairings.empty();
+        check(mp2p_b200_solve_gauss_newton(dev.ctx(), pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size(),
+                                           pairings.paired_pt2pl.data(), pairings.paired_pt2pl.size(),
+                                           last ? MP2P_B200_PAIRS_LAST_MATCH : 0, &prm,
                                            sc.guessRelativePose->m, out.optimalPose.m, &iters, &solved),
               "mp2p_b200_solve_gauss_newton");
         return solved != 0;

@@ -24,6 +24,7 @@
 #include <mrpt/maps/CPointsMap.h>
 #include <mrpt/rtti/CObject.h>
 
+#include <cstring>
 #include <mutex>
 #include <unordered_map>
 
@@ -119,6 +120,40 @@ inline MapCache& cache()
     static MapCache c;
     return c;
 }
+// Witness of the pairings a matcher call just returned to the host (count + 8 sample records). A
+// solver handed a list with the same count and samples takes it for that output — nothing modifies
+// the Pairings between run_matchers and run_solvers (ICP.cpp:143-170) — and passes
+// MP2P_B200_PAIRS_LAST_MATCH, so the library reads the copy still resident on the device instead of
+// uploading the same records again.
+struct Witness
+{
+    size_t        n = ~size_t(0);
+    unsigned char sample[8][sizeof(mp2p_b200_pair_pt2pl)];
+    template <class Rec>
+    void note(const Rec* recs, size_t cnt)
+    {
+        n = cnt;
+        for (size_t k = 0; k < 8 && cnt; k++) std::memcpy(sample[k], &recs[k * (cnt - 1) / 7], sizeof(Rec));
+    }
+    template <class Rec>
+    bool same(const Rec* recs, size_t cnt) const
+    {
+        if (!cnt || cnt != n) return false;
+        for (size_t k = 0; k < 8; k++)
+            if (std::memcmp(sample[k], &recs[k * (cnt - 1) / 7], sizeof(Rec)) != 0) return false;
+        return true;
+    }
+};
+inline Witness& witness2p()
+{
+    static Witness w;
+    return w;
+}
+inline Witness& witness2l()
+{
+    static Witness w;
+    return w;
+}
 inline std::vector<uint32_t> to_bits(const pointcloud_bitfield_t::DenseOrSparseBitField& bf, size_t n)
 {
     std::vector<uint32_t> w((n + 31) / 32, 0u);
@@ -194,6 +229,7 @@ class Matcher_Points_DistanceThreshold_B200 : public Matcher_Points_Base
                                     lx.size() * pairingsPerPoint, 0, &cnt, &pot));
         out.paired_pt2pt.resize(before + cnt);
         out.potential_pairings += pot;
+        witness2p().note(out.paired_pt2pt.data() + before, before == 0 ? cnt : 0);
         if (!allowMatchAlreadyMatchedGlobalPoints_)  // lambdaAddPair, …DistanceThreshold.cpp:116-120
             for (size_t i = before; i < out.paired_pt2pt.size(); i++)
             {
@@ -231,7 +267,11 @@ class Solver_Horn_B200 : public Solver_Horn
         double  T[12];
         int32_t solved = 0;
         check(mp2p_b200_solve_horn(ctx(), reinterpret_cast<const mp2p_b200_pair_pt2pt*>(pairings.paired_pt2pt.data()),
-                                   pairings.paired_pt2pt.size(), 0, &p, wc.data(), wv.data(), wc.size(), T, &solved));
+                                   pairings.paired_pt2pt.size(),
+                                   witness2p().same(pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size())
+                                       ? MP2P_B200_PAIRS_LAST_MATCH
+                                       : 0,
+                                   &p, wc.data(), wv.data(), wc.size(), T, &solved));
         if (!solved) return false;
         mrpt::math::CMatrixDouble44 M = mrpt::math::CMatrixDouble44::Identity();
         for (int r = 0; r < 3; r++)
@@ -293,6 +333,7 @@ class Matcher_Point2Plane_B200 : public Matcher_Points_Base
                                     lx.size(), 0, &cnt, &pot));
         out.paired_pt2pl.resize(before + cnt);
         out.potential_pairings += pot;
+        witness2l().note(out.paired_pt2pl.data() + before, before == 0 ? cnt : 0);
         // Matcher_Point2Plane.cpp:105-109: only the local point is marked. point_plane_pair_t carries
         // the local COORDINATES, not the index: re-identify by a parallel walk (the output is in
         // ascending local index and each local point pairs at most once)
@@ -336,10 +377,14 @@ class Solver_GaussNewton_B200 : public Solver_GaussNewton
         pose12(mrpt::poses::CPose3D(sc.guessRelativePose.value()), T0);
         int32_t  solved = 0;
         uint32_t iters  = 0;
-        check(mp2p_b200_solve_gauss_newton(ctx(), reinterpret_cast<const mp2p_b200_pair_pt2pt*>(pairings.paired_pt2pt.data()),
-                                           pairings.paired_pt2pt.size(),
-                                           reinterpret_cast<const mp2p_b200_pair_pt2pl*>(pairings.paired_pt2pl.data()),
-                                           pairings.paired_pt2pl.size(), 0, &p, T0, T, &iters, &solved));
+        // every non-empty list must be the witnessed output of the last matcher call of its kind
+        const auto& l2p  = pairings.paired_pt2pt;
+        const auto& l2l  = pairings.paired_pt2pl;
+        const bool  last = (l2p.empty() || witness2p().same(l2p.data(), l2p.size())) &&
+                          (l2l.empty() || witness2l().same(l2l.data(), l2l.size())) && !(l2p.empty() && l2l.empty());
+        check(mp2p_b200_solve_gauss_newton(ctx(), reinterpret_cast<const mp2p_b200_pair_pt2pt*>(l2p.data()), l2p.size(),
+                                           reinterpret_cast<const mp2p_b200_pair_pt2pl*>(l2l.data()), l2l.size(),
+                                           last ? MP2P_B200_PAIRS_LAST_MATCH : 0, &p, T0, T, &iters, &solved));
         if (!solved) return false;
         mrpt::math::CMatrixDouble44 M = mrpt::math::CMatrixDouble44::Identity();
         for (int r = 0; r < 3; r++)

@@ -503,6 +503,55 @@ def test_fused_iteration_pt2pl_gn_equals_two_calls(ctx):
     assert_pose_close(T, T0)
 
 
+# --------------------------------------------------------------------------- solver over the matcher's device copy
+def test_solver_reads_last_match_device_copy(ctx):
+    """MP2P_B200_PAIRS_LAST_MATCH: a solver handed the unmodified host output of the last matcher
+    call reads the copy that call left on the device — same pose as uploading the records again
+    (and as the oracle); a count that does not belong to the last matcher call is refused."""
+    M, L, gt = _c2(200_000, 10)
+    gmap = b200.Map(ctx, *xyz(M))
+    guess = fx.pose_xyzypr(0.25, -0.15, 0.08, 1.7 * DEG, -0.8 * DEG, 1.2 * DEG)
+    pairs, _ = gmap.match_pt2pt(*xyz(L), guess, b200.Pt2PtParams(threshold=1.0))
+    ok_a, T_a = ctx.solve_horn(pairs, last_match=True)
+    ok_b, T_b = ctx.solve_horn(pairs)
+    ok_c, T_c = orc.optimal_tf_horn(pairs)
+    assert ok_a and ok_b and ok_c
+    assert_pose_close(T_a, T_b, 1e-12)
+    assert_pose_close(T_a, T_c)
+    gn = b200.GNParams(maxInnerLoopIterations=4)
+    ok_a, T_a, it_a = ctx.solve_gauss_newton(pairs, None, gn, guess, last_match=True)
+    ok_b, T_b, it_b = ctx.solve_gauss_newton(pairs, None, gn, guess)
+    assert ok_a and ok_b and it_a == it_b
+    assert_pose_close(T_a, T_b, 1e-12)
+    with pytest.raises(b200.Mp2pError):
+        ctx.solve_horn(pairs[:-1], last_match=True)
+    # a later matcher call replaces the copy: the old list no longer qualifies unless the count matches
+    pairs2, _ = gmap.match_pt2pt(*xyz(L[: len(L) // 2]), guess, b200.Pt2PtParams(threshold=1.0))
+    assert len(pairs2) != len(pairs)
+    with pytest.raises(b200.Mp2pError):
+        ctx.solve_horn(pairs, last_match=True)
+    ok_a, T_a = ctx.solve_horn(pairs2, last_match=True)
+    assert_pose_close(T_a, orc.optimal_tf_horn(pairs2)[1])
+    # pt2pl list + Gauss-Newton, and the pre-bound plugin step (matcher call + solver call over host buffers)
+    S = fx.make_street_scene(n_map=200_000, length=40.0)
+    scan = fx.make_lidar_scan((20.0, 0.3, 0.0), n_rings=16, n_az=400, length=40.0)
+    g2 = fx.pose_xyzypr(20.05, 0.28, 0.01, 0.01, 0.0, 0.0)
+    smap = b200.Map(ctx, *xyz(S))
+    mprm = b200.Pt2PlParams(distanceThreshold=0.5, searchRadius=1.0, knn=8, minimumPlanePoints=5, planeEigenThreshold=0.01)
+    sprm = b200.GNParams(maxInnerLoopIterations=3, kernel="GemanMcClure", kernelParam=0.15)
+    q, _ = smap.match_pt2pl(*xyz(scan), g2, mprm)
+    ok_a, T_a, _ = ctx.solve_gauss_newton(None, q, sprm, g2, last_match=True)
+    ok_b, T_b, _ = ctx.solve_gauss_newton(None, q, sprm, g2)
+    assert ok_a and ok_b
+    assert_pose_close(T_a, T_b, 1e-12)
+    out = np.empty(len(scan), b200.PAIR_PT2PL)
+    for reuse in (True, False):
+        step = smap.make_plugin_step(*xyz(scan), mprm, sprm, out, reuse_device_pairs=reuse)
+        ok, T, n = step(g2)
+        assert ok and n == len(q) and out[:n].tobytes() == q.tobytes()
+        assert_pose_close(T, T_b, 1e-12)
+
+
 # --------------------------------------------------------------------------- resident (Morton-sorted) local cloud
 @pytest.mark.parametrize("kw", [dict(threshold=1.0), dict(threshold=2.5, pairingsPerPoint=3), dict(threshold=1.0, thresholdAngularDeg=0.5, allowMatchAlreadyMatchedGlobalPoints=True)])
 def test_resident_cloud_pt2pt_is_invisible(ctx, kw):
