@@ -262,6 +262,22 @@ int mp2p_b200_solve_horn(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* pairs, 
                          const uint64_t* weight_counts, const double* weight_values,
                          uint64_t n_weight_blocks, double pose_out[12], int32_t* solved);
 
+/* pt2ln_pl_to_pt2pt, plane part (mp2p_icp/src/pt2ln_pl_to_pt2pt.cpp:25-83): what Solver_Horn does to
+ * pt2pl pairings before optimal_tf_horn (Solver_Horn.cpp:51-55) — each pairing becomes the pt2pt
+ * pairing {local point -> its projection on the plane, computed at guess_pose}; those whose
+ * |distance| reaches 25 % of the largest one are kept, or the 3 largest. Indices are 0 (dummies) and
+ * errorSquareAfterTransformation is 0, as in the reference. ORDER: the reference emits the records by
+ * descending |distance| (multimap walk); this call keeps the input order — Horn's sums do not depend
+ * on it. mp2p_b200_solve_horn_pt2pl = conversion + optimal_tf_horn without leaving the device. */
+int mp2p_b200_pt2pl_to_pt2pt(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pl* pairs, uint64_t n,
+                             int pairs_on_device, const double guess_pose[12],
+                             mp2p_b200_pair_pt2pt* out_pairs, uint64_t capacity, int out_on_device,
+                             uint64_t* out_count);
+int mp2p_b200_solve_horn_pt2pl(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pl* pairs, uint64_t n,
+                               int pairs_on_device, const double guess_pose[12],
+                               const mp2p_b200_horn_params* params, double pose_out[12],
+                               int32_t* solved);
+
 /* optimal_tf_gauss_newton (mp2p_icp/src/optimal_tf_gauss_newton.cpp:36-372), pt2pt + pt2pl terms
  * (error_point2point / error_point2plane, errorTerms.cpp:36-66,115-161; robust_kernels.h:57-94).
  * H and g are zeroed every inner iteration. */

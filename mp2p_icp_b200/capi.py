@@ -161,6 +161,7 @@ EXPORTS = [
     "mp2p_b200_cloud_create", "mp2p_b200_cloud_destroy", "mp2p_b200_cloud_get_info",
     "mp2p_b200_shard_record_words",
     "mp2p_b200_gn_device_begin", "mp2p_b200_gn_device_accumulate", "mp2p_b200_gn_device_step",
+    "mp2p_b200_pt2pl_to_pt2pt", "mp2p_b200_solve_horn_pt2pl",
 ]
 GN_STATE_DOUBLES = 16
 COUNT_ON_DEVICE = (1 << 64) - 1  # MP2P_B200_COUNT_ON_DEVICE
@@ -301,6 +302,24 @@ class Context:
         T = np.zeros(12)
         solved = C.c_int32(0)
         _check(load_library().mp2p_b200_solve_horn(self._h, _ptr(pairs), C.c_uint64(n), int(on_device), C.byref(cp), _ptr(wc), _ptr(wv), C.c_uint64(nb), _ptr(T), C.byref(solved)))
+        return bool(solved.value), T.reshape(3, 4)
+
+    def pt2pl_to_pt2pt(self, p2l, T_guess):
+        """pt2ln_pl_to_pt2pt (plane part): host pt2pl records -> host pt2pt records (input order)."""
+        p2l = np.ascontiguousarray(p2l, dtype=PAIR_PT2PL)
+        out = np.zeros(max(p2l.size, 1), PAIR_PT2PT)
+        cnt = C.c_uint64(0)
+        _check(load_library().mp2p_b200_pt2pl_to_pt2pt(self._h, _ptr(p2l) if p2l.size else None, C.c_uint64(p2l.size), 0, _ptr(_pose(T_guess)), _ptr(out), C.c_uint64(out.size), 0, C.byref(cnt)))
+        return out[: cnt.value]
+
+    def solve_horn_pt2pl(self, p2l, T_guess, prm: HornParams = None, last_match=False):
+        """Solver_Horn over pt2pl pairings: conversion + optimal_tf_horn, all on the device."""
+        prm = prm or HornParams()
+        p2l = np.ascontiguousarray(p2l, dtype=PAIR_PT2PL)
+        cp = prm.c()
+        T = np.zeros(12)
+        solved = C.c_int32(0)
+        _check(load_library().mp2p_b200_solve_horn_pt2pl(self._h, _ptr(p2l) if p2l.size else None, C.c_uint64(p2l.size), PAIRS_LAST_MATCH if last_match else 0, _ptr(_pose(T_guess)), C.byref(cp), _ptr(T), C.byref(solved)))
         return bool(solved.value), T.reshape(3, 4)
 
     def solve_gauss_newton(self, p2p, p2l, prm: GNParams, T_init, n2p=None, n2l=None, on_device=False, last_match=False):

@@ -627,6 +627,60 @@ extern "C"
         return mp2p_b200_horn_finish(hp, hp + MP2P_B200_PACKET_DOUBLES, pose_out, solved);
     }
 
+    // ------------------------------------------------------------------------------ pt2pl -> pt2pt (Horn)
+    int mp2p_b200_pt2pl_to_pt2pt(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pl* pairs, uint64_t n, int pairs_on_device,
+                                 const double guess_pose[12], mp2p_b200_pair_pt2pt* out, uint64_t capacity,
+                                 int out_on_device, uint64_t* out_count)
+    {
+        if (!ctx || !guess_pose || !out_count || (n && !pairs) || (capacity && !out))
+        {
+            set_error("pt2pl_to_pt2pt: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        *out_count = 0;
+        if (n == 0) return 0;
+        DeviceGuard                 g(ctx->device);
+        const mp2p_b200_pair_pt2pl* d_in;
+        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2l, pairs, n, pairs_on_device, &d_in));
+        mp2p_b200_pair_pt2pt* d_out = out;
+        const uint64_t        cap   = std::min<uint64_t>(capacity, n);
+        if (!out_on_device)
+        {
+            MP2P_TRY(ctx->d_pairs2p.ensure(cap * sizeof(mp2p_b200_pair_pt2pt)));
+            d_out = ctx->d_pairs2p.as<mp2p_b200_pair_pt2pt>();
+        }
+        MP2P_TRY(run_pt2pl_to_pt2pt(ctx, d_in, n, guess_pose, d_out, cap, out_count));
+        if (!out_on_device && *out_count)
+        {
+            MP2P_CUDA_TRY(cudaMemcpyAsync(out, d_out, *out_count * sizeof(mp2p_b200_pair_pt2pt), cudaMemcpyDeviceToHost, ctx->stream));
+            MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+        return 0;
+    }
+
+    int mp2p_b200_solve_horn_pt2pl(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pl* pairs, uint64_t n, int pairs_on_device,
+                                   const double guess_pose[12], const mp2p_b200_horn_params* prm, double pose_out[12],
+                                   int32_t* solved)
+    {
+        if (!ctx || !guess_pose || !prm || !pose_out || !solved || (n && !pairs))
+        {
+            set_error("solve_horn_pt2pl: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        *solved = 0;
+        if (n == 0) return 0;
+        uint64_t kept = 0;
+        {
+            DeviceGuard                 g(ctx->device);
+            const mp2p_b200_pair_pt2pl* d_in;
+            MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2l, pairs, n, pairs_on_device, &d_in));
+            MP2P_TRY(ctx->d_pairs2p.ensure(n * sizeof(mp2p_b200_pair_pt2pt)));
+            MP2P_TRY(run_pt2pl_to_pt2pt(ctx, d_in, n, guess_pose, ctx->d_pairs2p.as<mp2p_b200_pair_pt2pt>(), n, &kept));
+        }
+        return mp2p_b200_solve_horn(ctx, ctx->d_pairs2p.as<mp2p_b200_pair_pt2pt>(), kept, 1, prm, nullptr, nullptr, 0,
+                                    pose_out, solved);
+    }
+
     // ------------------------------------------------------------------------------ Gauss-Newton
     int mp2p_b200_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* p2p, uint64_t n2p,
                                 const mp2p_b200_pair_pt2pl* p2l, uint64_t n2l, int pairs_on_device,

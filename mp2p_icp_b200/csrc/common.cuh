@@ -156,6 +156,7 @@ struct mp2p_b200_ctx
     mp2p::DevBuf d_pose;               // 12 doubles + flags
     mp2p::DevBuf d_weights;            // run-length point weights
     mp2p::DevBuf d_outlier;            // Horn scale-outlier flags
+    mp2p::DevBuf d_conv;               // pt2pl -> pt2pt conversion scratch and output
     // pinned host scratch
     void* h_pinned = nullptr;  // 4 KiB: counts, packets, poses
     // 1 KiB of MAPPED pinned memory a kernel writes results into directly (host view / device view)
@@ -257,6 +258,9 @@ int run_gn_device_loop(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint
                        const unsigned long long* d_n2p = nullptr, const unsigned long long* d_n2l = nullptr);
 int run_gn_step(mp2p_b200_ctx* ctx, const double* d_packet, const mp2p_b200_gn_params* prm, double* d_pose,
                 uint32_t* d_state);
+// pt2ln_pl_to_pt2pt (plane part) on the device; synchronises, *h_total = records kept
+int run_pt2pl_to_pt2pt(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pl* d_in, uint64_t n, const double pose[12],
+                       mp2p_b200_pair_pt2pt* d_out, uint64_t capacity, uint64_t* h_total);
 int run_horn_sums(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n,
                   const uint8_t* d_outlier, double* d_packet, const unsigned long long* d_n = nullptr);
 int run_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n,

@@ -16,6 +16,9 @@
 //
 // Pair records are AoS (36 / 72 bytes). A warp stages 32 consecutive records with fully coalesced
 // 128-byte loads into shared memory and each lane then reads its own record (stride 9 / 18 words).
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 #include "host_math.hpp"
 #include "reduce.cuh"
@@ -465,6 +468,188 @@ int run_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64
                                                              d_packet, d_n);
     prof_end(ctx, 3);
     count_launch(ctx);
+    return 0;
+}
+// ------------------------------------------------------------------------------------------
+// pt2ln_pl_to_pt2pt, plane part (pt2ln_pl_to_pt2pt.cpp:25-113): Solver_Horn turns every pt2pl
+// pairing into a pt2pt pairing "local point -> its projection on the plane" (Solver_Horn.cpp:51-55)
+// and keeps those whose |distance| is at least 25 % of the largest (or the 3 largest).
+//   k_pl2pt_project  one thread per pairing: g = T (+) l in double, d = n.g + D, record
+//                    {0, 0, float(g - n d), l, 0}, |d| kept aside, atomicMax of its bit pattern
+//   k_pl2pt_count / k_pl2pt_scan / k_pl2pt_write   ordered compaction of the records that pass
+// The reference emits them by descending |d|; Horn's sums do not depend on the order, this path
+// keeps the input order (documented in the header).
+// ------------------------------------------------------------------------------------------
+namespace
+{
+constexpr int kConvThreads = 256;
+struct PoseArg
+{
+    double m[12];
+};
+
+__global__ void __launch_bounds__(kConvThreads)
+    k_pl2pt_project(const mp2p_b200_pair_pt2pl* __restrict__ in, uint64_t n, PoseArg T,
+                    mp2p_b200_pair_pt2pt* __restrict__ rec, double* __restrict__ absd, unsigned long long* __restrict__ maxbits)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * kConvThreads + threadIdx.x;
+    double         a = 0.0;
+    if (i < n)
+    {
+        const mp2p_b200_pair_pt2pl p  = in[i];
+        const double               lx = p.local_x, ly = p.local_y, lz = p.local_z;
+        const double gx = T.m[0] * lx + T.m[1] * ly + T.m[2] * lz + T.m[3];  // composePoint, double
+        const double gy = T.m[4] * lx + T.m[5] * ly + T.m[6] * lz + T.m[7];
+        const double gz = T.m[8] * lx + T.m[9] * ly + T.m[10] * lz + T.m[11];
+        const double d  = p.plane_coefs[0] * gx + p.plane_coefs[1] * gy + p.plane_coefs[2] * gz + p.plane_coefs[3];
+        mp2p_b200_pair_pt2pt r;
+        r.globalIdx = 0, r.localIdx = 0;  // dummies, as in the reference
+        r.global_x = (float)(gx - p.plane_coefs[0] * d), r.global_y = (float)(gy - p.plane_coefs[1] * d);
+        r.global_z = (float)(gz - p.plane_coefs[2] * d);
+        r.local_x = p.local_x, r.local_y = p.local_y, r.local_z = p.local_z;
+        r.errorSquareAfterTransformation = 0.f;
+        rec[i]  = r;
+        a       = fabs(d);
+        absd[i] = a;
+    }
+    // non-negative doubles order like their bit patterns
+    unsigned long long b = (unsigned long long)__double_as_longlong(a);
+    for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(maxbits, b);
+}
+
+// thr = ratio * max unless thr_override >= 0
+__device__ __forceinline__ double conv_threshold(const unsigned long long* maxbits, double thr_override)
+{
+    return thr_override >= 0.0 ? thr_override : __longlong_as_double((long long)*maxbits) * 0.25;
+}
+
+__global__ void __launch_bounds__(kConvThreads)
+    k_pl2pt_count(const double* __restrict__ absd, uint64_t n, const unsigned long long* __restrict__ maxbits,
+                  double thr_override, uint32_t* __restrict__ counts)
+{
+    const double   thr  = conv_threshold(maxbits, thr_override);
+    const uint64_t i    = (uint64_t)blockIdx.x * kConvThreads + threadIdx.x;
+    const int      keep = (i < n && !(absd[i] < thr)) ? 1 : 0;
+    const int      c    = __syncthreads_count(keep);
+    if (threadIdx.x == 0) counts[blockIdx.x] = (uint32_t)c;
+}
+
+// one CTA: exclusive scan of the per-block counts in place, total -> *total
+__global__ void __launch_bounds__(1024) k_pl2pt_scan(uint32_t* __restrict__ counts, uint32_t n_blocks, unsigned long long* __restrict__ total)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += 1024)
+    {
+        const uint32_t b = b0 + threadIdx.x;
+        const uint32_t v = b < n_blocks ? counts[b] : 0u;
+        uint32_t       x = v;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32)
+        {
+            uint32_t w = s_warp[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += y;
+            }
+            s_warp[threadIdx.x] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t warp_excl = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0u;
+        const uint32_t base      = s_base;
+        if (b < n_blocks) counts[b] = base + warp_excl + x - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = base + s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_base;
+}
+
+__global__ void __launch_bounds__(kConvThreads)
+    k_pl2pt_write(const mp2p_b200_pair_pt2pt* __restrict__ rec, const double* __restrict__ absd, uint64_t n,
+                  const unsigned long long* __restrict__ maxbits, double thr_override, const uint32_t* __restrict__ offsets,
+                  mp2p_b200_pair_pt2pt* __restrict__ out, uint64_t capacity)
+{
+    __shared__ uint32_t s_warp[kConvThreads / 32];
+    const double        thr  = conv_threshold(maxbits, thr_override);
+    const uint64_t      i    = (uint64_t)blockIdx.x * kConvThreads + threadIdx.x;
+    const bool          keep = i < n && !(absd[i] < thr);
+    const unsigned      m    = __ballot_sync(0xffffffffu, keep);
+    const int           lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) s_warp[w] = __popc(m);
+    __syncthreads();
+    uint32_t off = offsets[blockIdx.x];
+    for (int k = 0; k < w; k++) off += s_warp[k];
+    off += __popc(m & ((1u << lane) - 1u));
+    if (keep && off < capacity) out[off] = rec[i];
+}
+}  // namespace
+
+// d_in: n pt2pl pairings (device). d_out: room for min(n, capacity) records (device). *h_total (host)
+// receives the number of records kept. Synchronises the stream.
+int run_pt2pl_to_pt2pt(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pl* d_in, uint64_t n, const double pose[12],
+                       mp2p_b200_pair_pt2pt* d_out, uint64_t capacity, uint64_t* h_total)
+{
+    *h_total = 0;
+    if (n == 0) return 0;
+    if (n >= 0xFFFFFFFFull)
+    {
+        set_error("pt2pl_to_pt2pt: n must be < 2^32-1");
+        return MP2P_B200_ERR_ARG;
+    }
+    const uint32_t blocks = (uint32_t)((n + kConvThreads - 1) / kConvThreads);
+    // scratch: [maxbits u64][total u64][counts u32 x blocks (padded)][absd f64 x n][records 36 B x n]
+    const size_t off_counts = 16, off_absd = (off_counts + (size_t)blocks * 4 + 15) & ~(size_t)15;
+    const size_t off_rec = off_absd + n * 8;
+    MP2P_TRY(ctx->d_conv.ensure(off_rec + n * sizeof(mp2p_b200_pair_pt2pt)));
+    char* base    = ctx->d_conv.as<char>();
+    auto* maxbits = reinterpret_cast<unsigned long long*>(base);
+    auto* total   = maxbits + 1;
+    auto* counts  = reinterpret_cast<uint32_t*>(base + off_counts);
+    auto* absd    = reinterpret_cast<double*>(base + off_absd);
+    auto* rec     = reinterpret_cast<mp2p_b200_pair_pt2pt*>(base + off_rec);
+    cudaStream_t st = ctx->stream;
+    MP2P_CUDA_TRY(cudaMemsetAsync(base, 0, 16, st));
+    PoseArg T;
+    for (int k = 0; k < 12; k++) T.m[k] = pose[k];
+    k_pl2pt_project<<<blocks, kConvThreads, 0, st>>>(d_in, n, T, rec, absd, maxbits);
+    count_launch(ctx);
+    unsigned long long* h = static_cast<unsigned long long*>(ctx->h_pinned);
+    double thr_override   = -1.0;
+    for (int pass = 0; pass < 2; pass++)
+    {
+        k_pl2pt_count<<<blocks, kConvThreads, 0, st>>>(absd, n, maxbits, thr_override, counts);
+        k_pl2pt_scan<<<1, 1024, 0, st>>>(counts, blocks, total);
+        k_pl2pt_write<<<blocks, kConvThreads, 0, st>>>(rec, absd, n, maxbits, thr_override, counts, d_out, capacity);
+        count_launch(ctx, 3);
+        MP2P_CUDA_TRY(cudaMemcpyAsync(h, total, 8, cudaMemcpyDeviceToHost, st));
+        MP2P_CUDA_TRY(cudaStreamSynchronize(st));
+        MP2P_CUDA_TRY(cudaGetLastError());
+        if (*h >= 3 || *h >= n || pass == 1) break;
+        // fewer than 3 pairings reach 25 % of the largest error: the reference keeps the 3 largest
+        // (pt2ln_pl_to_pt2pt.cpp:39-41). Rare: settle the threshold on the host.
+        std::vector<double> a(n);
+        MP2P_CUDA_TRY(cudaMemcpy(a.data(), absd, n * 8, cudaMemcpyDeviceToHost));
+        std::nth_element(a.begin(), a.begin() + 2, a.end(), [](double x, double y) { return x > y; });
+        thr_override = a[2];
+    }
+    *h_total = *h;
+    if (*h > capacity)
+    {
+        set_error("pt2pl_to_pt2pt: output capacity %llu too small for %llu pairings", (unsigned long long)capacity,
+                  (unsigned long long)*h);
+        return MP2P_B200_ERR_CAPACITY;
+    }
     return 0;
 }
 }  // namespace mp2p

@@ -636,8 +636,6 @@ class Solver_Horn : public Solver
     bool impl_optimal_pose(const Pairings& pairings, OptimalTF_Result& out, const SolverContext& sc) const override
     {
         out = OptimalTF_Result();
-        if (!pairings.paired_pt2pl.empty())
-            throw std::runtime_error("Solver_Horn on pt2pl pairings needs pt2ln_pl_to_pt2pt (host-side in the reference)");
         mp2p_b200_horn_params prm = pairingsWeightParameters;
         if (prm.robust_kernel != 0)
         {
@@ -649,6 +647,18 @@ class Solver_Horn : public Solver
         for (const auto& b : pairings.point_weights) wc.push_back(b.first), wv.push_back(b.second);
         int32_t solved = 0;
         Device&   dev    = Device::instance();
+        if (!pairings.paired_pt2pl.empty())
+        {
+            // Solver_Horn.cpp:51-55: pt2pl pairings are projected to pt2pt by pt2ln_pl_to_pt2pt and the
+            // solve runs over the projected list ONLY (the reference's `out` starts empty there)
+            if (!sc.guessRelativePose) throw std::runtime_error("Assert failed: sc.guessRelativePose.has_value()");
+            const auto& l2l = pairings.paired_pt2pl;
+            check(mp2p_b200_solve_horn_pt2pl(dev.ctx(), l2l.data(), l2l.size(),
+                                             dev.is_last_match_output(l2l.data(), l2l.size()) ? MP2P_B200_PAIRS_LAST_MATCH : 0,
+                                             sc.guessRelativePose->m, &prm, out.optimalPose.m, &solved),
+                  "mp2p_b200_solve_horn_pt2pl");
+            return solved != 0;
+        }
         const int origin = dev.is_last_match_output(pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size())
                                ? MP2P_B200_PAIRS_LAST_MATCH
                                : 0;

@@ -503,6 +503,39 @@ def test_fused_iteration_pt2pl_gn_equals_two_calls(ctx):
     assert_pose_close(T, T0)
 
 
+# --------------------------------------------------------------------------- Solver_Horn over pt2pl pairings (a14)
+def test_horn_over_pt2pl_pairings_matches_oracle(ctx):
+    """pt2ln_pl_to_pt2pt (plane part) + optimal_tf_horn on the device: the projected records are the
+    oracle's as a SET (the reference orders them by descending |distance|, the device keeps the input
+    order; Horn's sums do not depend on it), pose within 1e-5."""
+    S = fx.make_street_scene(n_map=200_000, length=40.0)
+    scan = fx.make_lidar_scan((20.0, 0.3, 0.0), n_rings=16, n_az=400, length=40.0)
+    guess = fx.pose_xyzypr(20.05, 0.28, 0.01, 0.01, 0.0, 0.0)
+    smap = b200.Map(ctx, *xyz(S))
+    mprm = b200.Pt2PlParams(distanceThreshold=0.5, searchRadius=1.0, knn=8, minimumPlanePoints=5, planeEigenThreshold=0.01)
+    q, _ = smap.match_pt2pl(*xyz(scan), guess, mprm)
+    assert len(q) > 1000
+    ref = orc.pt2pl_to_pt2pt(q, guess)
+    got = ctx.pt2pl_to_pt2pt(q, guess)
+    assert 3 <= len(ref) < len(q) and len(got) == len(ref)
+    key = lambda a: np.sort(np.frombuffer(a.tobytes(), dtype="S36"))
+    assert np.array_equal(key(ref), key(got))
+    ok_c, T_c = orc.optimal_tf_horn(ref)
+    ok_g, T_g = ctx.solve_horn_pt2pl(q, guess)
+    ok_l, T_l = ctx.solve_horn_pt2pl(q, guess, last_match=True)
+    assert ok_c and ok_g and ok_l
+    assert_pose_close(T_g, T_c)
+    assert_pose_close(T_l, T_g, 1e-12)
+    # "at least 3": one dominant error, everything else far below 25 % of it
+    few = q[:50].copy()
+    few["coefs"][0, 3] += 100.0
+    ref = orc.pt2pl_to_pt2pt(few, guess)
+    got = ctx.pt2pl_to_pt2pt(few, guess)
+    assert len(ref) == 3 and np.array_equal(key(ref), key(got))
+    assert len(ctx.pt2pl_to_pt2pt(q[:0], guess)) == 0
+    assert ctx.solve_horn_pt2pl(q[:2], guess)[0] is False  # fewer than 3 pairings (optimal_tf_horn.cpp:96)
+
+
 # --------------------------------------------------------------------------- solver over the matcher's device copy
 def test_solver_reads_last_match_device_copy(ctx):
     """MP2P_B200_PAIRS_LAST_MATCH: a solver handed the unmodified host output of the last matcher
