@@ -411,7 +411,8 @@ def run_ours(args):
         "config": {"workload": w["name"], "detail": w["desc"], "queries_per_gpu": nq, "map_points": len(w["map"]),
                    "pairs": int(n_pairs) if n_pairs >= 0 else None, "l2": "flushed between timed steps (256 MiB memset, outside the event bracket)",
                    "ms_per_step_l2_warm_informative": ms_warm,
-                   "device_path": "fused mp2p_b200_iterate_* call (N=1) / sharded search+all_gather+resolve+all_reduce (N>1)", "unit_note": "at N GPUs one step is one query-sharded iteration over N x queries_per_gpu; value counts N iteration-equivalents per step",
+                   "device_path": "fused mp2p_b200_iterate_* call (N=1) / sharded search+all_gather+resolve+all_reduce (N>1)",
+                   "collectives": (None if sh is None else ("own kernels over NVLink peer memory (csrc/peer.cu)" if sh.transport == "peer" else "NCCL via torch.distributed")), "unit_note": "at N GPUs one step is one query-sharded iteration over N x queries_per_gpu; value counts N iteration-equivalents per step",
                    "local_cloud": ({"resident": True, "order": "Morton-sorted copy, built once per align()", "build_ms": cloud.info["build_ms"]} if cloud is not None else {"resident": False}),
                    "index": {"build_ms": info["build_ms"], "finest_cell_m": info["finest_cell_size"], "levels": info["n_levels"], "bytes": info["index_bytes"]}},
         "e2e": {"value": unit_scale * 1e3 / ms_e2e, "unit": "iterations/s", "ms_per_step": ms_e2e,

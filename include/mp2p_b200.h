@@ -349,6 +349,52 @@ int mp2p_b200_horn_finish(const double sums_packet[MP2P_B200_PACKET_DOUBLES],
                           const double moments_packet[MP2P_B200_PACKET_DOUBLES], double pose_out[12],
                           int32_t* solved);
 
+/* ---- peer exchange over NVLink for the query-sharded path (one process per GPU) ----------------
+ * The two collectives of a sharded iteration — all-gather of the exchange records, all-reduce (SUM)
+ * of a 32-double packet — done by small kernels that write straight into the peers' HBM (CUDA IPC
+ * mappings) instead of by a collective library: no host call per collective, a few microseconds on
+ * the device (csrc/peer.cu). Setup: every rank calls peer_create (allocates its mailbox, returns an
+ * opaque handle of MP2P_B200_PEER_HANDLE_BYTES bytes), the caller all-gathers the handles by any
+ * means (torch.distributed, MPI, files) and passes all of them, rank order, to peer_connect.
+ * Every rank must issue the same sequence of exchanges. All calls only enqueue work on the context
+ * stream. record_words = mp2p_b200_shard_record_words(per_shard, pairingsPerPoint).
+ *   peer_record_slot        where THIS rank's next exchange record has to be written (pass it as
+ *                           record_out_device of ..._shard_search)
+ *   peer_allgather_records  pushes that record to every peer and waits for theirs; *records_device =
+ *                           the gathered records, rank order, contiguous (pass to ..._shard_resolve)
+ *   peer_allreduce_packet   packet_device[0..32) <- sum over ranks, in rank order: bit-identical on
+ *                           every rank. A peer that does not show up within 10 s traps the kernel. */
+#define MP2P_B200_PEER_HANDLE_BYTES 64
+typedef struct mp2p_b200_peer mp2p_b200_peer;
+int  mp2p_b200_peer_create(mp2p_b200_ctx* ctx, uint32_t rank, uint32_t world, uint64_t record_words,
+                           uint8_t handle_out[MP2P_B200_PEER_HANDLE_BYTES], mp2p_b200_peer** out);
+int  mp2p_b200_peer_connect(mp2p_b200_peer* peer, const uint8_t* all_handles /* world x 64 bytes */);
+void mp2p_b200_peer_destroy(mp2p_b200_peer* peer);
+int  mp2p_b200_peer_record_slot(mp2p_b200_peer* peer, uint64_t** slot_device);
+int  mp2p_b200_peer_allgather_records(mp2p_b200_peer* peer, const uint64_t** records_device);
+int  mp2p_b200_peer_allreduce_packet(mp2p_b200_peer* peer, double* packet_device);
+
+/* Whole query-sharded iterations over the peer exchange, enqueued natively with ONE host
+ * synchronisation (run_matchers + run_solvers, mp2p_icp/src/ICP.cpp:143,170, for the shard of this
+ * rank; every rank gets the same pose). peer_iterate_pt2pt: Matcher_Points_DistanceThreshold with
+ * exact cross-shard first-claim dedup, then Solver_Horn (`horn` != NULL; *n_pairs_total = pairings
+ * of the whole cloud) or Solver_GaussNewton (`gn` != NULL) — exactly one of the two.
+ * peer_iterate_pt2pl_gn: Matcher_Point2Plane + Solver_GaussNewton. `pairs_device` (device memory,
+ * `capacity` >= n_local * pairingsPerPoint records) receives this shard's pairings. */
+int mp2p_b200_peer_iterate_pt2pt(mp2p_b200_peer* peer, mp2p_b200_map* map, const float* lx, const float* ly,
+                                 const float* lz, uint64_t n_local, int local_on_device,
+                                 const double pose[12], const mp2p_b200_pt2pt_params* matcher_params,
+                                 const mp2p_b200_horn_params* horn, const mp2p_b200_gn_params* gn,
+                                 uint64_t per_shard, mp2p_b200_pair_pt2pt* pairs_device, uint64_t capacity,
+                                 double pose_out[12], int32_t* solved, uint64_t* n_pairs_total,
+                                 uint32_t* iterations_done);
+int mp2p_b200_peer_iterate_pt2pl_gn(mp2p_b200_peer* peer, mp2p_b200_map* map, const float* lx, const float* ly,
+                                    const float* lz, uint64_t n_local, int local_on_device,
+                                    const double pose[12], const mp2p_b200_pt2pl_params* matcher_params,
+                                    const mp2p_b200_gn_params* solver_params,
+                                    mp2p_b200_pair_pt2pl* pairs_device, uint64_t capacity,
+                                    double pose_out[12], int32_t* solved, uint32_t* iterations_done);
+
 /* ---- measurement hooks (bench.py): per-kernel CUDA-event timing and search statistics ----
  * With profiling on, every public call records CUDA events around its kernels on the context
  * stream; mp2p_b200_ctx_get_timings returns the durations (ms) of the LAST call:

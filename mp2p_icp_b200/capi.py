@@ -162,7 +162,11 @@ EXPORTS = [
     "mp2p_b200_shard_record_words",
     "mp2p_b200_gn_device_begin", "mp2p_b200_gn_device_accumulate", "mp2p_b200_gn_device_step",
     "mp2p_b200_pt2pl_to_pt2pt", "mp2p_b200_solve_horn_pt2pl",
+    "mp2p_b200_peer_create", "mp2p_b200_peer_connect", "mp2p_b200_peer_destroy", "mp2p_b200_peer_record_slot",
+    "mp2p_b200_peer_allgather_records", "mp2p_b200_peer_allreduce_packet",
+    "mp2p_b200_peer_iterate_pt2pt", "mp2p_b200_peer_iterate_pt2pl_gn",
 ]
+PEER_HANDLE_BYTES = 64
 GN_STATE_DOUBLES = 16
 COUNT_ON_DEVICE = (1 << 64) - 1  # MP2P_B200_COUNT_ON_DEVICE
 
@@ -192,6 +196,7 @@ def load_library():
     L.mp2p_b200_shard_record_words.restype = C.c_uint64
     L.mp2p_b200_shard_record_words.argtypes = [C.c_uint64, C.c_uint32]
     L.mp2p_b200_host_free.argtypes = [C.c_void_p]
+    L.mp2p_b200_peer_destroy.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -375,6 +380,78 @@ class Context:
         cp = prm.c()
         _check(load_library().mp2p_b200_horn_moments(self._h, _ptr(pairs) if n else None, C.c_uint64(n), int(on_device), C.byref(cp), _ptr(sums_packet), int(sums_on_device), C.c_uint64(n_total), _ptr(packet), int(packet_on_device)))
         return packet
+
+
+class Peer:
+    """NVLink mailbox exchange of one rank (csrc/peer.cu). `exchange_handles(bytes) -> list of bytes`
+    all-gathers the 64-byte IPC handles across ranks (rank order) by whatever means the caller has."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, record_words: int, exchange_handles):
+        L = load_library()
+        h = (C.c_uint8 * PEER_HANDLE_BYTES)()
+        p = C.c_void_p()
+        _check(L.mp2p_b200_peer_create(ctx._h, C.c_uint32(rank), C.c_uint32(world), C.c_uint64(record_words), h, C.byref(p)))
+        self._h, self.ctx, self.rank, self.world = p, ctx, rank, world
+        allh = exchange_handles(bytes(h))
+        if len(allh) != world or any(len(x) != PEER_HANDLE_BYTES for x in allh):
+            raise Mp2pError("exchange_handles must return one 64-byte handle per rank")
+        blob = (C.c_uint8 * (PEER_HANDLE_BYTES * world)).from_buffer_copy(b"".join(allh))
+        _check(L.mp2p_b200_peer_connect(self._h, blob))
+
+    def record_slot(self) -> int:
+        p = C.c_void_p()
+        _check(load_library().mp2p_b200_peer_record_slot(self._h, C.byref(p)))
+        return int(p.value)
+
+    def allgather_records(self) -> int:
+        p = C.c_void_p()
+        _check(load_library().mp2p_b200_peer_allgather_records(self._h, C.byref(p)))
+        return int(p.value)
+
+    def allreduce_packet(self, packet_device: int):
+        _check(load_library().mp2p_b200_peer_allreduce_packet(self._h, C.c_void_p(int(packet_device))))
+
+    def make_iterator(self, gmap, lx, ly, lz, n_local, matcher_prm, solver_prm, per_shard: int, pairs_device: int, capacity: int):
+        """Pre-binds one query-sharded ICP iteration of this rank (mp2p_b200_peer_iterate_*: every
+        kernel and exchange enqueued natively, one synchronisation). Returns
+        pose(3x4) -> (solved, pose_out 3x4, pairings of the whole cloud or -1, GN updates)."""
+        L = load_library()
+        mp, sp = matcher_prm.c(), solver_prm.c()
+        pose_in, pose_out = (C.c_double * 12)(), (C.c_double * 12)()
+        solved, n_all, iters = C.c_int32(0), C.c_uint64(0), C.c_uint32(0)
+        plx, ply, plz, n_local, kind = _local(lx, ly, lz, n_local, True)
+        head = [self._h, gmap._h, plx, ply, plz, C.c_uint64(n_local), kind, pose_in, C.byref(mp)]
+        if isinstance(matcher_prm, Pt2PtParams):
+            horn = isinstance(solver_prm, HornParams)
+            fn = L.mp2p_b200_peer_iterate_pt2pt
+            args = head + [C.byref(sp) if horn else None, None if horn else C.byref(sp), C.c_uint64(per_shard), C.c_void_p(int(pairs_device)), C.c_uint64(capacity), pose_out, C.byref(solved), C.byref(n_all), C.byref(iters)]
+        else:
+            horn = False
+            fn = L.mp2p_b200_peer_iterate_pt2pl_gn
+            args = head + [C.byref(sp), C.c_void_p(int(pairs_device)), C.c_uint64(capacity), pose_out, C.byref(solved), C.byref(iters)]
+        pose_in_np = np.frombuffer(pose_in, dtype=np.float64)
+        pose_out_np = np.frombuffer(pose_out, dtype=np.float64).reshape(3, 4)
+        keep = (lx, ly, lz, mp, sp)
+
+        def step(T, _keep=keep):
+            pose_in_np[:] = np.asarray(T, dtype=np.float64).reshape(-1)
+            rc = fn(*args)
+            if rc != 0:
+                _check(rc)
+            return bool(solved.value), pose_out_np.copy(), (int(n_all.value) if horn else -1), int(iters.value)
+
+        return step
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().mp2p_b200_peer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def gn_step_from_packet(packet, prm: GNParams, T):

@@ -120,6 +120,30 @@ struct mp2p_b200_ctx
         bool          valid = false;
         const double* sums  = nullptr;  // pt2pt: HORN1 packet the compaction produced on the way (device)
     } last2p, last2l;
+    // Speculative solve: when the previous solver call named the last matcher output
+    // (PAIRS_LAST_MATCH), the NEXT matcher call that returns pairings to the host also enqueues that
+    // solver over the device copy, on the compute stream, while the copy stream carries the records
+    // to the host; the solver call that follows — same parameters, same start pose — finds the
+    // result ready. A guess that does not come true costs a few idle-GPU microseconds; after two
+    // unused guesses in a row the library stops guessing until the pattern shows again.
+    struct SpecWant
+    {
+        int                   kind = 0;  // 0 none, 1 Solver_Horn (pt2pt), 2 Solver_GaussNewton
+        int                   list = 0;  // GN: 1 = pt2pt list, 2 = pt2pl list
+        mp2p_b200_horn_params horn{};
+        mp2p_b200_gn_params   gn{};
+    } spec_want;
+    int spec_unused = 0;  // speculations in a row nobody asked for: two and the guessing stops
+    struct SpecResult
+    {
+        bool     valid = false;
+        int      kind = 0, list = 0;
+        uint64_t n = 0;
+        double   pose_in[12] = {};
+    } spec_res;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t  ev_fork = nullptr;
+    mp2p::DevBuf d_spec;  // GN speculation: 12 doubles pose + state words
     // grid barrier state of the single-launch iteration (match.cu): counters only ever grow
     mp2p::DevBuf       d_coop;
     unsigned long long coop_arrivals = 0;
@@ -211,8 +235,16 @@ struct DeviceMatch
     // kernel, weights or scale-outlier pass) in want_horn_sums[32..64) if the matcher can fuse them
     double                    fuse_moments_w = 0.0;
     bool                      moments_done   = false;    // out: the matcher produced the moments too
+    // in: query-sharded single-launch iteration (peer.cu): this call is the shard `peer->view.rank` of
+    // a cloud cut into blocks of per_shard points; ONLY the single launch is acceptable — if it cannot
+    // be used run_match_pt2pt returns 1 without having enqueued anything and the caller takes the
+    // multi-kernel path (same mailbox protocol, so ranks may differ in their choice)
+    struct mp2p_b200_peer*    peer      = nullptr;
+    uint64_t                  per_shard = 0;
 };
 
+// api.cu
+int read_iteration_packets(mp2p_b200_ctx* ctx, bool polled, const double* d_packets, double** hp_out);
 // index.cu
 int build_index(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* x, const float* y,
                 const float* z, uint64_t n, int on_device);

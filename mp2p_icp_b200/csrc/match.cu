@@ -23,6 +23,7 @@
 
 #include "grid_search.cuh"
 #include "plane_fit.cuh"
+#include "peer.cuh"
 #include "reduce.cuh"
 
 namespace mp2p
@@ -211,6 +212,7 @@ struct Pt2PtArgs
     int      cand_sorted;    // candidate words go to the query's SORTED position (pt2pl path)
     uint32_t tile_stride;    // CTA b serves query tile (b * tile_stride) % n_tiles: spreads expensive
                              // neighbourhoods (sparse map regions cluster in any spatial order) over the grid
+    unsigned long long slot_offset;  // K = 1 sharded single-launch iteration: global proposal slot of local point 0
 };
 
 // ------------------------------------------------------------------------------------------
@@ -546,7 +548,7 @@ __device__ __forceinline__ void nn1_body(const GridView& g, const Pt2PtArgs& a, 
         if (c != ~0ull && !a.allowGlobal)
         {
             const uint32_t gi = (uint32_t)c;
-            if (!bit_set(gbits, gi)) atomicMin(claim + gi, a.tag | (unsigned long long)i);
+            if (!bit_set(gbits, gi)) atomicMin(claim + gi, a.tag | ((unsigned long long)i + a.slot_offset));
         }
     }
     flush_search_stats(sc, n_valid, stats);
@@ -659,6 +661,7 @@ struct CoopSync
     unsigned int*       sums_flag; // epoch of the launch whose HORN1 packet is complete
     unsigned int        epoch;
     double*             host_out;  // mapped pinned host memory: 64 packet doubles, then the flag word
+    unsigned int        scan_barrier;  // number of the barrier the resident scan uses (1; 3 in the sharded launch)
 };
 
 // barrier number `which` (0, 1, ...) of a cooperative launch: all CTAs are resident, so spinning is safe
@@ -805,7 +808,7 @@ __device__ __forceinline__ uint32_t compact_pt2pt_body(
         }
     }
     const unsigned long long w =
-        resident ? grid_exclusive_scan_resident(sm, tile, n_tiles, ok ? 1u : 0u, status, out_count, *resident, 1)
+        resident ? grid_exclusive_scan_resident(sm, tile, n_tiles, ok ? 1u : 0u, status, out_count, *resident, resident->scan_barrier)
                  : grid_exclusive_scan(sm, tile, n_tiles, ok ? 1u : 0u, status, out_count, a.scan_epoch);
     // The tile's records are consecutive in the output: stage them in shared memory and store the
     // byte range with fully coalesced 4-byte words (full sectors: no read-for-ownership fills),
@@ -874,6 +877,20 @@ __global__ void __launch_bounds__(kScanThreads)
 // Saves two launches, the solver's re-read of the pairings and the launch gaps; the numbers are the
 // same sums in a different grouping (poses agree to ~1e-15 with the three-kernel path).
 // ------------------------------------------------------------------------------------------
+// SHARDED (one process per GPU, csrc/peer.cuh): the same launch also carries the exchanges of a
+// query-sharded iteration through the peers' mailboxes over NVLink —
+//   phase 1   the shard's proposals claim directly under their GLOBAL slot numbers; candidate words
+//             go into this rank's record slot of its own mailbox
+//   -------- grid barrier 0
+//   phase 1b  every CTA stores a slice of the record (words, padding, bounding box) into EVERY peer's
+//             mailbox; grid barrier 1; CTA 0 releases the record flags; every CTA acquires the peers'
+//   phase 2a  replay of the OTHER shards' proposals into the claim array, fold of the bounding boxes
+//   -------- grid barrier 2
+//   phase 2   compaction (scan barrier 3) + HORN1 sums; the folding CTA all-reduces the packet with the
+//             peers before it publishes it
+//   phase 3   moments; the folding CTA all-reduces them and hands both packets to the host
+// so a sharded pt2pt + Horn iteration is ONE launch and no collective call.
+template <bool SHARDED>
 __global__ void __launch_bounds__(kScanThreads, 3)
     k_iterate_nn1_horn(GridView g, Pt2PtArgs a, CompactArgs ca, const float* __restrict__ qx, const float* __restrict__ qy,
                        const float* __restrict__ qz, const float* __restrict__ lx, const float* __restrict__ ly,
@@ -881,19 +898,84 @@ __global__ void __launch_bounds__(kScanThreads, 3)
                        unsigned long long* __restrict__ cand, float4* __restrict__ cand_xyz, uint32_t* __restrict__ bbox,
                        uint32_t* __restrict__ bbox_next, unsigned long long* __restrict__ status,
                        mp2p_b200_pair_pt2pt* __restrict__ out, unsigned long long* __restrict__ out_count, FusedSums fs,
-                       double* __restrict__ mom_partials, unsigned int* __restrict__ mom_ticket, double w_pt2pt, CoopSync cs)
+                       double* __restrict__ mom_partials, unsigned int* __restrict__ mom_ticket, double w_pt2pt, CoopSync cs,
+                       PeerLaunch pl, unsigned long long per_k, uint32_t* __restrict__ cloud_bbox)
 {
     __shared__ ScanSmem sm;
     __shared__ uint32_t s_rec[kScanThreads * 9];
+    const PeerView& pv = pl.view;
+    if (SHARDED)  // the candidate words of this shard live in its record slot of the own mailbox
+        cand = reinterpret_cast<unsigned long long*>(pv.box[pv.rank] + rec_offset(pv.rec_words, pv.world, pl.rec_epoch & 1u, pv.rank));
     // ---- phase 1
     nn1_body<kScanThreads>(g, a, qx, qy, qz, perm, nullptr, nullptr, claim, cand, cand_xyz, bbox, nullptr);
     grid_barrier(cs, 0);
+    const uint32_t* gate_box = bbox;
+    if (SHARDED)
+    {
+        const uint32_t parity = pl.rec_epoch & 1u;
+        // ---- phase 1b: record = [per_k words | 6 bbox words | pad] into every mailbox
+        for (unsigned long long j = (unsigned long long)blockIdx.x * kScanThreads + threadIdx.x; j < pv.rec_words;
+             j += (unsigned long long)gridDim.x * kScanThreads)
+        {
+            unsigned long long w = 0ull;
+            if (j < a.n_local)
+                w = __ldcg(cand + j);
+            else if (j < per_k)
+                w = ~0ull;  // slots of a short shard: "no candidate"
+            else if (j < per_k + 3)
+                w = (unsigned long long)__ldcg(bbox + 2 * (j - per_k)) | ((unsigned long long)__ldcg(bbox + 2 * (j - per_k) + 1) << 32);
+            if (j >= a.n_local) cand[j] = w;
+            for (uint32_t p = 1; p < pv.world; p++)
+            {
+                const uint32_t dst = (pv.rank + p) % pv.world;
+                reinterpret_cast<unsigned long long*>(pv.box[dst] + rec_offset(pv.rec_words, pv.world, parity, pv.rank))[j] = w;
+            }
+        }
+        __threadfence_system();
+        grid_barrier(cs, 1);
+        if (blockIdx.x == 0 && threadIdx.x < pv.world) st_release_sys(rec_flag(pv.box[threadIdx.x], parity, pv.rank), pl.rec_epoch);
+        if (threadIdx.x < pv.world) wait_flag(rec_flag(pv.box[pv.rank], parity, threadIdx.x), pl.rec_epoch);
+        __syncthreads();
+        // ---- phase 2a: the whole cloud's bounding box (every CTA writes the same six words), the
+        // other shards' proposals
+        const unsigned long long* recs =
+            reinterpret_cast<const unsigned long long*>(pv.box[pv.rank] + rec_offset(pv.rec_words, pv.world, parity, 0));
+        if (threadIdx.x < 6)
+        {
+            const int d = threadIdx.x;
+            uint32_t  r = d < 3 ? 0xFFFFFFFFu : 0u;
+            for (uint32_t p = 0; p < pv.world; p++)
+            {
+                const uint32_t v = __ldcg(reinterpret_cast<const uint32_t*>(recs + (size_t)p * pv.rec_words + per_k) + d);
+                r                = d < 3 ? min(r, v) : max(r, v);
+            }
+            cloud_bbox[d] = r;
+        }
+        if (!ca.allowGlobal)
+        {
+            const unsigned long long n_all = per_k * pv.world;
+            for (unsigned long long s = (unsigned long long)blockIdx.x * kScanThreads + threadIdx.x; s < n_all;
+                 s += (unsigned long long)gridDim.x * kScanThreads)
+            {
+                const unsigned long long r = s / per_k, j = s - r * per_k;
+                if (r == pv.rank) continue;  // claimed in phase 1
+                const unsigned long long c = __ldcg(recs + r * pv.rec_words + j);
+                if ((uint32_t)c == 0xFFFFFFFFu) continue;
+                atomicMin(claim + (uint32_t)c, ca.tag | s);
+            }
+        }
+        __threadfence();
+        grid_barrier(cs, 2);
+        gate_box = cloud_bbox;
+    }
     // ---- phase 2 (tile = CTA index: all CTAs are resident, the look-back cannot starve)
     bbox_rearm(bbox_next);
     bool           folded = false;  // CTA-uniform
-    const uint32_t n_rec  = compact_pt2pt_body(g, ca, lx, ly, lz, nullptr, claim, cand, cand_xyz, bbox, status, out, out_count, fs,
+    const uint32_t n_rec  = compact_pt2pt_body(g, ca, lx, ly, lz, nullptr, claim, cand, cand_xyz, gate_box, status, out, out_count, fs,
                                                blockIdx.x, sm, s_rec, &folded, &cs);
     // ---- the CTA that folded the HORN1 packet publishes it; everybody waits for it
+    __syncthreads();
+    if (SHARDED && folded && threadIdx.x < 32) peer_allreduce_warp(pv, pl.pkt_epoch, fs.packet, threadIdx.x);
     __syncthreads();
     if (threadIdx.x == 0)
     {
@@ -936,6 +1018,11 @@ __global__ void __launch_bounds__(kScanThreads, 3)
     }
     const bool last = block_reduce_to_packet<12>(acc, mom_partials, mom_ticket, fs.packet + MP2P_B200_PACKET_DOUBLES,
                                                  blockIdx.x, gridDim.x);
+    if (SHARDED && last)
+    {
+        __syncthreads();
+        if (threadIdx.x < 32) peer_allreduce_warp(pv, pl.pkt_epoch + 1u, fs.packet + MP2P_B200_PACKET_DOUBLES, threadIdx.x);
+    }
     if (last && cs.host_out)
     {
         // the CTA that folded the moments hands both packets to the host through mapped pinned memory
@@ -1252,20 +1339,84 @@ int prepare_stats(mp2p_b200_ctx* ctx, unsigned long long** stats)
 // Pairings back to the host with ONE synchronisation in the steady state: the record copy is
 // issued speculatively right behind the compaction, sized from the previous call's count (+12.5 %),
 // together with the count; only if the guess was too small a second copy fetches the remainder.
+// pinned host scratch of the speculative solve (h_pinned + 1024): [0..64) Horn packets | GN: pose 12, state
+inline double* spec_host(mp2p_b200_ctx* ctx) { return reinterpret_cast<double*>(static_cast<char*>(ctx->h_pinned) + 1024); }
+
+// Enqueues, on the compute stream, the solver the caller is expected to ask for next over the
+// pairings this matcher call leaves on the device (see mp2p_b200_ctx::SpecWant). `sums` = HORN1
+// packet produced by the compaction (pt2pt only).
+template <class Rec>
+int enqueue_speculation(mp2p_b200_ctx* ctx, const Rec* d_pairs, const unsigned long long* d_count, uint64_t capacity,
+                        const double pose[12], const double* sums)
+{
+    constexpr bool is2p = sizeof(Rec) == sizeof(mp2p_b200_pair_pt2pt);
+    auto&          w    = ctx->spec_want;
+    ctx->spec_res.valid = false;
+    if (w.kind && ctx->spec_unused >= 2) w.kind = 0;
+    double* h = spec_host(ctx);
+    if (w.kind == 1 && is2p && sums)
+    {
+        double* mom = ctx->d_packet.as<double>() + 6 * MP2P_B200_PACKET_DOUBLES;
+        MP2P_TRY(run_horn_moments(ctx, reinterpret_cast<const mp2p_b200_pair_pt2pt*>(d_pairs), capacity, &w.horn, sums, capacity,
+                                  nullptr, nullptr, 0, nullptr, mom, d_count, 1));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(h, sums, MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(h + MP2P_B200_PACKET_DOUBLES, mom, MP2P_B200_PACKET_DOUBLES * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->spec_res.kind = 1, ctx->spec_res.list = 1;
+    }
+    else if (w.kind == 2 && w.list == (is2p ? 1 : 2))
+    {
+        double*   d_pose  = ctx->d_spec.as<double>();
+        uint32_t* d_state = reinterpret_cast<uint32_t*>(ctx->d_spec.as<char>() + 128);
+        double*   hp      = h + 64;  // start pose staged in pinned memory, result comes back over it
+        std::memcpy(hp, pose, 96);
+        MP2P_CUDA_TRY(cudaMemcpyAsync(d_pose, hp, 96, cudaMemcpyHostToDevice, ctx->stream));
+        MP2P_TRY(run_gn_device_loop(ctx, is2p ? reinterpret_cast<const mp2p_b200_pair_pt2pt*>(d_pairs) : nullptr, is2p ? capacity : 0,
+                                    is2p ? nullptr : reinterpret_cast<const mp2p_b200_pair_pt2pl*>(d_pairs), is2p ? 0 : capacity,
+                                    &w.gn, d_pose, d_state, ctx->d_packet.as<double>(), is2p ? d_count : nullptr,
+                                    is2p ? nullptr : d_count));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(hp, d_pose, 96, cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(hp + 12, d_state, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->spec_res.kind = 2, ctx->spec_res.list = is2p ? 1 : 2;
+    }
+    else
+        return 0;
+    std::memcpy(ctx->spec_res.pose_in, pose, 96);
+    ctx->spec_res.valid = true;  // n is filled in by fetch_results once the count is known
+    ctx->spec_unused++;
+    return 0;
+}
+
 template <class Rec>
 int fetch_results(mp2p_b200_ctx* ctx, const unsigned long long* d_count, const Rec* d_pairs,
-                  Rec* out, uint64_t capacity, int out_on_device, uint64_t* out_count, uint64_t* hint)
+                  Rec* out, uint64_t capacity, int out_on_device, uint64_t* out_count, uint64_t* hint,
+                  const double* pose = nullptr, const double* sums = nullptr)
 {
     unsigned long long* h_count = static_cast<unsigned long long*>(ctx->h_pinned);
-    MP2P_CUDA_TRY(cudaMemcpyAsync(h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
     uint64_t spec = 0;
-    if (!out_on_device && capacity)
+    ctx->spec_res.valid = false;
+    if (!out_on_device && capacity && ctx->copy_stream && pose && ctx->spec_want.kind)
     {
+        // records to the host on the copy stream, the expected solver on the compute stream
         spec = *hint == ~0ull ? capacity : std::min<uint64_t>(capacity, *hint + *hint / 8 + 1024);
-        MP2P_CUDA_TRY(cudaMemcpyAsync(out, d_pairs, spec * sizeof(Rec), cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        MP2P_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(out, d_pairs, spec * sizeof(Rec), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        MP2P_TRY(enqueue_speculation(ctx, d_pairs, d_count, capacity, pose, sums));
+        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    }
+    else
+    {
+        MP2P_CUDA_TRY(cudaMemcpyAsync(h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (!out_on_device && capacity)
+        {
+            spec = *hint == ~0ull ? capacity : std::min<uint64_t>(capacity, *hint + *hint / 8 + 1024);
+            MP2P_CUDA_TRY(cudaMemcpyAsync(out, d_pairs, spec * sizeof(Rec), cudaMemcpyDeviceToHost, ctx->stream));
+        }
     }
     MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     MP2P_CUDA_TRY(cudaGetLastError());
+    ctx->spec_res.n = *h_count;
     const uint64_t cnt = *h_count;
     *out_count         = cnt;
     *hint              = cnt;
@@ -1290,25 +1441,33 @@ int fetch_results(mp2p_b200_ctx* ctx, const unsigned long long* d_count, const R
 }  // namespace
 
 // Launches k_iterate_nn1_horn if the whole grid can be co-resident; returns 1 if it cannot (the
-// caller then takes the three-kernel path), 0 after a successful launch.
+// caller then takes the three-kernel path), 0 after a successful launch. `peer` != NULL: the sharded
+// instantiation (exchanges through the peers' mailboxes inside the launch), per_k = per_shard * K.
 static int launch_iterate_nn1_horn(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const Pt2PtArgs& a, const CompactArgs& c,
                                    const SmallView& sv, unsigned long long* status, unsigned long long* cand,
                                    float4* cand_xyz, mp2p_b200_pair_pt2pt* d_out, double* d_packets, double w_pt2pt,
-                                   uint32_t n_tiles)
+                                   uint32_t n_tiles, mp2p_b200_peer* peer = nullptr, unsigned long long per_k = 0)
 {
-    static int blocks_per_sm = -1, n_sm = 0;
-    if (blocks_per_sm < 0)
+    static int blocks_per_sm[2] = {-1, -1}, n_sm = 0;
+    const int  which = peer ? 1 : 0;
+    if (blocks_per_sm[which] < 0)
     {
         int dev = 0, coop = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        blocks_per_sm = 0;
-        if (coop) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_iterate_nn1_horn, kScanThreads, 0);
-        const char* e = getenv("MP2P_FUSED_ITERATION");
-        if (e && atoi(e) == 0) blocks_per_sm = 0;
+        blocks_per_sm[which] = 0;
+        if (coop)
+        {
+            if (peer)
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[which], k_iterate_nn1_horn<true>, kScanThreads, 0);
+            else
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[which], k_iterate_nn1_horn<false>, kScanThreads, 0);
+        }
+        const char* e = getenv(peer ? "MP2P_FUSED_SHARDED_ITERATION" : "MP2P_FUSED_ITERATION");
+        if (e && atoi(e) == 0) blocks_per_sm[which] = 0;
     }
-    if ((uint64_t)n_tiles > (uint64_t)blocks_per_sm * (uint64_t)n_sm) return 1;
+    if ((uint64_t)n_tiles > (uint64_t)blocks_per_sm[which] * (uint64_t)n_sm) return 1;
     if (!ctx->d_coop.p)
     {
         MP2P_TRY(ctx->d_coop.ensure(64));
@@ -1320,12 +1479,23 @@ static int launch_iterate_nn1_horn(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const
     fs.packet                 = d_packets;
     double*       mom_partials = fs.partials + (size_t)n_tiles * 32;
     unsigned int* mom_ticket   = fs.ticket + 1;
+    // grid barriers of one launch: search | scan (2), sharded: search | records out | replay | scan (4)
+    const unsigned n_barriers = peer ? 4u : 2u;
     CoopSync      cs{};
     cs.arrivals  = ctx->d_coop.as<unsigned long long>();
-    cs.target    = ctx->coop_arrivals + n_tiles;  // barrier 0; barrier 1 completes at + 2 n_tiles
+    cs.target    = ctx->coop_arrivals + n_tiles;  // barrier 0; barrier b completes at + (b + 1) n_tiles
     cs.sums_flag = reinterpret_cast<unsigned int*>(ctx->d_coop.as<char>() + 16);
     cs.epoch     = ctx->coop_epoch + 1;
     cs.host_out  = ctx->h_mapped_dev;  // NULL if the mapping is not available: the caller then copies
+    cs.scan_barrier = n_barriers - 1;
+    PeerLaunch pl{};
+    if (peer)
+    {
+        pl.view      = peer->view;
+        pl.rec_epoch = peer->rec_epoch + 1;
+        pl.pkt_epoch = peer->pkt_epoch + 1;
+    }
+    uint32_t*      cloud_bbox = reinterpret_cast<uint32_t*>(ctx->d_coop.as<char>() + 32);  // 6 words
     GridView       gv = map->view;
     Pt2PtArgs      aa = a;
     CompactArgs    cc = c;
@@ -1335,16 +1505,17 @@ static int launch_iterate_nn1_horn(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const
     uint32_t *          bbox = sv.bbox, *bbox_next = sv.bbox_next;
     unsigned long long* count = sv.count;
     void* args[] = {&gv, &aa, &cc, &qx, &qy, &qz, &lx, &ly, &lz, &perm, &claim, &cand, &cand_xyz, &bbox, &bbox_next, &status,
-                    &d_out, &count, &fs, &mom_partials, &mom_ticket, &w_pt2pt, &cs};
-    const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_iterate_nn1_horn), dim3(n_tiles),
-                                                      dim3(kScanThreads), args, 0, ctx->stream);
+                    &d_out, &count, &fs, &mom_partials, &mom_ticket, &w_pt2pt, &cs, &pl, &per_k, &cloud_bbox};
+    void* fn = peer ? reinterpret_cast<void*>(k_iterate_nn1_horn<true>) : reinterpret_cast<void*>(k_iterate_nn1_horn<false>);
+    const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(n_tiles), dim3(kScanThreads), args, 0, ctx->stream);
     if (e != cudaSuccess)
     {
         cudaGetLastError();
         set_error("cooperative launch failed: %s", cudaGetErrorString(e));
         return MP2P_B200_ERR_CUDA;
     }
-    ctx->coop_arrivals += 2ull * n_tiles, ctx->coop_epoch += 1;
+    ctx->coop_arrivals += (unsigned long long)n_barriers * n_tiles, ctx->coop_epoch += 1;
+    if (peer) peer->rec_epoch += 1, peer->pkt_epoch += 2;
     count_launch(ctx);
     return 0;
 }
@@ -1358,7 +1529,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
 {
     *out_count          = 0;
     if (keep_on_device) keep_on_device->d_count = nullptr, keep_on_device->d_pairs = nullptr, keep_on_device->capacity = 0;
-    ctx->last2p.valid = false, ctx->last2p.sums = nullptr;
+    ctx->last2p.valid = false, ctx->last2p.sums = nullptr, ctx->spec_res.valid = false;
     const uint32_t K    = prm->pairingsPerPoint;
     const uint64_t nmap = map->view.n_points;
     if (nmap == 0 || n_local == 0) return 0;  // …DistanceThreshold.cpp:67
@@ -1418,6 +1589,13 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
 
     // whole iteration in one cooperative launch (k = 1, Horn sums AND moments wanted, no MatchState
     // bits, no search statistics), when the grid fits on the device
+    mp2p_b200_peer* peer = keep_on_device ? keep_on_device->peer : nullptr;
+    if (peer)  // shard of a bigger cloud: proposals and records carry whole-cloud numbers
+    {
+        const uint64_t per_k = keep_on_device->per_shard * K;
+        a.slot_offset = (unsigned long long)peer->view.rank * per_k;
+        c.slot_offset = a.slot_offset, c.index_offset = (uint32_t)(peer->view.rank * keep_on_device->per_shard);
+    }
     if (K == 1 && keep_on_device && keep_on_device->want_horn_sums && keep_on_device->fuse_moments_w > 0.0 && !lbits &&
         !gbits && !stats)
     {
@@ -1425,7 +1603,8 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
         cand_xyz = ctx->d_candxyz.as<float4>();
         prof_begin(ctx, 0);
         const int rc = launch_iterate_nn1_horn(ctx, map, a, c, sv, status, cand, cand_xyz, d_out, keep_on_device->want_horn_sums,
-                                               keep_on_device->fuse_moments_w, (uint32_t)n_tiles);
+                                               keep_on_device->fuse_moments_w, (uint32_t)n_tiles, peer,
+                                               keep_on_device->per_shard * K);
         if (rc < 0) return rc;
         if (rc == 0)
         {
@@ -1435,6 +1614,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
             return 0;
         }
     }
+    if (peer) return 1;  // nothing enqueued that the multi-kernel path does not redo
     prof_begin(ctx, 0);
 #define LAUNCH_MATCH(G)                                                                                    \
     {                                                                                                      \
@@ -1482,7 +1662,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
         keep_on_device->d_count = sv.count, keep_on_device->d_pairs = d_out, keep_on_device->capacity = c.capacity;
         return 0;
     }
-    return fetch_results(ctx, sv.count, d_out, out, c.capacity, out_on_device, out_count, &ctx->hint_pt2pt);
+    return fetch_results(ctx, sv.count, d_out, out, c.capacity, out_on_device, out_count, &ctx->hint_pt2pt, pose, fs.packet);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1598,7 +1778,7 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
 {
     if (out_count) *out_count = 0;
     ctx->last_count = nullptr, ctx->last_capacity = 0;
-    ctx->last2p.valid = false, ctx->last2p.sums = nullptr;
+    ctx->last2p.valid = false, ctx->last2p.sums = nullptr, ctx->spec_res.valid = false;
     const uint32_t K    = prm->pairingsPerPoint;
     const uint64_t nmap = map->view.n_points;
     const uint64_t per_k = per_shard * K, rec_words = shard_record_words(per_shard, K);
@@ -1674,7 +1854,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
 {
     *out_count          = 0;
     if (keep_on_device) *keep_on_device = DeviceMatch{};
-    ctx->last2l.valid   = false;
+    ctx->last2l.valid = false, ctx->spec_res.valid = false;
     const uint64_t nmap = map->view.n_points;
     if (nmap == 0 || n_local == 0) return 0;
     if (n_local >= 0xFFFFFFFFull || prm->knn < 1 || prm->knn > MP2P_B200_MAX_KNN)
@@ -1763,7 +1943,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
         keep_on_device->d_count = sv.count, keep_on_device->d_pairs = d_out, keep_on_device->capacity = cap;
         return 0;
     }
-    return fetch_results(ctx, sv.count, d_out, out, cap, out_on_device, out_count, &ctx->hint_pt2pl);
+    return fetch_results(ctx, sv.count, d_out, out, cap, out_on_device, out_count, &ctx->hint_pt2pl, pose);
 }
 
 int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const float* qy,

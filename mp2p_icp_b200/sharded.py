@@ -75,7 +75,14 @@ class ShardedMatcherSolver:
     records where they are — no packing or unpacking kernels on either side.
     """
 
-    def __init__(self, ctx: capi.Context, gmap: capi.Map, rank: int, world: int, n_total: int, k_max: int = 1):
+    def __init__(self, ctx: capi.Context, gmap: capi.Map, rank: int, world: int, n_total: int, k_max: int = 1, transport: str = None):
+        """transport: "peer" = the library's own NVLink mailbox exchange (csrc/peer.cu: kernels that
+        write into the peers' HBM, no host call per collective), "nccl" = torch.distributed
+        collectives, None = $MP2P_B200_TRANSPORT or "peer" (falls back to "nccl", with a warning, if
+        the mailboxes cannot be mapped)."""
+        import os
+        import warnings
+
         import torch
         import torch.distributed as dist
 
@@ -96,12 +103,62 @@ class ShardedMatcherSolver:
         self.h_packets = torch.zeros((64,), dtype=torch.float64).pin_memory()
         self.gn_state = torch.zeros((capi.GN_STATE_DOUBLES + 32,), dtype=torch.float64, device=dev)  # state | last packet
         self.h_gn_state = torch.zeros((capi.GN_STATE_DOUBLES + 32,), dtype=torch.float64).pin_memory()
+        self.peer = None
+        transport = transport or os.environ.get("MP2P_B200_TRANSPORT", "peer")
+        if world > 1 and transport == "peer":
+
+            def exchange(handle: bytes):
+                got = [None] * world
+                dist.all_gather_object(got, handle)
+                return got
+
+            err = None
+            try:
+                self.peer = capi.Peer(ctx, rank, world, self.rec_words, exchange)
+            except capi.Mp2pError as e:
+                err = str(e)
+            # all ranks or none: a rank that failed to map a mailbox drags everybody to NCCL
+            flags = [None] * world
+            dist.all_gather_object(flags, err)
+            if any(f is not None for f in flags):
+                if self.peer is not None:
+                    self.peer.close()
+                self.peer = None
+                warnings.warn(f"NVLink mailbox exchange unavailable ({[f for f in flags if f][0]}); using NCCL collectives")
+        self.transport = "peer" if self.peer is not None else ("nccl" if world > 1 else "single")
+        self._records_ptr = self.records.data_ptr()
+        self._iters = {}
+
+    def _native(self, local, mprm, sprm, d_pairs, capacity):
+        """Pre-bound native iteration (peer transport only), cached per argument set."""
+        # keyed on object identity (cheap; the entry keeps the objects alive): parameter objects are
+        # bound when first seen — mutate a copy, not the instance, to change them
+        key = (tuple(id(x) if not isinstance(x, int) else x for x in local), id(mprm), id(sprm), int(d_pairs), int(capacity))
+        ent = self._iters.get(key)
+        if ent is None:
+            lx, ly, lz = local
+            ent = (self.peer.make_iterator(self.map, lx, ly, lz, self.n_local, mprm, sprm, self.per, d_pairs, capacity), local, mprm, sprm)
+            self._iters[key] = ent
+        return ent[0]
+
+    def _allreduce(self, t):
+        """SUM over ranks of a 32-double device packet, in place, enqueued on the context stream."""
+        if self.peer is not None:
+            self.peer.allreduce_packet(t.data_ptr())
+        else:
+            self.dist.all_reduce(t)
 
     # ---- matcher -------------------------------------------------------------------------------
     def _search_gather(self, local, pose, prm):
         if prm.pairingsPerPoint != self.k:
             raise ValueError("exchange buffers were sized for another pairingsPerPoint")
         lx, ly, lz = local
+        if self.peer is not None:
+            # the search writes the record into this rank's mailbox slot; a push kernel stores it into
+            # every peer's mailbox over NVLink and a wait kernel acquires the peers' flags
+            self.map.shard_search_pt2pt(lx, ly, lz, pose, prm, self.per, self.peer.record_slot(), n_local=self.n_local, local_on_device=True)
+            self._records_ptr = self.peer.allgather_records()
+            return
         self.map.shard_search_pt2pt(lx, ly, lz, pose, prm, self.per, self.mine.data_ptr(), n_local=self.n_local, local_on_device=True)
         if self.world > 1:
             self.dist.all_gather_into_tensor(self.records, self.mine)
@@ -110,7 +167,7 @@ class ShardedMatcherSolver:
         """(d_lx, d_ly, d_lz) = device addresses of THIS rank's shard, or (Cloud, None, None).
         Returns the number of pairs written to d_out (synchronises)."""
         self._search_gather((d_lx, d_ly, d_lz), pose, prm)
-        return self.map.shard_resolve_pt2pt(self.n_local, self.rank, self.world, self.per, self.records.data_ptr(), prm, out=d_out, out_on_device=True, capacity=capacity)
+        return self.map.shard_resolve_pt2pt(self.n_local, self.rank, self.world, self.per, self._records_ptr, prm, out=d_out, out_on_device=True, capacity=capacity)
 
     # ---- whole iterations, ONE host synchronisation ----------------------------------------------
     def iterate_pt2pt_horn(self, local, pose, mprm: capi.Pt2PtParams, sprm: capi.HornParams, d_pairs: int, capacity: int):
@@ -119,12 +176,15 @@ class ShardedMatcherSolver:
         and reads the two packets back once. Returns (solved, pose 3x4, pairs in the whole cloud)."""
         if sprm.use_scale_outlier_detector:
             raise ValueError("use_scale_outlier_detector needs the two-call path (match_pt2pt + solve_horn)")
+        if self.peer is not None:
+            ok, T, n_all, _ = self._native(local, mprm, sprm, d_pairs, capacity)(pose)
+            return ok, T, n_all
         p = self.packets
         self._search_gather(local, pose, mprm)
-        self.map.shard_resolve_pt2pt(self.n_local, self.rank, self.world, self.per, self.records.data_ptr(), mprm, out=d_pairs, out_on_device=True, capacity=capacity, sync=False, horn_sums=p.data_ptr())
-        self.dist.all_reduce(p[:32])
+        self.map.shard_resolve_pt2pt(self.n_local, self.rank, self.world, self.per, self._records_ptr, mprm, out=d_pairs, out_on_device=True, capacity=capacity, sync=False, horn_sums=p.data_ptr())
+        self._allreduce(p[:32])
         self.ctx.horn_moments(d_pairs, p.data_ptr(), 0, n=capi.COUNT_ON_DEVICE, prm=sprm, on_device=True, sums_on_device=True, packet=p[32:].data_ptr(), packet_on_device=True)
-        self.dist.all_reduce(p[32:])
+        self._allreduce(p[32:])
         self.h_packets.copy_(p, non_blocking=True)
         self.torch.cuda.current_stream().synchronize()
         h = self.h_packets.numpy()
@@ -137,14 +197,20 @@ class ShardedMatcherSolver:
     def iterate_pt2pt_gn(self, local, pose, mprm: capi.Pt2PtParams, sprm: capi.GNParams, d_pairs: int, capacity: int):
         """Matcher_Points_DistanceThreshold + Solver_GaussNewton over the sharded cloud:
         one synchronisation per inner Gauss-Newton iteration (the reduced 6x6 system comes to the host)."""
+        if self.peer is not None:
+            ok, T, _, it = self._native(local, mprm, sprm, d_pairs, capacity)(pose)
+            return ok, T, it
         self._search_gather(local, pose, mprm)
-        self.map.shard_resolve_pt2pt(self.n_local, self.rank, self.world, self.per, self.records.data_ptr(), mprm, out=d_pairs, out_on_device=True, capacity=capacity, sync=False)
+        self.map.shard_resolve_pt2pt(self.n_local, self.rank, self.world, self.per, self._records_ptr, mprm, out=d_pairs, out_on_device=True, capacity=capacity, sync=False)
         return self.gn_device_loop(d_pairs, capi.COUNT_ON_DEVICE, None, 0, sprm, pose)
 
     def iterate_pt2pl_gn(self, local, pose, mprm: capi.Pt2PlParams, sprm: capi.GNParams, d_pairs: int, capacity: int):
         """Matcher_Point2Plane + Solver_GaussNewton (C3). pt2pl never dedups global points
         (Matcher_Point2Plane.cpp:87-90), so the shards match independently; the solver all-reduces one
         packet per inner iteration with the pose on the device. ONE host synchronisation."""
+        if self.peer is not None:
+            ok, T, _, it = self._native(local, mprm, sprm, d_pairs, capacity)(pose)
+            return ok, T, it
         lx, ly, lz = local
         self.map.match_pt2pl(lx, ly, lz, pose, mprm, n_local=self.n_local, local_on_device=True, out=d_pairs, out_on_device=True, capacity=capacity, sync=False)
         return self.gn_device_loop(None, 0, d_pairs, capi.COUNT_ON_DEVICE, sprm, pose)
@@ -157,7 +223,7 @@ class ShardedMatcherSolver:
         self.ctx.gn_device_begin(pose0, st.data_ptr())
         for _ in range(prm.maxInnerLoopIterations):
             self.ctx.gn_device_accumulate(d_p2p, n2p, d_p2l, n2l, cp, st.data_ptr(), p.data_ptr())
-            self.dist.all_reduce(p)
+            self._allreduce(p)
             self.ctx.gn_device_step(p.data_ptr(), cp, st.data_ptr())
         self.h_gn_state.copy_(st, non_blocking=True)
         self.torch.cuda.current_stream().synchronize()

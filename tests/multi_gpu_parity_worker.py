@@ -50,11 +50,29 @@ def main():
     cloud = b200.Cloud(ctx, *xyz(mine))
     d_pairs2 = torch.zeros(len(mine) * 36, dtype=torch.uint8, device=dev)
     ok_f, T_f, n_all = sh.iterate_pt2pt_horn((cloud, None, None), pose, prm, b200.HornParams(), d_pairs2.data_ptr(), len(mine))
-    ok_fg, T_fg, it_fg = sh.iterate_pt2pt_gn((cloud, None, None), pose, prm, gprm, d_pairs2.data_ptr(), len(mine))
+    d_pairs3 = torch.zeros(len(mine) * 36, dtype=torch.uint8, device=dev)
+    ok_fg, T_fg, it_fg = sh.iterate_pt2pt_gn((cloud, None, None), pose, prm, gprm, d_pairs3.data_ptr(), len(mine))
+    # repeated calls (mailbox parities alternate, epochs grow) and the plain-array form
+    ok_f2, T_f2, n_all2 = True, T_f, n_all
+    for _ in range(3):
+        ok_f2, T_f2, n_all2 = sh.iterate_pt2pt_horn((d_l[0].data_ptr(), d_l[1].data_ptr(), d_l[2].data_ptr()), pose, prm, b200.HornParams(), d_pairs2.data_ptr(), len(mine))
     torch.cuda.synchronize()
-    fused_same = bool((d_pairs2[: n_pairs * 36] == d_pairs[: n_pairs * 36]).all().item())
-    df = max(np.abs(T_f - T_h).max(), np.abs(T_fg - T_g).max())
-    fused_ok = torch.tensor([int(fused_same and ok_f and ok_fg and df < 1e-9 and it_fg == it_g)], device=dev)
+    fused_same = bool((d_pairs2[: n_pairs * 36] == d_pairs[: n_pairs * 36]).all().item()) and bool((d_pairs3[: n_pairs * 36] == d_pairs[: n_pairs * 36]).all().item())
+    df = max(np.abs(T_f - T_h).max(), np.abs(T_fg - T_g).max(), np.abs(T_f2 - T_h).max())
+    fused_ok = int(fused_same and ok_f and ok_fg and ok_f2 and n_all2 == n_all and df < 1e-9 and it_fg == it_g)
+    # a cloud that does not divide evenly: the last shard is short (its record is padded)
+    Lu = L[: len(L) - 37]
+    shu = ShardedMatcherSolver(ctx, gmap, rank, world, len(Lu), k_max=1)
+    mu = Lu[shu.lo : shu.hi]
+    d_pu = torch.zeros(max(len(mu), 1) * 36, dtype=torch.uint8, device=dev)
+    ok_u, T_u, n_all_u = shu.iterate_pt2pt_horn((b200.Cloud(ctx, *xyz(mu)), None, None), pose, prm, b200.HornParams(), d_pu.data_ptr(), len(mu))
+    if rank == 0:
+        ref_u, _ = gmap.match_pt2pt(*xyz(Lu), pose, prm)
+        ok_ru, T_ru = ctx.solve_horn(ref_u)
+        mine_u = ref_u[ref_u["localIdx"] < shu.hi]
+        got_u = d_pu[: len(mine_u) * 36].cpu().numpy().view(b200.PAIR_PT2PT)
+        fused_ok = int(fused_ok and ok_u and n_all_u == len(ref_u) and np.abs(T_u - T_ru).max() < 1e-9 and got_u.tobytes() == mine_u.tobytes())
+    fused_ok = torch.tensor([fused_ok], device=dev)
     dist.all_reduce(fused_ok, op=dist.ReduceOp.MIN)
     # pt2pl + Gauss-Newton over a sharded scan (independent shards, device-resident GN loop)
     Ms = fx.make_street_scene(n_map=200_000, length=40.0)
@@ -81,7 +99,7 @@ def main():
         ok_r2, T_r2, it_r = ctx.solve_gauss_newton(ref, None, gprm, pose)
         same = len(got) == len(ref) and got.tobytes() == ref.tobytes()
         dh, dg = np.abs(T_h - T_r).max(), np.abs(T_g - T_r2).max()
-        print(f"world={world} pairs={len(got)} identical={same} horn_diff={dh:.2e} gn_diff={dg:.2e} gn_iters={it_g}/{it_r} one_sync_path_ok={int(fused_ok.item())} n_all={n_all}")
+        print(f"world={world} transport={sh.transport} pairs={len(got)} identical={same} horn_diff={dh:.2e} gn_diff={dg:.2e} gn_iters={it_g}/{it_r} one_sync_path_ok={int(fused_ok.item())} n_all={n_all}")
         ref_l, _ = smap.match_pt2pl(*xyz(S), g2, mkw)
         ok_pr, T_pr, it_pr = ctx.solve_gauss_newton(None, ref_l, skw, g2)
         dp = np.abs(T_p - T_pr).max()

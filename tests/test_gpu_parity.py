@@ -585,6 +585,49 @@ def test_solver_reads_last_match_device_copy(ctx):
         assert_pose_close(T, T_b, 1e-12)
 
 
+def test_speculative_solver_matches_plain_calls(ctx):
+    """After a solver call over the last matcher output, the next matcher call runs that solver
+    speculatively while the records travel to the host; the solver call that follows must return what
+    the plain two-call sequence returns (and a solver call with other parameters / another start
+    pose must not be served from the speculation)."""
+    M, L, gt = _c2(200_000, 10)
+    gmap = b200.Map(ctx, *xyz(M))
+    poses = [fx.pose_xyzypr(0.25, -0.15, 0.08, 1.7 * DEG, -0.8 * DEG, 1.2 * DEG), fx.pose_xyzypr(0.28, -0.18, 0.09, 1.9 * DEG, -0.9 * DEG, 1.4 * DEG), gt]
+    mprm = b200.Pt2PtParams(threshold=1.0)
+    for T in poses * 2:  # Horn
+        pairs, _ = gmap.match_pt2pt(*xyz(L), T, mprm)
+        ok_s, T_s = ctx.solve_horn(pairs, last_match=True)  # from the 2nd round on: speculated
+        ok_p, T_p = ctx.solve_horn(pairs.copy())            # plain upload
+        ok_s2, T_s2 = ctx.solve_horn(pairs, last_match=True)
+        assert ok_s and ok_p and ok_s2
+        assert_pose_close(T_s, T_p, 1e-12)
+        assert_pose_close(T_s2, T_p, 1e-12)
+    gn = b200.GNParams(maxInnerLoopIterations=4, kernel="Cauchy", kernelParam=0.3)
+    for k, T in enumerate(poses * 2):  # Gauss-Newton over the pt2pt list
+        pairs, _ = gmap.match_pt2pt(*xyz(L), T, mprm)
+        ok_s, T_s, it_s = ctx.solve_gauss_newton(pairs, None, gn, T, last_match=True)
+        ok_p, T_p, it_p = ctx.solve_gauss_newton(pairs.copy(), None, gn, T)
+        assert ok_s and ok_p and it_s == it_p
+        assert_pose_close(T_s, T_p, 1e-12)
+        if k:  # another start pose than the matcher's: must be solved for real
+            T2 = poses[(k + 1) % 3]
+            pairs, _ = gmap.match_pt2pt(*xyz(L), T, mprm)
+            ok_a, T_a, _ = ctx.solve_gauss_newton(pairs, None, gn, T2, last_match=True)
+            ok_b, T_b, _ = ctx.solve_gauss_newton(pairs.copy(), None, gn, T2)
+            assert_pose_close(T_a, T_b, 1e-12)
+    S = fx.make_street_scene(n_map=200_000, length=40.0)
+    scan = fx.make_lidar_scan((20.0, 0.3, 0.0), n_rings=16, n_az=400, length=40.0)
+    smap = b200.Map(ctx, *xyz(S))
+    pl = b200.Pt2PlParams(distanceThreshold=0.5, searchRadius=1.0, knn=8, minimumPlanePoints=5, planeEigenThreshold=0.01)
+    gm = b200.GNParams(maxInnerLoopIterations=3, kernel="GemanMcClure", kernelParam=0.15)
+    for T in [fx.pose_xyzypr(20.05, 0.28, 0.01, 0.01, 0.0, 0.0), fx.pose_xyzypr(20.02, 0.29, 0.0, 0.01, 0.0, 0.0)] * 2:
+        q, _ = smap.match_pt2pl(*xyz(scan), T, pl)
+        ok_s, T_s, it_s = ctx.solve_gauss_newton(None, q, gm, T, last_match=True)
+        ok_p, T_p, it_p = ctx.solve_gauss_newton(None, q.copy(), gm, T)
+        assert ok_s and ok_p and it_s == it_p
+        assert_pose_close(T_s, T_p, 1e-12)
+
+
 # --------------------------------------------------------------------------- resident (Morton-sorted) local cloud
 @pytest.mark.parametrize("kw", [dict(threshold=1.0), dict(threshold=2.5, pairingsPerPoint=3), dict(threshold=1.0, thresholdAngularDeg=0.5, allowMatchAlreadyMatchedGlobalPoints=True)])
 def test_resident_cloud_pt2pt_is_invisible(ctx, kw):
@@ -657,7 +700,8 @@ def test_resident_cloud_edge_cases(ctx):
 
 
 # --------------------------------------------------------------------------- multi-GPU (needs >= 2 GPUs)
-def test_multi_gpu_sharded_iteration_equals_single_gpu():
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_multi_gpu_sharded_iteration_equals_single_gpu(transport):
     import subprocess
     import sys
 
@@ -669,6 +713,6 @@ def test_multi_gpu_sharded_iteration_equals_single_gpu():
     world = 2 if n < 4 else 4
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.join(here, "multi_gpu_parity_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MP2P_B200_TRANSPORT=transport))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-    assert "identical=True" in r.stdout
+    assert "identical=True" in r.stdout and f"transport={transport}" in r.stdout
