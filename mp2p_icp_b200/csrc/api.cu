@@ -628,6 +628,11 @@ extern "C"
                     ctx->spec_want.kind == 1 && same_params(ctx->spec_want.horn, *prm))
                 {
                     ctx->spec_unused = 0;
+                    if (r.pending)
+                    {
+                        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                        ctx->spec_res.pending = false;
+                    }
                     return mp2p_b200_horn_finish(spec_host(ctx), spec_host(ctx) + MP2P_B200_PACKET_DOUBLES, pose_out, solved);
                 }
                 ctx->spec_want.kind = 1, ctx->spec_want.list = 1, ctx->spec_want.horn = *prm, ctx->spec_unused = 0;
@@ -861,6 +866,11 @@ extern "C"
                 if (r.valid && r.kind == 2 && r.list == list && r.n == n && lm.valid && lm.n == n && ctx->spec_want.kind == 2 &&
                     same_params(ctx->spec_want.gn, *prm) && std::memcmp(r.pose_in, pose_init, 96) == 0)
                 {
+                    if (r.pending)
+                    {
+                        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                        ctx->spec_res.pending = false;
+                    }
                     const double* hp = spec_host(ctx) + 64;
                     std::memcpy(pose_out, hp, 96);
                     if (iterations_done) *iterations_done = reinterpret_cast<const uint32_t*>(hp + 12)[1];

@@ -137,6 +137,7 @@ struct mp2p_b200_ctx
     struct SpecResult
     {
         bool     valid = false;
+        bool     pending = false;  // enqueued on the compute stream, not yet synchronised (zero-copy matcher output)
         int      kind = 0, list = 0;
         uint64_t n = 0;
         double   pose_in[12] = {};
@@ -183,6 +184,7 @@ struct mp2p_b200_ctx
     mp2p::DevBuf d_conv;               // pt2pl -> pt2pt conversion scratch and output
     // pinned host scratch
     void* h_pinned = nullptr;  // 4 KiB: counts, packets, poses
+    void* h_pinned_dev = nullptr;  // its device alias (kernels that hand a count to the host themselves)
     // 1 KiB of MAPPED pinned memory a kernel writes results into directly (host view / device view)
     double* h_mapped = nullptr;
     double* h_mapped_dev = nullptr;

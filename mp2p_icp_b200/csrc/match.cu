@@ -213,6 +213,9 @@ struct Pt2PtArgs
     uint32_t tile_stride;    // CTA b serves query tile (b * tile_stride) % n_tiles: spreads expensive
                              // neighbourhoods (sparse map regions cluster in any spatial order) over the grid
     unsigned long long slot_offset;  // K = 1 sharded single-launch iteration: global proposal slot of local point 0
+    // K = 1, local cloud read straight from the caller's pinned host arrays (zero copy): the search
+    // kernel leaves a device copy here for the compaction (NULL = the arrays are device memory)
+    float *stage_x, *stage_y, *stage_z;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -307,17 +310,19 @@ __global__ void __launch_bounds__(kQueryTile, MP2P_MATCH_MIN_BLOCKS)
 // scan `count` consecutive points for the smallest (d2, index) key: loads go out four at a time
 // (clamped to the last point of the run — a duplicate never wins the strict compare), so a voxel
 // of <= 4 points costs ONE memory round trip; returns the key, *best_j = position inside the run
+template <int W = 4>
 __device__ __forceinline__ unsigned long long scan_run_min(const float4* __restrict__ run, uint32_t count, float qx,
-                                                           float qy, float qz, unsigned long long m, uint32_t& best_j)
+                                                           float qy, float qz, unsigned long long m, uint32_t& best_j,
+                                                           uint32_t first = 0)
 {
     const uint32_t last = count - 1;
-    for (uint32_t j0 = 0; j0 < count; j0 += 4)
+    for (uint32_t j0 = first; j0 < count; j0 += W)
     {
-        float4 q[4];
+        float4 q[W];
 #pragma unroll
-        for (int k = 0; k < 4; k++) q[k] = __ldg(run + min(j0 + k, last));
+        for (int k = 0; k < W; k++) q[k] = __ldg(run + min(j0 + k, last));
 #pragma unroll
-        for (int k = 0; k < 4; k++)
+        for (int k = 0; k < W; k++)
         {
             const unsigned long long c = point_key(qx, qy, qz, q[k]);
             if (c < m) m = c, best_j = min(j0 + k, last);
@@ -328,7 +333,10 @@ __device__ __forceinline__ unsigned long long scan_run_min(const float4* __restr
 
 // Body of the K = 1 matcher for a CTA of NT threads (NT queries); shared by the stand-alone kernel
 // and by the fused single-launch iteration (k_iterate_nn1_horn).
-template <int NT>
+// R = neighbour items a lane keeps in flight per pass (their hash probes go out together, then the
+// first W points of each run): the dependent memory round trips of a warp's item list shrink from
+// 2 x ceil(items / 32) to 2 x ceil(items / (32 R)). CW = points per step of the centre-voxel scan.
+template <int NT, int R, int W, int CW>
 __device__ __forceinline__ void nn1_body(const GridView& g, const Pt2PtArgs& a, const float* __restrict__ lx,
                                          const float* __restrict__ ly, const float* __restrict__ lz,
                                          const uint32_t* __restrict__ perm, const uint32_t* __restrict__ lbits,
@@ -353,6 +361,8 @@ __device__ __forceinline__ void nn1_body(const GridView& g, const Pt2PtArgs& a, 
 
     float gx = 0, gy = 0, gz = 0;
     if (valid) compose_point_f(a.pose, tile.x[threadIdx.x], tile.y[threadIdx.x], tile.z[threadIdx.x], gx, gy, gz);
+    if (a.stage_x && valid)
+        a.stage_x[qpos] = tile.x[threadIdx.x], a.stage_y[qpos] = tile.y[threadIdx.x], a.stage_z[qpos] = tile.z[threadIdx.x];
     bbox_accumulate(bacc, gx, gy, gz, valid, bbox_words);
 
     // …DistanceThreshold.cpp:230,256-257 (float, unfused); skipped locals (:218-220) get radius 0
@@ -413,7 +423,7 @@ __device__ __forceinline__ void nn1_body(const GridView& g, const Pt2PtArgs& a, 
             {
                 sc.cands += count;
                 uint32_t                 j = 0;
-                const unsigned long long m = scan_run_min(g.pts + start, count, gx, gy, gz, best, j);
+                const unsigned long long m = scan_run_min<CW>(g.pts + start, count, gx, gy, gz, best, j);
                 if (m < best) best = m, best_pos = start + j;
             }
         }
@@ -474,51 +484,89 @@ __device__ __forceinline__ void nn1_body(const GridView& g, const Pt2PtArgs& a, 
         __syncwarp();
         const uint32_t   shift = g.level_shift[rl], hmask = (1u << (64 - shift)) - 1u;
         const CellEntry* tab   = g.table + g.level_off[rl];
-        for (uint32_t b0 = 0; b0 < total; b0 += 32)
+        for (uint32_t b0 = 0; b0 < total; b0 += 32 * R)
         {
-            const uint32_t id = b0 + lane;
-            // the shuffles below are executed by all lanes; lanes past the end mirror item 0's owner
-            const uint32_t it    = id < total ? s_item[warp][id] : 0u;
-            const int      owner = (int)(it >> 5);
-            const uint32_t bit   = it & 31u;
-            const float    oqx = __shfl_sync(FULL, gx, owner), oqy = __shfl_sync(FULL, gy, owner), oqz = __shfl_sync(FULL, gz, owner);
-            const int      ocx = __shfl_sync(FULL, cx, owner), ocy = __shfl_sync(FULL, cy, owner), ocz = __shfl_sync(FULL, cz, owner);
-            unsigned long long m   = ~0ull;
-            uint32_t           pos = 0;
-            if (id < total)
+            // ---- A: decode up to R items of this lane, first hash probe of each goes out
+            float              oq[R][3];
+            int                owner[R];
+            bool               have[R];
+            uint4              raw[R];
+            unsigned long long ckey[R];
+            uint32_t           h[R];
+#pragma unroll
+            for (int r = 0; r < R; r++)
             {
+                have[r] = false, owner[r] = 0, ckey[r] = 0ull, h[r] = 0u, raw[r] = make_uint4(0u, 0u, 0u, 0u);
+                oq[r][0] = oq[r][1] = oq[r][2] = 0.f;
+                if (b0 + r * 32 >= total) continue;  // warp-uniform
+                const uint32_t id = b0 + r * 32 + lane;
+                // the shuffles below are executed by all lanes; lanes past the end mirror item 0's owner
+                have[r]            = id < total;
+                const uint32_t it  = have[r] ? s_item[warp][id] : 0u;
+                owner[r]           = (int)(it >> 5);
+                const uint32_t bit = it & 31u;
+                oq[r][0] = __shfl_sync(FULL, gx, owner[r]), oq[r][1] = __shfl_sync(FULL, gy, owner[r]), oq[r][2] = __shfl_sync(FULL, gz, owner[r]);
+                const int ocx = __shfl_sync(FULL, cx, owner[r]), ocy = __shfl_sync(FULL, cy, owner[r]), ocz = __shfl_sync(FULL, cz, owner[r]);
                 const int dz = (int)(bit / 9u), dy = (int)((bit % 9u) / 3u), dx = (int)(bit % 3u);
-                const unsigned long long ckey =
-                    cell_key((uint32_t)(ocx + dx - 1), (uint32_t)(ocy + dy - 1), (uint32_t)(ocz + dz - 1));
-                uint32_t h     = cell_hash(ckey, shift);
-                uint32_t start = 0, count = 0;
+                ckey[r] = cell_key((uint32_t)(ocx + dx - 1), (uint32_t)(ocy + dy - 1), (uint32_t)(ocz + dz - 1));
+                h[r]    = cell_hash(ckey[r], shift);
+                if (have[r]) raw[r] = __ldg(reinterpret_cast<const uint4*>(tab + h[r]));
+            }
+            // ---- B: resolve the probes (linear probing continues on a collision)
+            uint32_t start[R], count[R];
+#pragma unroll
+            for (int r = 0; r < R; r++)
+            {
+                start[r] = 0u, count[r] = 0u;
+                if (!have[r]) continue;
                 sc.probes++;
-                while (true)  // linear probing continues on a collision
+                while (true)
                 {
-                    const uint4              raw = __ldg(reinterpret_cast<const uint4*>(tab + h));
-                    const unsigned long long k   = (unsigned long long)raw.x | ((unsigned long long)raw.y << 32);
-                    if (k == ckey)
+                    const unsigned long long k = (unsigned long long)raw[r].x | ((unsigned long long)raw[r].y << 32);
+                    if (k == ckey[r])
                     {
-                        start = raw.z, count = raw.w;
+                        start[r] = raw[r].z, count[r] = raw[r].w;
                         break;
                     }
                     if (k == kEmptyKey) break;
-                    h = (h + 1) & hmask;
-                }
-                if (count)
-                {
-                    sc.cands += count;
-                    uint32_t j = 0;
-                    m          = scan_run_min(g.pts + start, count, oqx, oqy, oqz, ~0ull, j);
-                    pos        = start + j;
-                    atomicMin(&s_best[warp][owner], m);
+                    h[r]   = (h[r] + 1) & hmask;
+                    raw[r] = __ldg(reinterpret_cast<const uint4*>(tab + h[r]));
                 }
             }
-            // keys are unique (the map index is part of the key): once all items of the round have
+            // ---- C: the first W points of every run found (index clamped to the run)
+            float4 pw[R][W];
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int k = 0; k < W; k++)
+                    pw[r][k] = count[r] ? __ldg(g.pts + start[r] + min((uint32_t)k, count[r] - 1u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // ---- D: keys; longer runs continue four points at a time; results to the owners
+            unsigned long long m[R];
+            uint32_t           pos[R];
+#pragma unroll
+            for (int r = 0; r < R; r++)
+            {
+                m[r] = ~0ull, pos[r] = 0u;
+                if (!count[r]) continue;
+                sc.cands += count[r];
+                uint32_t j = 0;
+#pragma unroll
+                for (int k = 0; k < W; k++)
+                {
+                    const unsigned long long c = point_key(oq[r][0], oq[r][1], oq[r][2], pw[r][k]);
+                    if (c < m[r]) m[r] = c, j = min((uint32_t)k, count[r] - 1u);
+                }
+                if (count[r] > (uint32_t)W) m[r] = scan_run_min<4>(g.pts + start[r], count[r], oq[r][0], oq[r][1], oq[r][2], m[r], j, W);
+                pos[r] = start[r] + j;
+                atomicMin(&s_best[warp][owner[r]], m[r]);
+            }
+            // keys are unique (the map index is part of the key): once all items of the pass have
             // offered theirs, at most one of them equals the owner's slot — that one records where
             // its point sits (the owner's own centre candidate keeps its position otherwise)
             __syncwarp();
-            if (m != ~0ull && s_best[warp][owner] == m) s_run[warp][owner] = pos;
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (m[r] != ~0ull && s_best[warp][owner[r]] == m[r]) s_run[warp][owner[r]] = pos[r];
             __syncwarp();
         }
         best     = s_best[warp][lane];
@@ -554,6 +602,12 @@ __device__ __forceinline__ void nn1_body(const GridView& g, const Pt2PtArgs& a, 
     flush_search_stats(sc, n_valid, stats);
 }
 
+#ifndef MP2P_NN1_FUSED_R
+#define MP2P_NN1_FUSED_R 1  // variant built into the single-launch iteration (register budget: 85)
+#define MP2P_NN1_FUSED_W 4
+#define MP2P_NN1_FUSED_CW 4
+#endif
+template <int R, int W, int CW>
 __global__ void __launch_bounds__(kNN1Threads)
     k_match_pt2pt_nn1(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
                       const float* __restrict__ lz, const uint32_t* __restrict__ perm,
@@ -562,8 +616,32 @@ __global__ void __launch_bounds__(kNN1Threads)
                       unsigned long long* __restrict__ cand, float4* __restrict__ cand_xyz,
                       uint32_t* __restrict__ bbox_words, unsigned long long* __restrict__ stats)
 {
-    nn1_body<kNN1Threads>(g, a, lx, ly, lz, perm, lbits, gbits, claim, cand, cand_xyz, bbox_words, stats);
+    nn1_body<kNN1Threads, R, W, CW>(g, a, lx, ly, lz, perm, lbits, gbits, claim, cand, cand_xyz, bbox_words, stats);
 }
+// variant of the stand-alone K = 1 kernel: $MP2P_NN1_VARIANT (A/B on the device). Measured on C2
+// (gpurun visit 19, profiles/r01_nn1_variants_ab.txt): 0 -> 33.0 us, 1 -> 33.4, 2 -> 34.0, 3 -> 43.3,
+// 4 -> 46.8 (register pressure costs the single wave): more items in flight per lane do not pay,
+// the kernel is bound by the L1 tag rate of its divergent 16-byte loads, not by the chain length.
+inline int nn1_variant()
+{
+    static int v = -1;
+    if (v < 0)
+    {
+        const char* e = getenv("MP2P_NN1_VARIANT");
+        v             = e ? atoi(e) : 0;
+        if (v < 0 || v > 4) v = 0;
+    }
+    return v;
+}
+#define MP2P_LAUNCH_NN1(grid, st, ...)                                                       \
+    switch (nn1_variant())                                                                   \
+    {                                                                                        \
+    case 0: k_match_pt2pt_nn1<1, 4, 4><<<grid, kNN1Threads, 0, st>>>(__VA_ARGS__); break;    \
+    case 1: k_match_pt2pt_nn1<2, 4, 4><<<grid, kNN1Threads, 0, st>>>(__VA_ARGS__); break;    \
+    case 2: k_match_pt2pt_nn1<2, 4, 8><<<grid, kNN1Threads, 0, st>>>(__VA_ARGS__); break;    \
+    case 3: k_match_pt2pt_nn1<4, 2, 8><<<grid, kNN1Threads, 0, st>>>(__VA_ARGS__); break;    \
+    default: k_match_pt2pt_nn1<4, 4, 8><<<grid, kNN1Threads, 0, st>>>(__VA_ARGS__); break;   \
+    }
 
 // ------------------------------------------------------------------------------------------
 // Single-pass stream compaction (decoupled look-back over 1024-slot tiles).
@@ -737,6 +815,10 @@ struct CompactArgs
     uint32_t scan_epoch;    // stamps the look-back status words of this call
     uint64_t slot_offset;   // sharded runs: first global proposal slot of this shard (index_offset*K)
     uint32_t index_offset;  // sharded runs: first global local-point index of this shard
+    // zero-copy output: the caller's pinned host buffer (device alias) also receives the records, and
+    // the pairing count goes to pinned memory — no D2H copy behind the kernel
+    uint32_t*           out_host;
+    unsigned long long* count_host;
 };
 
 __device__ __forceinline__ bool bbox_gate(const GridView& g, const uint32_t* __restrict__ words, float eps)
@@ -829,6 +911,12 @@ __device__ __forceinline__ uint32_t compact_pt2pt_body(
         uint32_t* dst = reinterpret_cast<uint32_t*>(out) + tile_base * 9;
         for (uint32_t k = threadIdx.x; k < n_rec * 9; k += kScanThreads) dst[k] = s_rec[k];
     }
+    if (a.out_host)
+    {
+        uint32_t* dst = a.out_host + tile_base * 9;
+        for (uint32_t k = threadIdx.x; k < n_rec * 9; k += kScanThreads) dst[k] = s_rec[k];
+        if (tile == n_tiles - 1 && threadIdx.x == 0) *a.count_host = tile_base + sm.tile_total;
+    }
     if (fs.packet)
     {
         const bool in  = ok && w < a.capacity;
@@ -907,7 +995,7 @@ __global__ void __launch_bounds__(kScanThreads, 3)
     if (SHARDED)  // the candidate words of this shard live in its record slot of the own mailbox
         cand = reinterpret_cast<unsigned long long*>(pv.box[pv.rank] + rec_offset(pv.rec_words, pv.world, pl.rec_epoch & 1u, pv.rank));
     // ---- phase 1
-    nn1_body<kScanThreads>(g, a, qx, qy, qz, perm, nullptr, nullptr, claim, cand, cand_xyz, bbox, nullptr);
+    nn1_body<kScanThreads, MP2P_NN1_FUSED_R, MP2P_NN1_FUSED_W, MP2P_NN1_FUSED_CW>(g, a, qx, qy, qz, perm, nullptr, nullptr, claim, cand, cand_xyz, bbox, nullptr);
     grid_barrier(cs, 0);
     const uint32_t* gate_box = bbox;
     if (SHARDED)
@@ -1241,10 +1329,36 @@ int start_level(const GridView& v, uint32_t K)
 
 // Host clouds are copied into (aligned) staging arrays; device-resident clouds are used in place.
 // Sets ctx->cur_l{x,y,z} (what the kernels read) and ctx->cur_tma_ok.
+// Device alias of a pinned (page-locked, mapped) host pointer, NULL for anything else. Zero copy can
+// be switched off with MP2P_ZERO_COPY=0.
+template <class T>
+T* mapped_alias(T* host)
+{
+    static int enabled = -1;
+    if (enabled < 0)
+    {
+        const char* e = getenv("MP2P_ZERO_COPY");
+        enabled       = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (!enabled || !host) return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return static_cast<T*>(at.devicePointer);
+}
+
+// mapped_ok (optional, out): the caller can let its search kernel read pinned host arrays in place
+// (then cur_q* = the host arrays' device aliases, cur_l* = staging arrays the kernel must fill)
 int stage_local(mp2p_b200_ctx* ctx, const float* lx, const float* ly, const float* lz, uint64_t n,
-                int on_device)
+                int on_device, bool* mapped_ok = nullptr)
 {
     ctx->cur_perm = nullptr;
+    if (mapped_ok && on_device != 0) mapped_ok = nullptr;
+    if (mapped_ok) *mapped_ok = false;
     if (on_device == 2)  // resident cloud: search kernels walk the Morton-sorted copy
     {
         const auto* c = reinterpret_cast<const mp2p_b200_cloud*>(lx);
@@ -1270,6 +1384,20 @@ int stage_local(mp2p_b200_ctx* ctx, const float* lx, const float* ly, const floa
     MP2P_TRY(ctx->d_lx.ensure(bytes));
     MP2P_TRY(ctx->d_ly.ensure(bytes));
     MP2P_TRY(ctx->d_lz.ensure(bytes));
+    if (mapped_ok)
+    {
+        // pinned host arrays are read by the search kernel itself over PCIe (the transfer overlaps
+        // the search); it leaves a device copy in the staging arrays for the compaction
+        const float *mx = mapped_alias(lx), *my = mapped_alias(ly), *mz = mapped_alias(lz);
+        if (mx && my && mz)
+        {
+            ctx->cur_qx = mx, ctx->cur_qy = my, ctx->cur_qz = mz;
+            ctx->cur_lx = ctx->d_lx.as<float>(), ctx->cur_ly = ctx->d_ly.as<float>(), ctx->cur_lz = ctx->d_lz.as<float>();
+            ctx->cur_tma_ok = false;
+            *mapped_ok      = true;
+            return 0;
+        }
+    }
     MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_lx.p, lx, bytes, cudaMemcpyHostToDevice, ctx->stream));
     MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_ly.p, ly, bytes, cudaMemcpyHostToDevice, ctx->stream));
     MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_lz.p, lz, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -1389,12 +1517,29 @@ int enqueue_speculation(mp2p_b200_ctx* ctx, const Rec* d_pairs, const unsigned l
 template <class Rec>
 int fetch_results(mp2p_b200_ctx* ctx, const unsigned long long* d_count, const Rec* d_pairs,
                   Rec* out, uint64_t capacity, int out_on_device, uint64_t* out_count, uint64_t* hint,
-                  const double* pose = nullptr, const double* sums = nullptr)
+                  const double* pose = nullptr, const double* sums = nullptr, bool zero_copy = false)
 {
     unsigned long long* h_count = static_cast<unsigned long long*>(ctx->h_pinned);
     uint64_t spec = 0;
-    ctx->spec_res.valid = false;
-    if (!out_on_device && capacity && ctx->copy_stream && pose && ctx->spec_want.kind)
+    ctx->spec_res.valid = false, ctx->spec_res.pending = false;
+    if (zero_copy)
+    {
+        // the compaction kernel stored records and count straight into the caller's pinned memory;
+        // the solver the caller is expected to ask for next is enqueued behind it and runs while the
+        // caller looks at the pairings
+        MP2P_CUDA_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        MP2P_CUDA_TRY(cudaEventSynchronize(ctx->ev_fork));
+        MP2P_CUDA_TRY(cudaGetLastError());
+        // (enqueued only now: an earlier speculation nobody collected has drained, so its pinned
+        // scratch can be reused)
+        if (pose && ctx->spec_want.kind)
+        {
+            MP2P_TRY(enqueue_speculation(ctx, d_pairs, d_count, capacity, pose, sums));
+            ctx->spec_res.pending = ctx->spec_res.valid;
+        }
+        spec = ~0ull;  // nothing left to copy
+    }
+    else if (!out_on_device && capacity && ctx->copy_stream && pose && ctx->spec_want.kind)
     {
         // records to the host on the copy stream, the expected solver on the compute stream
         spec = *hint == ~0ull ? capacity : std::min<uint64_t>(capacity, *hint + *hint / 8 + 1024);
@@ -1414,8 +1559,11 @@ int fetch_results(mp2p_b200_ctx* ctx, const unsigned long long* d_count, const R
             MP2P_CUDA_TRY(cudaMemcpyAsync(out, d_pairs, spec * sizeof(Rec), cudaMemcpyDeviceToHost, ctx->stream));
         }
     }
-    MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    MP2P_CUDA_TRY(cudaGetLastError());
+    if (!zero_copy)
+    {
+        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        MP2P_CUDA_TRY(cudaGetLastError());
+    }
     ctx->spec_res.n = *h_count;
     const uint64_t cnt = *h_count;
     *out_count         = cnt;
@@ -1539,7 +1687,8 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
         return MP2P_B200_ERR_ARG;
     }
     cudaStream_t st = ctx->stream;
-    MP2P_TRY(stage_local(ctx, lx, ly, lz, n_local, local_on_device));
+    bool local_mapped = false;
+    MP2P_TRY(stage_local(ctx, lx, ly, lz, n_local, local_on_device, K == 1 ? &local_mapped : nullptr));
     const uint32_t *d_lbits, *d_gbits;
     MP2P_TRY(upload_bits(ctx, ctx->d_lbits, lbits, n_local, &d_lbits));
     MP2P_TRY(upload_bits(ctx, ctx->d_gbits, gbits, nmap, &d_gbits));
@@ -1566,6 +1715,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     a.tag = (unsigned long long)(0xFFFFFFFFu - map->epoch) << 32;
     a.tma_ok = ctx->cur_tma_ok;
     a.rl_start = start_level(map->view, K);
+    if (local_mapped) a.stage_x = ctx->d_lx.as<float>(), a.stage_y = ctx->d_ly.as<float>(), a.stage_z = ctx->d_lz.as<float>();
 
     const float *  dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;  // caller order (records)
     const float *  dqx = ctx->cur_qx, *dqy = ctx->cur_qy, *dqz = ctx->cur_qz;  // what the search walks
@@ -1586,6 +1736,17 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     c.gate_eps = (float)(prm->threshold + prm->bounding_box_intersection_check_epsilon);
     c.capacity = std::min<uint64_t>(capacity, n_slots);
     c.scan_epoch = ctx->scan_epoch;
+    if (!out_on_device && !keep_on_device && c.capacity)
+    {
+        // pinned host output: the compaction stores the records there itself (no copy behind it)
+        c.out_host = reinterpret_cast<uint32_t*>(mapped_alias(out));
+        if (c.out_host)
+        {
+            if (!ctx->h_pinned_dev) ctx->h_pinned_dev = mapped_alias(ctx->h_pinned);
+            c.count_host = static_cast<unsigned long long*>(ctx->h_pinned_dev);
+            if (!c.count_host) c.out_host = nullptr;
+        }
+    }
 
     // whole iteration in one cooperative launch (k = 1, Horn sums AND moments wanted, no MatchState
     // bits, no search statistics), when the grid fits on the device
@@ -1615,6 +1776,44 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
         }
     }
     if (peer) return 1;  // nothing enqueued that the multi-kernel path does not redo
+    // Host output into pinned memory + a plain Solver_Horn expected next (the caller's previous solver
+    // call named the last matcher output): the single launch does search, compaction straight into
+    // the caller's buffer AND both Horn passes; the solver call that follows costs no GPU work.
+    if (K == 1 && !keep_on_device && c.out_host && !lbits && !gbits && !stats && ctx->spec_want.kind == 1 &&
+        ctx->spec_unused < 2 && ctx->spec_want.horn.robust_kernel == 0 && ctx->spec_want.horn.w_pt2pt > 0.0 &&
+        !ctx->spec_want.horn.use_scale_outlier_detector && ctx->h_mapped)
+    {
+        MP2P_TRY(ctx->d_candxyz.ensure(n_slots * sizeof(float4)));
+        cand_xyz        = ctx->d_candxyz.as<float4>();
+        double* packets = ctx->d_packet.as<double>() + 6 * MP2P_B200_PACKET_DOUBLES;  // [6],[7]: sums, moments
+        prof_begin(ctx, 0);
+        const int rc = launch_iterate_nn1_horn(ctx, map, a, c, sv, status, cand, cand_xyz, d_out, packets,
+                                               ctx->spec_want.horn.w_pt2pt, (uint32_t)n_tiles);
+        if (rc < 0) return rc;
+        if (rc == 0)
+        {
+            prof_end(ctx, 0);
+            MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            MP2P_CUDA_TRY(cudaGetLastError());
+            const uint64_t cnt = *static_cast<unsigned long long*>(ctx->h_pinned);
+            *out_count = cnt, ctx->hint_pt2pt = cnt;
+            ctx->last2p.dev = d_out, ctx->last2p.n = cnt, ctx->last2p.valid = cnt <= c.capacity;
+            ctx->last2p.sums = packets;
+            if (cnt > c.capacity)
+            {
+                set_error("output capacity %llu too small for %llu pairings", (unsigned long long)c.capacity, (unsigned long long)cnt);
+                return MP2P_B200_ERR_CAPACITY;
+            }
+            double* hp = nullptr;  // packets -> the speculation's pinned scratch
+            MP2P_TRY(read_iteration_packets(ctx, true, packets, &hp));
+            std::memcpy(spec_host(ctx), hp, 2 * MP2P_B200_PACKET_DOUBLES * 8);
+            ctx->spec_res.valid = true, ctx->spec_res.pending = false, ctx->spec_res.kind = 1, ctx->spec_res.list = 1;
+            ctx->spec_res.n = cnt;
+            std::memcpy(ctx->spec_res.pose_in, pose, 96);
+            ctx->spec_unused++;
+            return 0;
+        }
+    }
     prof_begin(ctx, 0);
 #define LAUNCH_MATCH(G)                                                                                    \
     {                                                                                                      \
@@ -1626,8 +1825,8 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     {
         MP2P_TRY(ctx->d_candxyz.ensure(n_slots * sizeof(float4)));
         cand_xyz = ctx->d_candxyz.as<float4>();
-        k_match_pt2pt_nn1<<<(uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), kNN1Threads, 0, st>>>(
-            map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, cand_xyz, sv.bbox, stats);
+        MP2P_LAUNCH_NN1((uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), st, map->view, a, dqx, dqy, dqz, ctx->cur_perm,
+                        d_lbits, d_gbits, claim, cand, cand_xyz, sv.bbox, stats);
     }
     else
     {
@@ -1662,7 +1861,8 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
         keep_on_device->d_count = sv.count, keep_on_device->d_pairs = d_out, keep_on_device->capacity = c.capacity;
         return 0;
     }
-    return fetch_results(ctx, sv.count, d_out, out, c.capacity, out_on_device, out_count, &ctx->hint_pt2pt, pose, fs.packet);
+    return fetch_results(ctx, sv.count, d_out, out, c.capacity, out_on_device, out_count, &ctx->hint_pt2pt, pose, fs.packet,
+                         c.out_host != nullptr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1755,8 +1955,8 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     {
         MP2P_TRY(ctx->d_candxyz.ensure(n_local * sizeof(float4)));
         const uint32_t nb = (uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads);
-        k_match_pt2pt_nn1<<<nb, kNN1Threads, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr,
-                                                      d_record, ctx->d_candxyz.as<float4>(), d_bbox6, stats);
+        MP2P_LAUNCH_NN1(nb, st, map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, d_record,
+                        ctx->d_candxyz.as<float4>(), d_bbox6, stats);
     }
     else
     {

@@ -628,6 +628,47 @@ def test_speculative_solver_matches_plain_calls(ctx):
         assert_pose_close(T_s, T_p, 1e-12)
 
 
+def test_pinned_host_buffers_take_the_zero_copy_path_and_change_nothing(ctx):
+    """Pinned (page-locked) local arrays are read by the k = 1 search kernel in place and a pinned
+    pairings buffer is written by the compaction kernel itself (no copies around the kernels): the
+    records, the count and the solver results must be those of the pageable-buffer calls."""
+    import torch
+
+    M, L, gt = _c2(200_000, 10)
+    gmap = b200.Map(ctx, *xyz(M))
+    pinned = [torch.from_numpy(a).pin_memory() for a in xyz(L)]
+    px, py, pz = (t.numpy() for t in pinned)
+    out_t = torch.zeros(len(L) * 36, dtype=torch.uint8).pin_memory()
+    out = out_t.numpy().view(b200.PAIR_PT2PT)
+    poses = [fx.pose_xyzypr(0.25, -0.15, 0.08, 1.7 * DEG, -0.8 * DEG, 1.2 * DEG), gt, fx.pose_xyzypr(5.0, 0.0, 0.0, 0.0, 0.0, 0.0)]
+    for kw in (dict(threshold=1.0), dict(threshold=1.0, allowMatchAlreadyMatchedGlobalPoints=True), dict(threshold=0.05)):
+        prm = b200.Pt2PtParams(**kw)
+        for T in poses * 2:
+            ref, _ = gmap.match_pt2pt(*xyz(L), T, prm)
+            out_t.fill_(0xAB)
+            got, _ = gmap.match_pt2pt(px, py, pz, T, prm, out=out)
+            assert len(got) == len(ref) and got.tobytes() == ref.tobytes()
+            if len(ref) >= 3:
+                ok_a, T_a = ctx.solve_horn(got, last_match=True)  # second round on: speculated behind the kernel
+                ok_b, T_b = ctx.solve_horn(ref.copy())
+                assert ok_a and ok_b
+                assert_pose_close(T_a, T_b, 1e-12)
+    # a pinned output that is too small: same error as the copy path, nothing written past its end
+    small_t = torch.zeros(1000 * 36 + 36, dtype=torch.uint8).pin_memory()
+    small_t[-36:] = 0xCD
+    with pytest.raises(b200.Mp2pError):
+        gmap.match_pt2pt(px, py, pz, gt, b200.Pt2PtParams(threshold=1.0), out=small_t.numpy()[: 1000 * 36].view(b200.PAIR_PT2PT), capacity=1000)
+    assert bool((small_t[-36:] == 0xCD).all())
+    # empty local cloud / k > 1 (copy path for the local arrays, zero-copy output only for k = 1)
+    got, _ = gmap.match_pt2pt(px[:0], py[:0], pz[:0], gt, b200.Pt2PtParams(threshold=1.0), out=out)
+    assert len(got) == 0
+    prm3 = b200.Pt2PtParams(threshold=2.5, pairingsPerPoint=3)
+    ref, _ = gmap.match_pt2pt(*xyz(L[:20000]), gt, prm3)
+    out3 = torch.zeros(20000 * 3 * 36, dtype=torch.uint8).pin_memory()
+    got, _ = gmap.match_pt2pt(px[:20000], py[:20000], pz[:20000], gt, prm3, out=out3.numpy().view(b200.PAIR_PT2PT))
+    assert got.tobytes() == ref.tobytes()
+
+
 # --------------------------------------------------------------------------- resident (Morton-sorted) local cloud
 @pytest.mark.parametrize("kw", [dict(threshold=1.0), dict(threshold=2.5, pairingsPerPoint=3), dict(threshold=1.0, thresholdAngularDeg=0.5, allowMatchAlreadyMatchedGlobalPoints=True)])
 def test_resident_cloud_pt2pt_is_invisible(ctx, kw):
