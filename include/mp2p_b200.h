@@ -214,6 +214,31 @@ int mp2p_b200_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* l
                           uint64_t capacity, int out_on_device, uint64_t* out_count,
                           uint64_t* potential_pairings);
 
+/* Parameters of Matcher_Points_InlierRatio (mp2p_icp/include/mp2p_icp/Matcher_Points_InlierRatio.h:50-56,
+ * mp2p_icp/src/Matcher_Points_InlierRatio.cpp:35-39) + Matcher_Points_Base. */
+typedef struct
+{
+    double  inliersRatio; /* (0,1); class default 0.80 */
+    int32_t allowMatchAlreadyMatchedPoints;
+    int32_t allowMatchAlreadyMatchedGlobalPoints;
+    double  bounding_box_intersection_check_epsilon; /* default 0.20 */
+} mp2p_b200_inlier_ratio_params;
+
+/* Matcher_Points_InlierRatio::implMatchOneLayer (mp2p_icp/src/Matcher_Points_InlierRatio.cpp:41-143;
+ * SURVEY.md §8f N1): the unbounded nearest neighbour of every local point not yet paired, the tentative
+ * pairings ordered by errorSquareAfterTransformation (equal distances in reverse local order, as the
+ * reference's multimap::emplace_hint(begin()) leaves them, :104), the first
+ * mrpt::round(nTotal * inliersRatio) of them emitted IN THAT ORDER, skipping global points already paired
+ * on entry or named by an earlier pairing of this call (:121-137). Arguments as mp2p_b200_match_pt2pt;
+ * *potential_pairings is incremented by n_local (:55). Where the reference throws — inliersRatio outside
+ * (0,1) (:49-50), no tentative pairing at all (:117) — the call returns MP2P_B200_ERR_ARG. */
+int mp2p_b200_match_inlier_ratio(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                                 const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
+                                 const mp2p_b200_inlier_ratio_params* params, const uint32_t* local_paired_bits,
+                                 const uint32_t* global_paired_bits, mp2p_b200_pair_pt2pt* out_pairs,
+                                 uint64_t capacity, int out_on_device, uint64_t* out_count,
+                                 uint64_t* potential_pairings);
+
 /* ---- query-sharded pt2pt matching, one process per GPU --------------------------
  * The local cloud is split in contiguous shards of `per_shard` points (the last may be shorter, or
  * empty); shard r owns the local indices [r*per_shard, r*per_shard + n_local_r). The map (and its

@@ -13,6 +13,7 @@ from .capi import (  # noqa: F401
     Context,
     GNParams,
     HornParams,
+    InlierRatioParams,
     Map,
     Mp2pError,
     Pt2PlParams,

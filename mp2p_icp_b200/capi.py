@@ -55,6 +55,15 @@ class _Pt2PlParams(C.Structure):
     ]
 
 
+class _InlierRatioParams(C.Structure):
+    _fields_ = [
+        ("inliersRatio", C.c_double),
+        ("allowMatchAlreadyMatchedPoints", C.c_int32),
+        ("allowMatchAlreadyMatchedGlobalPoints", C.c_int32),
+        ("bounding_box_intersection_check_epsilon", C.c_double),
+    ]
+
+
 class _HornParams(C.Structure):
     _fields_ = [
         ("use_scale_outlier_detector", C.c_int32),
@@ -121,6 +130,19 @@ class Pt2PlParams:
 
 
 @dataclass
+class InlierRatioParams:
+    """Parameters of Matcher_Points_InlierRatio (same names as the reference's YAML keys)."""
+
+    inliersRatio: float = 0.80
+    allowMatchAlreadyMatchedPoints: bool = False
+    allowMatchAlreadyMatchedGlobalPoints: bool = False
+    bounding_box_intersection_check_epsilon: float = 0.20
+
+    def c(self):
+        return _InlierRatioParams(self.inliersRatio, int(self.allowMatchAlreadyMatchedPoints), int(self.allowMatchAlreadyMatchedGlobalPoints), self.bounding_box_intersection_check_epsilon)
+
+
+@dataclass
 class HornParams:
     use_scale_outlier_detector: bool = False
     scale_outlier_threshold: float = 1.20
@@ -151,7 +173,7 @@ class GNParams:
 EXPORTS = [
     "mp2p_b200_last_error", "mp2p_b200_device_count", "mp2p_b200_ctx_create", "mp2p_b200_ctx_destroy",
     "mp2p_b200_ctx_synchronize", "mp2p_b200_ctx_launch_count", "mp2p_b200_map_create", "mp2p_b200_map_destroy",
-    "mp2p_b200_map_get_info", "mp2p_b200_knn", "mp2p_b200_match_pt2pt", "mp2p_b200_match_pt2pl",
+    "mp2p_b200_map_get_info", "mp2p_b200_knn", "mp2p_b200_match_pt2pt", "mp2p_b200_match_pt2pl", "mp2p_b200_match_inlier_ratio",
     "mp2p_b200_solve_horn", "mp2p_b200_solve_gauss_newton", "mp2p_b200_gn_accumulate",
     "mp2p_b200_gn_step_from_packet", "mp2p_b200_horn_sums", "mp2p_b200_horn_moments", "mp2p_b200_horn_finish",
     "mp2p_b200_host_alloc", "mp2p_b200_host_free", "mp2p_b200_ctx_set_profiling",
@@ -577,6 +599,21 @@ class Map:
         _check(load_library().mp2p_b200_match_pt2pt(self.ctx._h, self._h, plx, ply, plz, C.c_uint64(n_local), kind, _ptr(_pose(T)), C.byref(cp), _ptr(lb), _ptr(gb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt) if sync else None, C.byref(pot)))
         if not sync:
             return None, pot.value
+        if out_on_device:
+            return cnt.value, pot.value
+        return out[: cnt.value], pot.value
+
+    def match_inlier_ratio(self, lx, ly, lz, T, prm: InlierRatioParams, local_paired=None, global_paired=None, n_local=None, local_on_device=False, out=None, out_on_device=False, capacity=None):
+        """Matcher_Points_InlierRatio. Returns (pairs in ascending-distance order, potential_pairings)."""
+        plx, ply, plz, n_local, kind = _local(lx, ly, lz, n_local, local_on_device)
+        cap = capacity if capacity is not None else n_local
+        if out is None and not out_on_device:
+            out = np.empty(max(cap, 1), PAIR_PT2PT)
+        lb = pack_bits(local_paired) if local_paired is not None else None
+        gb = pack_bits(global_paired) if global_paired is not None else None
+        cp = prm.c()
+        cnt, pot = C.c_uint64(0), C.c_uint64(0)
+        _check(load_library().mp2p_b200_match_inlier_ratio(self.ctx._h, self._h, plx, ply, plz, C.c_uint64(n_local), kind, _ptr(_pose(T)), C.byref(cp), _ptr(lb), _ptr(gb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt), C.byref(pot)))
         if out_on_device:
             return cnt.value, pot.value
         return out[: cnt.value], pot.value

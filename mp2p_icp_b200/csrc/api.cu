@@ -282,7 +282,7 @@ extern "C"
         cudaStreamSynchronize(c->stream);
         for (DevBuf* b : {&c->d_lx, &c->d_ly, &c->d_lz, &c->d_cand, &c->d_candxyz, &c->d_lbits, &c->d_gbits, &c->d_scan,
                           &c->d_small, &c->d_out2p, &c->d_out2l, &c->d_plcand, &c->d_okflags, &c->d_fitlist, &c->d_coop, &c->d_knn_idx, &c->d_knn_d2,
-                          &c->d_knn_found, &c->d_pairs2p, &c->d_pairs2l, &c->d_partials, &c->d_packet,
+                          &c->d_knn_found, &c->d_irk0, &c->d_irk1, &c->d_irv0, &c->d_irv1, &c->d_irtmp, &c->d_pairs2p, &c->d_pairs2l, &c->d_partials, &c->d_packet,
                           &c->d_pose, &c->d_weights, &c->d_outlier, &c->d_conv})
             b->release();
         if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -475,6 +475,33 @@ extern "C"
                                  out_pairs, capacity, 1, &dummy, &dm));
         ctx->last_count = dm.d_count, ctx->last_capacity = dm.d_count ? dm.capacity : 0;
         return 0;
+    }
+
+    int mp2p_b200_match_inlier_ratio(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                                     const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
+                                     const mp2p_b200_inlier_ratio_params* prm, const uint32_t* local_paired_bits,
+                                     const uint32_t* global_paired_bits, mp2p_b200_pair_pt2pt* out_pairs,
+                                     uint64_t capacity, int out_on_device, uint64_t* out_count,
+                                     uint64_t* potential_pairings)
+    {
+        if (!ctx || !map || !pose || !prm || !out_count || (n_local && bad_local(lx, ly, lz, local_on_device)) ||
+            (capacity && !out_pairs))
+        {
+            set_error("match_inlier_ratio: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        if (!(prm->inliersRatio > 0.0) || !(prm->inliersRatio < 1.0))
+        {
+            set_error("match_inlier_ratio: inliersRatio must be in (0,1)");  // Matcher_Points_InlierRatio.cpp:49-50
+            return MP2P_B200_ERR_ARG;
+        }
+        if (potential_pairings) *potential_pairings += n_local;  // :55
+        DeviceGuard g(ctx->device);
+        ProfScope   ps(ctx);
+        return run_match_inlier_ratio(ctx, map, lx, ly, lz, n_local, local_on_device, pose, prm->inliersRatio,
+                                      prm->allowMatchAlreadyMatchedPoints, prm->allowMatchAlreadyMatchedGlobalPoints,
+                                      prm->bounding_box_intersection_check_epsilon, local_paired_bits, global_paired_bits,
+                                      out_pairs, capacity, out_on_device, out_count);
     }
 
     uint64_t mp2p_b200_shard_record_words(uint64_t per_shard, uint32_t pairingsPerPoint)

@@ -105,7 +105,7 @@ struct mp2p_b200_ctx
     bool         own_stream = false;
     uint64_t     launches   = 0;
     uint32_t     scan_epoch = 0;  // stamps look-back status words (match.cu)
-    uint64_t     hint_pt2pt = ~0ull, hint_pt2pl = ~0ull;  // previous pairing counts (speculative D2H size)
+    uint64_t     hint_pt2pt = ~0ull, hint_pt2pl = ~0ull, hint_ir = ~0ull;  // previous pairing counts (speculative D2H size)
     // pairing count a matcher call left on the device without reading it back (shard_resolve with
     // out_count == NULL), consumed by solver calls given n = MP2P_B200_COUNT_ON_DEVICE
     const unsigned long long* last_count    = nullptr;
@@ -174,6 +174,7 @@ struct mp2p_b200_ctx
     mp2p::DevBuf d_plcand, d_okflags;  // per-query plane candidates + accepted flags (pt2pl)
     mp2p::DevBuf d_fitlist;            // [0] count, [1..] queries that qualify for a plane fit
     mp2p::DevBuf d_knn_idx, d_knn_d2, d_knn_found;
+    mp2p::DevBuf d_irk0, d_irk1, d_irv0, d_irv1, d_irtmp;  // Matcher_Points_InlierRatio: sort keys / values / scratch
     // solver scratch
     mp2p::DevBuf d_pairs2p, d_pairs2l; // H2D staging of host pairings
     mp2p::DevBuf d_partials;           // per-block partial sums
@@ -273,6 +274,10 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
                             const mp2p_b200_pt2pt_params* prm, const uint32_t* gbits,
                             mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device,
                             uint64_t* out_count, double* d_horn_sums);
+int run_match_inlier_ratio(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly, const float* lz,
+                           uint64_t n_local, int local_on_device, const double pose[12], double ratio, int allowLocal,
+                           int allowGlobal, double bbox_eps, const uint32_t* lbits, const uint32_t* gbits,
+                           mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device, uint64_t* out_count);
 int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const float* qy,
             const float* qz, uint64_t nq, uint32_t k, float radius2, uint32_t* out_idx,
             float* out_d2, int32_t* out_found);

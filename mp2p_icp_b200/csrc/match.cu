@@ -24,6 +24,7 @@
 #include "grid_search.cuh"
 #include "plane_fit.cuh"
 #include "peer.cuh"
+#include "radix_sort.cuh"
 #include "reduce.cuh"
 
 namespace mp2p
@@ -2182,6 +2183,210 @@ int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const
     MP2P_CUDA_TRY(cudaMemcpyAsync(out_found, ctx->d_knn_found.p, nq * 4, cudaMemcpyDeviceToHost, st));
     MP2P_CUDA_TRY(cudaStreamSynchronize(st));
     MP2P_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Matcher_Points_InlierRatio (mp2p_icp/src/Matcher_Points_InlierRatio.cpp:41-143):
+// unbounded 1-NN of every local point (the K = 1 search kernel with an infinite radius), all
+// tentative pairings ordered by errorSquareAfterTransformation, the first
+// mrpt::round(nTotal * inliersRatio) kept and emitted IN THAT ORDER, a global point going to the
+// first pairing (in sorted order) that names it.
+//   k_ir_keys     32-bit sort keys (the distance bits; "no candidate" sorts last) laid out by
+//                 DESCENDING local index + count of the tentative pairings
+//   rs::sort_pairs  stable LSD radix sort, 4 passes: equal distances stay in descending local index
+//                 = reverse insertion order = what multimap::emplace_hint(begin()) leaves (:104)
+//   k_ir_claim    positions p < nKeep propose  claim[g] = min(tag | p)
+//   k_ir_compact  acceptance + scan + records staged in shared memory, coalesced stores
+// ------------------------------------------------------------------------------------------
+namespace
+{
+__device__ __forceinline__ unsigned long long ir_keep(const unsigned long long* __restrict__ n_total, double ratio)
+{
+    // mrpt::round(double(nTotal) * inliersRatio), :119 — lrint: nearest, ties to even
+    return (unsigned long long)__double2ll_rn(__dmul_rn((double)__ldg(n_total), ratio));
+}
+
+__global__ void __launch_bounds__(256)
+    k_ir_keys(const unsigned long long* __restrict__ cand, uint32_t n, unsigned long long* __restrict__ keys,
+              uint32_t* __restrict__ vals, unsigned long long* __restrict__ n_total)
+{
+    const uint32_t j     = blockIdx.x * 256u + threadIdx.x;
+    bool           valid = false;
+    if (j < n)
+    {
+        const uint32_t           i = n - 1u - j;
+        const unsigned long long c = cand[i];
+        valid                      = (uint32_t)c != 0xFFFFFFFFu;
+        keys[j]                    = valid ? (c >> 32) : 0xFFFFFFFFull;
+        vals[j]                    = i;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_total, (unsigned long long)__popc(m));
+}
+
+__global__ void __launch_bounds__(256)
+    k_ir_claim(const unsigned long long* __restrict__ cand, const uint32_t* __restrict__ vals,
+               const unsigned long long* __restrict__ n_total, double ratio, unsigned long long tag,
+               const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim)
+{
+    const unsigned long long p = (unsigned long long)blockIdx.x * 256u + threadIdx.x;
+    if (p >= ir_keep(n_total, ratio)) return;
+    const uint32_t g = (uint32_t)cand[vals[p]];
+    if (!bit_set(gbits, g)) atomicMin(claim + g, tag | p);
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+    k_ir_compact(GridView g, uint32_t n_local, int allowGlobal, unsigned long long tag, float gate_eps, uint64_t capacity,
+                 uint32_t scan_epoch, double ratio, const float* __restrict__ lx, const float* __restrict__ ly,
+                 const float* __restrict__ lz, const uint32_t* __restrict__ gbits,
+                 const unsigned long long* __restrict__ claim, const unsigned long long* __restrict__ cand,
+                 const float4* __restrict__ cand_xyz, const uint32_t* __restrict__ vals,
+                 unsigned long long* __restrict__ n_total /* [0] tentative pairings, [1] out: bbox gate */,
+                 const uint32_t* __restrict__ bbox, uint32_t* __restrict__ bbox_next, unsigned long long* __restrict__ status,
+                 uint32_t* __restrict__ tile_counter, mp2p_b200_pair_pt2pt* __restrict__ out,
+                 unsigned long long* __restrict__ out_count)
+{
+    __shared__ ScanSmem sm;
+    __shared__ uint32_t s_rec[kScanThreads * 9];
+    bbox_rearm(bbox_next);
+    const uint32_t n_tiles = (n_local + kScanTile - 1) / kScanTile;
+    if (threadIdx.x == 0)
+    {
+        sm.tile_id = atomicAdd(tile_counter, 1u);
+        if (sm.tile_id == n_tiles - 1) *tile_counter = 0u;
+    }
+    __syncthreads();
+    const uint32_t tile = sm.tile_id;
+    const bool     gate = bbox_gate(g, bbox, gate_eps);
+    if (tile == 0 && threadIdx.x == 0) n_total[1] = gate ? 1ull : 0ull;
+    const unsigned long long p  = (unsigned long long)tile * kScanTile + threadIdx.x;
+    bool                     ok = gate && p < ir_keep(n_total, ratio);
+    uint32_t                 i = 0, gi = 0;
+    unsigned long long       c  = 0;
+    float4                   gp = make_float4(0.f, 0.f, 0.f, 0.f);
+    float                    px = 0.f, py = 0.f, pz = 0.f;
+    if (ok)
+    {
+        i  = vals[p];
+        c  = cand[i];
+        gi = (uint32_t)c;
+        gp = __ldg(cand_xyz + i);
+        px = lx[i], py = ly[i], pz = lz[i];
+        if (!allowGlobal) ok = !bit_set(gbits, gi) && __ldcg(claim + gi) == (tag | p);  // :126-128
+    }
+    const unsigned long long w         = grid_exclusive_scan(sm, tile, n_tiles, ok ? 1u : 0u, status, out_count, scan_epoch);
+    const unsigned long long tile_base = sm.tile_base;
+    if (ok)
+    {
+        uint32_t* o = s_rec + (uint32_t)(w - tile_base) * 9;
+        o[0] = gi, o[1] = i;
+        o[2] = __float_as_uint(gp.x), o[3] = __float_as_uint(gp.y), o[4] = __float_as_uint(gp.z);
+        o[5] = __float_as_uint(px), o[6] = __float_as_uint(py), o[7] = __float_as_uint(pz);
+        o[8] = (uint32_t)(c >> 32);
+    }
+    __syncthreads();
+    const unsigned long long room  = capacity > tile_base ? capacity - tile_base : 0ull;
+    const uint32_t           n_rec = (uint32_t)min((unsigned long long)sm.tile_total, room);
+    uint32_t*                dst   = reinterpret_cast<uint32_t*>(out) + tile_base * 9;
+    for (uint32_t k = threadIdx.x; k < n_rec * 9; k += kScanThreads) dst[k] = s_rec[k];
+}
+}  // namespace
+
+// *status_out: 0 ok, 1 = the reference would have thrown ASSERT_(nTotal > 0) (:117)
+int run_match_inlier_ratio(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly, const float* lz,
+                           uint64_t n_local, int local_on_device, const double pose[12], double ratio, int allowLocal,
+                           int allowGlobal, double bbox_eps, const uint32_t* lbits, const uint32_t* gbits,
+                           mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device, uint64_t* out_count)
+{
+    *out_count = 0;
+    ctx->last2p.valid = false, ctx->last2p.sums = nullptr, ctx->spec_res.valid = false;
+    const uint64_t nmap = map->view.n_points;
+    if (nmap == 0 || n_local == 0) return 0;  // :58
+    if (n_local >= 0x7FFFFFFFull)
+    {
+        set_error("match_inlier_ratio: n_local must be < 2^31");
+        return MP2P_B200_ERR_ARG;
+    }
+    cudaStream_t st = ctx->stream;
+    MP2P_TRY(stage_local(ctx, lx, ly, lz, n_local, local_on_device));
+    const uint32_t *d_lbits, *d_gbits;
+    MP2P_TRY(upload_bits(ctx, ctx->d_lbits, lbits, n_local, &d_lbits));
+    MP2P_TRY(upload_bits(ctx, ctx->d_gbits, gbits, nmap, &d_gbits));
+    const uint64_t      n_tiles = (n_local + kScanTile - 1) / kScanTile;
+    SmallView           sv;
+    unsigned long long* status;
+    MP2P_TRY(prepare_small(ctx, n_tiles, sv, &status));
+    MP2P_TRY(ctx->d_cand.ensure(n_local * 8));
+    MP2P_TRY(ctx->d_candxyz.ensure(n_local * sizeof(float4)));
+    const uint32_t sort_tiles = (uint32_t)((n_local + rs::kTile - 1) / rs::kTile);
+    MP2P_TRY(ctx->d_irk0.ensure(n_local * 8));
+    MP2P_TRY(ctx->d_irk1.ensure(n_local * 8));
+    MP2P_TRY(ctx->d_irv0.ensure(n_local * 4));
+    MP2P_TRY(ctx->d_irv1.ensure(n_local * 4));
+    MP2P_TRY(ctx->d_irtmp.ensure(((size_t)256 * sort_tiles + 256) * 4 + 64));
+    if (++map->epoch == 0xFFFFFFFFu)
+    {
+        MP2P_CUDA_TRY(cudaMemsetAsync(map->d_claim.p, 0xff, nmap * 8, st));
+        map->epoch = 1;
+    }
+    const unsigned long long tag = (unsigned long long)(0xFFFFFFFFu - map->epoch) << 32;
+
+    Pt2PtArgs a{};
+    for (int k = 0; k < 12; k++) a.pose.m[k] = pose[k];
+    a.maxDistSq = __builtin_inff(), a.angSq = 0.f;  // nn_single_search is unbounded (:89-91)
+    a.n_local = (uint32_t)n_local, a.K = 1;
+    a.allowLocal = allowLocal, a.allowGlobal = 1;  // no proposals from the search: claims follow the sort
+    a.tma_ok   = ctx->cur_tma_ok;
+    a.rl_start = start_level(map->view, 1);
+    auto*               cand     = ctx->d_cand.as<unsigned long long>();
+    auto*               cand_xyz = ctx->d_candxyz.as<float4>();
+    unsigned long long* stats    = nullptr;
+    MP2P_TRY(prepare_stats(ctx, &stats));
+    prof_begin(ctx, 0);
+    MP2P_LAUNCH_NN1((uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), st, map->view, a, ctx->cur_qx, ctx->cur_qy,
+                    ctx->cur_qz, ctx->cur_perm, d_lbits, nullptr, nullptr, cand, cand_xyz, sv.bbox, stats);
+    prof_end(ctx, 0);
+    count_launch(ctx);
+
+    prof_begin(ctx, 1);
+    // counters live behind the sort scratch: [0] tentative pairings, [1] bbox gate
+    auto* n_total = reinterpret_cast<unsigned long long*>(ctx->d_irtmp.as<char>() + ((size_t)256 * sort_tiles + 256) * 4);
+    n_total       = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(n_total) + 15) & ~uintptr_t(15));
+    MP2P_CUDA_TRY(cudaMemsetAsync(n_total, 0, 16, st));
+    const uint32_t nb = (uint32_t)((n_local + 255) / 256);
+    k_ir_keys<<<nb, 256, 0, st>>>(cand, (uint32_t)n_local, ctx->d_irk0.as<unsigned long long>(), ctx->d_irv0.as<uint32_t>(), n_total);
+    count_launch(ctx);
+    MP2P_TRY(rs::sort_pairs(ctx, ctx->d_irk0.as<unsigned long long>(), ctx->d_irv0.as<uint32_t>(),
+                            ctx->d_irk1.as<unsigned long long>(), ctx->d_irv1.as<uint32_t>(), (uint32_t)n_local, 32,
+                            ctx->d_irtmp.as<uint32_t>()));
+    auto* claim = map->d_claim.as<unsigned long long>();
+    if (!allowGlobal)
+    {
+        k_ir_claim<<<nb, 256, 0, st>>>(cand, ctx->d_irv0.as<uint32_t>(), n_total, ratio, tag, d_gbits, claim);
+        count_launch(ctx);
+    }
+    mp2p_b200_pair_pt2pt* d_out = out;
+    const uint64_t        cap   = std::min<uint64_t>(capacity, n_local);
+    if (!out_on_device)
+    {
+        MP2P_TRY(ctx->d_out2p.ensure(cap * sizeof(mp2p_b200_pair_pt2pt)));
+        d_out = ctx->d_out2p.as<mp2p_b200_pair_pt2pt>();
+    }
+    k_ir_compact<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, (uint32_t)n_local, allowGlobal, tag, (float)bbox_eps, cap,
+                                                            ctx->scan_epoch, ratio, ctx->cur_lx, ctx->cur_ly, ctx->cur_lz, d_gbits,
+                                                            claim, cand, cand_xyz, ctx->d_irv0.as<uint32_t>(), n_total, sv.bbox,
+                                                            sv.bbox_next, status, sv.tile_counter, d_out, sv.count);
+    prof_end(ctx, 1);
+    count_launch(ctx);
+    unsigned long long* h_tot = reinterpret_cast<unsigned long long*>(static_cast<char*>(ctx->h_pinned) + 64);
+    MP2P_CUDA_TRY(cudaMemcpyAsync(h_tot, n_total, 16, cudaMemcpyDeviceToHost, st));
+    MP2P_TRY(fetch_results(ctx, sv.count, d_out, out, cap, out_on_device, out_count, &ctx->hint_ir));
+    if (h_tot[1] && h_tot[0] == 0)
+    {
+        set_error("match_inlier_ratio: no tentative pairing at all (the reference asserts nTotal > 0, Matcher_Points_InlierRatio.cpp:117)");
+        return MP2P_B200_ERR_ARG;
+    }
     return 0;
 }
 }  // namespace mp2p

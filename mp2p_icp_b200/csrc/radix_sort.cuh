@@ -18,7 +18,7 @@ constexpr int kItems   = 8;
 constexpr int kTile    = kThreads * kItems;  // 2048 pairs per CTA
 constexpr int kWarps   = kThreads / 32;
 
-__global__ void __launch_bounds__(kThreads)
+static __global__ void __launch_bounds__(kThreads)
     k_rs_hist(const unsigned long long* __restrict__ keys, uint32_t n, int shift,
               uint32_t* __restrict__ hist /*[256][n_tiles]*/, uint32_t n_tiles)
 {
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // one CTA per digit: in-place exclusive scan over the tiles, total[digit] = sum
-__global__ void __launch_bounds__(kThreads)
+static __global__ void __launch_bounds__(kThreads)
     k_rs_scan_a(uint32_t* __restrict__ hist, uint32_t n_tiles, uint32_t* __restrict__ total)
 {
     __shared__ uint32_t wsum[kWarps];
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kThreads)
     if (threadIdx.x == 0) total[blockIdx.x] = carry;
 }
 
-__global__ void __launch_bounds__(256) k_rs_scan_b(uint32_t* __restrict__ total /*in: counts, out: exclusive*/)
+static __global__ void __launch_bounds__(256) k_rs_scan_b(uint32_t* __restrict__ total /*in: counts, out: exclusive*/)
 {
     __shared__ uint32_t wsum[8];
     const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) k_rs_scan_b(uint32_t* __restrict__ total 
     total[threadIdx.x] = off + x - v;
 }
 
-__global__ void __launch_bounds__(kThreads)
+static __global__ void __launch_bounds__(kThreads)
     k_rs_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                  unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
                  const uint32_t* __restrict__ prefix /*[256][n_tiles]*/, const uint32_t* __restrict__ dbase /*[256]*/,

@@ -72,6 +72,15 @@ extern "C"
         double   bounding_box_intersection_check_epsilon;
     };
 
+    // Matcher_Points_InlierRatio (mp2p_icp/include/mp2p_icp/Matcher_Points_InlierRatio.h) + Matcher_Points_Base
+    struct orc_match_inlier_params
+    {
+        double  inliersRatio;
+        int32_t allowMatchAlreadyMatchedPoints;
+        int32_t allowMatchAlreadyMatchedGlobalPoints;
+        double  bounding_box_intersection_check_epsilon;
+    };
+
     struct orc_horn_params
     {
         int32_t use_scale_outlier_detector;
@@ -329,6 +338,76 @@ extern "C"
             }
         }
         return nOut;
+    }
+
+    // ---------------------------------------------------------------- inlier-ratio matcher
+    // Matcher_Points_InlierRatio::implMatchOneLayer (mp2p_icp/src/Matcher_Points_InlierRatio.cpp:41-143):
+    // unbounded nn_single_search per local point (:89-91), all tentative pairings sorted by
+    // errorSquareAfterTransformation in a std::multimap filled with emplace_hint(begin()) (:104 —
+    // equal keys therefore end up in REVERSE insertion order: the hint puts a new element at the
+    // lower bound of its key), the first nKeep = mrpt::round(nTotal * inliersRatio) kept (:113),
+    // then emitted in sorted order skipping global points already paired, marking both bitfields as
+    // it goes (:121-137). The same std::multimap call is used here, so tie order is the reference's
+    // by construction. mrpt::round(double) is recalled from MRPT 2.x <mrpt/core/round.h> as
+    // lrint / _mm_cvtsd_si32, i.e. round-half-to-even in the default rounding mode (MRPT is not in
+    // this container: unverifiable here). Returns the number of pairings, or -1
+    // where the reference throws (ASSERT_(nTotal > 0), :111; ratio outside (0,1), :49-50).
+    long orc_match_inlier_ratio(void* tree, const float* lx, const float* ly, const float* lz, size_t nLocal,
+                                const double T[12], const orc_match_inlier_params* prm, uint8_t* local_paired,
+                                uint8_t* global_paired, orc_pair_pt2pt* out, size_t out_capacity,
+                                uint64_t* potential_pairings, int nthreads)
+    {
+        const auto* kd   = static_cast<const KDTree*>(tree);
+        const Pose  pose = to_pose(T);
+        if (!(prm->inliersRatio > 0.0) || !(prm->inliersRatio < 1.0)) return -1;  // :49-50
+        if (potential_pairings) *potential_pairings += nLocal;                    // :55
+        if (kd->n == 0 || nLocal == 0) return 0;                                   // :58
+
+        std::vector<float> gx(nLocal), gy(nLocal), gz(nLocal);
+        float              lmin[3], lmax[3];
+        transform_local_to_global(lx, ly, lz, nLocal, pose, gx.data(), gy.data(), gz.data(), lmin, lmax);  // :60
+        if (!bbox_intersects(kd->bbmin, kd->bbmax, lmin, lmax,
+                             static_cast<float>(prm->bounding_box_intersection_check_epsilon)))
+            return 0;  // :64-67
+
+        std::vector<uint32_t> nnIdx(nLocal);
+        std::vector<float>    nnD2(nLocal);
+        std::vector<int32_t>  nnCount(nLocal, 0);
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads > 0 ? nthreads : 1)
+        for (long i = 0; i < static_cast<long>(nLocal); i++)
+        {
+            if (!prm->allowMatchAlreadyMatchedPoints && local_paired && local_paired[i]) continue;  // :81-83
+            const float q[3] = {gx[i], gy[i], gz[i]};
+            nnCount[i]       = kd->knn(q, 1, std::numeric_limits<float>::infinity(), &nnIdx[i], &nnD2[i]);  // :89-91
+        }
+        std::multimap<double, orc_pair_pt2pt> sortedPairings;  // :76
+        for (size_t i = 0; i < nLocal; i++)
+        {
+            if (nnCount[i] < 1) continue;
+            orc_pair_pt2pt p;
+            const uint32_t g = nnIdx[i];
+            p.globalIdx = g, p.localIdx = static_cast<uint32_t>(i);
+            p.gx = kd->x[g], p.gy = kd->y[g], p.gz = kd->z[g];
+            p.lx = lx[i], p.ly = ly[i], p.lz = lz[i];
+            p.errSq = nnD2[i];
+            sortedPairings.emplace_hint(sortedPairings.begin(), static_cast<double>(nnD2[i]), p);  // :104
+        }
+        const size_t nTotal = sortedPairings.size();
+        if (nTotal == 0) return -1;  // :111
+        const long nKeep = lrint(static_cast<double>(nTotal) * prm->inliersRatio);  // :113
+        auto       itEnd = sortedPairings.begin();
+        std::advance(itEnd, nKeep);
+        size_t nOut = 0;
+        for (auto it = sortedPairings.begin(); it != itEnd; ++it)
+        {
+            const uint32_t li = it->second.localIdx, gi = it->second.globalIdx;
+            if (!prm->allowMatchAlreadyMatchedGlobalPoints && global_paired && global_paired[gi]) continue;  // :126-128
+            if (nOut < out_capacity) out[nOut] = it->second;
+            nOut++;
+            if (local_paired) local_paired[li] = 1;  // :133-135
+            if (global_paired) global_paired[gi] = 1;
+        }
+        return static_cast<long>(nOut);
     }
 
     // ---------------------------------------------------------------- pt2pl matcher (a7, a7')

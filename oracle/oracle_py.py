@@ -246,6 +246,43 @@ def match_pt2pt(tree: KDTree, lx, ly, lz, T, prm: MatchPt2PtParams, local_paired
     return out[:cnt], pot.value
 
 
+class _MatchInlierParams(C.Structure):
+    _fields_ = [
+        ("inliersRatio", C.c_double),
+        ("allowMatchAlreadyMatchedPoints", C.c_int32),
+        ("allowMatchAlreadyMatchedGlobalPoints", C.c_int32),
+        ("bounding_box_intersection_check_epsilon", C.c_double),
+    ]
+
+
+@dataclass
+class MatchInlierRatioParams:
+    inliersRatio: float
+    allowMatchAlreadyMatchedPoints: bool = False
+    allowMatchAlreadyMatchedGlobalPoints: bool = False
+    bounding_box_intersection_check_epsilon: float = 0.20
+
+
+def match_inlier_ratio(tree: KDTree, lx, ly, lz, T, prm: MatchInlierRatioParams, local_paired=None, global_paired=None, nthreads=1):
+    """Matcher_Points_InlierRatio (Matcher_Points_InlierRatio.cpp:41-143). The bitfields (one byte per
+    point) are updated in place like MatchState. Raises where the reference throws."""
+    lx, ly, lz = _f32(lx), _f32(ly), _f32(lz)
+    n = lx.size
+    cp = _MatchInlierParams(prm.inliersRatio, int(prm.allowMatchAlreadyMatchedPoints), int(prm.allowMatchAlreadyMatchedGlobalPoints), prm.bounding_box_intersection_check_epsilon)
+    if local_paired is None:
+        local_paired = np.zeros(n, np.uint8)
+    if global_paired is None:
+        global_paired = np.zeros(tree.n, np.uint8)
+    out = np.zeros(max(n, 1), PAIR_PT2PT)
+    pot = C.c_uint64(0)
+    fn = lib().orc_match_inlier_ratio
+    fn.restype = C.c_long
+    cnt = fn(C.c_void_p(tree._h), _p(lx), _p(ly), _p(lz), C.c_size_t(n), _p(_T(T)), C.byref(cp), _p(local_paired), _p(global_paired), _p(out), C.c_size_t(n), C.byref(pot), nthreads)
+    if cnt < 0:
+        raise RuntimeError("Matcher_Points_InlierRatio: reference assertion (inliersRatio outside (0,1), or no tentative pairing)")
+    return out[:cnt], pot.value
+
+
 def match_pt2pl(tree: KDTree, lx, ly, lz, T, prm: MatchPt2PlParams, local_paired=None, nthreads=1):
     lx, ly, lz = _f32(lx), _f32(ly), _f32(lz)
     n = lx.size

@@ -209,6 +209,95 @@ def test_match_pt2pl_parity_street_scene(ctx):
     del gt
 
 
+# --------------------------------------------------------------------------- Matcher_Points_InlierRatio (§8f N1)
+@pytest.mark.parametrize("ratio,allow_global", [(0.80, False), (0.5, False), (0.33, True), (0.999, False)])
+def test_match_inlier_ratio_bit_exact(ctx, ratio, allow_global):
+    """Records, their ORDER (ascending distance, ties in reverse local order) and the count must be the
+    oracle's (Matcher_Points_InlierRatio.cpp:41-143), byte for byte."""
+    M, L, gt = _c2(200_000, 10)
+    L = np.concatenate([L, L[:3000], L[100:1100] + np.float32(1e-3)])  # exact duplicates: distance ties + contested globals
+    tree, gmap = orc.KDTree(*xyz(M)), b200.Map(ctx, *xyz(M))
+    guess = fx.pose_xyzypr(0.25, -0.15, 0.08, 1.7 * DEG, -0.8 * DEG, 1.2 * DEG)
+    for T in (guess, gt):
+        p0, pot0 = orc.match_inlier_ratio(tree, *xyz(L), T, orc.MatchInlierRatioParams(ratio, allowMatchAlreadyMatchedGlobalPoints=allow_global), nthreads=8)
+        p1, pot1 = gmap.match_inlier_ratio(*xyz(L), T, b200.InlierRatioParams(ratio, allowMatchAlreadyMatchedGlobalPoints=allow_global))
+        assert pot0 == pot1 == len(L) and len(p0) == len(p1) > 1000
+        assert p0.tobytes() == p1.tobytes()
+        assert np.all(np.diff(p1["errSq"]) >= 0)
+    # resident (Morton-sorted) local cloud: same bytes
+    p2, _ = gmap.match_inlier_ratio(b200.Cloud(ctx, *xyz(L)), None, None, gt, b200.InlierRatioParams(ratio, allowMatchAlreadyMatchedGlobalPoints=allow_global))
+    assert p2.tobytes() == p0.tobytes()
+
+
+def test_match_inlier_ratio_matchstate_and_edge_cases(ctx):
+    M, L, gt = _c2(100_000, 10)
+    tree, gmap = orc.KDTree(*xyz(M)), b200.Map(ctx, *xyz(M))
+    rng = np.random.default_rng(3)
+    lp = (rng.random(len(L)) < 0.3).astype(np.uint8)
+    gp = (rng.random(len(M)) < 0.3).astype(np.uint8)
+    for kw in (dict(), dict(allowMatchAlreadyMatchedPoints=True), dict(allowMatchAlreadyMatchedGlobalPoints=True)):
+        lp0, gp0 = lp.copy(), gp.copy()
+        p0, _ = orc.match_inlier_ratio(tree, *xyz(L), gt, orc.MatchInlierRatioParams(0.7, **kw), lp0, gp0, nthreads=8)
+        p1, _ = gmap.match_inlier_ratio(*xyz(L), gt, b200.InlierRatioParams(0.7, **kw), local_paired=lp, global_paired=gp)
+        assert len(p0) > 100 and p0.tobytes() == p1.tobytes()
+    # the known-answer cases of tests/test_oracle_golden.py::test_inlier_ratio_semantics
+    g = np.array([[0, 0, 0], [10, 0, 0], [20, 0, 0], [30, 0, 0]], np.float32)
+    Ls = np.array([[0.5, 0, 0], [10.25, 0, 0], [9.75, 0, 0], [21, 0, 0], [32, 0, 0]], np.float32)
+    small = b200.Map(ctx, *xyz(g))
+    I = np.eye(3, 4)
+    p, pot = small.match_inlier_ratio(*xyz(Ls), I, b200.InlierRatioParams(0.5, allowMatchAlreadyMatchedGlobalPoints=True))
+    assert pot == 5 and list(p["localIdx"]) == [2, 1] and list(p["globalIdx"]) == [1, 1]
+    p, _ = small.match_inlier_ratio(*xyz(Ls), I, b200.InlierRatioParams(0.5))
+    assert list(p["localIdx"]) == [2]
+    for ratio, keep in [(0.7, 4), (0.9, 4), (0.95, 5), (0.1, 0)]:
+        p, _ = small.match_inlier_ratio(*xyz(Ls), I, b200.InlierRatioParams(ratio, allowMatchAlreadyMatchedGlobalPoints=True))
+        assert len(p) == keep
+    p, _ = small.match_inlier_ratio(*xyz(Ls), I, b200.InlierRatioParams(0.95, allowMatchAlreadyMatchedGlobalPoints=True))
+    assert list(p["localIdx"]) == [2, 1, 0, 3, 4] and np.array_equal(p["global"], g[[1, 1, 0, 2, 3]]) and np.array_equal(p["local"], Ls[[2, 1, 0, 3, 4]])
+    p, _ = small.match_inlier_ratio(*xyz(Ls), I, b200.InlierRatioParams(0.95), global_paired=np.array([1, 0, 0, 0], np.uint8))
+    assert list(p["localIdx"]) == [2, 3, 4]
+    with pytest.raises(b200.Mp2pError):  # the reference asserts 0 < ratio < 1
+        small.match_inlier_ratio(*xyz(Ls), I, b200.InlierRatioParams(1.0))
+    with pytest.raises(b200.Mp2pError):  # ... and nTotal > 0
+        small.match_inlier_ratio(*xyz(Ls), I, b200.InlierRatioParams(0.5), local_paired=np.ones(5, np.uint8))
+    p, _ = small.match_inlier_ratio(*xyz(Ls), fx.pose_xyzypr(1000, 0, 0, 0, 0, 0), b200.InlierRatioParams(0.5))
+    assert len(p) == 0  # no bounding-box overlap: nothing, no error
+    p, pot = small.match_inlier_ratio(*xyz(Ls[:0]), I, b200.InlierRatioParams(0.5))
+    assert len(p) == 0 and pot == 0
+
+
+@pytest.mark.parametrize("solver", ["horn", "gn"])
+def test_icp_align_bunny_inlier_ratio_matches_oracle(ctx, solver):
+    """tests/test-mp2p_icp_algos.cpp:250-262 protocol with Matcher_Points_InlierRatio: the GPU loop
+    must follow the oracle loop iteration by iteration and end within 0.1 of the ground truth."""
+    x, y, z = icp_harness.load_xyz_gz(os.path.join(GOLD, "bunny_decim.xyz.gz"))
+    x, y, z = x[::10], y[::10], z[::10]
+    P = np.stack([x, y, z], 1).astype(np.float64)
+    size = P.max(0) - P.min(0)
+    rng = np.random.default_rng(77)
+    gt = orc.pose_from_xyzypr(*(rng.uniform(-0.15, 0.15, 3) * size), *(rng.uniform(-10, 10, 3) * DEG))
+    L = ((P - gt[:, 3]) @ gt[:, :3]).astype(np.float32)
+    tree, gmap = orc.KDTree(x, y, z), b200.Map(ctx, x, y, z)
+    gn = dict(maxInnerLoopIterations=6)
+
+    def run(match, horn, gauss):
+        def solve(pairs, guess, it):
+            if solver == "horn":
+                return horn(pairs)
+            ok, T, _ = gauss(pairs, guess)
+            return ok, T
+
+        return icp_harness.align(match, solve, np.eye(3, 4), icp_harness.IcpParams(maxIterations=100))
+
+    r0 = run(lambda T, it: orc.match_inlier_ratio(tree, *xyz(L), T, orc.MatchInlierRatioParams(0.80), nthreads=4)[0], orc.optimal_tf_horn,
+             lambda p, T: orc.optimal_tf_gauss_newton(p, None, orc.GNParams(**gn), T))
+    r1 = run(lambda T, it: gmap.match_inlier_ratio(*xyz(L), T, b200.InlierRatioParams(0.80))[0], ctx.solve_horn,
+             lambda p, T: ctx.solve_gauss_newton(p, None, b200.GNParams(**gn), T))
+    assert r0.nIterations == r1.nIterations and r0.terminationReason == r1.terminationReason
+    assert_pose_close(r0.pose, r1.pose)
+    assert np.linalg.norm(orc.se3_log(orc.inverse_compose(r1.pose, gt))) < 0.1
+
+
 # --------------------------------------------------------------------------- solvers (a11-a14)
 def _random_pairs(n, seed, sigma=0.02):
     rng = np.random.default_rng(seed)

@@ -282,3 +282,78 @@ def test_transform_is_double_then_float():
     assert np.array_equal(np.stack([gx, gy, gz], 1), exp.astype(np.float32))
     assert np.allclose(ref, exp)
     assert np.array_equal(bmin, exp.astype(np.float32).min(0)) and np.array_equal(bmax, exp.astype(np.float32).max(0))
+
+
+# ---------------------------------------------------------------------------------------------
+# Matcher_Points_InlierRatio. The reference pins it only through the ICP protocol of
+# tests/test-mp2p_icp_algos.cpp:250-262 (class default inliersRatio = 0.80,
+# Matcher_Points_InlierRatio.h:56); the hand-made cases below pin the restatement's reading of
+# Matcher_Points_InlierRatio.cpp:41-143 (sorted emission, reverse-insertion tie order of
+# multimap::emplace_hint(begin()), mrpt::round, first-in-sorted-order dedup, bitfields).
+# ---------------------------------------------------------------------------------------------
+def test_inlier_ratio_semantics():
+    g = np.array([[0, 0, 0], [10, 0, 0], [20, 0, 0], [30, 0, 0]], np.float32)
+    tree = orc.KDTree(*(np.ascontiguousarray(g[:, k]) for k in range(3)))
+    # local points: distances to their NN 0.5 (g0), 0.25 (g1), 0.25 (g1, tie with the previous), 1.0 (g2), 2.0 (g3)
+    L = np.array([[0.5, 0, 0], [10.25, 0, 0], [9.75, 0, 0], [21, 0, 0], [32, 0, 0]], np.float32)
+    lx, ly, lz = (np.ascontiguousarray(L[:, k]) for k in range(3))
+    I = np.eye(3, 4)
+    # nTotal = 5, ratio 0.5 -> mrpt::round(2.5) = 2 (lrint: ties to even); sorted: d2 = 0.0625 twice
+    # (local 2 BEFORE local 1: reverse insertion order), then 0.25, 1, 4
+    p, pot = orc.match_inlier_ratio(tree, lx, ly, lz, I, orc.MatchInlierRatioParams(0.5, allowMatchAlreadyMatchedGlobalPoints=True))
+    assert pot == 5 and list(p["localIdx"]) == [2, 1] and list(p["globalIdx"]) == [1, 1]
+    # same with dedup: local 2 takes g1, local 1 is dropped (its global point is taken), NOT replaced
+    lp, gp = np.zeros(5, np.uint8), np.zeros(4, np.uint8)
+    p, _ = orc.match_inlier_ratio(tree, lx, ly, lz, I, orc.MatchInlierRatioParams(0.5), lp, gp)
+    assert list(p["localIdx"]) == [2] and list(lp) == [0, 0, 1, 0, 0] and list(gp) == [0, 1, 0, 0]
+    # ratio 0.7 -> round(3.5) = 4 (even); ratio 0.9 -> round(4.5) = 4; ratio 0.95 -> round(4.75) = 5
+    for ratio, keep in [(0.7, 4), (0.9, 4), (0.95, 5), (0.1, 0)]:
+        p, _ = orc.match_inlier_ratio(tree, lx, ly, lz, I, orc.MatchInlierRatioParams(ratio, allowMatchAlreadyMatchedGlobalPoints=True))
+        assert len(p) == keep
+    p, _ = orc.match_inlier_ratio(tree, lx, ly, lz, I, orc.MatchInlierRatioParams(0.95, allowMatchAlreadyMatchedGlobalPoints=True))
+    assert list(p["localIdx"]) == [2, 1, 0, 3, 4] and np.allclose(p["errSq"], [0.0625, 0.0625, 0.25, 1.0, 4.0])
+    assert np.array_equal(p["local"], L[[2, 1, 0, 3, 4]]) and np.array_equal(p["global"], g[[1, 1, 0, 2, 3]])
+    # locals already paired are not searched (:81-83) and do not count in nTotal
+    lp = np.array([0, 1, 1, 0, 0], np.uint8)
+    p, _ = orc.match_inlier_ratio(tree, lx, ly, lz, I, orc.MatchInlierRatioParams(0.7), lp, np.zeros(4, np.uint8))
+    assert list(p["localIdx"]) == [0, 3]  # nTotal 3 -> round(2.1) = 2
+    # global points paired on entry are skipped at emission (:126-128)
+    p, _ = orc.match_inlier_ratio(tree, lx, ly, lz, I, orc.MatchInlierRatioParams(0.95), None, np.array([1, 0, 0, 0], np.uint8))
+    assert list(p["localIdx"]) == [2, 3, 4]
+    # the reference throws: ratio outside (0,1) (:49-50); every local already paired (:117)
+    with pytest.raises(RuntimeError):
+        orc.match_inlier_ratio(tree, lx, ly, lz, I, orc.MatchInlierRatioParams(1.0))
+    with pytest.raises(RuntimeError):
+        orc.match_inlier_ratio(tree, lx, ly, lz, I, orc.MatchInlierRatioParams(0.5), np.ones(5, np.uint8), None)
+    # no bounding-box overlap (:64-67): nothing, no throw
+    far = orc.pose_from_xyzypr(1000, 0, 0)
+    p, _ = orc.match_inlier_ratio(tree, lx, ly, lz, far, orc.MatchInlierRatioParams(0.5))
+    assert len(p) == 0
+
+
+@pytest.mark.parametrize("solver", ["horn", "gn"])
+def test_icp_align_protocol_inlier_ratio(solver):
+    """tests/test-mp2p_icp_algos.cpp:250-262: Solver_Horn / Solver_GaussNewton with
+    Matcher_Points_InlierRatio (defaults) on the bunny, decimation 10, |log(GT - est)| < 0.1."""
+    x, y, z = icp_harness.load_xyz_gz(os.path.join(GOLD, "bunny_decim.xyz.gz"))
+    x, y, z = x[::10], y[::10], z[::10]
+    P = np.stack([x, y, z], 1).astype(np.float64)
+    size = P.max(0) - P.min(0)
+    rng = np.random.default_rng(4321)
+    tree = orc.KDTree(x, y, z)
+    for _ in range(3):
+        gt = orc.pose_from_xyzypr(*(rng.uniform(-0.15, 0.15, 3) * size), *(rng.uniform(-10, 10, 3) * DEG))
+        L = ((P - gt[:, 3]) @ gt[:, :3]).astype(np.float32)
+        lx, ly, lz = (np.ascontiguousarray(L[:, k]) for k in range(3))
+
+        def match(pose, it):
+            return orc.match_inlier_ratio(tree, lx, ly, lz, pose, orc.MatchInlierRatioParams(0.80), nthreads=4)[0]
+
+        def solve(pairs, guess, it):
+            if solver == "horn":
+                return orc.optimal_tf_horn(pairs)
+            ok, T, _ = orc.optimal_tf_gauss_newton(pairs, None, orc.GNParams(maxInnerLoopIterations=6), guess)
+            return ok, T
+
+        res = icp_harness.align(match, solve, np.eye(3, 4), icp_harness.IcpParams(maxIterations=100))
+        assert np.linalg.norm(orc.se3_log(orc.inverse_compose(res.pose, gt))) < 0.1
