@@ -14,7 +14,9 @@
 //   Solver, SolverContext                            mp2p_icp/include/mp2p_icp/Solver.h:43-102, src/Solver.cpp:28-64
 //   Solver_Horn / Solver_GaussNewton                 mp2p_icp/src/Solver_Horn.cpp:33-61, Solver_GaussNewton.cpp:29-67
 //   Pairings                                         mp2p_icp/include/mp2p_icp/Pairings.h:84-194, src/Pairings.cpp:123-147
-//   ICP::align loop (the caller)                     mp2p_icp/src/ICP.cpp:108-308
+//   Matcher_Points_InlierRatio                       mp2p_icp/src/Matcher_Points_InlierRatio.cpp:35-143
+//   QualityEvaluator, QualityEvaluator_PairedRatio   mp2p_icp/include/mp2p_icp/QualityEvaluator.h, src/QualityEvaluator_PairedRatio.cpp:27-73
+//   ICP::align loop (the caller)                     mp2p_icp/src/ICP.cpp:108-338, evaluate_quality :608-634
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -482,6 +484,48 @@ class Matcher_Points_DistanceThreshold : public Matcher_Points_Base
     }
 };
 
+/** Matcher_Points_InlierRatio (mp2p_icp/include/mp2p_icp/Matcher_Points_InlierRatio.h,
+ *  mp2p_icp/src/Matcher_Points_InlierRatio.cpp:35-143) over mp2p_b200_match_inlier_ratio. */
+class Matcher_Points_InlierRatio : public Matcher_Points_Base
+{
+   public:
+    double inliersRatio = 0.80;
+    void   initialize(const ParameterMap& params) override  // :35-39
+    {
+        Matcher_Points_Base::initialize(params);
+        inliersRatio = params.required<double>("inliersRatio");
+    }
+
+   private:
+    void implMatchOneLayer(const CPointsMap& pcGlobal, const CPointsMap& pcLocal, const CPose3D& localPose,
+                           MatchState& ms, const layer_name_t& globalName, const layer_name_t& localName,
+                           Pairings& out) const override
+    {
+        if (!(inliersRatio > 0.0)) throw std::runtime_error("Assert failed: inliersRatio > 0");  // :49-50
+        if (!(inliersRatio < 1.0)) throw std::runtime_error("Assert failed: inliersRatio < 1");
+        Device&                       dev = Device::instance();
+        mp2p_b200_inlier_ratio_params p{inliersRatio, allowMatchAlreadyMatchedPoints_, allowMatchAlreadyMatchedGlobalPoints_,
+                                        bounding_box_intersection_check_epsilon_};
+        auto&        lbits  = ms.localPaired.at(localName);
+        auto&        gbits  = ms.globalPaired.at(globalName);
+        const size_t before = out.paired_pt2pt.size(), cap = pcLocal.size();
+        out.paired_pt2pt.resize(before + cap);
+        uint64_t cnt = 0, pot = 0;
+        check(mp2p_b200_match_inlier_ratio(dev.ctx(), dev.map_for(pcGlobal), dev.cloud_for(pcLocal), nullptr, nullptr,
+                                           pcLocal.size(), MP2P_B200_LOCAL_CLOUD, localPose.m, &p, lbits.data(), gbits.data(),
+                                           out.paired_pt2pt.data() + before, cap, 0, &cnt, &pot),
+              "mp2p_b200_match_inlier_ratio");
+        out.paired_pt2pt.resize(before + cnt);
+        out.potential_pairings += pot;
+        dev.note_match_output(out.paired_pt2pt.data() + before, before == 0 ? cnt : 0);
+        for (size_t i = before; i < out.paired_pt2pt.size(); i++)  // :133-135 (unconditional in this matcher)
+        {
+            MatchState::mark(lbits, out.paired_pt2pt[i].localIdx);
+            MatchState::mark(gbits, out.paired_pt2pt[i].globalIdx);
+        }
+    }
+};
+
 class Matcher_Point2Plane : public Matcher_Points_Base
 {
    public:
@@ -708,32 +752,116 @@ class Solver_GaussNewton : public Solver
 };
 
 // ---- the caller: ICP::align (ICP.cpp:108-308), restated so whole alignments can be run --------
+// ------------------------------------------------------------------------------------------------
+/** QualityEvaluator (mp2p_icp/include/mp2p_icp/QualityEvaluator.h). */
+class QualityEvaluator
+{
+   public:
+    using Ptr                   = std::shared_ptr<QualityEvaluator>;
+    virtual ~QualityEvaluator() = default;
+    struct Result
+    {
+        double quality      = 0;      // [0,1]
+        bool   hard_discard = false;  // ICP::evaluate_quality then reports 0 (ICP.cpp:622-626)
+    };
+    virtual void   initialize(const ParameterMap& params) = 0;
+    virtual Result evaluate(const metric_map_t& pcGlobal, const metric_map_t& pcLocal, const CPose3D& localPose,
+                            const Pairings& pairingsFromICP) const = 0;
+};
+
+/** QualityEvaluator_PairedRatio (mp2p_icp/src/QualityEvaluator_PairedRatio.cpp:27-73): ratio of
+ *  pairings over potential pairings, from the last ICP pairings (reuse_icp_pairings, the default) or
+ *  from one more pass of a Matcher_Points_DistanceThreshold of its own that may pair a global point
+ *  several times (:37-40). That extra pass runs on the device; only its COUNT matters (:66-67). */
+class QualityEvaluator_PairedRatio : public QualityEvaluator
+{
+   public:
+    void initialize(const ParameterMap& params) override  // :27-44
+    {
+        reuse_icp_pairings             = params.getOrDefault<int>("reuse_icp_pairings", reuse_icp_pairings ? 1 : 0) != 0;
+        absolute_minimum_pairing_ratio = params.getOrDefault<double>("absolute_minimum_pairing_ratio", absolute_minimum_pairing_ratio);
+        if (!reuse_icp_pairings)
+        {
+            ParameterMap p = params;
+            if (!p.has("allowMatchAlreadyMatchedGlobalPoints")) p.set("allowMatchAlreadyMatchedGlobalPoints", 1);
+            matcher_.initialize(p);
+        }
+    }
+    Result evaluate(const metric_map_t& pcGlobal, const metric_map_t& pcLocal, const CPose3D& localPose,
+                    const Pairings& pairingsFromICP) const override  // :46-73
+    {
+        const Pairings* pairings = &pairingsFromICP;
+        Pairings        newPairings;
+        if (!reuse_icp_pairings)
+        {
+            MatchState ms(pcGlobal, pcLocal);
+            matcher_.match(pcGlobal, pcLocal, localPose, {}, ms, newPairings);
+            pairings = &newPairings;
+        }
+        Result r;
+        r.quality      = pairings->potential_pairings ? pairings->size() / double(pairings->potential_pairings) : .0;
+        r.hard_discard = r.quality < absolute_minimum_pairing_ratio;
+        return r;
+    }
+    bool   reuse_icp_pairings             = true;
+    double absolute_minimum_pairing_ratio = 0.20;
+
+   private:
+    Matcher_Points_DistanceThreshold matcher_;
+};
+
+struct QualityEvaluatorEntry  // ICP.h quality_eval_list_t
+{
+    QualityEvaluator::Ptr obj;
+    double                relativeWeight = 1.0;
+};
+using quality_eval_list_t = std::vector<QualityEvaluatorEntry>;
+
 enum class IterTermReason
 {
     Undefined,
     NoPairings,
     SolverError,
     MaxIterations,
-    Stalled
+    Stalled,
+    QualityCheckpointFailed
 };
 struct Parameters  // Parameters.h:42-52
 {
     uint32_t maxIterations    = 40;
     double   minAbsStep_trans = 5e-4, minAbsStep_rot = 1e-4;
+    std::map<uint32_t, double> quality_checkpoints;  // iteration -> minimum quality (Parameters.h:61-73)
 };
 struct Results
 {
     CPose3D        optimal_tf;
     uint32_t       nIterations       = 0;
     IterTermReason terminationReason = IterTermReason::Undefined;
+    double         quality           = 0;  // Results.h:41
     Pairings       finalPairings;
 };
 
 class ICP
 {
    public:
-    matcher_list_t& matchers() { return matchers_; }
-    solver_list_t&  solvers() { return solvers_; }
+    matcher_list_t&      matchers() { return matchers_; }
+    solver_list_t&       solvers() { return solvers_; }
+    quality_eval_list_t& quality_evaluators() { return quality_evaluators_; }
+    /** ICP::evaluate_quality, ICP.cpp:608-634 */
+    static double evaluate_quality(const quality_eval_list_t& evaluators, const metric_map_t& pcGlobal,
+                                   const metric_map_t& pcLocal, const CPose3D& localPose, const Pairings& finalPairings)
+    {
+        if (evaluators.empty()) throw std::runtime_error("Assert failed: !evaluators.empty()");
+        double sumW = .0, sumEvals = .0;
+        for (const auto& e : evaluators)
+        {
+            if (!(e.relativeWeight > 0)) throw std::runtime_error("Assert failed: relativeWeight > 0");
+            const auto r = e.obj->evaluate(pcGlobal, pcLocal, localPose, finalPairings);
+            if (r.hard_discard) return 0;
+            sumEvals += e.relativeWeight * r.quality, sumW += e.relativeWeight;
+        }
+        return sumEvals / sumW;
+    }
     void align(const metric_map_t& pcLocal, const metric_map_t& pcGlobal, const CPose3D& initialGuess,
                const Parameters& p, Results& result)
     {
@@ -785,16 +913,25 @@ class ICP
                 result.terminationReason = IterTermReason::Stalled;
                 break;
             }
+            if (auto itQ = p.quality_checkpoints.find(result.nIterations); itQ != p.quality_checkpoints.end())  // :257-280
+                if (evaluate_quality(quality_evaluators_, pcGlobal, pcLocal, current, pairings) < itQ->second)
+                {
+                    result.terminationReason = IterTermReason::QualityCheckpointFailed;
+                    break;
+                }
             prev2 = prev;
             prev  = current;
         }
+        if (!quality_evaluators_.empty())  // :322-324 (the reference asserts a non-empty list)
+            result.quality = evaluate_quality(quality_evaluators_, pcGlobal, pcLocal, current, pairings);
         result.optimal_tf    = current;
         result.finalPairings = std::move(pairings);
     }
 
    private:
-    matcher_list_t matchers_;
-    solver_list_t  solvers_;
+    matcher_list_t      matchers_;
+    solver_list_t       solvers_;
+    quality_eval_list_t quality_evaluators_;
 };
 
 }  // namespace mp2p_icp_b200

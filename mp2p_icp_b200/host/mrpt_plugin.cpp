@@ -7,7 +7,7 @@
 // mp2p_icp_map/src/load_plugin.cpp:70-134, then creates the class by name, ICP.cpp:507-516):
 //
 //   matchers:
-//     - class: mp2p_icp::Matcher_Points_DistanceThreshold_B200
+//     - class: mp2p_icp::Matcher_Points_DistanceThreshold_B200   (or Matcher_Points_InlierRatio_B200)
 //       plugin: libmp2p_icp_b200_plugin.so
 //       params: { threshold: 1.0, thresholdAngularDeg: 0, pairingsPerPoint: 1 }
 //   solvers:
@@ -16,6 +16,7 @@
 #if defined(MP2P_B200_WITH_MRPT)
 
 #include <mp2p_icp/Matcher_Points_Base.h>
+#include <mp2p_icp/QualityEvaluator.h>
 #include <mp2p_icp/Solver.h>
 #include <mp2p_icp/Solver_GaussNewton.h>
 #include <mp2p_icp/Solver_Horn.h>
@@ -240,6 +241,61 @@ class Matcher_Points_DistanceThreshold_B200 : public Matcher_Points_Base
 };
 IMPLEMENTS_MRPT_OBJECT(Matcher_Points_DistanceThreshold_B200, Matcher, mp2p_icp)
 
+/** Drop-in for Matcher_Points_InlierRatio (mp2p_icp/src/Matcher_Points_InlierRatio.cpp:35-143). */
+class Matcher_Points_InlierRatio_B200 : public Matcher_Points_Base
+{
+    DEFINE_MRPT_OBJECT(Matcher_Points_InlierRatio_B200, mp2p_icp)
+   public:
+    void initialize(const mrpt::containers::yaml& params) override
+    {
+        Matcher_Points_Base::initialize(params);
+        MCP_LOAD_REQ(params, inliersRatio);
+    }
+    double inliersRatio = 0.80;
+
+   private:
+    void implMatchOneLayer(const mrpt::maps::CMetricMap& pcGlobal, const mrpt::maps::CPointsMap& pcLocal,
+                           const mrpt::poses::CPose3D& localPose, MatchState& ms,
+                           const layer_name_t& globalName, const layer_name_t& localName,
+                           Pairings& out) const override
+    {
+        using namespace b200_detail;
+        ASSERT_GT_(inliersRatio, 0.0);
+        ASSERT_LT_(inliersRatio, 1.0);
+        mp2p_b200_map* gmap = cache().get(pcGlobal);
+        const auto&    lx   = pcLocal.getPointsBufferRef_x();
+        double         T[12];
+        pose12(localPose, T);
+        mp2p_b200_inlier_ratio_params p{inliersRatio, allowMatchAlreadyMatchedPoints_,
+                                        allowMatchAlreadyMatchedGlobalPoints_,
+                                        bounding_box_intersection_check_epsilon_};
+        auto&        lbf    = ms.localPairedBitField.point_layers[localName];
+        auto&        gbf    = ms.globalPairedBitField.point_layers[globalName];
+        const auto   lbits  = to_bits(lbf, lx.size());
+        const auto   gbits  = to_bits(gbf, mp2p_icp::MapToNN(pcGlobal, true)->nn_index_count());
+        const size_t before = out.paired_pt2pt.size();
+        out.paired_pt2pt.resize(before + lx.size());
+        uint64_t     cnt = 0, pot = 0;
+        const float* resident = cache().pinned_local(pcLocal);
+        check(mp2p_b200_match_inlier_ratio(ctx(), gmap, resident ? resident : lx.data(),
+                                           resident ? nullptr : pcLocal.getPointsBufferRef_y().data(),
+                                           resident ? nullptr : pcLocal.getPointsBufferRef_z().data(), lx.size(),
+                                           resident ? MP2P_B200_LOCAL_CLOUD : MP2P_B200_LOCAL_HOST, T, &p,
+                                           lbits.data(), gbits.data(),
+                                           reinterpret_cast<mp2p_b200_pair_pt2pt*>(out.paired_pt2pt.data() + before),
+                                           lx.size(), 0, &cnt, &pot));
+        out.paired_pt2pt.resize(before + cnt);
+        out.potential_pairings += pot;
+        witness2p().note(out.paired_pt2pt.data() + before, before == 0 ? cnt : 0);
+        for (size_t i = before; i < out.paired_pt2pt.size(); i++)  // :133-135
+        {
+            lbf.mark_as_set(out.paired_pt2pt[i].localIdx);
+            gbf.mark_as_set(out.paired_pt2pt[i].globalIdx);
+        }
+    }
+};
+IMPLEMENTS_MRPT_OBJECT(Matcher_Points_InlierRatio_B200, Matcher, mp2p_icp)
+
 /** Drop-in for Solver_Horn: pt2pt accumulation on the GPU. pt2ln / pt2pl pairings are first
  *  projected by the reference's own pt2ln_pl_to_pt2pt (host). */
 class Solver_Horn_B200 : public Solver_Horn
@@ -395,13 +451,64 @@ class Solver_GaussNewton_B200 : public Solver_GaussNewton
 };
 IMPLEMENTS_MRPT_OBJECT(Solver_GaussNewton_B200, Solver, mp2p_icp)
 
+/** Drop-in for QualityEvaluator_PairedRatio (mp2p_icp/src/QualityEvaluator_PairedRatio.cpp:27-73):
+ *  the extra matcher pass of the non-reuse mode runs on the GPU. The reference holds its matcher by
+ *  value (QualityEvaluator_PairedRatio.h:62), so the swap needs this class, named in the YAML's
+ *  `quality:` list (ICP.cpp:589-606). */
+class QualityEvaluator_PairedRatio_B200 : public QualityEvaluator
+{
+    DEFINE_MRPT_OBJECT(QualityEvaluator_PairedRatio_B200, mp2p_icp)
+   public:
+    void initialize(const mrpt::containers::yaml& params) override
+    {
+        MCP_LOAD_OPT(params, reuse_icp_pairings);
+        MCP_LOAD_OPT(params, absolute_minimum_pairing_ratio);
+        if (!reuse_icp_pairings)
+        {
+            mrpt::containers::yaml p = params;
+            if (!p.has("allowMatchAlreadyMatchedGlobalPoints")) p["allowMatchAlreadyMatchedGlobalPoints"] = true;
+            matcher_.initialize(p);
+        }
+    }
+    Result evaluate(const metric_map_t& pcGlobal, const metric_map_t& pcLocal, const mrpt::poses::CPose3D& localPose,
+                    const Pairings& pairingsFromICP) const override
+    {
+        const Pairings* pairings = &pairingsFromICP;
+        Pairings        newPairings;
+        if (!reuse_icp_pairings)
+        {
+            MatchState ms(pcGlobal, pcLocal);
+            matcher_.match(pcGlobal, pcLocal, localPose, {}, ms, newPairings);
+            pairings = &newPairings;
+        }
+        const auto nEffectiveLocalPoints = pairings->potential_pairings;
+        Result     r;
+        r.quality      = nEffectiveLocalPoints ? pairings->size() / double(nEffectiveLocalPoints) : .0;
+        r.hard_discard = r.quality < absolute_minimum_pairing_ratio;
+        return r;
+    }
+    void attachToParameterSource(ParameterSource& source) override
+    {
+        source.attach(*this);
+        source.attach(matcher_);
+    }
+
+   private:
+    Matcher_Points_DistanceThreshold_B200 matcher_;
+    bool                                  reuse_icp_pairings             = true;
+    double                                absolute_minimum_pairing_ratio = 0.20;
+};
+IMPLEMENTS_MRPT_OBJECT(QualityEvaluator_PairedRatio_B200, QualityEvaluator, mp2p_icp)
+
 MRPT_INITIALIZER(register_mp2p_icp_b200)
 {
     using mrpt::rtti::registerClass;
     registerClass(CLASS_ID(mp2p_icp::Matcher_Points_DistanceThreshold_B200));
+    registerClass(CLASS_ID(mp2p_icp::Matcher_Points_InlierRatio_B200));
     registerClass(CLASS_ID(mp2p_icp::Solver_Horn_B200));
     registerClass(CLASS_ID(mp2p_icp::Matcher_Point2Plane_B200));
     registerClass(CLASS_ID(mp2p_icp::Solver_GaussNewton_B200));
+    registerClass(CLASS_ID(mp2p_icp::QualityEvaluator_PairedRatio_B200));
 }
 }  // namespace mp2p_icp
 

@@ -105,6 +105,9 @@ int main(int argc, char** argv)
             const double max_dim = std::max(sz[0], std::max(sz[1], sz[2]));
             std::mt19937_64                        rng(1234);
             std::uniform_real_distribution<double> U(-1.0, 1.0);
+            // matcherKind 0: Matcher_Points_DistanceThreshold, 1: Matcher_Points_InlierRatio (defaults),
+            // tests/test-mp2p_icp_algos.cpp:250-262
+            for (int matcherKind = 0; matcherKind < 2; matcherKind++)
             for (int solverKind = 0; solverKind < 2; solverKind++)
                 for (int rep = 0; rep < 3; rep++)
                 {
@@ -122,12 +125,17 @@ int main(int argc, char** argv)
                     pc_ref.layers["raw"] = pts;
                     pc_mod.layers["raw"] = reg;
                     ICP  icp;
-                    auto matcher = std::make_shared<Matcher_Points_DistanceThreshold>();
-                    ParameterMap ps;
-                    ps.set("threshold", 0.40 * max_dim);
-                    ps.set("thresholdAngularDeg", 0);
-                    matcher->initialize(ps);
-                    icp.matchers().push_back(matcher);
+                    if (matcherKind == 0)
+                    {
+                        auto         matcher = std::make_shared<Matcher_Points_DistanceThreshold>();
+                        ParameterMap ps;
+                        ps.set("threshold", 0.40 * max_dim);
+                        ps.set("thresholdAngularDeg", 0);
+                        matcher->initialize(ps);
+                        icp.matchers().push_back(matcher);
+                    }
+                    else
+                        icp.matchers().push_back(std::make_shared<Matcher_Points_InlierRatio>());
                     if (solverKind == 0)
                         icp.solvers().push_back(std::make_shared<Solver_Horn>());
                     else
@@ -138,13 +146,40 @@ int main(int argc, char** argv)
                         s->initialize(sp);
                         icp.solvers().push_back(s);
                     }
+                    // QualityEvaluator_PairedRatio: from the last pairings (default) and from its own
+                    // matcher pass (QualityEvaluator_PairedRatio.cpp:27-73)
+                    auto qReuse = std::make_shared<QualityEvaluator_PairedRatio>();
+                    qReuse->initialize(ParameterMap());
+                    auto         qOwn = std::make_shared<QualityEvaluator_PairedRatio>();
+                    ParameterMap qp;
+                    qp.set("reuse_icp_pairings", 0);
+                    qp.set("threshold", 0.05 * max_dim);
+                    qp.set("thresholdAngularDeg", 0);
+                    qOwn->initialize(qp);
+                    icp.quality_evaluators().push_back({qReuse, 1.0});
+                    icp.quality_evaluators().push_back({qOwn, 3.0});
                     Parameters icp_params;
                     icp_params.maxIterations = 100;
                     Results res;
                     icp.align(pc_mod, pc_ref, CPose3D::Identity(), icp_params, res);
+                    {
+                        const auto   r1 = qReuse->evaluate(pc_ref, pc_mod, res.optimal_tf, res.finalPairings);
+                        const auto   r2 = qOwn->evaluate(pc_ref, pc_mod, res.optimal_tf, res.finalPairings);
+                        const double expect1 = res.finalPairings.size() / double(res.finalPairings.potential_pairings);
+                        ASSERT_(std::abs(r1.quality - expect1) < 1e-15 && !r1.hard_discard);
+                        // a converged alignment of a cloud with itself pairs (nearly) every point within 5 % of the size
+                        ASSERT_(r2.quality > 0.95 && r2.quality <= 1.0);
+                        ASSERT_(std::abs(res.quality - (1.0 * r1.quality + 3.0 * r2.quality) / 4.0) < 1e-12);
+                        // a checkpoint nobody can pass aborts the loop at that iteration (ICP.cpp:257-280)
+                        Parameters pq = icp_params;
+                        pq.quality_checkpoints[1] = 2.0;
+                        Results rq;
+                        icp.align(pc_mod, pc_ref, CPose3D::Identity(), pq, rq);
+                        ASSERT_(rq.terminationReason == IterTermReason::QualityCheckpointFailed && rq.nIterations == 1);
+                    }
                     double dxyz, drot;
                     (gt - res.optimal_tf).log_norms(dxyz, drot);
-                    std::printf("solver=%d rep=%d iters=%u err=%.3e\n", solverKind, rep, res.nIterations,
+                    std::printf("matcher=%d solver=%d rep=%d iters=%u err=%.3e\n", matcherKind, solverKind, rep, res.nIterations,
                                 std::sqrt(dxyz * dxyz + drot * drot));
                     ASSERT_(std::sqrt(dxyz * dxyz + drot * drot) < 0.1);
                     ASSERT_(!res.finalPairings.empty());
