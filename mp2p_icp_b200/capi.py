@@ -672,6 +672,7 @@ class Map:
                 _check(rc)
             return bool(solved.value), pose_out_np.copy(), int(n_pairs.value)
 
+        step._keep = (keep_local, keep, self)  # the closure owns its inputs (a temporary Cloud must outlive it)
         return step
 
     def make_plugin_step(self, hx, hy, hz, matcher_prm, solver_prm, out_pairs, reuse_device_pairs=True):
@@ -725,6 +726,7 @@ class Map:
                 _check(rc)
             return bool(solved.value), pose_out_np.copy(), int(cnt.value)
 
+        step._keep = (keep, self)
         return step
 
     def match_pt2pl(self, lx, ly, lz, T, prm: Pt2PlParams, local_paired=None, n_local=None, local_on_device=False, out=None, out_on_device=False, capacity=None, sync=True):

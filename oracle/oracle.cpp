@@ -51,6 +51,25 @@ extern "C"
         float  _pad;
     };
 
+    // mp2p_icp::point_line_pair_t (Pairings.h:61-73): TLine3D {pBase, director} + TPoint3D pt_local, 72 bytes
+    struct orc_pair_pt2ln
+    {
+        double pBase[3];
+        double director[3];
+        double lx, ly, lz;
+    };
+
+    // Matcher_Point2Line (Matcher_Point2Line.cpp:35-45) + Matcher_Points_Base
+    struct orc_match_pt2ln_params
+    {
+        double   distanceThreshold;
+        uint32_t knn;
+        uint32_t minimumLinePoints;
+        double   lineEigenThreshold;
+        int32_t  allowMatchAlreadyMatchedPoints;
+        double   bounding_box_intersection_check_epsilon;
+    };
+
     struct orc_match_pt2pt_params
     {
         double   threshold;
@@ -164,6 +183,7 @@ struct PlaneFit
     float  mean[3];
     double eigVals[3];
     double eigVec0[3];  // eigenvector of the smallest eigenvalue
+    double eigVec2[3];  // eigenvector of the largest eigenvalue
 };
 PlaneFit estimate_points_eigen(const float* xs, const float* ys, const float* zs, size_t count)
 {
@@ -187,6 +207,7 @@ PlaneFit estimate_points_eigen(const float* xs, const float* ys, const float* zs
     r.mean[0] = mx, r.mean[1] = my, r.mean[2] = mz;
     for (int i = 0; i < 3; i++) r.eigVals[i] = vals[i];
     r.eigVec0[0] = V[0], r.eigVec0[1] = V[3], r.eigVec0[2] = V[6];
+    r.eigVec2[0] = V[2], r.eigVec2[1] = V[5], r.eigVec2[2] = V[8];
     return r;
 }
 }  // namespace
@@ -408,6 +429,74 @@ extern "C"
             if (global_paired) global_paired[gi] = 1;
         }
         return static_cast<long>(nOut);
+    }
+
+    // ---------------------------------------------------------------- pt2ln matcher
+    // Matcher_Point2Line::implMatchOneLayer (mp2p_icp/src/Matcher_Point2Line.cpp:46-163): UNBOUNDED
+    // nn_multiple_search of `knn` points (:103-105); the neighbour list is cut at the first distance
+    // > distanceThreshold^2 (:110-127) and must keep >= minimumLinePoints entries (:130) — but only
+    // the index and distance vectors are cut, kddPts is not, so estimate_points_eigen runs over ALL
+    // knn points (:132-135). Restated as written. Line test :148-149, director = eigVectors[2]
+    // unitarized, pBase = the (float) mean (:151-156); the local point is marked, global points never
+    // (:92-95). No upstream test exercises this matcher: parity of this function is pinned only by the
+    // hand-made known answers in tests/test_oracle_golden.py.
+    size_t orc_match_pt2ln(void* tree, const float* lx, const float* ly, const float* lz, size_t nLocal,
+                           const double T[12], const orc_match_pt2ln_params* prm, uint8_t* local_paired,
+                           orc_pair_pt2ln* out, size_t out_capacity, uint64_t* potential_pairings, int nthreads)
+    {
+        const auto* kd   = static_cast<const KDTree*>(tree);
+        const Pose  pose = to_pose(T);
+        if (potential_pairings) *potential_pairings += nLocal;  // :58
+        if (kd->n == 0 || nLocal == 0) return 0;                 // :61
+        std::vector<float> gx(nLocal), gy(nLocal), gz(nLocal);
+        float              lmin[3], lmax[3];
+        transform_local_to_global(lx, ly, lz, nLocal, pose, gx.data(), gy.data(), gz.data(), lmin, lmax);
+        const float eps = static_cast<float>(prm->distanceThreshold + prm->bounding_box_intersection_check_epsilon);
+        if (!bbox_intersects(kd->bbmin, kd->bbmax, lmin, lmax, eps)) return 0;  // :67-70
+        const int   K      = static_cast<int>(prm->knn);
+        const float maxSqr = static_cast<float>(prm->distanceThreshold * prm->distanceThreshold);  // :77
+        std::vector<uint8_t>        ok(nLocal, 0);
+        std::vector<orc_pair_pt2ln> cand(nLocal);
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+        {
+            std::vector<uint32_t> idx(K);
+            std::vector<float>    d2(K), xs(K), ys(K), zs(K);
+#pragma omp for schedule(dynamic, 256)
+            for (long i = 0; i < static_cast<long>(nLocal); i++)
+            {
+                if (!prm->allowMatchAlreadyMatchedPoints && local_paired && local_paired[i]) continue;  // :88-90
+                const float q[3] = {gx[i], gy[i], gz[i]};
+                const int   cnt  = kd->knn(q, K, std::numeric_limits<float>::infinity(), idx.data(), d2.data());
+                int within = cnt;  // :110-127
+                for (int j = 0; j < cnt; j++)
+                    if (d2[j] > maxSqr)
+                    {
+                        within = j;
+                        break;
+                    }
+                if (within < static_cast<int>(prm->minimumLinePoints)) continue;  // :130
+                for (int k = 0; k < cnt; k++) xs[k] = kd->x[idx[k]], ys[k] = kd->y[idx[k]], zs[k] = kd->z[idx[k]];
+                const PlaneFit f = estimate_points_eigen(xs.data(), ys.data(), zs.data(), cnt);  // :134-135 (all cnt points)
+                if (f.eigVals[0] > prm->lineEigenThreshold * f.eigVals[2]) continue;  // :148
+                if (f.eigVals[1] > prm->lineEigenThreshold * f.eigVals[2]) continue;  // :149
+                orc_pair_pt2ln& p = cand[i];
+                p.lx = lx[i], p.ly = ly[i], p.lz = lz[i];  // :152
+                for (int d = 0; d < 3; d++) p.pBase[d] = f.mean[d];
+                const double* v = f.eigVec2;
+                const double  inv = 1.0 / std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);  // TPoint3D::unitarize
+                for (int d = 0; d < 3; d++) p.director[d] = v[d] * inv;
+                ok[i] = 1;
+            }
+        }
+        size_t nOut = 0;
+        for (size_t i = 0; i < nLocal; i++)
+        {
+            if (!ok[i]) continue;
+            if (nOut < out_capacity) out[nOut] = cand[i];
+            nOut++;
+            if (local_paired) local_paired[i] = 1;  // :159
+        }
+        return nOut;
     }
 
     // ---------------------------------------------------------------- pt2pl matcher (a7, a7')
@@ -666,9 +755,21 @@ extern "C"
     // -n n^T/|n|^2 (pt2pl), validated by the finite-difference test the reference
     // uses (tests/test-mp2p_error_terms_jacobians.cpp:63-101).
     // out_errNormSqr follows the TBB/pt2pt convention  sum weight*|e|^2.
+    // pt2ln term (optimal_tf_gauss_newton.cpp:182-203, errorTerms.cpp:67-113): e = q - u (u.q),
+    // q = T(+)l - pBase, J1 = (I - u u^T)-like matrix AS WRITTEN (:92-97, no assumption |u| = 1) times
+    // [l_x I .. I], weight = w_pt2ln * robust(|e|^2); the cost term is weight^2 |e|^2 there (:197).
+    void orc_gn_accumulate_ex(const orc_pair_pt2pt* p2p, size_t n2p, const orc_pair_pt2pl* p2l, size_t n2l,
+                              const orc_pair_pt2ln* p2ln, size_t n2ln, double w_pt2ln, const double T[12],
+                              const orc_gn_params* prm, double H[36], double g[6], double* out_errNormSqr, int nthreads);
     void orc_gn_accumulate(const orc_pair_pt2pt* p2p, size_t n2p, const orc_pair_pt2pl* p2l,
                            size_t n2l, const double T[12], const orc_gn_params* prm, double H[36],
                            double g[6], double* out_errNormSqr, int nthreads)
+    {
+        orc_gn_accumulate_ex(p2p, n2p, p2l, n2l, nullptr, 0, 1.0, T, prm, H, g, out_errNormSqr, nthreads);
+    }
+    void orc_gn_accumulate_ex(const orc_pair_pt2pt* p2p, size_t n2p, const orc_pair_pt2pl* p2l, size_t n2l,
+                              const orc_pair_pt2ln* p2ln, size_t n2ln, double w_pt2ln, const double T[12],
+                              const orc_gn_params* prm, double H[36], double g[6], double* out_errNormSqr, int nthreads)
     {
         const Pose pose = to_pose(T);
         const int  nt   = nthreads > 0 ? nthreads : 1;
@@ -737,6 +838,39 @@ extern "C"
                 acc[42] += w * e2;
                 add(J, e, w);
             }
+#pragma omp for schedule(static)
+            for (long i = 0; i < static_cast<long>(n2ln); i++)
+            {
+                const double  l[3] = {p2ln[i].lx, p2ln[i].ly, p2ln[i].lz};
+                const double* u    = p2ln[i].director;
+                double        gx, gy, gz;
+                compose_point(pose, l[0], l[1], l[2], gx, gy, gz);
+                const double q[3] = {gx - p2ln[i].pBase[0], gy - p2ln[i].pBase[1], gz - p2ln[i].pBase[2]};
+                const double uq   = u[0] * q[0] + u[1] * q[1] + u[2] * q[2];
+                const double e[3] = {q[0] - u[0] * uq, q[1] - u[1] * uq, q[2] - u[2] * uq};
+                double       B[3][6];
+                for (int r = 0; r < 3; r++)
+                {
+                    const double R0 = pose.R(r, 0), R1 = pose.R(r, 1), R2 = pose.R(r, 2);
+                    B[r][0] = R0, B[r][1] = R1, B[r][2] = R2;
+                    B[r][3] = R2 * l[1] - R1 * l[2];
+                    B[r][4] = R0 * l[2] - R2 * l[0];
+                    B[r][5] = R1 * l[0] - R0 * l[1];
+                }
+                double J[3][6];
+                for (int r = 0; r < 3; r++)
+                    for (int a = 0; a < 6; a++)
+                    {
+                        double v = 0;
+                        for (int c = 0; c < 3; c++) v += ((r == c ? 1.0 : 0.0) - u[r] * u[c]) * B[c][a];
+                        J[r][a] = v;
+                    }
+                const double e2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+                double       w  = w_pt2ln;
+                if (prm->kernel != 0) w *= robust_weight(prm->kernel, prm->kernelParam, e2);
+                acc[42] += w * w * e2;  // :197 (weight squared, as written)
+                add(J, e, w);
+            }
         }
         for (int k = 0; k < 36; k++) H[k] = 0;
         for (int k = 0; k < 6; k++) g[k] = 0;
@@ -753,16 +887,25 @@ extern "C"
     // optimal_tf_gauss_newton (optimal_tf_gauss_newton.cpp:36-372) restricted to pt2pt + pt2pl
     // terms, no prior. H and g are ZEROED every inner iteration (the TBB / mathematically intended
     // behaviour; the non-TBB build never zeroes them — SURVEY Q4, documented deviation).
+    int orc_optimal_tf_gauss_newton_ex(const orc_pair_pt2pt* p2p, size_t n2p, const orc_pair_pt2pl* p2l, size_t n2l,
+                                       const orc_pair_pt2ln* p2ln, size_t n2ln, double w_pt2ln, const orc_gn_params* prm,
+                                       const double T_init[12], double T_out[12], uint32_t* iters_done, int nthreads);
     int orc_optimal_tf_gauss_newton(const orc_pair_pt2pt* p2p, size_t n2p, const orc_pair_pt2pl* p2l,
                                     size_t n2l, const orc_gn_params* prm, const double T_init[12],
                                     double T_out[12], uint32_t* iters_done, int nthreads)
+    {
+        return orc_optimal_tf_gauss_newton_ex(p2p, n2p, p2l, n2l, nullptr, 0, 1.0, prm, T_init, T_out, iters_done, nthreads);
+    }
+    int orc_optimal_tf_gauss_newton_ex(const orc_pair_pt2pt* p2p, size_t n2p, const orc_pair_pt2pl* p2l, size_t n2l,
+                                       const orc_pair_pt2ln* p2ln, size_t n2ln, double w_pt2ln, const orc_gn_params* prm,
+                                       const double T_init[12], double T_out[12], uint32_t* iters_done, int nthreads)
     {
         Pose     pose = to_pose(T_init);  // :50
         uint32_t it = 0, updates = 0;
         for (; it < prm->maxInnerLoopIterations; it++)
         {
             double H[36], g[6], errSq = 0;
-            orc_gn_accumulate(p2p, n2p, p2l, n2l, pose.m, prm, H, g, &errSq, nthreads);
+            orc_gn_accumulate_ex(p2p, n2p, p2l, n2l, p2ln, n2ln, w_pt2ln, pose.m, prm, H, g, &errSq, nthreads);
             if (std::sqrt(errSq) <= prm->maxCost) break;  // :344-346
             double delta[6], mg[6];
             for (int k = 0; k < 6; k++) mg[k] = -g[k];
@@ -780,6 +923,34 @@ extern "C"
 
     // Raw residual/Jacobian of one pairing, for the finite-difference test
     // (tests/test-mp2p_error_terms_jacobians.cpp).  kind 0 = pt2pt, 1 = pt2pl.
+    void orc_error_and_jacobian_pt2ln(const orc_pair_pt2ln* pn, const double T[12], double e[3], double J[18])
+    {
+        const Pose   pose = to_pose(T);
+        const double l[3] = {pn->lx, pn->ly, pn->lz};
+        const double* u   = pn->director;
+        double       gx, gy, gz;
+        compose_point(pose, l[0], l[1], l[2], gx, gy, gz);
+        const double q[3] = {gx - pn->pBase[0], gy - pn->pBase[1], gz - pn->pBase[2]};
+        const double uq   = u[0] * q[0] + u[1] * q[1] + u[2] * q[2];
+        for (int r = 0; r < 3; r++) e[r] = q[r] - u[r] * uq;
+        for (int r = 0; r < 3; r++)
+        {
+            double B[3][6];
+            for (int c = 0; c < 3; c++)
+            {
+                const double R0 = pose.R(c, 0), R1 = pose.R(c, 1), R2 = pose.R(c, 2);
+                B[c][0] = R0, B[c][1] = R1, B[c][2] = R2;
+                B[c][3] = R2 * l[1] - R1 * l[2], B[c][4] = R0 * l[2] - R2 * l[0], B[c][5] = R1 * l[0] - R0 * l[1];
+            }
+            for (int a = 0; a < 6; a++)
+            {
+                double v = 0;
+                for (int c = 0; c < 3; c++) v += ((r == c ? 1.0 : 0.0) - u[r] * u[c]) * B[c][a];
+                J[6 * r + a] = v;
+            }
+        }
+    }
+
     void orc_error_and_jacobian(int kind, const orc_pair_pt2pt* pp, const orc_pair_pt2pl* pl,
                                 const double T[12], double e[3], double J[18])
     {

@@ -22,7 +22,8 @@ PAIR_PT2PT = np.dtype(
 PAIR_PT2PL = np.dtype(
     [("coefs", "<f8", 4), ("centroid", "<f8", 3), ("local", "<f4", 3), ("_pad", "<f4")]
 )
-assert PAIR_PT2PT.itemsize == 36 and PAIR_PT2PL.itemsize == 72
+PAIR_PT2LN = np.dtype([("pBase", "<f8", 3), ("director", "<f8", 3), ("local", "<f8", 3)])  # point_line_pair_t
+assert PAIR_PT2PT.itemsize == 36 and PAIR_PT2PL.itemsize == 72 and PAIR_PT2LN.itemsize == 72
 
 
 class _MatchPt2PtParams(C.Structure):
@@ -100,6 +101,7 @@ def lib():
         L.orc_pt2pl_to_pt2pt.restype = C.c_size_t
         L.orc_optimal_tf_horn.restype = C.c_int
         L.orc_optimal_tf_gauss_newton.restype = C.c_int
+        L.orc_optimal_tf_gauss_newton_ex.restype = C.c_int
         L.orc_knn.restype = C.c_int
         L.orc_max_threads.restype = C.c_int
         _lib = L
@@ -357,6 +359,69 @@ def optimal_tf_gauss_newton(p2p, p2l, prm: GNParams, T_init, nthreads=1):
     cp = prm.c()
     ok = lib().orc_optimal_tf_gauss_newton(_p(p2p), C.c_size_t(p2p.size), _p(p2l), C.c_size_t(p2l.size), C.byref(cp), _p(_T(T_init)), _p(T), C.byref(it), nthreads)
     return bool(ok), T.reshape(3, 4), it.value
+
+
+def optimal_tf_gauss_newton_ex(p2p, p2l, p2ln, prm: GNParams, T_init, w_pt2ln=1.0, nthreads=1):
+    """optimal_tf_gauss_newton over pt2pt + pt2pl + pt2ln pairings (optimal_tf_gauss_newton.cpp:36-372)."""
+    p2p, p2l = _pairs(p2p, p2l)
+    p2ln = np.zeros(0, PAIR_PT2LN) if p2ln is None else np.ascontiguousarray(p2ln, dtype=PAIR_PT2LN)
+    T = np.zeros(12)
+    it = C.c_uint32(0)
+    cp = prm.c()
+    ok = lib().orc_optimal_tf_gauss_newton_ex(_p(p2p), C.c_size_t(p2p.size), _p(p2l), C.c_size_t(p2l.size), _p(p2ln), C.c_size_t(p2ln.size), C.c_double(w_pt2ln), C.byref(cp), _p(_T(T_init)), _p(T), C.byref(it), nthreads)
+    return bool(ok), T.reshape(3, 4), it.value
+
+
+def gn_accumulate_ex(p2p, p2l, p2ln, T, prm: GNParams, w_pt2ln=1.0, nthreads=1):
+    p2p, p2l = _pairs(p2p, p2l)
+    p2ln = np.zeros(0, PAIR_PT2LN) if p2ln is None else np.ascontiguousarray(p2ln, dtype=PAIR_PT2LN)
+    H, g, err = np.zeros(36), np.zeros(6), C.c_double(0)
+    cp = prm.c()
+    lib().orc_gn_accumulate_ex(_p(p2p), C.c_size_t(p2p.size), _p(p2l), C.c_size_t(p2l.size), _p(p2ln), C.c_size_t(p2ln.size), C.c_double(w_pt2ln), _p(_T(T)), C.byref(cp), _p(H), _p(g), C.byref(err), nthreads)
+    return H.reshape(6, 6), g, err.value
+
+
+def error_and_jacobian_pt2ln(pair, T):
+    e, J = np.zeros(3), np.zeros((3, 6))
+    pp = np.ascontiguousarray(pair, dtype=PAIR_PT2LN)
+    lib().orc_error_and_jacobian_pt2ln(_p(pp), _p(_T(T)), _p(e), _p(J))
+    return e, J
+
+
+class _MatchPt2LnParams(C.Structure):
+    _fields_ = [
+        ("distanceThreshold", C.c_double),
+        ("knn", C.c_uint32),
+        ("minimumLinePoints", C.c_uint32),
+        ("lineEigenThreshold", C.c_double),
+        ("allowMatchAlreadyMatchedPoints", C.c_int32),
+        ("bounding_box_intersection_check_epsilon", C.c_double),
+    ]
+
+
+@dataclass
+class MatchPt2LnParams:
+    distanceThreshold: float
+    knn: int = 4
+    minimumLinePoints: int = 4
+    lineEigenThreshold: float = 0.01
+    allowMatchAlreadyMatchedPoints: bool = False
+    bounding_box_intersection_check_epsilon: float = 0.20
+
+
+def match_pt2ln(tree: KDTree, lx, ly, lz, T, prm: MatchPt2LnParams, local_paired=None, nthreads=1):
+    """Matcher_Point2Line (Matcher_Point2Line.cpp:46-163)."""
+    lx, ly, lz = _f32(lx), _f32(ly), _f32(lz)
+    n = lx.size
+    cp = _MatchPt2LnParams(prm.distanceThreshold, prm.knn, prm.minimumLinePoints, prm.lineEigenThreshold, int(prm.allowMatchAlreadyMatchedPoints), prm.bounding_box_intersection_check_epsilon)
+    if local_paired is None:
+        local_paired = np.zeros(n, np.uint8)
+    out = np.zeros(max(n, 1), PAIR_PT2LN)
+    pot = C.c_uint64(0)
+    fn = lib().orc_match_pt2ln
+    fn.restype = C.c_size_t
+    cnt = fn(C.c_void_p(tree._h), _p(lx), _p(ly), _p(lz), C.c_size_t(n), _p(_T(T)), C.byref(cp), _p(local_paired), _p(out), C.c_size_t(n), C.byref(pot), nthreads)
+    return out[:cnt], pot.value
 
 
 def pt2pl_to_pt2pt(p2l, T_guess):

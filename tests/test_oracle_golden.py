@@ -357,3 +357,83 @@ def test_icp_align_protocol_inlier_ratio(solver):
 
         res = icp_harness.align(match, solve, np.eye(3, 4), icp_harness.IcpParams(maxIterations=100))
         assert np.linalg.norm(orc.se3_log(orc.inverse_compose(res.pose, gt))) < 0.1
+
+
+# ---------------------------------------------------------------------------------------------
+# pt2ln: the error term and its Jacobian are pinned by the reference's own tests —
+# tests/test-mp2p_error_terms_jacobians.cpp:105-176 (finite differences on D*exp(eps), 1e-5) and
+# :492-512 (known answer) — and the Gauss-Newton solver over point-to-line pairings by
+# tests/test-mp2p_optimize_pt2ln.cpp:25-111 (three axis lines, 17 ground-truth poses, 1e-3).
+# Matcher_Point2Line has no upstream test: hand-made known answers below.
+# ---------------------------------------------------------------------------------------------
+def test_pt2ln_jacobian_vs_finite_differences_and_known_answer():
+    rng = np.random.default_rng(1234)
+    for _ in range(1000):
+        D = orc.pose_from_xyzypr(*rng.normal(0, 10, 3), rng.uniform(-np.pi, np.pi), *rng.uniform(-np.pi / 2, np.pi / 2, 2))
+        pair = np.zeros(1, orc.PAIR_PT2LN)
+        u = rng.normal(0, 1, 3)
+        pair["pBase"], pair["director"], pair["local"] = rng.normal(0, 20, 3), u / np.linalg.norm(u), rng.normal(0, 10, 3)
+        _, J = orc.error_and_jacobian_pt2ln(pair, D)
+        num = np.zeros((3, 6))
+        for a in range(6):
+            ep, em = np.zeros(6), np.zeros(6)
+            ep[a], em[a] = 1e-6, -1e-6
+            e_p, _ = orc.error_and_jacobian_pt2ln(pair, orc.compose(D, orc.se3_exp(ep)))
+            e_m, _ = orc.error_and_jacobian_pt2ln(pair, orc.compose(D, orc.se3_exp(em)))
+            num[:, a] = (e_p - e_m) / 2e-6
+        assert np.abs(num - J).max() < 1e-5
+    pair = np.zeros(1, orc.PAIR_PT2LN)  # :492-512
+    pair["pBase"], pair["director"], pair["local"] = [10, 11, 12], [0, 0, 1], [10, 11, -1.0]
+    e, _ = orc.error_and_jacobian_pt2ln(pair, np.eye(3, 4))
+    assert np.abs(e).max() < 1e-6
+
+
+PT2LN_GT = [(0, 0, 0, 0, 0, 0), (1, 0, 0, 0, 0, 0), (0, 1, 0, 0, 0, 0), (0, 0, 1, 0, 0, 0), (-2, 0, 0, 0, 0, 0), (0, -3, 0, 0, 0, 0),
+            (0, 0, -4, 0, 0, 0), (0, 0, 0, 20, 0, 0), (0, 0, 0, -20, 0, 0), (0, 0, 0, 0, 10, 0), (0, 0, 0, 0, -10, 0),
+            (0, 0, 0, 0, 0, 15), (0, 0, 0, 0, 0, -15), (1, 2, 3, 0, 0, 0), (1, 2, 3, -10, 5, 30)]
+
+
+def pt2ln_fixture(gt):
+    """tests/test-mp2p_optimize_pt2ln.cpp:36-50: the three axes as lines, one point on each."""
+    pairs = np.zeros(3, orc.PAIR_PT2LN)
+    for k, (axis, pt) in enumerate([((1, 0, 0), (0.5, 0, 0)), ((0, 1, 0), (0, 0.4, 0)), ((0, 0, 1), (0, 0, 0.2))]):
+        pairs["director"][k] = axis
+        pairs["local"][k] = (np.array(pt) - gt[:, 3]) @ gt[:, :3]  # groundTruth.inverseComposePoint
+    return pairs
+
+
+@pytest.mark.parametrize("gt6", PT2LN_GT)
+def test_gn_pt2ln_known_answers(gt6):
+    gt = orc.pose_from_xyzypr(*gt6[:3], *(np.array(gt6[3:]) * DEG))
+    ok, T, _ = orc.optimal_tf_gauss_newton_ex(None, None, pt2ln_fixture(gt), orc.GNParams(maxInnerLoopIterations=25), np.eye(3, 4))
+    assert ok and np.linalg.norm(orc.se3_log(orc.inverse_compose(T, gt))) < 1e-3
+
+
+def test_matcher_pt2ln_known_answers():
+    # global: a pole along z at (5, 5), 41 points 5 cm apart, and a plane patch z = 0 (must not look like a line)
+    zs = np.arange(41) * 0.05
+    pole = np.stack([np.full(41, 5.0), np.full(41, 5.0), zs], 1)
+    gx, gy = np.meshgrid(np.arange(20) * 0.1, np.arange(20) * 0.1)
+    plane = np.stack([gx.ravel(), gy.ravel(), np.zeros(400)], 1)
+    G = np.concatenate([pole, plane]).astype(np.float32)
+    tree = orc.KDTree(*(np.ascontiguousarray(G[:, k]) for k in range(3)))
+    L = np.array([[5.1, 5.0, 1.0], [5.0, 5.2, 0.52], [1.0, 1.0, 0.05], [5.0, 9.0, 1.0]], np.float32)
+    lx, ly, lz = (np.ascontiguousarray(L[:, k]) for k in range(3))
+    prm = orc.MatchPt2LnParams(distanceThreshold=0.5, knn=4, minimumLinePoints=4, lineEigenThreshold=0.01)
+    lp = np.zeros(4, np.uint8)
+    p, pot = orc.match_pt2ln(tree, lx, ly, lz, np.eye(3, 4), prm, lp)
+    # locals 0 and 1 sit next to the pole; local 2 is over the plane (eigen test fails); local 3 is 4 m away
+    assert pot == 4 and len(p) == 2 and list(lp) == [1, 1, 0, 0]
+    assert np.allclose(np.abs(p["director"]), [[0, 0, 1], [0, 0, 1]], atol=1e-6)
+    assert np.allclose(p["pBase"][:, :2], 5.0, atol=1e-6) and np.array_equal(p["local"], L[:2].astype(np.float64))
+    assert np.allclose(p["pBase"][:, 2], [0.975, 0.525], atol=1e-6)  # mean of the 4 nearest pole points (ties: lowest index)
+    # the count check is on the neighbours within the threshold, the PCA on all knn (as written upstream)
+    prm2 = orc.MatchPt2LnParams(distanceThreshold=0.12, knn=4, minimumLinePoints=4, lineEigenThreshold=0.01)
+    p2, _ = orc.match_pt2ln(tree, lx, ly, lz, np.eye(3, 4), prm2)
+    assert len(p2) == 0  # only 2-3 of the 4 nearest are within 12 cm
+    prm3 = orc.MatchPt2LnParams(distanceThreshold=0.12, knn=4, minimumLinePoints=2, lineEigenThreshold=0.01)
+    p3, _ = orc.match_pt2ln(tree, lx, ly, lz, np.eye(3, 4), prm3)
+    assert len(p3) == 1 and np.allclose(p3["pBase"][0, 2], 0.975, atol=1e-6)
+    # already-paired locals are skipped
+    p4, _ = orc.match_pt2ln(tree, lx, ly, lz, np.eye(3, 4), prm, np.array([1, 0, 0, 0], np.uint8))
+    assert len(p4) == 1 and np.array_equal(p4["local"][0], L[1].astype(np.float64))
