@@ -66,6 +66,15 @@ typedef struct
     float  _pad;
 } mp2p_b200_pair_pt2pl;
 
+/* mp2p_icp::point_line_pair_t (mp2p_icp/include/mp2p_icp/Pairings.h:61-73): mrpt::math::TLine3D
+ * {TPoint3D pBase, director[3]} + TPoint3D pt_local — 72 bytes, all doubles. */
+typedef struct
+{
+    double pBase[3];
+    double director[3];
+    double local[3];
+} mp2p_b200_pair_pt2ln;
+
 /* Parameters of Matcher_Points_DistanceThreshold (+ Matcher_Points_Base):
  * mp2p_icp/src/Matcher_Points_DistanceThreshold.cpp:39-46, Matcher_Points_Base.cpp:132-181. */
 typedef struct
@@ -214,6 +223,31 @@ int mp2p_b200_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* l
                           uint64_t capacity, int out_on_device, uint64_t* out_count,
                           uint64_t* potential_pairings);
 
+/* Parameters of Matcher_Point2Line (mp2p_icp/src/Matcher_Point2Line.cpp:35-45,
+ * mp2p_icp/include/mp2p_icp/Matcher_Point2Line.h:61-64) + Matcher_Points_Base. */
+typedef struct
+{
+    double   distanceThreshold;
+    uint32_t knn;
+    uint32_t minimumLinePoints; /* >= 2 */
+    double   lineEigenThreshold;
+    int32_t  allowMatchAlreadyMatchedPoints;
+    double   bounding_box_intersection_check_epsilon;
+} mp2p_b200_pt2ln_params;
+
+/* Matcher_Point2Line::implMatchOneLayer (mp2p_icp/src/Matcher_Point2Line.cpp:46-163):
+ * the `knn` nearest global points of every local point not yet paired (unbounded search, :103-105); at
+ * least minimumLinePoints of them within distanceThreshold (:110-130); estimate_points_eigen over all
+ * knn points (:132-135, as written upstream); line test e0, e1 <= lineEigenThreshold * e2 (:148-149);
+ * record = {mean, unit eigenvector of the largest eigenvalue, ORIGINAL local point}. Global points are
+ * never marked (:92-95); the caller marks the local bits of the returned pairs (:159). Output in
+ * ascending local index; *potential_pairings += n_local (:58). */
+int mp2p_b200_match_pt2ln(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                          const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
+                          const mp2p_b200_pt2ln_params* params, const uint32_t* local_paired_bits,
+                          mp2p_b200_pair_pt2ln* out_pairs, uint64_t capacity, int out_on_device,
+                          uint64_t* out_count, uint64_t* potential_pairings);
+
 /* Parameters of Matcher_Points_InlierRatio (mp2p_icp/include/mp2p_icp/Matcher_Points_InlierRatio.h:50-56,
  * mp2p_icp/src/Matcher_Points_InlierRatio.cpp:35-39) + Matcher_Points_Base. */
 typedef struct
@@ -311,6 +345,16 @@ int mp2p_b200_solve_gauss_newton(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt*
                                  uint64_t n_pt2pl, int pairs_on_device,
                                  const mp2p_b200_gn_params* params, const double pose_init[12],
                                  double pose_out[12], uint32_t* iterations_done, int32_t* solved);
+
+/* The same solver with the point-to-line term added (error_point2line, errorTerms.cpp:67-113;
+ * optimal_tf_gauss_newton.cpp:182-203: weight = w_pt2ln * robust(|e|^2), cost term weight^2 |e|^2 as
+ * written there). pairs_on_device: 0 = host lists, 1 = device lists (MP2P_B200_PAIRS_LAST_MATCH is not
+ * offered for this form). Reference tests: tests/test-mp2p_optimize_pt2ln.cpp. */
+int mp2p_b200_solve_gauss_newton_ex(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* pairs_pt2pt, uint64_t n_pt2pt,
+                                    const mp2p_b200_pair_pt2pl* pairs_pt2pl, uint64_t n_pt2pl,
+                                    const mp2p_b200_pair_pt2ln* pairs_pt2ln, uint64_t n_pt2ln, int pairs_on_device,
+                                    const mp2p_b200_gn_params* params, double w_pt2ln, const double pose_init[12],
+                                    double pose_out[12], uint32_t* iterations_done, int32_t* solved);
 
 /* ---- fused iterations: when BOTH plugins of an ICP iteration are ours, run_matchers + run_solvers
  * (mp2p_icp/src/ICP.cpp:143,170) are enqueued back to back on the device — the pairings never

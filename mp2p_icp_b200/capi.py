@@ -23,7 +23,8 @@ PAIR_PT2PT = np.dtype(
     [("globalIdx", "<u4"), ("localIdx", "<u4"), ("global", "<f4", 3), ("local", "<f4", 3), ("errSq", "<f4")]
 )
 PAIR_PT2PL = np.dtype([("coefs", "<f8", 4), ("centroid", "<f8", 3), ("local", "<f4", 3), ("_pad", "<f4")])
-assert PAIR_PT2PT.itemsize == 36 and PAIR_PT2PL.itemsize == 72
+PAIR_PT2LN = np.dtype([("pBase", "<f8", 3), ("director", "<f8", 3), ("local", "<f8", 3)])  # point_line_pair_t
+assert PAIR_PT2PT.itemsize == 36 and PAIR_PT2PL.itemsize == 72 and PAIR_PT2LN.itemsize == 72
 
 KERNELS = {"None": 0, "GemanMcClure": 1, "Cauchy": 2}
 
@@ -50,6 +51,17 @@ class _Pt2PlParams(C.Structure):
         ("knn", C.c_uint32),
         ("minimumPlanePoints", C.c_uint32),
         ("planeEigenThreshold", C.c_double),
+        ("allowMatchAlreadyMatchedPoints", C.c_int32),
+        ("bounding_box_intersection_check_epsilon", C.c_double),
+    ]
+
+
+class _Pt2LnParams(C.Structure):
+    _fields_ = [
+        ("distanceThreshold", C.c_double),
+        ("knn", C.c_uint32),
+        ("minimumLinePoints", C.c_uint32),
+        ("lineEigenThreshold", C.c_double),
         ("allowMatchAlreadyMatchedPoints", C.c_int32),
         ("bounding_box_intersection_check_epsilon", C.c_double),
     ]
@@ -130,6 +142,21 @@ class Pt2PlParams:
 
 
 @dataclass
+class Pt2LnParams:
+    """Parameters of Matcher_Point2Line (same names and defaults as the reference)."""
+
+    distanceThreshold: float = 0.50
+    knn: int = 4
+    minimumLinePoints: int = 4
+    lineEigenThreshold: float = 0.01
+    allowMatchAlreadyMatchedPoints: bool = False
+    bounding_box_intersection_check_epsilon: float = 0.20
+
+    def c(self):
+        return _Pt2LnParams(self.distanceThreshold, self.knn, self.minimumLinePoints, self.lineEigenThreshold, int(self.allowMatchAlreadyMatchedPoints), self.bounding_box_intersection_check_epsilon)
+
+
+@dataclass
 class InlierRatioParams:
     """Parameters of Matcher_Points_InlierRatio (same names as the reference's YAML keys)."""
 
@@ -173,7 +200,7 @@ class GNParams:
 EXPORTS = [
     "mp2p_b200_last_error", "mp2p_b200_device_count", "mp2p_b200_ctx_create", "mp2p_b200_ctx_destroy",
     "mp2p_b200_ctx_synchronize", "mp2p_b200_ctx_launch_count", "mp2p_b200_map_create", "mp2p_b200_map_destroy",
-    "mp2p_b200_map_get_info", "mp2p_b200_knn", "mp2p_b200_match_pt2pt", "mp2p_b200_match_pt2pl", "mp2p_b200_match_inlier_ratio",
+    "mp2p_b200_map_get_info", "mp2p_b200_knn", "mp2p_b200_match_pt2pt", "mp2p_b200_match_pt2pl", "mp2p_b200_match_inlier_ratio", "mp2p_b200_match_pt2ln", "mp2p_b200_solve_gauss_newton_ex",
     "mp2p_b200_solve_horn", "mp2p_b200_solve_gauss_newton", "mp2p_b200_gn_accumulate",
     "mp2p_b200_gn_step_from_packet", "mp2p_b200_horn_sums", "mp2p_b200_horn_moments", "mp2p_b200_horn_finish",
     "mp2p_b200_host_alloc", "mp2p_b200_host_free", "mp2p_b200_ctx_set_profiling",
@@ -360,6 +387,17 @@ class Context:
         T = np.zeros(12)
         it, solved = C.c_uint32(0), C.c_int32(0)
         _check(load_library().mp2p_b200_solve_gauss_newton(self._h, _ptr(p2p) if n2p else None, C.c_uint64(n2p or 0), _ptr(p2l) if n2l else None, C.c_uint64(n2l or 0), int(on_device), C.byref(cp), _ptr(_pose(T_init)), _ptr(T), C.byref(it), C.byref(solved)))
+        return bool(solved.value), T.reshape(3, 4), it.value
+
+    def solve_gauss_newton_ex(self, p2p, p2l, p2ln, prm: GNParams, T_init, w_pt2ln=1.0):
+        """optimal_tf_gauss_newton over host lists of pt2pt, pt2pl and pt2ln pairings."""
+        p2p = np.ascontiguousarray(p2p if p2p is not None else np.zeros(0, PAIR_PT2PT), dtype=PAIR_PT2PT)
+        p2l = np.ascontiguousarray(p2l if p2l is not None else np.zeros(0, PAIR_PT2PL), dtype=PAIR_PT2PL)
+        p2ln = np.ascontiguousarray(p2ln if p2ln is not None else np.zeros(0, PAIR_PT2LN), dtype=PAIR_PT2LN)
+        cp = prm.c()
+        T = np.zeros(12)
+        it, solved = C.c_uint32(0), C.c_int32(0)
+        _check(load_library().mp2p_b200_solve_gauss_newton_ex(self._h, _ptr(p2p) if p2p.size else None, C.c_uint64(p2p.size), _ptr(p2l) if p2l.size else None, C.c_uint64(p2l.size), _ptr(p2ln) if p2ln.size else None, C.c_uint64(p2ln.size), 0, C.byref(cp), C.c_double(w_pt2ln), _ptr(_pose(T_init)), _ptr(T), C.byref(it), C.byref(solved)))
         return bool(solved.value), T.reshape(3, 4), it.value
 
     def gn_accumulate(self, p2p, p2l, prm: GNParams, T, n2p=None, n2l=None, on_device=False, packet=None, packet_on_device=False):
@@ -728,6 +766,20 @@ class Map:
 
         step._keep = (keep, self)
         return step
+
+    def match_pt2ln(self, lx, ly, lz, T, prm: Pt2LnParams, local_paired=None, n_local=None, local_on_device=False, out=None, out_on_device=False, capacity=None):
+        """Matcher_Point2Line. Returns (point-to-line pairings in ascending local index, potential_pairings)."""
+        plx, ply, plz, n_local, kind = _local(lx, ly, lz, n_local, local_on_device)
+        cap = capacity if capacity is not None else n_local
+        if out is None and not out_on_device:
+            out = np.empty(max(cap, 1), PAIR_PT2LN)
+        lb = pack_bits(local_paired) if local_paired is not None else None
+        cp = prm.c()
+        cnt, pot = C.c_uint64(0), C.c_uint64(0)
+        _check(load_library().mp2p_b200_match_pt2ln(self.ctx._h, self._h, plx, ply, plz, C.c_uint64(n_local), kind, _ptr(_pose(T)), C.byref(cp), _ptr(lb), _ptr(out), C.c_uint64(cap), int(out_on_device), C.byref(cnt), C.byref(pot)))
+        if out_on_device:
+            return cnt.value, pot.value
+        return out[: cnt.value], pot.value
 
     def match_pt2pl(self, lx, ly, lz, T, prm: Pt2PlParams, local_paired=None, n_local=None, local_on_device=False, out=None, out_on_device=False, capacity=None, sync=True):
         plx, ply, plz, n_local, kind = _local(lx, ly, lz, n_local, local_on_device)

@@ -282,7 +282,7 @@ extern "C"
         cudaStreamSynchronize(c->stream);
         for (DevBuf* b : {&c->d_lx, &c->d_ly, &c->d_lz, &c->d_cand, &c->d_candxyz, &c->d_lbits, &c->d_gbits, &c->d_scan,
                           &c->d_small, &c->d_out2p, &c->d_out2l, &c->d_plcand, &c->d_okflags, &c->d_fitlist, &c->d_coop, &c->d_knn_idx, &c->d_knn_d2,
-                          &c->d_knn_found, &c->d_irk0, &c->d_irk1, &c->d_irv0, &c->d_irv1, &c->d_irtmp, &c->d_pairs2p, &c->d_pairs2l, &c->d_partials, &c->d_packet,
+                          &c->d_knn_found, &c->d_irk0, &c->d_irk1, &c->d_irv0, &c->d_irv1, &c->d_irtmp, &c->d_pairs2p, &c->d_pairs2l, &c->d_pairs2ln, &c->d_partials, &c->d_packet,
                           &c->d_pose, &c->d_weights, &c->d_outlier, &c->d_conv})
             b->release();
         if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -502,6 +502,39 @@ extern "C"
                                       prm->allowMatchAlreadyMatchedPoints, prm->allowMatchAlreadyMatchedGlobalPoints,
                                       prm->bounding_box_intersection_check_epsilon, local_paired_bits, global_paired_bits,
                                       out_pairs, capacity, out_on_device, out_count);
+    }
+
+    int mp2p_b200_match_pt2ln(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly, const float* lz,
+                              uint64_t n_local, int local_on_device, const double pose[12],
+                              const mp2p_b200_pt2ln_params* prm, const uint32_t* local_paired_bits,
+                              mp2p_b200_pair_pt2ln* out_pairs, uint64_t capacity, int out_on_device, uint64_t* out_count,
+                              uint64_t* potential_pairings)
+    {
+        static_assert(sizeof(mp2p_b200_pair_pt2ln) == sizeof(mp2p_b200_pair_pt2pl), "line and plane records share the pipeline");
+        if (!ctx || !map || !pose || !prm || !out_count || (n_local && bad_local(lx, ly, lz, local_on_device)) ||
+            (capacity && !out_pairs))
+        {
+            set_error("match_pt2ln: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        if (!(prm->distanceThreshold > 0.0) || prm->minimumLinePoints < 2 || prm->knn < prm->minimumLinePoints)
+        {
+            // Matcher_Point2Line.cpp:44 asserts minimumLinePoints >= 2; knn < minimumLinePoints can never pair
+            set_error("match_pt2ln: need distanceThreshold > 0, minimumLinePoints >= 2, knn >= minimumLinePoints");
+            return MP2P_B200_ERR_ARG;
+        }
+        if (potential_pairings) *potential_pairings += n_local;  // :58
+        DeviceGuard            g(ctx->device);
+        ProfScope              ps(ctx);
+        mp2p_b200_pt2pl_params pp{};  // the shared pipeline's view of the parameters
+        pp.distanceThreshold = prm->distanceThreshold, pp.searchRadius = prm->distanceThreshold, pp.knn = prm->knn;
+        pp.minimumPlanePoints = prm->minimumLinePoints, pp.planeEigenThreshold = prm->lineEigenThreshold;
+        pp.allowMatchAlreadyMatchedPoints = prm->allowMatchAlreadyMatchedPoints;
+        pp.bounding_box_intersection_check_epsilon = prm->bounding_box_intersection_check_epsilon;
+        const LineMode line{prm->minimumLinePoints, prm->lineEigenThreshold};
+        return run_match_pt2pl(ctx, map, lx, ly, lz, n_local, local_on_device, pose, &pp, local_paired_bits,
+                               reinterpret_cast<mp2p_b200_pair_pt2pl*>(out_pairs), capacity, out_on_device, out_count, nullptr,
+                               &line);
     }
 
     uint64_t mp2p_b200_shard_record_words(uint64_t per_shard, uint32_t pairingsPerPoint)
@@ -923,6 +956,45 @@ extern "C"
         uint32_t* d_state = reinterpret_cast<uint32_t*>(ctx->d_pose.as<char>() + 128);
         MP2P_CUDA_TRY(cudaMemcpyAsync(d_pose, hpose, 96, cudaMemcpyHostToDevice, ctx->stream));
         MP2P_TRY(run_gn_device_loop(ctx, d2p, n2p, d2l, n2l, prm, d_pose, d_state, ctx->d_packet.as<double>()));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(hpose, d_pose, 96, cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(hst, d_state, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        MP2P_CUDA_TRY(cudaGetLastError());
+        std::memcpy(pose_out, hpose, 96);
+        if (iterations_done) *iterations_done = hst[1];
+        *solved = 1;
+        return 0;
+    }
+
+    int mp2p_b200_solve_gauss_newton_ex(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* p2p, uint64_t n2p,
+                                        const mp2p_b200_pair_pt2pl* p2l, uint64_t n2l, const mp2p_b200_pair_pt2ln* p2ln,
+                                        uint64_t n2ln, int pairs_on_device, const mp2p_b200_gn_params* prm, double w_pt2ln,
+                                        const double pose_init[12], double pose_out[12], uint32_t* iterations_done,
+                                        int32_t* solved)
+    {
+        if (!ctx || !prm || !pose_init || !pose_out || !solved || (n2p && !p2p) || (n2l && !p2l) || (n2ln && !p2ln) ||
+            (pairs_on_device != 0 && pairs_on_device != 1))
+        {
+            set_error("solve_gauss_newton_ex: NULL argument, or pairs_on_device not 0 / 1");
+            return MP2P_B200_ERR_ARG;
+        }
+        *solved = 0;
+        DeviceGuard                 g(ctx->device);
+        ProfScope                   ps(ctx);
+        const mp2p_b200_pair_pt2pt* d2p;
+        const mp2p_b200_pair_pt2pl* d2l;
+        const mp2p_b200_pair_pt2ln* d2ln;
+        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2p, p2p, n2p, pairs_on_device, &d2p));
+        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2l, p2l, n2l, pairs_on_device, &d2l));
+        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2ln, p2ln, n2ln, pairs_on_device, &d2ln));
+        double*   hpose = reinterpret_cast<double*>(static_cast<char*>(ctx->h_pinned) + 2048);
+        uint32_t* hst   = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->h_pinned) + 2048 + 128);
+        std::memcpy(hpose, pose_init, 96);  // optimal_tf_gauss_newton.cpp:50
+        double*   d_pose  = ctx->d_pose.as<double>();
+        uint32_t* d_state = reinterpret_cast<uint32_t*>(ctx->d_pose.as<char>() + 128);
+        MP2P_CUDA_TRY(cudaMemcpyAsync(d_pose, hpose, 96, cudaMemcpyHostToDevice, ctx->stream));
+        MP2P_TRY(run_gn_device_loop(ctx, d2p, n2p, d2l, n2l, prm, d_pose, d_state, ctx->d_packet.as<double>(), nullptr, nullptr,
+                                    d2ln, n2ln, w_pt2ln));
         MP2P_CUDA_TRY(cudaMemcpyAsync(hpose, d_pose, 96, cudaMemcpyDeviceToHost, ctx->stream));
         MP2P_CUDA_TRY(cudaMemcpyAsync(hst, d_state, 8, cudaMemcpyDeviceToHost, ctx->stream));
         MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

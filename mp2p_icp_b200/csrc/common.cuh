@@ -105,7 +105,7 @@ struct mp2p_b200_ctx
     bool         own_stream = false;
     uint64_t     launches   = 0;
     uint32_t     scan_epoch = 0;  // stamps look-back status words (match.cu)
-    uint64_t     hint_pt2pt = ~0ull, hint_pt2pl = ~0ull, hint_ir = ~0ull;  // previous pairing counts (speculative D2H size)
+    uint64_t     hint_pt2pt = ~0ull, hint_pt2pl = ~0ull, hint_ir = ~0ull, hint_pt2ln = ~0ull;  // previous pairing counts (speculative D2H size)
     // pairing count a matcher call left on the device without reading it back (shard_resolve with
     // out_count == NULL), consumed by solver calls given n = MP2P_B200_COUNT_ON_DEVICE
     const unsigned long long* last_count    = nullptr;
@@ -176,7 +176,7 @@ struct mp2p_b200_ctx
     mp2p::DevBuf d_knn_idx, d_knn_d2, d_knn_found;
     mp2p::DevBuf d_irk0, d_irk1, d_irv0, d_irv1, d_irtmp;  // Matcher_Points_InlierRatio: sort keys / values / scratch
     // solver scratch
-    mp2p::DevBuf d_pairs2p, d_pairs2l; // H2D staging of host pairings
+    mp2p::DevBuf d_pairs2p, d_pairs2l, d_pairs2ln; // H2D staging of host pairings
     mp2p::DevBuf d_partials;           // per-block partial sums
     mp2p::DevBuf d_packet;             // 4 packets of 32 doubles
     mp2p::DevBuf d_pose;               // 12 doubles + flags
@@ -259,11 +259,17 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
                     const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits, const uint32_t* gbits,
                     mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device,
                     uint64_t* out_count, DeviceMatch* keep_on_device = nullptr);
+// Matcher_Point2Line rides on the pt2pl pipeline (k-NN search -> per-query fit -> compaction)
+struct LineMode
+{
+    uint32_t minimumLinePoints;
+    double   lineEigenThreshold;
+};
 int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
                     const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
                     const mp2p_b200_pt2pl_params* prm, const uint32_t* lbits,
                     mp2p_b200_pair_pt2pl* out, uint64_t capacity, int out_on_device,
-                    uint64_t* out_count, DeviceMatch* keep_on_device = nullptr);
+                    uint64_t* out_count, DeviceMatch* keep_on_device = nullptr, const LineMode* line = nullptr);
 uint64_t shard_record_words(uint64_t per_shard, uint32_t K);
 int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
                            const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
@@ -288,13 +294,15 @@ int run_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint6
                       const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l, const mp2p_b200_gn_params* prm,
                       const double* d_pose, double* d_packet, const unsigned long long* d_n2p = nullptr,
                       const unsigned long long* d_n2l = nullptr, const uint32_t* d_done = nullptr,
-                      uint32_t* d_step_state = nullptr /* != NULL: the launch also applies the GN update */);
+                      uint32_t* d_step_state = nullptr /* != NULL: the launch also applies the GN update */,
+                      const mp2p_b200_pair_pt2ln* d2ln = nullptr, uint64_t n2ln = 0, double w_pt2ln = 1.0);
 // whole inner loop of optimal_tf_gauss_newton on the device: (accumulate, solve+update) x maxIter,
 // no host synchronisation; d_pose in/out, d_state = {done flag, iterations done}
 int run_gn_device_loop(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p,
                        const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l, const mp2p_b200_gn_params* prm,
                        double* d_pose, uint32_t* d_state, double* d_packet,
-                       const unsigned long long* d_n2p = nullptr, const unsigned long long* d_n2l = nullptr);
+                       const unsigned long long* d_n2p = nullptr, const unsigned long long* d_n2l = nullptr,
+                       const mp2p_b200_pair_pt2ln* d2ln = nullptr, uint64_t n2ln = 0, double w_pt2ln = 1.0);
 int run_gn_step(mp2p_b200_ctx* ctx, const double* d_packet, const mp2p_b200_gn_params* prm, double* d_pose,
                 uint32_t* d_state);
 // pt2ln_pl_to_pt2pt (plane part) on the device; synchronises, *h_total = records kept

@@ -1142,6 +1142,10 @@ struct Pt2PlArgs
     float    gate_eps;
     uint64_t capacity;
     int      tma_ok;
+    // Matcher_Point2Line: line fit instead of plane fit; planeEigenThreshold = lineEigenThreshold,
+    // minPts = minimumLinePoints counted over the neighbours with d2 <= lineMaxSqr
+    int      line_mode;
+    float    lineMaxSqr;
 };
 
 // Plane fit of the pt2pl matcher, one THREAD per LISTED query (FitList: the k-NN search listed the
@@ -1164,7 +1168,7 @@ __global__ void __launch_bounds__(kFitThreads)
     const int      K    = (int)a.K;
     const uint32_t qpos = fit_list[t];  // position in the (possibly Morton-sorted) array the search walked
     const uint32_t i    = perm ? __ldg(perm + qpos) : qpos;
-    int            cnt  = 0;
+    int            cnt  = 0, within = 0;
     uint32_t       idx[KT];
 #pragma unroll
     for (int k = 0; k < KT; k++)
@@ -1173,6 +1177,8 @@ __global__ void __launch_bounds__(kFitThreads)
             const unsigned long long c = cand[(size_t)qpos * K + k];
             idx[k]                     = (uint32_t)c;
             cnt += ((uint32_t)c != 0xFFFFFFFFu);  // valid ranks come first
+            // Matcher_Point2Line.cpp:110-127: the list is cut at the first distance > threshold^2
+            if (a.line_mode && (uint32_t)c != 0xFFFFFFFFu && within == k && !(__uint_as_float((uint32_t)(c >> 32)) > a.lineMaxSqr)) within++;
         }
     float px[KT], py[KT], pz[KT];
 #pragma unroll
@@ -1186,7 +1192,9 @@ __global__ void __launch_bounds__(kFitThreads)
     compose_point_f(a.pose, qx[qpos], qy[qpos], qz[qpos], gx, gy, gz);
     PlaneCandidate pc;
     uint8_t        ok = 0;
-    if (fit_plane<KT>(px, py, pz, cnt, gx, gy, gz, a.planeEigenThreshold, a.distThr, pc))
+    // line mode: >= minimumLinePoints neighbours within the threshold (:130), PCA over ALL cnt (:132-135)
+    if (a.line_mode ? (within >= (int)a.minPts && fit_line<KT>(px, py, pz, cnt, a.planeEigenThreshold, pc))
+                    : fit_plane<KT>(px, py, pz, cnt, gx, gy, gz, a.planeEigenThreshold, a.distThr, pc))
     {
         plc[i] = pc;
         ok     = 1;
@@ -1202,7 +1210,7 @@ __global__ void __launch_bounds__(kScanThreads)
                     uint32_t* __restrict__ bbox_next, unsigned long long* __restrict__ status,
                     uint32_t* __restrict__ tile_counter,
                     mp2p_b200_pair_pt2pl* __restrict__ out, unsigned long long* __restrict__ out_count,
-                    uint32_t scan_epoch)
+                    uint32_t scan_epoch, int line_mode)
 {
     __shared__ ScanSmem sm;
     bbox_rearm(bbox_next);
@@ -1233,6 +1241,16 @@ __global__ void __launch_bounds__(kScanThreads)
         {
             const uint32_t       i  = i0 + j;
             const PlaneCandidate pc = plc[i];
+            if (line_mode)  // point_line_pair_t: TLine3D {pBase, director}, TPoint3D pt_local (Pairings.h:61-73)
+            {
+                mp2p_b200_pair_pt2ln r;
+                r.pBase[0] = pc.centroid[0], r.pBase[1] = pc.centroid[1], r.pBase[2] = pc.centroid[2];
+                r.director[0] = pc.coefs[0], r.director[1] = pc.coefs[1], r.director[2] = pc.coefs[2];
+                r.local[0] = lx[i], r.local[1] = ly[i], r.local[2] = lz[i];  // :152
+                reinterpret_cast<mp2p_b200_pair_pt2ln*>(out)[w] = r;
+                w++;
+                continue;
+            }
             mp2p_b200_pair_pt2pl r;
             r.plane_coefs[0] = pc.coefs[0], r.plane_coefs[1] = pc.coefs[1];
             r.plane_coefs[2] = pc.coefs[2], r.plane_coefs[3] = pc.coefs[3];
@@ -2051,7 +2069,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
                     const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
                     const mp2p_b200_pt2pl_params* prm, const uint32_t* lbits,
                     mp2p_b200_pair_pt2pl* out, uint64_t capacity, int out_on_device,
-                    uint64_t* out_count, DeviceMatch* keep_on_device)
+                    uint64_t* out_count, DeviceMatch* keep_on_device, const LineMode* line)
 {
     *out_count          = 0;
     if (keep_on_device) *keep_on_device = DeviceMatch{};
@@ -2083,6 +2101,12 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     a.n_local = (uint32_t)n_local, a.K = prm->knn, a.minPts = prm->minimumPlanePoints;
     a.allowLocal = prm->allowMatchAlreadyMatchedPoints;
     a.tma_ok     = ctx->cur_tma_ok;
+    if (line)  // Matcher_Point2Line: unbounded nn_multiple_search (:103-105), then the cut at threshold^2
+    {
+        a.line_mode = 1, a.radiusSq = __builtin_inff();
+        a.lineMaxSqr = (float)(prm->distanceThreshold * prm->distanceThreshold);  // :77
+        a.planeEigenThreshold = line->lineEigenThreshold, a.minPts = line->minimumLinePoints;
+    }
     const float gate_eps = (float)(prm->distanceThreshold + prm->bounding_box_intersection_check_epsilon);
 
     const float *  dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;  // caller order (records)
@@ -2100,7 +2124,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     MP2P_TRY(ctx->d_fitlist.ensure((n_local + 1) * 4));
     MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_fitlist.p, 0, 4, st));
     const FitList fit{ctx->d_fitlist.as<uint32_t>() + 1, ctx->d_fitlist.as<uint32_t>(), okf,
-                      (int)std::max<uint32_t>(3u, prm->minimumPlanePoints)};
+                      line ? (int)std::max<uint32_t>(1u, line->minimumLinePoints) : (int)std::max<uint32_t>(3u, prm->minimumPlanePoints)};
     prof_begin(ctx, 0);
 #define LAUNCH_SEARCH(G)                                                                                   \
     {                                                                                                      \
@@ -2136,13 +2160,19 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     k_compact_pt2pl<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, (uint32_t)n_local, gate_eps,
                                                                cap, dlx, dly, dlz, plc, okf, sv.bbox, sv.bbox_next,
                                                                status, sv.tile_counter, d_out, sv.count,
-                                                               ctx->scan_epoch);
+                                                               ctx->scan_epoch, line ? 1 : 0);
     prof_end(ctx, 1);
     count_launch(ctx);
     if (keep_on_device)
     {
         keep_on_device->d_count = sv.count, keep_on_device->d_pairs = d_out, keep_on_device->capacity = cap;
         return 0;
+    }
+    if (line)
+    {
+        const int rc      = fetch_results(ctx, sv.count, d_out, out, cap, out_on_device, out_count, &ctx->hint_pt2ln);
+        ctx->last2l.valid = false;  // the device copy holds LINE records: not a pt2pl list a solver may name
+        return rc;
     }
     return fetch_results(ctx, sv.count, d_out, out, cap, out_on_device, out_count, &ctx->hint_pt2pl, pose);
 }

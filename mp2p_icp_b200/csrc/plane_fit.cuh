@@ -146,4 +146,40 @@ __device__ __forceinline__ bool fit_plane(const float (&px)[KT], const float (&p
     out.centroid[0] = cx, out.centroid[1] = cy, out.centroid[2] = cz;
     return true;
 }
+
+// Line fit of the pt2ln matcher (mp2p_icp/src/Matcher_Point2Line.cpp:132-156): the same moments over
+// the cnt neighbours, line test e0 <= thr*e2 && e1 <= thr*e2 (:148-149), director = eigenvector of
+// the largest eigenvalue, unitarized; out.coefs[0..2] = director, out.centroid = pBase (the mean).
+template <int KT>
+__device__ __forceinline__ bool fit_line(const float (&px)[KT], const float (&py)[KT], const float (&pz)[KT], int cnt,
+                                         double lineEigenThreshold, PlaneCandidate& out)
+{
+    float mx = 0.f, my = 0.f, mz = 0.f;
+#pragma unroll
+    for (int k = 0; k < KT; k++)
+        if (k < cnt) mx += px[k], my += py[k], mz += pz[k];
+    const float inv_n = 1.0f / (float)cnt;
+    mx *= inv_n, my *= inv_n, mz *= inv_n;
+    double a00 = 0, a10 = 0, a20 = 0, a11 = 0, a21 = 0, a22 = 0;
+#pragma unroll
+    for (int k = 0; k < KT; k++)
+        if (k < cnt)
+        {
+            const float ax = px[k] - mx, ay = py[k] - my, az = pz[k] - mz;
+            a00 += (double)(ax * ax), a10 += (double)(ax * ay), a20 += (double)(ax * az);
+            a11 += (double)(ay * ay), a21 += (double)(ay * az), a22 += (double)(az * az);
+        }
+    const double dn = (double)inv_n;
+    a00 *= dn, a10 *= dn, a20 *= dn, a11 *= dn, a21 *= dn, a22 *= dn;
+    const double A[9] = {a00, a10, a20, a10, a11, a21, a20, a21, a22};
+    double       V[9], vals[3];
+    eig_sym3(A, V, vals);
+    if (vals[0] > lineEigenThreshold * vals[2]) return false;
+    if (vals[1] > lineEigenThreshold * vals[2]) return false;
+    const double ux = V[2], uy = V[5], uz = V[8];
+    const double inv = 1.0 / sqrt(ux * ux + uy * uy + uz * uz);
+    out.coefs[0] = ux * inv, out.coefs[1] = uy * inv, out.coefs[2] = uz * inv, out.coefs[3] = 0.0;
+    out.centroid[0] = mx, out.centroid[1] = my, out.centroid[2] = mz;
+    return true;
+}
 }  // namespace mp2p

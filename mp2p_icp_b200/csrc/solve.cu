@@ -65,6 +65,10 @@ struct GNArgs
     double   w2p, w2l;
     int      kernel;
     double   kparam;
+    // point-to-line pairings (optimal_tf_gauss_newton.cpp:182-203), 72-byte records
+    uint64_t        n2ln;
+    double          w2ln;
+    const uint32_t* p2ln;
 };
 
 constexpr int kGNV = 29;  // 21 H + 6 g + err + count
@@ -115,6 +119,8 @@ __device__ __forceinline__ void gn_step_device(const double* packet, double minD
 // (every other CTA has read the pose long before: they all passed the ticket) — the single-GPU inner
 // loop is then ONE launch per iteration. A multi-GPU caller all-reduces the packet first and uses
 // k_gn_step.
+// WITH_LINES = false compiles the point-to-line loop out (the pt2pt / pt2pl hot path keeps its registers)
+template <bool WITH_LINES>
 __global__ void __launch_bounds__(kSolveThreads)
     k_gn_accumulate(const uint32_t* __restrict__ p2p, const uint32_t* __restrict__ p2l, GNArgs a,
                     double* pose, double* __restrict__ partials,
@@ -201,6 +207,49 @@ __global__ void __launch_bounds__(kSolveThreads)
             const double q2 = n0 * R[2] + n1 * R[5] + n2 * R[8];
             const double row[6] = {q0, q1, q2, q2 * ly - q1 * lz, q0 * lz - q2 * lx, q1 * lx - q0 * ly};
             add_row(acc, row, ev * inv_n, w);
+        }
+        __syncwarp();
+    }
+    // ---- point-to-line (errorTerms.cpp:67-113): q = T(+)l - pBase, e = q - u (u.q),
+    //      J = M [R | -R [l]x] with M = I - u u^T formed as written (:92-97: no |u| = 1 assumption);
+    //      the cost term is weight^2 |e|^2 there (optimal_tf_gauss_newton.cpp:197)
+    for (uint64_t base = warp_global * 32; WITH_LINES && base < a.n2ln; base += warp_stride * 32)
+    {
+        warp_stage_records<18>(a.p2ln, base, a.n2ln, sh);
+        if (base + lane < a.n2ln)
+        {
+            const uint32_t* rec = sh + lane * 18;
+            double          v[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) v[k] = __longlong_as_double(((long long)rec[2 * k + 1] << 32) | (long long)rec[2 * k]);
+            const double lx = v[6], ly = v[7], lz = v[8];
+            double       q[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) q[r] = R[3 * r] * lx + R[3 * r + 1] * ly + R[3 * r + 2] * lz + t[r] - v[r];
+            const double ux = v[3], uy = v[4], uz = v[5];
+            const double uq = ux * q[0] + uy * q[1] + uz * q[2];
+            const double e[3] = {q[0] - ux * uq, q[1] - uy * uq, q[2] - uz * uq};
+            const double e2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+            double       w  = a.w2ln;
+            if (a.kernel) w *= robust_weight(a.kernel, a.kparam, e2);
+            acc[27] += w * w * e2;
+            acc[28] += 1.0;
+            const double u[3] = {ux, uy, uz};
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+            {
+                // row r of M [R | -R [l]x] = sum_c M[r][c] * B[c][:]
+                double row[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                {
+                    const double m  = (r == c ? 1.0 : 0.0) - u[r] * u[c];
+                    const double R0 = R[3 * c], R1 = R[3 * c + 1], R2 = R[3 * c + 2];
+                    row[0] += m * R0, row[1] += m * R1, row[2] += m * R2;
+                    row[3] += m * (R2 * ly - R1 * lz), row[4] += m * (R0 * lz - R2 * lx), row[5] += m * (R1 * lx - R0 * ly);
+                }
+                add_row(acc, row, e[r], w);
+            }
         }
         __syncwarp();
     }
@@ -381,17 +430,24 @@ int solve_grid(uint64_t n)
 int run_gn_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p,
                       const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l, const mp2p_b200_gn_params* prm,
                       const double* d_pose, double* d_packet, const unsigned long long* d_n2p,
-                      const unsigned long long* d_n2l, const uint32_t* d_done, uint32_t* d_step_state)
+                      const unsigned long long* d_n2l, const uint32_t* d_done, uint32_t* d_step_state,
+                      const mp2p_b200_pair_pt2ln* d2ln, uint64_t n2ln, double w_pt2ln)
 {
-    const int blocks = solve_grid(std::max(n2p, n2l));
+    const int blocks = solve_grid(std::max(std::max(n2p, n2l), n2ln));
     unsigned int* ticket;
     double*       partials;
     MP2P_TRY(solve_scratch(ctx, blocks, &ticket, &partials));
-    GNArgs a{n2p, n2l, prm->w_pt2pt, prm->w_pt2pl, prm->kernel, prm->kernelParam};
+    GNArgs a{n2p, n2l, prm->w_pt2pt, prm->w_pt2pl, prm->kernel, prm->kernelParam, n2ln, w_pt2ln,
+             reinterpret_cast<const uint32_t*>(d2ln)};
     prof_begin(ctx, 4);
-    k_gn_accumulate<<<blocks, kSolveThreads, 0, ctx->stream>>>(
-        reinterpret_cast<const uint32_t*>(d2p), reinterpret_cast<const uint32_t*>(d2l), a, const_cast<double*>(d_pose),
-        partials, ticket, d_packet, d_n2p, d_n2l, d_done, d_step_state, prm->minDelta, prm->maxCost);
+    if (n2ln)
+        k_gn_accumulate<true><<<blocks, kSolveThreads, 0, ctx->stream>>>(
+            reinterpret_cast<const uint32_t*>(d2p), reinterpret_cast<const uint32_t*>(d2l), a, const_cast<double*>(d_pose),
+            partials, ticket, d_packet, d_n2p, d_n2l, d_done, d_step_state, prm->minDelta, prm->maxCost);
+    else
+        k_gn_accumulate<false><<<blocks, kSolveThreads, 0, ctx->stream>>>(
+            reinterpret_cast<const uint32_t*>(d2p), reinterpret_cast<const uint32_t*>(d2l), a, const_cast<double*>(d_pose),
+            partials, ticket, d_packet, d_n2p, d_n2l, d_done, d_step_state, prm->minDelta, prm->maxCost);
     prof_end(ctx, 4);
     count_launch(ctx);
     return 0;
@@ -406,13 +462,15 @@ __global__ void k_gn_step(const double* __restrict__ packet, double minDelta, do
 int run_gn_device_loop(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p,
                        const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l, const mp2p_b200_gn_params* prm,
                        double* d_pose, uint32_t* d_state, double* d_packet,
-                       const unsigned long long* d_n2p, const unsigned long long* d_n2l)
+                       const unsigned long long* d_n2p, const unsigned long long* d_n2l,
+                       const mp2p_b200_pair_pt2ln* d2ln, uint64_t n2ln, double w_pt2ln)
 {
     MP2P_CUDA_TRY(cudaMemsetAsync(d_state, 0, 8, ctx->stream));
     for (uint32_t it = 0; it < prm->maxInnerLoopIterations; it++)  // optimal_tf_gauss_newton.cpp:70
     {
         // accumulate + update in one launch (the folding CTA applies the step)
-        MP2P_TRY(run_gn_accumulate(ctx, d2p, n2p, d2l, n2l, prm, d_pose, d_packet, d_n2p, d_n2l, d_state, d_state));
+        MP2P_TRY(run_gn_accumulate(ctx, d2p, n2p, d2l, n2l, prm, d_pose, d_packet, d_n2p, d_n2l, d_state, d_state, d2ln,
+                                   n2ln, w_pt2ln));
     }
     return 0;
 }

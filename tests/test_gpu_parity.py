@@ -298,6 +298,103 @@ def test_icp_align_bunny_inlier_ratio_matches_oracle(ctx, solver):
     assert np.linalg.norm(orc.se3_log(orc.inverse_compose(r1.pose, gt))) < 0.1
 
 
+# --------------------------------------------------------------------------- Matcher_Point2Line + pt2ln in GN (§8f N1)
+def _pole_scene(seed=3, n_poles=400, n_ground=150_000):
+    """Vertical and slanted poles (line-like neighbourhoods) over a ground plane."""
+    rng = np.random.default_rng(seed)
+    base = rng.uniform(0, 60, (n_poles, 2))
+    tilt = rng.normal(0, 0.15, (n_poles, 2))
+    h = np.arange(0, 3.0, 0.04)
+    poles = np.stack([(base[:, None, 0] + tilt[:, None, 0] * h[None, :]).ravel(), (base[:, None, 1] + tilt[:, None, 1] * h[None, :]).ravel(),
+                      np.broadcast_to(h, (n_poles, len(h))).ravel()], 1)
+    poles += rng.normal(0, 0.002, poles.shape)
+    ground = np.stack([rng.uniform(0, 60, n_ground), rng.uniform(0, 60, n_ground), rng.normal(-0.3, 0.005, n_ground)], 1)
+    M = np.concatenate([poles, ground]).astype(np.float32)
+    # local points: near poles (most), on the ground, and far away
+    pick = rng.integers(0, len(poles), 20_000)
+    near = poles[pick] + rng.normal(0, 0.05, (len(pick), 3))
+    L = np.concatenate([near, ground[:4000] + [0, 0, 0.05], rng.uniform(100, 120, (500, 3))]).astype(np.float32)
+    return M, L
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(distanceThreshold=0.12, knn=8, minimumLinePoints=3, lineEigenThreshold=0.02), dict(distanceThreshold=1.0, knn=16, minimumLinePoints=6, lineEigenThreshold=0.05)])
+def test_match_pt2ln_parity(ctx, kw):
+    """Same queries accepted, same order, local points bit-identical; line base / director within 1e-9
+    (float mean and fp64 moments as upstream; the 3x3 eigen-solve differs in the last bits)."""
+    M, L = _pole_scene()
+    tree, gmap = orc.KDTree(*xyz(M)), b200.Map(ctx, *xyz(M))
+    T = fx.pose_xyzypr(0.03, -0.02, 0.01, 0.004, -0.002, 0.003)
+    rng = np.random.default_rng(1)
+    lp = (rng.random(len(L)) < 0.2).astype(np.uint8)
+    for paired in (None, lp):
+        p0, pot0 = orc.match_pt2ln(tree, *xyz(L), T, orc.MatchPt2LnParams(**{**dict(distanceThreshold=0.5), **kw}), None if paired is None else paired.copy(), nthreads=8)
+        p1, pot1 = gmap.match_pt2ln(*xyz(L), T, b200.Pt2LnParams(**kw), local_paired=paired)
+        assert pot0 == pot1 == len(L) and len(p0) == len(p1) > 2000
+        assert np.array_equal(p0["local"], p1["local"])
+        np.testing.assert_allclose(p1["pBase"], p0["pBase"], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(p1["director"], p0["director"], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(np.linalg.norm(p1["director"], axis=1), 1.0, atol=1e-12)
+    p2, _ = gmap.match_pt2ln(b200.Cloud(ctx, *xyz(L)), None, None, T, b200.Pt2LnParams(**kw), local_paired=lp)
+    assert p2.tobytes() == p1.tobytes()  # resident (Morton-sorted) cloud: invisible
+    # the oracle's known answers (tests/test_oracle_golden.py::test_matcher_pt2ln_known_answers)
+    zs = np.arange(41) * 0.05
+    pole = np.stack([np.full(41, 5.0), np.full(41, 5.0), zs], 1)
+    gx, gy = np.meshgrid(np.arange(20) * 0.1, np.arange(20) * 0.1)
+    G = np.concatenate([pole, np.stack([gx.ravel(), gy.ravel(), np.zeros(400)], 1)]).astype(np.float32)
+    Ls = np.array([[5.1, 5.0, 1.0], [5.0, 5.2, 0.52], [1.0, 1.0, 0.05], [5.0, 9.0, 1.0]], np.float32)
+    small = b200.Map(ctx, *xyz(G))
+    p, pot = small.match_pt2ln(*xyz(Ls), np.eye(3, 4), b200.Pt2LnParams(distanceThreshold=0.5))
+    assert pot == 4 and len(p) == 2 and np.allclose(np.abs(p["director"]), [[0, 0, 1]] * 2, atol=1e-6)
+    assert np.allclose(p["pBase"][:, 2], [0.975, 0.525], atol=1e-6) and np.array_equal(p["local"], Ls[:2].astype(np.float64))
+    assert len(small.match_pt2ln(*xyz(Ls), np.eye(3, 4), b200.Pt2LnParams(distanceThreshold=0.12))[0]) == 0
+    p3, _ = small.match_pt2ln(*xyz(Ls), np.eye(3, 4), b200.Pt2LnParams(distanceThreshold=0.12, minimumLinePoints=2))
+    assert len(p3) == 1 and np.allclose(p3["pBase"][0, 2], 0.975, atol=1e-6)
+    with pytest.raises(b200.Mp2pError):
+        small.match_pt2ln(*xyz(Ls), np.eye(3, 4), b200.Pt2LnParams(minimumLinePoints=1))  # Matcher_Point2Line.cpp:44
+    assert len(small.match_pt2ln(*xyz(Ls[:0]), np.eye(3, 4), b200.Pt2LnParams())[0]) == 0
+
+
+def test_gn_pt2ln_known_answers_and_mixed_lists(ctx):
+    """tests/test-mp2p_optimize_pt2ln.cpp (three axis lines, 15 ground-truth poses, 1e-3), then random
+    mixed pt2pt + pt2pl + pt2ln lists with a robust kernel against the oracle."""
+    from tests.test_oracle_golden import PT2LN_GT, pt2ln_fixture
+
+    for gt6 in PT2LN_GT:
+        gt = orc.pose_from_xyzypr(*gt6[:3], *(np.array(gt6[3:]) * DEG))
+        pairs = pt2ln_fixture(gt)
+        ok1, T1, it1 = ctx.solve_gauss_newton_ex(None, None, pairs, b200.GNParams(maxInnerLoopIterations=25), np.eye(3, 4))
+        ok0, T0, it0 = orc.optimal_tf_gauss_newton_ex(None, None, pairs, orc.GNParams(maxInnerLoopIterations=25), np.eye(3, 4))
+        assert ok0 and ok1 and np.linalg.norm(orc.se3_log(orc.inverse_compose(T1, gt))) < 1e-3
+        assert_pose_close(T0, T1, 1e-7)
+    rng = np.random.default_rng(12)
+    p2p, gt = _random_pairs(5000, 77, sigma=0.02)
+    n = 3000
+    l = rng.uniform(0, 50, (n, 3))
+    g = l @ gt[:, :3].T + gt[:, 3]
+    u = rng.normal(0, 1, (n, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    p2ln = np.zeros(n, orc.PAIR_PT2LN)
+    p2ln["director"], p2ln["local"] = u, l + rng.normal(0, 0.02, (n, 3))
+    p2ln["pBase"] = g + u * rng.uniform(-5, 5, (n, 1))  # any point of the line through g
+    nrm = rng.normal(0, 1, (n, 3))
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    p2l = np.zeros(n, orc.PAIR_PT2PL)
+    p2l["coefs"][:, :3], p2l["coefs"][:, 3] = nrm, -(nrm * g).sum(1)
+    p2l["centroid"], p2l["local"] = g, (l + rng.normal(0, 0.02, (n, 3))).astype(np.float32)
+    guess = fx.pose_xyzypr(*(gt[:, 3] + 0.05), 0.0, 0.0, 0.0)
+    for kernel, w in (("None", 1.0), ("GemanMcClure", 2.5), ("Cauchy", 0.4)):
+        prm = dict(maxInnerLoopIterations=5, kernel=kernel, kernelParam=0.3)
+        for lists in ((None, None, p2ln), (p2p, None, p2ln), (p2p, p2l, p2ln)):
+            ok0, T0, it0 = orc.optimal_tf_gauss_newton_ex(*lists, orc.GNParams(**prm), guess, w_pt2ln=w, nthreads=8)
+            ok1, T1, it1 = ctx.solve_gauss_newton_ex(*lists, b200.GNParams(**prm), guess, w_pt2ln=w)
+            assert ok0 and ok1 and it0 == it1
+            assert_pose_close(T0, T1, 1e-9)
+    # without lines the extended entry point is the plain solver
+    ok0, T0, _ = ctx.solve_gauss_newton(p2p, p2l, b200.GNParams(maxInnerLoopIterations=4), guess)
+    ok1, T1, _ = ctx.solve_gauss_newton_ex(p2p, p2l, None, b200.GNParams(maxInnerLoopIterations=4), guess)
+    assert_pose_close(T0, T1, 1e-14)
+
+
 # --------------------------------------------------------------------------- solvers (a11-a14)
 def _random_pairs(n, seed, sigma=0.02):
     rng = np.random.default_rng(seed)
