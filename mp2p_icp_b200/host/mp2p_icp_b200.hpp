@@ -15,6 +15,7 @@
 //   Solver_Horn / Solver_GaussNewton                 mp2p_icp/src/Solver_Horn.cpp:33-61, Solver_GaussNewton.cpp:29-67
 //   Pairings                                         mp2p_icp/include/mp2p_icp/Pairings.h:84-194, src/Pairings.cpp:123-147
 //   Matcher_Points_InlierRatio                       mp2p_icp/src/Matcher_Points_InlierRatio.cpp:35-143
+//   Matcher_Point2Line                               mp2p_icp/src/Matcher_Point2Line.cpp:35-163
 //   QualityEvaluator, QualityEvaluator_PairedRatio   mp2p_icp/include/mp2p_icp/QualityEvaluator.h, src/QualityEvaluator_PairedRatio.cpp:27-73
 //   ICP::align loop (the caller)                     mp2p_icp/src/ICP.cpp:108-338, evaluate_quality :608-634
 #pragma once
@@ -172,16 +173,18 @@ struct Pairings
 {
     std::vector<mp2p_b200_pair_pt2pt>           paired_pt2pt;
     std::vector<mp2p_b200_pair_pt2pl>           paired_pt2pl;
+    std::vector<mp2p_b200_pair_pt2ln>           paired_pt2ln;
     std::vector<std::pair<std::size_t, double>> point_weights;
     uint64_t                                    potential_pairings = 0;
-    bool        empty() const { return paired_pt2pt.empty() && paired_pt2pl.empty(); }
-    std::size_t size() const { return paired_pt2pt.size() + paired_pt2pl.size(); }
+    bool        empty() const { return paired_pt2pt.empty() && paired_pt2pl.empty() && paired_pt2ln.empty(); }
+    std::size_t size() const { return paired_pt2pt.size() + paired_pt2pl.size() + paired_pt2ln.size(); }
     /** Pairings::push_back(const Pairings&): appends the lists and potential_pairings but NOT
      *  point_weights (Pairings.cpp:123-131) — kept as is. */
     void push_back(const Pairings& o)
     {
         paired_pt2pt.insert(paired_pt2pt.end(), o.paired_pt2pt.begin(), o.paired_pt2pt.end());
         paired_pt2pl.insert(paired_pt2pl.end(), o.paired_pt2pl.begin(), o.paired_pt2pl.end());
+        paired_pt2ln.insert(paired_pt2ln.end(), o.paired_pt2ln.begin(), o.paired_pt2ln.end());
         potential_pairings += o.potential_pairings;
     }
 };
@@ -576,6 +579,56 @@ class Matcher_Point2Plane : public Matcher_Points_Base
     }
 };
 
+/** Matcher_Point2Line (mp2p_icp/include/mp2p_icp/Matcher_Point2Line.h:38-70,
+ *  mp2p_icp/src/Matcher_Point2Line.cpp:35-163) over mp2p_b200_match_pt2ln. */
+class Matcher_Point2Line : public Matcher_Points_Base
+{
+   public:
+    double   distanceThreshold  = 0.50;
+    uint32_t knn                = 4;
+    uint32_t minimumLinePoints  = 4;
+    double   lineEigenThreshold = 0.01;
+    void     initialize(const ParameterMap& params) override  // :35-45
+    {
+        Matcher_Points_Base::initialize(params);
+        distanceThreshold  = params.required<double>("distanceThreshold");
+        knn                = params.required<uint32_t>("knn");
+        lineEigenThreshold = params.required<double>("lineEigenThreshold");
+        minimumLinePoints  = params.required<uint32_t>("minimumLinePoints");
+        if (!(minimumLinePoints >= 2)) throw std::runtime_error("Assert failed: minimumLinePoints >= 2");
+    }
+
+   private:
+    void implMatchOneLayer(const CPointsMap& pcGlobal, const CPointsMap& pcLocal, const CPose3D& localPose,
+                           MatchState& ms, const layer_name_t&, const layer_name_t& localName, Pairings& out) const override
+    {
+        Device&                dev = Device::instance();
+        mp2p_b200_pt2ln_params p{distanceThreshold, knn, minimumLinePoints, lineEigenThreshold,
+                                 allowMatchAlreadyMatchedPoints_, bounding_box_intersection_check_epsilon_};
+        auto&        lbits  = ms.localPaired.at(localName);
+        const size_t before = out.paired_pt2ln.size(), cap = pcLocal.size();
+        out.paired_pt2ln.resize(before + cap);
+        uint64_t cnt = 0, pot = 0;
+        check(mp2p_b200_match_pt2ln(dev.ctx(), dev.map_for(pcGlobal), dev.cloud_for(pcLocal), nullptr, nullptr, pcLocal.size(),
+                                    MP2P_B200_LOCAL_CLOUD, localPose.m, &p, lbits.data(), out.paired_pt2ln.data() + before, cap, 0,
+                                    &cnt, &pot),
+              "mp2p_b200_match_pt2ln");
+        out.paired_pt2ln.resize(before + cnt);
+        out.potential_pairings += pot;
+        // :159 — the local point is marked; re-identified by a parallel walk (ascending local index)
+        const auto &lx = pcLocal.getPointsBufferRef_x(), &ly = pcLocal.getPointsBufferRef_y(), &lz = pcLocal.getPointsBufferRef_z();
+        size_t      i  = 0;
+        for (size_t k = before; k < out.paired_pt2ln.size(); k++)
+        {
+            const auto& r = out.paired_pt2ln[k];
+            while (i < lx.size() && !((double)lx[i] == r.local[0] && (double)ly[i] == r.local[1] && (double)lz[i] == r.local[2] &&
+                                      !((lbits[i >> 5] >> (i & 31)) & 1u)))
+                i++;
+            if (i < lx.size()) MatchState::mark(lbits, i++);
+        }
+    }
+};
+
 /** run_matchers (Matcher.cpp:46-88) */
 inline Pairings run_matchers(const matcher_list_t& matchers, const metric_map_t& pcGlobal, const metric_map_t& pcLocal,
                              const CPose3D& local_wrt_global, const MatchContext& mc, MatchState* userMS = nullptr)
@@ -691,6 +744,9 @@ class Solver_Horn : public Solver
         for (const auto& b : pairings.point_weights) wc.push_back(b.first), wv.push_back(b.second);
         int32_t solved = 0;
         Device&   dev    = Device::instance();
+        if (!pairings.paired_pt2ln.empty())
+            throw std::runtime_error("Solver_Horn over point-to-line pairings (pt2ln_pl_to_pt2pt.cpp:88-108, TLine3D::closestPointTo) "
+                                     "is not offered: use Solver_GaussNewton");
         if (!pairings.paired_pt2pl.empty())
         {
             // Solver_Horn.cpp:51-55: pt2pl pairings are projected to pt2pt by pt2ln_pl_to_pt2pt and the
@@ -718,7 +774,7 @@ class Solver_GaussNewton : public Solver
    public:
     uint32_t    maxIterations = 5;
     std::string robustKernel  = "None";
-    double      robustKernelParam = 1.0, w_pt2pt = 1.0, w_pt2pl = 1.0;
+    double      robustKernelParam = 1.0, w_pt2pt = 1.0, w_pt2pl = 1.0, w_pt2ln = 1.0;
     void        initialize(const ParameterMap& p) override  // Solver_GaussNewton.cpp:29-40
     {
         Solver::initialize(p);
@@ -740,6 +796,14 @@ class Solver_GaussNewton : public Solver
         const auto &l2p = pairings.paired_pt2pt;
         const auto &l2l = pairings.paired_pt2pl;
         // every non-empty list must be the witnessed output of the last matcher call of its kind
+        if (!pairings.paired_pt2ln.empty())  // point-to-line term, optimal_tf_gauss_newton.cpp:182-203
+        {
+            check(mp2p_b200_solve_gauss_newton_ex(dev.ctx(), l2p.data(), l2p.size(), l2l.data(), l2l.size(),
+                                                  pairings.paired_pt2ln.data(), pairings.paired_pt2ln.size(), 0, &prm, w_pt2ln,
+                                                  sc.guessRelativePose->m, out.optimalPose.m, &iters, &solved),
+                  "mp2p_b200_solve_gauss_newton_ex");
+            return solved != 0;
+        }
         const bool last  = (l2p.empty() || dev.is_last_match_output(l2p.data(), l2p.size())) &&
                           (l2l.empty() || dev.is_last_match_output(l2l.data(), l2l.size())) && !pairings.empty();
         check(mp2p_b200_solve_gauss_newton(dev.ctx(), pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size(),

@@ -415,8 +415,8 @@ class Solver_GaussNewton_B200 : public Solver_GaussNewton
     bool impl_optimal_pose(const Pairings& pairings, OptimalTF_Result& out, const SolverContext& sc) const override
     {
         using namespace b200_detail;
-        if (sc.prior.has_value() || !pairings.paired_pt2ln.empty() || !pairings.paired_ln2ln.empty() ||
-            !pairings.paired_pl2pl.empty())
+        if (sc.prior.has_value() || !pairings.paired_ln2ln.empty() || !pairings.paired_pl2pl.empty() ||
+            (!pairings.paired_pt2ln.empty() && !pairings.point_weights.empty()))
             return Solver_GaussNewton::impl_optimal_pose(pairings, out, sc);  // terms that stay host-side
         checkAllParametersAreRealized();
         out = OptimalTF_Result();
@@ -438,7 +438,18 @@ class Solver_GaussNewton_B200 : public Solver_GaussNewton
         const auto& l2l  = pairings.paired_pt2pl;
         const bool  last = (l2p.empty() || witness2p().same(l2p.data(), l2p.size())) &&
                           (l2l.empty() || witness2l().same(l2l.data(), l2l.size())) && !(l2p.empty() && l2l.empty());
-        check(mp2p_b200_solve_gauss_newton(ctx(), reinterpret_cast<const mp2p_b200_pair_pt2pt*>(l2p.data()), l2p.size(),
+        if (const auto& l2n = pairings.paired_pt2ln; !l2n.empty())
+        {
+            // point-to-line term on the device too (optimal_tf_gauss_newton.cpp:182-203); point_line_pair_t
+            // = TLine3D {pBase, director} + TPoint3D pt_local = nine doubles, the layout of mp2p_b200_pair_pt2ln
+            static_assert(sizeof(mp2p_icp::point_line_pair_t) == sizeof(mp2p_b200_pair_pt2ln));
+            check(mp2p_b200_solve_gauss_newton_ex(ctx(), reinterpret_cast<const mp2p_b200_pair_pt2pt*>(l2p.data()), l2p.size(),
+                                                  reinterpret_cast<const mp2p_b200_pair_pt2pl*>(l2l.data()), l2l.size(),
+                                                  reinterpret_cast<const mp2p_b200_pair_pt2ln*>(l2n.data()), l2n.size(), 0, &p,
+                                                  pairWeights.pt2ln, T0, T, &iters, &solved));
+        }
+        else
+            check(mp2p_b200_solve_gauss_newton(ctx(), reinterpret_cast<const mp2p_b200_pair_pt2pt*>(l2p.data()), l2p.size(),
                                            reinterpret_cast<const mp2p_b200_pair_pt2pl*>(l2l.data()), l2l.size(),
                                            last ? MP2P_B200_PAIRS_LAST_MATCH : 0, &p, T0, T, &iters, &solved));
         if (!solved) return false;
@@ -450,6 +461,65 @@ class Solver_GaussNewton_B200 : public Solver_GaussNewton
     }
 };
 IMPLEMENTS_MRPT_OBJECT(Solver_GaussNewton_B200, Solver, mp2p_icp)
+
+/** Drop-in for Matcher_Point2Line (mp2p_icp/src/Matcher_Point2Line.cpp:35-163). */
+class Matcher_Point2Line_B200 : public Matcher_Points_Base
+{
+    DEFINE_MRPT_OBJECT(Matcher_Point2Line_B200, mp2p_icp)
+   public:
+    void initialize(const mrpt::containers::yaml& params) override
+    {
+        Matcher_Points_Base::initialize(params);
+        MCP_LOAD_REQ(params, distanceThreshold);
+        MCP_LOAD_REQ(params, knn);
+        MCP_LOAD_REQ(params, lineEigenThreshold);
+        MCP_LOAD_REQ(params, minimumLinePoints);
+        ASSERT_GE_(minimumLinePoints, 2UL);
+    }
+    double   distanceThreshold  = 0.50;
+    uint32_t knn                = 4;
+    uint32_t minimumLinePoints  = 4;
+    double   lineEigenThreshold = 0.01;
+
+   private:
+    void implMatchOneLayer(const mrpt::maps::CMetricMap& pcGlobal, const mrpt::maps::CPointsMap& pcLocal,
+                           const mrpt::poses::CPose3D& localPose, MatchState& ms, const layer_name_t&,
+                           const layer_name_t& localName, Pairings& out) const override
+    {
+        using namespace b200_detail;
+        mp2p_b200_map* gmap = cache().get(pcGlobal);
+        const auto&    lx   = pcLocal.getPointsBufferRef_x();
+        const auto&    ly   = pcLocal.getPointsBufferRef_y();
+        const auto&    lz   = pcLocal.getPointsBufferRef_z();
+        double         T[12];
+        pose12(localPose, T);
+        mp2p_b200_pt2ln_params p{distanceThreshold, knn, minimumLinePoints, lineEigenThreshold,
+                                 allowMatchAlreadyMatchedPoints_, bounding_box_intersection_check_epsilon_};
+        auto&        lbf    = ms.localPairedBitField.point_layers[localName];
+        const auto   lbits  = to_bits(lbf, lx.size());
+        const size_t before = out.paired_pt2ln.size();
+        out.paired_pt2ln.resize(before + lx.size());
+        static_assert(sizeof(mp2p_icp::point_line_pair_t) == sizeof(mp2p_b200_pair_pt2ln));
+        uint64_t     cnt = 0, pot = 0;
+        const float* resident = cache().pinned_local(pcLocal);
+        check(mp2p_b200_match_pt2ln(ctx(), gmap, resident ? resident : lx.data(), resident ? nullptr : ly.data(),
+                                    resident ? nullptr : lz.data(), lx.size(),
+                                    resident ? MP2P_B200_LOCAL_CLOUD : MP2P_B200_LOCAL_HOST, T, &p, lbits.data(),
+                                    reinterpret_cast<mp2p_b200_pair_pt2ln*>(out.paired_pt2ln.data() + before), lx.size(), 0,
+                                    &cnt, &pot));
+        out.paired_pt2ln.resize(before + cnt);
+        out.potential_pairings += pot;
+        // :159 — mark the local points (output is in ascending local index: parallel walk)
+        size_t i = 0;
+        for (size_t k = before; k < out.paired_pt2ln.size(); k++)
+        {
+            const auto& r = out.paired_pt2ln[k].pt_local;
+            while (i < lx.size() && !(double(lx[i]) == r.x && double(ly[i]) == r.y && double(lz[i]) == r.z && !lbf[i])) i++;
+            if (i < lx.size()) lbf.mark_as_set(i++);
+        }
+    }
+};
+IMPLEMENTS_MRPT_OBJECT(Matcher_Point2Line_B200, Matcher, mp2p_icp)
 
 /** Drop-in for QualityEvaluator_PairedRatio (mp2p_icp/src/QualityEvaluator_PairedRatio.cpp:27-73):
  *  the extra matcher pass of the non-reuse mode runs on the GPU. The reference holds its matcher by
@@ -505,6 +575,7 @@ MRPT_INITIALIZER(register_mp2p_icp_b200)
     using mrpt::rtti::registerClass;
     registerClass(CLASS_ID(mp2p_icp::Matcher_Points_DistanceThreshold_B200));
     registerClass(CLASS_ID(mp2p_icp::Matcher_Points_InlierRatio_B200));
+    registerClass(CLASS_ID(mp2p_icp::Matcher_Point2Line_B200));
     registerClass(CLASS_ID(mp2p_icp::Solver_Horn_B200));
     registerClass(CLASS_ID(mp2p_icp::Matcher_Point2Plane_B200));
     registerClass(CLASS_ID(mp2p_icp::Solver_GaussNewton_B200));

@@ -1,5 +1,6 @@
 // Mirrors the reference's tests/test-mp2p_optimize_pt2pl.cpp (Solver_GaussNewton on 3 pt2pl + 1 pt2pt
-// pairings recovers 15 ground-truth poses to 1e-3) and the protocol of tests/test-mp2p_icp_algos.cpp
+// pairings recovers 15 ground-truth poses to 1e-3), tests/test-mp2p_optimize_pt2ln.cpp (three
+// point-to-line pairings on the axes, same poses) and the protocol of tests/test-mp2p_icp_algos.cpp
 // (full ICP::align on a decimated cloud, |log(GT - est)| < 0.1) through the host mirror.
 #include <cstdio>
 #include <fstream>
@@ -53,6 +54,28 @@ static int test_opt_pt2pl(const CPose3D& groundTruth, const Solver& solver)
     return 0;
 }
 
+// tests/test-mp2p_optimize_pt2ln.cpp:25-78
+static int test_opt_pt2ln(const CPose3D& groundTruth, const Solver& solver)
+{
+    Pairings     p;
+    const double axis[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, pt[3][3] = {{0.5, 0, 0}, {0, 0.4, 0}, {0, 0, 0.2}};
+    for (int k = 0; k < 3; k++)
+    {
+        mp2p_b200_pair_pt2ln pp{};  // TLine3D::FromTwoPoints({0,0,0}, axis)
+        for (int d = 0; d < 3; d++) pp.director[d] = axis[k][d];
+        groundTruth.inverseComposePoint(pt[k][0], pt[k][1], pt[k][2], pp.local[0], pp.local[1], pp.local[2]);
+        p.paired_pt2ln.push_back(pp);
+    }
+    OptimalTF_Result result;
+    SolverContext    sc;
+    sc.guessRelativePose = CPose3D::Identity();
+    ASSERT_(solver.optimal_pose(p, result, sc));
+    double dxyz, drot;
+    (result.optimalPose - groundTruth).log_norms(dxyz, drot);
+    ASSERT_(std::sqrt(dxyz * dxyz + drot * drot) < 1e-3);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     try
@@ -71,6 +94,8 @@ int main(int argc, char** argv)
                                CPose3D(0, 0, 0, 0, 0, -15 * D), CPose3D(1, 2, 3, 0, 0, 0),     CPose3D(1, 2, 3, -10 * D, 5 * D, 30 * D)};
         for (const auto& gt : gts)
             if (test_opt_pt2pl(gt, solverGN)) return 1;
+        for (const auto& gt : gts)
+            if (test_opt_pt2ln(gt, solverGN)) return 1;
         {  // Solver: missing required parameter
             Solver_GaussNewton s2;
             bool               thrown = false;
