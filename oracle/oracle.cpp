@@ -100,6 +100,24 @@ extern "C"
         double  bounding_box_intersection_check_epsilon;
     };
 
+    // Matcher_Adaptive (mp2p_icp/include/mp2p_icp/Matcher_Adaptive.h:66-75, src/Matcher_Adaptive.cpp:32-57) + base
+    struct orc_match_adaptive_params
+    {
+        double   confidenceInterval;
+        double   firstToSecondDistanceMax;
+        double   absoluteMaxSearchDistance;
+        double   minimumCorrDist;
+        int32_t  enableDetectPlanes;
+        uint32_t planeSearchPoints;
+        uint32_t planeMinimumFoundPoints;
+        uint32_t maxPt2PtCorrespondences;
+        double   planeEigenThreshold;
+        double   planeMinimumDistance;
+        int32_t  allowMatchAlreadyMatchedPoints;
+        int32_t  allowMatchAlreadyMatchedGlobalPoints;
+        double   bounding_box_intersection_check_epsilon;
+    };
+
     struct orc_horn_params
     {
         int32_t use_scale_outlier_detector;
@@ -429,6 +447,152 @@ extern "C"
             if (global_paired) global_paired[gi] = 1;
         }
         return static_cast<long>(nOut);
+    }
+
+    // ---------------------------------------------------------------- adaptive matcher
+    // Matcher_Adaptive::implMatchOneLayer (mp2p_icp/src/Matcher_Adaptive.cpp:59-314), as written:
+    //  1. per local point not yet paired: nn_single_search (unbounded, then dropped if d2 > absMax^2,
+    //     :142-155,166) when one neighbour is wanted, else nn_radius_search(absMax^2, maxPoints)
+    //     (:156-162); at most MAX_CORRS_PER_LOCAL = 10 neighbours are kept (:108, Matcher_Adaptive.h:84);
+    //  2. min / max of the 1st and 2nd neighbour errors (:168-181) -> 50-bin histogram of those errors
+    //     (:188-194) -> upper confidence bound ci_high (:196-199) -> maxCorrDistSqr =
+    //     max(minimumCorrDist^2, ci_high) (:214);
+    //  3. per local point: optional plane through ALL its kept neighbours (:222-268; the point-plane
+    //     distance is evaluated with the LOCAL-frame point, :247, as written) -> pt2pl pairing; else
+    //     up to maxPt2PtCorrespondences pt2pt pairings with errSq < maxCorrDistSqr, stopping at the
+    //     first whose error exceeds firstToSecond^2 times the nearest's (:270-297). Global points are
+    //     never marked (:303-311).
+    // The two MRPT helpers the threshold rests on are NOT in the reference tree (mrpt-math, version
+    // ">= 2.11.5", unpinned) and are restated here from the MRPT 2.x sources as recalled — their
+    // parity is UNPINNED (no upstream test exercises this matcher either):
+    //   mrpt::math::CHistogram(min, max, nBins): binSizeInv = (nBins - 1) / (max - min);
+    //     add(x): ignored outside [min, max], bin = size_t(binSizeInv * (x - min));
+    //     getHistogramNormalized: x = linspace(min, max, nBins), hits[i] = bins[i] * binSizeInv / count;
+    //   mrpt::math::confidenceIntervalsFromHistogram(x, hits, lo, hi, ci): Hc = cumsum(hits) / max(Hc);
+    //     lo = x[lower_bound(Hc, ci)], hi = x[upper_bound(Hc, 1 - ci)].
+    // Returns 0, or -1 where the reference throws / dereferences an empty optional (no neighbour at
+    // all; all first/second errors equal: CHistogram asserts max > min).
+    long orc_match_adaptive(void* tree, const float* lx, const float* ly, const float* lz, size_t nLocal, const double T[12],
+                            const orc_match_adaptive_params* prm, uint8_t* local_paired, const uint8_t* global_paired,
+                            orc_pair_pt2pt* out2p, size_t cap2p, size_t* n2p_out, orc_pair_pt2pl* out2l, size_t cap2l,
+                            size_t* n2l_out, uint64_t* potential_pairings, double* ci_high_out, int nthreads)
+    {
+        constexpr int MAX_CORRS = 10;
+        const auto*   kd        = static_cast<const KDTree*>(tree);
+        const Pose    pose      = to_pose(T);
+        *n2p_out = *n2l_out = 0;
+        if (potential_pairings) *potential_pairings += nLocal * prm->maxPt2PtCorrespondences;  // :68
+        if (kd->n == 0 || nLocal == 0) return 0;                                                 // :71
+        std::vector<float> gx(nLocal), gy(nLocal), gz(nLocal);
+        float              lmin[3], lmax[3];
+        transform_local_to_global(lx, ly, lz, nLocal, pose, gx.data(), gy.data(), gz.data(), lmin, lmax);
+        if (!bbox_intersects(kd->bbmin, kd->bbmax, lmin, lmax, static_cast<float>(prm->bounding_box_intersection_check_epsilon)))
+            return 0;  // :77-80
+        const float absMaxSqr = static_cast<float>(prm->absoluteMaxSearchDistance * prm->absoluteMaxSearchDistance);  // :87
+        const uint32_t nnMax  = prm->enableDetectPlanes ? prm->planeSearchPoints : prm->maxPt2PtCorrespondences;     // :119-120
+        const int      K      = static_cast<int>(std::min<uint32_t>(nnMax, MAX_CORRS));
+        // nn_single_search keeps d2 <= absMax^2 (:166), nn_radius_search d2 < absMax^2 (nanoflann)
+        const float radius = nnMax == 1 ? std::nextafterf(absMaxSqr, std::numeric_limits<float>::infinity()) : absMaxSqr;
+        std::vector<uint32_t> idx(nLocal * K);
+        std::vector<float>    d2(nLocal * K);
+        std::vector<int32_t>  cnt(nLocal, 0);
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads > 0 ? nthreads : 1)
+        for (long i = 0; i < static_cast<long>(nLocal); i++)
+        {
+            if (!prm->allowMatchAlreadyMatchedPoints && local_paired && local_paired[i]) continue;  // :126-132
+            const float q[3] = {gx[i], gy[i], gz[i]};
+            cnt[i]           = kd->knn(q, K, radius, &idx[i * K], &d2[i * K]);
+        }
+        bool  any = false;
+        float emin = 0, emax = 0;
+        for (size_t i = 0; i < nLocal; i++)
+            for (int k = 0; k < std::min(cnt[i], 2); k++)  // :168-181
+            {
+                const float e = d2[i * K + k];
+                if (!any) emin = emax = e, any = true;
+                emin = std::min(emin, e), emax = std::max(emax, e);
+            }
+        if (!any) return -1;  // *minSqrErrorForHistogram on an empty optional
+        // ---- mrpt::math::CHistogram hist(min, max, 50) (:188-194)
+        constexpr int NB = 50;
+        const double  hmin = emin, hmax = emax;
+        if (!(hmax > hmin)) return -1;  // CHistogram: ASSERT_(max > min)
+        const double binSizeInv = (static_cast<double>(NB) - 1) / (hmax - hmin);
+        size_t       bins[NB]   = {0}, count = 0;
+        for (size_t i = 0; i < nLocal; i++)
+            for (int k = 0; k < std::min(cnt[i], 2); k++)
+            {
+                const double x = d2[i * K + k];
+                if (x < hmin || x > hmax) continue;
+                bins[static_cast<size_t>(binSizeInv * (x - hmin))]++;
+                count++;
+            }
+        double xs[NB], hits[NB], Hc[NB];
+        for (int b = 0; b < NB; b++) xs[b] = hmin + b * (hmax - hmin) / (NB - 1), hits[b] = (binSizeInv / count) * bins[b];
+        // ---- confidenceIntervalsFromHistogram(xs, hits, lo, hi, 1 - confidenceInterval) (:196-199)
+        double acc = 0;
+        for (int b = 0; b < NB; b++) acc += hits[b], Hc[b] = acc;
+        const double mx = *std::max_element(Hc, Hc + NB);
+        for (int b = 0; b < NB; b++) Hc[b] *= 1.0 / mx;
+        const double ci      = 1.0 - prm->confidenceInterval;
+        const double ci_high = xs[std::min<size_t>(NB - 1, std::upper_bound(Hc, Hc + NB, 1.0 - ci) - Hc)];
+        if (ci_high_out) *ci_high_out = ci_high;
+        const double maxCorrDistSqr = std::max(prm->minimumCorrDist * prm->minimumCorrDist, ci_high);  // :214
+        const float  maxSqr1to2     = static_cast<float>(prm->firstToSecondDistanceMax * prm->firstToSecondDistanceMax);  // :216
+
+        size_t n2p = 0, n2l = 0;
+        for (size_t i = 0; i < nLocal; i++)  // :219-298
+        {
+            const int c = cnt[i];
+            if (prm->enableDetectPlanes && c >= static_cast<int>(prm->planeMinimumFoundPoints))
+            {
+                float xs_[MAX_CORRS], ys_[MAX_CORRS], zs_[MAX_CORRS];
+                for (int k = 0; k < c; k++) xs_[k] = kd->x[idx[i * K + k]], ys_[k] = kd->y[idx[i * K + k]], zs_[k] = kd->z[idx[i * K + k]];
+                const PlaneFit f = estimate_points_eigen(xs_, ys_, zs_, c);
+                if (f.eigVals[0] < prm->planeEigenThreshold * f.eigVals[2] && f.eigVals[0] < prm->planeEigenThreshold * f.eigVals[1])
+                {
+                    const double n[3]  = {f.eigVec0[0], f.eigVec0[1], f.eigVec0[2]};
+                    const double cxyz[3] = {f.mean[0], f.mean[1], f.mean[2]};
+                    const double D     = -(n[0] * cxyz[0] + n[1] * cxyz[1] + n[2] * cxyz[2]);  // TPlane(point, normal)
+                    // :247 thePlane.distance(mspl.at(0).local): the LOCAL-frame point, as written
+                    const double ev   = n[0] * lx[i] + n[1] * ly[i] + n[2] * lz[i] + D;
+                    const double dist = std::fabs(std::fabs(ev) / std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]));
+                    if (dist < prm->planeMinimumDistance)
+                    {
+                        if (n2l < cap2l)
+                        {
+                            orc_pair_pt2pl& p = out2l[n2l];
+                            p.coefs[0] = n[0], p.coefs[1] = n[1], p.coefs[2] = n[2], p.coefs[3] = D;
+                            p.centroid[0] = cxyz[0], p.centroid[1] = cxyz[1], p.centroid[2] = cxyz[2];
+                            p.lx = lx[i], p.ly = ly[i], p.lz = lz[i], p._pad = 0;
+                        }
+                        n2l++;
+                        if (local_paired) local_paired[i] = 1;  // :262
+                        continue;
+                    }
+                }
+            }
+            for (int k = 0; k < std::min<int>(c, prm->maxPt2PtCorrespondences); k++)  // :270-297
+            {
+                const uint32_t g = idx[i * K + k];
+                const float    e = d2[i * K + k];
+                if (!prm->allowMatchAlreadyMatchedGlobalPoints && global_paired && global_paired[g]) continue;
+                if (e >= maxCorrDistSqr) continue;
+                if (k != 0 && e > d2[i * K] * maxSqr1to2) break;
+                if (n2p < cap2p)
+                {
+                    orc_pair_pt2pt& p = out2p[n2p];
+                    p.globalIdx = g, p.localIdx = static_cast<uint32_t>(i);
+                    p.gx = kd->x[g], p.gy = kd->y[g], p.gz = kd->z[g];
+                    p.lx = lx[i], p.ly = ly[i], p.lz = lz[i];
+                    p.errSq = e;
+                }
+                n2p++;
+                if (!prm->allowMatchAlreadyMatchedGlobalPoints && local_paired) local_paired[i] = 1;  // :291-295
+            }
+        }
+        *n2p_out = n2p, *n2l_out = n2l;
+        return 0;
     }
 
     // ---------------------------------------------------------------- pt2ln matcher

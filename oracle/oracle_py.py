@@ -424,6 +424,64 @@ def match_pt2ln(tree: KDTree, lx, ly, lz, T, prm: MatchPt2LnParams, local_paired
     return out[:cnt], pot.value
 
 
+class _MatchAdaptiveParams(C.Structure):
+    _fields_ = [
+        ("confidenceInterval", C.c_double),
+        ("firstToSecondDistanceMax", C.c_double),
+        ("absoluteMaxSearchDistance", C.c_double),
+        ("minimumCorrDist", C.c_double),
+        ("enableDetectPlanes", C.c_int32),
+        ("planeSearchPoints", C.c_uint32),
+        ("planeMinimumFoundPoints", C.c_uint32),
+        ("maxPt2PtCorrespondences", C.c_uint32),
+        ("planeEigenThreshold", C.c_double),
+        ("planeMinimumDistance", C.c_double),
+        ("allowMatchAlreadyMatchedPoints", C.c_int32),
+        ("allowMatchAlreadyMatchedGlobalPoints", C.c_int32),
+        ("bounding_box_intersection_check_epsilon", C.c_double),
+    ]
+
+
+@dataclass
+class MatchAdaptiveParams:  # Matcher_Adaptive.h:66-75
+    confidenceInterval: float = 0.80
+    firstToSecondDistanceMax: float = 1.2
+    absoluteMaxSearchDistance: float = 5.0
+    minimumCorrDist: float = 0.1
+    enableDetectPlanes: bool = False
+    planeSearchPoints: int = 8
+    planeMinimumFoundPoints: int = 4
+    maxPt2PtCorrespondences: int = 1
+    planeEigenThreshold: float = 0.01
+    planeMinimumDistance: float = 0.10
+    allowMatchAlreadyMatchedPoints: bool = False
+    allowMatchAlreadyMatchedGlobalPoints: bool = False
+    bounding_box_intersection_check_epsilon: float = 0.20
+
+    def c(self):
+        return _MatchAdaptiveParams(self.confidenceInterval, self.firstToSecondDistanceMax, self.absoluteMaxSearchDistance, self.minimumCorrDist, int(self.enableDetectPlanes), self.planeSearchPoints, self.planeMinimumFoundPoints, self.maxPt2PtCorrespondences, self.planeEigenThreshold, self.planeMinimumDistance, int(self.allowMatchAlreadyMatchedPoints), int(self.allowMatchAlreadyMatchedGlobalPoints), self.bounding_box_intersection_check_epsilon)
+
+
+def match_adaptive(tree: KDTree, lx, ly, lz, T, prm: MatchAdaptiveParams, local_paired=None, global_paired=None, nthreads=1):
+    """Matcher_Adaptive (Matcher_Adaptive.cpp:59-314). Returns (pt2pt pairs, pt2pl pairs, potential_pairings, ci_high)."""
+    lx, ly, lz = _f32(lx), _f32(ly), _f32(lz)
+    n = lx.size
+    cp = prm.c()
+    if local_paired is None:
+        local_paired = np.zeros(n, np.uint8)
+    if global_paired is None:
+        global_paired = np.zeros(tree.n, np.uint8)
+    cap2p = max(n * prm.maxPt2PtCorrespondences, 1)
+    out2p, out2l = np.zeros(cap2p, PAIR_PT2PT), np.zeros(max(n, 1), PAIR_PT2PL)
+    n2p, n2l, pot, ci = C.c_size_t(0), C.c_size_t(0), C.c_uint64(0), C.c_double(0)
+    fn = lib().orc_match_adaptive
+    fn.restype = C.c_long
+    rc = fn(C.c_void_p(tree._h), _p(lx), _p(ly), _p(lz), C.c_size_t(n), _p(_T(T)), C.byref(cp), _p(local_paired), _p(global_paired), _p(out2p), C.c_size_t(cap2p), C.byref(n2p), _p(out2l), C.c_size_t(n), C.byref(n2l), C.byref(pot), C.byref(ci), nthreads)
+    if rc < 0:
+        raise RuntimeError("Matcher_Adaptive: reference assertion (no neighbour within absoluteMaxSearchDistance, or all first/second errors equal)")
+    return out2p[: n2p.value], out2l[: n2l.value], pot.value, ci.value
+
+
 def pt2pl_to_pt2pt(p2l, T_guess):
     p2l = np.ascontiguousarray(p2l, dtype=PAIR_PT2PL)
     out = np.zeros(max(p2l.size, 1), PAIR_PT2PT)

@@ -437,3 +437,82 @@ def test_matcher_pt2ln_known_answers():
     # already-paired locals are skipped
     p4, _ = orc.match_pt2ln(tree, lx, ly, lz, np.eye(3, 4), prm, np.array([1, 0, 0, 0], np.uint8))
     assert len(p4) == 1 and np.array_equal(p4["local"][0], L[1].astype(np.float64))
+
+
+# ---------------------------------------------------------------------------------------------
+# Matcher_Adaptive — no upstream test; its threshold rests on two MRPT helpers that
+# are not in the reference tree (CHistogram, confidenceIntervalsFromHistogram: restated as recalled,
+# PARITY UNPINNED, see oracle.cpp). The cases below pin the restatement against an independent numpy
+# statement of the same steps and hand-made known answers.
+# ---------------------------------------------------------------------------------------------
+def _adaptive_threshold_numpy(errs_first_two, confidenceInterval, minimumCorrDist):
+    e = np.asarray(errs_first_two, np.float32).astype(np.float64)
+    lo, hi, nb = e.min(), e.max(), 50
+    inv = (nb - 1) / (hi - lo)
+    bins = np.bincount((inv * (e - lo)).astype(np.int64), minlength=nb)[:nb].astype(np.float64)
+    hits = bins * (inv / len(e))
+    Hc = np.cumsum(hits)
+    Hc = Hc * (1.0 / Hc.max())
+    xs = lo + np.arange(nb) * (hi - lo) / (nb - 1)
+    k = min(nb - 1, int(np.searchsorted(Hc, 1.0 - (1.0 - confidenceInterval), side="right")))
+    return max(minimumCorrDist**2, xs[k]), xs[k]
+
+
+def test_matcher_adaptive_against_numpy_statement():
+    rng = np.random.default_rng(2)
+    M = rng.uniform(0, 20, (30_000, 3)).astype(np.float32)
+    L = (M[::6] + rng.normal(0, 0.12, (5000, 3))).astype(np.float32)
+    L[:300] += 3.0  # gross outliers
+    tree = orc.KDTree(*(np.ascontiguousarray(M[:, k]) for k in range(3)))
+    lx, ly, lz = (np.ascontiguousarray(L[:, k]) for k in range(3))
+    I = np.eye(3, 4)
+    for ci, k in [(0.80, 1), (0.75, 1), (0.5, 3)]:
+        prm = orc.MatchAdaptiveParams(confidenceInterval=ci, absoluteMaxSearchDistance=0.5, maxPt2PtCorrespondences=k, minimumCorrDist=0.01)
+        p2p, p2l, pot, ci_high = orc.match_adaptive(tree, lx, ly, lz, I, prm, nthreads=4)
+        assert pot == len(L) * k and len(p2l) == 0
+        # independent statement: k-NN by the oracle's own search, thresholds by numpy
+        idx, d2, found = tree.knn(lx, ly, lz, k, np.nextafter(np.float32(0.25), np.float32(np.inf)) if k == 1 else 0.25, nthreads=4)
+        first_two = np.concatenate([d2[found > r, r] for r in range(min(k, 2))])
+        thr, xk = _adaptive_threshold_numpy(first_two, ci, 0.01)
+        assert abs(ci_high - xk) <= 1e-12 * max(1.0, xk)
+        exp = []
+        for i in range(len(L)):
+            for r in range(min(found[i], k)):
+                if d2[i, r] >= thr:
+                    continue
+                if r and np.float32(d2[i, r]) > np.float32(d2[i, 0]) * np.float32(1.2 * 1.2):
+                    break
+                exp.append((i, idx[i, r]))
+        assert [(int(a), int(b)) for a, b in zip(p2p["localIdx"], p2p["globalIdx"])] == exp and len(exp) > 2000
+        assert np.array_equal(p2p["local"], L[p2p["localIdx"]]) and np.array_equal(p2p["global"], M[p2p["globalIdx"]])
+
+
+def test_matcher_adaptive_planes_and_edge_cases():
+    # a plane patch z = 0 sampled every 5 cm; locals 3 cm above it (planar neighbourhood -> pt2pl) and far away
+    gx, gy = np.meshgrid(np.arange(40) * 0.05, np.arange(40) * 0.05)
+    G = np.stack([gx.ravel(), gy.ravel(), np.zeros(1600)], 1).astype(np.float32)
+    rng = np.random.default_rng(4)
+    G[:, 2] += rng.normal(0, 1e-4, len(G)).astype(np.float32)
+    tree = orc.KDTree(*(np.ascontiguousarray(G[:, k]) for k in range(3)))
+    L = np.array([[1.0, 1.0, 0.03], [0.52, 1.31, 0.05], [1.0, 1.0, 1.5], [30, 30, 30]], np.float32)
+    lx, ly, lz = (np.ascontiguousarray(L[:, k]) for k in range(3))
+    prm = orc.MatchAdaptiveParams(confidenceInterval=0.8, absoluteMaxSearchDistance=2.0, enableDetectPlanes=True, planeSearchPoints=8, planeMinimumFoundPoints=4, planeMinimumDistance=0.10, minimumCorrDist=0.1)
+    lp = np.zeros(4, np.uint8)
+    p2p, p2l, pot, _ = orc.match_adaptive(tree, lx, ly, lz, np.eye(3, 4), prm, lp)
+    # locals 0, 1: plane found, |distance of the LOCAL point| 0.03 / 0.05 < 0.10 -> pt2pl; local 2: plane found but
+    # 1.5 m away -> falls to the pt2pt branch (error 2.25 >= maxCorrDistSqr -> nothing); local 3: no neighbour
+    assert pot == 4 and len(p2l) == 2 and len(p2p) == 0 and list(lp) == [1, 1, 0, 0]
+    assert np.allclose(np.abs(p2l["coefs"][:, 2]), 1.0, atol=1e-4) and np.allclose(p2l["centroid"][:, 2], 0.0, atol=1e-3)
+    assert np.array_equal(p2l["local"], L[:2])
+    # planes off: pt2pt with the adaptive threshold, nearest neighbour only
+    prm2 = orc.MatchAdaptiveParams(confidenceInterval=0.8, absoluteMaxSearchDistance=2.0, minimumCorrDist=0.1)
+    p2p, p2l, _, ci_high = orc.match_adaptive(tree, lx, ly, lz, np.eye(3, 4), prm2)
+    assert len(p2l) == 0 and list(p2p["localIdx"]) == [0, 1]  # errors 0.0009, ~0.003 < max(0.01, ci_high); 2.25 is not
+    # the reference throws / crashes: no neighbour at all; a single error value (CHistogram asserts max > min)
+    with pytest.raises(RuntimeError):
+        orc.match_adaptive(tree, lx[:1], ly[:1], lz[:1], np.eye(3, 4), orc.MatchAdaptiveParams(absoluteMaxSearchDistance=0.01))
+    with pytest.raises(RuntimeError):
+        orc.match_adaptive(tree, lx[:1], ly[:1], lz[:1], np.eye(3, 4), prm2)
+    # no bounding-box overlap, empty cloud: nothing, no throw
+    assert len(orc.match_adaptive(tree, lx, ly, lz, orc.pose_from_xyzypr(500, 0, 0), prm2)[0]) == 0
+    assert len(orc.match_adaptive(tree, lx[:0], ly[:0], lz[:0], np.eye(3, 4), prm2)[0]) == 0
