@@ -248,6 +248,66 @@ int mp2p_b200_match_pt2ln(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* l
                           mp2p_b200_pair_pt2ln* out_pairs, uint64_t capacity, int out_on_device,
                           uint64_t* out_count, uint64_t* potential_pairings);
 
+/* Parameters of Matcher_Adaptive (mp2p_icp/include/mp2p_icp/Matcher_Adaptive.h:66-75,
+ * mp2p_icp/src/Matcher_Adaptive.cpp:32-57) + Matcher_Points_Base. */
+typedef struct
+{
+    double   confidenceInterval;        /* (0,1) */
+    double   firstToSecondDistanceMax;
+    double   absoluteMaxSearchDistance; /* m */
+    double   minimumCorrDist;           /* m */
+    int32_t  enableDetectPlanes;
+    uint32_t planeSearchPoints;
+    uint32_t planeMinimumFoundPoints; /* >= 3 */
+    uint32_t maxPt2PtCorrespondences; /* >= 1 */
+    double   planeEigenThreshold;
+    double   planeMinimumDistance;
+    int32_t  allowMatchAlreadyMatchedPoints;
+    int32_t  allowMatchAlreadyMatchedGlobalPoints;
+    double   bounding_box_intersection_check_epsilon;
+} mp2p_b200_adaptive_params;
+#define MP2P_B200_ADAPTIVE_BINS 50 /* mrpt::math::CHistogram hist(min, max, 50), Matcher_Adaptive.cpp:188 */
+
+/* Matcher_Adaptive::implMatchOneLayer (mp2p_icp/src/Matcher_Adaptive.cpp:59-314) in two
+ * device phases around the one step that is mrpt::math code:
+ *   adaptive_search    per local point the nearest neighbour(s) within absoluteMaxSearchDistance (at most
+ *                      MAX_CORRS_PER_LOCAL = 10 kept, Matcher_Adaptive.h:84); returns the 50-bin histogram of
+ *                      the 1st / 2nd neighbour squared errors exactly as CHistogram::add bins them
+ *                      (:168-194), its limits and sample count; *gate = 0 if the bounding boxes do not
+ *                      overlap (:77-80: the reference returns before anything else — ignore the histogram)
+ *   (host)             ci_high = upper confidence bound of that histogram (:196-199,
+ *                      mrpt::math::confidenceIntervalsFromHistogram); maxCorrDistSqr =
+ *                      max(minimumCorrDist^2, ci_high) (:214). A plugin built against MRPT calls MRPT here;
+ *                      mp2p_b200_adaptive_threshold is the library's restatement of the two MRPT helpers
+ *                      (recalled from MRPT 2.x, NOT in the reference tree: parity unpinned)
+ *   adaptive_emit      per local point a plane through its neighbours -> point-to-plane pairing (:222-268),
+ *                      else the point-to-point pairings below the threshold (:270-297); both lists in
+ *                      ascending local index. Must directly follow adaptive_search on the same context.
+ * mp2p_b200_match_adaptive = the three steps in one call; where the reference throws (no neighbour at all,
+ * all errors equal: CHistogram asserts max > min) it returns MP2P_B200_ERR_ARG. Global points are never
+ * marked by this matcher (:303-311); the caller marks the local bits of the returned pairings.
+ * *potential_pairings += n_local * maxPt2PtCorrespondences (:68). */
+int mp2p_b200_adaptive_search(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                              const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
+                              const mp2p_b200_adaptive_params* params, const uint32_t* local_paired_bits,
+                              uint64_t histogram_out[MP2P_B200_ADAPTIVE_BINS], double* err_min, double* err_max,
+                              uint64_t* n_samples, int32_t* gate, uint64_t* potential_pairings);
+int mp2p_b200_adaptive_threshold(const uint64_t histogram[MP2P_B200_ADAPTIVE_BINS], double err_min, double err_max,
+                                 uint64_t n_samples, double confidenceInterval, double minimumCorrDist,
+                                 double* ci_high, double* maxCorrDistSqr);
+int mp2p_b200_adaptive_emit(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const mp2p_b200_adaptive_params* params,
+                            double maxCorrDistSqr, const uint32_t* global_paired_bits,
+                            mp2p_b200_pair_pt2pt* out_pt2pt, uint64_t capacity_pt2pt,
+                            mp2p_b200_pair_pt2pl* out_pt2pl, uint64_t capacity_pt2pl, int out_on_device,
+                            uint64_t* n_pt2pt, uint64_t* n_pt2pl);
+int mp2p_b200_match_adaptive(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
+                             const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
+                             const mp2p_b200_adaptive_params* params, const uint32_t* local_paired_bits,
+                             const uint32_t* global_paired_bits, mp2p_b200_pair_pt2pt* out_pt2pt,
+                             uint64_t capacity_pt2pt, mp2p_b200_pair_pt2pl* out_pt2pl, uint64_t capacity_pt2pl,
+                             int out_on_device, uint64_t* n_pt2pt, uint64_t* n_pt2pl, double* ci_high,
+                             uint64_t* potential_pairings);
+
 /* Parameters of Matcher_Points_InlierRatio (mp2p_icp/include/mp2p_icp/Matcher_Points_InlierRatio.h:50-56,
  * mp2p_icp/src/Matcher_Points_InlierRatio.cpp:35-39) + Matcher_Points_Base. */
 typedef struct

@@ -7,6 +7,7 @@ benchmark and multi-process (torch.distributed) drivers. There is no CPU fallbac
 anywhere, every compute call needs the built library and a CUDA device.
 """
 from .capi import (  # noqa: F401
+    AdaptiveParams,
     PAIR_PT2LN,
     PAIR_PT2PL,
     PAIR_PT2PT,

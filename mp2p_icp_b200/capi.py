@@ -67,6 +67,24 @@ class _Pt2LnParams(C.Structure):
     ]
 
 
+class _AdaptiveParams(C.Structure):
+    _fields_ = [
+        ("confidenceInterval", C.c_double),
+        ("firstToSecondDistanceMax", C.c_double),
+        ("absoluteMaxSearchDistance", C.c_double),
+        ("minimumCorrDist", C.c_double),
+        ("enableDetectPlanes", C.c_int32),
+        ("planeSearchPoints", C.c_uint32),
+        ("planeMinimumFoundPoints", C.c_uint32),
+        ("maxPt2PtCorrespondences", C.c_uint32),
+        ("planeEigenThreshold", C.c_double),
+        ("planeMinimumDistance", C.c_double),
+        ("allowMatchAlreadyMatchedPoints", C.c_int32),
+        ("allowMatchAlreadyMatchedGlobalPoints", C.c_int32),
+        ("bounding_box_intersection_check_epsilon", C.c_double),
+    ]
+
+
 class _InlierRatioParams(C.Structure):
     _fields_ = [
         ("inliersRatio", C.c_double),
@@ -157,6 +175,28 @@ class Pt2LnParams:
 
 
 @dataclass
+class AdaptiveParams:
+    """Parameters of Matcher_Adaptive (same names and defaults as the reference, Matcher_Adaptive.h:66-75)."""
+
+    confidenceInterval: float = 0.80
+    firstToSecondDistanceMax: float = 1.2
+    absoluteMaxSearchDistance: float = 5.0
+    minimumCorrDist: float = 0.1
+    enableDetectPlanes: bool = False
+    planeSearchPoints: int = 8
+    planeMinimumFoundPoints: int = 4
+    maxPt2PtCorrespondences: int = 1
+    planeEigenThreshold: float = 0.01
+    planeMinimumDistance: float = 0.10
+    allowMatchAlreadyMatchedPoints: bool = False
+    allowMatchAlreadyMatchedGlobalPoints: bool = False
+    bounding_box_intersection_check_epsilon: float = 0.20
+
+    def c(self):
+        return _AdaptiveParams(self.confidenceInterval, self.firstToSecondDistanceMax, self.absoluteMaxSearchDistance, self.minimumCorrDist, int(self.enableDetectPlanes), self.planeSearchPoints, self.planeMinimumFoundPoints, self.maxPt2PtCorrespondences, self.planeEigenThreshold, self.planeMinimumDistance, int(self.allowMatchAlreadyMatchedPoints), int(self.allowMatchAlreadyMatchedGlobalPoints), self.bounding_box_intersection_check_epsilon)
+
+
+@dataclass
 class InlierRatioParams:
     """Parameters of Matcher_Points_InlierRatio (same names as the reference's YAML keys)."""
 
@@ -200,7 +240,7 @@ class GNParams:
 EXPORTS = [
     "mp2p_b200_last_error", "mp2p_b200_device_count", "mp2p_b200_ctx_create", "mp2p_b200_ctx_destroy",
     "mp2p_b200_ctx_synchronize", "mp2p_b200_ctx_launch_count", "mp2p_b200_map_create", "mp2p_b200_map_destroy",
-    "mp2p_b200_map_get_info", "mp2p_b200_knn", "mp2p_b200_match_pt2pt", "mp2p_b200_match_pt2pl", "mp2p_b200_match_inlier_ratio", "mp2p_b200_match_pt2ln", "mp2p_b200_solve_gauss_newton_ex",
+    "mp2p_b200_map_get_info", "mp2p_b200_knn", "mp2p_b200_match_pt2pt", "mp2p_b200_match_pt2pl", "mp2p_b200_match_inlier_ratio", "mp2p_b200_match_pt2ln", "mp2p_b200_solve_gauss_newton_ex", "mp2p_b200_adaptive_search", "mp2p_b200_adaptive_threshold", "mp2p_b200_adaptive_emit", "mp2p_b200_match_adaptive",
     "mp2p_b200_solve_horn", "mp2p_b200_solve_gauss_newton", "mp2p_b200_gn_accumulate",
     "mp2p_b200_gn_step_from_packet", "mp2p_b200_horn_sums", "mp2p_b200_horn_moments", "mp2p_b200_horn_finish",
     "mp2p_b200_host_alloc", "mp2p_b200_host_free", "mp2p_b200_ctx_set_profiling",
@@ -766,6 +806,30 @@ class Map:
 
         step._keep = (keep, self)
         return step
+
+    def match_adaptive(self, lx, ly, lz, T, prm: AdaptiveParams, local_paired=None, global_paired=None, n_local=None, local_on_device=False, threshold_fn=None):
+        """Matcher_Adaptive. Returns (pt2pt pairs, pt2pl pairs, potential_pairings, ci_high). With
+        `threshold_fn(hist[50], err_min, err_max, n_samples) -> maxCorrDistSqr` the two-phase form is used
+        (what a plugin built against MRPT does with mrpt::math::confidenceIntervalsFromHistogram)."""
+        L = load_library()
+        plx, ply, plz, n_local, kind = _local(lx, ly, lz, n_local, local_on_device)
+        cap2p = max(n_local * prm.maxPt2PtCorrespondences, 1)
+        out2p, out2l = np.empty(cap2p, PAIR_PT2PT), np.empty(max(n_local, 1), PAIR_PT2PL)
+        lb = pack_bits(local_paired) if local_paired is not None else None
+        gb = pack_bits(global_paired) if global_paired is not None else None
+        cp = prm.c()
+        n2p, n2l, pot, ci = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_double(0)
+        if threshold_fn is None:
+            _check(L.mp2p_b200_match_adaptive(self.ctx._h, self._h, plx, ply, plz, C.c_uint64(n_local), kind, _ptr(_pose(T)), C.byref(cp), _ptr(lb), _ptr(gb), _ptr(out2p), C.c_uint64(cap2p), _ptr(out2l), C.c_uint64(n_local), 0, C.byref(n2p), C.byref(n2l), C.byref(ci), C.byref(pot)))
+            return out2p[: n2p.value], out2l[: n2l.value], pot.value, ci.value
+        hist = np.zeros(50, np.uint64)
+        emin, emax, ns, gate = C.c_double(0), C.c_double(0), C.c_uint64(0), C.c_int32(0)
+        _check(L.mp2p_b200_adaptive_search(self.ctx._h, self._h, plx, ply, plz, C.c_uint64(n_local), kind, _ptr(_pose(T)), C.byref(cp), _ptr(lb), _ptr(hist), C.byref(emin), C.byref(emax), C.byref(ns), C.byref(gate), C.byref(pot)))
+        if not gate.value:
+            return out2p[:0], out2l[:0], pot.value, 0.0
+        thr = float(threshold_fn(hist, emin.value, emax.value, ns.value))
+        _check(L.mp2p_b200_adaptive_emit(self.ctx._h, self._h, C.byref(cp), C.c_double(thr), _ptr(gb), _ptr(out2p), C.c_uint64(cap2p), _ptr(out2l), C.c_uint64(n_local), 0, C.byref(n2p), C.byref(n2l)))
+        return out2p[: n2p.value], out2l[: n2l.value], pot.value, thr
 
     def match_pt2ln(self, lx, ly, lz, T, prm: Pt2LnParams, local_paired=None, n_local=None, local_on_device=False, out=None, out_on_device=False, capacity=None):
         """Matcher_Point2Line. Returns (point-to-line pairings in ascending local index, potential_pairings)."""

@@ -281,7 +281,7 @@ extern "C"
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
         for (DevBuf* b : {&c->d_lx, &c->d_ly, &c->d_lz, &c->d_cand, &c->d_candxyz, &c->d_lbits, &c->d_gbits, &c->d_scan,
-                          &c->d_small, &c->d_out2p, &c->d_out2l, &c->d_plcand, &c->d_okflags, &c->d_fitlist, &c->d_coop, &c->d_knn_idx, &c->d_knn_d2,
+                          &c->d_small, &c->d_out2p, &c->d_out2l, &c->d_plcand, &c->d_okflags, &c->d_fitlist, &c->d_adres, &c->d_adsel, &c->d_scan2, &c->d_coop, &c->d_knn_idx, &c->d_knn_d2,
                           &c->d_knn_found, &c->d_irk0, &c->d_irk1, &c->d_irv0, &c->d_irv1, &c->d_irtmp, &c->d_pairs2p, &c->d_pairs2l, &c->d_pairs2ln, &c->d_partials, &c->d_packet,
                           &c->d_pose, &c->d_weights, &c->d_outlier, &c->d_conv})
             b->release();
@@ -535,6 +535,120 @@ extern "C"
         return run_match_pt2pl(ctx, map, lx, ly, lz, n_local, local_on_device, pose, &pp, local_paired_bits,
                                reinterpret_cast<mp2p_b200_pair_pt2pl*>(out_pairs), capacity, out_on_device, out_count, nullptr,
                                &line);
+    }
+
+    // ------------------------------------------------------------------------------ Matcher_Adaptive
+    static bool bad_adaptive(const mp2p_b200_adaptive_params* p)
+    {
+        // Matcher_Adaptive.cpp:50-56
+        return !(p->confidenceInterval > 0.0 && p->confidenceInterval < 1.0) || !(p->absoluteMaxSearchDistance > 0.0) ||
+               p->maxPt2PtCorrespondences < 1 ||
+               (p->enableDetectPlanes && (p->planeSearchPoints < p->planeMinimumFoundPoints || p->planeMinimumFoundPoints < 3 ||
+                                          !(p->planeEigenThreshold > 0.0)));
+    }
+
+    int mp2p_b200_adaptive_search(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly, const float* lz,
+                                  uint64_t n_local, int local_on_device, const double pose[12],
+                                  const mp2p_b200_adaptive_params* prm, const uint32_t* local_paired_bits,
+                                  uint64_t histogram_out[MP2P_B200_ADAPTIVE_BINS], double* err_min, double* err_max,
+                                  uint64_t* n_samples, int32_t* gate, uint64_t* potential_pairings)
+    {
+        if (!ctx || !map || !pose || !prm || !histogram_out || !err_min || !err_max || !n_samples || !gate ||
+            (n_local && bad_local(lx, ly, lz, local_on_device)))
+        {
+            set_error("adaptive_search: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        if (bad_adaptive(prm))
+        {
+            set_error("adaptive_search: parameters outside the ranges Matcher_Adaptive::initialize asserts");
+            return MP2P_B200_ERR_ARG;
+        }
+        if (potential_pairings) *potential_pairings += n_local * prm->maxPt2PtCorrespondences;  // :68
+        DeviceGuard g(ctx->device);
+        ProfScope   ps(ctx);
+        int         gt = 0;
+        MP2P_TRY(run_adaptive_search(ctx, map, lx, ly, lz, n_local, local_on_device, pose, prm, local_paired_bits, histogram_out,
+                                     err_min, err_max, n_samples, &gt));
+        *gate = gt;
+        return 0;
+    }
+
+    // mrpt::math::CHistogram::getHistogramNormalized + mrpt::math::confidenceIntervalsFromHistogram as recalled
+    // from MRPT 2.x (the sources are not in the reference tree; parity UNPINNED):
+    //   x = linspace(min, max, N), hits[i] = bins[i] * ((N - 1) / (max - min)) / count,
+    //   Hc = cumsum(hits) / max(Hc), high = x[upper_bound(Hc, 1 - ci)] with ci = 1 - confidenceInterval (:196-199)
+    int mp2p_b200_adaptive_threshold(const uint64_t histogram[MP2P_B200_ADAPTIVE_BINS], double err_min, double err_max,
+                                     uint64_t n_samples, double confidenceInterval, double minimumCorrDist, double* ci_high,
+                                     double* maxCorrDistSqr)
+    {
+        constexpr int NB = MP2P_B200_ADAPTIVE_BINS;
+        if (!histogram || !ci_high || !maxCorrDistSqr) return MP2P_B200_ERR_ARG;
+        if (n_samples == 0 || !(err_max > err_min))
+        {
+            set_error("match_adaptive: no neighbour within absoluteMaxSearchDistance, or all first/second errors equal "
+                      "(the reference dereferences an empty optional / CHistogram asserts max > min, Matcher_Adaptive.cpp:188)");
+            return MP2P_B200_ERR_ARG;
+        }
+        const double binSizeInv = ((double)NB - 1) / (err_max - err_min);
+        uint64_t     count      = 0;
+        for (int b = 0; b < NB; b++) count += histogram[b];
+        double xs[NB], Hc[NB], acc = 0;
+        for (int b = 0; b < NB; b++)
+        {
+            xs[b] = err_min + b * (err_max - err_min) / (NB - 1);
+            acc += (binSizeInv / (double)count) * (double)histogram[b];
+            Hc[b] = acc;
+        }
+        const double mx = *std::max_element(Hc, Hc + NB);
+        for (int b = 0; b < NB; b++) Hc[b] *= 1.0 / mx;
+        const double ci = 1.0 - confidenceInterval;
+        const size_t k  = std::min<size_t>(NB - 1, std::upper_bound(Hc, Hc + NB, 1.0 - ci) - Hc);
+        *ci_high        = xs[k];
+        *maxCorrDistSqr = std::max(minimumCorrDist * minimumCorrDist, xs[k]);  // :214
+        return 0;
+    }
+
+    int mp2p_b200_adaptive_emit(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const mp2p_b200_adaptive_params* prm,
+                                double maxCorrDistSqr, const uint32_t* global_paired_bits, mp2p_b200_pair_pt2pt* out_pt2pt,
+                                uint64_t capacity_pt2pt, mp2p_b200_pair_pt2pl* out_pt2pl, uint64_t capacity_pt2pl,
+                                int out_on_device, uint64_t* n_pt2pt, uint64_t* n_pt2pl)
+    {
+        if (!ctx || !map || !prm || !n_pt2pt || !n_pt2pl || (capacity_pt2pt && !out_pt2pt) || (capacity_pt2pl && !out_pt2pl) ||
+            bad_adaptive(prm))
+        {
+            set_error("adaptive_emit: NULL argument or bad parameters");
+            return MP2P_B200_ERR_ARG;
+        }
+        DeviceGuard g(ctx->device);
+        ProfScope   ps(ctx);
+        return run_adaptive_emit(ctx, map, prm, maxCorrDistSqr, global_paired_bits, out_pt2pt, capacity_pt2pt, out_pt2pl,
+                                 capacity_pt2pl, out_on_device, n_pt2pt, n_pt2pl);
+    }
+
+    int mp2p_b200_match_adaptive(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly, const float* lz,
+                                 uint64_t n_local, int local_on_device, const double pose[12],
+                                 const mp2p_b200_adaptive_params* prm, const uint32_t* local_paired_bits,
+                                 const uint32_t* global_paired_bits, mp2p_b200_pair_pt2pt* out_pt2pt, uint64_t capacity_pt2pt,
+                                 mp2p_b200_pair_pt2pl* out_pt2pl, uint64_t capacity_pt2pl, int out_on_device, uint64_t* n_pt2pt,
+                                 uint64_t* n_pt2pl, double* ci_high, uint64_t* potential_pairings)
+    {
+        if (!n_pt2pt || !n_pt2pl)
+        {
+            set_error("match_adaptive: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        *n_pt2pt = *n_pt2pl = 0;
+        uint64_t hist[MP2P_B200_ADAPTIVE_BINS], ns = 0;
+        double   emin = 0, emax = 0, hi = 0, thr = 0;
+        int32_t  gate = 0;
+        MP2P_TRY(mp2p_b200_adaptive_search(ctx, map, lx, ly, lz, n_local, local_on_device, pose, prm, local_paired_bits, hist, &emin,
+                                           &emax, &ns, &gate, potential_pairings));
+        if (!gate) return 0;  // :71, :77-80 — empty map / cloud, or no bounding-box overlap: nothing, no throw
+        MP2P_TRY(mp2p_b200_adaptive_threshold(hist, emin, emax, ns, prm->confidenceInterval, prm->minimumCorrDist, &hi, &thr));
+        if (ci_high) *ci_high = hi;
+        return mp2p_b200_adaptive_emit(ctx, map, prm, thr, global_paired_bits, out_pt2pt, capacity_pt2pt, out_pt2pl, capacity_pt2pl,
+                                       out_on_device, n_pt2pt, n_pt2pl);
     }
 
     uint64_t mp2p_b200_shard_record_words(uint64_t per_shard, uint32_t pairingsPerPoint)

@@ -145,6 +145,18 @@ struct mp2p_b200_ctx
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t  ev_fork = nullptr;
     mp2p::DevBuf d_spec;  // GN speculation: 12 doubles pose + state words
+    // Matcher_Adaptive: what phase 2 (adaptive_emit) needs from phase 1 (adaptive_search)
+    struct AdaptiveState
+    {
+        bool                valid   = false;
+        mp2p_b200_map*      map     = nullptr;
+        uint64_t            n_local = 0;
+        uint32_t            K       = 0;
+        uint32_t *          sv_bbox = nullptr, *sv_bbox_next = nullptr, *sv_tile_counter = nullptr;
+        unsigned long long *sv_count = nullptr, *status = nullptr;
+        uint32_t            scan_epoch = 0;
+    } adaptive;
+    mp2p::DevBuf d_adres, d_adsel, d_scan2;  // phase-1 result block, selected pt2pt candidate words, 2nd scan status array
     // grid barrier state of the single-launch iteration (match.cu): counters only ever grow
     mp2p::DevBuf       d_coop;
     unsigned long long coop_arrivals = 0;
@@ -284,6 +296,13 @@ int run_match_inlier_ratio(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
                            uint64_t n_local, int local_on_device, const double pose[12], double ratio, int allowLocal,
                            int allowGlobal, double bbox_eps, const uint32_t* lbits, const uint32_t* gbits,
                            mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device, uint64_t* out_count);
+int run_adaptive_search(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly, const float* lz, uint64_t n_local,
+                        int local_on_device, const double pose[12], const mp2p_b200_adaptive_params* prm, const uint32_t* lbits,
+                        uint64_t hist_out[MP2P_B200_ADAPTIVE_BINS], double* err_min, double* err_max, uint64_t* n_samples,
+                        int* gate_out);
+int run_adaptive_emit(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const mp2p_b200_adaptive_params* prm, double maxCorrDistSqr,
+                      const uint32_t* gbits, mp2p_b200_pair_pt2pt* out2p, uint64_t cap2p, mp2p_b200_pair_pt2pl* out2l,
+                      uint64_t cap2l, int out_on_device, uint64_t* n2p, uint64_t* n2l);
 int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const float* qy,
             const float* qz, uint64_t nq, uint32_t k, float radius2, uint32_t* out_idx,
             float* out_d2, int32_t* out_found);

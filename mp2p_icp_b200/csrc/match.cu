@@ -2419,4 +2419,355 @@ int run_match_inlier_ratio(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     }
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// Matcher_Adaptive (mp2p_icp/src/Matcher_Adaptive.cpp:59-314), in two device phases
+// with the 50-bin histogram crossing to the host in between — the confidence-interval step is
+// mrpt::math code (CHistogram / confidenceIntervalsFromHistogram) that a plugin built against MRPT
+// calls itself; the library carries a restatement for everybody else (api.cu).
+//   phase 1  k-NN (k = 1: k_match_pt2pt_nn1, radius <= absMax; k > 1: k_match_pt2pt<G>, radius <
+//            absMax, at most MAX_CORRS_PER_LOCAL = 10 kept), k_ad_minmax (min / max / count of the
+//            1st and 2nd neighbour errors, :168-181), k_ad_hist (CHistogram::add, bin =
+//            size_t(binSizeInv * (x - min)) in fp64, + the bounding-box gate)
+//   phase 2  k_ad_decide (per local point: plane through its neighbours -> pt2pl, else the pt2pt
+//            candidates that pass the adaptive threshold and the 1st-to-2nd ratio, :219-298), then
+//            the two ordinary compactions
+// ------------------------------------------------------------------------------------------
+namespace
+{
+constexpr int kAdBins = MP2P_B200_ADAPTIVE_BINS;
+
+struct AdResult  // device block read back by the host after phase 1
+{
+    unsigned int       emin_bits, emax_bits;  // float bits (errors are >= 0: the bit patterns order like the values)
+    unsigned long long n_samples;
+    unsigned long long bins[kAdBins];
+    unsigned int       gate;
+};
+
+__global__ void __launch_bounds__(256)
+    k_ad_minmax(const unsigned long long* __restrict__ cand, uint32_t n_local, uint32_t K, AdResult* __restrict__ res)
+{
+    unsigned int lo = 0xFFFFFFFFu, hi = 0u, cnt = 0u;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n_local; i += gridDim.x * 256u)
+        for (uint32_t r = 0; r < min(K, 2u); r++)
+        {
+            const unsigned long long c = cand[(size_t)i * K + r];
+            if ((uint32_t)c == 0xFFFFFFFFu) break;  // valid ranks come first
+            const unsigned int e = (unsigned int)(c >> 32);
+            lo = min(lo, e), hi = max(hi, e), cnt++;
+        }
+    lo  = __reduce_min_sync(0xffffffffu, lo);
+    hi  = __reduce_max_sync(0xffffffffu, hi);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt)
+    {
+        atomicMin(&res->emin_bits, lo), atomicMax(&res->emax_bits, hi);
+        atomicAdd(&res->n_samples, (unsigned long long)cnt);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    k_ad_hist(GridView g, const unsigned long long* __restrict__ cand, uint32_t n_local, uint32_t K, const uint32_t* __restrict__ bbox,
+              uint32_t* __restrict__ bbox_next, float gate_eps, AdResult* __restrict__ res)
+{
+    __shared__ unsigned int sh[kAdBins];
+    bbox_rearm(bbox_next);  // phase 2 may never run (gate closed, reference assertion): the next call's slot is re-armed here
+    if (threadIdx.x < kAdBins) sh[threadIdx.x] = 0u;
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) res->gate = bbox_gate(g, bbox, gate_eps) ? 1u : 0u;
+    const double hmin = (double)__uint_as_float(res->emin_bits), hmax = (double)__uint_as_float(res->emax_bits);
+    if (res->n_samples && hmax > hmin)
+    {
+        const double inv = __ddiv_rn((double)kAdBins - 1.0, __dsub_rn(hmax, hmin));  // CHistogram: (nBins - 1) / (max - min)
+        for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n_local; i += gridDim.x * 256u)
+            for (uint32_t r = 0; r < min(K, 2u); r++)
+            {
+                const unsigned long long c = cand[(size_t)i * K + r];
+                if ((uint32_t)c == 0xFFFFFFFFu) break;
+                const double x = (double)__uint_as_float((uint32_t)(c >> 32));
+                if (x < hmin || x > hmax) continue;
+                const unsigned long long b = (unsigned long long)__double2ull_rz(__dmul_rn(inv, __dsub_rn(x, hmin)));
+                atomicAdd(&sh[min(b, (unsigned long long)(kAdBins - 1))], 1u);
+            }
+    }
+    __syncthreads();
+    if (threadIdx.x < kAdBins && sh[threadIdx.x]) atomicAdd(&res->bins[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+struct AdDecideArgs
+{
+    uint32_t n_local, K, Kp;  // neighbours kept per local, pt2pt slots per local (Kp <= K)
+    int      planes;
+    uint32_t planeMinFound;
+    double   planeEigenThreshold, planeMinimumDistance;
+    double   maxCorrDistSqr;
+    float    maxSqr1to2;
+    int      allowGlobal;
+};
+
+template <int KT>
+__global__ void __launch_bounds__(128)
+    k_ad_decide(GridView g, AdDecideArgs a, const float* __restrict__ lx, const float* __restrict__ ly, const float* __restrict__ lz,
+                const unsigned long long* __restrict__ cand, const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ sel,
+                PlaneCandidate* __restrict__ plc, uint8_t* __restrict__ ok_flags)
+{
+    const uint32_t i = blockIdx.x * 128u + threadIdx.x;
+    if (i >= a.n_local) return;
+    unsigned long long c[KT];
+    int                cnt = 0;
+#pragma unroll
+    for (int k = 0; k < KT; k++)
+    {
+        c[k] = (k < (int)a.K) ? cand[(size_t)i * a.K + k] : ~0ull;
+        cnt += ((uint32_t)c[k] != 0xFFFFFFFFu);
+    }
+    uint8_t plane_ok = 0;
+    if (a.planes && cnt >= (int)a.planeMinFound)  // :222-268
+    {
+        float px[KT], py[KT], pz[KT];
+#pragma unroll
+        for (int k = 0; k < KT; k++)
+            if (k < cnt)
+            {
+                const float4 p = __ldg(g.pts_orig + (uint32_t)c[k]);
+                px[k] = p.x, py[k] = p.y, pz[k] = p.z;
+            }
+        PlaneCandidate pc;
+        if (fit_plane_adaptive<KT>(px, py, pz, cnt, lx[i], ly[i], lz[i], a.planeEigenThreshold, a.planeMinimumDistance, pc))
+        {
+            plc[i]   = pc;
+            plane_ok = 1;
+        }
+    }
+    if (ok_flags) ok_flags[i] = plane_ok;
+    // :270-297
+    const float e0     = __uint_as_float((uint32_t)(c[0] >> 32));
+    bool        broken = plane_ok != 0;
+#pragma unroll
+    for (int k = 0; k < KT; k++)
+        if (k < (int)a.Kp)
+        {
+            unsigned long long w = ~0ull;
+            if (!broken && k < cnt)
+            {
+                const float e    = __uint_as_float((uint32_t)(c[k] >> 32));
+                bool        emit = true;
+                if (!a.allowGlobal && bit_set(gbits, (uint32_t)c[k])) emit = false;  // :276-278
+                if (emit && (double)e >= a.maxCorrDistSqr) emit = false;               // :281
+                if (emit && k != 0 && e > __fmul_rn(e0, a.maxSqr1to2)) emit = false, broken = true;  // :283-287
+                if (emit) w = c[k];
+            }
+            sel[(size_t)i * a.Kp + k] = w;
+        }
+}
+}  // namespace
+
+int run_adaptive_search(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly, const float* lz, uint64_t n_local,
+                        int local_on_device, const double pose[12], const mp2p_b200_adaptive_params* prm, const uint32_t* lbits,
+                        uint64_t hist_out[MP2P_B200_ADAPTIVE_BINS], double* err_min, double* err_max, uint64_t* n_samples,
+                        int* gate_out)
+{
+    auto& S = ctx->adaptive;
+    S       = mp2p_b200_ctx::AdaptiveState{};
+    for (int b = 0; b < kAdBins; b++) hist_out[b] = 0;
+    *err_min = *err_max = 0.0, *n_samples = 0, *gate_out = 0;
+    const uint64_t nmap = map->view.n_points;
+    if (nmap == 0 || n_local == 0) return 0;  // :71
+    const uint32_t nnMax = prm->enableDetectPlanes ? prm->planeSearchPoints : prm->maxPt2PtCorrespondences;  // :119-120
+    const uint32_t K     = std::min<uint32_t>(nnMax, 10u);                                                    // MAX_CORRS_PER_LOCAL
+    if (n_local * (uint64_t)std::max(K, 1u) >= 0xFFFFFFFFull || K < 1)
+    {
+        set_error("match_adaptive: need 1 <= neighbours per point and n_local * neighbours < 2^32-1");
+        return MP2P_B200_ERR_ARG;
+    }
+    cudaStream_t st = ctx->stream;
+    MP2P_TRY(stage_local(ctx, lx, ly, lz, n_local, local_on_device));
+    const uint32_t* d_lbits;
+    MP2P_TRY(upload_bits(ctx, ctx->d_lbits, lbits, n_local, &d_lbits));
+    const uint64_t      n_tiles = (n_local + kScanTile - 1) / kScanTile;
+    SmallView           sv;
+    unsigned long long* status;
+    MP2P_TRY(prepare_small(ctx, n_tiles, sv, &status));
+    MP2P_TRY(ctx->d_cand.ensure(n_local * K * 8));
+    MP2P_TRY(ctx->d_adres.ensure(sizeof(AdResult)));
+    const float absMaxSqr = (float)(prm->absoluteMaxSearchDistance * prm->absoluteMaxSearchDistance);  // :87
+    Pt2PtArgs   a{};
+    for (int k = 0; k < 12; k++) a.pose.m[k] = pose[k];
+    // nn_single_search keeps d2 <= absMax^2 (:166), nn_radius_search d2 < absMax^2; the kernels test d2 < maxDistSq
+    a.maxDistSq = nnMax == 1 ? nextafterf(absMaxSqr, __builtin_inff()) : absMaxSqr;
+    a.angSq     = 0.f;
+    a.n_local = (uint32_t)n_local, a.K = K;
+    a.allowLocal = prm->allowMatchAlreadyMatchedPoints, a.allowGlobal = 1;  // no first-claim dedup in this matcher
+    a.tma_ok   = ctx->cur_tma_ok;
+    a.rl_start = start_level(map->view, K);
+    auto*               cand  = ctx->d_cand.as<unsigned long long>();
+    unsigned long long* stats = nullptr;
+    MP2P_TRY(prepare_stats(ctx, &stats));
+    prof_begin(ctx, 0);
+    if (K == 1)
+    {
+        MP2P_TRY(ctx->d_candxyz.ensure(n_local * sizeof(float4)));
+        MP2P_LAUNCH_NN1((uint32_t)((n_local + kNN1Threads - 1) / kNN1Threads), st, map->view, a, ctx->cur_qx, ctx->cur_qy, ctx->cur_qz,
+                        ctx->cur_perm, d_lbits, nullptr, nullptr, cand, ctx->d_candxyz.as<float4>(), sv.bbox, stats);
+    }
+    else
+    {
+#define LAUNCH_MATCH(G)                                                                                    \
+    {                                                                                                      \
+        const uint32_t nb = (uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile);                       \
+        a.tile_stride = tile_stride_for(nb);                                                                \
+        k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, a, ctx->cur_qx, ctx->cur_qy, ctx->cur_qz, ctx->cur_perm, d_lbits, nullptr, nullptr, cand, sv.bbox, stats, FitList{nullptr, nullptr, nullptr, 0}); \
+    }
+        MP2P_DISPATCH_G(K, LAUNCH_MATCH)
+#undef LAUNCH_MATCH
+    }
+    prof_end(ctx, 0);
+    count_launch(ctx);
+    auto* res = ctx->d_adres.as<AdResult>();
+    {
+        AdResult init{};
+        init.emin_bits = 0xFFFFFFFFu;
+        AdResult* h = reinterpret_cast<AdResult*>(static_cast<char*>(ctx->h_pinned) + 3072);
+        *h          = init;
+        MP2P_CUDA_TRY(cudaMemcpyAsync(res, h, sizeof(AdResult), cudaMemcpyHostToDevice, st));
+    }
+    const uint32_t nb       = (uint32_t)std::min<uint64_t>((n_local + 255) / 256, 148 * 8);
+    const float    gate_eps = (float)prm->bounding_box_intersection_check_epsilon;  // :77-80
+    k_ad_minmax<<<nb, 256, 0, st>>>(cand, (uint32_t)n_local, K, res);
+    k_ad_hist<<<nb, 256, 0, st>>>(map->view, cand, (uint32_t)n_local, K, sv.bbox, sv.bbox_next, gate_eps, res);
+    count_launch(ctx, 2);
+    AdResult* h = reinterpret_cast<AdResult*>(static_cast<char*>(ctx->h_pinned) + 3072);
+    MP2P_CUDA_TRY(cudaMemcpyAsync(h, res, sizeof(AdResult), cudaMemcpyDeviceToHost, st));
+    MP2P_CUDA_TRY(cudaStreamSynchronize(st));
+    MP2P_CUDA_TRY(cudaGetLastError());
+    *gate_out = (int)h->gate;
+    *n_samples = h->n_samples;
+    if (h->n_samples)
+    {
+        float lo, hi;
+        std::memcpy(&lo, &h->emin_bits, 4), std::memcpy(&hi, &h->emax_bits, 4);
+        *err_min = lo, *err_max = hi;
+        for (int b = 0; b < kAdBins; b++) hist_out[b] = h->bins[b];
+    }
+    S.valid = true, S.map = map, S.n_local = n_local, S.K = K, S.sv_bbox = sv.bbox, S.sv_bbox_next = sv.bbox_next;
+    S.sv_count = sv.count, S.sv_tile_counter = sv.tile_counter, S.status = status, S.scan_epoch = ctx->scan_epoch;
+    return 0;
+}
+
+int run_adaptive_emit(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const mp2p_b200_adaptive_params* prm, double maxCorrDistSqr,
+                      const uint32_t* gbits, mp2p_b200_pair_pt2pt* out2p, uint64_t cap2p, mp2p_b200_pair_pt2pl* out2l,
+                      uint64_t cap2l, int out_on_device, uint64_t* n2p, uint64_t* n2l)
+{
+    *n2p = *n2l = 0;
+    ctx->last2p.valid = false, ctx->last2p.sums = nullptr, ctx->last2l.valid = false, ctx->spec_res.valid = false;
+    auto& S = ctx->adaptive;
+    if (!S.valid || S.map != map)
+    {
+        set_error("adaptive_emit: no matching adaptive_search on this context / map (or it reported gate = 0)");
+        return MP2P_B200_ERR_ARG;
+    }
+    S.valid                 = false;
+    cudaStream_t   st       = ctx->stream;
+    const uint64_t n_local  = S.n_local;
+    const uint32_t K        = S.K;
+    const uint32_t Kp       = std::min<uint32_t>(std::max<uint32_t>(prm->maxPt2PtCorrespondences, 1u), K);
+    const uint64_t nmap     = map->view.n_points;
+    const uint32_t* d_gbits;
+    MP2P_TRY(upload_bits(ctx, ctx->d_gbits, gbits, nmap, &d_gbits));
+    MP2P_TRY(ctx->d_adsel.ensure(n_local * Kp * 8));
+    MP2P_TRY(ctx->d_plcand.ensure(n_local * sizeof(PlaneCandidate)));
+    MP2P_TRY(ctx->d_okflags.ensure(n_local));
+    AdDecideArgs d{};
+    d.n_local = (uint32_t)n_local, d.K = K, d.Kp = Kp;
+    d.planes = prm->enableDetectPlanes, d.planeMinFound = prm->planeMinimumFoundPoints;
+    d.planeEigenThreshold = prm->planeEigenThreshold, d.planeMinimumDistance = prm->planeMinimumDistance;
+    d.maxCorrDistSqr = maxCorrDistSqr;
+    d.maxSqr1to2     = (float)(prm->firstToSecondDistanceMax * prm->firstToSecondDistanceMax);  // :216
+    d.allowGlobal    = prm->allowMatchAlreadyMatchedGlobalPoints;
+    auto*          cand = ctx->d_cand.as<unsigned long long>();
+    auto*          sel  = ctx->d_adsel.as<unsigned long long>();
+    auto*          plc  = ctx->d_plcand.as<PlaneCandidate>();
+    auto*          okf  = ctx->d_okflags.as<uint8_t>();
+    const uint32_t nbd  = (uint32_t)((n_local + 127) / 128);
+    prof_begin(ctx, 1);
+#define LAUNCH_DECIDE(KT) k_ad_decide<KT><<<nbd, 128, 0, st>>>(map->view, d, ctx->cur_lx, ctx->cur_ly, ctx->cur_lz, cand, d_gbits, sel, plc, okf)
+    if (K <= 1)
+        LAUNCH_DECIDE(1);
+    else if (K <= 4)
+        LAUNCH_DECIDE(4);
+    else if (K <= 8)
+        LAUNCH_DECIDE(8);
+    else
+        LAUNCH_DECIDE(10);
+#undef LAUNCH_DECIDE
+    count_launch(ctx);
+    const float gate_eps = (float)prm->bounding_box_intersection_check_epsilon;
+    // ---- point-to-plane pairings (ascending local index)
+    mp2p_b200_pair_pt2pl* d_out2l = out2l;
+    const uint64_t        capl    = std::min<uint64_t>(cap2l, n_local);
+    const uint64_t        n_tiles = (n_local + kScanTile - 1) / kScanTile;
+    if (prm->enableDetectPlanes)
+    {
+        if (!out_on_device)
+        {
+            MP2P_TRY(ctx->d_out2l.ensure(std::max<uint64_t>(capl, 1) * sizeof(mp2p_b200_pair_pt2pl)));
+            d_out2l = ctx->d_out2l.as<mp2p_b200_pair_pt2pl>();
+        }
+        k_compact_pt2pl<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, (uint32_t)n_local, gate_eps, capl, ctx->cur_lx, ctx->cur_ly,
+                                                                   ctx->cur_lz, plc, okf, S.sv_bbox, S.sv_bbox_next, S.status,
+                                                                   S.sv_tile_counter, d_out2l, S.sv_count, S.scan_epoch, 0);
+        count_launch(ctx);
+    }
+    // ---- point-to-point pairings: ordinary compaction over the selected candidate words, its own
+    //      status array and count word (two scans in one call)
+    const uint64_t n_slots  = n_local * Kp;
+    const uint64_t n_tiles2 = (n_slots + kScanTile - 1) / kScanTile;
+    if ((n_tiles2 + 1) * 8 > ctx->d_scan2.bytes)
+    {
+        MP2P_TRY(ctx->d_scan2.ensure((n_tiles2 + 1) * 8));
+        MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_scan2.p, 0, ctx->d_scan2.bytes, st));
+    }
+    auto*                 count2  = reinterpret_cast<unsigned long long*>(ctx->d_small.as<char>() + 80);
+    mp2p_b200_pair_pt2pt* d_out2p = out2p;
+    const uint64_t        capp    = std::min<uint64_t>(cap2p, n_slots);
+    if (!out_on_device)
+    {
+        MP2P_TRY(ctx->d_out2p.ensure(std::max<uint64_t>(capp, 1) * sizeof(mp2p_b200_pair_pt2pt)));
+        d_out2p = ctx->d_out2p.as<mp2p_b200_pair_pt2pt>();
+    }
+    CompactArgs c{};
+    c.n_local = (uint32_t)n_local, c.K = Kp, c.allowGlobal = 1, c.tag = 0;
+    c.gate_eps = gate_eps, c.capacity = capp, c.scan_epoch = S.scan_epoch;
+    k_compact_pt2pt<<<(uint32_t)n_tiles2, kScanThreads, 0, st>>>(map->view, c, ctx->cur_lx, ctx->cur_ly, ctx->cur_lz, nullptr,
+                                                                map->d_claim.as<unsigned long long>(), sel,
+                                                                K == 1 ? ctx->d_candxyz.as<float4>() : nullptr, S.sv_bbox, S.sv_bbox_next,
+                                                                ctx->d_scan2.as<unsigned long long>(), S.sv_tile_counter, d_out2p, count2,
+                                                                FusedSums{nullptr, nullptr, nullptr});
+    prof_end(ctx, 1);
+    count_launch(ctx);
+    // ---- counts and records back
+    unsigned long long* hc = reinterpret_cast<unsigned long long*>(static_cast<char*>(ctx->h_pinned) + 3072 + 512);
+    hc[0] = hc[1] = 0;
+    MP2P_CUDA_TRY(cudaMemcpyAsync(hc, count2, 8, cudaMemcpyDeviceToHost, st));
+    if (prm->enableDetectPlanes) MP2P_CUDA_TRY(cudaMemcpyAsync(hc + 1, S.sv_count, 8, cudaMemcpyDeviceToHost, st));
+    MP2P_CUDA_TRY(cudaStreamSynchronize(st));
+    MP2P_CUDA_TRY(cudaGetLastError());
+    *n2p = hc[0], *n2l = hc[1];
+    if (*n2p > capp || *n2l > capl)
+    {
+        set_error("match_adaptive: output capacity too small (%llu pt2pt, %llu pt2pl pairings)", (unsigned long long)*n2p,
+                  (unsigned long long)*n2l);
+        return MP2P_B200_ERR_CAPACITY;
+    }
+    if (!out_on_device)
+    {
+        if (*n2p) MP2P_CUDA_TRY(cudaMemcpyAsync(out2p, d_out2p, *n2p * sizeof(mp2p_b200_pair_pt2pt), cudaMemcpyDeviceToHost, st));
+        if (*n2l) MP2P_CUDA_TRY(cudaMemcpyAsync(out2l, d_out2l, *n2l * sizeof(mp2p_b200_pair_pt2pl), cudaMemcpyDeviceToHost, st));
+        MP2P_CUDA_TRY(cudaStreamSynchronize(st));
+        ctx->last2p.dev = d_out2p, ctx->last2p.n = *n2p, ctx->last2p.valid = true;
+        ctx->last2l.dev = d_out2l, ctx->last2l.n = *n2l, ctx->last2l.valid = prm->enableDetectPlanes != 0;
+    }
+    return 0;
+}
 }  // namespace mp2p

@@ -147,6 +147,47 @@ __device__ __forceinline__ bool fit_plane(const float (&px)[KT], const float (&p
     return true;
 }
 
+// Plane test of Matcher_Adaptive (mp2p_icp/src/Matcher_Adaptive.cpp:222-268): the same fit over the cnt
+// kept neighbours, planarity test :240-241, TPlane(centroid, eigenvector 0 AS IS), and the distance of
+// `(ex,ey,ez)` — the caller passes the LOCAL-frame point, as upstream does (:247) — strictly below
+// planeMinimumDistance (:249).
+template <int KT>
+__device__ __forceinline__ bool fit_plane_adaptive(const float (&px)[KT], const float (&py)[KT], const float (&pz)[KT], int cnt,
+                                                   float ex, float ey, float ez, double planeEigenThreshold,
+                                                   double planeMinimumDistance, PlaneCandidate& out)
+{
+    float mx = 0.f, my = 0.f, mz = 0.f;
+#pragma unroll
+    for (int k = 0; k < KT; k++)
+        if (k < cnt) mx += px[k], my += py[k], mz += pz[k];
+    const float inv_n = 1.0f / (float)cnt;
+    mx *= inv_n, my *= inv_n, mz *= inv_n;
+    double a00 = 0, a10 = 0, a20 = 0, a11 = 0, a21 = 0, a22 = 0;
+#pragma unroll
+    for (int k = 0; k < KT; k++)
+        if (k < cnt)
+        {
+            const float ax = px[k] - mx, ay = py[k] - my, az = pz[k] - mz;
+            a00 += (double)(ax * ax), a10 += (double)(ax * ay), a20 += (double)(ax * az);
+            a11 += (double)(ay * ay), a21 += (double)(ay * az), a22 += (double)(az * az);
+        }
+    const double dn = (double)inv_n;
+    a00 *= dn, a10 *= dn, a20 *= dn, a11 *= dn, a21 *= dn, a22 *= dn;
+    const double A[9] = {a00, a10, a20, a10, a11, a21, a20, a21, a22};
+    double       V[9], vals[3];
+    eig_sym3(A, V, vals);
+    if (!(vals[0] < planeEigenThreshold * vals[2] && vals[0] < planeEigenThreshold * vals[1])) return false;
+    const double cx = mx, cy = my, cz = mz;
+    const double nx = V[0], ny = V[3], nz = V[6];
+    const double D    = -(nx * cx + ny * cy + nz * cz);
+    const double ev   = nx * (double)ex + ny * (double)ey + nz * (double)ez + D;
+    const double dist = fabs(fabs(ev) / sqrt(nx * nx + ny * ny + nz * nz));
+    if (!(dist < planeMinimumDistance)) return false;
+    out.coefs[0] = nx, out.coefs[1] = ny, out.coefs[2] = nz, out.coefs[3] = D;
+    out.centroid[0] = cx, out.centroid[1] = cy, out.centroid[2] = cz;
+    return true;
+}
+
 // Line fit of the pt2ln matcher (mp2p_icp/src/Matcher_Point2Line.cpp:132-156): the same moments over
 // the cnt neighbours, line test e0 <= thr*e2 && e1 <= thr*e2 (:148-149), director = eigenvector of
 // the largest eigenvalue, unitarized; out.coefs[0..2] = director, out.centroid = pBase (the mean).

@@ -298,6 +298,82 @@ def test_icp_align_bunny_inlier_ratio_matches_oracle(ctx, solver):
     assert np.linalg.norm(orc.se3_log(orc.inverse_compose(r1.pose, gt))) < 0.1
 
 
+# --------------------------------------------------------------------------- Matcher_Adaptive (§8f N1)
+@pytest.mark.parametrize("kw", [dict(confidenceInterval=0.8, absoluteMaxSearchDistance=0.5, minimumCorrDist=0.01),
+                                dict(confidenceInterval=0.75, absoluteMaxSearchDistance=2.0, minimumCorrDist=0.1),
+                                dict(confidenceInterval=0.6, absoluteMaxSearchDistance=0.7, minimumCorrDist=0.02, maxPt2PtCorrespondences=3, firstToSecondDistanceMax=1.5),
+                                dict(confidenceInterval=0.9, absoluteMaxSearchDistance=1.0, minimumCorrDist=0.05, maxPt2PtCorrespondences=2, allowMatchAlreadyMatchedGlobalPoints=True)])
+def test_match_adaptive_pt2pt_bit_exact(ctx, kw):
+    """No planes: pt2pt records, their count, the histogram-derived threshold — all the oracle's."""
+    M, L, gt = _c2(200_000, 10)
+    rng = np.random.default_rng(8)
+    L = L.copy()
+    L[:1500] += rng.normal(0, 0.6, (1500, 3)).astype(np.float32)  # a tail of poor matches for the histogram
+    tree, gmap = orc.KDTree(*xyz(M)), b200.Map(ctx, *xyz(M))
+    lp = (rng.random(len(L)) < 0.1).astype(np.uint8)
+    gp = (rng.random(len(M)) < 0.1).astype(np.uint8)
+    for T in (fx.pose_xyzypr(0.25, -0.15, 0.08, 1.7 * DEG, -0.8 * DEG, 1.2 * DEG), gt):
+        for paired in (False, True):
+            a0, l0, pot0, ci0 = orc.match_adaptive(tree, *xyz(L), T, orc.MatchAdaptiveParams(**kw), lp.copy() if paired else None, gp if paired else None, nthreads=8)
+            a1, l1, pot1, ci1 = gmap.match_adaptive(*xyz(L), T, b200.AdaptiveParams(**kw), local_paired=lp if paired else None, global_paired=gp if paired else None)
+            assert pot0 == pot1 and ci0 == ci1 and len(l0) == len(l1) == 0
+            assert len(a0) == len(a1) > 100 and a0.tobytes() == a1.tobytes()
+    # two-phase form (the histogram crosses to the host: what an MRPT-linked plugin uses) with a caller's threshold
+    seen = {}
+
+    def thr(hist, emin, emax, ns):
+        seen.update(hist=hist.copy(), emin=emin, emax=emax, ns=ns)
+        return 0.04
+
+    a2, _, _, _ = gmap.match_adaptive(*xyz(L), gt, b200.AdaptiveParams(**kw), threshold_fn=thr)
+    k = kw.get("maxPt2PtCorrespondences", 1)
+    idx, d2, found = tree.knn(*orc.transform_local_to_global(*xyz(L), gt)[:3], min(k, 10), np.nextafter(np.float32(kw["absoluteMaxSearchDistance"] ** 2), np.float32(np.inf)) if k == 1 else np.float32(kw["absoluteMaxSearchDistance"] ** 2), nthreads=8)
+    first_two = np.concatenate([d2[found > r, r] for r in range(min(k, 2))])
+    assert seen["ns"] == len(first_two) == seen["hist"].sum() and seen["emin"] == first_two.min() and seen["emax"] == first_two.max()
+    inv = 49.0 / (float(first_two.max()) - float(first_two.min()))
+    assert np.array_equal(seen["hist"], np.bincount((inv * (first_two.astype(np.float64) - float(first_two.min()))).astype(np.int64), minlength=50)[:50].astype(np.uint64))
+    assert np.all(a2["errSq"] < 0.04) and len(a2) > 1000
+
+
+def test_match_adaptive_planes_and_edge_cases(ctx):
+    Ms = fx.make_street_scene(n_map=300_000, length=50.0)
+    S = fx.make_lidar_scan((25.0, 0.4, 0.0), n_rings=32, n_az=500, length=50.0)
+    tree, smap = orc.KDTree(*xyz(Ms)), b200.Map(ctx, *xyz(Ms))
+    T = fx.pose_xyzypr(25.03, 0.38, 0.01, 0.005, 0.0, 0.0)
+    for kw in (dict(enableDetectPlanes=True, absoluteMaxSearchDistance=1.0, confidenceInterval=0.8, planeMinimumDistance=50.0),
+               dict(enableDetectPlanes=True, absoluteMaxSearchDistance=0.6, confidenceInterval=0.7, planeSearchPoints=10, planeMinimumFoundPoints=5, planeEigenThreshold=0.02, planeMinimumDistance=30.0, maxPt2PtCorrespondences=2),
+               dict(enableDetectPlanes=True, absoluteMaxSearchDistance=1.0, planeSearchPoints=16, planeMinimumFoundPoints=8, planeMinimumDistance=0.10)):
+        lp0 = np.zeros(len(S), np.uint8)
+        a0, l0, pot0, ci0 = orc.match_adaptive(tree, *xyz(S), T, orc.MatchAdaptiveParams(**kw), lp0, nthreads=8)
+        a1, l1, pot1, ci1 = smap.match_adaptive(*xyz(S), T, b200.AdaptiveParams(**kw))
+        assert pot0 == pot1 and ci0 == ci1 and len(a0) == len(a1) and len(l0) == len(l1)
+        assert a0.tobytes() == a1.tobytes() and np.array_equal(l0["local"], l1["local"])
+        np.testing.assert_allclose(l1["coefs"], l0["coefs"], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(l1["centroid"], l0["centroid"], rtol=0, atol=1e-9)
+    assert len(l1) + len(a1) > 1000
+    # the known answers of tests/test_oracle_golden.py::test_matcher_adaptive_planes_and_edge_cases
+    gx, gy = np.meshgrid(np.arange(40) * 0.05, np.arange(40) * 0.05)
+    G = np.stack([gx.ravel(), gy.ravel(), np.zeros(1600)], 1).astype(np.float32)
+    G[:, 2] += np.random.default_rng(4).normal(0, 1e-4, len(G)).astype(np.float32)
+    Ls = np.array([[1.0, 1.0, 0.03], [0.52, 1.31, 0.05], [1.0, 1.0, 1.5], [30, 30, 30]], np.float32)
+    small = b200.Map(ctx, *xyz(G))
+    I = np.eye(3, 4)
+    prm = b200.AdaptiveParams(confidenceInterval=0.8, absoluteMaxSearchDistance=2.0, enableDetectPlanes=True, planeSearchPoints=8, planeMinimumFoundPoints=4, planeMinimumDistance=0.10, minimumCorrDist=0.1)
+    p2p, p2l, pot, _ = small.match_adaptive(*xyz(Ls), I, prm)
+    assert pot == 4 and len(p2l) == 2 and len(p2p) == 0 and np.array_equal(p2l["local"], Ls[:2])
+    prm2 = b200.AdaptiveParams(confidenceInterval=0.8, absoluteMaxSearchDistance=2.0, minimumCorrDist=0.1)
+    p2p, p2l, _, _ = small.match_adaptive(*xyz(Ls), I, prm2)
+    assert len(p2l) == 0 and list(p2p["localIdx"]) == [0, 1]
+    with pytest.raises(b200.Mp2pError):  # no neighbour at all
+        small.match_adaptive(*xyz(Ls[:1]), I, b200.AdaptiveParams(absoluteMaxSearchDistance=0.01))
+    with pytest.raises(b200.Mp2pError):  # one error value: CHistogram asserts max > min
+        small.match_adaptive(*xyz(Ls[:1]), I, prm2)
+    assert len(small.match_adaptive(*xyz(Ls), fx.pose_xyzypr(500, 0, 0, 0, 0, 0), prm2)[0]) == 0  # no bbox overlap
+    assert len(small.match_adaptive(*xyz(Ls[:0]), I, prm2)[0]) == 0
+    with pytest.raises(b200.Mp2pError):  # Matcher_Adaptive.cpp:50-51
+        small.match_adaptive(*xyz(Ls), I, b200.AdaptiveParams(confidenceInterval=1.0))
+
+
 # --------------------------------------------------------------------------- Matcher_Point2Line + pt2ln in GN (§8f N1)
 def _pole_scene(seed=3, n_poles=400, n_ground=150_000):
     """Vertical and slanted poles (line-like neighbourhoods) over a ground plane."""
