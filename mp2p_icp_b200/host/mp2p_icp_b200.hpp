@@ -16,6 +16,7 @@
 //   Pairings                                         mp2p_icp/include/mp2p_icp/Pairings.h:84-194, src/Pairings.cpp:123-147
 //   Matcher_Points_InlierRatio                       mp2p_icp/src/Matcher_Points_InlierRatio.cpp:35-143
 //   Matcher_Point2Line                               mp2p_icp/src/Matcher_Point2Line.cpp:35-163
+//   Matcher_Adaptive                                 mp2p_icp/src/Matcher_Adaptive.cpp:32-314
 //   QualityEvaluator, QualityEvaluator_PairedRatio   mp2p_icp/include/mp2p_icp/QualityEvaluator.h, src/QualityEvaluator_PairedRatio.cpp:27-73
 //   ICP::align loop (the caller)                     mp2p_icp/src/ICP.cpp:108-338, evaluate_quality :608-634
 #pragma once
@@ -623,6 +624,78 @@ class Matcher_Point2Line : public Matcher_Points_Base
             const auto& r = out.paired_pt2ln[k];
             while (i < lx.size() && !((double)lx[i] == r.local[0] && (double)ly[i] == r.local[1] && (double)lz[i] == r.local[2] &&
                                       !((lbits[i >> 5] >> (i & 31)) & 1u)))
+                i++;
+            if (i < lx.size()) MatchState::mark(lbits, i++);
+        }
+    }
+};
+
+/** Matcher_Adaptive (mp2p_icp/include/mp2p_icp/Matcher_Adaptive.h:39-98, mp2p_icp/src/Matcher_Adaptive.cpp:32-314)
+ *  over mp2p_b200_match_adaptive. The histogram -> confidence-interval step uses the library's
+ *  restatement of the two MRPT helpers (parity unpinned); the MRPT plugin calls MRPT. */
+class Matcher_Adaptive : public Matcher_Points_Base
+{
+   public:
+    double   confidenceInterval        = 0.80;
+    double   firstToSecondDistanceMax  = 1.2;
+    double   absoluteMaxSearchDistance = 5.0;
+    bool     enableDetectPlanes        = false;
+    uint32_t maxPt2PtCorrespondences   = 1;
+    uint32_t planeSearchPoints         = 8;
+    uint32_t planeMinimumFoundPoints   = 4;
+    double   planeMinimumDistance      = 0.10;
+    double   planeEigenThreshold       = 0.01;
+    double   minimumCorrDist           = 0.1;
+    void     initialize(const ParameterMap& params) override  // :32-57
+    {
+        Matcher_Points_Base::initialize(params);
+        confidenceInterval        = params.required<double>("confidenceInterval");
+        firstToSecondDistanceMax  = params.required<double>("firstToSecondDistanceMax");
+        absoluteMaxSearchDistance = params.required<double>("absoluteMaxSearchDistance");
+        minimumCorrDist           = params.getOrDefault<double>("minimumCorrDist", minimumCorrDist);
+        enableDetectPlanes        = params.required<int>("enableDetectPlanes") != 0;
+        planeSearchPoints         = params.getOrDefault<uint32_t>("planeSearchPoints", planeSearchPoints);
+        planeMinimumFoundPoints   = params.getOrDefault<uint32_t>("planeMinimumFoundPoints", planeMinimumFoundPoints);
+        planeEigenThreshold       = params.getOrDefault<double>("planeEigenThreshold", planeEigenThreshold);
+        maxPt2PtCorrespondences   = params.getOrDefault<uint32_t>("maxPt2PtCorrespondences", maxPt2PtCorrespondences);
+        planeMinimumDistance      = params.getOrDefault<double>("planeMinimumDistance", planeMinimumDistance);
+        if (!(confidenceInterval < 1.0)) throw std::runtime_error("Assert failed: confidenceInterval < 1.0");
+        if (!(confidenceInterval > 0.0)) throw std::runtime_error("Assert failed: confidenceInterval > 0.0");
+        if (!(planeSearchPoints >= planeMinimumFoundPoints)) throw std::runtime_error("Assert failed: planeSearchPoints >= planeMinimumFoundPoints");
+        if (!(planeMinimumFoundPoints >= 3)) throw std::runtime_error("Assert failed: planeMinimumFoundPoints >= 3");
+        if (!(planeEigenThreshold > 0.0)) throw std::runtime_error("Assert failed: planeEigenThreshold > 0.0");
+    }
+
+   private:
+    void implMatchOneLayer(const CPointsMap& pcGlobal, const CPointsMap& pcLocal, const CPose3D& localPose,
+                           MatchState& ms, const layer_name_t& globalName, const layer_name_t& localName, Pairings& out) const override
+    {
+        Device&                   dev = Device::instance();
+        mp2p_b200_adaptive_params p{confidenceInterval, firstToSecondDistanceMax, absoluteMaxSearchDistance, minimumCorrDist,
+                                    enableDetectPlanes, planeSearchPoints, planeMinimumFoundPoints, maxPt2PtCorrespondences,
+                                    planeEigenThreshold, planeMinimumDistance, allowMatchAlreadyMatchedPoints_,
+                                    allowMatchAlreadyMatchedGlobalPoints_, bounding_box_intersection_check_epsilon_};
+        auto&        lbits = ms.localPaired.at(localName);
+        auto&        gbits = ms.globalPaired.at(globalName);
+        const size_t b2p = out.paired_pt2pt.size(), b2l = out.paired_pt2pl.size();
+        const size_t cap2p = pcLocal.size() * maxPt2PtCorrespondences, cap2l = pcLocal.size();
+        out.paired_pt2pt.resize(b2p + cap2p), out.paired_pt2pl.resize(b2l + cap2l);
+        uint64_t n2p = 0, n2l = 0, pot = 0;
+        check(mp2p_b200_match_adaptive(dev.ctx(), dev.map_for(pcGlobal), dev.cloud_for(pcLocal), nullptr, nullptr, pcLocal.size(),
+                                       MP2P_B200_LOCAL_CLOUD, localPose.m, &p, lbits.data(), gbits.data(), out.paired_pt2pt.data() + b2p,
+                                       cap2p, out.paired_pt2pl.data() + b2l, cap2l, 0, &n2p, &n2l, nullptr, &pot),
+              "mp2p_b200_match_adaptive");
+        out.paired_pt2pt.resize(b2p + n2p), out.paired_pt2pl.resize(b2l + n2l);
+        out.potential_pairings += pot;
+        if (!allowMatchAlreadyMatchedGlobalPoints_)  // :291-295 (the local bit only; global points are never marked, :303-311)
+            for (size_t i = b2p; i < out.paired_pt2pt.size(); i++) MatchState::mark(lbits, out.paired_pt2pt[i].localIdx);
+        // :262 — local points that got a plane; re-identified by a parallel walk (ascending local index)
+        const auto &lx = pcLocal.getPointsBufferRef_x(), &ly = pcLocal.getPointsBufferRef_y(), &lz = pcLocal.getPointsBufferRef_z();
+        size_t      i  = 0;
+        for (size_t k = b2l; k < out.paired_pt2pl.size(); k++)
+        {
+            const auto& r = out.paired_pt2pl[k];
+            while (i < lx.size() && !(lx[i] == r.local_x && ly[i] == r.local_y && lz[i] == r.local_z && !((lbits[i >> 5] >> (i & 31)) & 1u)))
                 i++;
             if (i < lx.size()) MatchState::mark(lbits, i++);
         }

@@ -23,6 +23,8 @@
 #include <mp2p_icp/metricmap.h>
 #include <mrpt/core/initializer.h>
 #include <mrpt/maps/CPointsMap.h>
+#include <mrpt/math/distributions.h>
+#include <mrpt/math/utils.h>
 #include <mrpt/rtti/CObject.h>
 
 #include <cstring>
@@ -462,6 +464,101 @@ class Solver_GaussNewton_B200 : public Solver_GaussNewton
 };
 IMPLEMENTS_MRPT_OBJECT(Solver_GaussNewton_B200, Solver, mp2p_icp)
 
+/** Drop-in for Matcher_Adaptive (mp2p_icp/src/Matcher_Adaptive.cpp:32-314). The neighbour search, the
+ *  histogram binning and the per-point decisions run on the device; the ONE step in between — histogram
+ *  -> upper confidence bound — is done here by MRPT itself (mrpt::math::confidenceIntervalsFromHistogram,
+ *  :196-199), on the 50 numbers the device hands over, so the threshold is the reference's by construction. */
+class Matcher_Adaptive_B200 : public Matcher_Points_Base
+{
+    DEFINE_MRPT_OBJECT(Matcher_Adaptive_B200, mp2p_icp)
+   public:
+    void initialize(const mrpt::containers::yaml& params) override
+    {
+        Matcher_Points_Base::initialize(params);
+        MCP_LOAD_REQ(params, confidenceInterval);
+        MCP_LOAD_REQ(params, firstToSecondDistanceMax);
+        MCP_LOAD_REQ(params, absoluteMaxSearchDistance);
+        MCP_LOAD_OPT(params, minimumCorrDist);
+        MCP_LOAD_REQ(params, enableDetectPlanes);
+        MCP_LOAD_OPT(params, planeSearchPoints);
+        MCP_LOAD_OPT(params, planeMinimumFoundPoints);
+        MCP_LOAD_OPT(params, planeEigenThreshold);
+        MCP_LOAD_OPT(params, maxPt2PtCorrespondences);
+        MCP_LOAD_OPT(params, planeMinimumDistance);
+        ASSERT_LT_(confidenceInterval, 1.0);
+        ASSERT_GT_(confidenceInterval, 0.0);
+        ASSERT_GE_(planeSearchPoints, planeMinimumFoundPoints);
+        ASSERT_GE_(planeMinimumFoundPoints, 3);
+        ASSERT_GT_(planeEigenThreshold, 0.0);
+    }
+    double   confidenceInterval = 0.80, firstToSecondDistanceMax = 1.2, absoluteMaxSearchDistance = 5.0;
+    bool     enableDetectPlanes      = false;
+    uint32_t maxPt2PtCorrespondences = 1, planeSearchPoints = 8, planeMinimumFoundPoints = 4;
+    double   planeMinimumDistance = 0.10, planeEigenThreshold = 0.01, minimumCorrDist = 0.1;
+
+   private:
+    void implMatchOneLayer(const mrpt::maps::CMetricMap& pcGlobal, const mrpt::maps::CPointsMap& pcLocal,
+                           const mrpt::poses::CPose3D& localPose, MatchState& ms, const layer_name_t& globalName,
+                           const layer_name_t& localName, Pairings& out) const override
+    {
+        using namespace b200_detail;
+        mp2p_b200_map* gmap = cache().get(pcGlobal);
+        const auto&    lx   = pcLocal.getPointsBufferRef_x();
+        const auto&    ly   = pcLocal.getPointsBufferRef_y();
+        const auto&    lz   = pcLocal.getPointsBufferRef_z();
+        double         T[12];
+        pose12(localPose, T);
+        mp2p_b200_adaptive_params p{confidenceInterval, firstToSecondDistanceMax, absoluteMaxSearchDistance, minimumCorrDist,
+                                    enableDetectPlanes, planeSearchPoints, planeMinimumFoundPoints, maxPt2PtCorrespondences,
+                                    planeEigenThreshold, planeMinimumDistance, allowMatchAlreadyMatchedPoints_,
+                                    allowMatchAlreadyMatchedGlobalPoints_, bounding_box_intersection_check_epsilon_};
+        auto&      lbf   = ms.localPairedBitField.point_layers[localName];
+        auto&      gbf   = ms.globalPairedBitField.point_layers[globalName];
+        const auto lbits = to_bits(lbf, lx.size());
+        const auto gbits = to_bits(gbf, mp2p_icp::MapToNN(pcGlobal, true)->nn_index_count());
+        uint64_t   hist[MP2P_B200_ADAPTIVE_BINS], ns = 0, pot = 0;
+        double     emin = 0, emax = 0;
+        int32_t    gate = 0;
+        const float* resident = cache().pinned_local(pcLocal);
+        check(mp2p_b200_adaptive_search(ctx(), gmap, resident ? resident : lx.data(), resident ? nullptr : ly.data(),
+                                        resident ? nullptr : lz.data(), lx.size(),
+                                        resident ? MP2P_B200_LOCAL_CLOUD : MP2P_B200_LOCAL_HOST, T, &p, lbits.data(), hist, &emin,
+                                        &emax, &ns, &gate, &pot));
+        out.potential_pairings += pot;
+        if (!gate) return;  // :71, :77-80
+        // :188-199 — the histogram of the 1st / 2nd neighbour errors in MRPT's own normalisation, then MRPT's
+        // confidence interval (CHistogram(min, max, 50): binSizeInv = (nBins - 1) / (max - min))
+        ASSERT_(ns > 0);
+        ASSERT_(emax > emin);
+        std::vector<double> histXs, histValues(MP2P_B200_ADAPTIVE_BINS);
+        mrpt::math::linspace(emin, emax, size_t(MP2P_B200_ADAPTIVE_BINS), histXs);
+        const double K = ((MP2P_B200_ADAPTIVE_BINS - 1) / (emax - emin)) / double(ns);
+        for (int b = 0; b < MP2P_B200_ADAPTIVE_BINS; b++) histValues[b] = K * double(hist[b]);
+        double ci_low = 0, ci_high = 0;
+        mrpt::math::confidenceIntervalsFromHistogram(histXs, histValues, ci_low, ci_high, 1.0 - confidenceInterval);
+        const double maxCorrDistSqr = std::max(mrpt::square(minimumCorrDist), ci_high);  // :214
+
+        const size_t b2p = out.paired_pt2pt.size(), b2l = out.paired_pt2pl.size();
+        const size_t cap2p = lx.size() * maxPt2PtCorrespondences, cap2l = lx.size();
+        out.paired_pt2pt.resize(b2p + cap2p), out.paired_pt2pl.resize(b2l + cap2l);
+        uint64_t n2p = 0, n2l = 0;
+        check(mp2p_b200_adaptive_emit(ctx(), gmap, &p, maxCorrDistSqr, gbits.data(),
+                                      reinterpret_cast<mp2p_b200_pair_pt2pt*>(out.paired_pt2pt.data() + b2p), cap2p,
+                                      reinterpret_cast<mp2p_b200_pair_pt2pl*>(out.paired_pt2pl.data() + b2l), cap2l, 0, &n2p, &n2l));
+        out.paired_pt2pt.resize(b2p + n2p), out.paired_pt2pl.resize(b2l + n2l);
+        if (!allowMatchAlreadyMatchedGlobalPoints_)  // :291-295
+            for (size_t i = b2p; i < out.paired_pt2pt.size(); i++) lbf.mark_as_set(out.paired_pt2pt[i].localIdx);
+        size_t i = 0;  // :262 (output in ascending local index: parallel walk)
+        for (size_t k = b2l; k < out.paired_pt2pl.size(); k++)
+        {
+            const auto& r = out.paired_pt2pl[k].pt_local;
+            while (i < lx.size() && !(lx[i] == r.x && ly[i] == r.y && lz[i] == r.z && !lbf[i])) i++;
+            if (i < lx.size()) lbf.mark_as_set(i++);
+        }
+    }
+};
+IMPLEMENTS_MRPT_OBJECT(Matcher_Adaptive_B200, Matcher, mp2p_icp)
+
 /** Drop-in for Matcher_Point2Line (mp2p_icp/src/Matcher_Point2Line.cpp:35-163). */
 class Matcher_Point2Line_B200 : public Matcher_Points_Base
 {
@@ -576,6 +673,7 @@ MRPT_INITIALIZER(register_mp2p_icp_b200)
     registerClass(CLASS_ID(mp2p_icp::Matcher_Points_DistanceThreshold_B200));
     registerClass(CLASS_ID(mp2p_icp::Matcher_Points_InlierRatio_B200));
     registerClass(CLASS_ID(mp2p_icp::Matcher_Point2Line_B200));
+    registerClass(CLASS_ID(mp2p_icp::Matcher_Adaptive_B200));
     registerClass(CLASS_ID(mp2p_icp::Solver_Horn_B200));
     registerClass(CLASS_ID(mp2p_icp::Matcher_Point2Plane_B200));
     registerClass(CLASS_ID(mp2p_icp::Solver_GaussNewton_B200));

@@ -132,7 +132,9 @@ int main(int argc, char** argv)
             std::uniform_real_distribution<double> U(-1.0, 1.0);
             // matcherKind 0: Matcher_Points_DistanceThreshold, 1: Matcher_Points_InlierRatio (defaults),
             // tests/test-mp2p_icp_algos.cpp:250-262
-            for (int matcherKind = 0; matcherKind < 2; matcherKind++)
+            // 2: the schedule of demos/icp-settings-kitti.yaml:39-59 — Matcher_Points_DistanceThreshold for iterations
+            //    0-5, Matcher_Adaptive from iteration 6 on (confidenceInterval 0.75, firstToSecondDistanceMax 1.2)
+            for (int matcherKind = 0; matcherKind < 3; matcherKind++)
             for (int solverKind = 0; solverKind < 2; solverKind++)
                 for (int rep = 0; rep < 3; rep++)
                 {
@@ -159,8 +161,30 @@ int main(int argc, char** argv)
                         matcher->initialize(ps);
                         icp.matchers().push_back(matcher);
                     }
-                    else
+                    else if (matcherKind == 1)
                         icp.matchers().push_back(std::make_shared<Matcher_Points_InlierRatio>());
+                    else
+                    {
+                        auto         m1 = std::make_shared<Matcher_Points_DistanceThreshold>();
+                        ParameterMap p1;
+                        p1.set("threshold", 0.40 * max_dim);
+                        p1.set("thresholdAngularDeg", 0);
+                        p1.set("runFromIteration", 0);
+                        p1.set("runUpToIteration", 5);
+                        m1->initialize(p1);
+                        icp.matchers().push_back(m1);
+                        auto         m2 = std::make_shared<Matcher_Adaptive>();
+                        ParameterMap p2;
+                        p2.set("confidenceInterval", 0.75);
+                        p2.set("firstToSecondDistanceMax", 1.2);
+                        p2.set("absoluteMaxSearchDistance", 0.40 * max_dim);
+                        p2.set("minimumCorrDist", 0.02 * max_dim);
+                        p2.set("enableDetectPlanes", 0);
+                        p2.set("runFromIteration", 6);
+                        p2.set("runUpToIteration", 0);
+                        m2->initialize(p2);
+                        icp.matchers().push_back(m2);
+                    }
                     if (solverKind == 0)
                         icp.solvers().push_back(std::make_shared<Solver_Horn>());
                     else
