@@ -34,4 +34,11 @@ ok, T4, it = ctx.solve_gauss_newton(None, q, gn, g2)
 ok, T5, n5 = smap.make_iterator(b200.Cloud(ctx, *xyz(scan)), None, None, len(scan), b200.Pt2PlParams(**kw), gn)(g2)
 ok, T6 = ctx.solve_horn_pt2pl(q, g2)
 i, d, f = smap.knn(*xyz(scan[:2000]), 8, 1.0)
+# Matcher_Point2Line + the pt2ln term of Gauss-Newton, Matcher_Adaptive (both branches)
+ln, _ = smap.match_pt2ln(*xyz(scan), g2, b200.Pt2LnParams(distanceThreshold=1.0, knn=8, minimumLinePoints=4, lineEigenThreshold=0.5))
+if len(ln) >= 3:
+    ok, T7, it7 = ctx.solve_gauss_newton_ex(None, q[:500], ln[:2000], gn, g2, w_pt2ln=0.5)
+a1, l1, _, _ = smap.match_adaptive(*xyz(scan), g2, b200.AdaptiveParams(enableDetectPlanes=True, absoluteMaxSearchDistance=1.0, planeMinimumDistance=50.0))
+a2, l2, _, _ = gmap.match_adaptive(*xyz(L), pose, b200.AdaptiveParams(absoluteMaxSearchDistance=1.5, maxPt2PtCorrespondences=3))
+print("extra:", len(ln), len(a1), len(l1), len(a2))
 print("sanitize run OK:", len(p1), len(p3), len(pi), len(q), ctx.launch_count, "launches")
