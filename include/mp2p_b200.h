@@ -540,6 +540,19 @@ int mp2p_b200_ctx_set_profiling(mp2p_b200_ctx* ctx, int timings_on, int search_s
 int mp2p_b200_ctx_get_timings(mp2p_b200_ctx* ctx, float ms[MP2P_B200_N_TIMINGS]);
 int mp2p_b200_ctx_get_search_stats(mp2p_b200_ctx* ctx, uint64_t stats[8]);
 
+/* ---- KITTI .bin straight to the device ------------------------------------------
+ * A KITTI velodyne scan is a flat file of float32 (x, y, z, intensity) records — what the reference's
+ * kitti2mm reads through mrpt::obs::CObservationPointCloud / CPointsMapXYZI
+ * (apps/kitti2mm/main.cpp:55-69). read_kitti_bin loads such a file into PINNED host memory
+ * (release with mp2p_b200_host_free); map_create_xyzi / cloud_create_xyzi take the interleaved records
+ * (host or device memory) and split them into the library's SoA layout on the device — no host-side
+ * de-interleaving pass, and from pinned memory the upload is one DMA transfer. The intensity channel is
+ * not used by the matchers and is dropped. Results are those of the SoA entry points. */
+int mp2p_b200_read_kitti_bin(const char* path, float** xyzi_pinned_out, uint64_t* n_points_out);
+int mp2p_b200_map_create_xyzi(mp2p_b200_ctx* ctx, const float* xyzi, uint64_t n, int on_device, mp2p_b200_map** out);
+int mp2p_b200_cloud_create_xyzi(mp2p_b200_ctx* ctx, const float* xyzi, uint64_t n, int on_device,
+                                mp2p_b200_cloud** out);
+
 /* Pinned host memory helpers (so callers in any language can give the library DMA-able buffers). */
 int  mp2p_b200_host_alloc(size_t bytes, void** out);
 void mp2p_b200_host_free(void* p);

@@ -240,7 +240,7 @@ class GNParams:
 EXPORTS = [
     "mp2p_b200_last_error", "mp2p_b200_device_count", "mp2p_b200_ctx_create", "mp2p_b200_ctx_destroy",
     "mp2p_b200_ctx_synchronize", "mp2p_b200_ctx_launch_count", "mp2p_b200_map_create", "mp2p_b200_map_destroy",
-    "mp2p_b200_map_get_info", "mp2p_b200_knn", "mp2p_b200_match_pt2pt", "mp2p_b200_match_pt2pl", "mp2p_b200_match_inlier_ratio", "mp2p_b200_match_pt2ln", "mp2p_b200_solve_gauss_newton_ex", "mp2p_b200_adaptive_search", "mp2p_b200_adaptive_threshold", "mp2p_b200_adaptive_emit", "mp2p_b200_match_adaptive",
+    "mp2p_b200_map_get_info", "mp2p_b200_knn", "mp2p_b200_match_pt2pt", "mp2p_b200_match_pt2pl", "mp2p_b200_match_inlier_ratio", "mp2p_b200_match_pt2ln", "mp2p_b200_solve_gauss_newton_ex", "mp2p_b200_adaptive_search", "mp2p_b200_adaptive_threshold", "mp2p_b200_adaptive_emit", "mp2p_b200_match_adaptive", "mp2p_b200_read_kitti_bin", "mp2p_b200_map_create_xyzi", "mp2p_b200_cloud_create_xyzi",
     "mp2p_b200_solve_horn", "mp2p_b200_solve_gauss_newton", "mp2p_b200_gn_accumulate",
     "mp2p_b200_gn_step_from_packet", "mp2p_b200_horn_sums", "mp2p_b200_horn_moments", "mp2p_b200_horn_finish",
     "mp2p_b200_host_alloc", "mp2p_b200_host_free", "mp2p_b200_ctx_set_profiling",
@@ -588,6 +588,21 @@ class Cloud:
         self.n = int(n)
         ctx._maps.add(self)
 
+    @classmethod
+    def from_xyzi(cls, ctx: Context, xyzi, n=None, on_device=False):
+        """From interleaved KITTI (x, y, z, intensity) float32 records: an (n, 4) host array, or a
+        device address + n (mp2p_b200_cloud_create_xyzi)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        if not on_device:
+            xyzi = np.ascontiguousarray(xyzi, dtype=np.float32).reshape(-1, 4)
+            n = xyzi.shape[0]
+        h = C.c_void_p()
+        _check(load_library().mp2p_b200_cloud_create_xyzi(ctx._h, _ptr(xyzi), C.c_uint64(n), int(on_device), C.byref(h)))
+        self._h, self.n = h, int(n)
+        ctx._maps.add(self)
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
             if getattr(self.ctx, "_h", None):
@@ -617,8 +632,44 @@ def _local(lx, ly, lz, n_local, local_on_device):
     return _ptr(lx), _ptr(ly), _ptr(lz), n_local, 1
 
 
+def read_kitti_bin(path: str) -> np.ndarray:
+    """A KITTI velodyne .bin file as an (n, 4) float32 array living in PINNED memory owned by the
+    returned array's base object (mp2p_b200_read_kitti_bin)."""
+    L = load_library()
+    p, n = C.c_void_p(), C.c_uint64(0)
+    _check(L.mp2p_b200_read_kitti_bin(path.encode(), C.byref(p), C.byref(n)))
+
+    class _Owner:
+        def __init__(self, addr):
+            self.addr = addr
+
+        def __del__(self):
+            try:
+                load_library().mp2p_b200_host_free(C.c_void_p(self.addr))
+            except Exception:
+                pass
+
+    buf = (C.c_float * (4 * n.value)).from_address(p.value) if n.value else (C.c_float * 0)()
+    buf._owner = _Owner(p.value)  # the array's base is `buf`: the pinned block lives as long as any view of it
+    return np.frombuffer(buf, dtype=np.float32).reshape(-1, 4)
+
+
 class Map:
     """A global map layer resident on the GPU with its NN index (nn_prepare_for_3d_queries)."""
+
+    @classmethod
+    def from_xyzi(cls, ctx: Context, xyzi, n=None, on_device=False):
+        """From interleaved KITTI (x, y, z, intensity) float32 records (mp2p_b200_map_create_xyzi)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        if not on_device:
+            xyzi = np.ascontiguousarray(xyzi, dtype=np.float32).reshape(-1, 4)
+            n = xyzi.shape[0]
+        h = C.c_void_p()
+        _check(load_library().mp2p_b200_map_create_xyzi(ctx._h, _ptr(xyzi), C.c_uint64(n), int(on_device), C.byref(h)))
+        self._h, self.n = h, n
+        ctx._maps.add(self)
+        return self
 
     def __init__(self, ctx: Context, x, y, z, n=None, on_device=False):
         self.ctx = ctx

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <atomic>
 #include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -185,6 +186,16 @@ int read_iteration_packets(mp2p_b200_ctx* ctx, bool polled, const double* d_pack
     MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     MP2P_CUDA_TRY(cudaGetLastError());
     return 0;
+}
+// KITTI (x, y, z, intensity) records -> SoA, one 16-byte load per point, coalesced stores
+__global__ void __launch_bounds__(256)
+    k_split_xyzi(const float4* __restrict__ in, uint64_t n, float* __restrict__ x, float* __restrict__ y, float* __restrict__ z)
+{
+    for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256ull)
+    {
+        const float4 p = __ldg(in + i);
+        x[i] = p.x, y[i] = p.y, z[i] = p.z;
+    }
 }
 }  // namespace mp2p
 
@@ -1256,6 +1267,110 @@ extern "C"
         MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         std::memcpy(stats, ctx->h_pinned, 64);
         return 0;
+    }
+
+    // ------------------------------------------------------------------------------ KITTI .bin (xyzi records)
+    int mp2p_b200_read_kitti_bin(const char* path, float** xyzi_pinned_out, uint64_t* n_points_out)
+    {
+        if (!path || !xyzi_pinned_out || !n_points_out) return MP2P_B200_ERR_ARG;
+        *xyzi_pinned_out = nullptr, *n_points_out = 0;
+        FILE* f = std::fopen(path, "rb");
+        if (!f)
+        {
+            set_error("read_kitti_bin: cannot open %s", path);
+            return MP2P_B200_ERR_ARG;
+        }
+        std::fseek(f, 0, SEEK_END);
+        const long bytes = std::ftell(f);
+        std::fseek(f, 0, SEEK_SET);
+        if (bytes < 0 || bytes % 16 != 0)
+        {
+            std::fclose(f);
+            set_error("read_kitti_bin: %s is not a whole number of 16-byte (x, y, z, intensity) records", path);
+            return MP2P_B200_ERR_ARG;
+        }
+        void* p = nullptr;
+        if (mp2p_b200_host_alloc((size_t)bytes, &p) != 0)
+        {
+            std::fclose(f);
+            return MP2P_B200_ERR_CUDA;
+        }
+        const size_t got = bytes ? std::fread(p, 1, (size_t)bytes, f) : 0;
+        std::fclose(f);
+        if (got != (size_t)bytes)
+        {
+            mp2p_b200_host_free(p);
+            set_error("read_kitti_bin: short read on %s", path);
+            return MP2P_B200_ERR_ARG;
+        }
+        *xyzi_pinned_out = static_cast<float*>(p), *n_points_out = (uint64_t)bytes / 16;
+        return 0;
+    }
+
+    // interleaved records -> three device arrays in the context's staging buffers
+    static int split_xyzi(mp2p_b200_ctx* ctx, const float* xyzi, uint64_t n, int on_device, const float** x, const float** y,
+                          const float** z, DevBuf& tmp)
+    {
+        const size_t bytes = ((size_t)n + kQueryTile) * sizeof(float);
+        MP2P_TRY(ctx->d_lx.ensure(bytes));
+        MP2P_TRY(ctx->d_ly.ensure(bytes));
+        MP2P_TRY(ctx->d_lz.ensure(bytes));
+        const float4* src = reinterpret_cast<const float4*>(xyzi);
+        if (!on_device)
+        {
+            MP2P_TRY(tmp.ensure((size_t)n * 16));
+            MP2P_CUDA_TRY(cudaMemcpyAsync(tmp.p, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+            src = tmp.as<float4>();
+        }
+        else if (reinterpret_cast<uintptr_t>(xyzi) & 15u)
+        {
+            set_error("xyzi: device records must be 16-byte aligned");
+            return MP2P_B200_ERR_ARG;
+        }
+        k_split_xyzi<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(
+            src, n, ctx->d_lx.as<float>(), ctx->d_ly.as<float>(), ctx->d_lz.as<float>());
+        count_launch(ctx);
+        MP2P_CUDA_TRY(cudaGetLastError());
+        *x = ctx->d_lx.as<float>(), *y = ctx->d_ly.as<float>(), *z = ctx->d_lz.as<float>();
+        return 0;
+    }
+
+    int mp2p_b200_map_create_xyzi(mp2p_b200_ctx* ctx, const float* xyzi, uint64_t n, int on_device, mp2p_b200_map** out)
+    {
+        if (!ctx || !out || (n && !xyzi))
+        {
+            set_error("map_create_xyzi: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        *out = nullptr;
+        if (n == 0) return mp2p_b200_map_create(ctx, nullptr, nullptr, nullptr, 0, 1, out);
+        DeviceGuard  g(ctx->device);
+        DevBuf       tmp;
+        const float *x, *y, *z;
+        int          rc = split_xyzi(ctx, xyzi, n, on_device, &x, &y, &z, tmp);
+        if (rc == 0) rc = mp2p_b200_map_create(ctx, x, y, z, n, 1, out);  // synchronises the stream
+        cudaStreamSynchronize(ctx->stream);
+        tmp.release();
+        return rc;
+    }
+
+    int mp2p_b200_cloud_create_xyzi(mp2p_b200_ctx* ctx, const float* xyzi, uint64_t n, int on_device, mp2p_b200_cloud** out)
+    {
+        if (!ctx || !out || (n && !xyzi))
+        {
+            set_error("cloud_create_xyzi: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        *out = nullptr;
+        if (n == 0) return mp2p_b200_cloud_create(ctx, nullptr, nullptr, nullptr, 0, 1, out);
+        DeviceGuard  g(ctx->device);
+        DevBuf       tmp;
+        const float *x, *y, *z;
+        int          rc = split_xyzi(ctx, xyzi, n, on_device, &x, &y, &z, tmp);
+        if (rc == 0) rc = mp2p_b200_cloud_create(ctx, x, y, z, n, 1, out);
+        cudaStreamSynchronize(ctx->stream);
+        tmp.release();
+        return rc;
     }
 
     int mp2p_b200_host_alloc(size_t bytes, void** out)

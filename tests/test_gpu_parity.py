@@ -1002,6 +1002,47 @@ def test_resident_cloud_edge_cases(ctx):
     assert len(ref) == 1 and ref.tobytes() == got.tobytes()
 
 
+# --------------------------------------------------------------------------- KITTI .bin straight to the device (§8f N4)
+def test_kitti_bin_loader_and_xyzi_entry_points(ctx, tmp_path):
+    """A KITTI velodyne file (float32 x, y, z, intensity records, apps/kitti2mm/main.cpp:55-69) read into
+    pinned memory and split on the device: map and cloud built from the interleaved records must behave
+    exactly like the ones built from SoA arrays."""
+    import torch
+
+    Ms = fx.make_street_scene(n_map=150_000, length=40.0)
+    S = fx.make_lidar_scan((20.0, 0.4, 0.0), n_rings=32, n_az=400, length=40.0)
+    rng = np.random.default_rng(0)
+    scan4 = np.concatenate([S, rng.random((len(S), 1), dtype=np.float32)], axis=1).astype(np.float32)
+    path = str(tmp_path / "000000.bin")
+    scan4.tofile(path)
+    got = b200.capi.read_kitti_bin(path)
+    assert got.shape == scan4.shape and got.dtype == np.float32 and np.array_equal(got, scan4)
+    T = fx.pose_xyzypr(20.05, 0.38, 0.01, 0.01, 0.0, 0.0)
+    smap = b200.Map(ctx, *xyz(Ms))
+    kw = b200.Pt2PlParams(distanceThreshold=0.5, searchRadius=1.0, knn=8, minimumPlanePoints=5, planeEigenThreshold=0.01)
+    ref, _ = smap.match_pt2pl(b200.Cloud(ctx, *xyz(S)), None, None, T, kw)
+    c_host = b200.Cloud.from_xyzi(ctx, got)  # pinned host records
+    d4 = torch.from_numpy(scan4).cuda()
+    c_dev = b200.Cloud.from_xyzi(ctx, d4.data_ptr(), n=len(scan4), on_device=True)
+    for c in (c_host, c_dev):
+        assert c.n == len(S)
+        p, _ = smap.match_pt2pl(c, None, None, T, kw)
+        assert len(ref) > 1000 and p.tobytes() == ref.tobytes()
+    map4 = np.concatenate([Ms, np.zeros((len(Ms), 1), np.float32)], axis=1)
+    m2 = b200.Map.from_xyzi(ctx, map4)
+    q, _ = m2.match_pt2pl(c_host, None, None, T, kw)
+    assert q.tobytes() == ref.tobytes()
+    a, _ = m2.match_pt2pt(c_dev, None, None, T, b200.Pt2PtParams(threshold=0.3))
+    b, _ = smap.match_pt2pt(*xyz(S), T, b200.Pt2PtParams(threshold=0.3))
+    assert len(a) > 1000 and a.tobytes() == b.tobytes()
+    assert b200.Cloud.from_xyzi(ctx, scan4[:0]).n == 0
+    with pytest.raises(b200.Mp2pError):
+        b200.capi.read_kitti_bin(str(tmp_path / "missing.bin"))
+    (tmp_path / "bad.bin").write_bytes(b"\0" * 20)
+    with pytest.raises(b200.Mp2pError):  # not a whole number of 16-byte records
+        b200.capi.read_kitti_bin(str(tmp_path / "bad.bin"))
+
+
 # --------------------------------------------------------------------------- multi-GPU (needs >= 2 GPUs)
 @pytest.mark.parametrize("transport", ["peer", "nccl"])
 def test_multi_gpu_sharded_iteration_equals_single_gpu(transport):
