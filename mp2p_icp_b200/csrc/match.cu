@@ -7,7 +7,14 @@
 //   k_compact_pt2pt = lambdaAddPair (…DistanceThreshold.cpp:94-121): bounding-box gate (:73-75),
 //                    first-claim acceptance, stream compaction into 36-byte TMatchingPair records
 //                    in ascending (localIdx, rank) order.
-//   k_match_pt2pl / k_compact_pt2pl = Matcher_Point2Plane.cpp:41-114 with the k-NN + PCA plane fit.
+//   k_match_pt2pl / k_compact_pt2pl = Matcher_Point2Plane.cpp:41-114 with the k-NN + PCA plane fit;
+//                    in line mode the same pipeline is Matcher_Point2Line.cpp:46-163.
+//   k_match_pt2pt_nn1 = the k = 1 search (one lane per query, warp work redistribution);
+//   k_iterate_nn1_horn<SHARDED> = a whole pt2pt + Horn iteration in one cooperative launch, optionally
+//                    with the exchanges of a query-sharded iteration through the peers' mailboxes.
+//   k_ir_*          = Matcher_Points_InlierRatio.cpp:41-143 (sort by distance, keep a ratio).
+//   k_ad_*          = Matcher_Adaptive.cpp:59-314 (histogram of the 1st / 2nd errors out, adaptive
+//                    threshold in, per-point plane / pt2pt decision).
 //
 // Query tiles (256 points x 3 axes) are staged into shared memory with TMA bulk copies
 // (cp.async.bulk … mbarrier::complete_tx) so the per-thread search starts from on-chip data.
