@@ -338,6 +338,7 @@ extern "C"
             mp2p_b200_map_destroy(m);
             return rc;
         }
+        ctx->live_maps.insert(m);
         *out = m;
         return 0;
     }
@@ -347,6 +348,7 @@ extern "C"
         if (!m) return;
         if (m->ctx)
         {
+            m->ctx->live_maps.erase(m);
             DeviceGuard g(m->ctx->device);
             cudaStreamSynchronize(m->ctx->stream);
             m->d_pts.release(), m->d_pts_orig.release(), m->d_table.release(), m->d_claim.release();
@@ -380,6 +382,7 @@ extern "C"
             mp2p_b200_cloud_destroy(c);
             return rc;
         }
+        ctx->live_clouds.insert(c);
         *out = c;
         return 0;
     }
@@ -389,6 +392,7 @@ extern "C"
         if (!c) return;
         if (c->ctx)
         {
+            c->ctx->live_clouds.erase(c);
             DeviceGuard g(c->ctx->device);
             cudaStreamSynchronize(c->ctx->stream);
             for (DevBuf* b : {&c->d_x, &c->d_y, &c->d_z, &c->d_sx, &c->d_sy, &c->d_sz, &c->d_perm}) b->release();

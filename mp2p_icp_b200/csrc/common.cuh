@@ -1,5 +1,6 @@
 // Shared declarations of the B200 hot-path library (product code; never includes oracle/).
 #pragma once
+#include <unordered_set>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -145,6 +146,11 @@ struct mp2p_b200_ctx
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t  ev_fork = nullptr;
     mp2p::DevBuf d_spec;  // GN speculation: 12 doubles pose + state words
+    // live handles created on this context: a stale or foreign map / cloud handle is refused instead of
+    // being dereferenced (the objects are not thread-safe, like the reference's: no locking here)
+    std::unordered_set<const void*> live_maps, live_clouds;
+    bool owns_map(const void* m) const { return m && live_maps.count(m) != 0; }
+    bool owns_cloud(const void* c) const { return c && live_clouds.count(c) != 0; }
     // Matcher_Adaptive: what phase 2 (adaptive_emit) needs from phase 1 (adaptive_search)
     struct AdaptiveState
     {

@@ -1374,6 +1374,9 @@ T* mapped_alias(T* host)
         return nullptr;
     }
     if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    // page-locked under another device of this process: not necessarily mapped for ours — copy instead
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || at.device != dev) return nullptr;
     return static_cast<T*>(at.devicePointer);
 }
 
@@ -1388,6 +1391,11 @@ int stage_local(mp2p_b200_ctx* ctx, const float* lx, const float* ly, const floa
     if (on_device == 2)  // resident cloud: search kernels walk the Morton-sorted copy
     {
         const auto* c = reinterpret_cast<const mp2p_b200_cloud*>(lx);
+        if (!ctx->owns_cloud(c))
+        {
+            set_error("local cloud handle is not a live cloud of this context (destroyed, or created on another context)");
+            return MP2P_B200_ERR_ARG;
+        }
         if (c->ctx != ctx || c->n != n)
         {
             set_error("local cloud handle belongs to another context, or n_local differs from its size");
@@ -1702,6 +1710,11 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
                     uint64_t* out_count, DeviceMatch* keep_on_device)
 {
     *out_count          = 0;
+    if (!ctx->owns_map(map))
+    {
+        set_error("map handle is not a live map of this context (destroyed, or created on another context)");
+        return MP2P_B200_ERR_ARG;
+    }
     if (keep_on_device) keep_on_device->d_count = nullptr, keep_on_device->d_pairs = nullptr, keep_on_device->capacity = 0;
     ctx->last2p.valid = false, ctx->last2p.sums = nullptr, ctx->spec_res.valid = false;
     const uint32_t K    = prm->pairingsPerPoint;
@@ -1940,6 +1953,11 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
 {
     const uint32_t K  = prm->pairingsPerPoint;
     cudaStream_t   st = ctx->stream;
+    if (!ctx->owns_map(map))
+    {
+        set_error("map handle is not a live map of this context (destroyed, or created on another context)");
+        return MP2P_B200_ERR_ARG;
+    }
     if (n_local > per_shard)
     {
         set_error("shard_search: n_local exceeds per_shard");
@@ -2003,6 +2021,11 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
                             uint64_t* out_count, double* d_horn_sums)
 {
     if (out_count) *out_count = 0;
+    if (!ctx->owns_map(map))
+    {
+        set_error("map handle is not a live map of this context (destroyed, or created on another context)");
+        return MP2P_B200_ERR_ARG;
+    }
     ctx->last_count = nullptr, ctx->last_capacity = 0;
     ctx->last2p.valid = false, ctx->last2p.sums = nullptr, ctx->spec_res.valid = false;
     const uint32_t K    = prm->pairingsPerPoint;
@@ -2079,6 +2102,11 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
                     uint64_t* out_count, DeviceMatch* keep_on_device, const LineMode* line)
 {
     *out_count          = 0;
+    if (!ctx->owns_map(map))
+    {
+        set_error("map handle is not a live map of this context (destroyed, or created on another context)");
+        return MP2P_B200_ERR_ARG;
+    }
     if (keep_on_device) *keep_on_device = DeviceMatch{};
     ctx->last2l.valid = false, ctx->spec_res.valid = false;
     const uint64_t nmap = map->view.n_points;
@@ -2189,6 +2217,11 @@ int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const
             float* out_d2, int32_t* out_found)
 {
     if (nq == 0) return 0;
+    if (!ctx->owns_map(map))
+    {
+        set_error("map handle is not a live map of this context (destroyed, or created on another context)");
+        return MP2P_B200_ERR_ARG;
+    }
     if (K < 1 || K > MP2P_B200_MAX_KNN || nq >= 0xFFFFFFFFull)
     {
         set_error("knn: k must be in [1,%d]", MP2P_B200_MAX_KNN);
@@ -2337,6 +2370,11 @@ int run_match_inlier_ratio(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
                            mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device, uint64_t* out_count)
 {
     *out_count = 0;
+    if (!ctx->owns_map(map))
+    {
+        set_error("map handle is not a live map of this context (destroyed, or created on another context)");
+        return MP2P_B200_ERR_ARG;
+    }
     ctx->last2p.valid = false, ctx->last2p.sums = nullptr, ctx->spec_res.valid = false;
     const uint64_t nmap = map->view.n_points;
     if (nmap == 0 || n_local == 0) return 0;  // :58
@@ -2579,6 +2617,11 @@ int run_adaptive_search(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx,
     S       = mp2p_b200_ctx::AdaptiveState{};
     for (int b = 0; b < kAdBins; b++) hist_out[b] = 0;
     *err_min = *err_max = 0.0, *n_samples = 0, *gate_out = 0;
+    if (!ctx->owns_map(map))
+    {
+        set_error("map handle is not a live map of this context (destroyed, or created on another context)");
+        return MP2P_B200_ERR_ARG;
+    }
     const uint64_t nmap = map->view.n_points;
     if (nmap == 0 || n_local == 0) return 0;  // :71
     const uint32_t nnMax = prm->enableDetectPlanes ? prm->planeSearchPoints : prm->maxPt2PtCorrespondences;  // :119-120

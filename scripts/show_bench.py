@@ -7,7 +7,7 @@ for f in ('bench_c2','bench_c3'):
         print('  roof',round(d['roofline']['kernel_ms'],4),round(d['roofline']['achieved'],1),round(d['roofline']['frac'],4),{k:round(v,4) for k,v in d['roofline']['other_kernels_ms'].items()})
         if d.get('cpu_baseline'): print('  cpu',round(d['cpu_baseline']['value'],2),d['cpu_baseline']['cores'])
     except Exception as e: print(f,'ERR',e, open(f'gpurun_out/{f}.err').read()[-500:])
-rows=list(csv.reader(open('gpurun_out/launches_c2.csv')))
+rows=list(csv.reader(open('gpurun_out/launches_C2.csv')))
 for i,r in enumerate(rows):
     if 'Kernel Name' in r: h=i;break
 hdr=rows[h]; ki=hdr.index('Kernel Name'); vi=hdr.index('Metric Value'); gi=hdr.index('Grid Size')

@@ -92,3 +92,28 @@ def test_product_never_imports_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle|#include\s+[\"<].*oracle", txt, flags=re.M) or "liboracle" in txt:
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_adaptive_threshold_is_host_math_and_matches_the_oracle_statement():
+    """mp2p_b200_adaptive_threshold (the library's restatement of MRPT's CHistogram normalisation and
+    confidenceIntervalsFromHistogram, Matcher_Adaptive.cpp:188-214) needs no GPU; it must agree with the
+    numpy statement of the same steps used to pin the oracle (tests/test_oracle_golden.py)."""
+    import ctypes as C
+
+    from tests.test_oracle_golden import _adaptive_threshold_numpy
+
+    L = capi.load_library()
+    rng = np.random.default_rng(5)
+    for ci, mind in [(0.8, 0.1), (0.75, 0.01), (0.5, 0.0), (0.95, 0.3)]:
+        e = np.abs(rng.normal(0, 0.2, 5000)).astype(np.float32) ** 2
+        lo, hi = float(e.min()), float(e.max())
+        inv = 49.0 / (hi - lo)
+        hist = np.bincount((inv * (e.astype(np.float64) - lo)).astype(np.int64), minlength=50)[:50].astype(np.uint64)
+        ci_high, thr = C.c_double(0), C.c_double(0)
+        rc = L.mp2p_b200_adaptive_threshold(hist.ctypes.data_as(C.c_void_p), C.c_double(lo), C.c_double(hi), C.c_uint64(len(e)), C.c_double(ci), C.c_double(mind), C.byref(ci_high), C.byref(thr))
+        exp_thr, exp_hi = _adaptive_threshold_numpy(e, ci, mind)
+        assert rc == 0 and abs(ci_high.value - exp_hi) <= 1e-12 * max(1.0, exp_hi) and abs(thr.value - exp_thr) <= 1e-12 * max(1.0, exp_thr)
+    # the reference throws: no sample, or max == min
+    z = np.zeros(50, np.uint64)
+    assert L.mp2p_b200_adaptive_threshold(z.ctypes.data_as(C.c_void_p), C.c_double(0), C.c_double(0), C.c_uint64(0), C.c_double(0.8), C.c_double(0.1), C.byref(ci_high), C.byref(thr)) != 0
+    assert L.mp2p_b200_adaptive_threshold(z.ctypes.data_as(C.c_void_p), C.c_double(1.0), C.c_double(1.0), C.c_uint64(7), C.c_double(0.8), C.c_double(0.1), C.byref(ci_high), C.byref(thr)) != 0

@@ -1002,6 +1002,39 @@ def test_resident_cloud_edge_cases(ctx):
     assert len(ref) == 1 and ref.tobytes() == got.tobytes()
 
 
+def test_stale_and_foreign_handles_are_refused(ctx):
+    """A destroyed cloud / map handle, or one created on another context, is an argument error — not a
+    dereference of freed memory."""
+    import ctypes as C
+
+    M, L, gt = _c2(20_000, 10)
+    gmap = b200.Map(ctx, *xyz(M))
+    cloud = b200.Cloud(ctx, *xyz(L))
+    prm = b200.Pt2PtParams(threshold=1.0)
+    ok, _ = gmap.match_pt2pt(cloud, None, None, gt, prm)
+    assert len(ok) > 100
+    stale = b200.Cloud.__new__(b200.Cloud)  # a wrapper around the raw handle value that outlives the cloud
+    stale.ctx, stale._h, stale.n = ctx, C.c_void_p(cloud._h.value), cloud.n
+    cloud.close()
+    with pytest.raises(b200.Mp2pError):
+        gmap.match_pt2pt(stale, None, None, gt, prm)
+    stale._h = None
+    other = b200.Context(0)
+    try:
+        omap, ocloud = b200.Map(other, *xyz(M)), b200.Cloud(other, *xyz(L))
+        with pytest.raises(b200.Mp2pError):  # a cloud of another context
+            gmap.match_pt2pt(ocloud, None, None, gt, prm)
+        foreign = b200.Map.__new__(b200.Map)  # `omap`'s handle presented as a map of `ctx`
+        foreign.ctx, foreign._h, foreign.n = ctx, C.c_void_p(omap._h.value), omap.n
+        with pytest.raises(b200.Mp2pError):
+            foreign.match_pt2pt(*xyz(L), gt, prm)
+        foreign._h = None
+    finally:
+        other.close()
+    again, _ = gmap.match_pt2pt(*xyz(L), gt, prm)  # the context is still healthy
+    assert again.tobytes() == ok.tobytes()
+
+
 # --------------------------------------------------------------------------- KITTI .bin straight to the device (§8f N4)
 def test_kitti_bin_loader_and_xyzi_entry_points(ctx, tmp_path):
     """A KITTI velodyne file (float32 x, y, z, intensity records, apps/kitti2mm/main.cpp:55-69) read into
