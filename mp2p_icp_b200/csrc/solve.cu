@@ -10,9 +10,9 @@
 //
 // Reduction skeleton (shared by all three): every thread keeps NV double accumulators over a
 // grid-stride range, warp-shuffle tree -> one partial per warp in shared memory -> one partial per
-// CTA in global memory -> k_final_reduce sums the CTA partials in FIXED order into a 32-double
-// packet. Grid size is a pure function of N, so results are run-to-run bit-stable. The packet is
-// what a multi-GPU caller all-reduces.
+// CTA in global memory -> the LAST CTA to arrive (ticket) folds the CTA partials in FIXED order into a
+// 32-double packet (reduce.cuh) — one launch. Grid size is a pure function of N, so results are
+// run-to-run bit-stable. The packet is what a multi-GPU caller all-reduces.
 //
 // Pair records are AoS (36 / 72 bytes). A warp stages 32 consecutive records with fully coalesced
 // 128-byte loads into shared memory and each lane then reads its own record (stride 9 / 18 words).
