@@ -1373,10 +1373,9 @@ T* mapped_alias(T* host)
         cudaGetLastError();
         return nullptr;
     }
+    // (with unified addressing, page-locked host memory is portable and mapped for every device of the
+    // process, whichever device was current when it was allocated)
     if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
-    // page-locked under another device of this process: not necessarily mapped for ours — copy instead
-    int dev = -1;
-    if (cudaGetDevice(&dev) != cudaSuccess || at.device != dev) return nullptr;
     return static_cast<T*>(at.devicePointer);
 }
 
