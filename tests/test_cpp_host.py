@@ -18,8 +18,18 @@ def _build():
 def test_cpp_tests_compile():
     """CPU-side: the host mirror header and the C-ABI header are consistent (compile + link)."""
     _build()
-    for t in ("test_matcher_pt2pt", "test_matcher_pt2pl", "test_optimize_and_align"):
+    for t in ("test_matcher_pt2pt", "test_matcher_pt2pl", "test_optimize_and_align", "test_host_logic"):
         assert os.path.exists(os.path.join(BUILD, t))
+
+
+def test_cpp_host_logic_without_gpu():
+    """The host logic above the C ABI — matcher / solver gating, run_matchers, Pairings, the ICP::align loop
+    with every termination reason, quality evaluation and checkpoints, parameter errors — with mock
+    plugin classes: no device, no library call (tests/cpp/test_host_logic.cpp)."""
+    _build()
+    r = subprocess.run([os.path.join(BUILD, "test_host_logic")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "test_host_logic OK" in r.stdout
 
 
 @pytest.mark.gpu
