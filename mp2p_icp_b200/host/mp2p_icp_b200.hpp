@@ -14,13 +14,16 @@
 //   Solver, SolverContext                            mp2p_icp/include/mp2p_icp/Solver.h:43-102, src/Solver.cpp:28-64
 //   Solver_Horn / Solver_GaussNewton                 mp2p_icp/src/Solver_Horn.cpp:33-61, Solver_GaussNewton.cpp:29-67
 //   Pairings                                         mp2p_icp/include/mp2p_icp/Pairings.h:84-194, src/Pairings.cpp:123-147
+//   Parameterizable, ParameterSource                 mp2p_icp_map/include/mp2p_icp/Parameterizable.h, src/Parameterizable.cpp
 //   Matcher_Points_InlierRatio                       mp2p_icp/src/Matcher_Points_InlierRatio.cpp:35-143
 //   Matcher_Point2Line                               mp2p_icp/src/Matcher_Point2Line.cpp:35-163
 //   Matcher_Adaptive                                 mp2p_icp/src/Matcher_Adaptive.cpp:32-314
 //   QualityEvaluator, QualityEvaluator_PairedRatio   mp2p_icp/include/mp2p_icp/QualityEvaluator.h, src/QualityEvaluator_PairedRatio.cpp:27-73
 //   ICP::align loop (the caller)                     mp2p_icp/src/ICP.cpp:108-338, evaluate_quality :608-634
 #pragma once
+#include <cctype>
 #include <cmath>
+#include <deque>
 #include <cstdint>
 #include <cstring>
 #include <atomic>
@@ -250,6 +253,209 @@ class ParameterMap
     std::map<std::string, std::string> kv_;
 };
 
+// ---- formula-capable parameters (mp2p_icp_map/include/mp2p_icp/Parameterizable.h, src/Parameterizable.cpp) ----
+/** Arithmetic over named variables: numbers, identifiers, + - * / ^, unary minus, parentheses, and the
+ *  functions abs, sqrt, min, max — the subset of MRPT's expression language (mrpt::expr, exprtk) that the
+ *  reference's pipelines use (`threshold: "MATCH_THRESHOLD*2.0"`, tests/test-mp2p_matcher_pt2pt_parameterizable.cpp).
+ *  Throws std::runtime_error on syntax errors and unknown variables. */
+class Expression
+{
+   public:
+    static double eval(const std::string& text, const std::map<std::string, double>& vars)
+    {
+        Expression e{text, vars, 0};
+        const double v = e.sum();
+        e.skip();
+        if (e.pos_ != text.size()) throw std::runtime_error("expression: unexpected `" + text.substr(e.pos_) + "` in `" + text + "`");
+        return v;
+    }
+
+   private:
+    const std::string&                   s_;
+    const std::map<std::string, double>& vars_;
+    size_t                               pos_;
+    void skip()
+    {
+        while (pos_ < s_.size() && std::isspace((unsigned char)s_[pos_])) pos_++;
+    }
+    bool eat(char c)
+    {
+        skip();
+        if (pos_ < s_.size() && s_[pos_] == c) return pos_++, true;
+        return false;
+    }
+    double sum()
+    {
+        double v = product();
+        for (;;)
+        {
+            if (eat('+'))
+                v += product();
+            else if (eat('-'))
+                v -= product();
+            else
+                return v;
+        }
+    }
+    double product()
+    {
+        double v = power();
+        for (;;)
+        {
+            if (eat('*'))
+                v *= power();
+            else if (eat('/'))
+                v /= power();
+            else
+                return v;
+        }
+    }
+    double power()
+    {
+        const double b = unary();
+        return eat('^') ? std::pow(b, power()) : b;
+    }
+    double unary()
+    {
+        if (eat('-')) return -unary();
+        if (eat('+')) return unary();
+        return atom();
+    }
+    double atom()
+    {
+        skip();
+        if (eat('('))
+        {
+            const double v = sum();
+            if (!eat(')')) throw std::runtime_error("expression: missing `)` in `" + s_ + "`");
+            return v;
+        }
+        if (pos_ < s_.size() && (std::isdigit((unsigned char)s_[pos_]) || s_[pos_] == '.'))
+        {
+            size_t       used = 0;
+            const double v    = std::stod(s_.substr(pos_), &used);
+            pos_ += used;
+            return v;
+        }
+        if (pos_ < s_.size() && (std::isalpha((unsigned char)s_[pos_]) || s_[pos_] == '_'))
+        {
+            const size_t b = pos_;
+            while (pos_ < s_.size() && (std::isalnum((unsigned char)s_[pos_]) || s_[pos_] == '_')) pos_++;
+            const std::string name = s_.substr(b, pos_ - b);
+            if (name == "true") return 1.0;
+            if (name == "false") return 0.0;
+            if (eat('('))
+            {
+                const double a = sum();
+                double       r = 0;
+                if (name == "abs" || name == "sqrt")
+                    r = name == "abs" ? std::fabs(a) : std::sqrt(a);
+                else if (name == "min" || name == "max")
+                {
+                    if (!eat(',')) throw std::runtime_error("expression: `" + name + "` takes two arguments");
+                    const double c = sum();
+                    r              = name == "min" ? std::min(a, c) : std::max(a, c);
+                }
+                else
+                    throw std::runtime_error("expression: unknown function `" + name + "`");
+                if (!eat(')')) throw std::runtime_error("expression: missing `)` in `" + s_ + "`");
+                return r;
+            }
+            const auto it = vars_.find(name);
+            if (it == vars_.end()) throw std::runtime_error("expression: unknown variable `" + name + "`");
+            return it->second;
+        }
+        throw std::runtime_error("expression: cannot parse `" + s_ + "`");
+    }
+    Expression(const std::string& s, const std::map<std::string, double>& v, size_t p) : s_(s), vars_(v), pos_(p) {}
+};
+
+class ParameterSource;
+
+/** Parameterizable (Parameterizable.h:110-190): parameters declared from YAML text that may be formulas over
+ *  variables; constant ones are evaluated at declaration, the others whenever the attached ParameterSource
+ *  realizes (Parameterizable.cpp:107-140, :46-105). */
+class Parameterizable
+{
+   public:
+    struct Declared
+    {
+        std::string expression;
+        double*     target_d = nullptr;
+        uint32_t*   target_u = nullptr;
+        bool        is_constant = false, has_been_evaluated = false;
+        void        store(double v) const
+        {
+            if (target_d) *target_d = v;
+            if (target_u) *target_u = static_cast<uint32_t>(v);
+        }
+    };
+    /** checkAllParametersAreRealized (Parameterizable.cpp:142-154) */
+    void checkAllParametersAreRealized() const
+    {
+        for (const auto& d : declared_)
+            if (!d.has_been_evaluated)
+                throw std::runtime_error("Parameter `" + d.expression + "` was not realized: attach the object to a ParameterSource and call realize()");
+    }
+    std::deque<Declared>& declaredParameters() { return declared_; }
+    void                  unrealizeParameters() { declared_.clear(); }
+
+   protected:
+    /** DECLARE_PARAMETER_REQ / _OPT (Parameterizable.h:176-190) */
+    template <class T>
+    void declareParameter(const ParameterMap& p, const std::string& name, T& target, bool required)
+    {
+        if (!p.has(name))
+        {
+            if (required) throw std::invalid_argument("Required parameter `" + name + "` not an existing key");
+            return;
+        }
+        Declared& d  = declared_.emplace_back();
+        d.expression = p.getString(name, "");
+        if constexpr (std::is_same_v<T, double>)
+            d.target_d = &target;
+        else
+            d.target_u = &target;
+        try
+        {
+            d.store(Expression::eval(d.expression, {}));
+            d.is_constant = d.has_been_evaluated = true;
+        }
+        catch (const std::exception&)
+        {
+            // needs variables that are not defined yet: evaluated by ParameterSource::realize()
+        }
+    }
+
+   private:
+    std::deque<Declared> declared_;
+};
+
+/** ParameterSource (Parameterizable.h:46-96, Parameterizable.cpp:22-105) */
+class ParameterSource
+{
+   public:
+    void attach(Parameterizable& obj)
+    {
+        for (auto& d : obj.declaredParameters()) attached_.push_back(&d);
+    }
+    void updateVariable(const std::string& variable, double value) { variables_[variable] = value; }
+    void realize()
+    {
+        for (auto* d : attached_)
+        {
+            if (d->is_constant) continue;
+            d->store(Expression::eval(d->expression, variables_));  // throws on variables that are still unknown
+            d->has_been_evaluated = true;
+        }
+    }
+    std::map<std::string, double> getVariableValues() const { return variables_; }
+
+   private:
+    std::vector<Parameterizable::Declared*> attached_;
+    std::map<std::string, double>           variables_;
+};
+
 // ---- device context + map cache ------------------------------------------------------------
 class Device
 {
@@ -353,7 +559,7 @@ class Device
 };
 
 // ---- Matcher hierarchy -----------------------------------------------------------------------
-class Matcher
+class Matcher : public Parameterizable
 {
    public:
     using Ptr          = std::shared_ptr<Matcher>;
@@ -451,9 +657,10 @@ class Matcher_Points_DistanceThreshold : public Matcher_Points_Base
     void     initialize(const ParameterMap& params) override  // …DistanceThreshold.cpp:39-46
     {
         Matcher_Points_Base::initialize(params);
-        threshold           = params.required<double>("threshold");
-        thresholdAngularDeg = params.required<double>("thresholdAngularDeg");
-        pairingsPerPoint    = params.getOrDefault<uint32_t>("pairingsPerPoint", pairingsPerPoint);
+        unrealizeParameters();
+        declareParameter(params, "threshold", threshold, true);  // DECLARE_PARAMETER_REQ: may be formulas
+        declareParameter(params, "thresholdAngularDeg", thresholdAngularDeg, true);
+        declareParameter(params, "pairingsPerPoint", pairingsPerPoint, false);
     }
 
    private:
@@ -461,6 +668,7 @@ class Matcher_Points_DistanceThreshold : public Matcher_Points_Base
                            MatchState& ms, const layer_name_t& globalName, const layer_name_t& localName,
                            Pairings& out) const override
     {
+        checkAllParametersAreRealized();                                                                   // :56
         if (!(pairingsPerPoint >= 1)) throw std::runtime_error("Assert failed: pairingsPerPoint >= 1");  // :57-59
         if (!(threshold > .0)) throw std::runtime_error("Assert failed: threshold > 0");
         if (!(thresholdAngularDeg >= .0)) throw std::runtime_error("Assert failed: thresholdAngularDeg >= 0");

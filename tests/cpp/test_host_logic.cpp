@@ -274,6 +274,59 @@ int main()
             }
             ASSERT_(thrown && robust_kernel_from_string("RobustKernel::GemanMcClure") == 1);
         }
+        // ---- formula parameters: tests/test-mp2p_matcher_pt2pt_parameterizable.cpp:28-53
+        {
+            Matcher_Points_DistanceThreshold m;
+            ParameterMap                     p;
+            p.set("threshold", "MATCH_THRESHOLD*2.0");  // defined as an expression
+            p.set("thresholdAngularDeg", .0);
+            m.initialize(p);
+            bool thrown = false;
+            try
+            {
+                m.checkAllParametersAreRealized();  // `threshold` still waits for its variable
+            }
+            catch (const std::runtime_error&)
+            {
+                thrown = true;
+            }
+            ASSERT_(thrown);
+            ParameterSource globalParams;
+            globalParams.attach(m);
+            globalParams.updateVariable("MATCH_THRESHOLD", 1.5);
+            globalParams.realize();
+            ASSERT_(std::abs(m.threshold - 3.0) < 1e-4 && std::abs(m.thresholdAngularDeg) < 1e-4);
+            m.checkAllParametersAreRealized();
+            globalParams.updateVariable("MATCH_THRESHOLD", 0.5);
+            globalParams.realize();
+            ASSERT_(std::abs(m.threshold - 1.0) < 1e-4 && std::abs(m.thresholdAngularDeg) < 1e-4);
+            // plain numbers stay what the flat parser made of them (constants, realized at declaration)
+            Matcher_Points_DistanceThreshold m2;
+            ParameterMap                     p2;
+            p2.set("threshold", 0.40 * 0.1552);
+            p2.set("thresholdAngularDeg", 0);
+            p2.set("pairingsPerPoint", 3);
+            m2.initialize(p2);
+            m2.checkAllParametersAreRealized();
+            ASSERT_(m2.threshold == 0.40 * 0.1552 && m2.thresholdAngularDeg == 0.0 && m2.pairingsPerPoint == 3);
+            // the expression language itself
+            const std::map<std::string, double> v{{"A", 2.0}, {"b_1", -3.0}};
+            ASSERT_(Expression::eval("1e-3", v) == 1e-3 && Expression::eval(" ( A + 1 ) * -b_1 ", v) == 9.0);
+            ASSERT_(Expression::eval("max(A, abs(b_1)) / 2 ^ 2", v) == 0.75 && Expression::eval("sqrt(A*8)", v) == 4.0);
+            for (const char* bad : {"A +", "unknown*2", "(A", "2 $ 3", "foo(1)"})
+            {
+                thrown = false;
+                try
+                {
+                    Expression::eval(bad, v);
+                }
+                catch (const std::runtime_error&)
+                {
+                    thrown = true;
+                }
+                ASSERT_(thrown);
+            }
+        }
     }
     catch (std::exception& e)
     {
