@@ -1150,5 +1150,76 @@ extern "C"
         }
     }
 
+    // ---------------------------------------------------------------- voxel decimation (oracle first)
+    // FilterDecimateVoxels::filter (mp2p_icp_filters/src/FilterDecimateVoxels.cpp:109-378) over ONE input layer:
+    // voxel index per axis = int32(coordinate / resolution) — TRUNCATION toward zero, float division
+    // (PointCloudToVoxelGridSingle.h:105, PointCloudToVoxelGrid.h:118) — and per occupied voxel
+    //   method 0 FirstPoint        the first point that fell into it (PointCloudToVoxelGridSingle.cpp:60-95)
+    //   method 1 ClosestToAverage  the member closest to the voxel mean, first on ties (strict <, :279-298)
+    //   method 2 VoxelAverage      the mean itself: float sums, times float(1/n) (:265-277, :300-304)
+    // (RandomPoint draws from an unseeded mrpt::random generator, :247-248: not restatable.)
+    // flatten_to (optional): z is replaced and only the FIRST voxel visited of every (cx, cy) column emits (:210-224,
+    // :335-349). Visiting order: the reference walks a tsl::robin_map (implementation-defined order) unless
+    // use_tsl_robin_map = false, where FirstPoint walks a std::map ordered by (cx, cy, cz) (PointCloudToVoxelGridSingle.h:87-99);
+    // this restatement always emits in that ascending (cx, cy, cz) order — the SET of output points is the
+    // reference's in every configuration, the ORDER only in that one. Returns the number of output points;
+    // out_src[i] = index of the source point, or -1 for an averaged point.
+    size_t orc_decimate_voxels(const float* x, const float* y, const float* z, size_t n, float resolution, int method,
+                               int has_flatten, float flatten_to, float* ox, float* oy, float* oz, int64_t* out_src,
+                               size_t cap)
+    {
+        struct Key
+        {
+            int32_t cx, cy, cz;
+            bool    operator<(const Key& o) const { return cx != o.cx ? cx < o.cx : (cy != o.cy ? cy < o.cy : cz < o.cz); }
+        };
+        std::map<Key, std::vector<size_t>> vox;
+        for (size_t i = 0; i < n; i++)
+        {
+            const Key k{static_cast<int32_t>(x[i] / resolution), static_cast<int32_t>(y[i] / resolution),
+                        static_cast<int32_t>(z[i] / resolution)};
+            vox[k].push_back(i);
+        }
+        std::map<std::pair<int32_t, int32_t>, bool> usedColumn;
+        size_t                                       nOut = 0;
+        for (const auto& [k, idx] : vox)
+        {
+            float   px = 0, py = 0, pz = 0;
+            int64_t src = -1;
+            if (method == 0)
+                src = static_cast<int64_t>(idx[0]);
+            else
+            {
+                float       mx = 0, my = 0, mz = 0;
+                const float inv_n = 1.0f / idx.size();
+                for (size_t i : idx) mx += x[i], my += y[i], mz += z[i];
+                mx *= inv_n, my *= inv_n, mz *= inv_n;
+                if (method == 1)
+                {
+                    bool  have = false;
+                    float best = 0;
+                    for (size_t i : idx)
+                    {
+                        const float e = (x[i] - mx) * (x[i] - mx) + (y[i] - my) * (y[i] - my) + (z[i] - mz) * (z[i] - mz);
+                        if (!have || e < best) have = true, best = e, src = static_cast<int64_t>(i);
+                    }
+                }
+                else
+                    px = mx, py = my, pz = mz;
+            }
+            if (src >= 0) px = x[src], py = y[src], pz = z[src];
+            if (has_flatten)
+            {
+                auto& used = usedColumn[{k.cx, k.cy}];
+                if (used) continue;
+                used = true;
+                pz   = flatten_to;
+            }
+            if (nOut < cap) ox[nOut] = px, oy[nOut] = py, oz[nOut] = pz, out_src[nOut] = src;
+            nOut++;
+        }
+        return nOut;
+    }
+
     int orc_max_threads() { return omp_get_max_threads(); }
 }

@@ -496,5 +496,18 @@ def error_and_jacobian(kind: int, pair, T):
     return e, J
 
 
+def decimate_voxels(x, y, z, resolution: float, method: str = "FirstPoint", flatten_to=None):
+    """FilterDecimateVoxels over one layer (FilterDecimateVoxels.cpp:109-378). Returns (xyz (m, 3) float32, src (m,)
+    int64: source index or -1 for averaged points), in ascending (cx, cy, cz) voxel order."""
+    x, y, z = _f32(x), _f32(y), _f32(z)
+    n = x.size
+    ox, oy, oz = (np.zeros(max(n, 1), np.float32) for _ in range(3))
+    src = np.zeros(max(n, 1), np.int64)
+    fn = lib().orc_decimate_voxels
+    fn.restype = C.c_size_t
+    m = fn(_p(x), _p(y), _p(z), C.c_size_t(n), C.c_float(resolution), {"FirstPoint": 0, "ClosestToAverage": 1, "VoxelAverage": 2}[method], int(flatten_to is not None), C.c_float(0.0 if flatten_to is None else flatten_to), _p(ox), _p(oy), _p(oz), _p(src), C.c_size_t(n))
+    return np.stack([ox[:m], oy[:m], oz[:m]], 1), src[:m]
+
+
 def max_threads() -> int:
     return lib().orc_max_threads()

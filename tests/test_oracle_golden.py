@@ -556,3 +556,46 @@ def test_c4_kitti_schedule_converges():
     d = orc.se3_log(orc.inverse_compose(res.pose, gt))
     assert res.terminationReason in ("Stalled", "MaxIterations") and "adaptive" in used
     assert np.linalg.norm(d[:3]) < 5e-3 and np.linalg.norm(d[3:]) < 5e-4, (d, res.nIterations)
+
+
+# ---------------------------------------------------------------------------------------------
+# FilterDecimateVoxels — oracle first; the CUDA side is the next round's. No upstream test pins its
+# output; the cases below pin the restatement's reading of FilterDecimateVoxels.cpp:109-378 and of the voxel index
+# (truncation toward zero, PointCloudToVoxelGridSingle.h:105) against an independent numpy statement.
+# ---------------------------------------------------------------------------------------------
+def test_decimate_voxels_known_answers_and_numpy_statement():
+    P = np.array([[0.05, 0.05, 0.05], [0.15, 0.02, 0.01], [-0.15, 0.0, 0.0], [0.25, 0.0, 0.0], [0.26, 0.01, 0.0], [0.21, 0.19, 0.1],
+                  [0.25, 0.0, 0.35]], np.float32)
+    x, y, z = (np.ascontiguousarray(P[:, k]) for k in range(3))
+    # resolution 0.2: int32(c / 0.2) truncates toward zero, so (-0.2, 0.2) is ONE voxel per axis: points 0, 1, 2 share (0,0,0)
+    out, src = orc.decimate_voxels(x, y, z, 0.2, "FirstPoint")
+    assert list(src) == [0, 3, 6] and np.array_equal(out, P[[0, 3, 6]])  # voxels (0,0,0), (1,0,0), (1,0,1) in that order
+    out, src = orc.decimate_voxels(x, y, z, 0.2, "VoxelAverage")
+    assert list(src) == [-1, -1, -1]
+    assert np.allclose(out[0], P[:3].mean(0), atol=1e-7) and np.allclose(out[1], P[3:6].mean(0), atol=1e-7) and np.array_equal(out[2], P[6])
+    out, src = orc.decimate_voxels(x, y, z, 0.2, "ClosestToAverage")
+    assert list(src) == [0, 4, 6]  # mean of voxel (1,0,0) = (0.24, 0.0667, 0.0333): point 4 is the closest member
+    out, src = orc.decimate_voxels(x, y, z, 0.2, "FirstPoint", flatten_to=7.0)
+    assert list(src) == [0, 3] and np.array_equal(out[:, 2], [7.0, 7.0]) and np.array_equal(out[:, :2], P[[0, 3], :2])  # (1,0,1) shares a column
+    assert len(orc.decimate_voxels(x[:0], y[:0], z[:0], 0.2)[0]) == 0
+    # random cloud against a numpy statement of the same steps
+    rng = np.random.default_rng(6)
+    Q = rng.uniform(-3, 3, (20000, 3)).astype(np.float32)
+    res = np.float32(0.25)
+    key = (Q / res).astype(np.int32)  # float division, truncation toward zero
+    order = np.lexsort((np.arange(len(Q)), key[:, 2], key[:, 1], key[:, 0]))
+    ks = key[order]
+    first = np.ones(len(Q), bool)
+    first[1:] = np.any(ks[1:] != ks[:-1], axis=1)
+    out, src = orc.decimate_voxels(*(np.ascontiguousarray(Q[:, k]) for k in range(3)), float(res), "FirstPoint")
+    assert np.array_equal(src, order[first]) and np.array_equal(out, Q[order[first]])
+    out, src = orc.decimate_voxels(*(np.ascontiguousarray(Q[:, k]) for k in range(3)), float(res), "VoxelAverage")
+    starts = np.flatnonzero(first)
+    ends = np.append(starts[1:], len(Q))
+    for j in rng.choice(len(starts), 300, replace=False):
+        members = Q[np.sort(order[starts[j] : ends[j]])]
+        mean = np.zeros(3, np.float32)
+        for m in members:
+            mean = mean + m
+        mean = mean * (np.float32(1.0) / np.float32(len(members)))
+        assert np.array_equal(out[j], mean)
