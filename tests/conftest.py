@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no built artefacts (they are git-ignored): build them once, exactly as the
+    driver's build check does. The PRODUCT never builds or falls back by itself — it fails loudly when
+    libmp2p_b200.so is missing (tests/test_abi.py)."""
+    so = os.path.join(ROOT, "mp2p_icp_b200", "libmp2p_b200.so")
+    if not os.path.exists(so):
+        import __graft_entry__
+
+        __graft_entry__.build()
+
+
 def _has_gpu() -> bool:
     try:
         import torch
