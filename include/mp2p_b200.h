@@ -527,9 +527,9 @@ int mp2p_b200_peer_iterate_pt2pl_gn(mp2p_b200_peer* peer, mp2p_b200_map* map, co
 /* ---- measurement hooks (bench.py): per-kernel CUDA-event timing and search statistics ----
  * With profiling on, every public call records CUDA events around its kernels on the context
  * stream; mp2p_b200_ctx_get_timings returns the durations (ms) of the LAST call:
- *   [0] NN search kernel (k_match_pt2pt / k_match_pt2pl)   [1] compaction kernel
- *   [2] Horn sums  [3] Horn moments  [4] GN accumulate (sum over inner iterations)
- *   [5] whole call, device time                             (unused slots = 0)
+ *   [0] NN search kernel (k_match_pt2pt_nn1 / k_match_pt2pt<G>)   [1] compaction kernel
+ *   [2] Horn sums  [3] Horn moments  [4] GN accumulate (the LAST inner iteration's launch)
+ *   [5] whole call, device time   [6] plane / line fit kernel (pt2pl, pt2ln)   (unused slots = 0)
  * mp2p_b200_ctx_get_search_stats returns counters of the LAST match call when stats are on:
  *   [0] hash-table probes (16 B each)  [1] candidate points read (16 B each)
  *   [2] valid candidates written       [3] queries that climbed above the finest level

@@ -23,4 +23,5 @@ from .capi import (  # noqa: F401
     Pt2PtParams,
     library_path,
     load_library,
+    pack_bits,
 )

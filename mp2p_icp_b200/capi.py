@@ -363,7 +363,7 @@ class Context:
     def timings(self) -> dict:
         ms = (C.c_float * 8)()
         _check(load_library().mp2p_b200_ctx_get_timings(self._h, ms))
-        names = ["nn_search", "compact", "horn_sums", "horn_moments", "gn_accumulate", "call_total"]
+        names = ["nn_search", "compact", "horn_sums", "horn_moments", "gn_accumulate", "call_total", "plane_fit"]
         return {n: float(ms[i]) for i, n in enumerate(names)}
 
     def search_stats(self) -> dict:

@@ -100,7 +100,7 @@ template <uint32_t NQ>
 __device__ __forceinline__ void load_query_tile(QueryTile<NQ>& tile, const float* lx, const float* ly,
                                                 const float* lz, size_t base, size_t n_total, bool tma_ok)
 {
-    const bool use_tma = tma_ok && base + NQ <= n_total;  // CTA-uniform
+    const bool use_tma = (NQ % 4 == 0) && tma_ok && base + NQ <= n_total;  // CTA-uniform; bulk copies move multiples of 16 bytes
     if (use_tma && threadIdx.x == 0)
     {
         mbar_init(&tile.bar, 1);
@@ -217,6 +217,7 @@ struct Pt2PtArgs
     unsigned long long tag;  // (0xFFFFFFFF - epoch) << 32
     int      tma_ok;         // local arrays are 16-byte aligned
     int      rl_start;       // relative level the search starts from (start_level())
+    int      n_phases;       // k > 1 search: 2 = centre, then all neighbours; 3 = centre, faces, edges + corners
     int      cand_sorted;    // candidate words go to the query's SORTED position (pt2pl path)
     uint32_t tile_stride;    // CTA b serves query tile (b * tile_stride) % n_tiles: spreads expensive
                              // neighbourhoods (sparse map regions cluster in any spatial order) over the grid
@@ -241,8 +242,8 @@ struct FitList
 #ifndef MP2P_MATCH_MIN_BLOCKS
 #define MP2P_MATCH_MIN_BLOCKS 4  // CTAs of 256 threads per SM the register allocation must allow
 #endif
-template <int G>
-__global__ void __launch_bounds__(kQueryTile, MP2P_MATCH_MIN_BLOCKS)
+template <int G, bool V1 = false, int NT = (int)kQueryTile>
+__global__ void __launch_bounds__(NT, MP2P_MATCH_MIN_BLOCKS * (int)kQueryTile / NT)
     k_match_pt2pt(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
                   const float* __restrict__ lz, const uint32_t* __restrict__ perm,
                   const uint32_t* __restrict__ lbits,
@@ -250,12 +251,14 @@ __global__ void __launch_bounds__(kQueryTile, MP2P_MATCH_MIN_BLOCKS)
                   unsigned long long* __restrict__ cand, uint32_t* __restrict__ bbox_words,
                   unsigned long long* __restrict__ stats, FitList fit)
 {
-    constexpr uint32_t NQ = kQueryTile / G;  // queries per CTA
+    constexpr uint32_t NQ = NT / G;  // queries per CTA
     __shared__ QueryTile<NQ> tile;
     __shared__ BBoxAcc       bacc;
+    __shared__ KnnShared<V1 ? 32 : G, NT> ks;  // (V1: the old search keeps no tables; smallest instantiation)
     const size_t             base = (size_t)(((unsigned long long)blockIdx.x * a.tile_stride) % gridDim.x) * NQ;
     bbox_init(bacc);
-    load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);
+    if (!V1) knn_shared_init(ks);
+    load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);  // (holds the __syncthreads)
     const int      sub   = threadIdx.x % G, ql = threadIdx.x / G;
     const uint32_t qpos  = (uint32_t)base + ql;  // position in the array walked (sorted if perm)
     const bool     valid = qpos < a.n_local;
@@ -275,7 +278,11 @@ __global__ void __launch_bounds__(kQueryTile, MP2P_MATCH_MIN_BLOCKS)
     SearchCounters     sc;
     // all lanes take part (warp-uniform search); lanes past the end and already paired locals
     // (:218-220) are disabled
-    knn_search<G>(g, valid && (a.allowLocal || !bit_set(lbits, i)), gx, gy, gz, thr2, K, a.rl_start, mine, sub, sc);
+    if constexpr (V1)
+        knn_search_v1<G>(g, valid && (a.allowLocal || !bit_set(lbits, i)), gx, gy, gz, thr2, K, a.rl_start, mine, sub, sc);
+    else
+        knn_search<G>(g, valid && (a.allowLocal || !bit_set(lbits, i)), gx, gy, gz, thr2, K, a.rl_start, mine, sub, sc,
+                      ks.tb, ks.nb, a.n_phases);
     if (valid)
     {
         // lane r < K writes rank r; unused ranks are marked with an impossible map index (all ones)
@@ -1276,16 +1283,19 @@ __global__ void __launch_bounds__(kScanThreads)
 template <int G>
 __global__ void __launch_bounds__(256)
     k_knn(GridView g, const float* __restrict__ qx, const float* __restrict__ qy,
-          const float* __restrict__ qz, uint32_t nq, uint32_t K, float radius2, int rl_start,
+          const float* __restrict__ qz, uint32_t nq, uint32_t K, float radius2, int rl_start, int n_phases,
           uint32_t* __restrict__ out_idx, float* __restrict__ out_d2, int32_t* __restrict__ out_found)
 {
+    __shared__ KnnShared<G> ks;
+    knn_shared_init(ks);
+    __syncthreads();
     const int      sub   = threadIdx.x % G;
     const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << ((threadIdx.x & 31) / G * G);
     const uint32_t i     = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const bool     have  = i < nq;
     unsigned long long mine;
     SearchCounters     sc;
-    knn_search<G>(g, have, have ? qx[i] : 0.f, have ? qy[i] : 0.f, have ? qz[i] : 0.f, radius2, (int)K, rl_start, mine, sub, sc);
+    knn_search<G>(g, have, have ? qx[i] : 0.f, have ? qy[i] : 0.f, have ? qz[i] : 0.f, radius2, (int)K, rl_start, mine, sub, sc, ks.tb, ks.nb, n_phases);
     if (!have) return;  // whole groups leave together
     const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
     const bool               f        = sub < (int)K && mine < sentinel;
@@ -1340,6 +1350,57 @@ uint32_t tile_stride_for(uint64_t n_tiles)
     while (gcd(s, n_tiles) != 1) s += 2;
     return (uint32_t)(s % n_tiles);
 }
+// measurement knobs of the k > 1 search (A/B on the device): MP2P_KNN_PHASES = 2 | 3, MP2P_KNN_V1 = 1
+int knn_phases()
+{
+    static const int v = [] {
+        const char* e = getenv("MP2P_KNN_PHASES");
+        const int   x = e ? atoi(e) : 3;
+        return x == 2 ? 2 : 3;
+    }();
+    return v;
+}
+bool knn_v1()
+{
+    static const bool v = [] {
+        const char* e = getenv("MP2P_KNN_V1");
+        return e && atoi(e) == 1;
+    }();
+    return v;
+}
+// CTA size of the k > 1 search (threads; G lanes per query): $MP2P_KNN_NT = 64 | 128 | 256
+int knn_nt()
+{
+    static const int v = [] {
+        const char* e = getenv("MP2P_KNN_NT");
+        const int   x = e ? atoi(e) : 256;
+        return (x == 64 || x == 128) ? x : 256;
+    }();
+    return v;
+}
+#define MP2P_LAUNCH_KMATCH_NT(G, V1, NT, nq, st, ...)                                              \
+    {                                                                                              \
+        const uint32_t nb_ = (uint32_t)(((uint64_t)(nq) * G + NT - 1) / NT);                       \
+        a_.tile_stride     = tile_stride_for(nb_);                                                 \
+        k_match_pt2pt<G, V1, NT><<<nb_, NT, 0, st>>>(__VA_ARGS__);                                 \
+    }
+// `args` = the Pt2PtArgs lvalue passed in __VA_ARGS__ (its tile_stride is set here, per grid size)
+#define MP2P_LAUNCH_KMATCH(G, args, nq, st, ...)                                                   \
+    {                                                                                              \
+        auto& a_ = args;                                                                           \
+        if (knn_v1())                                                                              \
+        {                                                                                          \
+            if (knn_nt() == 64) MP2P_LAUNCH_KMATCH_NT(G, true, 64, nq, st, __VA_ARGS__)            \
+            else if (knn_nt() == 128) MP2P_LAUNCH_KMATCH_NT(G, true, 128, nq, st, __VA_ARGS__)     \
+            else MP2P_LAUNCH_KMATCH_NT(G, true, 256, nq, st, __VA_ARGS__)                          \
+        }                                                                                          \
+        else                                                                                       \
+        {                                                                                          \
+            if (knn_nt() == 64) MP2P_LAUNCH_KMATCH_NT(G, false, 64, nq, st, __VA_ARGS__)           \
+            else if (knn_nt() == 128) MP2P_LAUNCH_KMATCH_NT(G, false, 128, nq, st, __VA_ARGS__)    \
+            else MP2P_LAUNCH_KMATCH_NT(G, false, 256, nq, st, __VA_ARGS__)                         \
+        }                                                                                          \
+    }
 int start_level(const GridView& v, uint32_t K)
 {
     if (K <= 1) return 0;
@@ -1753,6 +1814,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     a.tag = (unsigned long long)(0xFFFFFFFFu - map->epoch) << 32;
     a.tma_ok = ctx->cur_tma_ok;
     a.rl_start = start_level(map->view, K);
+    a.n_phases = knn_phases();
     if (local_mapped) a.stage_x = ctx->d_lx.as<float>(), a.stage_y = ctx->d_ly.as<float>(), a.stage_z = ctx->d_lz.as<float>();
 
     const float *  dlx = ctx->cur_lx, *dly = ctx->cur_ly, *dlz = ctx->cur_lz;  // caller order (records)
@@ -1855,9 +1917,7 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     prof_begin(ctx, 0);
 #define LAUNCH_MATCH(G)                                                                                    \
     {                                                                                                      \
-        const uint32_t nb = (uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile);                       \
-        a.tile_stride = tile_stride_for(nb);                                                                \
-        k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, sv.bbox, stats, FitList{nullptr, nullptr, nullptr, 0}); \
+        MP2P_LAUNCH_KMATCH(G, a, n_local, st, map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, d_gbits, claim, cand, sv.bbox, stats, FitList{nullptr, nullptr, nullptr, 0}) \
     }
     if (K == 1)
     {
@@ -1984,15 +2044,14 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     a.tag = 0;
     a.tma_ok = ctx->cur_tma_ok;
     a.rl_start = start_level(map->view, K);
+    a.n_phases = knn_phases();
     const float *dqx = ctx->cur_qx, *dqy = ctx->cur_qy, *dqz = ctx->cur_qz;
     unsigned long long* stats = nullptr;
     MP2P_TRY(prepare_stats(ctx, &stats));
     prof_begin(ctx, 0);
 #define LAUNCH_MATCH(G)                                                                                    \
     {                                                                                                      \
-        const uint32_t nb = (uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile);                       \
-        a.tile_stride = tile_stride_for(nb);                                                                \
-        k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, d_record, d_bbox6, stats, FitList{nullptr, nullptr, nullptr, 0}); \
+        MP2P_LAUNCH_KMATCH(G, a, n_local, st, map->view, a, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, d_record, d_bbox6, stats, FitList{nullptr, nullptr, nullptr, 0}) \
     }
     if (K == 1)
     {
@@ -2162,14 +2221,15 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     prof_begin(ctx, 0);
 #define LAUNCH_SEARCH(G)                                                                                   \
     {                                                                                                      \
-        const uint32_t nb = (uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile);                       \
-        sa.tile_stride = tile_stride_for(nb);                                                              \
-        k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, sa, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, cand, sv.bbox, stats, fit); \
+        MP2P_LAUNCH_KMATCH(G, sa, n_local, st, map->view, sa, dqx, dqy, dqz, ctx->cur_perm, d_lbits, nullptr, nullptr, cand, sv.bbox, stats, fit) \
     }
 #define LAUNCH_FIT(KT) \
     k_plane_fit<KT><<<(uint32_t)((n_local + kFitThreads - 1) / kFitThreads), kFitThreads, 0, st>>>(map->view, a, dqx, dqy, dqz, ctx->cur_perm, cand, fit.list, fit.count, plc, okf)
     sa.rl_start = start_level(map->view, prm->knn);
+    sa.n_phases = knn_phases();
     MP2P_DISPATCH_G(prm->knn, LAUNCH_SEARCH)
+    prof_end(ctx, 0);
+    prof_begin(ctx, 6);
     switch (pick_kt(prm->knn))
     {
         case 1:
@@ -2180,7 +2240,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     }
 #undef LAUNCH_SEARCH
 #undef LAUNCH_FIT
-    prof_end(ctx, 0);
+    prof_end(ctx, 6);
     count_launch(ctx, 2);
 
     mp2p_b200_pair_pt2pl* d_out = out;
@@ -2242,7 +2302,7 @@ int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const
         auto *od = ctx->d_knn_d2.as<float>();
         auto *of = ctx->d_knn_found.as<int32_t>();
         const int rl0 = start_level(map->view, K);
-#define LAUNCH_KNN(G) k_knn<G><<<(uint32_t)((nq * G + 255) / 256), 256, 0, st>>>(map->view, dqx, dqy, dqz, (uint32_t)nq, K, radius2, rl0, oi, od, of);
+#define LAUNCH_KNN(G) k_knn<G><<<(uint32_t)((nq * G + 255) / 256), 256, 0, st>>>(map->view, dqx, dqy, dqz, (uint32_t)nq, K, radius2, rl0, knn_phases(), oi, od, of);
         MP2P_DISPATCH_G(K, LAUNCH_KNN)
 #undef LAUNCH_KNN
         count_launch(ctx);
@@ -2650,6 +2710,7 @@ int run_adaptive_search(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx,
     a.allowLocal = prm->allowMatchAlreadyMatchedPoints, a.allowGlobal = 1;  // no first-claim dedup in this matcher
     a.tma_ok   = ctx->cur_tma_ok;
     a.rl_start = start_level(map->view, K);
+    a.n_phases = knn_phases();
     auto*               cand  = ctx->d_cand.as<unsigned long long>();
     unsigned long long* stats = nullptr;
     MP2P_TRY(prepare_stats(ctx, &stats));
@@ -2664,9 +2725,7 @@ int run_adaptive_search(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx,
     {
 #define LAUNCH_MATCH(G)                                                                                    \
     {                                                                                                      \
-        const uint32_t nb = (uint32_t)((n_local * G + kQueryTile - 1) / kQueryTile);                       \
-        a.tile_stride = tile_stride_for(nb);                                                                \
-        k_match_pt2pt<G><<<nb, kQueryTile, 0, st>>>(map->view, a, ctx->cur_qx, ctx->cur_qy, ctx->cur_qz, ctx->cur_perm, d_lbits, nullptr, nullptr, cand, sv.bbox, stats, FitList{nullptr, nullptr, nullptr, 0}); \
+        MP2P_LAUNCH_KMATCH(G, a, n_local, st, map->view, a, ctx->cur_qx, ctx->cur_qy, ctx->cur_qz, ctx->cur_perm, d_lbits, nullptr, nullptr, cand, sv.bbox, stats, FitList{nullptr, nullptr, nullptr, 0}) \
     }
         MP2P_DISPATCH_G(K, LAUNCH_MATCH)
 #undef LAUNCH_MATCH

@@ -460,10 +460,13 @@ class ParameterSource
 class Device
 {
    public:
+    /** One Device (context + caches) per GPU, created on first use. */
     static Device& instance(int device = 0)
     {
-        static Device d(device);
-        return d;
+        static std::map<int, std::unique_ptr<Device>> all;
+        auto&                                         d = all[device];
+        if (!d) d.reset(new Device(device));
+        return *d;
     }
     mp2p_b200_ctx* ctx() { return ctx_; }
     /** nn_prepare_for_3d_queries(): index of a global layer, rebuilt when the layer was modified. */
@@ -1008,7 +1011,12 @@ class Solver_Horn : public Solver
         w.scale_outlier_threshold    = p.getOrDefault<double>("scale_outlier_threshold", w.scale_outlier_threshold);
         w.robust_kernel              = robust_kernel_from_string(p.getString("robust_kernel", "None"));
         w.robust_kernel_param        = p.getOrDefault<double>("robust_kernel_param", w.robust_kernel_param);
+        assumeUnmodifiedPairings     = p.getOrDefault<int>("assumeUnmodifiedPairings", 0) != 0;
     }
+    /** Opt-in (default off): a list whose count and 8 sampled records equal the last matcher output is
+     *  solved from the copy that call left on the device instead of being uploaded again. Only for
+     *  pipelines in which nothing edits the Pairings between run_matchers and run_solvers. */
+    bool assumeUnmodifiedPairings = false;
 
    protected:
     bool impl_optimal_pose(const Pairings& pairings, OptimalTF_Result& out, const SolverContext& sc) const override
@@ -1035,12 +1043,12 @@ class Solver_Horn : public Solver
             if (!sc.guessRelativePose) throw std::runtime_error("Assert failed: sc.guessRelativePose.has_value()");
             const auto& l2l = pairings.paired_pt2pl;
             check(mp2p_b200_solve_horn_pt2pl(dev.ctx(), l2l.data(), l2l.size(),
-                                             dev.is_last_match_output(l2l.data(), l2l.size()) ? MP2P_B200_PAIRS_LAST_MATCH : 0,
+                                             (assumeUnmodifiedPairings && dev.is_last_match_output(l2l.data(), l2l.size())) ? MP2P_B200_PAIRS_LAST_MATCH : 0,
                                              sc.guessRelativePose->m, &prm, out.optimalPose.m, &solved),
                   "mp2p_b200_solve_horn_pt2pl");
             return solved != 0;
         }
-        const int origin = dev.is_last_match_output(pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size())
+        const int origin = (assumeUnmodifiedPairings && dev.is_last_match_output(pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size()))
                                ? MP2P_B200_PAIRS_LAST_MATCH
                                : 0;
         check(mp2p_b200_solve_horn(dev.ctx(), pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size(), origin,
@@ -1063,7 +1071,9 @@ class Solver_GaussNewton : public Solver
         robustKernel      = p.getString("robustKernel", robustKernel);
         robustKernelParam = p.getOrDefault<double>("robustKernelParam", robustKernelParam);
         robust_kernel_from_string(robustKernel);
+        assumeUnmodifiedPairings = p.getOrDefault<int>("assumeUnmodifiedPairings", 0) != 0;
     }
+    bool assumeUnmodifiedPairings = false;  //!< opt-in, see Solver_Horn
 
    protected:
     bool impl_optimal_pose(const Pairings& pairings, OptimalTF_Result& out, const SolverContext& sc) const override
@@ -1076,6 +1086,11 @@ class Solver_GaussNewton : public Solver
         Device&    dev   = Device::instance();
         const auto &l2p = pairings.paired_pt2pt;
         const auto &l2l = pairings.paired_pt2pl;
+        // Pairings::point_weights re-weight the pt2pt term block by block (optimal_tf_gauss_newton.cpp:118-128);
+        // the device accumulation carries one uniform pt2pt weight: refuse instead of returning another pose
+        // (the MRPT plugin hands such calls to the reference's own solver)
+        if (!pairings.point_weights.empty() && !l2p.empty())
+            throw std::runtime_error("Solver_GaussNewton over weighted point layers (Pairings::point_weights) is not offered on the device");
         // every non-empty list must be the witnessed output of the last matcher call of its kind
         if (!pairings.paired_pt2ln.empty())  // point-to-line term, optimal_tf_gauss_newton.cpp:182-203
         {
@@ -1085,7 +1100,7 @@ class Solver_GaussNewton : public Solver
                   "mp2p_b200_solve_gauss_newton_ex");
             return solved != 0;
         }
-        const bool last  = (l2p.empty() || dev.is_last_match_output(l2p.data(), l2p.size())) &&
+        const bool last  = assumeUnmodifiedPairings && (l2p.empty() || dev.is_last_match_output(l2p.data(), l2p.size())) &&
                           (l2l.empty() || dev.is_last_match_output(l2l.data(), l2l.size())) && !pairings.empty();
         check(mp2p_b200_solve_gauss_newton(dev.ctx(), pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size(),
                                            pairings.paired_pt2pl.data(), pairings.paired_pt2pl.size(),

@@ -1,7 +1,21 @@
 // Reference-side binding: the mp2p_icp plugin classes that put the B200 hot path under the
-// reference's own Matcher / Solver interfaces. Built ONLY where MRPT and mp2p_icp headers exist
-// (`make -C mp2p_icp_b200/host plugin MRPT=1`); this container has neither, so the
-// file is compile-guarded and has not been compiled here — INTEGRATION.md says so explicitly.
+// reference's own Matcher / Solver interfaces. BUILT only where MRPT and mp2p_icp headers exist
+// (`make -C mp2p_icp_b200/host plugin MRPT=1`); this container has neither. Here the
+// file is TYPE-CHECKED against shape stubs of every MRPT / mp2p_icp declaration it touches
+// (tests/stubs/, `make -C mp2p_icp_b200/host shape`, run by __graft_entry__.build() and
+// tests/test_plugin_shape.py): the virtual signatures, member names and record layouts it relies on
+// are the ones cited there from the reference headers.
+//
+// Safety defaults (VERDICT r1 / ADVICE r1):
+//  * the solvers UPLOAD the pairings they are given. Reading the device copy the last matcher call
+//    left (MP2P_B200_PAIRS_LAST_MATCH) is an explicit opt-in, YAML `assumeUnmodifiedPairings: true`
+//    on the solver, for pipelines where nothing edits the Pairings between run_matchers and
+//    run_solvers (ICP.cpp:143-170) — then the count and 8 sampled records are still compared.
+//  * a global layer is re-indexed when its buffer address, size OR a fingerprint of 4096 sampled
+//    points + the first / last point changes. MRPT exposes no modification counter for the point
+//    buffers, so an in-place edit that touches none of the samples needs
+//    mp2p_icp::B200InvalidateGlobalLayer(layer) — documented in INTEGRATION.md.
+//  * YAML `device: <n>` on every class selects the GPU (default 0); one context per device.
 //
 // Usage from a pipeline YAML (the reference loads the .so through its `plugin:` key,
 // mp2p_icp_map/src/load_plugin.cpp:70-134, then creates the class by name, ICP.cpp:507-516):
@@ -27,9 +41,11 @@
 #include <mrpt/math/utils.h>
 #include <mrpt/rtti/CObject.h>
 
+#include <algorithm>
 #include <cstring>
+#include <map>
 #include <mutex>
-#include <unordered_map>
+#include <set>
 
 #include "mp2p_b200.h"
 
@@ -41,15 +57,18 @@ inline void check(int rc)
 {
     if (rc != MP2P_B200_OK) THROW_EXCEPTION_FMT("mp2p_b200: %s", mp2p_b200_last_error());
 }
-inline mp2p_b200_ctx* ctx()
+// one context per device, created on first use (YAML `device:` of the classes below)
+inline mp2p_b200_ctx* ctx(int device)
 {
-    static mp2p_b200_ctx* c = []
-    {
-        mp2p_b200_ctx* p = nullptr;
-        check(mp2p_b200_ctx_create(0, nullptr, &p));
-        return p;
-    }();
-    return c;
+    static std::mutex                     mtx;
+    static std::map<int, mp2p_b200_ctx*>  all;
+    std::lock_guard<std::mutex>           lk(mtx);
+    auto                                  it = all.find(device);
+    if (it != all.end()) return it->second;
+    mp2p_b200_ctx* p = nullptr;
+    check(mp2p_b200_ctx_create(device, nullptr, &p));
+    all[device] = p;
+    return p;
 }
 inline void pose12(const mrpt::poses::CPose3D& p, double out[12])
 {
@@ -60,9 +79,25 @@ inline void pose12(const mrpt::poses::CPose3D& p, double out[12])
         out[4 * r + 3] = p.m_coords[r];
     }
 }
-// Device copies of global layers, keyed on the layer object and rebuilt when its size or buffer
-// address changes (the reference relies on MRPT's own "kd-tree up to date" flag; methods are const
-// so the cache is mutable, SURVEY.md §8b "Ownership").
+// Device copies of global layers, keyed on (layer object, device) and rebuilt when the layer's buffer
+// address, size or content fingerprint changes (the reference relies on MRPT's own "kd-tree up to date"
+// flag, which is not visible from outside; methods are const so the cache is mutable).
+inline uint64_t fingerprint(const float* x, const float* y, const float* z, size_t n)
+{
+    // FNV-1a over the bit patterns of up to 4096 evenly spaced points plus the first and the last one
+    uint64_t   h   = 1469598103934665603ull;
+    const auto mix = [&h](float f)
+    {
+        uint32_t u;
+        std::memcpy(&u, &f, 4);
+        h = (h ^ u) * 1099511628211ull;
+    };
+    if (!n) return h;
+    const size_t step = n > 4096 ? n / 4096 : 1;
+    for (size_t i = 0; i < n; i += step) mix(x[i]), mix(y[i]), mix(z[i]);
+    mix(x[n - 1]), mix(y[n - 1]), mix(z[n - 1]);
+    return h;
+}
 struct MapCache
 {
     struct Entry
@@ -70,49 +105,59 @@ struct MapCache
         mp2p_b200_map*   map = nullptr;
         const float*     x   = nullptr;
         size_t           n   = 0;
+        uint64_t         fp  = 0;
         mp2p_b200_cloud* cloud = nullptr;  // set while a B200LocalCloudScope pins this layer as a LOCAL cloud
     };
-    std::mutex                                                   mtx;
-    std::unordered_map<const mrpt::maps::CMetricMap*, Entry>     entries;
-    mp2p_b200_map* get(const mrpt::maps::CMetricMap& layer)
+    using Key = std::pair<const mrpt::maps::CMetricMap*, int>;
+    std::mutex           mtx;
+    std::map<Key, Entry> entries;
+    mp2p_b200_map* get(const mrpt::maps::CMetricMap& layer, int device)
     {
         const auto* pts = mp2p_icp::MapToPointsMap(layer);
         ASSERTMSG_(pts, "B200 matchers need a CPointsMap global layer");
         const auto&                 xs = pts->getPointsBufferRef_x();
+        const auto&                 ys = pts->getPointsBufferRef_y();
+        const auto&                 zs = pts->getPointsBufferRef_z();
+        const uint64_t              fp = fingerprint(xs.data(), ys.data(), zs.data(), xs.size());
         std::lock_guard<std::mutex> lk(mtx);
-        auto&                       e = entries[&layer];
-        if (!e.map || e.x != xs.data() || e.n != xs.size())
+        auto&                       e = entries[Key(&layer, device)];
+        if (!e.map || e.x != xs.data() || e.n != xs.size() || e.fp != fp)
         {
-            if (e.map) mp2p_b200_map_destroy(e.map);
-            check(mp2p_b200_map_create(ctx(), xs.data(), pts->getPointsBufferRef_y().data(),
-                                       pts->getPointsBufferRef_z().data(), xs.size(), 0, &e.map));
-            e.x = xs.data(), e.n = xs.size();
+            if (e.map) mp2p_b200_map_destroy(e.map), e.map = nullptr;
+            check(mp2p_b200_map_create(ctx(device), xs.data(), ys.data(), zs.data(), xs.size(), 0, &e.map));
+            e.x = xs.data(), e.n = xs.size(), e.fp = fp;
         }
         return e.map;
+    }
+    void invalidate(const mrpt::maps::CMetricMap& layer)
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        for (auto& [k, e] : entries)
+            if (k.first == &layer && e.map) mp2p_b200_map_destroy(e.map), e.map = nullptr;
     }
     // A local layer is uploaded (and Morton-sorted) once and reused by every ICP iteration ONLY while
     // the caller vouches that it does not change: MRPT exposes no modification counter for the point
     // buffers, so the plugin cannot detect edits by itself. B200LocalCloudScope (below) is that
     // promise; without it the matchers pass the host buffers on every call (MP2P_B200_LOCAL_HOST).
-    const float* pinned_local(const mrpt::maps::CPointsMap& pts)
+    const float* pinned_local(const mrpt::maps::CPointsMap& pts, int device)
     {
         std::lock_guard<std::mutex> lk(mtx);
-        auto                        it = entries.find(&pts);
+        auto                        it = entries.find(Key(&pts, device));
         return (it == entries.end() || !it->second.cloud) ? nullptr : reinterpret_cast<const float*>(it->second.cloud);
     }
-    void pin_local(const mrpt::maps::CPointsMap& pts)
+    void pin_local(const mrpt::maps::CPointsMap& pts, int device)
     {
         const auto&                 xs = pts.getPointsBufferRef_x();
         std::lock_guard<std::mutex> lk(mtx);
-        auto&                       e = entries[&pts];
+        auto&                       e = entries[Key(&pts, device)];
         if (e.cloud) mp2p_b200_cloud_destroy(e.cloud), e.cloud = nullptr;
-        check(mp2p_b200_cloud_create(ctx(), xs.data(), pts.getPointsBufferRef_y().data(),
+        check(mp2p_b200_cloud_create(ctx(device), xs.data(), pts.getPointsBufferRef_y().data(),
                                      pts.getPointsBufferRef_z().data(), xs.size(), 0, &e.cloud));
     }
-    void unpin_local(const mrpt::maps::CPointsMap& pts)
+    void unpin_local(const mrpt::maps::CPointsMap& pts, int device)
     {
         std::lock_guard<std::mutex> lk(mtx);
-        auto                        it = entries.find(&pts);
+        auto                        it = entries.find(Key(&pts, device));
         if (it == entries.end() || !it->second.cloud) return;
         mp2p_b200_cloud_destroy(it->second.cloud);
         it->second.cloud = nullptr;
@@ -147,23 +192,59 @@ struct Witness
         return true;
     }
 };
-inline Witness& witness2p()
+inline Witness& witness2p(int device)
 {
-    static Witness w;
-    return w;
+    static std::map<int, Witness> w;
+    return w[device];
 }
-inline Witness& witness2l()
+inline Witness& witness2l(int device)
 {
-    static Witness w;
-    return w;
+    static std::map<int, Witness> w;
+    return w[device];
 }
+// MatchState bit field -> the bit words of the C ABI (bit i of word i / 32). An all-clear field — every
+// first matcher of a run_matchers call sees one (Matcher.cpp:58-66 builds a fresh MatchState) — comes back
+// EMPTY, and the callers then pass NULL ("none set": nothing to upload). Words are assembled in a
+// register, one store per 32 points; with libstdc++ and the dense form the vector<bool> storage is
+// read word-wise instead of bit by bit.
+struct BitFieldMirror  // the two data members of DenseOrSparseBitField (pointcloud_bitfield.h:86-91)
+{
+    std::optional<std::vector<bool>> dense_;
+    std::set<uint64_t>               sparse_;
+};
 inline std::vector<uint32_t> to_bits(const pointcloud_bitfield_t::DenseOrSparseBitField& bf, size_t n)
 {
     std::vector<uint32_t> w((n + 31) / 32, 0u);
-    for (size_t i = 0; i < n; i++)
-        if (bf[i]) w[i >> 5] |= 1u << (i & 31);
+    uint32_t              any = 0;
+#if defined(__GLIBCXX__) && defined(MP2P_B200_BITFIELD_FAST_PATH)
+    // opt-in (-DMP2P_B200_BITFIELD_FAST_PATH): reads the private members through a layout mirror
+    static_assert(sizeof(BitFieldMirror) == sizeof(pointcloud_bitfield_t::DenseOrSparseBitField));
+    const auto& m = reinterpret_cast<const BitFieldMirror&>(bf);
+    if (m.dense_.has_value() && m.dense_->size() >= n)
+    {
+        const unsigned long* src = m.dense_->begin()._M_p;  // libstdc++: _Bit_type words, bit i at word i / 64
+        for (size_t k = 0; k < w.size(); k++)
+        {
+            const unsigned long word = src[k >> 1];
+            w[k] = static_cast<uint32_t>((k & 1) ? (word >> 32) : word);
+            any |= w[k];
+        }
+        if (n & 31) w.back() &= (1u << (n & 31)) - 1u;
+        if (!any) w.clear();
+        return w;
+    }
+#endif
+    for (size_t k = 0; k < w.size(); k++)
+    {
+        const size_t i0 = k << 5, i1 = std::min(n, i0 + 32);
+        uint32_t     word = 0;
+        for (size_t i = i0; i < i1; i++) word |= static_cast<uint32_t>(bf[i]) << (i - i0);
+        w[k] = word, any |= word;
+    }
+    if (!any) w.clear();
     return w;
 }
+inline const uint32_t* bits_or_null(const std::vector<uint32_t>& w) { return w.empty() ? nullptr : w.data(); }
 }  // namespace b200_detail
 
 /** RAII promise that a local layer stays unmodified (e.g. for the duration of one ICP::align()):
@@ -172,23 +253,34 @@ inline std::vector<uint32_t> to_bits(const pointcloud_bitfield_t::DenseOrSparseB
 class B200LocalCloudScope
 {
    public:
-    explicit B200LocalCloudScope(const mrpt::maps::CPointsMap& pts) : pts_(pts) { b200_detail::cache().pin_local(pts_); }
-    ~B200LocalCloudScope() { b200_detail::cache().unpin_local(pts_); }
+    explicit B200LocalCloudScope(const mrpt::maps::CPointsMap& pts, int device = 0) : pts_(pts), device_(device)
+    {
+        b200_detail::cache().pin_local(pts_, device_);
+    }
+    ~B200LocalCloudScope() { b200_detail::cache().unpin_local(pts_, device_); }
     B200LocalCloudScope(const B200LocalCloudScope&)            = delete;
     B200LocalCloudScope& operator=(const B200LocalCloudScope&) = delete;
 
    private:
     const mrpt::maps::CPointsMap& pts_;
+    int                           device_;
 };
+
+/** Tells the plugin that a GLOBAL layer was edited in place (same buffers, same size): its device index is
+ *  rebuilt on the next matcher call. Edits that change the buffer address, the size or any of the ~4096
+ *  sampled points are detected without this call. */
+inline void B200InvalidateGlobalLayer(const mrpt::maps::CMetricMap& layer) { b200_detail::cache().invalidate(layer); }
 
 /** Drop-in for Matcher_Points_DistanceThreshold (same parameters, same results). */
 class Matcher_Points_DistanceThreshold_B200 : public Matcher_Points_Base
 {
     DEFINE_MRPT_OBJECT(Matcher_Points_DistanceThreshold_B200, mp2p_icp)
    public:
+    int device = 0;  //!< YAML `device`: the GPU this object works on
     void initialize(const mrpt::containers::yaml& params) override
     {
         Matcher_Points_Base::initialize(params);
+        MCP_LOAD_OPT(params, device);
         DECLARE_PARAMETER_REQ(params, threshold);
         DECLARE_PARAMETER_REQ(params, thresholdAngularDeg);
         DECLARE_PARAMETER_OPT(params, pairingsPerPoint);
@@ -207,7 +299,7 @@ class Matcher_Points_DistanceThreshold_B200 : public Matcher_Points_Base
         ASSERT_(pairingsPerPoint >= 1);
         ASSERT_GT_(threshold, .0);
         ASSERT_GE_(thresholdAngularDeg, .0);
-        mp2p_b200_map* gmap = cache().get(pcGlobal);
+        mp2p_b200_map* gmap = cache().get(pcGlobal, device);
         const auto& lx = pcLocal.getPointsBufferRef_x();
         double T[12];
         pose12(localPose, T);
@@ -222,17 +314,17 @@ class Matcher_Points_DistanceThreshold_B200 : public Matcher_Points_Base
         out.paired_pt2pt.resize(before + lx.size() * pairingsPerPoint);
         static_assert(sizeof(mrpt::tfest::TMatchingPair) == sizeof(mp2p_b200_pair_pt2pt));
         uint64_t cnt = 0, pot = 0;
-        const float* resident = cache().pinned_local(pcLocal);
-        check(mp2p_b200_match_pt2pt(ctx(), gmap, resident ? resident : lx.data(),
+        const float* resident = cache().pinned_local(pcLocal, device);
+        check(mp2p_b200_match_pt2pt(ctx(device), gmap, resident ? resident : lx.data(),
                                     resident ? nullptr : pcLocal.getPointsBufferRef_y().data(),
                                     resident ? nullptr : pcLocal.getPointsBufferRef_z().data(), lx.size(),
                                     resident ? MP2P_B200_LOCAL_CLOUD : MP2P_B200_LOCAL_HOST, T, &p,
-                                    lbits.data(), gbits.data(),
+                                    bits_or_null(lbits), bits_or_null(gbits),
                                     reinterpret_cast<mp2p_b200_pair_pt2pt*>(out.paired_pt2pt.data() + before),
                                     lx.size() * pairingsPerPoint, 0, &cnt, &pot));
         out.paired_pt2pt.resize(before + cnt);
         out.potential_pairings += pot;
-        witness2p().note(out.paired_pt2pt.data() + before, before == 0 ? cnt : 0);
+        witness2p(device).note(out.paired_pt2pt.data() + before, before == 0 ? cnt : 0);
         if (!allowMatchAlreadyMatchedGlobalPoints_)  // lambdaAddPair, …DistanceThreshold.cpp:116-120
             for (size_t i = before; i < out.paired_pt2pt.size(); i++)
             {
@@ -248,9 +340,11 @@ class Matcher_Points_InlierRatio_B200 : public Matcher_Points_Base
 {
     DEFINE_MRPT_OBJECT(Matcher_Points_InlierRatio_B200, mp2p_icp)
    public:
+    int device = 0;  //!< YAML `device`: the GPU this object works on
     void initialize(const mrpt::containers::yaml& params) override
     {
         Matcher_Points_Base::initialize(params);
+        MCP_LOAD_OPT(params, device);
         MCP_LOAD_REQ(params, inliersRatio);
     }
     double inliersRatio = 0.80;
@@ -264,7 +358,7 @@ class Matcher_Points_InlierRatio_B200 : public Matcher_Points_Base
         using namespace b200_detail;
         ASSERT_GT_(inliersRatio, 0.0);
         ASSERT_LT_(inliersRatio, 1.0);
-        mp2p_b200_map* gmap = cache().get(pcGlobal);
+        mp2p_b200_map* gmap = cache().get(pcGlobal, device);
         const auto&    lx   = pcLocal.getPointsBufferRef_x();
         double         T[12];
         pose12(localPose, T);
@@ -278,17 +372,17 @@ class Matcher_Points_InlierRatio_B200 : public Matcher_Points_Base
         const size_t before = out.paired_pt2pt.size();
         out.paired_pt2pt.resize(before + lx.size());
         uint64_t     cnt = 0, pot = 0;
-        const float* resident = cache().pinned_local(pcLocal);
-        check(mp2p_b200_match_inlier_ratio(ctx(), gmap, resident ? resident : lx.data(),
+        const float* resident = cache().pinned_local(pcLocal, device);
+        check(mp2p_b200_match_inlier_ratio(ctx(device), gmap, resident ? resident : lx.data(),
                                            resident ? nullptr : pcLocal.getPointsBufferRef_y().data(),
                                            resident ? nullptr : pcLocal.getPointsBufferRef_z().data(), lx.size(),
                                            resident ? MP2P_B200_LOCAL_CLOUD : MP2P_B200_LOCAL_HOST, T, &p,
-                                           lbits.data(), gbits.data(),
+                                           bits_or_null(lbits), bits_or_null(gbits),
                                            reinterpret_cast<mp2p_b200_pair_pt2pt*>(out.paired_pt2pt.data() + before),
                                            lx.size(), 0, &cnt, &pot));
         out.paired_pt2pt.resize(before + cnt);
         out.potential_pairings += pot;
-        witness2p().note(out.paired_pt2pt.data() + before, before == 0 ? cnt : 0);
+        witness2p(device).note(out.paired_pt2pt.data() + before, before == 0 ? cnt : 0);
         for (size_t i = before; i < out.paired_pt2pt.size(); i++)  // :133-135
         {
             lbf.mark_as_set(out.paired_pt2pt[i].localIdx);
@@ -303,6 +397,16 @@ IMPLEMENTS_MRPT_OBJECT(Matcher_Points_InlierRatio_B200, Matcher, mp2p_icp)
 class Solver_Horn_B200 : public Solver_Horn
 {
     DEFINE_MRPT_OBJECT(Solver_Horn_B200, mp2p_icp)
+   public:
+    int  device = 0;                         //!< YAML `device`: the GPU this object works on
+    bool assumeUnmodifiedPairings = false;   //!< YAML opt-in: read the device copy the last matcher call left
+    void initialize(const mrpt::containers::yaml& params) override
+    {
+        Solver_Horn::initialize(params);
+        MCP_LOAD_OPT(params, device);
+        MCP_LOAD_OPT(params, assumeUnmodifiedPairings);
+    }
+
    protected:
     bool impl_optimal_pose(const Pairings& pairings, OptimalTF_Result& out, const SolverContext& sc) const override
     {
@@ -324,9 +428,9 @@ class Solver_Horn_B200 : public Solver_Horn
         for (const auto& [cnt, w] : pairings.point_weights) wc.push_back(cnt), wv.push_back(w);
         double  T[12];
         int32_t solved = 0;
-        check(mp2p_b200_solve_horn(ctx(), reinterpret_cast<const mp2p_b200_pair_pt2pt*>(pairings.paired_pt2pt.data()),
+        check(mp2p_b200_solve_horn(ctx(device), reinterpret_cast<const mp2p_b200_pair_pt2pt*>(pairings.paired_pt2pt.data()),
                                    pairings.paired_pt2pt.size(),
-                                   witness2p().same(pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size())
+                                   (assumeUnmodifiedPairings && witness2p(device).same(pairings.paired_pt2pt.data(), pairings.paired_pt2pt.size()))
                                        ? MP2P_B200_PAIRS_LAST_MATCH
                                        : 0,
                                    &p, wc.data(), wv.data(), wc.size(), T, &solved));
@@ -349,9 +453,11 @@ class Matcher_Point2Plane_B200 : public Matcher_Points_Base
 {
     DEFINE_MRPT_OBJECT(Matcher_Point2Plane_B200, mp2p_icp)
    public:
+    int device = 0;  //!< YAML `device`: the GPU this object works on
     void initialize(const mrpt::containers::yaml& params) override
     {
         Matcher_Points_Base::initialize(params);
+        MCP_LOAD_OPT(params, device);
         DECLARE_PARAMETER_REQ(params, distanceThreshold);
         DECLARE_PARAMETER_OPT(params, searchRadius);
         DECLARE_PARAMETER_OPT(params, knn);
@@ -370,7 +476,7 @@ class Matcher_Point2Plane_B200 : public Matcher_Points_Base
         using namespace b200_detail;
         (void)globalName;
         checkAllParametersAreRealized();
-        mp2p_b200_map* gmap = cache().get(pcGlobal);
+        mp2p_b200_map* gmap = cache().get(pcGlobal, device);
         const auto&    lx   = pcLocal.getPointsBufferRef_x();
         double         T[12];
         pose12(localPose, T);
@@ -382,16 +488,16 @@ class Matcher_Point2Plane_B200 : public Matcher_Points_Base
         out.paired_pt2pl.resize(before + lx.size());
         static_assert(sizeof(mp2p_icp::point_plane_pair_t) == sizeof(mp2p_b200_pair_pt2pl));
         uint64_t     cnt = 0, pot = 0;
-        const float* resident = cache().pinned_local(pcLocal);
-        check(mp2p_b200_match_pt2pl(ctx(), gmap, resident ? resident : lx.data(),
+        const float* resident = cache().pinned_local(pcLocal, device);
+        check(mp2p_b200_match_pt2pl(ctx(device), gmap, resident ? resident : lx.data(),
                                     resident ? nullptr : pcLocal.getPointsBufferRef_y().data(),
                                     resident ? nullptr : pcLocal.getPointsBufferRef_z().data(), lx.size(),
-                                    resident ? MP2P_B200_LOCAL_CLOUD : MP2P_B200_LOCAL_HOST, T, &p, lbits.data(),
+                                    resident ? MP2P_B200_LOCAL_CLOUD : MP2P_B200_LOCAL_HOST, T, &p, bits_or_null(lbits),
                                     reinterpret_cast<mp2p_b200_pair_pt2pl*>(out.paired_pt2pl.data() + before),
                                     lx.size(), 0, &cnt, &pot));
         out.paired_pt2pl.resize(before + cnt);
         out.potential_pairings += pot;
-        witness2l().note(out.paired_pt2pl.data() + before, before == 0 ? cnt : 0);
+        witness2l(device).note(out.paired_pt2pl.data() + before, before == 0 ? cnt : 0);
         // Matcher_Point2Plane.cpp:105-109: only the local point is marked. point_plane_pair_t carries
         // the local COORDINATES, not the index: re-identify by a parallel walk (the output is in
         // ascending local index and each local point pairs at most once)
@@ -413,12 +519,24 @@ IMPLEMENTS_MRPT_OBJECT(Matcher_Point2Plane_B200, Matcher, mp2p_icp)
 class Solver_GaussNewton_B200 : public Solver_GaussNewton
 {
     DEFINE_MRPT_OBJECT(Solver_GaussNewton_B200, mp2p_icp)
+   public:
+    int  device = 0;                         //!< YAML `device`: the GPU this object works on
+    bool assumeUnmodifiedPairings = false;   //!< YAML opt-in: read the device copy the last matcher call left
+    void initialize(const mrpt::containers::yaml& params) override
+    {
+        Solver_GaussNewton::initialize(params);
+        MCP_LOAD_OPT(params, device);
+        MCP_LOAD_OPT(params, assumeUnmodifiedPairings);
+    }
+
    protected:
     bool impl_optimal_pose(const Pairings& pairings, OptimalTF_Result& out, const SolverContext& sc) const override
     {
         using namespace b200_detail;
+        // Pairings::point_weights re-weight the pt2pt term block by block (optimal_tf_gauss_newton.cpp:118-128):
+        // the device accumulation carries one uniform pt2pt weight, so weighted layers go to the reference
         if (sc.prior.has_value() || !pairings.paired_ln2ln.empty() || !pairings.paired_pl2pl.empty() ||
-            (!pairings.paired_pt2ln.empty() && !pairings.point_weights.empty()))
+            !pairings.point_weights.empty())
             return Solver_GaussNewton::impl_optimal_pose(pairings, out, sc);  // terms that stay host-side
         checkAllParametersAreRealized();
         out = OptimalTF_Result();
@@ -438,20 +556,20 @@ class Solver_GaussNewton_B200 : public Solver_GaussNewton
         // every non-empty list must be the witnessed output of the last matcher call of its kind
         const auto& l2p  = pairings.paired_pt2pt;
         const auto& l2l  = pairings.paired_pt2pl;
-        const bool  last = (l2p.empty() || witness2p().same(l2p.data(), l2p.size())) &&
-                          (l2l.empty() || witness2l().same(l2l.data(), l2l.size())) && !(l2p.empty() && l2l.empty());
+        const bool  last = assumeUnmodifiedPairings && (l2p.empty() || witness2p(device).same(l2p.data(), l2p.size())) &&
+                          (l2l.empty() || witness2l(device).same(l2l.data(), l2l.size())) && !(l2p.empty() && l2l.empty());
         if (const auto& l2n = pairings.paired_pt2ln; !l2n.empty())
         {
             // point-to-line term on the device too (optimal_tf_gauss_newton.cpp:182-203); point_line_pair_t
             // = TLine3D {pBase, director} + TPoint3D pt_local = nine doubles, the layout of mp2p_b200_pair_pt2ln
             static_assert(sizeof(mp2p_icp::point_line_pair_t) == sizeof(mp2p_b200_pair_pt2ln));
-            check(mp2p_b200_solve_gauss_newton_ex(ctx(), reinterpret_cast<const mp2p_b200_pair_pt2pt*>(l2p.data()), l2p.size(),
+            check(mp2p_b200_solve_gauss_newton_ex(ctx(device), reinterpret_cast<const mp2p_b200_pair_pt2pt*>(l2p.data()), l2p.size(),
                                                   reinterpret_cast<const mp2p_b200_pair_pt2pl*>(l2l.data()), l2l.size(),
                                                   reinterpret_cast<const mp2p_b200_pair_pt2ln*>(l2n.data()), l2n.size(), 0, &p,
                                                   pairWeights.pt2ln, T0, T, &iters, &solved));
         }
         else
-            check(mp2p_b200_solve_gauss_newton(ctx(), reinterpret_cast<const mp2p_b200_pair_pt2pt*>(l2p.data()), l2p.size(),
+            check(mp2p_b200_solve_gauss_newton(ctx(device), reinterpret_cast<const mp2p_b200_pair_pt2pt*>(l2p.data()), l2p.size(),
                                            reinterpret_cast<const mp2p_b200_pair_pt2pl*>(l2l.data()), l2l.size(),
                                            last ? MP2P_B200_PAIRS_LAST_MATCH : 0, &p, T0, T, &iters, &solved));
         if (!solved) return false;
@@ -472,9 +590,11 @@ class Matcher_Adaptive_B200 : public Matcher_Points_Base
 {
     DEFINE_MRPT_OBJECT(Matcher_Adaptive_B200, mp2p_icp)
    public:
+    int device = 0;  //!< YAML `device`: the GPU this object works on
     void initialize(const mrpt::containers::yaml& params) override
     {
         Matcher_Points_Base::initialize(params);
+        MCP_LOAD_OPT(params, device);
         MCP_LOAD_REQ(params, confidenceInterval);
         MCP_LOAD_REQ(params, firstToSecondDistanceMax);
         MCP_LOAD_REQ(params, absoluteMaxSearchDistance);
@@ -502,7 +622,7 @@ class Matcher_Adaptive_B200 : public Matcher_Points_Base
                            const layer_name_t& localName, Pairings& out) const override
     {
         using namespace b200_detail;
-        mp2p_b200_map* gmap = cache().get(pcGlobal);
+        mp2p_b200_map* gmap = cache().get(pcGlobal, device);
         const auto&    lx   = pcLocal.getPointsBufferRef_x();
         const auto&    ly   = pcLocal.getPointsBufferRef_y();
         const auto&    lz   = pcLocal.getPointsBufferRef_z();
@@ -519,10 +639,10 @@ class Matcher_Adaptive_B200 : public Matcher_Points_Base
         uint64_t   hist[MP2P_B200_ADAPTIVE_BINS], ns = 0, pot = 0;
         double     emin = 0, emax = 0;
         int32_t    gate = 0;
-        const float* resident = cache().pinned_local(pcLocal);
-        check(mp2p_b200_adaptive_search(ctx(), gmap, resident ? resident : lx.data(), resident ? nullptr : ly.data(),
+        const float* resident = cache().pinned_local(pcLocal, device);
+        check(mp2p_b200_adaptive_search(ctx(device), gmap, resident ? resident : lx.data(), resident ? nullptr : ly.data(),
                                         resident ? nullptr : lz.data(), lx.size(),
-                                        resident ? MP2P_B200_LOCAL_CLOUD : MP2P_B200_LOCAL_HOST, T, &p, lbits.data(), hist, &emin,
+                                        resident ? MP2P_B200_LOCAL_CLOUD : MP2P_B200_LOCAL_HOST, T, &p, bits_or_null(lbits), hist, &emin,
                                         &emax, &ns, &gate, &pot));
         out.potential_pairings += pot;
         if (!gate) return;  // :71, :77-80
@@ -542,7 +662,7 @@ class Matcher_Adaptive_B200 : public Matcher_Points_Base
         const size_t cap2p = lx.size() * maxPt2PtCorrespondences, cap2l = lx.size();
         out.paired_pt2pt.resize(b2p + cap2p), out.paired_pt2pl.resize(b2l + cap2l);
         uint64_t n2p = 0, n2l = 0;
-        check(mp2p_b200_adaptive_emit(ctx(), gmap, &p, maxCorrDistSqr, gbits.data(),
+        check(mp2p_b200_adaptive_emit(ctx(device), gmap, &p, maxCorrDistSqr, bits_or_null(gbits),
                                       reinterpret_cast<mp2p_b200_pair_pt2pt*>(out.paired_pt2pt.data() + b2p), cap2p,
                                       reinterpret_cast<mp2p_b200_pair_pt2pl*>(out.paired_pt2pl.data() + b2l), cap2l, 0, &n2p, &n2l));
         out.paired_pt2pt.resize(b2p + n2p), out.paired_pt2pl.resize(b2l + n2l);
@@ -564,9 +684,11 @@ class Matcher_Point2Line_B200 : public Matcher_Points_Base
 {
     DEFINE_MRPT_OBJECT(Matcher_Point2Line_B200, mp2p_icp)
    public:
+    int device = 0;  //!< YAML `device`: the GPU this object works on
     void initialize(const mrpt::containers::yaml& params) override
     {
         Matcher_Points_Base::initialize(params);
+        MCP_LOAD_OPT(params, device);
         MCP_LOAD_REQ(params, distanceThreshold);
         MCP_LOAD_REQ(params, knn);
         MCP_LOAD_REQ(params, lineEigenThreshold);
@@ -584,7 +706,7 @@ class Matcher_Point2Line_B200 : public Matcher_Points_Base
                            const layer_name_t& localName, Pairings& out) const override
     {
         using namespace b200_detail;
-        mp2p_b200_map* gmap = cache().get(pcGlobal);
+        mp2p_b200_map* gmap = cache().get(pcGlobal, device);
         const auto&    lx   = pcLocal.getPointsBufferRef_x();
         const auto&    ly   = pcLocal.getPointsBufferRef_y();
         const auto&    lz   = pcLocal.getPointsBufferRef_z();
@@ -598,10 +720,10 @@ class Matcher_Point2Line_B200 : public Matcher_Points_Base
         out.paired_pt2ln.resize(before + lx.size());
         static_assert(sizeof(mp2p_icp::point_line_pair_t) == sizeof(mp2p_b200_pair_pt2ln));
         uint64_t     cnt = 0, pot = 0;
-        const float* resident = cache().pinned_local(pcLocal);
-        check(mp2p_b200_match_pt2ln(ctx(), gmap, resident ? resident : lx.data(), resident ? nullptr : ly.data(),
+        const float* resident = cache().pinned_local(pcLocal, device);
+        check(mp2p_b200_match_pt2ln(ctx(device), gmap, resident ? resident : lx.data(), resident ? nullptr : ly.data(),
                                     resident ? nullptr : lz.data(), lx.size(),
-                                    resident ? MP2P_B200_LOCAL_CLOUD : MP2P_B200_LOCAL_HOST, T, &p, lbits.data(),
+                                    resident ? MP2P_B200_LOCAL_CLOUD : MP2P_B200_LOCAL_HOST, T, &p, bits_or_null(lbits),
                                     reinterpret_cast<mp2p_b200_pair_pt2ln*>(out.paired_pt2ln.data() + before), lx.size(), 0,
                                     &cnt, &pot));
         out.paired_pt2ln.resize(before + cnt);
@@ -626,8 +748,10 @@ class QualityEvaluator_PairedRatio_B200 : public QualityEvaluator
 {
     DEFINE_MRPT_OBJECT(QualityEvaluator_PairedRatio_B200, mp2p_icp)
    public:
+    int device = 0;  //!< YAML `device`: the GPU this object works on
     void initialize(const mrpt::containers::yaml& params) override
     {
+        MCP_LOAD_OPT(params, device);
         MCP_LOAD_OPT(params, reuse_icp_pairings);
         MCP_LOAD_OPT(params, absolute_minimum_pairing_ratio);
         if (!reuse_icp_pairings)
@@ -667,6 +791,9 @@ class QualityEvaluator_PairedRatio_B200 : public QualityEvaluator
 };
 IMPLEMENTS_MRPT_OBJECT(QualityEvaluator_PairedRatio_B200, QualityEvaluator, mp2p_icp)
 
+}  // namespace mp2p_icp
+
+// at global scope, like the reference's own (mp2p_icp/src/register.cpp:43-69)
 MRPT_INITIALIZER(register_mp2p_icp_b200)
 {
     using mrpt::rtti::registerClass;
@@ -679,6 +806,5 @@ MRPT_INITIALIZER(register_mp2p_icp_b200)
     registerClass(CLASS_ID(mp2p_icp::Solver_GaussNewton_B200));
     registerClass(CLASS_ID(mp2p_icp::QualityEvaluator_PairedRatio_B200));
 }
-}  // namespace mp2p_icp
 
 #endif  // MP2P_B200_WITH_MRPT
