@@ -619,12 +619,13 @@ class Bench:
             h_pairs_t = torch.empty(cap * rec, dtype=torch.uint8).pin_memory()
             h_pairs = h_pairs_t.numpy().view(b200.PAIR_PT2PT if rec == 36 else b200.PAIR_PT2PL)
             hx, hy, hz = (t.numpy() for t in h_l)
-            plugin_safe = gmap.make_plugin_step(hx, hy, hz, mprm, sprm, h_pairs, reuse_device_pairs=False)
+            plugin_safe = gmap.make_plugin_step(hx, hy, hz, mprm, sprm, h_pairs)  # the plugin classes' defaults
             plugin_reuse = gmap.make_plugin_step(hx, hy, hz, mprm, sprm, h_pairs, reuse_device_pairs=True)
+            plugin_nocache = gmap.make_plugin_step(hx, hy, hz, mprm, sprm, h_pairs, cache_local_cloud=False)
             # pageable buffers (std::vector storage) + MatchState bit marshalling: what icp-run would see
             px, py, pz = (np.array(a, copy=True) for a in xyz(L))
             p_pairs = np.empty(cap, b200.PAIR_PT2PT if rec == 36 else b200.PAIR_PT2PL)
-            plugin_pageable = gmap.make_plugin_step(px, py, pz, mprm, sprm, p_pairs, reuse_device_pairs=False)
+            plugin_pageable = gmap.make_plugin_step(px, py, pz, mprm, sprm, p_pairs)
             lbits_bool = np.zeros(nq, dtype=bool)
 
             def step_pageable():
@@ -640,17 +641,21 @@ class Bench:
 
             ms_e2e, (n_e, T_e) = self.timed(wrap(plugin_safe), steps, max(3, warmup), wall=True)
             ms_reuse, (n_r, T_r) = self.timed(wrap(plugin_reuse), steps, 3, wall=True)
+            ms_nocache, (n_c, T_c) = self.timed(wrap(plugin_nocache), max(3, steps // 2), 3, wall=True)
             ms_page, (n_p, T_p) = self.timed(step_pageable, max(3, steps // 2), 3, wall=True)
+            if n_c != n_e or float(np.abs(np.asarray(T_e) - np.asarray(T_c)).max()) > 1e-9:
+                raise SystemExit("e2e: cached and uncached local cloud disagree")
             if n_r != n_e or n_p != n_e or float(np.abs(np.asarray(T_e) - np.asarray(T_r)).max()) > 1e-9 or float(np.abs(np.asarray(T_e) - np.asarray(T_p)).max()) > 1e-9:
                 raise SystemExit("e2e: the three host-buffer paths disagree")
             pcie = self.pcie_gbs()
-            h2d = nq * 12 + 96 + n_e * rec + 96  # local cloud + pose (matcher), pairings + pose/params (solver)
+            h2d = 96 + n_e * rec + 96  # pose (matcher; the local layer is resident while its fingerprint holds), pairings + pose/params (solver)
             d2h = n_e * rec + 8 + (512 if w["solver"] == "horn" else 104)
             e2e = {"value": 1e3 / ms_e2e, "unit": "iterations/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "timing": "wall clock around the two C-ABI calls, pinned host buffers",
-                   "path": "matcher call (host local cloud in, host pairings out) + solver call over those host pairings, uploaded again (the plugin's safe default: nothing is assumed about what happened to the Pairings between the calls)",
-                   "assume_unmodified_pairings": {"ms_per_step": ms_reuse, "value": 1e3 / ms_reuse, "h2d_bytes_per_step": int(nq * 12 + 192),
+                   "path": "the plugin classes' defaults: matcher call (host local layer, kept on the device while address + size + sampled fingerprint are unchanged; host pairings out) + solver call over those host pairings, uploaded again and compared byte for byte with the matcher's device copy (equal: the result computed during the matcher call's read-back is used)",
+                   "local_cloud_uploaded_every_call": {"ms_per_step": ms_nocache, "value": 1e3 / ms_nocache, "h2d_bytes_per_step": int(h2d + nq * 12), "note": "YAML cacheLocalCloud: false"},
+                   "assume_unmodified_pairings": {"ms_per_step": ms_reuse, "value": 1e3 / ms_reuse, "h2d_bytes_per_step": 192,
                                                   "note": "opt-in (YAML assumeUnmodifiedPairings / MP2P_B200_PAIRS_LAST_MATCH): the solver reads the device copy the matcher left"},
                    "pageable": {"ms_per_step": ms_page, "value": 1e3 / ms_page, "note": "pageable host arrays for cloud and pairings + MatchState bit marshalling per matcher call"},
                    "pcie_h2d_gbs": pcie[0], "pcie_d2h_gbs": pcie[1],

@@ -189,6 +189,22 @@ int  mp2p_b200_cloud_create(mp2p_b200_ctx* ctx, const float* x, const float* y, 
 void mp2p_b200_cloud_destroy(mp2p_b200_cloud* cloud);
 int  mp2p_b200_cloud_get_info(const mp2p_b200_cloud* cloud, mp2p_b200_cloud_info* out);
 
+/* Device copies of HOST layers, cached by the library (what a plugin whose methods are `const` and whose
+ * callers hand it mrpt point maps needs; SURVEY.md §8b "Ownership"). The reference relies on MRPT's private
+ * "kd-tree up to date" flag; from outside only the buffers are visible, so a layer is taken for unchanged while
+ * its x-buffer address, its size and a FINGERPRINT (FNV-1a over the bit patterns of ~4096 evenly spaced points
+ * plus the first and the last one, ~3 us) are the same; anything else rebuilds the copy (*rebuilt = 1).
+ * An in-place edit that touches none of the sampled points is NOT seen: call mp2p_b200_layer_invalidate (or
+ * use the non-cached entry points, which never assume anything). The handles stay owned by the context (at
+ * most MP2P_B200_LAYER_CACHE_SLOTS layers per kind, least recently used first out) — do not destroy them. */
+#define MP2P_B200_LAYER_CACHE_SLOTS 8
+int  mp2p_b200_map_cached(mp2p_b200_ctx* ctx, const float* x, const float* y, const float* z, uint64_t n,
+                          mp2p_b200_map** out, int32_t* rebuilt);
+int  mp2p_b200_cloud_cached(mp2p_b200_ctx* ctx, const float* x, const float* y, const float* z, uint64_t n,
+                            mp2p_b200_cloud** out, int32_t* rebuilt);
+void mp2p_b200_layer_invalidate(mp2p_b200_ctx* ctx, const float* x);
+uint64_t mp2p_b200_layer_fingerprint(const float* x, const float* y, const float* z, uint64_t n);
+
 /* Raw k-NN of already-transformed query points (ascending (d2, index), d2 < radius2 strictly;
  * out_idx/out_d2 are [nq*k], out_found [nq]); replaces nn_single_search / nn_multiple_search /
  * nn_radius_search (Matcher_Points_DistanceThreshold.cpp:161-163,174-177,246-248). Host pointers. */
@@ -540,6 +556,11 @@ int mp2p_b200_ctx_set_profiling(mp2p_b200_ctx* ctx, int timings_on, int search_s
 int mp2p_b200_ctx_get_timings(mp2p_b200_ctx* ctx, float ms[MP2P_B200_N_TIMINGS]);
 int mp2p_b200_ctx_get_search_stats(mp2p_b200_ctx* ctx, uint64_t stats[8]);
 
+/* Per-CTA trace of the last k > 1 search over a resident cloud, recorded only when the environment variable
+ * MP2P_KNN_TRACE is set: 8 words per CTA {SM id, start ns (low 32 bits of %globaltimer), end ns, query tile,
+ * rounds, scan steps, list insertions, probes | levels << 16 of its first warp}. */
+int mp2p_b200_ctx_get_tile_trace(mp2p_b200_ctx* ctx, uint32_t* out, uint64_t capacity_tiles, uint64_t* n_tiles);
+
 /* ---- KITTI .bin straight to the device ------------------------------------------
  * A KITTI velodyne scan is a flat file of float32 (x, y, z, intensity) records — what the reference's
  * kitti2mm reads through mrpt::obs::CObservationPointCloud / CPointsMapXYZI
@@ -552,6 +573,58 @@ int mp2p_b200_read_kitti_bin(const char* path, float** xyzi_pinned_out, uint64_t
 int mp2p_b200_map_create_xyzi(mp2p_b200_ctx* ctx, const float* xyzi, uint64_t n, int on_device, mp2p_b200_map** out);
 int mp2p_b200_cloud_create_xyzi(mp2p_b200_ctx* ctx, const float* xyzi, uint64_t n, int on_device,
                                 mp2p_b200_cloud** out);
+
+/* ---- covariance() on the device -------------------------------------------------
+ * mp2p_icp::covariance (mp2p_icp/src/covariance.cpp:28-141; call site ICP.cpp:337, once per align()): the
+ * stacked error vector of the final pairings (pt2pt :75-82, pt2ln :85-93, pt2pl :107-115; three rows per
+ * pairing) differentiated numerically w.r.t. (x, y, z, yaw, pitch, roll) by central differences with the
+ * steps of CovarianceParameters (covariance.h:27-31: finDif_xyz, finDif_angles, default 1e-7; the
+ * mrpt::math::estimateJacobian scheme, recalled from MRPT 2.x: parity unpinned for that helper),
+ * hessian = J^T J, cov = hessian^-1 (inverse_LLt). The 12 sweeps over the pairings run in ONE launch.
+ *   x6 = the vector the Jacobian is taken at. AS WRITTEN UPSTREAM the z slot is never assigned
+ *        (covariance.cpp:41-47 sets [0], [1], [0] again, [3], [4], [5]) and a default-constructed
+ *        CMatrixDouble61 is zero-filled, so the reference evaluates at (x, y, 0, yaw, pitch, roll): a caller
+ *        that wants the reference's number passes x6[2] = 0 (the plugin and the host mirror do), one that wants
+ *        the covariance at the solution passes its z.
+ *   No pairings at all: cov = diag(1e6) (:33-38). ln2ln / pl2pl pairings are not taken (host-side upstream).
+ *   *positive_definite = 0 if the Cholesky factorisation of the hessian fails (upstream: undefined result);
+ *   cov_out then holds the hessian's pseudo-diagonal inverse and the call still returns MP2P_B200_OK.
+ * pairs_on_device: 0 host lists, 1 device lists. cov_out / hessian_out: 6x6 row-major (hessian_out may be NULL). */
+int mp2p_b200_covariance(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* pairs_pt2pt, uint64_t n_pt2pt,
+                         const mp2p_b200_pair_pt2pl* pairs_pt2pl, uint64_t n_pt2pl, const mp2p_b200_pair_pt2ln* pairs_pt2ln,
+                         uint64_t n_pt2ln, int pairs_on_device, const double x6[6], double finDif_xyz, double finDif_angles,
+                         double cov_out[36], double hessian_out[36], int32_t* positive_definite);
+
+/* ---- FilterDecimateVoxels on the device -----------------------------------------
+ * mp2p_icp_filters::FilterDecimateVoxels::filter over ONE input layer
+ * (mp2p_icp_filters/src/FilterDecimateVoxels.cpp:109-378; parameters FilterDecimateVoxels.h:84-116) — the
+ * step right before ICP::align() in the reference's pipelines (demos/icp-settings-kitti.yaml:76-82).
+ * Voxel index per axis = int32(coordinate / resolution): float division, truncation toward zero
+ * (PointCloudToVoxelGridSingle.h:105). decimate_method: 0 FirstPoint (the first point inserted into the
+ * voxel), 1 ClosestToAverage (the member closest to the voxel mean, first on ties), 2 VoxelAverage (float
+ * sums in insertion order times float(1/n)); RandomPoint (an unseeded generator upstream) is refused.
+ * has_flatten_to: z is replaced by flatten_to and only the first voxel of every (cx, cy) column emits
+ * (:210-224, :335-349). OUTPUT ORDER: ascending (cx, cy, cz) — the order of the reference's std::map walk
+ * (use_tsl_robin_map = false); with the default tsl::robin_map the reference's own order is
+ * implementation-defined and only the set of points is comparable. out_src_index[i] = index of the input
+ * point output i is a copy of, -1 for an averaged point (may be NULL). Returns MP2P_B200_ERR_CAPACITY
+ * (with *out_count = the number needed) if capacity is too small; capacity = n always suffices.
+ * mp2p_b200_cloud_create_decimated = the filter followed by mp2p_b200_cloud_create without leaving the
+ * device: the decimated local layer of an align() goes from the filter to the matchers in HBM. */
+typedef struct
+{
+    float   voxel_filter_resolution; /* metres, > 0 */
+    int32_t decimate_method;
+    int32_t has_flatten_to;
+    float   flatten_to;
+} mp2p_b200_decimate_params;
+int mp2p_b200_filter_decimate_voxels(mp2p_b200_ctx* ctx, const float* x, const float* y, const float* z, uint64_t n,
+                                     int on_device, const mp2p_b200_decimate_params* params, float* out_x, float* out_y,
+                                     float* out_z, int64_t* out_src_index, uint64_t capacity, int out_on_device,
+                                     uint64_t* out_count);
+int mp2p_b200_cloud_create_decimated(mp2p_b200_ctx* ctx, const float* x, const float* y, const float* z, uint64_t n,
+                                     int on_device, const mp2p_b200_decimate_params* params, mp2p_b200_cloud** out,
+                                     uint64_t* out_count);
 
 /* Pinned host memory helpers (so callers in any language can give the library DMA-able buffers). */
 int  mp2p_b200_host_alloc(size_t bytes, void** out);

@@ -117,6 +117,17 @@ class _GNParams(C.Structure):
     ]
 
 
+class _DecimateParams(C.Structure):
+    _fields_ = [("voxel_filter_resolution", C.c_float), ("decimate_method", C.c_int32), ("has_flatten_to", C.c_int32), ("flatten_to", C.c_float)]
+
+
+DECIMATE_METHODS = {"FirstPoint": 0, "ClosestToAverage": 1, "VoxelAverage": 2, "RandomPoint": 3}
+
+
+def _decimate_params(resolution, method, flatten_to):
+    return _DecimateParams(float(resolution), DECIMATE_METHODS[method] if isinstance(method, str) else int(method), int(flatten_to is not None), float(flatten_to or 0.0))
+
+
 class _MapInfo(C.Structure):
     _fields_ = [
         ("n_points", C.c_uint64),
@@ -254,6 +265,7 @@ EXPORTS = [
     "mp2p_b200_peer_create", "mp2p_b200_peer_connect", "mp2p_b200_peer_destroy", "mp2p_b200_peer_record_slot",
     "mp2p_b200_peer_allgather_records", "mp2p_b200_peer_allreduce_packet",
     "mp2p_b200_peer_iterate_pt2pt", "mp2p_b200_peer_iterate_pt2pl_gn",
+    "mp2p_b200_filter_decimate_voxels", "mp2p_b200_cloud_create_decimated", "mp2p_b200_covariance", "mp2p_b200_ctx_get_tile_trace",
 ]
 PEER_HANDLE_BYTES = 64
 GN_STATE_DOUBLES = 16
@@ -377,6 +389,58 @@ class Context:
         return int(load_library().mp2p_b200_ctx_launch_count(self._h))
 
     # ---------------------------------------------------------------- solvers
+    def cached_map(self, x, y, z):
+        """(Map view of the library-owned cached index of a HOST layer, rebuilt flag) — mp2p_b200_map_cached."""
+        h, rb = C.c_void_p(), C.c_int32(0)
+        _check(load_library().mp2p_b200_map_cached(self._h, _ptr(x), _ptr(y), _ptr(z), C.c_uint64(x.size), C.byref(h), C.byref(rb)))
+        m = Map.__new__(Map)
+        m.ctx, m._h, m._borrowed = self, h, True
+        return m, bool(rb.value)
+
+    def cached_cloud(self, x, y, z):
+        h, rb = C.c_void_p(), C.c_int32(0)
+        _check(load_library().mp2p_b200_cloud_cached(self._h, _ptr(x), _ptr(y), _ptr(z), C.c_uint64(x.size), C.byref(h), C.byref(rb)))
+        c = Cloud.__new__(Cloud)
+        c.ctx, c._h, c.n, c._borrowed = self, h, int(x.size), True
+        return c, bool(rb.value)
+
+    def invalidate_layer(self, x):
+        load_library().mp2p_b200_layer_invalidate(self._h, _ptr(x))
+
+    def tile_trace(self):
+        """(n, 8) uint32 {SM, start ns, end ns, tile, rounds, steps, inserts, probes | levels << 16} of the last k > 1 search (needs $MP2P_KNN_TRACE)."""
+        n = C.c_uint64(0)
+        _check(load_library().mp2p_b200_ctx_get_tile_trace(self._h, None, C.c_uint64(0), C.byref(n)))
+        out = np.zeros((n.value, 8), np.uint32)
+        if n.value:
+            _check(load_library().mp2p_b200_ctx_get_tile_trace(self._h, _ptr(out), C.c_uint64(n.value), C.byref(n)))
+        return out
+
+    def covariance(self, p2p, p2l, p2ln, x6, finDif_xyz=1e-7, finDif_angles=1e-7):
+        """mp2p_icp::covariance on the device. Returns (cov 6x6, hessian 6x6, positive_definite)."""
+        def arr(a, dt):
+            return np.zeros(0, dt) if a is None else np.ascontiguousarray(a, dtype=dt)
+        p2p, p2l, p2ln = arr(p2p, PAIR_PT2PT), arr(p2l, PAIR_PT2PL), arr(p2ln, PAIR_PT2LN)
+        cov, hes, pd = np.zeros(36), np.zeros(36), C.c_int32(0)
+        x6 = np.ascontiguousarray(x6, dtype=np.float64)
+        _check(load_library().mp2p_b200_covariance(self._h, _ptr(p2p) if p2p.size else None, C.c_uint64(p2p.size), _ptr(p2l) if p2l.size else None, C.c_uint64(p2l.size), _ptr(p2ln) if p2ln.size else None, C.c_uint64(p2ln.size), 0, _ptr(x6), C.c_double(finDif_xyz), C.c_double(finDif_angles), _ptr(cov), _ptr(hes), C.byref(pd)))
+        return cov.reshape(6, 6), hes.reshape(6, 6), bool(pd.value)
+
+    def decimate_voxels(self, x, y, z, resolution: float, method="FirstPoint", flatten_to=None, n=None, on_device=False):
+        """FilterDecimateVoxels over one layer on the device. Returns (xyz (m, 3) float32, src (m,) int64: source index,
+        -1 for an averaged point), ascending (cx, cy, cz) voxel order."""
+        if not on_device:
+            x, y, z = _f32(x), _f32(y), _f32(z)
+            n = x.size
+        ox, oy, oz = (np.zeros(max(n, 1), np.float32) for _ in range(3))
+        src = np.zeros(max(n, 1), np.int64)
+        cnt = C.c_uint64(0)
+        prm = _decimate_params(resolution, method, flatten_to)
+        px, py, pz = (C.c_void_p(int(a)) for a in (x, y, z)) if on_device else (_ptr(x), _ptr(y), _ptr(z))
+        _check(load_library().mp2p_b200_filter_decimate_voxels(self._h, px, py, pz, C.c_uint64(n), int(on_device), C.byref(prm), _ptr(ox), _ptr(oy), _ptr(oz), _ptr(src), C.c_uint64(n), 0, C.byref(cnt)))
+        m = cnt.value
+        return np.stack([ox[:m], oy[:m], oz[:m]], 1), src[:m]
+
     def solve_horn(self, pairs, n=None, prm: HornParams = None, point_weights=None, on_device=False, last_match=False):
         """last_match=True: `pairs` is the unmodified host output of the last matcher call on this
         context; the solver reads the copy that call left on the device (MP2P_B200_PAIRS_LAST_MATCH)."""
@@ -603,9 +667,25 @@ class Cloud:
         ctx._maps.add(self)
         return self
 
+    @classmethod
+    def decimated(cls, ctx: "Context", x, y, z, resolution: float, method="FirstPoint", flatten_to=None, n=None, on_device=False):
+        """FilterDecimateVoxels followed by cloud_create without leaving the device (the `decimated` local layer of
+        demos/icp-settings-kitti.yaml:76-82 goes from the filter to the matchers in HBM)."""
+        if not on_device:
+            x, y, z = _f32(x), _f32(y), _f32(z)
+            n = x.size
+        self = cls.__new__(cls)
+        p, cnt = C.c_void_p(), C.c_uint64(0)
+        prm = _decimate_params(resolution, method, flatten_to)
+        px, py, pz = (C.c_void_p(int(a)) for a in (x, y, z)) if on_device else (_ptr(x), _ptr(y), _ptr(z))
+        _check(load_library().mp2p_b200_cloud_create_decimated(ctx._h, px, py, pz, C.c_uint64(n), int(on_device), C.byref(prm), C.byref(p), C.byref(cnt)))
+        self._h, self.ctx, self.n = p, ctx, int(cnt.value)
+        ctx._maps.add(self)
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
-            if getattr(self.ctx, "_h", None):
+            if getattr(self.ctx, "_h", None) and not getattr(self, "_borrowed", False):  # cached layers belong to the library
                 load_library().mp2p_b200_cloud_destroy(self._h)
             self._h = None
 
@@ -684,7 +764,7 @@ class Map:
 
     def close(self):
         if getattr(self, "_h", None):
-            if getattr(self.ctx, "_h", None):  # a map never outlives its context
+            if getattr(self.ctx, "_h", None) and not getattr(self, "_borrowed", False):  # a map never outlives its context; cached layers belong to the library
                 load_library().mp2p_b200_map_destroy(self._h)
             self._h = None
 
@@ -804,14 +884,17 @@ class Map:
         step._keep = (keep_local, keep, self)  # the closure owns its inputs (a temporary Cloud must outlive it)
         return step
 
-    def make_plugin_step(self, hx, hy, hz, matcher_prm, solver_prm, out_pairs, reuse_device_pairs=True):
+    def make_plugin_step(self, hx, hy, hz, matcher_prm, solver_prm, out_pairs, reuse_device_pairs=False, cache_local_cloud=True):
         """Pre-binds what the reference's ICP loop does per iteration through the two plugin classes
         (run_matchers then run_solvers, ICP.cpp:143,170) over HOST buffers: a matcher call that
         uploads the local cloud `hx, hy, hz` and returns the pairings into `out_pairs` (host), then a
-        solver call over those host pairings. reuse_device_pairs: the solver names them as the
-        unmodified output of the last matcher call (MP2P_B200_PAIRS_LAST_MATCH, what the plugin's
-        witness check does) instead of uploading them again. Returns pose(3x4) -> (solved, pose_out,
-        n_pairs); all ctypes marshalling happens once here."""
+        solver call over those host pairings. Defaults = the plugin classes' defaults: the local layer
+        goes through the library's fingerprinted cache (mp2p_b200_cloud_cached, YAML cacheLocalCloud),
+        the solver uploads the pairings it is given (the library compares them with the matcher's
+        device copy and may hand out the result computed ahead of time). reuse_device_pairs = the YAML
+        opt-in assumeUnmodifiedPairings: the solver names the pairings as the unmodified output of the
+        last matcher call (MP2P_B200_PAIRS_LAST_MATCH) instead of uploading them. Returns
+        pose(3x4) -> (solved, pose_out, n_pairs); all ctypes marshalling happens once here."""
         L = load_library()
         is_pt2pt = isinstance(matcher_prm, Pt2PtParams)
         mp, sp = matcher_prm.c(), solver_prm.c()
@@ -844,8 +927,19 @@ class Map:
         pose_in_np = np.frombuffer(pose_in, dtype=np.float64)
         pose_out_np = np.frombuffer(pose_out, dtype=np.float64).reshape(3, 4)
 
+        cloud_h = C.c_void_p()
+        c_args = [self.ctx._h, _ptr(hx), _ptr(hy), _ptr(hz), C.c_uint64(n_local), C.byref(cloud_h), None]
+        host_lx = m_args[2]
+
         def step(T):
             pose_in_np[:] = np.asarray(T, dtype=np.float64).reshape(-1)
+            if cache_local_cloud:
+                rc = L.mp2p_b200_cloud_cached(*c_args)
+                if rc != 0:
+                    _check(rc)
+                m_args[2], m_args[6] = cloud_h, 2
+            else:
+                m_args[2], m_args[6] = host_lx, 0
             rc = m_fn(*m_args)
             if rc != 0:
                 _check(rc)

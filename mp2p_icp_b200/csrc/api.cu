@@ -131,6 +131,52 @@ int stage_pairs(mp2p_b200_ctx* ctx, DevBuf& buf, const Rec* pairs, uint64_t n, i
     return 0;
 }
 
+// Safe form of the device-copy shortcut: the host records a solver is handed are UPLOADED (as always) and
+// compared, word by word on the device, with the copy the last matcher call left there. Only if every
+// byte is equal may the solver hand out the result that matcher call computed ahead of time over its copy
+// (ctx->spec_res); any edit of the Pairings between the two calls — a filter, a hook, a re-weighting — is
+// seen and the solve runs over the uploaded records. Costs one pass over 2 x n records at HBM speed
+// instead of the solver's own passes, and nothing is assumed about the caller.
+__global__ void __launch_bounds__(256) k_words_differ(const uint4* __restrict__ a, const uint4* __restrict__ b, uint64_t n16,
+                                                       const uint32_t* __restrict__ ta, const uint32_t* __restrict__ tb, uint32_t n_tail,
+                                                       uint32_t* __restrict__ flag)
+{
+    bool diff = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x)
+    {
+        const uint4 x = __ldg(a + i), y = __ldg(b + i);
+        diff |= (x.x != y.x) | (x.y != y.y) | (x.z != y.z) | (x.w != y.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n_tail) diff |= ta[threadIdx.x] != tb[threadIdx.x];
+    if (__any_sync(0xffffffffu, diff) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+
+// uploads `pairs` into buf (*d_out) and reports in *same whether they equal the last matcher output's device copy
+template <class Rec>
+int upload_and_compare(mp2p_b200_ctx* ctx, DevBuf& buf, const Rec* pairs, uint64_t n, const Rec** d_out, bool* same)
+{
+    *same = false;
+    const mp2p_b200_ctx::LastMatch& lm = sizeof(Rec) == sizeof(mp2p_b200_pair_pt2pt) ? ctx->last2p : ctx->last2l;
+    MP2P_TRY(buf.ensure(n * sizeof(Rec) + 16));
+    MP2P_CUDA_TRY(cudaMemcpyAsync(buf.p, pairs, n * sizeof(Rec), cudaMemcpyHostToDevice, ctx->stream));
+    *d_out = buf.as<Rec>();
+    if (!lm.valid || lm.n != n || !lm.dev || (reinterpret_cast<uintptr_t>(lm.dev) & 15u)) return 0;
+    uint32_t* h_flag = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->h_pinned) + 4032);
+    uint32_t* d_flag = reinterpret_cast<uint32_t*>(ctx->d_pose.as<char>() + 192);
+    MP2P_CUDA_TRY(cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
+    const uint64_t bytes = n * sizeof(Rec), n16 = bytes / 16;
+    const uint32_t tail  = (uint32_t)((bytes - n16 * 16) / 4);
+    const int      grid  = (int)std::max<uint64_t>(1, std::min<uint64_t>((n16 + 255) / 256, 148 * 8));
+    k_words_differ<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint4*>(buf.p), static_cast<const uint4*>(lm.dev), n16,
+                                                  reinterpret_cast<const uint32_t*>(buf.as<char>() + n16 * 16),
+                                                  reinterpret_cast<const uint32_t*>(static_cast<const char*>(lm.dev) + n16 * 16), tail, d_flag);
+    count_launch(ctx);
+    MP2P_CUDA_TRY(cudaMemcpyAsync(h_flag, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *same = *h_flag == 0u;
+    return 0;
+}
+
 int packet_out(mp2p_b200_ctx* ctx, const double* d_packet, double* packet, int packet_on_device)
 {
     if (packet_on_device)
@@ -256,6 +302,9 @@ extern "C"
         cudaEventCreate(&c->ev1);
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
         if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) c->copy_stream = nullptr;
+        cudaEventCreateWithFlags(&c->ev_rank_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_rank, cudaEventDisableTiming);
+        if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess) c->aux_stream = nullptr;
         cudaGetLastError();
         for (auto& e : c->pev) cudaEventCreate(&e);
         {
@@ -289,23 +338,34 @@ extern "C"
     void mp2p_b200_ctx_destroy(mp2p_b200_ctx* c)
     {
         if (!c) return;
+        for (auto& e : c->layer_cache)
+        {
+            if (e.map) mp2p_b200_map_destroy(e.map);
+            if (e.cloud) mp2p_b200_cloud_destroy(e.cloud);
+        }
+        c->layer_cache.clear();
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
         for (DevBuf* b : {&c->d_lx, &c->d_ly, &c->d_lz, &c->d_cand, &c->d_candxyz, &c->d_lbits, &c->d_gbits, &c->d_scan,
                           &c->d_small, &c->d_out2p, &c->d_out2l, &c->d_plcand, &c->d_okflags, &c->d_fitlist, &c->d_adres, &c->d_adsel, &c->d_scan2, &c->d_coop, &c->d_knn_idx, &c->d_knn_d2,
                           &c->d_knn_found, &c->d_irk0, &c->d_irk1, &c->d_irv0, &c->d_irv1, &c->d_irtmp, &c->d_pairs2p, &c->d_pairs2l, &c->d_pairs2ln, &c->d_partials, &c->d_packet,
-                          &c->d_pose, &c->d_weights, &c->d_outlier, &c->d_conv})
+                          &c->d_pose, &c->d_weights, &c->d_outlier, &c->d_conv, &c->d_fd_small, &c->d_fd_keys, &c->d_fd_vals, &c->d_fd_flags,
+                          &c->d_fd_rs, &c->d_fd_in, &c->d_fd_out})
             b->release();
         if (c->h_pinned) cudaFreeHost(c->h_pinned);
         if (c->h_mapped) cudaFreeHost(c->h_mapped);
         if (c->copy_stream) cudaStreamSynchronize(c->copy_stream), cudaStreamDestroy(c->copy_stream);
         if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+        if (c->aux_stream) cudaStreamSynchronize(c->aux_stream), cudaStreamDestroy(c->aux_stream);
+        if (c->ev_rank_fork) cudaEventDestroy(c->ev_rank_fork);
+        if (c->ev_rank) cudaEventDestroy(c->ev_rank);
         c->d_spec.release();
         if (c->ev0) cudaEventDestroy(c->ev0);
         if (c->ev1) cudaEventDestroy(c->ev1);
         for (auto& e : c->pev)
             if (e) cudaEventDestroy(e);
         c->d_stats.release();
+        c->d_trace.release();
         if (c->own_stream) cudaStreamDestroy(c->stream);
         delete c;
     }
@@ -395,9 +455,102 @@ extern "C"
             c->ctx->live_clouds.erase(c);
             DeviceGuard g(c->ctx->device);
             cudaStreamSynchronize(c->ctx->stream);
-            for (DevBuf* b : {&c->d_x, &c->d_y, &c->d_z, &c->d_sx, &c->d_sy, &c->d_sz, &c->d_perm}) b->release();
+            if (c->ctx->aux_stream) cudaStreamSynchronize(c->ctx->aux_stream);
+            for (DevBuf* b : {&c->d_x, &c->d_y, &c->d_z, &c->d_sx, &c->d_sy, &c->d_sz, &c->d_perm, &c->d_tile_cost, &c->d_tile_order}) b->release();
         }
         delete c;
+    }
+
+    uint64_t mp2p_b200_layer_fingerprint(const float* x, const float* y, const float* z, uint64_t n)
+    {
+        uint64_t   h   = 1469598103934665603ull;  // FNV-1a
+        const auto mix = [&h](float f)
+        {
+            uint32_t u;
+            std::memcpy(&u, &f, 4);
+            h = (h ^ u) * 1099511628211ull;
+        };
+        if (!n || !x || !y || !z) return h;
+        const uint64_t step = n > 4096 ? n / 4096 : 1;
+        for (uint64_t i = 0; i < n; i += step) mix(x[i]), mix(y[i]), mix(z[i]);
+        mix(x[n - 1]), mix(y[n - 1]), mix(z[n - 1]);
+        return h ^ n;
+    }
+
+    // kind 0 = map, 1 = cloud
+    static int layer_cached(mp2p_b200_ctx* ctx, int kind, const float* x, const float* y, const float* z, uint64_t n, void** out,
+                            int32_t* rebuilt)
+    {
+        if (!ctx || !out || (n && (!x || !y || !z)))
+        {
+            set_error("layer cache: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        *out = nullptr;
+        if (rebuilt) *rebuilt = 0;
+        const uint64_t fp = mp2p_b200_layer_fingerprint(x, y, z, n);
+        ctx->layer_clock++;
+        mp2p_b200_ctx::CachedLayer* slot = nullptr;
+        for (auto& e : ctx->layer_cache)
+            if (e.x == x && (kind == 0 ? (void*)e.map : (void*)e.cloud)) slot = &e;
+        if (slot && slot->n == n && slot->fingerprint == fp)
+        {
+            slot->last_use = ctx->layer_clock;
+            *out           = kind == 0 ? (void*)slot->map : (void*)slot->cloud;
+            return 0;
+        }
+        if (!slot)
+        {
+            size_t used = 0;
+            for (auto& e : ctx->layer_cache) used += (kind == 0 ? (void*)e.map : (void*)e.cloud) != nullptr;
+            if (used >= MP2P_B200_LAYER_CACHE_SLOTS)  // evict the least recently used layer of this kind
+            {
+                for (auto& e : ctx->layer_cache)
+                    if ((kind == 0 ? (void*)e.map : (void*)e.cloud) && (!slot || e.last_use < slot->last_use)) slot = &e;
+            }
+            else
+            {
+                ctx->layer_cache.emplace_back();
+                slot = &ctx->layer_cache.back();
+            }
+        }
+        if (kind == 0 && slot->map) mp2p_b200_map_destroy(slot->map), slot->map = nullptr;
+        if (kind == 1 && slot->cloud) mp2p_b200_cloud_destroy(slot->cloud), slot->cloud = nullptr;
+        slot->x = x, slot->n = n, slot->fingerprint = fp, slot->last_use = ctx->layer_clock;
+        int rc;
+        if (kind == 0)
+            rc = mp2p_b200_map_create(ctx, x, y, z, n, 0, &slot->map);
+        else
+            rc = mp2p_b200_cloud_create(ctx, x, y, z, n, 0, &slot->cloud);
+        if (rc != 0)
+        {
+            slot->x = nullptr;
+            return rc;
+        }
+        if (rebuilt) *rebuilt = 1;
+        *out = kind == 0 ? (void*)slot->map : (void*)slot->cloud;
+        return 0;
+    }
+    int mp2p_b200_map_cached(mp2p_b200_ctx* ctx, const float* x, const float* y, const float* z, uint64_t n, mp2p_b200_map** out,
+                             int32_t* rebuilt)
+    {
+        return layer_cached(ctx, 0, x, y, z, n, reinterpret_cast<void**>(out), rebuilt);
+    }
+    int mp2p_b200_cloud_cached(mp2p_b200_ctx* ctx, const float* x, const float* y, const float* z, uint64_t n, mp2p_b200_cloud** out,
+                               int32_t* rebuilt)
+    {
+        return layer_cached(ctx, 1, x, y, z, n, reinterpret_cast<void**>(out), rebuilt);
+    }
+    void mp2p_b200_layer_invalidate(mp2p_b200_ctx* ctx, const float* x)
+    {
+        if (!ctx) return;
+        for (auto& e : ctx->layer_cache)
+            if (e.x == x)
+            {
+                if (e.map) mp2p_b200_map_destroy(e.map), e.map = nullptr;
+                if (e.cloud) mp2p_b200_cloud_destroy(e.cloud), e.cloud = nullptr;
+                e.x = nullptr;
+            }
     }
 
     int mp2p_b200_cloud_get_info(const mp2p_b200_cloud* c, mp2p_b200_cloud_info* out)
@@ -808,29 +961,40 @@ extern "C"
         }
         // Speculative solve (common.cuh, SpecWant): a plain Solver_Horn over the last matcher output
         // is what that matcher call already ran while the records travelled to the host
+        const mp2p_b200_pair_pt2pt* staged = nullptr;  // host records already uploaded by the comparison below
         {
             const bool weights = n_weight_blocks && weight_counts && weight_values;
-            if (pairs_on_device == MP2P_B200_PAIRS_LAST_MATCH && !weights && !prm->use_scale_outlier_detector && prm->robust_kernel == 0)
+            if ((pairs_on_device == MP2P_B200_PAIRS_LAST_MATCH || pairs_on_device == 0) && !weights && !prm->use_scale_outlier_detector &&
+                prm->robust_kernel == 0)
             {
                 const auto& r = ctx->spec_res;
                 if (r.valid && r.kind == 1 && r.n == n && ctx->last2p.valid && ctx->last2p.n == n &&
                     ctx->spec_want.kind == 1 && same_params(ctx->spec_want.horn, *prm))
                 {
-                    ctx->spec_unused = 0;
-                    if (r.pending)
+                    bool use = pairs_on_device == MP2P_B200_PAIRS_LAST_MATCH;  // the caller vouches for the identity...
+                    if (!use)  // ...or the library checks it (see upload_and_compare)
                     {
-                        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-                        ctx->spec_res.pending = false;
+                        DeviceGuard g(ctx->device);
+                        MP2P_TRY(upload_and_compare(ctx, ctx->d_pairs2p, pairs, n, &staged, &use));
                     }
-                    return mp2p_b200_horn_finish(spec_host(ctx), spec_host(ctx) + MP2P_B200_PACKET_DOUBLES, pose_out, solved);
+                    if (use)
+                    {
+                        ctx->spec_unused = 0;
+                        if (r.pending)
+                        {
+                            MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                            ctx->spec_res.pending = false;
+                        }
+                        return mp2p_b200_horn_finish(spec_host(ctx), spec_host(ctx) + MP2P_B200_PACKET_DOUBLES, pose_out, solved);
+                    }
                 }
                 ctx->spec_want.kind = 1, ctx->spec_want.list = 1, ctx->spec_want.horn = *prm, ctx->spec_unused = 0;
             }
         }
         DeviceGuard                 g(ctx->device);
         ProfScope   ps(ctx);
-        const mp2p_b200_pair_pt2pt* d;
-        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2p, pairs, n, pairs_on_device, &d));
+        const mp2p_b200_pair_pt2pt* d = staged;
+        if (!staged) MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2p, pairs, n, pairs_on_device, &d));
 
         const uint64_t* d_wprefix = nullptr;
         const double*   d_wvalue  = nullptr;
@@ -1044,10 +1208,12 @@ extern "C"
             return MP2P_B200_ERR_ARG;
         }
         *solved = 0;
+        const mp2p_b200_pair_pt2pt* staged2p = nullptr;  // host records already uploaded by the comparison below
+        const mp2p_b200_pair_pt2pl* staged2l = nullptr;
         {
             // speculative solve (see mp2p_b200_solve_horn): one list, the last matcher's, same start pose
             const int list = (n2p && !n2l) ? 1 : ((!n2p && n2l) ? 2 : 0);
-            if (pairs_on_device == MP2P_B200_PAIRS_LAST_MATCH && list)
+            if ((pairs_on_device == MP2P_B200_PAIRS_LAST_MATCH || pairs_on_device == 0) && list)
             {
                 const auto&    r = ctx->spec_res;
                 const uint64_t n = list == 1 ? n2p : n2l;
@@ -1055,27 +1221,39 @@ extern "C"
                 if (r.valid && r.kind == 2 && r.list == list && r.n == n && lm.valid && lm.n == n && ctx->spec_want.kind == 2 &&
                     same_params(ctx->spec_want.gn, *prm) && std::memcmp(r.pose_in, pose_init, 96) == 0)
                 {
-                    if (r.pending)
+                    bool use = pairs_on_device == MP2P_B200_PAIRS_LAST_MATCH;  // the caller vouches for the identity...
+                    if (!use)  // ...or the library checks it: upload, compare with the device copy byte for byte
                     {
-                        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-                        ctx->spec_res.pending = false;
+                        DeviceGuard g(ctx->device);
+                        if (list == 1)
+                            MP2P_TRY(upload_and_compare(ctx, ctx->d_pairs2p, p2p, n2p, &staged2p, &use));
+                        else
+                            MP2P_TRY(upload_and_compare(ctx, ctx->d_pairs2l, p2l, n2l, &staged2l, &use));
                     }
-                    const double* hp = spec_host(ctx) + 64;
-                    std::memcpy(pose_out, hp, 96);
-                    if (iterations_done) *iterations_done = reinterpret_cast<const uint32_t*>(hp + 12)[1];
-                    *solved          = 1;
-                    ctx->spec_unused = 0;
-                    return 0;
+                    if (use)
+                    {
+                        if (r.pending)
+                        {
+                            MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                            ctx->spec_res.pending = false;
+                        }
+                        const double* hp = spec_host(ctx) + 64;
+                        std::memcpy(pose_out, hp, 96);
+                        if (iterations_done) *iterations_done = reinterpret_cast<const uint32_t*>(hp + 12)[1];
+                        *solved          = 1;
+                        ctx->spec_unused = 0;
+                        return 0;
+                    }
                 }
                 ctx->spec_want.kind = 2, ctx->spec_want.list = list, ctx->spec_want.gn = *prm, ctx->spec_unused = 0;
             }
         }
         DeviceGuard                 g(ctx->device);
         ProfScope   ps(ctx);
-        const mp2p_b200_pair_pt2pt* d2p;
-        const mp2p_b200_pair_pt2pl* d2l;
-        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2p, p2p, n2p, pairs_on_device, &d2p));
-        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2l, p2l, n2l, pairs_on_device, &d2l));
+        const mp2p_b200_pair_pt2pt* d2p = staged2p;
+        const mp2p_b200_pair_pt2pl* d2l = staged2l;
+        if (!staged2p) MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2p, p2p, n2p, pairs_on_device, &d2p));
+        if (!staged2l) MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2l, p2l, n2l, pairs_on_device, &d2l));
         // the whole inner loop runs on the device (accumulate -> LDL^T step -> pose update, repeated),
         // one synchronisation at the end
         double*   hpose = reinterpret_cast<double*>(static_cast<char*>(ctx->h_pinned) + 2048);
@@ -1375,6 +1553,196 @@ extern "C"
         cudaStreamSynchronize(ctx->stream);
         tmp.release();
         return rc;
+    }
+
+    int mp2p_b200_covariance(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* p2p, uint64_t n2p, const mp2p_b200_pair_pt2pl* p2l,
+                             uint64_t n2l, const mp2p_b200_pair_pt2ln* p2ln, uint64_t n2ln, int pairs_on_device, const double x6[6],
+                             double finDif_xyz, double finDif_angles, double cov_out[36], double hessian_out[36],
+                             int32_t* positive_definite)
+    {
+        if (!ctx || !x6 || !cov_out || (n2p && !p2p) || (n2l && !p2l) || (n2ln && !p2ln) || !(finDif_xyz > 0) || !(finDif_angles > 0))
+        {
+            set_error("covariance: NULL argument or non-positive finite-difference step");
+            return MP2P_B200_ERR_ARG;
+        }
+        for (int k = 0; k < 36; k++) cov_out[k] = 0;
+        if (hessian_out)
+            for (int k = 0; k < 36; k++) hessian_out[k] = 0;
+        if (positive_definite) *positive_definite = 1;
+        if (n2p + n2l + n2ln == 0)  // covariance.cpp:33-38
+        {
+            for (int k = 0; k < 6; k++) cov_out[7 * k] = 1e6;
+            return 0;
+        }
+        DeviceGuard                 g(ctx->device);
+        const mp2p_b200_pair_pt2pt* d2p;
+        const mp2p_b200_pair_pt2pl* d2l;
+        const mp2p_b200_pair_pt2ln* d2n;
+        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2p, p2p, n2p, pairs_on_device ? 1 : 0, &d2p));
+        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2l, p2l, n2l, pairs_on_device ? 1 : 0, &d2l));
+        MP2P_TRY(stage_pairs(ctx, ctx->d_pairs2ln, p2ln, n2ln, pairs_on_device ? 1 : 0, &d2n));
+        // CPose3D::setFromValues(x, y, z, yaw, pitch, roll): R = Rz(yaw) Ry(pitch) Rx(roll)
+        double poses[12][12], inv2h[6];
+        for (int i = 0; i < 6; i++)
+        {
+            const double h = i < 3 ? finDif_xyz : finDif_angles;
+            inv2h[i]       = 0.5 / h;
+            for (int sgn = 0; sgn < 2; sgn++)
+            {
+                double x[6];
+                for (int k = 0; k < 6; k++) x[k] = x6[k];
+                x[i] = sgn == 0 ? x6[i] + h : x6[i] - h;
+                const double cy = std::cos(x[3]), sy = std::sin(x[3]), cp = std::cos(x[4]), sp = std::sin(x[4]), cr = std::cos(x[5]),
+                             sr = std::sin(x[5]);
+                double* m = poses[2 * i + sgn];
+                m[0] = cy * cp, m[1] = cy * sp * sr - sy * cr, m[2] = cy * sp * cr + sy * sr, m[3] = x[0];
+                m[4] = sy * cp, m[5] = sy * sp * sr + cy * cr, m[6] = sy * sp * cr - cy * sr, m[7] = x[1];
+                m[8] = -sp, m[9] = cp * sr, m[10] = cp * cr, m[11] = x[2];
+            }
+        }
+        double* d_packet = ctx->d_packet.as<double>();
+        MP2P_TRY(run_cov_accumulate(ctx, d2p, n2p, d2l, n2l, d2n, n2ln, poses, inv2h, d_packet));
+        double* hp = reinterpret_cast<double*>(static_cast<char*>(ctx->h_pinned) + 2048);
+        MP2P_CUDA_TRY(cudaMemcpyAsync(hp, d_packet, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        MP2P_CUDA_TRY(cudaGetLastError());
+        double H[36];
+        int    idx = 0;
+        for (int a = 0; a < 6; a++)
+            for (int b = a; b < 6; b++) H[6 * a + b] = H[6 * b + a] = hp[idx++];
+        if (hessian_out) std::memcpy(hessian_out, H, sizeof(H));
+        // inverse_LLt: H = L L^T, cov = L^-T L^-1
+        double L[36] = {0}, Li[36] = {0};
+        bool   pd = true;
+        for (int i = 0; i < 6 && pd; i++)
+            for (int j = 0; j <= i; j++)
+            {
+                double s = H[6 * i + j];
+                for (int k = 0; k < j; k++) s -= L[6 * i + k] * L[6 * j + k];
+                if (i == j)
+                {
+                    if (!(s > 0))
+                    {
+                        pd = false;
+                        break;
+                    }
+                    L[6 * i + j] = std::sqrt(s);
+                }
+                else
+                    L[6 * i + j] = s / L[6 * j + j];
+            }
+        if (!pd)
+        {
+            if (positive_definite) *positive_definite = 0;
+            for (int k = 0; k < 6; k++) cov_out[7 * k] = H[7 * k] > 0 ? 1.0 / H[7 * k] : 1e6;
+            return 0;
+        }
+        for (int c = 0; c < 6; c++)
+            for (int i = c; i < 6; i++)
+            {
+                double s = i == c ? 1.0 : 0.0;
+                for (int k = c; k < i; k++) s -= L[6 * i + k] * Li[6 * k + c];
+                Li[6 * i + c] = s / L[6 * i + i];
+            }
+        for (int a = 0; a < 6; a++)
+            for (int b = 0; b < 6; b++)
+            {
+                double s = 0;
+                for (int k = 0; k < 6; k++) s += Li[6 * k + a] * Li[6 * k + b];
+                cov_out[6 * a + b] = s;
+            }
+        return 0;
+    }
+
+    // stages host input into ctx->d_fd_in (device input is used in place); out: device pointers
+    static int fd_stage(mp2p_b200_ctx* ctx, const float* x, const float* y, const float* z, uint64_t n, int on_device,
+                        const float** dx, const float** dy, const float** dz)
+    {
+        if (on_device)
+        {
+            *dx = x, *dy = y, *dz = z;
+            return 0;
+        }
+        MP2P_TRY(ctx->d_fd_in.ensure(n * 12 + 16));
+        float* b = ctx->d_fd_in.as<float>();
+        MP2P_CUDA_TRY(cudaMemcpyAsync(b, x, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(b + n, y, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        MP2P_CUDA_TRY(cudaMemcpyAsync(b + 2 * n, z, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        *dx = b, *dy = b + n, *dz = b + 2 * n;
+        return 0;
+    }
+
+    int mp2p_b200_filter_decimate_voxels(mp2p_b200_ctx* ctx, const float* x, const float* y, const float* z, uint64_t n,
+                                         int on_device, const mp2p_b200_decimate_params* params, float* out_x, float* out_y,
+                                         float* out_z, int64_t* out_src_index, uint64_t capacity, int out_on_device,
+                                         uint64_t* out_count)
+    {
+        if (!ctx || !params || !out_count || (n && (!x || !y || !z)) || (capacity && (!out_x || !out_y || !out_z)))
+        {
+            set_error("filter_decimate_voxels: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        *out_count = 0;
+        if (n == 0) return 0;
+        DeviceGuard g(ctx->device);
+        const float *dx, *dy, *dz;
+        MP2P_TRY(fd_stage(ctx, x, y, z, n, on_device, &dx, &dy, &dz));
+        float *    ox = out_x, *oy = out_y, *oz = out_z;
+        long long* os = reinterpret_cast<long long*>(out_src_index);
+        const uint64_t cap = std::min<uint64_t>(capacity, n);
+        if (!out_on_device)
+        {
+            MP2P_TRY(ctx->d_fd_out.ensure(cap * 20 + 32));
+            ox = ctx->d_fd_out.as<float>(), oy = ox + cap, oz = oy + cap;
+            os = out_src_index ? reinterpret_cast<long long*>(ctx->d_fd_out.as<char>() + ((cap * 12 + 15) & ~(uint64_t)15)) : nullptr;
+        }
+        uint64_t  cnt = 0;
+        const int rc  = run_decimate_voxels(ctx, dx, dy, dz, n, params, ox, oy, oz, os, cap, &cnt);
+        *out_count    = cnt;
+        if (rc != 0) return rc;
+        if (!out_on_device && cnt)
+        {
+            MP2P_CUDA_TRY(cudaMemcpyAsync(out_x, ox, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            MP2P_CUDA_TRY(cudaMemcpyAsync(out_y, oy, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            MP2P_CUDA_TRY(cudaMemcpyAsync(out_z, oz, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            if (out_src_index) MP2P_CUDA_TRY(cudaMemcpyAsync(out_src_index, os, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+        return 0;
+    }
+
+    int mp2p_b200_cloud_create_decimated(mp2p_b200_ctx* ctx, const float* x, const float* y, const float* z, uint64_t n,
+                                         int on_device, const mp2p_b200_decimate_params* params, mp2p_b200_cloud** out,
+                                         uint64_t* out_count)
+    {
+        if (!ctx || !params || !out || (n && (!x || !y || !z)))
+        {
+            set_error("cloud_create_decimated: NULL argument");
+            return MP2P_B200_ERR_ARG;
+        }
+        *out = nullptr;
+        if (out_count) *out_count = 0;
+        if (n == 0) return mp2p_b200_cloud_create(ctx, nullptr, nullptr, nullptr, 0, 1, out);
+        DeviceGuard g(ctx->device);
+        const float *dx, *dy, *dz;
+        MP2P_TRY(fd_stage(ctx, x, y, z, n, on_device, &dx, &dy, &dz));
+        MP2P_TRY(ctx->d_fd_out.ensure(n * 12 + 32));
+        float *  ox = ctx->d_fd_out.as<float>(), *oy = ox + n, *oz = oy + n;
+        uint64_t cnt = 0;
+        MP2P_TRY(run_decimate_voxels(ctx, dx, dy, dz, n, params, ox, oy, oz, nullptr, n, &cnt));
+        if (out_count) *out_count = cnt;
+        return mp2p_b200_cloud_create(ctx, ox, oy, oz, cnt, 1, out);
+    }
+
+    int mp2p_b200_ctx_get_tile_trace(mp2p_b200_ctx* ctx, uint32_t* out, uint64_t capacity_tiles, uint64_t* n_tiles)
+    {
+        if (!ctx || !n_tiles) return MP2P_B200_ERR_ARG;
+        *n_tiles = ctx->trace_tiles;
+        if (!out || !ctx->trace_tiles) return 0;
+        DeviceGuard g(ctx->device);
+        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        MP2P_CUDA_TRY(cudaMemcpy(out, ctx->d_trace.p, std::min<uint64_t>(capacity_tiles, ctx->trace_tiles) * 32, cudaMemcpyDeviceToHost));
+        return 0;
     }
 
     int mp2p_b200_host_alloc(size_t bytes, void** out)

@@ -1,7 +1,9 @@
 // Shared declarations of the B200 hot-path library (product code; never includes oracle/).
 #pragma once
 #include <unordered_set>
+#include <vector>
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 
 #include <cstdarg>
@@ -145,10 +147,23 @@ struct mp2p_b200_ctx
     } spec_res;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t  ev_fork = nullptr;
+    // side stream of the k > 1 search's scheduling hint (k_tile_rank runs behind the search, match.cu)
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t  ev_rank_fork = nullptr, ev_rank = nullptr;
     mp2p::DevBuf d_spec;  // GN speculation: 12 doubles pose + state words
     // live handles created on this context: a stale or foreign map / cloud handle is refused instead of
     // being dereferenced (the objects are not thread-safe, like the reference's: no locking here)
     std::unordered_set<const void*> live_maps, live_clouds;
+    // host layers the library keeps a device copy of (mp2p_b200_map_cached / mp2p_b200_cloud_cached)
+    struct CachedLayer
+    {
+        const float*     x = nullptr;
+        uint64_t         n = 0, fingerprint = 0, last_use = 0;
+        mp2p_b200_map*   map   = nullptr;
+        mp2p_b200_cloud* cloud = nullptr;
+    };
+    std::vector<CachedLayer> layer_cache;
+    uint64_t                 layer_clock = 0;
     bool owns_map(const void* m) const { return m && live_maps.count(m) != 0; }
     bool owns_cloud(const void* c) const { return c && live_clouds.count(c) != 0; }
     // Matcher_Adaptive: what phase 2 (adaptive_emit) needs from phase 1 (adaptive_search)
@@ -174,6 +189,8 @@ struct mp2p_b200_ctx
     bool         pev_used[8]  = {};
     float        timings[MP2P_B200_N_TIMINGS] = {};
     mp2p::DevBuf d_stats;               // 8 x u64 search counters
+    mp2p::DevBuf d_trace;               // measurement hook ($MP2P_KNN_TRACE): per-CTA {SM, start, end, tile} of the last k > 1 search
+    uint32_t     trace_tiles = 0;
 
     // matcher scratch
     const float *cur_lx = nullptr, *cur_ly = nullptr, *cur_lz = nullptr;  // local cloud, caller's order
@@ -181,6 +198,7 @@ struct mp2p_b200_ctx
     // (then cur_perm[j] = caller's index of sorted position j)
     const float *   cur_qx = nullptr, *cur_qy = nullptr, *cur_qz = nullptr;
     const uint32_t* cur_perm   = nullptr;
+    mp2p_b200_cloud* cur_cloud = nullptr;  // the resident cloud being searched (scheduling hint), or NULL
     bool            cur_tma_ok = false;
     mp2p::DevBuf d_lx, d_ly, d_lz;     // local cloud staging (padded to kQueryTile)
     mp2p::DevBuf d_cand;               // u64 [n_local*K]  (d2 bits << 32 | map index)
@@ -201,6 +219,8 @@ struct mp2p_b200_ctx
     mp2p::DevBuf d_weights;            // run-length point weights
     mp2p::DevBuf d_outlier;            // Horn scale-outlier flags
     mp2p::DevBuf d_conv;               // pt2pl -> pt2pt conversion scratch and output
+    // FilterDecimateVoxels scratch (filter.cu): extrema + count | sort keys a/b | values a/b | flags + tile sums | radix scratch | staged input / output
+    mp2p::DevBuf d_fd_small, d_fd_keys, d_fd_vals, d_fd_flags, d_fd_rs, d_fd_in, d_fd_out;
     // pinned host scratch
     void* h_pinned = nullptr;  // 4 KiB: counts, packets, poses
     void* h_pinned_dev = nullptr;  // its device alias (kernels that hand a count to the host themselves)
@@ -228,6 +248,10 @@ struct mp2p_b200_cloud
     mp2p::DevBuf   d_sx, d_sy, d_sz;  // sorted by Morton code of the cloud's own bounding box
     mp2p::DevBuf   d_perm;            // u32 [n]: sorted position -> caller index
     float          build_ms = 0.f;
+    // scheduling hint of the k > 1 search (match.cu): how long every query tile took in the previous call
+    // over this cloud, and the tile order (longest first) derived from it for the next one
+    mp2p::DevBuf   d_tile_cost, d_tile_order;
+    uint64_t       hint_key = 0;  // (tiles, lanes per query, CTA size) the order was made for; 0 = none
 };
 
 namespace mp2p
@@ -312,6 +336,10 @@ int run_adaptive_emit(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const mp2p_b200_ad
 int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const float* qy,
             const float* qz, uint64_t nq, uint32_t k, float radius2, uint32_t* out_idx,
             float* out_d2, int32_t* out_found);
+// filter.cu — FilterDecimateVoxels over device arrays; synchronises, *h_count = points produced
+int run_decimate_voxels(mp2p_b200_ctx* ctx, const float* dx, const float* dy, const float* dz, uint64_t n,
+                        const mp2p_b200_decimate_params* prm, float* d_ox, float* d_oy, float* d_oz, long long* d_osrc,
+                        uint64_t capacity, uint64_t* h_count);
 // solve.cu
 // `d_n*` (optional): pair counts read from DEVICE memory at kernel time (n* then are upper bounds
 // used for the grid size) — lets a solver be enqueued behind a matcher without a host round trip.
@@ -340,4 +368,8 @@ int run_horn_moments(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64
                      uint64_t n_total_pairs, const uint64_t* d_wcount_prefix, const double* d_wvalue,
                      uint32_t n_wblocks, uint8_t* d_outlier, double* d_packet,
                      const unsigned long long* d_n = nullptr, int n_total_mode = 0);
+// covariance(): J^T J of the numerically differentiated error vector (solve.cu)
+int run_cov_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p, const mp2p_b200_pair_pt2pl* d2l,
+                       uint64_t n2l, const mp2p_b200_pair_pt2ln* d2ln, uint64_t n2ln, const double poses[12][12],
+                       const double inv2h[6], double* d_packet);
 }  // namespace mp2p

@@ -96,6 +96,7 @@ __constant__ uint8_t kNeighbourOrder[27] = {
 struct SearchCounters
 {
     uint32_t probes = 0, cands = 0, levels = 0;
+    uint32_t rounds = 0, steps = 0, inserts = 0;  // warp-uniform loop trip counts (trace hook)
 };
 
 // ---- sub-warp cooperative search --------------------------------------------------------------
@@ -377,39 +378,40 @@ __device__ __forceinline__ void knn_search_v1(const GridView& g, bool enabled, f
     }
 }
 
-// ---- dense-list search with pruned descent (round 2) ------------------------------------------
+// ---- stack-driven search with pruned descent (round 2) ----------------------------------------
 // Same index, same exactness argument, same group layout (G lanes per query, the K best keys
 // distributed over the group in ascending order) as knn_search_v1. What changes:
-//  (1) DENSE LISTS. v1 offered every voxel's run on its own (a warp-uniform call per run, ~9 per
-//      level, each with its fixed cost and at least one scan step even when three of the four groups
-//      of the warp had nothing to offer). Here the voxels of a ROUND — the centre voxel; then the
-//      neighbours the K-th distance found so far cannot exclude, the 6 faces before the 20 edges /
-//      corners; then whatever the descent stack holds — are taken by the lanes of the group by
-//      static assignment (voxel n -> lane n % G, no bit-select), bounded, hash-probed with all probes
-//      of a lane in flight, and the runs found go into the group's RUN TABLE in shared memory
-//      (ballot-ranked positions, one in-group prefix scan: end[r] = inclusive prefix of the run
-//      lengths, adj[r] = start - exclusive prefix, so candidate v of the concatenated list sits at
-//      pts[adj[r] + v]). The list is scanned densely: step s offers candidates [s*G, s*G + G)
-//      whatever run they belong to (each lane walks the table with a cursor), four steps of loads in
-//      flight. A long list is scanned by the whole warp for its owner group, 32 candidates a step.
+//  (1) ONE MECHANISM. Every voxel that may matter — the centre voxel of a level, then its face
+//      neighbours, then its edge / corner neighbours, then the children of a voxel that was split —
+//      is an entry (cell key, level) on the group's STACK in shared memory. A ROUND pops up to G
+//      entries, one per lane: the lane bounds its voxel against the K-th distance found so far,
+//      hash-probes it if it survives (the probes of a round are in flight together), and either
+//      lists the run found in the group's RUN TABLE or splits it. The table (ballot-ranked
+//      positions, one in-group prefix scan: end[r] = inclusive prefix of the run lengths, adj[r] =
+//      start - exclusive prefix, so candidate v of the round's concatenated list sits at
+//      pts[adj[r] + v]) is then scanned DENSELY: step s offers candidates [s*G, s*G + G) whatever
+//      run they belong to, four steps of loads in flight. v1 offered every run on its own (~9
+//      warp-uniform calls per level, each with its fixed cost and at least one scan step even when
+//      three of the four groups of the warp had nothing to offer). The kernel holds one copy of the
+//      round and one of the scan: its code is half of v1's (the first cut of this design inlined
+//      them per phase, 108 KB of SASS, and stalled on instruction fetch).
 //  (2) PRUNED DESCENT. A query that has to climb (a far return the pose error moved off its surface:
 //      7 % of a C3 scan) met voxels of hundreds to thousands of points in v1 and read all of them —
 //      half of all candidates of the launch, and whole CTAs of such queries formed its tail (ncu:
 //      one SM busy for 400 k cycles, the average 284 k). Here a voxel holding more than kDescend
-//      points is not scanned: its 8 children (one table level down — every level's voxel is the
-//      union of its children, and their runs are sub-runs of its run) go on the group's stack, are
-//      bounded against the current K-th distance, probed, and scanned or split again. Depth first,
-//      so the first leaves tighten the bound for everything still on the stack. The candidates of a
-//      climbing query scale with the surface inside its search sphere, not with the coarse block.
+//      points is not scanned: its 8 children (one table level down — a voxel is the union of its
+//      children and their runs are sub-runs of its run) go on the stack. Depth first, so the first
+//      leaves tighten the bound for everything still waiting.
 // Exactness: within one level every voxel of the 3x3x3 block is scanned, or excluded by a lower
 // bound that exceeds an upper bound of the K-th distance, or replaced by its children, which
 // partition it; no point is offered twice (the list is rebuilt per level, as before).
 constexpr uint32_t kDescend  = 64;  // points above which a voxel is split instead of scanned
-constexpr int      kStackCap = 64;  // descent stack entries per group (overflow: the voxel is scanned)
+constexpr uint32_t kLongList = 64;  // candidates from which a round's list is scanned by the whole warp
+constexpr int      kStackCap = 64;  // stack entries per group (a voxel that cannot be split for lack of room is scanned)
 struct RunTable  // one per query group, shared memory
 {
-    uint32_t           end[36];
-    uint32_t           adj[36];
+    uint32_t           end[32];
+    uint32_t           adj[32];
     unsigned long long stk_key[kStackCap];  // cell_key of a voxel waiting to be visited
     uint8_t            stk_rl[kStackCap];   // its relative level
 };
@@ -432,14 +434,13 @@ __device__ __forceinline__ void knn_search(const GridView& g, bool enabled, floa
                                            SearchCounters& sc, RunTable* tables, const uint8_t* nb_order, int n_phases)
 {
     constexpr unsigned       FULL     = 0xffffffffu;
-    constexpr int            T        = (26 + G - 1) / G;  // voxels a lane may have to take per round
+    constexpr int            T        = (20 + G - 1) / G;  // neighbour voxels a lane may have to bound per phase
     const int                lane     = threadIdx.x & 31;
     const int                gbase    = lane - sub;
     const unsigned           gmask    = (G == 32 ? FULL : ((1u << (G & 31)) - 1u)) << gbase;
     const unsigned           below    = gmask & ((1u << lane) - 1u);
     const int                kth_lane = gbase + K - 1;  // warp lane holding the K-th best
-    RunTable* const          tb_warp  = tables + (threadIdx.x >> 5) * (32 / G);  // the tables of this warp's groups
-    RunTable&                tb       = tb_warp[gbase / G];
+    RunTable&                tb       = tables[(threadIdx.x >> 5) * (32 / G) + gbase / G];
     const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
     mine                              = sentinel;
     bool live = enabled && radius2 > 0.f;  // group-uniform
@@ -458,20 +459,12 @@ __device__ __forceinline__ void knn_search(const GridView& g, bool enabled, floa
     const int   Ix = (int)floorf(ux), Iy = (int)floorf(uy), Iz = (int)floorf(uz);
     const float q2 = g.s0_lo * g.s0_lo * 0.999999f;  // quanta^2 -> metres^2, rounded down
     float       kth = radius2;  // upper bound of the K-th best distance found so far (all levels)
-    int         sp  = 0;        // descent stack height (group-uniform)
-
-    // one offer of a candidate key to the owner group's list (all 32 lanes; `ins` = this lane's group
-    // takes part): lanes with cc < mine form a suffix of the group, its first lane takes cc, the others
-    // take their left neighbour's key
-#define MP2P_KNN_INSERT(ins_, cc_)                                                     \
-    {                                                                                  \
-        const unsigned long long up_ = __shfl_up_sync(FULL, mine, 1, G);               \
-        if ((ins_) && (cc_) < mine) mine = (sub == 0 || !((cc_) < up_)) ? (cc_) : up_; \
-    }
+    int         sp  = 0;        // stack height (group-uniform)
+    int         next_rl = rl_start;  // the next level this group searches (levels in between are skipped)
 
     // lower bound (metres^2, conservative by 4 quanta per axis) of the distance from the query to the
     // voxel (vx,vy,vz) of absolute level L; for the neighbours of the query's own voxel this is the
-    // per-axis gap formula of v1 (fx = ux - cx * s is the gap to the -1 slab, s - fx to the +1 slab)
+    // per-axis gap formula of v1 (ux - cx * s is the gap to the -1 slab, (cx + 1) * s - ux to the +1 slab)
     auto voxel_bound = [&](int L, int vx, int vy, int vz) -> float
     {
         const float s  = (float)(1 << L);
@@ -482,327 +475,284 @@ __device__ __forceinline__ void knn_search(const GridView& g, bool enabled, floa
         return gx * gx * q2 + gy * gy * q2 + gz * gz * q2;
     };
 
-    // scan of the round's list (table already in shared memory); total = its length for this group
-    auto dense_scan = [&](uint32_t total)
+    for (int rl = rl_start; rl < g.n_levels; rl++)
     {
-        if (G < 32)
+        if (!__any_sync(FULL, live)) break;
+        const int  L    = g.level_first + rl;
+        const bool top  = L == kGridBits;         // the single voxel holding every point
+        const bool here = live && rl >= next_rl;  // this group searches this level
+        if (here) mine = sentinel;                // the list is rebuilt at every level: no key is ever offered twice
+        const int   cmax = ((1 << kGridBits) - 1) >> L;
+        const float s    = (float)(1 << L);  // voxel edge in finest quanta
+        const int   cx = top ? 0 : (Ix >> L), cy = top ? 0 : (Iy >> L), cz = top ? 0 : (Iz >> L);
+        const int   nph = top ? 1 : n_phases;
+        // smallest bound any face voxel / any edge or corner voxel of the block can have (the per-axis gaps of
+        // voxel_bound): a phase none of whose voxels can matter to any group of the warp is skipped outright
+        float min_face, min_edge;
         {
-            unsigned big = __ballot_sync(FULL, total >= kLongRun && sub == 0);
-            while (big)  // warp-uniform: the whole warp scans the list of the group starting at lane o
+            const float fx = ux - (float)cx * s, fy = uy - (float)cy * s, fz = uz - (float)cz * s;
+            const float ax = fmaxf(fminf(fx, s - fx) - 4.f, 0.f), ay = fmaxf(fminf(fy, s - fy) - 4.f, 0.f), az = fmaxf(fminf(fz, s - fz) - 4.f, 0.f);
+            const float mnx = ax * ax * q2, mny = ay * ay * q2, mnz = az * az * q2;
+            min_face = fminf(mnx, fminf(mny, mnz)) * 0.999999f;
+            min_edge = fminf(mnx + mny, fminf(mnx + mnz, mny + mnz)) * 0.999999f;
+        }
+
+#pragma unroll 1
+        for (int phase = 0; phase < nph; phase++)
+        {
+            // ---- this phase's voxels onto the stack: the centre | the 6 faces | the 20 edges and corners
+            // (n_phases == 2: all 26 neighbours at once), each bounded against kth first
             {
-                const int o = __ffs(big) - 1;
-                big &= big - 1;
-                const RunTable& ot     = tb_warp[o / G];
-                const uint32_t  ototal = __shfl_sync(FULL, total, o);
-                const float     oqx = __shfl_sync(FULL, qx, o), oqy = __shfl_sync(FULL, qy, o), oqz = __shfl_sync(FULL, qz, o);
-                const float     okth  = __shfl_sync(FULL, kth, o);
-                const int       okl   = o + K - 1;
-                const bool      owner = (unsigned)(lane - o) < (unsigned)G;
-                constexpr int   kAheadW = 4;
-                uint32_t        r = 0, re = ot.end[0], ra = ot.adj[0];
-                for (uint32_t j0 = 0; j0 < ototal; j0 += kAheadW * 32)
+                const int lo = phase == 0 ? 0 : (phase == 1 ? 1 : 7), hi = phase == 0 ? 1 : ((phase == 1 && n_phases == 3) ? 7 : 27);
+                if (phase > 0 && !__any_sync(FULL, here && !((phase == 1 ? min_face : min_edge) > kth))) continue;
+                __syncwarp();
+#pragma unroll 1
+                for (int n0 = lo; n0 < hi; n0 += G)  // (warp-uniform; at most T passes)
                 {
-                    float4 p[kAheadW];
-#pragma unroll
-                    for (int u = 0; u < kAheadW; u++)
+                    const int n  = n0 + sub;
+                    bool      ok = false;
+                    int       vx = 0, vy = 0, vz = 0;
+                    if (here && n < hi)
                     {
-                        const uint32_t v = j0 + u * 32 + lane;
-                        p[u]             = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (v < ototal)
+                        const uint32_t code = nb_order[n];
+                        vx = cx + (int)(code & 3u) - 1, vy = cy + (int)((code >> 2) & 3u) - 1, vz = cz + (int)((code >> 4) & 3u) - 1;
+                        ok = (unsigned)vx <= (unsigned)cmax && (unsigned)vy <= (unsigned)cmax && (unsigned)vz <= (unsigned)cmax &&
+                             !(voxel_bound(L, vx, vy, vz) > kth);  // strict `>`: an equal-distance lower index must still be seen
+                    }
+                    const unsigned b = __ballot_sync(FULL, ok) & gmask;
+                    if (ok)
+                    {
+                        // (pushed in reverse so that the nearer voxels of kNeighbourOrder pop first)
+                        const int at   = sp + __popc(b) - 1 - __popc(b & below);
+                        tb.stk_key[at] = cell_key((uint32_t)vx, (uint32_t)vy, (uint32_t)vz);
+                        tb.stk_rl[at]  = (uint8_t)rl;
+                    }
+                    sp += __popc(b);
+                }
+                __syncwarp();
+            }
+            // ---- rounds until every stack of the warp is empty
+#pragma unroll 1
+            while (__any_sync(FULL, sp > 0))
+            {
+                // pop: lane `sub` takes the sub-th entry from the top, bounds it again (kth may have
+                // tightened since it was pushed) and probes it
+                const int          n_pop = min(sp, G);
+                sc.rounds++;
+                uint32_t           start = 0, count = 0;
+                int                erl   = 0;
+                unsigned long long ckey  = 0;
+                if (sub < n_pop)
+                {
+                    ckey = tb.stk_key[sp - 1 - sub];
+                    erl  = tb.stk_rl[sp - 1 - sub];
+                    const int vx = (int)(ckey & 0x1fffffu), vy = (int)((ckey >> 21) & 0x1fffffu), vz = (int)((ckey >> 42) & 0x1fffffu);
+                    if (!(voxel_bound(g.level_first + erl, vx, vy, vz) > kth))
+                    {
+                        sc.probes++;
+                        if (!grid_lookup(g, erl, (uint32_t)vx, (uint32_t)vy, (uint32_t)vz, start, count)) count = 0;
+                    }
+                }
+                sp -= n_pop;
+                __syncwarp();  // the popped entries are in registers before anybody pushes over them
+                // split the large voxels (while the stack has room), list the others. The children of a voxel
+                // are bounded BEFORE they take a stack slot — lane c of the group looks at child c — so that
+                // only those the K-th distance cannot exclude cost a round later (three of four fail for a
+                // query that climbed through empty space)
+                const bool large = count > kDescend && erl > 0;
+                bool       split = false;
+                unsigned   bl    = __ballot_sync(FULL, large);
+                while (bl)  // warp-uniform: one large voxel of one group per pass
+                {
+                    const int o = __ffs(bl) - 1;  // the lane holding it
+                    bl &= bl - 1;
+                    const bool               mine_grp = (unsigned)(o - gbase) < (unsigned)G;
+                    const unsigned long long pk  = __shfl_sync(FULL, ckey, o);
+                    const int                prl = __shfl_sync(FULL, erl, o) - 1;
+                    const bool               room = sp + 8 <= kStackCap;  // (group-uniform)
+                    bool                     ok   = false;
+                    unsigned long long       ck   = 0;
+                    if (mine_grp && room && sub < 8)
+                    {
+                        const int vx = (int)((pk & 0x1fffffull) << 1) | (sub & 1), vy = (int)(((pk >> 21) & 0x1fffffull) << 1) | ((sub >> 1) & 1),
+                                  vz = (int)(((pk >> 42) & 0x1fffffull) << 1) | (sub >> 2);
+                        ok = !(voxel_bound(g.level_first + prl, vx, vy, vz) > kth);
+                        ck = cell_key((uint32_t)vx, (uint32_t)vy, (uint32_t)vz);
+                    }
+                    const unsigned bc = __ballot_sync(FULL, ok) & gmask;
+                    if (ok)
+                    {
+                        const int at   = sp + __popc(bc & below);
+                        tb.stk_key[at] = ck;
+                        tb.stk_rl[at]  = (uint8_t)prl;
+                    }
+                    if (mine_grp && room)
+                    {
+                        sp += __popc(bc);
+                        if (lane == o) split = true;
+                    }
+                }
+                const bool     listed = count != 0u && !split;
+                const unsigned b      = __ballot_sync(FULL, listed) & gmask;
+                const uint32_t n_runs = __popc(b);
+                if (listed) sc.cands += count;
+                // run table: lengths -> inclusive prefix, starts -> start - exclusive prefix (n_runs <= G: one pass)
+                uint32_t total;
+                {
+                    if (listed)
+                    {
+                        const int at2 = __popc(b & below);
+                        tb.end[at2] = count, tb.adj[at2] = start;
+                    }
+                    __syncwarp();
+                    const bool     mine_e = (uint32_t)sub < n_runs;  // lane `sub` finishes entry `sub`
+                    const uint32_t len    = mine_e ? tb.end[sub] : 0u;
+                    uint32_t       incl   = len;
+#pragma unroll
+                    for (int o = 1; o < G; o <<= 1)
+                    {
+                        const uint32_t y = __shfl_up_sync(FULL, incl, o, G);
+                        if (sub >= o) incl += y;
+                    }
+                    if (mine_e) tb.end[sub] = incl, tb.adj[sub] -= incl - len;
+                    total = __shfl_sync(FULL, incl, gbase + G - 1);
+                }
+                __syncwarp();
+
+                // ---- a LONG list (a query that climbed: its groups' lists are long in different rounds, so
+                // stepping them side by side would cost the warp the SUM of their lengths) is scanned by the
+                // whole warp for its owner group, 32 candidates per step, through the owner's table
+                if (G < 32)
+                {
+                    unsigned big = __ballot_sync(FULL, total >= kLongList && sub == 0);
+                    while (big)  // warp-uniform
+                    {
+                        const int o = __ffs(big) - 1;  // first lane of the owner group
+                        big &= big - 1;
+                        const RunTable& ot     = tables[(threadIdx.x >> 5) * (32 / G) + o / G];
+                        const uint32_t  ototal = __shfl_sync(FULL, total, o);
+                        const float     oqx = __shfl_sync(FULL, qx, o), oqy = __shfl_sync(FULL, qy, o), oqz = __shfl_sync(FULL, qz, o);
+                        const float     okth  = __shfl_sync(FULL, kth, o);
+                        const int       okl   = o + K - 1;  // lane holding the owner's K-th key
+                        const bool      owner = (unsigned)(lane - o) < (unsigned)G;
+                        uint32_t        r = 0, re = ot.end[0], ra = ot.adj[0];
+#pragma unroll 1
+                        for (uint32_t j0 = 0; j0 < ototal; j0 += 64)
                         {
-                            while (v >= re) r++, re = ot.end[r], ra = ot.adj[r];
+                            float4 p[2];
+#pragma unroll
+                            for (int u = 0; u < 2; u++)
+                            {
+                                const uint32_t v = j0 + u * 32 + lane;
+                                p[u]             = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (v < ototal)
+                                {
+                                    while (v >= re) r++, re = ot.end[r], ra = ot.adj[r];
+                                    p[u] = __ldg(g.pts + (uint32_t)(ra + v));
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 2; u++)
+                            {
+                                if (j0 + u * 32 >= ototal) break;  // warp-uniform
+                                sc.steps++;
+                                const bool               in   = j0 + u * 32 + lane < ototal;
+                                const unsigned long long c    = in ? point_key(oqx, oqy, oqz, p[u]) : ~0ull;
+                                const unsigned long long kkey = __shfl_sync(FULL, mine, okl);
+                                const bool pass = in && c < kkey && __uint_as_float((uint32_t)(c >> 32)) <= okth;
+                                unsigned   pm   = __ballot_sync(FULL, pass);
+                                while (pm)  // warp-uniform
+                                {
+                                    const int src = __ffs(pm) - 1;
+                                    pm &= pm - 1;
+                                    sc.inserts++;
+                                    const unsigned long long cc = __shfl_sync(FULL, c, src);
+                                    const unsigned long long up = __shfl_up_sync(FULL, mine, 1, G);
+                                    if (owner && cc < mine) mine = (sub == 0 || !(cc < up)) ? cc : up;
+                                }
+                            }
+                        }
+                        const unsigned long long kkey = __shfl_sync(FULL, mine, okl);
+                        if (owner) kth = fminf(kth, __uint_as_float((uint32_t)(kkey >> 32))), total = 0;
+                    }
+                }
+                // ---- dense scan of the round's list, G candidates per step, four steps of loads in flight
+                const uint32_t steps = __reduce_max_sync(FULL, total);
+                constexpr int  kAhead = 4;
+                uint32_t       r = 0, re = tb.end[0], ra = tb.adj[0];  // stale values if total == 0: never used then
+#pragma unroll 1
+                for (uint32_t j0 = 0; j0 < steps; j0 += kAhead * G)
+                {
+                    float4 p[kAhead];
+#pragma unroll
+                    for (int u = 0; u < kAhead; u++)
+                    {
+                        const uint32_t v = j0 + u * G + sub;
+                        p[u]             = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (v < total)
+                        {
+                            while (v >= re) r++, re = tb.end[r], ra = tb.adj[r];
                             p[u] = __ldg(g.pts + (uint32_t)(ra + v));
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < kAheadW; u++)
+                    for (int u = 0; u < kAhead; u++)
                     {
-                        if (j0 + u * 32 >= ototal) break;  // warp-uniform
-                        const bool               in   = j0 + u * 32 + lane < ototal;
-                        const unsigned long long c    = in ? point_key(oqx, oqy, oqz, p[u]) : ~0ull;
-                        const unsigned long long kkey = __shfl_sync(FULL, mine, okl);
-                        const bool pass = in && c < kkey && __uint_as_float((uint32_t)(c >> 32)) <= okth;
-                        unsigned   pm   = __ballot_sync(FULL, pass);
-                        while (pm)  // warp-uniform
+                        if (j0 + u * G >= steps) break;  // warp-uniform
+                        sc.steps++;
+                        const bool               in   = j0 + u * G + sub < total;
+                        const unsigned long long c    = in ? point_key(qx, qy, qz, p[u]) : ~0ull;
+                        const unsigned long long kkey = __shfl_sync(FULL, mine, kth_lane);
+                        const bool pass = in && c < kkey && __uint_as_float((uint32_t)(c >> 32)) <= kth;
+                        unsigned   pm   = __ballot_sync(FULL, pass) & gmask;
+                        while (__any_sync(FULL, pm != 0))
                         {
-                            const int src = __ffs(pm) - 1;
+                            // one offer to the group's list: lanes with cc < mine form a suffix of the group, its
+                            // first lane takes cc, the others take their left neighbour's key
+                            const bool ins = pm != 0;
+                            const int  src = ins ? __ffs(pm) - 1 : lane;
                             pm &= pm - 1;
+                            sc.inserts++;
                             const unsigned long long cc = __shfl_sync(FULL, c, src);
-                            MP2P_KNN_INSERT(owner, cc)
+                            const unsigned long long up = __shfl_up_sync(FULL, mine, 1, G);
+                            if (ins && cc < mine) mine = (sub == 0 || !(cc < up)) ? cc : up;
                         }
                     }
                 }
-                const unsigned long long kkey = __shfl_sync(FULL, mine, okl);
-                if (owner) kth = fminf(kth, __uint_as_float((uint32_t)(kkey >> 32))), total = 0;
-            }
-        }
-        const uint32_t steps = __reduce_max_sync(FULL, total);
-        constexpr int  kAhead = 4;  // steps whose loads are issued together
-        uint32_t       r = 0, re = tb.end[0], ra = tb.adj[0];  // stale values if total == 0: never used then
-        for (uint32_t j0 = 0; j0 < steps; j0 += kAhead * G)
-        {
-            float4 p[kAhead];
-#pragma unroll
-            for (int u = 0; u < kAhead; u++)
-            {
-                const uint32_t v = j0 + u * G + sub;
-                p[u]             = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (v < total)
-                {
-                    while (v >= re) r++, re = tb.end[r], ra = tb.adj[r];
-                    p[u] = __ldg(g.pts + (uint32_t)(ra + v));
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kAhead; u++)
-            {
-                if (j0 + u * G >= steps) break;  // warp-uniform
-                const bool               in   = j0 + u * G + sub < total;
-                const unsigned long long c    = in ? point_key(qx, qy, qz, p[u]) : ~0ull;
                 const unsigned long long kkey = __shfl_sync(FULL, mine, kth_lane);
-                const bool pass = in && c < kkey && __uint_as_float((uint32_t)(c >> 32)) <= kth;
-                unsigned   pm   = __ballot_sync(FULL, pass) & gmask;
-                while (__any_sync(FULL, pm != 0))
-                {
-                    const bool ins = pm != 0;
-                    const int  src = ins ? __ffs(pm) - 1 : lane;
-                    pm &= pm - 1;
-                    const unsigned long long cc = __shfl_sync(FULL, c, src);
-                    MP2P_KNN_INSERT(ins, cc)
-                }
-            }
-        }
-        const unsigned long long kkey = __shfl_sync(FULL, mine, kth_lane);
-        if (total) kth = fminf(kth, __uint_as_float((uint32_t)(kkey >> 32)));
-    };
-
-    // One ROUND: every lane takes up to T voxels — from the 3x3x3 neighbourhood of the level's centre
-    // voxel (from_stack = false: neighbour numbers [lo, hi) of kNeighbourOrder) or from the top of the
-    // group's descent stack — bounds them against kth, probes the survivors, splits the large ones
-    // (8 children onto the stack) and lists the others in the run table. Returns the list's length.
-    // (rl, cx, cy, cz = the level being searched and its centre voxel; only used if !from_stack.)
-    auto round = [&](bool from_stack, int lo, int hi, bool want, int rl, int cx, int cy, int cz) -> uint32_t
-    {
-        uint32_t           st[T], cn[T], h[T];
-        unsigned long long ckey[T];
-        uint4              raw[T];
-        int                erl[T];
-        bool               need[T];
-        const int          n_pop = from_stack ? min(sp, G * T) : 0;
-#pragma unroll
-        for (int t = 0; t < T; t++)
-        {
-            const int n = sub + G * t;
-            st[t] = cn[t] = h[t] = 0u, ckey[t] = 0ull, need[t] = false, erl[t] = rl, raw[t] = make_uint4(0u, 0u, 0u, 0u);
-            int  vx = 0, vy = 0, vz = 0;
-            bool have = false;
-            if (from_stack)
-            {
-                if (n < n_pop)
-                {
-                    const unsigned long long e = tb.stk_key[sp - 1 - n];
-                    erl[t]                     = tb.stk_rl[sp - 1 - n];
-                    vx = (int)(e & 0x1fffffu), vy = (int)((e >> 21) & 0x1fffffu), vz = (int)((e >> 42) & 0x1fffffu);
-                    have = true;
-                }
-            }
-            else if (want && lo + n < hi)
-            {
-                const uint32_t code = nb_order[lo + n];
-                vx = cx + (int)(code & 3u) - 1, vy = cy + (int)((code >> 2) & 3u) - 1, vz = cz + (int)((code >> 4) & 3u) - 1;
-                const int cmax = ((1 << kGridBits) - 1) >> (g.level_first + rl);
-                have = (unsigned)vx <= (unsigned)cmax && (unsigned)vy <= (unsigned)cmax && (unsigned)vz <= (unsigned)cmax;
-            }
-            // strict `>`: an equal-distance lower index must still be seen
-            if (have && !(voxel_bound(g.level_first + erl[t], vx, vy, vz) > kth))
-            {
-                need[t] = true;
-                ckey[t] = cell_key((uint32_t)vx, (uint32_t)vy, (uint32_t)vz);
-                h[t]    = cell_hash(ckey[t], g.level_shift[erl[t]]);
-                raw[t]  = __ldg(reinterpret_cast<const uint4*>(g.table + g.level_off[erl[t]] + h[t]));  // the lane's probes go out together
-            }
-        }
-        sp -= n_pop;
-        __syncwarp();  // the popped entries are in registers before anybody pushes over them
-#pragma unroll
-        for (int t = 0; t < T; t++)
-        {
-            if (!need[t]) continue;
-            sc.probes++;
-            const uint32_t   hmask = (1u << (64 - g.level_shift[erl[t]])) - 1u;
-            const CellEntry* tab   = g.table + g.level_off[erl[t]];
-            while (true)  // linear probing continues on a collision
-            {
-                const unsigned long long k = (unsigned long long)raw[t].x | ((unsigned long long)raw[t].y << 32);
-                if (k == ckey[t])
-                {
-                    st[t] = raw[t].z, cn[t] = raw[t].w;
-                    break;
-                }
-                if (k == kEmptyKey) break;
-                h[t]   = (h[t] + 1) & hmask;
-                raw[t] = __ldg(reinterpret_cast<const uint4*>(tab + h[t]));
-            }
-        }
-        // large voxels are split (while the stack has room), the others listed: positions by ballot rank
-        uint32_t n_runs = 0, pos[T];
-        int      sp_new = sp;
-        bool     split[T];
-#pragma unroll
-        for (int t = 0; t < T; t++)
-        {
-            const bool     large = cn[t] > kDescend && erl[t] > 0;
-            const unsigned bl    = __ballot_sync(FULL, large) & gmask;
-            const int      at    = sp_new + 8 * __popc(bl & below);
-            split[t]             = large && at + 8 <= kStackCap;
-            // (lanes are served in order, so the ones that fit form a prefix of the large ones)
-            const unsigned bs = __ballot_sync(FULL, split[t]) & gmask;
-            if (split[t])
-            {
-                const unsigned long long e  = ckey[t];
-                const unsigned long long x2 = (e & 0x1fffffull) << 1, y2 = ((e >> 21) & 0x1fffffull) << 1, z2 = ((e >> 42) & 0x1fffffull) << 1;
-#pragma unroll
-                for (int c = 0; c < 8; c++)
-                {
-                    tb.stk_key[at + c] = (x2 | (unsigned long long)(c & 1)) | ((y2 | (unsigned long long)((c >> 1) & 1)) << 21) |
-                                         ((z2 | (unsigned long long)(c >> 2)) << 42);
-                    tb.stk_rl[at + c] = (uint8_t)(erl[t] - 1);
-                }
-            }
-            sp_new += 8 * __popc(bs);
-            const bool     listed = cn[t] != 0u && !split[t];
-            const unsigned b      = __ballot_sync(FULL, listed) & gmask;
-            pos[t]                = n_runs + __popc(b & below);
-            n_runs += __popc(b);
-            if (listed) sc.cands += cn[t];
-        }
-        sp = sp_new;
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < T; t++)
-            if (cn[t] != 0u && !split[t]) tb.end[pos[t]] = cn[t], tb.adj[pos[t]] = st[t];
-        __syncwarp();
-        // lengths -> inclusive prefix, starts -> start - exclusive prefix; G entries per pass
-        uint32_t       carry  = 0;
-        const uint32_t passes = __reduce_max_sync(FULL, (n_runs + G - 1) / G);
-        for (uint32_t c = 0; c < passes; c++)
-        {
-            const uint32_t e    = c * G + sub;
-            const uint32_t x    = e < n_runs ? tb.end[e] : 0u;
-            uint32_t       incl = x;
-#pragma unroll
-            for (int o = 1; o < G; o <<= 1)
-            {
-                const uint32_t y = __shfl_up_sync(FULL, incl, o, G);
-                if (sub >= o) incl += y;
-            }
-            incl += carry;
-            if (e < n_runs) tb.end[e] = incl, tb.adj[e] -= incl - x;
-            carry = __shfl_sync(FULL, incl, gbase + G - 1);
-        }
-        __syncwarp();
-        return carry;
-    };
-
-    // visits everything the rounds so far put on the stacks, depth first
-    auto drain = [&]()
-    {
-        while (__any_sync(FULL, sp > 0))
-        {
-            const uint32_t total = round(true, 0, 0, false, 0, 0, 0, 0);
-            dense_scan(total);
-        }
-    };
-
-    for (int rl = rl_start; rl < g.n_levels; rl++)
-    {
-        if (!__any_sync(FULL, live)) break;
-        const int  L   = g.level_first + rl;
-        const bool top = L == kGridBits;  // the single voxel holding every point
-        if (live) mine = sentinel;        // the list is rebuilt at every level: no key is ever offered twice
-
-        const int   cmax = ((1 << kGridBits) - 1) >> L;
-        const float s    = (float)(1 << L);  // voxel edge in finest quanta
-        const int   cx = Ix >> L, cy = Iy >> L, cz = Iz >> L;
-        const float fx = ux - (float)cx * s, fy = uy - (float)cy * s, fz = uz - (float)cz * s;
-        // smallest bound any face voxel / any edge or corner voxel can have (per-axis gaps as in voxel_bound)
-        const float gxl = fmaxf(fx - 4.f, 0.f), gxh = fmaxf(s - fx - 4.f, 0.f);
-        const float gyl = fmaxf(fy - 4.f, 0.f), gyh = fmaxf(s - fy - 4.f, 0.f);
-        const float gzl = fmaxf(fz - 4.f, 0.f), gzh = fmaxf(s - fz - 4.f, 0.f);
-        const float mnx = fminf(gxl * gxl * q2, gxh * gxh * q2), mny = fminf(gyl * gyl * q2, gyh * gyh * q2),
-                    mnz = fminf(gzl * gzl * q2, gzh * gzh * q2);
-        const float min_face = fminf(mnx, fminf(mny, mnz));
-        const float min_edge = fminf(mnx + mny, fminf(mnx + mnz, mny + mnz)) * 0.999999f;
-
-        // ---- centre voxel: every lane of the group makes the same probe (one broadcast request)
-        {
-            uint32_t start = 0, count = 0;
-            if (top)
-            {
-                if (live) count = g.n_points;
-                if (live && sub == 0) sc.probes++;
-            }
-            else if (live && (unsigned)cx <= (unsigned)cmax && (unsigned)cy <= (unsigned)cmax && (unsigned)cz <= (unsigned)cmax)
-            {
-                if (!grid_lookup(g, rl, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz, start, count)) count = 0;
-                if (sub == 0) sc.probes++;
-            }
-            const bool split = count > kDescend && rl > 0;  // (sp == 0 here: the stack has room)
-            __syncwarp();
-            if (split)
-            {
-                if (sub < 8)
-                {
-                    const unsigned long long x2 = (unsigned long long)(top ? 0 : cx) << 1, y2 = (unsigned long long)(top ? 0 : cy) << 1,
-                                             z2 = (unsigned long long)(top ? 0 : cz) << 1;
-                    tb.stk_key[sub] = (x2 | (unsigned long long)(sub & 1)) | ((y2 | (unsigned long long)((sub >> 1) & 1)) << 21) |
-                                      ((z2 | (unsigned long long)(sub >> 2)) << 42);
-                    tb.stk_rl[sub]  = (uint8_t)(rl - 1);
-                }
-                sp = 8, count = 0;
-            }
-            else if (sub == 0)
-            {
-                tb.end[0] = count, tb.adj[0] = start;
-                sc.cands += count;
-            }
-            __syncwarp();
-            dense_scan(count);
-            drain();
-        }
-        // ---- the neighbours the bound cannot exclude: faces, then edges and corners (or all at once)
-        if (!top)
-        {
-#pragma unroll 1
-            for (int phase = 1; phase < n_phases; phase++)
-            {
-                const int   lo = phase == 1 ? 1 : 7, hi = (phase == 1 && n_phases == 3) ? 7 : 27;
-                const float mn = phase == 1 ? min_face : min_edge;
-                const bool  want = live && !(mn > kth);
-                if (!__any_sync(FULL, want)) continue;  // nothing of this phase can matter to any group
-                const uint32_t total = round(false, lo, hi, want, rl, cx, cy, cz);
-                dense_scan(total);
-                drain();
+                if (total) kth = fminf(kth, __uint_as_float((uint32_t)(kkey >> 32)));
             }
         }
         if (top)
         {
-            if (live && sub == 0) sc.levels++;
+            if (here && sub == 0) sc.levels++;
             break;
         }
         // `mine` now holds the exact K best of this level's block; everything outside the 3x3x3
         // block is at least m quanta away
+        const float fx = ux - (float)cx * s, fy = uy - (float)cy * s, fz = uz - (float)cz * s;
         const float mx = s + fminf(fx, s - fx), my = s + fminf(fy, s - fy), mz = s + fminf(fz, s - fz);
         const float m  = fmaxf(fminf(mx, fminf(my, mz)) - 4.f, 0.f);
-        if (live)
+        if (here)
         {
             if (sub == 0) sc.levels++;
-            if (kth <= m * m * q2) live = false;
+            if (kth <= m * m * q2)
+                live = false;
+            else
+            {
+                // not settled: go straight to the first level whose block is certain to settle the bound found
+                // (its margin is at least one voxel edge) instead of trying every level in between
+                next_rl = rl + 1;
+                while (next_rl < g.n_levels - 1)
+                {
+                    const float e = fmaxf((float)(1 << (g.level_first + next_rl)) - 4.f, 0.f);
+                    if (e * e * q2 >= kth) break;
+                    next_rl++;
+                }
+            }
         }
     }
-#undef MP2P_KNN_INSERT
 }
-
 
 // warp-aggregated accumulation of the per-thread counters into stats[0..3] (measurement hook)
 __device__ __forceinline__ void flush_search_stats(const SearchCounters& sc, uint32_t n_valid,

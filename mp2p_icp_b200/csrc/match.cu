@@ -225,6 +225,11 @@ struct Pt2PtArgs
     // K = 1, local cloud read straight from the caller's pinned host arrays (zero copy): the search
     // kernel leaves a device copy here for the compaction (NULL = the arrays are device memory)
     float *stage_x, *stage_y, *stage_z;
+    // k > 1 search over a resident cloud: tile served by CTA b (longest tiles of the previous call first;
+    // NULL = the strided order above) and where every tile reports how long it took (NULL = nowhere)
+    const uint32_t* tile_order;
+    uint32_t*       tile_cost;
+    uint32_t*       tile_trace;  // measurement hook: 8 words per CTA {SM, start ns, end ns, tile, rounds, steps, inserts, probes | levels << 16 of warp 0}
 };
 
 // ------------------------------------------------------------------------------------------
@@ -255,7 +260,11 @@ __global__ void __launch_bounds__(NT, MP2P_MATCH_MIN_BLOCKS * (int)kQueryTile / 
     __shared__ QueryTile<NQ> tile;
     __shared__ BBoxAcc       bacc;
     __shared__ KnnShared<V1 ? 32 : G, NT> ks;  // (V1: the old search keeps no tables; smallest instantiation)
-    const size_t             base = (size_t)(((unsigned long long)blockIdx.x * a.tile_stride) % gridDim.x) * NQ;
+    const long long    t_start = clock64();
+    unsigned long long t_trace0 = 0;
+    if (a.tile_trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_trace0));
+    const uint32_t  tile_id = a.tile_order ? __ldg(a.tile_order + blockIdx.x) : (uint32_t)(((unsigned long long)blockIdx.x * a.tile_stride) % gridDim.x);
+    const size_t    base    = (size_t)tile_id * NQ;
     bbox_init(bacc);
     if (!V1) knn_shared_init(ks);
     load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);  // (holds the __syncthreads)
@@ -310,6 +319,53 @@ __global__ void __launch_bounds__(NT, MP2P_MATCH_MIN_BLOCKS * (int)kQueryTile / 
         if (has) fit.list[at + __popc(m & ((1u << lane) - 1u))] = qpos;
         if (q_lane && !has) fit.ok_flags[i] = 0;
         if (valid && fit.need > G && sub == 0) fit.ok_flags[i] = 0;  // cannot hold `need` neighbours at all
+    }
+    // how long this tile took (its slowest warp, in units of 64 clocks): the next call over the same cloud
+    // starts the long tiles first (k_tile_rank)
+    if (a.tile_cost && (threadIdx.x & 31) == 0) atomicMax(a.tile_cost + tile_id, (uint32_t)min((clock64() - t_start) >> 6, 0xffffffffll));
+    if (a.tile_trace)  // measurement hook ($MP2P_KNN_TRACE=1): where and when every CTA ran
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            unsigned long long t1;
+            uint32_t           smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            a.tile_trace[8 * blockIdx.x + 0] = smid, a.tile_trace[8 * blockIdx.x + 1] = (uint32_t)t_trace0;
+            a.tile_trace[8 * blockIdx.x + 2] = (uint32_t)t1, a.tile_trace[8 * blockIdx.x + 3] = tile_id;
+            a.tile_trace[8 * blockIdx.x + 4] = sc.rounds, a.tile_trace[8 * blockIdx.x + 5] = sc.steps;
+            a.tile_trace[8 * blockIdx.x + 6] = sc.inserts, a.tile_trace[8 * blockIdx.x + 7] = sc.probes | (sc.levels << 16);
+        }
+    }
+}
+
+// Tile order for the next call: tiles by DESCENDING cost, 256 cost classes (counting sort by one CTA; the order
+// inside a class is arbitrary — it only decides which CTA serves which tile, never a result).
+__global__ void __launch_bounds__(1024) k_tile_rank(uint32_t* __restrict__ cost, uint32_t n_tiles, uint32_t* __restrict__ order)
+{
+    __shared__ uint32_t hist[256], cursor[256], mx;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) mx = 1;
+    __syncthreads();
+    uint32_t m = 0;
+    for (uint32_t t = threadIdx.x; t < n_tiles; t += blockDim.x) m = max(m, cost[t]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) atomicMax(&mx, m);
+    __syncthreads();
+    const float scale = 255.f / (float)mx;
+    for (uint32_t t = threadIdx.x; t < n_tiles; t += blockDim.x) atomicAdd(&hist[255 - min(255u, (uint32_t)((float)cost[t] * scale))], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        uint32_t acc = 0;
+        for (int b = 0; b < 256; b++) cursor[b] = acc, acc += hist[b];
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < n_tiles; t += blockDim.x)
+    {
+        order[atomicAdd(&cursor[255 - min(255u, (uint32_t)((float)cost[t] * scale))], 1u)] = t;
+        cost[t] = 0u;  // re-armed for the next search (atomicMax accumulates into it)
     }
 }
 
@@ -1224,9 +1280,12 @@ __global__ void __launch_bounds__(kScanThreads)
                     uint32_t* __restrict__ bbox_next, unsigned long long* __restrict__ status,
                     uint32_t* __restrict__ tile_counter,
                     mp2p_b200_pair_pt2pl* __restrict__ out, unsigned long long* __restrict__ out_count,
-                    uint32_t scan_epoch, int line_mode)
+                    uint32_t scan_epoch, int line_mode, uint32_t* __restrict__ out_host,
+                    unsigned long long* __restrict__ count_host)
 {
+    static_assert(kScanItems == 1, "one local point per thread");
     __shared__ ScanSmem sm;
+    __shared__ uint32_t s_rec[kScanThreads * 18];  // this tile's 72-byte records, staged for coalesced stores
     bbox_rearm(bbox_next);
     const uint32_t n_tiles = (n_local + kScanTile - 1) / kScanTile;
     if (threadIdx.x == 0)
@@ -1235,45 +1294,46 @@ __global__ void __launch_bounds__(kScanThreads)
         if (sm.tile_id == n_tiles - 1) *tile_counter = 0u;
     }
     __syncthreads();
-    const uint32_t tile    = sm.tile_id;
-    const bool     gate    = bbox_gate(g, bbox, gate_eps);
-    const uint32_t i0      = tile * kScanTile + threadIdx.x * kScanItems;
-    uint32_t       flags = 0, local = 0;
-#pragma unroll
-    for (int j = 0; j < kScanItems; j++)
+    const uint32_t tile = sm.tile_id;
+    const bool     gate = bbox_gate(g, bbox, gate_eps);
+    const uint32_t i    = tile * kScanTile + threadIdx.x;
+    const bool     ok   = gate && i < n_local && ok_flags[i];
+    // everything the record needs is requested before the scan (one dependent round trip)
+    PlaneCandidate pc{};
+    float          px = 0.f, py = 0.f, pz = 0.f;
+    if (ok) pc = plc[i], px = lx[i], py = ly[i], pz = lz[i];  // ORIGINAL local point (Matcher_Point2Plane.cpp:105)
+    const unsigned long long w = grid_exclusive_scan(sm, tile, n_tiles, ok ? 1u : 0u, status, out_count, scan_epoch);
+    const unsigned long long tile_base = sm.tile_base;
+    if (ok)
     {
-        const uint32_t i = i0 + j;
-        if (gate && i < n_local && ok_flags[i]) flags |= 1u << j, local++;
-    }
-    const unsigned long long off = grid_exclusive_scan(sm, tile, n_tiles, local, status, out_count, scan_epoch);
-    unsigned long long       w   = off;
-#pragma unroll
-    for (int j = 0; j < kScanItems; j++)
-    {
-        if (!(flags & (1u << j))) continue;
-        if (w < capacity)
+        double* o = reinterpret_cast<double*>(s_rec + (uint32_t)(w - tile_base) * 18);
+        if (line_mode)  // point_line_pair_t: TLine3D {pBase, director}, TPoint3D pt_local (Pairings.h:61-73; Matcher_Point2Line.cpp:152)
         {
-            const uint32_t       i  = i0 + j;
-            const PlaneCandidate pc = plc[i];
-            if (line_mode)  // point_line_pair_t: TLine3D {pBase, director}, TPoint3D pt_local (Pairings.h:61-73)
-            {
-                mp2p_b200_pair_pt2ln r;
-                r.pBase[0] = pc.centroid[0], r.pBase[1] = pc.centroid[1], r.pBase[2] = pc.centroid[2];
-                r.director[0] = pc.coefs[0], r.director[1] = pc.coefs[1], r.director[2] = pc.coefs[2];
-                r.local[0] = lx[i], r.local[1] = ly[i], r.local[2] = lz[i];  // :152
-                reinterpret_cast<mp2p_b200_pair_pt2ln*>(out)[w] = r;
-                w++;
-                continue;
-            }
-            mp2p_b200_pair_pt2pl r;
-            r.plane_coefs[0] = pc.coefs[0], r.plane_coefs[1] = pc.coefs[1];
-            r.plane_coefs[2] = pc.coefs[2], r.plane_coefs[3] = pc.coefs[3];
-            r.centroid[0] = pc.centroid[0], r.centroid[1] = pc.centroid[1], r.centroid[2] = pc.centroid[2];
-            r.local_x = lx[i], r.local_y = ly[i], r.local_z = lz[i];  // ORIGINAL point (:105)
-            r._pad = 0.f;
-            out[w] = r;
+            o[0] = pc.centroid[0], o[1] = pc.centroid[1], o[2] = pc.centroid[2];
+            o[3] = pc.coefs[0], o[4] = pc.coefs[1], o[5] = pc.coefs[2];
+            o[6] = px, o[7] = py, o[8] = pz;
         }
-        w++;
+        else  // point_plane_pair_t: plane_patch_t {TPlane coefs[4], TPoint3D centroid}, TPoint3Df pt_local, pad
+        {
+            o[0] = pc.coefs[0], o[1] = pc.coefs[1], o[2] = pc.coefs[2], o[3] = pc.coefs[3];
+            o[4] = pc.centroid[0], o[5] = pc.centroid[1], o[6] = pc.centroid[2];
+            uint32_t* t = reinterpret_cast<uint32_t*>(o + 7);
+            t[0] = __float_as_uint(px), t[1] = __float_as_uint(py);
+            t[2] = __float_as_uint(pz), t[3] = 0u;
+        }
+    }
+    __syncthreads();
+    const unsigned long long room  = capacity > tile_base ? capacity - tile_base : 0ull;
+    const uint32_t           n_rec = (uint32_t)min((unsigned long long)sm.tile_total, room);
+    {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out) + tile_base * 18;
+        for (uint32_t k = threadIdx.x; k < n_rec * 18; k += kScanThreads) dst[k] = s_rec[k];
+    }
+    if (out_host)  // zero-copy output: the caller's pinned buffer receives the records, pinned memory the count
+    {
+        uint32_t* dst = out_host + tile_base * 18;
+        for (uint32_t k = threadIdx.x; k < n_rec * 18; k += kScanThreads) dst[k] = s_rec[k];
+        if (tile == n_tiles - 1 && threadIdx.x == 0) *count_host = tile_base + sm.tile_total;
     }
 }
 
@@ -1378,11 +1438,66 @@ int knn_nt()
     }();
     return v;
 }
+// Scheduling hint of a search over a RESIDENT cloud (knn_tile_hint): the kernel reports per-tile durations
+// into the cloud handle, k_tile_rank turns them into the next call's tile order (longest first). The pose
+// moves little between ICP iterations, so the expensive tiles of one call — queries that climb through empty
+// space — are the expensive tiles of the next; started first they overlap with everything else instead of
+// forming the tail of the launch. $MP2P_KNN_LPT=0 switches the hint off.
+bool knn_lpt()
+{
+    static const bool v = [] {
+        const char* e = getenv("MP2P_KNN_LPT");
+        return !(e && atoi(e) == 0);
+    }();
+    return v;
+}
+int knn_tile_hint(mp2p_b200_ctx* ctx, uint32_t n_tiles, int G, int NT, Pt2PtArgs& a)
+{
+    a.tile_order = nullptr, a.tile_cost = nullptr, a.tile_trace = nullptr;
+    mp2p_b200_cloud* c = ctx->cur_cloud;
+    static const char* trace_path = getenv("MP2P_KNN_TRACE");
+    if (trace_path && c)
+    {
+        MP2P_TRY(ctx->d_trace.ensure((size_t)n_tiles * 32));
+        a.tile_trace = ctx->d_trace.as<uint32_t>(), ctx->trace_tiles = n_tiles;
+    }
+    if (!c || !knn_lpt() || !ctx->aux_stream || n_tiles < 2 * 148) return 0;  // (a launch of less than two CTAs per SM has no tail to hide)
+    const uint64_t key = ((uint64_t)n_tiles << 20) | ((uint64_t)G << 12) | (uint64_t)NT;
+    if (c->hint_key == key)
+    {
+        // the order was made on the side stream behind the previous search: this search waits for it
+        a.tile_order = c->d_tile_order.as<uint32_t>();
+        MP2P_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_rank, 0));
+    }
+    else
+    {
+        if (c->hint_key) MP2P_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_rank, 0));  // a rank kernel may still read / clear the arrays
+        MP2P_TRY(c->d_tile_cost.ensure((size_t)n_tiles * 4));
+        MP2P_TRY(c->d_tile_order.ensure((size_t)n_tiles * 4));
+        MP2P_CUDA_TRY(cudaMemsetAsync(c->d_tile_cost.p, 0, (size_t)n_tiles * 4, ctx->stream));  // later calls: k_tile_rank re-arms it
+    }
+    c->hint_key = key;
+    a.tile_cost = c->d_tile_cost.as<uint32_t>();
+    return 0;
+}
+// behind the search, on the side stream: the next call's tile order (nothing of this call waits for it)
+int knn_tile_rank(mp2p_b200_ctx* ctx, uint32_t n_tiles, const Pt2PtArgs& a)
+{
+    if (!a.tile_cost) return 0;
+    MP2P_CUDA_TRY(cudaEventRecord(ctx->ev_rank_fork, ctx->stream));
+    MP2P_CUDA_TRY(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_rank_fork, 0));
+    k_tile_rank<<<1, 1024, 0, ctx->aux_stream>>>(a.tile_cost, n_tiles, ctx->cur_cloud->d_tile_order.as<uint32_t>());
+    MP2P_CUDA_TRY(cudaEventRecord(ctx->ev_rank, ctx->aux_stream));
+    count_launch(ctx);
+    return 0;
+}
 #define MP2P_LAUNCH_KMATCH_NT(G, V1, NT, nq, st, ...)                                              \
     {                                                                                              \
         const uint32_t nb_ = (uint32_t)(((uint64_t)(nq) * G + NT - 1) / NT);                       \
         a_.tile_stride     = tile_stride_for(nb_);                                                 \
+        MP2P_TRY(knn_tile_hint(ctx, nb_, G, NT, a_));                                              \
         k_match_pt2pt<G, V1, NT><<<nb_, NT, 0, st>>>(__VA_ARGS__);                                 \
+        MP2P_TRY(knn_tile_rank(ctx, nb_, a_));                                                     \
     }
 // `args` = the Pt2PtArgs lvalue passed in __VA_ARGS__ (its tile_stride is set here, per grid size)
 #define MP2P_LAUNCH_KMATCH(G, args, nq, st, ...)                                                   \
@@ -1445,7 +1560,7 @@ T* mapped_alias(T* host)
 int stage_local(mp2p_b200_ctx* ctx, const float* lx, const float* ly, const float* lz, uint64_t n,
                 int on_device, bool* mapped_ok = nullptr)
 {
-    ctx->cur_perm = nullptr;
+    ctx->cur_perm = nullptr, ctx->cur_cloud = nullptr;
     if (mapped_ok && on_device != 0) mapped_ok = nullptr;
     if (mapped_ok) *mapped_ok = false;
     if (on_device == 2)  // resident cloud: search kernels walk the Morton-sorted copy
@@ -1464,6 +1579,7 @@ int stage_local(mp2p_b200_ctx* ctx, const float* lx, const float* ly, const floa
         ctx->cur_lx = c->d_x.as<float>(), ctx->cur_ly = c->d_y.as<float>(), ctx->cur_lz = c->d_z.as<float>();
         ctx->cur_qx = c->d_sx.as<float>(), ctx->cur_qy = c->d_sy.as<float>(), ctx->cur_qz = c->d_sz.as<float>();
         ctx->cur_perm   = c->d_perm.as<uint32_t>();
+        ctx->cur_cloud  = const_cast<mp2p_b200_cloud*>(c);
         ctx->cur_tma_ok = true;
         return 0;
     }
@@ -2250,11 +2366,31 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
         MP2P_TRY(ctx->d_out2l.ensure(cap * sizeof(mp2p_b200_pair_pt2pl)));
         d_out = ctx->d_out2l.as<mp2p_b200_pair_pt2pl>();
     }
+    // pinned host output: the compaction CAN store records and count straight into the caller's buffer like the
+    // pt2pt matcher does — measured on C3 (4.5 MB of 72-byte records) the stores over PCIe take 55 us longer than
+    // the DMA copy behind the kernel (round 2, visit 13: e2e 0.534 vs 0.478 ms), so it is off unless
+    // $MP2P_PT2PL_ZERO_COPY=1
+    uint32_t*           out_host   = nullptr;
+    unsigned long long* count_host = nullptr;
+    static const bool   zc_pt2pl   = [] {
+        const char* e = getenv("MP2P_PT2PL_ZERO_COPY");
+        return e && atoi(e) == 1;
+    }();
+    if (zc_pt2pl && !keep_on_device && !out_on_device)
+    {
+        out_host = reinterpret_cast<uint32_t*>(mapped_alias(out));
+        if (out_host)
+        {
+            if (!ctx->h_pinned_dev) ctx->h_pinned_dev = mapped_alias(ctx->h_pinned);
+            count_host = static_cast<unsigned long long*>(ctx->h_pinned_dev);
+            if (!count_host) out_host = nullptr;
+        }
+    }
     prof_begin(ctx, 1);
     k_compact_pt2pl<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, (uint32_t)n_local, gate_eps,
                                                                cap, dlx, dly, dlz, plc, okf, sv.bbox, sv.bbox_next,
                                                                status, sv.tile_counter, d_out, sv.count,
-                                                               ctx->scan_epoch, line ? 1 : 0);
+                                                               ctx->scan_epoch, line ? 1 : 0, out_host, count_host);
     prof_end(ctx, 1);
     count_launch(ctx);
     if (keep_on_device)
@@ -2264,11 +2400,13 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
     }
     if (line)
     {
-        const int rc      = fetch_results(ctx, sv.count, d_out, out, cap, out_on_device, out_count, &ctx->hint_pt2ln);
+        const int rc = fetch_results(ctx, sv.count, d_out, out, cap, out_on_device, out_count, &ctx->hint_pt2ln, nullptr, nullptr,
+                                     out_host != nullptr);
         ctx->last2l.valid = false;  // the device copy holds LINE records: not a pt2pl list a solver may name
         return rc;
     }
-    return fetch_results(ctx, sv.count, d_out, out, cap, out_on_device, out_count, &ctx->hint_pt2pl, pose);
+    return fetch_results(ctx, sv.count, d_out, out, cap, out_on_device, out_count, &ctx->hint_pt2pl, pose, nullptr,
+                         out_host != nullptr);
 }
 
 int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const float* qy,
@@ -2824,7 +2962,7 @@ int run_adaptive_emit(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const mp2p_b200_ad
         }
         k_compact_pt2pl<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, (uint32_t)n_local, gate_eps, capl, ctx->cur_lx, ctx->cur_ly,
                                                                    ctx->cur_lz, plc, okf, S.sv_bbox, S.sv_bbox_next, S.status,
-                                                                   S.sv_tile_counter, d_out2l, S.sv_count, S.scan_epoch, 0);
+                                                                   S.sv_tile_counter, d_out2l, S.sv_count, S.scan_epoch, 0, nullptr, nullptr);
         count_launch(ctx);
     }
     // ---- point-to-point pairings: ordinary compaction over the selected candidate words, its own

@@ -7,6 +7,32 @@ namespace mp2p
 constexpr int    kReduceThreads  = 256;
 constexpr int    kReduceWarps    = kReduceThreads / 32;
 
+// (compile-time recursion: every index below is a constant, the values stay in registers)
+template <int P>
+__device__ __forceinline__ void warp_plain_steps(double (&v)[P])
+{
+#pragma unroll
+    for (int off = 16; off >= P; off >>= 1)
+#pragma unroll
+        for (int i = 0; i < P; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+}
+template <int P, int OFF>
+__device__ __forceinline__ void warp_halving_steps(double (&v)[P], int lane)
+{
+    if constexpr (OFF >= 1)
+    {
+        const bool up = (lane & OFF) != 0;
+#pragma unroll
+        for (int i = 0; i < OFF; i++)  // 2 * OFF values are still held
+        {
+            const double send = up ? v[i] : v[i + OFF];
+            const double keep = up ? v[i + OFF] : v[i];
+            v[i]              = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        warp_halving_steps<P, OFF / 2>(v, lane);
+    }
+}
+
 // Block reduction + grid fold without a second launch: every CTA stores its NV partial sums in row
 // `slot` (a CTA-unique index in [0, n_slots)) and takes a ticket; the LAST CTA to arrive sums the
 // rows of all CTAs in a FIXED order (8 chunks of rows in parallel, then the 8 chunk sums in order)
@@ -23,13 +49,20 @@ __device__ __forceinline__ bool block_reduce_to_packet(double (&acc)[NV], double
     __shared__ double   sh[kReduceWarps][32];
     __shared__ unsigned is_last;
     const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int v = 0; v < NV; v++)
+    // Warp sums of the NV values by RECURSIVE HALVING instead of NV separate shuffle trees: at every
+    // step the lanes of a pair trade half of the values they still hold (the lane whose bit is clear
+    // keeps the lower half and receives its partner's, and vice versa), so the P = 2^k >= NV values
+    // cost P - 1 exchanges in total — 31 for the 29 Gauss-Newton sums, where the trees cost 29 x 5 = 145
+    // (59 % of that kernel's instructions, profiles/r01_v20_ncu_lines_c3_gn.txt). Lane l ends with the
+    // sum of value l & (P - 1). The order of additions is fixed, so results stay run-to-run identical.
     {
-        double x = acc[v];
+        constexpr int P = NV <= 1 ? 1 : (NV <= 2 ? 2 : (NV <= 4 ? 4 : (NV <= 8 ? 8 : (NV <= 16 ? 16 : 32))));
+        double        v[P];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        if (lane == 0) sh[warp][v] = x;
+        for (int i = 0; i < P; i++) v[i] = i < NV ? acc[i] : 0.0;
+        if (P <= 16) warp_plain_steps<P>(v);  // more lanes than values: plain exchanges first
+        warp_halving_steps<P, P / 2>(v, lane);
+        if (lane < P) sh[warp][lane] = v[0];
     }
     __syncthreads();
     if (threadIdx.x < NV)

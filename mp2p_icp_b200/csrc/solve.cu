@@ -17,6 +17,7 @@
 // Pair records are AoS (36 / 72 bytes). A warp stages 32 consecutive records with fully coalesced
 // 128-byte loads into shared memory and each lane then reads its own record (stride 9 / 18 words).
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -708,6 +709,160 @@ int run_pt2pl_to_pt2pt(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pl* d_in, uin
                   (unsigned long long)*h);
         return MP2P_B200_ERR_CAPACITY;
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// covariance() (mp2p_icp/src/covariance.cpp:28-141): the stacked error vector of the final
+// pairings — error_point2point / error_point2line / error_point2plane, 3 rows per pairing — differentiated
+// numerically w.r.t. (x, y, z, yaw, pitch, roll) by central differences (mrpt::math::estimateJacobian:
+// column i = (f(x + h_i e_i) - f(x - h_i e_i)) * 0.5 / h_i), hessian = J^T J. The 12 perturbed poses come
+// from the host; one thread per pairing evaluates its 3 x 12 error values exactly as the host loop would,
+// forms its 3 x 6 block of J and adds the block's J^T J (upper triangle, 21 values) to its accumulators;
+// the grid reduction is the solvers' (reduce.cuh). cov = hessian^-1 on the host.
+// ------------------------------------------------------------------------------------------
+namespace
+{
+struct CovPoses
+{
+    double m[12][12];  // [2 * i] = x + h_i e_i, [2 * i + 1] = x - h_i e_i, row-major 3x4 each
+    double inv2h[6];
+};
+constexpr int kCovV = 21;
+
+__device__ __forceinline__ void cov_point(const double* T, double lx, double ly, double lz, double (&g)[3])
+{
+#pragma unroll
+    for (int r = 0; r < 3; r++) g[r] = T[4 * r] * lx + T[4 * r + 1] * ly + T[4 * r + 2] * lz + T[4 * r + 3];
+}
+__device__ __forceinline__ void cov_add_block(double (&acc)[kCovV], const double (&J)[3][6])
+{
+    int idx = 0;
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = a; b < 6; b++) acc[idx++] += J[0][a] * J[0][b] + J[1][a] * J[1][b] + J[2][a] * J[2][b];
+}
+
+__global__ void __launch_bounds__(kSolveThreads)
+    k_cov_accumulate(const uint32_t* __restrict__ p2p, uint64_t n2p, const uint32_t* __restrict__ p2l, uint64_t n2l,
+                     const uint32_t* __restrict__ p2ln, uint64_t n2ln, CovPoses P, double* __restrict__ partials,
+                     unsigned int* __restrict__ ticket, double* __restrict__ packet)
+{
+    __shared__ uint32_t stage[kWarps][32 * 18];
+    const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t*           sh = stage[warp];
+    double              acc[kCovV];
+#pragma unroll
+    for (int v = 0; v < kCovV; v++) acc[v] = 0;
+    const uint64_t warp_global = (uint64_t)blockIdx.x * kWarps + warp;
+    const uint64_t warp_stride = (uint64_t)gridDim.x * kWarps;
+
+    for (uint64_t base = warp_global * 32; base < n2p; base += warp_stride * 32)  // covariance.cpp:75-82
+    {
+        warp_stage_records<9>(p2p, base, n2p, sh);
+        if (base + lane < n2p)
+        {
+            const uint32_t* rec = sh + lane * 9;
+            const double    gx = __uint_as_float(rec[2]), gy = __uint_as_float(rec[3]), gz = __uint_as_float(rec[4]);
+            const double    lx = __uint_as_float(rec[5]), ly = __uint_as_float(rec[6]), lz = __uint_as_float(rec[7]);
+            double          J[3][6];
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+            {
+                double gp[3], gm[3];
+                cov_point(P.m[2 * i], lx, ly, lz, gp), cov_point(P.m[2 * i + 1], lx, ly, lz, gm);
+                J[0][i] = P.inv2h[i] * ((gp[0] - gx) - (gm[0] - gx));
+                J[1][i] = P.inv2h[i] * ((gp[1] - gy) - (gm[1] - gy));
+                J[2][i] = P.inv2h[i] * ((gp[2] - gz) - (gm[2] - gz));
+            }
+            cov_add_block(acc, J);
+        }
+        __syncwarp();
+    }
+    for (uint64_t base = warp_global * 32; base < n2ln; base += warp_stride * 32)  // :85-93, errorTerms.cpp:67-113
+    {
+        warp_stage_records<18>(p2ln, base, n2ln, sh);
+        if (base + lane < n2ln)
+        {
+            const uint32_t* rec = sh + lane * 18;
+            double          v[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) v[k] = __longlong_as_double(((long long)rec[2 * k + 1] << 32) | (long long)rec[2 * k]);
+            double J[3][6];
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+            {
+                double e[2][3];
+#pragma unroll
+                for (int sgn = 0; sgn < 2; sgn++)
+                {
+                    double g[3];
+                    cov_point(P.m[2 * i + sgn], v[6], v[7], v[8], g);
+                    const double q[3] = {g[0] - v[0], g[1] - v[1], g[2] - v[2]};
+                    const double uq   = v[3] * q[0] + v[4] * q[1] + v[5] * q[2];
+                    e[sgn][0] = q[0] - v[3] * uq, e[sgn][1] = q[1] - v[4] * uq, e[sgn][2] = q[2] - v[5] * uq;
+                }
+#pragma unroll
+                for (int r = 0; r < 3; r++) J[r][i] = P.inv2h[i] * (e[0][r] - e[1][r]);
+            }
+            cov_add_block(acc, J);
+        }
+        __syncwarp();
+    }
+    for (uint64_t base = warp_global * 32; base < n2l; base += warp_stride * 32)  // :107-115, errorTerms.cpp:115-161
+    {
+        warp_stage_records<18>(p2l, base, n2l, sh);
+        if (base + lane < n2l)
+        {
+            const uint32_t* rec = sh + lane * 18;
+            double          c[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) c[k] = __longlong_as_double(((long long)rec[2 * k + 1] << 32) | (long long)rec[2 * k]);
+            const double lx = __uint_as_float(rec[14]), ly = __uint_as_float(rec[15]), lz = __uint_as_float(rec[16]);
+            const double mod_n = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+            double       J[3][6];
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+            {
+                double e[2][3];
+#pragma unroll
+                for (int sgn = 0; sgn < 2; sgn++)
+                {
+                    double g[3];
+                    cov_point(P.m[2 * i + sgn], lx, ly, lz, g);
+                    const double ev = c[0] * g[0] + c[1] * g[1] + c[2] * g[2] + c[3];
+#pragma unroll
+                    for (int r = 0; r < 3; r++) e[sgn][r] = -(c[r] / mod_n) * ev;
+                }
+#pragma unroll
+                for (int r = 0; r < 3; r++) J[r][i] = P.inv2h[i] * (e[0][r] - e[1][r]);
+            }
+            cov_add_block(acc, J);
+        }
+        __syncwarp();
+    }
+    block_reduce_to_packet<kCovV>(acc, partials, ticket, packet, blockIdx.x, gridDim.x);
+}
+}  // namespace
+
+// poses[12][12]: the perturbed poses (see CovPoses); d_packet[0..21) <- upper triangle of J^T J, row-major
+int run_cov_accumulate(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p, const mp2p_b200_pair_pt2pl* d2l,
+                       uint64_t n2l, const mp2p_b200_pair_pt2ln* d2ln, uint64_t n2ln, const double poses[12][12],
+                       const double inv2h[6], double* d_packet)
+{
+    const int     blocks = solve_grid(std::max(std::max(n2p, n2l), n2ln));
+    unsigned int* ticket;
+    double*       partials;
+    MP2P_TRY(solve_scratch(ctx, blocks, &ticket, &partials));
+    CovPoses P;
+    std::memcpy(P.m, poses, sizeof(P.m));
+    std::memcpy(P.inv2h, inv2h, sizeof(P.inv2h));
+    k_cov_accumulate<<<blocks, kSolveThreads, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d2p), n2p,
+                                                                reinterpret_cast<const uint32_t*>(d2l), n2l,
+                                                                reinterpret_cast<const uint32_t*>(d2ln), n2ln, P, partials, ticket,
+                                                                d_packet);
+    count_launch(ctx);
     return 0;
 }
 }  // namespace mp2p

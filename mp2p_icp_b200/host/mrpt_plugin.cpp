@@ -11,10 +11,13 @@
 //    left (MP2P_B200_PAIRS_LAST_MATCH) is an explicit opt-in, YAML `assumeUnmodifiedPairings: true`
 //    on the solver, for pipelines where nothing edits the Pairings between run_matchers and
 //    run_solvers (ICP.cpp:143-170) — then the count and 8 sampled records are still compared.
-//  * a global layer is re-indexed when its buffer address, size OR a fingerprint of 4096 sampled
-//    points + the first / last point changes. MRPT exposes no modification counter for the point
-//    buffers, so an in-place edit that touches none of the samples needs
-//    mp2p_icp::B200InvalidateGlobalLayer(layer) — documented in INTEGRATION.md.
+//  * a global layer is re-indexed (and a local layer re-uploaded) when its buffer address, size OR a
+//    fingerprint of ~4096 sampled points + the first / last point changes (mp2p_b200_map_cached /
+//    mp2p_b200_cloud_cached). MRPT exposes no modification counter for the point buffers, so an
+//    in-place edit that touches none of the samples needs mp2p_icp::B200InvalidateLayer(layer) —
+//    documented in INTEGRATION.md. YAML `cacheLocalCloud: false` uploads the local layer every call.
+//  * the solvers' uploaded pairings are compared on the device, byte for byte, with the copy the last
+//    matcher call left there; only on equality is the result that call computed ahead of time used.
 //  * YAML `device: <n>` on every class selects the GPU (default 0); one context per device.
 //
 // Usage from a pipeline YAML (the reference loads the .so through its `plugin:` key,
@@ -35,6 +38,8 @@
 #include <mp2p_icp/Solver_GaussNewton.h>
 #include <mp2p_icp/Solver_Horn.h>
 #include <mp2p_icp/metricmap.h>
+#include <mp2p_icp_filters/FilterDecimateVoxels.h>
+#include <mp2p_icp_filters/GetOrCreatePointLayer.h>
 #include <mrpt/core/initializer.h>
 #include <mrpt/maps/CPointsMap.h>
 #include <mrpt/math/distributions.h>
@@ -79,94 +84,31 @@ inline void pose12(const mrpt::poses::CPose3D& p, double out[12])
         out[4 * r + 3] = p.m_coords[r];
     }
 }
-// Device copies of global layers, keyed on (layer object, device) and rebuilt when the layer's buffer
-// address, size or content fingerprint changes (the reference relies on MRPT's own "kd-tree up to date"
-// flag, which is not visible from outside; methods are const so the cache is mutable).
-inline uint64_t fingerprint(const float* x, const float* y, const float* z, size_t n)
+// Device copies of the layers: kept by the LIBRARY (mp2p_b200_map_cached / mp2p_b200_cloud_cached), keyed on
+// the layer's x-buffer address, its size and a fingerprint of ~4096 sampled points — the reference relies on
+// MRPT's own "kd-tree up to date" flag, which is not visible from outside, and the methods here are const
+// (SURVEY.md §8b "Ownership"). A global layer is re-indexed, a local layer re-uploaded, whenever one of the
+// three changes; B200InvalidateLayer() covers in-place edits that miss every sample.
+inline mp2p_b200_map* device_map(const mrpt::maps::CMetricMap& layer, int device)
 {
-    // FNV-1a over the bit patterns of up to 4096 evenly spaced points plus the first and the last one
-    uint64_t   h   = 1469598103934665603ull;
-    const auto mix = [&h](float f)
-    {
-        uint32_t u;
-        std::memcpy(&u, &f, 4);
-        h = (h ^ u) * 1099511628211ull;
-    };
-    if (!n) return h;
-    const size_t step = n > 4096 ? n / 4096 : 1;
-    for (size_t i = 0; i < n; i += step) mix(x[i]), mix(y[i]), mix(z[i]);
-    mix(x[n - 1]), mix(y[n - 1]), mix(z[n - 1]);
-    return h;
+    const auto* pts = mp2p_icp::MapToPointsMap(layer);
+    ASSERTMSG_(pts, "B200 matchers need a CPointsMap global layer");
+    const auto&    xs = pts->getPointsBufferRef_x();
+    mp2p_b200_map* m  = nullptr;
+    check(mp2p_b200_map_cached(ctx(device), xs.data(), pts->getPointsBufferRef_y().data(), pts->getPointsBufferRef_z().data(),
+                               xs.size(), &m, nullptr));
+    return m;
 }
-struct MapCache
+// the local layer of an align() does not change between iterations (ICP.cpp:123-308 only moves the pose): with
+// `cacheLocalCloud` (default) it crosses PCIe once and is searched in Morton order; NULL = pass the host buffers
+inline const float* device_cloud(const mrpt::maps::CPointsMap& pts, int device, bool cache)
 {
-    struct Entry
-    {
-        mp2p_b200_map*   map = nullptr;
-        const float*     x   = nullptr;
-        size_t           n   = 0;
-        uint64_t         fp  = 0;
-        mp2p_b200_cloud* cloud = nullptr;  // set while a B200LocalCloudScope pins this layer as a LOCAL cloud
-    };
-    using Key = std::pair<const mrpt::maps::CMetricMap*, int>;
-    std::mutex           mtx;
-    std::map<Key, Entry> entries;
-    mp2p_b200_map* get(const mrpt::maps::CMetricMap& layer, int device)
-    {
-        const auto* pts = mp2p_icp::MapToPointsMap(layer);
-        ASSERTMSG_(pts, "B200 matchers need a CPointsMap global layer");
-        const auto&                 xs = pts->getPointsBufferRef_x();
-        const auto&                 ys = pts->getPointsBufferRef_y();
-        const auto&                 zs = pts->getPointsBufferRef_z();
-        const uint64_t              fp = fingerprint(xs.data(), ys.data(), zs.data(), xs.size());
-        std::lock_guard<std::mutex> lk(mtx);
-        auto&                       e = entries[Key(&layer, device)];
-        if (!e.map || e.x != xs.data() || e.n != xs.size() || e.fp != fp)
-        {
-            if (e.map) mp2p_b200_map_destroy(e.map), e.map = nullptr;
-            check(mp2p_b200_map_create(ctx(device), xs.data(), ys.data(), zs.data(), xs.size(), 0, &e.map));
-            e.x = xs.data(), e.n = xs.size(), e.fp = fp;
-        }
-        return e.map;
-    }
-    void invalidate(const mrpt::maps::CMetricMap& layer)
-    {
-        std::lock_guard<std::mutex> lk(mtx);
-        for (auto& [k, e] : entries)
-            if (k.first == &layer && e.map) mp2p_b200_map_destroy(e.map), e.map = nullptr;
-    }
-    // A local layer is uploaded (and Morton-sorted) once and reused by every ICP iteration ONLY while
-    // the caller vouches that it does not change: MRPT exposes no modification counter for the point
-    // buffers, so the plugin cannot detect edits by itself. B200LocalCloudScope (below) is that
-    // promise; without it the matchers pass the host buffers on every call (MP2P_B200_LOCAL_HOST).
-    const float* pinned_local(const mrpt::maps::CPointsMap& pts, int device)
-    {
-        std::lock_guard<std::mutex> lk(mtx);
-        auto                        it = entries.find(Key(&pts, device));
-        return (it == entries.end() || !it->second.cloud) ? nullptr : reinterpret_cast<const float*>(it->second.cloud);
-    }
-    void pin_local(const mrpt::maps::CPointsMap& pts, int device)
-    {
-        const auto&                 xs = pts.getPointsBufferRef_x();
-        std::lock_guard<std::mutex> lk(mtx);
-        auto&                       e = entries[Key(&pts, device)];
-        if (e.cloud) mp2p_b200_cloud_destroy(e.cloud), e.cloud = nullptr;
-        check(mp2p_b200_cloud_create(ctx(device), xs.data(), pts.getPointsBufferRef_y().data(),
-                                     pts.getPointsBufferRef_z().data(), xs.size(), 0, &e.cloud));
-    }
-    void unpin_local(const mrpt::maps::CPointsMap& pts, int device)
-    {
-        std::lock_guard<std::mutex> lk(mtx);
-        auto                        it = entries.find(Key(&pts, device));
-        if (it == entries.end() || !it->second.cloud) return;
-        mp2p_b200_cloud_destroy(it->second.cloud);
-        it->second.cloud = nullptr;
-    }
-};
-inline MapCache& cache()
-{
-    static MapCache c;
-    return c;
+    if (!cache) return nullptr;
+    const auto&      xs = pts.getPointsBufferRef_x();
+    mp2p_b200_cloud* c  = nullptr;
+    check(mp2p_b200_cloud_cached(ctx(device), xs.data(), pts.getPointsBufferRef_y().data(), pts.getPointsBufferRef_z().data(),
+                                 xs.size(), &c, nullptr));
+    return reinterpret_cast<const float*>(c);
 }
 // Witness of the pairings a matcher call just returned to the host (count + 8 sample records). A
 // solver handed a list with the same count and samples takes it for that output — nothing modifies
@@ -247,40 +189,26 @@ inline std::vector<uint32_t> to_bits(const pointcloud_bitfield_t::DenseOrSparseB
 inline const uint32_t* bits_or_null(const std::vector<uint32_t>& w) { return w.empty() ? nullptr : w.data(); }
 }  // namespace b200_detail
 
-/** RAII promise that a local layer stays unmodified (e.g. for the duration of one ICP::align()):
- *  the layer is kept on the device, Morton-sorted, instead of crossing PCIe at every iteration.
- *      { mp2p_icp::B200LocalCloudScope keep(*pcLocal); icp.align(pcLocal, pcGlobal, ...); }        */
-class B200LocalCloudScope
-{
-   public:
-    explicit B200LocalCloudScope(const mrpt::maps::CPointsMap& pts, int device = 0) : pts_(pts), device_(device)
-    {
-        b200_detail::cache().pin_local(pts_, device_);
-    }
-    ~B200LocalCloudScope() { b200_detail::cache().unpin_local(pts_, device_); }
-    B200LocalCloudScope(const B200LocalCloudScope&)            = delete;
-    B200LocalCloudScope& operator=(const B200LocalCloudScope&) = delete;
-
-   private:
-    const mrpt::maps::CPointsMap& pts_;
-    int                           device_;
-};
-
-/** Tells the plugin that a GLOBAL layer was edited in place (same buffers, same size): its device index is
- *  rebuilt on the next matcher call. Edits that change the buffer address, the size or any of the ~4096
+/** Tells the plugin that a layer (global or local) was edited IN PLACE — same buffers, same size: its device copy
+ *  is rebuilt on the next matcher call. Edits that change the buffer address, the size or any of the ~4096
  *  sampled points are detected without this call. */
-inline void B200InvalidateGlobalLayer(const mrpt::maps::CMetricMap& layer) { b200_detail::cache().invalidate(layer); }
+inline void B200InvalidateLayer(const mrpt::maps::CPointsMap& layer, int device = 0)
+{
+    mp2p_b200_layer_invalidate(b200_detail::ctx(device), layer.getPointsBufferRef_x().data());
+}
 
 /** Drop-in for Matcher_Points_DistanceThreshold (same parameters, same results). */
 class Matcher_Points_DistanceThreshold_B200 : public Matcher_Points_Base
 {
     DEFINE_MRPT_OBJECT(Matcher_Points_DistanceThreshold_B200, mp2p_icp)
    public:
-    int device = 0;  //!< YAML `device`: the GPU this object works on
+    int  device = 0;              //!< YAML `device`: the GPU this object works on
+    bool cacheLocalCloud = true;  //!< YAML: keep the local layer on the device while its fingerprint is unchanged
     void initialize(const mrpt::containers::yaml& params) override
     {
         Matcher_Points_Base::initialize(params);
         MCP_LOAD_OPT(params, device);
+        MCP_LOAD_OPT(params, cacheLocalCloud);
         DECLARE_PARAMETER_REQ(params, threshold);
         DECLARE_PARAMETER_REQ(params, thresholdAngularDeg);
         DECLARE_PARAMETER_OPT(params, pairingsPerPoint);
@@ -299,7 +227,7 @@ class Matcher_Points_DistanceThreshold_B200 : public Matcher_Points_Base
         ASSERT_(pairingsPerPoint >= 1);
         ASSERT_GT_(threshold, .0);
         ASSERT_GE_(thresholdAngularDeg, .0);
-        mp2p_b200_map* gmap = cache().get(pcGlobal, device);
+        mp2p_b200_map* gmap = device_map(pcGlobal, device);
         const auto& lx = pcLocal.getPointsBufferRef_x();
         double T[12];
         pose12(localPose, T);
@@ -314,7 +242,7 @@ class Matcher_Points_DistanceThreshold_B200 : public Matcher_Points_Base
         out.paired_pt2pt.resize(before + lx.size() * pairingsPerPoint);
         static_assert(sizeof(mrpt::tfest::TMatchingPair) == sizeof(mp2p_b200_pair_pt2pt));
         uint64_t cnt = 0, pot = 0;
-        const float* resident = cache().pinned_local(pcLocal, device);
+        const float* resident = device_cloud(pcLocal, device, cacheLocalCloud);
         check(mp2p_b200_match_pt2pt(ctx(device), gmap, resident ? resident : lx.data(),
                                     resident ? nullptr : pcLocal.getPointsBufferRef_y().data(),
                                     resident ? nullptr : pcLocal.getPointsBufferRef_z().data(), lx.size(),
@@ -340,11 +268,13 @@ class Matcher_Points_InlierRatio_B200 : public Matcher_Points_Base
 {
     DEFINE_MRPT_OBJECT(Matcher_Points_InlierRatio_B200, mp2p_icp)
    public:
-    int device = 0;  //!< YAML `device`: the GPU this object works on
+    int  device = 0;              //!< YAML `device`: the GPU this object works on
+    bool cacheLocalCloud = true;  //!< YAML: keep the local layer on the device while its fingerprint is unchanged
     void initialize(const mrpt::containers::yaml& params) override
     {
         Matcher_Points_Base::initialize(params);
         MCP_LOAD_OPT(params, device);
+        MCP_LOAD_OPT(params, cacheLocalCloud);
         MCP_LOAD_REQ(params, inliersRatio);
     }
     double inliersRatio = 0.80;
@@ -358,7 +288,7 @@ class Matcher_Points_InlierRatio_B200 : public Matcher_Points_Base
         using namespace b200_detail;
         ASSERT_GT_(inliersRatio, 0.0);
         ASSERT_LT_(inliersRatio, 1.0);
-        mp2p_b200_map* gmap = cache().get(pcGlobal, device);
+        mp2p_b200_map* gmap = device_map(pcGlobal, device);
         const auto&    lx   = pcLocal.getPointsBufferRef_x();
         double         T[12];
         pose12(localPose, T);
@@ -372,7 +302,7 @@ class Matcher_Points_InlierRatio_B200 : public Matcher_Points_Base
         const size_t before = out.paired_pt2pt.size();
         out.paired_pt2pt.resize(before + lx.size());
         uint64_t     cnt = 0, pot = 0;
-        const float* resident = cache().pinned_local(pcLocal, device);
+        const float* resident = device_cloud(pcLocal, device, cacheLocalCloud);
         check(mp2p_b200_match_inlier_ratio(ctx(device), gmap, resident ? resident : lx.data(),
                                            resident ? nullptr : pcLocal.getPointsBufferRef_y().data(),
                                            resident ? nullptr : pcLocal.getPointsBufferRef_z().data(), lx.size(),
@@ -453,11 +383,13 @@ class Matcher_Point2Plane_B200 : public Matcher_Points_Base
 {
     DEFINE_MRPT_OBJECT(Matcher_Point2Plane_B200, mp2p_icp)
    public:
-    int device = 0;  //!< YAML `device`: the GPU this object works on
+    int  device = 0;              //!< YAML `device`: the GPU this object works on
+    bool cacheLocalCloud = true;  //!< YAML: keep the local layer on the device while its fingerprint is unchanged
     void initialize(const mrpt::containers::yaml& params) override
     {
         Matcher_Points_Base::initialize(params);
         MCP_LOAD_OPT(params, device);
+        MCP_LOAD_OPT(params, cacheLocalCloud);
         DECLARE_PARAMETER_REQ(params, distanceThreshold);
         DECLARE_PARAMETER_OPT(params, searchRadius);
         DECLARE_PARAMETER_OPT(params, knn);
@@ -476,7 +408,7 @@ class Matcher_Point2Plane_B200 : public Matcher_Points_Base
         using namespace b200_detail;
         (void)globalName;
         checkAllParametersAreRealized();
-        mp2p_b200_map* gmap = cache().get(pcGlobal, device);
+        mp2p_b200_map* gmap = device_map(pcGlobal, device);
         const auto&    lx   = pcLocal.getPointsBufferRef_x();
         double         T[12];
         pose12(localPose, T);
@@ -488,7 +420,7 @@ class Matcher_Point2Plane_B200 : public Matcher_Points_Base
         out.paired_pt2pl.resize(before + lx.size());
         static_assert(sizeof(mp2p_icp::point_plane_pair_t) == sizeof(mp2p_b200_pair_pt2pl));
         uint64_t     cnt = 0, pot = 0;
-        const float* resident = cache().pinned_local(pcLocal, device);
+        const float* resident = device_cloud(pcLocal, device, cacheLocalCloud);
         check(mp2p_b200_match_pt2pl(ctx(device), gmap, resident ? resident : lx.data(),
                                     resident ? nullptr : pcLocal.getPointsBufferRef_y().data(),
                                     resident ? nullptr : pcLocal.getPointsBufferRef_z().data(), lx.size(),
@@ -590,11 +522,13 @@ class Matcher_Adaptive_B200 : public Matcher_Points_Base
 {
     DEFINE_MRPT_OBJECT(Matcher_Adaptive_B200, mp2p_icp)
    public:
-    int device = 0;  //!< YAML `device`: the GPU this object works on
+    int  device = 0;              //!< YAML `device`: the GPU this object works on
+    bool cacheLocalCloud = true;  //!< YAML: keep the local layer on the device while its fingerprint is unchanged
     void initialize(const mrpt::containers::yaml& params) override
     {
         Matcher_Points_Base::initialize(params);
         MCP_LOAD_OPT(params, device);
+        MCP_LOAD_OPT(params, cacheLocalCloud);
         MCP_LOAD_REQ(params, confidenceInterval);
         MCP_LOAD_REQ(params, firstToSecondDistanceMax);
         MCP_LOAD_REQ(params, absoluteMaxSearchDistance);
@@ -622,7 +556,7 @@ class Matcher_Adaptive_B200 : public Matcher_Points_Base
                            const layer_name_t& localName, Pairings& out) const override
     {
         using namespace b200_detail;
-        mp2p_b200_map* gmap = cache().get(pcGlobal, device);
+        mp2p_b200_map* gmap = device_map(pcGlobal, device);
         const auto&    lx   = pcLocal.getPointsBufferRef_x();
         const auto&    ly   = pcLocal.getPointsBufferRef_y();
         const auto&    lz   = pcLocal.getPointsBufferRef_z();
@@ -639,7 +573,7 @@ class Matcher_Adaptive_B200 : public Matcher_Points_Base
         uint64_t   hist[MP2P_B200_ADAPTIVE_BINS], ns = 0, pot = 0;
         double     emin = 0, emax = 0;
         int32_t    gate = 0;
-        const float* resident = cache().pinned_local(pcLocal, device);
+        const float* resident = device_cloud(pcLocal, device, cacheLocalCloud);
         check(mp2p_b200_adaptive_search(ctx(device), gmap, resident ? resident : lx.data(), resident ? nullptr : ly.data(),
                                         resident ? nullptr : lz.data(), lx.size(),
                                         resident ? MP2P_B200_LOCAL_CLOUD : MP2P_B200_LOCAL_HOST, T, &p, bits_or_null(lbits), hist, &emin,
@@ -684,11 +618,13 @@ class Matcher_Point2Line_B200 : public Matcher_Points_Base
 {
     DEFINE_MRPT_OBJECT(Matcher_Point2Line_B200, mp2p_icp)
    public:
-    int device = 0;  //!< YAML `device`: the GPU this object works on
+    int  device = 0;              //!< YAML `device`: the GPU this object works on
+    bool cacheLocalCloud = true;  //!< YAML: keep the local layer on the device while its fingerprint is unchanged
     void initialize(const mrpt::containers::yaml& params) override
     {
         Matcher_Points_Base::initialize(params);
         MCP_LOAD_OPT(params, device);
+        MCP_LOAD_OPT(params, cacheLocalCloud);
         MCP_LOAD_REQ(params, distanceThreshold);
         MCP_LOAD_REQ(params, knn);
         MCP_LOAD_REQ(params, lineEigenThreshold);
@@ -706,7 +642,7 @@ class Matcher_Point2Line_B200 : public Matcher_Points_Base
                            const layer_name_t& localName, Pairings& out) const override
     {
         using namespace b200_detail;
-        mp2p_b200_map* gmap = cache().get(pcGlobal, device);
+        mp2p_b200_map* gmap = device_map(pcGlobal, device);
         const auto&    lx   = pcLocal.getPointsBufferRef_x();
         const auto&    ly   = pcLocal.getPointsBufferRef_y();
         const auto&    lz   = pcLocal.getPointsBufferRef_z();
@@ -720,7 +656,7 @@ class Matcher_Point2Line_B200 : public Matcher_Points_Base
         out.paired_pt2ln.resize(before + lx.size());
         static_assert(sizeof(mp2p_icp::point_line_pair_t) == sizeof(mp2p_b200_pair_pt2ln));
         uint64_t     cnt = 0, pot = 0;
-        const float* resident = cache().pinned_local(pcLocal, device);
+        const float* resident = device_cloud(pcLocal, device, cacheLocalCloud);
         check(mp2p_b200_match_pt2ln(ctx(device), gmap, resident ? resident : lx.data(), resident ? nullptr : ly.data(),
                                     resident ? nullptr : lz.data(), lx.size(),
                                     resident ? MP2P_B200_LOCAL_CLOUD : MP2P_B200_LOCAL_HOST, T, &p, bits_or_null(lbits),
@@ -748,7 +684,8 @@ class QualityEvaluator_PairedRatio_B200 : public QualityEvaluator
 {
     DEFINE_MRPT_OBJECT(QualityEvaluator_PairedRatio_B200, mp2p_icp)
    public:
-    int device = 0;  //!< YAML `device`: the GPU this object works on
+    int  device = 0;              //!< YAML `device`: the GPU this object works on
+    bool cacheLocalCloud = true;  //!< YAML: keep the local layer on the device while its fingerprint is unchanged
     void initialize(const mrpt::containers::yaml& params) override
     {
         MCP_LOAD_OPT(params, device);
@@ -793,6 +730,84 @@ IMPLEMENTS_MRPT_OBJECT(QualityEvaluator_PairedRatio_B200, QualityEvaluator, mp2p
 
 }  // namespace mp2p_icp
 
+namespace mp2p_icp_filters
+{
+/** Drop-in for FilterDecimateVoxels (mp2p_icp_filters/src/FilterDecimateVoxels.cpp:109-378): same
+ *  YAML parameters (initialize() is the reference's own), the voxel grid on the GPU. The points of all input layers
+ *  go through ONE grid, as upstream. Output ORDER: ascending (cx, cy, cz) — the reference's order only with
+ *  use_tsl_robin_map = false; with the default hash map its order is implementation-defined, the point SET is equal.
+ *  DecimateMethod::RandomPoint (an unseeded generator upstream) goes to the reference implementation. */
+class FilterDecimateVoxels_B200 : public FilterDecimateVoxels
+{
+    DEFINE_MRPT_OBJECT(FilterDecimateVoxels_B200, mp2p_icp_filters)
+   public:
+    int  device = 0;  //!< YAML `device`
+    void initialize(const mrpt::containers::yaml& c) override
+    {
+        FilterDecimateVoxels::initialize(c);
+        MCP_LOAD_OPT(c, device);
+    }
+    void filter(mp2p_icp::metric_map_t& inOut) const override
+    {
+        using namespace mp2p_icp::b200_detail;
+        if (params_.decimate_method == DecimateMethod::RandomPoint) return FilterDecimateVoxels::filter(inOut);
+        checkAllParametersAreRealized();
+        std::vector<const mrpt::maps::CPointsMap*> in;  // :116-141
+        for (const auto& name : params_.input_pointcloud_layer)
+        {
+            auto it = inOut.layers.find(name);
+            if (it == inOut.layers.end())
+            {
+                if (params_.error_on_missing_input_layer) THROW_EXCEPTION_FMT("Input layer '%s' not found on input map.", name.c_str());
+                continue;
+            }
+            const auto* pc = mp2p_icp::MapToPointsMap(*it->second);
+            if (!pc) THROW_EXCEPTION_FMT("Layer '%s' must be of point cloud type.", name.c_str());
+            in.push_back(pc);
+        }
+        ASSERT_(!in.empty());
+        ASSERT_(!params_.output_pointcloud_layer.empty());
+        auto outPc = GetOrCreatePointLayer(inOut, params_.output_pointcloud_layer, false, in.at(0)->GetRuntimeClass()->className);
+        // small layers are copied whole (:156-189), the others go through the grid
+        std::vector<float> cx, cy, cz;  // only used when several layers have to be put behind each other
+        const float *      x = nullptr, *y = nullptr, *z = nullptr;
+        size_t             n = 0, n_grid_layers = 0;
+        for (const auto* pc : in)
+        {
+            const auto &xs = pc->getPointsBufferRef_x(), &ys = pc->getPointsBufferRef_y(), &zs = pc->getPointsBufferRef_z();
+            if (params_.minimum_input_points_to_filter > 0 && xs.size() <= params_.minimum_input_points_to_filter)
+            {
+                for (size_t i = 0; i < xs.size(); i++)
+                    if (params_.flatten_to.has_value())
+                        outPc->insertPointFast(xs[i], ys[i], static_cast<float>(*params_.flatten_to));
+                    else
+                        outPc->insertPointFrom(*pc, i);
+                continue;
+            }
+            if (n_grid_layers++ == 0)
+                x = xs.data(), y = ys.data(), z = zs.data(), n = xs.size();
+            else
+            {
+                if (cx.empty()) cx.assign(x, x + n), cy.assign(y, y + n), cz.assign(z, z + n);
+                cx.insert(cx.end(), xs.begin(), xs.end()), cy.insert(cy.end(), ys.begin(), ys.end()), cz.insert(cz.end(), zs.begin(), zs.end());
+                x = cx.data(), y = cy.data(), z = cz.data(), n = cx.size();
+            }
+        }
+        if (!n) return;
+        mp2p_b200_decimate_params p{params_.voxel_filter_resolution, static_cast<int32_t>(params_.decimate_method),
+                                    params_.flatten_to.has_value() ? 1 : 0,
+                                    params_.flatten_to.has_value() ? static_cast<float>(*params_.flatten_to) : 0.f};
+        std::vector<float> ox(n), oy(n), oz(n);
+        uint64_t           cnt = 0;
+        check(mp2p_b200_filter_decimate_voxels(ctx(device), x, y, z, n, 0, &p, ox.data(), oy.data(), oz.data(), nullptr, n, 0, &cnt));
+        outPc->reserve(outPc->size() + cnt);
+        for (uint64_t i = 0; i < cnt; i++) outPc->insertPointFast(ox[i], oy[i], oz[i]);
+        outPc->mark_as_modified();
+    }
+};
+IMPLEMENTS_MRPT_OBJECT(FilterDecimateVoxels_B200, FilterDecimateVoxels, mp2p_icp_filters)
+}  // namespace mp2p_icp_filters
+
 // at global scope, like the reference's own (mp2p_icp/src/register.cpp:43-69)
 MRPT_INITIALIZER(register_mp2p_icp_b200)
 {
@@ -805,6 +820,7 @@ MRPT_INITIALIZER(register_mp2p_icp_b200)
     registerClass(CLASS_ID(mp2p_icp::Matcher_Point2Plane_B200));
     registerClass(CLASS_ID(mp2p_icp::Solver_GaussNewton_B200));
     registerClass(CLASS_ID(mp2p_icp::QualityEvaluator_PairedRatio_B200));
+    registerClass(CLASS_ID(mp2p_icp_filters::FilterDecimateVoxels_B200));
 }
 
 #endif  // MP2P_B200_WITH_MRPT

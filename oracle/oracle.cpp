@@ -1221,5 +1221,98 @@ extern "C"
         return nOut;
     }
 
+    // ---------------------------------------------------------------- covariance() (oracle first)
+    // mp2p_icp::covariance (mp2p_icp/src/covariance.cpp:28-141): the stacked error vector of the final pairings
+    // (pt2pt :75-82, pt2ln :85-93, pt2pl :107-115; 3 rows per pairing, error_point2point / error_point2line /
+    // error_point2plane of errorTerms.cpp) is differentiated numerically w.r.t. (x, y, z, yaw, pitch, roll) by
+    // mrpt::math::estimateJacobian — central differences, column i = (f(x + h_i e_i) - f(x - h_i e_i)) * (0.5 / h_i),
+    // recalled from MRPT 2.x num_jacobian.h (not in the reference tree: parity unpinned for that helper) —
+    // hessian = J^T J (:134), cov = hessian.inverse_LLt() (:136). `x6` is the vector the Jacobian is taken at.
+    // NOTE (as written upstream, :41-47): the reference fills xInitial[0], [1], [0] again, [3], [4], [5] — slot 2 (z)
+    // is never assigned; a default-constructed CMatrixDouble61 is zero-filled, so the reference evaluates at z = 0.
+    // Callers that want the reference's number pass x6[2] = 0; this function takes the vector as given.
+    // Empty pairings: diag(1e6) (:33-38). ln2ln / pl2pl terms are not restated (they stay host-side upstream).
+    void orc_covariance(const orc_pair_pt2pt* p2p, size_t n2p, const orc_pair_pt2pl* p2l, size_t n2l,
+                        const orc_pair_pt2ln* p2ln, size_t n2ln, const double x6[6], double finDif_xyz,
+                        double finDif_angles, double cov_out[36], double hessian_out[36])
+    {
+        for (int k = 0; k < 36; k++) cov_out[k] = 0, hessian_out[k] = 0;
+        if (n2p + n2l + n2ln == 0)
+        {
+            for (int k = 0; k < 6; k++) cov_out[7 * k] = 1e6;
+            return;
+        }
+        const size_t        rows = 3 * (n2p + n2ln + n2l);
+        std::vector<double> fp(rows), fm(rows), J(rows * 6);
+        auto                eval = [&](const double x[6], std::vector<double>& err)
+        {
+            const Pose pose = pose_from_xyzypr(x[0], x[1], x[2], x[3], x[4], x[5]);  // CPose3D::setFromValues
+            size_t     r    = 0;
+            for (size_t i = 0; i < n2p; i++, r += 3)  // error_point2point, errorTerms.cpp:36-66
+            {
+                double gx, gy, gz;
+                compose_point(pose, p2p[i].lx, p2p[i].ly, p2p[i].lz, gx, gy, gz);
+                err[r] = gx - p2p[i].gx, err[r + 1] = gy - p2p[i].gy, err[r + 2] = gz - p2p[i].gz;
+            }
+            for (size_t i = 0; i < n2ln; i++, r += 3)  // error_point2line, errorTerms.cpp:67-113
+            {
+                double gx, gy, gz;
+                compose_point(pose, p2ln[i].lx, p2ln[i].ly, p2ln[i].lz, gx, gy, gz);
+                const double* u    = p2ln[i].director;
+                const double  q[3] = {gx - p2ln[i].pBase[0], gy - p2ln[i].pBase[1], gz - p2ln[i].pBase[2]};
+                const double  uq   = u[0] * q[0] + u[1] * q[1] + u[2] * q[2];
+                for (int c = 0; c < 3; c++) err[r + c] = q[c] - u[c] * uq;
+            }
+            for (size_t i = 0; i < n2l; i++, r += 3)  // error_point2plane, errorTerms.cpp:115-161
+            {
+                double gx, gy, gz;
+                compose_point(pose, p2l[i].lx, p2l[i].ly, p2l[i].lz, gx, gy, gz);
+                const double* c     = p2l[i].coefs;
+                const double  mod_n = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+                const double  ev    = c[0] * gx + c[1] * gy + c[2] * gz + c[3];
+                for (int k = 0; k < 3; k++) err[r + k] = -(c[k] / mod_n) * ev;
+            }
+        };
+        for (int i = 0; i < 6; i++)
+        {
+            const double h = i < 3 ? finDif_xyz : finDif_angles;
+            double       xp[6], xm[6];
+            for (int k = 0; k < 6; k++) xp[k] = xm[k] = x6[k];
+            xp[i] = x6[i] + h, xm[i] = x6[i] - h;
+            eval(xp, fp), eval(xm, fm);
+            const double inv2h = 0.5 / h;
+            for (size_t r = 0; r < rows; r++) J[r * 6 + i] = inv2h * (fp[r] - fm[r]);
+        }
+        double H[36] = {0};
+        for (size_t r = 0; r < rows; r++)
+            for (int a = 0; a < 6; a++)
+                for (int b = 0; b < 6; b++) H[6 * a + b] += J[r * 6 + a] * J[r * 6 + b];
+        for (int k = 0; k < 36; k++) hessian_out[k] = H[k];
+        // inverse_LLt: H = L L^T (Cholesky), cov = L^-T L^-1
+        double Lm[36] = {0};
+        for (int i = 0; i < 6; i++)
+            for (int j = 0; j <= i; j++)
+            {
+                double s = H[6 * i + j];
+                for (int k = 0; k < j; k++) s -= Lm[6 * i + k] * Lm[6 * j + k];
+                Lm[6 * i + j] = i == j ? std::sqrt(s) : s / Lm[6 * j + j];
+            }
+        double Li[36] = {0};  // L^-1 (lower)
+        for (int c = 0; c < 6; c++)
+            for (int i = c; i < 6; i++)
+            {
+                double s = i == c ? 1.0 : 0.0;
+                for (int k = c; k < i; k++) s -= Lm[6 * i + k] * Li[6 * k + c];
+                Li[6 * i + c] = s / Lm[6 * i + i];
+            }
+        for (int a = 0; a < 6; a++)
+            for (int b = 0; b < 6; b++)
+            {
+                double s = 0;
+                for (int k = 0; k < 6; k++) s += Li[6 * k + a] * Li[6 * k + b];
+                cov_out[6 * a + b] = s;
+            }
+    }
+
     int orc_max_threads() { return omp_get_max_threads(); }
 }

@@ -372,6 +372,17 @@ def optimal_tf_gauss_newton_ex(p2p, p2l, p2ln, prm: GNParams, T_init, w_pt2ln=1.
     return bool(ok), T.reshape(3, 4), it.value
 
 
+def covariance(p2p, p2l, p2ln, x6, finDif_xyz=1e-7, finDif_angles=1e-7):
+    """mp2p_icp::covariance (covariance.cpp:28-141) at x6 = (x, y, z, yaw, pitch, roll). Returns (cov 6x6, hessian 6x6).
+    The reference never assigns the z slot of its xInitial (:41-47) — pass x6[2] = 0 for its number."""
+    p2p, p2l = _pairs(p2p, p2l)
+    p2ln = np.zeros(0, PAIR_PT2LN) if p2ln is None else np.ascontiguousarray(p2ln, dtype=PAIR_PT2LN)
+    cov, hes = np.zeros(36), np.zeros(36)
+    x6 = np.ascontiguousarray(x6, dtype=np.float64)
+    lib().orc_covariance(_p(p2p), C.c_size_t(p2p.size), _p(p2l), C.c_size_t(p2l.size), _p(p2ln), C.c_size_t(p2ln.size), _p(x6), C.c_double(finDif_xyz), C.c_double(finDif_angles), _p(cov), _p(hes))
+    return cov.reshape(6, 6), hes.reshape(6, 6)
+
+
 def gn_accumulate_ex(p2p, p2l, p2ln, T, prm: GNParams, w_pt2ln=1.0, nthreads=1):
     p2p, p2l = _pairs(p2p, p2l)
     p2ln = np.zeros(0, PAIR_PT2LN) if p2ln is None else np.ascontiguousarray(p2ln, dtype=PAIR_PT2LN)

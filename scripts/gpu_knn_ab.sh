@@ -21,7 +21,12 @@ for tag in "$@"; do
     p3) run p3 MP2P_KNN_PHASES=3 ;;
     p2) run p2 MP2P_KNN_PHASES=2 ;;
     v1) run v1 MP2P_KNN_V1=1 ;;
+    nolpt) run nolpt MP2P_KNN_LPT=0 ;;
+    v1nolpt) run v1nolpt MP2P_KNN_V1=1 MP2P_KNN_LPT=0 ;;
+    fast:*) tag2=${tag#fast:}; IFS=, read -ra envs <<< "$tag2"; env "${envs[@]}" timeout 600 python bench.py --workload C3 --steps 10 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_c3_fast.json 2> gpurun_out/bench_c3_fast.err; echo "fast $tag2"; show gpurun_out/bench_c3_fast.json; tail -2 gpurun_out/bench_c3_fast.err ;;
     ncu) timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_match_pt2pt" -s 4 -c 1 -f -o gpurun_out/prof_r2_knn_v3 python bench.py --workload C3 --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_r2_knn_v3.log 2>&1; echo "ncu rc=$?" ;;
+    trace) MP2P_KNN_TRACE=1 timeout 300 python scripts/knn_trace.py > gpurun_out/knn_trace_v4.txt 2>&1; tail -8 gpurun_out/knn_trace_v4.txt ;;
+    filter) timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "filter_decimate or covariance" > gpurun_out/pytest_filter.log 2>&1; echo "filter pytest rc=$?"; tail -5 gpurun_out/pytest_filter.log ;;
     full) timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "full pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log ;;
   esac
 done

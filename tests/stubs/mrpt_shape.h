@@ -162,6 +162,14 @@ class CMetricMap : public serialization::CSerializable  // Matcher_Points_Base.h
 {
    public:
     using Ptr = std::shared_ptr<CMetricMap>;
+    struct ClassInfo
+    {
+        const char* className = "";
+    };
+    const ClassInfo* GetRuntimeClass() const { return &info_; }  // FilterDecimateVoxels.cpp:150
+
+   private:
+    ClassInfo info_;
 };
 class CPointsMap : public CMetricMap, public NearestNeighborsCapable  // Matcher_Points_Base.cpp:201-203
 {
@@ -170,6 +178,11 @@ class CPointsMap : public CMetricMap, public NearestNeighborsCapable  // Matcher
     const mrpt::aligned_std_vector<float>& getPointsBufferRef_y() const { return y_; }
     const mrpt::aligned_std_vector<float>& getPointsBufferRef_z() const { return z_; }
     size_t                                 size() const { return x_.size(); }
+    using Ptr = std::shared_ptr<CPointsMap>;
+    void reserve(size_t n) { x_.reserve(n), y_.reserve(n), z_.reserve(n); }                         // FilterDecimateVoxels.cpp:152
+    void insertPointFast(float x, float y, float z) { x_.push_back(x), y_.push_back(y), z_.push_back(z); }  // :175
+    void insertPointFrom(const CPointsMap& o, size_t i) { insertPointFast(o.x_[i], o.y_[i], o.z_[i]); }     // :179
+    void mark_as_modified() {}                                                                      // Matcher_Points_Base.cpp:112
     size_t                                 nn_index_count() const override { return x_.size(); }
     bool                                   nn_has_indices_or_ids() const override { return true; }
 

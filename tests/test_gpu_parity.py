@@ -1093,3 +1093,124 @@ def test_multi_gpu_sharded_iteration_equals_single_gpu(transport):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MP2P_B200_TRANSPORT=transport))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "identical=True" in r.stdout and f"transport={transport}" in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------
+# FilterDecimateVoxels on the device: points AND order equal to the oracle
+# (FilterDecimateVoxels.cpp:109-378; order = the reference's std::map walk, ascending (cx, cy, cz))
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["FirstPoint", "ClosestToAverage", "VoxelAverage"])
+@pytest.mark.parametrize("flatten_to", [None, -1.5])
+def test_filter_decimate_voxels_bit_exact(ctx, method, flatten_to):
+    rng = np.random.default_rng(11)
+    # a scan-shaped cloud around the origin: negative coordinates exercise the truncation toward zero
+    P = np.concatenate([fx.make_lidar_scan((20.0, 0.3, 0.0), n_rings=16, n_az=600, length=40.0), rng.uniform(-3, 3, (5000, 3)).astype(np.float32)])
+    x, y, z = (np.ascontiguousarray(P[:, k]) for k in range(3))
+    for res in (2.0, 0.35):
+        want_xyz, want_src = orc.decimate_voxels(x, y, z, res, method, flatten_to)
+        got_xyz, got_src = ctx.decimate_voxels(x, y, z, res, method, flatten_to)
+        assert len(got_xyz) == len(want_xyz) > 50
+        assert got_xyz.tobytes() == want_xyz.tobytes(), (method, flatten_to, res)
+        assert np.array_equal(got_src, want_src)
+
+
+@pytest.mark.gpu
+def test_filter_decimate_voxels_edge_cases_and_resident_cloud(ctx):
+    x, y, z = (np.ascontiguousarray(a) for a in (np.array([0.1, 0.2, -0.1, 5.0, 5.1], np.float32), np.zeros(5, np.float32), np.zeros(5, np.float32)))
+    got, src = ctx.decimate_voxels(x, y, z, 1.0)  # -0.1 and 0.1 truncate to the SAME voxel 0 (PointCloudToVoxelGridSingle.h:105)
+    assert src.tolist() == [0, 3] and got.tobytes() == np.array([[0.1, 0, 0], [5.0, 0, 0]], np.float32).tobytes()
+    e, es = ctx.decimate_voxels(x[:0], y[:0], z[:0], 1.0)
+    assert len(e) == 0 and len(es) == 0
+    one, osrc = ctx.decimate_voxels(x[:1], y[:1], z[:1], 0.5, "VoxelAverage")
+    assert osrc.tolist() == [-1] and one.tobytes() == np.array([[0.1, 0, 0]], np.float32).tobytes()
+    with pytest.raises(b200.Mp2pError):
+        ctx.decimate_voxels(x, y, z, 1.0, "RandomPoint")  # unseeded generator upstream: refused
+    with pytest.raises(b200.Mp2pError):
+        ctx.decimate_voxels(x, y, z, 0.0)
+    with pytest.raises(b200.Mp2pError):  # voxel indices spanning more than 64 bits
+        ctx.decimate_voxels(np.array([-3e9, 3e9], np.float32), np.array([-3e9, 3e9], np.float32), np.array([-3e9, 3e9], np.float32), 1.0)
+    # filter -> resident cloud -> matcher without leaving the device == matcher over the oracle's decimated cloud
+    M, L, gt = fx.make_c2(n_map=50_000, decim=5)
+    gmap = b200.Map(ctx, *xyz(M))
+    want_xyz, _ = orc.decimate_voxels(*xyz(L), 4.0)
+    cloud = b200.Cloud.decimated(ctx, *xyz(L), 4.0)
+    assert cloud.n == len(want_xyz)
+    prm = b200.Pt2PtParams(threshold=1.0)
+    a, _ = gmap.match_pt2pt(cloud, None, None, np.eye(3, 4), prm)
+    b, _ = gmap.match_pt2pt(*xyz(want_xyz), np.eye(3, 4), prm)
+    assert len(a) > 10 and a.tobytes() == b.tobytes()
+
+
+# ---------------------------------------------------------------------------------------------
+# covariance() on the device (covariance.cpp:28-141) vs the oracle's restatement
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_covariance_matches_oracle(ctx):
+    rng = np.random.default_rng(3)
+    x6 = np.array([0.3, -0.2, 0.0, 0.2, -0.1, 0.05])  # z slot = 0: what the reference evaluates at (covariance.cpp:41-47)
+    T = orc.pose_from_xyzypr(*x6)
+    n, m, k = 5000, 3000, 700
+    L = rng.uniform(-20, 20, (n, 3))
+    p2p = np.zeros(n, b200.PAIR_PT2PT)
+    p2p["global"], p2p["local"] = (L @ T[:, :3].T + T[:, 3] + rng.normal(0, 0.02, (n, 3))).astype(np.float32), L.astype(np.float32)
+    Lp = rng.uniform(-20, 20, (m, 3))
+    nrm = rng.normal(size=(m, 3))
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    p2l = np.zeros(m, b200.PAIR_PT2PL)
+    p2l["coefs"][:, :3] = nrm
+    p2l["coefs"][:, 3] = -(nrm * (Lp @ T[:, :3].T + T[:, 3])).sum(1) + rng.normal(0, 0.02, m)
+    p2l["local"] = Lp.astype(np.float32)
+    Ln = rng.uniform(-20, 20, (k, 3))
+    u = rng.normal(size=(k, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    p2ln = np.zeros(k, b200.PAIR_PT2LN)
+    p2ln["pBase"], p2ln["director"], p2ln["local"] = Ln @ T[:, :3].T + T[:, 3] + rng.normal(0, 0.02, (k, 3)), u, Ln
+    for lists in ((p2p, None, None), (None, p2l, None), (p2p, p2l, p2ln)):
+        cov_c, hes_c = orc.covariance(*lists, x6)
+        cov_g, hes_g, pd = ctx.covariance(*lists, x6)
+        assert pd
+        assert np.allclose(hes_g, hes_c, rtol=1e-9, atol=1e-9 * np.abs(hes_c).max())
+        assert np.allclose(cov_g, cov_c, rtol=1e-6, atol=1e-9 * np.abs(cov_c).max())
+    c0, _, _ = ctx.covariance(None, None, None, x6)
+    assert np.array_equal(c0, np.eye(6) * 1e6)  # no pairings (covariance.cpp:33-38)
+    # a single pt2pl pairing: the hessian is singular -> reported, no exception
+    _, _, pd1 = ctx.covariance(None, p2l[:1], None, x6)
+    assert not pd1
+
+
+@pytest.mark.gpu
+def test_solver_over_host_pairings_is_checked_against_the_device_copy(ctx):
+    """The safe default of the plugin (no assumeUnmodifiedPairings): the solver uploads the host pairings and the
+    library compares them byte for byte with the copy the matcher call left on the device. Unmodified -> the
+    result the matcher call computed ahead of time is handed out; ANY edit in between -> the solve runs over
+    the edited records (here: the oracle's result over the edited list)."""
+    S = fx.make_street_scene(n_map=300_000, length=60.0)
+    scan = fx.make_lidar_scan((30.0, 0.3, 0.0), n_rings=32, n_az=600, length=60.0)
+    guess = fx.pose_xyzypr(30.05, 0.28, 0.01, 0.01, 0.0, 0.0)
+    smap = b200.Map(ctx, *xyz(S))
+    mprm = b200.Pt2PlParams(distanceThreshold=0.5, searchRadius=1.0, knn=8, minimumPlanePoints=5, planeEigenThreshold=0.01)
+    gprm = b200.GNParams(maxInnerLoopIterations=3, kernel="GemanMcClure", kernelParam=0.15)
+    ogp = orc.GNParams(maxInnerLoopIterations=3, kernel="GemanMcClure", kernelParam=0.15)
+    for rep in range(4):  # the matcher starts computing ahead once it has seen the solver's request
+        pairs, _ = smap.match_pt2pl(*xyz(scan), guess, mprm)
+        assert len(pairs) > 500
+        if rep == 3:  # an edit of ONE record in the middle of the list (what a sampled witness would miss)
+            pairs = pairs.copy()
+            pairs["coefs"][len(pairs) // 2 + 1, 3] += 0.05
+        ok, T, _ = ctx.solve_gauss_newton(None, pairs, gprm, guess)
+        _, T_ref, _ = orc.optimal_tf_gauss_newton(None, pairs, ogp, guess, nthreads=4)
+        assert ok
+        assert_pose_close(T, T_ref, 1e-9)
+    # the same for pt2pt + Horn
+    M, L, gt = fx.make_c2(n_map=100_000, decim=10)
+    gmap = b200.Map(ctx, *xyz(M))
+    for rep in range(4):
+        p2p, _ = gmap.match_pt2pt(*xyz(L), np.eye(3, 4), b200.Pt2PtParams(threshold=1.0))
+        if rep == 3:
+            p2p = p2p.copy()
+            p2p["global"][len(p2p) // 3, 0] += 0.5
+        ok, T = ctx.solve_horn(p2p)
+        _, T_ref = orc.optimal_tf_horn(p2p)
+        assert ok
+        assert_pose_close(T, T_ref, 1e-9)

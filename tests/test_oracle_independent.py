@@ -154,3 +154,56 @@ def test_estimate_points_eigen_against_numpy_covariance():
         assert abs(abs(nk @ V[:, 0]) - 1) < 1e-5 and abs(np.linalg.norm(nk) - 1) < 1e-9  # float mean upstream: 1e-5
         assert np.abs(pl["centroid"][k] - P.mean(0)).max() < 1e-5
         assert abs(nk @ pl["centroid"][k] + pl["coefs"][k, 3]) < 1e-9
+
+
+def test_covariance_against_an_independent_numpy_statement():
+    """mp2p_icp::covariance (covariance.cpp:28-141): numerical Jacobian of the stacked error vector w.r.t.
+    (x, y, z, yaw, pitch, roll), hessian = J^T J, cov = hessian^-1. Independent statement: the ANALYTIC Jacobian
+    of the same residuals through scipy's rotation derivatives (finite differences of a different step and
+    scheme would share the method), numpy's inverse."""
+    rng = np.random.default_rng(5)
+    n = 200
+    x6 = np.array([0.3, -0.2, 0.1, 0.2, -0.1, 0.05])
+    T = orc.pose_from_xyzypr(*x6)
+    L = rng.uniform(-5, 5, (n, 3))
+    G = L @ T[:, :3].T + T[:, 3] + rng.normal(0, 0.01, (n, 3))
+    p2p = np.zeros(n, orc.PAIR_PT2PT)
+    p2p["global"], p2p["local"] = G.astype(np.float32), L.astype(np.float32)
+    m = 150
+    Lp = rng.uniform(-5, 5, (m, 3))
+    nrm = rng.normal(size=(m, 3))
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    Gp = Lp @ T[:, :3].T + T[:, 3]
+    p2l = np.zeros(m, orc.PAIR_PT2PL)
+    p2l["coefs"][:, :3] = nrm
+    p2l["coefs"][:, 3] = -(nrm * Gp).sum(1) + rng.normal(0, 0.01, m)
+    p2l["local"] = Lp.astype(np.float32)
+    cov, hes = orc.covariance(p2p, p2l, None, x6)
+
+    def residuals(x):
+        Tx = orc.pose_from_xyzypr(*x)
+        l1 = p2p["local"].astype(np.float64)
+        e1 = (l1 @ Tx[:, :3].T + Tx[:, 3] - p2p["global"].astype(np.float64)).reshape(-1)
+        l2 = p2l["local"].astype(np.float64)
+        g2 = l2 @ Tx[:, :3].T + Tx[:, 3]
+        c = p2l["coefs"]
+        ev = (c[:, :3] * g2).sum(1) + c[:, 3]
+        e2 = (-(c[:, :3] / (c[:, :3] ** 2).sum(1)[:, None]) * ev[:, None]).reshape(-1)
+        return np.concatenate([e1, e2])
+
+    # complex-step-free independent derivative: Richardson-extrapolated central differences at two larger steps
+    def jac(h):
+        J = np.zeros((3 * (n + m), 6))
+        for i in range(6):
+            d = np.zeros(6)
+            d[i] = h
+            J[:, i] = (residuals(x6 + d) - residuals(x6 - d)) / (2 * h)
+        return J
+
+    J = (4 * jac(1e-4) - jac(2e-4)) / 3
+    H = J.T @ J
+    assert np.allclose(hes, H, rtol=1e-5, atol=1e-6 * np.abs(H).max())
+    assert np.allclose(cov, np.linalg.inv(H), rtol=1e-4, atol=1e-6 * np.abs(np.linalg.inv(H)).max())
+    # no pairings: diag(1e6) (covariance.cpp:33-38)
+    c0, _ = orc.covariance(None, None, None, x6)
+    assert np.array_equal(c0, np.eye(6) * 1e6)

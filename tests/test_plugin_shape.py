@@ -42,5 +42,5 @@ def test_a_signature_drift_is_caught(tmp_path):
 def test_safe_defaults_are_in_the_source():
     txt = open(SRC).read()
     assert "bool assumeUnmodifiedPairings = false;" in txt  # device-copy shortcut is opt-in
-    assert "fingerprint(" in txt and "B200InvalidateGlobalLayer" in txt  # in-place edits of the global layer
+    assert "mp2p_b200_map_cached" in txt and "mp2p_b200_cloud_cached" in txt and "B200InvalidateLayer" in txt  # in-place edits of a layer
     assert "ctx_create(0," not in txt and "MCP_LOAD_OPT(params, device);" in txt  # no hard-coded device 0
