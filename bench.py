@@ -566,15 +566,19 @@ class Bench:
         ctx.set_profiling(False, True)
         if world == 1:
             step_device()
-        else:  # the sharded calls do not bracket a single matcher call: one plain matcher call for the counters
-            (gmap.match_pt2pt if pt2pt else gmap.match_pt2pl)(*lp, pose, mprm, n_local=nq, local_on_device=True, out=d_pairs.data_ptr(), out_on_device=True, capacity=cap)
+        else:  # the sharded calls do not bracket a single matcher call: one plain matcher call (over this shard alone) for the counters
+            d_tmp = torch.empty(cap * rec, dtype=torch.uint8, device=dev)
+            (gmap.match_pt2pt if pt2pt else gmap.match_pt2pl)(*lp, pose, mprm, n_local=nq, local_on_device=True, out=d_tmp.data_ptr(), out_on_device=True, capacity=cap)
+            del d_tmp
         st = ctx.search_stats()
         ctx.set_profiling(False, False)
         kms = {k: float(np.mean(v)) for k, v in kt.items()}
-        if n_pairs < 0:  # sharded GN paths do not return the count: this rank's own
-            n_pairs_rank = int((gmap.match_pt2pt if pt2pt else gmap.match_pt2pl)(*lp, pose, mprm, n_local=nq, local_on_device=True, out=d_pairs.data_ptr(), out_on_device=True, capacity=cap)[0])
+        self._last_kernel_ms = kms
+        if world > 1:  # this rank's share of the pairings: one more sharded step, its count read from the device
+            step_device()
+            n_pairs_rank = ctx.last_count()
         else:
-            n_pairs_rank = int(n_pairs) if world == 1 else None
+            n_pairs_rank = int(n_pairs)
 
         # ---- roofline of the matcher kernels (SURVEY §8d unit sizes)
         peak, peak_src = measured_peaks()
@@ -681,7 +685,7 @@ class Bench:
             self._cpu_tree = tree
 
         unit_scale = 1 if strong else world  # weak: a step processes `world` clouds of the base size
-        return {"ms": ms_dev, "value": unit_scale * 1e3 / ms_dev, "ms_warm": ms_warm, "launches": int(launches), "n_pairs": n_pairs, "n_pairs_rank": n_pairs_rank,
+        return {"ms": ms_dev, "value": unit_scale * 1e3 / ms_dev, "ms_warm": ms_warm, "kernel_ms": kms, "ms_with_events": ms_dev_events, "launches": int(launches), "n_pairs": n_pairs, "n_pairs_rank": n_pairs_rank,
                 "T": T_dev, "roofline": roof, "e2e": e2e, "cpu": cpu, "nq": nq, "n_total": n_total, "n_map": n_map, "info": info, "cloud": cloud, "gmap": gmap, "sh": sh,
                 "d_pairs": d_pairs, "rec": rec, "cap": cap}
 
@@ -837,7 +841,8 @@ def run_ours(args):
                               "index": {"build_ms": info["build_ms"], "finest_cell_m": info["finest_cell_size"], "levels": info["n_levels"], "bytes": info["index_bytes"]}},
                    "e2e": r["e2e"] if r["e2e"] is not None else {"value": None, "unit": "iterations/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                                                                   "note": "N > 1: no sharded host-buffer path is offered (the plugin classes are single-GPU); null rather than N replicas"},
-                   "gpu_launches": int(r["launches"] * args.steps), "roofline": r["roofline"], "cpu_baseline": r["cpu"], "clocks": clocks}
+                   "gpu_launches": int(r["launches"] * args.steps), "roofline": r["roofline"], "cpu_baseline": r["cpu"], "clocks": clocks,
+                   "kernel_ms_rank0": r["kernel_ms"]}
             out.update(extras)
     if rank == 0 and out is not None:
         if "clocks" not in out or out["clocks"] is None:
@@ -863,7 +868,7 @@ def c5_extra(B, args):
     if B.rank == 0:
         res = {"workload": "C5", "detail": w["desc"], "n_gpus": B.world, "scaling": "strong", "ms_per_step": r["ms"], "value": r["value"], "unit": "iterations/s",
                "steps": steps, "queries_total": r["n_total"], "queries_per_gpu": r["nq"], "map_points": r["n_map"], "index_build_ms": r["info"]["build_ms"],
-               "index_bytes": r["info"]["index_bytes"], "gpu_launches_per_step": r["launches"], "parity_vs_n1": par, "roofline": r["roofline"],
+               "index_bytes": r["info"]["index_bytes"], "gpu_launches_per_step": r["launches"], "parity_vs_n1": par, "roofline": r["roofline"], "kernel_ms_rank0": r["kernel_ms"],
                "ms_per_step_l2_warm_informative": r["ms_warm"]}
     r["gmap"].close()
     return res

@@ -162,6 +162,10 @@ int  mp2p_b200_ctx_synchronize(mp2p_b200_ctx* ctx);
 /* number of kernels this context launched so far (bench.py's `gpu_launches`). */
 uint64_t mp2p_b200_ctx_launch_count(const mp2p_b200_ctx* ctx);
 
+/* Number of pairings the last matcher call of this context left on the DEVICE without reading it back
+ * (out_count == NULL, the fused and the query-sharded iterations); synchronises. */
+int mp2p_b200_ctx_last_count(mp2p_b200_ctx* ctx, uint64_t* n_pairs);
+
 /* Upload a global map layer and build its NN index. Replaces
  * mrpt::maps::NearestNeighborsCapable::nn_prepare_for_3d_queries() on a CPointsMap
  * (call site mp2p_icp/src/Matcher_Points_DistanceThreshold.cpp:92); rebuilt whenever the layer is
@@ -515,6 +519,16 @@ int  mp2p_b200_peer_create(mp2p_b200_ctx* ctx, uint32_t rank, uint32_t world, ui
                            uint8_t handle_out[MP2P_B200_PEER_HANDLE_BYTES], mp2p_b200_peer** out);
 int  mp2p_b200_peer_connect(mp2p_b200_peer* peer, const uint8_t* all_handles /* world x 64 bytes */);
 void mp2p_b200_peer_destroy(mp2p_b200_peer* peer);
+/* OWNER-PARTITIONED first claims (optional, after peer_connect): global point g belongs to rank g % world, which
+ * keeps its claim word in memory every rank maps over NVLink. peer_iterate_pt2pt then proposes straight into the
+ * owners' HBM (system-scope atomicMin), gathers only the shards' 32-byte bounding boxes (the flags of that exchange
+ * are also the barrier "everybody has proposed") and reads each claim word back from its owner: no record
+ * all-gather, no replay of the other shards' proposals — NVLink bytes and atomics per GPU are the shard's own,
+ * whatever the world size. Same results, bit for bit. Setup like the mailboxes: every rank calls claims_create
+ * (n_map_points = size of the replicated map; allocates 8 * ceil(n / world) bytes), the caller all-gathers the
+ * 64-byte handles, every rank calls claims_connect with all of them in rank order. */
+int  mp2p_b200_peer_claims_create(mp2p_b200_peer* peer, uint64_t n_map_points, uint8_t handle_out[MP2P_B200_PEER_HANDLE_BYTES]);
+int  mp2p_b200_peer_claims_connect(mp2p_b200_peer* peer, const uint8_t* all_handles /* world x 64 bytes */);
 int  mp2p_b200_peer_record_slot(mp2p_b200_peer* peer, uint64_t** slot_device);
 int  mp2p_b200_peer_allgather_records(mp2p_b200_peer* peer, const uint64_t** records_device);
 int  mp2p_b200_peer_allreduce_packet(mp2p_b200_peer* peer, double* packet_device);

@@ -249,6 +249,7 @@ class GNParams:
 
 
 EXPORTS = [
+    "mp2p_b200_ctx_last_count",
     "mp2p_b200_last_error", "mp2p_b200_device_count", "mp2p_b200_ctx_create", "mp2p_b200_ctx_destroy",
     "mp2p_b200_ctx_synchronize", "mp2p_b200_ctx_launch_count", "mp2p_b200_map_create", "mp2p_b200_map_destroy",
     "mp2p_b200_map_get_info", "mp2p_b200_knn", "mp2p_b200_match_pt2pt", "mp2p_b200_match_pt2pl", "mp2p_b200_match_inlier_ratio", "mp2p_b200_match_pt2ln", "mp2p_b200_solve_gauss_newton_ex", "mp2p_b200_adaptive_search", "mp2p_b200_adaptive_threshold", "mp2p_b200_adaptive_emit", "mp2p_b200_match_adaptive", "mp2p_b200_read_kitti_bin", "mp2p_b200_map_create_xyzi", "mp2p_b200_cloud_create_xyzi",
@@ -266,6 +267,12 @@ EXPORTS = [
     "mp2p_b200_peer_allgather_records", "mp2p_b200_peer_allreduce_packet",
     "mp2p_b200_peer_iterate_pt2pt", "mp2p_b200_peer_iterate_pt2pl_gn",
     "mp2p_b200_filter_decimate_voxels", "mp2p_b200_cloud_create_decimated", "mp2p_b200_covariance", "mp2p_b200_ctx_get_tile_trace",
+    "mp2p_b200_cloud_cached",
+    "mp2p_b200_layer_fingerprint",
+    "mp2p_b200_layer_invalidate",
+    "mp2p_b200_map_cached",
+    "mp2p_b200_peer_claims_connect",
+    "mp2p_b200_peer_claims_create",
 ]
 PEER_HANDLE_BYTES = 64
 GN_STATE_DOUBLES = 16
@@ -365,6 +372,12 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def last_count(self) -> int:
+        """Pairings the last matcher call left on the device (fused / sharded iterations)."""
+        n = C.c_uint64(0)
+        _check(load_library().mp2p_b200_ctx_last_count(self._h, C.byref(n)))
+        return int(n.value)
 
     def synchronize(self):
         _check(load_library().mp2p_b200_ctx_synchronize(self._h))
@@ -561,6 +574,16 @@ class Peer:
             raise Mp2pError("exchange_handles must return one 64-byte handle per rank")
         blob = (C.c_uint8 * (PEER_HANDLE_BYTES * world)).from_buffer_copy(b"".join(allh))
         _check(L.mp2p_b200_peer_connect(self._h, blob))
+
+    def enable_owner_claims(self, n_map_points: int, exchange_handles):
+        """Owner-partitioned first claims over NVLink (mp2p_b200_peer_claims_*): every rank calls this with the same
+        map size; `exchange_handles` as in the constructor."""
+        L = load_library()
+        h = (C.c_uint8 * PEER_HANDLE_BYTES)()
+        _check(L.mp2p_b200_peer_claims_create(self._h, C.c_uint64(n_map_points), h))
+        allh = exchange_handles(bytes(h))
+        blob = (C.c_uint8 * (PEER_HANDLE_BYTES * self.world)).from_buffer_copy(b"".join(allh))
+        _check(L.mp2p_b200_peer_claims_connect(self._h, blob))
 
     def record_slot(self) -> int:
         p = C.c_void_p()

@@ -8,6 +8,8 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "host_math.hpp"
 
@@ -42,6 +44,16 @@ void prof_collect(mp2p_b200_ctx* c)
 
 namespace
 {
+// NVTX range of one public call, named after the reference's own profiler sections (mrpt::system::CTimeLogger
+// entries of ICP::align, mp2p_icp/src/ICP.cpp:141 "align.3.1_matchers", :162 "align.3.2_solvers") so that a
+// timeline of icp-run with the plugin reads like the reference's profile. Header-only NVTX 3: no-ops (a few ns)
+// unless a profiler is attached.
+struct NvtxRange
+{
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 // RAII bracket of one public compute call: timing slot 5 = whole call (device time)
 struct ProfScope
 {
@@ -380,9 +392,23 @@ extern "C"
 
     uint64_t mp2p_b200_ctx_launch_count(const mp2p_b200_ctx* c) { return c ? c->launches : 0; }
 
+    int mp2p_b200_ctx_last_count(mp2p_b200_ctx* ctx, uint64_t* n_pairs)
+    {
+        if (!ctx || !n_pairs) return MP2P_B200_ERR_ARG;
+        *n_pairs = 0;
+        if (!ctx->last_count) return 0;
+        DeviceGuard g(ctx->device);
+        unsigned long long h = 0;
+        MP2P_CUDA_TRY(cudaMemcpyAsync(&h, ctx->last_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        *n_pairs = std::min<uint64_t>(h, ctx->last_capacity);
+        return 0;
+    }
+
     int mp2p_b200_map_create(mp2p_b200_ctx* ctx, const float* x, const float* y, const float* z,
                              uint64_t n, int on_device, mp2p_b200_map** out)
     {
+        NvtxRange nvtx_("nn_prepare_for_3d_queries (mp2p_b200_map_create)");
         if (!ctx || !out || (n && (!x || !y || !z)))
         {
             set_error("map_create: NULL argument");
@@ -427,6 +453,7 @@ extern "C"
     int mp2p_b200_cloud_create(mp2p_b200_ctx* ctx, const float* x, const float* y, const float* z, uint64_t n,
                                int on_device, mp2p_b200_cloud** out)
     {
+        NvtxRange nvtx_("align.1_prepare (mp2p_b200_cloud_create)");
         if (!ctx || !out || (n && (!x || !y || !z)))
         {
             set_error("cloud_create: NULL argument");
@@ -581,6 +608,7 @@ extern "C"
                               mp2p_b200_pair_pt2pt* out_pairs, uint64_t capacity, int out_on_device,
                               uint64_t* out_count, uint64_t* potential_pairings)
     {
+        NvtxRange nvtx_("align.3.1_matchers (Matcher_Points_DistanceThreshold)");
         if (!ctx || !map || !pose || !prm || (!out_count && !out_on_device) ||
             (n_local && bad_local(lx, ly, lz, local_on_device)) || (capacity && !out_pairs))
         {
@@ -619,6 +647,7 @@ extern "C"
                               uint64_t capacity, int out_on_device, uint64_t* out_count,
                               uint64_t* potential_pairings)
     {
+        NvtxRange nvtx_("align.3.1_matchers (Matcher_Point2Plane)");
         if (!ctx || !map || !pose || !prm || (!out_count && !out_on_device) ||
             (n_local && bad_local(lx, ly, lz, local_on_device)) || (capacity && !out_pairs))
         {
@@ -652,6 +681,7 @@ extern "C"
                                      uint64_t capacity, int out_on_device, uint64_t* out_count,
                                      uint64_t* potential_pairings)
     {
+        NvtxRange nvtx_("align.3.1_matchers (Matcher_Points_InlierRatio)");
         if (!ctx || !map || !pose || !prm || !out_count || (n_local && bad_local(lx, ly, lz, local_on_device)) ||
             (capacity && !out_pairs))
         {
@@ -678,6 +708,7 @@ extern "C"
                               mp2p_b200_pair_pt2ln* out_pairs, uint64_t capacity, int out_on_device, uint64_t* out_count,
                               uint64_t* potential_pairings)
     {
+        NvtxRange nvtx_("align.3.1_matchers (Matcher_Point2Line)");
         static_assert(sizeof(mp2p_b200_pair_pt2ln) == sizeof(mp2p_b200_pair_pt2pl), "line and plane records share the pipeline");
         if (!ctx || !map || !pose || !prm || !out_count || (n_local && bad_local(lx, ly, lz, local_on_device)) ||
             (capacity && !out_pairs))
@@ -721,6 +752,7 @@ extern "C"
                                   uint64_t histogram_out[MP2P_B200_ADAPTIVE_BINS], double* err_min, double* err_max,
                                   uint64_t* n_samples, int32_t* gate, uint64_t* potential_pairings)
     {
+        NvtxRange nvtx_("align.3.1_matchers (Matcher_Adaptive, search)");
         if (!ctx || !map || !pose || !prm || !histogram_out || !err_min || !err_max || !n_samples || !gate ||
             (n_local && bad_local(lx, ly, lz, local_on_device)))
         {
@@ -782,6 +814,7 @@ extern "C"
                                 uint64_t capacity_pt2pt, mp2p_b200_pair_pt2pl* out_pt2pl, uint64_t capacity_pt2pl,
                                 int out_on_device, uint64_t* n_pt2pt, uint64_t* n_pt2pl)
     {
+        NvtxRange nvtx_("align.3.1_matchers (Matcher_Adaptive, emit)");
         if (!ctx || !map || !prm || !n_pt2pt || !n_pt2pl || (capacity_pt2pt && !out_pt2pt) || (capacity_pt2pl && !out_pt2pl) ||
             bad_adaptive(prm))
         {
@@ -947,6 +980,7 @@ extern "C"
                              const uint64_t* weight_counts, const double* weight_values,
                              uint64_t n_weight_blocks, double pose_out[12], int32_t* solved)
     {
+        NvtxRange nvtx_("align.3.2_solvers (Solver_Horn)");
         if (!ctx || !prm || !pose_out || !solved || (n && !pairs))
         {
             set_error("solve_horn: NULL argument");
@@ -1088,6 +1122,7 @@ extern "C"
                                    const double guess_pose[12], const mp2p_b200_horn_params* prm, double pose_out[12],
                                    int32_t* solved)
     {
+        NvtxRange nvtx_("align.3.2_solvers (Solver_Horn over pt2pl)");
         if (!ctx || !guess_pose || !prm || !pose_out || !solved || (n && !pairs))
         {
             set_error("solve_horn_pt2pl: NULL argument");
@@ -1202,6 +1237,7 @@ extern "C"
                                      const mp2p_b200_gn_params* prm, const double pose_init[12],
                                      double pose_out[12], uint32_t* iterations_done, int32_t* solved)
     {
+        NvtxRange nvtx_("align.3.2_solvers (Solver_GaussNewton)");
         if (!ctx || !prm || !pose_init || !pose_out || !solved || (n2p && !p2p) || (n2l && !p2l))
         {
             set_error("solve_gauss_newton: NULL argument");
@@ -1279,6 +1315,7 @@ extern "C"
                                         const double pose_init[12], double pose_out[12], uint32_t* iterations_done,
                                         int32_t* solved)
     {
+        NvtxRange nvtx_("align.3.2_solvers (Solver_GaussNewton, pt2ln)");
         if (!ctx || !prm || !pose_init || !pose_out || !solved || (n2p && !p2p) || (n2l && !p2l) || (n2ln && !p2ln) ||
             (pairs_on_device != 0 && pairs_on_device != 1))
         {
@@ -1320,6 +1357,7 @@ extern "C"
                                      uint64_t capacity, double pose_out[12], int32_t* solved,
                                      uint64_t* n_pairs, uint64_t* potential_pairings)
     {
+        NvtxRange nvtx_("align.3_iter (fused pt2pt + Horn)");
         if (!ctx || !map || !pose || !mprm || !sprm || !pose_out || !solved || !n_pairs || (n_local && bad_local(lx, ly, lz, local_on_device)))
         {
             set_error("iterate_pt2pt_horn: NULL argument");
@@ -1379,6 +1417,7 @@ extern "C"
                                    int32_t* solved, uint64_t* n_pairs, uint32_t* iterations_done,
                                    uint64_t* potential_pairings)
     {
+        NvtxRange nvtx_("align.3_iter (fused pt2pl + GaussNewton)");
         if (!ctx || !map || !pose || !mprm || !sprm || !pose_out || !solved || !n_pairs || (n_local && bad_local(lx, ly, lz, local_on_device)))
         {
             set_error("iterate_pt2pl_gn: NULL argument");
@@ -1560,6 +1599,7 @@ extern "C"
                              double finDif_xyz, double finDif_angles, double cov_out[36], double hessian_out[36],
                              int32_t* positive_definite)
     {
+        NvtxRange nvtx_("covariance");
         if (!ctx || !x6 || !cov_out || (n2p && !p2p) || (n2l && !p2l) || (n2ln && !p2ln) || !(finDif_xyz > 0) || !(finDif_angles > 0))
         {
             set_error("covariance: NULL argument or non-positive finite-difference step");
@@ -1677,6 +1717,7 @@ extern "C"
                                          float* out_z, int64_t* out_src_index, uint64_t capacity, int out_on_device,
                                          uint64_t* out_count)
     {
+        NvtxRange nvtx_("FilterDecimateVoxels");
         if (!ctx || !params || !out_count || (n && (!x || !y || !z)) || (capacity && (!out_x || !out_y || !out_z)))
         {
             set_error("filter_decimate_voxels: NULL argument");

@@ -313,15 +313,25 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
                     mp2p_b200_pair_pt2pl* out, uint64_t capacity, int out_on_device,
                     uint64_t* out_count, DeviceMatch* keep_on_device = nullptr, const LineMode* line = nullptr);
 uint64_t shard_record_words(uint64_t per_shard, uint32_t K);
+// OWNER-PARTITIONED first claims of a query-sharded run (peer.cu): global point g belongs to rank g % world,
+// which keeps its claim word at parts[g % world][g / world] in memory every rank has mapped (CUDA IPC over
+// NVLink). Proposals are system-scope atomicMin's straight into the owner's HBM, acceptance reads the word back
+// from there: nothing is gathered and nothing replayed, per-GPU work is the shard's own proposals.
+struct OwnerClaims
+{
+    unsigned long long* const* parts = nullptr;  // device array of `world` pointers
+    uint32_t                   world = 0;
+    unsigned long long         tag   = 0;        // (0xFFFFFFFF - epoch) << 32, the same on every rank
+};
 int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
                            const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
                            const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits, uint64_t per_shard,
-                           unsigned long long* d_record);
+                           unsigned long long* d_record, const OwnerClaims* oc = nullptr, uint32_t shard_rank = 0);
 int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_local, uint32_t shard_rank,
                             uint32_t n_shards, uint64_t per_shard, const unsigned long long* d_records,
                             const mp2p_b200_pt2pt_params* prm, const uint32_t* gbits,
                             mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device,
-                            uint64_t* out_count, double* d_horn_sums);
+                            uint64_t* out_count, double* d_horn_sums, const OwnerClaims* oc = nullptr);
 int run_match_inlier_ratio(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly, const float* lz,
                            uint64_t n_local, int local_on_device, const double pose[12], double ratio, int allowLocal,
                            int allowGlobal, double bbox_eps, const uint32_t* lbits, const uint32_t* gbits,
@@ -356,6 +366,9 @@ int run_gn_device_loop(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint
                        double* d_pose, uint32_t* d_state, double* d_packet,
                        const unsigned long long* d_n2p = nullptr, const unsigned long long* d_n2l = nullptr,
                        const mp2p_b200_pair_pt2ln* d2ln = nullptr, uint64_t n2ln = 0, double w_pt2ln = 1.0);
+int run_gn_coop_loop(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p, const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l,
+                     const mp2p_b200_gn_params* prm, double* d_pose, uint32_t* d_state, double* d_packet,
+                     const unsigned long long* d_n2p, const unsigned long long* d_n2l, struct mp2p_b200_peer* peer);
 int run_gn_step(mp2p_b200_ctx* ctx, const double* d_packet, const mp2p_b200_gn_params* prm, double* d_pose,
                 uint32_t* d_state);
 // pt2ln_pl_to_pt2pt (plane part) on the device; synchronises, *h_total = records kept

@@ -208,6 +208,22 @@ __device__ __forceinline__ bool bit_set(const uint32_t* bits, uint32_t i)
     return bits && ((bits[i >> 5] >> (i & 31)) & 1u);
 }
 
+// first-claim word of global point gi: the map's own array, or the owner rank's part over NVLink
+__device__ __forceinline__ void claim_propose(unsigned long long* claim, unsigned long long* const* parts, uint32_t world,
+                                              uint32_t gi, unsigned long long word)
+{
+    if (parts)
+        atomicMin_system(parts[gi % world] + gi / world, word);
+    else
+        atomicMin(claim + gi, word);
+}
+__device__ __forceinline__ unsigned long long claim_read(const unsigned long long* claim, unsigned long long* const* parts,
+                                                         uint32_t world, uint32_t gi)
+{
+    if (parts) return *reinterpret_cast<const volatile unsigned long long*>(parts[gi % world] + gi / world);
+    return __ldcg(claim + gi);
+}
+
 struct Pt2PtArgs
 {
     PoseArg  pose;
@@ -227,6 +243,9 @@ struct Pt2PtArgs
     float *stage_x, *stage_y, *stage_z;
     // k > 1 search over a resident cloud: tile served by CTA b (longest tiles of the previous call first;
     // NULL = the strided order above) and where every tile reports how long it took (NULL = nowhere)
+    // query-sharded run with owner-partitioned claims (OwnerClaims, common.cuh): NULL = the map's own claim array
+    unsigned long long* const* claim_parts;
+    uint32_t                   claim_world;
     const uint32_t* tile_order;
     uint32_t*       tile_cost;
     uint32_t*       tile_trace;  // measurement hook: 8 words per CTA {SM, start ns, end ns, tile, rounds, steps, inserts, probes | levels << 16 of warp 0}
@@ -302,7 +321,7 @@ __global__ void __launch_bounds__(NT, MP2P_MATCH_MIN_BLOCKS * (int)kQueryTile / 
             if (c != ~0ull && !a.allowGlobal)
             {
                 const uint32_t gi = (uint32_t)c;
-                if (!bit_set(gbits, gi)) atomicMin(claim + gi, a.tag | (unsigned long long)(i * (uint32_t)K + sub));
+                if (!bit_set(gbits, gi)) claim_propose(claim, a.claim_parts, a.claim_world, gi, a.tag | ((unsigned long long)(i * (uint32_t)K + sub) + a.slot_offset));
             }
         }
         flush_search_stats(sc, c != ~0ull ? 1u : 0u, stats);
@@ -667,7 +686,7 @@ __device__ __forceinline__ void nn1_body(const GridView& g, const Pt2PtArgs& a, 
         if (c != ~0ull && !a.allowGlobal)
         {
             const uint32_t gi = (uint32_t)c;
-            if (!bit_set(gbits, gi)) atomicMin(claim + gi, a.tag | ((unsigned long long)i + a.slot_offset));
+            if (!bit_set(gbits, gi)) claim_propose(claim, a.claim_parts, a.claim_world, gi, a.tag | ((unsigned long long)i + a.slot_offset));
         }
     }
     flush_search_stats(sc, n_valid, stats);
@@ -890,6 +909,9 @@ struct CompactArgs
     // the pairing count goes to pinned memory — no D2H copy behind the kernel
     uint32_t*           out_host;
     unsigned long long* count_host;
+    // owner-partitioned claims of a query-sharded run (NULL = the map's own claim array)
+    unsigned long long* const* claim_parts;
+    uint32_t                   claim_world;
 };
 
 __device__ __forceinline__ bool bbox_gate(const GridView& g, const uint32_t* __restrict__ words, float eps)
@@ -951,7 +973,7 @@ __device__ __forceinline__ uint32_t compact_pt2pt_body(
             gi = (uint32_t)c;
             i  = (uint32_t)(a.K == 1 ? slot : slot / a.K);
             unsigned long long cw = a.tag | (unsigned long long)(slot + a.slot_offset);
-            if (!a.allowGlobal) cw = __ldcg(claim + gi);
+            if (!a.allowGlobal) cw = claim_read(claim, a.claim_parts, a.claim_world, gi);
             // the K = 1 matcher hands the matched point's coordinates over with the candidate
             // (sequential read); the K > 1 matcher does not (random gather from the map)
             gp = cand_xyz ? __ldcs(cand_xyz + slot) : __ldg(g.pts_orig + gi);
@@ -1806,12 +1828,19 @@ static int launch_iterate_nn1_horn(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const
                                    float4* cand_xyz, mp2p_b200_pair_pt2pt* d_out, double* d_packets, double w_pt2pt,
                                    uint32_t n_tiles, mp2p_b200_peer* peer = nullptr, unsigned long long per_k = 0)
 {
-    static int blocks_per_sm[2] = {-1, -1}, n_sm = 0;
+    // co-residency bound, cached per DEVICE and per instantiation (contexts on different GPUs of one process,
+    // e.g. the plugin's `device:` parameter, must not share it)
+    static int per_dev[64][2], sm_dev[64];
+    static bool init_dev[64][2] = {};
     const int  which = peer ? 1 : 0;
-    if (blocks_per_sm[which] < 0)
+    const int  devi  = ctx->device;
+    if (devi < 0 || devi >= 64) return 1;
+    int* blocks_per_sm = per_dev[devi];
+    int& n_sm          = sm_dev[devi];
+    if (!init_dev[devi][which])
     {
-        int dev = 0, coop = 0;
-        cudaGetDevice(&dev);
+        init_dev[devi][which] = true;
+        int dev = devi, coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         blocks_per_sm[which] = 0;
@@ -1866,6 +1895,11 @@ static int launch_iterate_nn1_horn(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const
                     &d_out, &count, &fs, &mom_partials, &mom_ticket, &w_pt2pt, &cs, &pl, &per_k, &cloud_bbox};
     void* fn = peer ? reinterpret_cast<void*>(k_iterate_nn1_horn<true>) : reinterpret_cast<void*>(k_iterate_nn1_horn<false>);
     const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(n_tiles), dim3(kScanThreads), args, 0, ctx->stream);
+    if (e == cudaErrorCooperativeLaunchTooLarge)
+    {
+        cudaGetLastError();  // the grid does not fit after all (another context holds SM resources): three-kernel path
+        return 1;
+    }
     if (e != cudaSuccess)
     {
         cudaGetLastError();
@@ -2124,7 +2158,7 @@ uint64_t shard_record_words(uint64_t per_shard, uint32_t K) { return per_shard *
 int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, const float* ly,
                            const float* lz, uint64_t n_local, int local_on_device, const double pose[12],
                            const mp2p_b200_pt2pt_params* prm, const uint32_t* lbits, uint64_t per_shard,
-                           unsigned long long* d_record)
+                           unsigned long long* d_record, const OwnerClaims* oc, uint32_t shard_rank)
 {
     const uint32_t K  = prm->pairingsPerPoint;
     cudaStream_t   st = ctx->stream;
@@ -2158,6 +2192,12 @@ int run_shard_search_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* 
     a.n_local = (uint32_t)n_local, a.K = K;
     a.allowLocal = prm->allowMatchAlreadyMatchedPoints, a.allowGlobal = 1;  // claims happen in phase B
     a.tag = 0;
+    if (oc && !prm->allowMatchAlreadyMatchedGlobalPoints)
+    {
+        // owner-partitioned claims: the search proposes straight into the owners' memory, under the GLOBAL slot numbers
+        a.allowGlobal = 0, a.tag = oc->tag, a.claim_parts = oc->parts, a.claim_world = oc->world;
+        a.slot_offset = (unsigned long long)shard_rank * per_shard * K;
+    }
     a.tma_ok = ctx->cur_tma_ok;
     a.rl_start = start_level(map->view, K);
     a.n_phases = knn_phases();
@@ -2192,7 +2232,7 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
                             uint32_t n_shards, uint64_t per_shard, const unsigned long long* d_records,
                             const mp2p_b200_pt2pt_params* prm, const uint32_t* gbits,
                             mp2p_b200_pair_pt2pt* out, uint64_t capacity, int out_on_device,
-                            uint64_t* out_count, double* d_horn_sums)
+                            uint64_t* out_count, double* d_horn_sums, const OwnerClaims* oc)
 {
     if (out_count) *out_count = 0;
     if (!ctx->owns_map(map))
@@ -2230,9 +2270,9 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
         MP2P_CUDA_TRY(cudaMemsetAsync(map->d_claim.p, 0xff, nmap * 8, st));
         map->epoch = 1;
     }
-    const unsigned long long tag   = (unsigned long long)(0xFFFFFFFFu - map->epoch) << 32;
+    const unsigned long long tag   = oc ? oc->tag : (unsigned long long)(0xFFFFFFFFu - map->epoch) << 32;
     auto*                    claim = map->d_claim.as<unsigned long long>();
-    if (!prm->allowMatchAlreadyMatchedGlobalPoints)
+    if (!prm->allowMatchAlreadyMatchedGlobalPoints && !oc)  // (owner-partitioned claims were proposed by the searches)
     {
         const uint64_t all_slots = per_k * n_shards;
         const uint32_t blocks    = (uint32_t)std::min<uint64_t>((all_slots + 255) / 256, 148 * 16);
@@ -2251,6 +2291,7 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
     c.capacity = std::min<uint64_t>(capacity, n_slots);
     c.slot_offset = (uint64_t)shard_rank * per_k, c.index_offset = (uint32_t)(shard_rank * per_shard);
     c.scan_epoch = ctx->scan_epoch;
+    if (oc) c.claim_parts = oc->parts, c.claim_world = oc->world;
     FusedSums fs{nullptr, nullptr, nullptr};
     if (d_horn_sums)
     {

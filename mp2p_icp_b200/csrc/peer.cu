@@ -31,9 +31,10 @@ namespace mp2p
 namespace
 {
 __global__ void __launch_bounds__(256)
-    k_peer_push_record(PeerView pv, uint32_t parity, uint32_t epoch, unsigned int* __restrict__ ticket)
+    k_peer_push_record(PeerView pv, uint32_t parity, uint32_t epoch, unsigned int* __restrict__ ticket, uint64_t first_word)
 {
-    // the record sits in the own mailbox already (the search kernel wrote it there)
+    // the record sits in the own mailbox already (the search kernel wrote it there); words [first_word, rec_words)
+    // travel (everything, or — with owner-partitioned claims — only the shard's bounding box at its end)
     const size_t              off   = rec_offset(pv.rec_words, pv.world, parity, pv.rank);
     const unsigned long long* src   = reinterpret_cast<const unsigned long long*>(pv.box[pv.rank] + off);
     const size_t              n_vec = pv.rec_words;
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(256)
     {
         const uint32_t      dst_rank = (pv.rank + p) % pv.world;  // start with the right neighbour: spreads the traffic
         unsigned long long* dst      = reinterpret_cast<unsigned long long*>(pv.box[dst_rank] + off);
-        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x)
+        for (size_t i = first_word + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x)
             dst[i] = src[i];
     }
     __threadfence_system();
@@ -135,6 +136,10 @@ extern "C"
         cudaStreamSynchronize(p->ctx->stream);
         for (void* o : p->opened)
             if (o) cudaIpcCloseMemHandle(o);
+        for (void* o : p->claims_opened)
+            if (o) cudaIpcCloseMemHandle(o);
+        if (p->d_claim_parts) cudaFree(p->d_claim_parts);
+        if (p->claims_own) cudaFree(p->claims_own);
         if (p->own) cudaFree(p->own);
         delete p;
     }
@@ -147,7 +152,8 @@ extern "C"
         return 0;
     }
 
-    int mp2p_b200_peer_allgather_records(mp2p_b200_peer* p, const uint64_t** records_device)
+    // first_word: only words [first_word, rec_words) of the records are exchanged (0 = whole records)
+    static int peer_allgather_tail(mp2p_b200_peer* p, const uint64_t** records_device, uint64_t first_word)
     {
         if (!p || !records_device || !p->connected)
         {
@@ -157,9 +163,9 @@ extern "C"
         MP2P_CUDA_TRY(cudaSetDevice(p->ctx->device));
         const uint32_t epoch = ++p->rec_epoch, parity = epoch & 1u;
         cudaStream_t   st    = p->ctx->stream;
-        const size_t   n_vec = p->view.rec_words;
+        const size_t   n_vec = p->view.rec_words - first_word;
         const int      blocks = (int)std::max<size_t>(1, std::min<size_t>((n_vec + 255) / 256, 148 * 2));
-        k_peer_push_record<<<blocks, 256, 0, st>>>(p->view, parity, epoch, p->ticket);
+        k_peer_push_record<<<blocks, 256, 0, st>>>(p->view, parity, epoch, p->ticket, first_word);
         k_peer_wait_records<<<1, 32, 0, st>>>(p->view, parity, epoch);
         count_launch(p->ctx, 2);
         MP2P_CUDA_TRY(cudaGetLastError());
@@ -167,6 +173,73 @@ extern "C"
         return 0;
     }
 
+    int mp2p_b200_peer_claims_create(mp2p_b200_peer* p, uint64_t n_map_points, uint8_t handle_out[MP2P_B200_PEER_HANDLE_BYTES])
+    {
+        if (!p || !handle_out || !n_map_points)
+        {
+            set_error("peer_claims_create: NULL argument or empty map");
+            return MP2P_B200_ERR_ARG;
+        }
+        MP2P_CUDA_TRY(cudaSetDevice(p->ctx->device));
+        if (p->claims_own)
+        {
+            set_error("peer_claims_create: this peer object already owns a claim part");
+            return MP2P_B200_ERR_ARG;
+        }
+        const uint64_t words = (n_map_points + p->view.world - 1) / p->view.world + 1;
+        cudaError_t    e     = cudaMalloc(&p->claims_own, words * 8);
+        if (e == cudaSuccess) e = cudaMemset(p->claims_own, 0xff, words * 8);  // "unclaimed": loses against any proposal
+        if (e == cudaSuccess) e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle_out), p->claims_own);
+        if (e != cudaSuccess)
+        {
+            set_error("peer_claims_create: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            if (p->claims_own) cudaFree(p->claims_own), p->claims_own = nullptr;
+            return MP2P_B200_ERR_CUDA;
+        }
+        p->claims_n = n_map_points;
+        return 0;
+    }
+
+    int mp2p_b200_peer_claims_connect(mp2p_b200_peer* p, const uint8_t* handles)
+    {
+        if (!p || !handles || !p->claims_own)
+        {
+            set_error("peer_claims_connect: call peer_claims_create first");
+            return MP2P_B200_ERR_ARG;
+        }
+        MP2P_CUDA_TRY(cudaSetDevice(p->ctx->device));
+        unsigned long long* parts[kMaxPeers] = {};
+        for (uint32_t r = 0; r < p->view.world; r++)
+        {
+            if (r == p->view.rank)
+            {
+                parts[r] = static_cast<unsigned long long*>(p->claims_own);
+                continue;
+            }
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, handles + (size_t)r * MP2P_B200_PEER_HANDLE_BYTES, sizeof(h));
+            void*             ptr = nullptr;
+            const cudaError_t e   = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess)
+            {
+                set_error("peer_claims_connect: cannot map the claim part of rank %u: %s", r, cudaGetErrorString(e));
+                cudaGetLastError();
+                return MP2P_B200_ERR_CUDA;
+            }
+            p->claims_opened[r] = ptr;
+            parts[r]            = static_cast<unsigned long long*>(ptr);
+        }
+        MP2P_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&p->d_claim_parts), sizeof(parts)));
+        MP2P_CUDA_TRY(cudaMemcpy(p->d_claim_parts, parts, sizeof(parts), cudaMemcpyHostToDevice));
+        p->claims_connected = true;
+        return 0;
+    }
+
+    int mp2p_b200_peer_allgather_records(mp2p_b200_peer* p, const uint64_t** records_device)
+    {
+        return peer_allgather_tail(p, records_device, 0);
+    }
     int mp2p_b200_peer_allreduce_packet(mp2p_b200_peer* p, double* packet_device)
     {
         if (!p || !packet_device || !p->connected)
@@ -192,7 +265,18 @@ extern "C"
         double*        state  = ctx->d_pose.as<double>();  // MP2P_B200_GN_STATE_DOUBLES doubles
         double*        packet = ctx->d_packet.as<double>() + 5 * MP2P_B200_PACKET_DOUBLES;
         MP2P_TRY(mp2p_b200_gn_device_begin(ctx, pose, state));
-        for (uint32_t it = 0; it < sprm->maxInnerLoopIterations; it++)
+        // the whole inner loop, all-reduces included, as one cooperative launch (solve.cu, k_gn_loop<true>);
+        // rc 1 = not possible here: one launch per accumulate / all-reduce / step instead (same protocol, same epochs)
+        uint64_t                  n2p_h = n2p, n2l_h = n2l;
+        const unsigned long long *dn2p = nullptr, *dn2l = nullptr;
+        if (n2p == MP2P_B200_COUNT_ON_DEVICE) n2p_h = ctx->last_count ? ctx->last_capacity : 0, dn2p = ctx->last_count;
+        if (n2l == MP2P_B200_COUNT_ON_DEVICE) n2l_h = ctx->last_count ? ctx->last_capacity : 0, dn2l = ctx->last_count;
+        int rc_coop = 1;
+        if ((n2p != MP2P_B200_COUNT_ON_DEVICE || ctx->last_count) && (n2l != MP2P_B200_COUNT_ON_DEVICE || ctx->last_count))
+            rc_coop = run_gn_coop_loop(ctx, d2p, n2p_h, d2l, n2l_h, sprm, state, reinterpret_cast<uint32_t*>(state + 12), packet, dn2p,
+                                       dn2l, p);
+        if (rc_coop < 0) return rc_coop;
+        for (uint32_t it = 0; rc_coop == 1 && it < sprm->maxInnerLoopIterations; it++)
         {
             MP2P_TRY(mp2p_b200_gn_device_accumulate(ctx, d2p, n2p, d2l, n2l, sprm, state, packet));
             MP2P_TRY(mp2p_b200_peer_allreduce_packet(p, packet));
@@ -228,6 +312,12 @@ extern "C"
         mp2p_b200_ctx* ctx = p->ctx;
         *solved            = 0;
         if (n_pairs_total) *n_pairs_total = 0;
+        struct Prof  // timing slot 5 = the whole call (measurement hook, no-op unless profiling is on)
+        {
+            mp2p_b200_ctx* c;
+            explicit Prof(mp2p_b200_ctx* x) : c(x) { prof_reset(c); }
+            ~Prof() { prof_collect(c); }
+        } prof(ctx);
         double* p0 = ctx->d_packet.as<double>() + 5 * MP2P_B200_PACKET_DOUBLES;
         double* p1 = p0 + MP2P_B200_PACKET_DOUBLES;
         if (horn && mprm->pairingsPerPoint == 1 && horn->robust_kernel == 0 && horn->w_pt2pt > 0.0 &&
@@ -258,10 +348,38 @@ extern "C"
         uint64_t*       slot = nullptr;
         const uint64_t* recs = nullptr;
         MP2P_TRY(mp2p_b200_peer_record_slot(p, &slot));
-        MP2P_TRY(mp2p_b200_match_pt2pt_shard_search(ctx, map, lx, ly, lz, n_local, local_on_device, pose, mprm, nullptr, per_shard, slot));
-        MP2P_TRY(mp2p_b200_peer_allgather_records(p, &recs));
-        MP2P_TRY(mp2p_b200_match_pt2pt_shard_resolve(ctx, map, n_local, p->view.rank, p->view.world, per_shard, recs, mprm, nullptr,
-                                                     pairs_device, capacity, 1, nullptr, horn ? p0 : nullptr));
+        if (p->claims_connected && p->claims_n >= map->view.n_points && !mprm->allowMatchAlreadyMatchedGlobalPoints &&
+            n_local <= per_shard && per_shard * mprm->pairingsPerPoint * p->view.world < 0xFFFFFFFFull)
+        {
+            // OWNER-PARTITIONED claims: the search proposes straight into the owners' HBM over NVLink (system-scope
+            // atomicMin), only the 32-byte bounding boxes are gathered (the flags of that exchange are also the
+            // barrier "every rank has proposed"), the compaction reads each claim word back from its owner. No
+            // record all-gather, no replay: the per-GPU work is the shard's own proposals, whatever the world size.
+            // (The next call's proposals cannot overtake this call's reads: every rank passes at least one packet
+            // all-reduce behind its compaction before it returns.)
+            MP2P_CUDA_TRY(cudaSetDevice(ctx->device));
+            if (++p->claim_epoch == 0xFFFFFFFFu)
+            {
+                set_error("peer_iterate_pt2pt: claim epochs exhausted (2^32 sharded calls): recreate the peer object");
+                return MP2P_B200_ERR_ARG;
+            }
+            OwnerClaims oc;
+            oc.parts = p->d_claim_parts, oc.world = p->view.world;
+            oc.tag   = (unsigned long long)(0xFFFFFFFFu - p->claim_epoch) << 32;
+            MP2P_TRY(run_shard_search_pt2pt(ctx, map, lx, ly, lz, n_local, local_on_device, pose, mprm, nullptr, per_shard,
+                                            reinterpret_cast<unsigned long long*>(slot), &oc, p->view.rank));
+            MP2P_TRY(peer_allgather_tail(p, &recs, per_shard * mprm->pairingsPerPoint));
+            MP2P_TRY(run_shard_resolve_pt2pt(ctx, map, n_local, p->view.rank, p->view.world, per_shard,
+                                             reinterpret_cast<const unsigned long long*>(recs), mprm, nullptr, pairs_device, capacity, 1,
+                                             nullptr, horn ? p0 : nullptr, &oc));
+        }
+        else
+        {
+            MP2P_TRY(mp2p_b200_match_pt2pt_shard_search(ctx, map, lx, ly, lz, n_local, local_on_device, pose, mprm, nullptr, per_shard, slot));
+            MP2P_TRY(mp2p_b200_peer_allgather_records(p, &recs));
+            MP2P_TRY(mp2p_b200_match_pt2pt_shard_resolve(ctx, map, n_local, p->view.rank, p->view.world, per_shard, recs, mprm, nullptr,
+                                                         pairs_device, capacity, 1, nullptr, horn ? p0 : nullptr));
+        }
         if (gn)
             return peer_gn_loop(p, pairs_device, MP2P_B200_COUNT_ON_DEVICE, nullptr, 0, gn, pose, pose_out, solved, iterations_done);
         // Solver_Horn: HORN1 sums came out of the compaction; reduce, moments, reduce, one read-back

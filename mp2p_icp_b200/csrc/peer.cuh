@@ -90,4 +90,12 @@ struct mp2p_b200_peer
     uint32_t       rec_epoch = 0, pkt_epoch = 0;
     unsigned int*  ticket    = nullptr;
     bool           connected = false;
+    // owner-partitioned first claims (mp2p_b200_peer_claims_*): this rank's part, the peers' parts (IPC mappings),
+    // the device array of the `world` part pointers, the map size they were made for, the call counter
+    void*                 claims_own = nullptr;
+    void*                 claims_opened[mp2p::kMaxPeers] = {};
+    unsigned long long**  d_claim_parts = nullptr;
+    uint64_t              claims_n = 0;
+    uint32_t              claim_epoch = 0;
+    bool                  claims_connected = false;
 };

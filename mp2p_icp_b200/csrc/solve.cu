@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "host_math.hpp"
 #include "reduce.cuh"
+#include "peer.cuh"
 
 namespace mp2p
 {
@@ -121,20 +122,13 @@ __device__ __forceinline__ void gn_step_device(const double* packet, double minD
 // loop is then ONE launch per iteration. A multi-GPU caller all-reduces the packet first and uses
 // k_gn_step.
 // WITH_LINES = false compiles the point-to-line loop out (the pt2pt / pt2pl hot path keeps its registers)
+// The pair loops of one Gauss-Newton accumulation at `pose` into the caller's accumulators (shared by the
+// one-launch-per-iteration kernel and the whole-inner-loop kernel). `sh` = this warp's staging buffer.
 template <bool WITH_LINES>
-__global__ void __launch_bounds__(kSolveThreads)
-    k_gn_accumulate(const uint32_t* __restrict__ p2p, const uint32_t* __restrict__ p2l, GNArgs a,
-                    double* pose, double* __restrict__ partials,
-                    unsigned int* __restrict__ ticket, double* __restrict__ packet,
-                    const unsigned long long* __restrict__ d_n2p, const unsigned long long* __restrict__ d_n2l,
-                    const uint32_t* d_done, uint32_t* step_state, double minDelta, double maxCost)
+__device__ __forceinline__ void gn_accumulate_body(const uint32_t* __restrict__ p2p, const uint32_t* __restrict__ p2l, const GNArgs& a,
+                                                   const double* pose, uint32_t* sh, double (&acc)[kGNV])
 {
-    if (d_done && *d_done) return;  // the device-side GN loop already converged
-    if (d_n2p) a.n2p = *d_n2p;
-    if (d_n2l) a.n2l = *d_n2l;
-    __shared__ uint32_t stage[kWarps][32 * 18];
-    const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t*           sh = stage[warp];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double              R[9], t[3];
 #pragma unroll
     for (int r = 0; r < 3; r++)
@@ -142,7 +136,6 @@ __global__ void __launch_bounds__(kSolveThreads)
         R[3 * r] = pose[4 * r], R[3 * r + 1] = pose[4 * r + 1], R[3 * r + 2] = pose[4 * r + 2];
         t[r] = pose[4 * r + 3];
     }
-    double acc[kGNV];
 #pragma unroll
     for (int v = 0; v < kGNV; v++) acc[v] = 0;
 
@@ -254,11 +247,98 @@ __global__ void __launch_bounds__(kSolveThreads)
         }
         __syncwarp();
     }
+}
+
+template <bool WITH_LINES>
+__global__ void __launch_bounds__(kSolveThreads)
+    k_gn_accumulate(const uint32_t* __restrict__ p2p, const uint32_t* __restrict__ p2l, GNArgs a,
+                    double* pose, double* __restrict__ partials,
+                    unsigned int* __restrict__ ticket, double* __restrict__ packet,
+                    const unsigned long long* __restrict__ d_n2p, const unsigned long long* __restrict__ d_n2l,
+                    const uint32_t* d_done, uint32_t* step_state, double minDelta, double maxCost)
+{
+    if (d_done && *d_done) return;  // the device-side GN loop already converged
+    if (d_n2p) a.n2p = *d_n2p;
+    if (d_n2l) a.n2l = *d_n2l;
+    __shared__ uint32_t stage[kWarps][32 * 18];
+    double              acc[kGNV];
+    gn_accumulate_body<WITH_LINES>(p2p, p2l, a, pose, stage[threadIdx.x >> 5], acc);
     const bool folded = block_reduce_to_packet<kGNV>(acc, partials, ticket, packet, blockIdx.x, gridDim.x);
     if (folded && step_state && threadIdx.x < 32)
     {
         __syncwarp();  // the packet was written by this warp's lanes
         if (threadIdx.x == 0) gn_step_device(packet, minDelta, maxCost, pose, step_state);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// The WHOLE inner loop of optimal_tf_gauss_newton (optimal_tf_gauss_newton.cpp:70-366) in ONE cooperative
+// launch of co-resident CTAs: per inner iteration  accumulate -> block partials -> the last CTA folds the
+// packet (reduce.cuh) [-> SHARDED: all-reduces it with the peers through the NVLink mailboxes, rank order,
+// bit-identical everywhere] -> applies the LDL^T step to the pose -> ONE grid barrier -> next iteration.
+// Against one launch per iteration this saves the launch gaps and, for a query-sharded run, the two extra
+// launches per iteration of the stand-alone all-reduce and step kernels: the 6x6 / 6x1 all-reduce the north
+// star names costs one mailbox round trip inside the kernel. After convergence the remaining iterations only
+// pass their barrier (the barrier count of a launch must not depend on the data: the arrival counter is
+// shared with the next launch).
+struct GNCoop
+{
+    unsigned long long* arrivals;  // monotonically increasing across launches (never reset)
+    unsigned long long  target;    // arrivals value that completes this launch's barrier 0 (+ grid per further one)
+};
+__device__ __forceinline__ void gn_grid_barrier(const GNCoop& cs, unsigned which)
+{
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const unsigned long long target = cs.target + (unsigned long long)which * gridDim.x;
+        __threadfence();
+        atomicAdd(cs.arrivals, 1ull);
+        while (*reinterpret_cast<volatile unsigned long long*>(cs.arrivals) < target) __nanosleep(20);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <bool SHARDED>
+__global__ void __launch_bounds__(kSolveThreads)
+    k_gn_loop(const uint32_t* __restrict__ p2p, const uint32_t* __restrict__ p2l, GNArgs a, double* pose, double* __restrict__ partials,
+              unsigned int* __restrict__ ticket, double* __restrict__ packet, const unsigned long long* __restrict__ d_n2p,
+              const unsigned long long* __restrict__ d_n2l, uint32_t* state, double minDelta, double maxCost, uint32_t max_iter,
+              GNCoop cs, PeerLaunch pl)
+{
+    if (d_n2p) a.n2p = *d_n2p;
+    if (d_n2l) a.n2l = *d_n2l;
+    __shared__ uint32_t stage[kWarps][32 * 18];
+    __shared__ double   s_pose[12];
+    __shared__ uint32_t s_done;
+    for (uint32_t it = 0; it < max_iter; it++)
+    {
+        // pose and flag as the folding CTA of the previous iteration left them (behind the barrier)
+        if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(pose + threadIdx.x);
+        if (threadIdx.x == 12) s_done = __ldcg(state);
+        __syncthreads();
+        if (!s_done)  // (the same on every CTA — and, sharded, on every rank: the reduced packets are bit-identical)
+        {
+            double acc[kGNV];
+            gn_accumulate_body<false>(p2p, p2l, a, s_pose, stage[threadIdx.x >> 5], acc);
+            const bool folded = block_reduce_to_packet<kGNV>(acc, partials, ticket, packet, blockIdx.x, gridDim.x);
+            if (folded && threadIdx.x < 32)
+            {
+                __syncwarp();  // the packet was written by this warp's lanes
+                if (SHARDED) peer_allreduce_warp(pl.view, pl.pkt_epoch + it, packet, threadIdx.x), __syncwarp();
+                if (threadIdx.x == 0)
+                {
+                    gn_step_device(packet, minDelta, maxCost, pose, state);
+                    __threadfence();
+                }
+            }
+        }
+        else if (SHARDED && blockIdx.x == 0 && threadIdx.x < 32)
+            // converged: the exchange still takes place (on a packet nobody reads) — the number of exchanges of a
+            // call must not depend on the data, a peer on the multi-launch path is waiting for this one
+            peer_allreduce_warp(pl.view, pl.pkt_epoch + it, packet, threadIdx.x);
+        gn_grid_barrier(cs, it);
     }
 }
 
@@ -460,12 +540,82 @@ __global__ void k_gn_step(const double* __restrict__ packet, double minDelta, do
     if (threadIdx.x == 0) gn_step_device(packet, minDelta, maxCost, pose, state);
 }
 
+// The inner loop as ONE cooperative launch (k_gn_loop). Returns 1 — nothing enqueued — when that is not possible
+// (no cooperative launch on the device, switched off by $MP2P_GN_COOP=0): the caller then enqueues one launch per
+// iteration. `peer` != NULL: the packet is all-reduced with the peers inside the kernel (epochs pkt_epoch+1 ...).
+int run_gn_coop_loop(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p, const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l,
+                     const mp2p_b200_gn_params* prm, double* d_pose, uint32_t* d_state, double* d_packet,
+                     const unsigned long long* d_n2p, const unsigned long long* d_n2l, mp2p_b200_peer* peer)
+{
+    if (prm->maxInnerLoopIterations == 0) return 1;
+    // co-residency bound per device (contexts on different GPUs of one process must not share it)
+    static int occ[64][2];
+    static bool have[64] = {};
+    const int  dev = ctx->device;
+    if (dev < 0 || dev >= 64) return 1;
+    if (!have[dev])
+    {
+        int coop = 0, n_sm = 0, b0 = 0, b1 = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (coop)
+        {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_gn_loop<false>, kSolveThreads, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_gn_loop<true>, kSolveThreads, 0);
+        }
+        const char* e = getenv("MP2P_GN_COOP");
+        if (e && atoi(e) == 0) b0 = b1 = 0;
+        occ[dev][0] = b0 * n_sm, occ[dev][1] = b1 * n_sm;
+        have[dev]   = true;
+    }
+    const int cap = occ[dev][peer ? 1 : 0];
+    if (cap <= 0) return 1;
+    const int     blocks = std::min(solve_grid(std::max(n2p, n2l)), cap);
+    unsigned int* ticket;
+    double*       partials;
+    MP2P_TRY(solve_scratch(ctx, blocks, &ticket, &partials));
+    if (!ctx->d_coop.p)
+    {
+        MP2P_TRY(ctx->d_coop.ensure(64));
+        MP2P_CUDA_TRY(cudaMemsetAsync(ctx->d_coop.p, 0, 64, ctx->stream));
+        ctx->coop_arrivals = 0, ctx->coop_epoch = 0;
+    }
+    GNArgs a{n2p, n2l, prm->w_pt2pt, prm->w_pt2pl, prm->kernel, prm->kernelParam, 0, 1.0, nullptr};
+    GNCoop cs{ctx->d_coop.as<unsigned long long>(), ctx->coop_arrivals + (unsigned long long)blocks};
+    PeerLaunch pl{};
+    if (peer) pl.view = peer->view, pl.pkt_epoch = peer->pkt_epoch + 1;
+    const uint32_t* p2p   = reinterpret_cast<const uint32_t*>(d2p);
+    const uint32_t* p2l   = reinterpret_cast<const uint32_t*>(d2l);
+    double          minDelta = prm->minDelta, maxCost = prm->maxCost;
+    uint32_t        max_iter = prm->maxInnerLoopIterations;
+    MP2P_CUDA_TRY(cudaMemsetAsync(d_state, 0, 8, ctx->stream));
+    void* args[] = {&p2p, &p2l, &a, &d_pose, &partials, &ticket, &d_packet, &d_n2p, &d_n2l, &d_state, &minDelta, &maxCost, &max_iter, &cs, &pl};
+    void* fn = peer ? reinterpret_cast<void*>(k_gn_loop<true>) : reinterpret_cast<void*>(k_gn_loop<false>);
+    prof_begin(ctx, 4);
+    const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(kSolveThreads), args, 0, ctx->stream);
+    prof_end(ctx, 4);
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();  // e.g. cudaErrorCooperativeLaunchTooLarge: take the multi-launch path
+        return 1;
+    }
+    ctx->coop_arrivals += (unsigned long long)max_iter * blocks;
+    if (peer) peer->pkt_epoch += max_iter;
+    count_launch(ctx);
+    return 0;
+}
+
 int run_gn_device_loop(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64_t n2p,
                        const mp2p_b200_pair_pt2pl* d2l, uint64_t n2l, const mp2p_b200_gn_params* prm,
                        double* d_pose, uint32_t* d_state, double* d_packet,
                        const unsigned long long* d_n2p, const unsigned long long* d_n2l,
                        const mp2p_b200_pair_pt2ln* d2ln, uint64_t n2ln, double w_pt2ln)
 {
+    if (!n2ln)  // the pt2pt / pt2pl loop in one cooperative launch
+    {
+        const int rc = run_gn_coop_loop(ctx, d2p, n2p, d2l, n2l, prm, d_pose, d_state, d_packet, d_n2p, d_n2l, nullptr);
+        if (rc <= 0) return rc;
+    }
     MP2P_CUDA_TRY(cudaMemsetAsync(d_state, 0, 8, ctx->stream));
     for (uint32_t it = 0; it < prm->maxInnerLoopIterations; it++)  // optimal_tf_gauss_newton.cpp:70
     {

@@ -115,6 +115,10 @@ class ShardedMatcherSolver:
             err = None
             try:
                 self.peer = capi.Peer(ctx, rank, world, self.rec_words, exchange)
+                if os.environ.get("MP2P_B200_OWNER_CLAIMS", "1") != "0":
+                    # first claims partitioned by owner (global point g -> rank g % world): proposals and their
+                    # acceptance go straight to the owner's HBM over NVLink, nothing is gathered or replayed
+                    self.peer.enable_owner_claims(gmap.info["n_points"], exchange)
             except capi.Mp2pError as e:
                 err = str(e)
             # all ranks or none: a rank that failed to map a mailbox drags everybody to NCCL

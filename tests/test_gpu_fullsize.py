@@ -169,3 +169,77 @@ def test_c5_scale_properties(ctx, n_map, n_query, n_sample):
     ok1, T1 = ctx.solve_horn(pairs)
     assert ok0 and ok1 and pose_err(T0, T1) < 1e-8 < POSE_TOL
     gmap.close()
+
+
+def test_c4_kitti_schedule_at_full_size_follows_the_oracle_iteration_by_iteration(ctx):
+    """C4: the C3 data (10M-point map, 118,808-point scan) through the schedule of
+    demos/icp-settings-kitti.yaml:10-60 — Matcher_Points_DistanceThreshold(2.0) + Solver_Horn for iterations 0-5,
+    Matcher_Adaptive + Solver_GaussNewton(3, GemanMcClure 0.15) after, maxIterations 200, minAbsStep 1e-4 — run by
+    the SAME ICP::align loop (tests/icp_harness.py, ICP.cpp:123-308) once over the oracle and once over the device:
+    the pairing counts, the pose after every iteration (1e-9) and the termination are the same."""
+    from tests import icp_harness
+
+    w = bench.make_workload("C4")
+    M, S, guess, al = w["map"], w["local"], w["pose"], w["align"]
+    nt = orc.max_threads()
+    tree, gmap = orc.KDTree(*xyz(M)), b200.Map(ctx, *xyz(M))
+    L = xyz(S)
+    cloud = b200.Cloud(ctx, *L)
+    trace = {"cpu": [], "gpu": []}
+
+    def cpu_match(pose, it):
+        if it < al["switch_at"]:
+            return orc.match_pt2pt(tree, *L, pose, orc.MatchPt2PtParams(**al["pt2pt"]), nthreads=nt)[0]
+        p2p, p2l, _, _ = orc.match_adaptive(tree, *L, pose, orc.MatchAdaptiveParams(**al["adaptive"]), nthreads=nt)
+        return (p2p, p2l)
+
+    def cpu_solve(pairs, cur, it):
+        if it < al["switch_at"]:
+            ok, T = orc.optimal_tf_horn(pairs)
+        else:
+            ok, T, _ = orc.optimal_tf_gauss_newton(pairs[0], pairs[1] if len(pairs[1]) else None, orc.GNParams(**al["gn"]), cur, nthreads=nt)
+        trace["cpu"].append((it, len(pairs) if it < al["switch_at"] else len(pairs[0]) + len(pairs[1]), np.array(T)))
+        return ok, T
+
+    def gpu_match(pose, it):
+        if it < al["switch_at"]:
+            return gmap.match_pt2pt(cloud, None, None, pose, b200.Pt2PtParams(**al["pt2pt"]))[0]
+        p2p, p2l, _, _ = gmap.match_adaptive(cloud, None, None, pose, b200.AdaptiveParams(**al["adaptive"]), n_local=len(S), local_on_device=True)
+        return (p2p, p2l)
+
+    def gpu_solve(pairs, cur, it):
+        if it < al["switch_at"]:
+            ok, T = ctx.solve_horn(pairs)
+        else:
+            ok, T, _ = ctx.solve_gauss_newton(pairs[0] if len(pairs[0]) else None, pairs[1] if len(pairs[1]) else None, b200.GNParams(**al["gn"]), cur)
+        trace["gpu"].append((it, len(pairs) if it < al["switch_at"] else len(pairs[0]) + len(pairs[1]), np.array(T)))
+        return ok, T
+
+    prm = icp_harness.IcpParams(maxIterations=al["maxIterations"], minAbsStep_trans=al["minAbsStep_trans"], minAbsStep_rot=al["minAbsStep_rot"])
+    r_cpu = icp_harness.align(cpu_match, cpu_solve, guess, prm)
+    r_gpu = icp_harness.align(gpu_match, gpu_solve, guess, prm)
+    assert r_gpu.terminationReason == r_cpu.terminationReason and r_gpu.nIterations == r_cpu.nIterations > al["switch_at"]
+    assert len(trace["cpu"]) == len(trace["gpu"])
+    for (it_c, n_c, T_c), (it_g, n_g, T_g) in zip(trace["cpu"], trace["gpu"]):
+        assert it_c == it_g and n_c == n_g, (it_c, n_c, n_g)
+        assert pose_err(T_c, T_g) < 1e-9, (it_c, pose_err(T_c, T_g))
+    assert pose_err(r_cpu.pose, r_gpu.pose) < 1e-9 < POSE_TOL
+
+
+def test_quality_evaluator_paired_ratio_matches_oracle(ctx):
+    """QualityEvaluator_PairedRatio, non-reuse mode (QualityEvaluator_PairedRatio.cpp:27-73): its own
+    Matcher_Points_DistanceThreshold pass with allowMatchAlreadyMatchedGlobalPoints = true (:34-41), quality =
+    pairings / potential_pairings (:65-68), hard_discard below absolute_minimum_pairing_ratio (:70). On C2 data at
+    the ground-truth pose, a mid-ICP pose and a far pose."""
+    w = bench.make_workload("C2")
+    M, L = w["map"], w["local"]
+    tree, gmap = orc.KDTree(*xyz(M)), b200.Map(ctx, *xyz(M))
+    far = fx.pose_xyzypr(3.0, -2.0, 1.0, 0.2, 0.0, 0.0)
+    for pose, thr in ((w["gt"], 0.25), (w["pose"], 0.25), (far, 0.25), (w["pose"], 1.0)):
+        kw = dict(threshold=thr, thresholdAngularDeg=0.0, pairingsPerPoint=1, allowMatchAlreadyMatchedGlobalPoints=True)
+        p_c, pot_c = orc.match_pt2pt(tree, *xyz(L), pose, orc.MatchPt2PtParams(**kw), nthreads=orc.max_threads())
+        p_g, pot_g = gmap.match_pt2pt(*xyz(L), pose, b200.Pt2PtParams(**kw))
+        assert pot_c == pot_g == len(L) and p_g.tobytes() == p_c.tobytes()
+        q_c, q_g = len(p_c) / pot_c, len(p_g) / pot_g
+        assert q_c == q_g and (q_g < 0.20) == (q_c < 0.20)
+    assert 0.9 < len(gmap.match_pt2pt(*xyz(L), w["gt"], b200.Pt2PtParams(threshold=0.25, allowMatchAlreadyMatchedGlobalPoints=True))[0]) / len(L)

@@ -1077,7 +1077,7 @@ def test_kitti_bin_loader_and_xyzi_entry_points(ctx, tmp_path):
 
 
 # --------------------------------------------------------------------------- multi-GPU (needs >= 2 GPUs)
-@pytest.mark.parametrize("transport", ["peer", "nccl"])
+@pytest.mark.parametrize("transport", ["peer", "peer_replay", "nccl"])
 def test_multi_gpu_sharded_iteration_equals_single_gpu(transport):
     import subprocess
     import sys
@@ -1090,9 +1090,13 @@ def test_multi_gpu_sharded_iteration_equals_single_gpu(transport):
     world = 2 if n < 4 else 4
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.join(here, "multi_gpu_parity_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MP2P_B200_TRANSPORT=transport))
+    # "peer" = NVLink mailboxes + owner-partitioned claims (the default), "peer_replay" = mailboxes with the record
+    # all-gather and replicated claim replay of round 1, "nccl" = torch.distributed collectives
+    env = dict(os.environ, MP2P_B200_TRANSPORT="peer" if transport.startswith("peer") else transport,
+               MP2P_B200_OWNER_CLAIMS="0" if transport == "peer_replay" else "1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-    assert "identical=True" in r.stdout and f"transport={transport}" in r.stdout
+    assert "identical=True" in r.stdout and f"transport={env['MP2P_B200_TRANSPORT']}" in r.stdout
 
 
 # ---------------------------------------------------------------------------------------------
