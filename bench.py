@@ -199,6 +199,8 @@ def make_workload(name: str, shard: int = 0, n_shards: int = 1):
         S = fx.make_lidar_scan(sensor, seed=8 + shard)
         gt = fx.pose_xyzypr(*sensor, 0.01, 0.0, 0.0)
         pose = fx.pose_xyzypr(sensor[0] + 0.12, sensor[1] - 0.07, 0.03, 0.016, 0.002, -0.002)
+        if os.environ.get("MP2P_BENCH_GT_POSE") == "1":  # experiment: no pose error (every query on its surface)
+            pose = gt
         w = dict(name="C3", map=M, local=S, gt=gt, pose=pose, matcher="pt2pl", solver="gn",
                  pt2pl=dict(distanceThreshold=0.5, searchRadius=1.0, knn=8, minimumPlanePoints=5, planeEigenThreshold=0.01),
                  gn=dict(maxInnerLoopIterations=3, kernel="GemanMcClure", kernelParam=0.15),

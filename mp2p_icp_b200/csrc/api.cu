@@ -359,7 +359,7 @@ extern "C"
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
         for (DevBuf* b : {&c->d_lx, &c->d_ly, &c->d_lz, &c->d_cand, &c->d_candxyz, &c->d_lbits, &c->d_gbits, &c->d_scan,
-                          &c->d_small, &c->d_out2p, &c->d_out2l, &c->d_plcand, &c->d_okflags, &c->d_fitlist, &c->d_adres, &c->d_adsel, &c->d_scan2, &c->d_coop, &c->d_knn_idx, &c->d_knn_d2,
+                          &c->d_small, &c->d_out2p, &c->d_out2l, &c->d_plcand, &c->d_okflags, &c->d_fitlist, &c->d_defer, &c->d_adres, &c->d_adsel, &c->d_scan2, &c->d_coop, &c->d_knn_idx, &c->d_knn_d2,
                           &c->d_knn_found, &c->d_irk0, &c->d_irk1, &c->d_irv0, &c->d_irv1, &c->d_irtmp, &c->d_pairs2p, &c->d_pairs2l, &c->d_pairs2ln, &c->d_partials, &c->d_packet,
                           &c->d_pose, &c->d_weights, &c->d_outlier, &c->d_conv, &c->d_fd_small, &c->d_fd_keys, &c->d_fd_vals, &c->d_fd_flags,
                           &c->d_fd_rs, &c->d_fd_in, &c->d_fd_out})
@@ -437,7 +437,7 @@ extern "C"
             m->ctx->live_maps.erase(m);
             DeviceGuard g(m->ctx->device);
             cudaStreamSynchronize(m->ctx->stream);
-            m->d_pts.release(), m->d_pts_orig.release(), m->d_table.release(), m->d_claim.release();
+            m->d_pts.release(), m->d_pts_orig.release(), m->d_table.release(), m->d_box.release(), m->d_claim.release();
         }
         delete m;
     }

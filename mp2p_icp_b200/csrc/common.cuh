@@ -53,6 +53,10 @@ struct GridView
     const float4*    pts;       // Morton-sorted points: x,y,z, original index (int bits)
     const float4*    pts_orig;  // original order: x,y,z,0  (for emitting TMatchingPair::global)
     const CellEntry* table;     // all level tables back to back
+    // per table slot: the TIGHT box of the voxel's points, 8 bits per bound relative to the voxel (box_lo / box_hi
+    // in grid_search.cuh). A voxel is a cube, the points in it usually a patch of surface: its cube says a far
+    // query must look at it, its box says it need not. NULL = not built ($MP2P_INDEX_BOX=0)
+    const uint2*     box;
     float            ox, oy, oz;  // grid origin = map bbox min
     float            inv_s0;      // 1 / finest quantum
     float            s0_lo;       // finest quantum, rounded DOWN (conservative bounds)
@@ -209,6 +213,8 @@ struct mp2p_b200_ctx
     mp2p::DevBuf d_out2p, d_out2l;     // compacted pairs when the caller wants them on the host
     mp2p::DevBuf d_plcand, d_okflags;  // per-query plane candidates + accepted flags (pt2pl)
     mp2p::DevBuf d_fitlist;            // [0] count, [1..] queries that qualify for a plane fit
+    mp2p::DevBuf d_defer;              // [0], [1] counters used in turn, [2..] queries the thread-per-query search handed over
+    uint32_t     defer_turn = 0;
     mp2p::DevBuf d_knn_idx, d_knn_d2, d_knn_found;
     mp2p::DevBuf d_irk0, d_irk1, d_irv0, d_irv1, d_irtmp;  // Matcher_Points_InlierRatio: sort keys / values / scratch
     // solver scratch
@@ -234,7 +240,7 @@ struct mp2p_b200_map
     mp2p_b200_ctx*     ctx = nullptr;
     mp2p::GridView     view{};
     mp2p_b200_map_info info{};
-    mp2p::DevBuf       d_pts, d_pts_orig, d_table, d_claim;
+    mp2p::DevBuf       d_pts, d_pts_orig, d_table, d_box, d_claim;
     uint32_t           epoch = 0;  // first-claim epoch (see match.cu)
 };
 

@@ -53,7 +53,7 @@ __device__ __forceinline__ uint32_t cell_hash(unsigned long long key, uint32_t s
 }
 
 __device__ __forceinline__ bool grid_lookup(const GridView& g, int rl, uint32_t cx, uint32_t cy,
-                                            uint32_t cz, uint32_t& start, uint32_t& count)
+                                            uint32_t cz, uint32_t& start, uint32_t& count, uint32_t* slot = nullptr)
 {
     const unsigned long long key   = cell_key(cx, cy, cz);
     const uint32_t           shift = g.level_shift[rl];
@@ -68,11 +68,31 @@ __device__ __forceinline__ bool grid_lookup(const GridView& g, int rl, uint32_t 
         {
             start = raw.z;
             count = raw.w;
+            if (slot) *slot = h;
             return true;
         }
         if (k == kEmptyKey) return false;
         h = (h + 1) & mask;
     }
+}
+
+// Lower bound (metres^2, conservative by the same 4 quanta per axis as the cube bounds below) of the distance from
+// a query at (ux,uy,uz) finest quanta to the TIGHT box of the points of voxel (vx,vy,vz), absolute level L, found in
+// slot `slot` of table rl (GridView::box; layout in index.cu). q2 = quanta^2 -> metres^2, rounded down.
+constexpr uint32_t kBoxMin = 4;  // voxels with fewer points are scanned without looking at their box
+__device__ __forceinline__ float box_bound(const GridView& g, int rl, uint32_t slot, int L, int vx, int vy, int vz, float ux,
+                                           float uy, float uz, float q2)
+{
+    const uint2 b    = __ldg(g.box + g.level_off[rl] + slot);
+    const float unit = (float)(1 << max(L - 8, 0)), s = (float)(1 << L);  // (all products below are integers < 2^24: exact)
+    const float ox = (float)vx * s, oy = (float)vy * s, oz = (float)vz * s;
+    const float lx = ox + (float)(b.x & 255u) * unit, hx = ox + (float)((b.y & 255u) + 1u) * unit;
+    const float ly = oy + (float)((b.x >> 8) & 255u) * unit, hy = oy + (float)(((b.y >> 8) & 255u) + 1u) * unit;
+    const float lz = oz + (float)((b.x >> 16) & 255u) * unit, hz = oz + (float)(((b.y >> 16) & 255u) + 1u) * unit;
+    const float gx = fmaxf(fmaxf(lx - ux, ux - hx) - 4.f, 0.f);
+    const float gy = fmaxf(fmaxf(ly - uy, uy - hy) - 4.f, 0.f);
+    const float gz = fmaxf(fmaxf(lz - uz, uz - hz) - 4.f, 0.f);
+    return gx * gx * q2 + gy * gy * q2 + gz * gz * q2;
 }
 
 // reference float metric, never fused
@@ -434,7 +454,6 @@ __device__ __forceinline__ void knn_search(const GridView& g, bool enabled, floa
                                            SearchCounters& sc, RunTable* tables, const uint8_t* nb_order, int n_phases)
 {
     constexpr unsigned       FULL     = 0xffffffffu;
-    constexpr int            T        = (20 + G - 1) / G;  // neighbour voxels a lane may have to bound per phase
     const int                lane     = threadIdx.x & 31;
     const int                gbase    = lane - sub;
     const unsigned           gmask    = (G == 32 ? FULL : ((1u << (G & 31)) - 1u)) << gbase;
@@ -507,7 +526,7 @@ __device__ __forceinline__ void knn_search(const GridView& g, bool enabled, floa
                 if (phase > 0 && !__any_sync(FULL, here && !((phase == 1 ? min_face : min_edge) > kth))) continue;
                 __syncwarp();
 #pragma unroll 1
-                for (int n0 = lo; n0 < hi; n0 += G)  // (warp-uniform; at most T passes)
+                for (int n0 = lo; n0 < hi; n0 += G)  // (warp-uniform; at most ceil(20 / G) passes)
                 {
                     const int n  = n0 + sub;
                     bool      ok = false;
@@ -550,7 +569,11 @@ __device__ __forceinline__ void knn_search(const GridView& g, bool enabled, floa
                     if (!(voxel_bound(g.level_first + erl, vx, vy, vz) > kth))
                     {
                         sc.probes++;
-                        if (!grid_lookup(g, erl, (uint32_t)vx, (uint32_t)vy, (uint32_t)vz, start, count)) count = 0;
+                        uint32_t slot;
+                        if (!grid_lookup(g, erl, (uint32_t)vx, (uint32_t)vy, (uint32_t)vz, start, count, &slot))
+                            count = 0;
+                        else if (g.box && count >= kBoxMin && box_bound(g, erl, slot, g.level_first + erl, vx, vy, vz, ux, uy, uz, q2) > kth)
+                            count = 0;  // the voxel's points sit in a corner of it the K-th distance does not reach
                     }
                 }
                 sp -= n_pop;
@@ -752,6 +775,323 @@ __device__ __forceinline__ void knn_search(const GridView& g, bool enabled, floa
             }
         }
     }
+}
+
+// ---- one thread per query (k <= kThreadKMax) ---------------------------------------------------
+// The group searches above spread ONE query's candidates over G lanes and pay for it at every step: the
+// K best keys live in G different lanes, so a candidate enters the list through a ballot, two shuffles of
+// the key and a shuffle-up, one candidate at a time per group (per-line profile r02_ncu_lines_c3_knn.txt:
+// half of the kernel's instructions are that bookkeeping, a quarter is the stack / run table it shares
+// through shared memory). Here a query is ONE thread:
+//   * the K best keys sit in the thread's registers, descending (best[0] = the K-th best, the only key a
+//     candidate is compared with); a candidate that passes sinks through a branch-free chain of KM - 1
+//     compare-exchanges. 32 queries take a candidate each per step and nothing is exchanged;
+//   * queries are walked in Morton order, so the lanes of a warp stand in the same or adjacent voxels:
+//     their hash probes and point reads mostly hit the same addresses (one L1 transaction) and their
+//     loops have nearly the same trip counts;
+//   * per level the same three phases as above (centre | faces | edges + corners), the bound of the 26
+//     neighbours from three per-axis gaps (two adds per voxel); the runs found in a phase go into the
+//     thread's run list (shared memory, column per thread: no bank conflict whatever row a lane is in)
+//     and are scanned densely, four loads in flight; a voxel above kDescend points is split depth-first
+//     WITHOUT a stack (the walk derives the next sibling / the parent from the voxel coordinates), every
+//     leaf bounded first and scanned at once so that the bound tightens on the way.
+// Exactness: as knn_search — every voxel of the level's block is scanned, or excluded by a conservative
+// lower bound above an upper bound of the K-th distance, or replaced by its children.
+constexpr int kThreadKMax = 20;
+constexpr int kRunCap     = 8;  // runs a thread lists before it scans them
+constexpr int kDfsFlush   = 4;  // inside a split voxel: leaves listed before they are scanned (nearest first)
+template <int NT>
+struct KnnThreadShared
+{
+    uint32_t start[kRunCap][NT];
+    uint32_t count[kRunCap][NT];
+    float    bound[kRunCap][NT];  // lower bound of the distance to the run's points (its voxel's tight box)
+};
+
+// Work budget of a thread: a query that has cost more probes / candidates than this without settling hands itself
+// over (its position goes on the deferred list, served afterwards by the warp-per-query group search) — a lone
+// lane walking 700 candidates through a split voxel holds its warp for longer than the rest of the launch takes.
+// list == NULL: no deferral. A full list (cap entries) means the thread carries on by itself.
+struct DeferList
+{
+    uint32_t* list;
+    uint32_t* count;
+    uint32_t  cap, max_probes, max_cands;
+};
+
+// returns true if the query was deferred (best[] is meaningless then)
+template <int KM, int NT>
+__device__ __forceinline__ bool knn_search_thread(const GridView& g, bool enabled, float qx, float qy, float qz, float radius2,
+                                                  int K, int rl_start, unsigned long long (&best)[KM], SearchCounters& sc,
+                                                  KnnThreadShared<NT>& ks, const DeferList& df, uint32_t qpos)
+{
+    const int                tid      = threadIdx.x;
+    const unsigned long long sentinel = (unsigned long long)__float_as_uint(radius2) << 32;
+#pragma unroll
+    for (int j = 0; j < KM; j++) best[j] = j < K ? sentinel : 0ull;  // (unused slots hold the smallest key: nothing sinks past them)
+    bool live = enabled && radius2 > 0.f;
+    if (live)
+    {
+        // reject queries farther than the radius from the map bbox (conservative: strictly greater)
+        const float ex = fmaxf(fmaxf(g.bbmin[0] - qx, qx - g.bbmax[0]), 0.f);
+        const float ey = fmaxf(fmaxf(g.bbmin[1] - qy, qy - g.bbmax[1]), 0.f);
+        const float ez = fmaxf(fmaxf(g.bbmin[2] - qz, qz - g.bbmax[2]), 0.f);
+        if ((ex * ex + ey * ey + ez * ez) * 0.999999f > radius2) live = false;
+    }
+    const float lim = 4194304.f;  // 2^22
+    const float ux  = fminf(fmaxf(grid_u(qx, g.ox, g.inv_s0), -lim), lim);
+    const float uy  = fminf(fmaxf(grid_u(qy, g.oy, g.inv_s0), -lim), lim);
+    const float uz  = fminf(fmaxf(grid_u(qz, g.oz, g.inv_s0), -lim), lim);
+    const int   Ix = (int)floorf(ux), Iy = (int)floorf(uy), Iz = (int)floorf(uz);
+    const float q2 = g.s0_lo * g.s0_lo * 0.999999f;  // quanta^2 -> metres^2, rounded down
+    float       kth = radius2;  // upper bound of the K-th best distance found so far (all levels)
+    uint32_t    n_runs = 0;
+
+    // The walk is a state machine with ONE producer loop and ONE scan in the code (a scan inlined at every
+    // place a list can fill up made the first group search of this round stall on instruction fetch), and
+    // the scan — where the instructions go — is where the lanes of a warp meet again after producing.
+    // (Every lane of the warp runs the outer loop and takes part in its votes, finished lanes with nothing to
+    // do: left to themselves the lanes never reconverged after their first different probe count and the
+    // kernel ran them one after the other, 20x slower.)
+    constexpr unsigned FULL = 0xffffffffu;
+    int      rl    = rl_start;
+    int      phase = 0;         // 0 = the centre voxel, 1 = the 6 face neighbours, 2 = the 20 edge / corner neighbours
+    uint32_t mask  = 1u << 13;  // voxels of the phase still to visit: bit dz*9 + dy*3 + dx (each 0..2)
+    bool     dfs   = false;     // inside a voxel that was split: (erl, vx, vy, vz) is the next voxel of the walk
+    int      erl = 0, vx = 0, vy = 0, vz = 0;
+    bool     deferred = false, may_defer = df.list != nullptr;
+    // the child of voxel (px,py,pz), relative level prl, the query is in or nearest to: bit 0 = upper half in x, ...
+    auto near_child = [&](int prl, int px, int py, int pz) -> int
+    {
+        const float h = (float)(1 << (g.level_first + prl - 1));  // child edge, finest quanta
+        return (int)(ux >= (float)(2 * px + 1) * h) | ((int)(uy >= (float)(2 * py + 1) * h) << 1) | ((int)(uz >= (float)(2 * pz + 1) * h) << 2);
+    };
+#pragma unroll 1
+    while (__any_sync(FULL, live))
+    {
+        const int  L    = g.level_first + rl;
+        const bool top  = L == kGridBits;  // the single voxel holding every point
+        const int  cmax = ((1 << kGridBits) - 1) >> L;
+        const int  cx = top ? 0 : (Ix >> L), cy = top ? 0 : (Iy >> L), cz = top ? 0 : (Iz >> L);
+        bool       phase_done = false;
+        // ---- produce: list runs until the phase is through, the list is full or a split voxel's leaves are due
+#pragma unroll 1
+        while (live)
+        {
+            if (may_defer && (sc.probes > df.max_probes || sc.cands > df.max_cands))
+            {
+                const uint32_t at = atomicAdd(df.count, 1u);
+                may_defer         = false;
+                if (at < df.cap)
+                {
+                    df.list[at] = qpos;
+                    deferred = true, live = false, n_runs = 0;
+                    break;
+                }
+            }
+            uint32_t start = 0, count = 0;
+            int      prl, px, py, pz;  // the voxel probed in this step
+            if (dfs)
+                prl = erl, px = vx, py = vy, pz = vz;
+            else
+            {
+                if (!mask)
+                {
+                    phase_done = true;
+                    break;
+                }
+                if (n_runs == (uint32_t)kRunCap) break;
+                const int bit = __ffs(mask) - 1;
+                mask &= mask - 1;
+                prl = rl, px = cx + bit % 3 - 1, py = cy + (bit % 9) / 3 - 1, pz = cz + bit / 9 - 1;
+            }
+            bool  found = false;
+            float bnd;
+            {
+                // lower bound (metres^2, conservative by 4 quanta per axis) of the distance to the voxel; for the
+                // block's own voxels it was tested when the mask was made, against a K-th distance that may have
+                // tightened since
+                const float e  = (float)(1 << (g.level_first + prl));
+                const float lx = (float)px * e, ly = (float)py * e, lz = (float)pz * e;
+                const float gx = fmaxf(fmaxf(lx - ux, ux - (lx + e)) - 4.f, 0.f);
+                const float gy = fmaxf(fmaxf(ly - uy, uy - (ly + e)) - 4.f, 0.f);
+                const float gz = fmaxf(fmaxf(lz - uz, uz - (lz + e)) - 4.f, 0.f);
+                bnd            = gx * gx * q2 + gy * gy * q2 + gz * gz * q2;
+                const unsigned pmax = (unsigned)(((1 << kGridBits) - 1) >> (g.level_first + prl));
+                if ((unsigned)px <= pmax && (unsigned)py <= pmax && (unsigned)pz <= pmax && !(bnd > kth))  // strict `>`: an equal-distance lower index must still be seen
+                {
+                    sc.probes++;
+                    uint32_t slot;
+                    found = grid_lookup(g, prl, (uint32_t)px, (uint32_t)py, (uint32_t)pz, start, count, &slot);
+                    if (found && g.box && count >= kBoxMin)
+                    {
+                        // (the voxel's points may sit in a corner of it the K-th distance does not reach)
+                        bnd = box_bound(g, prl, slot, g.level_first + prl, px, py, pz, ux, uy, uz, q2);
+                        if (bnd > kth) found = false;
+                    }
+                }
+            }
+            const bool split = found && count > kDescend && prl > 0;
+            if (found && !split)
+            {
+                ks.start[n_runs][tid] = start, ks.count[n_runs][tid] = count, ks.bound[n_runs][tid] = bnd;
+                n_runs++;
+            }
+            if (split)
+            {
+                // into the child nearest to the query. No stack: from a finished voxel the walk goes to the next
+                // sibling (the i-th visited child is nearest ^ i), from the last one up to the parent's next sibling
+                const int c = near_child(prl, px, py, pz);
+                dfs = true, erl = prl - 1, vx = (px << 1) | (c & 1), vy = (py << 1) | ((c >> 1) & 1), vz = (pz << 1) | (c >> 2);
+                if (n_runs) break;  // what is listed so far first: it tightens the bound the children are held against
+                continue;
+            }
+            if (dfs)
+            {
+                int i;
+                for (;;)
+                {
+                    const int c = near_child(erl + 1, vx >> 1, vy >> 1, vz >> 1);
+                    i           = ((vx & 1) | ((vy & 1) << 1) | ((vz & 1) << 2)) ^ c;
+                    if (i < 7)
+                    {
+                        const int b = (i + 1) ^ c;
+                        vx = (vx & ~1) | (b & 1), vy = (vy & ~1) | ((b >> 1) & 1), vz = (vz & ~1) | (b >> 2);
+                        break;
+                    }
+                    vx >>= 1, vy >>= 1, vz >>= 1, erl++;
+                    if (erl == rl)
+                    {
+                        dfs = false;
+                        break;
+                    }
+                }
+                if (n_runs >= (uint32_t)(dfs ? kDfsFlush : 1)) break;  // leaves are scanned a few at a time: depth first, the bound tightens on the way
+            }
+        }
+        // ---- scan the listed runs, nearest first, for as long as the K-th distance reaches them; four loads in
+        // flight per lane (warp-uniform loop: a lane that is through idles)
+        __syncwarp();
+        {
+            uint32_t todo = (1u << n_runs) - 1u, p = 0, e = 0;
+#pragma unroll 1
+            for (;;)
+            {
+                if (p >= e && todo)
+                {
+                    const float kcur = fminf(kth, __uint_as_float((uint32_t)(best[0] >> 32)));
+                    int         pick = -1;
+                    float       bmin = 3.4e38f;
+#pragma unroll
+                    for (int r = 0; r < kRunCap; r++)
+                        if ((todo >> r) & 1u)
+                        {
+                            const float b = ks.bound[r][tid];
+                            if (b < bmin) bmin = b, pick = r;
+                        }
+                    if (bmin > kcur)
+                        todo = 0;  // nothing left that could hold a better point
+                    else
+                    {
+                        todo &= ~(1u << pick), p = ks.start[pick][tid], e = p + ks.count[pick][tid];
+                        sc.cands += e - p;  // (runs listed but never scanned are not candidates)
+                    }
+                }
+                const bool busy = p < e;
+                if (!__any_sync(FULL, busy)) break;
+                constexpr int kAhead = 4;
+                float4        pt[kAhead];
+#pragma unroll
+                for (int u = 0; u < kAhead; u++) pt[u] = (busy && p + u < e) ? __ldg(g.pts + p + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < kAhead; u++)
+                {
+                    const unsigned long long c = (busy && p + u < e) ? point_key(qx, qy, qz, pt[u]) : ~0ull;
+                    if (c < best[0] && __uint_as_float((uint32_t)(c >> 32)) <= kth)
+                    {
+                        // the old K-th best drops out, c sinks to its place (branch-free compare-exchange chain)
+                        unsigned long long x = c;
+#pragma unroll
+                        for (int j = 1; j < KM; j++)
+                        {
+                            const bool               lt = x < best[j];
+                            const unsigned long long hi = lt ? best[j] : x;
+                            x                           = lt ? x : best[j];
+                            best[j - 1]                 = hi;
+                        }
+                        best[KM - 1] = x;
+                    }
+                }
+                if (busy) p += kAhead;
+            }
+            if (n_runs) kth = fminf(kth, __uint_as_float((uint32_t)(best[0] >> 32)));
+            n_runs = 0;
+        }
+        __syncwarp();
+        if (!phase_done) continue;  // (lanes that are through: phase_done is false, they only take part in the votes)
+        if (phase < 2 && !top)
+        {
+            // ---- next phase: the neighbours the bound does not exclude, from the squared conservative gaps
+            // (metres^2) to the -1 / 0 / +1 slabs per axis
+            phase++;
+            const float s  = (float)(1 << L);
+            const float fx = ux - (float)cx * s, fy = uy - (float)cy * s, fz = uz - (float)cz * s;
+            const float glx = fmaxf(fx - 4.f, 0.f), ghx = fmaxf(s - fx - 4.f, 0.f);
+            const float gly = fmaxf(fy - 4.f, 0.f), ghy = fmaxf(s - fy - 4.f, 0.f);
+            const float glz = fmaxf(fz - 4.f, 0.f), ghz = fmaxf(s - fz - 4.f, 0.f);
+            const float ax[3] = {glx * glx * q2, 0.f, ghx * ghx * q2};
+            const float ay[3] = {gly * gly * q2, 0.f, ghy * ghy * q2};
+            const float az[3] = {glz * glz * q2, 0.f, ghz * ghz * q2};
+            const bool  okx[3] = {cx >= 1 && cx - 1 <= cmax, (unsigned)cx <= (unsigned)cmax, cx + 1 >= 0 && cx + 1 <= cmax};
+            const bool  oky[3] = {cy >= 1 && cy - 1 <= cmax, (unsigned)cy <= (unsigned)cmax, cy + 1 >= 0 && cy + 1 <= cmax};
+            const bool  okz[3] = {cz >= 1 && cz - 1 <= cmax, (unsigned)cz <= (unsigned)cmax, cz + 1 >= 0 && cz + 1 <= cmax};
+            uint32_t    m = 0;
+#pragma unroll
+            for (int dz = 0; dz < 3; dz++)
+#pragma unroll
+                for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+                    for (int dx = 0; dx < 3; dx++)
+                    {
+                        if (dx == 1 && dy == 1 && dz == 1) continue;
+                        if (okx[dx] && oky[dy] && okz[dz] && !(az[dz] + ay[dy] + ax[dx] > kth)) m |= 1u << (dz * 9 + dy * 3 + dx);
+                    }
+            constexpr uint32_t kFaces = (1u << 4) | (1u << 10) | (1u << 12) | (1u << 14) | (1u << 16) | (1u << 22);
+            mask = m & (phase == 1 ? kFaces : ~kFaces);
+            continue;
+        }
+        // ---- the level is through: best[] holds the exact K best of its block; everything outside the 3x3x3
+        // block is at least m quanta away
+        sc.levels++;
+        if (top)
+        {
+            live = false;
+            continue;
+        }
+        const float s  = (float)(1 << L);
+        const float fx = ux - (float)cx * s, fy = uy - (float)cy * s, fz = uz - (float)cz * s;
+        const float mx = s + fminf(fx, s - fx), my = s + fminf(fy, s - fy), mz = s + fminf(fz, s - fz);
+        const float mq = fmaxf(fminf(mx, fminf(my, mz)) - 4.f, 0.f);
+        if (kth <= mq * mq * q2)
+        {
+            live = false;
+            continue;
+        }
+        // not settled: go straight to the first level whose block is certain to settle the bound found (its
+        // margin is at least one voxel edge) instead of trying every level in between
+        rl++;
+        while (rl < g.n_levels - 1)
+        {
+            const float e = fmaxf((float)(1 << (g.level_first + rl)) - 4.f, 0.f);
+            if (e * e * q2 >= kth) break;
+            rl++;
+        }
+        phase = 0, mask = 1u << 13;
+#pragma unroll
+        for (int j = 0; j < KM; j++)
+            if (j < K) best[j] = sentinel;  // the list is rebuilt at every level: no key is ever offered twice
+    }
+    return deferred;
 }
 
 // warp-aggregated accumulation of the per-thread counters into stats[0..3] (measurement hook)

@@ -220,6 +220,80 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ---- tight boxes (GridView::box) --------------------------------------------------------------
+// Box of the voxel in table slot `slot` of level L (edge 2^L finest quanta), per axis the smallest and the
+// largest finest-voxel coordinate of its points relative to the voxel, in units of 2^max(L - 8, 0) quanta:
+// word x = lo_x | lo_y << 8 | lo_z << 16, word y = hi_x | hi_y << 8 | hi_z << 16 (hi inclusive: the box ends at
+// (hi + 1) units). Finest table: from the points' Morton keys. Every level above: the union of the children's
+// boxes (eight lookups one table down), rounded outwards.
+constexpr uint32_t kBoxScanMax = 4096;  // a finest-level voxel holding more points (duplicates) keeps the full cube
+__global__ void __launch_bounds__(256)
+    k_box_finest(const unsigned long long* __restrict__ keys, const CellEntry* __restrict__ table, uint32_t n_slots, int L,
+                 uint2* __restrict__ box)
+{
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const CellEntry e = table[slot];
+    if (e.key == kEmptyKey) return;
+    const int sh = max(L - 8, 0);
+    uint32_t  lo[3] = {255u, 255u, 255u}, hi[3] = {0u, 0u, 0u};
+    if (e.count > kBoxScanMax)
+        for (int d = 0; d < 3; d++) lo[d] = 0u, hi[d] = (uint32_t)min((1 << L) - 1, 255);
+    else
+    {
+        const uint32_t o[3] = {(uint32_t)(e.key & 0x1fffffu) << L, (uint32_t)((e.key >> 21) & 0x1fffffu) << L, (uint32_t)((e.key >> 42) & 0x1fffffu) << L};
+        for (uint32_t j = e.start; j < e.start + e.count; j++)
+        {
+            const unsigned long long mk = keys[j];
+            for (int d = 0; d < 3; d++)
+            {
+                const uint32_t q = (compact3(mk >> d) - o[d]) >> sh;
+                lo[d] = min(lo[d], q), hi[d] = max(hi[d], q);
+            }
+        }
+    }
+    box[slot] = make_uint2(lo[0] | (lo[1] << 8) | (lo[2] << 16), hi[0] | (hi[1] << 8) | (hi[2] << 16));
+}
+__global__ void __launch_bounds__(256)
+    k_box_merge(const CellEntry* __restrict__ table, LevelLayout lay, int rl, uint32_t n_slots, uint2* __restrict__ box)
+{
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const CellEntry e = table[lay.level_off[rl] + slot];
+    if (e.key == kEmptyKey) return;
+    const int      L   = lay.level_first + rl;
+    const int      shp = max(L - 8, 0), shc = max(L - 1 - 8, 0);
+    const uint32_t v[3] = {(uint32_t)(e.key & 0x1fffffu), (uint32_t)((e.key >> 21) & 0x1fffffu), (uint32_t)((e.key >> 42) & 0x1fffffu)};
+    uint32_t       lo[3] = {255u, 255u, 255u}, hi[3] = {0u, 0u, 0u};
+    const uint32_t   shift = lay.level_shift[rl - 1], mask = (1u << (64 - shift)) - 1u;
+    const CellEntry* t     = table + lay.level_off[rl - 1];
+    for (uint32_t c = 0; c < 8; c++)
+    {
+        const uint32_t           b[3] = {c & 1u, (c >> 1) & 1u, c >> 2};
+        const unsigned long long key  = cell_key(2 * v[0] + b[0], 2 * v[1] + b[1], 2 * v[2] + b[2]);
+        uint32_t                 h    = cell_hash(key, shift);
+        while (true)
+        {
+            const unsigned long long k = t[h].key;
+            if (k == key)
+            {
+                const uint2 cb = box[lay.level_off[rl - 1] + h];
+                for (int d = 0; d < 3; d++)
+                {
+                    const uint32_t off = b[d] << (L - 1);  // the child's origin inside this voxel, finest quanta
+                    const uint32_t l   = off + (((cb.x >> (8 * d)) & 255u) << shc);
+                    const uint32_t u   = off + ((((cb.y >> (8 * d)) & 255u) + 1u) << shc) - 1u;
+                    lo[d] = min(lo[d], l >> shp), hi[d] = max(hi[d], u >> shp);
+                }
+                break;
+            }
+            if (k == kEmptyKey) break;
+            h = (h + 1) & mask;
+        }
+    }
+    box[lay.level_off[rl] + slot] = make_uint2(lo[0] | (lo[1] << 8) | (lo[2] << 16), hi[0] | (hi[1] << 8) | (hi[2] << 16));
+}
+
 __global__ void k_fill_u64(unsigned long long* p, size_t n, unsigned long long v)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -484,6 +558,28 @@ int build_index(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* x, const fl
         v.level_occupancy[rl] = (float)((double)n / (double)cells[Lf + rl]);
     }
 
+    // ---- tight boxes, finest table first, then level by level upwards
+    static const bool with_boxes = [] {
+        const char* e = getenv("MP2P_INDEX_BOX");
+        return !(e && atoi(e) == 0);
+    }();
+    v.box = nullptr;
+    if (with_boxes)
+    {
+        MP2P_TRY(map->d_box.ensure(total * sizeof(uint2)));
+        uint2* box = map->d_box.as<uint2>();
+        for (int rl = 0; rl < lay.n_levels; rl++)
+        {
+            const uint32_t n_slots = 1u << (64 - lay.level_shift[rl]);
+            if (rl == 0)
+                k_box_finest<<<(n_slots + 255) / 256, 256, 0, st>>>(d_keys, map->d_table.as<CellEntry>(), n_slots, Lf, box);
+            else
+                k_box_merge<<<(n_slots + 255) / 256, 256, 0, st>>>(map->d_table.as<CellEntry>(), lay, rl, n_slots, box);
+            count_launch(ctx);
+        }
+        v.box = box;
+    }
+
     // ---- first-claim words (see match.cu): one u64 per map point, all ones = "never claimed"
     MP2P_TRY(map->d_claim.ensure(n * 8ull));
     k_fill_u64<<<148 * 4, 256, 0, st>>>(map->d_claim.as<unsigned long long>(), n, ~0ull);
@@ -502,7 +598,7 @@ int build_index(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* x, const fl
     inf.finest_cell_size = (float)(s0_eff * (double)(1u << Lf));
     inf.n_levels         = (uint32_t)lay.n_levels;
     inf.n_finest_cells   = cells[Lf];
-    inf.index_bytes      = n * 40ull + total * sizeof(CellEntry);
+    inf.index_bytes      = n * 40ull + total * (sizeof(CellEntry) + (v.box ? sizeof(uint2) : 0));
     inf.build_ms         = ms;
     return 0;
 }

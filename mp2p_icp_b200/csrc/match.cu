@@ -246,6 +246,14 @@ struct Pt2PtArgs
     // query-sharded run with owner-partitioned claims (OwnerClaims, common.cuh): NULL = the map's own claim array
     unsigned long long* const* claim_parts;
     uint32_t                   claim_world;
+    // thread-per-query search: where over-budget queries hand themselves over (DeferList, grid_search.cuh), and the
+    // group kernel serving that list: query positions come from qlist[0 .. min(*qlist_count, qlist_cap)) instead of
+    // the tile; it also clears *defer_reset (the counter the NEXT call's thread pass will use)
+    DeferList       defer;
+    const uint32_t* qlist;
+    const uint32_t* qlist_count;
+    uint32_t        qlist_cap;
+    uint32_t*       defer_reset;
     const uint32_t* tile_order;
     uint32_t*       tile_cost;
     uint32_t*       tile_trace;  // measurement hook: 8 words per CTA {SM, start ns, end ns, tile, rounds, steps, inserts, probes | levels << 16 of warp 0}
@@ -282,20 +290,36 @@ __global__ void __launch_bounds__(NT, MP2P_MATCH_MIN_BLOCKS * (int)kQueryTile / 
     const long long    t_start = clock64();
     unsigned long long t_trace0 = 0;
     if (a.tile_trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_trace0));
-    const uint32_t  tile_id = a.tile_order ? __ldg(a.tile_order + blockIdx.x) : (uint32_t)(((unsigned long long)blockIdx.x * a.tile_stride) % gridDim.x);
+    const bool      listed  = a.qlist != nullptr;  // serving the deferred list of a thread-per-query pass
+    const uint32_t  tile_id = listed ? blockIdx.x : (a.tile_order ? __ldg(a.tile_order + blockIdx.x) : (uint32_t)(((unsigned long long)blockIdx.x * a.tile_stride) % gridDim.x));
     const size_t    base    = (size_t)tile_id * NQ;
+    uint32_t        n_listed = 0;
+    if (listed)
+    {
+        n_listed = min(__ldg(a.qlist_count), a.qlist_cap);
+        if (a.defer_reset && blockIdx.x == 0 && threadIdx.x == 0) *a.defer_reset = 0u;
+        if (base >= n_listed) return;  // (CTA-uniform)
+    }
     bbox_init(bacc);
     if (!V1) knn_shared_init(ks);
-    load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);  // (holds the __syncthreads)
-    const int      sub   = threadIdx.x % G, ql = threadIdx.x / G;
-    const uint32_t qpos  = (uint32_t)base + ql;  // position in the array walked (sorted if perm)
+    const int sub = threadIdx.x % G, ql = threadIdx.x / G;
+    if (!listed)
+        load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);  // (holds the __syncthreads)
+    else
+    {
+        const bool     in = base + ql < n_listed;
+        const uint32_t q  = in ? __ldg(a.qlist + base + ql) : 0u;
+        if (sub == 0) tile.x[ql] = in ? lx[q] : 0.f, tile.y[ql] = in ? ly[q] : 0.f, tile.z[ql] = in ? lz[q] : 0.f;
+        __syncthreads();
+    }
+    const uint32_t qpos  = listed ? (base + ql < n_listed ? __ldg(a.qlist + base + ql) : 0xFFFFFFFFu) : (uint32_t)base + ql;  // position in the array walked (sorted if perm)
     const bool     valid = qpos < a.n_local;
     const uint32_t i     = (perm && valid) ? __ldg(perm + qpos) : qpos;  // the caller's index of this query
     const uint32_t co    = a.cand_sorted ? qpos : i;                     // where its candidate words go
 
     float gx = 0, gy = 0, gz = 0;
     if (valid) compose_point_f(a.pose, tile.x[ql], tile.y[ql], tile.z[ql], gx, gy, gz);
-    bbox_accumulate(bacc, gx, gy, gz, valid && sub == 0, bbox_words);
+    bbox_accumulate(bacc, gx, gy, gz, valid && sub == 0 && !listed, bbox_words);  // (the thread pass counted the listed queries)
     const int K = (int)a.K;
     // …DistanceThreshold.cpp:230,256-257 (float, unfused)
     const float normSq = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
@@ -355,6 +379,102 @@ __global__ void __launch_bounds__(NT, MP2P_MATCH_MIN_BLOCKS * (int)kQueryTile / 
             a.tile_trace[8 * blockIdx.x + 2] = (uint32_t)t1, a.tile_trace[8 * blockIdx.x + 3] = tile_id;
             a.tile_trace[8 * blockIdx.x + 4] = sc.rounds, a.tile_trace[8 * blockIdx.x + 5] = sc.steps;
             a.tile_trace[8 * blockIdx.x + 6] = sc.inserts, a.tile_trace[8 * blockIdx.x + 7] = sc.probes | (sc.levels << 16);
+        }
+    }
+}
+
+// The same contract served by ONE THREAD per query (knn_search_thread, grid_search.cuh): a CTA of NT threads
+// takes a tile of NT queries; thread t leaves rank r of its query at cand[.. * K + r] like lane r of a group.
+template <int KM, int NT>
+__global__ void __launch_bounds__(NT)
+    k_match_knn_thread(GridView g, Pt2PtArgs a, const float* __restrict__ lx, const float* __restrict__ ly,
+                       const float* __restrict__ lz, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ lbits,
+                       const uint32_t* __restrict__ gbits, unsigned long long* __restrict__ claim,
+                       unsigned long long* __restrict__ cand, uint32_t* __restrict__ bbox_words,
+                       unsigned long long* __restrict__ stats, FitList fit)
+{
+    __shared__ QueryTile<NT>       tile;
+    __shared__ BBoxAcc             bacc;
+    __shared__ KnnThreadShared<NT> ks;
+    const long long    t_start  = clock64();
+    unsigned long long t_trace0 = 0;
+    if (a.tile_trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_trace0));
+    const uint32_t tile_id = a.tile_order ? __ldg(a.tile_order + blockIdx.x) : (uint32_t)(((unsigned long long)blockIdx.x * a.tile_stride) % gridDim.x);
+    const size_t   base    = (size_t)tile_id * NT;
+    bbox_init(bacc);
+    load_query_tile(tile, lx, ly, lz, base, a.n_local, a.tma_ok != 0);  // (holds the __syncthreads)
+    const uint32_t qpos  = (uint32_t)base + threadIdx.x;  // position in the array walked (sorted if perm)
+    const bool     valid = qpos < a.n_local;
+    const uint32_t i     = (perm && valid) ? __ldg(perm + qpos) : qpos;  // the caller's index of this query
+    const uint32_t co    = a.cand_sorted ? qpos : i;                     // where its candidate words go
+
+    float gx = 0, gy = 0, gz = 0;
+    if (valid) compose_point_f(a.pose, tile.x[threadIdx.x], tile.y[threadIdx.x], tile.z[threadIdx.x], gx, gy, gz);
+    bbox_accumulate(bacc, gx, gy, gz, valid, bbox_words);
+    const int K = (int)a.K;
+    // …DistanceThreshold.cpp:230,256-257 (float, unfused)
+    const float normSq = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+    const float thr2   = __fadd_rn(a.maxDistSq, __fmul_rn(a.angSq, normSq));
+    const unsigned long long sentinel = (unsigned long long)__float_as_uint(thr2) << 32;
+
+    unsigned long long best[KM];  // descending: best[K - 1 - r] = the r-th best key
+    SearchCounters     sc;
+    // lanes past the end and already paired locals (:218-220) do not search
+    const bool deferred = knn_search_thread<KM, NT>(g, valid && (a.allowLocal || !bit_set(lbits, i)), gx, gy, gz, thr2, K, a.rl_start, best, sc, ks, a.defer, qpos);
+    __syncwarp();
+    unsigned long long need_key = ~0ull;  // the key of rank fit.need - 1
+    if (deferred) flush_search_stats(sc, 0u, stats);  // (the work done before handing over is work done)
+    if (valid && !deferred)
+    {
+        uint32_t n_found = 0;
+#pragma unroll
+        for (int j = 0; j < KM; j++)
+        {
+            if (j >= K) break;
+            const int                r = K - 1 - j;
+            const unsigned long long c = best[j] < sentinel ? best[j] : ~0ull;  // unused ranks: an impossible map index (all ones)
+            cand[(size_t)co * K + r]   = c;
+            if (r == fit.need - 1) need_key = c;
+            n_found += c != ~0ull;
+        }
+        if (!a.allowGlobal)  // first claims (one rolled loop over the words just written: the unrolled one was half of the kernel's code)
+#pragma unroll 1
+            for (int r = 0; r < K; r++)
+            {
+                const unsigned long long c = cand[(size_t)co * K + r];
+                if (c == ~0ull) continue;
+                const uint32_t gi = (uint32_t)c;
+                if (!bit_set(gbits, gi)) claim_propose(claim, a.claim_parts, a.claim_world, gi, a.tag | ((unsigned long long)(i * (uint32_t)K + r) + a.slot_offset));
+            }
+        flush_search_stats(sc, n_found, stats);
+    }
+    __syncwarp();
+    if (fit.list)  // all lanes: warp-aggregated append of the queries that qualify for a plane fit
+    {
+        const bool     has  = valid && !deferred && fit.need <= K && need_key != ~0ull;
+        const unsigned m    = __ballot_sync(0xffffffffu, has);
+        const int      lane = threadIdx.x & 31;
+        uint32_t       at   = 0;
+        if (m && lane == __ffs(m) - 1) at = atomicAdd(fit.count, (uint32_t)__popc(m));
+        at = __shfl_sync(0xffffffffu, at, m ? __ffs(m) - 1 : 0);
+        if (has) fit.list[at + __popc(m & ((1u << lane) - 1u))] = qpos;
+        if (valid && !deferred && !has) fit.ok_flags[i] = 0;
+    }
+    // how long this tile took (its slowest warp, in units of 64 clocks): see k_match_pt2pt
+    if (a.tile_cost && (threadIdx.x & 31) == 0) atomicMax(a.tile_cost + tile_id, (uint32_t)min((clock64() - t_start) >> 6, 0xffffffffll));
+    if (a.tile_trace)  // measurement hook ($MP2P_KNN_TRACE=1): where and when every CTA ran
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            unsigned long long t1;
+            uint32_t           smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            a.tile_trace[8 * blockIdx.x + 0] = smid, a.tile_trace[8 * blockIdx.x + 1] = (uint32_t)t_trace0;
+            a.tile_trace[8 * blockIdx.x + 2] = (uint32_t)t1, a.tile_trace[8 * blockIdx.x + 3] = tile_id;
+            a.tile_trace[8 * blockIdx.x + 4] = sc.levels, a.tile_trace[8 * blockIdx.x + 5] = sc.cands;
+            a.tile_trace[8 * blockIdx.x + 6] = 0u, a.tile_trace[8 * blockIdx.x + 7] = sc.probes | (sc.levels << 16);
         }
     }
 }
@@ -1513,6 +1633,84 @@ int knn_tile_rank(mp2p_b200_ctx* ctx, uint32_t n_tiles, const Pt2PtArgs& a)
     count_launch(ctx);
     return 0;
 }
+// k <= kThreadKMax: one thread per query, A/B variant ($MP2P_KNN_THREAD=1; $MP2P_KNN_TNT = 64 | 128 | 256 queries per
+// CTA). NOT the default: measured on C3 (profiles/r02_knn_ab.txt) it executes 2.3x fewer instructions than the group
+// search and is still slower — a 119k-query scan is 3.7k warps, 25 per SM, one wave, and every SM waits for its
+// slowest warp; with G = 8 lanes per query the same scan is 30k warps and the tail hides behind the bulk.
+bool knn_thread_mode()
+{
+    static const bool v = [] {
+        const char* e = getenv("MP2P_KNN_THREAD");
+        return e && atoi(e) == 1;
+    }();
+    return v && !knn_v1();
+}
+int knn_thread_nt()
+{
+    static const int v = [] {
+        const char* e = getenv("MP2P_KNN_TNT");
+        const int   x = e ? atoi(e) : 128;
+        return (x == 64 || x == 256) ? x : 128;
+    }();
+    return v;
+}
+template <int KM, int NT>
+int launch_knn_thread_nt(mp2p_b200_ctx* ctx, size_t nq, cudaStream_t st, const GridView& g, Pt2PtArgs& a, const float* lx, const float* ly,
+                         const float* lz, const uint32_t* perm, const uint32_t* lbits, const uint32_t* gbits, unsigned long long* claim,
+                         unsigned long long* cand, uint32_t* bbox_words, unsigned long long* stats, const FitList& fit)
+{
+    const uint32_t nb = (uint32_t)((nq + NT - 1) / NT);
+    a.tile_stride     = tile_stride_for(nb);
+    MP2P_TRY(knn_tile_hint(ctx, nb, 1, NT, a));
+    // over-budget queries: two counters used in turn (this call's, cleared by the previous call's second kernel)
+    static const uint32_t max_probes = [] { const char* e = getenv("MP2P_KNN_DEFER_PROBES"); return e ? (uint32_t)atoi(e) : 24u; }();
+    static const uint32_t max_cands  = [] { const char* e = getenv("MP2P_KNN_DEFER_CANDS"); return e ? (uint32_t)atoi(e) : 160u; }();
+    const bool     defer = max_probes && max_cands && nq >= 4096;
+    const uint32_t cap   = (uint32_t)(nq / 8);
+    a.defer = DeferList{nullptr, nullptr, 0, 0, 0}, a.qlist = nullptr, a.qlist_count = nullptr, a.qlist_cap = 0, a.defer_reset = nullptr;
+    uint32_t* cnt = nullptr;
+    if (defer)
+    {
+        const bool fresh = ctx->d_defer.bytes < (size_t)(cap + 2) * 4;
+        MP2P_TRY(ctx->d_defer.ensure((size_t)(cap + 2) * 4));
+        cnt = ctx->d_defer.as<uint32_t>();
+        if (fresh) MP2P_CUDA_TRY(cudaMemsetAsync(cnt, 0, 8, st));
+        ctx->defer_turn ^= 1u;
+        a.defer = DeferList{cnt + 2, cnt + ctx->defer_turn, cap, max_probes, max_cands};
+    }
+    k_match_knn_thread<KM, NT><<<nb, NT, 0, st>>>(g, a, lx, ly, lz, perm, lbits, gbits, claim, cand, bbox_words, stats, fit);
+    if (defer)
+    {
+        // the deferred queries, one WARP per query (the group search with G = 32: probes, candidates and list are
+        // spread over the lanes), eight queries per CTA
+        Pt2PtArgs b = a;
+        b.defer = DeferList{nullptr, nullptr, 0, 0, 0}, b.tile_order = nullptr, b.tile_cost = nullptr, b.tile_trace = nullptr;
+        b.qlist = cnt + 2, b.qlist_count = cnt + ctx->defer_turn, b.qlist_cap = cap, b.defer_reset = cnt + (ctx->defer_turn ^ 1u);
+        k_match_pt2pt<32, false, 256><<<(cap + 7) / 8, 256, 0, st>>>(g, b, lx, ly, lz, perm, lbits, gbits, claim, cand, bbox_words, stats, fit);
+        count_launch(ctx);
+    }
+    MP2P_TRY(knn_tile_rank(ctx, nb, a));
+    return 0;
+}
+template <int KM, class... Args>
+int launch_knn_thread_km(mp2p_b200_ctx* ctx, size_t nq, cudaStream_t st, Args&&... args)
+{
+    switch (knn_thread_nt())
+    {
+        case 64: return launch_knn_thread_nt<KM, 64>(ctx, nq, st, args...);
+        case 256: return launch_knn_thread_nt<KM, 256>(ctx, nq, st, args...);
+        default: return launch_knn_thread_nt<KM, 128>(ctx, nq, st, args...);
+    }
+}
+template <class... Args>
+int launch_knn_thread(mp2p_b200_ctx* ctx, uint32_t K, size_t nq, cudaStream_t st, Args&&... args)
+{
+    if (K <= 4) return launch_knn_thread_km<4>(ctx, nq, st, args...);
+    if (K <= 8) return launch_knn_thread_km<8>(ctx, nq, st, args...);
+    if (K <= 12) return launch_knn_thread_km<12>(ctx, nq, st, args...);
+    if (K <= 16) return launch_knn_thread_km<16>(ctx, nq, st, args...);
+    return launch_knn_thread_km<20>(ctx, nq, st, args...);
+}
 #define MP2P_LAUNCH_KMATCH_NT(G, V1, NT, nq, st, ...)                                              \
     {                                                                                              \
         const uint32_t nb_ = (uint32_t)(((uint64_t)(nq) * G + NT - 1) / NT);                       \
@@ -1525,7 +1723,11 @@ int knn_tile_rank(mp2p_b200_ctx* ctx, uint32_t n_tiles, const Pt2PtArgs& a)
 #define MP2P_LAUNCH_KMATCH(G, args, nq, st, ...)                                                   \
     {                                                                                              \
         auto& a_ = args;                                                                           \
-        if (knn_v1())                                                                              \
+        if (knn_thread_mode() && a_.K <= (uint32_t)kThreadKMax)                                    \
+        {                                                                                          \
+            MP2P_TRY(launch_knn_thread(ctx, a_.K, nq, st, __VA_ARGS__));                           \
+        }                                                                                          \
+        else if (knn_v1())                                                                         \
         {                                                                                          \
             if (knn_nt() == 64) MP2P_LAUNCH_KMATCH_NT(G, true, 64, nq, st, __VA_ARGS__)            \
             else if (knn_nt() == 128) MP2P_LAUNCH_KMATCH_NT(G, true, 128, nq, st, __VA_ARGS__)     \

@@ -13,11 +13,14 @@ P
 }
 run() {  # tag, env...
   tag=$1; shift
-  env "$@" timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "knn or pt2pl or pt2ln or adaptive or c2_small" > gpurun_out/pytest_knn_$tag.log 2>&1; echo "$tag pytest rc=$?"; tail -1 gpurun_out/pytest_knn_$tag.log
+  env "$@" timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "knn or pt2pl or pt2ln or adaptive or c2_small" > gpurun_out/pytest_knn_$tag.log 2>&1; echo "$tag pytest rc=$?"; tail -1 gpurun_out/pytest_knn_$tag.log
   env "$@" timeout 600 python bench.py --workload C3 --steps 10 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_c3_$tag.json 2> gpurun_out/bench_c3_$tag.err; show gpurun_out/bench_c3_$tag.json; tail -2 gpurun_out/bench_c3_$tag.err
 }
 for tag in "$@"; do
   case $tag in
+    thr) run thr MP2P_KNN_THREAD=1 ;;
+    grp) run grp MP2P_KNN_THREAD=0 ;;
+    ncut) timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_match_knn_thread" -s 4 -c 1 -f -o gpurun_out/prof_r2_knn_thread python bench.py --workload C3 --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_r2_knn_thread.log 2>&1; echo "ncut rc=$?" ;;
     p3) run p3 MP2P_KNN_PHASES=3 ;;
     p2) run p2 MP2P_KNN_PHASES=2 ;;
     v1) run v1 MP2P_KNN_V1=1 ;;
