@@ -55,7 +55,7 @@ struct GridView
     const CellEntry* table;     // all level tables back to back
     // per table slot: the TIGHT box of the voxel's points, 8 bits per bound relative to the voxel (box_lo / box_hi
     // in grid_search.cuh). A voxel is a cube, the points in it usually a patch of surface: its cube says a far
-    // query must look at it, its box says it need not. NULL = not built ($MP2P_INDEX_BOX=0)
+    // query must look at it, its box says it need not. NULL = not built (the default; $MP2P_INDEX_BOX=1 builds them)
     const uint2*     box;
     float            ox, oy, oz;  // grid origin = map bbox min
     float            inv_s0;      // 1 / finest quantum

@@ -558,10 +558,12 @@ int build_index(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* x, const fl
         v.level_occupancy[rl] = (float)((double)n / (double)cells[Lf + rl]);
     }
 
-    // ---- tight boxes, finest table first, then level by level upwards
+    // ---- tight boxes, finest table first, then level by level upwards. Optional ($MP2P_INDEX_BOX=1): on C3 they
+    // cut the candidates of the k > 1 search by 23 % and its time by 4 % (the search is bound by its per-round
+    // costs, not by the candidates), 0.5 % of an iteration, for 8 more bytes per table slot and 11 % more build time
     static const bool with_boxes = [] {
         const char* e = getenv("MP2P_INDEX_BOX");
-        return !(e && atoi(e) == 0);
+        return e && atoi(e) == 1;
     }();
     v.box = nullptr;
     if (with_boxes)

@@ -860,8 +860,16 @@ inline int nn1_variant()
 // array is never cleared between calls.
 // ------------------------------------------------------------------------------------------
 constexpr int      kScanThreads = 256;
-constexpr int      kScanItems   = 1;  // latency-bound at ICP sizes: one slot per thread, many small tiles
+constexpr int      kScanItems   = 1;  // the fused iteration, inlier-ratio and adaptive compactions: one slot per thread
 constexpr uint32_t kScanTile    = kScanThreads * kScanItems;
+// The stand-alone compactions take several CONSECUTIVE slots per thread. With one slot per thread the 1M slots
+// of C5 are 3,907 tiles whose look-back walks (32 tiles per step, one L2 round trip each) run ~120 steps deep
+// when every tile starts at once: 119 us for 44 MB. Four slots per thread quarter the chain; the loads of the
+// four slots are in flight together.
+constexpr int      kCompactItems2p = 4;  // 36-byte records: 36 KB of staging per CTA
+constexpr int      kCompactItems2l = 2;  // 72-byte records: 36 KB
+inline uint32_t compact_tiles_2p(uint64_t n_slots) { return (uint32_t)((n_slots + kScanThreads * kCompactItems2p - 1) / (kScanThreads * kCompactItems2p)); }
+inline uint32_t compact_tiles_2l(uint64_t n_local) { return (uint32_t)((n_local + kScanThreads * kCompactItems2l - 1) / (kScanThreads * kCompactItems2l)); }
 
 struct ScanSmem
 {
@@ -907,6 +915,8 @@ __device__ __forceinline__ unsigned long long grid_exclusive_scan(
             __threadfence();
             vstatus[tile] = (1ull << 62) | ep | block_total;  // aggregate available
         }
+        // (a window of 128 tiles per step — four statuses per lane — was measured and is slower: 68.9 us against
+        // 62.9 us on the 1M slots of C5; once the tiles hold four slots per thread the walk is not the bound)
         unsigned long long base = 0;
         int                t    = (int)tile - 1;
         while (t >= 0)
@@ -1064,6 +1074,7 @@ struct FusedSums
 // Body of the pt2pt compaction for tile `tile` of a CTA of kScanThreads threads. On return the
 // tile's accepted records sit in s_rec[0 .. n_rec*9) (n_rec returned); shared by the stand-alone
 // kernel and by the fused single-launch iteration.
+template <int ITEMS = 1>
 __device__ __forceinline__ uint32_t compact_pt2pt_body(
     const GridView& g, const CompactArgs& a, const float* __restrict__ lx, const float* __restrict__ ly,
     const float* __restrict__ lz, const uint32_t* __restrict__ gbits, const unsigned long long* __restrict__ claim,
@@ -1072,50 +1083,70 @@ __device__ __forceinline__ uint32_t compact_pt2pt_body(
     unsigned long long* __restrict__ out_count, const FusedSums& fs, uint32_t tile, ScanSmem& sm, uint32_t* s_rec,
     bool* folded_sums = nullptr, const CoopSync* resident = nullptr)
 {
+    constexpr uint32_t TILE = kScanThreads * ITEMS;
     const uint64_t n_slots = (uint64_t)a.n_local * a.K;
-    const uint32_t n_tiles = (uint32_t)((n_slots + kScanTile - 1) / kScanTile);
+    const uint32_t n_tiles = (uint32_t)((n_slots + TILE - 1) / TILE);
     const bool     gate    = bbox_gate(g, bbox, a.gate_eps);
 
     // Everything a record needs is requested up front (cand -> {claim word, global point, local
-    // point} in parallel) so that only ONE dependent memory round trip precedes the scan.
-    const uint64_t     slot = (uint64_t)tile * kScanTile + threadIdx.x;
-    bool               ok   = false;
-    unsigned long long c    = ~0ull;
-    uint32_t           i = 0, gi = 0;
-    float4             gp = make_float4(0.f, 0.f, 0.f, 0.f);
-    float              px = 0.f, py = 0.f, pz = 0.f;
-    if (gate && slot < n_slots)
+    // point} in parallel, for all of the thread's slots) so that only ONE dependent memory round trip
+    // precedes the scan.
+    const uint64_t     slot0 = (uint64_t)tile * TILE + (uint64_t)threadIdx.x * ITEMS;
+    bool               ok[ITEMS];
+    unsigned long long c[ITEMS];
+    uint32_t           i[ITEMS], gi[ITEMS];
+    float4             gp[ITEMS];
+    float              px[ITEMS], py[ITEMS], pz[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++)
     {
-        c  = cand[slot];
-        ok = ((uint32_t)c != 0xFFFFFFFFu);  // unused ranks carry an all-ones map index
-        if (ok)
+        const uint64_t slot = slot0 + j;
+        ok[j] = false, c[j] = ~0ull, i[j] = 0, gi[j] = 0, gp[j] = make_float4(0.f, 0.f, 0.f, 0.f), px[j] = py[j] = pz[j] = 0.f;
+        if (gate && slot < n_slots)
         {
-            gi = (uint32_t)c;
-            i  = (uint32_t)(a.K == 1 ? slot : slot / a.K);
-            unsigned long long cw = a.tag | (unsigned long long)(slot + a.slot_offset);
-            if (!a.allowGlobal) cw = claim_read(claim, a.claim_parts, a.claim_world, gi);
-            // the K = 1 matcher hands the matched point's coordinates over with the candidate
-            // (sequential read); the K > 1 matcher does not (random gather from the map)
-            gp = cand_xyz ? __ldcs(cand_xyz + slot) : __ldg(g.pts_orig + gi);
-            px = lx[i], py = ly[i], pz = lz[i];
-            if (!a.allowGlobal)
-                ok = !bit_set(gbits, gi) && (cw == (a.tag | (unsigned long long)(slot + a.slot_offset)));
+            c[j]  = cand[slot];
+            ok[j] = ((uint32_t)c[j] != 0xFFFFFFFFu);  // unused ranks carry an all-ones map index
         }
     }
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++)
+        if (ok[j])
+        {
+            const uint64_t slot = slot0 + j;
+            gi[j] = (uint32_t)c[j];
+            i[j]  = (uint32_t)(a.K == 1 ? slot : slot / a.K);
+            unsigned long long cw = a.tag | (unsigned long long)(slot + a.slot_offset);
+            if (!a.allowGlobal) cw = claim_read(claim, a.claim_parts, a.claim_world, gi[j]);
+            // the K = 1 matcher hands the matched point's coordinates over with the candidate
+            // (sequential read); the K > 1 matcher does not (random gather from the map)
+            gp[j] = cand_xyz ? __ldcs(cand_xyz + slot) : __ldg(g.pts_orig + gi[j]);
+            px[j] = lx[i[j]], py[j] = ly[i[j]], pz[j] = lz[i[j]];
+            if (!a.allowGlobal)
+                ok[j] = !bit_set(gbits, gi[j]) && (cw == (a.tag | (unsigned long long)(slot + a.slot_offset)));
+        }
+    uint32_t local = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) local += ok[j] ? 1u : 0u;
     const unsigned long long w =
-        resident ? grid_exclusive_scan_resident(sm, tile, n_tiles, ok ? 1u : 0u, status, out_count, *resident, resident->scan_barrier)
-                 : grid_exclusive_scan(sm, tile, n_tiles, ok ? 1u : 0u, status, out_count, a.scan_epoch);
+        resident ? grid_exclusive_scan_resident(sm, tile, n_tiles, local, status, out_count, *resident, resident->scan_barrier)
+                 : grid_exclusive_scan(sm, tile, n_tiles, local, status, out_count, a.scan_epoch);
     // The tile's records are consecutive in the output: stage them in shared memory and store the
     // byte range with fully coalesced 4-byte words (full sectors: no read-for-ownership fills),
     // instead of nine strided stores per thread.
     const unsigned long long tile_base = sm.tile_base;
-    if (ok)
     {
-        uint32_t* o = s_rec + (uint32_t)(w - tile_base) * 9;
-        o[0] = gi, o[1] = i + a.index_offset;
-        o[2] = __float_as_uint(gp.x), o[3] = __float_as_uint(gp.y), o[4] = __float_as_uint(gp.z);
-        o[5] = __float_as_uint(px), o[6] = __float_as_uint(py), o[7] = __float_as_uint(pz);
-        o[8] = (uint32_t)(c >> 32);
+        uint32_t at = (uint32_t)(w - tile_base);
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++)
+            if (ok[j])
+            {
+                uint32_t* o = s_rec + at * 9;
+                at++;
+                o[0] = gi[j], o[1] = i[j] + a.index_offset;
+                o[2] = __float_as_uint(gp[j].x), o[3] = __float_as_uint(gp[j].y), o[4] = __float_as_uint(gp[j].z);
+                o[5] = __float_as_uint(px[j]), o[6] = __float_as_uint(py[j]), o[7] = __float_as_uint(pz[j]);
+                o[8] = (uint32_t)(c[j] >> 32);
+            }
     }
     __syncthreads();
     const unsigned long long room  = a.capacity > tile_base ? a.capacity - tile_base : 0ull;
@@ -1132,9 +1163,20 @@ __device__ __forceinline__ uint32_t compact_pt2pt_body(
     }
     if (fs.packet)
     {
-        const bool in  = ok && w < a.capacity;
-        double     acc[8] = {in ? (double)px : 0.0,   in ? (double)py : 0.0,   in ? (double)pz : 0.0, in ? (double)gp.x : 0.0,
-                             in ? (double)gp.y : 0.0, in ? (double)gp.z : 0.0, in ? 1.0 : 0.0,       in ? 1.0 : 0.0};
+        double             acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long at     = w;
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++)  // (sequential per thread, slot order)
+            if (ok[j])
+            {
+                if (at < a.capacity)
+                {
+                    acc[0] += (double)px[j], acc[1] += (double)py[j], acc[2] += (double)pz[j];
+                    acc[3] += (double)gp[j].x, acc[4] += (double)gp[j].y, acc[5] += (double)gp[j].z;
+                    acc[6] += 1.0, acc[7] += 1.0;
+                }
+                at++;
+            }
         const bool folded = block_reduce_to_packet<8>(acc, fs.partials, fs.ticket, fs.packet, tile, n_tiles);
         if (folded_sums) *folded_sums = folded;
     }
@@ -1151,20 +1193,21 @@ __global__ void __launch_bounds__(kScanThreads)
                     mp2p_b200_pair_pt2pt* __restrict__ out, unsigned long long* __restrict__ out_count,
                     FusedSums fs)
 {
-    static_assert(kScanItems == 1 && kScanThreads == kReduceThreads, "one slot per thread");
+    static_assert(kScanThreads == kReduceThreads, "the sums use the solvers' block reduction");
+    constexpr uint32_t TILE = kScanThreads * kCompactItems2p;
     __shared__ ScanSmem sm;
-    __shared__ uint32_t s_rec[kScanThreads * 9];  // this tile's records, staged for coalesced stores
+    __shared__ uint32_t s_rec[TILE * 9];  // this tile's records, staged for coalesced stores
     bbox_rearm(bbox_next);
     const uint64_t n_slots = (uint64_t)a.n_local * a.K;
-    const uint32_t n_tiles = (uint32_t)((n_slots + kScanTile - 1) / kScanTile);
+    const uint32_t n_tiles = (uint32_t)((n_slots + TILE - 1) / TILE);
     if (threadIdx.x == 0)
     {
         sm.tile_id = atomicAdd(tile_counter, 1u);
         if (sm.tile_id == n_tiles - 1) *tile_counter = 0u;  // last ticket handed out: re-arm
     }
     __syncthreads();
-    compact_pt2pt_body(g, a, lx, ly, lz, gbits, claim, cand, cand_xyz, bbox, status, out, out_count, fs, sm.tile_id, sm,
-                       s_rec);
+    compact_pt2pt_body<kCompactItems2p>(g, a, lx, ly, lz, gbits, claim, cand, cand_xyz, bbox, status, out, out_count, fs, sm.tile_id,
+                                        sm, s_rec);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1425,11 +1468,12 @@ __global__ void __launch_bounds__(kScanThreads)
                     uint32_t scan_epoch, int line_mode, uint32_t* __restrict__ out_host,
                     unsigned long long* __restrict__ count_host)
 {
-    static_assert(kScanItems == 1, "one local point per thread");
+    constexpr int      ITEMS = kCompactItems2l;
+    constexpr uint32_t TILE  = kScanThreads * ITEMS;
     __shared__ ScanSmem sm;
-    __shared__ uint32_t s_rec[kScanThreads * 18];  // this tile's 72-byte records, staged for coalesced stores
+    __shared__ uint32_t s_rec[TILE * 18];  // this tile's 72-byte records, staged for coalesced stores
     bbox_rearm(bbox_next);
-    const uint32_t n_tiles = (n_local + kScanTile - 1) / kScanTile;
+    const uint32_t n_tiles = (n_local + TILE - 1) / TILE;
     if (threadIdx.x == 0)
     {
         sm.tile_id = atomicAdd(tile_counter, 1u);
@@ -1438,32 +1482,45 @@ __global__ void __launch_bounds__(kScanThreads)
     __syncthreads();
     const uint32_t tile = sm.tile_id;
     const bool     gate = bbox_gate(g, bbox, gate_eps);
-    const uint32_t i    = tile * kScanTile + threadIdx.x;
-    const bool     ok   = gate && i < n_local && ok_flags[i];
-    // everything the record needs is requested before the scan (one dependent round trip)
-    PlaneCandidate pc{};
-    float          px = 0.f, py = 0.f, pz = 0.f;
-    if (ok) pc = plc[i], px = lx[i], py = ly[i], pz = lz[i];  // ORIGINAL local point (Matcher_Point2Plane.cpp:105)
-    const unsigned long long w = grid_exclusive_scan(sm, tile, n_tiles, ok ? 1u : 0u, status, out_count, scan_epoch);
-    const unsigned long long tile_base = sm.tile_base;
-    if (ok)
+    const uint32_t i0   = tile * TILE + threadIdx.x * ITEMS;  // the thread's consecutive local points
+    // everything the records need is requested before the scan (one dependent round trip)
+    bool           ok[ITEMS];
+    PlaneCandidate pc[ITEMS];
+    float          px[ITEMS], py[ITEMS], pz[ITEMS];
+    uint32_t       local = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++)
     {
-        double* o = reinterpret_cast<double*>(s_rec + (uint32_t)(w - tile_base) * 18);
-        if (line_mode)  // point_line_pair_t: TLine3D {pBase, director}, TPoint3D pt_local (Pairings.h:61-73; Matcher_Point2Line.cpp:152)
-        {
-            o[0] = pc.centroid[0], o[1] = pc.centroid[1], o[2] = pc.centroid[2];
-            o[3] = pc.coefs[0], o[4] = pc.coefs[1], o[5] = pc.coefs[2];
-            o[6] = px, o[7] = py, o[8] = pz;
-        }
-        else  // point_plane_pair_t: plane_patch_t {TPlane coefs[4], TPoint3D centroid}, TPoint3Df pt_local, pad
-        {
-            o[0] = pc.coefs[0], o[1] = pc.coefs[1], o[2] = pc.coefs[2], o[3] = pc.coefs[3];
-            o[4] = pc.centroid[0], o[5] = pc.centroid[1], o[6] = pc.centroid[2];
-            uint32_t* t = reinterpret_cast<uint32_t*>(o + 7);
-            t[0] = __float_as_uint(px), t[1] = __float_as_uint(py);
-            t[2] = __float_as_uint(pz), t[3] = 0u;
-        }
+        const uint32_t i = i0 + j;
+        ok[j] = gate && i < n_local && ok_flags[i];
+        pc[j] = PlaneCandidate{}, px[j] = py[j] = pz[j] = 0.f;
+        if (ok[j]) pc[j] = plc[i], px[j] = lx[i], py[j] = ly[i], pz[j] = lz[i];  // ORIGINAL local point (Matcher_Point2Plane.cpp:105)
+        local += ok[j] ? 1u : 0u;
     }
+    const unsigned long long w = grid_exclusive_scan(sm, tile, n_tiles, local, status, out_count, scan_epoch);
+    const unsigned long long tile_base = sm.tile_base;
+    uint32_t                 at        = (uint32_t)(w - tile_base);
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++)
+        if (ok[j])
+        {
+            double* o = reinterpret_cast<double*>(s_rec + at * 18);
+            at++;
+            if (line_mode)  // point_line_pair_t: TLine3D {pBase, director}, TPoint3D pt_local (Pairings.h:61-73; Matcher_Point2Line.cpp:152)
+            {
+                o[0] = pc[j].centroid[0], o[1] = pc[j].centroid[1], o[2] = pc[j].centroid[2];
+                o[3] = pc[j].coefs[0], o[4] = pc[j].coefs[1], o[5] = pc[j].coefs[2];
+                o[6] = px[j], o[7] = py[j], o[8] = pz[j];
+            }
+            else  // point_plane_pair_t: plane_patch_t {TPlane coefs[4], TPoint3D centroid}, TPoint3Df pt_local, pad
+            {
+                o[0] = pc[j].coefs[0], o[1] = pc[j].coefs[1], o[2] = pc[j].coefs[2], o[3] = pc[j].coefs[3];
+                o[4] = pc[j].centroid[0], o[5] = pc[j].centroid[1], o[6] = pc[j].centroid[2];
+                uint32_t* t = reinterpret_cast<uint32_t*>(o + 7);
+                t[0] = __float_as_uint(px[j]), t[1] = __float_as_uint(py[j]);
+                t[2] = __float_as_uint(pz[j]), t[3] = 0u;
+            }
+        }
     __syncthreads();
     const unsigned long long room  = capacity > tile_base ? capacity - tile_base : 0ull;
     const uint32_t           n_rec = (uint32_t)min((unsigned long long)sm.tile_total, room);
@@ -2301,9 +2358,9 @@ int run_match_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
         fs.packet        = ctx->d_packet.as<double>() + 4 * MP2P_B200_PACKET_DOUBLES;
         ctx->last2p.sums = fs.packet;
     }
-    k_compact_pt2pt<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, c, dlx, dly, dlz, d_gbits,
-                                                               claim, cand, cand_xyz, sv.bbox, sv.bbox_next, status,
-                                                               sv.tile_counter, d_out, sv.count, fs);
+    k_compact_pt2pt<<<compact_tiles_2p(n_slots), kScanThreads, 0, st>>>(map->view, c, dlx, dly, dlz, d_gbits,
+                                                                       claim, cand, cand_xyz, sv.bbox, sv.bbox_next, status,
+                                                                       sv.tile_counter, d_out, sv.count, fs);
     prof_end(ctx, 1);
     count_launch(ctx);
     if (keep_on_device)  // fused iteration: the caller enqueues the solver and synchronises once
@@ -2501,7 +2558,7 @@ int run_shard_resolve_pt2pt(mp2p_b200_ctx* ctx, mp2p_b200_map* map, uint64_t n_l
         fs.packet = d_horn_sums;
     }
     prof_begin(ctx, 1);
-    k_compact_pt2pt<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(
+    k_compact_pt2pt<<<compact_tiles_2p(n_slots), kScanThreads, 0, st>>>(
         map->view, c, ctx->cur_lx, ctx->cur_ly, ctx->cur_lz, d_gbits, claim,
         d_records + (uint64_t)shard_rank * rec_words, K == 1 ? ctx->d_candxyz.as<float4>() : nullptr, sv.bbox,
         sv.bbox_next, status, sv.tile_counter, d_out, sv.count, fs);
@@ -2630,7 +2687,7 @@ int run_match_pt2pl(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const float* lx, con
         }
     }
     prof_begin(ctx, 1);
-    k_compact_pt2pl<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, (uint32_t)n_local, gate_eps,
+    k_compact_pt2pl<<<compact_tiles_2l(n_local), kScanThreads, 0, st>>>(map->view, (uint32_t)n_local, gate_eps,
                                                                cap, dlx, dly, dlz, plc, okf, sv.bbox, sv.bbox_next,
                                                                status, sv.tile_counter, d_out, sv.count,
                                                                ctx->scan_epoch, line ? 1 : 0, out_host, count_host);
@@ -3195,7 +3252,6 @@ int run_adaptive_emit(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const mp2p_b200_ad
     // ---- point-to-plane pairings (ascending local index)
     mp2p_b200_pair_pt2pl* d_out2l = out2l;
     const uint64_t        capl    = std::min<uint64_t>(cap2l, n_local);
-    const uint64_t        n_tiles = (n_local + kScanTile - 1) / kScanTile;
     if (prm->enableDetectPlanes)
     {
         if (!out_on_device)
@@ -3203,7 +3259,7 @@ int run_adaptive_emit(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const mp2p_b200_ad
             MP2P_TRY(ctx->d_out2l.ensure(std::max<uint64_t>(capl, 1) * sizeof(mp2p_b200_pair_pt2pl)));
             d_out2l = ctx->d_out2l.as<mp2p_b200_pair_pt2pl>();
         }
-        k_compact_pt2pl<<<(uint32_t)n_tiles, kScanThreads, 0, st>>>(map->view, (uint32_t)n_local, gate_eps, capl, ctx->cur_lx, ctx->cur_ly,
+        k_compact_pt2pl<<<compact_tiles_2l(n_local), kScanThreads, 0, st>>>(map->view, (uint32_t)n_local, gate_eps, capl, ctx->cur_lx, ctx->cur_ly,
                                                                    ctx->cur_lz, plc, okf, S.sv_bbox, S.sv_bbox_next, S.status,
                                                                    S.sv_tile_counter, d_out2l, S.sv_count, S.scan_epoch, 0, nullptr, nullptr);
         count_launch(ctx);
@@ -3228,7 +3284,7 @@ int run_adaptive_emit(mp2p_b200_ctx* ctx, mp2p_b200_map* map, const mp2p_b200_ad
     CompactArgs c{};
     c.n_local = (uint32_t)n_local, c.K = Kp, c.allowGlobal = 1, c.tag = 0;
     c.gate_eps = gate_eps, c.capacity = capp, c.scan_epoch = S.scan_epoch;
-    k_compact_pt2pt<<<(uint32_t)n_tiles2, kScanThreads, 0, st>>>(map->view, c, ctx->cur_lx, ctx->cur_ly, ctx->cur_lz, nullptr,
+    k_compact_pt2pt<<<compact_tiles_2p(n_slots), kScanThreads, 0, st>>>(map->view, c, ctx->cur_lx, ctx->cur_ly, ctx->cur_lz, nullptr,
                                                                 map->d_claim.as<unsigned long long>(), sel,
                                                                 K == 1 ? ctx->d_candxyz.as<float4>() : nullptr, S.sv_bbox, S.sv_bbox_next,
                                                                 ctx->d_scan2.as<unsigned long long>(), S.sv_tile_counter, d_out2p, count2,

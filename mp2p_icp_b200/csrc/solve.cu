@@ -570,7 +570,14 @@ int run_gn_coop_loop(mp2p_b200_ctx* ctx, const mp2p_b200_pair_pt2pt* d2p, uint64
     }
     const int cap = occ[dev][peer ? 1 : 0];
     if (cap <= 0) return 1;
-    const int     blocks = std::min(solve_grid(std::max(n2p, n2l)), cap);
+    // (the loop is bound by its grid barrier and the fold of the CTA partials, not by the pass over the records:
+    // $MP2P_GN_BLOCKS caps the grid for measurements)
+    static const int max_blocks = [] {
+        const char* e = getenv("MP2P_GN_BLOCKS");
+        return e ? atoi(e) : 0;
+    }();
+    int blocks = std::min(solve_grid(std::max(n2p, n2l)), cap);
+    if (max_blocks > 0) blocks = std::min(blocks, max_blocks);
     unsigned int* ticket;
     double*       partials;
     MP2P_TRY(solve_scratch(ctx, blocks, &ticket, &partials));

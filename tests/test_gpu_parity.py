@@ -15,6 +15,7 @@ from tests import icp_harness
 pytestmark = pytest.mark.gpu
 DEG = np.pi / 180.0
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 POSE_TOL = 1e-5
 
 
@@ -86,6 +87,49 @@ def test_knn_edge_cases(ctx):
     i0, d0, f0 = tree.knn(*xyz(Q), 4)
     i1, d1, f1 = gmap.knn(*xyz(Q), 4)
     assert np.array_equal(i0, i1) and np.array_equal(d0, d1) and np.array_equal(f0, f1)
+
+
+_VARIANT_CHILD = r"""
+import sys, hashlib, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import fixtures as fx, mp2p_icp_b200 as b200
+M = fx.make_street_scene(n_map=400_000, length=60.0)
+S = fx.make_lidar_scan((30.0, 0.4, 0.0), seed=3, length=60.0, max_range=28.0)
+pose = fx.pose_xyzypr(30.1, 0.3, 0.05, 0.02, 0.003, -0.002)
+ctx = b200.Context(0); gmap = b200.Map(ctx, M[:, 0].copy(), M[:, 1].copy(), M[:, 2].copy())
+l = [S[:, 0].copy(), S[:, 1].copy(), S[:, 2].copy()]
+h = hashlib.blake2b(digest_size=8)
+p2l, _ = gmap.match_pt2pl(*l, pose, b200.Pt2PlParams(distanceThreshold=0.5, searchRadius=1.0, knn=8, minimumPlanePoints=5, planeEigenThreshold=0.01))
+h.update(p2l.tobytes())
+p2p, _ = gmap.match_pt2pt(*l, pose, b200.Pt2PtParams(threshold=0.6, thresholdAngularDeg=0.0, pairingsPerPoint=3))
+h.update(p2p.tobytes())
+G = (S.astype(np.float64) @ pose[:, :3].T + pose[:, 3]).astype(np.float32)
+i, d, f = gmap.knn(G[:, 0].copy(), G[:, 1].copy(), G[:, 2].copy(), 20, 4.0)
+mask = np.arange(20)[None, :] < f[:, None]
+h.update(f.tobytes()); h.update(i[mask].tobytes()); h.update(d[mask].tobytes())
+print("HASH", h.hexdigest(), len(S), len(p2l), len(p2p))
+"""
+
+
+@pytest.mark.parametrize("env", [{"MP2P_KNN_THREAD": "1"}, {"MP2P_KNN_THREAD": "1", "MP2P_KNN_DEFER_PROBES": "6", "MP2P_KNN_DEFER_CANDS": "40"}, {"MP2P_INDEX_BOX": "1"}, {"MP2P_INDEX_BOX": "1", "MP2P_KNN_THREAD": "1"}, {"MP2P_KNN_V1": "1"}])
+def test_search_variants_return_the_same_keys(env):
+    """The A/B variants of the k > 1 search (one thread per query, with and without most queries handed over to
+    the warp-per-query pass; tight voxel boxes; the round-1 search) are all exact searches over the same (d2, index)
+    order: on a street scene with off-surface queries the pt2pl records (k = 8), the pt2pt records with three
+    pairings per point (first claims) and a raw 20-NN must be byte-identical to the default's. The knobs are
+    read once per process, hence the child processes."""
+    import subprocess, sys
+
+    def run(extra):
+        e = dict(os.environ, **extra)
+        out = subprocess.run([sys.executable, "-c", _VARIANT_CHILD, ROOT], env=e, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return [l for l in out.stdout.splitlines() if l.startswith("HASH")][-1]
+
+    base = run({"MP2P_KNN_THREAD": "0"})
+    n_scan, n_2l, n_2p = (int(v) for v in base.split()[-3:])
+    assert n_scan > 100_000 and n_2l > 20_000 and n_2p > 50_000
+    assert run(env) == base
 
 
 # --------------------------------------------------------------------------- pt2pt matcher (a3,a4)
