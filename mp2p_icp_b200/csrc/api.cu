@@ -11,10 +11,41 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include "common.cuh"
+#include "hostcopy.hpp"
 #include "host_math.hpp"
 
 namespace mp2p
 {
+bool copy_wants_helpers(mp2p_b200_ctx* ctx, const void* host, size_t bytes)
+{
+    if (bytes < PageableCopier::kMinBytes || !host) return false;
+    if (!ctx->copier) ctx->copier = new PageableCopier(ctx->device);
+    return ctx->copier->enabled() && PageableCopier::pageable(host);
+}
+int copy_to_host_sync(mp2p_b200_ctx* ctx, void* dst, const void* src_dev, size_t bytes, cudaStream_t st)
+{
+    if (!bytes) return 0;
+    if (copy_wants_helpers(ctx, dst, bytes))
+    {
+        MP2P_CUDA_TRY(ctx->copier->to_host(dst, src_dev, bytes, st));
+        return 0;
+    }
+    MP2P_CUDA_TRY(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+    MP2P_CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+int copy_to_device(mp2p_b200_ctx* ctx, void* dst_dev, const void* src, size_t bytes, cudaStream_t st)
+{
+    if (!bytes) return 0;
+    if (copy_wants_helpers(ctx, src, bytes))
+    {
+        MP2P_CUDA_TRY(ctx->copier->to_device(dst_dev, src, bytes, st));
+        return 0;
+    }
+    MP2P_CUDA_TRY(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
 static thread_local char g_err[512] = "";
 void                     set_error(const char* fmt, ...)
 {
@@ -138,7 +169,7 @@ int stage_pairs(mp2p_b200_ctx* ctx, DevBuf& buf, const Rec* pairs, uint64_t n, i
         return 0;
     }
     MP2P_TRY(buf.ensure(n * sizeof(Rec)));
-    MP2P_CUDA_TRY(cudaMemcpyAsync(buf.p, pairs, n * sizeof(Rec), cudaMemcpyHostToDevice, ctx->stream));
+    MP2P_TRY(copy_to_device(ctx, buf.p, pairs, n * sizeof(Rec), ctx->stream));
     *d_out = buf.as<Rec>();
     return 0;
 }
@@ -170,7 +201,7 @@ int upload_and_compare(mp2p_b200_ctx* ctx, DevBuf& buf, const Rec* pairs, uint64
     *same = false;
     const mp2p_b200_ctx::LastMatch& lm = sizeof(Rec) == sizeof(mp2p_b200_pair_pt2pt) ? ctx->last2p : ctx->last2l;
     MP2P_TRY(buf.ensure(n * sizeof(Rec) + 16));
-    MP2P_CUDA_TRY(cudaMemcpyAsync(buf.p, pairs, n * sizeof(Rec), cudaMemcpyHostToDevice, ctx->stream));
+    MP2P_TRY(copy_to_device(ctx, buf.p, pairs, n * sizeof(Rec), ctx->stream));
     *d_out = buf.as<Rec>();
     if (!lm.valid || lm.n != n || !lm.dev || (reinterpret_cast<uintptr_t>(lm.dev) & 15u)) return 0;
     uint32_t* h_flag = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->h_pinned) + 4032);
@@ -364,6 +395,8 @@ extern "C"
                           &c->d_pose, &c->d_weights, &c->d_outlier, &c->d_conv, &c->d_fd_small, &c->d_fd_keys, &c->d_fd_vals, &c->d_fd_flags,
                           &c->d_fd_rs, &c->d_fd_in, &c->d_fd_out})
             b->release();
+        delete c->copier;
+        c->copier = nullptr;
         if (c->h_pinned) cudaFreeHost(c->h_pinned);
         if (c->h_mapped) cudaFreeHost(c->h_mapped);
         if (c->copy_stream) cudaStreamSynchronize(c->copy_stream), cudaStreamDestroy(c->copy_stream);

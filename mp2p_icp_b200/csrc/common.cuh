@@ -69,6 +69,8 @@ struct GridView
     float            level_occupancy[kMaxLevels];  // mean points per occupied voxel, per table
 };
 
+class PageableCopier;
+
 struct DevBuf
 {
     void*  p     = nullptr;
@@ -229,6 +231,7 @@ struct mp2p_b200_ctx
     mp2p::DevBuf d_fd_small, d_fd_keys, d_fd_vals, d_fd_flags, d_fd_rs, d_fd_in, d_fd_out;
     // pinned host scratch
     void* h_pinned = nullptr;  // 4 KiB: counts, packets, poses
+    mp2p::PageableCopier* copier = nullptr;  // pageable host buffers: bounce buffer + helper threads (hostcopy.hpp), made on first use
     void* h_pinned_dev = nullptr;  // its device alias (kernels that hand a count to the host themselves)
     // 1 KiB of MAPPED pinned memory a kernel writes results into directly (host view / device view)
     double* h_mapped = nullptr;
@@ -353,6 +356,14 @@ int run_knn(mp2p_b200_ctx* ctx, const mp2p_b200_map* map, const float* qx, const
             const float* qz, uint64_t nq, uint32_t k, float radius2, uint32_t* out_idx,
             float* out_d2, int32_t* out_found);
 // filter.cu — FilterDecimateVoxels over device arrays; synchronises, *h_count = points produced
+// Host <-> device copies of caller buffers: pinned memory and small transfers go straight to cudaMemcpyAsync,
+// large PAGEABLE buffers through the context's bounce buffer and helper threads (hostcopy.hpp).
+// copy_to_host_sync = cudaMemcpyAsync(DeviceToHost, st) + cudaStreamSynchronize(st);
+// copy_to_device    = cudaMemcpyAsync(HostToDevice, st): the source may be reused when it returns.
+int copy_to_host_sync(mp2p_b200_ctx* ctx, void* dst, const void* src_dev, size_t bytes, cudaStream_t st);
+int copy_to_device(mp2p_b200_ctx* ctx, void* dst_dev, const void* src, size_t bytes, cudaStream_t st);
+bool copy_wants_helpers(mp2p_b200_ctx* ctx, const void* host, size_t bytes);
+
 int run_decimate_voxels(mp2p_b200_ctx* ctx, const float* dx, const float* dy, const float* dz, uint64_t n,
                         const mp2p_b200_decimate_params* prm, float* d_ox, float* d_oy, float* d_oz, long long* d_osrc,
                         uint64_t capacity, uint64_t* h_count);

@@ -1889,9 +1889,9 @@ int stage_local(mp2p_b200_ctx* ctx, const float* lx, const float* ly, const floa
             return 0;
         }
     }
-    MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_lx.p, lx, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_ly.p, ly, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    MP2P_CUDA_TRY(cudaMemcpyAsync(ctx->d_lz.p, lz, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MP2P_TRY(copy_to_device(ctx, ctx->d_lx.p, lx, bytes, ctx->stream));
+    MP2P_TRY(copy_to_device(ctx, ctx->d_ly.p, ly, bytes, ctx->stream));
+    MP2P_TRY(copy_to_device(ctx, ctx->d_lz.p, lz, bytes, ctx->stream));
     ctx->cur_lx = ctx->cur_qx = ctx->d_lx.as<float>(), ctx->cur_ly = ctx->cur_qy = ctx->d_ly.as<float>();
     ctx->cur_lz = ctx->cur_qz = ctx->d_lz.as<float>();
     ctx->cur_tma_ok = true;
@@ -1905,7 +1905,7 @@ int upload_bits(mp2p_b200_ctx* ctx, DevBuf& buf, const uint32_t* bits, uint64_t 
     if (!bits) return 0;
     const size_t bytes = ((n_bits + 31) / 32) * 4;
     MP2P_TRY(buf.ensure(bytes));
-    MP2P_CUDA_TRY(cudaMemcpyAsync(buf.p, bits, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MP2P_TRY(copy_to_device(ctx, buf.p, bits, bytes, ctx->stream));
     *d_out = buf.as<uint32_t>();
     return 0;
 }
@@ -2037,9 +2037,18 @@ int fetch_results(mp2p_b200_ctx* ctx, const unsigned long long* d_count, const R
         MP2P_CUDA_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
         MP2P_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
         MP2P_CUDA_TRY(cudaMemcpyAsync(h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
-        MP2P_CUDA_TRY(cudaMemcpyAsync(out, d_pairs, spec * sizeof(Rec), cudaMemcpyDeviceToHost, ctx->copy_stream));
-        MP2P_TRY(enqueue_speculation(ctx, d_pairs, d_count, capacity, pose, sums));
-        MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+        if (copy_wants_helpers(ctx, out, spec * sizeof(Rec)))
+        {
+            // pageable output: the solver is enqueued first, then this thread and the helpers drain the bounce buffer
+            MP2P_TRY(enqueue_speculation(ctx, d_pairs, d_count, capacity, pose, sums));
+            MP2P_TRY(copy_to_host_sync(ctx, out, d_pairs, spec * sizeof(Rec), ctx->copy_stream));
+        }
+        else
+        {
+            MP2P_CUDA_TRY(cudaMemcpyAsync(out, d_pairs, spec * sizeof(Rec), cudaMemcpyDeviceToHost, ctx->copy_stream));
+            MP2P_TRY(enqueue_speculation(ctx, d_pairs, d_count, capacity, pose, sums));
+            MP2P_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+        }
     }
     else
     {
@@ -2047,7 +2056,10 @@ int fetch_results(mp2p_b200_ctx* ctx, const unsigned long long* d_count, const R
         if (!out_on_device && capacity)
         {
             spec = *hint == ~0ull ? capacity : std::min<uint64_t>(capacity, *hint + *hint / 8 + 1024);
-            MP2P_CUDA_TRY(cudaMemcpyAsync(out, d_pairs, spec * sizeof(Rec), cudaMemcpyDeviceToHost, ctx->stream));
+            if (copy_wants_helpers(ctx, out, spec * sizeof(Rec)))
+                MP2P_TRY(copy_to_host_sync(ctx, out, d_pairs, spec * sizeof(Rec), ctx->stream));
+            else
+                MP2P_CUDA_TRY(cudaMemcpyAsync(out, d_pairs, spec * sizeof(Rec), cudaMemcpyDeviceToHost, ctx->stream));
         }
     }
     if (!zero_copy)

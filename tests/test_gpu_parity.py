@@ -111,13 +111,15 @@ print("HASH", h.hexdigest(), len(S), len(p2l), len(p2p))
 """
 
 
-@pytest.mark.parametrize("env", [{"MP2P_KNN_THREAD": "1"}, {"MP2P_KNN_THREAD": "1", "MP2P_KNN_DEFER_PROBES": "6", "MP2P_KNN_DEFER_CANDS": "40"}, {"MP2P_INDEX_BOX": "1"}, {"MP2P_INDEX_BOX": "1", "MP2P_KNN_THREAD": "1"}, {"MP2P_KNN_V1": "1"}])
+@pytest.mark.parametrize("env", [{"MP2P_KNN_THREAD": "1"}, {"MP2P_KNN_THREAD": "1", "MP2P_KNN_DEFER_PROBES": "6", "MP2P_KNN_DEFER_CANDS": "40"}, {"MP2P_INDEX_BOX": "1"}, {"MP2P_INDEX_BOX": "1", "MP2P_KNN_THREAD": "1"}, {"MP2P_KNN_V1": "1"},
+                                 {"MP2P_HOST_COPY_THREADS": "0"}, {"MP2P_HOST_COPY_THREADS": "3"}])
 def test_search_variants_return_the_same_keys(env):
     """The A/B variants of the k > 1 search (one thread per query, with and without most queries handed over to
     the warp-per-query pass; tight voxel boxes; the round-1 search) are all exact searches over the same (d2, index)
     order: on a street scene with off-surface queries the pt2pl records (k = 8), the pt2pt records with three
-    pairings per point (first claims) and a raw 20-NN must be byte-identical to the default's. The knobs are
-    read once per process, hence the child processes."""
+    pairings per point (first claims) and a raw 20-NN must be byte-identical to the default's. The last two
+    settings move the (pageable) record arrays with plain cudaMemcpyAsync / with three helper threads instead of
+    the default bounce-buffer path (hostcopy.hpp). The knobs are read once per process, hence the child processes."""
     import subprocess, sys
 
     def run(extra):
