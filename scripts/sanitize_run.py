@@ -40,5 +40,15 @@ if len(ln) >= 3:
     ok, T7, it7 = ctx.solve_gauss_newton_ex(None, q[:500], ln[:2000], gn, g2, w_pt2ln=0.5)
 a1, l1, _, _ = smap.match_adaptive(*xyz(scan), g2, b200.AdaptiveParams(enableDetectPlanes=True, absoluteMaxSearchDistance=1.0, planeMinimumDistance=50.0))
 a2, l2, _, _ = gmap.match_adaptive(*xyz(L), pose, b200.AdaptiveParams(absoluteMaxSearchDistance=1.5, maxPt2PtCorrespondences=3))
-print("extra:", len(ln), len(a1), len(l1), len(a2))
+# round 2: voxel decimation filter, covariance(), library-side layer cache, pageable records >= 256 KB (hostcopy.hpp)
+dv, src = ctx.decimate_voxels(*xyz(scan), 0.5, method="VoxelAverage")
+dx = dv
+cov, hes, pd = ctx.covariance(p1, None, None, np.zeros(6))
+cov = np.asarray(cov)
+cm, _ = ctx.cached_map(*xyz(S))
+q2, _ = cm.match_pt2pl(*xyz(scan), g2, b200.Pt2PlParams(**kw))
+assert q2.tobytes() == q.tobytes()
+big, _ = gmap.match_pt2pt(*xyz(M[:30_000]), fx.pose_xyzypr(0, 0, 0, 0, 0, 0), b200.Pt2PtParams(threshold=0.5))  # 1 MB of records
+ok, T8 = ctx.solve_horn(big)
+print("extra:", len(ln), len(a1), len(l1), len(a2), len(dx), cov.shape, len(big))
 print("sanitize run OK:", len(p1), len(p3), len(pi), len(q), ctx.launch_count, "launches")
