@@ -14,7 +14,9 @@
 // small transfers. The workers sleep on a condition variable between transfers (no spinning while idle).
 #pragma once
 #include <atomic>
+#include <algorithm>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
